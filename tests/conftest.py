@@ -1,0 +1,54 @@
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def read_fasta(path):
+    """Minimal FASTA reader -> list of (name, bytes)."""
+    opener = gzip.open if path.endswith(".gz") else open
+    recs, name, chunks = [], None, []
+    with opener(path, "rb") as fh:
+        for line in fh:
+            line = line.rstrip(b"\r\n")
+            if line.startswith(b">"):
+                if name is not None:
+                    recs.append((name, b"".join(chunks)))
+                name, chunks = line[1:].decode(), []
+            elif line:
+                chunks.append(line)
+    if name is not None:
+        recs.append((name, b"".join(chunks)))
+    return recs
+
+
+@pytest.fixture(scope="session")
+def golden():
+    arrays = np.load(os.path.join(GOLDEN, "golden_arrays.npz"))
+    with open(os.path.join(GOLDEN, "golden_meta.json")) as fh:
+        meta = json.load(fh)
+    return {"arrays": arrays, "meta": meta}
+
+
+@pytest.fixture(scope="session")
+def ecoli_seq():
+    recs = read_fasta(os.path.join(GOLDEN, "ecoli_k12.fna.gz"))
+    assert len(recs) == 1
+    return recs[0][1]
+
+
+@pytest.fixture(scope="session")
+def s10_records():
+    return read_fasta(os.path.join(GOLDEN, "genome-s10.fa.gz"))
