@@ -1,0 +1,283 @@
+/*
+ * sourmash_b200.h -- C ABI of libsourmash_b200.so, the B200 (sm_100a) implementation of
+ * sourmash's two data-parallel hot paths (FracMinHash sketching, sorted-u64 intersection).
+ *
+ * The library is a drop-in for the subset of the reference's C ABI
+ * (/root/reference/include/sourmash.h, generated from src/core/src/ffi/ *.rs) that the
+ * Python object model binds for these paths, plus NEW batched entry points (smb_*) that
+ * replace the reference's per-pair / per-record Python loops.  Part 1 keeps the reference's
+ * names, argument order, ownership and error protocol; each group cites what it replaces.
+ * Everything is plain C: opaque handles, pointers and sizes, no torch / C++ types.
+ *
+ * Error protocol (reference: src/core/src/ffi/utils.rs:17-19,58-86,195-208; Python side
+ * src/sourmash/utils.py:65-78): no return codes.  A failing call stores (code, message) in a
+ * thread-local slot and returns a zeroed value; callers do
+ *     sourmash_err_clear(); r = f(...); if (sourmash_err_get_last_code()) -> raise.
+ * All hashing and set-intersection arithmetic runs on the GPU; if no CUDA device is usable
+ * the call fails with SOURMASH_ERROR_CODE_CUDA (there is no CPU fallback).
+ */
+#ifndef SOURMASH_B200_H_INCLUDED
+#define SOURMASH_B200_H_INCLUDED
+
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================== */
+/* Part 1: reference-compatible ABI (same symbols as include/sourmash.h)                  */
+/* ===================================================================================== */
+
+/* include/sourmash.h:11-17 */
+enum { /* HashFunctions */
+  HASH_FUNCTIONS_MURMUR64_DNA = 1,
+  HASH_FUNCTIONS_MURMUR64_PROTEIN = 2,
+  HASH_FUNCTIONS_MURMUR64_DAYHOFF = 3,
+  HASH_FUNCTIONS_MURMUR64_HP = 4,
+};
+typedef uint32_t HashFunctions;
+
+/* include/sourmash.h:19-53 (numeric values from src/core/src/errors.rs:101-141).
+ * SOURMASH_ERROR_CODE_CUDA is new: raised when the GPU path cannot run. */
+enum { /* SourmashErrorCode */
+  SOURMASH_ERROR_CODE_NO_ERROR = 0,
+  SOURMASH_ERROR_CODE_PANIC = 1,
+  SOURMASH_ERROR_CODE_INTERNAL = 2,
+  SOURMASH_ERROR_CODE_MSG = 3,
+  SOURMASH_ERROR_CODE_UNKNOWN = 4,
+  SOURMASH_ERROR_CODE_MISMATCH_K_SIZES = 101,
+  SOURMASH_ERROR_CODE_MISMATCH_DNA_PROT = 102,
+  SOURMASH_ERROR_CODE_MISMATCH_SCALED = 103,
+  SOURMASH_ERROR_CODE_MISMATCH_SEED = 104,
+  SOURMASH_ERROR_CODE_MISMATCH_SIGNATURE_TYPE = 105,
+  SOURMASH_ERROR_CODE_NON_EMPTY_MIN_HASH = 106,
+  SOURMASH_ERROR_CODE_MISMATCH_NUM = 107,
+  SOURMASH_ERROR_CODE_NEEDS_ABUNDANCE_TRACKING = 108,
+  SOURMASH_ERROR_CODE_CANNOT_UPSAMPLE_SCALED = 109,
+  SOURMASH_ERROR_CODE_NO_MIN_HASH_FOUND = 110,
+  SOURMASH_ERROR_CODE_EMPTY_SIGNATURE = 111,
+  SOURMASH_ERROR_CODE_MULTIPLE_SKETCHES_FOUND = 112,
+  SOURMASH_ERROR_CODE_INVALID_DNA = 1101,
+  SOURMASH_ERROR_CODE_INVALID_PROT = 1102,
+  SOURMASH_ERROR_CODE_INVALID_CODON_LENGTH = 1103,
+  SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION = 1104,
+  SOURMASH_ERROR_CODE_READ_DATA = 1201,
+  SOURMASH_ERROR_CODE_STORAGE = 1202,
+  SOURMASH_ERROR_CODE_HLL_PRECISION_BOUNDS = 1301,
+  SOURMASH_ERROR_CODE_ANI_ESTIMATION_ERROR = 1401,
+  SOURMASH_ERROR_CODE_IO = 100001,
+  SOURMASH_ERROR_CODE_UTF8_ERROR = 100002,
+  SOURMASH_ERROR_CODE_PARSE_INT = 100003,
+  SOURMASH_ERROR_CODE_SERDE_ERROR = 100004,
+  SOURMASH_ERROR_CODE_NIFFLER_ERROR = 100005,
+  SOURMASH_ERROR_CODE_CSV_ERROR = 100006,
+  SOURMASH_ERROR_CODE_ROCKS_DB_ERROR = 100007,
+  SOURMASH_ERROR_CODE_CUDA = 200001,
+};
+typedef uint32_t SourmashErrorCode;
+
+typedef struct SourmashComputeParameters SourmashComputeParameters;
+typedef struct SourmashKmerMinHash SourmashKmerMinHash;
+typedef struct SourmashSignature SourmashSignature;
+
+/* include/sourmash.h:75-88: string returned by value; free with sourmash_str_free if owned */
+typedef struct {
+  char *data;
+  uintptr_t len;
+  bool owned;
+} SourmashStr;
+
+/* --- errors / init / strings: src/core/src/ffi/utils.rs:95-165,211-320 ------------------ */
+void sourmash_init(void);
+void sourmash_err_clear(void);
+SourmashErrorCode sourmash_err_get_last_code(void);
+SourmashStr sourmash_err_get_last_message(void);
+SourmashStr sourmash_err_get_backtrace(void);
+void sourmash_str_free(SourmashStr *s);
+SourmashStr sourmash_str_from_cstr(const char *s);
+
+/* --- hash primitive: src/core/src/ffi/mod.rs:22-31 -> lib.rs:57-59 ---------------------- */
+uint64_t hash_murmur(const char *kmer, uint64_t seed);
+
+/* --- KmerMinHash: src/core/src/ffi/minhash.rs:18-483 (include/sourmash.h:169-273) -------- */
+SourmashKmerMinHash *kmerminhash_new(uint64_t scaled, uint32_t k, HashFunctions hash_function,
+                                     uint64_t seed, bool track_abundance, uint32_t n);
+void kmerminhash_free(SourmashKmerMinHash *ptr);
+void kmerminhash_slice_free(uint64_t *ptr, uintptr_t insize);
+void kmerminhash_add_sequence(SourmashKmerMinHash *ptr, const char *sequence, bool force);
+void kmerminhash_add_protein(SourmashKmerMinHash *ptr, const char *sequence);
+const uint64_t *kmerminhash_seq_to_hashes(SourmashKmerMinHash *ptr, const char *sequence,
+                                          uintptr_t insize, bool force, bool bad_kmers_as_zeroes,
+                                          bool is_protein, uintptr_t *size);
+void kmerminhash_clear(SourmashKmerMinHash *ptr);
+void kmerminhash_add_hash(SourmashKmerMinHash *ptr, uint64_t h);
+void kmerminhash_add_hash_with_abundance(SourmashKmerMinHash *ptr, uint64_t h, uint64_t abundance);
+void kmerminhash_add_word(SourmashKmerMinHash *ptr, const char *word);
+void kmerminhash_add_many(SourmashKmerMinHash *ptr, const uint64_t *hashes_ptr, uintptr_t insize);
+void kmerminhash_add_from(SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other);
+void kmerminhash_remove_hash(SourmashKmerMinHash *ptr, uint64_t h);
+void kmerminhash_remove_many(SourmashKmerMinHash *ptr, const uint64_t *hashes_ptr, uintptr_t insize);
+void kmerminhash_remove_from(SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other);
+const uint64_t *kmerminhash_get_mins(const SourmashKmerMinHash *ptr, uintptr_t *size);
+uintptr_t kmerminhash_get_mins_size(const SourmashKmerMinHash *ptr);
+const uint64_t *kmerminhash_get_abunds(SourmashKmerMinHash *ptr, uintptr_t *size);
+void kmerminhash_set_abundances(SourmashKmerMinHash *ptr, const uint64_t *hashes_ptr,
+                                const uint64_t *abunds_ptr, uintptr_t insize, bool clear);
+SourmashStr kmerminhash_md5sum(const SourmashKmerMinHash *ptr);
+bool kmerminhash_is_protein(const SourmashKmerMinHash *ptr);
+bool kmerminhash_dayhoff(const SourmashKmerMinHash *ptr);
+bool kmerminhash_hp(const SourmashKmerMinHash *ptr);
+uint64_t kmerminhash_seed(const SourmashKmerMinHash *ptr);
+bool kmerminhash_track_abundance(const SourmashKmerMinHash *ptr);
+void kmerminhash_disable_abundance(SourmashKmerMinHash *ptr);
+void kmerminhash_enable_abundance(SourmashKmerMinHash *ptr);
+uint32_t kmerminhash_num(const SourmashKmerMinHash *ptr);
+uint32_t kmerminhash_ksize(const SourmashKmerMinHash *ptr);
+uint64_t kmerminhash_max_hash(const SourmashKmerMinHash *ptr);
+HashFunctions kmerminhash_hash_function(const SourmashKmerMinHash *ptr);
+void kmerminhash_hash_function_set(SourmashKmerMinHash *ptr, HashFunctions hash_function);
+void kmerminhash_merge(SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other);
+bool kmerminhash_is_compatible(const SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other);
+uint64_t kmerminhash_count_common(const SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other,
+                                  bool downsample);
+SourmashKmerMinHash *kmerminhash_intersection(const SourmashKmerMinHash *ptr,
+                                              const SourmashKmerMinHash *other);
+uint64_t kmerminhash_intersection_union_size(const SourmashKmerMinHash *ptr,
+                                             const SourmashKmerMinHash *other, uint64_t *union_size);
+double kmerminhash_jaccard(const SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other);
+double kmerminhash_similarity(const SourmashKmerMinHash *ptr, const SourmashKmerMinHash *other,
+                              bool ignore_abundance, bool downsample);
+double kmerminhash_angular_similarity(const SourmashKmerMinHash *ptr,
+                                      const SourmashKmerMinHash *other);
+
+/* --- Signature (subset): src/core/src/ffi/signature.rs:24-217 (include/sourmash.h:364-396) */
+SourmashSignature *signature_new(void);
+void signature_free(SourmashSignature *ptr);
+SourmashSignature *signature_from_params(const SourmashComputeParameters *ptr);
+uintptr_t signature_len(const SourmashSignature *ptr);
+bool signature_eq(const SourmashSignature *ptr, const SourmashSignature *other);
+void signature_add_sequence(SourmashSignature *ptr, const char *sequence, bool force);
+void signature_add_protein(SourmashSignature *ptr, const char *sequence);
+SourmashKmerMinHash *signature_first_mh(const SourmashSignature *ptr);
+SourmashKmerMinHash **signature_get_mhs(const SourmashSignature *ptr, uintptr_t *size);
+void signature_set_mh(SourmashSignature *ptr, const SourmashKmerMinHash *other);
+void signature_push_mh(SourmashSignature *ptr, const SourmashKmerMinHash *other);
+SourmashStr signature_get_name(const SourmashSignature *ptr);
+SourmashStr signature_get_filename(const SourmashSignature *ptr);
+SourmashStr signature_get_license(const SourmashSignature *ptr);
+void signature_set_name(SourmashSignature *ptr, const char *name);
+void signature_set_filename(SourmashSignature *ptr, const char *name);
+
+/* --- ComputeParameters: src/core/src/ffi/cmd/compute.rs:14-170 (include/sourmash.h:89-131) */
+SourmashComputeParameters *computeparams_new(void);
+void computeparams_free(SourmashComputeParameters *ptr);
+const uint32_t *computeparams_ksizes(const SourmashComputeParameters *ptr, uintptr_t *size);
+void computeparams_ksizes_free(uint32_t *ptr, uintptr_t insize);
+void computeparams_set_ksizes(SourmashComputeParameters *ptr, const uint32_t *ksizes_ptr,
+                              uintptr_t insize);
+bool computeparams_dna(const SourmashComputeParameters *ptr);
+bool computeparams_protein(const SourmashComputeParameters *ptr);
+bool computeparams_dayhoff(const SourmashComputeParameters *ptr);
+bool computeparams_hp(const SourmashComputeParameters *ptr);
+bool computeparams_track_abundance(const SourmashComputeParameters *ptr);
+uint32_t computeparams_num_hashes(const SourmashComputeParameters *ptr);
+uint64_t computeparams_scaled(const SourmashComputeParameters *ptr);
+uint64_t computeparams_seed(const SourmashComputeParameters *ptr);
+void computeparams_set_dna(SourmashComputeParameters *ptr, bool v);
+void computeparams_set_protein(SourmashComputeParameters *ptr, bool v);
+void computeparams_set_dayhoff(SourmashComputeParameters *ptr, bool v);
+void computeparams_set_hp(SourmashComputeParameters *ptr, bool v);
+void computeparams_set_track_abundance(SourmashComputeParameters *ptr, bool v);
+void computeparams_set_num_hashes(SourmashComputeParameters *ptr, uint32_t num);
+void computeparams_set_scaled(SourmashComputeParameters *ptr, uint64_t scaled);
+void computeparams_set_seed(SourmashComputeParameters *ptr, uint64_t new_seed);
+
+/* ===================================================================================== */
+/* Part 2: batched entry points (NEW; the reference iterates these in Python)             */
+/* ===================================================================================== */
+
+/* A set of sketches resident in HBM: CSR of sorted-unique u64 rows
+ * (offsets[n_rows+1], hashes[offsets[n_rows]]), optionally with abundances. */
+typedef struct SmbSketchSet SmbSketchSet;
+
+/* device / context ------------------------------------------------------------------- */
+int32_t smb_device_count(void);                 /* 0 if no usable CUDA device (no error set) */
+void smb_set_device(int32_t device);            /* per-thread; default = current CUDA device  */
+void smb_set_stream(void *cuda_stream);         /* run subsequent work on this cudaStream_t   */
+void smb_synchronize(void);
+uint64_t smb_kernel_launches(void);             /* number of kernels launched by this library */
+void *smb_alloc_pinned(uintptr_t nbytes);       /* page-locked host memory for e2e transfers  */
+void smb_free_pinned(void *ptr);
+uint64_t smb_max_hash_for_scaled(uint64_t scaled);   /* sketch/minhash.rs:21-27 */
+
+/* sketch sets ------------------------------------------------------------------------ */
+/* copy host CSR to the device (abunds may be NULL) */
+SmbSketchSet *smb_sketchset_from_host(const uint64_t *hashes, const uint64_t *offsets,
+                                      uintptr_t n_rows, const uint64_t *abunds);
+/* wrap device-resident CSR without copying (caller keeps the buffers alive);
+ * h_offsets is the same offsets array on the host */
+SmbSketchSet *smb_sketchset_from_device(const uint64_t *d_hashes, const uint64_t *d_offsets,
+                                        const uint64_t *h_offsets, uintptr_t n_rows);
+void smb_sketchset_free(SmbSketchSet *set);
+uintptr_t smb_sketchset_len(const SmbSketchSet *set);
+uint64_t smb_sketchset_total_hashes(const SmbSketchSet *set);
+bool smb_sketchset_has_abunds(const SmbSketchSet *set);
+void smb_sketchset_offsets(const SmbSketchSet *set, uint64_t *offsets_out);   /* n_rows+1 */
+void smb_sketchset_to_host(const SmbSketchSet *set, uint64_t *hashes_out, uint64_t *abunds_out);
+const uint64_t *smb_sketchset_device_hashes(const SmbSketchSet *set);
+const uint64_t *smb_sketchset_device_offsets(const SmbSketchSet *set);
+/* new set holding, for every row, the prefix h <= max_hash (downsample_scaled,
+ * sketch/minhash.rs:777-798) */
+SmbSketchSet *smb_sketchset_downsample(const SmbSketchSet *set, uint64_t max_hash);
+
+/* sketching (replaces the per-record loop command_sketch.py:662-789 ->
+ * signature_add_sequence -> SeqToHashes::next) --------------------------------------- */
+/* Input: n_seqs records concatenated in `seqs` (record r = bytes [seq_offsets[r],
+ * seq_offsets[r+1])); seq_to_sketch[r] (NULL = one sketch per record) says which output
+ * sketch a record feeds.  Output row (sketch s, ksizes[j]) is s * n_ksizes + j.
+ * scaled > 0: FracMinHash rows (h <= max_hash_for_scaled(scaled)); scaled == 0: bottom-`num`.
+ * Invalid (non-ACGT) bases skip the windows covering them (force=True semantics).
+ * n_kmers_out (nullable) receives the number of k-mer windows hashed. */
+SmbSketchSet *smb_sketch_sequences(const uint8_t *seqs, const uint64_t *seq_offsets,
+                                   uintptr_t n_seqs, const uint32_t *seq_to_sketch,
+                                   uintptr_t n_sketches, const uint32_t *ksizes,
+                                   uintptr_t n_ksizes, uint64_t scaled, uint32_t num, uint64_t seed,
+                                   bool track_abundance, uint64_t *n_kmers_out);
+/* Same with the bases already in HBM: d_bases holds the streams back to back, stream s at
+ * byte h_stream_offsets[s] (16-byte aligned) with length h_stream_lens[s]; records inside a
+ * stream separated by any non-ACGT byte.  One sketch per stream. */
+SmbSketchSet *smb_sketch_streams_dev(const uint8_t *d_bases, const uint64_t *h_stream_offsets,
+                                     const uint64_t *h_stream_lens, uintptr_t n_streams,
+                                     const uint32_t *ksizes, uintptr_t n_ksizes, uint64_t scaled,
+                                     uint32_t num, uint64_t seed, bool track_abundance,
+                                     uint64_t *n_kmers_out);
+
+/* intersection ------------------------------------------------------------------------ */
+/* common[i*n_b + j] = |A_i ∩ B_j| (b == NULL: b = a, only i<j computed, mirrored, diagonal
+ * = |A_i|).  num > 0 selects bottom-k semantics (minhash.rs:593-617) and fills usize_out
+ * (nullable) with |M|.  Output on the host. */
+void smb_pairwise_common(const SmbSketchSet *a, const SmbSketchSet *b, uint32_t num,
+                         uint32_t *common_out, uint32_t *usize_out);
+/* compare_all_pairs / compare_serial (src/sourmash/compare.py:14-64,328-358): float64
+ * (n, n) Jaccard matrix, ones on the diagonal.  out on the host (pinned or pageable). */
+void smb_compare_jaccard(const SmbSketchSet *set, uint32_t num, double *out);
+/* same, result left in HBM (d_out: n*n doubles) -- used to time the kernels alone */
+void smb_compare_jaccard_dev(const SmbSketchSet *set, uint32_t num, double *d_out);
+/* Index.find inner loop (src/sourmash/index/__init__.py:115-170): one query vs every row */
+void smb_one_vs_many(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
+                     uint32_t *common_out);
+/* gather (CounterGather + GatherDatabases, src/sourmash/index/__init__.py:777-909,
+ * src/sourmash/search.py:877-949): iterative min-set-cover.  Returns number of rounds;
+ * match_ids/isect_sizes receive, per round, the chosen row and |match ∩ remaining query|.
+ * threshold: stop when the best remaining overlap is < threshold (at least 1). */
+uintptr_t smb_gather(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
+                     uint32_t threshold, uint32_t *match_ids, uint32_t *isect_sizes,
+                     uintptr_t max_rounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOURMASH_B200_H_INCLUDED */

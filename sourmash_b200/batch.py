@@ -1,0 +1,223 @@
+"""Batched GPU entry points: the Python face of Part 2 of include/sourmash_b200.h.
+
+These replace the reference's per-record / per-pair Python loops
+(command_sketch.py:662-789, compare.py:14-187, index/__init__.py:115-170,777-909) with one
+C-ABI call per batch.  Arrays are numpy on the host side; ``SketchSet`` keeps the sketches
+resident in HBM between calls.
+"""
+import numpy as np
+
+from ._lowlevel import ffi, lib
+from .utils import rustcall
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a, ctype):
+    return ffi.cast(ctype, a.ctypes.data) if a is not None and a.size else ffi.cast(ctype, 0)
+
+
+def device_count():
+    return int(lib.smb_device_count())
+
+
+def set_device(i):
+    lib.smb_set_device(int(i))
+
+
+def set_stream(cuda_stream_handle):
+    """Run subsequent library work on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    lib.smb_set_stream(ffi.cast("void *", int(cuda_stream_handle)))
+
+
+def synchronize():
+    rustcall(lib.smb_synchronize)
+
+
+def kernel_launches():
+    return int(lib.smb_kernel_launches())
+
+
+def max_hash_for_scaled(scaled):
+    return int(lib.smb_max_hash_for_scaled(int(scaled)))
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (for end-to-end transfers)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._ptr = rustcall(lib.smb_alloc_pinned, max(nbytes, 16))
+        buf = ffi.buffer(self._ptr, max(nbytes, 16))
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p is not None:
+            self.array = None
+            lib.smb_free_pinned(p)
+
+
+def pinned_empty(shape, dtype):
+    return PinnedArray(shape, dtype)
+
+
+class SketchSet:
+    """CSR set of sorted-unique u64 sketches resident on the GPU."""
+
+    def __init__(self, ptr, keepalive=None):
+        self._ptr = ptr
+        self._keepalive = keepalive
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p:
+            lib.smb_sketchset_free(p)
+
+    @classmethod
+    def from_host(cls, hashes, offsets, abunds=None):
+        hashes, offsets = _u64(hashes), _u64(offsets)
+        ab = _u64(abunds) if abunds is not None else None
+        n = len(offsets) - 1
+        p = rustcall(lib.smb_sketchset_from_host, _ptr(hashes, "uint64_t *"), _ptr(offsets, "uint64_t *"),
+                     n, _ptr(ab, "uint64_t *") if ab is not None else ffi.NULL)
+        return cls(p)
+
+    @classmethod
+    def from_rows(cls, rows, abund_rows=None):
+        offsets = np.zeros(len(rows) + 1, dtype=np.uint64)
+        if len(rows):
+            offsets[1:] = np.cumsum([len(r) for r in rows])
+        hashes = np.concatenate([_u64(r) for r in rows]) if len(rows) else np.zeros(0, np.uint64)
+        ab = None
+        if abund_rows is not None:
+            ab = np.concatenate([_u64(r) for r in abund_rows]) if len(rows) else np.zeros(0, np.uint64)
+        return cls.from_host(hashes, offsets, ab)
+
+    @classmethod
+    def from_device(cls, d_hashes_ptr, d_offsets_ptr, h_offsets, keepalive=None):
+        h_offsets = _u64(h_offsets)
+        p = rustcall(lib.smb_sketchset_from_device, ffi.cast("uint64_t *", int(d_hashes_ptr)),
+                     ffi.cast("uint64_t *", int(d_offsets_ptr)), _ptr(h_offsets, "uint64_t *"),
+                     len(h_offsets) - 1)
+        return cls(p, keepalive=keepalive)
+
+    def __len__(self):
+        return int(lib.smb_sketchset_len(self._ptr))
+
+    @property
+    def total_hashes(self):
+        return int(lib.smb_sketchset_total_hashes(self._ptr))
+
+    @property
+    def has_abunds(self):
+        return bool(lib.smb_sketchset_has_abunds(self._ptr))
+
+    def offsets(self):
+        out = np.zeros(len(self) + 1, dtype=np.uint64)
+        lib.smb_sketchset_offsets(self._ptr, _ptr(out, "uint64_t *"))
+        return out
+
+    def sizes(self):
+        return np.diff(self.offsets().astype(np.int64))
+
+    def to_host(self, with_abunds=False):
+        off = self.offsets()
+        h = np.zeros(int(off[-1]), dtype=np.uint64)
+        ab = np.zeros(int(off[-1]), dtype=np.uint64) if (with_abunds and self.has_abunds) else None
+        rustcall(lib.smb_sketchset_to_host, self._ptr, _ptr(h, "uint64_t *"),
+                 _ptr(ab, "uint64_t *") if ab is not None else ffi.NULL)
+        return (h, off, ab) if with_abunds else (h, off)
+
+    def rows(self):
+        h, off = self.to_host()
+        return [h[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+    def downsample(self, max_hash):
+        return SketchSet(rustcall(lib.smb_sketchset_downsample, self._ptr, int(max_hash)))
+
+    def device_pointers(self):
+        return (int(ffi.cast("uintptr_t", lib.smb_sketchset_device_hashes(self._ptr))),
+                int(ffi.cast("uintptr_t", lib.smb_sketchset_device_offsets(self._ptr))))
+
+
+def sketch_sequences(seqs, seq_offsets, ksizes, scaled=0, num=0, seed=42, track_abundance=False,
+                     seq_to_sketch=None, n_sketches=None):
+    """Sketch a batch of records.  Returns (SketchSet, n_kmers); row = sketch * len(ksizes) + k_index."""
+    if isinstance(seqs, (bytes, bytearray)):
+        seqs = np.frombuffer(seqs, dtype=np.uint8)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_offsets = _u64(seq_offsets)
+    ks = np.ascontiguousarray(ksizes, dtype=np.uint32)
+    n_seqs = len(seq_offsets) - 1
+    s2s = None
+    if seq_to_sketch is not None:
+        s2s = np.ascontiguousarray(seq_to_sketch, dtype=np.uint32)
+        if n_sketches is None:
+            n_sketches = int(s2s.max()) + 1 if len(s2s) else 0
+    else:
+        n_sketches = n_seqs
+    nk = ffi.new("uint64_t *")
+    p = rustcall(lib.smb_sketch_sequences, _ptr(seqs, "uint8_t *"), _ptr(seq_offsets, "uint64_t *"), n_seqs,
+                 _ptr(s2s, "uint32_t *") if s2s is not None else ffi.NULL, n_sketches,
+                 _ptr(ks, "uint32_t *"), len(ks), int(scaled), int(num), int(seed), bool(track_abundance), nk)
+    return SketchSet(p), int(nk[0])
+
+
+def sketch_streams_device(d_bases_ptr, stream_offsets, stream_lens, ksizes, scaled=0, num=0, seed=42,
+                          track_abundance=False):
+    """Sketch streams that already live in HBM (device pointer as int)."""
+    so, sl = _u64(stream_offsets), _u64(stream_lens)
+    ks = np.ascontiguousarray(ksizes, dtype=np.uint32)
+    nk = ffi.new("uint64_t *")
+    p = rustcall(lib.smb_sketch_streams_dev, ffi.cast("uint8_t *", int(d_bases_ptr)), _ptr(so, "uint64_t *"),
+                 _ptr(sl, "uint64_t *"), len(so), _ptr(ks, "uint32_t *"), len(ks), int(scaled), int(num),
+                 int(seed), bool(track_abundance), nk)
+    return SketchSet(p), int(nk[0])
+
+
+def pairwise_common(a, b=None, num=0, want_usize=False):
+    """(n_a, n_b) uint32 matrix of |A_i ∩ B_j| (b None: all-vs-all of a)."""
+    na, nb = len(a), len(b) if b is not None else len(a)
+    out = np.zeros((na, nb), dtype=np.uint32)
+    us = np.zeros((na, nb), dtype=np.uint32) if (num and want_usize) else None
+    rustcall(lib.smb_pairwise_common, a._ptr, b._ptr if b is not None else ffi.NULL, int(num),
+             _ptr(out, "uint32_t *"), _ptr(us, "uint32_t *") if us is not None else ffi.NULL)
+    return (out, us) if want_usize else out
+
+
+def compare_jaccard(sset, num=0, out=None):
+    """float64 (n, n) Jaccard matrix with ones on the diagonal (compare_serial's contract)."""
+    n = len(sset)
+    if out is None:
+        out = np.empty((n, n), dtype=np.float64)
+    assert out.dtype == np.float64 and out.shape == (n, n) and out.flags.c_contiguous
+    rustcall(lib.smb_compare_jaccard, sset._ptr, int(num), _ptr(out, "double *"))
+    return out
+
+
+def compare_jaccard_device(sset, d_out_ptr, num=0):
+    rustcall(lib.smb_compare_jaccard_dev, sset._ptr, int(num), ffi.cast("double *", int(d_out_ptr)))
+
+
+def one_vs_many(query, db):
+    q = _u64(query)
+    out = np.zeros(len(db), dtype=np.uint32)
+    rustcall(lib.smb_one_vs_many, _ptr(q, "uint64_t *"), len(q), db._ptr, _ptr(out, "uint32_t *"))
+    return out
+
+
+def gather(query, db, threshold=1, max_rounds=None):
+    """Iterative min-set-cover; returns (match_ids, intersect_sizes) in pick order."""
+    q = _u64(query)
+    if max_rounds is None:
+        max_rounds = len(db)
+    ids = np.zeros(max(max_rounds, 1), dtype=np.uint32)
+    sizes = np.zeros(max(max_rounds, 1), dtype=np.uint32)
+    n = rustcall(lib.smb_gather, _ptr(q, "uint64_t *"), len(q), db._ptr, int(threshold),
+                 _ptr(ids, "uint32_t *"), _ptr(sizes, "uint32_t *"), int(max_rounds))
+    return ids[:n].copy(), sizes[:n].copy()

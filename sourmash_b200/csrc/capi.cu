@@ -1,0 +1,1374 @@
+// capi.cu -- the C ABI of libsourmash_b200.so (see include/sourmash_b200.h).
+//
+// Host-side object model (KmerMinHash, Signature, ComputeParameters: sorted containers,
+// parameter checks, error protocol) written in C++ against the behaviour of the reference's
+// Rust core, with every hashing / set-intersection computation dispatched to the sm_100a
+// kernels in sketch_kernels.cu / compare_kernels.cu.  There is no CPU implementation of
+// those computations in this library: without a CUDA device the calls fail with
+// SOURMASH_ERROR_CODE_CUDA.
+//
+// Reference behaviour cited per function (paths relative to /root/reference/).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sourmash_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "md5.h"
+
+namespace smb {
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+}  // namespace smb
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error protocol: src/core/src/ffi/utils.rs:17-19 (TLS LAST_ERROR), :195-208 (landingpad)
+// ------------------------------------------------------------------------------------------
+struct SmbError {
+    uint32_t code;
+    std::string msg;
+};
+thread_local bool t_has_error = false;
+thread_local SmbError t_error;
+
+void set_error(uint32_t code, const std::string& msg) {
+    t_has_error = true;
+    t_error.code = code;
+    t_error.msg = msg;
+}
+
+[[noreturn]] void fail(uint32_t code, const std::string& msg) { throw SmbError{code, msg}; }
+
+// messages: src/core/src/errors.rs:10-59
+[[noreturn]] void fail_ksize() { fail(SOURMASH_ERROR_CODE_MISMATCH_K_SIZES, "different ksizes cannot be compared"); }
+[[noreturn]] void fail_dnaprot() { fail(SOURMASH_ERROR_CODE_MISMATCH_DNA_PROT, "DNA/prot minhashes cannot be compared"); }
+[[noreturn]] void fail_scaled() { fail(SOURMASH_ERROR_CODE_MISMATCH_SCALED, "mismatch in scaled; comparison fail"); }
+[[noreturn]] void fail_seed() { fail(SOURMASH_ERROR_CODE_MISMATCH_SEED, "mismatch in seed; comparison fail"); }
+
+template <typename R, typename F>
+R guarded(F&& f) {
+    try {
+        return f();
+    } catch (const SmbError& e) {
+        set_error(e.code, e.msg);
+    } catch (const std::bad_alloc&) {
+        set_error(SOURMASH_ERROR_CODE_PANIC, "out of host memory");
+    } catch (const std::exception& e) {
+        set_error(SOURMASH_ERROR_CODE_PANIC, std::string("panic: ") + e.what());
+    }
+    return R{};
+}
+template <typename F>
+void guarded_void(F&& f) {
+    try {
+        f();
+    } catch (const SmbError& e) {
+        set_error(e.code, e.msg);
+    } catch (const std::bad_alloc&) {
+        set_error(SOURMASH_ERROR_CODE_PANIC, "out of host memory");
+    } catch (const std::exception& e) {
+        set_error(SOURMASH_ERROR_CODE_PANIC, std::string("panic: ") + e.what());
+    }
+}
+
+SourmashStr make_str(const std::string& s) {
+    SourmashStr r;
+    r.len = s.size();
+    r.data = (char*)malloc(s.size() + 1);
+    memcpy(r.data, s.data(), s.size());
+    r.data[s.size()] = 0;
+    r.owned = true;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA context
+// ------------------------------------------------------------------------------------------
+thread_local int t_device = -1;
+thread_local cudaStream_t t_stream = 0;
+std::once_flag g_probe_once;
+int g_device_count = 0;
+std::string g_probe_error;
+
+void probe_devices() {
+    std::call_once(g_probe_once, [] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            g_probe_error = cudaGetErrorString(e);
+            n = 0;
+            cudaGetLastError();
+        }
+        g_device_count = n;
+    });
+}
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        fail(SOURMASH_ERROR_CODE_CUDA, m);
+    }
+}
+#define CK(x) cuda_check((x), #x)
+
+cudaStream_t need_gpu() {
+    probe_devices();
+    if (g_device_count <= 0)
+        fail(SOURMASH_ERROR_CODE_CUDA,
+             "no usable CUDA device (" + (g_probe_error.empty() ? std::string("device count 0") : g_probe_error) +
+                 "); sourmash_b200 has no CPU fallback for hashing / intersection");
+    if (t_device >= 0) CK(cudaSetDevice(t_device));
+    return t_stream;
+}
+
+// stream-ordered device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = 0;
+    DevBuf() {}
+    DevBuf(size_t count, cudaStream_t st) { alloc(count, st); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    void alloc(size_t count, cudaStream_t st) {
+        release();
+        n = count; s = st;
+        size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+        bytes = (bytes + 15) & ~size_t(15);
+        CK(cudaMallocAsync((void**)&p, bytes, st));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    }
+    ~DevBuf() { release(); }
+    void upload(const T* h, size_t count) {
+        if (count) CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* h, size_t count) const {
+        if (count) CK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void zero() { CK(cudaMemsetAsync(p, 0, std::max<size_t>(n * sizeof(T), 16), s)); }
+};
+
+void sync(cudaStream_t s) { CK(cudaStreamSynchronize(s)); }
+
+// max_hash_for_scaled / scaled_for_max_hash: src/core/src/sketch/minhash.rs:21-34
+uint64_t max_hash_for_scaled(uint64_t scaled) {
+    if (scaled == 0) return 0;
+    if (scaled == 1) return UINT64_MAX;
+    double v = 18446744073709551616.0 / (double)scaled;   // u64::MAX as f64 == 2^64
+    return (uint64_t)v;
+}
+uint64_t scaled_for_max_hash(uint64_t max_hash) {
+    if (max_hash == 0) return 0;
+    double v = 18446744073709551616.0 / (double)max_hash;
+    if (v >= 18446744073709551616.0) return UINT64_MAX;
+    return (uint64_t)v;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// device-resident CSR sketch set
+// ==========================================================================================
+struct SmbSketchSet {
+    size_t n_rows = 0;
+    std::vector<uint64_t> h_off;          // host copy of offsets (n_rows + 1)
+    DevBuf<uint64_t> own_hashes, own_off, own_abunds;
+    const uint64_t* d_hashes = nullptr;   // either own_* or borrowed
+    const uint64_t* d_off = nullptr;
+    const uint64_t* d_abunds = nullptr;
+    uint64_t max_len = 0;
+    uint64_t total() const { return h_off.empty() ? 0 : h_off.back(); }
+    void finish_offsets() {
+        max_len = 0;
+        for (size_t i = 0; i < n_rows; ++i) max_len = std::max(max_len, h_off[i + 1] - h_off[i]);
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// sketching core: streams in HBM -> CSR rows in HBM
+// ------------------------------------------------------------------------------------------
+struct StreamList {
+    const uint8_t* d_bases = nullptr;        // 16-byte aligned, padded allocation
+    std::vector<uint64_t> off, len;          // per stream
+    std::vector<uint32_t> row;               // per stream -> sketch index (empty: identity)
+    size_t n_sketches = 0;
+};
+
+struct SketchParams {
+    std::vector<uint32_t> ksizes;
+    uint64_t max_hash = 0;                   // scaled mode threshold (0 in num mode)
+    uint32_t num = 0;
+    uint64_t seed = 42;
+    bool track = false;
+};
+
+// expected survivors -> capacity with slack
+uint64_t cap_for(uint64_t nwin, uint64_t thr) {
+    if (thr == UINT64_MAX) return nwin;
+    long double frac = ((long double)thr + 1.0L) / 18446744073709551616.0L;
+    long double e = (long double)nwin * frac;
+    uint64_t c = (uint64_t)(e * 1.25L + 8.0L * sqrtl(e + 1.0L) + 64.0L);
+    return std::min<uint64_t>(nwin, c);
+}
+
+std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchParams& P,
+                                             cudaStream_t s, uint64_t* n_kmers_out) {
+    const size_t ns = in.off.size();
+    const size_t nk = P.ksizes.size();
+    const size_t n_sk = in.n_sketches;
+    const size_t n_rows = n_sk * nk;
+    auto set = std::make_unique<SmbSketchSet>();
+    set->n_rows = n_rows;
+    set->h_off.assign(n_rows + 1, 0);
+    uint64_t n_kmers = 0;
+
+    // per-sketch byte totals and per-row window counts
+    std::vector<uint64_t> row_windows(n_rows, 0);
+    uint64_t total_bytes = 0, longest = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        size_t sk = in.row.empty() ? i : in.row[i];
+        total_bytes += in.len[i];
+        longest = std::max(longest, in.len[i]);
+        for (size_t j = 0; j < nk; ++j) {
+            uint64_t k = P.ksizes[j];
+            uint64_t nw = (k > 0 && in.len[i] >= k) ? in.len[i] - k + 1 : 0;
+            row_windows[sk * nk + j] += nw;
+            n_kmers += nw;
+        }
+    }
+    if (n_kmers_out) *n_kmers_out = n_kmers;
+    bool never_stores = (P.num == 0 && P.max_hash == 0);     // minhash.rs:324-327
+    if (n_rows == 0 || n_kmers == 0 || never_stores) {
+        set->own_off.alloc(n_rows + 1, s);
+        set->own_off.zero();
+        set->own_hashes.alloc(1, s);
+        if (P.track) set->own_abunds.alloc(1, s);
+        set->d_off = set->own_off.p; set->d_hashes = set->own_hashes.p;
+        set->d_abunds = P.track ? set->own_abunds.p : nullptr;
+        set->finish_offsets();
+        return set;
+    }
+
+    // windows per thread: keep >= ~8 CTAs per SM in flight when the input allows it
+    const int threads = smb::hash_threads();
+    int W = 128;
+    while (W > 16 && total_bytes / ((uint64_t)threads * W) < (uint64_t)SMB_B200_SMS * 8) W -= 16;
+
+    std::vector<uint32_t> tile_r(ns + 1, 0), tile_g(ns + 1, 0);
+    for (size_t i = 0; i < ns; ++i) {
+        uint64_t lp = (in.off[i] & 15) + in.len[i];
+        uint64_t per = (uint64_t)threads * W;
+        tile_r[i + 1] = tile_r[i] + (uint32_t)((lp + per - 1) / per);
+        tile_g[i + 1] = tile_g[i] + (uint32_t)((in.len[i] + 255) / 256);
+    }
+    DevBuf<uint64_t> d_soff(ns, s), d_slen(ns, s);
+    DevBuf<uint32_t> d_tile_r(ns + 1, s), d_tile_g(ns + 1, s), d_srow;
+    d_soff.upload(in.off.data(), ns);
+    d_slen.upload(in.len.data(), ns);
+    d_tile_r.upload(tile_r.data(), ns + 1);
+    d_tile_g.upload(tile_g.data(), ns + 1);
+    if (!in.row.empty()) { d_srow.alloc(ns, s); d_srow.upload(in.row.data(), ns); }
+
+    // num mode keeps the `num` smallest distinct hashes: hash with a threshold that keeps a
+    // few times `num` survivors, widen to "everything" if a row comes back short.
+    std::vector<uint64_t> thr(n_rows, P.max_hash);
+    if (P.num > 0) {
+        for (size_t r = 0; r < n_rows; ++r) {
+            long double want = 4.0L * P.num + 1024.0L;
+            long double nw = (long double)std::max<uint64_t>(row_windows[r], 1);
+            thr[r] = want >= nw ? UINT64_MAX : (uint64_t)(want / nw * 18446744073709551615.0L);
+        }
+    }
+    // one threshold per launch: use the widest of the rows handled by the launch (per k)
+    std::vector<uint64_t> cap(n_rows, 0);
+    std::vector<uint32_t> cnt(n_rows, 0), ucnt(n_rows, 0);
+    DevBuf<uint64_t> d_cand, d_cand_off(n_rows + 1, s), d_abund;
+    DevBuf<uint32_t> d_cnt(n_rows, s), d_ucnt(n_rows, s);
+    std::vector<uint64_t> cand_off(n_rows + 1, 0);
+    std::vector<uint64_t> kthr(nk, 0);
+    for (size_t j = 0; j < nk; ++j) {
+        uint64_t t = 0;
+        for (size_t sk = 0; sk < n_sk; ++sk) t = std::max(t, thr[sk * nk + j]);
+        kthr[j] = t;
+    }
+    for (size_t r = 0; r < n_rows; ++r) cap[r] = cap_for(row_windows[r], kthr[r % nk]);
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        for (size_t r = 0; r < n_rows; ++r) cand_off[r + 1] = cand_off[r] + cap[r];
+        d_cand.alloc(cand_off[n_rows], s);
+        if (P.track) d_abund.alloc(cand_off[n_rows], s);
+        d_cand_off.upload(cand_off.data(), n_rows + 1);
+        d_cnt.zero();
+        smb::HashLaunch L{};
+        L.bases = in.d_bases; L.stream_off = d_soff.p; L.stream_len = d_slen.p;
+        L.stream_row = in.row.empty() ? nullptr : d_srow.p;
+        L.n_streams = (int)ns;
+        L.tile_start_rolled = d_tile_r.p; L.total_tiles_rolled = tile_r[ns];
+        L.tile_start_generic = d_tile_g.p; L.total_tiles_generic = tile_g[ns];
+        L.W = W; L.seed = P.seed;
+        L.cand = d_cand.p; L.cand_off = d_cand_off.p; L.cand_cnt = d_cnt.p;
+        L.row_stride = (int)nk;
+        for (size_t j = 0; j < nk; ++j) {
+            L.max_hash = kthr[j];
+            smb::launch_hash_kmers_k(L, P.ksizes[j], (int)j, s);
+        }
+        CK(cudaGetLastError());
+        d_cnt.download(cnt.data(), n_rows);
+        sync(s);
+        bool overflow = false;
+        for (size_t r = 0; r < n_rows; ++r)
+            if (cnt[r] > cap[r]) { overflow = true; cap[r] = std::min<uint64_t>(row_windows[r], (uint64_t)cnt[r] + 64); }
+        if (overflow) continue;                      // rerun with exact capacities
+
+        // sort + unique
+        smb::launch_sort_unique_small(d_cand.p, d_cand_off.p, d_cnt.p, (int)n_rows, d_ucnt.p,
+                                      P.track ? d_abund.p : nullptr, s);
+        const uint32_t small_max = (uint32_t)smb::sort_small_max();
+        for (size_t r = 0; r < n_rows; ++r) {
+            if (cnt[r] > small_max) {
+                DevBuf<uint64_t> sorted(cnt[r], s), heads(cnt[r], s);
+                CK(smb::sort_unique_big_row(d_cand.p + cand_off[r], cnt[r], sorted.p, heads.p,
+                                            P.track ? d_abund.p + cand_off[r] : nullptr,
+                                            d_ucnt.p + r, s));
+            }
+        }
+        CK(cudaGetLastError());
+        d_ucnt.download(ucnt.data(), n_rows);
+        sync(s);
+        if (P.num > 0) {
+            bool shortfall = false;
+            for (size_t j = 0; j < nk; ++j) {
+                if (kthr[j] == UINT64_MAX) continue;
+                for (size_t sk = 0; sk < n_sk; ++sk)
+                    if (ucnt[sk * nk + j] < P.num) { shortfall = true; kthr[j] = UINT64_MAX; break; }
+            }
+            if (shortfall) {
+                for (size_t r = 0; r < n_rows; ++r) cap[r] = cap_for(row_windows[r], kthr[r % nk]);
+                continue;
+            }
+            for (size_t r = 0; r < n_rows; ++r) ucnt[r] = std::min(ucnt[r], P.num);
+        }
+        // dense CSR
+        for (size_t r = 0; r < n_rows; ++r) set->h_off[r + 1] = set->h_off[r] + ucnt[r];
+        DevBuf<uint32_t> d_final_cnt(n_rows, s);
+        d_final_cnt.upload(ucnt.data(), n_rows);
+        set->own_off.alloc(n_rows + 1, s);
+        set->own_off.upload(set->h_off.data(), n_rows + 1);
+        set->own_hashes.alloc(set->total(), s);
+        smb::launch_compact_rows(d_cand.p, d_cand_off.p, d_final_cnt.p, set->own_off.p,
+                                 set->own_hashes.p, (int)n_rows, s);
+        if (P.track) {
+            set->own_abunds.alloc(set->total(), s);
+            smb::launch_compact_rows(d_abund.p, d_cand_off.p, d_final_cnt.p, set->own_off.p,
+                                     set->own_abunds.p, (int)n_rows, s);
+        }
+        CK(cudaGetLastError());
+        sync(s);      // h_off vector / ucnt are host temporaries used by the async uploads
+        set->d_off = set->own_off.p; set->d_hashes = set->own_hashes.p;
+        set->d_abunds = P.track ? set->own_abunds.p : nullptr;
+        set->finish_offsets();
+        return set;
+    }
+    fail(SOURMASH_ERROR_CODE_INTERNAL, "sketch candidate buffers kept overflowing");
+}
+
+// ------------------------------------------------------------------------------------------
+// pairwise counts core (device in, device out)
+// ------------------------------------------------------------------------------------------
+struct CountsDev {
+    DevBuf<uint32_t> common, usize;
+    size_t ldo = 0;
+};
+
+void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t num, uint32_t* d_common,
+                         uint32_t* d_usize, size_t ldo, cudaStream_t s) {
+    const bool symmetric = (Bp == nullptr);
+    const SmbSketchSet& B = symmetric ? A : *Bp;
+    const int nA = (int)A.n_rows, nB = (int)B.n_rows;
+    if (nA == 0 || nB == 0) return;
+    if (num > 0) {
+        smb::launch_pairwise_num(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, num, d_common,
+                                 d_usize, ldo, symmetric, s);
+        return;
+    }
+    smb::PairwisePlan plan = smb::plan_pairwise(A.max_len, nB);
+    if (plan.tables_per_cta == 0) {
+        smb::launch_pairwise_generic(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
+                                     symmetric, s);
+        return;
+    }
+    DevBuf<uint32_t> d_shift(4, s);
+    smb::launch_bucket_shift(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, plan.nb_log2,
+                             d_shift.p, s);
+    smb::launch_pairwise_tile(plan, A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
+                              d_shift.p, symmetric, s);
+}
+
+// upload one sorted row as a 1-row set
+std::unique_ptr<SmbSketchSet> single_row_set(const uint64_t* h, size_t n, const uint64_t* ab,
+                                             cudaStream_t s) {
+    auto set = std::make_unique<SmbSketchSet>();
+    set->n_rows = 1;
+    set->h_off = {0, (uint64_t)n};
+    set->own_off.alloc(2, s);
+    set->own_off.upload(set->h_off.data(), 2);
+    set->own_hashes.alloc(n, s);
+    set->own_hashes.upload(h, n);
+    if (ab) { set->own_abunds.alloc(n, s); set->own_abunds.upload(ab, n); }
+    set->d_off = set->own_off.p; set->d_hashes = set->own_hashes.p;
+    set->d_abunds = ab ? set->own_abunds.p : nullptr;
+    set->finish_offsets();
+    return set;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// KmerMinHash host object: src/core/src/sketch/minhash.rs:41-64
+// ==========================================================================================
+struct SourmashKmerMinHash {
+    uint32_t num = 0, ksize = 0;
+    HashFunctions hash_function = HASH_FUNCTIONS_MURMUR64_DNA;
+    uint64_t seed = 42, max_hash = 0;
+    bool track = false;
+    std::vector<uint64_t> mins, abunds;     // abunds parallel to mins when track
+
+    uint64_t scaled() const { return scaled_for_max_hash(max_hash); }   // minhash.rs:233-235
+
+    // minhash.rs:886-912
+    void check_compatible(const SourmashKmerMinHash& o) const {
+        if (ksize != o.ksize) fail_ksize();
+        if (hash_function != o.hash_function) fail_dnaprot();
+        if (max_hash != o.max_hash) fail_scaled();
+        if (seed != o.seed) fail_seed();
+    }
+    void remove_hash(uint64_t h) {          // minhash.rs:406-416
+        auto it = std::lower_bound(mins.begin(), mins.end(), h);
+        if (it != mins.end() && *it == h) {
+            size_t p = it - mins.begin();
+            mins.erase(it);
+            if (track) abunds.erase(abunds.begin() + p);
+        }
+    }
+    void add_hash_with_abundance(uint64_t h, uint64_t abundance) {   // minhash.rs:313-383
+        uint64_t current_max = mins.empty() ? UINT64_MAX : mins.back();
+        if (h > max_hash && max_hash != 0) return;
+        if (num == 0 && max_hash == 0) return;
+        if (abundance == 0) { remove_hash(h); return; }
+        if (mins.empty()) { mins.push_back(h); if (track) abunds.push_back(abundance); return; }
+        if (h <= max_hash || h <= current_max || mins.size() < (size_t)num) {
+            auto it = std::lower_bound(mins.begin(), mins.end(), h);
+            size_t pos = it - mins.begin();
+            if (it == mins.end()) {
+                mins.push_back(h);
+                if (track) abunds.push_back(abundance);
+            } else if (*it != h) {
+                mins.insert(it, h);
+                if (track) abunds.insert(abunds.begin() + pos, abundance);
+                if (num != 0 && mins.size() > (size_t)num) { mins.pop_back(); if (track) abunds.pop_back(); }
+            } else if (track) {
+                abunds[pos] += abundance;
+            }
+        }
+    }
+    // bulk union with a sorted-unique batch (same result as add_hash_with_abundance per item)
+    void absorb_sorted(const uint64_t* h, const uint64_t* ab, size_t n) {
+        if (num == 0 && max_hash == 0) return;
+        std::vector<uint64_t> m, a;
+        m.reserve(mins.size() + n);
+        if (track) a.reserve(mins.size() + n);
+        size_t i = 0, j = 0;
+        while (i < mins.size() || j < n) {
+            if (j < n && max_hash != 0 && h[j] > max_hash) { ++j; continue; }
+            bool take_i = j >= n || (i < mins.size() && mins[i] <= h[j]);
+            bool take_j = i >= mins.size() || (j < n && h[j] <= mins[i]);
+            uint64_t v = take_i ? mins[i] : h[j];
+            uint64_t c = 0;
+            if (track) c = (take_i ? abunds[i] : 0) + (take_j ? (ab ? ab[j] : 1) : 0);
+            m.push_back(v);
+            if (track) a.push_back(c);
+            if (take_i) ++i;
+            if (take_j) ++j;
+        }
+        if (num != 0 && m.size() > (size_t)num) { m.resize(num); if (track) a.resize(num); }
+        mins.swap(m);
+        if (track) abunds.swap(a);
+    }
+    // minhash.rs:432-516
+    void merge(const SourmashKmerMinHash& o) {
+        check_compatible(o);
+        const bool both = track && o.track;
+        std::vector<uint64_t> m, a;
+        m.reserve(mins.size() + o.mins.size());
+        size_t i = 0, j = 0;
+        while (i < mins.size() && j < o.mins.size()) {
+            if (o.mins[j] < mins[i]) { m.push_back(o.mins[j]); if (both) a.push_back(o.abunds[j]); ++j; }
+            else if (o.mins[j] == mins[i]) { m.push_back(mins[i]); if (both) a.push_back(abunds[i] + o.abunds[j]); ++i; ++j; }
+            else { m.push_back(mins[i]); if (both) a.push_back(abunds[i]); ++i; }
+        }
+        for (; i < mins.size(); ++i) { m.push_back(mins[i]); if (both) a.push_back(abunds[i]); }
+        for (; j < o.mins.size(); ++j) { m.push_back(o.mins[j]); if (both) a.push_back(o.abunds[j]); }
+        if (num != 0 && m.size() > (size_t)num) { m.resize(num); if (both) a.resize(num); }
+        mins.swap(m);
+        abunds.swap(a);
+        track = both;            // merged_abunds = None unless both sides track
+    }
+    // minhash.rs:777-798 (errors on upsampling; identity when scaled() equal or num sketch)
+    SourmashKmerMinHash downsample_scaled(uint64_t new_scaled) const {
+        if (scaled() == new_scaled || scaled() == 0) return *this;
+        if (scaled() > new_scaled)
+            fail(SOURMASH_ERROR_CODE_CANNOT_UPSAMPLE_SCALED, "new scaled smaller than previous; cannot upsample");
+        SourmashKmerMinHash r;
+        r.num = num; r.ksize = ksize; r.hash_function = hash_function; r.seed = seed;
+        r.track = track; r.max_hash = max_hash_for_scaled(new_scaled);
+        size_t keep = std::upper_bound(mins.begin(), mins.end(), r.max_hash) - mins.begin();
+        r.mins.assign(mins.begin(), mins.begin() + keep);
+        if (track) r.abunds.assign(abunds.begin(), abunds.begin() + keep);
+        return r;
+    }
+    std::string md5sum() const {   // minhash.rs:290-307
+        smb::Md5 ctx;
+        char buf[32];
+        int l = snprintf(buf, sizeof buf, "%u", ksize);
+        ctx.update((const uint8_t*)buf, (size_t)l);
+        for (uint64_t v : mins) {
+            l = snprintf(buf, sizeof buf, "%llu", (unsigned long long)v);
+            ctx.update((const uint8_t*)buf, (size_t)l);
+        }
+        return ctx.hexdigest();
+    }
+};
+
+namespace {
+
+typedef SourmashKmerMinHash MH;
+
+// hash one sequence on the GPU and fold the survivors into the sketch.
+// signature.rs:38-58 (+ :271-279 for the !force error, raised after earlier windows were added)
+void mh_add_sequence(MH& mh, const uint8_t* seq, size_t len, bool force) {
+    if (mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA)
+        fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
+             "Invalid hash function: translated / protein k-mers are outside the B200 hot path");
+    const size_t k = mh.ksize;
+    if (k == 0 || len < k) return;                       // signature.rs:206-210
+    cudaStream_t s = need_gpu();
+    DevBuf<uint8_t> d_seq(len + 32, s);
+    d_seq.upload(seq, len);
+    size_t use_len = len;
+    int64_t bad_window = -1;
+    if (!force) {
+        DevBuf<unsigned long long> d_pos(1, s);
+        smb::launch_first_invalid(d_seq.p, len, d_pos.p, s);
+        unsigned long long pos = 0;
+        d_pos.download(&pos, 1);
+        sync(s);
+        if (pos != ~0ull) {
+            bad_window = pos + 1 >= k ? (int64_t)(pos - k + 1) : 0;
+            use_len = (size_t)bad_window + k - 1;         // windows [0, bad_window) only
+        }
+    }
+    if (use_len >= k) {
+        StreamList in;
+        in.d_bases = d_seq.p;
+        in.off = {0}; in.len = {use_len}; in.n_sketches = 1;
+        SketchParams P;
+        P.ksizes = {mh.ksize}; P.max_hash = mh.max_hash; P.num = mh.num; P.seed = mh.seed;
+        P.track = mh.track;
+        auto set = sketch_streams(in, P, s, nullptr);
+        size_t n = set->total();
+        std::vector<uint64_t> h(n), ab(mh.track ? n : 0);
+        if (n) {
+            CK(cudaMemcpyAsync(h.data(), set->d_hashes, n * 8, cudaMemcpyDeviceToHost, s));
+            if (mh.track) CK(cudaMemcpyAsync(ab.data(), set->d_abunds, n * 8, cudaMemcpyDeviceToHost, s));
+            sync(s);
+        }
+        mh.absorb_sorted(h.data(), mh.track ? ab.data() : nullptr, n);
+    }
+    if (bad_window >= 0) {
+        std::string km((const char*)seq + bad_window, k);
+        for (auto& c : km) if (c >= 'a' && c <= 'z') c -= 32;
+        fail(SOURMASH_ERROR_CODE_INVALID_DNA, "invalid DNA character in input k-mer: " + km);
+    }
+}
+
+struct PairCounts { uint64_t common, usize; };
+
+// |A ∩ B| (and |M| for num sketches) of two host sketches, computed on the GPU
+PairCounts mh_pair_counts(const MH& a, const MH& b, bool num_semantics) {
+    cudaStream_t s = need_gpu();
+    auto sa = single_row_set(a.mins.data(), a.mins.size(), nullptr, s);
+    auto sb = single_row_set(b.mins.data(), b.mins.size(), nullptr, s);
+    DevBuf<uint32_t> d_out(2, s);
+    d_out.zero();
+    uint32_t num = num_semantics ? a.num : 0;
+    pairwise_counts_dev(*sa, sb.get(), num, d_out.p, d_out.p + 1, 1, s);
+    CK(cudaGetLastError());
+    uint32_t out[2] = {0, 0};
+    d_out.download(out, 2);
+    sync(s);
+    PairCounts r;
+    r.common = out[0];
+    r.usize = num ? out[1] : (uint64_t)a.mins.size() + b.mins.size() - out[0];
+    return r;
+}
+
+// minhash.rs:593-621
+PairCounts mh_intersection_size(const MH& a, const MH& b) {
+    a.check_compatible(b);
+    return mh_pair_counts(a, b, a.num != 0);
+}
+
+double mh_jaccard(const MH& a, const MH& b) {       // minhash.rs:624-631
+    a.check_compatible(b);
+    PairCounts c = mh_intersection_size(a, b);
+    return (double)c.common / (double)std::max<uint64_t>(1, c.usize);
+}
+
+double mh_angular(const MH& a, const MH& b) {       // minhash.rs:635-680
+    a.check_compatible(b);
+    if (!a.track || !b.track)
+        fail(SOURMASH_ERROR_CODE_NEEDS_ABUNDANCE_TRACKING, "sketch needs abundance for this operation");
+    cudaStream_t s = need_gpu();
+    auto sa = single_row_set(a.mins.data(), a.mins.size(), a.abunds.data(), s);
+    auto sb = single_row_set(b.mins.data(), b.mins.size(), b.abunds.data(), s);
+    DevBuf<unsigned long long> d_out(3, s);
+    smb::launch_angular_terms(sa->d_hashes, sa->d_abunds, a.mins.size(), sb->d_hashes, sb->d_abunds,
+                              b.mins.size(), d_out.p, s);
+    unsigned long long t[3];
+    d_out.download(t, 3);
+    sync(s);
+    double norm_a = std::sqrt((double)t[1]), norm_b = std::sqrt((double)t[2]);
+    if (norm_a == 0. || norm_b == 0.) return 0.0;
+    double prod = std::min((double)t[0] / (norm_a * norm_b), 1.0);
+    double distance = 2. * std::acos(prod) / 3.14159265358979323846264338327950288;
+    return 1. - distance;
+}
+
+double mh_similarity(const MH& a, const MH& b, bool ignore_abundance, bool downsample) {
+    // minhash.rs:682-702
+    if (downsample && a.scaled() != b.scaled()) {
+        const MH& first = a.scaled() > b.scaled() ? a : b;
+        const MH& second = a.scaled() > b.scaled() ? b : a;
+        MH ds = second.downsample_scaled(first.scaled());
+        return mh_similarity(first, ds, ignore_abundance, false);
+    }
+    if (ignore_abundance || !a.track || !b.track) return mh_jaccard(a, b);
+    return mh_angular(a, b);
+}
+
+uint64_t mh_count_common(const MH& a, const MH& b, bool downsample) {   // minhash.rs:539-558
+    if (downsample && a.scaled() != b.scaled()) {
+        const MH& first = a.scaled() > b.scaled() ? a : b;
+        const MH& second = a.scaled() > b.scaled() ? b : a;
+        MH ds = second.downsample_scaled(first.scaled());
+        return mh_count_common(first, ds, false);
+    }
+    a.check_compatible(b);
+    return mh_pair_counts(a, b, false).common;
+}
+
+// minhash.rs:560-589 + ffi/minhash.rs:428-441
+MH* mh_intersection(const MH& a, const MH& b) {
+    a.check_compatible(b);
+    cudaStream_t s = need_gpu();
+    auto sa = single_row_set(a.mins.data(), a.mins.size(), nullptr, s);
+    auto sb = single_row_set(b.mins.data(), b.mins.size(), nullptr, s);
+    DevBuf<uint64_t> d_out(std::min(a.mins.size(), b.mins.size()) + 1, s);
+    DevBuf<uint32_t> d_n(1, s);
+    smb::launch_intersect_rows(sa->d_hashes, a.mins.size(), sb->d_hashes, b.mins.size(), d_out.p, d_n.p, s);
+    uint32_t n = 0;
+    d_n.download(&n, 1);
+    sync(s);
+    size_t keep = n;
+    if (a.num != 0) keep = std::min<size_t>(keep, mh_pair_counts(a, b, true).common);
+    std::vector<uint64_t> common(keep);
+    if (keep) { CK(cudaMemcpyAsync(common.data(), d_out.p, keep * 8, cudaMemcpyDeviceToHost, s)); sync(s); }
+    MH* r = new MH(a);
+    r->mins.clear();
+    r->abunds.clear();
+    for (uint64_t h : common) r->add_hash_with_abundance(h, 1);
+    return r;
+}
+
+uint64_t murmur_on_gpu(const uint8_t* data, size_t len, uint64_t seed) {
+    cudaStream_t s = need_gpu();
+    DevBuf<uint8_t> d(len + 16, s);
+    d.upload(data, len);
+    DevBuf<uint64_t> d_out(1, s);
+    smb::launch_murmur_bytes(d.p, len, seed, d_out.p, s);
+    uint64_t h = 0;
+    d_out.download(&h, 1);
+    sync(s);
+    return h;
+}
+
+uint64_t* to_boxed(const std::vector<uint64_t>& v, uintptr_t* size) {
+    uint64_t* p = (uint64_t*)malloc(std::max<size_t>(v.size(), 1) * 8);
+    if (!v.empty()) memcpy(p, v.data(), v.size() * 8);
+    *size = v.size();
+    return p;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// Signature / ComputeParameters: src/core/src/signature.rs:401-445, cmd.rs:22-188
+// ==========================================================================================
+struct SourmashComputeParameters {
+    std::vector<uint32_t> ksizes{21, 31, 51};    // cmd.rs:60-84 defaults
+    bool dna = true, protein = false, dayhoff = false, hp = false, track_abundance = false;
+    uint32_t num_hashes = 500;
+    uint64_t scaled = 0, seed = 42;
+};
+
+struct SourmashSignature {
+    std::string name, filename;
+    std::string license = "CC0";
+    std::vector<MH> sketches;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+void sourmash_init(void) {}
+void sourmash_err_clear(void) { t_has_error = false; }
+SourmashErrorCode sourmash_err_get_last_code(void) { return t_has_error ? t_error.code : 0; }
+SourmashStr sourmash_err_get_last_message(void) {
+    if (t_has_error) return make_str(t_error.msg);
+    SourmashStr r{nullptr, 0, false};
+    return r;
+}
+SourmashStr sourmash_err_get_backtrace(void) { SourmashStr r{nullptr, 0, false}; return r; }
+void sourmash_str_free(SourmashStr* s) {
+    if (s && s->owned && s->data) { free(s->data); s->data = nullptr; s->len = 0; s->owned = false; }
+}
+SourmashStr sourmash_str_from_cstr(const char* s) { return make_str(s ? s : ""); }
+
+uint64_t hash_murmur(const char* kmer, uint64_t seed) {
+    return guarded<uint64_t>([&] { return murmur_on_gpu((const uint8_t*)kmer, strlen(kmer), seed); });
+}
+
+// ------------------------------------------------------------------------------------------
+SourmashKmerMinHash* kmerminhash_new(uint64_t scaled, uint32_t k, HashFunctions hash_function,
+                                     uint64_t seed, bool track_abundance, uint32_t n) {
+    MH* m = new MH();
+    m->num = n; m->ksize = k; m->hash_function = hash_function; m->seed = seed;
+    m->track = track_abundance; m->max_hash = max_hash_for_scaled(scaled);
+    return m;
+}
+void kmerminhash_free(SourmashKmerMinHash* ptr) { delete ptr; }
+void kmerminhash_slice_free(uint64_t* ptr, uintptr_t) { free(ptr); }
+
+void kmerminhash_add_sequence(SourmashKmerMinHash* ptr, const char* sequence, bool force) {
+    guarded_void([&] { mh_add_sequence(*ptr, (const uint8_t*)sequence, strlen(sequence), force); });
+}
+void kmerminhash_add_protein(SourmashKmerMinHash*, const char*) {
+    set_error(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
+              "Invalid hash function: protein k-mers are outside the B200 hot path");
+}
+
+const uint64_t* kmerminhash_seq_to_hashes(SourmashKmerMinHash* ptr, const char* sequence,
+                                          uintptr_t insize, bool force, bool bad_kmers_as_zeroes,
+                                          bool is_protein, uintptr_t* size) {
+    return guarded<const uint64_t*>([&]() -> const uint64_t* {
+        // ffi/minhash.rs:63-99
+        MH& mh = *ptr;
+        if (is_protein || mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA)
+            fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
+                 "Invalid hash function: translated / protein k-mers are outside the B200 hot path");
+        std::vector<uint64_t> out;
+        const size_t k = mh.ksize, len = insize;
+        if (k > 0 && len >= k) {
+            cudaStream_t s = need_gpu();
+            const size_t nwin = len - k + 1;
+            DevBuf<uint8_t> d_seq(len + 32, s);
+            d_seq.upload((const uint8_t*)sequence, len);
+            DevBuf<uint64_t> d_raw(nwin, s);
+            uint64_t off = 0, ln = len;
+            uint32_t tr[2] = {0, 0}, tg[2] = {0, 0};
+            const int W = 64;
+            tr[1] = (uint32_t)((len + (size_t)smb::hash_threads() * W - 1) / ((size_t)smb::hash_threads() * W));
+            tg[1] = (uint32_t)((len + 255) / 256);
+            DevBuf<uint64_t> d_off(1, s), d_len(1, s);
+            DevBuf<uint32_t> d_tr(2, s), d_tg(2, s);
+            d_off.upload(&off, 1); d_len.upload(&ln, 1); d_tr.upload(tr, 2); d_tg.upload(tg, 2);
+            smb::HashLaunch L{};
+            L.bases = d_seq.p; L.stream_off = d_off.p; L.stream_len = d_len.p; L.stream_row = nullptr;
+            L.n_streams = 1; L.tile_start_rolled = d_tr.p; L.total_tiles_rolled = tr[1];
+            L.tile_start_generic = d_tg.p; L.total_tiles_generic = tg[1];
+            L.W = W; L.seed = mh.seed; L.max_hash = UINT64_MAX;
+            smb::launch_window_hashes(L, mh.ksize, d_raw.p, s);
+            CK(cudaGetLastError());
+            std::vector<uint64_t> raw(nwin);
+            d_raw.download(raw.data(), nwin);
+            // validity needs the bases (a genuine hash of 0 is indistinguishable in `raw`)
+            sync(s);
+            const uint8_t* sq = (const uint8_t*)sequence;
+            auto ok = [&](uint8_t c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; };
+            size_t bad_until = 0;                       // windows < bad_until contain a bad base
+            for (size_t p = 0; p + 1 < k; ++p) if (!ok(sq[p])) bad_until = p + 1;
+            out.reserve(nwin);
+            for (size_t w = 0; w < nwin; ++w) {
+                if (!ok(sq[w + k - 1])) bad_until = w + k;
+                if (w < bad_until) {
+                    if (!force) {
+                        std::string km((const char*)sq + w, k);
+                        for (auto& c : km) if (c >= 'a' && c <= 'z') c -= 32;
+                        fail(SOURMASH_ERROR_CODE_INVALID_DNA, "invalid DNA character in input k-mer: " + km);
+                    }
+                    if (bad_kmers_as_zeroes) out.push_back(0);
+                } else if (raw[w] != 0 || (force && bad_kmers_as_zeroes)) {
+                    out.push_back(raw[w]);
+                }
+            }
+        }
+        return to_boxed(out, size);
+    });
+}
+
+void kmerminhash_clear(SourmashKmerMinHash* ptr) { ptr->mins.clear(); ptr->abunds.clear(); }
+void kmerminhash_add_hash(SourmashKmerMinHash* ptr, uint64_t h) { ptr->add_hash_with_abundance(h, 1); }
+void kmerminhash_add_hash_with_abundance(SourmashKmerMinHash* ptr, uint64_t h, uint64_t abundance) {
+    ptr->add_hash_with_abundance(h, abundance);
+}
+void kmerminhash_add_word(SourmashKmerMinHash* ptr, const char* word) {
+    guarded_void([&] {
+        ptr->add_hash_with_abundance(murmur_on_gpu((const uint8_t*)word, strlen(word), ptr->seed), 1);
+    });
+}
+void kmerminhash_add_many(SourmashKmerMinHash* ptr, const uint64_t* hashes_ptr, uintptr_t insize) {
+    for (uintptr_t i = 0; i < insize; ++i) ptr->add_hash_with_abundance(hashes_ptr[i], 1);
+}
+void kmerminhash_add_from(SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other) {
+    for (uint64_t h : other->mins) ptr->add_hash_with_abundance(h, 1);
+}
+void kmerminhash_remove_hash(SourmashKmerMinHash* ptr, uint64_t h) { ptr->remove_hash(h); }
+void kmerminhash_remove_many(SourmashKmerMinHash* ptr, const uint64_t* hashes_ptr, uintptr_t insize) {
+    for (uintptr_t i = 0; i < insize; ++i) ptr->remove_hash(hashes_ptr[i]);
+}
+void kmerminhash_remove_from(SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other) {
+    for (uint64_t h : other->mins) ptr->remove_hash(h);
+}
+const uint64_t* kmerminhash_get_mins(const SourmashKmerMinHash* ptr, uintptr_t* size) {
+    return to_boxed(ptr->mins, size);
+}
+uintptr_t kmerminhash_get_mins_size(const SourmashKmerMinHash* ptr) { return ptr->mins.size(); }
+const uint64_t* kmerminhash_get_abunds(SourmashKmerMinHash* ptr, uintptr_t* size) {
+    if (!ptr->track) {
+        set_error(SOURMASH_ERROR_CODE_PANIC, "panic: not implemented (sketch does not track abundance)");
+        *size = 0;
+        return nullptr;
+    }
+    return to_boxed(ptr->abunds, size);
+}
+void kmerminhash_set_abundances(SourmashKmerMinHash* ptr, const uint64_t* hashes_ptr,
+                                const uint64_t* abunds_ptr, uintptr_t insize, bool clear) {
+    // ffi/minhash.rs:269-301: sort pairs, optional clear, add_many_with_abund
+    std::vector<std::pair<uint64_t, uint64_t>> pairs(insize);
+    for (uintptr_t i = 0; i < insize; ++i) pairs[i] = {hashes_ptr[i], abunds_ptr[i]};
+    std::sort(pairs.begin(), pairs.end());
+    if (clear) { ptr->mins.clear(); ptr->abunds.clear(); }
+    for (auto& pr : pairs) ptr->add_hash_with_abundance(pr.first, pr.second);
+}
+SourmashStr kmerminhash_md5sum(const SourmashKmerMinHash* ptr) { return make_str(ptr->md5sum()); }
+bool kmerminhash_is_protein(const SourmashKmerMinHash* ptr) { return ptr->hash_function == HASH_FUNCTIONS_MURMUR64_PROTEIN; }
+bool kmerminhash_dayhoff(const SourmashKmerMinHash* ptr) { return ptr->hash_function == HASH_FUNCTIONS_MURMUR64_DAYHOFF; }
+bool kmerminhash_hp(const SourmashKmerMinHash* ptr) { return ptr->hash_function == HASH_FUNCTIONS_MURMUR64_HP; }
+uint64_t kmerminhash_seed(const SourmashKmerMinHash* ptr) { return ptr->seed; }
+bool kmerminhash_track_abundance(const SourmashKmerMinHash* ptr) { return ptr->track; }
+void kmerminhash_disable_abundance(SourmashKmerMinHash* ptr) { ptr->track = false; ptr->abunds.clear(); }
+void kmerminhash_enable_abundance(SourmashKmerMinHash* ptr) {
+    if (!ptr->mins.empty()) {     // minhash.rs:265-275
+        set_error(SOURMASH_ERROR_CODE_NON_EMPTY_MIN_HASH, "Can only set \"track_abundance=True\" if the MinHash is empty");
+        return;
+    }
+    ptr->track = true;
+    ptr->abunds.clear();
+}
+uint32_t kmerminhash_num(const SourmashKmerMinHash* ptr) { return ptr->num; }
+uint32_t kmerminhash_ksize(const SourmashKmerMinHash* ptr) { return ptr->ksize; }
+uint64_t kmerminhash_max_hash(const SourmashKmerMinHash* ptr) { return ptr->max_hash; }
+HashFunctions kmerminhash_hash_function(const SourmashKmerMinHash* ptr) { return ptr->hash_function; }
+void kmerminhash_hash_function_set(SourmashKmerMinHash* ptr, HashFunctions hash_function) {
+    if (ptr->hash_function == hash_function) return;      // minhash.rs:247-259
+    if (!ptr->mins.empty()) {
+        set_error(SOURMASH_ERROR_CODE_NON_EMPTY_MIN_HASH, "Can only set \"hash_function\" if the MinHash is empty");
+        return;
+    }
+    ptr->hash_function = hash_function;
+}
+void kmerminhash_merge(SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other) {
+    guarded_void([&] { ptr->merge(*other); });
+}
+bool kmerminhash_is_compatible(const SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other) {
+    try { ptr->check_compatible(*other); return true; } catch (const SmbError&) { return false; }
+}
+uint64_t kmerminhash_count_common(const SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other,
+                                  bool downsample) {
+    return guarded<uint64_t>([&] { return mh_count_common(*ptr, *other, downsample); });
+}
+SourmashKmerMinHash* kmerminhash_intersection(const SourmashKmerMinHash* ptr,
+                                              const SourmashKmerMinHash* other) {
+    return guarded<SourmashKmerMinHash*>([&] { return mh_intersection(*ptr, *other); });
+}
+uint64_t kmerminhash_intersection_union_size(const SourmashKmerMinHash* ptr,
+                                             const SourmashKmerMinHash* other, uint64_t* union_size) {
+    // ffi/minhash.rs:443-457: incompatibility is swallowed -> (0, 0); GPU failures still raise
+    *union_size = 0;
+    try {
+        ptr->check_compatible(*other);
+    } catch (const SmbError&) {
+        return 0;
+    }
+    return guarded<uint64_t>([&] {
+        PairCounts c = mh_intersection_size(*ptr, *other);
+        *union_size = c.usize;
+        return c.common;
+    });
+}
+double kmerminhash_jaccard(const SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other) {
+    return guarded<double>([&] { return mh_jaccard(*ptr, *other); });
+}
+double kmerminhash_similarity(const SourmashKmerMinHash* ptr, const SourmashKmerMinHash* other,
+                              bool ignore_abundance, bool downsample) {
+    return guarded<double>([&] { return mh_similarity(*ptr, *other, ignore_abundance, downsample); });
+}
+double kmerminhash_angular_similarity(const SourmashKmerMinHash* ptr,
+                                      const SourmashKmerMinHash* other) {
+    return guarded<double>([&] { return mh_angular(*ptr, *other); });
+}
+
+// ------------------------------------------------------------------------------------------
+// Signature subset (ffi/signature.rs:24-217)
+// ------------------------------------------------------------------------------------------
+SourmashSignature* signature_new(void) { return new SourmashSignature(); }
+void signature_free(SourmashSignature* ptr) { delete ptr; }
+SourmashSignature* signature_from_params(const SourmashComputeParameters* p) {
+    // cmd.rs:109-188 build_template: one sketch per ksize for each enabled molecule type
+    return guarded<SourmashSignature*>([&]() -> SourmashSignature* {
+        if (p->protein || p->dayhoff || p->hp)
+            fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
+                 "Invalid hash function: protein / dayhoff / hp sketches are outside the B200 hot path");
+        auto* sig = new SourmashSignature();
+        if (p->dna) {
+            for (uint32_t k : p->ksizes) {
+                MH m;
+                m.num = p->num_hashes; m.ksize = k; m.seed = p->seed; m.track = p->track_abundance;
+                m.max_hash = max_hash_for_scaled(p->scaled);
+                sig->sketches.push_back(m);
+            }
+        }
+        return sig;
+    });
+}
+uintptr_t signature_len(const SourmashSignature* ptr) { return ptr->sketches.size(); }
+bool signature_eq(const SourmashSignature* a, const SourmashSignature* b) {
+    // signature.rs PartialEq (:883-905): class/license/name-independent metadata + sketches' mins
+    if (a->sketches.size() != b->sketches.size()) return false;
+    for (size_t i = 0; i < a->sketches.size(); ++i) {
+        const MH &x = a->sketches[i], &y = b->sketches[i];
+        if (x.ksize != y.ksize || x.num != y.num || x.max_hash != y.max_hash || x.seed != y.seed ||
+            x.hash_function != y.hash_function || x.mins != y.mins) return false;
+        if (x.track && y.track && x.abunds != y.abunds) return false;
+    }
+    return true;
+}
+void signature_add_sequence(SourmashSignature* ptr, const char* sequence, bool force) {
+    // signature.rs:661-677: every sketch of the signature sees the sequence.  One upload, one
+    // hash launch per ksize.
+    guarded_void([&] {
+        size_t len = strlen(sequence);
+        for (auto& mh : ptr->sketches) mh_add_sequence(mh, (const uint8_t*)sequence, len, force);
+    });
+}
+void signature_add_protein(SourmashSignature*, const char*) {
+    set_error(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
+              "Invalid hash function: protein k-mers are outside the B200 hot path");
+}
+SourmashKmerMinHash* signature_first_mh(const SourmashSignature* ptr) {
+    // ffi/signature.rs:169-185 returns a clone
+    if (ptr->sketches.empty()) {
+        set_error(SOURMASH_ERROR_CODE_INTERNAL, "internal error: \"found unsupported sketch type\"");
+        return nullptr;
+    }
+    return new MH(ptr->sketches[0]);
+}
+SourmashKmerMinHash** signature_get_mhs(const SourmashSignature* ptr, uintptr_t* size) {
+    size_t n = ptr->sketches.size();
+    SourmashKmerMinHash** arr = (SourmashKmerMinHash**)malloc(std::max<size_t>(n, 1) * sizeof(void*));
+    for (size_t i = 0; i < n; ++i) arr[i] = new MH(ptr->sketches[i]);
+    *size = n;
+    return arr;
+}
+void signature_set_mh(SourmashSignature* ptr, const SourmashKmerMinHash* other) {
+    ptr->sketches.clear();
+    ptr->sketches.push_back(*other);
+}
+void signature_push_mh(SourmashSignature* ptr, const SourmashKmerMinHash* other) {
+    ptr->sketches.push_back(*other);
+}
+SourmashStr signature_get_name(const SourmashSignature* ptr) { return make_str(ptr->name); }
+SourmashStr signature_get_filename(const SourmashSignature* ptr) { return make_str(ptr->filename); }
+SourmashStr signature_get_license(const SourmashSignature* ptr) { return make_str(ptr->license); }
+void signature_set_name(SourmashSignature* ptr, const char* name) { ptr->name = name ? name : ""; }
+void signature_set_filename(SourmashSignature* ptr, const char* name) { ptr->filename = name ? name : ""; }
+
+// ------------------------------------------------------------------------------------------
+// ComputeParameters (ffi/cmd/compute.rs:14-170)
+// ------------------------------------------------------------------------------------------
+SourmashComputeParameters* computeparams_new(void) { return new SourmashComputeParameters(); }
+void computeparams_free(SourmashComputeParameters* ptr) { delete ptr; }
+const uint32_t* computeparams_ksizes(const SourmashComputeParameters* ptr, uintptr_t* size) {
+    size_t n = ptr->ksizes.size();
+    uint32_t* p = (uint32_t*)malloc(std::max<size_t>(n, 1) * 4);
+    if (n) memcpy(p, ptr->ksizes.data(), n * 4);
+    *size = n;
+    return p;
+}
+void computeparams_ksizes_free(uint32_t* ptr, uintptr_t) { free(ptr); }
+void computeparams_set_ksizes(SourmashComputeParameters* ptr, const uint32_t* ksizes_ptr, uintptr_t insize) {
+    ptr->ksizes.assign(ksizes_ptr, ksizes_ptr + insize);
+}
+bool computeparams_dna(const SourmashComputeParameters* p) { return p->dna; }
+bool computeparams_protein(const SourmashComputeParameters* p) { return p->protein; }
+bool computeparams_dayhoff(const SourmashComputeParameters* p) { return p->dayhoff; }
+bool computeparams_hp(const SourmashComputeParameters* p) { return p->hp; }
+bool computeparams_track_abundance(const SourmashComputeParameters* p) { return p->track_abundance; }
+uint32_t computeparams_num_hashes(const SourmashComputeParameters* p) { return p->num_hashes; }
+uint64_t computeparams_scaled(const SourmashComputeParameters* p) { return p->scaled; }
+uint64_t computeparams_seed(const SourmashComputeParameters* p) { return p->seed; }
+void computeparams_set_dna(SourmashComputeParameters* p, bool v) { p->dna = v; }
+void computeparams_set_protein(SourmashComputeParameters* p, bool v) { p->protein = v; }
+void computeparams_set_dayhoff(SourmashComputeParameters* p, bool v) { p->dayhoff = v; }
+void computeparams_set_hp(SourmashComputeParameters* p, bool v) { p->hp = v; }
+void computeparams_set_track_abundance(SourmashComputeParameters* p, bool v) { p->track_abundance = v; }
+void computeparams_set_num_hashes(SourmashComputeParameters* p, uint32_t num) { p->num_hashes = num; }
+void computeparams_set_scaled(SourmashComputeParameters* p, uint64_t scaled) { p->scaled = scaled; }
+void computeparams_set_seed(SourmashComputeParameters* p, uint64_t new_seed) { p->seed = new_seed; }
+
+// ==========================================================================================
+// Part 2: batched entry points
+// ==========================================================================================
+int32_t smb_device_count(void) { probe_devices(); return g_device_count; }
+void smb_set_device(int32_t device) { t_device = device; }
+void smb_set_stream(void* cuda_stream) { t_stream = (cudaStream_t)cuda_stream; }
+void smb_synchronize(void) { guarded_void([&] { cudaStream_t s = need_gpu(); sync(s); }); }
+uint64_t smb_kernel_launches(void) { return smb::g_launches.load(); }
+void* smb_alloc_pinned(uintptr_t nbytes) {
+    return guarded<void*>([&]() -> void* {
+        need_gpu();
+        void* p = nullptr;
+        CK(cudaHostAlloc(&p, std::max<size_t>(nbytes, 16), cudaHostAllocDefault));
+        return p;
+    });
+}
+void smb_free_pinned(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+uint64_t smb_max_hash_for_scaled(uint64_t scaled) { return max_hash_for_scaled(scaled); }
+
+SmbSketchSet* smb_sketchset_from_host(const uint64_t* hashes, const uint64_t* offsets,
+                                      uintptr_t n_rows, const uint64_t* abunds) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        cudaStream_t s = need_gpu();
+        auto set = std::make_unique<SmbSketchSet>();
+        set->n_rows = n_rows;
+        set->h_off.assign(offsets, offsets + n_rows + 1);
+        uint64_t total = set->total();
+        set->own_off.alloc(n_rows + 1, s);
+        set->own_off.upload(offsets, n_rows + 1);
+        set->own_hashes.alloc(total, s);
+        set->own_hashes.upload(hashes, total);
+        if (abunds) { set->own_abunds.alloc(total, s); set->own_abunds.upload(abunds, total); }
+        sync(s);
+        set->d_off = set->own_off.p; set->d_hashes = set->own_hashes.p;
+        set->d_abunds = abunds ? set->own_abunds.p : nullptr;
+        set->finish_offsets();
+        return set.release();
+    });
+}
+SmbSketchSet* smb_sketchset_from_device(const uint64_t* d_hashes, const uint64_t* d_offsets,
+                                        const uint64_t* h_offsets, uintptr_t n_rows) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        need_gpu();
+        auto set = std::make_unique<SmbSketchSet>();
+        set->n_rows = n_rows;
+        set->h_off.assign(h_offsets, h_offsets + n_rows + 1);
+        set->d_hashes = d_hashes; set->d_off = d_offsets;
+        set->finish_offsets();
+        return set.release();
+    });
+}
+void smb_sketchset_free(SmbSketchSet* set) { delete set; }
+uintptr_t smb_sketchset_len(const SmbSketchSet* set) { return set->n_rows; }
+uint64_t smb_sketchset_total_hashes(const SmbSketchSet* set) { return set->total(); }
+bool smb_sketchset_has_abunds(const SmbSketchSet* set) { return set->d_abunds != nullptr; }
+void smb_sketchset_offsets(const SmbSketchSet* set, uint64_t* offsets_out) {
+    memcpy(offsets_out, set->h_off.data(), (set->n_rows + 1) * 8);
+}
+void smb_sketchset_to_host(const SmbSketchSet* set, uint64_t* hashes_out, uint64_t* abunds_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        uint64_t total = set->total();
+        if (total && hashes_out) CK(cudaMemcpyAsync(hashes_out, set->d_hashes, total * 8, cudaMemcpyDeviceToHost, s));
+        if (total && abunds_out && set->d_abunds)
+            CK(cudaMemcpyAsync(abunds_out, set->d_abunds, total * 8, cudaMemcpyDeviceToHost, s));
+        sync(s);
+    });
+}
+const uint64_t* smb_sketchset_device_hashes(const SmbSketchSet* set) { return set->d_hashes; }
+const uint64_t* smb_sketchset_device_offsets(const SmbSketchSet* set) { return set->d_off; }
+
+SmbSketchSet* smb_sketchset_downsample(const SmbSketchSet* set, uint64_t max_hash) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        auto out = std::make_unique<SmbSketchSet>();
+        out->n_rows = n;
+        out->h_off.assign(n + 1, 0);
+        DevBuf<uint32_t> d_cnt(n, s);
+        smb::launch_row_prefix_counts(set->d_hashes, set->d_off, (int)n, max_hash, d_cnt.p, s);
+        std::vector<uint32_t> cnt(n);
+        d_cnt.download(cnt.data(), n);
+        sync(s);
+        for (size_t r = 0; r < n; ++r) out->h_off[r + 1] = out->h_off[r] + cnt[r];
+        out->own_off.alloc(n + 1, s);
+        out->own_off.upload(out->h_off.data(), n + 1);
+        out->own_hashes.alloc(out->total(), s);
+        smb::launch_compact_rows(set->d_hashes, set->d_off, d_cnt.p, out->own_off.p, out->own_hashes.p, (int)n, s);
+        if (set->d_abunds) {
+            out->own_abunds.alloc(out->total(), s);
+            smb::launch_compact_rows(set->d_abunds, set->d_off, d_cnt.p, out->own_off.p, out->own_abunds.p, (int)n, s);
+        }
+        CK(cudaGetLastError());
+        sync(s);
+        out->d_off = out->own_off.p; out->d_hashes = out->own_hashes.p;
+        out->d_abunds = set->d_abunds ? out->own_abunds.p : nullptr;
+        out->finish_offsets();
+        return out.release();
+    });
+}
+
+static SketchParams make_params(const uint32_t* ksizes, uintptr_t n_ksizes, uint64_t scaled,
+                                uint32_t num, uint64_t seed, bool track) {
+    SketchParams P;
+    P.ksizes.assign(ksizes, ksizes + n_ksizes);
+    P.max_hash = max_hash_for_scaled(scaled);
+    P.num = num; P.seed = seed; P.track = track;
+    return P;
+}
+
+SmbSketchSet* smb_sketch_sequences(const uint8_t* seqs, const uint64_t* seq_offsets,
+                                   uintptr_t n_seqs, const uint32_t* seq_to_sketch,
+                                   uintptr_t n_sketches, const uint32_t* ksizes,
+                                   uintptr_t n_ksizes, uint64_t scaled, uint32_t num, uint64_t seed,
+                                   bool track_abundance, uint64_t* n_kmers_out) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        cudaStream_t s = need_gpu();
+        const uint64_t total = n_seqs ? seq_offsets[n_seqs] : 0;
+        DevBuf<uint8_t> d_bases(total + 32, s);
+        d_bases.upload(seqs, total);                 // one H2D copy of the caller's buffer
+        StreamList in;
+        in.d_bases = d_bases.p;
+        in.off.assign(seq_offsets, seq_offsets + n_seqs);
+        in.len.resize(n_seqs);
+        for (size_t i = 0; i < n_seqs; ++i) in.len[i] = seq_offsets[i + 1] - seq_offsets[i];
+        if (seq_to_sketch) in.row.assign(seq_to_sketch, seq_to_sketch + n_seqs);
+        in.n_sketches = seq_to_sketch ? n_sketches : n_seqs;
+        SketchParams P = make_params(ksizes, n_ksizes, scaled, num, seed, track_abundance);
+        return sketch_streams(in, P, s, n_kmers_out).release();
+    });
+}
+
+SmbSketchSet* smb_sketch_streams_dev(const uint8_t* d_bases, const uint64_t* h_stream_offsets,
+                                     const uint64_t* h_stream_lens, uintptr_t n_streams,
+                                     const uint32_t* ksizes, uintptr_t n_ksizes, uint64_t scaled,
+                                     uint32_t num, uint64_t seed, bool track_abundance,
+                                     uint64_t* n_kmers_out) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        cudaStream_t s = need_gpu();
+        StreamList in;
+        in.d_bases = d_bases;
+        in.off.assign(h_stream_offsets, h_stream_offsets + n_streams);
+        in.len.assign(h_stream_lens, h_stream_lens + n_streams);
+        in.n_sketches = n_streams;
+        SketchParams P = make_params(ksizes, n_ksizes, scaled, num, seed, track_abundance);
+        return sketch_streams(in, P, s, n_kmers_out).release();
+    });
+}
+
+void smb_pairwise_common(const SmbSketchSet* a, const SmbSketchSet* b, uint32_t num,
+                         uint32_t* common_out, uint32_t* usize_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t nA = a->n_rows, nB = b ? b->n_rows : a->n_rows;
+        if (nA == 0 || nB == 0) return;
+        DevBuf<uint32_t> d_c(nA * nB, s), d_u;
+        d_c.zero();
+        if (num) { d_u.alloc(nA * nB, s); d_u.zero(); }
+        pairwise_counts_dev(*a, b, num, d_c.p, num ? d_u.p : nullptr, nB, s);
+        CK(cudaGetLastError());
+        d_c.download(common_out, nA * nB);
+        if (num && usize_out) d_u.download(usize_out, nA * nB);
+        sync(s);
+        if (!b) {   // mirror the strict upper triangle; diagonal = |A_i| (num: min(num,|A_i|))
+            for (size_t i = 0; i < nA; ++i) {
+                uint64_t li = a->h_off[i + 1] - a->h_off[i];
+                if (num && li > num) li = num;
+                common_out[i * nB + i] = (uint32_t)li;
+                if (num && usize_out) usize_out[i * nB + i] = (uint32_t)li;
+                for (size_t j = i + 1; j < nB; ++j) {
+                    common_out[j * nB + i] = common_out[i * nB + j];
+                    if (num && usize_out) usize_out[j * nB + i] = usize_out[i * nB + j];
+                }
+            }
+        }
+    });
+}
+
+static void compare_jaccard_impl(const SmbSketchSet* set, uint32_t num, double* d_out, cudaStream_t s) {
+    const size_t n = set->n_rows;
+    if (n == 0) return;
+    DevBuf<uint32_t> d_c(n * n, s), d_u;
+    if (num) d_u.alloc(n * n, s);
+    pairwise_counts_dev(*set, nullptr, num, d_c.p, num ? d_u.p : nullptr, n, s);
+    smb::launch_finalize_matrix(d_c.p, num ? d_u.p : nullptr, n, set->d_off, set->d_off, (int)n, (int)n,
+                                num ? 1 : 0, true, d_out, s);
+    CK(cudaGetLastError());
+}
+
+void smb_compare_jaccard_dev(const SmbSketchSet* set, uint32_t num, double* d_out) {
+    guarded_void([&] { cudaStream_t s = need_gpu(); compare_jaccard_impl(set, num, d_out, s); });
+}
+
+void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (n == 0) return;
+        DevBuf<double> d_out(n * n, s);
+        compare_jaccard_impl(set, num, d_out.p, s);
+        d_out.download(out, n * n);
+        sync(s);
+    });
+}
+
+static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& db, uint32_t* d_counts,
+                            cudaStream_t s) {
+    // query small enough for shared memory: it becomes the (single) table of the tile kernel;
+    // otherwise a global-memory directory over the query.
+    const int nB = (int)db.n_rows;
+    if (nB == 0) return;
+    smb::PairwisePlan plan = smb::plan_pairwise(nq, nB);
+    SmbSketchSet q;
+    q.n_rows = 1; q.h_off = {0, (uint64_t)nq};
+    q.own_off.alloc(2, s); q.own_off.upload(q.h_off.data(), 2);
+    q.d_off = q.own_off.p; q.d_hashes = d_q; q.finish_offsets();
+    DevBuf<uint32_t> d_shift(4, s);
+    if (plan.tables_per_cta > 0) {
+        plan.tables_per_cta = 1;
+        plan.smem_bytes = (size_t)(plan.cap + 2) * 8 + ((size_t(1) << plan.nb_log2) + 2) * 2;
+        plan.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
+        smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, plan.nb_log2, d_shift.p, s);
+        smb::launch_pairwise_tile(plan, q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, d_counts,
+                                  (size_t)nB, d_shift.p, false, s);
+    } else {
+        int nb_log2 = 12;
+        while (nb_log2 < 26 && (1ull << nb_log2) < 2 * (uint64_t)nq) ++nb_log2;
+        smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, q.d_hashes, q.d_off, 1, nb_log2, d_shift.p, s);
+        DevBuf<uint32_t> d_dir((size_t(1) << nb_log2) + 2, s);
+        smb::launch_build_global_dir(d_q, nq, nb_log2, d_shift.p, d_dir.p, s);
+        smb::launch_one_vs_many_global(d_q, nq, d_dir.p, d_shift.p, nb_log2, db.d_hashes, db.d_off, nB,
+                                       d_counts, s);
+    }
+    CK(cudaGetLastError());
+    sync(s);      // q's offsets upload reads a host temporary
+}
+
+void smb_one_vs_many(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
+                     uint32_t* common_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t nB = db->n_rows;
+        if (nB == 0) return;
+        DevBuf<uint64_t> d_q(n_query, s);
+        d_q.upload(query, n_query);
+        DevBuf<uint32_t> d_counts(nB, s);
+        d_counts.zero();
+        one_vs_many_dev(d_q.p, n_query, *db, d_counts.p, s);
+        d_counts.download(common_out, nB);
+        sync(s);
+    });
+}
+
+uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
+                     uint32_t threshold, uint32_t* match_ids, uint32_t* isect_sizes,
+                     uintptr_t max_rounds) {
+    return guarded<uintptr_t>([&]() -> uintptr_t {
+        // CounterGather (index/__init__.py:777-909): counters[j] = |query ∩ S_j| once, then per
+        // round: best = argmax (first inserted wins ties); intersect = remaining_query ∩ best;
+        // every counter -= |intersect ∩ S_j|; remaining_query -= best.
+        cudaStream_t s = need_gpu();
+        const size_t nB = db->n_rows;
+        if (nB == 0 || n_query == 0 || max_rounds == 0) return 0;
+        if (threshold < 1) threshold = 1;
+        DevBuf<uint64_t> d_q(n_query, s), d_q2(n_query, s), d_isect(n_query, s);
+        d_q.upload(query, n_query);
+        DevBuf<uint32_t> d_counts(nB, s), d_delta(nB, s), d_n(2, s);
+        DevBuf<unsigned long long> d_best(2, s);
+        d_counts.zero();
+        one_vs_many_dev(d_q.p, n_query, *db, d_counts.p, s);
+        size_t nq = n_query;
+        uint64_t* cur = d_q.p;
+        uint64_t* other = d_q2.p;
+        const uint32_t* delta = nullptr;
+        uintptr_t rounds = 0;
+        while (rounds < max_rounds) {
+            smb::launch_counter_update_argmax(d_counts.p, delta, (int)nB, d_best.p, s);
+            unsigned long long best[2];
+            d_best.download(best, 2);
+            sync(s);
+            if (best[0] < threshold || best[0] == 0) break;
+            const size_t j = (size_t)best[1];
+            const uint64_t* row = db->d_hashes + db->h_off[j];
+            const size_t rn = db->h_off[j + 1] - db->h_off[j];
+            // intersect = cur ∩ row ; new query = cur \ row
+            smb::launch_intersect_rows(cur, nq, row, rn, d_isect.p, d_n.p, s);
+            smb::launch_subtract_rows(cur, nq, row, rn, other, d_n.p + 1, s);
+            uint32_t nn[2];
+            d_n.download(nn, 2);
+            sync(s);
+            match_ids[rounds] = (uint32_t)j;
+            isect_sizes[rounds] = nn[0];
+            ++rounds;
+            // counters -= |intersect ∩ S_j| for all j (the chosen row drops to 0 by itself)
+            d_delta.zero();
+            if (nn[0] > 0) one_vs_many_dev(d_isect.p, nn[0], *db, d_delta.p, s);
+            delta = d_delta.p;
+            std::swap(cur, other);
+            nq = nn[1];
+            if (nq == 0) break;
+        }
+        return rounds;
+    });
+}
+
+}  // extern "C"

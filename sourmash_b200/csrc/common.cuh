@@ -1,0 +1,30 @@
+// common.cuh -- shared device/host helpers for the sm_100a kernels of sourmash_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+#define SMB_U64_MAX 0xffffffffffffffffULL
+
+// Number of SMs on a B200; grids for persistent-style kernels are sized in multiples of it.
+#define SMB_B200_SMS 148
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
+    return __ldg(reinterpret_cast<const unsigned long long*>(p));
+}
+
+// MurmurHash3 x64-128 building blocks (device + host), see murmur.cuh.
+__host__ __device__ __forceinline__ u64 smb_rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__host__ __device__ __forceinline__ u64 smb_fmix64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33; return x;
+}
+#define SMB_C1 0x87c37b91114253d5ULL
+#define SMB_C2 0x4cf5ad432745937fULL

@@ -1,0 +1,534 @@
+// compare_kernels.cu -- sorted-u64 hash-set intersection kernels for sm_100a.
+//
+// Replaces the reference's per-pair CPU loops:
+//   count_common          src/core/src/sketch/minhash.rs:539-558 (+ Intersection :915-953)
+//   intersection_size     src/core/src/sketch/minhash.rs:593-621, free fn :1765-1807
+//   intersection          src/core/src/sketch/minhash.rs:560-589, free fn :1721-1763
+//   jaccard               src/core/src/sketch/minhash.rs:624-631
+// driven in the reference by Python loops (src/sourmash/compare.py:14-187,
+// src/sourmash/index/__init__.py:115-170,777-909).
+//
+// Design (B200): integer/byte work, no tensor cores.  The hot kernel keeps TA "table" rows
+// resident in shared memory as sorted keys + a bucket directory (bucket = key >> shift, the
+// keys are murmur outputs, i.e. uniform), and streams the other operand's rows through
+// registers with coalesced 8-byte loads: each streamed element costs one directory lookup
+// plus two key compares per table ("directory galloping"), instead of a two-pointer walk
+// over |A|+|B| elements.  Counts are reduced with warp REDUX and written as u32.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+static constexpr int TILE_THREADS = 512;
+static constexpr int MAX_DYN_SMEM = 227 * 1024;
+
+// ------------------------------------------------------------------------------------
+// bucket shift: (max key) >> shift < 2^nb_log2
+// ------------------------------------------------------------------------------------
+__global__ void max_last_kernel(const u64* __restrict__ hA, const u64* __restrict__ offA, int nA,
+                                const u64* __restrict__ hB, const u64* __restrict__ offB, int nB,
+                                unsigned long long* __restrict__ d_max) {
+    u64 m = 0;
+    int total = nA + nB;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += gridDim.x * blockDim.x) {
+        const u64* h = r < nA ? hA : hB;
+        const u64* off = r < nA ? offA : offB;
+        int i = r < nA ? r : r - nA;
+        u64 beg = off[i], end = off[i + 1];
+        if (end > beg) { u64 v = h[end - 1]; m = v > m ? v : m; }
+    }
+    for (int d = 16; d; d >>= 1) { u64 o = __shfl_xor_sync(0xffffffffu, m, d); m = o > m ? o : m; }
+    if (lane_id() == 0 && m) atomicMax(d_max, (unsigned long long)m);
+}
+
+__global__ void shift_from_max_kernel(const unsigned long long* __restrict__ d_max, int nb_log2,
+                                      u32* __restrict__ d_shift) {
+    u64 m = *d_max;
+    int bits = m ? 64 - __clzll((long long)m) : 0;
+    int sh = bits - nb_log2;
+    d_shift[0] = sh > 0 ? (u32)sh : 0u;
+}
+
+void launch_bucket_shift(const u64* hA, const u64* offA, int nA, const u64* hB, const u64* offB,
+                         int nB, int nb_log2, u32* d_shift, cudaStream_t s) {
+    // d_shift[0] = shift, d_shift[2..3] = scratch for the 64-bit max
+    unsigned long long* d_max = reinterpret_cast<unsigned long long*>(d_shift + 2);
+    cudaMemsetAsync(d_shift, 0, 4 * sizeof(u32), s);
+    int total = nA + nB;
+    int blocks = (total + 255) / 256;
+    if (blocks > SMB_B200_SMS * 4) blocks = SMB_B200_SMS * 4;
+    if (blocks < 1) blocks = 1;
+    max_last_kernel<<<blocks, 256, 0, s>>>(hA, offA, nA, hB, offB, nB, d_max); count_launches(1);
+    shift_from_max_kernel<<<1, 1, 0, s>>>(d_max, nb_log2, d_shift); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// tile kernel
+// ------------------------------------------------------------------------------------
+PairwisePlan plan_pairwise(uint64_t max_len_a, int n_b) {
+    PairwisePlan p{};
+    uint64_t cap = (max_len_a + 1 + 3) & ~3ULL;          // +1: room even if a row is empty
+    if (cap < 64) cap = 64;
+    // directory: about 2-4 buckets per key, 2^10 .. 2^14 buckets
+    int nb_log2 = 10;
+    while (nb_log2 < 14 && (1ULL << nb_log2) < 2 * cap) ++nb_log2;
+    for (;; --nb_log2) {
+        size_t per_table = (cap + 2) * 8 + ((size_t(1) << nb_log2) + 2) * 2;
+        int ta = (int)(MAX_DYN_SMEM / per_table);
+        if (ta >= 1) {
+            if (ta > 4) ta = 4;
+            p.tables_per_cta = ta; p.nb_log2 = nb_log2; p.cap = (int)cap;
+            p.smem_bytes = per_table * ta;
+            break;
+        }
+        if (nb_log2 == 10) { p.tables_per_cta = 0; return p; }   // row too large for smem
+    }
+    // columns per CTA: enough streamed rows to amortise the table build
+    p.cols_per_cta = 512;
+    (void)n_b;
+    return p;
+}
+
+struct TileArgs {
+    const u64* hA; const u64* offA; int nA;
+    const u64* hB; const u64* offB; int nB;
+    u32* out; size_t ldo;
+    const u32* d_shift;
+    int nb_log2, cap, cols_per_cta, symmetric;
+};
+
+template <int TA>
+__device__ __forceinline__ void probe_one(u64 q, u32 b, const u64* const (&keys)[TA],
+                                          const u16* const (&dirs)[TA], u32 (&cnt)[TA], u32 valid) {
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        u32 st = dirs[t][b];
+        const u64* kp = keys[t] + st;
+        u64 k0 = kp[0], k1 = kp[1];
+        u32 m = (k0 == q) | (k1 == q);
+        if (k1 < q) {                       // rare: >2 keys of this bucket precede q
+            const u64* pp = kp + 2;
+            u64 kk;
+            while ((kk = *pp) < q) ++pp;
+            m = (kk == q);
+        }
+        cnt[t] += m & valid;
+    }
+}
+
+template <int TA, int U>
+__global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int i0 = blockIdx.x * TA;
+    int jbeg = blockIdx.y * a.cols_per_cta;
+    int jend = min(jbeg + a.cols_per_cta, a.nB);
+    if (a.symmetric) jbeg = max(jbeg, i0 + 1);
+    if (jbeg >= jend) return;
+
+    const u32 shift = a.d_shift[0];
+    const int nb = 1 << a.nb_log2;
+    const int tid = threadIdx.x;
+    const int kstride = a.cap + 2;
+    const int dstride = nb + 2;
+    u64* keys_base = reinterpret_cast<u64*>(smem_raw);
+    u16* dirs_base = reinterpret_cast<u16*>(smem_raw + (size_t)TA * kstride * 8);
+
+    __shared__ int s_n[TA];
+    __shared__ int s_hasmax[TA];
+
+    // ---- load table rows (coalesced), strip a trailing UINT64_MAX key, add sentinels
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        int i = i0 + t;
+        u64 beg = 0; int n = 0; int hm = 0;
+        if (i < a.nA) {
+            beg = a.offA[i];
+            n = (int)(a.offA[i + 1] - beg);
+            if (n > 0 && ld_nc_u64(a.hA + beg + n - 1) == SMB_U64_MAX) { --n; hm = 1; }
+        }
+        u64* kt = keys_base + (size_t)t * kstride;
+        for (int p = tid; p < n; p += TILE_THREADS) kt[p] = ld_nc_u64(a.hA + beg + p);
+        if (tid < 2) kt[n + tid] = SMB_U64_MAX;
+        if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
+    }
+    __syncthreads();
+    // ---- build directories: dir[b] = #keys with bucket < b, b in [0, nb]
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        const u64* kt = keys_base + (size_t)t * kstride;
+        u16* dt = dirs_base + (size_t)t * dstride;
+        int n = s_n[t];
+        for (int p = tid; p <= n; p += TILE_THREADS) {
+            int bp = p < n ? (int)(kt[p] >> shift) : nb;
+            int bprev = p == 0 ? -1 : (int)(kt[p - 1] >> shift);
+            for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)p;
+        }
+    }
+    __syncthreads();
+
+    const u64* keys[TA];
+    const u16* dirs[TA];
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        keys[t] = keys_base + (size_t)t * kstride;
+        dirs[t] = dirs_base + (size_t)t * dstride;
+    }
+
+    // ---- stream columns: one warp per streamed row
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARPS = TILE_THREADS / 32;
+    for (int j = jbeg + warp; j < jend; j += NWARPS) {
+        const u64 bbeg = a.offB[j];
+        int nbj = (int)(a.offB[j + 1] - bbeg);
+        int bmax = 0;
+        if (nbj > 0 && ld_nc_u64(a.hB + bbeg + nbj - 1) == SMB_U64_MAX) { --nbj; bmax = 1; }
+        const u64* row = a.hB + bbeg;
+        u32 cnt[TA];
+#pragma unroll
+        for (int t = 0; t < TA; ++t) cnt[t] = 0;
+
+        int base = 0;
+        const int full = nbj - (nbj % (32 * U));
+        u64 q[U];
+        if (full > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + u * 32 + lane);
+        }
+        for (; base < full; base += 32 * U) {
+            u64 cur[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = q[u];
+            if (base + 32 * U < full) {       // prefetch next batch before probing this one
+#pragma unroll
+                for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + base + 32 * U + u * 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) probe_one<TA>(cur[u], (u32)(cur[u] >> shift), keys, dirs, cnt, 1u);
+        }
+        for (; base < nbj; base += 32) {      // ragged tail
+            int e = base + lane;
+            u32 valid = e < nbj;
+            u64 qq = valid ? ld_nc_u64(row + e) : 0ULL;
+            probe_one<TA>(qq, (u32)(qq >> shift), keys, dirs, cnt, valid);
+        }
+#pragma unroll
+        for (int t = 0; t < TA; ++t) {
+            u32 c = __reduce_add_sync(0xffffffffu, cnt[t]);
+            int i = i0 + t;
+            if (lane == 0 && i < a.nA && (!a.symmetric || j > i))
+                a.out[(size_t)i * a.ldo + j] = c + (u32)(s_hasmax[t] & bmax);
+        }
+    }
+}
+
+template <int TA>
+static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
+    auto kern = pairwise_tile_kernel<TA, 4>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((args.nA + TA - 1) / TA, (args.nB + args.cols_per_cta - 1) / args.cols_per_cta);
+    kern<<<grid, TILE_THREADS, smem, s>>>(args); count_launches(1);
+}
+
+void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* offA, int nA,
+                          const u64* hB, const u64* offB, int nB, u32* out, size_t ldo,
+                          const u32* d_shift, bool symmetric, cudaStream_t s) {
+    if (nA <= 0 || nB <= 0) return;
+    TileArgs a{hA, offA, nA, hB, offB, nB, out, ldo, d_shift,
+               plan.nb_log2, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0};
+    switch (plan.tables_per_cta) {
+        case 1: launch_tile_ta<1>(a, plan.smem_bytes, s); break;
+        case 2: launch_tile_ta<2>(a, plan.smem_bytes, s); break;
+        case 3: launch_tile_ta<3>(a, plan.smem_bytes, s); break;
+        default: launch_tile_ta<4>(a, plan.smem_bytes, s); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// generic fallback: warp per pair, binary search of the shorter row in the longer row
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool row_contains(const u64* __restrict__ r, u64 n, u64 x) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        u64 v = ld_nc_u64(r + mid);
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && ld_nc_u64(r + lo) == x;
+}
+
+__global__ void __launch_bounds__(256) pairwise_generic_kernel(
+    const u64* __restrict__ hA, const u64* __restrict__ offA, int nA, const u64* __restrict__ hB,
+    const u64* __restrict__ offB, int nB, u32* __restrict__ out, size_t ldo, int symmetric) {
+    const u64 npairs = (u64)nA * (u64)nB;
+    const u64 wstride = (u64)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < npairs; w += wstride) {
+        int i = (int)(w / (u64)nB), j = (int)(w % (u64)nB);
+        if (symmetric && j <= i) continue;
+        const u64* ra = hA + offA[i]; u64 na = offA[i + 1] - offA[i];
+        const u64* rb = hB + offB[j]; u64 nb = offB[j + 1] - offB[j];
+        if (na > nb) { const u64* tr = ra; ra = rb; rb = tr; u64 tn = na; na = nb; nb = tn; }
+        u32 c = 0;
+        for (u64 e = lane; e < na; e += 32) c += row_contains(rb, nb, ld_nc_u64(ra + e)) ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) out[(size_t)i * ldo + j] = c;
+    }
+}
+
+void launch_pairwise_generic(const u64* hA, const u64* offA, int nA, const u64* hB,
+                             const u64* offB, int nB, u32* out, size_t ldo, bool symmetric,
+                             cudaStream_t s) {
+    if (nA <= 0 || nB <= 0) return;
+    u64 npairs = (u64)nA * (u64)nB;
+    u64 blocks = (npairs + 7) / 8;
+    if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
+    pairwise_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(hA, offA, nA, hB, offB, nB, out, ldo,
+                                                            symmetric ? 1 : 0); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// bottom-k ("num") sketches -- minhash.rs:593-617.  M = first `num` of A ∪ B.
+// The union rank of a_i is i + lower_bound(B, a_i) - (#matches among a_0..a_{i-1}); a common
+// element counts iff its rank < num.  One warp per pair; prefix of matches by ballot.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pairwise_num_kernel(
+    const u64* __restrict__ hA, const u64* __restrict__ offA, int nA, const u64* __restrict__ hB,
+    const u64* __restrict__ offB, int nB, u32 num, u32* __restrict__ common,
+    u32* __restrict__ usize, size_t ldo, int symmetric) {
+    const u64 npairs = (u64)nA * (u64)nB;
+    const u64 wstride = (u64)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < npairs; w += wstride) {
+        int i = (int)(w / (u64)nB), j = (int)(w % (u64)nB);
+        if (symmetric && j <= i) continue;
+        const u64* ra = hA + offA[i]; u64 na = offA[i + 1] - offA[i];
+        const u64* rb = hB + offB[j]; u64 nb = offB[j + 1] - offB[j];
+        u64 matches_before = 0;     // matches among a_0 .. a_{base-1}
+        u32 c_in_m = 0, c_total = 0;
+        for (u64 base = 0; base < na; base += 32) {
+            u64 e = base + lane;
+            bool valid = e < na;
+            u64 x = valid ? ld_nc_u64(ra + e) : 0;
+            u64 lo = 0, hi = valid ? nb : 0;
+            while (lo < hi) {
+                u64 mid = (lo + hi) >> 1;
+                if (ld_nc_u64(rb + mid) < x) lo = mid + 1; else hi = mid;
+            }
+            bool m = valid && lo < nb && ld_nc_u64(rb + lo) == x;
+            u32 bal = __ballot_sync(0xffffffffu, m);
+            u64 prior = matches_before + __popc(bal & ((1u << lane) - 1u));
+            u64 rank = e + lo - prior;
+            if (m) { ++c_total; if (num == 0 || rank < (u64)num) ++c_in_m; }
+            matches_before += __popc(bal);
+        }
+        c_in_m = __reduce_add_sync(0xffffffffu, c_in_m);
+        c_total = __reduce_add_sync(0xffffffffu, c_total);
+        if (lane == 0) {
+            u64 un = na + nb - c_total;
+            if (num != 0 && un > num) un = num;
+            common[(size_t)i * ldo + j] = c_in_m;
+            if (usize) usize[(size_t)i * ldo + j] = (u32)un;
+        }
+    }
+}
+
+void launch_pairwise_num(const u64* hA, const u64* offA, int nA, const u64* hB, const u64* offB,
+                         int nB, u32 num, u32* common, u32* usize, size_t ldo, bool symmetric,
+                         cudaStream_t s) {
+    if (nA <= 0 || nB <= 0) return;
+    u64 npairs = (u64)nA * (u64)nB;
+    u64 blocks = (npairs + 7) / 8;
+    if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
+    pairwise_num_kernel<<<(unsigned)blocks, 256, 0, s>>>(hA, offA, nA, hB, offB, nB, num, common,
+                                                        usize, ldo, symmetric ? 1 : 0); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// counts -> float64 matrix (jaccard = common / max(1, union), minhash.rs:624-631;
+// IEEE div.rn.f64 is bit-identical to the reference's f64 divide).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_matrix_kernel(
+    const u32* __restrict__ common, const u32* __restrict__ usize, size_t ldo,
+    const u64* __restrict__ offA, const u64* __restrict__ offB, int nA, int nB, int mode,
+    int symmetric, double* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= nB || i >= nA) return;
+    double v;
+    if (symmetric && i == j) {
+        v = 1.0;                                  // compare.py:38 np.ones diagonal
+    } else {
+        int r = i, c = j;
+        if (symmetric && j < i) { r = j; c = i; }
+        u64 cm = common[(size_t)r * ldo + c];
+        if (mode == 0) {
+            u64 na = offA[r + 1] - offA[r], nbb = offB[c + 1] - offB[c];
+            u64 un = na + nbb - cm;
+            v = (double)cm / (double)(un > 1 ? un : 1);
+        } else if (mode == 1) {
+            u64 un = usize[(size_t)r * ldo + c];
+            v = (double)cm / (double)(un > 1 ? un : 1);
+        } else {
+            v = (double)cm;
+        }
+    }
+    out[(size_t)i * nB + j] = v;
+}
+
+void launch_finalize_matrix(const u32* common, const u32* usize, size_t ldo, const u64* offA,
+                            const u64* offB, int nA, int nB, int mode, bool symmetric, double* out,
+                            cudaStream_t s) {
+    if (nA <= 0 || nB <= 0) return;
+    dim3 grid((nB + 255) / 256, nA);
+    finalize_matrix_kernel<<<grid, 256, 0, s>>>(common, usize, ldo, offA, offB, nA, nB, mode,
+                                                symmetric ? 1 : 0, out); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// one (large) query vs many subjects: global-memory directory over the query
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_global_dir_kernel(
+    const u64* __restrict__ q, u64 nq, int nb_log2, const u32* __restrict__ d_shift,
+    u32* __restrict__ dir) {
+    const u32 shift = d_shift[0];
+    const u64 nb = 1ULL << nb_log2;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p <= nq;
+         p += (u64)gridDim.x * blockDim.x) {
+        long long bp = p < nq ? (long long)(q[p] >> shift) : (long long)nb;
+        if (bp > (long long)nb) bp = (long long)nb;
+        long long bprev = p == 0 ? -1 : (long long)(q[p - 1] >> shift);
+        if (bprev > (long long)nb) bprev = (long long)nb;
+        for (long long b = bprev + 1; b <= bp; ++b) dir[b] = (u32)p;
+    }
+}
+
+void launch_build_global_dir(const u64* q, u64 nq, int nb_log2, const u32* d_shift, u32* dir,
+                             cudaStream_t s) {
+    u64 blocks = (nq + 1 + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 32) blocks = (u64)SMB_B200_SMS * 32;
+    build_global_dir_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, nb_log2, d_shift, dir); count_launches(1);
+}
+
+__global__ void __launch_bounds__(256) one_vs_many_global_kernel(
+    const u64* __restrict__ q, u64 nq, const u32* __restrict__ dir, const u32* __restrict__ d_shift,
+    int nb_log2, const u64* __restrict__ hB, const u64* __restrict__ offB, int nB,
+    u32* __restrict__ out) {
+    const u32 shift = d_shift[0];
+    const u64 nbk = 1ULL << nb_log2;
+    const int lane = lane_id();
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    for (int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nB; j += wstride) {
+        const u64* row = hB + offB[j];
+        u64 n = offB[j + 1] - offB[j];
+        u32 c = 0;
+        for (u64 e = lane; e < n; e += 32) {
+            u64 x = ld_nc_u64(row + e);
+            u64 b = x >> shift;
+            if (b >= nbk) continue;                 // beyond the query's key range
+            u64 p = dir[b], pe = dir[b + 1];
+            for (; p < pe; ++p) {
+                u64 k = ld_nc_u64(q + p);
+                if (k >= x) { c += (k == x); break; }
+            }
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) out[j] = c;
+    }
+}
+
+void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, const u32* d_shift,
+                               int nb_log2, const u64* hB, const u64* offB, int nB, u32* out,
+                               cudaStream_t s) {
+    if (nB <= 0) return;
+    int blocks = (nB + 7) / 8;
+    if (blocks > SMB_B200_SMS * 16) blocks = SMB_B200_SMS * 16;
+    one_vs_many_global_kernel<<<blocks, 256, 0, s>>>(q, nq, dir, d_shift, nb_log2, hB, offB, nB, out); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// row-level set operations used by gather (single block; rows are a few 1e3..1e6 keys)
+// ------------------------------------------------------------------------------------
+template <bool KEEP_COMMON>
+__global__ void __launch_bounds__(1024) setop_rows_kernel(const u64* __restrict__ a, u64 na,
+                                                         const u64* __restrict__ b, u64 nb,
+                                                         u64* __restrict__ out,
+                                                         u32* __restrict__ d_n) {
+    // stable compaction of a's elements that are (KEEP_COMMON ? in : not in) b.
+    __shared__ u32 warp_tot[32];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    for (u64 base = 0; base < na; base += blockDim.x) {
+        u64 e = base + threadIdx.x;
+        bool valid = e < na;
+        u64 x = valid ? a[e] : 0;
+        bool in_b = valid && row_contains(b, nb, x);
+        bool keep = valid && (KEEP_COMMON ? in_b : !in_b);
+        u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u32 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (keep) out[pos] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 t = 0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += warp_tot[w2];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *d_n = carry;
+}
+
+void launch_intersect_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, u32* d_n,
+                           cudaStream_t s) {
+    setop_rows_kernel<true><<<1, 1024, 0, s>>>(a, na, b, nb, out, d_n); count_launches(1);
+}
+void launch_subtract_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, u32* d_n,
+                          cudaStream_t s) {
+    setop_rows_kernel<false><<<1, 1024, 0, s>>>(a, na, b, nb, out, d_n); count_launches(1);
+}
+
+// counters[j] -= delta[j] (delta nullable), then argmax with lowest-index tie break
+// (Counter.most_common()[0] on insertion-ordered dict: src/sourmash/index/__init__.py:841).
+__global__ void __launch_bounds__(1024) counter_update_argmax_kernel(
+    u32* __restrict__ counters, const u32* __restrict__ delta, int n,
+    unsigned long long* __restrict__ d_best) {
+    // key = (value << 32) | (0xffffffff - index): max key == max value, then min index
+    unsigned long long best = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        u32 v = counters[j];
+        if (delta) { u32 d = delta[j]; v = d > v ? 0u : v - d; counters[j] = v; }
+        unsigned long long key = ((unsigned long long)v << 32) | (unsigned long long)(0xffffffffu - (u32)j);
+        best = key > best ? key : best;
+    }
+    for (int d = 16; d; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o > best ? o : best;
+    }
+    __shared__ unsigned long long sb[32];
+    if (lane_id() == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : 0ULL;
+        for (int d = 16; d; d >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+            best = o > best ? o : best;
+        }
+        if (threadIdx.x == 0) {
+            d_best[0] = best >> 32;                                   // value
+            d_best[1] = 0xffffffffu - (u32)(best & 0xffffffffu);      // index
+        }
+    }
+}
+
+void launch_counter_update_argmax(u32* counters, const u32* delta, int n,
+                                  unsigned long long* d_best, cudaStream_t s) {
+    counter_update_argmax_kernel<<<1, 1024, 0, s>>>(counters, delta, n, d_best); count_launches(1);
+}
+
+}  // namespace smb
+

@@ -1,0 +1,125 @@
+// kernels.h -- host-callable launchers for the sm_100a kernels (internal C++ interface
+// between capi.cu and the .cu kernel files; the public boundary is include/sourmash_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace smb {
+
+// ---------------------------------------------------------------- intersection path
+struct PairwisePlan {
+    int tables_per_cta;   // TA (1..4); 0 => tile kernel not applicable, use generic kernel
+    int nb_log2;          // log2(#buckets) of the shared-memory directory
+    int cap;              // key capacity per table
+    int cols_per_cta;
+    size_t smem_bytes;
+};
+
+// Chooses the tile-kernel configuration for table rows of at most max_len_a keys.
+PairwisePlan plan_pairwise(uint64_t max_len_a, int n_b);
+
+// Writes the bucket shift (a device u32) such that (max key >> shift) < 2^nb_log2, where the
+// max runs over the last element of every row of both CSR sets.  d_shift must hold 2 u32.
+void launch_bucket_shift(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
+                         const uint64_t* offB, int nB, int nb_log2, uint32_t* d_shift,
+                         cudaStream_t s);
+
+// common[i*ldo + j] = |A_i ∩ B_j| for every (i, j) (symmetric: only j > i, A == B).
+// Tile kernel: A rows become shared-memory bucket tables, B rows stream through registers.
+void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const uint64_t* offA,
+                          int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
+                          size_t ldo, const uint32_t* d_shift, bool symmetric, cudaStream_t s);
+
+// Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
+// elements in the longer row.
+void launch_pairwise_generic(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
+                             const uint64_t* offB, int nB, uint32_t* out, size_t ldo,
+                             bool symmetric, cudaStream_t s);
+
+// Bottom-k ("num") sketches: common = |A ∩ B ∩ M|, usize = |M|, M = first `num` of A ∪ B.
+void launch_pairwise_num(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
+                         const uint64_t* offB, int nB, uint32_t num, uint32_t* common,
+                         uint32_t* usize, size_t ldo, bool symmetric, cudaStream_t s);
+
+// counts -> float64 matrix.  mode: 0 jaccard (scaled), 1 jaccard (num; needs usize),
+// 2 raw containment c/|col j| written at [i][j] (no bias correction; host applies it).
+void launch_finalize_matrix(const uint32_t* common, const uint32_t* usize, size_t ldo,
+                            const uint64_t* offA, const uint64_t* offB, int nA, int nB, int mode,
+                            bool symmetric, double* out, cudaStream_t s);
+
+// One query vs many subjects with a query too large for shared memory: global-memory bucket
+// directory over the query, every subject element probes it.
+void launch_build_global_dir(const uint64_t* q, uint64_t nq, int nb_log2, const uint32_t* d_shift,
+                             uint32_t* dir, cudaStream_t s);
+void launch_one_vs_many_global(const uint64_t* q, uint64_t nq, const uint32_t* dir,
+                               const uint32_t* d_shift, int nb_log2, const uint64_t* hB,
+                               const uint64_t* offB, int nB, uint32_t* out, cudaStream_t s);
+
+// Materialise A ∩ B of two sorted rows (gather's intersect_mh); returns count in *d_n.
+void launch_intersect_rows(const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb,
+                           uint64_t* out, uint32_t* d_n, cudaStream_t s);
+// out = a \ b (sorted rows), count in *d_n  (gather's query.remove_many(found)).
+void launch_subtract_rows(const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb,
+                          uint64_t* out, uint32_t* d_n, cudaStream_t s);
+// counters[j] -= delta[j]; then (best value, lowest index) of counters -> d_best[0..1].
+void launch_counter_update_argmax(uint32_t* counters, const uint32_t* delta, int n,
+                                  unsigned long long* d_best, cudaStream_t s);
+
+// ---------------------------------------------------------------- sketch path
+// Streams are byte sequences inside one 16-byte aligned HBM allocation that is readable up to
+// the next 16-byte boundary past its end.  Any non-ACGT byte inside a stream (record separator,
+// N, ...) invalidates the windows covering it.  Output row = stream * row_stride + row_index.
+struct HashLaunch {
+    const uint8_t* bases;
+    const uint64_t* stream_off;          // device [n_streams] byte offsets (any alignment)
+    const uint64_t* stream_len;          // device [n_streams]
+    const uint32_t* stream_row;          // device [n_streams] sketch fed by each stream (NULL: identity)
+    int n_streams;
+    const uint32_t* tile_start_rolled;   // device [n_streams+1] prefix of ceil((off%16+len)/(threads*W))
+    uint32_t total_tiles_rolled;
+    const uint32_t* tile_start_generic;  // device [n_streams+1] prefix of ceil(len/256)
+    uint32_t total_tiles_generic;
+    int W;                               // windows per thread, multiple of 16
+    uint64_t seed, max_hash;
+    uint64_t* cand;                      // candidate storage
+    const uint64_t* cand_off;            // device [n_rows+1]
+    uint32_t* cand_cnt;                  // device [n_rows] (zeroed by caller)
+    int row_stride;
+};
+bool k_has_rolled_kernel(uint32_t k);
+int hash_threads();
+// survivors (0 < h <= max_hash, all k bases valid) of every window -> candidate rows
+void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cudaStream_t s);
+// per-window hashes of stream 0 in order; 0 marks an invalid window (seq_to_hashes)
+void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s);
+// first non-ACGT position of a sequence (UINT64_MAX if none)
+void launch_first_invalid(const uint8_t* bases, uint64_t len, unsigned long long* d_pos,
+                          cudaStream_t s);
+// murmur3 of an arbitrary byte string (hash_murmur / add_word)
+void launch_murmur_bytes(const uint8_t* data, uint64_t len, uint64_t seed, uint64_t* d_out,
+                         cudaStream_t s);
+
+// rows with <= sort_small_max() candidates: block bitonic sort + unique (+ run lengths) in place
+int sort_small_max();
+void launch_sort_unique_small(uint64_t* cand, const uint64_t* cand_off, const uint32_t* cand_cnt,
+                              int n_rows, uint32_t* out_cnt, uint64_t* abund, cudaStream_t s);
+// bigger rows: CUB radix sort + unique; scratch_sorted / scratch_heads hold n u64 each
+cudaError_t sort_unique_big_row(uint64_t* row, uint64_t n, uint64_t* scratch_sorted,
+                                uint64_t* scratch_heads, uint64_t* abund_row, uint32_t* d_out_cnt,
+                                cudaStream_t s);
+void launch_compact_rows(const uint64_t* src, const uint64_t* src_off, const uint32_t* cnt,
+                         const uint64_t* dst_off, uint64_t* dst, int n_rows, cudaStream_t s);
+// angular similarity terms (minhash.rs:635-680): out[0] = sum a_i*b_j over common hashes,
+// out[1] = sum a_i^2, out[2] = sum b_j^2
+void launch_angular_terms(const uint64_t* a, const uint64_t* aa, uint64_t na, const uint64_t* b,
+                          const uint64_t* ba, uint64_t nb, unsigned long long* d_out,
+                          cudaStream_t s);
+// per row: number of hashes <= max_hash (downsample_scaled == prefix of the sorted row)
+void launch_row_prefix_counts(const uint64_t* h, const uint64_t* off, int n_rows,
+                              uint64_t max_hash, uint32_t* out_cnt, cudaStream_t s);
+
+// kernel-launch accounting (smb_kernel_launches)
+void count_launches(int n);
+
+}  // namespace smb

@@ -1,0 +1,597 @@
+// sketch_kernels.cu -- FracMinHash / MinHash sketch construction kernels for sm_100a.
+//
+// Replaces the reference's per-k-mer CPU loop:
+//   SeqToHashes::new / ::next (DNA branch)   src/core/src/signature.rs:190-232, 246-306
+//   revcomp / COMPLEMENT / VALID             src/core/src/encodings.rs:85-101, 370-377
+//   _hash_murmur                             src/core/src/lib.rs:57-59 (murmurhash3 0.0.5 x64_128 .0)
+//   SigsTrait::add_sequence                  src/core/src/signature.rs:38-58 (drop Ok(0))
+//   add_hash_with_abundance (scaled filter)  src/core/src/sketch/minhash.rs:313-383
+//
+// Design (B200): this path is integer-issue bound (~150 SASS integer ops per k-mer, 1 byte of
+// HBM traffic per k-mer), so the kernel is organised around instruction count, not bytes:
+// every thread owns W consecutive windows and rolls the forward and reverse-complement
+// k-mers through registers as little-endian ASCII words (exactly the words murmur3 consumes)
+// plus a 2-bit packed copy used only for the lexicographic min(kmer, revcomp) decision.  Input
+// bases are read with 16-byte vector loads; survivors (h <= max_hash, h != 0) are staged in a
+// shared-memory buffer and flushed with one atomicAdd per CTA.  A block-level bitonic sort +
+// unique materialises each sketch row.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+static constexpr int HASH_THREADS = 128;
+static constexpr int STAGE_CAP = 1024;          // per-CTA survivor staging (u64 entries)
+
+// ---------------------------------------------------------------------------------------
+// murmur3 x64_128 (first word) over K ASCII bytes held as little-endian 32-bit words.
+// Bytes >= K in the top word are zero.  Matches oracle/oracle.c orc_hash_murmur.
+// ---------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ u64 murmur_words(const u32 (&w)[(K + 3) / 4], u64 seed) {
+    constexpr int N32 = (K + 3) / 4;
+    constexpr int NBLK = K / 16;
+    constexpr int TAIL = K % 16;
+    u64 h1 = seed, h2 = seed;
+    auto word64 = [&](int i) -> u64 {          // i-th little-endian u64 of the k-mer (zero padded)
+        u32 lo = (2 * i < N32) ? w[2 * i] : 0u;
+        u32 hi = (2 * i + 1 < N32) ? w[2 * i + 1] : 0u;
+        return ((u64)hi << 32) | lo;
+    };
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+        u64 k1 = word64(2 * b), k2 = word64(2 * b + 1);
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+        h1 = smb_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+        h2 = smb_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    }
+    if (TAIL > 8) {
+        u64 k2 = word64(2 * NBLK + 1);
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+    }
+    if (TAIL > 0) {
+        u64 k1 = word64(2 * NBLK);
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+    }
+    h1 ^= (u64)K; h2 ^= (u64)K;
+    h1 += h2; h2 += h1;
+    h1 = smb_fmix64(h1); h2 = smb_fmix64(h2);
+    return h1 + h2;
+}
+
+// ---------------------------------------------------------------------------------------
+// Rolling k-mer state for compile-time K.
+//   fw[]  forward k-mer, byte t of the k-mer at byte t (little endian words)
+//   rc[]  reverse complement, same layout
+//   cf/cr 2-bit codes (A0 C1 G2 T3), first base most significant -> integer order ==
+//         byte-lexicographic order of the ASCII strings (signature.rs:304 std::cmp::min)
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct Roll {
+    static constexpr int N32 = (K + 3) / 4;
+    static constexpr int NC = (2 * K + 31) / 32;       // 32-bit words of 2-bit codes
+    u32 fw[N32], rc[N32];
+    u32 cf[NC], cr[NC];
+    u32 run;                                            // consecutive valid bases so far
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < N32; ++i) { fw[i] = 0; rc[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cf[i] = 0; cr[i] = 0; }
+        run = 0;
+    }
+
+    // push one raw input byte
+    __device__ __forceinline__ void push(u32 x) {
+        const u32 up = x & 0xDFu;                        // to_ascii_uppercase for letters
+        const u32 c2 = (up >> 1) & 3u;                   // A0 C1 T2 G3
+        const u32 expect = __byte_perm(0x47544341u, 0u, c2);   // "ACTG"[c2]
+        const bool ok = (expect == up);
+        const u32 comp = __byte_perm(0x43414754u, 0u, c2);     // complement: "TGAC"[c2]
+        const u32 code = c2 ^ (c2 >> 1);                 // A0 C1 G2 T3
+        run = ok ? run + 1u : 0u;
+        // forward: drop byte 0, append `up` at byte K-1
+#pragma unroll
+        for (int i = 0; i < N32 - 1; ++i) fw[i] = __funnelshift_r(fw[i], fw[i + 1], 8);
+        fw[N32 - 1] >>= 8;
+        fw[(K - 1) / 4] |= up << (8 * ((K - 1) % 4));
+        // reverse complement: prepend `comp` at byte 0, drop byte K
+#pragma unroll
+        for (int i = N32 - 1; i > 0; --i) rc[i] = __funnelshift_l(rc[i - 1], rc[i], 8);
+        rc[0] = (rc[0] << 8) | comp;
+        if (K % 4 != 0) rc[N32 - 1] &= (1u << (8 * (K % 4))) - 1u;
+        // 2-bit forward: shift left by 2, insert code at the bottom, keep 2K bits
+#pragma unroll
+        for (int i = NC - 1; i > 0; --i) cf[i] = __funnelshift_l(cf[i - 1], cf[i], 2);
+        cf[0] = (cf[0] << 2) | code;
+        if ((2 * K) % 32 != 0) cf[NC - 1] &= (1u << ((2 * K) % 32)) - 1u;
+        // 2-bit revcomp: shift right by 2, insert (3-code) at the top (bit 2K-2)
+#pragma unroll
+        for (int i = 0; i < NC - 1; ++i) cr[i] = __funnelshift_r(cr[i], cr[i + 1], 2);
+        cr[NC - 1] >>= 2;
+        cr[(2 * K - 2) / 32] |= (code ^ 3u) << ((2 * K - 2) % 32);
+    }
+
+    __device__ __forceinline__ bool fwd_is_canonical() const {
+        // multiword compare, most significant word first; tie -> forward (identical strings)
+        bool lt = false, decided = false;
+#pragma unroll
+        for (int i = NC - 1; i >= 0; --i) {
+            if (!decided && cf[i] != cr[i]) { lt = cf[i] < cr[i]; decided = true; }
+        }
+        return decided ? lt : true;
+    }
+
+    __device__ __forceinline__ u64 hash(u64 seed) const {
+        const bool f = fwd_is_canonical();
+        u32 sel[N32];
+#pragma unroll
+        for (int i = 0; i < N32; ++i) sel[i] = f ? fw[i] : rc[i];
+        return murmur_words<K>(sel, seed);
+    }
+};
+
+struct HashArgs {
+    const u8* bases;              // 16-byte aligned allocation, readable up to the next 16-byte boundary
+    const u64* stream_off;        // [n_streams] byte offset of stream s (any alignment)
+    const u64* stream_len;        // [n_streams] length in bytes
+    const u32* stream_row;        // [n_streams] output sketch of stream s (NULL: s)
+    const u32* tile_start;        // [n_streams + 1] prefix sum of tiles per stream
+    int n_streams;
+    int W;                        // windows per thread (multiple of 16)
+    u64 seed, max_hash;
+    u64* cand;                    // candidate storage
+    const u64* cand_off;          // [n_rows + 1]
+    u32* cand_cnt;                // [n_rows]
+    int row_stride, row_index;    // row = sketch * row_stride + row_index
+    u64* raw_out;                 // RAW mode: per-window hashes of stream 0 (0 = invalid)
+};
+
+__device__ __forceinline__ int find_stream(const u32* __restrict__ tile_start, int n_streams, u32 tile) {
+    int lo = 0, hi = n_streams;                    // last stream with tile_start <= tile
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_start[mid] <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+
+template <int K, bool RAW>
+__global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
+    __shared__ u64 s_buf[STAGE_CAP];
+    __shared__ u32 s_cnt;
+    __shared__ u32 s_base;
+    __shared__ int s_stream;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_cnt = 0;
+        s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x);
+    }
+    __syncthreads();
+    const int stream = s_stream;
+    // aligned coordinates: the stream starts `lead` bytes into its first 16-byte line; the
+    // lead bytes belong to whatever precedes the stream and are masked to "invalid".
+    const u64 s0 = a.stream_off[stream];
+    const u64 b0 = s0 & ~15ull;
+    const u32 lead = (u32)(s0 - b0);
+    const u64 Lp = (u64)lead + a.stream_len[stream];
+    const u8* __restrict__ base = a.bases + b0;
+    const u64 nwin = Lp >= (u64)K ? Lp - K + 1 : 0;
+    const u64 tile = blockIdx.x - a.tile_start[stream];
+    const u64 w0 = (tile * HASH_THREADS + tid) * (u64)a.W;
+    const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
+    const int row = sk * a.row_stride + a.row_index;
+
+    if (w0 < nwin) {
+        Roll<K> st;
+        st.init();
+        const int nbytes = a.W + K - 1;                   // bytes this thread consumes
+        const int nchunks = (nbytes + 15) >> 4;
+        int j = 0;                                        // byte index within the thread's run
+        for (int c = 0; c < nchunks; ++c) {
+            const u64 pos = w0 + 16ull * c;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            u32 vm = 0;                                   // bit jj: byte pos+jj lies inside the stream
+            if (pos < Lp) {
+                v = __ldg(reinterpret_cast<const uint4*>(base + pos));
+                const u32 hi = (u32)min((u64)16, Lp - pos);
+                const u32 lo = pos < lead ? min(16u, (u32)(lead - pos)) : 0u;
+                vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            }
+            const u32 words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj, ++j) {
+                if (j < nbytes) {
+                    u32 x = (words[jj >> 2] >> (8 * (jj & 3))) & 0xffu;
+                    if (!((vm >> jj) & 1u)) x = 0;        // outside the stream: invalid base
+                    st.push(x);
+                    if (j >= K - 1) {
+                        const u64 w = w0 + (u64)(j - (K - 1));
+                        if (w < nwin) {
+                            const bool valid = st.run >= (u32)K;
+                            u64 h = st.hash(a.seed);
+                            if (RAW) {
+                                if (w >= lead) a.raw_out[w - lead] = valid ? h : 0ull;
+                            } else if (valid && h != 0ull && h <= a.max_hash) {
+                                u32 slot = atomicAdd(&s_cnt, 1u);
+                                if (slot < STAGE_CAP) {
+                                    s_buf[slot] = h;
+                                } else {                  // staging full: append directly
+                                    u32 g = atomicAdd(&a.cand_cnt[row], 1u);
+                                    u64 capr = a.cand_off[row + 1] - a.cand_off[row];
+                                    if (g < capr) a.cand[a.cand_off[row] + g] = h;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (RAW) return;
+    __syncthreads();
+    const u32 n = min(s_cnt, (u32)STAGE_CAP);
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(&a.cand_cnt[row], n);
+    __syncthreads();
+    const u64 off = a.cand_off[row];
+    const u64 capr = a.cand_off[row + 1] - off;
+    for (u32 i = tid; i < n; i += HASH_THREADS) {
+        u64 g = (u64)s_base + i;
+        if (g < capr) a.cand[off + g] = s_buf[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Any other k: one thread per window, bytes straight from global/L1 (slow path, same results).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 up_byte(u32 x) { return (x >= 'a' && x <= 'z') ? x - 32u : x; }
+__device__ __forceinline__ bool valid_base(u32 u) { return u == 'A' || u == 'C' || u == 'G' || u == 'T'; }
+__device__ __forceinline__ u32 comp_base(u32 u) { return u == 'A' ? 'T' : u == 'C' ? 'G' : u == 'G' ? 'C' : 'A'; }
+
+template <bool RAW>
+__global__ void __launch_bounds__(256) hash_kmers_generic_kernel(HashArgs a, u32 K) {
+    __shared__ int s_stream;
+    if (threadIdx.x == 0) s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x);
+    __syncthreads();
+    const int stream = s_stream;
+    const u64 L = a.stream_len[stream];
+    const u8* __restrict__ base = a.bases + a.stream_off[stream];
+    if (L < K || K == 0) return;
+    const u64 nwin = L - K + 1;
+    const u64 tile = blockIdx.x - a.tile_start[stream];
+    const u64 w = tile * 256ull + threadIdx.x;
+    if (w >= nwin) return;
+    const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
+    const int row = sk * a.row_stride + a.row_index;
+    bool valid = true;
+    for (u32 t = 0; t < K; ++t) valid = valid && valid_base(up_byte(base[w + t]));
+    u64 h = 0;
+    if (valid) {
+        bool fwd = true;
+        for (u32 t = 0; t < K; ++t) {
+            u32 f = up_byte(base[w + t]), r = comp_base(up_byte(base[w + K - 1 - t]));
+            if (f != r) { fwd = f < r; break; }
+        }
+        auto at = [&](u32 t) -> u64 {
+            return fwd ? up_byte(base[w + t]) : comp_base(up_byte(base[w + K - 1 - t]));
+        };
+        u64 h1 = a.seed, h2 = a.seed;
+        const u32 nblk = K / 16;
+        for (u32 b = 0; b < nblk; ++b) {
+            u64 k1 = 0, k2 = 0;
+            for (int i = 7; i >= 0; --i) { k1 = (k1 << 8) | at(16 * b + i); k2 = (k2 << 8) | at(16 * b + 8 + i); }
+            k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+            h1 = smb_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+            k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+            h2 = smb_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+        }
+        const u32 tail = K & 15u, tb = 16 * nblk;
+        if (tail > 8) {
+            u64 k2 = 0;
+            for (u32 i = tail; i > 8; --i) k2 = (k2 << 8) | at(tb + i - 1);
+            k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+        }
+        if (tail > 0) {
+            u64 k1 = 0;
+            for (u32 i = tail < 8 ? tail : 8; i > 0; --i) k1 = (k1 << 8) | at(tb + i - 1);
+            k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+        }
+        h1 ^= (u64)K; h2 ^= (u64)K;
+        h1 += h2; h2 += h1;
+        h1 = smb_fmix64(h1); h2 = smb_fmix64(h2);
+        h = h1 + h2;
+    }
+    if (RAW) {
+        a.raw_out[w] = valid ? h : 0ull;
+    } else if (valid && h != 0ull && h <= a.max_hash) {
+        u32 g = atomicAdd(&a.cand_cnt[row], 1u);
+        u64 capr = a.cand_off[row + 1] - a.cand_off[row];
+        if (g < capr) a.cand[a.cand_off[row] + g] = h;
+    }
+}
+
+template <bool RAW>
+static void launch_hash_one_k(HashArgs a, u32 K, u32 total_tiles_rolled, u32 total_tiles_generic,
+                              cudaStream_t s) {
+    switch (K) {
+        case 21: if (total_tiles_rolled) hash_kmers_kernel<21, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
+        case 31: if (total_tiles_rolled) hash_kmers_kernel<31, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
+        case 51: if (total_tiles_rolled) hash_kmers_kernel<51, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
+        default: if (total_tiles_generic) hash_kmers_generic_kernel<RAW><<<total_tiles_generic, 256, 0, s>>>(a, K); count_launches(1); break;
+    }
+}
+
+bool k_has_rolled_kernel(uint32_t k) { return k == 21 || k == 31 || k == 51; }
+int hash_threads() { return HASH_THREADS; }
+
+void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cudaStream_t s) {
+    HashArgs a{};
+    a.bases = L.bases; a.stream_off = L.stream_off; a.stream_len = L.stream_len;
+    a.stream_row = L.stream_row;
+    a.n_streams = L.n_streams; a.W = L.W; a.seed = L.seed; a.max_hash = L.max_hash;
+    a.cand = L.cand; a.cand_off = L.cand_off; a.cand_cnt = L.cand_cnt;
+    a.row_stride = L.row_stride; a.row_index = row_index; a.raw_out = nullptr;
+    const bool rolled = k_has_rolled_kernel(ksize);
+    a.tile_start = rolled ? L.tile_start_rolled : L.tile_start_generic;
+    launch_hash_one_k<false>(a, ksize, L.total_tiles_rolled, L.total_tiles_generic, s);
+}
+
+void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s) {
+    HashArgs a{};
+    a.bases = L.bases; a.stream_off = L.stream_off; a.stream_len = L.stream_len;
+    a.stream_row = nullptr;
+    a.n_streams = L.n_streams; a.W = L.W; a.seed = L.seed; a.max_hash = L.max_hash;
+    a.row_stride = 1; a.row_index = 0; a.raw_out = raw_out;
+    const bool rolled = k_has_rolled_kernel(ksize);
+    a.tile_start = rolled ? L.tile_start_rolled : L.tile_start_generic;
+    launch_hash_one_k<true>(a, ksize, L.total_tiles_rolled, L.total_tiles_generic, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// first invalid base of a sequence (force == false path: signature.rs:271-279)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) first_invalid_kernel(const u8* __restrict__ b, u64 len,
+                                                           unsigned long long* __restrict__ d_pos) {
+    unsigned long long best = ~0ull;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < len; p += (u64)gridDim.x * blockDim.x) {
+        if (!valid_base(up_byte(b[p]))) { best = p; break; }      // positions ascend per thread
+    }
+    for (int d = 16; d; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o < best ? o : best;
+    }
+    if (lane_id() == 0 && best != ~0ull) atomicMin(d_pos, best);
+}
+
+void launch_first_invalid(const u8* bases, u64 len, unsigned long long* d_pos, cudaStream_t s) {
+    cudaMemsetAsync(d_pos, 0xff, sizeof(unsigned long long), s);
+    if (len == 0) return;
+    u64 blocks = (len + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 8) blocks = (u64)SMB_B200_SMS * 8;
+    first_invalid_kernel<<<(unsigned)blocks, 256, 0, s>>>(bases, len, d_pos); count_launches(1);
+}
+
+// ---------------------------------------------------------------------------------------
+// row materialisation: sort + unique (+ run lengths) of each row's candidates
+// ---------------------------------------------------------------------------------------
+static constexpr int SORT_THREADS = 1024;
+static constexpr int SORT_MAX = 16384;            // rows up to this many candidates sort in smem
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_unique_small_kernel(
+    u64* __restrict__ cand, const u64* __restrict__ cand_off, const u32* __restrict__ cand_cnt,
+    u32* __restrict__ out_cnt, u64* __restrict__ abund) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = blockIdx.x;
+    const u64 off = cand_off[r];
+    const u64 capr = cand_off[r + 1] - off;
+    u32 n = cand_cnt[r];
+    if ((u64)n > capr || n > SORT_MAX) return;          // overflowed / big row: handled on host path
+    if (n == 0) { if (threadIdx.x == 0) out_cnt[r] = 0; return; }
+    u32 np2 = 1; while (np2 < n) np2 <<= 1;
+    u64* s = reinterpret_cast<u64*>(smem_raw);
+    u32* heads = reinterpret_cast<u32*>(smem_raw + (size_t)np2 * 8);
+    const int tid = threadIdx.x;
+    for (u32 i = tid; i < np2; i += SORT_THREADS) s[i] = i < n ? cand[off + i] : SMB_U64_MAX;
+    __syncthreads();
+    for (u32 k = 2; k <= np2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = tid; i < np2; i += SORT_THREADS) {
+                u32 ixj = i ^ j;
+                if (ixj > i) {
+                    u64 x = s[i], y = s[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { s[i] = y; s[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // unique: stable compaction of run heads
+    __shared__ u32 warp_tot[32];
+    __shared__ u32 carry;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (u32 base = 0; base < n; base += SORT_THREADS) {
+        u32 i = base + tid;
+        bool head = i < n && (i == 0 || s[i] != s[i - 1]);
+        u32 bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u32 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (head) { cand[off + pos] = s[i]; heads[pos] = i; }
+        __syncthreads();
+        if (tid == 0) { u32 t = 0; for (int w2 = 0; w2 < SORT_THREADS / 32; ++w2) t += warp_tot[w2]; carry += t; }
+        __syncthreads();
+    }
+    const u32 m = carry;
+    if (abund) {
+        for (u32 p = tid; p < m; p += SORT_THREADS) {
+            u32 nxt = p + 1 < m ? heads[p + 1] : n;
+            abund[off + p] = (u64)(nxt - heads[p]);
+        }
+    }
+    if (tid == 0) out_cnt[r] = m;
+}
+
+// unique (+ run lengths) of an already sorted row, in place; single block.
+__global__ void __launch_bounds__(SORT_THREADS) unique_sorted_row_kernel(
+    const u64* __restrict__ sorted, u64 n, u64* __restrict__ out, u64* __restrict__ abund,
+    u64* __restrict__ head_idx, u32* __restrict__ out_cnt) {
+    __shared__ u32 warp_tot[32];
+    __shared__ u64 carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n; base += SORT_THREADS) {
+        u64 i = base + tid;
+        bool head = i < n && (i == 0 || sorted[i] != sorted[i - 1]);
+        u32 bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u64 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (head) { out[pos] = sorted[i]; head_idx[pos] = i; }
+        __syncthreads();
+        if (tid == 0) { u32 t = 0; for (int w2 = 0; w2 < SORT_THREADS / 32; ++w2) t += warp_tot[w2]; carry += t; }
+        __syncthreads();
+    }
+    const u64 m = carry;
+    if (abund) {
+        for (u64 p = tid; p < m; p += SORT_THREADS) {
+            u64 nxt = p + 1 < m ? head_idx[p + 1] : n;
+            abund[p] = nxt - head_idx[p];
+        }
+    }
+    if (tid == 0) *out_cnt = (u32)m;
+}
+
+int sort_small_max() { return SORT_MAX; }
+
+// murmur3 of an arbitrary byte string, single thread (hash_murmur / add_word utility)
+__global__ void murmur_bytes_kernel(const u8* __restrict__ d, u64 len, u64 seed, u64* __restrict__ out) {
+    u64 h1 = seed, h2 = seed;
+    const u64 nblk = len / 16;
+    for (u64 b = 0; b < nblk; ++b) {
+        u64 k1 = 0, k2 = 0;
+        for (int i = 7; i >= 0; --i) { k1 = (k1 << 8) | d[16 * b + i]; k2 = (k2 << 8) | d[16 * b + 8 + i]; }
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+        h1 = smb_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+        h2 = smb_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    }
+    const u64 tail = len & 15, tb = 16 * nblk;
+    if (tail > 8) {
+        u64 k2 = 0;
+        for (u64 i = tail; i > 8; --i) k2 = (k2 << 8) | d[tb + i - 1];
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+    }
+    if (tail > 0) {
+        u64 k1 = 0;
+        for (u64 i = tail < 8 ? tail : 8; i > 0; --i) k1 = (k1 << 8) | d[tb + i - 1];
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+    }
+    h1 ^= len; h2 ^= len;
+    h1 += h2; h2 += h1;
+    h1 = smb_fmix64(h1); h2 = smb_fmix64(h2);
+    *out = h1 + h2;
+}
+void launch_murmur_bytes(const u8* data, u64 len, u64 seed, u64* d_out, cudaStream_t s) {
+    murmur_bytes_kernel<<<1, 1, 0, s>>>(data, len, seed, d_out); count_launches(1);
+}
+
+// angular similarity terms -- single block; rows are sketches with abundances
+__global__ void __launch_bounds__(1024) angular_terms_kernel(
+    const u64* __restrict__ a, const u64* __restrict__ aa, u64 na, const u64* __restrict__ b,
+    const u64* __restrict__ ba, u64 nb, unsigned long long* __restrict__ out) {
+    unsigned long long prod = 0, asq = 0, bsq = 0;
+    for (u64 i = threadIdx.x; i < na; i += blockDim.x) {
+        u64 x = a[i], ab = aa[i];
+        asq += ab * ab;
+        u64 lo = 0, hi = nb;
+        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (b[mid] < x) lo = mid + 1; else hi = mid; }
+        if (lo < nb && b[lo] == x) prod += ab * ba[lo];
+    }
+    for (u64 j = threadIdx.x; j < nb; j += blockDim.x) bsq += ba[j] * ba[j];
+    for (int d = 16; d; d >>= 1) {
+        prod += __shfl_xor_sync(0xffffffffu, prod, d);
+        asq += __shfl_xor_sync(0xffffffffu, asq, d);
+        bsq += __shfl_xor_sync(0xffffffffu, bsq, d);
+    }
+    if (lane_id() == 0) { atomicAdd(out + 0, prod); atomicAdd(out + 1, asq); atomicAdd(out + 2, bsq); }
+}
+void launch_angular_terms(const u64* a, const u64* aa, u64 na, const u64* b, const u64* ba, u64 nb,
+                          unsigned long long* d_out, cudaStream_t s) {
+    cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), s);
+    angular_terms_kernel<<<1, 1024, 0, s>>>(a, aa, na, b, ba, nb, d_out); count_launches(1);
+}
+
+__global__ void __launch_bounds__(256) row_prefix_counts_kernel(const u64* __restrict__ h,
+                                                               const u64* __restrict__ off, int n_rows,
+                                                               u64 max_hash, u32* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const u64* row = h + off[r];
+    u64 lo = 0, hi = off[r + 1] - off[r];
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (row[mid] <= max_hash) lo = mid + 1; else hi = mid; }
+    out[r] = (u32)lo;
+}
+void launch_row_prefix_counts(const u64* h, const u64* off, int n_rows, u64 max_hash, u32* out_cnt,
+                              cudaStream_t s) {
+    if (n_rows <= 0) return;
+    row_prefix_counts_kernel<<<(n_rows + 255) / 256, 256, 0, s>>>(h, off, n_rows, max_hash, out_cnt); count_launches(1);
+}
+
+void launch_sort_unique_small(u64* cand, const u64* cand_off, const u32* cand_cnt, int n_rows,
+                              u32* out_cnt, u64* abund, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    size_t smem = (size_t)SORT_MAX * 8 + (size_t)SORT_MAX * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sort_unique_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    sort_unique_small_kernel<<<n_rows, SORT_THREADS, smem, s>>>(cand, cand_off, cand_cnt, out_cnt, abund); count_launches(1);
+}
+
+// Big row: CUB radix sort into scratch, then unique back into the row.  scratch must hold
+// 2*n u64 (+ CUB temp, allocated here with cudaMallocAsync).
+cudaError_t sort_unique_big_row(u64* row, u64 n, u64* scratch_sorted, u64* scratch_heads,
+                                u64* abund_row, u32* d_out_cnt, cudaStream_t s) {
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, row, scratch_sorted, (long long)n, 0, 64, s);
+    void* temp = nullptr;
+    cudaError_t e = cudaMallocAsync(&temp, temp_bytes ? temp_bytes : 16, s);
+    if (e != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortKeys(temp, temp_bytes, row, scratch_sorted, (long long)n, 0, 64, s);
+    unique_sorted_row_kernel<<<1, SORT_THREADS, 0, s>>>(scratch_sorted, n, row, abund_row, scratch_heads, d_out_cnt); count_launches(1);
+    cudaFreeAsync(temp, s);
+    return cudaGetLastError();
+}
+
+// gather rows into a dense CSR buffer: dst[dst_off[r] + i] = src[src_off[r] + i], i < cnt[r]
+__global__ void __launch_bounds__(256) compact_rows_kernel(const u64* __restrict__ src,
+                                                          const u64* __restrict__ src_off,
+                                                          const u32* __restrict__ cnt,
+                                                          const u64* __restrict__ dst_off,
+                                                          u64* __restrict__ dst) {
+    const int r = blockIdx.x;
+    const u64 so = src_off[r], d0 = dst_off[r];
+    const u32 n = cnt[r];
+    for (u32 i = threadIdx.x + blockIdx.y * blockDim.x; i < n; i += blockDim.x * gridDim.y)
+        dst[d0 + i] = src[so + i];
+}
+
+void launch_compact_rows(const u64* src, const u64* src_off, const u32* cnt, const u64* dst_off,
+                         u64* dst, int n_rows, cudaStream_t s) {
+    if (n_rows <= 0) return;
+    dim3 grid(n_rows, 4);
+    compact_rows_kernel<<<grid, 256, 0, s>>>(src, src_off, cnt, dst_off, dst); count_launches(1);
+}
+
+}  // namespace smb
