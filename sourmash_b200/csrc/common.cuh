@@ -13,11 +13,13 @@ typedef uint8_t u8;
 // Number of SMs on a B200; grids for persistent-style kernels are sized in multiples of it.
 #define SMB_B200_SMS 148
 
+#ifdef __CUDACC__
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
 
 __device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
     return __ldg(reinterpret_cast<const unsigned long long*>(p));
 }
+#endif
 
 // MurmurHash3 x64-128 building blocks (device + host), see murmur.cuh.
 __host__ __device__ __forceinline__ u64 smb_rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }

@@ -1,0 +1,183 @@
+// kmer_roll.cuh -- rolling canonical k-mer state + murmur3 over register-resident words.
+// __host__ __device__ so that tests/host_emul can run exactly this code on the CPU.
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+
+namespace smb {
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ u32 fshr(u32 lo, u32 hi, u32 s) { return __funnelshift_r(lo, hi, s); }
+__device__ __forceinline__ u32 fshl(u32 lo, u32 hi, u32 s) { return __funnelshift_l(lo, hi, s); }
+__device__ __forceinline__ u32 pick_byte(u32 table, u32 idx) { return __byte_perm(table, 0u, idx) & 0xffu; }
+#else
+inline u32 fshr(u32 lo, u32 hi, u32 s) { return (u32)((((u64)hi << 32) | lo) >> (s & 31)); }
+inline u32 fshl(u32 lo, u32 hi, u32 s) { return (u32)(((((u64)hi << 32) | lo) << (s & 31)) >> 32); }
+inline u32 pick_byte(u32 table, u32 idx) { return (table >> (8 * (idx & 3))) & 0xffu; }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// murmur3 x64_128 (first word) over K ASCII bytes held as little-endian 32-bit words.
+// Bytes >= K in the top word are zero.  Matches oracle/oracle.c orc_hash_murmur.
+// ---------------------------------------------------------------------------------------
+template <int K>
+__host__ __device__ __forceinline__ u64 murmur_words(const u32 (&w)[(K + 3) / 4], u64 seed) {
+    constexpr int N32 = (K + 3) / 4;
+    constexpr int NBLK = K / 16;
+    constexpr int TAIL = K % 16;
+    u64 h1 = seed, h2 = seed;
+    auto word64 = [&](int i) -> u64 {          // i-th little-endian u64 of the k-mer (zero padded)
+        u32 lo = (2 * i < N32) ? w[2 * i] : 0u;
+        u32 hi = (2 * i + 1 < N32) ? w[2 * i + 1] : 0u;
+        return ((u64)hi << 32) | lo;
+    };
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+        u64 k1 = word64(2 * b), k2 = word64(2 * b + 1);
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+        h1 = smb_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+        h2 = smb_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
+    }
+    if (TAIL > 8) {
+        u64 k2 = word64(2 * NBLK + 1);
+        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
+    }
+    if (TAIL > 0) {
+        u64 k1 = word64(2 * NBLK);
+        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
+    }
+    h1 ^= (u64)K; h2 ^= (u64)K;
+    h1 += h2; h2 += h1;
+    h1 = smb_fmix64(h1); h2 = smb_fmix64(h2);
+    return h1 + h2;
+}
+
+// ---------------------------------------------------------------------------------------
+// Rolling k-mer state for compile-time K.
+//   fw[]  forward k-mer, byte t of the k-mer at byte t (little endian words)
+//   rc[]  reverse complement, same layout
+//   cf/cr 2-bit codes (A0 C1 G2 T3), first base most significant -> integer order ==
+//         byte-lexicographic order of the ASCII strings (signature.rs:304 std::cmp::min)
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct Roll {
+    static constexpr int N32 = (K + 3) / 4;
+    static constexpr int NC = (2 * K + 31) / 32;       // 32-bit words of 2-bit codes
+    u32 fw[N32], rc[N32];
+    u32 cf[NC], cr[NC];
+    u32 run;                                            // consecutive valid bases so far
+
+    __host__ __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < N32; ++i) { fw[i] = 0; rc[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cf[i] = 0; cr[i] = 0; }
+        run = 0;
+    }
+
+    // push one raw input byte
+    __host__ __device__ __forceinline__ void push(u32 x) {
+        const u32 up = x & 0xDFu;                        // to_ascii_uppercase for letters
+        const u32 c2 = (up >> 1) & 3u;                   // A0 C1 T2 G3
+        const u32 expect = pick_byte(0x47544341u, c2);   // "ACTG"[c2]
+        const bool ok = (expect == up);
+        const u32 comp = pick_byte(0x43414754u, c2);     // complement: "TGAC"[c2]
+        const u32 code = c2 ^ (c2 >> 1);                 // A0 C1 G2 T3
+        run = ok ? run + 1u : 0u;
+        // forward: drop byte 0, append `up` at byte K-1
+#pragma unroll
+        for (int i = 0; i < N32 - 1; ++i) fw[i] = fshr(fw[i], fw[i + 1], 8);
+        fw[N32 - 1] >>= 8;
+        fw[(K - 1) / 4] |= up << (8 * ((K - 1) % 4));
+        // reverse complement: prepend `comp` at byte 0, drop byte K
+#pragma unroll
+        for (int i = N32 - 1; i > 0; --i) rc[i] = fshl(rc[i - 1], rc[i], 8);
+        rc[0] = (rc[0] << 8) | comp;
+        if (K % 4 != 0) rc[N32 - 1] &= (1u << (8 * (K % 4))) - 1u;
+        // 2-bit forward: shift left by 2, insert code at the bottom, keep 2K bits
+#pragma unroll
+        for (int i = NC - 1; i > 0; --i) cf[i] = fshl(cf[i - 1], cf[i], 2);
+        cf[0] = (cf[0] << 2) | code;
+        if ((2 * K) % 32 != 0) cf[NC - 1] &= (1u << ((2 * K) % 32)) - 1u;
+        // 2-bit revcomp: shift right by 2, insert (3-code) at the top (bit 2K-2)
+#pragma unroll
+        for (int i = 0; i < NC - 1; ++i) cr[i] = fshr(cr[i], cr[i + 1], 2);
+        cr[NC - 1] >>= 2;
+        cr[(2 * K - 2) / 32] |= (code ^ 3u) << ((2 * K - 2) % 32);
+    }
+
+    __host__ __device__ __forceinline__ bool fwd_is_canonical() const {
+        // multiword compare, most significant word first; tie -> forward (identical strings)
+        bool lt = false, decided = false;
+#pragma unroll
+        for (int i = NC - 1; i >= 0; --i) {
+            if (!decided && cf[i] != cr[i]) { lt = cf[i] < cr[i]; decided = true; }
+        }
+        return decided ? lt : true;
+    }
+
+    __host__ __device__ __forceinline__ u64 hash(u64 seed) const {
+        const bool f = fwd_is_canonical();
+        u32 sel[N32];
+#pragma unroll
+        for (int i = 0; i < N32; ++i) sel[i] = f ? fw[i] : rc[i];
+        return murmur_words<K>(sel, seed);
+    }
+};
+
+
+struct Bytes16 { u32 w[4]; };
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ Bytes16 load16(const u8* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    Bytes16 b; b.w[0] = v.x; b.w[1] = v.y; b.w[2] = v.z; b.w[3] = v.w; return b;
+}
+#else
+inline Bytes16 load16(const u8* p) { Bytes16 b; memcpy(b.w, p, 16); return b; }
+#endif
+
+// One thread's share of a stream: windows [w0, w0 + W) in "aligned coordinates".
+//   base   16-byte aligned pointer to the line holding the stream's first byte
+//   lead   bytes of that line that precede the stream (masked invalid)
+//   Lp     lead + stream length
+// emit(w, valid, h) is called for every window w < Lp - K + 1 of the share (w includes lead).
+template <int K, class Emit>
+__host__ __device__ __forceinline__ void hash_thread_windows(const u8* __restrict__ base, u64 Lp, u32 lead,
+                                                             u64 w0, int W, u64 seed, Emit&& emit) {
+    const u64 nwin = Lp >= (u64)K ? Lp - K + 1 : 0;
+    if (w0 >= nwin) return;
+    Roll<K> st;
+    st.init();
+    const int nbytes = W + K - 1;                     // bytes this thread consumes
+    const int nchunks = (nbytes + 15) >> 4;
+    int j = 0;                                        // byte index within the thread's run
+    for (int c = 0; c < nchunks; ++c) {
+        const u64 pos = w0 + 16ull * c;
+        Bytes16 v; v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0u;
+        u32 vm = 0;                                   // bit jj: byte pos+jj lies inside the stream
+        if (pos < Lp) {
+            v = load16(base + pos);
+            const u64 rem = Lp - pos;
+            const u32 hi = rem < 16 ? (u32)rem : 16u;
+            u32 lo = 0;
+            if (pos < lead) { const u64 d = lead - pos; lo = d < 16 ? (u32)d : 16u; }
+            vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj, ++j) {
+            if (j < nbytes) {
+                u32 x = (v.w[jj >> 2] >> (8 * (jj & 3))) & 0xffu;
+                if (!((vm >> jj) & 1u)) x = 0;        // outside the stream: invalid base
+                st.push(x);
+                if (j >= K - 1) {
+                    const u64 w = w0 + (u64)(j - (K - 1));
+                    if (w < nwin) emit(w, st.run >= (u32)K, st.hash(seed));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace smb

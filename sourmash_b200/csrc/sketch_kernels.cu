@@ -19,121 +19,12 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "kmer_roll.cuh"
 
 namespace smb {
 
 static constexpr int HASH_THREADS = 128;
 static constexpr int STAGE_CAP = 1024;          // per-CTA survivor staging (u64 entries)
-
-// ---------------------------------------------------------------------------------------
-// murmur3 x64_128 (first word) over K ASCII bytes held as little-endian 32-bit words.
-// Bytes >= K in the top word are zero.  Matches oracle/oracle.c orc_hash_murmur.
-// ---------------------------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ u64 murmur_words(const u32 (&w)[(K + 3) / 4], u64 seed) {
-    constexpr int N32 = (K + 3) / 4;
-    constexpr int NBLK = K / 16;
-    constexpr int TAIL = K % 16;
-    u64 h1 = seed, h2 = seed;
-    auto word64 = [&](int i) -> u64 {          // i-th little-endian u64 of the k-mer (zero padded)
-        u32 lo = (2 * i < N32) ? w[2 * i] : 0u;
-        u32 hi = (2 * i + 1 < N32) ? w[2 * i + 1] : 0u;
-        return ((u64)hi << 32) | lo;
-    };
-#pragma unroll
-    for (int b = 0; b < NBLK; ++b) {
-        u64 k1 = word64(2 * b), k2 = word64(2 * b + 1);
-        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
-        h1 = smb_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
-        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
-        h2 = smb_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ULL;
-    }
-    if (TAIL > 8) {
-        u64 k2 = word64(2 * NBLK + 1);
-        k2 *= SMB_C2; k2 = smb_rotl64(k2, 33); k2 *= SMB_C1; h2 ^= k2;
-    }
-    if (TAIL > 0) {
-        u64 k1 = word64(2 * NBLK);
-        k1 *= SMB_C1; k1 = smb_rotl64(k1, 31); k1 *= SMB_C2; h1 ^= k1;
-    }
-    h1 ^= (u64)K; h2 ^= (u64)K;
-    h1 += h2; h2 += h1;
-    h1 = smb_fmix64(h1); h2 = smb_fmix64(h2);
-    return h1 + h2;
-}
-
-// ---------------------------------------------------------------------------------------
-// Rolling k-mer state for compile-time K.
-//   fw[]  forward k-mer, byte t of the k-mer at byte t (little endian words)
-//   rc[]  reverse complement, same layout
-//   cf/cr 2-bit codes (A0 C1 G2 T3), first base most significant -> integer order ==
-//         byte-lexicographic order of the ASCII strings (signature.rs:304 std::cmp::min)
-// ---------------------------------------------------------------------------------------
-template <int K>
-struct Roll {
-    static constexpr int N32 = (K + 3) / 4;
-    static constexpr int NC = (2 * K + 31) / 32;       // 32-bit words of 2-bit codes
-    u32 fw[N32], rc[N32];
-    u32 cf[NC], cr[NC];
-    u32 run;                                            // consecutive valid bases so far
-
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < N32; ++i) { fw[i] = 0; rc[i] = 0; }
-#pragma unroll
-        for (int i = 0; i < NC; ++i) { cf[i] = 0; cr[i] = 0; }
-        run = 0;
-    }
-
-    // push one raw input byte
-    __device__ __forceinline__ void push(u32 x) {
-        const u32 up = x & 0xDFu;                        // to_ascii_uppercase for letters
-        const u32 c2 = (up >> 1) & 3u;                   // A0 C1 T2 G3
-        const u32 expect = __byte_perm(0x47544341u, 0u, c2);   // "ACTG"[c2]
-        const bool ok = (expect == up);
-        const u32 comp = __byte_perm(0x43414754u, 0u, c2);     // complement: "TGAC"[c2]
-        const u32 code = c2 ^ (c2 >> 1);                 // A0 C1 G2 T3
-        run = ok ? run + 1u : 0u;
-        // forward: drop byte 0, append `up` at byte K-1
-#pragma unroll
-        for (int i = 0; i < N32 - 1; ++i) fw[i] = __funnelshift_r(fw[i], fw[i + 1], 8);
-        fw[N32 - 1] >>= 8;
-        fw[(K - 1) / 4] |= up << (8 * ((K - 1) % 4));
-        // reverse complement: prepend `comp` at byte 0, drop byte K
-#pragma unroll
-        for (int i = N32 - 1; i > 0; --i) rc[i] = __funnelshift_l(rc[i - 1], rc[i], 8);
-        rc[0] = (rc[0] << 8) | comp;
-        if (K % 4 != 0) rc[N32 - 1] &= (1u << (8 * (K % 4))) - 1u;
-        // 2-bit forward: shift left by 2, insert code at the bottom, keep 2K bits
-#pragma unroll
-        for (int i = NC - 1; i > 0; --i) cf[i] = __funnelshift_l(cf[i - 1], cf[i], 2);
-        cf[0] = (cf[0] << 2) | code;
-        if ((2 * K) % 32 != 0) cf[NC - 1] &= (1u << ((2 * K) % 32)) - 1u;
-        // 2-bit revcomp: shift right by 2, insert (3-code) at the top (bit 2K-2)
-#pragma unroll
-        for (int i = 0; i < NC - 1; ++i) cr[i] = __funnelshift_r(cr[i], cr[i + 1], 2);
-        cr[NC - 1] >>= 2;
-        cr[(2 * K - 2) / 32] |= (code ^ 3u) << ((2 * K - 2) % 32);
-    }
-
-    __device__ __forceinline__ bool fwd_is_canonical() const {
-        // multiword compare, most significant word first; tie -> forward (identical strings)
-        bool lt = false, decided = false;
-#pragma unroll
-        for (int i = NC - 1; i >= 0; --i) {
-            if (!decided && cf[i] != cr[i]) { lt = cf[i] < cr[i]; decided = true; }
-        }
-        return decided ? lt : true;
-    }
-
-    __device__ __forceinline__ u64 hash(u64 seed) const {
-        const bool f = fwd_is_canonical();
-        u32 sel[N32];
-#pragma unroll
-        for (int i = 0; i < N32; ++i) sel[i] = f ? fw[i] : rc[i];
-        return murmur_words<K>(sel, seed);
-    }
-};
 
 struct HashArgs {
     const u8* bases;              // 16-byte aligned allocation, readable up to the next 16-byte boundary
@@ -177,58 +68,25 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
     const u32 lead = (u32)(s0 - b0);
     const u64 Lp = (u64)lead + a.stream_len[stream];
     const u8* __restrict__ base = a.bases + b0;
-    const u64 nwin = Lp >= (u64)K ? Lp - K + 1 : 0;
     const u64 tile = blockIdx.x - a.tile_start[stream];
     const u64 w0 = (tile * HASH_THREADS + tid) * (u64)a.W;
     const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
     const int row = sk * a.row_stride + a.row_index;
 
-    if (w0 < nwin) {
-        Roll<K> st;
-        st.init();
-        const int nbytes = a.W + K - 1;                   // bytes this thread consumes
-        const int nchunks = (nbytes + 15) >> 4;
-        int j = 0;                                        // byte index within the thread's run
-        for (int c = 0; c < nchunks; ++c) {
-            const u64 pos = w0 + 16ull * c;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            u32 vm = 0;                                   // bit jj: byte pos+jj lies inside the stream
-            if (pos < Lp) {
-                v = __ldg(reinterpret_cast<const uint4*>(base + pos));
-                const u32 hi = (u32)min((u64)16, Lp - pos);
-                const u32 lo = pos < lead ? min(16u, (u32)(lead - pos)) : 0u;
-                vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-            }
-            const u32 words[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj, ++j) {
-                if (j < nbytes) {
-                    u32 x = (words[jj >> 2] >> (8 * (jj & 3))) & 0xffu;
-                    if (!((vm >> jj) & 1u)) x = 0;        // outside the stream: invalid base
-                    st.push(x);
-                    if (j >= K - 1) {
-                        const u64 w = w0 + (u64)(j - (K - 1));
-                        if (w < nwin) {
-                            const bool valid = st.run >= (u32)K;
-                            u64 h = st.hash(a.seed);
-                            if (RAW) {
-                                if (w >= lead) a.raw_out[w - lead] = valid ? h : 0ull;
-                            } else if (valid && h != 0ull && h <= a.max_hash) {
-                                u32 slot = atomicAdd(&s_cnt, 1u);
-                                if (slot < STAGE_CAP) {
-                                    s_buf[slot] = h;
-                                } else {                  // staging full: append directly
-                                    u32 g = atomicAdd(&a.cand_cnt[row], 1u);
-                                    u64 capr = a.cand_off[row + 1] - a.cand_off[row];
-                                    if (g < capr) a.cand[a.cand_off[row] + g] = h;
-                                }
-                            }
-                        }
-                    }
-                }
+    hash_thread_windows<K>(base, Lp, lead, w0, a.W, a.seed, [&](u64 w, bool valid, u64 h) {
+        if (RAW) {
+            if (w >= lead) a.raw_out[w - lead] = valid ? h : 0ull;
+        } else if (valid && h != 0ull && h <= a.max_hash) {
+            u32 slot = atomicAdd(&s_cnt, 1u);
+            if (slot < STAGE_CAP) {
+                s_buf[slot] = h;
+            } else {                                  // staging full: append directly
+                u32 g = atomicAdd(&a.cand_cnt[row], 1u);
+                u64 capr = a.cand_off[row + 1] - a.cand_off[row];
+                if (g < capr) a.cand[a.cand_off[row] + g] = h;
             }
         }
-    }
+    });
     if (RAW) return;
     __syncthreads();
     const u32 n = min(s_cnt, (u32)STAGE_CAP);
