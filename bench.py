@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of sourmash_b200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Primary workload (BASELINE.json configs[2]): `compare` of 10 000 synthetic FracMinHash sketches
+(k=31, scaled=1000, ~5000 hashes each, 100 families) -> all-vs-all Jaccard matrix; metric
+sketch-pairs/s.  Secondary workload (configs[1], reported under "sketch"): `sketch dna`
+k=21,31,51 scaled=1000 over 100 synthetic 5 Mbp genomes; metric k-mers hashed/s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                  # this framework on cuda:0
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                           # CPU restatement on host cores
+
+One JSON line on stdout (rank 0).  Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SKETCHES = 10_000
+KSIZES = (21, 31, 51)
+N_GENOMES = 100
+GENOME_LEN = 5_000_000
+SCALED = 1000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- workloads
+def compare_workload():
+    from sourmash_b200.synth import synth_sketches
+    t = time.time()
+    h, off = synth_sketches(N_SKETCHES)
+    log(f"[bench] compare workload: {N_SKETCHES} sketches, {len(h)} hashes ({time.time() - t:.1f}s)")
+    return h, off
+
+
+def sketch_workload(n_genomes=N_GENOMES):
+    from sourmash_b200.synth import synth_genome
+    t = time.time()
+    total = n_genomes * GENOME_LEN
+    seqs = np.empty(total, dtype=np.uint8)
+    for g in range(n_genomes):
+        seqs[g * GENOME_LEN:(g + 1) * GENOME_LEN] = synth_genome(GENOME_LEN, 1000 + g)
+    offs = (np.arange(n_genomes + 1, dtype=np.uint64) * np.uint64(GENOME_LEN))
+    log(f"[bench] sketch workload: {n_genomes} genomes x {GENOME_LEN} bp ({time.time() - t:.1f}s)")
+    return seqs, offs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh).get(kernel)
+    return None
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_compare_sample(h, off, ncores, target_pairs):
+    """Time the oracle's compare_serial restatement on rows [0, R) (all columns j > i)."""
+    import oracle as orc
+    n = len(off) - 1
+    rows, pairs = 0, 0
+    while rows < n and pairs < target_pairs:
+        pairs += n - 1 - rows
+        rows += 1
+    t = time.perf_counter()
+    orc.compare_all_pairs(h, off, first_row=0, n_rows=rows, nthreads=ncores)
+    dt = time.perf_counter() - t
+    return pairs, dt, f"rows 0..{rows - 1} x all later columns of the {n}-sketch matrix = {pairs} pairs"
+
+
+def cpu_sketch_sample(seqs, offs, ncores, n_genomes):
+    import oracle as orc
+    sub_off = offs[: n_genomes + 1]
+    sub = seqs[: int(sub_off[-1])]
+    mx = orc.max_hash_for_scaled(SCALED)
+    kmers, t = 0, time.perf_counter()
+    for k in KSIZES:
+        orc.sketch_batch(sub, sub_off, k, mx, nthreads=ncores, cap_per_seq=20000)
+        kmers += int(sum(int(sub_off[i + 1] - sub_off[i]) - k + 1 for i in range(n_genomes)))
+    dt = time.perf_counter() - t
+    return kmers, dt, f"{n_genomes} of the {N_GENOMES} genomes x k={list(KSIZES)} = {kmers} k-mers"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    if args.workload == "compare":
+        h, off = compare_workload()
+        target = int(1.2e5 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
+        times = []
+        for i in range(args.warmup + args.steps):
+            units, dt, sample = cpu_compare_sample(h, off, ncores, target)
+            if i >= args.warmup:
+                times.append(dt)
+        metric, unit = "sketch-pairs/sec (compare)", "pairs/s"
+        config = {"workload": "configs[2]: compare 10000 synthetic sketches k=31 scaled=1000 all-vs-all jaccard",
+                  "n_sketches": N_SKETCHES}
+    else:
+        ng = min(N_GENOMES, max(8, ncores))
+        seqs, offs = sketch_workload(ng)
+        times = []
+        for i in range(args.warmup + args.steps):
+            units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, ng)
+            if i >= args.warmup:
+                times.append(dt)
+        metric, unit = "k-mers hashed/sec (sketch)", "k-mers/s"
+        config = {"workload": "configs[1]: sketch dna k=21,31,51 scaled=1000, 100 synthetic 5 Mbp genomes"}
+    ms = 1000.0 * float(np.mean(times))
+    value = units / (ms / 1000.0)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU restatement of src/core (oracle/oracle.c, OpenMP), not the Rust binary: no Rust toolchain in the image"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from sourmash_b200 import batch as B
+    B.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    B.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = B.kernel_launches()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0.record(stream)
+        extra = [step_fn() for _ in range(steps)]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, B.kernel_launches() - launches0, clocks, extra
+
+    hbm_peak, peak_src = peaks()
+    out = {}
+    if args.workload in ("compare", "both"):
+        out["compare"] = bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src)
+    if args.workload in ("sketch", "both"):
+        out["sketch"] = bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src)
+    if rank == 0:
+        primary = out.get("compare") or out.get("sketch")
+        line = dict(primary)
+        if "compare" in out and "sketch" in out:
+            line["sketch"] = out["sketch"]
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
+    h, off = compare_workload()
+    n = len(off) - 1
+    n_pairs = n * (n - 1) // 2
+    sizes = np.diff(off.astype(np.int64))
+    # algorithmic bytes of the intersection kernel: every pair reads both rows once, writes a u32
+    alg_bytes = 8.0 * (n - 1) * float(sizes.sum()) + 4.0 * n_pairs
+    dev = torch.device("cuda")
+    B.set_profiling(True)
+
+    if world == 1:
+        sset = B.SketchSet.from_host(h, off)
+        d_out = torch.empty((n, n), dtype=torch.float64, device=dev)
+        kernel_ms = []
+
+        def step():
+            B.compare_jaccard_device(sset, d_out.data_ptr())
+
+        def step_prof():
+            step()
+            kernel_ms.append(B.last_kernel_ms(0))
+
+        ms, launches, clocks, _ = timed(step_prof, args.steps, args.warmup)
+        kernel_ms = kernel_ms[-args.steps:]
+        # end to end: host CSR (pinned) -> H2D -> kernels -> D2H of the float64 matrix (pinned)
+        ph, po = B.pinned_empty(len(h), np.uint64), B.pinned_empty(len(off), np.uint64)
+        ph.array[:] = h
+        po.array[:] = off
+        pout = B.pinned_empty((n, n), np.float64)
+
+        def step_e2e():
+            s2 = B.SketchSet.from_host(ph.array, po.array)
+            B.compare_jaccard(s2, out=pout.array)
+            return float(pout.array[0, 1])
+
+        ms_e2e, _, _, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+        h2d, d2h = int(h.nbytes + off.nbytes), int(n * n * 8)
+        parallelism = "1 gpu"
+    else:
+        # shard rows across ranks as if each rank had sketched its own genomes; one all-gather
+        # of the shards, cyclic row tiles per rank, all-reduce of the partial count matrices,
+        # each rank finalises a block of rows.
+        from sourmash_b200.distributed import CompareShard
+        cs = CompareShard(torch, dist, B, h, off, rank, world)
+        kernel_ms = []
+
+        def step_prof():
+            cs.step(e2e=False)
+            kernel_ms.append(B.last_kernel_ms(0))
+
+        ms, launches, clocks, _ = timed(step_prof, args.steps, args.warmup)
+        kernel_ms = kernel_ms[-args.steps:]
+        ms_e2e, _, _, _ = timed(lambda: cs.step(e2e=True), max(2, args.steps // 2), 1)
+        h2d, d2h = cs.h2d_bytes, cs.d2h_bytes
+        alg_bytes = alg_bytes / world
+        parallelism = f"{world} gpus: sketches all-gathered, row tiles cyclic, counts all-reduced"
+
+    value = n_pairs / (ms / 1e3)
+    kms = float(np.mean(kernel_ms))
+    achieved = alg_bytes / (kms / 1e3) / 1e9
+    res = {
+        "metric": "sketch-pairs/sec (compare)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[2]: compare 10000 synthetic sketches (k=31, scaled=1000, ~5000 hashes, "
+                               "100 families) all-vs-all jaccard float64 matrix",
+                   "n_sketches": n, "pairs_per_step": n_pairs, "parallelism": parallelism,
+                   "l2_policy": "inputs 400 MB + 800 MB output per step exceed the 126 MB L2; no flush"},
+        "e2e": {"value": n_pairs / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "pairwise_tile_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("pairwise_tile_kernel"),
+                     "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
+                             "memory / L2, so DRAM traffic is far below this"},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        units, dt, sample = cpu_compare_sample(h, off, ncores, int(1.2e5 * ncores))
+        res["cpu_baseline"] = {"value": units / dt, "unit": "pairs/s", "cores": ncores, "kind": "port",
+                               "sample": sample, "seconds": dt}
+    return res
+
+
+def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
+    seqs, offs = sketch_workload()
+    ng = len(offs) - 1
+    mine = list(range(rank, ng, world))                   # genomes dealt round-robin to ranks
+    my_off = np.zeros(len(mine) + 1, dtype=np.uint64)
+    my_off[1:] = np.cumsum([int(offs[g + 1] - offs[g]) for g in mine])
+    my_seqs = np.concatenate([seqs[int(offs[g]):int(offs[g + 1])] for g in mine]) if world > 1 else seqs
+    total_kmers = sum(int(offs[g + 1] - offs[g]) - k + 1 for g in range(ng) for k in KSIZES)
+    my_kmers = sum(int(offs[g + 1] - offs[g]) - k + 1 for g in mine for k in KSIZES)
+    dev = torch.device("cuda")
+    d_bases = torch.empty(len(my_seqs) + 64, dtype=torch.uint8, device=dev)
+    d_bases[: len(my_seqs)].copy_(torch.from_numpy(my_seqs))
+    lens = np.diff(my_off.astype(np.int64)).astype(np.uint64)
+    B.set_profiling(True)
+    kernel_ms = []
+
+    def gather_shards(sset):
+        if dist is None:
+            return
+        from sourmash_b200.distributed import allgather_sketchset
+        allgather_sketchset(torch, dist, B, sset)
+
+    def step():
+        sset, nk = B.sketch_streams_device(d_bases.data_ptr(), my_off[:-1], lens, KSIZES, scaled=SCALED)
+        assert nk == my_kmers
+        kernel_ms.append(B.last_kernel_ms(1))
+        gather_shards(sset)
+        return sset
+
+    ms, launches, clocks, _ = timed(step, args.steps, args.warmup)
+    kernel_ms = kernel_ms[-args.steps:]
+    pin = B.pinned_empty(len(my_seqs), np.uint8)
+    pin.array[:] = my_seqs
+
+    def step_e2e():
+        sset, nk = B.sketch_sequences(pin.array, my_off, KSIZES, scaled=SCALED)
+        gather_shards(sset)
+        hh, oo = sset.to_host()
+        return int(oo[-1])
+
+    ms_e2e, _, _, ex = timed(step_e2e, max(2, args.steps // 2), 1)
+    kms = float(np.mean(kernel_ms))
+    alg_bytes = float(my_kmers) * (1.0 + 8.0 / SCALED)
+    achieved = alg_bytes / (kms / 1e3) / 1e9
+    res = {
+        "metric": "k-mers hashed/sec (sketch)", "value": total_kmers / (ms / 1e3), "unit": "k-mers/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: sketch dna k=21,31,51 scaled=1000 on 100 synthetic 5 Mbp genomes",
+                   "kmers_per_step": total_kmers,
+                   "parallelism": "1 gpu" if world == 1 else f"{world} gpus: genomes round-robin, sketches all-gathered",
+                   "l2_policy": "500 MB of bases per pass exceed the 126 MB L2; no flush"},
+        "e2e": {"value": total_kmers / (ms_e2e / 1e3), "unit": "k-mers/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(len(my_seqs)), "d2h_bytes_per_step": int(ex[-1]) * 8},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"kernel": "hash_kmers_kernel (3 launches, k=21,31,51)", "bound": "hbm", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": ncu_traffic("hash_kmers_kernel"), "kernel_ms": kms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "note": "integer-issue bound by construction (~150 int ops per k-mer vs 1 B): "
+                             "HBM fraction is expected to be small"},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, min(ng, max(8, ncores)))
+        res["cpu_baseline"] = {"value": units / dt, "unit": "k-mers/s", "cores": ncores, "kind": "port",
+                               "sample": sample, "seconds": dt}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=["compare", "sketch", "both"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "compare" if args.impl == "reference" else "both"
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -209,6 +209,8 @@ void smb_set_device(int32_t device);            /* per-thread; default = current
 void smb_set_stream(void *cuda_stream);         /* run subsequent work on this cudaStream_t   */
 void smb_synchronize(void);
 uint64_t smb_kernel_launches(void);             /* number of kernels launched by this library */
+void smb_set_profiling(bool on);                /* record CUDA events around the dominant kernels */
+double smb_last_kernel_ms(int32_t which);       /* 0: last pairwise tile kernel, 1: last hash pass */
 void *smb_alloc_pinned(uintptr_t nbytes);       /* page-locked host memory for e2e transfers  */
 void smb_free_pinned(void *ptr);
 uint64_t smb_max_hash_for_scaled(uint64_t scaled);   /* sketch/minhash.rs:21-27 */
@@ -227,6 +229,9 @@ uint64_t smb_sketchset_total_hashes(const SmbSketchSet *set);
 bool smb_sketchset_has_abunds(const SmbSketchSet *set);
 void smb_sketchset_offsets(const SmbSketchSet *set, uint64_t *offsets_out);   /* n_rows+1 */
 void smb_sketchset_to_host(const SmbSketchSet *set, uint64_t *hashes_out, uint64_t *abunds_out);
+/* device-to-device copy into caller-owned buffers (e.g. torch tensors), stream ordered */
+void smb_sketchset_copy_to_device(const SmbSketchSet *set, uint64_t *d_hashes_out,
+                                  uint64_t *d_offsets_out);
 const uint64_t *smb_sketchset_device_hashes(const SmbSketchSet *set);
 const uint64_t *smb_sketchset_device_offsets(const SmbSketchSet *set);
 /* new set holding, for every row, the prefix h <= max_hash (downsample_scaled,
@@ -266,6 +271,16 @@ void smb_pairwise_common(const SmbSketchSet *a, const SmbSketchSet *b, uint32_t 
 void smb_compare_jaccard(const SmbSketchSet *set, uint32_t num, double *out);
 /* same, result left in HBM (d_out: n*n doubles) -- used to time the kernels alone */
 void smb_compare_jaccard_dev(const SmbSketchSet *set, uint32_t num, double *d_out);
+/* Multi-GPU building blocks.  Shard `shard` of `n_shards` computes the common counts of its
+ * share of row tiles (dealt cyclically) into d_common (n*n u32, zero-initialised by the
+ * caller; only entries j > i of owned rows are written) -- partial matrices are then summed
+ * across ranks (NCCL all-reduce) and each rank finalises a block of rows. */
+void smb_pairwise_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint32_t n_shards,
+                                   uint32_t *d_common);
+/* d_out[(i - row_begin) * n + j] = jaccard(i, j) for row_begin <= i < row_end, from a complete
+ * upper-triangular count matrix */
+void smb_finalize_jaccard_rows_dev(const SmbSketchSet *set, const uint32_t *d_common,
+                                   uint64_t row_begin, uint64_t row_end, double *d_out);
 /* Index.find inner loop (src/sourmash/index/__init__.py:115-170): one query vs every row */
 void smb_one_vs_many(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
                      uint32_t *common_out);

@@ -40,6 +40,15 @@ def kernel_launches():
     return int(lib.smb_kernel_launches())
 
 
+def set_profiling(on):
+    lib.smb_set_profiling(bool(on))
+
+
+def last_kernel_ms(which):
+    """CUDA-event duration of the last pairwise tile kernel (0) / hash pass (1); -1 if none."""
+    return float(rustcall(lib.smb_last_kernel_ms, int(which)))
+
+
 def max_hash_for_scaled(scaled):
     return int(lib.smb_max_hash_for_scaled(int(scaled)))
 
@@ -140,6 +149,10 @@ class SketchSet:
     def downsample(self, max_hash):
         return SketchSet(rustcall(lib.smb_sketchset_downsample, self._ptr, int(max_hash)))
 
+    def copy_to_device(self, d_hashes_ptr, d_offsets_ptr=0):
+        rustcall(lib.smb_sketchset_copy_to_device, self._ptr, ffi.cast("uint64_t *", int(d_hashes_ptr)),
+                 ffi.cast("uint64_t *", int(d_offsets_ptr)))
+
     def device_pointers(self):
         return (int(ffi.cast("uintptr_t", lib.smb_sketchset_device_hashes(self._ptr))),
                 int(ffi.cast("uintptr_t", lib.smb_sketchset_device_offsets(self._ptr))))
@@ -202,6 +215,16 @@ def compare_jaccard(sset, num=0, out=None):
 
 def compare_jaccard_device(sset, d_out_ptr, num=0):
     rustcall(lib.smb_compare_jaccard_dev, sset._ptr, int(num), ffi.cast("double *", int(d_out_ptr)))
+
+
+def pairwise_counts_shard_device(sset, shard, n_shards, d_common_ptr):
+    rustcall(lib.smb_pairwise_counts_shard_dev, sset._ptr, int(shard), int(n_shards),
+             ffi.cast("uint32_t *", int(d_common_ptr)))
+
+
+def finalize_jaccard_rows_device(sset, d_common_ptr, row_begin, row_end, d_out_ptr):
+    rustcall(lib.smb_finalize_jaccard_rows_dev, sset._ptr, ffi.cast("uint32_t *", int(d_common_ptr)),
+             int(row_begin), int(row_end), ffi.cast("double *", int(d_out_ptr)))
 
 
 def one_vs_many(query, db):

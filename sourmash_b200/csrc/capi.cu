@@ -168,6 +168,26 @@ struct DevBuf {
 
 void sync(cudaStream_t s) { CK(cudaStreamSynchronize(s)); }
 
+// optional CUDA-event timing of the dominant kernels (smb_set_profiling / smb_last_kernel_ms)
+struct KernelTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool armed = false;
+    void begin(cudaStream_t s) {
+        if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); }
+        CK(cudaEventRecord(e0, s));
+    }
+    void end(cudaStream_t s) { CK(cudaEventRecord(e1, s)); armed = true; }
+    double ms() {
+        if (!armed) return -1.0;
+        float t = 0.f;
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        return (double)t;
+    }
+};
+thread_local bool t_profiling = false;
+thread_local KernelTimer t_timer_pairwise, t_timer_hash;
+
 // max_hash_for_scaled / scaled_for_max_hash: src/core/src/sketch/minhash.rs:21-34
 uint64_t max_hash_for_scaled(uint64_t scaled) {
     if (scaled == 0) return 0;
@@ -328,10 +348,12 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
         L.W = W; L.seed = P.seed;
         L.cand = d_cand.p; L.cand_off = d_cand_off.p; L.cand_cnt = d_cnt.p;
         L.row_stride = (int)nk;
+        if (t_profiling) t_timer_hash.begin(s);
         for (size_t j = 0; j < nk; ++j) {
             L.max_hash = kthr[j];
             smb::launch_hash_kmers_k(L, P.ksizes[j], (int)j, s);
         }
+        if (t_profiling) t_timer_hash.end(s);
         CK(cudaGetLastError());
         d_cnt.download(cnt.data(), n_rows);
         sync(s);
@@ -401,7 +423,8 @@ struct CountsDev {
 };
 
 void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t num, uint32_t* d_common,
-                         uint32_t* d_usize, size_t ldo, cudaStream_t s) {
+                         uint32_t* d_usize, size_t ldo, cudaStream_t s,
+                         smb::TileShard tiles = smb::TileShard{0, 1}) {
     const bool symmetric = (Bp == nullptr);
     const SmbSketchSet& B = symmetric ? A : *Bp;
     const int nA = (int)A.n_rows, nB = (int)B.n_rows;
@@ -420,8 +443,10 @@ void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t
     DevBuf<uint32_t> d_shift(4, s);
     smb::launch_bucket_shift(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, plan.nb_log2,
                              d_shift.p, s);
+    if (t_profiling) t_timer_pairwise.begin(s);
     smb::launch_pairwise_tile(plan, A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
-                              d_shift.p, symmetric, s);
+                              d_shift.p, symmetric, tiles, s);
+    if (t_profiling) t_timer_pairwise.end(s);
 }
 
 // upload one sorted row as a 1-row set
@@ -1074,6 +1099,10 @@ void smb_set_device(int32_t device) { t_device = device; }
 void smb_set_stream(void* cuda_stream) { t_stream = (cudaStream_t)cuda_stream; }
 void smb_synchronize(void) { guarded_void([&] { cudaStream_t s = need_gpu(); sync(s); }); }
 uint64_t smb_kernel_launches(void) { return smb::g_launches.load(); }
+void smb_set_profiling(bool on) { t_profiling = on; }
+double smb_last_kernel_ms(int32_t which) {
+    return guarded<double>([&] { return which == 0 ? t_timer_pairwise.ms() : t_timer_hash.ms(); });
+}
 void* smb_alloc_pinned(uintptr_t nbytes) {
     return guarded<void*>([&]() -> void* {
         need_gpu();
@@ -1132,6 +1161,16 @@ void smb_sketchset_to_host(const SmbSketchSet* set, uint64_t* hashes_out, uint64
         if (total && abunds_out && set->d_abunds)
             CK(cudaMemcpyAsync(abunds_out, set->d_abunds, total * 8, cudaMemcpyDeviceToHost, s));
         sync(s);
+    });
+}
+void smb_sketchset_copy_to_device(const SmbSketchSet* set, uint64_t* d_hashes_out, uint64_t* d_offsets_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        uint64_t total = set->total();
+        if (total && d_hashes_out)
+            CK(cudaMemcpyAsync(d_hashes_out, set->d_hashes, total * 8, cudaMemcpyDeviceToDevice, s));
+        if (d_offsets_out)
+            CK(cudaMemcpyAsync(d_offsets_out, set->d_off, (set->n_rows + 1) * 8, cudaMemcpyDeviceToDevice, s));
     });
 }
 const uint64_t* smb_sketchset_device_hashes(const SmbSketchSet* set) { return set->d_hashes; }
@@ -1244,6 +1283,30 @@ void smb_pairwise_common(const SmbSketchSet* a, const SmbSketchSet* b, uint32_t 
     });
 }
 
+void smb_pairwise_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint32_t n_shards,
+                                   uint32_t* d_common) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        if (set->n_rows == 0) return;
+        if (n_shards == 0 || shard >= n_shards) fail(SOURMASH_ERROR_CODE_MSG, "bad shard index");
+        pairwise_counts_dev(*set, nullptr, 0, d_common, nullptr, set->n_rows, s,
+                            smb::TileShard{(int)shard, (int)n_shards});
+        CK(cudaGetLastError());
+    });
+}
+
+void smb_finalize_jaccard_rows_dev(const SmbSketchSet* set, const uint32_t* d_common, uint64_t row_begin,
+                                   uint64_t row_end, double* d_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (row_end > n) row_end = n;
+        if (row_begin >= row_end) return;
+        smb::launch_finalize_rows(d_common, n, set->d_off, (int)n, (int)row_begin, (int)row_end, d_out, s);
+        CK(cudaGetLastError());
+    });
+}
+
 static void compare_jaccard_impl(const SmbSketchSet* set, uint32_t num, double* d_out, cudaStream_t s) {
     const size_t n = set->n_rows;
     if (n == 0) return;
@@ -1289,7 +1352,7 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
         plan.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
         smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, plan.nb_log2, d_shift.p, s);
         smb::launch_pairwise_tile(plan, q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, d_counts,
-                                  (size_t)nB, d_shift.p, false, s);
+                                  (size_t)nB, d_shift.p, false, smb::TileShard{0, 1}, s);
     } else {
         int nb_log2 = 12;
         while (nb_log2 < 26 && (1ull << nb_log2) < 2 * (uint64_t)nq) ++nb_log2;

@@ -95,6 +95,7 @@ struct TileArgs {
     u32* out; size_t ldo;
     const u32* d_shift;
     int nb_log2, cap, cols_per_cta, symmetric;
+    int tile_offset, tile_stride;       // row tile = blockIdx.x * tile_stride + tile_offset
 };
 
 template <int TA>
@@ -119,7 +120,7 @@ __device__ __forceinline__ void probe_one(u64 q, u32 b, const u64* const (&keys)
 template <int TA, int U>
 __global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int i0 = blockIdx.x * TA;
+    const int i0 = (blockIdx.x * a.tile_stride + a.tile_offset) * TA;
     int jbeg = blockIdx.y * a.cols_per_cta;
     int jend = min(jbeg + a.cols_per_cta, a.nB);
     if (a.symmetric) jbeg = max(jbeg, i0 + 1);
@@ -225,16 +226,20 @@ template <int TA>
 static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
     auto kern = pairwise_tile_kernel<TA, 4>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((args.nA + TA - 1) / TA, (args.nB + args.cols_per_cta - 1) / args.cols_per_cta);
+    const int tiles = (args.nA + TA - 1) / TA;
+    const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
+    if (my_tiles <= 0) return;
+    dim3 grid(my_tiles, (args.nB + args.cols_per_cta - 1) / args.cols_per_cta);
     kern<<<grid, TILE_THREADS, smem, s>>>(args); count_launches(1);
 }
 
 void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* offA, int nA,
                           const u64* hB, const u64* offB, int nB, u32* out, size_t ldo,
-                          const u32* d_shift, bool symmetric, cudaStream_t s) {
+                          const u32* d_shift, bool symmetric, TileShard tiles, cudaStream_t s) {
     if (nA <= 0 || nB <= 0) return;
     TileArgs a{hA, offA, nA, hB, offB, nB, out, ldo, d_shift,
-               plan.nb_log2, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0};
+               plan.nb_log2, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0,
+               tiles.shard, tiles.n_shards > 0 ? tiles.n_shards : 1};
     switch (plan.tables_per_cta) {
         case 1: launch_tile_ta<1>(a, plan.smem_bytes, s); break;
         case 2: launch_tile_ta<2>(a, plan.smem_bytes, s); break;
@@ -382,6 +387,30 @@ void launch_finalize_matrix(const u32* common, const u32* usize, size_t ldo, con
     dim3 grid((nB + 255) / 256, nA);
     finalize_matrix_kernel<<<grid, 256, 0, s>>>(common, usize, ldo, offA, offB, nA, nB, mode,
                                                 symmetric ? 1 : 0, out); count_launches(1);
+}
+
+__global__ void __launch_bounds__(256) finalize_rows_kernel(const u32* __restrict__ common, size_t n,
+                                                           const u64* __restrict__ off, int row_begin,
+                                                           int row_end, double* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = row_begin + blockIdx.y;
+    if (j >= (int)n || i >= row_end) return;
+    double v = 1.0;
+    if (i != j) {
+        int r = i < j ? i : j, c = i < j ? j : i;
+        u64 cm = common[(size_t)r * n + c];
+        u64 un = (off[r + 1] - off[r]) + (off[c + 1] - off[c]) - cm;
+        v = (double)cm / (double)(un > 1 ? un : 1);
+    }
+    out[(size_t)(i - row_begin) * n + j] = v;
+}
+
+void launch_finalize_rows(const u32* common, size_t n, const u64* off, int n_rows, int row_begin,
+                          int row_end, double* out, cudaStream_t s) {
+    (void)n_rows;
+    if (row_end <= row_begin) return;
+    dim3 grid(((int)n + 255) / 256, row_end - row_begin);
+    finalize_rows_kernel<<<grid, 256, 0, s>>>(common, n, off, row_begin, row_end, out); count_launches(1);
 }
 
 // ------------------------------------------------------------------------------------

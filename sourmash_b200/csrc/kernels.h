@@ -25,11 +25,15 @@ void launch_bucket_shift(const uint64_t* hA, const uint64_t* offA, int nA, const
                          const uint64_t* offB, int nB, int nb_log2, uint32_t* d_shift,
                          cudaStream_t s);
 
+// Multi-GPU sharding of row tiles: this launch handles tiles shard, shard + n_shards, ...
+struct TileShard { int shard; int n_shards; };
+
 // common[i*ldo + j] = |A_i ∩ B_j| for every (i, j) (symmetric: only j > i, A == B).
 // Tile kernel: A rows become shared-memory bucket tables, B rows stream through registers.
 void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const uint64_t* offA,
                           int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
-                          size_t ldo, const uint32_t* d_shift, bool symmetric, cudaStream_t s);
+                          size_t ldo, const uint32_t* d_shift, bool symmetric, TileShard tiles,
+                          cudaStream_t s);
 
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
 // elements in the longer row.
@@ -47,6 +51,10 @@ void launch_pairwise_num(const uint64_t* hA, const uint64_t* offA, int nA, const
 void launch_finalize_matrix(const uint32_t* common, const uint32_t* usize, size_t ldo,
                             const uint64_t* offA, const uint64_t* offB, int nA, int nB, int mode,
                             bool symmetric, double* out, cudaStream_t s);
+
+// rows [row_begin, row_end) of the symmetric jaccard matrix from upper-triangular counts
+void launch_finalize_rows(const uint32_t* common, size_t n, const uint64_t* off, int n_rows,
+                          int row_begin, int row_end, double* out, cudaStream_t s);
 
 // One query vs many subjects with a query too large for shared memory: global-memory bucket
 // directory over the query, every subject element probes it.

@@ -1,0 +1,106 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+The reference has no distributed path at all; sharding follows SURVEY §8e:
+  * sketching shards by genome, followed by ONE variable-length all-gather of the shards;
+  * compare replicates the gathered sketches, deals row tiles cyclically to ranks, sums the
+    partial count matrices with an all-reduce, and every rank finalises a block of rows.
+Host-side logic (shard bounds, padded all-gather + compaction, offsets) is backend agnostic
+and is what the gloo tests exercise; the compute calls need a GPU.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world):
+    """Contiguous row blocks: rank r owns rows [b[r], b[r+1])."""
+    return [n * r // world for r in range(world + 1)]
+
+
+def allgather_csr(torch, dist, local_hashes, local_sizes, device):
+    """All-gather variable-length CSR shards (rank order == row order).
+
+    local_hashes: int64 tensor (hashes viewed as int64) on `device`; local_sizes: int64 tensor.
+    Returns (hashes int64 tensor [total], sizes int64 numpy [n_rows_total]).
+    """
+    world = dist.get_world_size()
+    meta = torch.tensor([local_hashes.numel(), local_sizes.numel()], dtype=torch.int64, device=device)
+    metas = torch.empty(2 * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(metas, meta)
+    metas = metas.cpu().numpy().reshape(world, 2)
+    max_h, max_r = int(metas[:, 0].max()), int(metas[:, 1].max())
+    pad_h = torch.zeros(max(max_h, 1), dtype=torch.int64, device=device)
+    pad_h[: local_hashes.numel()] = local_hashes
+    pad_s = torch.zeros(max(max_r, 1), dtype=torch.int64, device=device)
+    pad_s[: local_sizes.numel()] = local_sizes
+    all_h = torch.empty(world * pad_h.numel(), dtype=torch.int64, device=device)
+    all_s = torch.empty(world * pad_s.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_h, pad_h)
+    dist.all_gather_into_tensor(all_s, pad_s)
+    total = int(metas[:, 0].sum())
+    hashes = torch.empty(max(total, 1), dtype=torch.int64, device=device)
+    sizes = []
+    pos = 0
+    all_s_host = all_s.cpu().numpy()
+    for r in range(world):
+        nh, nr = int(metas[r, 0]), int(metas[r, 1])
+        hashes[pos:pos + nh] = all_h[r * pad_h.numel(): r * pad_h.numel() + nh]
+        sizes.append(all_s_host[r * pad_s.numel(): r * pad_s.numel() + nr])
+        pos += nh
+    return hashes[:total], np.concatenate(sizes) if sizes else np.zeros(0, np.int64)
+
+
+def allgather_sketchset(torch, dist, B, sset):
+    """All-gather a per-rank SketchSet into a full SketchSet on every rank."""
+    device = torch.device("cuda", torch.cuda.current_device())
+    off = sset.offsets()
+    local = torch.empty(max(int(off[-1]), 1), dtype=torch.int64, device=device)
+    sset.copy_to_device(local.data_ptr())
+    sizes = torch.from_numpy(np.diff(off.astype(np.int64))).to(device)
+    hashes, all_sizes = allgather_csr(torch, dist, local[: int(off[-1])], sizes, device)
+    h_off = np.zeros(len(all_sizes) + 1, dtype=np.uint64)
+    h_off[1:] = np.cumsum(all_sizes)
+    d_off = torch.from_numpy(h_off.view(np.int64)).to(device)
+    return B.SketchSet.from_device(hashes.data_ptr(), d_off.data_ptr(), h_off, keepalive=(hashes, d_off))
+
+
+class CompareShard:
+    """One rank's part of an N-GPU all-vs-all compare (see module docstring)."""
+
+    def __init__(self, torch, dist, B, hashes, offsets, rank, world):
+        self.torch, self.dist, self.B, self.rank, self.world = torch, dist, B, rank, world
+        n = len(offsets) - 1
+        self.n = n
+        self.bounds = shard_bounds(n, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        local = hashes[int(offsets[lo]):int(offsets[hi])].view(np.int64)
+        sizes = np.diff(offsets.astype(np.int64))[lo:hi]
+        self.pin_h = torch.from_numpy(local.copy()).pin_memory()
+        self.pin_s = torch.from_numpy(sizes.copy()).pin_memory()
+        self.d_local = self.pin_h.to(self.device)
+        self.d_sizes = self.pin_s.to(self.device)
+        self.d_common = torch.zeros((n, n), dtype=torch.int32, device=self.device)
+        self.d_out = torch.empty((hi - lo, n), dtype=torch.float64, device=self.device)
+        self.pin_out = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
+        self.h2d_bytes = int(local.nbytes + sizes.nbytes)
+        self.d2h_bytes = int((hi - lo) * n * 8)
+
+    def step(self, e2e):
+        torch, dist, B = self.torch, self.dist, self.B
+        if e2e:
+            self.d_local.copy_(self.pin_h, non_blocking=True)
+            self.d_sizes.copy_(self.pin_s, non_blocking=True)
+        hashes, sizes = allgather_csr(torch, dist, self.d_local, self.d_sizes, self.device)
+        h_off = np.zeros(self.n + 1, dtype=np.uint64)
+        h_off[1:] = np.cumsum(sizes)
+        d_off = torch.from_numpy(h_off.view(np.int64)).to(self.device)
+        sset = B.SketchSet.from_device(hashes.data_ptr(), d_off.data_ptr(), h_off, keepalive=(hashes, d_off))
+        self.d_common.zero_()
+        B.pairwise_counts_shard_device(sset, self.rank, self.world, self.d_common.data_ptr())
+        dist.all_reduce(self.d_common)
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        B.finalize_jaccard_rows_device(sset, self.d_common.data_ptr(), lo, hi, self.d_out.data_ptr())
+        if e2e:
+            self.pin_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(self.pin_out[0, 1 if self.n > 1 else 0])
+        return None

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from tests.synth import MAX_HASH_1000, rows_of, synth_genome, synth_sketches
+from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_genome, synth_sketches
 
 pytestmark = pytest.mark.gpu
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from tests.synth import synth_genome
+from sourmash_b200.synth import synth_genome
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "roll_emul.cu")
