@@ -157,7 +157,7 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     if args.workload == "compare":
         h, off = compare_workload()
-        target = int(1.2e5 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
+        target = int(4e4 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
         times = []
         for i in range(args.warmup + args.steps):
             units, dt, sample = cpu_compare_sample(h, off, ncores, target)
@@ -329,7 +329,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     }
     if rank == 0 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
-        units, dt, sample = cpu_compare_sample(h, off, ncores, int(1.2e5 * ncores))
+        units, dt, sample = cpu_compare_sample(h, off, ncores, int(4e4 * ncores))
         res["cpu_baseline"] = {"value": units / dt, "unit": "pairs/s", "cores": ncores, "kind": "port",
                                "sample": sample, "seconds": dt}
     return res
