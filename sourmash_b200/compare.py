@@ -1,0 +1,141 @@
+"""All-vs-all comparison of signatures on the GPU.
+
+Function-for-function replacement of /root/reference/src/sourmash/compare.py (:14-358): the
+reference walks ``itertools.combinations`` in Python and crosses the FFI three times per
+pair; here a list of signatures becomes one CSR SketchSet in HBM and one batched call
+produces the whole count matrix.  Float post-processing follows the reference's operation
+order (similarity = common / max(1, union) on the device as an IEEE f64 divide; containment
+bias factors computed with Python floats exactly like minhash.py:827-841).
+"""
+import numpy as np
+
+from . import batch as B
+
+
+def _flat_minhashes(siglist):
+    return [s.minhash if hasattr(s, "minhash") else s for s in siglist]
+
+
+def _check_and_build(siglist, *, downsample, need_scaled=False):
+    """Validate compatibility like the per-pair calls would, return (SketchSet, num, scaled, sizes)."""
+    mhs = _flat_minhashes(siglist)
+    if not mhs:
+        return None, 0, 0, np.zeros(0, np.int64)
+    first = mhs[0]
+    for mh in mhs[1:]:
+        if mh.ksize != first.ksize:
+            raise ValueError("different ksizes cannot be compared")
+        if mh.moltype != first.moltype:
+            raise ValueError("DNA/prot minhashes cannot be compared")
+        if mh.seed != first.seed:
+            raise ValueError("mismatch in seed; comparison fail")
+        if mh.num != first.num:
+            raise TypeError(f"incompatible num values: self={first.num} other={mh.num}")
+    if need_scaled and not all(mh.scaled for mh in mhs):
+        raise TypeError("Error: can only calculate containment for scaled MinHashes")
+    scaleds = {mh.scaled for mh in mhs}
+    scaled = max(scaleds)
+    if len(scaleds) > 1:
+        if not downsample:
+            raise ValueError("mismatch in scaled; comparison fail")
+        mhs = [mh.downsample(scaled=scaled) if mh.scaled != scaled else mh for mh in mhs]
+    rows = [mh._mins_array() for mh in mhs]
+    sset = B.SketchSet.from_rows(rows)
+    return sset, first.num, scaled, np.array([len(r) for r in rows], dtype=np.int64)
+
+
+def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=None, return_ani=False):
+    """Similarity matrix (n, n) float64, ones on the diagonal -- ``compare_all_pairs`` /
+    ``compare_serial`` / ``compare_parallel`` of the reference (compare.py:14-64,241-358).
+    ``n_jobs`` is accepted for signature compatibility; the GPU does the whole matrix."""
+    if return_ani:
+        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
+    mhs = _flat_minhashes(siglist)
+    n = len(mhs)
+    if n == 0:
+        return np.ones((0, 0))
+    if not ignore_abundance and all(mh.track_abundance for mh in mhs):
+        # angular similarity between abundance sketches: per-pair GPU calls (not the batched path)
+        out = np.ones((n, n))
+        for i in range(n):
+            for j in range(i + 1, n):
+                out[i][j] = out[j][i] = mhs[i].similarity(mhs[j], ignore_abundance=False, downsample=downsample)
+        return out
+    sset, num, _, _ = _check_and_build(siglist, downsample=downsample)
+    return B.compare_jaccard(sset, num=num)
+
+
+def compare_serial(siglist, ignore_abundance, *, downsample=False, return_ani=False):
+    return compare_all_pairs(siglist, ignore_abundance, downsample=downsample, return_ani=return_ani)
+
+
+def compare_parallel(siglist, ignore_abundance, downsample, n_jobs, return_ani=False):
+    return compare_all_pairs(siglist, ignore_abundance, downsample=downsample, n_jobs=n_jobs, return_ani=return_ani)
+
+
+def _bias_factors(sizes, scaled):
+    "bias_factor(n) = 1 - (1 - 1/scaled) ** float(n * scaled), Python floats (minhash.py:830-833)"
+    table = {}
+    for n in set(int(x) for x in sizes):
+        table[n] = 1.0 - (1.0 - 1.0 / scaled) ** float(n * scaled) if n else 1.0
+    return np.array([table[int(x)] for x in sizes], dtype=np.float64)
+
+
+def _clamp01(m):
+    m = np.where(m >= 1, 1.0, m)
+    return np.where(m <= 0, 0.0, m)
+
+
+def _containment_parts(siglist, downsample):
+    sset, _, scaled, sizes = _check_and_build(siglist, downsample=downsample, need_scaled=True)
+    n = len(sizes)
+    if n == 0:
+        return None, sizes, scaled
+    common = B.pairwise_common(sset).astype(np.float64)
+    return common, sizes, scaled
+
+
+def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
+    """containments[i][j] = siglist[j].contained_by(siglist[i]) (compare.py:67-106)."""
+    if return_ani:
+        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
+    common, sizes, scaled = _containment_parts(siglist, downsample)
+    n = len(sizes)
+    if n == 0:
+        return np.ones((0, 0))
+    denom = sizes.astype(np.float64) * _bias_factors(sizes, scaled)       # per column j
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = common / denom[np.newaxis, :]
+    m = _clamp01(m)
+    m[:, sizes == 0] = 0.0
+    np.fill_diagonal(m, 1.0)
+    return m
+
+
+def compare_serial_max_containment(siglist, *, downsample=False, return_ani=False):
+    """max_containment matrix (compare.py:109-147): common / (min(|A|,|B|) * bias(min))."""
+    if return_ani:
+        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
+    common, sizes, scaled = _containment_parts(siglist, downsample)
+    n = len(sizes)
+    if n == 0:
+        return np.ones((0, 0))
+    mins = np.minimum(sizes[:, None], sizes[None, :])
+    flat = mins.ravel()
+    bias = _bias_factors(np.unique(flat), scaled)
+    lut = dict(zip(np.unique(flat).tolist(), bias.tolist()))
+    denom = mins.astype(np.float64) * np.vectorize(lut.get, otypes=[np.float64])(mins)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = common / denom
+    m = _clamp01(m)
+    m[mins == 0] = 0.0
+    np.fill_diagonal(m, 1.0)
+    return m
+
+
+def compare_serial_avg_containment(siglist, *, downsample=False, return_ani=False):
+    """avg_containment matrix (compare.py:150-187): mean of the two directed containments."""
+    c = compare_serial_containment(siglist, downsample=downsample, return_ani=return_ani)
+    m = (c + c.T) / 2
+    np.fill_diagonal(m, 1.0)
+    return m

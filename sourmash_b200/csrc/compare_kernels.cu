@@ -14,12 +14,22 @@
 // registers with coalesced 8-byte loads: each streamed element costs one directory lookup
 // plus two key compares per table ("directory galloping"), instead of a two-pointer walk
 // over |A|+|B| elements.  Counts are reduced with warp REDUX and written as u32.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace smb {
 
-static constexpr int TILE_THREADS = 512;
+static constexpr int TILE_THREADS_MAX = 1024;
+static int tile_threads() {
+    static int v = [] { const char* e = getenv("SMB_TILE_THREADS"); int t = e ? atoi(e) : 512; return (t == 256 || t == 512 || t == 1024) ? t : 512; }();
+    return v;
+}
+static int tile_cols_override() {
+    static int v = [] { const char* e = getenv("SMB_TILE_COLS"); return e ? atoi(e) : 0; }();
+    return v;
+}
 static constexpr int MAX_DYN_SMEM = 227 * 1024;
 
 // ------------------------------------------------------------------------------------
@@ -84,7 +94,7 @@ PairwisePlan plan_pairwise(uint64_t max_len_a, int n_b) {
         if (nb_log2 == 10) { p.tables_per_cta = 0; return p; }   // row too large for smem
     }
     // columns per CTA: enough streamed rows to amortise the table build
-    p.cols_per_cta = 512;
+    p.cols_per_cta = tile_cols_override() > 0 ? tile_cols_override() : 512;
     (void)n_b;
     return p;
 }
@@ -118,7 +128,7 @@ __device__ __forceinline__ void probe_one(u64 q, u32 b, const u64* const (&keys)
 }
 
 template <int TA, int U>
-__global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs a) {
+__global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int i0 = (blockIdx.x * a.tile_stride + a.tile_offset) * TA;
     int jbeg = blockIdx.y * a.cols_per_cta;
@@ -129,6 +139,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs
     const u32 shift = a.d_shift[0];
     const int nb = 1 << a.nb_log2;
     const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
     const int kstride = a.cap + 2;
     const int dstride = nb + 2;
     u64* keys_base = reinterpret_cast<u64*>(smem_raw);
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs
             if (n > 0 && ld_nc_u64(a.hA + beg + n - 1) == SMB_U64_MAX) { --n; hm = 1; }
         }
         u64* kt = keys_base + (size_t)t * kstride;
-        for (int p = tid; p < n; p += TILE_THREADS) kt[p] = ld_nc_u64(a.hA + beg + p);
+        for (int p = tid; p < n; p += nthreads) kt[p] = ld_nc_u64(a.hA + beg + p);
         if (tid < 2) kt[n + tid] = SMB_U64_MAX;
         if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
     }
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs
         const u64* kt = keys_base + (size_t)t * kstride;
         u16* dt = dirs_base + (size_t)t * dstride;
         int n = s_n[t];
-        for (int p = tid; p <= n; p += TILE_THREADS) {
+        for (int p = tid; p <= n; p += nthreads) {
             int bp = p < n ? (int)(kt[p] >> shift) : nb;
             int bprev = p == 0 ? -1 : (int)(kt[p - 1] >> shift);
             for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)p;
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) pairwise_tile_kernel(TileArgs
 
     // ---- stream columns: one warp per streamed row
     const int warp = tid >> 5, lane = tid & 31;
-    constexpr int NWARPS = TILE_THREADS / 32;
+    const int NWARPS = nthreads >> 5;
     for (int j = jbeg + warp; j < jend; j += NWARPS) {
         const u64 bbeg = a.offB[j];
         int nbj = (int)(a.offB[j + 1] - bbeg);
@@ -230,7 +241,7 @@ static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
     const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
     if (my_tiles <= 0) return;
     dim3 grid(my_tiles, (args.nB + args.cols_per_cta - 1) / args.cols_per_cta);
-    kern<<<grid, TILE_THREADS, smem, s>>>(args); count_launches(1);
+    kern<<<grid, tile_threads(), smem, s>>>(args); count_launches(1);
 }
 
 void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* offA, int nA,

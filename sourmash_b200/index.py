@@ -1,0 +1,261 @@
+"""In-memory index with GPU-batched search / prefetch / gather.
+
+Mirrors the reference's ``Index`` protocol (src/sourmash/index/__init__.py:115-320) and its
+``CounterGather`` helper (:735-909) for the linear (flat) case: the per-subject Python loop
+of ``Index.find`` and the per-dataset loop of ``CounterGather.consume`` become single
+one-vs-many kernel launches over a SketchSet kept in HBM.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import batch as B
+from .minhash import flatten_and_intersect_scaled
+from .search import calc_threshold_from_bp, make_containment_query, make_jaccard_search_query
+
+IndexSearchResult = namedtuple("IndexSearchResult", "score, signature, location")
+GatherResult = namedtuple("GatherResult", "match, intersect_size, containment, location")
+
+
+class LinearIndex:
+    "A list of signatures searched on the GPU (reference: LinearIndex, index/__init__.py:380-470)."
+
+    is_database = False
+
+    def __init__(self, _signatures=None, filename=None):
+        self._signatures = list(_signatures) if _signatures else []
+        self.filename = filename
+        self._device = None          # (scaled -> (SketchSet, sizes)) cache
+
+    @property
+    def location(self):
+        return self.filename
+
+    def signatures(self):
+        return iter(self._signatures)
+
+    def signatures_with_location(self):
+        for ss in self._signatures:
+            yield ss, self.location
+
+    def __len__(self):
+        return len(self._signatures)
+
+    def __bool__(self):
+        return bool(self._signatures)
+
+    def insert(self, node):
+        self._signatures.append(node)
+        self._device = None
+
+    # -- device cache ----------------------------------------------------------------------
+    def _groups(self):
+        """Subjects grouped by their own scaled (or num): {key: (indices, SketchSet)}; rows flat."""
+        if self._device is None:
+            groups = {}
+            for idx, ss in enumerate(self._signatures):
+                mh = ss.minhash
+                key = ("scaled", mh.scaled) if mh.scaled else ("num", mh.num)
+                groups.setdefault(key, []).append((idx, mh._mins_array()))
+            self._device = {k: ([i for i, _ in v], B.SketchSet.from_rows([r for _, r in v]))
+                            for k, v in groups.items()}
+        return self._device
+
+    # -- the 1 x N scoring loop ------------------------------------------------------------
+    def find(self, search_fn, query, **kwargs):
+        """Yield IndexSearchResult for subjects passing search_fn, in index order
+        (Index.find, index/__init__.py:115-170)."""
+        search_fn.check_is_compatible(query)
+        query_mh = query.minhash
+        assert not query_mh.track_abundance
+        scored = []
+        for (kind, val), (indices, sset) in self._groups().items():
+            if query_mh.scaled:
+                if kind != "scaled":
+                    raise ValueError("cannot compare scaled query against num sketches")
+                s = max(query_mh.scaled, val)
+                q = query_mh.downsample(scaled=s) if s > query_mh.scaled else query_mh
+                sub = sset.downsample(B.max_hash_for_scaled(s)) if s > val else sset
+                qarr = q._mins_array()
+                shared = B.one_vs_many(qarr, sub)
+                sizes = sub.sizes()
+                total = len(qarr) + sizes - shared
+                qsize = np.full(len(indices), len(qarr))
+            else:
+                if kind != "num":
+                    raise ValueError("cannot compare num query against scaled sketches")
+                n = min(query_mh.num, val)
+                rows = sset.rows()
+                sub = B.SketchSet.from_rows([r[:n] for r in rows])
+                qarr = query_mh._mins_array()[:n]
+                cm, us = B.pairwise_common(B.SketchSet.from_rows([qarr]), sub, num=n, want_usize=True)
+                shared, total = cm[0], us[0]
+                sizes = sub.sizes()
+                qsize = np.full(len(indices), len(qarr))
+            for pos, idx in enumerate(indices):
+                scored.append((idx, int(qsize[pos]), int(shared[pos]), int(sizes[pos]), int(total[pos])))
+        scored.sort()
+        for idx, qs, sh, ss_size, tot in scored:
+            score = search_fn.score_fn(qs, sh, ss_size, tot)
+            if search_fn.passes(score):
+                subj = self._signatures[idx]
+                if search_fn.collect(score, subj):
+                    yield IndexSearchResult(score, subj, self.location)
+
+    def search(self, query, *, threshold=None, do_containment=False, do_max_containment=False,
+               best_only=False, **kwargs):
+        "Sorted (best first) matches at or above threshold (Index.search, :202-239)."
+        if threshold is None:
+            raise TypeError("'search' requires 'threshold'")
+        threshold = float(threshold)
+        search_obj = make_jaccard_search_query(do_containment=do_containment,
+                                               do_max_containment=do_max_containment,
+                                               best_only=best_only, threshold=threshold)
+        matches = list(self.find(search_obj, query, **kwargs))
+        matches.sort(key=lambda x: -x.score)
+        return matches
+
+    def prefetch(self, query, threshold_bp, **kwargs):
+        "All subjects overlapping the query by at least threshold_bp (Index.prefetch, :241-256)."
+        if not self:
+            raise ValueError("no signatures to search")
+        search_fn = make_containment_query(query.minhash, threshold_bp, best_only=False)
+        yield from self.find(search_fn, query, **kwargs)
+
+    def counter_gather(self, query, threshold_bp, **kwargs):
+        "CounterGather pre-loaded with every prefetch match (Index.counter_gather, :302-320)."
+        counter = CounterGather(query)
+        for result in self.prefetch(query, threshold_bp, **kwargs):
+            counter.add(result.signature, location=result.location, require_overlap=False)
+        return counter
+
+    def best_containment(self, query, threshold_bp=None, **kwargs):
+        results = self.prefetch(query, threshold_bp, best_only=True, **kwargs)
+        results = sorted(results, key=lambda x: (-x.score, x.signature.md5sum()))
+        return results[0] if results else None
+
+
+class CounterGather:
+    """Tracks overlaps between a query and candidate matches for min-set-cover ``gather``
+    (protocol of index/__init__.py:735-909; conformance: tests/test_index_protocol.py of the
+    reference).  ``add`` records candidates, the first ``peek`` moves them to HBM, ``consume``
+    decrements every counter with one one-vs-many launch."""
+
+    def __init__(self, query):
+        query_mh = query.minhash
+        if not query_mh.scaled:
+            raise ValueError("gather requires scaled signatures")
+        self.orig_query_mh = query_mh.copy().flatten()
+        self.scaled = query_mh.scaled
+        self.siglist = {}
+        self.locations = {}
+        self.counter = {}            # md5 -> overlap, insertion ordered (ties: first added wins)
+        self.query_started = 0
+        self._pending = []           # signatures added but not yet counted
+        self._sset = None
+        self._order = None
+
+    def _count_pending(self):
+        if not self._pending:
+            return
+        qarr = self.orig_query_mh._mins_array()
+        rows = [ss.minhash._mins_array() for ss, _, _ in self._pending]
+        counts = B.one_vs_many(qarr, B.SketchSet.from_rows(rows))
+        pending, self._pending = self._pending, []
+        for (ss, location, require_overlap), overlap in zip(pending, counts.tolist()):
+            if overlap:
+                md5 = ss.md5sum()
+                self.counter[md5] = overlap
+                self.siglist[md5] = ss
+                self.locations[md5] = location
+                self.downsample(ss.minhash.scaled)
+            elif require_overlap:
+                raise ValueError("no overlap between query and signature!?")
+
+    def add(self, ss, *, location=None, require_overlap=True):
+        "Register a candidate match (overlap counted on the GPU)."
+        if self.query_started:
+            raise ValueError("cannot add more signatures to counter after peek/consume")
+        self._pending.append((ss, location, require_overlap))
+        if require_overlap:
+            self._count_pending()          # the reference raises at add() time
+
+    def downsample(self, scaled):
+        if scaled > self.scaled:
+            self.scaled = scaled
+        return self.scaled
+
+    def signatures(self):
+        self._count_pending()
+        yield from self.siglist.values()
+
+    @property
+    def union_found(self):
+        self._count_pending()
+        found_mh = self.orig_query_mh.copy_and_clear()
+        for ss in self.siglist.values():
+            found_mh.add_many(flatten_and_intersect_scaled(ss.minhash, self.orig_query_mh))
+        return found_mh
+
+    def _start(self):
+        self._count_pending()
+        self.query_started = 1
+        if self._sset is None and self.siglist:
+            self._order = list(self.siglist.keys())
+            self._sset = B.SketchSet.from_rows([self.siglist[m].minhash._mins_array() for m in self._order])
+
+    def peek(self, cur_query_mh, *, threshold_bp=0):
+        "Best remaining match and its intersection with the current query; [] if none."
+        self._start()
+        if not self.counter:
+            return []
+        scaled = self.downsample(cur_query_mh.scaled)
+        cur_query_mh = cur_query_mh.downsample(scaled=scaled)
+        if not cur_query_mh:
+            return []
+        if cur_query_mh.contained_by(self.orig_query_mh, downsample=True) < 1:
+            raise ValueError("current query not a subset of original query")
+        try:
+            threshold, n_threshold_hashes = calc_threshold_from_bp(threshold_bp, scaled, len(cur_query_mh))
+        except ValueError:
+            return []
+        best = max(self.counter.values())
+        dataset_id = next(k for k, v in self.counter.items() if v == best)   # first inserted wins ties
+        if best < n_threshold_hashes:
+            return []
+        match = self.siglist[dataset_id]
+        cont = cur_query_mh.contained_by(match.minhash, downsample=True)
+        assert cont
+        assert cont >= threshold
+        match_mh = match.minhash.downsample(scaled=scaled).flatten()
+        intersect_mh = cur_query_mh & match_mh
+        return (IndexSearchResult(cont, match, self.locations[dataset_id]), intersect_mh)
+
+    def consume(self, intersect_mh):
+        "Subtract the hashes of the chosen match from every remaining counter."
+        self._start()
+        if not intersect_mh:
+            return
+        deltas = B.one_vs_many(intersect_mh._mins_array(), self._sset)
+        for md5, d in zip(self._order, deltas.tolist()):
+            if d and md5 in self.counter:
+                self.counter[md5] -= d
+                if self.counter[md5] == 0:
+                    del self.counter[md5]
+
+
+def gather(query, index, threshold_bp=0):
+    """Iterative min-set-cover of ``query`` by the signatures of ``index`` (the loop of
+    GatherDatabases.__next__, search.py:877-949).  Yields GatherResult in pick order."""
+    counter = index.counter_gather(query, threshold_bp)
+    cur = query.minhash.flatten().to_mutable()
+    while True:
+        result = counter.peek(cur, threshold_bp=threshold_bp)
+        if not result:
+            return
+        sr, intersect_mh = result
+        counter.consume(intersect_mh)
+        yield GatherResult(sr.signature, len(intersect_mh), sr.score, sr.location)
+        cur = cur.downsample(scaled=counter.scaled).to_mutable() if counter.scaled > cur.scaled else cur
+        cur.remove_many(sr.signature.minhash.downsample(scaled=cur.scaled) if
+                        sr.signature.minhash.scaled < cur.scaled else sr.signature.minhash)
