@@ -138,44 +138,81 @@ __device__ __forceinline__ Bytes16 load16(const u8* p) {
 inline Bytes16 load16(const u8* p) { Bytes16 b; memcpy(b.w, p, 16); return b; }
 #endif
 
-// One thread's share of a stream: windows [w0, w0 + W) in "aligned coordinates".
+// Sequential 32-bit word reader over a thread's byte range, in "aligned coordinates":
 //   base   16-byte aligned pointer to the line holding the stream's first byte
-//   lead   bytes of that line that precede the stream (masked invalid)
-//   Lp     lead + stream length
-// emit(w, valid, h) is called for every window w < Lp - K + 1 of the share (w includes lead).
+//   lead   bytes of that line that precede the stream; Lp = lead + stream length
+// Bytes outside [lead, Lp) read as 0 (an invalid base), so windows that touch them never emit.
+struct WordStream {
+    const u8* base;
+    u64 Lp, pos;
+    u32 lead, r0, r1, r2, r3, i;
+    __host__ __device__ __forceinline__ WordStream(const u8* b, u64 lp, u32 ld, u64 start)
+        : base(b), Lp(lp), pos(start), lead(ld), r0(0), r1(0), r2(0), r3(0), i(0) {}
+    __host__ __device__ __forceinline__ void refill() {
+        r0 = r1 = r2 = r3 = 0u;
+        if (pos < Lp) {
+            Bytes16 v = load16(base + pos);
+            r0 = v.w[0]; r1 = v.w[1]; r2 = v.w[2]; r3 = v.w[3];
+            const u64 rem = Lp - pos;
+            if (rem < 16 || pos < lead) {              // partial line: zero the bytes outside the stream
+                const u32 hi = rem < 16 ? (u32)rem : 16u;
+                u32 lo = 0;
+                if (pos < lead) { const u64 d = lead - pos; lo = d < 16 ? (u32)d : 16u; }
+                const u32 vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                u32* r[4] = {&r0, &r1, &r2, &r3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    u32 m = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) if ((vm >> (4 * q + b)) & 1u) m |= 0xffu << (8 * b);
+                    *r[q] &= m;
+                }
+            }
+        }
+        pos += 16;
+    }
+    __host__ __device__ __forceinline__ u32 next() {
+        if ((i & 3u) == 0u) refill();
+        ++i;
+        const u32 w = r0;
+        r0 = r1; r1 = r2; r2 = r3;
+        return w;
+    }
+};
+
+// One thread's share of a stream: windows [w0, w0 + W), W a multiple of 4.  emit(w, valid, h)
+// is called for each of them in order (w in aligned coordinates, i.e. including `lead`; windows
+// past the end of the stream come out with valid == false).
 template <int K, class Emit>
 __host__ __device__ __forceinline__ void hash_thread_windows(const u8* __restrict__ base, u64 Lp, u32 lead,
                                                              u64 w0, int W, u64 seed, Emit&& emit) {
     const u64 nwin = Lp >= (u64)K ? Lp - K + 1 : 0;
     if (w0 >= nwin) return;
+    constexpr int Q = (K - 1) / 4, R = (K - 1) % 4;
+    WordStream ws(base, Lp, lead, w0);
     Roll<K> st;
     st.init();
-    const int nbytes = W + K - 1;                     // bytes this thread consumes
-    const int nchunks = (nbytes + 15) >> 4;
-    int j = 0;                                        // byte index within the thread's run
-    for (int c = 0; c < nchunks; ++c) {
-        const u64 pos = w0 + 16ull * c;
-        Bytes16 v; v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0u;
-        u32 vm = 0;                                   // bit jj: byte pos+jj lies inside the stream
-        if (pos < Lp) {
-            v = load16(base + pos);
-            const u64 rem = Lp - pos;
-            const u32 hi = rem < 16 ? (u32)rem : 16u;
-            u32 lo = 0;
-            if (pos < lead) { const u64 d = lead - pos; lo = d < 16 ? (u32)d : 16u; }
-            vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-        }
+    // warm-up: the first K-1 bases only fill the rolling state
+#pragma unroll 1
+    for (int q = 0; q < Q; ++q) {
+        const u32 word = ws.next();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj, ++j) {
-            if (j < nbytes) {
-                u32 x = (v.w[jj >> 2] >> (8 * (jj & 3))) & 0xffu;
-                if (!((vm >> jj) & 1u)) x = 0;        // outside the stream: invalid base
-                st.push(x);
-                if (j >= K - 1) {
-                    const u64 w = w0 + (u64)(j - (K - 1));
-                    if (w < nwin) emit(w, st.run >= (u32)K, st.hash(seed));
-                }
-            }
+        for (int b = 0; b < 4; ++b) st.push((word >> (8 * b)) & 0xffu);
+    }
+    u32 cur = ws.next();
+#pragma unroll
+    for (int b = 0; b < R; ++b) st.push((cur >> (8 * b)) & 0xffu);
+    // main phase: one window per base; bases come 4 at a time, re-aligned by a funnel shift
+    u64 w = w0;
+#pragma unroll 1
+    for (int q = 0; q < (W >> 2); ++q) {
+        const u32 nxt = ws.next();
+        const u32 word = R ? fshr(cur, nxt, 8 * R) : cur;
+        cur = nxt;
+#pragma unroll
+        for (int b = 0; b < 4; ++b, ++w) {
+            st.push((word >> (8 * b)) & 0xffu);
+            emit(w, st.run >= (u32)K, st.hash(seed));
         }
     }
 }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
 
     hash_thread_windows<K>(base, Lp, lead, w0, a.W, a.seed, [&](u64 w, bool valid, u64 h) {
         if (RAW) {
-            if (w >= lead) a.raw_out[w - lead] = valid ? h : 0ull;
+            if (w >= lead && w + K <= Lp) a.raw_out[w - lead] = valid ? h : 0ull;
         } else if (valid && h != 0ull && h <= a.max_hash) {
             u32 slot = atomicAdd(&s_cnt, 1u);
             if (slot < STAGE_CAP) {

@@ -23,7 +23,7 @@ static void run(const std::vector<u8>& buf, u32 lead, int W, u64 seed, std::vect
     const u64 nwin = Lp >= (u64)K ? Lp - K + 1 : 0;
     for (u64 w0 = 0; w0 < nwin; w0 += (u64)W) {
         hash_thread_windows<K>(padded.data(), Lp, lead, w0, W, seed, [&](u64 w, bool valid, u64 h) {
-            if (w >= lead) out[w - lead] = valid ? h : 0ULL;
+            if (w >= lead && w + K <= Lp) out[w - lead] = valid ? h : 0ULL;
         });
     }
 }
