@@ -128,6 +128,20 @@ cudaStream_t need_gpu() {
              "no usable CUDA device (" + (g_probe_error.empty() ? std::string("device count 0") : g_probe_error) +
                  "); sourmash_b200 has no CPU fallback for hashing / intersection");
     if (t_device >= 0) CK(cudaSetDevice(t_device));
+    // keep freed stream-ordered allocations cached in the pool (default threshold 0 returns
+    // them to the driver at every synchronisation, i.e. a fresh cudaMalloc per call)
+    thread_local int t_pool_ready_for = -2;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (t_pool_ready_for != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        t_pool_ready_for = dev;
+    }
     return t_stream;
 }
 

@@ -23,7 +23,7 @@ namespace smb {
 
 static constexpr int TILE_THREADS_MAX = 1024;
 static int tile_threads() {
-    static int v = [] { const char* e = getenv("SMB_TILE_THREADS"); int t = e ? atoi(e) : 512; return (t == 256 || t == 512 || t == 1024) ? t : 512; }();
+    static int v = [] { const char* e = getenv("SMB_TILE_THREADS"); int t = e ? atoi(e) : 1024; return (t == 256 || t == 512 || t == 1024) ? t : 1024; }();
     return v;
 }
 static int tile_cols_override() {
