@@ -1,0 +1,75 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: shard bounds, the
+variable-length all-gather of CSR shards and the bookkeeping around it.  The compute calls
+themselves need GPUs and are exercised by bench.py --gpus N."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sourmash_b200.distributed import allgather_csr, shard_bounds
+        from sourmash_b200.synth import synth_sketches
+        h, off = synth_sketches(37, mean=200, sd=40, lo=0, hi=400, n_families=3, pool=250, seed=5)
+        bounds = shard_bounds(37, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        local = torch.from_numpy(h[int(off[lo]):int(off[hi])].view(np.int64).copy())
+        sizes = torch.from_numpy(np.diff(off.astype(np.int64))[lo:hi].copy())
+        hashes, all_sizes = allgather_csr(torch, dist, local, sizes, torch.device("cpu"))
+        ok = (np.array_equal(hashes.numpy().view(np.uint64), h)
+              and np.array_equal(all_sizes, np.diff(off.astype(np.int64))))
+        # an empty shard on one rank must also work
+        e_local = local if rank == 0 else local[:0]
+        e_sizes = sizes if rank == 0 else sizes[:0]
+        eh, es = allgather_csr(torch, dist, e_local, e_sizes, torch.device("cpu"))
+        ok = ok and eh.numel() == local.numel() if rank == 0 else ok
+        q.put((rank, bool(ok), int(hashes.numel()), len(all_sizes)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    sys.path.insert(0, ROOT)
+    from sourmash_b200.distributed import shard_bounds
+    assert shard_bounds(10, 1) == [0, 10]
+    assert shard_bounds(10, 4) == [0, 2, 5, 7, 10]
+    b = shard_bounds(10000, 8)
+    assert b[0] == 0 and b[-1] == 10000 and all(b[i + 1] - b[i] == 1250 for i in range(8))
+    assert shard_bounds(3, 8)[-1] == 3
+
+
+@pytest.mark.timeout(120)
+def test_allgather_csr_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in results) == [0, 1]
+    assert all(r[1] for r in results), results
+    assert results[0][2] == results[1][2] and results[0][3] == 37
