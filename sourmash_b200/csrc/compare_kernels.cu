@@ -108,26 +108,41 @@ struct TileArgs {
     int tile_offset, tile_stride;       // row tile = blockIdx.x * tile_stride + tile_offset
 };
 
-template <int TA>
-__device__ __forceinline__ void probe_one(u64 q, u32 b, const u64* const (&keys)[TA],
-                                          const u16* const (&dirs)[TA], u32 (&cnt)[TA], u32 valid) {
+// Directory entries are u16.  When every table row has < 16384 keys (OCC), the top two bits
+// carry min(bucket occupancy, 3) so the probe knows, without touching the keys, whether more
+// than two keys share the bucket; otherwise the entry is the plain start index and the
+// "more keys" test is k1 < q.
+template <int TA, bool OCC>
+__device__ __forceinline__ void probe_fast(u64 q, u32 b, const u64* const (&keys)[TA],
+                                           const u16* const (&dirs)[TA], u32 (&cnt)[TA], u32 valid,
+                                           u32& pend, int ubit) {
 #pragma unroll
     for (int t = 0; t < TA; ++t) {
-        u32 st = dirs[t][b];
+        const u32 ent = dirs[t][b];
+        const u32 st = OCC ? (ent & 0x3fffu) : ent;
         const u64* kp = keys[t] + st;
-        u64 k0 = kp[0], k1 = kp[1];
-        u32 m = (k0 == q) | (k1 == q);
-        if (k1 < q) {                       // rare: >2 keys of this bucket precede q
-            const u64* pp = kp + 2;
-            u64 kk;
-            while ((kk = *pp) < q) ++pp;
-            m = (kk == q);
-        }
+        const u64 k0 = kp[0], k1 = kp[1];
+        const u32 m = (k0 == q) | (k1 == q);
         cnt[t] += m & valid;
+        const bool more = OCC ? (ent >= 0xC000u) : (k1 < q);
+        if (more && valid) pend |= 1u << (ubit * TA + t);      // predicated OR, no branch
     }
 }
 
-template <int TA, int U>
+// rare: a bucket holds more than two keys below/at q -- continue the scan past the two
+// keys the fast path already compared
+template <int TA, bool OCC>
+__device__ __forceinline__ void probe_rest(u64 q, u32 b, int t, const u64* const (&keys)[TA],
+                                           const u16* const (&dirs)[TA], u32 (&cnt)[TA]) {
+    const u32 ent = dirs[t][b];
+    const u32 st = OCC ? (ent & 0x3fffu) : ent;
+    const u64* pp = keys[t] + st + 2;
+    u64 kk;
+    while ((kk = *pp) < q) ++pp;
+    cnt[t] += (kk == q);
+}
+
+template <int TA, int U, bool OCC>
 __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int i0 = (blockIdx.x * a.tile_stride + a.tile_offset) * TA;
@@ -177,6 +192,18 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
         }
     }
     __syncthreads();
+    if (OCC) {          // fold min(occupancy, 3) into the top two bits
+#pragma unroll
+        for (int t = 0; t < TA; ++t) {
+            u16* dt = dirs_base + (size_t)t * dstride;
+            for (int b = tid; b < nb; b += nthreads) {
+                u32 st = dt[b] & 0x3fffu, en = dt[b + 1] & 0x3fffu;
+                u32 occ = en - st;
+                dt[b] = (u16)(st | ((occ > 3u ? 3u : occ) << 14));
+            }
+        }
+        __syncthreads();
+    }
 
     const u64* keys[TA];
     const u16* dirs[TA];
@@ -214,14 +241,30 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
 #pragma unroll
                 for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + base + 32 * U + u * 32 + lane);
             }
+            u32 pend = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) probe_one<TA>(cur[u], (u32)(cur[u] >> shift), keys, dirs, cnt, 1u);
+            for (int u = 0; u < U; ++u)
+                probe_fast<TA, OCC>(cur[u], (u32)(cur[u] >> shift), keys, dirs, cnt, 1u, pend, u);
+            if (pend) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int t = 0; t < TA; ++t)
+                        if (pend & (1u << (u * TA + t)))
+                            probe_rest<TA, OCC>(cur[u], (u32)(cur[u] >> shift), t, keys, dirs, cnt);
+            }
         }
         for (; base < nbj; base += 32) {      // ragged tail
             int e = base + lane;
             u32 valid = e < nbj;
             u64 qq = valid ? ld_nc_u64(row + e) : 0ULL;
-            probe_one<TA>(qq, (u32)(qq >> shift), keys, dirs, cnt, valid);
+            u32 pend = 0;
+            probe_fast<TA, OCC>(qq, (u32)(qq >> shift), keys, dirs, cnt, valid, pend, 0);
+            if (pend) {
+#pragma unroll
+                for (int t = 0; t < TA; ++t)
+                    if (pend & (1u << t)) probe_rest<TA, OCC>(qq, (u32)(qq >> shift), t, keys, dirs, cnt);
+            }
         }
 #pragma unroll
         for (int t = 0; t < TA; ++t) {
@@ -235,7 +278,7 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
 
 template <int TA>
 static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
-    auto kern = pairwise_tile_kernel<TA, 4>;
+    auto kern = args.cap < 16380 ? pairwise_tile_kernel<TA, 4, true> : pairwise_tile_kernel<TA, 4, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles = (args.nA + TA - 1) / TA;
     const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
