@@ -199,6 +199,23 @@ struct KernelTimer {
         return (double)t;
     }
 };
+// second stream for uploads that overlap with kernels, and a small pool of timing-less events
+thread_local cudaStream_t t_copy_stream = nullptr;
+thread_local std::vector<cudaEvent_t> t_events;
+thread_local size_t t_event_next = 0;
+cudaStream_t copy_stream() {
+    if (!t_copy_stream) CK(cudaStreamCreateWithFlags(&t_copy_stream, cudaStreamNonBlocking));
+    return t_copy_stream;
+}
+cudaEvent_t pool_event() {
+    if (t_events.size() < 64) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        t_events.push_back(e);
+        return e;
+    }
+    return t_events[t_event_next++ % t_events.size()];
+}
 thread_local bool t_profiling = false;
 thread_local KernelTimer t_timer_pairwise, t_timer_hash;
 
@@ -243,6 +260,8 @@ namespace {
 // ------------------------------------------------------------------------------------------
 struct StreamList {
     const uint8_t* d_bases = nullptr;        // 16-byte aligned, padded allocation
+    const uint8_t* h_bases = nullptr;        // if set: host copy still to be uploaded to d_bases
+    uint64_t total_bytes = 0;                //         (done in groups, overlapped with hashing)
     std::vector<uint64_t> off, len;          // per stream
     std::vector<uint32_t> row;               // per stream -> sketch index (empty: identity)
     size_t n_sketches = 0;
@@ -347,6 +366,7 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
     }
     for (size_t r = 0; r < n_rows; ++r) cap[r] = cap_for(row_windows[r], kthr[r % nk]);
 
+    bool uploaded = false;
     for (int attempt = 0; attempt < 4; ++attempt) {
         for (size_t r = 0; r < n_rows; ++r) cand_off[r + 1] = cand_off[r] + cap[r];
         d_cand.alloc(cand_off[n_rows], s);
@@ -363,9 +383,37 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
         L.cand = d_cand.p; L.cand_off = d_cand_off.p; L.cand_cnt = d_cnt.p;
         L.row_stride = (int)nk;
         if (t_profiling) t_timer_hash.begin(s);
-        for (size_t j = 0; j < nk; ++j) {
-            L.max_hash = kthr[j];
-            smb::launch_hash_kmers_k(L, P.ksizes[j], (int)j, s);
+        if (in.h_bases && !uploaded) {
+            // pipeline: copy a group of streams on the copy stream, hash it on `s` as soon as it
+            // has landed, while the next group is in flight
+            cudaStream_t cs = copy_stream();
+            cudaEvent_t ready = pool_event();
+            CK(cudaEventRecord(ready, s));                  // d_bases allocation is ordered on s
+            CK(cudaStreamWaitEvent(cs, ready, 0));
+            const uint64_t group_bytes = 48ull << 20;
+            size_t g0 = 0;
+            while (g0 < ns) {
+                size_t g1 = g0;
+                uint64_t lo = in.off[g0], hi = lo;
+                while (g1 < ns && (hi - lo < group_bytes || g1 == g0)) { hi = in.off[g1] + in.len[g1]; ++g1; }
+                if (g1 == ns) hi = in.total_bytes;
+                CK(cudaMemcpyAsync((void*)(in.d_bases + lo), in.h_bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                cudaEvent_t ev = pool_event();
+                CK(cudaEventRecord(ev, cs));
+                CK(cudaStreamWaitEvent(s, ev, 0));
+                for (size_t j = 0; j < nk; ++j) {
+                    L.max_hash = kthr[j];
+                    smb::launch_hash_kmers_range(L, P.ksizes[j], (int)j, tile_r[g0], tile_r[g1], tile_g[g0],
+                                                 tile_g[g1], s);
+                }
+                g0 = g1;
+            }
+            uploaded = true;
+        } else {
+            for (size_t j = 0; j < nk; ++j) {
+                L.max_hash = kthr[j];
+                smb::launch_hash_kmers_k(L, P.ksizes[j], (int)j, s);
+            }
         }
         if (t_profiling) t_timer_hash.end(s);
         CK(cudaGetLastError());
@@ -1238,9 +1286,10 @@ SmbSketchSet* smb_sketch_sequences(const uint8_t* seqs, const uint64_t* seq_offs
         cudaStream_t s = need_gpu();
         const uint64_t total = n_seqs ? seq_offsets[n_seqs] : 0;
         DevBuf<uint8_t> d_bases(total + 32, s);
-        d_bases.upload(seqs, total);                 // one H2D copy of the caller's buffer
         StreamList in;
         in.d_bases = d_bases.p;
+        in.h_bases = seqs;                           // uploaded in groups, overlapped with hashing
+        in.total_bytes = total;
         in.off.assign(seq_offsets, seq_offsets + n_seqs);
         in.len.resize(n_seqs);
         for (size_t i = 0; i < n_seqs; ++i) in.len[i] = seq_offsets[i + 1] - seq_offsets[i];

@@ -99,6 +99,9 @@ bool k_has_rolled_kernel(uint32_t k);
 int hash_threads();
 // survivors (0 < h <= max_hash, all k bases valid) of every window -> candidate rows
 void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cudaStream_t s);
+// same, restricted to a range of tiles (a group of streams) -- lets uploads and hashing overlap
+void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index, uint32_t tile_lo_r,
+                             uint32_t tile_hi_r, uint32_t tile_lo_g, uint32_t tile_hi_g, cudaStream_t s);
 // per-window hashes of stream 0 in order; 0 marks an invalid window (seq_to_hashes)
 void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s);
 // first non-ACGT position of a sequence (UINT64_MAX if none)

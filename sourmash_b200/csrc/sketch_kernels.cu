@@ -38,6 +38,7 @@ struct HashArgs {
     u64* cand;                    // candidate storage
     const u64* cand_off;          // [n_rows + 1]
     u32* cand_cnt;                // [n_rows]
+    u32 tile_base;                // first tile of this launch (launches may cover a range of tiles)
     int row_stride, row_index;    // row = sketch * row_stride + row_index
     u64* raw_out;                 // RAW mode: per-window hashes of stream 0 (0 = invalid)
 };
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         s_cnt = 0;
-        s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x);
+        s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x + a.tile_base);
     }
     __syncthreads();
     const int stream = s_stream;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
     const u32 lead = (u32)(s0 - b0);
     const u64 Lp = (u64)lead + a.stream_len[stream];
     const u8* __restrict__ base = a.bases + b0;
-    const u64 tile = blockIdx.x - a.tile_start[stream];
+    const u64 tile = blockIdx.x + a.tile_base - a.tile_start[stream];
     const u64 w0 = (tile * HASH_THREADS + tid) * (u64)a.W;
     const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
     const int row = sk * a.row_stride + a.row_index;
@@ -111,14 +112,14 @@ __device__ __forceinline__ u32 comp_base(u32 u) { return u == 'A' ? 'T' : u == '
 template <bool RAW>
 __global__ void __launch_bounds__(256) hash_kmers_generic_kernel(HashArgs a, u32 K) {
     __shared__ int s_stream;
-    if (threadIdx.x == 0) s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x);
+    if (threadIdx.x == 0) s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x + a.tile_base);
     __syncthreads();
     const int stream = s_stream;
     const u64 L = a.stream_len[stream];
     const u8* __restrict__ base = a.bases + a.stream_off[stream];
     if (L < K || K == 0) return;
     const u64 nwin = L - K + 1;
-    const u64 tile = blockIdx.x - a.tile_start[stream];
+    const u64 tile = blockIdx.x + a.tile_base - a.tile_start[stream];
     const u64 w = tile * 256ull + threadIdx.x;
     if (w >= nwin) return;
     const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
@@ -171,40 +172,53 @@ __global__ void __launch_bounds__(256) hash_kmers_generic_kernel(HashArgs a, u32
 }
 
 template <bool RAW>
-static void launch_hash_one_k(HashArgs a, u32 K, u32 total_tiles_rolled, u32 total_tiles_generic,
-                              cudaStream_t s) {
-    switch (K) {
-        case 21: if (total_tiles_rolled) hash_kmers_kernel<21, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
-        case 31: if (total_tiles_rolled) hash_kmers_kernel<31, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
-        case 51: if (total_tiles_rolled) hash_kmers_kernel<51, RAW><<<total_tiles_rolled, HASH_THREADS, 0, s>>>(a); count_launches(1); break;
-        default: if (total_tiles_generic) hash_kmers_generic_kernel<RAW><<<total_tiles_generic, 256, 0, s>>>(a, K); count_launches(1); break;
+static void launch_hash_one_k(HashArgs a, u32 K, bool rolled, u32 n_tiles, cudaStream_t s) {
+    if (n_tiles == 0) return;
+    if (rolled) {
+        switch (K) {
+            case 21: hash_kmers_kernel<21, RAW><<<n_tiles, HASH_THREADS, 0, s>>>(a); break;
+            case 31: hash_kmers_kernel<31, RAW><<<n_tiles, HASH_THREADS, 0, s>>>(a); break;
+            default: hash_kmers_kernel<51, RAW><<<n_tiles, HASH_THREADS, 0, s>>>(a); break;
+        }
+    } else {
+        hash_kmers_generic_kernel<RAW><<<n_tiles, 256, 0, s>>>(a, K);
     }
+    count_launches(1);
 }
 
 bool k_has_rolled_kernel(uint32_t k) { return k == 21 || k == 31 || k == 51; }
 int hash_threads() { return HASH_THREADS; }
 
-void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cudaStream_t s) {
+static HashArgs make_hash_args(const HashLaunch& L, bool rolled, u32 tile_lo) {
     HashArgs a{};
     a.bases = L.bases; a.stream_off = L.stream_off; a.stream_len = L.stream_len;
     a.stream_row = L.stream_row;
     a.n_streams = L.n_streams; a.W = L.W; a.seed = L.seed; a.max_hash = L.max_hash;
     a.cand = L.cand; a.cand_off = L.cand_off; a.cand_cnt = L.cand_cnt;
-    a.row_stride = L.row_stride; a.row_index = row_index; a.raw_out = nullptr;
-    const bool rolled = k_has_rolled_kernel(ksize);
+    a.row_stride = L.row_stride; a.raw_out = nullptr;
     a.tile_start = rolled ? L.tile_start_rolled : L.tile_start_generic;
-    launch_hash_one_k<false>(a, ksize, L.total_tiles_rolled, L.total_tiles_generic, s);
+    a.tile_base = tile_lo;
+    return a;
+}
+
+void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cudaStream_t s) {
+    launch_hash_kmers_range(L, ksize, row_index, 0, L.total_tiles_rolled, 0, L.total_tiles_generic, s);
+}
+
+void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index, uint32_t tile_lo_r,
+                             uint32_t tile_hi_r, uint32_t tile_lo_g, uint32_t tile_hi_g, cudaStream_t s) {
+    const bool rolled = k_has_rolled_kernel(ksize);
+    const u32 lo = rolled ? tile_lo_r : tile_lo_g, hi = rolled ? tile_hi_r : tile_hi_g;
+    HashArgs a = make_hash_args(L, rolled, lo);
+    a.row_index = row_index;
+    launch_hash_one_k<false>(a, ksize, rolled, hi - lo, s);
 }
 
 void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s) {
-    HashArgs a{};
-    a.bases = L.bases; a.stream_off = L.stream_off; a.stream_len = L.stream_len;
-    a.stream_row = nullptr;
-    a.n_streams = L.n_streams; a.W = L.W; a.seed = L.seed; a.max_hash = L.max_hash;
-    a.row_stride = 1; a.row_index = 0; a.raw_out = raw_out;
     const bool rolled = k_has_rolled_kernel(ksize);
-    a.tile_start = rolled ? L.tile_start_rolled : L.tile_start_generic;
-    launch_hash_one_k<true>(a, ksize, L.total_tiles_rolled, L.total_tiles_generic, s);
+    HashArgs a = make_hash_args(L, rolled, 0);
+    a.stream_row = nullptr; a.row_stride = 1; a.row_index = 0; a.raw_out = raw_out;
+    launch_hash_one_k<true>(a, ksize, rolled, rolled ? L.total_tiles_rolled : L.total_tiles_generic, s);
 }
 
 // ---------------------------------------------------------------------------------------
