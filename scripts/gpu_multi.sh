@@ -1,0 +1,18 @@
+#!/bin/bash
+# N-GPU bench (torchrun, NCCL) -- run with: gpurun --gpus N -- 'bash scripts/gpu_multi.sh N'
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+N=${1:-2}
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n${N}.json 2> gpurun_out/bench_n${N}.err
+echo "rc=$?"
+tail -15 gpurun_out/bench_n${N}.err
+python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/bench_n${N}.json"))
+    for x in (d, d.get("sketch", {})):
+        if x: print(x["metric"], "n_gpus", x["n_gpus"], "value %.4g"%x["value"], "ms %.2f"%x["ms_per_step"], "e2e %.4g (%.1f ms)"%(x["e2e"]["value"], x["e2e"]["ms_per_step"]), "kernel_ms %.2f"%x["roofline"]["kernel_ms"])
+except Exception as e:
+    print("no json:", e); print(open("gpurun_out/bench_n${N}.json").read()[:2000])
+PY
