@@ -269,6 +269,9 @@ void smb_pairwise_common(const SmbSketchSet *a, const SmbSketchSet *b, uint32_t 
 /* compare_all_pairs / compare_serial (src/sourmash/compare.py:14-64,328-358): float64
  * (n, n) Jaccard matrix, ones on the diagonal.  out on the host (pinned or pageable). */
 void smb_compare_jaccard(const SmbSketchSet *set, uint32_t num, double *out);
+/* all-vs-all angular similarity (KmerMinHash::angular_similarity, sketch/minhash.rs:635-680) of
+ * a set that carries abundances; float64 (n, n), ones on the diagonal */
+void smb_compare_angular(const SmbSketchSet *set, double *out);
 /* same, result left in HBM (d_out: n*n doubles) -- used to time the kernels alone */
 void smb_compare_jaccard_dev(const SmbSketchSet *set, uint32_t num, double *d_out);
 /* Multi-GPU building blocks.  Shard `shard` of `n_shards` computes the common counts of its

@@ -16,3 +16,5 @@ try:
 except Exception as e:
     print("no json:", e); print(open("gpurun_out/bench_n${N}.json").read()[:2000])
 PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+    scripts/multi_gpu_verify.py 2>&1 | tail -5

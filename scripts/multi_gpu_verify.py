@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Correctness of the N-GPU paths against the oracle (run under torchrun on N GPUs):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_verify.py
+
+Every rank runs CompareShard on a 700-sketch problem and checks its block of rows of the
+float64 matrix bit-for-bit against the oracle; the sketch shards are all-gathered and
+compared with single-rank sketching."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle as orc  # noqa: E402
+from sourmash_b200 import batch as B  # noqa: E402
+from sourmash_b200.distributed import CompareShard, allgather_sketchset  # noqa: E402
+from sourmash_b200.synth import synth_genome, synth_sketches  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+B.set_device(local)
+B.set_stream(torch.cuda.current_stream().cuda_stream)
+
+# ---- compare
+h, off = synth_sketches(700, mean=1500, sd=300, lo=100, hi=3000, n_families=7, pool=1800, seed=4)
+cs = CompareShard(torch, dist, B, h, off, rank, world)
+cs.step(e2e=True)
+lo, hi = cs.bounds[rank], cs.bounds[rank + 1]
+want = orc.compare_all_pairs(h, off, nthreads=8)
+got = cs.pin_out.numpy()
+assert got.shape == (hi - lo, 700)
+assert np.array_equal(got, want[lo:hi]), f"rank {rank}: compare rows {lo}:{hi} differ"
+
+# ---- sketch shards + all-gather
+genomes = [synth_genome(200_000 + 1000 * g, seed=50 + g) for g in range(6)]
+mine = list(range(rank, 6, world))
+seqs = np.concatenate([genomes[g] for g in mine])
+offs = np.cumsum([0] + [len(genomes[g]) for g in mine]).astype(np.uint64)
+sset, _ = B.sketch_sequences(seqs, offs, [21, 31], scaled=100)
+full = allgather_sketchset(torch, dist, B, sset)
+rows = full.rows()
+order = [g for r in range(world) for g in range(r, 6, world)]          # rank-major gather order
+mx = orc.max_hash_for_scaled(100)
+for pos, g in enumerate(order):
+    for ki, k in enumerate((21, 31)):
+        assert np.array_equal(rows[pos * 2 + ki], orc.sketch_scaled(genomes[g], k, mx)), (rank, g, k)
+dist.barrier()
+if rank == 0:
+    print(f"multi-GPU verify ok on {world} GPUs: compare rows bit-identical to the oracle, "
+          f"{len(rows)} gathered sketch rows identical")
+dist.destroy_process_group()

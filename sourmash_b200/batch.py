@@ -213,6 +213,15 @@ def compare_jaccard(sset, num=0, out=None):
     return out
 
 
+def compare_angular(sset, out=None):
+    """float64 (n, n) angular-similarity matrix of a SketchSet that carries abundances."""
+    n = len(sset)
+    if out is None:
+        out = np.empty((n, n), dtype=np.float64)
+    rustcall(lib.smb_compare_angular, sset._ptr, _ptr(out, "double *"))
+    return out
+
+
 def compare_jaccard_device(sset, d_out_ptr, num=0):
     rustcall(lib.smb_compare_jaccard_dev, sset._ptr, int(num), ffi.cast("double *", int(d_out_ptr)))
 

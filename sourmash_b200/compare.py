@@ -54,15 +54,23 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
     n = len(mhs)
     if n == 0:
         return np.ones((0, 0))
-    if not ignore_abundance and all(mh.track_abundance for mh in mhs):
-        # angular similarity between abundance sketches: per-pair GPU calls (not the batched path)
-        out = np.ones((n, n))
-        for i in range(n):
-            for j in range(i + 1, n):
-                out[i][j] = out[j][i] = mhs[i].similarity(mhs[j], ignore_abundance=False, downsample=downsample)
-        return out
-    sset, num, _, _ = _check_and_build(siglist, downsample=downsample)
-    return B.compare_jaccard(sset, num=num)
+    has_ab = np.array([bool(mh.track_abundance) for mh in mhs])
+    sset, num, scaled, _ = _check_and_build(siglist, downsample=downsample)
+    jac = B.compare_jaccard(sset, num=num)
+    if ignore_abundance or not has_ab.any():
+        return jac
+    # angular similarity where both sketches track abundance, Jaccard elsewhere (minhash.rs:682-702)
+    rows, abs_ = [], []
+    for mh in mhs:
+        if mh.scaled and mh.scaled != scaled:
+            mh = mh.downsample(scaled=scaled)
+        rows.append(mh._mins_array())
+        abs_.append(mh._abunds_array() if mh.track_abundance else np.ones(len(rows[-1]), dtype=np.uint64))
+    ang = B.compare_angular(B.SketchSet.from_rows(rows, abs_))
+    both = has_ab[:, None] & has_ab[None, :]
+    out = np.where(both, ang, jac)
+    np.fill_diagonal(out, 1.0)
+    return out
 
 
 def compare_serial(siglist, ignore_abundance, *, downsample=False, return_ani=False):

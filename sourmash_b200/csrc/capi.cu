@@ -1397,6 +1397,22 @@ void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
     });
 }
 
+void smb_compare_angular(const SmbSketchSet* set, double* out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (n == 0) return;
+        if (!set->d_abunds)
+            fail(SOURMASH_ERROR_CODE_NEEDS_ABUNDANCE_TRACKING, "sketch needs abundance for this operation");
+        DevBuf<double> d_out(n * n, s);
+        DevBuf<unsigned long long> d_sq(n, s);
+        smb::launch_pairwise_angular(set->d_hashes, set->d_abunds, set->d_off, (int)n, d_sq.p, d_out.p, s);
+        CK(cudaGetLastError());
+        d_out.download(out, n * n);
+        sync(s);
+    });
+}
+
 static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& db, uint32_t* d_counts,
                             cudaStream_t s) {
     // query small enough for shared memory: it becomes the (single) table of the tile kernel;

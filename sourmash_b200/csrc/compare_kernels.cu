@@ -403,6 +403,67 @@ void launch_pairwise_num(const u64* hA, const u64* offA, int nA, const u64* hB, 
 }
 
 // ------------------------------------------------------------------------------------
+// angular similarity of abundance sketches (minhash.rs:635-680): warp per pair,
+// dot = sum a_i*b_j over common hashes (u64, wrapping like the reference's release build),
+// value = 1 - 2*acos(min(dot / (|a| |b|), 1)) / pi.  acos runs on the device (<= 2 ulp from
+// libm, far inside the 1e-12 tolerance).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const u64* __restrict__ ab, const u64* __restrict__ off,
+                                                       int n, unsigned long long* __restrict__ out) {
+    const int lane = lane_id();
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += wstride) {
+        unsigned long long acc = 0;
+        for (u64 e = off[r] + lane; e < off[r + 1]; e += 32) { u64 v = ab[e]; acc += v * v; }
+        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) out[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) pairwise_angular_kernel(
+    const u64* __restrict__ h, const u64* __restrict__ ab, const u64* __restrict__ off, int n,
+    const unsigned long long* __restrict__ sumsq, double* __restrict__ out) {
+    const u64 npairs = (u64)n * (u64)n;
+    const u64 wstride = (u64)gridDim.x * (blockDim.x >> 5);
+    const int lane = lane_id();
+    for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < npairs; w += wstride) {
+        int i = (int)(w / (u64)n), j = (int)(w % (u64)n);
+        if (j < i) continue;
+        if (i == j) { if (lane == 0) out[(size_t)i * n + i] = 1.0; continue; }
+        const u64 ao = off[i], na = off[i + 1] - ao, bo = off[j], nb = off[j + 1] - bo;
+        unsigned long long dot = 0;
+        for (u64 e = lane; e < na; e += 32) {
+            u64 x = ld_nc_u64(h + ao + e);
+            u64 lo = 0, hi = nb;
+            while (lo < hi) { u64 mid = (lo + hi) >> 1; if (ld_nc_u64(h + bo + mid) < x) lo = mid + 1; else hi = mid; }
+            if (lo < nb && ld_nc_u64(h + bo + lo) == x) dot += ab[ao + e] * ab[bo + lo];
+        }
+        for (int d = 16; d; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+        if (lane == 0) {
+            double na_ = sqrt((double)sumsq[i]), nb_ = sqrt((double)sumsq[j]);
+            double v = 0.0;
+            if (na_ != 0.0 && nb_ != 0.0) {
+                double p = fmin((double)dot / (na_ * nb_), 1.0);
+                v = 1.0 - 2.0 * acos(p) / 3.14159265358979323846264338327950288;
+            }
+            out[(size_t)i * n + j] = v;
+            out[(size_t)j * n + i] = v;
+        }
+    }
+}
+
+void launch_pairwise_angular(const u64* h, const u64* ab, const u64* off, int n,
+                             unsigned long long* d_sumsq, double* out, cudaStream_t s) {
+    if (n <= 0) return;
+    int b1 = (n + 7) / 8; if (b1 > SMB_B200_SMS * 16) b1 = SMB_B200_SMS * 16;
+    row_sumsq_kernel<<<b1, 256, 0, s>>>(ab, off, n, d_sumsq); count_launches(1);
+    u64 npairs = (u64)n * (u64)n;
+    u64 blocks = (npairs + 7) / 8;
+    if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
+    pairwise_angular_kernel<<<(unsigned)blocks, 256, 0, s>>>(h, ab, off, n, d_sumsq, out); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
 // counts -> float64 matrix (jaccard = common / max(1, union), minhash.rs:624-631;
 // IEEE div.rn.f64 is bit-identical to the reference's f64 divide).
 // ------------------------------------------------------------------------------------

@@ -52,6 +52,10 @@ void launch_finalize_matrix(const uint32_t* common, const uint32_t* usize, size_
                             const uint64_t* offA, const uint64_t* offB, int nA, int nB, int mode,
                             bool symmetric, double* out, cudaStream_t s);
 
+// all-vs-all angular similarity of abundance sketches (symmetric f64 matrix, ones on the diagonal)
+void launch_pairwise_angular(const uint64_t* h, const uint64_t* ab, const uint64_t* off, int n,
+                             unsigned long long* d_sumsq, double* out, cudaStream_t s);
+
 // rows [row_begin, row_end) of the symmetric jaccard matrix from upper-triangular counts
 void launch_finalize_rows(const uint32_t* common, size_t n, const uint64_t* off, int n_rows,
                           int row_begin, int row_end, double* out, cudaStream_t s);

@@ -243,6 +243,35 @@ def test_compare_matrices_vs_per_pair_calls(smb):
         C.compare_all_pairs(sigs[:2] + [_sig(smb, rows[0], "k21", ksize=21)], True)
 
 
+def test_compare_abundance_angular_matrix(smb):
+    from sourmash_b200 import compare as C
+    rng = np.random.Generator(np.random.PCG64(77))
+    pool = np.unique(rng.integers(1, 10**12, size=3000, dtype=np.uint64))
+    sigs = []
+    for i in range(9):
+        pick = np.sort(rng.choice(pool, size=int(rng.integers(200, 1500)), replace=False))
+        mh = smb.MinHash(0, 21, scaled=1, track_abundance=(i != 4))
+        if i != 4:
+            mh.set_abundances(dict(zip(pick.tolist(), rng.integers(1, 50, size=len(pick)).tolist())))
+        else:
+            mh.add_many(pick)
+        sigs.append(smb.SourmashSignature(mh, name=f"a{i}"))
+    m = C.compare_all_pairs(sigs, ignore_abundance=False)
+    mi = C.compare_all_pairs(sigs, ignore_abundance=True)
+    for i in range(9):
+        for j in range(9):
+            if i == j:
+                assert m[i, j] == 1.0
+                continue
+            a, b = sigs[i].minhash, sigs[j].minhash
+            assert abs(m[i, j] - a.similarity(b)) < 1e-12                     # angular, or jaccard if one is flat
+            assert mi[i, j] == a.similarity(b, ignore_abundance=True)
+            if i != 4 and j != 4:
+                ha, hb = a.hashes, b.hashes
+                want = orc.angular_similarity(list(ha), list(ha.values()), list(hb), list(hb.values()))
+                assert abs(m[i, j] - want) < 1e-12
+
+
 def test_compare_downsample_mixed_scaled(smb):
     from sourmash_b200 import compare as C
     h, off = synth_sketches(6, mean=3000, sd=300, lo=2000, hi=4000, n_families=2, pool=3500, seed=2)
