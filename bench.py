@@ -234,6 +234,12 @@ def run_b200(args):
         return ms / steps, B.kernel_launches() - launches0, clocks, extra
 
     hbm_peak, peak_src = peaks()
+    if args.workload in ("search", "gather"):
+        r = bench_search_gather(args, torch, dist, B, rank, world, timed, args.workload)
+        if rank == 0:
+            r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "data": "synthetic", "dtype": "u64"})
+            print(json.dumps(r), flush=True)
+        return
     out = {}
     if args.workload in ("compare", "both"):
         out["compare"] = bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src)
@@ -405,13 +411,60 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     return res
 
 
+def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
+    """configs[3] / configs[4] shapes (parity-test cases, not the headline): one query vs a
+    large resident database; reported for completeness, single GPU only."""
+    from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_sketches
+    h, off = synth_sketches(N_SKETCHES)
+    rows = rows_of(h, off)
+    rng = np.random.Generator(np.random.PCG64(4000))
+    if which == "search":
+        n_db = 300_000
+        reps = n_db // N_SKETCHES
+        db_h = np.tile(h, reps)
+        db_off = np.concatenate([[0], np.cumsum(np.tile(np.diff(off.astype(np.int64)), reps))]).astype(np.uint64)
+        planted = rng.choice(N_SKETCHES, size=100, replace=False)
+        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=10_000_000, dtype=np.uint64)] +
+                                         [rows[j][: len(rows[j]) // 2] for j in planted]))
+        db = B.SketchSet.from_host(db_h, db_off)
+        pq = B.pinned_empty(len(query), np.uint64)
+        pq.array[:] = query
+        ms, launches, clocks, ex = timed(lambda: int(B.one_vs_many(pq.array, db).sum()), args.steps, args.warmup)
+        alg = 8.0 * (len(db_h) + len(query))
+        return {"metric": "query-vs-DB passes/sec (search)", "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms,
+                "config": {"workload": "configs[3]: 1e7-hash query vs 300000-sketch DB (12 GB resident), containment counts",
+                           "db_hashes": int(len(db_h)), "query_hashes": int(len(query))},
+                "subjects_per_s": n_db / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9, "gpu_launches": launches,
+                "note": "query uploaded from pinned host memory every step; counts downloaded"}
+    n_db = 50_000
+    reps = n_db // N_SKETCHES
+    db_h = np.tile(h, reps)
+    db_off = np.concatenate([[0], np.cumsum(np.tile(np.diff(off.astype(np.int64)), reps))]).astype(np.uint64)
+    planted = rng.choice(N_SKETCHES, size=200, replace=False)
+    query = np.unique(np.concatenate([rows[j][rng.random(len(rows[j])) < 0.6] for j in planted] +
+                                     [rng.integers(1, MAX_HASH_1000, size=20_000, dtype=np.uint64)]))
+    db = B.SketchSet.from_host(db_h, db_off)
+    res = {}
+
+    def step():
+        ids, sizes = B.gather(query, db, threshold=50)
+        res["rounds"] = len(ids)
+        return len(ids)
+
+    ms, launches, clocks, ex = timed(step, args.steps, args.warmup)
+    return {"metric": "gather wall time", "value": ms, "unit": "ms", "higher_is_better": False, "ms_per_step": ms,
+            "config": {"workload": "configs[4]: ~1e5-hash query vs 50000-sketch DB, 200 planted overlapping matches, "
+                                   "threshold 50 hashes", "query_hashes": int(len(query)), "db_hashes": int(len(db_h))},
+            "rounds": res["rounds"], "rounds_per_s": res["rounds"] / (ms / 1e3), "gpu_launches": launches}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["compare", "sketch", "both"])
+    ap.add_argument("--workload", default=None, choices=["compare", "sketch", "both", "search", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
