@@ -179,7 +179,10 @@ def _sketch_from_json(d):
     if max_hash:
         num = 0                       # old files carry num=2**32-1 together with max_hash
     track = "abundances" in d
-    mh = MinHash(num, int(d["ksize"]), is_protein=(molecule == "protein"), dayhoff=(molecule == "dayhoff"),
+    ksize = int(d["ksize"])
+    if molecule != "dna":
+        ksize //= 3                   # the file stores the internal (x3) ksize for protein-family sketches
+    mh = MinHash(num, ksize, is_protein=(molecule == "protein"), dayhoff=(molecule == "dayhoff"),
                  hp=(molecule == "hp"), track_abundance=track, seed=int(d.get("seed", 42)), max_hash=max_hash)
     mins = d.get("mins", [])
     if track:

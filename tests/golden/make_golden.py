@@ -102,6 +102,10 @@ for rec, s in sketches(os.path.join(TD, "genome-s10.fa.gz.sig")):
                             "max_hash": s.get("max_hash", 0), "n": len(s["mins"])}
 meta["genome_s10"] = s10
 
+# --- two reference-written .sig files, byte copies, for the JSON loader tests ----------------
+shutil.copyfile(os.path.join(TD, "47.fa.sig"), os.path.join(HERE, "47.fa.sig"))
+shutil.copyfile(os.path.join(TD, "genome-s10.fa.gz.sig"), os.path.join(HERE, "genome-s10.fa.gz.sig"))
+
 # --- known-answer values quoted from the reference's tests ----------------------------------
 meta["kat"] = {
     "hash_murmur_ACG_42": 1731421407650554201,            # tests/test_minhash.py:1239-1262

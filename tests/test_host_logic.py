@@ -243,3 +243,28 @@ def test_search_scoring_protocol():
     b = JaccardSearchBestOnly(s.search_type, 0.1)
     b.collect(0.7, None)
     assert b.threshold == 0.7
+
+
+def test_load_reference_written_sig_files(golden):
+    import os
+    from tests.conftest import GOLDEN
+    sigs = list(smb.load_signatures(os.path.join(GOLDEN, "47.fa.sig")))
+    assert len(sigs) == 1
+    mh = sigs[0].minhash
+    assert (mh.ksize, mh.scaled, mh.num, len(mh)) == (31, 1000, 0, 5177)
+    assert sigs[0].md5sum() == golden["meta"]["s47_md5"] == "09a08691ce52952152f0e866a59f6261"
+    assert mh._mins_array().tolist() == golden["arrays"]["s47"].tolist()
+    # multi-sketch file with DNA and protein sketches (num=500)
+    s10 = list(smb.load_signatures(os.path.join(GOLDEN, "genome-s10.fa.gz.sig")))
+    dna = [s for s in s10 if s.minhash.is_dna]
+    assert {s.minhash.ksize for s in dna} == {21, 30} and len(s10) > len(dna)
+    for s in dna:
+        assert s.md5sum() == golden["meta"]["genome_s10"][str(s.minhash.ksize)]["md5sum"]
+    prot = [s for s in s10 if s.minhash.moltype == "protein"]
+    assert prot and all(len(s.minhash) == 500 for s in prot)
+    only21 = list(smb.load_signatures_from_json(os.path.join(GOLDEN, "genome-s10.fa.gz.sig"), ksize=21,
+                                                select_moltype="dna"))
+    assert len(only21) == 1
+    # round trip through our writer keeps identity
+    again = list(smb.load_signatures_from_json(smb.save_signatures_to_json(s10)))
+    assert [a.md5sum() for a in again] == [a.md5sum() for a in s10]
