@@ -698,6 +698,33 @@ void mh_add_sequence(MH& mh, const uint8_t* seq, size_t len, bool force) {
     }
 }
 
+// force=True over several sketches that differ only in ksize (the `sketch dna -p k=21,k=31,k=51`
+// case, signature.rs:661-677): one upload, one hash launch per ksize, one sort pass.
+void add_sequence_group(std::vector<MH*>& group, const uint8_t* seq, size_t len) {
+    cudaStream_t s = need_gpu();
+    DevBuf<uint8_t> d_seq(len + 32, s);
+    d_seq.upload(seq, len);
+    StreamList in;
+    in.d_bases = d_seq.p;
+    in.off = {0}; in.len = {len}; in.n_sketches = 1;
+    SketchParams P;
+    for (MH* m : group) P.ksizes.push_back(m->ksize);
+    const MH& f = *group[0];
+    P.max_hash = f.max_hash; P.num = f.num; P.seed = f.seed; P.track = f.track;
+    auto set = sketch_streams(in, P, s, nullptr);
+    const size_t n = set->total();
+    std::vector<uint64_t> h(n), ab(f.track ? n : 0);
+    if (n) {
+        CK(cudaMemcpyAsync(h.data(), set->d_hashes, n * 8, cudaMemcpyDeviceToHost, s));
+        if (f.track) CK(cudaMemcpyAsync(ab.data(), set->d_abunds, n * 8, cudaMemcpyDeviceToHost, s));
+        sync(s);
+    }
+    for (size_t j = 0; j < group.size(); ++j) {
+        const size_t o = set->h_off[j], c = set->h_off[j + 1] - o;
+        group[j]->absorb_sorted(h.data() + o, f.track ? ab.data() + o : nullptr, c);
+    }
+}
+
 struct PairCounts { uint64_t common, usize; };
 
 // |A ∩ B| (and |M| for num sketches) of two host sketches, computed on the GPU
@@ -1085,7 +1112,19 @@ void signature_add_sequence(SourmashSignature* ptr, const char* sequence, bool f
     // hash launch per ksize.
     guarded_void([&] {
         size_t len = strlen(sequence);
-        for (auto& mh : ptr->sketches) mh_add_sequence(mh, (const uint8_t*)sequence, len, force);
+        auto& sk = ptr->sketches;
+        bool groupable = force && sk.size() > 1;
+        for (auto& mh : sk)
+            groupable = groupable && mh.hash_function == HASH_FUNCTIONS_MURMUR64_DNA && mh.num == sk[0].num &&
+                        mh.max_hash == sk[0].max_hash && mh.seed == sk[0].seed && mh.track == sk[0].track &&
+                        mh.ksize > 0;
+        if (groupable) {
+            std::vector<MH*> group;
+            for (auto& mh : sk) if (len >= mh.ksize) group.push_back(&mh);
+            if (!group.empty()) add_sequence_group(group, (const uint8_t*)sequence, len);
+        } else {
+            for (auto& mh : sk) mh_add_sequence(mh, (const uint8_t*)sequence, len, force);
+        }
     });
 }
 void signature_add_protein(SourmashSignature*, const char*) {
