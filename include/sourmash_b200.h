@@ -295,6 +295,20 @@ uintptr_t smb_gather(const uint64_t *query, uintptr_t n_query, const SmbSketchSe
                      uint32_t threshold, uint32_t *match_ids, uint32_t *isect_sizes,
                      uintptr_t max_rounds);
 
+/* gather as a session -- the building blocks of smb_gather, exposed so that a database sharded
+ * over several GPUs can run the same rounds with two tiny collectives per round
+ * (all-gather of (count, row), broadcast of the winning intersection):
+ *   begin      counters[j] = |query ∩ S_j| for the local shard
+ *   peek       best remaining (count, local row), lowest row wins ties
+ *   intersect  remaining query ∩ local row -> host buffer, returns its size
+ *   apply      counters -= |intersect ∩ S_j|, query -= intersect; returns remaining query size */
+typedef struct SmbGatherState SmbGatherState;
+SmbGatherState *smb_gather_begin(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db);
+void smb_gather_peek(SmbGatherState *st, uint32_t *best_count, uint32_t *best_row);
+uintptr_t smb_gather_intersect(SmbGatherState *st, uint32_t row, uint64_t *out_hashes);
+uintptr_t smb_gather_apply(SmbGatherState *st, const uint64_t *intersect, uintptr_t n);
+void smb_gather_end(SmbGatherState *st);
+
 #ifdef __cplusplus
 }
 #endif

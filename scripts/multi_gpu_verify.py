@@ -50,8 +50,22 @@ mx = orc.max_hash_for_scaled(100)
 for pos, g in enumerate(order):
     for ki, k in enumerate((21, 31)):
         assert np.array_equal(rows[pos * 2 + ki], orc.sketch_scaled(genomes[g], k, mx)), (rank, g, k)
+# ---- sharded search / gather vs the single-GPU result
+from sourmash_b200.distributed import ShardedDatabase, shard_bounds  # noqa: E402
+from sourmash_b200.synth import rows_of  # noqa: E402
+hh, oo = synth_sketches(400, mean=800, sd=100, lo=300, hi=1200, n_families=8, pool=1000, seed=12)
+rws = rows_of(hh, oo)
+bb = shard_bounds(400, world)
+shard = B.SketchSet.from_rows(rws[bb[rank]:bb[rank + 1]])
+sdb = ShardedDatabase(torch, dist, B, shard, 400, bb[rank])
+query = np.unique(np.concatenate([rws[5], rws[123][:500], rws[250][100:700], rws[399][::2], rws[77][:30]]))
+whole = B.SketchSet.from_host(hh, oo)
+assert np.array_equal(sdb.search_counts(query), B.one_vs_many(query, whole))
+ids, sizes = sdb.gather(query, threshold=3)
+ids1, sizes1 = B.gather(query, whole, threshold=3)
+assert np.array_equal(ids, ids1) and np.array_equal(sizes, sizes1) and len(ids) >= 4, (ids, ids1)
 dist.barrier()
 if rank == 0:
     print(f"multi-GPU verify ok on {world} GPUs: compare rows bit-identical to the oracle, "
-          f"{len(rows)} gathered sketch rows identical")
+          f"{len(rows)} gathered sketch rows identical, sharded search/gather == single GPU ({len(ids)} rounds)")
 dist.destroy_process_group()

@@ -253,3 +253,37 @@ def gather(query, db, threshold=1, max_rounds=None):
     n = rustcall(lib.smb_gather, _ptr(q, "uint64_t *"), len(q), db._ptr, int(threshold),
                  _ptr(ids, "uint32_t *"), _ptr(sizes, "uint32_t *"), int(max_rounds))
     return ids[:n].copy(), sizes[:n].copy()
+
+
+class GatherSession:
+    """Step-wise gather over one (local) database: begin / peek / intersect / apply
+    (smb_gather_* of the C ABI).  ``gather()`` above is this loop run inside the library;
+    ``distributed.ShardedDatabase.gather`` runs it across ranks."""
+
+    def __init__(self, query, db):
+        q = _u64(query)
+        self._db = db
+        self._cap = int(db.sizes().max()) if len(db) else 0
+        self._ptr = rustcall(lib.smb_gather_begin, _ptr(q, "uint64_t *"), len(q), db._ptr)
+        self.remaining = len(q)
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p:
+            lib.smb_gather_end(p)
+
+    def peek(self):
+        "(best_count, local_row)"
+        c, r = ffi.new("uint32_t *"), ffi.new("uint32_t *")
+        rustcall(lib.smb_gather_peek, self._ptr, c, r)
+        return int(c[0]), int(r[0])
+
+    def intersect(self, row):
+        out = np.zeros(max(self._cap, 1), dtype=np.uint64)
+        n = rustcall(lib.smb_gather_intersect, self._ptr, int(row), _ptr(out, "uint64_t *"))
+        return out[:n].copy()
+
+    def apply(self, intersect_hashes):
+        h = _u64(intersect_hashes)
+        self.remaining = int(rustcall(lib.smb_gather_apply, self._ptr, _ptr(h, "uint64_t *"), len(h)))
+        return self.remaining

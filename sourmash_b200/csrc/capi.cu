@@ -530,6 +530,16 @@ std::unique_ptr<SmbSketchSet> single_row_set(const uint64_t* h, size_t n, const 
 
 }  // namespace
 
+struct SmbGatherState {
+    const SmbSketchSet* db = nullptr;
+    DevBuf<uint64_t> q[2], isect;
+    DevBuf<uint32_t> counts, delta, d_n;
+    DevBuf<unsigned long long> d_best;
+    size_t nq = 0;
+    int cur = 0;
+    bool delta_pending = false;
+};
+
 // ==========================================================================================
 // KmerMinHash host object: src/core/src/sketch/minhash.rs:41-64
 // ==========================================================================================
@@ -1500,56 +1510,107 @@ void smb_one_vs_many(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
     });
 }
 
+// ---- gather as a session: the single-GPU loop and the sharded multi-GPU loop
+// (sourmash_b200/distributed.py) are both built from these four steps.
+SmbGatherState* smb_gather_begin(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db) {
+    return guarded<SmbGatherState*>([&]() -> SmbGatherState* {
+        cudaStream_t s = need_gpu();
+        auto st = std::make_unique<SmbGatherState>();
+        st->db = db;
+        st->nq = n_query;
+        const size_t nB = db->n_rows;
+        st->q[0].alloc(n_query, s); st->q[1].alloc(n_query, s); st->isect.alloc(n_query, s);
+        st->q[0].upload(query, n_query);
+        st->counts.alloc(nB, s); st->delta.alloc(nB, s); st->d_n.alloc(2, s); st->d_best.alloc(2, s);
+        st->counts.zero();
+        // CounterGather.add (index/__init__.py:777-794): counters[j] = |query ∩ S_j|
+        if (n_query && nB) one_vs_many_dev(st->q[0].p, n_query, *db, st->counts.p, s);
+        sync(s);
+        return st.release();
+    });
+}
+
+void smb_gather_end(SmbGatherState* st) { delete st; }
+
+// best remaining (count, row); lowest row index wins ties (Counter.most_common()[0], :841)
+void smb_gather_peek(SmbGatherState* st, uint32_t* best_count, uint32_t* best_row) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        *best_count = 0; *best_row = 0;
+        if (st->db->n_rows == 0) return;
+        smb::launch_counter_update_argmax(st->counts.p, st->delta_pending ? st->delta.p : nullptr,
+                                          (int)st->db->n_rows, st->d_best.p, s);
+        st->delta_pending = false;
+        unsigned long long best[2];
+        st->d_best.download(best, 2);
+        sync(s);
+        *best_count = (uint32_t)best[0];
+        *best_row = (uint32_t)best[1];
+    });
+}
+
+// intersect = remaining query ∩ row `row` of the local database -> host buffer (capacity = |row|)
+uintptr_t smb_gather_intersect(SmbGatherState* st, uint32_t row, uint64_t* out_hashes) {
+    return guarded<uintptr_t>([&]() -> uintptr_t {
+        cudaStream_t s = need_gpu();
+        const SmbSketchSet* db = st->db;
+        const uint64_t* r = db->d_hashes + db->h_off[row];
+        const size_t rn = db->h_off[row + 1] - db->h_off[row];
+        smb::launch_intersect_rows(st->q[st->cur].p, st->nq, r, rn, st->isect.p, st->d_n.p, s);
+        uint32_t n = 0;
+        st->d_n.download(&n, 1);
+        sync(s);
+        if (n && out_hashes) { CK(cudaMemcpyAsync(out_hashes, st->isect.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s)); sync(s); }
+        return n;
+    });
+}
+
+// consume (index/__init__.py:882-909): every counter -= |intersect ∩ S_j|; query -= intersect.
+// `intersect` is a host array (it may come from another rank).  Returns the remaining query size.
+uintptr_t smb_gather_apply(SmbGatherState* st, const uint64_t* intersect, uintptr_t n) {
+    return guarded<uintptr_t>([&]() -> uintptr_t {
+        cudaStream_t s = need_gpu();
+        if (n == 0) return st->nq;
+        DevBuf<uint64_t> d_i(n, s);
+        d_i.upload(intersect, n);
+        st->delta.zero();
+        if (st->db->n_rows) one_vs_many_dev(d_i.p, n, *st->db, st->delta.p, s);
+        st->delta_pending = true;
+        const int nxt = st->cur ^ 1;
+        smb::launch_subtract_rows(st->q[st->cur].p, st->nq, d_i.p, n, st->q[nxt].p, st->d_n.p + 1, s);
+        uint32_t rem = 0;
+        CK(cudaMemcpyAsync(&rem, st->d_n.p + 1, 4, cudaMemcpyDeviceToHost, s));
+        sync(s);
+        st->cur = nxt;
+        st->nq = rem;
+        return rem;
+    });
+}
+
 uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
                      uint32_t threshold, uint32_t* match_ids, uint32_t* isect_sizes,
                      uintptr_t max_rounds) {
-    return guarded<uintptr_t>([&]() -> uintptr_t {
-        // CounterGather (index/__init__.py:777-909): counters[j] = |query ∩ S_j| once, then per
-        // round: best = argmax (first inserted wins ties); intersect = remaining_query ∩ best;
-        // every counter -= |intersect ∩ S_j|; remaining_query -= best.
-        cudaStream_t s = need_gpu();
-        const size_t nB = db->n_rows;
-        if (nB == 0 || n_query == 0 || max_rounds == 0) return 0;
-        if (threshold < 1) threshold = 1;
-        DevBuf<uint64_t> d_q(n_query, s), d_q2(n_query, s), d_isect(n_query, s);
-        d_q.upload(query, n_query);
-        DevBuf<uint32_t> d_counts(nB, s), d_delta(nB, s), d_n(2, s);
-        DevBuf<unsigned long long> d_best(2, s);
-        d_counts.zero();
-        one_vs_many_dev(d_q.p, n_query, *db, d_counts.p, s);
-        size_t nq = n_query;
-        uint64_t* cur = d_q.p;
-        uint64_t* other = d_q2.p;
-        const uint32_t* delta = nullptr;
-        uintptr_t rounds = 0;
-        while (rounds < max_rounds) {
-            smb::launch_counter_update_argmax(d_counts.p, delta, (int)nB, d_best.p, s);
-            unsigned long long best[2];
-            d_best.download(best, 2);
-            sync(s);
-            if (best[0] < threshold || best[0] == 0) break;
-            const size_t j = (size_t)best[1];
-            const uint64_t* row = db->d_hashes + db->h_off[j];
-            const size_t rn = db->h_off[j + 1] - db->h_off[j];
-            // intersect = cur ∩ row ; new query = cur \ row
-            smb::launch_intersect_rows(cur, nq, row, rn, d_isect.p, d_n.p, s);
-            smb::launch_subtract_rows(cur, nq, row, rn, other, d_n.p + 1, s);
-            uint32_t nn[2];
-            d_n.download(nn, 2);
-            sync(s);
-            match_ids[rounds] = (uint32_t)j;
-            isect_sizes[rounds] = nn[0];
-            ++rounds;
-            // counters -= |intersect ∩ S_j| for all j (the chosen row drops to 0 by itself)
-            d_delta.zero();
-            if (nn[0] > 0) one_vs_many_dev(d_isect.p, nn[0], *db, d_delta.p, s);
-            delta = d_delta.p;
-            std::swap(cur, other);
-            nq = nn[1];
-            if (nq == 0) break;
-        }
-        return rounds;
-    });
+    // CounterGather + GatherDatabases loop (index/__init__.py:777-909, search.py:877-949)
+    if (db->n_rows == 0 || n_query == 0 || max_rounds == 0) return 0;
+    if (threshold < 1) threshold = 1;
+    SmbGatherState* st = smb_gather_begin(query, n_query, db);
+    if (!st) return 0;
+    std::vector<uint64_t> isect(db->max_len + 1);
+    uintptr_t rounds = 0;
+    while (rounds < max_rounds) {
+        uint32_t cnt = 0, row = 0;
+        smb_gather_peek(st, &cnt, &row);
+        if (t_has_error || cnt < threshold || cnt == 0) break;
+        uintptr_t n = smb_gather_intersect(st, row, isect.data());
+        if (t_has_error) break;
+        match_ids[rounds] = row;
+        isect_sizes[rounds] = (uint32_t)n;
+        ++rounds;
+        uintptr_t rem = smb_gather_apply(st, isect.data(), n);
+        if (t_has_error || rem == 0) break;
+    }
+    smb_gather_end(st);
+    return t_has_error ? 0 : rounds;
 }
 
 }  // extern "C"

@@ -104,3 +104,74 @@ class CompareShard:
             torch.cuda.current_stream().synchronize()
             return float(self.pin_out[0, 1 if self.n > 1 else 0])
         return None
+
+
+class ShardedDatabase:
+    """A sketch database sharded by subject over the ranks: every rank keeps its
+    block of rows in HBM; a query is replicated.
+
+    * ``search_counts(query)``: local one-vs-many, then one all-gather of the u32 counts.
+    * ``gather(query, threshold)``: the CounterGather rounds with two tiny collectives per
+      round -- all-gather of (best count, global row), broadcast of the winner's intersection.
+    Works with any backend for the collectives (NCCL on GPUs; tensors for gloo live on the CPU).
+    """
+
+    def __init__(self, torch, dist, B, local_rows_sset, n_rows_total, row_begin):
+        self.torch, self.dist, self.B = torch, dist, B
+        self.sset, self.n_total, self.row_begin = local_rows_sset, n_rows_total, row_begin
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+            else torch.device("cpu")
+
+    def search_counts(self, query):
+        "|query ∩ S_j| for every row of the whole database, on every rank."
+        torch, dist = self.torch, self.dist
+        local = self.B.one_vs_many(query, self.sset).astype(np.int64)
+        sizes = torch.tensor([len(local)], dtype=torch.int64, device=self.device)
+        all_sizes = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(all_sizes, sizes)
+        all_sizes = all_sizes.cpu().numpy()
+        pad = torch.zeros(int(all_sizes.max()) if len(all_sizes) else 1, dtype=torch.int64, device=self.device)
+        pad[: len(local)] = torch.from_numpy(local).to(self.device)
+        out = torch.empty(self.world * pad.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, pad)
+        out = out.cpu().numpy().reshape(self.world, -1)
+        return np.concatenate([out[r, : all_sizes[r]] for r in range(self.world)]).astype(np.uint32)
+
+    def gather(self, query, threshold=1, max_rounds=None):
+        "Returns (global match rows, intersect sizes) in pick order -- identical on every rank."
+        torch, dist = self.torch, self.dist
+        session = self.B.GatherSession(query, self.sset)
+        ids, sizes = [], []
+        max_rounds = self.n_total if max_rounds is None else max_rounds
+        threshold = max(int(threshold), 1)
+        while len(ids) < max_rounds:
+            cnt, row = session.peek() if len(self.sset) else (0, 0)
+            mine = torch.tensor([cnt, self.row_begin + row], dtype=torch.int64, device=self.device)
+            allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allv, mine)
+            allv = allv.cpu().numpy().reshape(self.world, 2)
+            best = int(allv[:, 0].max())
+            if best < threshold:
+                break
+            # ties: lowest global row (== first inserted in the reference's Counter)
+            cand = allv[allv[:, 0] == best]
+            grow = int(cand[:, 1].min())
+            owner = int(np.nonzero((allv[:, 0] == best) & (allv[:, 1] == grow))[0][0])
+            if owner == self.rank:
+                isect = session.intersect(grow - self.row_begin)
+                n = torch.tensor([len(isect)], dtype=torch.int64, device=self.device)
+            else:
+                isect, n = None, torch.zeros(1, dtype=torch.int64, device=self.device)
+            dist.broadcast(n, src=owner)
+            buf = torch.empty(int(n.item()), dtype=torch.int64, device=self.device)
+            if owner == self.rank and len(isect):
+                buf.copy_(torch.from_numpy(isect.view(np.int64)))
+            if buf.numel():
+                dist.broadcast(buf, src=owner)
+            isect = buf.cpu().numpy().view(np.uint64)
+            ids.append(grow)
+            sizes.append(len(isect))
+            if session.apply(isect) == 0:
+                break
+        return np.array(ids, dtype=np.uint32), np.array(sizes, dtype=np.uint32)

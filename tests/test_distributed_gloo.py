@@ -48,6 +48,96 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _FakeSet:
+    "host-only stand-in for batch.SketchSet (rows kept in numpy)"
+    def __init__(self, rows):
+        self._rows = rows
+    def __len__(self):
+        return len(self._rows)
+    def sizes(self):
+        return np.array([len(r) for r in self._rows], dtype=np.int64)
+
+
+class _FakeBatch:
+    """oracle-backed stand-in for sourmash_b200.batch so that the collective logic of
+    ShardedDatabase (tie-breaking, ownership, broadcasts) runs on CPU/gloo."""
+    @staticmethod
+    def one_vs_many(query, sset):
+        import oracle as orc
+        return np.array([orc.count_common(query, r) for r in sset._rows], dtype=np.uint32)
+
+    class GatherSession:
+        def __init__(self, query, sset):
+            import oracle as orc
+            self.q = np.array(query, dtype=np.uint64)
+            self.rows = sset._rows
+            self.counts = np.array([orc.count_common(self.q, r) for r in self.rows], dtype=np.int64)
+        def peek(self):
+            if not len(self.counts):
+                return 0, 0
+            j = int(np.argmax(self.counts))
+            return int(self.counts[j]), j
+        def intersect(self, row):
+            return np.intersect1d(self.q, self.rows[row])
+        def apply(self, isect):
+            import oracle as orc
+            self.counts -= np.array([orc.count_common(isect, r) for r in self.rows], dtype=np.int64)
+            self.q = np.setdiff1d(self.q, isect)
+            return len(self.q)
+
+
+def _sharded_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle as orc
+        from sourmash_b200.distributed import ShardedDatabase, shard_bounds
+        from sourmash_b200.synth import rows_of, synth_sketches
+        h, off = synth_sketches(31, mean=300, sd=50, lo=100, hi=500, n_families=3, pool=380, seed=8)
+        rows = rows_of(h, off)
+        rows[17] = rows[4].copy()                       # an exact tie across shards: lowest global row must win
+        b = shard_bounds(31, world)
+        db = ShardedDatabase(torch, dist, _FakeBatch, _FakeSet(rows[b[rank]:b[rank + 1]]), 31, b[rank])
+        query = np.unique(np.concatenate([rows[4], rows[9][:150], rows[25][50:250], rows[30][::2]]))
+        counts = db.search_counts(query)
+        ok = np.array_equal(counts, np.array([orc.count_common(query, r) for r in rows], dtype=np.uint32))
+        ids, sizes = db.gather(query, threshold=5)
+        # single-process reference loop
+        cur, cnt, want = query.copy(), np.array([orc.count_common(query, r) for r in rows]), []
+        while True:
+            j = int(np.argmax(cnt))
+            if cnt[j] < 5:
+                break
+            isect = np.intersect1d(cur, rows[j])
+            want.append((j, len(isect)))
+            cnt = cnt - np.array([orc.count_common(isect, r) for r in rows])
+            cur = np.setdiff1d(cur, isect)
+            if not len(cur):
+                break
+        ok = ok and list(zip(ids.tolist(), sizes.tolist())) == want and ids[0] == 4
+        q.put((rank, bool(ok), len(ids)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_search_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert all(r[1] for r in results), results
+    assert results[0][2] == results[1][2] >= 3
+
+
 def test_shard_bounds():
     sys.path.insert(0, ROOT)
     from sourmash_b200.distributed import shard_bounds

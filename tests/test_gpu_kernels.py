@@ -218,3 +218,23 @@ def test_gather_vs_oracle(B):
     ids, sizes = B.gather(query, db, threshold=3)
     want = _gather_oracle(query, rows, threshold=3)
     assert list(zip(ids.tolist(), sizes.tolist())) == want
+
+
+def test_gather_session_steps_equal_library_loop(B):
+    h, off = synth_sketches(80, mean=700, sd=90, lo=300, hi=1000, n_families=5, pool=900, seed=44)
+    rows = rows_of(h, off)
+    query = np.unique(np.concatenate([rows[2], rows[11][:400], rows[40][100:600], rows[77][::3]]))
+    db = B.SketchSet.from_host(h, off)
+    ids, sizes = B.gather(query, db, threshold=4)
+    sess = B.GatherSession(query, db)
+    got = []
+    while True:
+        cnt, row = sess.peek()
+        if cnt < 4:
+            break
+        isect = sess.intersect(row)
+        assert len(isect) == cnt and np.array_equal(isect, np.intersect1d(isect, rows[row]))
+        got.append((row, len(isect)))
+        if sess.apply(isect) == 0:
+            break
+    assert got == list(zip(ids.tolist(), sizes.tolist())) == _gather_oracle(query, rows, threshold=4)
