@@ -376,3 +376,36 @@ def _minus(smb, mh, remove):
     m = mh.to_mutable()
     m.remove_many(remove)
     return m
+
+
+def test_sketch_fasta_files_matches_golden_signatures(smb, golden):
+    """`sourmash sketch dna` on the two reference genomes -> the reference's own .sig contents."""
+    import os
+    from sourmash_b200.sketch import read_sequences, sketch_fasta_files
+    from tests.conftest import GOLDEN
+    ecoli, s10 = os.path.join(GOLDEN, "ecoli_k12.fna.gz"), os.path.join(GOLDEN, "genome-s10.fa.gz")
+    sigs = sketch_fasta_files([ecoli, s10], ksizes=[21, 31, 51], scaled=1000, name_from_first=True)
+    assert len(sigs) == 2 and len(sigs[0]) == 3 and sigs[0].filename == ecoli
+    assert sigs[0].name.startswith("NC_000913.3 Escherichia coli")
+    for mh in sigs[0].sketches():
+        assert mh.md5sum() == golden["meta"]["ecoli"][str(mh.ksize)]["md5sum"]
+    # num=500 sketches of the multi-record file equal the reference's golden sig
+    nsig, = sketch_fasta_files([s10], ksizes=[21, 30], scaled=0, num=500)
+    assert [m.md5sum() for m in nsig.sketches()] == [golden["meta"]["genome_s10"][k]["md5sum"] for k in ("21", "30")]
+    # singleton: one signature per record; abundance tracking
+    recs = read_sequences(s10)
+    single = sketch_fasta_files([s10], ksizes=[21], scaled=100, singleton=True, track_abundance=True)
+    assert len(single) == len(recs) and single[0].name == recs[0][0]
+    om = orc.OracleMinHash(scaled=100, ksize=21, track_abundance=True)
+    om.add_sequence(recs[0][1], force=True)
+    assert single[0].minhash._mins_array().tolist() == om.mins().tolist()
+    assert single[0].minhash._abunds_array().tolist() == om.abunds().tolist()
+    # --check-sequence semantics
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as fh:
+        fh.write(">bad\nACGTACGTNACGTACGTACGTAGCATGCATGCA\n")
+    with pytest.raises(ValueError, match="invalid DNA character"):
+        sketch_fasta_files([fh.name], ksizes=[5], scaled=1, check_sequence=True)
+    ok, = sketch_fasta_files([fh.name], ksizes=[5], scaled=1)
+    assert len(ok.minhash) > 0
+    os.unlink(fh.name)
