@@ -14,4 +14,4 @@ ncu --set full --clock-control none --import-source on -k regex:hash_kmers -s 3 
     -o gpurun_out/prof_hash_${TAG} -f python bench.py --workload sketch --steps 1 --warmup 3 --no-cpu-baseline \
     > /dev/null 2> gpurun_out/prof_hash_${TAG}.err
 ls -la gpurun_out/
-tail -3 gpurun_out/*.err
+for f in gpurun_out/*_${TAG}.err; do tail -n 3 "$f"; done
