@@ -199,6 +199,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # keep stdout clean for the single JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from sourmash_b200 import batch as B

@@ -10,11 +10,14 @@ tail -15 gpurun_out/bench_n${N}.err
 python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_n${N}.json"))
+    lines=[l for l in open("gpurun_out/bench_n${N}.json") if l.startswith("{")]
+    print("stdout lines:", sum(1 for _ in open("gpurun_out/bench_n${N}.json")))
+    d=json.loads(lines[-1])
     for x in (d, d.get("sketch", {})):
         if x: print(x["metric"], "n_gpus", x["n_gpus"], "value %.4g"%x["value"], "ms %.2f"%x["ms_per_step"], "e2e %.4g (%.1f ms)"%(x["e2e"]["value"], x["e2e"]["ms_per_step"]), "kernel_ms %.2f"%x["roofline"]["kernel_ms"])
 except Exception as e:
     print("no json:", e); print(open("gpurun_out/bench_n${N}.json").read()[:2000])
 PY
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-    scripts/multi_gpu_verify.py 2>&1 | tail -5
+    scripts/multi_gpu_verify.py > gpurun_out/verify_n${N}.log 2>&1
+grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_n${N}.log | head -10

@@ -66,7 +66,7 @@ class PinnedArray:
 
     def __del__(self):
         p, self._ptr = getattr(self, "_ptr", None), None
-        if p is not None:
+        if p is not None and lib is not None:
             self.array = None
             lib.smb_free_pinned(p)
 
@@ -84,7 +84,7 @@ class SketchSet:
 
     def __del__(self):
         p, self._ptr = getattr(self, "_ptr", None), None
-        if p:
+        if p and lib is not None:                    # lib is None during interpreter shutdown
             lib.smb_sketchset_free(p)
 
     @classmethod
@@ -269,7 +269,7 @@ class GatherSession:
 
     def __del__(self):
         p, self._ptr = getattr(self, "_ptr", None), None
-        if p:
+        if p and lib is not None:
             lib.smb_gather_end(p)
 
     def peek(self):

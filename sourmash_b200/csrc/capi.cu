@@ -1487,8 +1487,13 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
         smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, q.d_hashes, q.d_off, 1, nb_log2, d_shift.p, s);
         DevBuf<uint32_t> d_dir((size_t(1) << nb_log2) + 2, s);
         smb::launch_build_global_dir(d_q, nq, nb_log2, d_shift.p, d_dir.p, s);
-        smb::launch_one_vs_many_global(d_q, nq, d_dir.p, d_shift.p, nb_log2, db.d_hashes, db.d_off, nB,
-                                       d_counts, s);
+        // L2-resident occupancy bitmap, 8x finer than the directory (1 byte per bucket)
+        const int fine_log2 = 3;
+        DevBuf<uint32_t> d_bm(((size_t(1) << nb_log2) << fine_log2) / 32 + 2, s);
+        d_bm.zero();
+        smb::launch_build_query_bitmap(d_q, nq, d_shift.p, fine_log2, d_bm.p, s);
+        smb::launch_one_vs_many_global(d_q, nq, d_dir.p, d_shift.p, nb_log2, d_bm.p, fine_log2, db.d_hashes,
+                                       db.d_off, nB, d_counts, s);
     }
     CK(cudaGetLastError());
     sync(s);      // q's offsets upload reads a host temporary

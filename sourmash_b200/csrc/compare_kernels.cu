@@ -553,11 +553,35 @@ void launch_build_global_dir(const u64* q, u64 nq, int nb_log2, const u32* d_shi
     build_global_dir_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, nb_log2, d_shift, dir); count_launches(1);
 }
 
+// occupancy bitmap over the query: bit (key >> bm_shift) set iff some query key maps there.  It
+// is 8-16x smaller than directory + keys, stays in L2, and rejects most probes of a subject
+// element before the directory / key lines (DRAM for a 1e7-hash query) are touched.
+__global__ void __launch_bounds__(256) build_query_bitmap_kernel(const u64* __restrict__ q, u64 nq,
+                                                                const u32* __restrict__ d_shift,
+                                                                int fine_log2,
+                                                                u32* __restrict__ bitmap) {
+    const u32 sh = d_shift[0];                       // bitmap is 2^fine_log2 times finer than the directory
+    const u32 bm_shift = sh >= (u32)fine_log2 ? sh - (u32)fine_log2 : 0u;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+        const u64 bit = q[p] >> bm_shift;
+        atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    }
+}
+
+void launch_build_query_bitmap(const u64* q, u64 nq, const u32* d_shift, int fine_log2,
+                               u32* bitmap, cudaStream_t s) {
+    if (nq == 0) return;
+    u64 blocks = (nq + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 32) blocks = (u64)SMB_B200_SMS * 32;
+    build_query_bitmap_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, d_shift, fine_log2, bitmap); count_launches(1);
+}
+
 __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
     const u64* __restrict__ q, u64 nq, const u32* __restrict__ dir, const u32* __restrict__ d_shift,
-    int nb_log2, const u64* __restrict__ hB, const u64* __restrict__ offB, int nB,
-    u32* __restrict__ out) {
+    int nb_log2, const u32* __restrict__ bitmap, int fine_log2, const u64* __restrict__ hB,
+    const u64* __restrict__ offB, int nB, u32* __restrict__ out) {
     const u32 shift = d_shift[0];
+    const u32 bm_shift = shift >= (u32)fine_log2 ? shift - (u32)fine_log2 : 0u;
     const u64 nbk = 1ULL << nb_log2;
     const int lane = lane_id();
     const int wstride = gridDim.x * (blockDim.x >> 5);
@@ -569,6 +593,10 @@ __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
             u64 x = ld_nc_u64(row + e);
             u64 b = x >> shift;
             if (b >= nbk) continue;                 // beyond the query's key range
+            if (bitmap) {
+                const u64 bit = x >> bm_shift;
+                if (!((__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u)) continue;
+            }
             u64 p = dir[b], pe = dir[b + 1];
             for (; p < pe; ++p) {
                 u64 k = ld_nc_u64(q + p);
@@ -581,12 +609,13 @@ __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
 }
 
 void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, const u32* d_shift,
-                               int nb_log2, const u64* hB, const u64* offB, int nB, u32* out,
-                               cudaStream_t s) {
+                               int nb_log2, const u32* bitmap, int fine_log2, const u64* hB,
+                               const u64* offB, int nB, u32* out, cudaStream_t s) {
     if (nB <= 0) return;
     int blocks = (nB + 7) / 8;
     if (blocks > SMB_B200_SMS * 16) blocks = SMB_B200_SMS * 16;
-    one_vs_many_global_kernel<<<blocks, 256, 0, s>>>(q, nq, dir, d_shift, nb_log2, hB, offB, nB, out); count_launches(1);
+    one_vs_many_global_kernel<<<blocks, 256, 0, s>>>(q, nq, dir, d_shift, nb_log2, bitmap, fine_log2,
+                                                     hB, offB, nB, out); count_launches(1);
 }
 
 // ------------------------------------------------------------------------------------

@@ -64,9 +64,14 @@ void launch_finalize_rows(const uint32_t* common, size_t n, const uint64_t* off,
 // directory over the query, every subject element probes it.
 void launch_build_global_dir(const uint64_t* q, uint64_t nq, int nb_log2, const uint32_t* d_shift,
                              uint32_t* dir, cudaStream_t s);
+// bitmap (nullable, zeroed by the caller, (2^nb_log2 << fine_log2) bits): occupancy of the query at
+// 2^fine_log2 times the directory's resolution, bit index = key >> max(shift - fine_log2, 0)
+void launch_build_query_bitmap(const uint64_t* q, uint64_t nq, const uint32_t* d_shift,
+                               int fine_log2, uint32_t* bitmap, cudaStream_t s);
 void launch_one_vs_many_global(const uint64_t* q, uint64_t nq, const uint32_t* dir,
-                               const uint32_t* d_shift, int nb_log2, const uint64_t* hB,
-                               const uint64_t* offB, int nB, uint32_t* out, cudaStream_t s);
+                               const uint32_t* d_shift, int nb_log2, const uint32_t* bitmap,
+                               int fine_log2, const uint64_t* hB, const uint64_t* offB, int nB,
+                               uint32_t* out, cudaStream_t s);
 
 // Materialise A ∩ B of two sorted rows (gather's intersect_mh); returns count in *d_n.
 void launch_intersect_rows(const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb,

@@ -55,7 +55,7 @@ class RustObject:
         if self._objptr is None or self._shared:
             return
         f = self.__class__.__dealloc_func__
-        if f is not None:
+        if f is not None and lib is not None:
             try:
                 f(self._objptr)
             finally:
