@@ -304,6 +304,10 @@ uintptr_t smb_gather(const uint64_t *query, uintptr_t n_query, const SmbSketchSe
  *   apply      counters -= |intersect ∩ S_j|, query -= intersect; returns remaining query size */
 typedef struct SmbGatherState SmbGatherState;
 SmbGatherState *smb_gather_begin(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db);
+/* same; rows overlapping the query by fewer than min_count hashes are dropped up front (they
+ * can never be picked), so later rounds only stream the surviving candidates */
+SmbGatherState *smb_gather_begin_min(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
+                                     uint32_t min_count);
 void smb_gather_peek(SmbGatherState *st, uint32_t *best_count, uint32_t *best_row);
 uintptr_t smb_gather_intersect(SmbGatherState *st, uint32_t row, uint64_t *out_hashes);
 uintptr_t smb_gather_apply(SmbGatherState *st, const uint64_t *intersect, uintptr_t n);

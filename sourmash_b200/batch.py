@@ -260,11 +260,11 @@ class GatherSession:
     (smb_gather_* of the C ABI).  ``gather()`` above is this loop run inside the library;
     ``distributed.ShardedDatabase.gather`` runs it across ranks."""
 
-    def __init__(self, query, db):
+    def __init__(self, query, db, min_count=1):
         q = _u64(query)
         self._db = db
         self._cap = int(db.sizes().max()) if len(db) else 0
-        self._ptr = rustcall(lib.smb_gather_begin, _ptr(q, "uint64_t *"), len(q), db._ptr)
+        self._ptr = rustcall(lib.smb_gather_begin_min, _ptr(q, "uint64_t *"), len(q), db._ptr, int(min_count))
         self.remaining = len(q)
 
     def __del__(self):

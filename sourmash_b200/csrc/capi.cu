@@ -531,7 +531,9 @@ std::unique_ptr<SmbSketchSet> single_row_set(const uint64_t* h, size_t n, const 
 }  // namespace
 
 struct SmbGatherState {
-    const SmbSketchSet* db = nullptr;
+    const SmbSketchSet* db = nullptr;        // the set the rounds run on (== sub.get() when compacted)
+    std::unique_ptr<SmbSketchSet> sub;       // rows of the caller's database with overlap >= min_count
+    std::vector<uint32_t> rowmap;            // compact row -> caller's row (empty: identity)
     DevBuf<uint64_t> q[2], isect;
     DevBuf<uint32_t> counts, delta, d_n;
     DevBuf<unsigned long long> d_best;
@@ -1517,22 +1519,68 @@ void smb_one_vs_many(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
 
 // ---- gather as a session: the single-GPU loop and the sharded multi-GPU loop
 // (sourmash_b200/distributed.py) are both built from these four steps.
-SmbGatherState* smb_gather_begin(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db) {
+SmbGatherState* smb_gather_begin_min(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
+                                     uint32_t min_count) {
     return guarded<SmbGatherState*>([&]() -> SmbGatherState* {
         cudaStream_t s = need_gpu();
         auto st = std::make_unique<SmbGatherState>();
         st->db = db;
         st->nq = n_query;
+        if (min_count < 1) min_count = 1;
         const size_t nB = db->n_rows;
         st->q[0].alloc(n_query, s); st->q[1].alloc(n_query, s); st->isect.alloc(n_query, s);
         st->q[0].upload(query, n_query);
-        st->counts.alloc(nB, s); st->delta.alloc(nB, s); st->d_n.alloc(2, s); st->d_best.alloc(2, s);
+        st->counts.alloc(nB, s); st->d_n.alloc(2, s); st->d_best.alloc(2, s);
         st->counts.zero();
         // CounterGather.add (index/__init__.py:777-794): counters[j] = |query ∩ S_j|
         if (n_query && nB) one_vs_many_dev(st->q[0].p, n_query, *db, st->counts.p, s);
+        // Rows whose overlap is below min_count can never be picked and their counters only
+        // shrink: drop them once, so that every later round streams the surviving rows only
+        // (the reference's counter holds prefetch matches only, index/__init__.py:302-320).
+        std::vector<uint32_t> cnt(nB);
+        st->counts.download(cnt.data(), nB);
         sync(s);
+        std::vector<uint32_t> keep;
+        for (size_t j = 0; j < nB; ++j) if (cnt[j] >= min_count) keep.push_back((uint32_t)j);
+        if (keep.size() * 4 < nB * 3) {
+            const size_t m = keep.size();
+            auto sub = std::make_unique<SmbSketchSet>();
+            sub->n_rows = m;
+            sub->h_off.assign(m + 1, 0);
+            std::vector<uint64_t> src_off(m + 1, 0);
+            std::vector<uint32_t> len(m + 1, 0), kept(m + 1, 0);
+            for (size_t i = 0; i < m; ++i) {
+                const size_t j = keep[i];
+                src_off[i] = db->h_off[j];
+                len[i] = (uint32_t)(db->h_off[j + 1] - db->h_off[j]);
+                sub->h_off[i + 1] = sub->h_off[i] + len[i];
+                kept[i] = cnt[j];
+            }
+            DevBuf<uint64_t> d_src(m + 1, s);
+            DevBuf<uint32_t> d_len(m + 1, s);
+            d_src.upload(src_off.data(), m + 1);
+            d_len.upload(len.data(), m + 1);
+            sub->own_off.alloc(m + 1, s);
+            sub->own_off.upload(sub->h_off.data(), m + 1);
+            sub->own_hashes.alloc(sub->total(), s);
+            smb::launch_compact_rows(db->d_hashes, d_src.p, d_len.p, sub->own_off.p, sub->own_hashes.p, (int)m, s);
+            st->counts.alloc(m, s);
+            st->counts.upload(kept.data(), m);
+            CK(cudaGetLastError());
+            sync(s);
+            sub->d_off = sub->own_off.p; sub->d_hashes = sub->own_hashes.p;
+            sub->finish_offsets();
+            st->rowmap = std::move(keep);
+            st->sub = std::move(sub);
+            st->db = st->sub.get();
+        }
+        st->delta.alloc(st->db->n_rows, s);
         return st.release();
     });
+}
+
+SmbGatherState* smb_gather_begin(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db) {
+    return smb_gather_begin_min(query, n_query, db, 1);
 }
 
 void smb_gather_end(SmbGatherState* st) { delete st; }
@@ -1550,7 +1598,7 @@ void smb_gather_peek(SmbGatherState* st, uint32_t* best_count, uint32_t* best_ro
         st->d_best.download(best, 2);
         sync(s);
         *best_count = (uint32_t)best[0];
-        *best_row = (uint32_t)best[1];
+        *best_row = st->rowmap.empty() ? (uint32_t)best[1] : st->rowmap[(size_t)best[1]];
     });
 }
 
@@ -1559,6 +1607,11 @@ uintptr_t smb_gather_intersect(SmbGatherState* st, uint32_t row, uint64_t* out_h
     return guarded<uintptr_t>([&]() -> uintptr_t {
         cudaStream_t s = need_gpu();
         const SmbSketchSet* db = st->db;
+        if (!st->rowmap.empty()) {           // caller's row -> compact row
+            auto it = std::lower_bound(st->rowmap.begin(), st->rowmap.end(), row);
+            if (it == st->rowmap.end() || *it != row) fail(SOURMASH_ERROR_CODE_MSG, "row is not an active gather candidate");
+            row = (uint32_t)(it - st->rowmap.begin());
+        }
         const uint64_t* r = db->d_hashes + db->h_off[row];
         const size_t rn = db->h_off[row + 1] - db->h_off[row];
         smb::launch_intersect_rows(st->q[st->cur].p, st->nq, r, rn, st->isect.p, st->d_n.p, s);
@@ -1598,7 +1651,7 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
     // CounterGather + GatherDatabases loop (index/__init__.py:777-909, search.py:877-949)
     if (db->n_rows == 0 || n_query == 0 || max_rounds == 0) return 0;
     if (threshold < 1) threshold = 1;
-    SmbGatherState* st = smb_gather_begin(query, n_query, db);
+    SmbGatherState* st = smb_gather_begin_min(query, n_query, db, threshold);
     if (!st) return 0;
     std::vector<uint64_t> isect(db->max_len + 1);
     uintptr_t rounds = 0;

@@ -562,9 +562,19 @@ __global__ void __launch_bounds__(256) build_query_bitmap_kernel(const u64* __re
                                                                 u32* __restrict__ bitmap) {
     const u32 sh = d_shift[0];                       // bitmap is 2^fine_log2 times finer than the directory
     const u32 bm_shift = sh >= (u32)fine_log2 ? sh - (u32)fine_log2 : 0u;
+    // q is sorted, so the keys of one 32-bit bitmap word are a contiguous run: the first key of
+    // a run ORs the whole run together and stores the word -- no atomics, one writer per word.
     for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
         const u64 bit = q[p] >> bm_shift;
-        atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+        const u64 word = bit >> 5;
+        if (p > 0 && ((q[p - 1] >> bm_shift) >> 5) == word) continue;
+        u32 acc = 1u << (bit & 31);
+        for (u64 r = p + 1; r < nq; ++r) {
+            const u64 b2 = q[r] >> bm_shift;
+            if ((b2 >> 5) != word) break;
+            acc |= 1u << (b2 & 31);
+        }
+        bitmap[word] = acc;
     }
 }
 
@@ -585,22 +595,43 @@ __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
     const u64 nbk = 1ULL << nb_log2;
     const int lane = lane_id();
     const int wstride = gridDim.x * (blockDim.x >> 5);
+    constexpr int U = 4;
     for (int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nB; j += wstride) {
         const u64* row = hB + offB[j];
-        u64 n = offB[j + 1] - offB[j];
+        const u64 n = offB[j + 1] - offB[j];
         u32 c = 0;
-        for (u64 e = lane; e < n; e += 32) {
-            u64 x = ld_nc_u64(row + e);
-            u64 b = x >> shift;
-            if (b >= nbk) continue;                 // beyond the query's key range
-            if (bitmap) {
-                const u64 bit = x >> bm_shift;
-                if (!((__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u)) continue;
+        for (u64 base = 0; base < n; base += 32 * U) {
+            u64 x[U];
+            u32 word[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                       // U independent loads in flight
+                const u64 e = base + (u64)u * 32 + lane;
+                x[u] = e < n ? ld_nc_u64(row + e) : SMB_U64_MAX;
             }
-            u64 p = dir[b], pe = dir[b + 1];
-            for (; p < pe; ++p) {
-                u64 k = ld_nc_u64(q + p);
-                if (k >= x) { c += (k == x); break; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool in_range = (x[u] >> shift) < nbk;    // false for padding / beyond the query
+                word[u] = 0u;
+                if (in_range) {
+                    if (bitmap) {
+                        const u64 bit = x[u] >> bm_shift;
+                        word[u] = (__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u;
+                    } else {
+                        word[u] = 1u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (word[u]) {                                   // ~4 % of the elements get here
+                    const u64 b = x[u] >> shift;
+                    u64 p = dir[b];
+                    const u64 pe = dir[b + 1];
+                    for (; p < pe; ++p) {
+                        const u64 k = ld_nc_u64(q + p);
+                        if (k >= x[u]) { c += (k == x[u]); break; }
+                    }
+                }
             }
         }
         c = __reduce_add_sync(0xffffffffu, c);

@@ -141,10 +141,10 @@ class ShardedDatabase:
     def gather(self, query, threshold=1, max_rounds=None):
         "Returns (global match rows, intersect sizes) in pick order -- identical on every rank."
         torch, dist = self.torch, self.dist
-        session = self.B.GatherSession(query, self.sset)
+        threshold = max(int(threshold), 1)
+        session = self.B.GatherSession(query, self.sset, threshold)
         ids, sizes = [], []
         max_rounds = self.n_total if max_rounds is None else max_rounds
-        threshold = max(int(threshold), 1)
         while len(ids) < max_rounds:
             cnt, row = session.peek() if len(self.sset) else (0, 0)
             mine = torch.tensor([cnt, self.row_begin + row], dtype=torch.int64, device=self.device)

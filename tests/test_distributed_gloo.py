@@ -67,7 +67,7 @@ class _FakeBatch:
         return np.array([orc.count_common(query, r) for r in sset._rows], dtype=np.uint32)
 
     class GatherSession:
-        def __init__(self, query, sset):
+        def __init__(self, query, sset, min_count=1):
             import oracle as orc
             self.q = np.array(query, dtype=np.uint64)
             self.rows = sset._rows
