@@ -246,6 +246,8 @@ struct SmbSketchSet {
     const uint64_t* d_off = nullptr;
     const uint64_t* d_abunds = nullptr;
     uint64_t max_len = 0;
+    mutable uint64_t max_key = 0;         // largest hash of any row (lazily computed on the device)
+    mutable bool max_key_known = false;
     uint64_t total() const { return h_off.empty() ? 0 : h_off.back(); }
     void finish_offsets() {
         max_len = 0;
@@ -484,6 +486,25 @@ struct CountsDev {
     size_t ldo = 0;
 };
 
+// largest key of a set: one tiny reduction kernel + an 8-byte readback, cached on the set
+uint64_t set_max_key(const SmbSketchSet& A, cudaStream_t s) {
+    if (!A.max_key_known) {
+        uint64_t m = 0;
+        if (A.n_rows && A.total()) {
+            DevBuf<unsigned long long> d_max(1, s);
+            d_max.zero();
+            smb::launch_max_last(A.d_hashes, A.d_off, (int)A.n_rows, nullptr, nullptr, 0, d_max.p, s);
+            unsigned long long v = 0;
+            d_max.download(&v, 1);
+            sync(s);
+            m = v;
+        }
+        A.max_key = m;
+        A.max_key_known = true;
+    }
+    return A.max_key;
+}
+
 void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t num, uint32_t* d_common,
                          uint32_t* d_usize, size_t ldo, cudaStream_t s,
                          smb::TileShard tiles = smb::TileShard{0, 1}) {
@@ -496,18 +517,16 @@ void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t
                                  d_usize, ldo, symmetric, s);
         return;
     }
-    smb::PairwisePlan plan = smb::plan_pairwise(A.max_len, nB);
+    const uint64_t max_key = std::max(set_max_key(A, s), symmetric ? 0 : set_max_key(B, s));
+    smb::PairwisePlan plan = smb::plan_pairwise(A.max_len, max_key, nB);
     if (plan.tables_per_cta == 0) {
         smb::launch_pairwise_generic(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
                                      symmetric, s);
         return;
     }
-    DevBuf<uint32_t> d_shift(4, s);
-    smb::launch_bucket_shift(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, plan.nb_log2,
-                             d_shift.p, s);
     if (t_profiling) t_timer_pairwise.begin(s);
     smb::launch_pairwise_tile(plan, A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
-                              d_shift.p, symmetric, tiles, s);
+                              symmetric, tiles, s);
     if (t_profiling) t_timer_pairwise.end(s);
 }
 
@@ -534,11 +553,11 @@ struct SmbGatherState {
     const SmbSketchSet* db = nullptr;        // the set the rounds run on (== sub.get() when compacted)
     std::unique_ptr<SmbSketchSet> sub;       // rows of the caller's database with overlap >= min_count
     std::vector<uint32_t> rowmap;            // compact row -> caller's row (empty: identity)
-    DevBuf<uint64_t> q[2], isect;
+    DevBuf<uint64_t> q, isect;               // the original query stays in place ...
+    DevBuf<uint8_t> alive;                   // ... consumed hashes are flagged, not removed
     DevBuf<uint32_t> counts, delta, d_n;
     DevBuf<unsigned long long> d_best;
-    size_t nq = 0;
-    int cur = 0;
+    size_t nq = 0, remaining = 0;
     bool delta_pending = false;
 };
 
@@ -1470,31 +1489,43 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
     // otherwise a global-memory directory over the query.
     const int nB = (int)db.n_rows;
     if (nB == 0) return;
-    smb::PairwisePlan plan = smb::plan_pairwise(nq, nB);
     SmbSketchSet q;
     q.n_rows = 1; q.h_off = {0, (uint64_t)nq};
     q.own_off.alloc(2, s); q.own_off.upload(q.h_off.data(), 2);
     q.d_off = q.own_off.p; q.d_hashes = d_q; q.finish_offsets();
-    DevBuf<uint32_t> d_shift(4, s);
+    const uint64_t q_max = set_max_key(q, s);
+    const uint64_t max_key = std::max(q_max, set_max_key(db, s));
+    smb::PairwisePlan plan = smb::plan_pairwise(nq, max_key, nB);
     if (plan.tables_per_cta > 0) {
-        plan.tables_per_cta = 1;
-        plan.smem_bytes = (size_t)(plan.cap + 2) * 8 + ((size_t(1) << plan.nb_log2) + 2) * 2;
-        plan.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
-        smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, plan.nb_log2, d_shift.p, s);
-        smb::launch_pairwise_tile(plan, q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, d_counts,
-                                  (size_t)nB, d_shift.p, false, smb::TileShard{0, 1}, s);
+        // query small enough for shared memory: it is the single table of the tile kernel
+        smb::PairwisePlan one = smb::plan_pairwise(nq, max_key, nB);
+        one.tables_per_cta = 1;
+        {   // with one table the whole 227 KB is available: take the finest directory that fits
+            const size_t key_bytes = (size_t)(one.cap + 2) * 8;
+            const uint64_t max_entries = std::min<uint64_t>((227 * 1024 - key_bytes) / 2 - 2, 60000);
+            int sh = 0;
+            while (sh < 63 && (max_key >> sh) + 1 > max_entries) ++sh;
+            one.shift = sh; one.nb = (int)((max_key >> sh) + 1);
+            one.smem_bytes = key_bytes + ((size_t)one.nb + 2) * 2;
+        }
+        one.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
+        smb::launch_pairwise_tile(one, q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, d_counts,
+                                  (size_t)nB, false, smb::TileShard{0, 1}, s);
     } else {
+        // large query: directory over the query's own key range (subject keys beyond it are skipped)
         int nb_log2 = 12;
         while (nb_log2 < 26 && (1ull << nb_log2) < 2 * (uint64_t)nq) ++nb_log2;
-        smb::launch_bucket_shift(q.d_hashes, q.d_off, 1, q.d_hashes, q.d_off, 1, nb_log2, d_shift.p, s);
-        DevBuf<uint32_t> d_dir((size_t(1) << nb_log2) + 2, s);
-        smb::launch_build_global_dir(d_q, nq, nb_log2, d_shift.p, d_dir.p, s);
+        int shift = 0;
+        while (shift < 63 && (q_max >> shift) >= (1ull << nb_log2)) ++shift;
+        const uint64_t nb = (q_max >> shift) + 1;
+        DevBuf<uint32_t> d_dir(nb + 2, s);
+        smb::launch_build_global_dir(d_q, nq, shift, nb, d_dir.p, s);
         // L2-resident occupancy bitmap, 8x finer than the directory (1 byte per bucket)
         const int fine_log2 = 3;
-        DevBuf<uint32_t> d_bm(((size_t(1) << nb_log2) << fine_log2) / 32 + 2, s);
+        DevBuf<uint32_t> d_bm(((size_t)nb << fine_log2) / 32 + 2, s);
         d_bm.zero();
-        smb::launch_build_query_bitmap(d_q, nq, d_shift.p, fine_log2, d_bm.p, s);
-        smb::launch_one_vs_many_global(d_q, nq, d_dir.p, d_shift.p, nb_log2, d_bm.p, fine_log2, db.d_hashes,
+        smb::launch_build_query_bitmap(d_q, nq, shift, fine_log2, d_bm.p, s);
+        smb::launch_one_vs_many_global(d_q, nq, d_dir.p, shift, nb, d_bm.p, fine_log2, db.d_hashes,
                                        db.d_off, nB, d_counts, s);
     }
     CK(cudaGetLastError());
@@ -1528,12 +1559,15 @@ SmbGatherState* smb_gather_begin_min(const uint64_t* query, uintptr_t n_query, c
         st->nq = n_query;
         if (min_count < 1) min_count = 1;
         const size_t nB = db->n_rows;
-        st->q[0].alloc(n_query, s); st->q[1].alloc(n_query, s); st->isect.alloc(n_query, s);
-        st->q[0].upload(query, n_query);
+        st->remaining = n_query;
+        st->q.alloc(n_query, s); st->isect.alloc(std::max<size_t>(db->max_len, 1), s);
+        st->q.upload(query, n_query);
+        st->alive.alloc(n_query, s);
+        CK(cudaMemsetAsync(st->alive.p, 1, std::max<size_t>(n_query, 1), s));
         st->counts.alloc(nB, s); st->d_n.alloc(2, s); st->d_best.alloc(2, s);
         st->counts.zero();
         // CounterGather.add (index/__init__.py:777-794): counters[j] = |query ∩ S_j|
-        if (n_query && nB) one_vs_many_dev(st->q[0].p, n_query, *db, st->counts.p, s);
+        if (n_query && nB) one_vs_many_dev(st->q.p, n_query, *db, st->counts.p, s);
         // Rows whose overlap is below min_count can never be picked and their counters only
         // shrink: drop them once, so that every later round streams the surviving rows only
         // (the reference's counter holds prefetch matches only, index/__init__.py:302-320).
@@ -1614,7 +1648,7 @@ uintptr_t smb_gather_intersect(SmbGatherState* st, uint32_t row, uint64_t* out_h
         }
         const uint64_t* r = db->d_hashes + db->h_off[row];
         const size_t rn = db->h_off[row + 1] - db->h_off[row];
-        smb::launch_intersect_rows(st->q[st->cur].p, st->nq, r, rn, st->isect.p, st->d_n.p, s);
+        smb::launch_intersect_alive(st->q.p, st->nq, st->alive.p, r, rn, st->isect.p, st->d_n.p, s);
         uint32_t n = 0;
         st->d_n.download(&n, 1);
         sync(s);
@@ -1628,20 +1662,17 @@ uintptr_t smb_gather_intersect(SmbGatherState* st, uint32_t row, uint64_t* out_h
 uintptr_t smb_gather_apply(SmbGatherState* st, const uint64_t* intersect, uintptr_t n) {
     return guarded<uintptr_t>([&]() -> uintptr_t {
         cudaStream_t s = need_gpu();
-        if (n == 0) return st->nq;
+        if (n == 0) return st->remaining;
         DevBuf<uint64_t> d_i(n, s);
         d_i.upload(intersect, n);
         st->delta.zero();
         if (st->db->n_rows) one_vs_many_dev(d_i.p, n, *st->db, st->delta.p, s);
         st->delta_pending = true;
-        const int nxt = st->cur ^ 1;
-        smb::launch_subtract_rows(st->q[st->cur].p, st->nq, d_i.p, n, st->q[nxt].p, st->d_n.p + 1, s);
-        uint32_t rem = 0;
-        CK(cudaMemcpyAsync(&rem, st->d_n.p + 1, 4, cudaMemcpyDeviceToHost, s));
-        sync(s);
-        st->cur = nxt;
-        st->nq = rem;
-        return rem;
+        smb::launch_mark_dead(st->q.p, st->nq, st->alive.p, d_i.p, n, s);
+        CK(cudaGetLastError());
+        sync(s);                                   // d_i is released on return
+        st->remaining = st->remaining > n ? st->remaining - n : 0;
+        return st->remaining;
     });
 }
 

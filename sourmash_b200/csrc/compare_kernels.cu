@@ -16,6 +16,8 @@
 // over |A|+|B| elements.  Counts are reduced with warp REDUX and written as u32.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -51,51 +53,52 @@ __global__ void max_last_kernel(const u64* __restrict__ hA, const u64* __restric
     if (lane_id() == 0 && m) atomicMax(d_max, (unsigned long long)m);
 }
 
-__global__ void shift_from_max_kernel(const unsigned long long* __restrict__ d_max, int nb_log2,
-                                      u32* __restrict__ d_shift) {
-    u64 m = *d_max;
-    int bits = m ? 64 - __clzll((long long)m) : 0;
-    int sh = bits - nb_log2;
-    d_shift[0] = sh > 0 ? (u32)sh : 0u;
-}
-
-void launch_bucket_shift(const u64* hA, const u64* offA, int nA, const u64* hB, const u64* offB,
-                         int nB, int nb_log2, u32* d_shift, cudaStream_t s) {
-    // d_shift[0] = shift, d_shift[2..3] = scratch for the 64-bit max
-    unsigned long long* d_max = reinterpret_cast<unsigned long long*>(d_shift + 2);
-    cudaMemsetAsync(d_shift, 0, 4 * sizeof(u32), s);
+// max over the last (largest) key of every row -> *d_max (zeroed by the caller)
+void launch_max_last(const u64* hA, const u64* offA, int nA, const u64* hB, const u64* offB, int nB,
+                     unsigned long long* d_max, cudaStream_t s) {
     int total = nA + nB;
+    if (total <= 0) return;
     int blocks = (total + 255) / 256;
     if (blocks > SMB_B200_SMS * 4) blocks = SMB_B200_SMS * 4;
-    if (blocks < 1) blocks = 1;
     max_last_kernel<<<blocks, 256, 0, s>>>(hA, offA, nA, hB, offB, nB, d_max); count_launches(1);
-    shift_from_max_kernel<<<1, 1, 0, s>>>(d_max, nb_log2, d_shift); count_launches(1);
 }
 
 // ------------------------------------------------------------------------------------
 // tile kernel
 // ------------------------------------------------------------------------------------
-PairwisePlan plan_pairwise(uint64_t max_len_a, int n_b) {
+// Bucket = key >> shift with buckets 0 .. (max_key >> shift): the directory covers exactly the
+// occupied key range, and shift is the finest one whose directory still fits next to the keys.
+// Prefer more tables per CTA (fewer passes over the streamed rows) as long as the buckets stay
+// sparse (<= ~0.45 keys per bucket at the largest row), because denser buckets mean the
+// deferred long-bucket scan runs in nearly every batch.
+PairwisePlan plan_pairwise(uint64_t max_len_a, uint64_t max_key, int n_b) {
+    (void)n_b;
     PairwisePlan p{};
     uint64_t cap = (max_len_a + 1 + 3) & ~3ULL;          // +1: room even if a row is empty
     if (cap < 64) cap = 64;
-    // directory: about 2-4 buckets per key, 2^10 .. 2^14 buckets
-    int nb_log2 = 10;
-    while (nb_log2 < 14 && (1ULL << nb_log2) < 2 * cap) ++nb_log2;
-    for (;; --nb_log2) {
-        size_t per_table = (cap + 2) * 8 + ((size_t(1) << nb_log2) + 2) * 2;
-        int ta = (int)(MAX_DYN_SMEM / per_table);
-        if (ta >= 1) {
-            if (ta > 4) ta = 4;
-            p.tables_per_cta = ta; p.nb_log2 = nb_log2; p.cap = (int)cap;
-            p.smem_bytes = per_table * ta;
-            break;
-        }
-        if (nb_log2 == 10) { p.tables_per_cta = 0; return p; }   // row too large for smem
+    const size_t key_bytes = (cap + 2) * 8;
+    auto config = [&](int ta, int& shift, uint64_t& nb) -> bool {
+        const size_t per_table = (size_t)MAX_DYN_SMEM / ta;
+        if (per_table < key_bytes + 64) return false;
+        const uint64_t max_entries = std::min<uint64_t>((per_table - key_bytes) / 2 - 2, 60000);
+        shift = 0;
+        while (shift < 63 && (max_key >> shift) + 1 > max_entries) ++shift;
+        nb = (max_key >> shift) + 1;
+        return nb <= max_entries;
+    };
+    int best_ta = 0, best_shift = 0;
+    uint64_t best_nb = 0;
+    for (int ta = 4; ta >= 1; --ta) {
+        int sh; uint64_t nb;
+        if (!config(ta, sh, nb)) continue;
+        if (best_ta == 0) { best_ta = ta; best_shift = sh; best_nb = nb; }      // densest acceptable fallback
+        if ((double)cap / (double)nb <= 0.45 || sh == 0) { best_ta = ta; best_shift = sh; best_nb = nb; break; }
+        best_ta = ta; best_shift = sh; best_nb = nb;                             // keep the sparsest seen so far
     }
-    // columns per CTA: enough streamed rows to amortise the table build
+    if (best_ta == 0) { p.tables_per_cta = 0; return p; }                        // row too large for smem
+    p.tables_per_cta = best_ta; p.shift = best_shift; p.nb = (int)best_nb; p.cap = (int)cap;
+    p.smem_bytes = (size_t)best_ta * (key_bytes + (best_nb + 2) * 2);
     p.cols_per_cta = tile_cols_override() > 0 ? tile_cols_override() : 512;
-    (void)n_b;
     return p;
 }
 
@@ -103,8 +106,7 @@ struct TileArgs {
     const u64* hA; const u64* offA; int nA;
     const u64* hB; const u64* offB; int nB;
     u32* out; size_t ldo;
-    const u32* d_shift;
-    int nb_log2, cap, cols_per_cta, symmetric;
+    int shift, nb, cap, cols_per_cta, symmetric;
     int tile_offset, tile_stride;       // row tile = blockIdx.x * tile_stride + tile_offset
 };
 
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
     if (a.symmetric) jbeg = max(jbeg, i0 + 1);
     if (jbeg >= jend) return;
 
-    const u32 shift = a.d_shift[0];
-    const int nb = 1 << a.nb_log2;
+    const u32 shift = (u32)a.shift;
+    const int nb = a.nb;                      // buckets 0 .. nb-1; dir has nb+1 entries
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
     const int kstride = a.cap + 2;
@@ -177,6 +179,10 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
         for (int p = tid; p < n; p += nthreads) kt[p] = ld_nc_u64(a.hA + beg + p);
         if (tid < 2) kt[n + tid] = SMB_U64_MAX;
         if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
+        // directory default: "no key at or after this bucket" (= n); overwritten below up to the
+        // bucket of the row's last key
+        u16* dt = dirs_base + (size_t)t * dstride;
+        for (int b = tid; b <= nb; b += nthreads) dt[b] = (u16)n;
     }
     __syncthreads();
     // ---- build directories: dir[b] = #keys with bucket < b, b in [0, nb]
@@ -185,8 +191,8 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
         const u64* kt = keys_base + (size_t)t * kstride;
         u16* dt = dirs_base + (size_t)t * dstride;
         int n = s_n[t];
-        for (int p = tid; p <= n; p += nthreads) {
-            int bp = p < n ? (int)(kt[p] >> shift) : nb;
+        for (int p = tid; p < n; p += nthreads) {
+            int bp = (int)(kt[p] >> shift);
             int bprev = p == 0 ? -1 : (int)(kt[p - 1] >> shift);
             for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)p;
         }
@@ -289,10 +295,10 @@ static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
 
 void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* offA, int nA,
                           const u64* hB, const u64* offB, int nB, u32* out, size_t ldo,
-                          const u32* d_shift, bool symmetric, TileShard tiles, cudaStream_t s) {
+                          bool symmetric, TileShard tiles, cudaStream_t s) {
     if (nA <= 0 || nB <= 0) return;
-    TileArgs a{hA, offA, nA, hB, offB, nB, out, ldo, d_shift,
-               plan.nb_log2, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0,
+    TileArgs a{hA, offA, nA, hB, offB, nB, out, ldo,
+               plan.shift, plan.nb, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0,
                tiles.shard, tiles.n_shards > 0 ? tiles.n_shards : 1};
     switch (plan.tables_per_cta) {
         case 1: launch_tile_ta<1>(a, plan.smem_bytes, s); break;
@@ -531,36 +537,57 @@ void launch_finalize_rows(const u32* common, size_t n, const u64* off, int n_row
 // ------------------------------------------------------------------------------------
 // one (large) query vs many subjects: global-memory directory over the query
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_global_dir_kernel(
-    const u64* __restrict__ q, u64 nq, int nb_log2, const u32* __restrict__ d_shift,
-    u32* __restrict__ dir) {
-    const u32 shift = d_shift[0];
-    const u64 nb = 1ULL << nb_log2;
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p <= nq;
-         p += (u64)gridDim.x * blockDim.x) {
-        long long bp = p < nq ? (long long)(q[p] >> shift) : (long long)nb;
-        if (bp > (long long)nb) bp = (long long)nb;
-        long long bprev = p == 0 ? -1 : (long long)(q[p - 1] >> shift);
-        if (bprev > (long long)nb) bprev = (long long)nb;
-        for (long long b = bprev + 1; b <= bp; ++b) dir[b] = (u32)p;
+// dir[b] = #query keys with (key >> shift) < b, b in [0, nb].  Pass 1 presets "unset", pass 2
+// lets every key that opens a bucket write its index and fill short runs of empty buckets
+// behind it, pass 3 resolves the remaining (long) empty runs by binary search -- no thread ever
+// walks a long gap serially, whatever the key distribution.
+static constexpr u32 DIR_UNSET = 0xffffffffu;
+
+__global__ void __launch_bounds__(256) global_dir_fill_kernel(u32* __restrict__ dir, u64 n_entries, u32 v) {
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_entries; b += (u64)gridDim.x * blockDim.x)
+        dir[b] = v;
+}
+
+__global__ void __launch_bounds__(256) global_dir_heads_kernel(const u64* __restrict__ q, u64 nq, u32 shift,
+                                                              u32* __restrict__ dir) {
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
+        const u64 bp = q[p] >> shift;
+        const long long bprev = p == 0 ? -1 : (long long)(q[p - 1] >> shift);
+        if ((long long)bp == bprev) continue;
+        long long lo = (long long)bp - 32;                      // short gaps: fill directly
+        if (lo < bprev + 1) lo = bprev + 1;
+        for (long long b = lo; b <= (long long)bp; ++b) dir[b] = (u32)p;
     }
 }
 
-void launch_build_global_dir(const u64* q, u64 nq, int nb_log2, const u32* d_shift, u32* dir,
-                             cudaStream_t s) {
-    u64 blocks = (nq + 1 + 255) / 256;
-    if (blocks > (u64)SMB_B200_SMS * 32) blocks = (u64)SMB_B200_SMS * 32;
-    build_global_dir_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, nb_log2, d_shift, dir); count_launches(1);
+__global__ void __launch_bounds__(256) global_dir_resolve_kernel(const u64* __restrict__ q, u64 nq, u32 shift,
+                                                                u64 nb, u32* __restrict__ dir) {
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += (u64)gridDim.x * blockDim.x) {
+        if (dir[b] != DIR_UNSET) continue;
+        u64 lo = 0, hi = nq;                                    // first key with bucket >= b
+        while (lo < hi) { u64 mid = (lo + hi) >> 1; if ((q[mid] >> shift) < b) lo = mid + 1; else hi = mid; }
+        dir[b] = (u32)lo;
+    }
+}
+
+void launch_build_global_dir(const u64* q, u64 nq, int shift, u64 nb, u32* dir, cudaStream_t s) {
+    const u64 cap_blocks = (u64)SMB_B200_SMS * 32;
+    u64 b1 = (nb + 1 + 255) / 256; if (b1 > cap_blocks) b1 = cap_blocks;
+    global_dir_fill_kernel<<<(unsigned)b1, 256, 0, s>>>(dir, nb + 1, DIR_UNSET); count_launches(1);
+    if (nq) {
+        u64 b2 = (nq + 255) / 256; if (b2 > cap_blocks) b2 = cap_blocks;
+        global_dir_heads_kernel<<<(unsigned)b2, 256, 0, s>>>(q, nq, (u32)shift, dir); count_launches(1);
+    }
+    global_dir_resolve_kernel<<<(unsigned)b1, 256, 0, s>>>(q, nq, (u32)shift, nb, dir); count_launches(1);
 }
 
 // occupancy bitmap over the query: bit (key >> bm_shift) set iff some query key maps there.  It
 // is 8-16x smaller than directory + keys, stays in L2, and rejects most probes of a subject
 // element before the directory / key lines (DRAM for a 1e7-hash query) are touched.
 __global__ void __launch_bounds__(256) build_query_bitmap_kernel(const u64* __restrict__ q, u64 nq,
-                                                                const u32* __restrict__ d_shift,
-                                                                int fine_log2,
+                                                                u32 sh, int fine_log2,
                                                                 u32* __restrict__ bitmap) {
-    const u32 sh = d_shift[0];                       // bitmap is 2^fine_log2 times finer than the directory
+    // bitmap is 2^fine_log2 times finer than the directory
     const u32 bm_shift = sh >= (u32)fine_log2 ? sh - (u32)fine_log2 : 0u;
     // q is sorted, so the keys of one 32-bit bitmap word are a contiguous run: the first key of
     // a run ORs the whole run together and stores the word -- no atomics, one writer per word.
@@ -578,21 +605,19 @@ __global__ void __launch_bounds__(256) build_query_bitmap_kernel(const u64* __re
     }
 }
 
-void launch_build_query_bitmap(const u64* q, u64 nq, const u32* d_shift, int fine_log2,
+void launch_build_query_bitmap(const u64* q, u64 nq, int shift, int fine_log2,
                                u32* bitmap, cudaStream_t s) {
     if (nq == 0) return;
     u64 blocks = (nq + 255) / 256;
     if (blocks > (u64)SMB_B200_SMS * 32) blocks = (u64)SMB_B200_SMS * 32;
-    build_query_bitmap_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, d_shift, fine_log2, bitmap); count_launches(1);
+    build_query_bitmap_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, (u32)shift, fine_log2, bitmap); count_launches(1);
 }
 
 __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
-    const u64* __restrict__ q, u64 nq, const u32* __restrict__ dir, const u32* __restrict__ d_shift,
-    int nb_log2, const u32* __restrict__ bitmap, int fine_log2, const u64* __restrict__ hB,
+    const u64* __restrict__ q, u64 nq, const u32* __restrict__ dir, u32 shift, u64 nbk,
+    const u32* __restrict__ bitmap, int fine_log2, const u64* __restrict__ hB,
     const u64* __restrict__ offB, int nB, u32* __restrict__ out) {
-    const u32 shift = d_shift[0];
     const u32 bm_shift = shift >= (u32)fine_log2 ? shift - (u32)fine_log2 : 0u;
-    const u64 nbk = 1ULL << nb_log2;
     const int lane = lane_id();
     const int wstride = gridDim.x * (blockDim.x >> 5);
     constexpr int U = 4;
@@ -639,13 +664,13 @@ __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
     }
 }
 
-void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, const u32* d_shift,
-                               int nb_log2, const u32* bitmap, int fine_log2, const u64* hB,
+void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, int shift, u64 nb,
+                               const u32* bitmap, int fine_log2, const u64* hB,
                                const u64* offB, int nB, u32* out, cudaStream_t s) {
     if (nB <= 0) return;
     int blocks = (nB + 7) / 8;
     if (blocks > SMB_B200_SMS * 16) blocks = SMB_B200_SMS * 16;
-    one_vs_many_global_kernel<<<blocks, 256, 0, s>>>(q, nq, dir, d_shift, nb_log2, bitmap, fine_log2,
+    one_vs_many_global_kernel<<<blocks, 256, 0, s>>>(q, nq, dir, (u32)shift, nb, bitmap, fine_log2,
                                                      hB, offB, nB, out); count_launches(1);
 }
 
@@ -687,8 +712,76 @@ __global__ void __launch_bounds__(1024) setop_rows_kernel(const u64* __restrict_
     if (threadIdx.x == 0) *d_n = carry;
 }
 
+// gather keeps its query fixed and flags consumed hashes instead of re-materialising the
+// remaining query every round: intersect = row elements present in q and still alive.
+__device__ __forceinline__ long long row_find(const u64* __restrict__ r, u64 n, u64 x) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (ld_nc_u64(r + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && ld_nc_u64(r + lo) == x) ? (long long)lo : -1;
+}
+
+__global__ void __launch_bounds__(1024) intersect_alive_kernel(const u64* __restrict__ q, u64 nq,
+                                                              const u8* __restrict__ alive,
+                                                              const u64* __restrict__ row, u64 rn,
+                                                              u64* __restrict__ out, u32* __restrict__ d_n) {
+    __shared__ u32 warp_tot[32];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    for (u64 base = 0; base < rn; base += blockDim.x) {
+        u64 e = base + threadIdx.x;
+        bool keep = false;
+        u64 x = 0;
+        if (e < rn) {
+            x = row[e];
+            long long pos = row_find(q, nq, x);
+            keep = pos >= 0 && alive[pos];
+        }
+        u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u32 pos_out = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (keep) out[pos_out] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 t = 0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += warp_tot[w2];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *d_n = carry;
+}
+
+void launch_intersect_alive(const u64* q, u64 nq, const u8* alive, const u64* row, u64 rn, u64* out,
+                            u32* d_n, cudaStream_t s) {
+    intersect_alive_kernel<<<1, 1024, 0, s>>>(q, nq, alive, row, rn, out, d_n); count_launches(1);
+}
+
+__global__ void __launch_bounds__(256) mark_dead_kernel(const u64* __restrict__ q, u64 nq, u8* __restrict__ alive,
+                                                       const u64* __restrict__ gone, u64 n) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        long long pos = row_find(q, nq, gone[e]);
+        if (pos >= 0) alive[pos] = 0;
+    }
+}
+
+void launch_mark_dead(const u64* q, u64 nq, u8* alive, const u64* gone, u64 n, cudaStream_t s) {
+    if (n == 0) return;
+    u64 blocks = (n + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 8) blocks = (u64)SMB_B200_SMS * 8;
+    mark_dead_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, alive, gone, n); count_launches(1);
+}
+
 void launch_intersect_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, u32* d_n,
                            cudaStream_t s) {
+    if (nb < na) { const u64* t = a; a = b; b = t; u64 tn = na; na = nb; nb = tn; }   // probe with the shorter row
     setop_rows_kernel<true><<<1, 1024, 0, s>>>(a, na, b, nb, out, d_n); count_launches(1);
 }
 void launch_subtract_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, u32* d_n,

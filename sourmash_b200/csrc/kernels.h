@@ -10,20 +10,20 @@ namespace smb {
 // ---------------------------------------------------------------- intersection path
 struct PairwisePlan {
     int tables_per_cta;   // TA (1..4); 0 => tile kernel not applicable, use generic kernel
-    int nb_log2;          // log2(#buckets) of the shared-memory directory
+    int shift;            // bucket = key >> shift
+    int nb;               // number of buckets = (max_key >> shift) + 1
     int cap;              // key capacity per table
     int cols_per_cta;
     size_t smem_bytes;
 };
 
-// Chooses the tile-kernel configuration for table rows of at most max_len_a keys.
-PairwisePlan plan_pairwise(uint64_t max_len_a, int n_b);
+// Chooses the tile-kernel configuration for table rows of at most max_len_a keys when no key
+// of either operand exceeds max_key.
+PairwisePlan plan_pairwise(uint64_t max_len_a, uint64_t max_key, int n_b);
 
-// Writes the bucket shift (a device u32) such that (max key >> shift) < 2^nb_log2, where the
-// max runs over the last element of every row of both CSR sets.  d_shift must hold 2 u32.
-void launch_bucket_shift(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
-                         const uint64_t* offB, int nB, int nb_log2, uint32_t* d_shift,
-                         cudaStream_t s);
+// max over the last (largest) key of every row of both CSR sets -> *d_max (zeroed by the caller)
+void launch_max_last(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
+                     const uint64_t* offB, int nB, unsigned long long* d_max, cudaStream_t s);
 
 // Multi-GPU sharding of row tiles: this launch handles tiles shard, shard + n_shards, ...
 struct TileShard { int shard; int n_shards; };
@@ -32,8 +32,7 @@ struct TileShard { int shard; int n_shards; };
 // Tile kernel: A rows become shared-memory bucket tables, B rows stream through registers.
 void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const uint64_t* offA,
                           int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
-                          size_t ldo, const uint32_t* d_shift, bool symmetric, TileShard tiles,
-                          cudaStream_t s);
+                          size_t ldo, bool symmetric, TileShard tiles, cudaStream_t s);
 
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
 // elements in the longer row.
@@ -61,17 +60,23 @@ void launch_finalize_rows(const uint32_t* common, size_t n, const uint64_t* off,
                           int row_begin, int row_end, double* out, cudaStream_t s);
 
 // One query vs many subjects with a query too large for shared memory: global-memory bucket
-// directory over the query, every subject element probes it.
-void launch_build_global_dir(const uint64_t* q, uint64_t nq, int nb_log2, const uint32_t* d_shift,
-                             uint32_t* dir, cudaStream_t s);
-// bitmap (nullable, zeroed by the caller, (2^nb_log2 << fine_log2) bits): occupancy of the query at
+// directory over the query (dir has nb+1 u32 entries), every subject element probes it.
+void launch_build_global_dir(const uint64_t* q, uint64_t nq, int shift, uint64_t nb, uint32_t* dir,
+                             cudaStream_t s);
+// bitmap (nullable, zeroed by the caller, (nb << fine_log2) bits): occupancy of the query at
 // 2^fine_log2 times the directory's resolution, bit index = key >> max(shift - fine_log2, 0)
-void launch_build_query_bitmap(const uint64_t* q, uint64_t nq, const uint32_t* d_shift,
-                               int fine_log2, uint32_t* bitmap, cudaStream_t s);
-void launch_one_vs_many_global(const uint64_t* q, uint64_t nq, const uint32_t* dir,
-                               const uint32_t* d_shift, int nb_log2, const uint32_t* bitmap,
-                               int fine_log2, const uint64_t* hB, const uint64_t* offB, int nB,
-                               uint32_t* out, cudaStream_t s);
+void launch_build_query_bitmap(const uint64_t* q, uint64_t nq, int shift, int fine_log2,
+                               uint32_t* bitmap, cudaStream_t s);
+void launch_one_vs_many_global(const uint64_t* q, uint64_t nq, const uint32_t* dir, int shift,
+                               uint64_t nb, const uint32_t* bitmap, int fine_log2, const uint64_t* hB,
+                               const uint64_t* offB, int nB, uint32_t* out, cudaStream_t s);
+
+// gather: query fixed in HBM + per-hash alive flags.  intersect_alive: hashes of `row` that are in q
+// and alive (sorted, count in *d_n); mark_dead: clear the flags of the given hashes.
+void launch_intersect_alive(const uint64_t* q, uint64_t nq, const uint8_t* alive, const uint64_t* row,
+                            uint64_t rn, uint64_t* out, uint32_t* d_n, cudaStream_t s);
+void launch_mark_dead(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* gone, uint64_t n,
+                      cudaStream_t s);
 
 // Materialise A ∩ B of two sorted rows (gather's intersect_mh); returns count in *d_n.
 void launch_intersect_rows(const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb,
