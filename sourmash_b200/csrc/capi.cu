@@ -1504,7 +1504,7 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
             const size_t key_bytes = (size_t)(one.cap + 2) * 8;
             const uint64_t max_entries = std::min<uint64_t>((227 * 1024 - key_bytes) / 2 - 2, 60000);
             int sh = 0;
-            while (sh < 63 && (max_key >> sh) + 1 > max_entries) ++sh;
+            while (sh < 63 && (max_key >> sh) >= max_entries) ++sh;
             one.shift = sh; one.nb = (int)((max_key >> sh) + 1);
             one.smem_bytes = key_bytes + ((size_t)one.nb + 2) * 2;
         }

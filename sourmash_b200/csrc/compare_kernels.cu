@@ -82,7 +82,7 @@ PairwisePlan plan_pairwise(uint64_t max_len_a, uint64_t max_key, int n_b) {
         if (per_table < key_bytes + 64) return false;
         const uint64_t max_entries = std::min<uint64_t>((per_table - key_bytes) / 2 - 2, 60000);
         shift = 0;
-        while (shift < 63 && (max_key >> shift) + 1 > max_entries) ++shift;
+        while (shift < 63 && (max_key >> shift) >= max_entries) ++shift;   // (no +1: max_key may be 2^64-1)
         nb = (max_key >> shift) + 1;
         return nb <= max_entries;
     };
