@@ -1483,6 +1483,28 @@ void smb_compare_angular(const SmbSketchSet* set, double* out) {
     });
 }
 
+// Launch-only variant for a query that (a) fits the tile kernel and (b) whose true length lives on
+// the device: d_qoff = {0, n} is written by the producing kernel, `nq_cap` bounds n, `key_bound`
+// bounds every key of the query.  No host synchronisation.
+static void one_vs_many_small_async(const uint64_t* d_q, const uint64_t* d_qoff, size_t nq_cap,
+                                    uint64_t key_bound, const SmbSketchSet& db, uint32_t* d_counts,
+                                    cudaStream_t s) {
+    const int nB = (int)db.n_rows;
+    if (nB == 0) return;
+    const uint64_t max_key = std::max(key_bound, set_max_key(db, s));
+    smb::PairwisePlan one = smb::plan_pairwise(nq_cap, max_key, nB);
+    one.tables_per_cta = 1;
+    const size_t key_bytes = (size_t)(one.cap + 2) * 8;
+    const uint64_t max_entries = std::min<uint64_t>((227 * 1024 - key_bytes) / 2 - 2, 60000);
+    int sh = 0;
+    while (sh < 63 && (max_key >> sh) >= max_entries) ++sh;
+    one.shift = sh; one.nb = (int)((max_key >> sh) + 1);
+    one.smem_bytes = key_bytes + ((size_t)one.nb + 2) * 2;
+    one.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
+    smb::launch_pairwise_tile(one, d_q, d_qoff, 1, db.d_hashes, db.d_off, nB, d_counts, (size_t)nB, false,
+                              smb::TileShard{0, 1}, s);
+}
+
 static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& db, uint32_t* d_counts,
                             cudaStream_t s) {
     // query small enough for shared memory: it becomes the (single) table of the tile kernel;
@@ -1679,27 +1701,71 @@ uintptr_t smb_gather_apply(SmbGatherState* st, const uint64_t* intersect, uintpt
 uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
                      uint32_t threshold, uint32_t* match_ids, uint32_t* isect_sizes,
                      uintptr_t max_rounds) {
-    // CounterGather + GatherDatabases loop (index/__init__.py:777-909, search.py:877-949)
+    // CounterGather + GatherDatabases loop (index/__init__.py:777-909, search.py:877-949), all
+    // state in HBM.  Per round: argmax (one 24-byte readback = the only synchronisation),
+    // intersect kernel, one-vs-many of the intersection, flag the consumed hashes.
     if (db->n_rows == 0 || n_query == 0 || max_rounds == 0) return 0;
     if (threshold < 1) threshold = 1;
     SmbGatherState* st = smb_gather_begin_min(query, n_query, db, threshold);
     if (!st) return 0;
-    std::vector<uint64_t> isect(db->max_len + 1);
-    uintptr_t rounds = 0;
-    while (rounds < max_rounds) {
-        uint32_t cnt = 0, row = 0;
-        smb_gather_peek(st, &cnt, &row);
-        if (t_has_error || cnt < threshold || cnt == 0) break;
-        uintptr_t n = smb_gather_intersect(st, row, isect.data());
-        if (t_has_error) break;
-        match_ids[rounds] = row;
-        isect_sizes[rounds] = (uint32_t)n;
-        ++rounds;
-        uintptr_t rem = smb_gather_apply(st, isect.data(), n);
-        if (t_has_error || rem == 0) break;
-    }
-    smb_gather_end(st);
-    return t_has_error ? 0 : rounds;
+    return guarded<uintptr_t>([&]() -> uintptr_t {
+        std::unique_ptr<SmbGatherState> owner(st);
+        cudaStream_t s = need_gpu();
+        const SmbSketchSet* cdb = st->db;
+        if (cdb->n_rows == 0) return 0;
+        const uint64_t q_max = query[n_query - 1];             // query is sorted: bounds every intersection
+        const bool small_rows = smb::plan_pairwise(cdb->max_len, std::max(q_max, set_max_key(*cdb, s)),
+                                                   (int)cdb->n_rows).tables_per_cta > 0;
+        DevBuf<uint64_t> d_qoff(2, s);
+        DevBuf<unsigned long long> d_info(4, s);               // {best count, best row, previous |intersect|}
+        uintptr_t rounds = 0;
+        bool have_delta = false;
+        while (rounds < max_rounds) {
+            smb::launch_counter_update_argmax(st->counts.p, have_delta ? st->delta.p : nullptr, (int)cdb->n_rows,
+                                              st->d_best.p, s);
+            unsigned long long best[2];
+            uint32_t prev_n = 0;
+            st->d_best.download(best, 2);
+            if (rounds) CK(cudaMemcpyAsync(&prev_n, st->d_n.p, 4, cudaMemcpyDeviceToHost, s));
+            sync(s);
+            if (rounds) {
+                isect_sizes[rounds - 1] = prev_n;
+                st->remaining = st->remaining > prev_n ? st->remaining - prev_n : 0;
+                if (st->remaining == 0) break;
+            }
+            if (best[0] < threshold || best[0] == 0) break;
+            const uint32_t row = (uint32_t)best[1];
+            match_ids[rounds] = st->rowmap.empty() ? row : st->rowmap[row];
+            isect_sizes[rounds] = (uint32_t)best[0];            // == |intersect|; confirmed next round
+            ++rounds;
+            const uint64_t* r = cdb->d_hashes + cdb->h_off[row];
+            const size_t rn = cdb->h_off[row + 1] - cdb->h_off[row];
+            smb::launch_intersect_alive(st->q.p, st->nq, st->alive.p, r, rn, st->isect.p, st->d_n.p, s);
+            if (small_rows) {
+                smb::launch_make_row_offsets(st->d_n.p, d_qoff.p, s);
+                st->delta.zero();
+                one_vs_many_small_async(st->isect.p, d_qoff.p, rn, q_max, *cdb, st->delta.p, s);
+                smb::launch_mark_dead_n(st->q.p, st->nq, st->alive.p, st->isect.p, st->d_n.p, s);
+            } else {                                           // huge rows: synchronous path
+                uint32_t n = 0;
+                st->d_n.download(&n, 1);
+                sync(s);
+                st->delta.zero();
+                if (n) one_vs_many_dev(st->isect.p, n, *cdb, st->delta.p, s);
+                smb::launch_mark_dead(st->q.p, st->nq, st->alive.p, st->isect.p, n, s);
+            }
+            have_delta = true;
+            CK(cudaGetLastError());
+        }
+        if (rounds && st->remaining) {                          // size of the last intersection
+            uint32_t last_n = 0;
+            CK(cudaMemcpyAsync(&last_n, st->d_n.p, 4, cudaMemcpyDeviceToHost, s));
+            sync(s);
+            if (isect_sizes[rounds - 1] != last_n) isect_sizes[rounds - 1] = last_n;
+        }
+        sync(s);
+        return rounds;
+    });
 }
 
 }  // extern "C"

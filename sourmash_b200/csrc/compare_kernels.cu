@@ -779,6 +779,26 @@ void launch_mark_dead(const u64* q, u64 nq, u8* alive, const u64* gone, u64 n, c
     mark_dead_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, alive, gone, n); count_launches(1);
 }
 
+__global__ void make_row_offsets_kernel(const u32* __restrict__ d_n, u64* __restrict__ off2) {
+    off2[0] = 0;
+    off2[1] = *d_n;
+}
+void launch_make_row_offsets(const u32* d_n, u64* d_off2, cudaStream_t s) {
+    make_row_offsets_kernel<<<1, 1, 0, s>>>(d_n, d_off2); count_launches(1);
+}
+
+__global__ void __launch_bounds__(256) mark_dead_n_kernel(const u64* __restrict__ q, u64 nq, u8* __restrict__ alive,
+                                                         const u64* __restrict__ gone, const u32* __restrict__ d_n) {
+    const u64 n = *d_n;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        long long pos = row_find(q, nq, gone[e]);
+        if (pos >= 0) alive[pos] = 0;
+    }
+}
+void launch_mark_dead_n(const u64* q, u64 nq, u8* alive, const u64* gone, const u32* d_n, cudaStream_t s) {
+    mark_dead_n_kernel<<<64, 256, 0, s>>>(q, nq, alive, gone, d_n); count_launches(1);
+}
+
 void launch_intersect_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, u32* d_n,
                            cudaStream_t s) {
     if (nb < na) { const u64* t = a; a = b; b = t; u64 tn = na; na = nb; nb = tn; }   // probe with the shorter row

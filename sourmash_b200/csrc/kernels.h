@@ -78,6 +78,12 @@ void launch_intersect_alive(const uint64_t* q, uint64_t nq, const uint8_t* alive
 void launch_mark_dead(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* gone, uint64_t n,
                       cudaStream_t s);
 
+// device-side glue for the sync-free gather round: offsets {0, *d_n} of a 1-row CSR, and
+// mark_dead with the count read from the device
+void launch_make_row_offsets(const uint32_t* d_n, uint64_t* d_off2, cudaStream_t s);
+void launch_mark_dead_n(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* gone,
+                        const uint32_t* d_n, cudaStream_t s);
+
 // Materialise A ∩ B of two sorted rows (gather's intersect_mh); returns count in *d_n.
 void launch_intersect_rows(const uint64_t* a, uint64_t na, const uint64_t* b, uint64_t nb,
                            uint64_t* out, uint32_t* d_n, cudaStream_t s);
