@@ -36,6 +36,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: keep a private handle to the real stdout and point fd 1
+# at stderr, so that library banners (e.g. "NCCL version ..." printed from C) cannot pollute it.
+_JSON_FD = None
+
+
+def protect_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -185,7 +207,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "CPU restatement of src/core (oracle/oracle.c, OpenMP), not the Rust binary: no Rust toolchain in the image"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -240,7 +262,7 @@ def run_b200(args):
         r = bench_search_gather(args, torch, dist, B, rank, world, timed, args.workload)
         if rank == 0:
             r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "data": "synthetic", "dtype": "u64"})
-            print(json.dumps(r), flush=True)
+            emit_json(r)
         return
     out = {}
     if args.workload in ("compare", "both"):
@@ -252,7 +274,7 @@ def run_b200(args):
         line = dict(primary)
         if "compare" in out and "sketch" in out:
             line["sketch"] = out["sketch"]
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -473,6 +495,7 @@ def main():
         args.workload = "compare" if args.impl == "reference" else "both"
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -38,14 +38,15 @@ assert got.shape == (hi - lo, 700)
 assert np.array_equal(got, want[lo:hi]), f"rank {rank}: compare rows {lo}:{hi} differ"
 
 # ---- sketch shards + all-gather
-genomes = [synth_genome(200_000 + 1000 * g, seed=50 + g) for g in range(6)]
-mine = list(range(rank, 6, world))
+NG = 2 * world + 1
+genomes = [synth_genome(100_000 + 1000 * g, seed=50 + g) for g in range(NG)]
+mine = list(range(rank, NG, world))
 seqs = np.concatenate([genomes[g] for g in mine])
 offs = np.cumsum([0] + [len(genomes[g]) for g in mine]).astype(np.uint64)
 sset, _ = B.sketch_sequences(seqs, offs, [21, 31], scaled=100)
 full = allgather_sketchset(torch, dist, B, sset)
 rows = full.rows()
-order = [g for r in range(world) for g in range(r, 6, world)]          # rank-major gather order
+order = [g for r in range(world) for g in range(r, NG, world)]          # rank-major gather order
 mx = orc.max_hash_for_scaled(100)
 for pos, g in enumerate(order):
     for ki, k in enumerate((21, 31)):
