@@ -238,3 +238,21 @@ def test_gather_session_steps_equal_library_loop(B):
         if sess.apply(isect) == 0:
             break
     assert got == list(zip(ids.tolist(), sizes.tolist())) == _gather_oracle(query, rows, threshold=4)
+
+
+def test_one_vs_many_medium_query_and_big_row_gather(B):
+    rng = np.random.Generator(np.random.PCG64(91))
+    # query of 20 000 hashes: single shared-memory table without occupancy flags
+    h, off = synth_sketches(150, mean=3000, sd=400, lo=1500, hi=5000, n_families=4, pool=3600, seed=17)
+    rows = rows_of(h, off)
+    db = B.SketchSet.from_host(h, off)
+    q = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=20_000, dtype=np.uint64), rows[3], rows[77]]))
+    assert 16_380 < len(q) < 28_000
+    assert np.array_equal(B.one_vs_many(q, db), orc.one_vs_many(q, h, off).astype(np.uint32))
+    # gather over a database whose rows do not fit shared memory (synchronous round path)
+    pool = np.unique(rng.integers(1, 2**62, size=200_000, dtype=np.uint64))
+    big_rows = [np.sort(rng.choice(pool, size=40_000, replace=False)) for _ in range(6)]
+    bdb = B.SketchSet.from_rows(big_rows)
+    query = np.unique(np.concatenate([big_rows[2][:30_000], big_rows[4][5_000:25_000], big_rows[0][::7]]))
+    ids, sizes = B.gather(query, bdb, threshold=10)
+    assert list(zip(ids.tolist(), sizes.tolist())) == _gather_oracle(query, big_rows, threshold=10)
