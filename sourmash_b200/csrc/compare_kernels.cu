@@ -282,9 +282,209 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Split-word variant of the tile kernel (rows < 16380 keys).  The v1 kernel above runs at
+// ~98 % of the SM's shared-memory wavefront rate (ncu), two LDS.64 per probe being the bulk.
+// Here the table keeps the low and high 32-bit halves of the keys in separate arrays: the
+// fast path touches only the low words (two LDS.32, ~1/2 the wavefronts) and remembers, per
+// probe, where a low word matched; the high words are read only for those probes, inside a
+// warp-uniform branch that unrelated pairs never enter.  Exact: a low-word match is always
+// verified against the high word (both slots if both low words match).
+// ------------------------------------------------------------------------------------
+template <int TA, int U>
+__global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kernel(TileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int i0 = (blockIdx.x * a.tile_stride + a.tile_offset) * TA;
+    int jbeg = blockIdx.y * a.cols_per_cta;
+    int jend = min(jbeg + a.cols_per_cta, a.nB);
+    if (a.symmetric) jbeg = max(jbeg, i0 + 1);
+    if (jbeg >= jend) return;
+
+    const u32 shift = (u32)a.shift;
+    const int nb = a.nb;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int kstride = a.cap + 2;                       // same footprint as the u64 layout
+    const int dstride = nb + 2;
+    u32* lo_base = reinterpret_cast<u32*>(smem_raw);
+    u32* hi_base = lo_base + (size_t)TA * kstride;
+    u16* dirs_base = reinterpret_cast<u16*>(smem_raw + (size_t)TA * kstride * 8);
+
+    __shared__ int s_n[TA];
+    __shared__ int s_hasmax[TA];
+
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        int i = i0 + t;
+        u64 beg = 0; int n = 0; int hm = 0;
+        if (i < a.nA) {
+            beg = a.offA[i];
+            n = (int)(a.offA[i + 1] - beg);
+            if (n > 0 && ld_nc_u64(a.hA + beg + n - 1) == SMB_U64_MAX) { --n; hm = 1; }
+        }
+        u32* lt = lo_base + (size_t)t * kstride;
+        u32* ht = hi_base + (size_t)t * kstride;
+        for (int p = tid; p < n; p += nthreads) {
+            const u64 k = ld_nc_u64(a.hA + beg + p);
+            lt[p] = (u32)k; ht[p] = (u32)(k >> 32);
+        }
+        if (tid < 2) { lt[n + tid] = 0xffffffffu; ht[n + tid] = 0xffffffffu; }   // sentinel = 2^64-1
+        if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
+        u16* dt = dirs_base + (size_t)t * dstride;
+        for (int b = tid; b <= nb; b += nthreads) dt[b] = (u16)n;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        const u32* lt = lo_base + (size_t)t * kstride;
+        const u32* ht = hi_base + (size_t)t * kstride;
+        u16* dt = dirs_base + (size_t)t * dstride;
+        int n = s_n[t];
+        for (int p = tid; p < n; p += nthreads) {
+            int bp = (int)((((u64)ht[p] << 32) | lt[p]) >> shift);
+            int bprev = p == 0 ? -1 : (int)((((u64)ht[p - 1] << 32) | lt[p - 1]) >> shift);
+            for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)p;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {                      // fold min(occupancy, 3) into the top two bits
+        u16* dt = dirs_base + (size_t)t * dstride;
+        for (int b = tid; b < nb; b += nthreads) {
+            u32 st = dt[b] & 0x3fffu, en = dt[b + 1] & 0x3fffu;
+            u32 occ = en - st;
+            dt[b] = (u16)(st | ((occ > 3u ? 3u : occ) << 14));
+        }
+    }
+    __syncthreads();
+
+    const u32* los[TA];
+    const u32* his[TA];
+    const u16* dirs[TA];
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+        los[t] = lo_base + (size_t)t * kstride;
+        his[t] = hi_base + (size_t)t * kstride;
+        dirs[t] = dirs_base + (size_t)t * dstride;
+    }
+
+    // one probe: low words only.  info = start | (slot0 low-match) << 14 | (slot1 low-match) << 15
+    auto probe = [&](u64 q, int t, u32& info, u32& pend, int bit, u32 valid) {
+        const u32 b = (u32)(q >> shift);
+        const u32 ent = dirs[t][b];
+        const u32 st = ent & 0x3fffu;
+        const u32 l0 = los[t][st], l1 = los[t][st + 1];
+        const u32 qlo = (u32)q;
+        info = st | (l0 == qlo ? 0x4000u : 0u) | (l1 == qlo ? 0x8000u : 0u);
+        if (!valid) info = st;
+        if (ent >= 0xC000u && valid) pend |= 1u << bit;
+    };
+    // high-word check of the slots whose low word matched
+    auto verify = [&](u64 q, int t, u32 info, u32& cnt) {
+        const u32 st = info & 0x3fffu;
+        const u32 qhi = (u32)(q >> 32);
+        u32 m = 0;
+        if (info & 0x4000u) m |= (his[t][st] == qhi);
+        if (info & 0x8000u) m |= (his[t][st + 1] == qhi);
+        cnt += m;
+    };
+    // more than two keys in the bucket: continue past the two slots of the fast path
+    auto rest = [&](u64 q, int t, u32& cnt) {
+        const u32 b = (u32)(q >> shift);
+        u32 p = (dirs[t][b] & 0x3fffu) + 2;
+        for (;;) {
+            const u64 k = ((u64)his[t][p] << 32) | los[t][p];
+            if (k >= q) { cnt += (k == q); break; }
+            ++p;
+        }
+    };
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NWARPS = nthreads >> 5;
+    for (int j = jbeg + warp; j < jend; j += NWARPS) {
+        const u64 bbeg = a.offB[j];
+        int nbj = (int)(a.offB[j + 1] - bbeg);
+        int bmax = 0;
+        if (nbj > 0 && ld_nc_u64(a.hB + bbeg + nbj - 1) == SMB_U64_MAX) { --nbj; bmax = 1; }
+        const u64* row = a.hB + bbeg;
+        u32 cnt[TA];
+#pragma unroll
+        for (int t = 0; t < TA; ++t) cnt[t] = 0;
+
+        int base = 0;
+        const int full = nbj - (nbj % (32 * U));
+        u64 q[U];
+        if (full > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + u * 32 + lane);
+        }
+        for (; base < full; base += 32 * U) {
+            u64 cur[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = q[u];
+            if (base + 32 * U < full) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + base + 32 * U + u * 32 + lane);
+            }
+            u32 info[U * TA];
+            u32 pend = 0, anyhit = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int t = 0; t < TA; ++t) {
+                    probe(cur[u], t, info[u * TA + t], pend, u * TA + t, 1u);
+                    anyhit |= info[u * TA + t];
+                }
+            if (__any_sync(0xffffffffu, (anyhit >> 14) != 0u)) {      // related rows only
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int t = 0; t < TA; ++t) verify(cur[u], t, info[u * TA + t], cnt[t]);
+            }
+            if (pend) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int t = 0; t < TA; ++t)
+                        if (pend & (1u << (u * TA + t))) rest(cur[u], t, cnt[t]);
+            }
+        }
+        for (; base < nbj; base += 32) {      // ragged tail
+            int e = base + lane;
+            u32 valid = e < nbj;
+            u64 qq = valid ? ld_nc_u64(row + e) : 0ULL;
+            u32 pend = 0;
+#pragma unroll
+            for (int t = 0; t < TA; ++t) {
+                u32 info;
+                probe(qq, t, info, pend, t, valid);
+                verify(qq, t, info, cnt[t]);
+            }
+            if (pend) {
+#pragma unroll
+                for (int t = 0; t < TA; ++t)
+                    if (pend & (1u << t)) rest(qq, t, cnt[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TA; ++t) {
+            u32 c = __reduce_add_sync(0xffffffffu, cnt[t]);
+            int i = i0 + t;
+            if (lane == 0 && i < a.nA && (!a.symmetric || j > i))
+                a.out[(size_t)i * a.ldo + j] = c + (u32)(s_hasmax[t] & bmax);
+        }
+    }
+}
+
+static int tile_variant() {       // SMB_TILE_VARIANT=u64 selects the v1 kernel for A/B measurements
+    static int v = [] { const char* e = getenv("SMB_TILE_VARIANT"); return (e && e[0] == 'u') ? 0 : 1; }();
+    return v;
+}
+
 template <int TA>
 static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
-    auto kern = args.cap < 16380 ? pairwise_tile_kernel<TA, 4, true> : pairwise_tile_kernel<TA, 4, false>;
+    auto kern = args.cap < 16380 ? (tile_variant() ? pairwise_tile_split_kernel<TA, 4> : pairwise_tile_kernel<TA, 4, true>)
+                                 : pairwise_tile_kernel<TA, 4, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles = (args.nA + TA - 1) / TA;
     const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
