@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_kernel(Tile
 }
 
 // ------------------------------------------------------------------------------------
-// Split-word variant of the tile kernel (rows < 16380 keys).  The v1 kernel above runs at
+// Split-word variant of the tile kernel (rows < 32760 keys, i.e. everything that fits).  The v1 kernel above runs at
 // ~98 % of the SM's shared-memory wavefront rate (ncu), two LDS.64 per probe being the bulk.
 // Here the table keeps the low and high 32-bit halves of the keys in separate arrays: the
 // fast path touches only the low words (two LDS.32, ~1/2 the wavefronts) and remembers, per
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
         if (tid < 2) { lt[n + tid] = 0xffffffffu; ht[n + tid] = 0xffffffffu; }   // sentinel = 2^64-1
         if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
         u16* dt = dirs_base + (size_t)t * dstride;
-        for (int b = tid; b <= nb; b += nthreads) dt[b] = (u16)n;
+        for (int b = tid; b <= nb; b += nthreads) dt[b] = (u16)(n << 1);     // entry = (start << 1) | crowded
     }
     __syncthreads();
 #pragma unroll
@@ -343,17 +343,16 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
         for (int p = tid; p < n; p += nthreads) {
             int bp = (int)((((u64)ht[p] << 32) | lt[p]) >> shift);
             int bprev = p == 0 ? -1 : (int)((((u64)ht[p - 1] << 32) | lt[p - 1]) >> shift);
-            for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)p;
+            for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)(p << 1);
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < TA; ++t) {                      // fold min(occupancy, 3) into the top two bits
+    for (int t = 0; t < TA; ++t) {                      // bit 0 <- "three or more keys share this bucket"
         u16* dt = dirs_base + (size_t)t * dstride;
         for (int b = tid; b < nb; b += nthreads) {
-            u32 st = dt[b] & 0x3fffu, en = dt[b + 1] & 0x3fffu;
-            u32 occ = en - st;
-            dt[b] = (u16)(st | ((occ > 3u ? 3u : occ) << 14));
+            u32 st2 = dt[b] & 0xfffeu, en2 = dt[b + 1] & 0xfffeu;
+            dt[b] = (u16)(st2 | (en2 - st2 >= 6u ? 1u : 0u));
         }
     }
     __syncthreads();
@@ -368,30 +367,20 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
         dirs[t] = dirs_base + (size_t)t * dstride;
     }
 
-    // one probe: low words only.  info = start | (slot0 low-match) << 14 | (slot1 low-match) << 15
-    auto probe = [&](u64 q, int t, u32& info, u32& pend, int bit, u32 valid) {
-        const u32 b = (u32)(q >> shift);
-        const u32 ent = dirs[t][b];
-        const u32 st = ent & 0x3fffu;
-        const u32 l0 = los[t][st], l1 = los[t][st + 1];
-        const u32 qlo = (u32)q;
-        info = st | (l0 == qlo ? 0x4000u : 0u) | (l1 == qlo ? 0x8000u : 0u);
-        if (!valid) info = st;
-        if (ent >= 0xC000u && valid) pend |= 1u << bit;
-    };
-    // high-word check of the slots whose low word matched
-    auto verify = [&](u64 q, int t, u32 info, u32& cnt) {
-        const u32 st = info & 0x3fffu;
-        const u32 qhi = (u32)(q >> 32);
+    // exact check of the two slots of q's bucket: high words are read only where a low word matched
+    auto verify = [&](u64 q, int t, u32& cnt) {
+        const u32 st = (dirs[t][(u32)(q >> shift)] & 0xfffeu) >> 1;
+        const u32 qlo = (u32)q, qhi = (u32)(q >> 32);
         u32 m = 0;
-        if (info & 0x4000u) m |= (his[t][st] == qhi);
-        if (info & 0x8000u) m |= (his[t][st + 1] == qhi);
+        if (los[t][st] == qlo) m |= (his[t][st] == qhi);
+        if (los[t][st + 1] == qlo) m |= (his[t][st + 1] == qhi);
         cnt += m;
     };
-    // more than two keys in the bucket: continue past the two slots of the fast path
+    // three or more keys in the bucket: continue past the two slots of the fast path
     auto rest = [&](u64 q, int t, u32& cnt) {
-        const u32 b = (u32)(q >> shift);
-        u32 p = (dirs[t][b] & 0x3fffu) + 2;
+        const u32 ent = dirs[t][(u32)(q >> shift)];
+        if (!(ent & 1u)) return;
+        u32 p = (ent >> 1) + 2;
         for (;;) {
             const u64 k = ((u64)his[t][p] << 32) | los[t][p];
             if (k >= q) { cnt += (k == q); break; }
@@ -426,44 +415,44 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
 #pragma unroll
                 for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + base + 32 * U + u * 32 + lane);
             }
-            u32 info[U * TA];
-            u32 pend = 0, anyhit = 0;
+            // fast path: directory entry + two low words per probe; one predicate and one OR
+            // accumulator for the whole batch, nothing else is kept
+            bool hit = false;
+            u32 ovacc = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                const u32 b = (u32)(cur[u] >> shift);
+                const u32 qlo = (u32)cur[u];
 #pragma unroll
                 for (int t = 0; t < TA; ++t) {
-                    probe(cur[u], t, info[u * TA + t], pend, u * TA + t, 1u);
-                    anyhit |= info[u * TA + t];
+                    const u32 ent = dirs[t][b];
+                    ovacc |= ent;
+                    // byte offset of slot 0 = start * 4 = (entry & ~1) * 2: one LOP + one LEA
+                    const u32* slot = reinterpret_cast<const u32*>(
+                        reinterpret_cast<const unsigned char*>(los[t]) + ((ent & 0xfffeu) << 1));
+                    hit |= (slot[0] == qlo);
+                    hit |= (slot[1] == qlo);
                 }
-            if (__any_sync(0xffffffffu, (anyhit >> 14) != 0u)) {      // related rows only
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int t = 0; t < TA; ++t) verify(cur[u], t, info[u * TA + t], cnt[t]);
             }
-            if (pend) {
+            if (__any_sync(0xffffffffu, hit)) {                       // related rows only
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int t = 0; t < TA; ++t)
-                        if (pend & (1u << (u * TA + t))) rest(cur[u], t, cnt[t]);
+                    for (int t = 0; t < TA; ++t) verify(cur[u], t, cnt[t]);
+            }
+            if (ovacc & 1u) {                                          // rare: a crowded bucket was hit
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int t = 0; t < TA; ++t) rest(cur[u], t, cnt[t]);
             }
         }
         for (; base < nbj; base += 32) {      // ragged tail
             int e = base + lane;
-            u32 valid = e < nbj;
-            u64 qq = valid ? ld_nc_u64(row + e) : 0ULL;
-            u32 pend = 0;
+            if (e < nbj) {
+                u64 qq = ld_nc_u64(row + e);
 #pragma unroll
-            for (int t = 0; t < TA; ++t) {
-                u32 info;
-                probe(qq, t, info, pend, t, valid);
-                verify(qq, t, info, cnt[t]);
-            }
-            if (pend) {
-#pragma unroll
-                for (int t = 0; t < TA; ++t)
-                    if (pend & (1u << t)) rest(qq, t, cnt[t]);
+                for (int t = 0; t < TA; ++t) { verify(qq, t, cnt[t]); rest(qq, t, cnt[t]); }
             }
         }
 #pragma unroll
@@ -483,8 +472,10 @@ static int tile_variant() {       // SMB_TILE_VARIANT=u64 selects the v1 kernel 
 
 template <int TA>
 static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
-    auto kern = args.cap < 16380 ? (tile_variant() ? pairwise_tile_split_kernel<TA, 4> : pairwise_tile_kernel<TA, 4, true>)
-                                 : pairwise_tile_kernel<TA, 4, false>;
+    // split-word kernel for every row size that fits shared memory (15-bit positions); the u64
+    // kernels stay selectable (SMB_TILE_VARIANT=u64) for A/B measurements
+    auto kern = tile_variant() && args.cap < 32760 ? pairwise_tile_split_kernel<TA, 4>
+              : (args.cap < 16380 ? pairwise_tile_kernel<TA, 4, true> : pairwise_tile_kernel<TA, 4, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles = (args.nA + TA - 1) / TA;
     const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
