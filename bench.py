@@ -351,8 +351,8 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "pairwise_tile_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("pairwise_tile_kernel"),
+        "roofline": {"kernel": "pairwise_tile_split_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("pairwise_tile_split_kernel"),
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
                              "memory / L2, so DRAM traffic is far below this"},

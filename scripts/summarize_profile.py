@@ -52,7 +52,7 @@ if os.path.exists(src):
 # ---- full captures
 traffic_path = os.path.join(P, "ncu_traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-for short, key in (("tile", "pairwise_tile_kernel"), ("hash", "hash_kmers_kernel")):
+for short, key in (("tile", "pairwise_tile_split_kernel"), ("hash", "hash_kmers_kernel")):
     rep = os.path.join(G, f"prof_{short}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
