@@ -418,15 +418,16 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
             // fast path: directory entry + two low words per probe; one predicate and one OR
             // accumulator for the whole batch, nothing else is kept
             bool hit = false;
-            u32 ovacc = 0;
+            u32 ov[U];                                  // per element: OR of its directory entries
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const u32 b = (u32)(cur[u] >> shift);
                 const u32 qlo = (u32)cur[u];
+                ov[u] = 0;
 #pragma unroll
                 for (int t = 0; t < TA; ++t) {
                     const u32 ent = dirs[t][b];
-                    ovacc |= ent;
+                    ov[u] |= ent;
                     // byte offset of slot 0 = start * 4 = (entry & ~1) * 2: one LOP + one LEA
                     const u32* slot = reinterpret_cast<const u32*>(
                         reinterpret_cast<const unsigned char*>(los[t]) + ((ent & 0xfffeu) << 1));
@@ -440,11 +441,16 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
 #pragma unroll
                     for (int t = 0; t < TA; ++t) verify(cur[u], t, cnt[t]);
             }
-            if (ovacc & 1u) {                                          // rare: a crowded bucket was hit
+            u32 ovany = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) ovany |= ov[u];
+            if (ovany & 1u) {                                          // rare: a crowded bucket was hit
 #pragma unroll
                 for (int u = 0; u < U; ++u)
+                    if (ov[u] & 1u) {
 #pragma unroll
-                    for (int t = 0; t < TA; ++t) rest(cur[u], t, cnt[t]);
+                        for (int t = 0; t < TA; ++t) rest(cur[u], t, cnt[t]);
+                    }
             }
         }
         for (; base < nbj; base += 32) {      // ragged tail
