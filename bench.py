@@ -128,6 +128,23 @@ def sketch_workload(n_genomes=N_GENOMES):
     return seqs, offs
 
 
+def host_cores():
+    """Usable host threads: the smallest of cpu_count, the affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -176,7 +193,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
+    ncores = host_cores()
     if args.workload == "compare":
         h, off = compare_workload()
         target = int(4e4 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
@@ -358,7 +375,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                              "memory / L2, so DRAM traffic is far below this"},
     }
     if rank == 0 and not args.no_cpu_baseline:
-        ncores = os.cpu_count() or 1
+        ncores = host_cores()
         units, dt, sample = cpu_compare_sample(h, off, ncores, int(4e4 * ncores))
         res["cpu_baseline"] = {"value": units / dt, "unit": "pairs/s", "cores": ncores, "kind": "port",
                                "sample": sample, "seconds": dt}
@@ -428,7 +445,7 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                              "HBM fraction is expected to be small"},
     }
     if rank == 0 and not args.no_cpu_baseline:
-        ncores = os.cpu_count() or 1
+        ncores = host_cores()
         units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, min(ng, max(8, ncores)))
         res["cpu_baseline"] = {"value": units / dt, "unit": "k-mers/s", "cores": ncores, "kind": "port",
                                "sample": sample, "seconds": dt}
