@@ -374,7 +374,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "note": "algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
                              "memory / L2, so DRAM traffic is far below this"},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # CPU baseline: rank 0 at N=1 only
         ncores = host_cores()
         units, dt, sample = cpu_compare_sample(h, off, ncores, int(4e4 * ncores))
         res["cpu_baseline"] = {"value": units / dt, "unit": "pairs/s", "cores": ncores, "kind": "port",
@@ -444,7 +444,7 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "note": "integer-issue bound by construction (~150 int ops per k-mer vs 1 B): "
                              "HBM fraction is expected to be small"},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = host_cores()
         units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, min(ng, max(8, ncores)))
         res["cpu_baseline"] = {"value": units / dt, "unit": "k-mers/s", "cores": ncores, "kind": "port",
