@@ -1461,6 +1461,37 @@ void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
         const size_t n = set->n_rows;
         if (n == 0) return;
         DevBuf<double> d_out(n * n, s);
+        smb::PairwisePlan plan{};
+        if (num == 0 && n >= 1024) plan = smb::plan_pairwise(set->max_len, set_max_key(*set, s), (int)n);
+        if (plan.tables_per_cta > 0) {
+            // Large matrix: compute groups of row tiles in order and download every finished block
+            // of rows on the copy stream while the next group is being computed (rows of group g
+            // only need counts from groups <= g: c[min(i,j)][max(i,j)]).
+            DevBuf<uint32_t> d_c(n * n, s);
+            const int ta = plan.tables_per_cta;
+            const int tiles = (int)((n + ta - 1) / ta);
+            const int groups = 8;
+            const int per = (tiles + groups - 1) / groups;
+            cudaStream_t cs = copy_stream();
+            if (t_profiling) t_timer_pairwise.begin(s);
+            for (int t0 = 0; t0 < tiles; t0 += per) {
+                const int cnt = std::min(per, tiles - t0);
+                smb::launch_pairwise_tile(plan, set->d_hashes, set->d_off, (int)n, set->d_hashes, set->d_off, (int)n,
+                                          d_c.p, n, true, smb::TileShard{t0, 1, cnt}, s);
+                const size_t r0 = (size_t)t0 * ta, r1 = std::min(n, (size_t)(t0 + cnt) * ta);
+                smb::launch_finalize_rows(d_c.p, n, set->d_off, (int)n, (int)r0, (int)r1, d_out.p + r0 * n, s);
+                cudaEvent_t ev = pool_event();
+                CK(cudaEventRecord(ev, s));
+                CK(cudaStreamWaitEvent(cs, ev, 0));
+                CK(cudaMemcpyAsync(out + r0 * n, d_out.p + r0 * n, (r1 - r0) * n * sizeof(double),
+                                   cudaMemcpyDeviceToHost, cs));
+            }
+            if (t_profiling) t_timer_pairwise.end(s);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(cs));
+            sync(s);
+            return;
+        }
         compare_jaccard_impl(set, num, d_out.p, s);
         d_out.download(out, n * n);
         sync(s);

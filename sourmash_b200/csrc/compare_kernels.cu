@@ -108,6 +108,7 @@ struct TileArgs {
     u32* out; size_t ldo;
     int shift, nb, cap, cols_per_cta, symmetric;
     int tile_offset, tile_stride;       // row tile = blockIdx.x * tile_stride + tile_offset
+    int tile_count;                     // >= 0: launch at most this many tiles
 };
 
 // Directory entries are u16.  When every table row has < 16384 keys (OCC), the top two bits
@@ -484,7 +485,8 @@ static void launch_tile_ta(const TileArgs& args, size_t smem, cudaStream_t s) {
               : (args.cap < 16380 ? pairwise_tile_kernel<TA, 4, true> : pairwise_tile_kernel<TA, 4, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int tiles = (args.nA + TA - 1) / TA;
-    const int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
+    int my_tiles = (tiles - args.tile_offset + args.tile_stride - 1) / args.tile_stride;
+    if (args.tile_count >= 0 && my_tiles > args.tile_count) my_tiles = args.tile_count;
     if (my_tiles <= 0) return;
     dim3 grid(my_tiles, (args.nB + args.cols_per_cta - 1) / args.cols_per_cta);
     kern<<<grid, tile_threads(), smem, s>>>(args); count_launches(1);
@@ -496,7 +498,7 @@ void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* of
     if (nA <= 0 || nB <= 0) return;
     TileArgs a{hA, offA, nA, hB, offB, nB, out, ldo,
                plan.shift, plan.nb, plan.cap, plan.cols_per_cta, symmetric ? 1 : 0,
-               tiles.shard, tiles.n_shards > 0 ? tiles.n_shards : 1};
+               tiles.shard, tiles.n_shards > 0 ? tiles.n_shards : 1, tiles.count};
     switch (plan.tables_per_cta) {
         case 1: launch_tile_ta<1>(a, plan.smem_bytes, s); break;
         case 2: launch_tile_ta<2>(a, plan.smem_bytes, s); break;

@@ -26,7 +26,7 @@ void launch_max_last(const uint64_t* hA, const uint64_t* offA, int nA, const uin
                      const uint64_t* offB, int nB, unsigned long long* d_max, cudaStream_t s);
 
 // Multi-GPU sharding of row tiles: this launch handles tiles shard, shard + n_shards, ...
-struct TileShard { int shard; int n_shards; };
+struct TileShard { int shard; int n_shards; int count = -1; };   // count >= 0: at most that many tiles
 
 // common[i*ldo + j] = |A_i ∩ B_j| for every (i, j) (symmetric: only j > i, A == B).
 // Tile kernel: A rows become shared-memory bucket tables, B rows stream through registers.
