@@ -196,7 +196,7 @@ def run_reference(args):
     ncores = host_cores()
     if args.workload == "compare":
         h, off = compare_workload()
-        target = int(4e4 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
+        target = int(1.5e5 * ncores)            # ~8 s per step at ~1.5e4 pairs/s/core
         times = []
         for i in range(args.warmup + args.steps):
             units, dt, sample = cpu_compare_sample(h, off, ncores, target)
@@ -206,7 +206,7 @@ def run_reference(args):
         config = {"workload": "configs[2]: compare 10000 synthetic sketches k=31 scaled=1000 all-vs-all jaccard",
                   "n_sketches": N_SKETCHES}
     else:
-        ng = min(N_GENOMES, max(8, ncores))
+        ng = N_GENOMES                           # the whole configs[1] workload (a few seconds on 16 cores)
         seqs, offs = sketch_workload(ng)
         times = []
         for i in range(args.warmup + args.steps):
@@ -376,7 +376,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # CPU baseline: rank 0 at N=1 only
         ncores = host_cores()
-        units, dt, sample = cpu_compare_sample(h, off, ncores, int(4e4 * ncores))
+        units, dt, sample = cpu_compare_sample(h, off, ncores, int(1.5e5 * ncores))
         res["cpu_baseline"] = {"value": units / dt, "unit": "pairs/s", "cores": ncores, "kind": "port",
                                "sample": sample, "seconds": dt}
     return res
@@ -446,7 +446,7 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = host_cores()
-        units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, min(ng, max(8, ncores)))
+        units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, ng)
         res["cpu_baseline"] = {"value": units / dt, "unit": "k-mers/s", "cores": ncores, "kind": "port",
                                "sample": sample, "seconds": dt}
     return res
