@@ -12,8 +12,24 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _ensure_built():
+    """Compile libsourmash_b200.so if it is missing or stale (needs nvcc; the GPU box receives the
+    prebuilt file with the snapshot).  Loaded by path so the package is not imported first."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_smb_build", os.path.join(ROOT, "sourmash_b200", "_build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        if mod.needs_build():
+            mod.build()
+    except Exception as exc:                      # no nvcc on this machine: use what is there
+        if not os.path.exists(mod.LIB):
+            raise RuntimeError(f"cannot build {mod.LIB}: {exc}")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    _ensure_built()
 
 
 def read_fasta(path):
