@@ -8,7 +8,7 @@ resident in HBM between calls.
 import numpy as np
 
 from ._lowlevel import ffi, lib
-from .utils import rustcall
+from ._ffi import rustcall
 
 
 def _u64(a):

@@ -17,7 +17,7 @@ from collections.abc import Mapping
 import numpy as np
 
 from ._lowlevel import ffi, lib
-from .utils import RustObject, decode_str, rustcall
+from ._ffi import RustObject, decode_str, rustcall
 
 MINHASH_DEFAULT_SEED = 42
 MINHASH_MAX_HASH = 0xFFFFFFFFFFFFFFFF
@@ -327,29 +327,10 @@ class MinHash(RustObject):
         return self.hashes.keys()
 
     @property
-    def seed(self):
-        return self._methodcall(lib.kmerminhash_seed)
-
-    @property
-    def num(self):
-        return self._methodcall(lib.kmerminhash_num)
-
-    @property
     def scaled(self):
-        mx = self._methodcall(lib.kmerminhash_max_hash)
+        "Python-visible scaled = round(2**64 / max_hash) (0 for num sketches)."
+        mx = self._max_hash
         return _get_scaled_for_max_hash(mx) if mx else 0
-
-    @property
-    def is_protein(self):
-        return self._methodcall(lib.kmerminhash_is_protein)
-
-    @property
-    def dayhoff(self):
-        return self._methodcall(lib.kmerminhash_dayhoff)
-
-    @property
-    def hp(self):
-        return self._methodcall(lib.kmerminhash_hp)
 
     @property
     def is_dna(self):
@@ -357,19 +338,12 @@ class MinHash(RustObject):
 
     @property
     def ksize(self):
+        "k in residues: protein-family sketches store 3*k below the ABI."
         k = self._methodcall(lib.kmerminhash_ksize)
-        if not self.is_dna:
-            assert k % 3 == 0
-            k //= 3
-        return k
-
-    @property
-    def max_hash(self):
-        return self._methodcall(lib.kmerminhash_max_hash)
-
-    @property
-    def _max_hash(self):
-        return self._methodcall(lib.kmerminhash_max_hash)
+        if self.is_dna:
+            return k
+        assert k % 3 == 0
+        return k // 3
 
     @property
     def moltype(self):
@@ -584,6 +558,23 @@ class MinHash(RustObject):
         if not self.scaled:
             raise TypeError("can only approximate unique_dataset_hashes for scaled MinHashes")
         return len(self) * self.scaled
+
+
+def _scalar_getter(c_function, doc):
+    return property(lambda self: self._methodcall(c_function), doc=doc)
+
+
+# plain scalar attributes: one C getter each (ffi/minhash.rs:303-378)
+for _name, _cfn, _doc in (
+        ("seed", lib.kmerminhash_seed, "murmurhash seed"),
+        ("num", lib.kmerminhash_num, "bottom-k size (0 for scaled sketches)"),
+        ("is_protein", lib.kmerminhash_is_protein, "protein k-mers"),
+        ("dayhoff", lib.kmerminhash_dayhoff, "dayhoff-encoded protein k-mers"),
+        ("hp", lib.kmerminhash_hp, "hydrophobic/polar-encoded protein k-mers"),
+        ("max_hash", lib.kmerminhash_max_hash, "largest retained hash (deprecated alias of _max_hash)"),
+        ("_max_hash", lib.kmerminhash_max_hash, "largest retained hash; 0 for num sketches")):
+    setattr(MinHash, _name, _scalar_getter(_cfn, _doc))
+del _name, _cfn, _doc
 
 
 def _frozen(name):

@@ -12,7 +12,7 @@ import os
 
 from ._lowlevel import ffi, lib
 from .minhash import FrozenMinHash, MinHash
-from .utils import RustObject, decode_str, rustcall
+from ._ffi import RustObject, decode_str, rustcall
 
 SIGNATURE_VERSION = 0.4
 

@@ -16,7 +16,7 @@ from . import batch as B
 from ._lowlevel import lib
 from .minhash import MinHash
 from .signature import SourmashSignature
-from .utils import rustcall
+from ._ffi import rustcall
 
 
 def read_sequences(path):
