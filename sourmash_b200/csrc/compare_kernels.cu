@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "split_table.cuh"
 
 namespace smb {
 
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
     __shared__ int s_n[TA];
     __shared__ int s_hasmax[TA];
 
+    // ---- build the tables (split_table.cuh: the same three phases run on the host in the tests)
 #pragma unroll
     for (int t = 0; t < TA; ++t) {
         int i = i0 + t;
@@ -323,71 +325,27 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
             n = (int)(a.offA[i + 1] - beg);
             if (n > 0 && ld_nc_u64(a.hA + beg + n - 1) == SMB_U64_MAX) { --n; hm = 1; }
         }
-        u32* lt = lo_base + (size_t)t * kstride;
-        u32* ht = hi_base + (size_t)t * kstride;
-        for (int p = tid; p < n; p += nthreads) {
-            const u64 k = ld_nc_u64(a.hA + beg + p);
-            lt[p] = (u32)k; ht[p] = (u32)(k >> 32);
-        }
-        if (tid < 2) { lt[n + tid] = 0xffffffffu; ht[n + tid] = 0xffffffffu; }   // sentinel = 2^64-1
         if (tid == 0) { s_n[t] = n; s_hasmax[t] = hm; }
-        u16* dt = dirs_base + (size_t)t * dstride;
-        for (int b = tid; b <= nb; b += nthreads) dt[b] = (u16)(n << 1);     // entry = (start << 1) | crowded
+        split_table_load(lo_base + (size_t)t * kstride, hi_base + (size_t)t * kstride,
+                         dirs_base + (size_t)t * dstride, a.hA + beg, n, nb, tid, nthreads);
     }
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < TA; ++t) {
-        const u32* lt = lo_base + (size_t)t * kstride;
-        const u32* ht = hi_base + (size_t)t * kstride;
-        u16* dt = dirs_base + (size_t)t * dstride;
-        int n = s_n[t];
-        for (int p = tid; p < n; p += nthreads) {
-            int bp = (int)((((u64)ht[p] << 32) | lt[p]) >> shift);
-            int bprev = p == 0 ? -1 : (int)((((u64)ht[p - 1] << 32) | lt[p - 1]) >> shift);
-            for (int b = bprev + 1; b <= bp; ++b) dt[b] = (u16)(p << 1);
-        }
-    }
+    for (int t = 0; t < TA; ++t)
+        split_table_heads(lo_base + (size_t)t * kstride, hi_base + (size_t)t * kstride,
+                          dirs_base + (size_t)t * dstride, s_n[t], shift, tid, nthreads);
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < TA; ++t) {                      // bit 0 <- "three or more keys share this bucket"
-        u16* dt = dirs_base + (size_t)t * dstride;
-        for (int b = tid; b < nb; b += nthreads) {
-            u32 st2 = dt[b] & 0xfffeu, en2 = dt[b + 1] & 0xfffeu;
-            dt[b] = (u16)(st2 | (en2 - st2 >= 6u ? 1u : 0u));
-        }
-    }
+    for (int t = 0; t < TA; ++t) split_table_flags(dirs_base + (size_t)t * dstride, nb, tid, nthreads);
     __syncthreads();
 
-    const u32* los[TA];
-    const u32* his[TA];
-    const u16* dirs[TA];
+    SplitTable tab[TA];
 #pragma unroll
     for (int t = 0; t < TA; ++t) {
-        los[t] = lo_base + (size_t)t * kstride;
-        his[t] = hi_base + (size_t)t * kstride;
-        dirs[t] = dirs_base + (size_t)t * dstride;
+        tab[t].lo = lo_base + (size_t)t * kstride;
+        tab[t].hi = hi_base + (size_t)t * kstride;
+        tab[t].dir = dirs_base + (size_t)t * dstride;
     }
-
-    // exact check of the two slots of q's bucket: high words are read only where a low word matched
-    auto verify = [&](u64 q, int t, u32& cnt) {
-        const u32 st = (dirs[t][(u32)(q >> shift)] & 0xfffeu) >> 1;
-        const u32 qlo = (u32)q, qhi = (u32)(q >> 32);
-        u32 m = 0;
-        if (los[t][st] == qlo) m |= (his[t][st] == qhi);
-        if (los[t][st + 1] == qlo) m |= (his[t][st + 1] == qhi);
-        cnt += m;
-    };
-    // three or more keys in the bucket: continue past the two slots of the fast path
-    auto rest = [&](u64 q, int t, u32& cnt) {
-        const u32 ent = dirs[t][(u32)(q >> shift)];
-        if (!(ent & 1u)) return;
-        u32 p = (ent >> 1) + 2;
-        for (;;) {
-            const u64 k = ((u64)his[t][p] << 32) | los[t][p];
-            if (k >= q) { cnt += (k == q); break; }
-            ++p;
-        }
-    };
 
     const int warp = tid >> 5, lane = tid & 31;
     const int NWARPS = nthreads >> 5;
@@ -417,30 +375,20 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
                 for (int u = 0; u < U; ++u) q[u] = ld_nc_u64(row + base + 32 * U + u * 32 + lane);
             }
             // fast path: directory entry + two low words per probe; one predicate and one OR
-            // accumulator for the whole batch, nothing else is kept
+            // accumulator per element for the whole batch, nothing else is kept
             bool hit = false;
-            u32 ov[U];                                  // per element: OR of its directory entries
+            u32 ov[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const u32 b = (u32)(cur[u] >> shift);
-                const u32 qlo = (u32)cur[u];
                 ov[u] = 0;
 #pragma unroll
-                for (int t = 0; t < TA; ++t) {
-                    const u32 ent = dirs[t][b];
-                    ov[u] |= ent;
-                    // byte offset of slot 0 = start * 4 = (entry & ~1) * 2: one LOP + one LEA
-                    const u32* slot = reinterpret_cast<const u32*>(
-                        reinterpret_cast<const unsigned char*>(los[t]) + ((ent & 0xfffeu) << 1));
-                    hit |= (slot[0] == qlo);
-                    hit |= (slot[1] == qlo);
-                }
+                for (int t = 0; t < TA; ++t) hit |= split_probe_low(tab[t], cur[u], shift, ov[u]);
             }
             if (__any_sync(0xffffffffu, hit)) {                       // related rows only
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int t = 0; t < TA; ++t) verify(cur[u], t, cnt[t]);
+                    for (int t = 0; t < TA; ++t) cnt[t] += split_probe_verify(tab[t], cur[u], shift);
             }
             u32 ovany = 0;
 #pragma unroll
@@ -450,7 +398,7 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
                 for (int u = 0; u < U; ++u)
                     if (ov[u] & 1u) {
 #pragma unroll
-                        for (int t = 0; t < TA; ++t) rest(cur[u], t, cnt[t]);
+                        for (int t = 0; t < TA; ++t) cnt[t] += split_probe_rest(tab[t], cur[u], shift);
                     }
             }
         }
@@ -459,7 +407,8 @@ __global__ void __launch_bounds__(TILE_THREADS_MAX, 1) pairwise_tile_split_kerne
             if (e < nbj) {
                 u64 qq = ld_nc_u64(row + e);
 #pragma unroll
-                for (int t = 0; t < TA; ++t) { verify(qq, t, cnt[t]); rest(qq, t, cnt[t]); }
+                for (int t = 0; t < TA; ++t)
+                    cnt[t] += split_probe_verify(tab[t], qq, shift) + split_probe_rest(tab[t], qq, shift);
             }
         }
 #pragma unroll

@@ -53,3 +53,59 @@ def test_roll_short_and_exact_lengths(emul):
                 continue
             want, _ = orc.seq_to_hashes(bytes(g), k, force=True, keep_zeros=True)
             assert np.array_equal(emul(g, k, 16, 3), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# intersection kernel: table build + probes (csrc/split_table.cuh) driven like the CUDA kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tile_emul():
+    exe = os.path.join(tempfile.gettempdir(), "smb_tile_emul")
+    src = os.path.join(HERE, "host_emul", "tile_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(rows, max_entries=30000):
+        hashes, offsets = orc.to_csr(rows)
+        finite = hashes[hashes != np.uint64(2**64 - 1)]
+        max_key = int(finite.max()) if len(finite) else 0
+        if len(hashes) and int(hashes.max()) == 2**64 - 1:
+            max_key = 2**64 - 1                               # the planner sees the raw maximum
+        shift = 0
+        while shift < 63 and (max_key >> shift) >= max_entries:
+            shift += 1
+        nb = (max_key >> shift) + 1
+        with tempfile.TemporaryDirectory() as td:
+            fin, fout = os.path.join(td, "in"), os.path.join(td, "out")
+            with open(fin, "wb") as fh:
+                fh.write(np.uint64(len(rows)).tobytes()); fh.write(offsets.tobytes()); fh.write(hashes.tobytes())
+            subprocess.check_call([exe, str(shift), str(nb), fin, fout])
+            n = len(rows)
+            return np.fromfile(fout, dtype=np.uint32).reshape(n, n), (hashes, offsets)
+    return run
+
+
+def test_tile_table_logic_matches_oracle(tile_emul):
+    from sourmash_b200.synth import rows_of, synth_sketches
+    h, off = synth_sketches(24, mean=700, sd=150, lo=5, hi=1500, n_families=3, pool=900, seed=31)
+    rows = rows_of(h, off)
+    got, (hh, oo) = tile_emul(rows)
+    assert np.array_equal(got, orc.pairwise_common(hh, oo))
+    # coarse directory (few buckets => crowded buckets everywhere): the rare path becomes the main path
+    got, _ = tile_emul(rows, max_entries=64)
+    assert np.array_equal(got, orc.pairwise_common(hh, oo))
+
+
+def test_tile_table_logic_edge_rows(tile_emul):
+    rng = np.random.Generator(np.random.PCG64(3))
+    big = 2**64 - 1
+    rows = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, 3, big], np.uint64),
+            np.array([big], np.uint64), np.array([big - 1, big], np.uint64),
+            np.arange(1, 700, dtype=np.uint64),                                       # dense: one bucket
+            np.unique(rng.integers(0, 2**63, size=900, dtype=np.uint64)),
+            # equal low words, different high words in neighbouring slots (low-word false positives)
+            np.array([(7 << 32) | 5, (8 << 32) | 5, (9 << 32) | 5, (9 << 32) | 6], dtype=np.uint64),
+            np.array([(8 << 32) | 5, (9 << 32) | 6, (10 << 32) | 5], dtype=np.uint64),
+            np.unique(rng.integers(0, 1000, size=300, dtype=np.uint64))]
+    for max_entries in (30000, 16, 2):
+        got, (hh, oo) = tile_emul(rows, max_entries=max_entries)
+        assert np.array_equal(got, orc.pairwise_common(hh, oo)), max_entries
