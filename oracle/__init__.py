@@ -77,10 +77,23 @@ def _load():
                                       C.POINTER(C.c_uint64)]
     lib.orc_sketch_batch.argtypes = [u8p, u64p, sz, C.c_uint32, C.c_uint64, C.c_uint64, u64p,
                                      u64p, u64p, C.c_int]
+    lib.orc_translate_codon.restype = C.c_uint8
+    lib.orc_translate_codon.argtypes = [C.c_char_p, sz]
+    lib.orc_aa_to_dayhoff.restype = C.c_uint8
+    lib.orc_aa_to_dayhoff.argtypes = [C.c_uint8]
+    lib.orc_aa_to_hp.restype = C.c_uint8
+    lib.orc_aa_to_hp.argtypes = [C.c_uint8]
+    for fn in (lib.orc_seq_to_hashes_protein, lib.orc_seq_to_hashes_translate):
+        fn.restype = C.c_int64
+        fn.argtypes = [C.c_char_p, sz, C.c_uint32, C.c_uint64, C.c_int, C.c_int, u64p]
+    lib.orc_mh_add_protein_family.restype = C.c_int64
+    lib.orc_mh_add_protein_family.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_int, C.c_int]
     return lib
 
 
 lib = _load()
+
+HASH_FUNCTIONS = {"dna": 1, "DNA": 1, "protein": 2, "dayhoff": 3, "hp": 4}
 
 
 def _u64(a):
@@ -110,6 +123,40 @@ def seq_to_hashes(seq, ksize, seed=42, force=False, keep_zeros=False):
     if r < 0:
         return out[: nb.value].copy(), int(err.value)
     return out[:r].copy(), None
+
+
+def translate_codon(codon):
+    """encodings.rs:298-326; raises ValueError for lengths outside 1..3."""
+    if isinstance(codon, str):
+        codon = codon.encode()
+    r = lib.orc_translate_codon(codon, len(codon))
+    if r == 0:
+        raise ValueError("Codon is invalid length: %d" % len(codon))
+    return chr(r)
+
+
+def seq_to_hashes_protein(seq, ksize_aa, moltype="protein", seed=42, keep_zeros=False):
+    """SeqToHashes(is_protein=True): residues -> hashes in order (signature.rs:358-388).
+    ksize_aa is in residues.  Raises ValueError for a DNA sketch (InvalidHashFunction)."""
+    if isinstance(seq, str):
+        seq = seq.encode()
+    out = np.zeros(len(seq) + 1, dtype=np.uint64)
+    n = lib.orc_seq_to_hashes_protein(seq, len(seq), 3 * ksize_aa, seed, HASH_FUNCTIONS[moltype],
+                                      int(keep_zeros), out)
+    if n < 0:
+        raise ValueError("Invalid hash function")
+    return out[:n].copy()
+
+
+def seq_to_hashes_translate(seq, ksize_aa, moltype="protein", seed=42, keep_zeros=False):
+    """SeqToHashes(is_protein=False) on a protein-family sketch: six-frame translation
+    (signature.rs:307-357)."""
+    if isinstance(seq, str):
+        seq = seq.encode()
+    out = np.zeros(2 * len(seq) + 4, dtype=np.uint64)
+    n = lib.orc_seq_to_hashes_translate(seq, len(seq), 3 * ksize_aa, seed, HASH_FUNCTIONS[moltype],
+                                        int(keep_zeros), out)
+    return out[:n].copy()
 
 
 class OracleMinHash:
@@ -164,6 +211,16 @@ class OracleMinHash:
             seq = seq.encode()
         r = lib.orc_mh_add_sequence(self._p, seq, len(seq), int(force))
         return None if r == 0 else int(r - 1)
+
+    def add_protein_family(self, seq, moltype, input_is_protein):
+        """add_protein (input_is_protein) / add_sequence (translate) on a protein-family sketch;
+        self.ksize must be the ABI value (3 x residues)."""
+        if isinstance(seq, str):
+            seq = seq.encode()
+        r = lib.orc_mh_add_protein_family(self._p, seq, len(seq), HASH_FUNCTIONS[moltype],
+                                          int(input_is_protein))
+        if r < 0:
+            raise ValueError("Invalid hash function")
 
     def merge(self, other):
         lib.orc_mh_merge(self._p, other._p)

@@ -52,6 +52,17 @@ size_t orc_sketch_scaled(const uint8_t *seq, size_t len, uint32_t k, uint64_t se
 void orc_sketch_batch(const uint8_t *seqs, const uint64_t *seq_off, size_t n_seqs, uint32_t k,
                       uint64_t seed, uint64_t max_hash, uint64_t *out, const uint64_t *out_off,
                       uint64_t *out_n, int nthreads);
+
+/* protein-family hashing (hash_function: 2 protein, 3 dayhoff, 4 hp; ksize = 3 x residues) */
+uint8_t orc_translate_codon(const uint8_t *codon, size_t n);
+uint8_t orc_aa_to_dayhoff(uint8_t aa);
+uint8_t orc_aa_to_hp(uint8_t aa);
+int64_t orc_seq_to_hashes_protein(const uint8_t *seq, size_t len, uint32_t ksize, uint64_t seed,
+                                  int hash_function, int keep_zeros, uint64_t *out);
+int64_t orc_seq_to_hashes_translate(const uint8_t *seq, size_t len, uint32_t ksize, uint64_t seed,
+                                    int hash_function, int keep_zeros, uint64_t *out);
+int64_t orc_mh_add_protein_family(orc_mh *m, const uint8_t *seq, size_t len, int hash_function,
+                                  int input_is_protein);
 #ifdef __cplusplus
 }
 #endif

@@ -68,3 +68,9 @@ def ecoli_seq():
 @pytest.fixture(scope="session")
 def s10_records():
     return read_fasta(os.path.join(GOLDEN, "genome-s10.fa.gz"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    import pathlib
+    return pathlib.Path(GOLDEN)

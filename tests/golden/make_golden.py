@@ -10,6 +10,7 @@ Outputs (committed):
   golden_meta.json    md5sums, parameters and known-answer values quoted from the reference tests
   ecoli_k12.fna.gz    byte copy of data/GCF_000005845.2_ASM584v2_genomic.fna.gz (BASELINE config 1 input)
   genome-s10.fa.gz    byte copy of tests/test-data/genome-s10.fa.gz (multi-record FASTA, num=500 golden sig)
+  ecoli.faa, ecoli.genes.fna   byte copies of the protein / gene inputs of the known-good protein tests
 
 Nothing here imports the reference's code (it cannot be built in this image: no Rust toolchain);
 the .sig files are plain JSON written by the reference and are the pinned expected outputs.
@@ -106,6 +107,23 @@ meta["genome_s10"] = s10
 shutil.copyfile(os.path.join(TD, "47.fa.sig"), os.path.join(HERE, "47.fa.sig"))
 shutil.copyfile(os.path.join(TD, "genome-s10.fa.gz.sig"), os.path.join(HERE, "genome-s10.fa.gz.sig"))
 
+# --- protein-family fixtures: tests/test_sourmash_sketch.py:1340-1376 ---------
+# ecoli.faa (2 protein records) and ecoli.genes.fna (the 2 genes) are the inputs of the
+# reference's known-good tests; benchmark.input_prot.sig / benchmark.prot.sig are their expected
+# num=500, k=7 (ksize 21) protein sketches (input protein / six-frame translation).
+shutil.copyfile(os.path.join(TD, "ecoli.faa"), os.path.join(HERE, "ecoli.faa"))
+shutil.copyfile(os.path.join(TD, "ecoli.genes.fna"), os.path.join(HERE, "ecoli.genes.fna"))
+prot = {}
+for tag, fn in (("input_prot", "benchmark.input_prot.sig"), ("translate_prot", "benchmark.prot.sig"),
+                ("benchmark_dna", "benchmark.dna.sig")):
+    (rec, s), = list(sketches(os.path.join(TD, fn)))
+    arrays[f"bench_{tag}"] = np.array(s["mins"], dtype=np.uint64)
+    prot[tag] = {"name": rec["name"], "ksize": s["ksize"], "num": s["num"], "seed": s["seed"],
+                 "molecule": s["molecule"], "md5sum": s["md5sum"], "n": len(s["mins"])}
+meta["protein_benchmarks"] = prot
+# 2 x 2 similarities of tests/test_sourmash_compute.py:810-860 (round(., 3)), k=21 (7 residues), num=500
+meta["protein_2x2"] = {"aa1_trans1": 0.0, "aa2_trans1": 0.166, "aa1_trans2": 0.174, "aa2_trans2": 0.0}
+
 # --- known-answer values quoted from the reference's tests ----------------------------------
 meta["kat"] = {
     "hash_murmur_ACG_42": 1731421407650554201,            # tests/test_minhash.py:1239-1262
@@ -118,6 +136,13 @@ meta["kat"] = {
                    9390240264282449587, 11085758717695534616, 11668188995231815419,
                    11760449009842383350, 14682565545778736889]},
     "invalid_dna_k3": {"AAANNCCCTN": 3, "NAAA": 1},        # src/core/tests/minhash.rs:56-66
+    # tests/test_minhash.py:390-454: residues are re-encoded before hashing
+    "dayhoff_CADHIFC": "abcdefa", "dayhoff_CADHIF*": "abcdef*", "hp_ANA": "hph", "hp_AN*": "hp*",
+    # tests/test_minhash.py:313-358, src/core/tests/minhash.rs:153-175, signature.rs:1031-1039
+    "AGYYG_k2": {"protein": 4, "dayhoff": 4, "hp": 1}, "ACTGAC_translate_k2": 2,
+    "AGY_k2_protein": 2, "AGY_k1_protein": 3,
+    # tests/test_minhash.py:361-370
+    "translate_codon": {"TCT": "S", "TC": "S", "T": "X"},
 }
 
 np.savez_compressed(os.path.join(HERE, "golden_arrays.npz"), **arrays)

@@ -122,3 +122,86 @@ def test_angular_similarity_small():
     b = np.array([2, 6], dtype=np.uint64)
     bb = np.array([1, 1], dtype=np.uint64)
     assert orc.angular_similarity(a, ab, b, bb) == 0.0
+
+
+# ------------------------------------------------------------------ protein family
+def _fasta_records(path):
+    name, seq, out = None, [], []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            if name is not None:
+                out.append((name, "".join(seq)))
+            name, seq = line[1:], []
+        elif line:
+            seq.append(line)
+    out.append((name, "".join(seq)))
+    return out
+
+
+def test_protein_encoding_kats(golden):
+    kat = golden["meta"]["kat"]
+    for codon, aa in kat["translate_codon"].items():
+        assert orc.translate_codon(codon) == aa
+    with pytest.raises(ValueError):
+        orc.translate_codon("")
+    with pytest.raises(ValueError):
+        orc.translate_codon("TCTA")
+    # tests/test_minhash.py:390-454
+    assert orc.seq_to_hashes_protein("CADHIFC", 7, "dayhoff").tolist() == [orc.hash_murmur(kat["dayhoff_CADHIFC"])]
+    assert orc.seq_to_hashes_protein("CADHIF*", 7, "dayhoff").tolist() == [orc.hash_murmur(kat["dayhoff_CADHIF*"])]
+    assert orc.seq_to_hashes_protein("ANA", 3, "hp").tolist() == [orc.hash_murmur(kat["hp_ANA"])]
+    assert orc.seq_to_hashes_protein("AN*", 3, "hp").tolist() == [orc.hash_murmur(kat["hp_AN*"])]
+    for mol, n in kat["AGYYG_k2"].items():
+        assert len(set(orc.seq_to_hashes_protein("AGYYG", 2, mol).tolist())) == n
+    for mol in ("protein", "dayhoff", "hp"):
+        assert len(set(orc.seq_to_hashes_translate("ACTGAC", 2, mol).tolist())) == kat["ACTGAC_translate_k2"]
+    assert len(orc.seq_to_hashes_translate("ACTGA", 2, "dayhoff")) == 0      # test_minhash.py:283-287
+    assert len(orc.seq_to_hashes_protein("AG", 9, "protein")) == 0          # test_minhash.py:456-461
+    assert len(orc.seq_to_hashes_protein("AGY", 2, "protein")) == kat["AGY_k2_protein"]
+    assert len(orc.seq_to_hashes_protein("AGY", 1, "protein")) == kat["AGY_k1_protein"]
+    with pytest.raises(ValueError):
+        orc.seq_to_hashes_protein("ATGAGAGACGATAGACAGATGACC", 7, "dna")     # test_minhash.py:242-249
+    # lower case is folded before hashing (signature.rs:214)
+    assert orc.seq_to_hashes_protein("agyyg", 2).tolist() == orc.seq_to_hashes_protein("AGYYG", 2).tolist()
+    # force && bad_kmers_as_zeroes: the iterator's two bookkeeping zeros surround the hashes
+    hz = orc.seq_to_hashes_translate("ACTGACTGA", 2, keep_zeros=True)
+    h = orc.seq_to_hashes_translate("ACTGACTGA", 2)
+    assert hz[0] == 0 and hz[-1] == 0 and hz[1:-1].tolist() == h.tolist() and len(h) == 2 * (9 - 6 + 1)
+
+
+def test_protein_benchmark_sigs(golden, golden_dir):
+    """tests/test_sourmash_sketch.py:1340-1376: the reference's own known-good protein sketches."""
+    info = golden["meta"]["protein_benchmarks"]
+    prots = dict((n.split()[0], s) for n, s in _fasta_records(golden_dir / "ecoli.faa"))
+    genes = dict((n.split()[0], s) for n, s in _fasta_records(golden_dir / "ecoli.genes.fna"))
+    i = info["input_prot"]
+    mh = orc.OracleMinHash(scaled=0, ksize=i["ksize"], num=i["num"], seed=i["seed"])
+    mh.add_protein_family(prots[i["name"].split()[0]], "protein", True)
+    assert np.array_equal(mh.mins(), golden["arrays"]["bench_input_prot"])
+    assert mh.md5sum() == i["md5sum"]
+    t = info["translate_prot"]
+    mh = orc.OracleMinHash(scaled=0, ksize=t["ksize"], num=t["num"], seed=t["seed"])
+    mh.add_protein_family(genes[t["name"].split()[0]], "protein", False)
+    assert np.array_equal(mh.mins(), golden["arrays"]["bench_translate_prot"])
+    assert mh.md5sum() == t["md5sum"]
+
+
+def test_protein_2x2_similarities(golden, golden_dir):
+    """tests/test_sourmash_compute.py:810-860: protein input vs translated genes, k=21, num=500."""
+    want = golden["meta"]["protein_2x2"]
+    prots = sorted(_fasta_records(golden_dir / "ecoli.faa"))
+    genes = sorted(_fasta_records(golden_dir / "ecoli.genes.fna"))
+    aa, tr = [], []
+    for _, s in prots:
+        mh = orc.OracleMinHash(scaled=0, ksize=21, num=500)
+        mh.add_protein_family(s, "protein", True)
+        aa.append(mh.mins())
+    for _, s in genes:
+        mh = orc.OracleMinHash(scaled=0, ksize=21, num=500)
+        mh.add_protein_family(s, "protein", False)
+        tr.append(mh.mins())
+    assert round(orc.jaccard(aa[0], tr[0], num=500), 3) == want["aa1_trans1"]
+    assert round(orc.jaccard(aa[1], tr[0], num=500), 3) == want["aa2_trans1"]
+    assert round(orc.jaccard(aa[0], tr[1], num=500), 3) == want["aa1_trans2"]
+    assert round(orc.jaccard(aa[1], tr[1], num=500), 3) == want["aa2_trans2"]
