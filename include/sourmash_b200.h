@@ -102,6 +102,11 @@ SourmashStr sourmash_str_from_cstr(const char *s);
 /* --- hash primitive: src/core/src/ffi/mod.rs:22-31 -> lib.rs:57-59 ---------------------- */
 uint64_t hash_murmur(const char *kmer, uint64_t seed);
 
+/* --- residue encodings: src/core/src/ffi/minhash.rs:157-178 -> encodings.rs:298-343 ------- */
+char sourmash_translate_codon(const char *codon);   /* 1..3 bases; else InvalidCodonLength */
+char sourmash_aa_to_dayhoff(char aa);
+char sourmash_aa_to_hp(char aa);
+
 /* --- KmerMinHash: src/core/src/ffi/minhash.rs:18-483 (include/sourmash.h:169-273) -------- */
 SourmashKmerMinHash *kmerminhash_new(uint64_t scaled, uint32_t k, HashFunctions hash_function,
                                      uint64_t seed, bool track_abundance, uint32_t n);

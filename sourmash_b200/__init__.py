@@ -10,7 +10,7 @@ Drop-in for the two hot paths of sourmash (include/sourmash_b200.h):
 from . import batch  # noqa: F401
 from ._lowlevel import ffi, lib  # noqa: F401
 from .minhash import (FrozenMinHash, MinHash, get_minhash_default_seed, get_minhash_max_hash,  # noqa: F401
-                      hash_murmur)
+                      hash_murmur, translate_codon)
 from .signature import (ComputeParameters, SourmashSignature, load_signatures,  # noqa: F401
                         load_signatures_from_json, save_signatures_to_json)
 

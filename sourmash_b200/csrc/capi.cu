@@ -275,6 +275,11 @@ struct SketchParams {
     uint32_t num = 0;
     uint64_t seed = 42;
     bool track = false;
+    // protein-family sketches: ksizes hold the ABI value (3 x residues, signature.rs:200-203);
+    // input_is_protein: streams are residues (add_protein) instead of DNA to translate
+    HashFunctions hash_function = HASH_FUNCTIONS_MURMUR64_DNA;
+    bool input_is_protein = false;
+    bool aa_mode() const { return hash_function != HASH_FUNCTIONS_MURMUR64_DNA; }
 };
 
 // expected survivors -> capacity with slack
@@ -307,6 +312,12 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
         for (size_t j = 0; j < nk; ++j) {
             uint64_t k = P.ksizes[j];
             uint64_t nw = (k > 0 && in.len[i] >= k) ? in.len[i] - k + 1 : 0;
+            if (P.aa_mode()) {
+                // residues: windows of k/3; DNA: every window of 3*(k/3) bases is hashed on both
+                // strands (signature.rs:307-345)
+                const uint64_t kaa = k / 3, span = P.input_is_protein ? kaa : 3 * kaa;
+                nw = (kaa > 0 && in.len[i] >= span) ? (in.len[i] - span + 1) * (P.input_is_protein ? 1 : 2) : 0;
+            }
             row_windows[sk * nk + j] += nw;
             n_kmers += nw;
         }
@@ -368,6 +379,24 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
     }
     for (size_t r = 0; r < n_rows; ++r) cap[r] = cap_for(row_windows[r], kthr[r % nk]);
 
+    DevBuf<uint8_t> d_aa_tables;
+    if (P.aa_mode()) {
+        for (uint32_t k : P.ksizes)
+            if (k / 3 > smb::aa_max_k(!P.input_is_protein))
+                fail(SOURMASH_ERROR_CODE_INTERNAL, "protein-family ksize too large for the shared-memory tile");
+        const smb::AaTables T = smb::build_aa_tables((int)P.hash_function);
+        d_aa_tables.alloc(sizeof T, s);
+        d_aa_tables.upload((const uint8_t*)&T, sizeof T);
+        sync(s);                                           // T is a stack temporary
+    }
+    const smb::AaTables* d_tabs = (const smb::AaTables*)d_aa_tables.p;
+    auto launch_k = [&](smb::HashLaunch& L, size_t j, uint32_t r0, uint32_t r1, uint32_t g0, uint32_t g1) {
+        if (P.aa_mode())
+            smb::launch_hash_aa_range(L, d_tabs, P.ksizes[j] / 3, !P.input_is_protein, (int)j, g0, g1, s);
+        else
+            smb::launch_hash_kmers_range(L, P.ksizes[j], (int)j, r0, r1, g0, g1, s);
+    };
+
     bool uploaded = false;
     for (int attempt = 0; attempt < 4; ++attempt) {
         for (size_t r = 0; r < n_rows; ++r) cand_off[r + 1] = cand_off[r] + cap[r];
@@ -405,8 +434,7 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
                 CK(cudaStreamWaitEvent(s, ev, 0));
                 for (size_t j = 0; j < nk; ++j) {
                     L.max_hash = kthr[j];
-                    smb::launch_hash_kmers_range(L, P.ksizes[j], (int)j, tile_r[g0], tile_r[g1], tile_g[g0],
-                                                 tile_g[g1], s);
+                    launch_k(L, j, tile_r[g0], tile_r[g1], tile_g[g0], tile_g[g1]);
                 }
                 g0 = g1;
             }
@@ -414,7 +442,7 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
         } else {
             for (size_t j = 0; j < nk; ++j) {
                 L.max_hash = kthr[j];
-                smb::launch_hash_kmers_k(L, P.ksizes[j], (int)j, s);
+                launch_k(L, j, 0, tile_r[ns], 0, tile_g[ns]);
             }
         }
         if (t_profiling) t_timer_hash.end(s);
@@ -683,10 +711,36 @@ typedef SourmashKmerMinHash MH;
 
 // hash one sequence on the GPU and fold the survivors into the sketch.
 // signature.rs:38-58 (+ :271-279 for the !force error, raised after earlier windows were added)
+// protein-family sketch fed residues (add_protein, signature.rs:60-80) or DNA to translate in six
+// frames (add_sequence on such a sketch, signature.rs:307-357; no validity check, `force` unused)
+void mh_add_aa(MH& mh, const uint8_t* seq, size_t len, bool input_is_protein) {
+    const size_t kaa = mh.ksize / 3;                     // signature.rs:200-203
+    if (len < kaa) return;                               // max_index == 0: the iterator ends at once
+    if (mh.hash_function == HASH_FUNCTIONS_MURMUR64_DNA) // only reachable with input_is_protein
+        fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION, "Invalid hash function: \"DNA\"");   // :376-380
+    if (kaa == 0 || (!input_is_protein && len < 3 * kaa)) return;       // signature.rs:259-262
+    cudaStream_t s = need_gpu();
+    DevBuf<uint8_t> d_seq(len + 32, s);
+    d_seq.upload(seq, len);
+    StreamList in;
+    in.d_bases = d_seq.p;
+    in.off = {0}; in.len = {len}; in.n_sketches = 1;
+    SketchParams P;
+    P.ksizes = {mh.ksize}; P.max_hash = mh.max_hash; P.num = mh.num; P.seed = mh.seed;
+    P.track = mh.track; P.hash_function = mh.hash_function; P.input_is_protein = input_is_protein;
+    auto set = sketch_streams(in, P, s, nullptr);
+    const size_t n = set->total();
+    std::vector<uint64_t> h(n), ab(mh.track ? n : 0);
+    if (n) {
+        CK(cudaMemcpyAsync(h.data(), set->d_hashes, n * 8, cudaMemcpyDeviceToHost, s));
+        if (mh.track) CK(cudaMemcpyAsync(ab.data(), set->d_abunds, n * 8, cudaMemcpyDeviceToHost, s));
+        sync(s);
+    }
+    mh.absorb_sorted(h.data(), mh.track ? ab.data() : nullptr, n);
+}
+
 void mh_add_sequence(MH& mh, const uint8_t* seq, size_t len, bool force) {
-    if (mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA)
-        fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
-             "Invalid hash function: translated / protein k-mers are outside the B200 hot path");
+    if (mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA) { mh_add_aa(mh, seq, len, false); return; }
     const size_t k = mh.ksize;
     if (k == 0 || len < k) return;                       // signature.rs:206-210
     cudaStream_t s = need_gpu();
@@ -754,6 +808,50 @@ void add_sequence_group(std::vector<MH*>& group, const uint8_t* seq, size_t len)
         const size_t o = set->h_off[j], c = set->h_off[j + 1] - o;
         group[j]->absorb_sorted(h.data() + o, f.track ? ab.data() + o : nullptr, c);
     }
+}
+
+// seq_to_hashes for protein-family sketches (ffi/minhash.rs:63-99 over signature.rs:307-392):
+// hashes in the reference's order; zeros dropped unless keep_zeros, in which case the translate
+// iterator's two bookkeeping Ok(0) items (signature.rs:346,351) are part of the output too.
+std::vector<uint64_t> aa_seq_to_hashes(const MH& mh, const uint8_t* seq, size_t len, bool is_protein,
+                                       bool keep_zeros) {
+    std::vector<uint64_t> out;
+    const size_t kaa = mh.ksize / 3;
+    if (len < kaa) return out;
+    if (is_protein && mh.hash_function == HASH_FUNCTIONS_MURMUR64_DNA)
+        fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION, "Invalid hash function: \"DNA\"");
+    const bool translate = !is_protein;
+    if (kaa == 0 || (translate && len < 3 * kaa)) return out;
+    if (kaa > smb::aa_max_k(translate))
+        fail(SOURMASH_ERROR_CODE_INTERNAL, "protein-family ksize too large for the shared-memory tile");
+    cudaStream_t s = need_gpu();
+    const size_t span = translate ? 3 * kaa : kaa;
+    const size_t nraw = (len - span + 1) * (translate ? 2 : 1);
+    DevBuf<uint8_t> d_seq(len + 32, s), d_tabs(sizeof(smb::AaTables), s);
+    d_seq.upload(seq, len);
+    const smb::AaTables T = smb::build_aa_tables((int)mh.hash_function);
+    d_tabs.upload((const uint8_t*)&T, sizeof T);
+    DevBuf<uint64_t> d_raw(nraw, s);
+    uint64_t off = 0, ln = len;
+    uint32_t tg[2] = {0, (uint32_t)((len + 255) / 256)};
+    DevBuf<uint64_t> d_off(1, s), d_len(1, s);
+    DevBuf<uint32_t> d_tg(2, s);
+    d_off.upload(&off, 1); d_len.upload(&ln, 1); d_tg.upload(tg, 2);
+    smb::HashLaunch L{};
+    L.bases = d_seq.p; L.stream_off = d_off.p; L.stream_len = d_len.p; L.stream_row = nullptr;
+    L.n_streams = 1; L.tile_start_rolled = d_tg.p; L.total_tiles_rolled = 0;
+    L.tile_start_generic = d_tg.p; L.total_tiles_generic = tg[1];
+    L.W = 16; L.seed = mh.seed; L.max_hash = UINT64_MAX;
+    smb::launch_aa_window_hashes(L, (const smb::AaTables*)d_tabs.p, (uint32_t)kaa, translate, len, d_raw.p, s);
+    CK(cudaGetLastError());
+    std::vector<uint64_t> raw(nraw);
+    d_raw.download(raw.data(), nraw);
+    sync(s);
+    out.reserve(nraw + 2);
+    if (translate && keep_zeros) out.push_back(0);
+    for (uint64_t h : raw) if (h != 0 || keep_zeros) out.push_back(h);
+    if (translate && keep_zeros) out.push_back(0);
+    return out;
 }
 
 struct PairCounts { uint64_t common, usize; };
@@ -913,6 +1011,23 @@ uint64_t hash_murmur(const char* kmer, uint64_t seed) {
     return guarded<uint64_t>([&] { return murmur_on_gpu((const uint8_t*)kmer, strlen(kmer), seed); });
 }
 
+// residue encodings (ffi/minhash.rs:157-178): scalar table lookups on the tables the kernel uses
+char sourmash_translate_codon(const char* codon) {
+    return guarded<char>([&]() -> char {
+        const size_t n = strlen(codon);
+        if (n == 1) return 'X';                                            // encodings.rs:299-301
+        if (n != 2 && n != 3)
+            fail(SOURMASH_ERROR_CODE_INVALID_CODON_LENGTH, "Codon is invalid length: " + std::to_string(n));
+        const smb::AaTables T = smb::build_aa_tables((int)HASH_FUNCTIONS_MURMUR64_PROTEIN);
+        // no case folding here: translate_codon looks the bytes up as they are (encodings.rs:303-321)
+        auto code = [&](char c) -> uint32_t { return (c >= 'a' && c <= 'z') ? 5u : T.base_code[(uint8_t)c]; };
+        const uint32_t c2 = n == 3 ? code(codon[2]) : 4u;                  // two bases: third is 'N'
+        return (char)T.codon[code(codon[0]) * 36 + code(codon[1]) * 6 + c2];
+    });
+}
+char sourmash_aa_to_dayhoff(char aa) { return (char)smb::aa_reencode((uint8_t)aa, (int)HASH_FUNCTIONS_MURMUR64_DAYHOFF); }
+char sourmash_aa_to_hp(char aa) { return (char)smb::aa_reencode((uint8_t)aa, (int)HASH_FUNCTIONS_MURMUR64_HP); }
+
 // ------------------------------------------------------------------------------------------
 SourmashKmerMinHash* kmerminhash_new(uint64_t scaled, uint32_t k, HashFunctions hash_function,
                                      uint64_t seed, bool track_abundance, uint32_t n) {
@@ -927,9 +1042,8 @@ void kmerminhash_slice_free(uint64_t* ptr, uintptr_t) { free(ptr); }
 void kmerminhash_add_sequence(SourmashKmerMinHash* ptr, const char* sequence, bool force) {
     guarded_void([&] { mh_add_sequence(*ptr, (const uint8_t*)sequence, strlen(sequence), force); });
 }
-void kmerminhash_add_protein(SourmashKmerMinHash*, const char*) {
-    set_error(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
-              "Invalid hash function: protein k-mers are outside the B200 hot path");
+void kmerminhash_add_protein(SourmashKmerMinHash* ptr, const char* sequence) {
+    guarded_void([&] { mh_add_aa(*ptr, (const uint8_t*)sequence, strlen(sequence), true); });
 }
 
 const uint64_t* kmerminhash_seq_to_hashes(SourmashKmerMinHash* ptr, const char* sequence,
@@ -938,9 +1052,11 @@ const uint64_t* kmerminhash_seq_to_hashes(SourmashKmerMinHash* ptr, const char* 
     return guarded<const uint64_t*>([&]() -> const uint64_t* {
         // ffi/minhash.rs:63-99
         MH& mh = *ptr;
-        if (is_protein || mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA)
-            fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
-                 "Invalid hash function: translated / protein k-mers are outside the B200 hot path");
+        if (is_protein || mh.hash_function != HASH_FUNCTIONS_MURMUR64_DNA) {
+            std::vector<uint64_t> out = aa_seq_to_hashes(mh, (const uint8_t*)sequence, insize, is_protein,
+                                                         force && bad_kmers_as_zeroes);
+            return to_boxed(out, size);
+        }
         std::vector<uint64_t> out;
         const size_t k = mh.ksize, len = insize;
         if (k > 0 && len >= k) {
@@ -1111,14 +1227,16 @@ void signature_free(SourmashSignature* ptr) { delete ptr; }
 SourmashSignature* signature_from_params(const SourmashComputeParameters* p) {
     // cmd.rs:109-188 build_template: one sketch per ksize for each enabled molecule type
     return guarded<SourmashSignature*>([&]() -> SourmashSignature* {
-        if (p->protein || p->dayhoff || p->hp)
-            fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
-                 "Invalid hash function: protein / dayhoff / hp sketches are outside the B200 hot path");
         auto* sig = new SourmashSignature();
-        if (p->dna) {
-            for (uint32_t k : p->ksizes) {
+        for (uint32_t k : p->ksizes) {                      // per ksize: protein, dayhoff, hp, dna
+            const std::pair<bool, HashFunctions> kinds[4] = {
+                {p->protein, HASH_FUNCTIONS_MURMUR64_PROTEIN}, {p->dayhoff, HASH_FUNCTIONS_MURMUR64_DAYHOFF},
+                {p->hp, HASH_FUNCTIONS_MURMUR64_HP}, {p->dna, HASH_FUNCTIONS_MURMUR64_DNA}};
+            for (const auto& kind : kinds) {
+                if (!kind.first) continue;
                 MH m;
                 m.num = p->num_hashes; m.ksize = k; m.seed = p->seed; m.track = p->track_abundance;
+                m.hash_function = kind.second;
                 m.max_hash = max_hash_for_scaled(p->scaled);
                 sig->sketches.push_back(m);
             }
@@ -1158,9 +1276,12 @@ void signature_add_sequence(SourmashSignature* ptr, const char* sequence, bool f
         }
     });
 }
-void signature_add_protein(SourmashSignature*, const char*) {
-    set_error(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION,
-              "Invalid hash function: protein k-mers are outside the B200 hot path");
+void signature_add_protein(SourmashSignature* ptr, const char* sequence) {
+    // signature.rs:679-697: every sketch of the signature sees the residues
+    guarded_void([&] {
+        const size_t len = strlen(sequence);
+        for (auto& mh : ptr->sketches) mh_add_aa(mh, (const uint8_t*)sequence, len, true);
+    });
 }
 SourmashKmerMinHash* signature_first_mh(const SourmashSignature* ptr) {
     // ffi/signature.rs:169-185 returns a clone

@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "aa_kmers.cuh"
+
 namespace smb {
 
 // ---------------------------------------------------------------- intersection path
@@ -124,6 +126,15 @@ void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index,
                              uint32_t tile_hi_r, uint32_t tile_lo_g, uint32_t tile_hi_g, cudaStream_t s);
 // per-window hashes of stream 0 in order; 0 marks an invalid window (seq_to_hashes)
 void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s);
+// protein-family sketches (aa_kmers.cuh): windows of kaa residues, read as they are
+// (translate == false; streams hold residues) or from DNA translated in six frames (two hashes per
+// window of 3*kaa bases).  Uses the generic (256 positions per CTA) tiling of HashLaunch.
+uint32_t aa_max_k(bool translate);
+void launch_hash_aa_range(const HashLaunch& L, const AaTables* d_tables, uint32_t kaa, bool translate,
+                          int row_index, uint32_t tile_lo, uint32_t tile_hi, cudaStream_t s);
+// per-window hashes of stream 0 (length len) in the reference's seq_to_hashes order
+void launch_aa_window_hashes(const HashLaunch& L, const AaTables* d_tables, uint32_t kaa, bool translate,
+                             uint64_t len, uint64_t* raw_out, cudaStream_t s);
 // first non-ACGT position of a sequence (UINT64_MAX if none)
 void launch_first_invalid(const uint8_t* bases, uint64_t len, unsigned long long* d_pos,
                           cudaStream_t s);

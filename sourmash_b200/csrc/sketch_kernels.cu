@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "kmer_roll.cuh"
+#include "aa_kmers.cuh"
 
 namespace smb {
 
@@ -219,6 +220,112 @@ void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out
     HashArgs a = make_hash_args(L, rolled, 0);
     a.stream_row = nullptr; a.row_stride = 1; a.row_index = 0; a.raw_out = raw_out;
     launch_hash_one_k<true>(a, ksize, rolled, rolled ? L.total_tiles_rolled : L.total_tiles_generic, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// Protein-family sketches (csrc/aa_kmers.cuh): residues, or DNA translated in six frames.
+// One CTA = AA_TILE window starts.  The residue of every position of the tile (forward codon and
+// reverse-complement codon for translated input) is computed once into shared memory; each
+// thread then hashes its window from there (byte gathers at stride 1 or 3 are conflict free:
+// consecutive threads read consecutive bytes).  Survivors are staged per CTA as in the DNA kernel.
+// ---------------------------------------------------------------------------------------
+static constexpr int AA_TABLE_BYTES = (sizeof(AaTables) + 15) & ~15;
+
+template <bool RAW>
+__global__ void __launch_bounds__(AA_TILE) hash_aa_kernel(HashArgs a, const AaTables* __restrict__ tabs,
+                                                          u32 kaa, u32 translate, AaFrames F) {
+    extern __shared__ __align__(16) unsigned char aa_smem[];
+    __shared__ u64 s_buf[2 * AA_TILE];
+    __shared__ u32 s_cnt, s_base;
+    __shared__ int s_stream;
+    const int tid = threadIdx.x;
+    AaTables* T = reinterpret_cast<AaTables*>(aa_smem);
+    const u32 stride = translate ? 3u : 1u;
+    const u32 nst = aa_stage_len(kaa, stride);
+    u8* sf = aa_smem + AA_TABLE_BYTES;
+    u8* sr = sf + ((nst + 15u) & ~15u);
+    for (u32 i = tid; i < sizeof(AaTables) / 4; i += AA_TILE)
+        reinterpret_cast<u32*>(T)[i] = reinterpret_cast<const u32*>(tabs)[i];
+    if (tid == 0) {
+        s_cnt = 0;
+        s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x + a.tile_base);
+    }
+    __syncthreads();
+    const int stream = s_stream;
+    const u64 L = a.stream_len[stream];
+    const u8* __restrict__ seq = a.bases + a.stream_off[stream];
+    const u64 span = (u64)kaa * stride;
+    if (kaa == 0 || L < span) return;
+    const u64 t0 = (u64)(blockIdx.x + a.tile_base - a.tile_start[stream]) * AA_TILE;
+    if (t0 + span > L) return;                          // no window starts in this tile
+    for (u32 i = tid; i < nst; i += AA_TILE) aa_stage(*T, translate != 0, seq, L, t0, i, sf, sr);
+    __syncthreads();
+    const u64 p = t0 + tid;
+    const bool valid = p + span <= L;
+    const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
+    const int row = sk * a.row_stride + a.row_index;
+    if (valid) {
+        const u64 hf = aa_hash_fwd(sf, (u32)tid, kaa, stride, a.seed);
+        u64 hr = 0;
+        if (translate) hr = aa_hash_rev(sr, (u32)tid, kaa, a.seed);
+        if (RAW) {
+            if (translate) {
+                a.raw_out[aa_raw_index(F, p, false)] = hf;
+                a.raw_out[aa_raw_index(F, L - p - span, true)] = hr;
+            } else {
+                a.raw_out[p] = hf;
+            }
+        } else {
+            if (hf != 0ull && hf <= a.max_hash) s_buf[atomicAdd(&s_cnt, 1u)] = hf;
+            if (translate && hr != 0ull && hr <= a.max_hash) s_buf[atomicAdd(&s_cnt, 1u)] = hr;
+        }
+    }
+    if (RAW) return;
+    __syncthreads();
+    const u32 n = s_cnt;
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(&a.cand_cnt[row], n);
+    __syncthreads();
+    const u64 off = a.cand_off[row];
+    const u64 capr = a.cand_off[row + 1] - off;
+    for (u32 i = tid; i < n; i += AA_TILE) {
+        u64 g = (u64)s_base + i;
+        if (g < capr) a.cand[off + g] = s_buf[i];
+    }
+}
+
+size_t aa_smem_bytes(uint32_t kaa, bool translate) {
+    const u32 nst = aa_stage_len(kaa ? kaa : 1, translate ? 3u : 1u);
+    return (size_t)AA_TABLE_BYTES + 2 * (size_t)((nst + 15u) & ~15u);
+}
+uint32_t aa_max_k(bool translate) {
+    // both staging arrays must fit next to the tables in 200 KB of dynamic shared memory
+    const size_t budget = 200 * 1024 - AA_TABLE_BYTES - 64;
+    return (uint32_t)((budget / 2 - AA_TILE) / (translate ? 3 : 1));
+}
+
+template <bool RAW>
+static void launch_hash_aa(HashArgs a, const AaTables* d_tables, u32 kaa, bool translate, AaFrames F,
+                           u32 n_tiles, cudaStream_t s) {
+    if (n_tiles == 0 || kaa == 0) return;
+    const size_t smem = aa_smem_bytes(kaa, translate);
+    cudaFuncSetAttribute(hash_aa_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    hash_aa_kernel<RAW><<<n_tiles, AA_TILE, smem, s>>>(a, d_tables, kaa, translate ? 1u : 0u, F);
+    count_launches(1);
+}
+
+void launch_hash_aa_range(const HashLaunch& L, const AaTables* d_tables, uint32_t kaa, bool translate,
+                          int row_index, uint32_t tile_lo, uint32_t tile_hi, cudaStream_t s) {
+    HashArgs a = make_hash_args(L, false, tile_lo);
+    a.row_index = row_index;
+    launch_hash_aa<false>(a, d_tables, kaa, translate, AaFrames{}, tile_hi - tile_lo, s);
+}
+
+void launch_aa_window_hashes(const HashLaunch& L, const AaTables* d_tables, uint32_t kaa, bool translate,
+                             uint64_t len, uint64_t* raw_out, cudaStream_t s) {
+    HashArgs a = make_hash_args(L, false, 0);
+    a.stream_row = nullptr; a.row_stride = 1; a.row_index = 0; a.raw_out = raw_out;
+    launch_hash_aa<true>(a, d_tables, kaa, translate, aa_frames(len, kaa), L.total_tiles_generic, s);
 }
 
 // ---------------------------------------------------------------------------------------

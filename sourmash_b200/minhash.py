@@ -8,9 +8,8 @@ execute on the GPU.  Float formulas that the reference evaluates in Python
 (bias-corrected containment, minhash.py:819-959) are evaluated here in Python too, in the
 same operation order, so results are bit-identical.
 
-Not ported in this round (outside the hot-path scope): protein / dayhoff / hp
-hashing (objects can be constructed and hold hashes; ``add_protein`` raises) and the ANI
-estimators (``*_ani`` methods).
+Protein / dayhoff / hp sketches hash on the GPU as well (``add_protein`` for residues,
+``add_sequence`` for DNA translated in six frames; csrc/aa_kmers.cuh).
 """
 from collections.abc import Mapping
 
@@ -22,7 +21,7 @@ from ._ffi import RustObject, decode_str, rustcall
 MINHASH_DEFAULT_SEED = 42
 MINHASH_MAX_HASH = 0xFFFFFFFFFFFFFFFF
 
-__all__ = ["MinHash", "FrozenMinHash", "hash_murmur", "get_minhash_default_seed", "get_minhash_max_hash",
+__all__ = ["MinHash", "FrozenMinHash", "hash_murmur", "translate_codon", "get_minhash_default_seed", "get_minhash_max_hash",
            "flatten_and_downsample_scaled", "flatten_and_downsample_num", "flatten_and_intersect_scaled"]
 
 
@@ -51,6 +50,9 @@ def _get_scaled_for_max_hash(max_hash):
     return min(int(round(MINHASH_MAX_HASH / max_hash, 0)), MINHASH_MAX_HASH)
 
 
+_RC_TABLE = str.maketrans("ACGTNacgtn", "TGCANtgcan")     # screed.rc equivalent
+
+
 def to_bytes(s):
     "str / bytes / single int -> bytes"
     if isinstance(s, bytes):
@@ -62,6 +64,15 @@ def to_bytes(s):
     if isinstance(s, (bytearray, memoryview, np.ndarray)):
         return bytes(s)
     raise TypeError("Requires a string-like sequence")
+
+
+def translate_codon(codon):
+    "Translate a codon into an amino acid (minhash.py:96-101)."
+    from .exceptions import SourmashError
+    try:
+        return rustcall(lib.sourmash_translate_codon, to_bytes(codon)).decode("utf-8")
+    except SourmashError as e:
+        raise ValueError(e.message)
 
 
 def hash_murmur(kmer, seed=MINHASH_DEFAULT_SEED):
@@ -226,15 +237,38 @@ class MinHash(RustObject):
             lib.kmerminhash_slice_free(ptr, n)
 
     def kmers_and_hashes(self, sequence, *, force=False, is_protein=False):
-        "Yield (kmer, hash) for every k-mer of a DNA sequence (hash None for invalid k-mers)."
-        if not self.is_dna or is_protein:
-            raise ValueError("kmers_and_hashes: only DNA sketches are on the B200 path")
-        seq = to_bytes(sequence).decode("utf-8") if not isinstance(sequence, str) else sequence
-        k = self.ksize
-        hashes = self.seq_to_hashes(seq, force=force, bad_kmers_as_zeroes=force)
-        for i, h in enumerate(hashes):
-            kmer = seq[i:i + k]
-            yield kmer, (None if (h == 0 and force) else h)
+        """Yield (kmer, hash) for every k-mer without adding them (minhash.py:392-456).
+        DNA into a protein-family sketch is translated in six frames; with ``force`` invalid
+        k-mers come out with hash None."""
+        bad_kmers_as_zeroes = bool(force)
+        sequence = (to_bytes(sequence).decode("utf-8") if not isinstance(sequence, str) else sequence).upper()
+        hashvals = self.seq_to_hashes(sequence, force=force, is_protein=is_protein,
+                                      bad_kmers_as_zeroes=bad_kmers_as_zeroes)
+        if bad_kmers_as_zeroes:
+            hashvals = [None if h == 0 else h for h in hashvals]
+        ksize = self.ksize
+        translate = False
+        if self.moltype == "DNA" or is_protein:
+            pass
+        else:                                   # DNA into protein / dayhoff / hp: translate
+            translate = True
+            ksize = self.ksize * 3
+        if translate:
+            # forward AND reverse complement => twice the k-mers
+            n_kmers = (len(sequence) - ksize + 1) * 2
+            assert n_kmers == len(hashvals)
+            seqrc = sequence[::-1].translate(_RC_TABLE)
+            hash_i = 0
+            for frame in (0, 1, 2):
+                for strand in (sequence, seqrc):
+                    for start in range(0, len(strand) - ksize + 1 - frame, 3):
+                        yield strand[start + frame:start + frame + ksize], hashvals[hash_i]
+                        hash_i += 1
+        else:
+            n_kmers = len(sequence) - ksize + 1
+            assert n_kmers == len(hashvals)
+            for i, hashval in zip(range(0, n_kmers), hashvals):
+                yield sequence[i:i + ksize], hashval
 
     def add_kmer(self, kmer):
         "Add one k-mer."

@@ -109,3 +109,54 @@ def test_tile_table_logic_edge_rows(tile_emul):
     for max_entries in (30000, 16, 2):
         got, (hh, oo) = tile_emul(rows, max_entries=max_entries)
         assert np.array_equal(got, orc.pairwise_common(hh, oo)), max_entries
+
+
+# ---------------------------------------------------------------------------------------------
+# protein-family kernel logic (csrc/aa_kmers.cuh): tables, staging, strided gathers, frame order
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def aa_emul():
+    exe = os.path.join(tempfile.gettempdir(), "smb_aa_emul")
+    src = os.path.join(HERE, "host_emul", "aa_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(seq, moltype, kaa, translate):
+        with tempfile.TemporaryDirectory() as td:
+            fin, fout = os.path.join(td, "in"), os.path.join(td, "out")
+            with open(fin, "wb") as fh:
+                fh.write(bytes(seq))
+            subprocess.check_call([exe, str(orc.HASH_FUNCTIONS[moltype]), str(kaa), str(int(translate)), fin, fout])
+            return np.fromfile(fout, dtype=np.uint64)
+    return run
+
+
+def _messy_dna(n, seed):
+    g = synth_genome(n, seed=seed, n_every=53)
+    g[100:160] = np.frombuffer(bytes(g[100:160]).lower(), dtype=np.uint8)
+    g[200] = ord("R"); g[201] = 0; g[202] = ord("n"); g[-2] = ord("N")
+    return g
+
+
+@pytest.mark.parametrize("moltype", ["protein", "dayhoff", "hp"])
+@pytest.mark.parametrize("kaa", [1, 2, 7, 8, 9, 16, 17, 33, 42])
+def test_aa_translate_matches_oracle(aa_emul, moltype, kaa):
+    for n in (3 * kaa - 1, 3 * kaa, 3 * kaa + 1, 3 * kaa + 2, 700, 1031):
+        g = _messy_dna(max(n, 300), seed=n + kaa)[:n]
+        want = orc.seq_to_hashes_translate(bytes(g), kaa, moltype, keep_zeros=True)
+        got = aa_emul(g, moltype, kaa, True)
+        if n < 3 * kaa:
+            assert len(want) == 0 and len(got) == 0
+        else:
+            assert np.array_equal(got, want[1:-1]), (moltype, kaa, n)
+
+
+@pytest.mark.parametrize("moltype", ["protein", "dayhoff", "hp"])
+@pytest.mark.parametrize("kaa", [1, 3, 7, 10, 16, 19, 42])
+def test_aa_protein_matches_oracle(aa_emul, moltype, kaa):
+    rng = np.random.default_rng(kaa)
+    alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXBZJUO*acdefghiklmnpqrstvwy-\x00", dtype=np.uint8)
+    for n in (kaa - 1, kaa, kaa + 1, 255, 256, 257, 900):
+        seq = alphabet[rng.integers(0, len(alphabet), size=max(n, 0))]
+        want = orc.seq_to_hashes_protein(bytes(seq), kaa, moltype, keep_zeros=True)
+        got = aa_emul(seq, moltype, kaa, False)
+        assert np.array_equal(got, want), (moltype, kaa, n)

@@ -268,3 +268,28 @@ def test_load_reference_written_sig_files(golden):
     # round trip through our writer keeps identity
     again = list(smb.load_signatures_from_json(smb.save_signatures_to_json(s10)))
     assert [a.md5sum() for a in again] == [a.md5sum() for a in s10]
+
+
+def test_residue_encodings_and_protein_guards(golden):
+    """Scalar parts of the protein path that need no GPU (encodings.rs:298-343)."""
+    from sourmash_b200 import translate_codon
+    from sourmash_b200._lowlevel import lib
+    for codon, aa in golden["meta"]["kat"]["translate_codon"].items():
+        assert translate_codon(codon) == aa
+    assert translate_codon("tct") == "X" and translate_codon("TCN") == "S" and translate_codon("TTN") == "X"
+    assert translate_codon("ATG") == "M" and translate_codon("TGA") == "*" and translate_codon("NNN") == "X"
+    for bad in ("", "TCTA"):
+        with pytest.raises(ValueError, match="Codon is invalid length"):
+            translate_codon(bad)
+    for aa in b"ACDEFGHIKLMNPQRSTVWY*XBZ":
+        assert lib.sourmash_aa_to_dayhoff(bytes([aa])) == bytes([orc.lib.orc_aa_to_dayhoff(aa)])
+        assert lib.sourmash_aa_to_hp(bytes([aa])) == bytes([orc.lib.orc_aa_to_hp(aa)])
+    all_codons = ["".join(c) for c in __import__("itertools").product("ACGTNR", repeat=3)]
+    for c in all_codons:
+        assert translate_codon(c) == orc.translate_codon(c), c
+    # shorter than k: nothing happens, even without a GPU and even on a DNA sketch (max_index == 0)
+    smb.MinHash(10, 9, is_protein=True).add_protein("AG")
+    smb.MinHash(0, 31, scaled=1).add_protein("AG")
+    assert smb.MinHash(0, 2, dayhoff=True, scaled=1).seq_to_hashes("ACTGA") == []
+    with pytest.raises(ValueError):
+        smb.MinHash(0, 21, scaled=1).seq_to_hashes("ATGAGAGACGATAGACAGATGACC", is_protein=True)
