@@ -256,6 +256,16 @@ SmbSketchSet *smb_sketch_sequences(const uint8_t *seqs, const uint64_t *seq_offs
                                    uintptr_t n_sketches, const uint32_t *ksizes,
                                    uintptr_t n_ksizes, uint64_t scaled, uint32_t num, uint64_t seed,
                                    bool track_abundance, uint64_t *n_kmers_out);
+/* Protein-family sketches (`sourmash sketch protein` / `sketch translate`,
+ * signature.rs:307-392): hash_function is PROTEIN, DAYHOFF or HP; ksizes carry the ABI value
+ * (3 x residues).  input_is_protein: records are residues (add_protein); otherwise DNA that is
+ * translated in six frames (two hashes per window of ksize bases, no validity filter). */
+SmbSketchSet *smb_sketch_sequences_aa(const uint8_t *seqs, const uint64_t *seq_offsets,
+                                      uintptr_t n_seqs, const uint32_t *seq_to_sketch,
+                                      uintptr_t n_sketches, const uint32_t *ksizes,
+                                      uintptr_t n_ksizes, HashFunctions hash_function,
+                                      bool input_is_protein, uint64_t scaled, uint32_t num,
+                                      uint64_t seed, bool track_abundance, uint64_t *n_kmers_out);
 /* Same with the bases already in HBM: d_bases holds the streams back to back, stream s at
  * byte h_stream_offsets[s] (16-byte aligned) with length h_stream_lens[s]; records inside a
  * stream separated by any non-ACGT byte.  One sketch per stream. */

@@ -158,9 +158,16 @@ class SketchSet:
                 int(ffi.cast("uintptr_t", lib.smb_sketchset_device_offsets(self._ptr))))
 
 
+_HASH_FUNCTIONS = {"dna": 1, "protein": 2, "dayhoff": 3, "hp": 4}
+
+
 def sketch_sequences(seqs, seq_offsets, ksizes, scaled=0, num=0, seed=42, track_abundance=False,
-                     seq_to_sketch=None, n_sketches=None):
-    """Sketch a batch of records.  Returns (SketchSet, n_kmers); row = sketch * len(ksizes) + k_index."""
+                     seq_to_sketch=None, n_sketches=None, moltype="DNA", input_is_protein=False):
+    """Sketch a batch of records.  Returns (SketchSet, n_kmers); row = sketch * len(ksizes) + k_index.
+
+    ``moltype`` "protein" / "dayhoff" / "hp" builds protein-family sketches (ksizes in residues):
+    from residues when ``input_is_protein`` (sketch protein), else from DNA translated in six
+    frames (sketch translate)."""
     if isinstance(seqs, (bytes, bytearray)):
         seqs = np.frombuffer(seqs, dtype=np.uint8)
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
@@ -175,6 +182,16 @@ def sketch_sequences(seqs, seq_offsets, ksizes, scaled=0, num=0, seed=42, track_
     else:
         n_sketches = n_seqs
     nk = ffi.new("uint64_t *")
+    hf = _HASH_FUNCTIONS[moltype.lower()]
+    if hf != 1:
+        ks = np.ascontiguousarray(ks * np.uint32(3))           # ABI ksize of protein-family sketches
+        p = rustcall(lib.smb_sketch_sequences_aa, _ptr(seqs, "uint8_t *"), _ptr(seq_offsets, "uint64_t *"), n_seqs,
+                     _ptr(s2s, "uint32_t *") if s2s is not None else ffi.NULL, n_sketches,
+                     _ptr(ks, "uint32_t *"), len(ks), hf, bool(input_is_protein), int(scaled), int(num),
+                     int(seed), bool(track_abundance), nk)
+        return SketchSet(p), int(nk[0])
+    if input_is_protein:
+        raise ValueError("cannot add protein sequence to DNA MinHash")
     p = rustcall(lib.smb_sketch_sequences, _ptr(seqs, "uint8_t *"), _ptr(seq_offsets, "uint64_t *"), n_seqs,
                  _ptr(s2s, "uint32_t *") if s2s is not None else ffi.NULL, n_sketches,
                  _ptr(ks, "uint32_t *"), len(ks), int(scaled), int(num), int(seed), bool(track_abundance), nk)

@@ -1491,6 +1491,35 @@ SmbSketchSet* smb_sketch_sequences(const uint8_t* seqs, const uint64_t* seq_offs
     });
 }
 
+SmbSketchSet* smb_sketch_sequences_aa(const uint8_t* seqs, const uint64_t* seq_offsets,
+                                      uintptr_t n_seqs, const uint32_t* seq_to_sketch,
+                                      uintptr_t n_sketches, const uint32_t* ksizes,
+                                      uintptr_t n_ksizes, HashFunctions hash_function,
+                                      bool input_is_protein, uint64_t scaled, uint32_t num,
+                                      uint64_t seed, bool track_abundance, uint64_t* n_kmers_out) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        if (hash_function != HASH_FUNCTIONS_MURMUR64_PROTEIN && hash_function != HASH_FUNCTIONS_MURMUR64_DAYHOFF &&
+            hash_function != HASH_FUNCTIONS_MURMUR64_HP)
+            fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION, "Invalid hash function: \"DNA\"");
+        cudaStream_t s = need_gpu();
+        const uint64_t total = n_seqs ? seq_offsets[n_seqs] : 0;
+        DevBuf<uint8_t> d_bases(total + 32, s);
+        StreamList in;
+        in.d_bases = d_bases.p;
+        in.h_bases = seqs;
+        in.total_bytes = total;
+        in.off.assign(seq_offsets, seq_offsets + n_seqs);
+        in.len.resize(n_seqs);
+        for (size_t i = 0; i < n_seqs; ++i) in.len[i] = seq_offsets[i + 1] - seq_offsets[i];
+        if (seq_to_sketch) in.row.assign(seq_to_sketch, seq_to_sketch + n_seqs);
+        in.n_sketches = seq_to_sketch ? n_sketches : n_seqs;
+        SketchParams P = make_params(ksizes, n_ksizes, scaled, num, seed, track_abundance);
+        P.hash_function = hash_function;
+        P.input_is_protein = input_is_protein;
+        return sketch_streams(in, P, s, n_kmers_out).release();
+    });
+}
+
 SmbSketchSet* smb_sketch_streams_dev(const uint8_t* d_bases, const uint64_t* h_stream_offsets,
                                      const uint64_t* h_stream_lens, uintptr_t n_streams,
                                      const uint32_t* ksizes, uintptr_t n_ksizes, uint64_t scaled,

@@ -178,3 +178,36 @@ def test_signature_template_all_moltypes(smb, golden_dir):             # signatu
     sig2 = smb.SourmashSignature.from_params(p2)                       # signature.rs:1020-1039
     sig2.add_protein("AGY")
     assert [len(m) for m in sig2.sketches()] == [3, 2]
+
+
+@pytest.mark.parametrize("moltype,input_is_protein", [("protein", True), ("dayhoff", True), ("hp", False), ("protein", False)])
+def test_batched_protein_sketching(smb, moltype, input_is_protein, golden_dir):
+    """smb_sketch_sequences_aa: many records, two ksizes, records grouped into sketches."""
+    from sourmash_b200 import batch as B
+    from sourmash_b200.synth import synth_genome
+    rng = np.random.default_rng(7)
+    if input_is_protein:
+        alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY*X", dtype=np.uint8)
+        recs = [bytes(alphabet[rng.integers(0, len(alphabet), size=n)]) for n in (5000, 3, 0, 1200, 257, 256, 9000)]
+    else:
+        recs = [bytes(synth_genome(n, seed=n, n_every=97 if n % 2 else 0)) for n in (30000, 20, 0, 7001, 768, 40000, 29)]
+    owner = [0, 0, 1, 1, 2, 3, 3]
+    offs = np.cumsum([0] + [len(r) for r in recs]).astype(np.uint64)
+    seqs = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    ks = [7, 10]
+    sset, nk = B.sketch_sequences(seqs, offs, ks, scaled=10, moltype=moltype, input_is_protein=input_is_protein,
+                                  seq_to_sketch=np.array(owner, dtype=np.uint32), n_sketches=4, track_abundance=True)
+    h, off, ab = sset.to_host(with_abunds=True)
+    total = 0
+    for s in range(4):
+        for j, k in enumerate(ks):
+            o = orc.OracleMinHash(scaled=10, ksize=3 * k, track_abundance=True)
+            for r, ow in zip(recs, owner):
+                if ow == s:
+                    o.add_protein_family(r, moltype, input_is_protein)
+                    span = k if input_is_protein else 3 * k
+                    total += max(len(r) - span + 1, 0) * (1 if input_is_protein else 2)
+            row = slice(int(off[s * 2 + j]), int(off[s * 2 + j + 1]))
+            assert np.array_equal(h[row], o.mins()), (s, k)
+            assert np.array_equal(ab[row], o.abunds()), (s, k)
+    assert nk == total
