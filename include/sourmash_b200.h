@@ -328,6 +328,83 @@ uintptr_t smb_gather_intersect(SmbGatherState *st, uint32_t row, uint64_t *out_h
 uintptr_t smb_gather_apply(SmbGatherState *st, const uint64_t *intersect, uintptr_t n);
 void smb_gather_end(SmbGatherState *st);
 
+/* ==========================================================================================
+ * Part 3: native ingest -- the data formats either side of the hot paths,
+ * read without per-record Python so that they do not dominate end to end.
+ * ======================================================================================== */
+/* FASTA / FASTQ, plain or gzip (decided per file from its content); replaces the screed record
+ * loop of src/sourmash/command_sketch.py:697-766.  Record name = the header line after the
+ * marker, sequence = the record's lines joined.  Files are read by up to n_threads threads
+ * (<= 0: one per core, at most 32); records keep input order.  The sequence bytes live in
+ * page-locked memory when a GPU is present, so smb_sketch_records uploads them at full speed. */
+typedef struct SmbRecords SmbRecords;
+SmbRecords *smb_records_read(const char *const *paths, uintptr_t n_paths, int32_t n_threads);
+void smb_records_free(SmbRecords *r);
+uintptr_t smb_records_len(const SmbRecords *r);
+uint64_t smb_records_total_bytes(const SmbRecords *r);
+const uint8_t *smb_records_data(const SmbRecords *r);
+const uint64_t *smb_records_offsets(const SmbRecords *r);          /* n + 1 */
+const uint32_t *smb_records_files(const SmbRecords *r);            /* n: index into paths */
+const char *smb_records_names(const SmbRecords *r, const uint64_t **name_offsets);
+/* sketch the records of a batch (smb_sketch_sequences / smb_sketch_sequences_aa on its buffers);
+ * hash_function DNA ignores input_is_protein */
+SmbSketchSet *smb_sketch_records(const SmbRecords *r, const uint32_t *rec_to_sketch,
+                                 uintptr_t n_sketches, const uint32_t *ksizes, uintptr_t n_ksizes,
+                                 HashFunctions hash_function, bool input_is_protein, uint64_t scaled,
+                                 uint32_t num, uint64_t seed, bool track_abundance,
+                                 uint64_t *n_kmers_out);
+
+/* .sig / .sig.gz JSON (src/core/src/signature.rs:401-445, sketch/minhash.rs:103-184) parsed
+ * straight into CSR: every sketch of every signature of every file is one row (unsorted mins
+ * are sorted like the reference's loader does).  Replaces loading N objects through
+ * signatures_load_path + kmerminhash_get_mins for compare / search / gather over many files. */
+typedef struct SmbSigs SmbSigs;
+typedef struct {
+  uint32_t sig_index;      /* signature object the sketch belongs to (name / filename) */
+  uint32_t file;           /* index into paths */
+  uint32_t ksize;          /* as stored: 3 x residues for protein-family sketches */
+  uint32_t num;            /* 0 when max_hash != 0 (minhash.rs:146) */
+  uint64_t max_hash;
+  uint64_t seed;
+  uint32_t hash_function;  /* HashFunctions */
+  bool has_abund;
+  uint64_t n_mins;
+} SmbSketchInfo;
+SmbSigs *smb_sigs_read(const char *const *paths, uintptr_t n_paths, int32_t n_threads);
+SmbSigs *smb_sigs_parse(const char *data, uintptr_t len);          /* JSON text or gzip of it */
+void smb_sigs_free(SmbSigs *s);
+uintptr_t smb_sigs_n_signatures(const SmbSigs *s);
+uintptr_t smb_sigs_n_sketches(const SmbSigs *s);
+bool smb_sigs_any_abund(const SmbSigs *s);
+void smb_sigs_sketch_info(const SmbSigs *s, uintptr_t i, SmbSketchInfo *out);
+SourmashStr smb_sigs_sketch_md5(const SmbSigs *s, uintptr_t i);
+SourmashStr smb_sigs_sig_name(const SmbSigs *s, uintptr_t j);
+SourmashStr smb_sigs_sig_filename(const SmbSigs *s, uintptr_t j);
+SourmashStr smb_sigs_sig_license(const SmbSigs *s, uintptr_t j);
+const uint64_t *smb_sigs_offsets(const SmbSigs *s);                /* n_sketches + 1 */
+const uint64_t *smb_sigs_mins(const SmbSigs *s);
+const uint64_t *smb_sigs_abunds(const SmbSigs *s);                 /* 1 where a sketch has none */
+SourmashKmerMinHash *smb_sigs_minhash(const SmbSigs *s, uintptr_t i);   /* new owned object */
+/* rows (NULL: all) -> device-resident CSR; max_hash != 0 keeps the prefix h <= max_hash of every
+ * row (downsample_scaled, sketch/minhash.rs:777-798) */
+SmbSketchSet *smb_sigs_to_sketchset(const SmbSigs *s, const uint32_t *rows, uintptr_t n_rows,
+                                    uint64_t max_hash, bool with_abunds);
+
+/* reference ABI for .sig I/O: src/core/src/ffi/signature.rs:219-343 (include/sourmash.h:389-414).
+ * One SourmashSignature per sketch, filtered by ksize (0: any; compared with the stored ksize)
+ * and molecule type (NULL: any).  The returned array is freed with signatures_array_free, the
+ * objects with signature_free; buffers with nodegraph_buffer_free (the reference's name). */
+SourmashSignature **signatures_load_path(const char *ptr, bool ignore_md5sum, uintptr_t ksize,
+                                         const char *select_moltype, uintptr_t *size);
+SourmashSignature **signatures_load_buffer(const char *ptr, uintptr_t insize, bool ignore_md5sum,
+                                           uintptr_t ksize, const char *select_moltype,
+                                           uintptr_t *size);
+const uint8_t *signatures_save_buffer(const SourmashSignature *const *ptr, uintptr_t size,
+                                      uint8_t compression, uintptr_t *osize);
+SourmashStr signature_save_json(const SourmashSignature *ptr);
+void nodegraph_buffer_free(uint8_t *ptr, uintptr_t insize);
+void signatures_array_free(SourmashSignature **ptr, uintptr_t size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,8 +5,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsourmash_b200.so")
-SOURCES = ["capi.cu", "sketch_kernels.cu", "compare_kernels.cu"]
-DEPS = SOURCES + ["common.cuh", "kernels.h", "md5.h", "kmer_roll.cuh", "split_table.cuh", "aa_kmers.cuh", os.path.join("..", "..", "include", "sourmash_b200.h")]
+SOURCES = ["capi.cu", "sketch_kernels.cu", "compare_kernels.cu", "ingest.cu"]
+DEPS = SOURCES + ["common.cuh", "kernels.h", "md5.h", "kmer_roll.cuh", "split_table.cuh", "aa_kmers.cuh", "ingest.h", os.path.join("..", "..", "include", "sourmash_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -28,7 +28,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES + ["-lz"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)

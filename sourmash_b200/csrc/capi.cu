@@ -16,11 +16,15 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <zlib.h>
 
 #include "../../include/sourmash_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "ingest.h"
 #include "md5.h"
 
 namespace smb {
@@ -973,7 +977,6 @@ uint64_t* to_boxed(const std::vector<uint64_t>& v, uintptr_t* size) {
 }
 
 }  // namespace
-
 // ==========================================================================================
 // Signature / ComputeParameters: src/core/src/signature.rs:401-445, cmd.rs:22-188
 // ==========================================================================================
@@ -983,14 +986,167 @@ struct SourmashComputeParameters {
     uint32_t num_hashes = 500;
     uint64_t scaled = 0, seed = 42;
 };
-
-struct SourmashSignature {
+struct SourmashSignature {                 // signature.rs:401-445
     std::string name, filename;
     std::string license = "CC0";
+    std::string email, klass = "sourmash_signature", hash_function = "0.murmur64";
+    double version = 0.4;
     std::vector<MH> sketches;
 };
+struct SmbRecords { smb::RecordBatch b; };
+struct SmbSigs { smb::SigBatch b; };
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// .sig JSON writer (serde field order of signature.rs:401-445 and sketch/minhash.rs:103-131)
+// ------------------------------------------------------------------------------------------
+void json_escape(std::string& out, const std::string& s) {
+    out.push_back('"');
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\n': out += "\\n"; break;
+            case '\r': out += "\\r"; break;
+            case '\t': out += "\\t"; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); out += b; }
+                else out.push_back((char)c);
+        }
+    }
+    out.push_back('"');
+}
+void json_u64_array(std::string& out, const std::vector<uint64_t>& v) {
+    out.push_back('[');
+    char b[24];
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i) out.push_back(',');
+        int l = snprintf(b, sizeof b, "%llu", (unsigned long long)v[i]);
+        out.append(b, (size_t)l);
+    }
+    out.push_back(']');
+}
+const char* molecule_name(HashFunctions hf) {          // encodings.rs:55-69 (Display)
+    return hf == HASH_FUNCTIONS_MURMUR64_PROTEIN ? "protein" : hf == HASH_FUNCTIONS_MURMUR64_DAYHOFF ? "dayhoff"
+         : hf == HASH_FUNCTIONS_MURMUR64_HP ? "hp" : "DNA";
+}
+void json_signature(std::string& out, const SourmashSignature& sig) {
+    out += "{\"class\":"; json_escape(out, sig.klass);
+    out += ",\"email\":"; json_escape(out, sig.email);
+    out += ",\"hash_function\":"; json_escape(out, sig.hash_function);
+    out += ",\"filename\":";
+    if (sig.filename.empty()) out += "null"; else json_escape(out, sig.filename);
+    if (!sig.name.empty()) { out += ",\"name\":"; json_escape(out, sig.name); }
+    out += ",\"license\":"; json_escape(out, sig.license);
+    out += ",\"signatures\":[";
+    for (size_t i = 0; i < sig.sketches.size(); ++i) {
+        const MH& m = sig.sketches[i];
+        if (i) out.push_back(',');
+        out += "{\"num\":" + std::to_string(m.num) + ",\"ksize\":" + std::to_string(m.ksize) +
+               ",\"seed\":" + std::to_string(m.seed) + ",\"max_hash\":" + std::to_string(m.max_hash) + ",\"mins\":";
+        json_u64_array(out, m.mins);
+        out += ",\"md5sum\":\"" + m.md5sum() + "\"";
+        if (m.track) { out += ",\"abundances\":"; json_u64_array(out, m.abunds); }
+        out += std::string(",\"molecule\":\"") + molecule_name(m.hash_function) + "\"}";
+    }
+    char vb[32];
+    snprintf(vb, sizeof vb, "%.17g", sig.version);
+    double back = strtod(vb, nullptr);
+    for (int prec = 1; prec < 17; ++prec) {                // shortest representation that round-trips
+        char t[32]; snprintf(t, sizeof t, "%.*g", prec, sig.version);
+        if (strtod(t, nullptr) == sig.version) { memcpy(vb, t, sizeof t); break; }
+    }
+    (void)back;
+    out += std::string("],\"version\":") + vb + "}";
+}
+std::string json_signatures(const SourmashSignature* const* sigs, size_t n) {
+    std::string out = "[";
+    for (size_t i = 0; i < n; ++i) { if (i) out.push_back(','); json_signature(out, *sigs[i]); }
+    out.push_back(']');
+    return out;
+}
+std::string gzip_bytes(const std::string& in, int level) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+        fail(SOURMASH_ERROR_CODE_INTERNAL, "zlib deflateInit2 failed");
+    std::string out(deflateBound(&zs, in.size()) + 32, '\0');
+    zs.next_in = (Bytef*)in.data(); zs.avail_in = (uInt)in.size();
+    zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
+    int r = deflate(&zs, Z_FINISH);
+    deflateEnd(&zs);
+    if (r != Z_STREAM_END) fail(SOURMASH_ERROR_CODE_INTERNAL, "zlib deflate failed");
+    out.resize(zs.total_out);
+    return out;
+}
+std::string gunzip_bytes(const uint8_t* p, size_t n) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) fail(SOURMASH_ERROR_CODE_INTERNAL, "zlib inflateInit2 failed");
+    std::string out;
+    std::vector<char> buf(1 << 20);
+    zs.next_in = (Bytef*)p; zs.avail_in = (uInt)n;
+    int r;
+    do {
+        zs.next_out = (Bytef*)buf.data(); zs.avail_out = (uInt)buf.size();
+        r = inflate(&zs, Z_NO_FLUSH);
+        if (r != Z_OK && r != Z_STREAM_END) { inflateEnd(&zs); fail(SOURMASH_ERROR_CODE_NIFFLER_ERROR, "gzip stream is corrupt"); }
+        out.append(buf.data(), buf.size() - zs.avail_out);
+    } while (r != Z_STREAM_END);
+    inflateEnd(&zs);
+    return out;
+}
+
+// one host sketch object from row i of a parsed batch
+MH mh_from_batch(const smb::SigBatch& B, size_t i) {
+    const smb::SigSketch& sk = B.sketches[i];
+    MH m;
+    m.num = sk.num; m.ksize = sk.ksize; m.seed = sk.seed; m.max_hash = sk.max_hash;
+    m.hash_function = (HashFunctions)sk.hash_function; m.track = sk.has_abund;
+    m.mins.assign(B.mins.begin() + B.off[i], B.mins.begin() + B.off[i + 1]);
+    if (sk.has_abund) m.abunds.assign(B.abunds.begin() + B.off[i], B.abunds.begin() + B.off[i + 1]);
+    return m;
+}
+// Signature::load_signatures (signature.rs:583-658): one signature per sketch, filtered by ksize
+// (as stored) and molecule type
+SourmashSignature** sigs_from_batch(const smb::SigBatch& B, uintptr_t ksize, const char* select_moltype,
+                                    uintptr_t* size) {
+    int want_hf = 0;
+    if (select_moltype) {
+        std::string m(select_moltype);
+        for (auto& c : m) if (c >= 'A' && c <= 'Z') c = (char)(c + 32);
+        want_hf = m == "dna" ? 1 : m == "protein" ? 2 : m == "dayhoff" ? 3 : m == "hp" ? 4 : -1;
+        if (want_hf < 0) fail(SOURMASH_ERROR_CODE_INVALID_HASH_FUNCTION, "Invalid hash function: \"" + std::string(select_moltype) + "\"");
+    }
+    std::vector<SourmashSignature*> out;
+    for (size_t i = 0; i < B.sketches.size(); ++i) {
+        const smb::SigSketch& sk = B.sketches[i];
+        if (ksize != 0 && sk.ksize != ksize) continue;
+        if (want_hf && (int)sk.hash_function != want_hf) continue;
+        const smb::SigRecord& r = B.sigs[sk.sig_index];
+        auto* sig = new SourmashSignature();
+        sig->name = r.name; sig->filename = r.filename; sig->license = r.license; sig->email = r.email;
+        sig->klass = r.klass; sig->hash_function = r.hash_function; sig->version = r.version;
+        sig->sketches.push_back(mh_from_batch(B, i));
+        out.push_back(sig);
+    }
+    *size = out.size();
+    auto** arr = (SourmashSignature**)malloc(std::max<size_t>(out.size(), 1) * sizeof(void*));
+    if (!out.empty()) memcpy(arr, out.data(), out.size() * sizeof(void*));
+    return arr;
+}
+int default_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(std::max<unsigned>(n, 1u), 32u);
+}
+
+}  // namespace
 
 extern "C" {
+
 
 // ------------------------------------------------------------------------------------------
 void sourmash_init(void) {}
@@ -1948,5 +2104,147 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
         return rounds;
     });
 }
+
+// ==========================================================================================
+// Part 3: native ingest (csrc/ingest.cu) -- sequence files and .sig JSON without per-record Python
+// ==========================================================================================
+SmbRecords* smb_records_read(const char* const* paths, uintptr_t n_paths, int32_t n_threads) {
+    return guarded<SmbRecords*>([&]() -> SmbRecords* {
+        auto r = std::make_unique<SmbRecords>();
+        probe_devices();
+        std::string err = smb::read_sequence_files(paths, n_paths, n_threads > 0 ? n_threads : default_threads(),
+                                                   g_device_count > 0, r->b);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_IO, err);
+        return r.release();
+    });
+}
+void smb_records_free(SmbRecords* r) { delete r; }
+uintptr_t smb_records_len(const SmbRecords* r) { return r->b.file.size(); }
+uint64_t smb_records_total_bytes(const SmbRecords* r) { return r->b.total; }
+const uint8_t* smb_records_data(const SmbRecords* r) { return r->b.seqs; }
+const uint64_t* smb_records_offsets(const SmbRecords* r) { return r->b.off.data(); }
+const uint32_t* smb_records_files(const SmbRecords* r) { return r->b.file.data(); }
+const char* smb_records_names(const SmbRecords* r, const uint64_t** name_offsets) {
+    *name_offsets = r->b.name_off.data();
+    return r->b.names.data();
+}
+SmbSketchSet* smb_sketch_records(const SmbRecords* r, const uint32_t* rec_to_sketch, uintptr_t n_sketches,
+                                 const uint32_t* ksizes, uintptr_t n_ksizes, HashFunctions hash_function,
+                                 bool input_is_protein, uint64_t scaled, uint32_t num, uint64_t seed,
+                                 bool track_abundance, uint64_t* n_kmers_out) {
+    const uintptr_t n = r->b.file.size();
+    if (hash_function == HASH_FUNCTIONS_MURMUR64_DNA)
+        return smb_sketch_sequences(r->b.seqs, r->b.off.data(), n, rec_to_sketch, n_sketches, ksizes, n_ksizes,
+                                    scaled, num, seed, track_abundance, n_kmers_out);
+    return smb_sketch_sequences_aa(r->b.seqs, r->b.off.data(), n, rec_to_sketch, n_sketches, ksizes, n_ksizes,
+                                   hash_function, input_is_protein, scaled, num, seed, track_abundance, n_kmers_out);
+}
+
+SmbSigs* smb_sigs_read(const char* const* paths, uintptr_t n_paths, int32_t n_threads) {
+    return guarded<SmbSigs*>([&]() -> SmbSigs* {
+        auto r = std::make_unique<SmbSigs>();
+        std::string err = smb::read_signature_files(paths, n_paths, n_threads > 0 ? n_threads : default_threads(), r->b);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
+        return r.release();
+    });
+}
+SmbSigs* smb_sigs_parse(const char* data, uintptr_t len) {
+    return guarded<SmbSigs*>([&]() -> SmbSigs* {
+        auto r = std::make_unique<SmbSigs>();
+        std::string text;
+        if (len >= 2 && (uint8_t)data[0] == 0x1f && (uint8_t)data[1] == 0x8b) {
+            text = gunzip_bytes((const uint8_t*)data, len);
+            data = text.data(); len = text.size();
+        }
+        std::string err = smb::parse_signature_json(data, len, 0, r->b);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
+        return r.release();
+    });
+}
+void smb_sigs_free(SmbSigs* s) { delete s; }
+uintptr_t smb_sigs_n_signatures(const SmbSigs* s) { return s->b.sigs.size(); }
+uintptr_t smb_sigs_n_sketches(const SmbSigs* s) { return s->b.sketches.size(); }
+bool smb_sigs_any_abund(const SmbSigs* s) { return s->b.any_abund; }
+void smb_sigs_sketch_info(const SmbSigs* s, uintptr_t i, SmbSketchInfo* out) {
+    const smb::SigSketch& k = s->b.sketches[i];
+    out->sig_index = k.sig_index; out->file = k.file; out->ksize = k.ksize; out->num = k.num;
+    out->max_hash = k.max_hash; out->seed = k.seed; out->hash_function = k.hash_function;
+    out->has_abund = k.has_abund; out->n_mins = s->b.off[i + 1] - s->b.off[i];
+}
+SourmashStr smb_sigs_sketch_md5(const SmbSigs* s, uintptr_t i) { return make_str(s->b.sketches[i].md5sum); }
+SourmashStr smb_sigs_sig_name(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].name); }
+SourmashStr smb_sigs_sig_filename(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].filename); }
+SourmashStr smb_sigs_sig_license(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].license); }
+const uint64_t* smb_sigs_offsets(const SmbSigs* s) { return s->b.off.data(); }
+const uint64_t* smb_sigs_mins(const SmbSigs* s) { return s->b.mins.data(); }
+const uint64_t* smb_sigs_abunds(const SmbSigs* s) { return s->b.abunds.data(); }
+SourmashKmerMinHash* smb_sigs_minhash(const SmbSigs* s, uintptr_t i) {
+    return guarded<SourmashKmerMinHash*>([&] { return new MH(mh_from_batch(s->b, i)); });
+}
+// rows (NULL: all) of the parsed sketches -> device CSR, optionally cut at max_hash (0: as stored)
+SmbSketchSet* smb_sigs_to_sketchset(const SmbSigs* s, const uint32_t* rows, uintptr_t n_rows, uint64_t max_hash,
+                                    bool with_abunds) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        const smb::SigBatch& B = s->b;
+        const size_t n = rows ? n_rows : B.sketches.size();
+        std::vector<uint64_t> off(n + 1, 0), h, ab;
+        for (size_t r = 0; r < n; ++r) {
+            const size_t i = rows ? rows[r] : r;
+            if (i >= B.sketches.size()) fail(SOURMASH_ERROR_CODE_INTERNAL, "sketch row out of range");
+            const uint64_t* b = B.mins.data() + B.off[i];
+            const uint64_t* e = B.mins.data() + B.off[i + 1];
+            if (max_hash) e = std::upper_bound(b, e, max_hash);        // downsample_scaled == prefix
+            h.insert(h.end(), b, e);
+            if (with_abunds) ab.insert(ab.end(), B.abunds.data() + B.off[i], B.abunds.data() + B.off[i] + (e - b));
+            off[r + 1] = h.size();
+        }
+        return smb_sketchset_from_host(h.data(), off.data(), n, with_abunds ? ab.data() : nullptr);
+    });
+}
+
+// reference ABI: ffi/signature.rs:219-343
+SourmashSignature** signatures_load_path(const char* ptr, bool, uintptr_t ksize, const char* select_moltype,
+                                         uintptr_t* size) {
+    return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
+        smb::SigBatch B;
+        const char* paths[1] = {ptr};
+        std::string err = smb::read_signature_files(paths, 1, 1, B);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
+        return sigs_from_batch(B, ksize, select_moltype, size);
+    });
+}
+SourmashSignature** signatures_load_buffer(const char* ptr, uintptr_t insize, bool, uintptr_t ksize,
+                                           const char* select_moltype, uintptr_t* size) {
+    return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
+        smb::SigBatch B;
+        std::string text;
+        if (insize >= 2 && (uint8_t)ptr[0] == 0x1f && (uint8_t)ptr[1] == 0x8b) {   // niffler sniffing
+            text = gunzip_bytes((const uint8_t*)ptr, insize);
+            ptr = text.data(); insize = text.size();
+        }
+        std::string err = smb::parse_signature_json(ptr, insize, 0, B);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
+        return sigs_from_batch(B, ksize, select_moltype, size);
+    });
+}
+const uint8_t* signatures_save_buffer(const SourmashSignature* const* ptr, uintptr_t size, uint8_t compression,
+                                      uintptr_t* osize) {
+    return guarded<const uint8_t*>([&]() -> const uint8_t* {
+        std::string text = json_signatures(ptr, size);
+        if (compression > 0) text = gzip_bytes(text, compression > 9 ? 9 : compression);
+        uint8_t* out = (uint8_t*)malloc(text.size() + 1);
+        memcpy(out, text.data(), text.size());
+        out[text.size()] = 0;
+        *osize = text.size();
+        return out;
+    });
+}
+SourmashStr signature_save_json(const SourmashSignature* ptr) {
+    std::string out;
+    json_signature(out, *ptr);
+    return make_str(out);
+}
+void nodegraph_buffer_free(uint8_t* ptr, uintptr_t) { free(ptr); }
+void signatures_array_free(SourmashSignature** ptr, uintptr_t) { free(ptr); }
 
 }  // extern "C"

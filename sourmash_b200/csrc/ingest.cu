@@ -1,0 +1,464 @@
+// ingest.cu -- native host-side readers (see ingest.h).  Host code only (no kernels); compiled
+// with the rest of the library so that the boundary stays one C-ABI shared object.
+//
+// FASTA/FASTQ parsing follows what the reference's CLI gets from screed
+// (src/sourmash/command_sketch.py:697-766): record name = the whole header line after the
+// marker, sequence = the record's lines joined, with line ends stripped.  The reference's Rust
+// benches use needletail + niffler for the same job (src/core/benches/compute.rs:36-45).
+#include "ingest.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
+namespace smb {
+
+RecordBatch::~RecordBatch() {
+    if (seqs) { if (pinned) cudaFreeHost(seqs); else free(seqs); }
+}
+
+namespace {
+
+// Growable byte buffer without value-initialisation (std::vector would zero every growth).
+struct Bytes {
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    Bytes() {}
+    Bytes(const Bytes&) = delete;
+    Bytes& operator=(const Bytes&) = delete;
+    ~Bytes() { free(p); }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t c = std::max<size_t>(want, cap * 2);
+        uint8_t* q = (uint8_t*)realloc(p, c);
+        if (!q) return false;
+        p = q; cap = c;
+        return true;
+    }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+};
+
+// whole file into memory; gzip members are inflated (magic 1f 8b), anything else is read as is
+std::string slurp(const char* path, Bytes& data) {
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return std::string("cannot open ") + path;
+    unsigned char magic[2] = {0, 0};
+    size_t got = fread(magic, 1, 2, fh);
+    fseek(fh, 0, SEEK_END);
+    const long fsize = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz) {
+        if (!data.reserve((size_t)std::max<long>(fsize, 0) + 16)) { fclose(fh); return "out of host memory"; }
+        data.n = fread(data.p, 1, (size_t)std::max<long>(fsize, 0), fh);
+        fclose(fh);
+        return "";
+    }
+    fclose(fh);
+    gzFile f = gzopen(path, "rb");
+    if (!f) return std::string("cannot open ") + path;
+    gzbuffer(f, 1 << 20);
+    if (!data.reserve((size_t)std::max<long>(fsize, 1) * 4 + (1 << 16))) { gzclose(f); return "out of host memory"; }
+    for (;;) {
+        if (data.cap - data.n < (1u << 20) && !data.reserve(data.cap * 2)) { gzclose(f); return "out of host memory"; }
+        size_t want = std::min<size_t>(data.cap - data.n, 1u << 30);
+        int n = gzread(f, data.p + data.n, (unsigned)want);
+        if (n < 0) { int e; std::string m = gzerror(f, &e); gzclose(f); return std::string(path) + ": " + m; }
+        if (n == 0) break;
+        data.n += (size_t)n;
+    }
+    gzclose(f);
+    return "";
+}
+
+struct FileRecords {
+    std::vector<uint8_t> seqs;
+    std::vector<uint64_t> off{0};
+    std::string names;
+    std::vector<uint64_t> name_off{0};
+    std::string error;
+};
+
+inline const uint8_t* line_end(const uint8_t* p, const uint8_t* end) {
+    const void* q = memchr(p, '\n', (size_t)(end - p));
+    return q ? (const uint8_t*)q : end;
+}
+// append [p, e) without trailing '\r' / blanks
+inline void append_trimmed(std::vector<uint8_t>& dst, const uint8_t* p, const uint8_t* e) {
+    while (e > p && (e[-1] == '\r' || e[-1] == ' ' || e[-1] == '\t')) --e;
+    dst.insert(dst.end(), p, e);
+}
+
+void parse_records(const Bytes& data, FileRecords& R) {
+    const uint8_t* p = data.data();
+    const uint8_t* end = p + data.size();
+    while (p < end && (*p == '\n' || *p == '\r' || *p == ' ')) ++p;
+    if (p == end) return;
+    if (*p != '>' && *p != '@') { R.error = "neither FASTA nor FASTQ (first byte is not '>' or '@')"; return; }
+    R.seqs.reserve(data.size());
+    const bool fastq = *p == '@';
+    while (p < end) {
+        const uint8_t* e = line_end(p, end);
+        if (e == p || *p == '\r') { p = e + 1; continue; }          // blank line between records
+        if (*p != (fastq ? '@' : '>')) { R.error = "malformed record header"; return; }
+        const uint8_t* he = e;
+        while (he > p + 1 && (he[-1] == '\r' || he[-1] == ' ')) --he;
+        R.names.append((const char*)p + 1, (size_t)(he - p - 1));
+        R.name_off.push_back(R.names.size());
+        p = e < end ? e + 1 : end;
+        const size_t seq_begin = R.seqs.size();
+        if (!fastq) {
+            while (p < end && *p != '>') {
+                e = line_end(p, end);
+                append_trimmed(R.seqs, p, e);
+                p = e < end ? e + 1 : end;
+            }
+        } else {
+            while (p < end && *p != '+') {                           // sequence lines up to the '+' line
+                e = line_end(p, end);
+                append_trimmed(R.seqs, p, e);
+                p = e < end ? e + 1 : end;
+            }
+            if (p < end) { e = line_end(p, end); p = e < end ? e + 1 : end; }   // '+' line
+            size_t need = R.seqs.size() - seq_begin, got = 0;       // quality: as many symbols as bases
+            while (p < end && got < need) {
+                e = line_end(p, end);
+                const uint8_t* qe = e;
+                while (qe > p && (qe[-1] == '\r')) --qe;
+                got += (size_t)(qe - p);
+                p = e < end ? e + 1 : end;
+            }
+        }
+        R.off.push_back(R.seqs.size());
+    }
+}
+
+}  // namespace
+
+std::string read_sequence_files(const char* const* paths, size_t n_paths, int n_threads, bool want_pinned,
+                                RecordBatch& out) {
+    std::vector<FileRecords> files(n_paths);
+    std::atomic<size_t> next{0};
+    auto worker = [&] {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_paths) return;
+            Bytes data;
+            files[i].error = slurp(paths[i], data);
+            if (files[i].error.empty()) {
+                parse_records(data, files[i]);
+                if (!files[i].error.empty()) files[i].error = std::string(paths[i]) + ": " + files[i].error;
+            }
+        }
+    };
+    size_t nt = (size_t)std::max(1, n_threads);
+    nt = std::min(nt, std::max<size_t>(n_paths, 1));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    for (auto& f : files) if (!f.error.empty()) return f.error;
+
+    uint64_t total = 0, n_rec = 0, name_bytes = 0;
+    for (auto& f : files) { total += f.seqs.size(); n_rec += f.off.size() - 1; name_bytes += f.names.size(); }
+    out.total = total;
+    const size_t alloc = (size_t)((total + 64 + 4095) & ~4095ull);
+    out.pinned = false;
+    if (want_pinned && cudaHostAlloc((void**)&out.seqs, alloc, cudaHostAllocDefault) == cudaSuccess) out.pinned = true;
+    else { cudaGetLastError(); out.seqs = (uint8_t*)aligned_alloc(4096, alloc); }
+    if (!out.seqs) return "out of host memory";
+    out.off.assign(1, 0); out.off.reserve(n_rec + 1);
+    out.file.clear(); out.file.reserve(n_rec);
+    out.names.clear(); out.names.reserve(name_bytes);
+    out.name_off.assign(1, 0); out.name_off.reserve(n_rec + 1);
+    // per-file base offsets, then copy the sequence bytes in parallel
+    std::vector<uint64_t> base(n_paths + 1, 0);
+    for (size_t i = 0; i < n_paths; ++i) base[i + 1] = base[i] + files[i].seqs.size();
+    for (size_t i = 0; i < n_paths; ++i) {
+        const FileRecords& f = files[i];
+        for (size_t r = 0; r + 1 < f.off.size(); ++r) {
+            out.off.push_back(base[i] + f.off[r + 1]);
+            out.file.push_back((uint32_t)i);
+            out.name_off.push_back(out.names.size() + f.name_off[r + 1]);
+        }
+        out.names += f.names;
+    }
+    next = 0;
+    auto copier = [&] {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_paths) return;
+            if (!files[i].seqs.empty()) memcpy(out.seqs + base[i], files[i].seqs.data(), files[i].seqs.size());
+        }
+    };
+    pool.clear();
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(copier);
+    copier();
+    for (auto& t : pool) t.join();
+    memset(out.seqs + total, 0, alloc - total);
+    return "";
+}
+
+// =============================================================================================
+// .sig JSON
+// =============================================================================================
+namespace {
+
+struct Json {
+    const char* p;
+    const char* end;
+    std::string err;
+    bool fail(const char* m) { if (err.empty()) err = m; return false; }
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p; }
+    bool lit(char c) { ws(); if (p < end && *p == c) { ++p; return true; } return false; }
+    bool expect(char c) { return lit(c) ? true : fail("malformed JSON"); }
+
+    bool string(std::string& out) {
+        ws();
+        if (p >= end || *p != '"') return fail("expected a string");
+        ++p;
+        out.clear();
+        while (p < end && *p != '"') {
+            if (*p != '\\') { out.push_back(*p++); continue; }
+            if (++p >= end) break;
+            switch (*p++) {
+                case 'n': out.push_back('\n'); break;
+                case 't': out.push_back('\t'); break;
+                case 'r': out.push_back('\r'); break;
+                case 'b': out.push_back('\b'); break;
+                case 'f': out.push_back('\f'); break;
+                case 'u': {
+                    if (end - p < 4) return fail("bad \\u escape");
+                    unsigned cp = (unsigned)strtoul(std::string(p, 4).c_str(), nullptr, 16);
+                    p += 4;
+                    if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                        unsigned lo = (unsigned)strtoul(std::string(p + 2, 4).c_str(), nullptr, 16);
+                        p += 6;
+                        cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                    }
+                    if (cp < 0x80) out.push_back((char)cp);
+                    else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 63))); }
+                    else if (cp < 0x10000) { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 63))); out.push_back((char)(0x80 | (cp & 63))); }
+                    else { out.push_back((char)(0xF0 | (cp >> 18))); out.push_back((char)(0x80 | ((cp >> 12) & 63))); out.push_back((char)(0x80 | ((cp >> 6) & 63))); out.push_back((char)(0x80 | (cp & 63))); }
+                    break;
+                }
+                default: out.push_back(p[-1]);
+            }
+        }
+        if (p >= end) return fail("unterminated string");
+        ++p;
+        return true;
+    }
+    bool u64(uint64_t& v) {
+        ws();
+        if (p >= end || *p < '0' || *p > '9') return fail("expected an unsigned integer");
+        uint64_t x = 0;
+        while (p < end && *p >= '0' && *p <= '9') x = x * 10 + (uint64_t)(*p++ - '0');
+        if (p < end && (*p == '.' || *p == 'e' || *p == 'E')) {       // tolerate 1.0-style integers
+            while (p < end && (*p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-' || (*p >= '0' && *p <= '9'))) ++p;
+        }
+        v = x;
+        return true;
+    }
+    bool number(double& v) {
+        ws();
+        char* e = nullptr;
+        v = strtod(p, &e);
+        if (e == p) return fail("expected a number");
+        p = e;
+        return true;
+    }
+    bool u64_array(std::vector<uint64_t>& dst) {
+        if (!expect('[')) return false;
+        if (lit(']')) return true;
+        for (;;) {
+            uint64_t v;
+            if (!u64(v)) return false;
+            dst.push_back(v);
+            if (lit(',')) continue;
+            return expect(']');
+        }
+    }
+    bool skip() {                                   // any value
+        ws();
+        if (p >= end) return fail("unexpected end of JSON");
+        if (*p == '"') { std::string s; return string(s); }
+        if (*p == '{' || *p == '[') {
+            const char open = *p, close = open == '{' ? '}' : ']';
+            ++p;
+            if (lit(close)) return true;
+            for (;;) {
+                if (open == '{') { std::string k; if (!string(k) || !expect(':')) return false; }
+                if (!skip()) return false;
+                if (lit(',')) continue;
+                return expect(close);
+            }
+        }
+        while (p < end && *p != ',' && *p != '}' && *p != ']' && *p != ' ' && *p != '\n') ++p;   // number / literal
+        return true;
+    }
+    bool null_or_string(std::string& s, bool& present) {
+        ws();
+        if (end - p >= 4 && !memcmp(p, "null", 4)) { p += 4; present = false; return true; }
+        present = true;
+        return string(s);
+    }
+};
+
+bool parse_sketch(Json& J, SigBatch& B, uint32_t sig_index, uint32_t file) {
+    SigSketch sk;
+    sk.sig_index = sig_index; sk.file = file;
+    std::vector<uint64_t> mins, abunds;
+    std::string molecule = "dna", key;
+    bool have_abund = false;
+    if (!J.expect('{')) return false;
+    if (!J.lit('}')) for (;;) {
+        if (!J.string(key) || !J.expect(':')) return false;
+        uint64_t v = 0;
+        if (key == "num") { if (!J.u64(v)) return false; sk.num = (uint32_t)v; }
+        else if (key == "ksize") { if (!J.u64(v)) return false; sk.ksize = (uint32_t)v; }
+        else if (key == "seed") { if (!J.u64(sk.seed)) return false; }
+        else if (key == "max_hash") { if (!J.u64(sk.max_hash)) return false; }
+        else if (key == "md5sum") { if (!J.string(sk.md5sum)) return false; }
+        else if (key == "molecule") { if (!J.string(molecule)) return false; }
+        else if (key == "mins") { if (!J.u64_array(mins)) return false; }
+        else if (key == "abundances") {
+            J.ws();
+            if (J.end - J.p >= 4 && !memcmp(J.p, "null", 4)) J.p += 4;
+            else { have_abund = true; if (!J.u64_array(abunds)) return false; }
+        } else if (!J.skip()) return false;
+        if (J.lit(',')) continue;
+        if (!J.expect('}')) return false;
+        break;
+    }
+    for (auto& c : molecule) if (c >= 'A' && c <= 'Z') c = (char)(c + 32);
+    if (molecule == "dna") sk.hash_function = 1;
+    else if (molecule == "protein") sk.hash_function = 2;
+    else if (molecule == "dayhoff") sk.hash_function = 3;
+    else if (molecule == "hp") sk.hash_function = 4;
+    else return J.fail("unknown molecule type");
+    if (sk.max_hash != 0) sk.num = 0;                                   // minhash.rs:146
+    if (have_abund && abunds.size() != mins.size()) return J.fail("mins and abundances differ in length");
+    sk.has_abund = have_abund;
+    // minhash.rs:159-171: files with unsorted mins exist; sort (pairs when abundances are present)
+    if (!std::is_sorted(mins.begin(), mins.end())) {
+        if (have_abund) {
+            std::vector<std::pair<uint64_t, uint64_t>> v(mins.size());
+            for (size_t i = 0; i < mins.size(); ++i) v[i] = {mins[i], abunds[i]};
+            std::sort(v.begin(), v.end());
+            for (size_t i = 0; i < mins.size(); ++i) { mins[i] = v[i].first; abunds[i] = v[i].second; }
+        } else {
+            std::sort(mins.begin(), mins.end());
+        }
+    }
+    B.mins.insert(B.mins.end(), mins.begin(), mins.end());
+    if (have_abund) B.abunds.insert(B.abunds.end(), abunds.begin(), abunds.end());
+    else B.abunds.insert(B.abunds.end(), mins.size(), 1);
+    B.any_abund = B.any_abund || have_abund;
+    B.off.push_back(B.mins.size());
+    B.sketches.push_back(std::move(sk));
+    return true;
+}
+
+bool parse_signature(Json& J, SigBatch& B, uint32_t file) {
+    SigRecord rec;
+    rec.file = file; rec.license = "CC0"; rec.klass = "sourmash_signature";
+    const uint32_t sig_index = (uint32_t)B.sigs.size();
+    B.sigs.push_back(rec);                                             // sketches refer to it by index
+    std::string key;
+    if (!J.expect('{')) return false;
+    if (!J.lit('}')) for (;;) {
+        if (!J.string(key) || !J.expect(':')) return false;
+        SigRecord& r = B.sigs[sig_index];
+        if (key == "signatures") {
+            if (!J.expect('[')) return false;
+            if (!J.lit(']')) for (;;) {
+                if (!parse_sketch(J, B, sig_index, file)) return false;
+                if (J.lit(',')) continue;
+                if (!J.expect(']')) return false;
+                break;
+            }
+        } else if (key == "name") { if (!J.null_or_string(r.name, r.has_name)) return false; }
+        else if (key == "filename") { if (!J.null_or_string(r.filename, r.has_filename)) return false; }
+        else if (key == "license") { if (!J.string(r.license)) return false; }
+        else if (key == "email") { if (!J.string(r.email)) return false; }
+        else if (key == "class") { if (!J.string(r.klass)) return false; }
+        else if (key == "hash_function") { if (!J.string(r.hash_function)) return false; }
+        else if (key == "version") { if (!J.number(r.version)) return false; }
+        else if (!J.skip()) return false;
+        if (J.lit(',')) continue;
+        if (!J.expect('}')) return false;
+        break;
+    }
+    return true;
+}
+
+}  // namespace
+
+std::string parse_signature_json(const char* text, size_t len, uint32_t file_index, SigBatch& B) {
+    if (B.off.empty()) B.off.push_back(0);
+    Json J{text, text + len, ""};
+    J.ws();
+    if (J.p < J.end && *J.p == '[') {
+        ++J.p;
+        if (!J.lit(']')) for (;;) {
+            if (!parse_signature(J, B, file_index)) return J.err;
+            if (J.lit(',')) continue;
+            if (!J.expect(']')) return J.err;
+            break;
+        }
+    } else if (!parse_signature(J, B, file_index)) {
+        return J.err;
+    }
+    return J.err;
+}
+
+std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, SigBatch& out) {
+    std::vector<SigBatch> parts(n_paths);
+    std::vector<std::string> errs(n_paths);
+    std::atomic<size_t> next{0};
+    auto worker = [&] {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_paths) return;
+            Bytes data;
+            errs[i] = slurp(paths[i], data);
+            if (errs[i].empty()) {
+                errs[i] = parse_signature_json((const char*)data.data(), data.size(), (uint32_t)i, parts[i]);
+                if (!errs[i].empty()) errs[i] = std::string(paths[i]) + ": " + errs[i];
+            }
+        }
+    };
+    size_t nt = std::min<size_t>((size_t)std::max(1, n_threads), std::max<size_t>(n_paths, 1));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    for (auto& e : errs) if (!e.empty()) return e;
+    if (out.off.empty()) out.off.push_back(0);
+    size_t tot = 0, nsk = 0;
+    for (auto& p : parts) { tot += p.mins.size(); nsk += p.sketches.size(); }
+    out.mins.reserve(out.mins.size() + tot);
+    out.abunds.reserve(out.abunds.size() + tot);
+    out.sketches.reserve(out.sketches.size() + nsk);
+    for (auto& p : parts) {
+        const uint32_t sig_base = (uint32_t)out.sigs.size();
+        const uint64_t h_base = out.mins.size();
+        for (auto& s : p.sigs) out.sigs.push_back(std::move(s));
+        for (auto& sk : p.sketches) { sk.sig_index += sig_base; out.sketches.push_back(std::move(sk)); }
+        for (size_t r = 1; r < p.off.size(); ++r) out.off.push_back(h_base + p.off[r]);
+        out.mins.insert(out.mins.end(), p.mins.begin(), p.mins.end());
+        out.abunds.insert(out.abunds.end(), p.abunds.begin(), p.abunds.end());
+        out.any_abund = out.any_abund || p.any_abund;
+    }
+    return "";
+}
+
+}  // namespace smb

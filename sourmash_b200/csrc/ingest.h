@@ -1,0 +1,61 @@
+// ingest.h -- native host-side readers that feed the GPU paths without per-record Python:
+//   * FASTA / FASTQ (optionally gzip) -> concatenated sequence bytes + record table
+//     (replaces the screed record loop of src/sourmash/command_sketch.py:697-766)
+//   * sourmash .sig JSON (optionally gzip) -> CSR of sketches + per-sketch metadata
+//     (replaces per-object loading through signature.py:383-527 / ffi/signature.rs:219-343;
+//      format: src/core/src/signature.rs:401-445, sketch fields sketch/minhash.rs:103-184)
+// Internal C++ interface; the public boundary is include/sourmash_b200.h (smb_records_*, smb_sigs_*).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace smb {
+
+struct RecordBatch {
+    uint8_t* seqs = nullptr;            // all sequences back to back (allocated by alloc_bytes)
+    uint64_t total = 0;
+    bool pinned = false;
+    std::vector<uint64_t> off;          // [n + 1]
+    std::vector<uint32_t> file;         // [n] index of the input file
+    std::string names;                  // header lines back to back
+    std::vector<uint64_t> name_off;     // [n + 1]
+    ~RecordBatch();
+};
+
+// Reads every file (FASTA or FASTQ, plain or gzip, decided per file from its content) with up to
+// n_threads worker threads, records in input order.  Returns an error message, empty on success.
+std::string read_sequence_files(const char* const* paths, size_t n_paths, int n_threads, bool want_pinned,
+                                RecordBatch& out);
+
+struct SigSketch {
+    uint32_t sig_index = 0;             // which signature object of which file it came from
+    uint32_t file = 0;
+    uint32_t ksize = 0, num = 0;        // ksize as stored in the file (3 x residues for proteins)
+    uint64_t max_hash = 0, seed = 42;
+    uint32_t hash_function = 1;         // 1 dna, 2 protein, 3 dayhoff, 4 hp
+    bool has_abund = false;
+    std::string md5sum;
+};
+struct SigRecord {                      // one signature object (signature.rs:401-445)
+    uint32_t file = 0;
+    std::string name, filename, license, email, klass, hash_function;
+    double version = 0.4;
+    bool has_name = false, has_filename = false;
+};
+struct SigBatch {
+    std::vector<SigRecord> sigs;
+    std::vector<SigSketch> sketches;
+    std::vector<uint64_t> off;          // [n_sketches + 1] into mins / abunds
+    std::vector<uint64_t> mins;         // each row sorted ascending (loader re-sorts, minhash.rs:159-171)
+    std::vector<uint64_t> abunds;       // parallel to mins; 1 where a sketch has no abundances
+    bool any_abund = false;
+};
+
+// Parses .sig / .sig.gz files (JSON array of signatures, or one signature object).
+std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, SigBatch& out);
+// Same from memory (one document).
+std::string parse_signature_json(const char* text, size_t len, uint32_t file_index, SigBatch& out);
+
+}  // namespace smb

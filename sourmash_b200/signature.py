@@ -2,12 +2,9 @@
 
 Mirrors the part of /root/reference/src/sourmash/signature.py (:29-527) that sits on the
 hot path: construction from a MinHash, ``add_sequence`` (every sketch of the signature sees
-the sequence), the comparison delegates, md5sum identity, and a plain-JSON reader/writer
-for ``.sig`` files (format: signature.rs:401-445; kept in Python -- "next" row f1 of the
-scope table -- so fixtures and results can be exchanged with the reference).
+the sequence), the comparison delegates, md5sum identity, and ``.sig`` JSON I/O through the
+library's native reader / writer (csrc/ingest.cu; format: signature.rs:401-445).
 """
-import gzip
-import json
 import os
 
 from ._lowlevel import ffi, lib
@@ -171,71 +168,74 @@ class ComputeParameters(RustObject):
 
 
 # ---------------------------------------------------------------------------------------------
-# .sig JSON (signature.rs:401-445; sketch fields sketch/minhash.rs:103-184)
+# .sig JSON (signature.rs:401-445; sketch fields sketch/minhash.rs:103-184): parsed and written
+# by the library (csrc/ingest.cu) through the reference's own entry points
+# signatures_load_path / signatures_load_buffer / signatures_save_buffer
+# (signature.py:383-527 -> ffi/signature.rs:219-343).
 # ---------------------------------------------------------------------------------------------
-def _sketch_from_json(d):
-    molecule = d.get("molecule", "DNA").lower()
-    num, max_hash = int(d.get("num", 0)), int(d.get("max_hash", 0))
-    if max_hash:
-        num = 0                       # old files carry num=2**32-1 together with max_hash
-    track = "abundances" in d
-    ksize = int(d["ksize"])
-    if molecule != "dna":
-        ksize //= 3                   # the file stores the internal (x3) ksize for protein-family sketches
-    mh = MinHash(num, ksize, is_protein=(molecule == "protein"), dayhoff=(molecule == "dayhoff"),
-                 hp=(molecule == "hp"), track_abundance=track, seed=int(d.get("seed", 42)), max_hash=max_hash)
-    mins = d.get("mins", [])
-    if track:
-        mh.set_abundances(dict(zip(mins, d["abundances"])))
-    else:
-        mh.add_many(mins)
-    return mh
-
-
-def load_signatures_from_json(data, *, ksize=None, select_moltype=None):
-    """Yield SourmashSignature objects (one per sketch) from a .sig path, JSON text or bytes."""
-    if isinstance(data, (str, os.PathLike)) and os.path.exists(str(data)):
-        opener = gzip.open if str(data).endswith(".gz") else open
-        with opener(str(data), "rt") as fh:
-            data = fh.read()
-    if isinstance(data, bytes):
-        if data[:2] == b"\x1f\x8b":
-            data = gzip.decompress(data)
-        data = data.decode("utf-8")
-    for rec in json.loads(data):
-        for sk in rec.get("signatures", []):
-            if ksize is not None and int(sk["ksize"]) != ksize:
-                continue
-            if select_moltype is not None and sk.get("molecule", "DNA").lower() != select_moltype.lower():
-                continue
-            yield SourmashSignature(_sketch_from_json(sk), name=rec.get("name", ""),
-                                    filename=rec.get("filename", ""))
+def load_signatures_from_json(data, *, ksize=None, select_moltype=None, ignore_md5sum=False, do_raise=False):
+    """Yield SourmashSignature objects (one per sketch) from a .sig / .sig.gz path, JSON text,
+    bytes (optionally gzipped) or a file object.  ``ksize`` is compared with the stored value
+    (3 x residues for protein-family sketches), like the reference (signature.rs:611-616)."""
+    if not data:
+        return
+    if hasattr(data, "read"):
+        if hasattr(data, "mode") and "t" in data.mode and hasattr(data, "buffer"):
+            data = data.buffer
+        data = data.read()
+    moltype = ffi.NULL if select_moltype is None else select_moltype.encode("utf-8")
+    size = ffi.new("uintptr_t *")
+    try:
+        if isinstance(data, (str, os.PathLike)) and os.path.exists(str(data)):
+            arr = rustcall(lib.signatures_load_path, str(data).encode("utf-8"), ignore_md5sum,
+                           int(ksize or 0), moltype, size)
+        else:
+            if isinstance(data, os.PathLike):
+                raise ValueError(f"cannot open {data}")
+            buf = data.encode("utf-8") if isinstance(data, str) else bytes(data)
+            arr = rustcall(lib.signatures_load_buffer, buf, len(buf), ignore_md5sum,
+                           int(ksize or 0), moltype, size)
+    except Exception:
+        if do_raise:
+            raise
+        return
+    sigs = [SourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
+    lib.signatures_array_free(arr, size[0])
+    yield from sigs
 
 
 load_signatures = load_signatures_from_json
 
 
-def save_signatures_to_json(siglist, fp=None):
+def load_one_signature_from_json(data, *, ksize=None, select_moltype=None, ignore_md5sum=False):
+    it = load_signatures_from_json(data, ksize=ksize, select_moltype=select_moltype, ignore_md5sum=ignore_md5sum)
+    try:
+        first = next(it)
+    except StopIteration:
+        raise ValueError("no signatures to load")
+    try:
+        next(it)
+    except StopIteration:
+        return first
+    raise ValueError("expected to load exactly one signature")
+
+
+def save_signatures_to_json(siglist, fp=None, compression=0):
     "Serialise signatures in the reference's .sig JSON layout; returns the text if fp is None."
-    records = []
-    for sig in siglist:
-        sketches = []
-        for mh in sig.sketches():
-            hashes = mh.hashes
-            d = {"num": mh.num, "ksize": mh.ksize if mh.is_dna else mh.ksize * 3, "seed": mh.seed,
-                 "max_hash": mh._max_hash, "mins": list(hashes.keys()), "md5sum": mh.md5sum(),
-                 "molecule": mh.moltype if mh.moltype != "DNA" else "dna"}
-            if mh.track_abundance:
-                d["abundances"] = list(hashes.values())
-            sketches.append(d)
-        rec = {"class": "sourmash_signature", "email": "", "hash_function": "0.murmur64",
-               "filename": sig.filename, "license": sig.license, "signatures": sketches,
-               "version": SIGNATURE_VERSION}
-        if sig.name:
-            rec["name"] = sig.name
-        records.append(rec)
-    text = json.dumps(records)
+    siglist = list(siglist)
+    ptrs = ffi.new("SourmashSignature *[]", [sig._get_objptr() for sig in siglist])
+    size = ffi.new("uintptr_t *")
+    raw = rustcall(lib.signatures_save_buffer, ptrs, len(siglist), int(compression), size)
+    try:
+        result = bytes(ffi.buffer(raw, size[0]))
+    finally:
+        lib.nodegraph_buffer_free(raw, size[0])
+    if not compression:
+        result = result.decode("utf-8")
     if fp is None:
-        return text
-    fp.write(text)
+        return result
+    try:
+        fp.write(result)
+    except TypeError:
+        fp.write(result.decode("utf-8") if isinstance(result, bytes) else result.encode("utf-8"))
     return None

@@ -1,0 +1,130 @@
+"""Bulk .sig loading straight into a GPU-resident SketchSet.
+
+The reference loads N signatures as N Python objects (signature.py:383-527), and ``compare`` /
+``search`` / ``gather`` then pull every sketch's hashes back out through the FFI one object at a
+time.  Here the library parses all files in parallel threads into one CSR (csrc/ingest.cu) and the
+rows go to HBM in one copy; Python only sees per-sketch metadata.
+"""
+import numpy as np
+
+from . import batch as B
+from ._ffi import decode_str, rustcall
+from ._lowlevel import ffi, lib
+
+_MOLTYPES = {1: "DNA", 2: "protein", 3: "dayhoff", 4: "hp"}
+
+
+class SignatureSet:
+    """Parsed .sig files: per-sketch metadata on the host, hashes as CSR (numpy views), and
+    ``to_sketchset`` to put any selection of rows on the GPU."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+        n = int(lib.smb_sigs_n_sketches(ptr))
+        info = ffi.new("SmbSketchInfo *")
+        self.ksize = np.zeros(n, np.uint32); self.num = np.zeros(n, np.uint32)
+        self.max_hash = np.zeros(n, np.uint64); self.seed = np.zeros(n, np.uint64)
+        self.hash_function = np.zeros(n, np.uint32); self.has_abund = np.zeros(n, bool)
+        self.sig_index = np.zeros(n, np.uint32); self.file = np.zeros(n, np.uint32)
+        self.n_mins = np.zeros(n, np.uint64)
+        for i in range(n):
+            lib.smb_sigs_sketch_info(ptr, i, info)
+            self.ksize[i], self.num[i], self.max_hash[i], self.seed[i] = info.ksize, info.num, info.max_hash, info.seed
+            self.hash_function[i], self.has_abund[i] = info.hash_function, info.has_abund
+            self.sig_index[i], self.file[i], self.n_mins[i] = info.sig_index, info.file, info.n_mins
+        self.offsets = np.frombuffer(ffi.buffer(lib.smb_sigs_offsets(ptr), (n + 1) * 8), dtype=np.uint64)
+        tot = int(self.offsets[-1]) if n else 0
+        self.mins = np.frombuffer(ffi.buffer(lib.smb_sigs_mins(ptr), tot * 8), dtype=np.uint64) if tot else np.zeros(0, np.uint64)
+        self.abunds = np.frombuffer(ffi.buffer(lib.smb_sigs_abunds(ptr), tot * 8), dtype=np.uint64) if tot else np.zeros(0, np.uint64)
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p and lib is not None:
+            self.offsets = self.mins = self.abunds = None
+            lib.smb_sigs_free(p)
+
+    @classmethod
+    def from_files(cls, paths, n_threads=0):
+        paths = [str(p).encode("utf-8") for p in paths]
+        keep = [ffi.new("char[]", p) for p in paths]
+        arr = ffi.new("char *[]", keep)
+        return cls(rustcall(lib.smb_sigs_read, arr, len(paths), int(n_threads)))
+
+    @classmethod
+    def from_json(cls, data):
+        buf = data.encode("utf-8") if isinstance(data, str) else bytes(data)
+        return cls(rustcall(lib.smb_sigs_parse, buf, len(buf)))
+
+    def __len__(self):
+        return len(self.ksize)
+
+    def moltype(self, i):
+        return _MOLTYPES[int(self.hash_function[i])]
+
+    def name(self, i):
+        return decode_str(lib.smb_sigs_sig_name(self._ptr, int(self.sig_index[i])))
+
+    def filename(self, i):
+        return decode_str(lib.smb_sigs_sig_filename(self._ptr, int(self.sig_index[i])))
+
+    def md5sum(self, i):
+        return decode_str(lib.smb_sigs_sketch_md5(self._ptr, int(i)))
+
+    def row(self, i):
+        return self.mins[int(self.offsets[i]):int(self.offsets[i + 1])]
+
+    def select(self, ksize=None, moltype=None, scaled=None, num=None):
+        """Indices of the sketches matching the filters (ksize as stored; scaled: sketches that can
+        be downsampled to it, i.e. stored scaled <= requested)."""
+        keep = np.ones(len(self), bool)
+        if ksize is not None:
+            keep &= self.ksize == ksize
+        if moltype is not None:
+            code = {v.lower(): k for k, v in _MOLTYPES.items()}[moltype.lower()]
+            keep &= self.hash_function == code
+        if scaled is not None:
+            keep &= (self.max_hash >= np.uint64(B.max_hash_for_scaled(scaled))) & (self.max_hash != 0)
+        if num is not None:
+            keep &= self.num == num
+        return np.nonzero(keep)[0].astype(np.uint32)
+
+    def minhash(self, i):
+        "One sketch as a (frozen) MinHash object."
+        from .minhash import FrozenMinHash
+        return FrozenMinHash._from_objptr(rustcall(lib.smb_sigs_minhash, self._ptr, int(i)))
+
+    def to_sketchset(self, rows=None, scaled=None, with_abunds=False):
+        """Rows (default: all) as a GPU-resident SketchSet; ``scaled`` downsamples every row
+        (prefix h <= max_hash_for_scaled(scaled), sketch/minhash.rs:777-798)."""
+        max_hash = B.max_hash_for_scaled(scaled) if scaled else 0
+        if rows is None:
+            p = rustcall(lib.smb_sigs_to_sketchset, self._ptr, ffi.NULL, 0, max_hash, bool(with_abunds))
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.uint32)
+            p = rustcall(lib.smb_sigs_to_sketchset, self._ptr, ffi.cast("uint32_t *", rows.ctypes.data),
+                         len(rows), max_hash, bool(with_abunds))
+        return B.SketchSet(p)
+
+
+def compare_signature_files(paths, *, ksize=None, moltype="DNA", scaled=None, n_threads=0):
+    """`sourmash compare *.sig` without per-object Python: parse all files natively, downsample to
+    the coarsest scaled (commands.py:167-194), one N x N launch.  Returns (matrix, labels)."""
+    ss = SignatureSet.from_files(paths, n_threads)
+    rows = ss.select(ksize=ksize, moltype=moltype)
+    if len(rows) == 0:
+        raise ValueError("no signatures match the selection")
+    nums = set(int(x) for x in ss.num[rows])
+    is_scaled = bool((ss.max_hash[rows] != 0).all())
+    if not is_scaled and (len(nums) != 1 or (ss.max_hash[rows] != 0).any()):
+        raise ValueError("cannot mix scaled signatures with num signatures / different nums")
+    if len(set(int(x) for x in ss.ksize[rows])) != 1:
+        raise ValueError("multiple k-mer sizes loaded; please specify one with ksize")
+    labels = [ss.name(i) or ss.filename(i) or ss.md5sum(i)[:8] for i in rows]
+    if is_scaled:
+        coarsest = int(ss.max_hash[rows].min())                     # largest scaled == smallest max_hash
+        if scaled:
+            coarsest = min(coarsest, B.max_hash_for_scaled(scaled))
+        p = rustcall(lib.smb_sigs_to_sketchset, ss._ptr, ffi.cast("uint32_t *", rows.ctypes.data), len(rows),
+                     coarsest, False)
+        return B.compare_jaccard(B.SketchSet(p)), labels
+    return B.compare_jaccard(ss.to_sketchset(rows), num=nums.pop()), labels

@@ -1,48 +1,85 @@
-"""`sourmash sketch dna` driver on the batched GPU path.
+"""`sourmash sketch dna | protein | translate` driver on the batched GPU path.
 
 Counterpart of the record loop of /root/reference/src/sourmash/command_sketch.py:662-789
-(`_compute_individual`: screed record loop -> ``sig.add_sequence(seq, force=not check_sequence)``)
-: all records of all input files go to the GPU in one ``smb_sketch_sequences`` call, and one
+(`_compute_individual`: screed record loop -> ``sig.add_sequence(seq, force=not check_sequence)``
+or ``sig.add_protein(seq)`` when ``input_is_protein``): the input files are read natively
+(``smb_records_read``: FASTA/FASTQ, plain or gzip, one thread per file, sequence bytes in
+page-locked memory), all records go to the GPU in one ``smb_sketch_records`` call, and one
 ``SourmashSignature`` per file (or per record with ``singleton=True``) comes back carrying one
-sketch per ksize.  The FASTA/FASTQ reader is a minimal host-side parser ("next" row f2 of the
-scope table: not accelerated).
+sketch per ksize.
 """
-import gzip
-import os
-
 import numpy as np
 
 from . import batch as B
-from ._lowlevel import lib
+from ._ffi import rustcall
+from ._lowlevel import ffi, lib
 from .minhash import MinHash
 from .signature import SourmashSignature
-from ._ffi import rustcall
+
+
+class RecordBatch:
+    """Sequence records of a set of FASTA/FASTQ(.gz) files, parsed by the library."""
+
+    def __init__(self, paths, n_threads=0):
+        self.paths = [str(p) for p in paths]
+        keep = [ffi.new("char[]", p.encode("utf-8")) for p in self.paths]
+        self._ptr = rustcall(lib.smb_records_read, ffi.new("char *[]", keep), len(keep), int(n_threads))
+        n = int(lib.smb_records_len(self._ptr))
+        self.offsets = np.frombuffer(ffi.buffer(lib.smb_records_offsets(self._ptr), (n + 1) * 8), dtype=np.uint64)
+        self.files = np.frombuffer(ffi.buffer(lib.smb_records_files(self._ptr), n * 4), dtype=np.uint32) if n else np.zeros(0, np.uint32)
+        self.total_bytes = int(lib.smb_records_total_bytes(self._ptr))
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p and lib is not None:
+            self.offsets = self.files = None
+            lib.smb_records_free(p)
+
+    def __len__(self):
+        return len(self.files)
+
+    def names(self):
+        noff = ffi.new("uint64_t **")
+        base = lib.smb_records_names(self._ptr, noff)
+        n = len(self)
+        off = np.frombuffer(ffi.buffer(noff[0], (n + 1) * 8), dtype=np.uint64)
+        blob = bytes(ffi.buffer(base, int(off[-1]))) if n and off[-1] else b""
+        return [blob[int(off[i]):int(off[i + 1])].decode("utf-8", "replace") for i in range(n)]
+
+    def sequence(self, i):
+        lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
+        return bytes(ffi.buffer(lib.smb_records_data(self._ptr) + lo, hi - lo)) if hi > lo else b""
+
+    def sketch(self, rec_to_sketch, n_sketches, ksizes, *, moltype="DNA", input_is_protein=False, scaled=0, num=0,
+               seed=42, track_abundance=False):
+        ks = np.ascontiguousarray(ksizes, dtype=np.uint32)
+        hf = B._HASH_FUNCTIONS[moltype.lower()]
+        if hf != 1:
+            ks = np.ascontiguousarray(ks * np.uint32(3))
+        elif input_is_protein:
+            raise ValueError("cannot add protein sequence to DNA MinHash")
+        r2s = np.ascontiguousarray(rec_to_sketch, dtype=np.uint32)
+        nk = ffi.new("uint64_t *")
+        p = rustcall(lib.smb_sketch_records, self._ptr, ffi.cast("uint32_t *", r2s.ctypes.data) if len(r2s) else ffi.NULL,
+                     int(n_sketches), ffi.cast("uint32_t *", ks.ctypes.data), len(ks), hf, bool(input_is_protein),
+                     int(scaled), int(num), int(seed), bool(track_abundance), nk)
+        return B.SketchSet(p), int(nk[0])
 
 
 def read_sequences(path):
     """[(name, sequence bytes)] of a FASTA or FASTQ file (optionally gzipped)."""
-    opener = gzip.open if str(path).endswith(".gz") else open
-    with opener(path, "rb") as fh:
-        data = fh.read()
-    if not data:
-        return []
-    if data[:1] == b"@":                                   # FASTQ: 4-line records
-        lines = data.split(b"\n")
-        return [(lines[i][1:].decode("utf-8", "replace"), lines[i + 1].strip())
-                for i in range(0, len(lines) - 1, 4) if lines[i].startswith(b"@")]
-    out = []
-    for chunk in data.split(b">")[1:]:
-        head, _, body = chunk.partition(b"\n")
-        out.append((head.strip().decode("utf-8", "replace"), body.replace(b"\n", b"").replace(b"\r", b"")))
-    return out
+    rb = RecordBatch([path])
+    return list(zip(rb.names(), (rb.sequence(i) for i in range(len(rb)))))
 
 
-def _signature_from_rows(rows, abunds, ksizes, scaled, num, seed, track, name, filename):
+def _signature_from_rows(rows, abunds, ksizes, scaled, num, seed, track, name, filename, moltype="DNA"):
     sig = SourmashSignature.__new__(SourmashSignature)
     sig._objptr = lib.signature_new()
     sig._shared = False
+    mol = moltype.lower()
     for i, k in enumerate(ksizes):
-        mh = MinHash(num, k, scaled=scaled, seed=seed, track_abundance=track)
+        mh = MinHash(num, k, scaled=scaled, seed=seed, track_abundance=track, is_protein=mol == "protein",
+                     dayhoff=mol == "dayhoff", hp=mol == "hp")
         if track:
             mh.set_abundances(dict(zip(rows[i].tolist(), abunds[i].tolist())))
         else:
@@ -56,47 +93,52 @@ def _signature_from_rows(rows, abunds, ksizes, scaled, num, seed, track, name, f
 
 
 def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, seed=42, track_abundance=False,
-                       singleton=False, name_from_first=False, check_sequence=False):
+                       singleton=False, name_from_first=False, check_sequence=False, moltype="DNA",
+                       input_is_protein=False, n_threads=0):
     """Sketch every input file on the GPU; returns a list of SourmashSignature (one sketch per ksize).
 
+    ``moltype`` "protein" / "dayhoff" / "hp" with ``input_is_protein`` is `sketch protein`; without
+    it the DNA is translated in six frames (`sketch translate`); ksizes are then in residues.
     ``check_sequence=True`` reproduces ``--check-sequence`` (force=False: the first invalid k-mer
     raises ValueError) through the per-record ABI call; the default skips invalid k-mers like
     the reference CLI (command_sketch.py:827-832)."""
     ksizes = list(ksizes)
-    records, owner, names, files = [], [], [], []
-    for path in filenames:
-        recs = read_sequences(path)
-        if singleton:
-            for name, seq in recs:
-                owner.append(len(names)); names.append(name); files.append(str(path)); records.append(seq)
-        else:
-            first = recs[0][0] if recs and name_from_first else ""
-            for _, seq in recs:
-                owner.append(len(names)); records.append(seq)
-            names.append(first); files.append(str(path))
+    rb = RecordBatch(filenames, n_threads)
+    rec_names = rb.names() if (singleton or name_from_first) else None
+    names, files = [], []
+    if singleton:
+        owner = np.arange(len(rb), dtype=np.uint32)
+        names = rec_names
+        files = [rb.paths[int(f)] for f in rb.files]
+    else:
+        owner = rb.files.copy()
+        first_of = {}
+        if name_from_first:
+            for i, f in enumerate(rb.files):
+                first_of.setdefault(int(f), rec_names[i])
+        names = [first_of.get(i, "") for i in range(len(rb.paths))]
+        files = list(rb.paths)
     n_sk = len(names)
-    if check_sequence:
+    if check_sequence and moltype.lower() == "dna":
         sigs = []
+        empty = [np.zeros(0, np.uint64)] * len(ksizes)
         for s in range(n_sk):
-            sig = _signature_from_rows([np.zeros(0, np.uint64)] * len(ksizes), [np.zeros(0, np.uint64)] * len(ksizes),
-                                       ksizes, scaled, num, seed, track_abundance, names[s], files[s])
-            for seq, o in zip(records, owner):
-                if o == s:
-                    sig.add_sequence(seq, force=False)
+            sig = _signature_from_rows(empty, empty, ksizes, scaled, num, seed, track_abundance, names[s], files[s])
+            for i in np.nonzero(owner == s)[0]:
+                sig.add_sequence(rb.sequence(int(i)), force=False)
             sigs.append(sig)
         return sigs
-    lens = np.array([len(r) for r in records], dtype=np.uint64)
-    offs = np.zeros(len(records) + 1, dtype=np.uint64)
-    offs[1:] = np.cumsum(lens)
-    seqs = np.frombuffer(b"".join(records), dtype=np.uint8) if records else np.zeros(0, np.uint8)
-    sset, _ = B.sketch_sequences(seqs, offs, ksizes, scaled=scaled, num=num, seed=seed,
-                                 track_abundance=track_abundance,
-                                 seq_to_sketch=np.array(owner, dtype=np.uint32), n_sketches=n_sk)
-    h, off, ab = sset.to_host(with_abunds=True)
     nk = len(ksizes)
+    if len(rb) == 0:                                       # nothing to hash: empty sketches
+        empty = [np.zeros(0, np.uint64)] * nk
+        return [_signature_from_rows(empty, empty, ksizes, scaled, num, seed, track_abundance, names[s], files[s], moltype)
+                for s in range(n_sk)]
+    sset, _ = rb.sketch(owner, n_sk, ksizes, moltype=moltype, input_is_protein=input_is_protein, scaled=scaled,
+                        num=num, seed=seed, track_abundance=track_abundance)
+    h, off, ab = sset.to_host(with_abunds=True)
     sigs = []
     for s in range(n_sk):
         rows = [h[int(off[s * nk + j]):int(off[s * nk + j + 1])] for j in range(nk)]
         abr = [ab[int(off[s * nk + j]):int(off[s * nk + j + 1])] for j in range(nk)] if ab is not None else None
-        sigs.append(_signature_from_rows(rows, abr, ksizes, scaled, num, seed, track_abundance, names[s], files[s]))
+        sigs.append(_signature_from_rows(rows, abr, ksizes, scaled, num, seed, track_abundance, names[s], files[s], moltype))
     return sigs

@@ -36,7 +36,7 @@ def _mh(smb, moltype, k, **kw):
 
 
 def _records(path):
-    from conftest import read_fasta
+    from tests.conftest import read_fasta
     return [(n, s) for n, s in read_fasta(str(path))]
 
 
