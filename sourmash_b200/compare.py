@@ -7,9 +7,42 @@ produces the whole count matrix.  Float post-processing follows the reference's 
 order (similarity = common / max(1, union) on the device as an IEEE f64 divide; containment
 bias factors computed with Python floats exactly like minhash.py:827-841).
 """
+import sys
+
 import numpy as np
 
 from . import batch as B
+from . import distance_utils as DU
+
+_FALSE_NEG_WARNING = ("WARNING: Some of these sketches may have no hashes in common based on chance alone "
+                      "(false negatives). Consider decreasing your scaled value to prevent this.")
+_JACCARD_WARNING = ("WARNING: Jaccard estimation for at least one of these comparisons is likely inaccurate. "
+                    "Could not estimate ANI for these comparisons.")
+
+
+def notify(msg):
+    print(msg, file=sys.stderr)
+
+
+def _sizes_accurate(mhs, relative_error=0.20, confidence=0.95):
+    "size_is_accurate() of every sketch, one vectorised binomial evaluation (minhash.py:1129-1150)."
+    if not all(mh.scaled for mh in mhs):
+        raise TypeError("Error: can only calculate ANI for scaled MinHashes")
+    out = np.zeros(len(mhs), dtype=bool)
+    cache = {}
+    for i, mh in enumerate(mhs):
+        key = (len(mh), mh.scaled)
+        if key not in cache:
+            cache[key] = bool(DU.set_size_exact_prob(key[0] * key[1], key[1], relative_error=relative_error) >= confidence)
+        out[i] = cache[key]
+    return out
+
+
+def _p_nothing_in_common(dist, n_unique_kmers, ksize, scaled):
+    "get_exp_probability_nothing_common for arrays (distance_utils.py:247-270)."
+    q = 1 - (1 - dist) ** ksize
+    p = np.exp((n_unique_kmers - n_unique_kmers * q) * np.log(1.0 - 1.0 / float(scaled)))
+    return np.where(dist == 1.0, 1.0, np.where(dist == 0.0, 0.0, p))
 
 
 def _flat_minhashes(siglist):
@@ -48,15 +81,24 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
     """Similarity matrix (n, n) float64, ones on the diagonal -- ``compare_all_pairs`` /
     ``compare_serial`` / ``compare_parallel`` of the reference (compare.py:14-64,241-358).
     ``n_jobs`` is accepted for signature compatibility; the GPU does the whole matrix."""
-    if return_ani:
-        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
     mhs = _flat_minhashes(siglist)
     n = len(mhs)
     if n == 0:
         return np.ones((0, 0))
     has_ab = np.array([bool(mh.track_abundance) for mh in mhs])
-    sset, num, scaled, _ = _check_and_build(siglist, downsample=downsample)
+    if return_ani:
+        accurate = _sizes_accurate(mhs)                   # also raises for num sketches, like jaccard_ani
+    sset, num, scaled, sizes = _check_and_build(siglist, downsample=downsample)
     jac = B.compare_jaccard(sset, num=num)
+    if return_ani:
+        # compare.py:36-54: ANI from Jaccard for every pair; untrustworthy estimates become 0
+        ani, untrustworthy, false_neg = DU.jaccard_to_ani_matrix(jac, sizes, mhs[0].ksize, scaled,
+                                                                  size_accurate=accurate)
+        if untrustworthy:
+            notify(_JACCARD_WARNING)
+        if false_neg:
+            notify(_FALSE_NEG_WARNING)
+        return ani
     if ignore_abundance or not has_ab.any():
         return jac
     # angular similarity where both sketches track abundance, Jaccard elsewhere (minhash.rs:682-702)
@@ -104,9 +146,9 @@ def _containment_parts(siglist, downsample):
 
 
 def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
-    """containments[i][j] = siglist[j].contained_by(siglist[i]) (compare.py:67-106)."""
-    if return_ani:
-        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
+    """containments[i][j] = siglist[j].contained_by(siglist[i]) (compare.py:67-106); with
+    ``return_ani`` the containment ANI of j in i (0.0 where it cannot be trusted)."""
+    accurate = _sizes_accurate(_flat_minhashes(siglist)) if return_ani else None
     common, sizes, scaled = _containment_parts(siglist, downsample)
     n = len(sizes)
     if n == 0:
@@ -116,14 +158,22 @@ def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
         m = common / denom[np.newaxis, :]
     m = _clamp01(m)
     m[:, sizes == 0] = 0.0
+    if return_ani:
+        ksize = _flat_minhashes(siglist)[0].ksize
+        ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
+        p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize),
+                                 (sizes * scaled).astype(np.float64)[np.newaxis, :], ksize, scaled)
+        np.fill_diagonal(p, 0.0)
+        if (p > 1e-3).any():
+            notify(_FALSE_NEG_WARNING)
+        m = ani
     np.fill_diagonal(m, 1.0)
     return m
 
 
 def compare_serial_max_containment(siglist, *, downsample=False, return_ani=False):
     """max_containment matrix (compare.py:109-147): common / (min(|A|,|B|) * bias(min))."""
-    if return_ani:
-        raise NotImplementedError("ANI estimation is outside the B200 hot path (SURVEY §8 f4)")
+    accurate = _sizes_accurate(_flat_minhashes(siglist)) if return_ani else None
     common, sizes, scaled = _containment_parts(siglist, downsample)
     n = len(sizes)
     if n == 0:
@@ -137,13 +187,26 @@ def compare_serial_max_containment(siglist, *, downsample=False, return_ani=Fals
         m = common / denom
     m = _clamp01(m)
     m[mins == 0] = 0.0
+    if return_ani:
+        ksize = _flat_minhashes(siglist)[0].ksize
+        ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
+        p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize), (mins * scaled).astype(np.float64),
+                                 ksize, scaled)
+        np.fill_diagonal(p, 0.0)
+        if (p > 1e-3).any():
+            notify(_FALSE_NEG_WARNING)
+        m = ani
     np.fill_diagonal(m, 1.0)
     return m
 
 
 def compare_serial_avg_containment(siglist, *, downsample=False, return_ani=False):
-    """avg_containment matrix (compare.py:150-187): mean of the two directed containments."""
+    """avg_containment matrix (compare.py:150-187): mean of the two directed containments; with
+    ``return_ani`` the mean of the two containment ANIs, 0.0 if either cannot be trusted."""
     c = compare_serial_containment(siglist, downsample=downsample, return_ani=return_ani)
     m = (c + c.T) / 2
+    if return_ani:
+        accurate = _sizes_accurate(_flat_minhashes(siglist))
+        m = np.where(accurate[:, None] & accurate[None, :], m, 0.0)
     np.fill_diagonal(m, 1.0)
     return m

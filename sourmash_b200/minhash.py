@@ -593,6 +593,86 @@ class MinHash(RustObject):
             raise TypeError("can only approximate unique_dataset_hashes for scaled MinHashes")
         return len(self) * self.scaled
 
+    def size_is_accurate(self, relative_error=0.20, confidence=0.95):
+        """True if len(self) * scaled is, with probability >= confidence, within relative_error
+        of the true number of distinct k-mers (minhash.py:1129-1150)."""
+        from .distance_utils import set_size_exact_prob
+        if not self.scaled:
+            raise TypeError("Error: can only estimate dataset size for scaled MinHashes")
+        if not (0 <= relative_error <= 1) or not (0 <= confidence <= 1):
+            raise ValueError("Error: relative error and confidence values must be between 0 and 1.")
+        return set_size_exact_prob(self.unique_dataset_hashes, self.scaled, relative_error=relative_error) >= confidence
+
+    def inflate(self, from_mh):
+        """New sketch holding self's hashes with the abundances they have in ``from_mh``
+        (hashes absent there are dropped; minhash.py:1071-1092)."""
+        if self.track_abundance or not from_mh.track_abundance:
+            raise ValueError("inflate operates on a flat MinHash and takes a MinHash object with track_abundance=True")
+        orig = from_mh.hashes
+        abund_mh = from_mh.copy_and_clear()
+        abund_mh.downsample(scaled=self.scaled)
+        abund_mh.set_abundances({h: orig.get(h, 0) for h in self.hashes})
+        return abund_mh
+
+    # ------------------------------------------------------------------ ANI (minhash.py:749-976)
+    def _ani_operands(self, other, downsample):
+        if not (self.scaled and other.scaled):
+            raise TypeError("Error: can only calculate ANI for scaled MinHashes")
+        a, b, scaled = self, other, self.scaled
+        if downsample:
+            scaled = max(a.scaled, b.scaled)
+            a, b = a.downsample(scaled=scaled), b.downsample(scaled=scaled)
+        return a, b, scaled
+
+    def jaccard_ani(self, other, *, downsample=False, jaccard=None, prob_threshold=1e-3, err_threshold=1e-4):
+        "ANI estimated from the Jaccard similarity of two scaled sketches."
+        from .distance_utils import jaccard_to_distance
+        a, b, scaled = self._ani_operands(other, downsample)
+        if jaccard is None:
+            jaccard = a.similarity(b, ignore_abundance=True)
+        avg_n_kmers = round((len(a) + len(b)) / 2 * scaled)
+        res = jaccard_to_distance(jaccard, a.ksize, scaled, n_unique_kmers=avg_n_kmers,
+                                  prob_threshold=prob_threshold, err_threshold=err_threshold)
+        if not self.size_is_accurate() or not other.size_is_accurate():
+            res.size_is_inaccurate = True
+        return res
+
+    def containment_ani(self, other, *, downsample=False, containment=None, confidence=0.95, estimate_ci=False,
+                        prob_threshold=1e-3):
+        "ANI estimated from the containment of self in other."
+        from .distance_utils import containment_to_distance
+        a, b, scaled = self._ani_operands(other, downsample)
+        if containment is None:
+            containment = a.contained_by(b)
+        res = containment_to_distance(containment, a.ksize, a.scaled, n_unique_kmers=len(a) * scaled,
+                                      confidence=confidence, estimate_ci=estimate_ci, prob_threshold=prob_threshold)
+        if not self.size_is_accurate() or not other.size_is_accurate():
+            res.size_is_inaccurate = True
+        return res
+
+    def max_containment_ani(self, other, *, downsample=False, max_containment=None, confidence=0.95,
+                            estimate_ci=False, prob_threshold=1e-3):
+        "ANI estimated from the containment relative to the smaller sketch."
+        from .distance_utils import containment_to_distance
+        a, b, scaled = self._ani_operands(other, downsample)
+        if max_containment is None:
+            max_containment = a.max_containment(b)
+        res = containment_to_distance(max_containment, a.ksize, scaled, n_unique_kmers=min(len(a), len(b)) * scaled,
+                                      confidence=confidence, estimate_ci=estimate_ci, prob_threshold=prob_threshold)
+        if not self.size_is_accurate() or not other.size_is_accurate():
+            res.size_is_inaccurate = True
+        return res
+
+    def avg_containment_ani(self, other, *, downsample=False, prob_threshold=1e-3):
+        "Mean of the two containment ANIs (None if either is not trustworthy)."
+        if not (self.scaled and other.scaled):
+            raise TypeError("Error: can only calculate ANI for scaled MinHashes")
+        a1 = self.containment_ani(other, downsample=downsample, prob_threshold=prob_threshold).ani
+        a2 = other.containment_ani(self, downsample=downsample, prob_threshold=prob_threshold).ani
+        if a1 is None or a2 is None:
+            return None
+        return (a1 + a2) / 2
+
 
 def _scalar_getter(c_function, doc):
     return property(lambda self: self._methodcall(c_function), doc=doc)
