@@ -1,0 +1,232 @@
+"""`sourmash gather` with its full per-match report, driven by the GPU gather session.
+
+The reference (src/sourmash/search.py:763-949) runs one Python round per match: pick the best
+counter, intersect, subtract, rebuild MinHash objects, and build a ``GatherResult``
+(search.py:471-655) whose columns come from two ``FracMinHashComparison`` objects
+(sketchcomparison.py:99-256).  Here the database, the query and the counters stay in HBM
+(``batch.GatherSession``); each round returns the winning row and the hashes it newly covers,
+and every report column is evaluated from those integers with the reference's own float
+formulas (Python floats, same operation order).  Abundance-weighted columns (f_unique_weighted,
+average / median / std abundance; search.py:596-620) use the query's abundances of exactly those
+hashes, in ascending hash order like ``MinHash.hashes``.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import batch as B
+from . import distance_utils as DU
+from .search import calc_threshold_from_bp
+
+GATHER_COLUMNS = [  # search.py:480-513
+    "intersect_bp", "f_orig_query", "f_match", "f_unique_to_query", "f_unique_weighted", "average_abund",
+    "median_abund", "std_abund", "filename", "name", "md5", "f_match_orig", "unique_intersect_bp",
+    "gather_result_rank", "remaining_bp", "query_filename", "query_name", "query_md5", "query_bp", "ksize",
+    "moltype", "scaled", "query_n_hashes", "query_abundance", "query_containment_ani", "match_containment_ani",
+    "average_containment_ani", "max_containment_ani", "potential_false_negative", "n_unique_weighted_found",
+    "sum_weighted_found", "total_weighted_hashes"]
+CI_COLUMNS = ["query_containment_ani_low", "query_containment_ani_high", "match_containment_ani_low",
+              "match_containment_ani_high"]
+
+
+@dataclass
+class GatherRow:
+    "One gather match; attribute names are the reference's CSV columns."
+    row: int                       # row of the database SketchSet
+    intersect_bp: int = 0
+    f_orig_query: float = 0.0
+    f_match: float = 0.0
+    f_unique_to_query: float = 0.0
+    f_unique_weighted: float = 0.0
+    average_abund: float = None
+    median_abund: float = None
+    std_abund: float = None
+    filename: str = None
+    name: str = None
+    md5: str = None
+    f_match_orig: float = 0.0
+    unique_intersect_bp: int = 0
+    gather_result_rank: int = 0
+    remaining_bp: int = 0
+    query_filename: str = None
+    query_name: str = None
+    query_md5: str = None
+    query_bp: int = 0
+    ksize: int = 0
+    moltype: str = "DNA"
+    scaled: int = 0
+    query_n_hashes: int = 0
+    query_abundance: bool = False
+    query_containment_ani: float = None
+    match_containment_ani: float = None
+    average_containment_ani: float = None
+    max_containment_ani: float = None
+    potential_false_negative: bool = False
+    n_unique_weighted_found: int = None
+    sum_weighted_found: int = 0
+    total_weighted_hashes: int = 0
+    query_containment_ani_low: float = None
+    query_containment_ani_high: float = None
+    match_containment_ani_low: float = None
+    match_containment_ani_high: float = None
+
+    def to_dict(self, estimate_ani_ci=False):
+        cols = GATHER_COLUMNS + (CI_COLUMNS if estimate_ani_ci else [])
+        return {c: getattr(self, c) for c in cols if getattr(self, c) is not None}
+
+
+def _contained_by(common, size, scaled):
+    "MinHash.contained_by from counts (minhash.py:819-841): bias-corrected, clamped to [0, 1]."
+    if size == 0:
+        return 0
+    bias = 1.0 - (1.0 - 1.0 / scaled) ** float(size * scaled)
+    c = common / (size * bias)
+    return 1.0 if c >= 1 else 0.0 if c <= 0 else c
+
+
+def _size_ok(n, scaled, cache):
+    key = (n, scaled)
+    if key not in cache:
+        cache[key] = bool(DU.set_size_exact_prob(n * scaled, scaled, relative_error=0.20) >= 0.95)
+    return cache[key]
+
+
+def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, estimate_ani_ci=False,
+                     names=None, md5s=None, filenames=None, query_name="", query_filename="", max_rounds=None):
+    """Min-set-cover of ``query_mh`` by the rows of the GPU-resident SketchSet ``db`` (same ksize,
+    seed and scaled as the query; use ``SketchSet.downsample`` / ``SignatureSet.to_sketchset``).
+    Returns the list of GatherRow in pick order -- the reference's GatherDatabases loop with the
+    columns of GatherResult.gatherresultdict."""
+    if not query_mh.scaled:
+        raise TypeError("query signature must be calculated with scaled")
+    scaled, ksize = query_mh.scaled, query_mh.ksize
+    q_hashes = query_mh._mins_array()
+    track = bool(query_mh.track_abundance) and not ignore_abundance
+    q_abunds = query_mh._abunds_array() if track else np.ones(len(q_hashes), dtype=np.uint64)
+    orig_len = len(q_hashes)
+    rows = []
+    if orig_len == 0 or len(db) == 0:
+        return rows
+    total_weighted = int(q_abunds.sum(dtype=object)) if track else orig_len
+    query_md5 = query_mh.md5sum()[:8]
+    sizes = db.sizes()
+    counts0 = B.one_vs_many(q_hashes, db)                     # |match ∩ original query| for every row
+    cache = {}
+    q_size_ok = _size_ok(orig_len, scaled, cache)
+    alive = np.ones(orig_len, dtype=bool)                      # hashes of the query not yet covered
+    remaining = orig_len
+    sess = B.GatherSession(q_hashes, db, min_count=1)
+    if max_rounds is None:
+        max_rounds = len(db)
+    while remaining > 0 and len(rows) < max_rounds:
+        try:                                                   # search.py:15-37, per current query size
+            _, n_threshold = calc_threshold_from_bp(threshold_bp, scaled, remaining)
+        except ValueError:
+            break
+        best, r = sess.peek()
+        if best == 0 or best < n_threshold:
+            break
+        isect = sess.intersect(r)                              # remaining query ∩ row r (ascending)
+        u, m, c0 = len(isect), int(sizes[r]), int(counts0[r])
+        pos = np.searchsorted(q_hashes, isect)
+        ab = q_abunds[pos]
+        alive[pos] = False
+        left = sess.apply(isect)
+        g = GatherRow(row=int(r), gather_result_rank=len(rows), ksize=ksize, moltype=query_mh.moltype,
+                      scaled=scaled, query_name=query_name, query_filename=query_filename, query_md5=query_md5,
+                      query_bp=orig_len * scaled, query_n_hashes=orig_len, total_weighted_hashes=total_weighted)
+        g.name = names[r] if names is not None else None
+        g.md5 = md5s[r] if md5s is not None else None
+        g.filename = filenames[r] if filenames is not None else None
+        g.intersect_bp = c0 * scaled
+        g.unique_intersect_bp = u * scaled
+        g.f_orig_query = c0 / orig_len
+        g.f_unique_to_query = u / orig_len
+        g.f_match_orig = _contained_by(c0, m, scaled)          # match.contained_by(original query)
+        g.f_match = _contained_by(u, m, scaled)                # match.contained_by(remaining query)
+        g.remaining_bp = (remaining - u) * scaled
+        if track:
+            g.query_abundance = True
+            g.n_unique_weighted_found = int(ab.sum(dtype=object))
+            g.f_unique_weighted = g.n_unique_weighted_found / total_weighted
+            vals = ab.tolist()
+            g.average_abund, g.median_abund, g.std_abund = np.mean(vals), np.median(vals), np.std(vals)
+        else:
+            g.f_unique_weighted = g.f_unique_to_query
+        g.sum_weighted_found = total_weighted - (int(q_abunds[alive].sum(dtype=object)) if track else int(alive.sum()))
+        # ANI columns: FracMinHashComparison(original query, match) (search.py:389-420, sketchcomparison.py:162-236)
+        ok = q_size_ok and _size_ok(m, scaled, cache)
+        qc = DU.containment_to_distance(_contained_by(c0, orig_len, scaled), ksize, scaled,
+                                        n_unique_kmers=orig_len * scaled, estimate_ci=estimate_ani_ci)
+        mc = DU.containment_to_distance(g.f_match_orig, ksize, scaled, n_unique_kmers=m * scaled,
+                                        estimate_ci=estimate_ani_ci)
+        qc.size_is_inaccurate = mc.size_is_inaccurate = not ok
+        g.query_containment_ani, g.match_containment_ani = qc.ani, mc.ani
+        g.potential_false_negative = bool(qc.p_exceeds_threshold or mc.p_exceeds_threshold)
+        if estimate_ani_ci:
+            g.query_containment_ani_low, g.query_containment_ani_high = qc.ani_low, qc.ani_high
+            g.match_containment_ani_low, g.match_containment_ani_high = mc.ani_low, mc.ani_high
+        if qc.ani is not None and mc.ani is not None:
+            g.average_containment_ani = (qc.ani + mc.ani) / 2
+            g.max_containment_ani = max(qc.ani, mc.ani)
+        rows.append(g)
+        remaining = left
+    return rows
+
+
+PREFETCH_COLUMNS = [  # search.py:364-388
+    "intersect_bp", "jaccard", "max_containment", "f_query_match", "f_match_query", "match_filename", "match_name",
+    "match_md5", "match_bp", "query_filename", "query_name", "query_md5", "query_bp", "ksize", "moltype", "scaled",
+    "query_n_hashes", "query_abundance", "query_containment_ani", "match_containment_ani",
+    "average_containment_ani", "max_containment_ani", "potential_false_negative"]
+
+
+def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, names=None, md5s=None, filenames=None,
+                      query_name="", query_filename=""):
+    """All rows of ``db`` sharing at least ``threshold_bp`` with the query, in database order, as
+    dictionaries with the reference's prefetch columns (search.py:953-998 + PrefetchResult
+    :357-470).  One pass of the one-vs-many kernel; everything else is per-match scalar work."""
+    if not query_mh.scaled:
+        raise TypeError("query signature must be calculated with scaled")
+    scaled, ksize = query_mh.scaled, query_mh.ksize
+    q = query_mh._mins_array()
+    nq = len(q)
+    if nq == 0:
+        raise ValueError("query is empty!?")
+    calc_threshold_from_bp(threshold_bp, scaled, nq)           # ValueError if unattainable (search.py:15-37)
+    counts = B.one_vs_many(q, db)
+    sizes = db.sizes()
+    cache = {}
+    q_ok = _size_ok(nq, scaled, cache)
+    out = []
+    query_md5 = query_mh.md5sum()[:8]
+    for r in np.nonzero(counts.astype(np.int64) * scaled >= max(threshold_bp, 1))[0]:
+        c, m = int(counts[r]), int(sizes[r])
+        qc_c, mc_c = _contained_by(c, nq, scaled), _contained_by(c, m, scaled)
+        qc = DU.containment_to_distance(qc_c, ksize, scaled, n_unique_kmers=nq * scaled, estimate_ci=estimate_ani_ci)
+        mc = DU.containment_to_distance(mc_c, ksize, scaled, n_unique_kmers=m * scaled, estimate_ci=estimate_ani_ci)
+        qc.size_is_inaccurate = mc.size_is_inaccurate = not (q_ok and _size_ok(m, scaled, cache))
+        d = {"row": int(r), "intersect_bp": c * scaled, "jaccard": c / max(1, nq + m - c),
+             "max_containment": _contained_by(c, min(nq, m), scaled), "f_query_match": mc_c, "f_match_query": qc_c,
+             "match_bp": m * scaled, "query_bp": nq * scaled, "ksize": ksize, "moltype": query_mh.moltype,
+             "scaled": scaled, "query_n_hashes": nq, "query_abundance": bool(query_mh.track_abundance),
+             "query_name": query_name, "query_filename": query_filename, "query_md5": query_md5,
+             "potential_false_negative": bool(qc.p_exceeds_threshold or mc.p_exceeds_threshold)}
+        if names is not None:
+            d["match_name"] = names[r]
+        if md5s is not None:
+            d["match_md5"] = md5s[r][:8]
+        if filenames is not None:
+            d["match_filename"] = filenames[r]
+        if qc.ani is not None:
+            d["query_containment_ani"] = qc.ani
+        if mc.ani is not None:
+            d["match_containment_ani"] = mc.ani
+        if qc.ani is not None and mc.ani is not None:
+            d["average_containment_ani"] = (qc.ani + mc.ani) / 2
+            d["max_containment_ani"] = max(qc.ani, mc.ani)
+        if estimate_ani_ci:
+            d.update(query_containment_ani_low=qc.ani_low, query_containment_ani_high=qc.ani_high,
+                     match_containment_ani_low=mc.ani_low, match_containment_ani_high=mc.ani_high)
+        out.append(d)
+    return out
