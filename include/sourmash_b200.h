@@ -343,16 +343,27 @@ void smb_records_free(SmbRecords *r);
 uintptr_t smb_records_len(const SmbRecords *r);
 uint64_t smb_records_total_bytes(const SmbRecords *r);
 const uint8_t *smb_records_data(const SmbRecords *r);
-const uint64_t *smb_records_offsets(const SmbRecords *r);          /* n + 1 */
+const uint64_t *smb_records_starts(const SmbRecords *r);           /* n: byte offset of each record */
+const uint64_t *smb_records_lengths(const SmbRecords *r);          /* n */
 const uint32_t *smb_records_files(const SmbRecords *r);            /* n: index into paths */
 const char *smb_records_names(const SmbRecords *r, const uint64_t **name_offsets);
-/* sketch the records of a batch (smb_sketch_sequences / smb_sketch_sequences_aa on its buffers);
- * hash_function DNA ignores input_is_protein */
+/* The sequence bytes sit in one buffer (every file owns a 16-byte aligned region, records packed
+ * inside it); a one-buffer pool keeps the page-locked allocation alive between calls.
+ * smb_sketch_records sketches the records of a batch like smb_sketch_sequences /
+ * smb_sketch_sequences_aa; hash_function DNA ignores input_is_protein */
 SmbSketchSet *smb_sketch_records(const SmbRecords *r, const uint32_t *rec_to_sketch,
                                  uintptr_t n_sketches, const uint32_t *ksizes, uintptr_t n_ksizes,
                                  HashFunctions hash_function, bool input_is_protein, uint64_t scaled,
                                  uint32_t num, uint64_t seed, bool track_abundance,
                                  uint64_t *n_kmers_out);
+
+/* Signature objects straight from a sketch set (the tail of _compute_individual,
+ * command_sketch.py:770-789): signature g owns rows [g * n_ksizes, (g + 1) * n_ksizes); ksizes
+ * are the ABI values.  Array freed with signatures_array_free, objects with signature_free. */
+SourmashSignature **smb_signatures_from_sketchset(const SmbSketchSet *set, const uint32_t *ksizes,
+                                                  uintptr_t n_ksizes, HashFunctions hash_function,
+                                                  uint64_t scaled, uint32_t num, uint64_t seed,
+                                                  uintptr_t *size);
 
 /* .sig / .sig.gz JSON (src/core/src/signature.rs:401-445, sketch/minhash.rs:103-184) parsed
  * straight into CSR: every sketch of every signature of every file is one row (unsorted mins

@@ -120,8 +120,24 @@ if "files" in what:
             text = smb.save_signatures_to_json(sigs)
             ts.append(time.perf_counter() - t)
         kmers = sum(5_000_000 - k + 1 for k in (21, 31, 51)) * len(paths)
+        # phases of the last iteration, timed separately
+        from sourmash_b200.sketch import RecordBatch
+        t0 = time.perf_counter()
+        rb = RecordBatch(paths)
+        t1 = time.perf_counter()
+        sset, _ = rb.sketch(rb.files.copy(), len(paths), [21, 31, 51], scaled=1000)
+        B.synchronize()
+        t2 = time.perf_counter()
+        del rb, sset
+        t3 = time.perf_counter()
+        sigs = sketch_fasta_files(paths, ksizes=[21, 31, 51], scaled=1000)
+        t4 = time.perf_counter()
+        text = smb.save_signatures_to_json(sigs)
+        t5 = time.perf_counter()
         res[tag] = {"files": len(paths), "wall_s_best": round(min(ts[1:]), 4), "kmers_per_s": kmers / min(ts[1:]),
-                    "sig_json_bytes": len(text)}
+                    "sig_json_bytes": len(text),
+                    "phases_s": {"read_parse": round(t1 - t0, 4), "upload_hash_sort": round(t2 - t1, 4),
+                                 "all_but_json": round(t4 - t3, 4), "sig_json": round(t5 - t4, 4)}}
     out["files"] = res
 
 if "sigs" in what:

@@ -2122,7 +2122,8 @@ void smb_records_free(SmbRecords* r) { delete r; }
 uintptr_t smb_records_len(const SmbRecords* r) { return r->b.file.size(); }
 uint64_t smb_records_total_bytes(const SmbRecords* r) { return r->b.total; }
 const uint8_t* smb_records_data(const SmbRecords* r) { return r->b.seqs; }
-const uint64_t* smb_records_offsets(const SmbRecords* r) { return r->b.off.data(); }
+const uint64_t* smb_records_starts(const SmbRecords* r) { return r->b.start.data(); }
+const uint64_t* smb_records_lengths(const SmbRecords* r) { return r->b.len.data(); }
 const uint32_t* smb_records_files(const SmbRecords* r) { return r->b.file.data(); }
 const char* smb_records_names(const SmbRecords* r, const uint64_t** name_offsets) {
     *name_offsets = r->b.name_off.data();
@@ -2132,12 +2133,61 @@ SmbSketchSet* smb_sketch_records(const SmbRecords* r, const uint32_t* rec_to_ske
                                  const uint32_t* ksizes, uintptr_t n_ksizes, HashFunctions hash_function,
                                  bool input_is_protein, uint64_t scaled, uint32_t num, uint64_t seed,
                                  bool track_abundance, uint64_t* n_kmers_out) {
-    const uintptr_t n = r->b.file.size();
-    if (hash_function == HASH_FUNCTIONS_MURMUR64_DNA)
-        return smb_sketch_sequences(r->b.seqs, r->b.off.data(), n, rec_to_sketch, n_sketches, ksizes, n_ksizes,
-                                    scaled, num, seed, track_abundance, n_kmers_out);
-    return smb_sketch_sequences_aa(r->b.seqs, r->b.off.data(), n, rec_to_sketch, n_sketches, ksizes, n_ksizes,
-                                   hash_function, input_is_protein, scaled, num, seed, track_abundance, n_kmers_out);
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        const smb::RecordBatch& b = r->b;
+        const size_t n = b.file.size();
+        cudaStream_t s = need_gpu();
+        DevBuf<uint8_t> d_bases(b.extent + 32, s);
+        StreamList in;
+        in.d_bases = d_bases.p;
+        in.h_bases = b.seqs;                             // uploaded in groups, overlapped with hashing
+        in.total_bytes = b.extent;
+        in.off = b.start;
+        in.len = b.len;
+        if (rec_to_sketch) in.row.assign(rec_to_sketch, rec_to_sketch + n);
+        in.n_sketches = rec_to_sketch ? n_sketches : n;
+        SketchParams P = make_params(ksizes, n_ksizes, scaled, num, seed, track_abundance);
+        P.hash_function = hash_function;
+        P.input_is_protein = hash_function != HASH_FUNCTIONS_MURMUR64_DNA && input_is_protein;
+        return sketch_streams(in, P, s, n_kmers_out).release();
+    });
+}
+
+// signatures straight from a sketch set (the tail of _compute_individual, command_sketch.py:770-789):
+// signature s gets rows [s * n_ksizes, (s + 1) * n_ksizes) of `set` as its sketches
+SourmashSignature** smb_signatures_from_sketchset(const SmbSketchSet* set, const uint32_t* ksizes,
+                                                  uintptr_t n_ksizes, HashFunctions hash_function,
+                                                  uint64_t scaled, uint32_t num, uint64_t seed,
+                                                  uintptr_t* size) {
+    return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
+        cudaStream_t s = need_gpu();
+        const size_t n_rows = set->n_rows, nk = n_ksizes;
+        if (nk == 0 || n_rows % nk != 0) fail(SOURMASH_ERROR_CODE_INTERNAL, "sketch set does not hold n_ksizes rows per signature");
+        const size_t tot = set->total();
+        std::vector<uint64_t> h(tot), ab(set->d_abunds ? tot : 0);
+        if (tot) {
+            CK(cudaMemcpyAsync(h.data(), set->d_hashes, tot * 8, cudaMemcpyDeviceToHost, s));
+            if (set->d_abunds) CK(cudaMemcpyAsync(ab.data(), set->d_abunds, tot * 8, cudaMemcpyDeviceToHost, s));
+            sync(s);
+        }
+        const size_t n_sig = n_rows / nk;
+        auto** arr = (SourmashSignature**)malloc(std::max<size_t>(n_sig, 1) * sizeof(void*));
+        for (size_t g = 0; g < n_sig; ++g) {
+            auto* sig = new SourmashSignature();
+            for (size_t j = 0; j < nk; ++j) {
+                const size_t r0 = set->h_off[g * nk + j], r1 = set->h_off[g * nk + j + 1];
+                MH m;
+                m.num = num; m.ksize = ksizes[j]; m.seed = seed; m.hash_function = hash_function;
+                m.max_hash = max_hash_for_scaled(scaled); m.track = set->d_abunds != nullptr;
+                m.mins.assign(h.begin() + r0, h.begin() + r1);
+                if (m.track) m.abunds.assign(ab.begin() + r0, ab.begin() + r1);
+                sig->sketches.push_back(std::move(m));
+            }
+            arr[g] = sig;
+        }
+        *size = n_sig;
+        return arr;
+    });
 }
 
 SmbSigs* smb_sigs_read(const char* const* paths, uintptr_t n_paths, int32_t n_threads) {

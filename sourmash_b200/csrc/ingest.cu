@@ -8,20 +8,21 @@
 #include "ingest.h"
 
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 
 namespace smb {
-
-RecordBatch::~RecordBatch() {
-    if (seqs) { if (pinned) cudaFreeHost(seqs); else free(seqs); }
-}
 
 namespace {
 
@@ -78,11 +79,45 @@ std::string slurp(const char* path, Bytes& data) {
     return "";
 }
 
+// One input file held in memory: plain files are mapped (no copy), gzip files inflated.
+struct Loaded {
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    void* map = nullptr;
+    size_t map_len = 0;
+    Bytes owned;
+    std::string error;
+    ~Loaded() { if (map) munmap(map, map_len); }
+};
+
+void load_file(const char* path, Loaded& L) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { L.error = std::string("cannot open ") + path; return; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); L.error = std::string("cannot stat ") + path; return; }
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd, magic, 2, 0);
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz && st.st_size > 0 && S_ISREG(st.st_mode)) {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+            L.map = m; L.map_len = (size_t)st.st_size;
+            L.p = (const uint8_t*)m; L.n = (size_t)st.st_size;
+            close(fd);
+            return;
+        }
+    }
+    close(fd);
+    L.error = slurp(path, L.owned);
+    L.p = L.owned.p; L.n = L.owned.n;
+}
+
 struct FileRecords {
-    std::vector<uint8_t> seqs;
-    std::vector<uint64_t> off{0};
+    std::vector<uint64_t> start, len;     // per record, relative to the file's output region
     std::string names;
     std::vector<uint64_t> name_off{0};
+    uint64_t used = 0;                     // bytes written to the region
     std::string error;
 };
 
@@ -90,20 +125,23 @@ inline const uint8_t* line_end(const uint8_t* p, const uint8_t* end) {
     const void* q = memchr(p, '\n', (size_t)(end - p));
     return q ? (const uint8_t*)q : end;
 }
-// append [p, e) without trailing '\r' / blanks
-inline void append_trimmed(std::vector<uint8_t>& dst, const uint8_t* p, const uint8_t* e) {
+// copy [p, e) without trailing '\r' / blanks to dst + w; returns the new write position
+inline uint64_t put_trimmed(uint8_t* dst, uint64_t w, const uint8_t* p, const uint8_t* e) {
     while (e > p && (e[-1] == '\r' || e[-1] == ' ' || e[-1] == '\t')) --e;
-    dst.insert(dst.end(), p, e);
+    memcpy(dst + w, p, (size_t)(e - p));
+    return w + (uint64_t)(e - p);
 }
 
-void parse_records(const Bytes& data, FileRecords& R) {
-    const uint8_t* p = data.data();
-    const uint8_t* end = p + data.size();
+// Records of one file; sequence bytes go straight to `dst` (a region of at least data-size bytes:
+// the sequence lines of a file never outgrow the file).
+void parse_records(const uint8_t* data, size_t size, uint8_t* dst, FileRecords& R) {
+    const uint8_t* p = data;
+    const uint8_t* end = p + size;
     while (p < end && (*p == '\n' || *p == '\r' || *p == ' ')) ++p;
     if (p == end) return;
     if (*p != '>' && *p != '@') { R.error = "neither FASTA nor FASTQ (first byte is not '>' or '@')"; return; }
-    R.seqs.reserve(data.size());
     const bool fastq = *p == '@';
+    uint64_t w = 0;
     while (p < end) {
         const uint8_t* e = line_end(p, end);
         if (e == p || *p == '\r') { p = e + 1; continue; }          // blank line between records
@@ -113,96 +151,127 @@ void parse_records(const Bytes& data, FileRecords& R) {
         R.names.append((const char*)p + 1, (size_t)(he - p - 1));
         R.name_off.push_back(R.names.size());
         p = e < end ? e + 1 : end;
-        const size_t seq_begin = R.seqs.size();
+        const uint64_t seq_begin = w;
         if (!fastq) {
             while (p < end && *p != '>') {
                 e = line_end(p, end);
-                append_trimmed(R.seqs, p, e);
+                w = put_trimmed(dst, w, p, e);
                 p = e < end ? e + 1 : end;
             }
         } else {
             while (p < end && *p != '+') {                           // sequence lines up to the '+' line
                 e = line_end(p, end);
-                append_trimmed(R.seqs, p, e);
+                w = put_trimmed(dst, w, p, e);
                 p = e < end ? e + 1 : end;
             }
             if (p < end) { e = line_end(p, end); p = e < end ? e + 1 : end; }   // '+' line
-            size_t need = R.seqs.size() - seq_begin, got = 0;       // quality: as many symbols as bases
+            uint64_t need = w - seq_begin, got = 0;                 // quality: as many symbols as bases
             while (p < end && got < need) {
                 e = line_end(p, end);
                 const uint8_t* qe = e;
                 while (qe > p && (qe[-1] == '\r')) --qe;
-                got += (size_t)(qe - p);
+                got += (uint64_t)(qe - p);
                 p = e < end ? e + 1 : end;
             }
         }
-        R.off.push_back(R.seqs.size());
+        R.start.push_back(seq_begin);
+        R.len.push_back(w - seq_begin);
     }
+    R.used = w;
 }
 
-}  // namespace
+// One page-locked staging buffer is kept between calls: pinning hundreds of MB costs far more
+// than filling them, and sketching runs are repeated over similar-sized batches.
+std::mutex g_pin_mu;
+uint8_t* g_pin_buf = nullptr;
+size_t g_pin_cap = 0;
 
-std::string read_sequence_files(const char* const* paths, size_t n_paths, int n_threads, bool want_pinned,
-                                RecordBatch& out) {
-    std::vector<FileRecords> files(n_paths);
-    std::atomic<size_t> next{0};
-    auto worker = [&] {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n_paths) return;
-            Bytes data;
-            files[i].error = slurp(paths[i], data);
-            if (files[i].error.empty()) {
-                parse_records(data, files[i]);
-                if (!files[i].error.empty()) files[i].error = std::string(paths[i]) + ": " + files[i].error;
-            }
+uint8_t* pinned_acquire(size_t bytes, size_t& cap) {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (g_pin_buf && g_pin_cap >= bytes) {
+            uint8_t* p = g_pin_buf; cap = g_pin_cap;
+            g_pin_buf = nullptr; g_pin_cap = 0;
+            return p;
         }
-    };
-    size_t nt = (size_t)std::max(1, n_threads);
-    nt = std::min(nt, std::max<size_t>(n_paths, 1));
+        if (g_pin_buf) { cudaFreeHost(g_pin_buf); g_pin_buf = nullptr; g_pin_cap = 0; }
+    }
+    uint8_t* p = nullptr;
+    cap = (bytes + (bytes >> 3) + (1u << 20)) & ~size_t(4095);
+    if (cudaHostAlloc((void**)&p, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pinned_release(uint8_t* p, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_buf) { g_pin_buf = p; g_pin_cap = cap; return; }
+    if (cap > g_pin_cap) { cudaFreeHost(g_pin_buf); g_pin_buf = p; g_pin_cap = cap; return; }
+    cudaFreeHost(p);
+}
+
+template <class F>
+void run_parallel(size_t n_items, size_t nt, F&& fn) {
+    std::atomic<size_t> next{0};
+    auto worker = [&] { for (;;) { size_t i = next.fetch_add(1); if (i >= n_items) return; fn(i); } };
+    nt = std::min(std::max<size_t>(nt, 1), std::max<size_t>(n_items, 1));
     std::vector<std::thread> pool;
     for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
-    for (auto& f : files) if (!f.error.empty()) return f.error;
+}
 
-    uint64_t total = 0, n_rec = 0, name_bytes = 0;
-    for (auto& f : files) { total += f.seqs.size(); n_rec += f.off.size() - 1; name_bytes += f.names.size(); }
-    out.total = total;
-    const size_t alloc = (size_t)((total + 64 + 4095) & ~4095ull);
+}  // namespace
+
+RecordBatch::~RecordBatch() {
+    if (seqs) { if (pinned) pinned_release(seqs, cap); else free(seqs); }
+}
+
+std::string read_sequence_files(const char* const* paths, size_t n_paths, int n_threads, bool want_pinned,
+                                RecordBatch& out) {
+    const size_t nt = (size_t)std::max(1, n_threads);
+    // 1. every file into memory (mmap / inflate), in parallel
+    std::vector<Loaded> loaded(n_paths);
+    run_parallel(n_paths, nt, [&](size_t i) { load_file(paths[i], loaded[i]); });
+    for (auto& l : loaded) if (!l.error.empty()) return l.error;
+    // 2. one destination buffer; file i owns a region as large as the file (sequence bytes never
+    //    outgrow it), 16-byte aligned.  Gaps between regions are never read as sequence.
+    std::vector<uint64_t> base(n_paths + 1, 0);
+    for (size_t i = 0; i < n_paths; ++i) base[i + 1] = (base[i] + loaded[i].n + 15) & ~15ull;
+    const size_t need = (size_t)base[n_paths] + 64;
     out.pinned = false;
-    if (want_pinned && cudaHostAlloc((void**)&out.seqs, alloc, cudaHostAllocDefault) == cudaSuccess) out.pinned = true;
-    else { cudaGetLastError(); out.seqs = (uint8_t*)aligned_alloc(4096, alloc); }
+    if (want_pinned) { out.seqs = pinned_acquire(need, out.cap); out.pinned = out.seqs != nullptr; }
+    if (!out.seqs) { out.cap = (need + 4095) & ~size_t(4095); out.seqs = (uint8_t*)aligned_alloc(4096, out.cap); }
     if (!out.seqs) return "out of host memory";
-    out.off.assign(1, 0); out.off.reserve(n_rec + 1);
+    // 3. parse straight into the regions, in parallel
+    std::vector<FileRecords> files(n_paths);
+    run_parallel(n_paths, nt, [&](size_t i) {
+        parse_records(loaded[i].p, loaded[i].n, out.seqs + base[i], files[i]);
+        if (!files[i].error.empty()) files[i].error = std::string(paths[i]) + ": " + files[i].error;
+        // zero the tail of the region so that the buffer holds no stale bytes
+        memset(out.seqs + base[i] + files[i].used, 0, (size_t)(base[i + 1] - base[i] - files[i].used));
+    });
+    for (auto& f : files) if (!f.error.empty()) return f.error;
+    memset(out.seqs + base[n_paths], 0, 64);
+    // 4. record table
+    uint64_t n_rec = 0, name_bytes = 0, seq_bytes = 0;
+    for (auto& f : files) { n_rec += f.start.size(); name_bytes += f.names.size(); }
+    out.start.clear(); out.start.reserve(n_rec);
+    out.len.clear(); out.len.reserve(n_rec);
     out.file.clear(); out.file.reserve(n_rec);
     out.names.clear(); out.names.reserve(name_bytes);
     out.name_off.assign(1, 0); out.name_off.reserve(n_rec + 1);
-    // per-file base offsets, then copy the sequence bytes in parallel
-    std::vector<uint64_t> base(n_paths + 1, 0);
-    for (size_t i = 0; i < n_paths; ++i) base[i + 1] = base[i] + files[i].seqs.size();
     for (size_t i = 0; i < n_paths; ++i) {
         const FileRecords& f = files[i];
-        for (size_t r = 0; r + 1 < f.off.size(); ++r) {
-            out.off.push_back(base[i] + f.off[r + 1]);
+        for (size_t r = 0; r < f.start.size(); ++r) {
+            out.start.push_back(base[i] + f.start[r]);
+            out.len.push_back(f.len[r]);
+            seq_bytes += f.len[r];
             out.file.push_back((uint32_t)i);
             out.name_off.push_back(out.names.size() + f.name_off[r + 1]);
         }
         out.names += f.names;
     }
-    next = 0;
-    auto copier = [&] {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n_paths) return;
-            if (!files[i].seqs.empty()) memcpy(out.seqs + base[i], files[i].seqs.data(), files[i].seqs.size());
-        }
-    };
-    pool.clear();
-    for (size_t t = 1; t < nt; ++t) pool.emplace_back(copier);
-    copier();
-    for (auto& t : pool) t.join();
-    memset(out.seqs + total, 0, alloc - total);
+    out.extent = base[n_paths];
+    out.total = seq_bytes;
     return "";
 }
 

@@ -14,10 +14,12 @@
 namespace smb {
 
 struct RecordBatch {
-    uint8_t* seqs = nullptr;            // all sequences back to back (allocated by alloc_bytes)
-    uint64_t total = 0;
-    bool pinned = false;
-    std::vector<uint64_t> off;          // [n + 1]
+    uint8_t* seqs = nullptr;            // one buffer; every file owns a 16-byte aligned region of it
+    size_t cap = 0;                     // allocated bytes
+    uint64_t extent = 0;                // bytes of the buffer in use (what gets uploaded)
+    uint64_t total = 0;                 // sum of the record lengths
+    bool pinned = false;                // page-locked (taken from / returned to a one-buffer pool)
+    std::vector<uint64_t> start, len;   // [n] byte offset and length of every record
     std::vector<uint32_t> file;         // [n] index of the input file
     std::string names;                  // header lines back to back
     std::vector<uint64_t> name_off;     // [n + 1]

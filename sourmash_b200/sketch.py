@@ -25,14 +25,15 @@ class RecordBatch:
         keep = [ffi.new("char[]", p.encode("utf-8")) for p in self.paths]
         self._ptr = rustcall(lib.smb_records_read, ffi.new("char *[]", keep), len(keep), int(n_threads))
         n = int(lib.smb_records_len(self._ptr))
-        self.offsets = np.frombuffer(ffi.buffer(lib.smb_records_offsets(self._ptr), (n + 1) * 8), dtype=np.uint64)
+        self.starts = np.frombuffer(ffi.buffer(lib.smb_records_starts(self._ptr), n * 8), dtype=np.uint64) if n else np.zeros(0, np.uint64)
+        self.lengths = np.frombuffer(ffi.buffer(lib.smb_records_lengths(self._ptr), n * 8), dtype=np.uint64) if n else np.zeros(0, np.uint64)
         self.files = np.frombuffer(ffi.buffer(lib.smb_records_files(self._ptr), n * 4), dtype=np.uint32) if n else np.zeros(0, np.uint32)
         self.total_bytes = int(lib.smb_records_total_bytes(self._ptr))
 
     def __del__(self):
         p, self._ptr = getattr(self, "_ptr", None), None
         if p and lib is not None:
-            self.offsets = self.files = None
+            self.starts = self.lengths = self.files = None
             lib.smb_records_free(p)
 
     def __len__(self):
@@ -47,8 +48,8 @@ class RecordBatch:
         return [blob[int(off[i]):int(off[i + 1])].decode("utf-8", "replace") for i in range(n)]
 
     def sequence(self, i):
-        lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
-        return bytes(ffi.buffer(lib.smb_records_data(self._ptr) + lo, hi - lo)) if hi > lo else b""
+        lo, n = int(self.starts[i]), int(self.lengths[i])
+        return bytes(ffi.buffer(lib.smb_records_data(self._ptr) + lo, n)) if n else b""
 
     def sketch(self, rec_to_sketch, n_sketches, ksizes, *, moltype="DNA", input_is_protein=False, scaled=0, num=0,
                seed=42, track_abundance=False):
@@ -135,10 +136,16 @@ def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, se
                 for s in range(n_sk)]
     sset, _ = rb.sketch(owner, n_sk, ksizes, moltype=moltype, input_is_protein=input_is_protein, scaled=scaled,
                         num=num, seed=seed, track_abundance=track_abundance)
-    h, off, ab = sset.to_host(with_abunds=True)
-    sigs = []
-    for s in range(n_sk):
-        rows = [h[int(off[s * nk + j]):int(off[s * nk + j + 1])] for j in range(nk)]
-        abr = [ab[int(off[s * nk + j]):int(off[s * nk + j + 1])] for j in range(nk)] if ab is not None else None
-        sigs.append(_signature_from_rows(rows, abr, ksizes, scaled, num, seed, track_abundance, names[s], files[s], moltype))
+    hf = B._HASH_FUNCTIONS[moltype.lower()]
+    ks = np.ascontiguousarray(ksizes, dtype=np.uint32) * np.uint32(3 if hf != 1 else 1)
+    size = ffi.new("uintptr_t *")
+    arr = rustcall(lib.smb_signatures_from_sketchset, sset._ptr, ffi.cast("uint32_t *", ks.ctypes.data), nk, hf,
+                   int(scaled), int(num), int(seed), size)
+    sigs = [SourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
+    lib.signatures_array_free(arr, size[0])
+    for s_, sig in enumerate(sigs):
+        if names[s_]:
+            sig._name = names[s_]
+        if files[s_]:
+            sig.filename = files[s_]
     return sigs

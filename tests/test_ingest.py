@@ -26,7 +26,11 @@ def test_fasta_reader_matches_python_reader():
         assert int(rb.files[r]) == fi and names[r] == name
         assert rb.sequence(r) == seq
     assert rb.total_bytes == sum(len(s) for _, _, s in want)
-    assert [int(x) for x in rb.offsets[:3]] == [0, len(want[0][2]), len(want[0][2]) + len(want[1][2])]
+    assert [int(x) for x in rb.lengths[:3]] == [len(w[2]) for w in want[:3]]
+    first = np.concatenate([[True], rb.files[1:] != rb.files[:-1]])
+    assert int(rb.starts[0]) == 0 and all(int(x) % 16 == 0 for x in rb.starts[first])      # file regions
+    inner = np.nonzero(~first)[0]                                                           # records packed inside
+    assert all(int(rb.starts[i]) == int(rb.starts[i - 1]) + int(rb.lengths[i - 1]) for i in inner) and len(inner) > 0
 
 
 def test_fastq_crlf_blank_lines_and_errors(tmp_path):
