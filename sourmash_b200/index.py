@@ -176,6 +176,17 @@ class CounterGather:
         "Register a candidate match (overlap counted on the GPU)."
         if self.query_started:
             raise ValueError("cannot add more signatures to counter after peek/consume")
+        # count_common(query, match, downsample=True) of the reference checks compatibility first
+        # (sketch/minhash.rs:539-547,886-912): same ksize / molecule / seed, both scaled
+        mh, q = ss.minhash, self.orig_query_mh
+        if mh.ksize != q.ksize:
+            raise ValueError("different ksizes cannot be compared")
+        if mh.moltype != q.moltype:
+            raise ValueError("DNA/prot minhashes cannot be compared")
+        if not mh.scaled:
+            raise ValueError("mismatch in scaled; comparison fail")
+        if mh.seed != q.seed:
+            raise ValueError("mismatch in seed; comparison fail")
         self._pending.append((ss, location, require_overlap))
         if require_overlap:
             self._count_pending()          # the reference raises at add() time

@@ -124,6 +124,17 @@ meta["protein_benchmarks"] = prot
 # 2 x 2 similarities of tests/test_sourmash_compute.py:810-860 (round(., 3)), k=21 (7 residues), num=500
 meta["protein_2x2"] = {"aa1_trans1": 0.0, "aa2_trans1": 0.166, "aa1_trans2": 0.174, "aa2_trans2": 0.0}
 
+# --- gather fixtures: tests/test_index_protocol.py:1057-1097 (12 genomes + their combined query,
+# k=21 / 31 / 51 scaled sketches); byte copies of the reference-written .sig files ------------
+os.makedirs(os.path.join(HERE, "gather"), exist_ok=True)
+for f in sorted(os.listdir(os.path.join(TD, "gather"))):
+    if f.endswith(".sig"):
+        shutil.copyfile(os.path.join(TD, "gather", f), os.path.join(HERE, "gather", f))
+meta["gather_k21_expected"] = [  # (first word of the match name, new hashes covered), in pick order
+    ["NC_003198.1", 487], ["NC_000853.1", 192], ["NC_011978.1", 169], ["NC_002163.1", 157],
+    ["NC_003197.2", 152], ["NC_009486.1", 92], ["NC_006905.1", 76], ["NC_011080.1", 59],
+    ["NC_011274.1", 42], ["NC_006511.1", 31], ["NC_011294.1", 7], ["NC_004631.1", 2]]
+
 # --- known-answer values quoted from the reference's tests ----------------------------------
 meta["kat"] = {
     "hash_murmur_ACG_42": 1731421407650554201,            # tests/test_minhash.py:1239-1262

@@ -136,3 +136,31 @@ def test_reference_written_files_roundtrip_through_the_writer(tmp_path):
         assert [a.name for a in again] == [s.name for s in sigs]
         want = {sk["md5sum"] for _, sk in _py_sketches(os.path.join(GOLDEN, f))}
         assert {a.md5sum() for a in again} == want
+
+
+def test_gather_fixture_bruteforce_matches_reference_expectation(golden):
+    """The 12-genome gather of tests/test_index_protocol.py:1057-1097, replayed with Python sets on
+    the natively parsed fixtures: pins the fixture copies, the parser and the brute-force loop the
+    GPU gather tests use as their checker."""
+    import glob
+    d = os.path.join(GOLDEN, "gather")
+    q = SignatureSet.from_files([os.path.join(d, "combined.sig")])
+    qi, = q.select(ksize=21)
+    subjects = SignatureSet.from_files(sorted(glob.glob(os.path.join(d, "GCF*.sig"))))
+    rows = subjects.select(ksize=21)
+    assert len(rows) == 12 and int(q.max_hash[qi]) == int(subjects.max_hash[rows[0]])
+    remaining = set(q.row(qi).tolist())
+    sets = {int(i): set(subjects.row(i).tolist()) for i in rows}
+    counters = {i: len(remaining & s) for i, s in sets.items() if remaining & s}
+    got = []
+    while counters:
+        best = max(counters.values())
+        i = next(k for k, v in counters.items() if v == best)
+        isect = remaining & sets[i]
+        got.append([subjects.name(i).split()[0], len(isect)])
+        remaining -= sets[i]
+        for k in list(counters):
+            counters[k] -= len(isect & sets[k])
+            if counters[k] <= 0:
+                del counters[k]
+    assert got == golden["meta"]["gather_k21_expected"]
