@@ -1847,7 +1847,7 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
     // query small enough for shared memory: it becomes the (single) table of the tile kernel;
     // otherwise a global-memory directory over the query.
     const int nB = (int)db.n_rows;
-    if (nB == 0) return;
+    if (nB == 0 || nq == 0) return;                  // callers zero the counters: nothing is shared
     SmbSketchSet q;
     q.n_rows = 1; q.h_off = {0, (uint64_t)nq};
     q.own_off.alloc(2, s); q.own_off.upload(q.h_off.data(), 2);

@@ -97,3 +97,40 @@ def test_gather(B, rows, query, threshold):
         if not len(q):
             break
     assert list(zip(ids.tolist(), sizes.tolist())) == want
+
+
+residues = st.text(alphabet="ACDEFGHIKLMNPQRSTVWYXBZ*acdefghiklmnpqrstvwy-", min_size=0, max_size=300)
+
+
+@given(st.lists(dna, min_size=1, max_size=4), st.sampled_from(["protein", "dayhoff", "hp"]),
+       st.sampled_from([1, 2, 5, 7, 10, 16, 17, 42]), st.sampled_from([1, 3, 200]), st.booleans())
+@settings(**COMMON)
+def test_sketch_translate(B, seqs, moltype, kaa, scaled, track):
+    raw = [s.encode() for s in seqs]
+    data = np.frombuffer(b"".join(raw), dtype=np.uint8) if any(raw) else np.zeros(0, np.uint8)
+    offs = np.cumsum([0] + [len(r) for r in raw]).astype(np.uint64)
+    sset, nk = B.sketch_sequences(data, offs, [kaa], scaled=scaled, moltype=moltype, track_abundance=track)
+    h, off, ab = sset.to_host(with_abunds=True)
+    for i, r in enumerate(raw):
+        om = orc.OracleMinHash(scaled=scaled, ksize=3 * kaa, track_abundance=track)
+        om.add_protein_family(r, moltype, False)
+        assert h[int(off[i]):int(off[i + 1])].tolist() == om.mins().tolist()
+        if track:
+            assert ab[int(off[i]):int(off[i + 1])].tolist() == om.abunds().tolist()
+    assert nk == sum(2 * max(len(r) - 3 * kaa + 1, 0) for r in raw)
+
+
+@given(st.lists(residues, min_size=1, max_size=4), st.sampled_from(["protein", "dayhoff", "hp"]),
+       st.sampled_from([1, 3, 7, 10, 16, 19, 42]), st.integers(0, 9))
+@settings(**COMMON)
+def test_sketch_protein_num(B, seqs, moltype, kaa, num):
+    raw = [s.encode() for s in seqs]
+    data = np.frombuffer(b"".join(raw), dtype=np.uint8) if any(raw) else np.zeros(0, np.uint8)
+    offs = np.cumsum([0] + [len(r) for r in raw]).astype(np.uint64)
+    scaled = 1 if num == 0 else 0
+    sset, nk = B.sketch_sequences(data, offs, [kaa], scaled=scaled, num=num, moltype=moltype, input_is_protein=True)
+    for row, r in zip(sset.rows(), raw):
+        om = orc.OracleMinHash(scaled=scaled, ksize=3 * kaa, num=num)
+        om.add_protein_family(r, moltype, True)
+        assert row.tolist() == om.mins().tolist()
+    assert nk == sum(max(len(r) - kaa + 1, 0) for r in raw)
