@@ -537,6 +537,32 @@ uint64_t set_max_key(const SmbSketchSet& A, cudaStream_t s) {
     return A.max_key;
 }
 
+// Which algorithm computes the symmetric (all-vs-all) scaled count matrix?  The inverted join
+// (compare_kernels.cu) costs one sort plus one increment per shared hash per pair; the tile kernel
+// costs |A_i| probes per pair.  Decided from a deterministic 1/64 key-range sample of the set, so
+// every rank holding the same set decides alike.  SMB_COMPARE_ALGO=join|tile overrides.
+struct JoinDecision { bool use = false; double increments = 0, elements = 0; unsigned long long max_group = 0; };
+thread_local JoinDecision t_last_join;
+
+JoinDecision plan_join(const SmbSketchSet& A, uint64_t max_key, cudaStream_t s) {
+    JoinDecision d;
+    const char* env = getenv("SMB_COMPARE_ALGO");
+    if (env && !strcmp(env, "tile")) return d;
+    const size_t n = A.n_rows;
+    if (n < 64 || A.total() == 0) return d;
+    DevBuf<unsigned long long> scratch(2, s);
+    CK(smb::join_estimate(A.d_hashes, A.d_off, (int)n, max_key, scratch.p, &d.increments, &d.elements,
+                          &d.max_group, s));
+    // cost model (ms), constants measured on B200 (profiles/): radix sort + gather ~ 0.35 ns per
+    // element, ~ 0.025 ns per increment; tile kernel 185 ms for 5e7 pairs of 5000-hash rows
+    const double join_ms = d.elements * 3.5e-7 + d.increments * 2.5e-8 + 0.3;
+    const double pairs = 0.5 * (double)n * (double)(n - 1);
+    const double avg_len = (double)A.total() / (double)n;
+    const double tile_ms = pairs * avg_len * 7.4e-10 + 0.05;
+    d.use = (env && !strcmp(env, "join")) || join_ms < tile_ms;
+    return d;
+}
+
 void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t num, uint32_t* d_common,
                          uint32_t* d_usize, size_t ldo, cudaStream_t s,
                          smb::TileShard tiles = smb::TileShard{0, 1}) {
@@ -544,6 +570,17 @@ void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t
     const SmbSketchSet& B = symmetric ? A : *Bp;
     const int nA = (int)A.n_rows, nB = (int)B.n_rows;
     if (nA == 0 || nB == 0) return;
+    if (symmetric && num == 0 && tiles.count < 0) {
+        const uint64_t mk = set_max_key(A, s);
+        t_last_join = plan_join(A, mk, s);
+        if (t_last_join.use) {
+            if (t_profiling) t_timer_pairwise.begin(s);
+            CK(cudaMemsetAsync(d_common, 0, (size_t)nA * ldo * sizeof(uint32_t), s));
+            CK(smb::join_counts(A.d_hashes, A.d_off, nA, mk, tiles.shard, tiles.n_shards, d_common, ldo, s));
+            if (t_profiling) t_timer_pairwise.end(s);
+            return;
+        }
+    }
     if (num > 0) {
         smb::launch_pairwise_num(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, num, d_common,
                                  d_usize, ldo, symmetric, s);
@@ -1768,7 +1805,35 @@ void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
         if (n == 0) return;
         DevBuf<double> d_out(n * n, s);
         smb::PairwisePlan plan{};
-        if (num == 0 && n >= 1024) plan = smb::plan_pairwise(set->max_len, set_max_key(*set, s), (int)n);
+        if (num == 0 && n >= 1024) {
+            const uint64_t mk = set_max_key(*set, s);
+            t_last_join = plan_join(*set, mk, s);
+            if (t_last_join.use) {
+                // counts by inverted join, then finalise blocks of rows and download each block on
+                // the copy stream while the next one is being finalised
+                DevBuf<uint32_t> d_c(n * n, s);
+                if (t_profiling) t_timer_pairwise.begin(s);
+                CK(cudaMemsetAsync(d_c.p, 0, n * n * sizeof(uint32_t), s));
+                CK(smb::join_counts(set->d_hashes, set->d_off, (int)n, mk, 0, 1, d_c.p, n, s));
+                if (t_profiling) t_timer_pairwise.end(s);
+                cudaStream_t cs = copy_stream();
+                const size_t per = (n + 7) / 8;
+                for (size_t r0 = 0; r0 < n; r0 += per) {
+                    const size_t r1 = std::min(n, r0 + per);
+                    smb::launch_finalize_rows(d_c.p, n, set->d_off, (int)n, (int)r0, (int)r1, d_out.p + r0 * n, s);
+                    cudaEvent_t ev = pool_event();
+                    CK(cudaEventRecord(ev, s));
+                    CK(cudaStreamWaitEvent(cs, ev, 0));
+                    CK(cudaMemcpyAsync(out + r0 * n, d_out.p + r0 * n, (r1 - r0) * n * sizeof(double),
+                                       cudaMemcpyDeviceToHost, cs));
+                }
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(cs));
+                sync(s);
+                return;
+            }
+            plan = smb::plan_pairwise(set->max_len, mk, (int)n);
+        }
         if (plan.tables_per_cta > 0) {
             // Large matrix: compute groups of row tiles in order and download every finished block
             // of rows on the copy stream while the next group is being computed (rows of group g

@@ -16,6 +16,9 @@
 // over |A|+|B| elements.  Counts are reduced with warp REDUX and written as u32.
 #include <stdlib.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -993,6 +996,173 @@ __global__ void __launch_bounds__(1024) counter_update_argmax_kernel(
 void launch_counter_update_argmax(u32* counters, const u32* delta, int n,
                                   unsigned long long* d_best, cudaStream_t s) {
     counter_update_argmax_kernel<<<1, 1024, 0, s>>>(counters, delta, n, d_best); count_launches(1);
+}
+
+// ------------------------------------------------------------------------------------
+// All-vs-all counts by inverted join (sort by hash, count co-occurrences).
+//
+// |A_i ∩ A_j| = number of hashes that occur in both rows, so the whole count matrix is the sum,
+// over every distinct hash h, of one increment for every pair of rows containing h.  Sorting the
+// (hash, row) pairs of the whole set groups the rows of each hash together (radix sort, ~55 key
+// bits, stable => row ids ascending inside a group); a group of m rows contributes C(m,2)
+// increments.  The work is output sensitive: sum over pairs of |A_i ∩ A_j| increments plus one
+// sort, instead of |A_i| + |A_j| probes for every pair -- unrelated pairs, the bulk of a real
+// all-vs-all matrix, cost nothing.  The planner falls back to the tile kernel when the estimated
+// number of increments says the join would be slower (e.g. thousands of near-identical sketches).
+// Multi-GPU: rank r joins the hashes of key range r (every hash lives in exactly one range), the
+// partial matrices add up.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) join_row_range_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
+                                                            int n_rows, u64 key_lo, u64 key_hi, int bounded_hi,
+                                                            u64* __restrict__ beg, u64* __restrict__ cnt) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    if (r == n_rows) { cnt[r] = 0; return; }              // extra slot: the scan then yields the total
+    const u64* row = h + off[r];
+    const u64 len = off[r + 1] - off[r];
+    u64 lo = 0, hi = len;
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (row[mid] < key_lo) lo = mid + 1; else hi = mid; }
+    const u64 b = lo;
+    u64 e = len;
+    if (bounded_hi) {
+        lo = b; hi = len;
+        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (row[mid] < key_hi) lo = mid + 1; else hi = mid; }
+        e = lo;
+    }
+    beg[r] = b;
+    cnt[r] = e - b;
+}
+
+__global__ void __launch_bounds__(256) join_gather_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
+                                                         const u64* __restrict__ beg, const u64* __restrict__ dst_off,
+                                                         int n_rows, u64* __restrict__ keys, u32* __restrict__ ids) {
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const u64 src = off[r] + beg[r], d0 = dst_off[r], n = dst_off[r + 1] - d0;
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) { keys[d0 + i] = h[src + i]; ids[d0 + i] = (u32)r; }
+    }
+}
+
+// out[0] += sum over groups of C(m,2); out[1] = max m
+__global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restrict__ keys, u64 T,
+                                                           unsigned long long* __restrict__ out) {
+    unsigned long long pairs = 0, mmax = 0;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < T; p += (u64)gridDim.x * blockDim.x) {
+        const u64 k = keys[p];
+        if (p > 0 && keys[p - 1] == k) continue;          // not the head of its group
+        u64 m = 1;
+        while (p + m < T && keys[p + m] == k) ++m;
+        pairs += m * (m - 1) / 2;
+        mmax = m > mmax ? m : mmax;
+    }
+    for (int d = 16; d; d >>= 1) {
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, mmax, d);
+        mmax = o > mmax ? o : mmax;
+    }
+    if (lane_id() == 0) { if (pairs) atomicAdd(out, pairs); if (mmax) atomicMax(out + 1, mmax); }
+}
+
+// Every element pairs with the later elements of its group: ids ascend inside a group, so
+// (ids[p], ids[b]) is an upper-triangle cell.  Increments are fire-and-forget reductions (RED).
+__global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                        u64 T, u32* __restrict__ common, size_t ld) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T) return;
+    const u64 k = keys[p];
+    u64 b = p + 1;
+    if (b >= T || keys[b] != k) return;
+    u32* __restrict__ row = common + (size_t)ids[p] * ld;
+    do {
+        atomicAdd(row + ids[b], 1u);
+        ++b;
+    } while (b < T && keys[b] == k);
+}
+
+// Slice rows to [key_lo, key_hi) (bounded_hi == 0: no upper bound), sort the (hash, row) pairs.
+// Returns the number of elements; *keys_out / *ids_out point into `work`, which the caller frees.
+struct JoinWork {
+    void* mem = nullptr;
+    u64 *keys_a = nullptr, *keys_b = nullptr;
+    u32 *ids_a = nullptr, *ids_b = nullptr;
+    u64 T = 0;
+};
+static cudaError_t join_sort_slice(const u64* h, const u64* off, int n, u64 upper_T, u64 key_lo, u64 key_hi,
+                                   int bounded_hi, int key_bits, JoinWork& W, cudaStream_t s) {
+    u64 *d_beg = nullptr, *d_cnt = nullptr, *d_doff = nullptr;
+    cudaError_t e;
+    const size_t nn = (size_t)n + 1;
+    if ((e = cudaMallocAsync((void**)&d_beg, nn * 3 * sizeof(u64), s)) != cudaSuccess) return e;
+    d_cnt = d_beg + nn; d_doff = d_cnt + nn;
+    join_row_range_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(h, off, n, key_lo, key_hi, bounded_hi, d_beg, d_cnt);
+    count_launches(1);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt, d_doff, (int)nn, s);
+    void* d_scan = nullptr;
+    if ((e = cudaMallocAsync(&d_scan, scan_bytes ? scan_bytes : 16, s)) != cudaSuccess) return e;
+    cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_cnt, d_doff, (int)nn, s);
+    u64 T = 0;
+    cudaMemcpyAsync(&T, d_doff + n, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    (void)upper_T;
+    W.T = T;
+    if (T == 0) { cudaFreeAsync(d_scan, s); cudaFreeAsync(d_beg, s); return cudaSuccess; }
+    const size_t Tp = (size_t)((T + 63) & ~63ull);
+    if ((e = cudaMallocAsync(&W.mem, Tp * (2 * sizeof(u64) + 2 * sizeof(u32)), s)) != cudaSuccess) return e;
+    W.keys_a = (u64*)W.mem; W.keys_b = W.keys_a + Tp;
+    W.ids_a = (u32*)(W.keys_b + Tp); W.ids_b = W.ids_a + Tp;
+    int blocks = n < SMB_B200_SMS * 16 ? n : SMB_B200_SMS * 16;
+    join_gather_kernel<<<blocks, 256, 0, s>>>(h, off, d_beg, d_doff, n, W.keys_a, W.ids_a); count_launches(1);
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
+    void* d_sort = nullptr;
+    if ((e = cudaMallocAsync(&d_sort, sort_bytes ? sort_bytes : 16, s)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
+    count_launches(1);
+    cudaFreeAsync(d_sort, s); cudaFreeAsync(d_scan, s); cudaFreeAsync(d_beg, s);
+    return cudaGetLastError();
+}
+
+static int key_bit_length(u64 max_key) { int b = 1; while (b < 64 && (max_key >> b)) ++b; return b; }
+
+cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsigned long long* d_out2,
+                          double* est_increments, double* est_elements, unsigned long long* max_group,
+                          cudaStream_t s) {
+    // deterministic sample: the lowest 1/64 of the key range (identical on every rank that holds the
+    // same set, so all ranks take the same decision)
+    const u64 hi = max_key / JOIN_SAMPLE + 1;
+    JoinWork W;
+    cudaError_t e = join_sort_slice(h, off, n, 0, 0, hi, 1, key_bit_length(hi), W, s);
+    if (e != cudaSuccess) return e;
+    unsigned long long r[2] = {0, 0};
+    cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned long long), s);
+    if (W.T) {
+        u64 blocks = (W.T + 255) / 256;
+        if (blocks > (u64)SMB_B200_SMS * 32) blocks = (u64)SMB_B200_SMS * 32;
+        join_estimate_kernel<<<(unsigned)blocks, 256, 0, s>>>(W.keys_b, W.T, d_out2); count_launches(1);
+    }
+    cudaMemcpyAsync(r, d_out2, sizeof r, cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    if (W.mem) cudaFreeAsync(W.mem, s);
+    *est_increments = (double)r[0] * JOIN_SAMPLE;
+    *est_elements = (double)W.T * JOIN_SAMPLE;
+    *max_group = r[1];
+    return e;
+}
+
+cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
+                        u32* common, size_t ld, cudaStream_t s) {
+    const u64 step = max_key / (u64)n_shards + 1;
+    const u64 lo = (u64)shard * step;
+    const int bounded = shard + 1 < n_shards;
+    JoinWork W;
+    cudaError_t e = join_sort_slice(h, off, n, 0, lo, lo + step, bounded, key_bit_length(max_key), W, s);
+    if (e != cudaSuccess) return e;
+    if (W.T) {
+        join_count_kernel<<<(unsigned)((W.T + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
+        count_launches(1);
+    }
+    if (W.mem) cudaFreeAsync(W.mem, s);
+    return cudaGetLastError();
 }
 
 }  // namespace smb

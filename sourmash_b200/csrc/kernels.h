@@ -36,6 +36,17 @@ void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const ui
                           int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
                           size_t ldo, bool symmetric, TileShard tiles, cudaStream_t s);
 
+// All-vs-all counts by inverted join (compare_kernels.cu): sort the (hash, row) pairs of the set,
+// one increment per pair of rows sharing a hash.  join_estimate sorts the lowest 1/JOIN_SAMPLE of
+// the key range and extrapolates the number of increments / elements (d_out2: 2 x u64 scratch);
+// join_counts adds the counts of key range `shard` of `n_shards` into the zeroed upper triangle.
+static constexpr unsigned long long JOIN_SAMPLE = 64;
+cudaError_t join_estimate(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key,
+                          unsigned long long* d_out2, double* est_increments, double* est_elements,
+                          unsigned long long* max_group, cudaStream_t s);
+cudaError_t join_counts(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key, int shard,
+                        int n_shards, uint32_t* common, size_t ld, cudaStream_t s);
+
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
 // elements in the longer row.
 void launch_pairwise_generic(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,

@@ -256,3 +256,84 @@ def test_one_vs_many_medium_query_and_big_row_gather(B):
     query = np.unique(np.concatenate([big_rows[2][:30_000], big_rows[4][5_000:25_000], big_rows[0][::7]]))
     ids, sizes = B.gather(query, bdb, threshold=10)
     assert list(zip(ids.tolist(), sizes.tolist())) == _gather_oracle(query, big_rows, threshold=10)
+
+
+# ---------------------------------------------------------------------------------------------
+# inverted join (sort by hash + co-occurrence counts) vs tile kernel vs oracle
+# ---------------------------------------------------------------------------------------------
+def _with_algo(algo, fn):
+    import os
+    old = os.environ.get("SMB_COMPARE_ALGO")
+    os.environ["SMB_COMPARE_ALGO"] = algo
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["SMB_COMPARE_ALGO"]
+        else:
+            os.environ["SMB_COMPARE_ALGO"] = old
+
+
+@pytest.mark.parametrize("seed,n,mean", [(1, 300, 400), (2, 1100, 120), (3, 70, 3000)])
+def test_join_and_tile_agree_with_oracle(seed, n, mean):
+    from sourmash_b200 import batch as B
+    from sourmash_b200.synth import synth_sketches
+    h, off = synth_sketches(n, mean=mean, sd=mean // 5, lo=mean // 3, hi=mean * 2, n_families=max(n // 25, 2),
+                            pool=int(mean * 1.3), seed=seed)
+    want_c = orc.pairwise_common(h, off, nthreads=8)
+    want_j = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    iu = np.triu_indices(n, 1)
+    for algo in ("join", "tile"):
+        c = _with_algo(algo, lambda: B.pairwise_common(sset))
+        assert np.array_equal(c[iu], want_c[iu]), algo
+        assert np.array_equal(_with_algo(algo, lambda: B.compare_jaccard(sset)), want_j), algo
+
+
+def test_join_edge_cases():
+    from sourmash_b200 import batch as B
+    rng = np.random.default_rng(0)
+    big = np.uint64(2**64 - 1)
+    shared = np.unique(rng.integers(0, 2**63, size=50, dtype=np.uint64))
+    rows = []
+    for i in range(130):
+        own = np.unique(rng.integers(0, 2**64 - 1, size=int(rng.integers(0, 40)), dtype=np.uint64))
+        parts = [own]
+        if i % 3 == 0:
+            parts.append(shared)                      # one hash group spanning 44 rows
+        if i % 7 == 0:
+            parts.append(np.array([0, 1, 2, big], dtype=np.uint64))
+        rows.append(np.unique(np.concatenate(parts)) if i != 5 else np.zeros(0, np.uint64))   # row 5 empty
+    rows[10] = rows[9].copy()                         # identical rows
+    dense = [np.arange(i % 5, 40, dtype=np.uint64) for i in range(70)]   # tiny dense keys: every hash in ~all rows
+    for rr in (rows, dense):
+        h, off = orc.to_csr(rr)
+        n = len(rr)
+        want = orc.pairwise_common(h, off)
+        sset = B.SketchSet.from_host(h, off)
+        iu = np.triu_indices(n, 1)
+        for algo in ("join", "tile"):
+            assert np.array_equal(_with_algo(algo, lambda: B.pairwise_common(sset))[iu], want[iu]), algo
+            assert np.array_equal(_with_algo(algo, lambda: B.compare_jaccard(sset)), orc.compare_all_pairs(h, off)), algo
+
+
+def test_join_key_range_shards_sum_to_full():
+    import torch
+    from sourmash_b200 import batch as B
+    from sourmash_b200.synth import synth_sketches
+    n = 400
+    h, off = synth_sketches(n, mean=300, sd=60, lo=100, hi=600, n_families=8, pool=400, seed=4)
+    sset = B.SketchSet.from_host(h, off)
+    want = orc.pairwise_common(h, off, nthreads=8)
+    iu = np.triu_indices(n, 1)
+    B.set_stream(torch.cuda.current_stream().cuda_stream)
+    for algo in ("join", "tile"):
+        for shards in (1, 3, 8):
+            total = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+            for r in range(shards):
+                part = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+                _with_algo(algo, lambda: B.pairwise_counts_shard_device(sset, r, shards, part.data_ptr()))
+                total += part
+            torch.cuda.synchronize()
+            assert np.array_equal(total.cpu().numpy().astype(np.uint32)[iu], want[iu]), (algo, shards)
+    B.set_stream(0)
