@@ -356,6 +356,17 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     value = n_pairs / (ms / 1e3)
     kms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (kms / 1e3) / 1e9
+    plan = B.last_compare_plan()
+    if plan["algo"] == "join":
+        kname = "inverted join (join_gather + cub::DeviceRadixSort + join_count_kernel)"
+        knote = ("counts by sorting the (hash,row) pairs and incrementing one cell per pair of rows sharing a hash "
+                 "(planner estimate: %.3g increments over %.3g elements); algorithmic bytes keep SURVEY 8d's "
+                 "definition, 8*(|A|+|B|) per pair + 4 B out" % (plan["est_increments"], plan["est_elements"]))
+        tkey = "inverted_join"
+    else:
+        kname, tkey = "pairwise_tile_split_kernel", "pairwise_tile_split_kernel"
+        knote = ("algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
+                 "memory / L2, so DRAM traffic is far below this")
     res = {
         "metric": "sketch-pairs/sec (compare)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -368,11 +379,10 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "pairwise_tile_split_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("pairwise_tile_split_kernel"),
+        "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(tkey),
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "note": "algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
-                             "memory / L2, so DRAM traffic is far below this"},
+                     "algorithm": plan, "note": knote},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # CPU baseline: rank 0 at N=1 only
         ncores = host_cores()

@@ -216,6 +216,9 @@ void smb_synchronize(void);
 uint64_t smb_kernel_launches(void);             /* number of kernels launched by this library */
 void smb_set_profiling(bool on);                /* record CUDA events around the dominant kernels */
 double smb_last_kernel_ms(int32_t which);       /* 0: last pairwise tile kernel, 1: last hash pass */
+/* planner of the last all-vs-all count (this thread): {1 = inverted join / 0 = tile kernel,
+ * estimated increments, estimated elements, largest hash group seen in the sample} */
+void smb_last_compare_plan(double *out4);
 void *smb_alloc_pinned(uintptr_t nbytes);       /* page-locked host memory for e2e transfers  */
 void smb_free_pinned(void *ptr);
 uint64_t smb_max_hash_for_scaled(uint64_t scaled);   /* sketch/minhash.rs:21-27 */

@@ -49,6 +49,14 @@ def last_kernel_ms(which):
     return float(rustcall(lib.smb_last_kernel_ms, int(which)))
 
 
+def last_compare_plan():
+    "Planner decision of the last all-vs-all count: dict(algo, est_increments, est_elements, max_group)."
+    out = ffi.new("double[4]")
+    lib.smb_last_compare_plan(out)
+    return {"algo": "join" if out[0] else "tile", "est_increments": out[1], "est_elements": out[2],
+            "max_group": int(out[3])}
+
+
 def max_hash_for_scaled(scaled):
     return int(lib.smb_max_hash_for_scaled(int(scaled)))
 

@@ -1549,6 +1549,12 @@ void smb_set_profiling(bool on) { t_profiling = on; }
 double smb_last_kernel_ms(int32_t which) {
     return guarded<double>([&] { return which == 0 ? t_timer_pairwise.ms() : t_timer_hash.ms(); });
 }
+void smb_last_compare_plan(double* out4) {
+    out4[0] = t_last_join.use ? 1.0 : 0.0;
+    out4[1] = t_last_join.increments;
+    out4[2] = t_last_join.elements;
+    out4[3] = (double)t_last_join.max_group;
+}
 void* smb_alloc_pinned(uintptr_t nbytes) {
     return guarded<void*>([&]() -> void* {
         need_gpu();
