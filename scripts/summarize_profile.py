@@ -36,10 +36,18 @@ if os.path.exists(src):
     start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     hdr = rows[start]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    mi = hdr.index("Metric Name")
     agg = collections.OrderedDict()
+    dram = collections.OrderedDict()       # per kernel: DRAM bytes (when the capture carried them)
+    BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     for r in rows[start + 1:]:
-        if len(r) > vi:
-            agg.setdefault(r[ki].split("(")[0], []).append(unit_ms(r[vi], r[ui]))
+        if len(r) <= vi:
+            continue
+        name = r[ki].split("(")[0].split("<")[0]
+        if r[mi] == "gpu__time_duration.sum":
+            agg.setdefault(name, []).append(unit_ms(r[vi], r[ui]))
+        elif r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            dram[name] = dram.get(name, 0.0) + float(r[vi].replace(",", "")) * BYTES.get(r[ui], 1)
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as fh:
         fh.write(f"# ncu launch list `{tag}` (gpu__time_duration.sum, --clock-control none)\n\n")
@@ -47,6 +55,11 @@ if os.path.exists(src):
                  "cold-cache and serialised, compare shares.\n\n| kernel | launches | total ms | avg ms | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in agg.items():
             fh.write(f"| `{k}` | {len(v)} | {sum(v):.3f} | {sum(v) / len(v):.4f} | {100 * sum(v) / tot:.1f}% |\n")
+        if dram:
+            fh.write("\nDRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, same capture):\n\n"
+                     "| kernel | MB / launch |\n|---|---:|\n")
+            for k, b in dram.items():
+                fh.write(f"| `{k}` | {b / len(agg[k]) / 1e6:.1f} |\n")
     print(open(os.path.join(P, f"{tag}_launches.md")).read())
 
 # ---- full captures

@@ -553,9 +553,11 @@ JoinDecision plan_join(const SmbSketchSet& A, uint64_t max_key, cudaStream_t s) 
     DevBuf<unsigned long long> scratch(2, s);
     CK(smb::join_estimate(A.d_hashes, A.d_off, (int)n, max_key, scratch.p, &d.increments, &d.elements,
                           &d.max_group, s));
-    // cost model (ms), constants measured on B200 (profiles/): radix sort + gather ~ 0.35 ns per
-    // element, ~ 0.025 ns per increment; tile kernel 185 ms for 5e7 pairs of 5000-hash rows
-    const double join_ms = d.elements * 3.5e-7 + d.increments * 2.5e-8 + 0.3;
+    // cost model (ms), constants measured on B200 (profiles/r1p_launches.md): gather + 7-pass radix
+    // sort 3.1 ms per 5e7 elements, 16.7 ms per 1.44e9 increments (L2 reductions), with a 1.5x
+    // margin on the increments (hot cells serialise); tile kernel 185 ms for 5e7 pairs of
+    // 5000-hash rows
+    const double join_ms = d.elements * 7e-8 + d.increments * 1.8e-8 + 0.5;
     const double pairs = 0.5 * (double)n * (double)(n - 1);
     const double avg_len = (double)A.total() / (double)n;
     const double tile_ms = pairs * avg_len * 7.4e-10 + 0.05;
