@@ -1063,19 +1063,31 @@ __global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restric
 }
 
 // Every element pairs with the later elements of its group: ids ascend inside a group, so
-// (ids[p], ids[b]) is an upper-triangle cell.  Increments are fire-and-forget reductions (RED).
+// (ids[p], ids[b]) is an upper-triangle cell.  Increments are fire-and-forget reductions (RED)
+// resolved in L2.  The (hash, row) stream is read once, the cells of related rows are hit thousands
+// of times: the stream is loaded evict-first and the reductions carry an evict-last policy so that
+// the streaming reads do not push the hot cells out of L2 (VARIANT 0: plain loads / atomics, kept
+// for A/B runs through SMB_JOIN_VARIANT).
+__device__ __forceinline__ void red_add_evict_last(u32* p, unsigned long long policy) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(1u), "l"(policy) : "memory");
+}
+template <int VARIANT>
 __global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
                                                         u64 T, u32* __restrict__ common, size_t ld) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= T) return;
-    const u64 k = keys[p];
+    const u64 k = VARIANT ? __ldcs(keys + p) : keys[p];
     u64 b = p + 1;
-    if (b >= T || keys[b] != k) return;
-    u32* __restrict__ row = common + (size_t)ids[p] * ld;
+    if (b >= T || (VARIANT ? __ldcs(keys + b) : keys[b]) != k) return;
+    u32* __restrict__ row = common + (size_t)(VARIANT ? __ldcs(ids + p) : ids[p]) * ld;
+    unsigned long long policy = 0;
+    if (VARIANT == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
     do {
-        atomicAdd(row + ids[b], 1u);
+        const u32 j = VARIANT ? __ldcs(ids + b) : ids[b];
+        if (VARIANT == 2) red_add_evict_last(row + j, policy);
+        else atomicAdd(row + j, 1u);
         ++b;
-    } while (b < T && keys[b] == k);
+    } while (b < T && (VARIANT ? __ldcs(keys + b) : keys[b]) == k);
 }
 
 // Slice rows to [key_lo, key_hi) (bounded_hi == 0: no upper bound), sort the (hash, row) pairs.
@@ -1158,7 +1170,12 @@ cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int sh
     cudaError_t e = join_sort_slice(h, off, n, 0, lo, lo + step, bounded, key_bit_length(max_key), W, s);
     if (e != cudaSuccess) return e;
     if (W.T) {
-        join_count_kernel<<<(unsigned)((W.T + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
+        const unsigned grid = (unsigned)((W.T + 255) / 256);
+        const char* v = getenv("SMB_JOIN_VARIANT");
+        const int variant = v ? atoi(v) : 2;
+        if (variant == 0) join_count_kernel<0><<<grid, 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
+        else if (variant == 1) join_count_kernel<1><<<grid, 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
+        else join_count_kernel<2><<<grid, 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
         count_launches(1);
     }
     if (W.mem) cudaFreeAsync(W.mem, s);
