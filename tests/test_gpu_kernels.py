@@ -306,7 +306,10 @@ def test_join_edge_cases():
         rows.append(np.unique(np.concatenate(parts)) if i != 5 else np.zeros(0, np.uint64))   # row 5 empty
     rows[10] = rows[9].copy()                         # identical rows
     dense = [np.arange(i % 5, 40, dtype=np.uint64) for i in range(70)]   # tiny dense keys: every hash in ~all rows
-    for rr in (rows, dense):
+    # two hashes shared by thousands of rows: groups far longer than the kernel's staged window
+    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64),
+                                      np.array([7] if i % 4 else [7, 2**61], dtype=np.uint64)])) for i in range(3300)]
+    for rr in (rows, dense, wide):
         h, off = orc.to_csr(rr)
         n = len(rr)
         want = orc.pairwise_common(h, off)
