@@ -1064,52 +1064,25 @@ __global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restric
 
 // Every element pairs with the later elements of its group: ids ascend inside a group, so
 // (ids[p], ids[b]) is an upper-triangle cell.  Increments are fire-and-forget reductions (RED)
-// resolved in L2.
-//
-// VARIANT 0 walks the group in global memory: every step is a dependent L2 load (key, then id),
-// and ncu shows the kernel latency bound (issue slots 10 % busy, 105 long-scoreboard stall cycles
-// per issue, L2 35 % busy; profiles/r1q_join.txt).  VARIANT 1 (default) stages a tile of the
-// sorted stream plus a look-ahead window in shared memory, so the walk runs at shared-memory
-// latency and only groups that outgrow the window continue in global memory.
-// (Evict-first loads / evict-last reductions were tried: DRAM write-back fell from 7.1 to 1.4 GB
-// per launch with no change in time -- the kernel is not DRAM bound.)
-static constexpr int JOIN_TILE = 2048, JOIN_AHEAD = 1024, JOIN_THREADS = 256;
-
-template <int VARIANT>
-__global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(const u64* __restrict__ keys,
-                                                                 const u32* __restrict__ ids, u64 T,
-                                                                 u32* __restrict__ common, size_t ld) {
-    if (VARIANT == 0) {
-        const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        if (p >= T) return;
-        const u64 k = keys[p];
-        u64 b = p + 1;
-        if (b >= T || keys[b] != k) return;
-        u32* __restrict__ row = common + (size_t)ids[p] * ld;
-        do {
-            atomicAdd(row + ids[b], 1u);
-            ++b;
-        } while (b < T && keys[b] == k);
-        return;
-    }
-    __shared__ u64 sk[JOIN_TILE + JOIN_AHEAD];
-    __shared__ u32 si[JOIN_TILE + JOIN_AHEAD];
-    const u64 t0 = (u64)blockIdx.x * JOIN_TILE;
-    const u64 left = T - t0;
-    const u32 n_loaded = left < (u64)(JOIN_TILE + JOIN_AHEAD) ? (u32)left : (u32)(JOIN_TILE + JOIN_AHEAD);
-    for (u32 q = threadIdx.x; q < n_loaded; q += JOIN_THREADS) { sk[q] = keys[t0 + q]; si[q] = ids[t0 + q]; }
-    __syncthreads();
-    const u32 n_own = n_loaded < (u32)JOIN_TILE ? n_loaded : (u32)JOIN_TILE;
-    for (u32 q = threadIdx.x; q < n_own; q += JOIN_THREADS) {
-        const u64 k = sk[q];
-        u32 b = q + 1;
-        if (b >= n_loaded ? (t0 + b >= T || keys[t0 + b] != k) : sk[b] != k) continue;
-        u32* __restrict__ row = common + (size_t)si[q] * ld;
-        while (b < n_loaded && sk[b] == k) { atomicAdd(row + si[b], 1u); ++b; }
-        if (b == n_loaded) {                        // the group outgrows the staged window
-            for (u64 g = t0 + b; g < T && keys[g] == k; ++g) atomicAdd(row + ids[g], 1u);
-        }
-    }
+// resolved in L2, and their rate is what bounds the kernel: 1.455e9 reductions in 16.7 ms =
+// 8.7e10 /s = 0.31 per clock per SM on the 10 000-sketch matrix, and three rewrites that attack
+// everything else left the time unchanged to 0.1 % (profiles/r1q_join.txt, r1s_join.txt):
+// evict-first stream loads + evict-last reductions (DRAM write-back 7.1 -> 1.4 GB, same time) and
+// walking the groups from a shared-memory tile instead of dependent L2 loads (long-scoreboard
+// stalls 105 -> 33 per issue, same time).  Going faster needs fewer reductions (accumulating in
+// shared-memory tiles of the matrix), see DESIGN.md section 4.7.
+__global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                        u64 T, u32* __restrict__ common, size_t ld) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T) return;
+    const u64 k = keys[p];
+    u64 b = p + 1;
+    if (b >= T || keys[b] != k) return;
+    u32* __restrict__ row = common + (size_t)ids[p] * ld;
+    do {
+        atomicAdd(row + ids[b], 1u);
+        ++b;
+    } while (b < T && keys[b] == k);
 }
 
 // Slice rows to [key_lo, key_hi) (bounded_hi == 0: no upper bound), sort the (hash, row) pairs.
@@ -1192,14 +1165,7 @@ cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int sh
     cudaError_t e = join_sort_slice(h, off, n, 0, lo, lo + step, bounded, key_bit_length(max_key), W, s);
     if (e != cudaSuccess) return e;
     if (W.T) {
-        const char* v = getenv("SMB_JOIN_VARIANT");
-        const int variant = v ? atoi(v) : 1;
-        if (variant == 0)
-            join_count_kernel<0><<<(unsigned)((W.T + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, s>>>(
-                W.keys_b, W.ids_b, W.T, common, ld);
-        else
-            join_count_kernel<1><<<(unsigned)((W.T + JOIN_TILE - 1) / JOIN_TILE), JOIN_THREADS, 0, s>>>(
-                W.keys_b, W.ids_b, W.T, common, ld);
+        join_count_kernel<<<(unsigned)((W.T + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
         count_launches(1);
     }
     if (W.mem) cudaFreeAsync(W.mem, s);
