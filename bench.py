@@ -66,6 +66,13 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def start(self):
         try:
@@ -79,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -91,7 +98,18 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # the sampler runs from before the warm-up (nvidia-smi needs ~0.2 s to deliver its first
+        # line); keep the samples taken inside the timed region, widened to the closest ones when
+        # the region is shorter than the 20 ms sampling period
+        rows = self.rows
+        window = "timed region"
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end + 0.03]
+            if len(inside) >= 2:
+                rows = inside
+            else:
+                window = "warm-up + timed region (timed region shorter than two sampling periods)"
+        for _, r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -104,7 +122,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ----------------------------------------------------------------------------- workloads
@@ -254,18 +272,20 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def timed(step_fn, steps, warmup):
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         for _ in range(warmup):
             step_fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = B.kernel_launches()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         e0.record(stream)
         extra = [step_fn() for _ in range(steps)]
         e1.record(stream)
         barrier()
+        sampler.mark_end()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
         if dist is not None:

@@ -635,6 +635,15 @@ struct SmbGatherState {
 // ==========================================================================================
 // KmerMinHash host object: src/core/src/sketch/minhash.rs:41-64
 // ==========================================================================================
+// u64 -> decimal digits (no locale, no format parsing); returns the number of characters
+inline int u64_to_dec(uint64_t v, char* out) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (int i = 0; i < n; ++i) out[i] = tmp[n - 1 - i];
+    return n;
+}
+
 struct SourmashKmerMinHash {
     uint32_t num = 0, ksize = 0;
     HashFunctions hash_function = HASH_FUNCTIONS_MURMUR64_DNA;
@@ -737,13 +746,13 @@ struct SourmashKmerMinHash {
     }
     std::string md5sum() const {   // minhash.rs:290-307
         smb::Md5 ctx;
-        char buf[32];
-        int l = snprintf(buf, sizeof buf, "%u", ksize);
-        ctx.update((const uint8_t*)buf, (size_t)l);
+        char buf[4096];
+        size_t fill = (size_t)u64_to_dec(ksize, buf);
         for (uint64_t v : mins) {
-            l = snprintf(buf, sizeof buf, "%llu", (unsigned long long)v);
-            ctx.update((const uint8_t*)buf, (size_t)l);
+            if (fill > sizeof buf - 24) { ctx.update((const uint8_t*)buf, fill); fill = 0; }
+            fill += (size_t)u64_to_dec(v, buf + fill);
         }
+        ctx.update((const uint8_t*)buf, fill);
         return ctx.hexdigest();
     }
 };
@@ -1060,12 +1069,14 @@ void json_escape(std::string& out, const std::string& s) {
 }
 void json_u64_array(std::string& out, const std::vector<uint64_t>& v) {
     out.push_back('[');
-    char b[24];
+    const size_t base = out.size();
+    out.resize(base + v.size() * 21 + 1);
+    char* w = &out[base];
     for (size_t i = 0; i < v.size(); ++i) {
-        if (i) out.push_back(',');
-        int l = snprintf(b, sizeof b, "%llu", (unsigned long long)v[i]);
-        out.append(b, (size_t)l);
+        if (i) *w++ = ',';
+        w += u64_to_dec(v[i], w);
     }
+    out.resize((size_t)(w - out.data()));
     out.push_back(']');
 }
 const char* molecule_name(HashFunctions hf) {          // encodings.rs:55-69 (Display)
@@ -1102,8 +1113,21 @@ void json_signature(std::string& out, const SourmashSignature& sig) {
     out += std::string("],\"version\":") + vb + "}";
 }
 std::string json_signatures(const SourmashSignature* const* sigs, size_t n) {
-    std::string out = "[";
-    for (size_t i = 0; i < n; ++i) { if (i) out.push_back(','); json_signature(out, *sigs[i]); }
+    // one string per signature, rendered by a few threads (digits + md5 are the whole cost)
+    std::vector<std::string> parts(n);
+    std::atomic<size_t> next{0};
+    auto worker = [&] { for (;;) { size_t i = next.fetch_add(1); if (i >= n) return; json_signature(parts[i], *sigs[i]); } };
+    const size_t nt = std::min<size_t>(n < 8 ? 1 : 16, std::max<unsigned>(std::thread::hardware_concurrency(), 1u));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    size_t tot = 2 + n;
+    for (auto& p : parts) tot += p.size();
+    std::string out;
+    out.reserve(tot);
+    out.push_back('[');
+    for (size_t i = 0; i < n; ++i) { if (i) out.push_back(','); out += parts[i]; }
     out.push_back(']');
     return out;
 }
