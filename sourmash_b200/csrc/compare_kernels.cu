@@ -1070,7 +1070,7 @@ __global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restric
 // evict-first stream loads + evict-last reductions (DRAM write-back 7.1 -> 1.4 GB, same time) and
 // walking the groups from a shared-memory tile instead of dependent L2 loads (long-scoreboard
 // stalls 105 -> 33 per issue, same time).  Going faster needs fewer reductions (accumulating in
-// shared-memory tiles of the matrix), see DESIGN.md section 4.7.
+// shared-memory tiles of the matrix), see DESIGN.md section 4.5.
 __global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
                                                         u64 T, u32* __restrict__ common, size_t ld) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
