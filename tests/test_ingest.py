@@ -164,3 +164,91 @@ def test_gather_fixture_bruteforce_matches_reference_expectation(golden):
             if counters[k] <= 0:
                 del counters[k]
     assert got == golden["meta"]["gather_k21_expected"]
+
+
+REF_DATA = "/root/reference/tests/test-data"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference checkout not present (build container only)")
+def test_native_parser_on_the_reference_fixture_corpus():
+    """Every .sig / .sig.gz the reference ships as test data (hundreds of files: old writers,
+    abundances, protein / dayhoff / hp, num and scaled, multi-signature files) through the native
+    parser, against Python's json on the same bytes."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(REF_DATA, "**", "*.sig"), recursive=True) +
+                   glob.glob(os.path.join(REF_DATA, "**", "*.sig.gz"), recursive=True))
+    assert len(paths) > 100
+    checked = sketches = 0
+    for p in paths:
+        try:
+            want = list(_py_sketches(p))
+        except Exception:
+            continue                                   # deliberately broken fixtures
+        if not all("mins" in sk and "ksize" in sk for _, sk in want):
+            continue                                   # other sketch types (e.g. HLL) are out of scope
+        ss = SignatureSet.from_files([p])
+        assert len(ss) == len(want), p
+        for i, (rec, sk) in enumerate(want):
+            mins = np.array(sk["mins"], dtype=np.uint64)
+            order = np.argsort(mins, kind="stable")
+            assert np.array_equal(ss.row(i), mins[order]), p
+            if "abundances" in sk:
+                assert np.array_equal(ss.abunds[int(ss.offsets[i]):int(ss.offsets[i + 1])],
+                                      np.array(sk["abundances"], dtype=np.uint64)[order]), p
+            assert int(ss.ksize[i]) == sk["ksize"] and ss.moltype(i).lower() == sk.get("molecule", "dna").lower()
+            assert ss.md5sum(i) == sk.get("md5sum", "") and ss.name(i) == (rec.get("name") or "")
+            sketches += 1
+        checked += 1
+    assert checked > 90 and sketches > 150, (checked, sketches)
+
+
+def _py_records(path):
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rb") as fh:
+        data = fh.read()
+    lines = data.split(b"\n")
+    out, i = [], 0
+    fastq = data[:1] == b"@"
+    while i < len(lines):
+        ln = lines[i].rstrip(b"\r ")
+        if not ln:
+            i += 1
+            continue
+        name = ln[1:].decode("utf-8", "replace")
+        i += 1
+        seq = []
+        if fastq:
+            while i < len(lines) and not lines[i].startswith(b"+"):
+                seq.append(lines[i].strip()); i += 1
+            i += 1
+            need, got = sum(len(s) for s in seq), 0
+            while i < len(lines) and got < need:
+                got += len(lines[i].rstrip(b"\r")); i += 1
+        else:
+            while i < len(lines) and not lines[i].startswith(b">"):
+                seq.append(lines[i].strip()); i += 1
+        out.append((name, b"".join(seq)))
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference checkout not present (build container only)")
+def test_native_reader_on_the_reference_sequence_files():
+    import glob
+    paths = []
+    for pat in ("*.fa", "*.fa.gz", "*.fna", "*.fna.gz", "*.faa", "*.faa.gz", "*.fq.gz", "*.fq", "*.fastq", "*.fasta"):
+        paths += glob.glob(os.path.join(REF_DATA, "**", pat), recursive=True)
+        paths += glob.glob(os.path.join(os.path.dirname(os.path.dirname(REF_DATA)), "data", pat))
+    paths = sorted(set(p for p in paths if os.path.getsize(p) > 0))
+    assert len(paths) > 12
+    checked = 0
+    for p in paths:
+        with (gzip.open if p.endswith(".gz") else open)(p, "rb") as fh:
+            head = fh.read(1)
+        if head not in (b">", b"@"):
+            continue
+        want = _py_records(p)
+        got = read_sequences(p)
+        assert [n for n, _ in got] == [n for n, _ in want], p
+        assert [s for _, s in got] == [s for _, s in want], p
+        checked += 1
+    assert checked > 10, checked
