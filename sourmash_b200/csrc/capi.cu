@@ -425,12 +425,15 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
             cudaEvent_t ready = pool_event();
             CK(cudaEventRecord(ready, s));                  // d_bases allocation is ordered on s
             CK(cudaStreamWaitEvent(cs, ready, 0));
-            const uint64_t group_bytes = 48ull << 20;
+            // groups ramp up (8, 16, 32, 48, 48, ... MB): hashing starts after the first few MB have
+            // landed instead of after a full-size group
+            uint64_t group_bytes = 8ull << 20;
             size_t g0 = 0;
             while (g0 < ns) {
                 size_t g1 = g0;
                 uint64_t lo = in.off[g0], hi = lo;
                 while (g1 < ns && (hi - lo < group_bytes || g1 == g0)) { hi = in.off[g1] + in.len[g1]; ++g1; }
+                group_bytes = std::min<uint64_t>(group_bytes * 2, 48ull << 20);
                 if (g1 == ns) hi = in.total_bytes;
                 CK(cudaMemcpyAsync((void*)(in.d_bases + lo), in.h_bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
                 cudaEvent_t ev = pool_event();
