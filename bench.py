@@ -60,19 +60,17 @@ def emit_json(obj):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """`nvidia-smi -lms 20` running for the whole benchmark (it needs ~0.3 s to deliver its first
+    line, longer than some timed regions); every timed region reports the samples whose arrival
+    time falls inside it, widened to the nearest samples when the region is shorter than the
+    sampling period."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
-        self.t_begin = self.t_end = None
-
-    def mark_begin(self):
-        self.t_begin = time.monotonic()
-
-    def mark_end(self):
-        self.t_end = time.monotonic()
 
     def start(self):
         try:
@@ -89,27 +87,27 @@ class ClockSampler:
             self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def window(self, t_begin, t_end):
+        "Clock statistics of the samples taken in [t_begin, t_end] (monotonic seconds)."
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)                                  # let the last in-region line arrive
+        rows = list(self.rows)
+        inside = [r for r in rows if t_begin <= r[0] <= t_end + 0.03]
+        note = "timed region"
+        if len(inside) < 2:                               # region shorter than two sampling periods
+            mid = 0.5 * (t_begin + t_end)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "3 samples nearest to the timed region (region shorter than two 20 ms sampling periods)"
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        # the sampler runs from before the warm-up (nvidia-smi needs ~0.2 s to deliver its first
-        # line); keep the samples taken inside the timed region, widened to the closest ones when
-        # the region is shorter than the 20 ms sampling period
-        rows = self.rows
-        window = "timed region"
-        if self.t_begin is not None and self.t_end is not None:
-            inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end + 0.03]
-            if len(inside) >= 2:
-                rows = inside
-            else:
-                window = "warm-up + timed region (timed region shorter than two sampling periods)"
-        for _, r in rows:
+        for _, r in inside:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -118,11 +116,11 @@ class ClockSampler:
                 mx = float(parts[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
+            for nm, v in zip(self.NAMES, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons), "window": window}
+                "samples": len(sm), "reasons": sorted(reasons), "window": note}
 
 
 # ----------------------------------------------------------------------------- workloads
@@ -271,23 +269,26 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                   # runs until the process exits (daemon reader)
+        import atexit
+        atexit.register(sampler.stop)
+
     def timed(step_fn, steps, warmup):
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         for _ in range(warmup):
             step_fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = B.kernel_launches()
-        sampler.mark_begin()
+        t_begin = time.monotonic()
         e0.record(stream)
         extra = [step_fn() for _ in range(steps)]
         e1.record(stream)
         barrier()
-        sampler.mark_end()
+        t_end = time.monotonic()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.window(t_begin, t_end) if rank == 0 else None
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
