@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsourmash_b200.so")
 SOURCES = ["capi.cu", "sketch_kernels.cu", "compare_kernels.cu", "ingest.cu"]
-DEPS = SOURCES + ["common.cuh", "kernels.h", "md5.h", "kmer_roll.cuh", "split_table.cuh", "aa_kmers.cuh", "ingest.h", os.path.join("..", "..", "include", "sourmash_b200.h")]
+DEPS = SOURCES + ["common.cuh", "kernels.h", "md5.h", "kmer_roll.cuh", "split_table.cuh", "aa_kmers.cuh", "ingest.h", "join_walk.cuh", os.path.join("..", "..", "include", "sourmash_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "split_table.cuh"
+#include "join_walk.cuh"
 
 namespace smb {
 
@@ -1047,11 +1048,8 @@ __global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restric
                                                            unsigned long long* __restrict__ out) {
     unsigned long long pairs = 0, mmax = 0;
     for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < T; p += (u64)gridDim.x * blockDim.x) {
-        const u64 k = keys[p];
-        if (p > 0 && keys[p - 1] == k) continue;          // not the head of its group
-        u64 m = 1;
-        while (p + m < T && keys[p + m] == k) ++m;
-        pairs += m * (m - 1) / 2;
+        const u64 m = join_group_size_at_head(keys, T, p);
+        pairs += m * (m - (m ? 1 : 0)) / 2;
         mmax = m > mmax ? m : mmax;
     }
     for (int d = 16; d; d >>= 1) {
@@ -1075,44 +1073,53 @@ __global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__
                                                         u64 T, u32* __restrict__ common, size_t ld) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= T) return;
-    const u64 k = keys[p];
-    u64 b = p + 1;
-    if (b >= T || keys[b] != k) return;
-    u32* __restrict__ row = common + (size_t)ids[p] * ld;
-    do {
-        atomicAdd(row + ids[b], 1u);
-        ++b;
-    } while (b < T && keys[b] == k);
+    join_walk(keys, ids, T, p, [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
 }
 
 // Slice rows to [key_lo, key_hi) (bounded_hi == 0: no upper bound), sort the (hash, row) pairs.
 // Returns the number of elements; *keys_out / *ids_out point into `work`, which the caller frees.
 struct JoinWork {
     void* mem = nullptr;
+    cudaStream_t stream = 0;
+    ~JoinWork() { if (mem) cudaFreeAsync(mem, stream); }
     u64 *keys_a = nullptr, *keys_b = nullptr;
     u32 *ids_a = nullptr, *ids_b = nullptr;
     u64 T = 0;
 };
-static cudaError_t join_sort_slice(const u64* h, const u64* off, int n, u64 upper_T, u64 key_lo, u64 key_hi,
+// stream-ordered scratch allocations released at scope exit, error paths included
+struct JoinScratch {
+    cudaStream_t s;
+    void* p[3] = {nullptr, nullptr, nullptr};
+    int n = 0;
+    explicit JoinScratch(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
+        if (e == cudaSuccess) p[n++] = *out;
+        return e;
+    }
+    ~JoinScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s); }
+};
+
+static cudaError_t join_sort_slice(const u64* h, const u64* off, int n, u64 key_lo, u64 key_hi,
                                    int bounded_hi, int key_bits, JoinWork& W, cudaStream_t s) {
-    u64 *d_beg = nullptr, *d_cnt = nullptr, *d_doff = nullptr;
+    JoinScratch scratch(s);
+    u64* d_beg = nullptr;
     cudaError_t e;
     const size_t nn = (size_t)n + 1;
-    if ((e = cudaMallocAsync((void**)&d_beg, nn * 3 * sizeof(u64), s)) != cudaSuccess) return e;
-    d_cnt = d_beg + nn; d_doff = d_cnt + nn;
+    if ((e = scratch.alloc((void**)&d_beg, nn * 3 * sizeof(u64))) != cudaSuccess) return e;
+    u64 *d_cnt = d_beg + nn, *d_doff = d_cnt + nn;
     join_row_range_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(h, off, n, key_lo, key_hi, bounded_hi, d_beg, d_cnt);
     count_launches(1);
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt, d_doff, (int)nn, s);
     void* d_scan = nullptr;
-    if ((e = cudaMallocAsync(&d_scan, scan_bytes ? scan_bytes : 16, s)) != cudaSuccess) return e;
+    if ((e = scratch.alloc(&d_scan, scan_bytes)) != cudaSuccess) return e;
     cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_cnt, d_doff, (int)nn, s);
     u64 T = 0;
     cudaMemcpyAsync(&T, d_doff + n, sizeof(u64), cudaMemcpyDeviceToHost, s);
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-    (void)upper_T;
     W.T = T;
-    if (T == 0) { cudaFreeAsync(d_scan, s); cudaFreeAsync(d_beg, s); return cudaSuccess; }
+    if (T == 0) return cudaSuccess;
     const size_t Tp = (size_t)((T + 63) & ~63ull);
     if ((e = cudaMallocAsync(&W.mem, Tp * (2 * sizeof(u64) + 2 * sizeof(u32)), s)) != cudaSuccess) return e;
     W.keys_a = (u64*)W.mem; W.keys_b = W.keys_a + Tp;
@@ -1122,10 +1129,9 @@ static cudaError_t join_sort_slice(const u64* h, const u64* off, int n, u64 uppe
     size_t sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
     void* d_sort = nullptr;
-    if ((e = cudaMallocAsync(&d_sort, sort_bytes ? sort_bytes : 16, s)) != cudaSuccess) return e;
+    if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) return e;
     cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
     count_launches(1);
-    cudaFreeAsync(d_sort, s); cudaFreeAsync(d_scan, s); cudaFreeAsync(d_beg, s);
     return cudaGetLastError();
 }
 
@@ -1138,7 +1144,8 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
     // same set, so all ranks take the same decision)
     const u64 hi = max_key / JOIN_SAMPLE + 1;
     JoinWork W;
-    cudaError_t e = join_sort_slice(h, off, n, 0, 0, hi, 1, key_bit_length(hi), W, s);
+    cudaError_t e = join_sort_slice(h, off, n, 0, hi, 1, key_bit_length(hi), W, s);
+    W.stream = s;
     if (e != cudaSuccess) return e;
     unsigned long long r[2] = {0, 0};
     cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned long long), s);
@@ -1149,7 +1156,6 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
     }
     cudaMemcpyAsync(r, d_out2, sizeof r, cudaMemcpyDeviceToHost, s);
     e = cudaStreamSynchronize(s);
-    if (W.mem) cudaFreeAsync(W.mem, s);
     *est_increments = (double)r[0] * JOIN_SAMPLE;
     *est_elements = (double)W.T * JOIN_SAMPLE;
     *max_group = r[1];
@@ -1158,17 +1164,17 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
 
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                         u32* common, size_t ld, cudaStream_t s) {
-    const u64 step = max_key / (u64)n_shards + 1;
-    const u64 lo = (u64)shard * step;
-    const int bounded = shard + 1 < n_shards;
+    u64 lo, hi;
+    bool bounded;
+    join_shard_range(max_key, shard, n_shards, lo, hi, bounded);
     JoinWork W;
-    cudaError_t e = join_sort_slice(h, off, n, 0, lo, lo + step, bounded, key_bit_length(max_key), W, s);
+    cudaError_t e = join_sort_slice(h, off, n, lo, hi, bounded ? 1 : 0, key_bit_length(max_key), W, s);
+    W.stream = s;
     if (e != cudaSuccess) return e;
     if (W.T) {
         join_count_kernel<<<(unsigned)((W.T + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, W.T, common, ld);
         count_launches(1);
     }
-    if (W.mem) cudaFreeAsync(W.mem, s);
     return cudaGetLastError();
 }
 

@@ -160,3 +160,45 @@ def test_aa_protein_matches_oracle(aa_emul, moltype, kaa):
         want = orc.seq_to_hashes_protein(bytes(seq), kaa, moltype, keep_zeros=True)
         got = aa_emul(seq, moltype, kaa, False)
         assert np.array_equal(got, want), (moltype, kaa, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# inverted join (csrc/join_walk.cuh): group walk, group sizes, key-range shards
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def join_emul():
+    exe = os.path.join(tempfile.gettempdir(), "smb_join_emul")
+    src = os.path.join(HERE, "host_emul", "join_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(rows, n_shards):
+        hashes, offsets = orc.to_csr(rows)
+        n = len(rows)
+        with tempfile.TemporaryDirectory() as td:
+            fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
+            hashes.tofile(fh); offsets.tofile(fo)
+            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp])
+            return np.fromfile(fc, dtype=np.uint32).reshape(n, n), int(np.fromfile(fp, dtype=np.uint64)[0])
+    return run
+
+
+def test_join_walk_matches_oracle(join_emul):
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(3)
+    h, off = synth_sketches(90, mean=300, sd=60, lo=100, hi=600, n_families=6, pool=400, seed=9)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(90)]
+    big = np.uint64(2**64 - 1)
+    edge = [np.unique(np.concatenate([rng.integers(0, 2**64 - 1, size=int(rng.integers(0, 30)), dtype=np.uint64),
+                                      np.array([0, 5, big] if i % 3 == 0 else [5], dtype=np.uint64)])) for i in range(40)]
+    edge[7] = np.zeros(0, np.uint64)
+    edge[9] = edge[8].copy()
+    dense = [np.arange(i % 4, 30, dtype=np.uint64) for i in range(25)]
+    for rows in (fam, edge, dense):
+        hh, oo = orc.to_csr(rows)
+        want = orc.pairwise_common(hh, oo)
+        iu = np.triu_indices(len(rows), 1)
+        for shards in (1, 2, 5):
+            got, pairs = join_emul(rows, shards)
+            assert np.array_equal(got[iu], want[iu]), shards
+            assert int(np.tril(got).sum()) == 0                      # only the upper triangle is touched
+            assert pairs == int(want[iu].sum())                       # sum of C(m,2) == sum of all intersections
