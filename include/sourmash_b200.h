@@ -391,6 +391,7 @@ uintptr_t smb_sigs_n_signatures(const SmbSigs *s);
 uintptr_t smb_sigs_n_sketches(const SmbSigs *s);
 bool smb_sigs_any_abund(const SmbSigs *s);
 void smb_sigs_sketch_info(const SmbSigs *s, uintptr_t i, SmbSketchInfo *out);
+void smb_sigs_sketch_info_all(const SmbSigs *s, SmbSketchInfo *out);   /* out[n_sketches] */
 SourmashStr smb_sigs_sketch_md5(const SmbSigs *s, uintptr_t i);
 SourmashStr smb_sigs_sig_name(const SmbSigs *s, uintptr_t j);
 SourmashStr smb_sigs_sig_filename(const SmbSigs *s, uintptr_t j);

@@ -2321,6 +2321,9 @@ void smb_sigs_sketch_info(const SmbSigs* s, uintptr_t i, SmbSketchInfo* out) {
     out->max_hash = k.max_hash; out->seed = k.seed; out->hash_function = k.hash_function;
     out->has_abund = k.has_abund; out->n_mins = s->b.off[i + 1] - s->b.off[i];
 }
+void smb_sigs_sketch_info_all(const SmbSigs* s, SmbSketchInfo* out) {
+    for (uintptr_t i = 0; i < s->b.sketches.size(); ++i) smb_sigs_sketch_info(s, i, out + i);
+}
 SourmashStr smb_sigs_sketch_md5(const SmbSigs* s, uintptr_t i) { return make_str(s->b.sketches[i].md5sum); }
 SourmashStr smb_sigs_sig_name(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].name); }
 SourmashStr smb_sigs_sig_filename(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].filename); }

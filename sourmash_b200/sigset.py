@@ -12,6 +12,11 @@ from ._ffi import decode_str, rustcall
 from ._lowlevel import ffi, lib
 
 _MOLTYPES = {1: "DNA", 2: "protein", 3: "dayhoff", 4: "hp"}
+# layout of SmbSketchInfo (include/sourmash_b200.h), natural C alignment
+_INFO_DTYPE = np.dtype({"names": ["sig_index", "file", "ksize", "num", "max_hash", "seed", "hash_function",
+                                  "has_abund", "n_mins"],
+                        "formats": ["<u4", "<u4", "<u4", "<u4", "<u8", "<u8", "<u4", "u1", "<u8"],
+                        "offsets": [0, 4, 8, 12, 16, 24, 32, 36, 40], "itemsize": 48})
 
 
 class SignatureSet:
@@ -21,17 +26,14 @@ class SignatureSet:
     def __init__(self, ptr):
         self._ptr = ptr
         n = int(lib.smb_sigs_n_sketches(ptr))
-        info = ffi.new("SmbSketchInfo *")
-        self.ksize = np.zeros(n, np.uint32); self.num = np.zeros(n, np.uint32)
-        self.max_hash = np.zeros(n, np.uint64); self.seed = np.zeros(n, np.uint64)
-        self.hash_function = np.zeros(n, np.uint32); self.has_abund = np.zeros(n, bool)
-        self.sig_index = np.zeros(n, np.uint32); self.file = np.zeros(n, np.uint32)
-        self.n_mins = np.zeros(n, np.uint64)
-        for i in range(n):
-            lib.smb_sigs_sketch_info(ptr, i, info)
-            self.ksize[i], self.num[i], self.max_hash[i], self.seed[i] = info.ksize, info.num, info.max_hash, info.seed
-            self.hash_function[i], self.has_abund[i] = info.hash_function, info.has_abund
-            self.sig_index[i], self.file[i], self.n_mins[i] = info.sig_index, info.file, info.n_mins
+        info = ffi.new("SmbSketchInfo[]", max(n, 1))       # one call for all sketches
+        lib.smb_sigs_sketch_info_all(ptr, info)
+        rec = np.frombuffer(ffi.buffer(info, n * ffi.sizeof("SmbSketchInfo")), dtype=_INFO_DTYPE) if n else \
+            np.zeros(0, dtype=_INFO_DTYPE)
+        self.ksize, self.num = rec["ksize"].copy(), rec["num"].copy()
+        self.max_hash, self.seed = rec["max_hash"].copy(), rec["seed"].copy()
+        self.hash_function, self.has_abund = rec["hash_function"].copy(), rec["has_abund"].astype(bool)
+        self.sig_index, self.file, self.n_mins = rec["sig_index"].copy(), rec["file"].copy(), rec["n_mins"].copy()
         self.offsets = np.frombuffer(ffi.buffer(lib.smb_sigs_offsets(ptr), (n + 1) * 8), dtype=np.uint64)
         tot = int(self.offsets[-1]) if n else 0
         self.mins = np.frombuffer(ffi.buffer(lib.smb_sigs_mins(ptr), tot * 8), dtype=np.uint64) if tot else np.zeros(0, np.uint64)
