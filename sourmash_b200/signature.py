@@ -5,6 +5,7 @@ hot path: construction from a MinHash, ``add_sequence`` (every sketch of the sig
 the sequence), the comparison delegates, md5sum identity, and ``.sig`` JSON I/O through the
 library's native reader / writer (csrc/ingest.cu; format: signature.rs:401-445).
 """
+import contextlib
 import os
 
 from ._lowlevel import ffi, lib
@@ -49,6 +50,10 @@ class SourmashSignature(RustObject):
     @property
     def name(self):
         return decode_str(self._methodcall(lib.signature_get_name))
+
+    @name.setter
+    def name(self, value):
+        self._methodcall(lib.signature_set_name, value.encode("utf-8"))
 
     @property
     def _name(self):
@@ -122,8 +127,110 @@ class SourmashSignature(RustObject):
         rv._shared = False
         return rv
 
+    # -- ANI delegates (signature.py:186-222 of the reference) ---------------------------------
+    def jaccard_ani(self, other, *, downsample=False, jaccard=None, prob_threshold=1e-3, err_threshold=1e-4):
+        return self.minhash.jaccard_ani(other.minhash, downsample=downsample, jaccard=jaccard,
+                                        prob_threshold=prob_threshold, err_threshold=err_threshold)
+
+    def containment_ani(self, other, *, downsample=False, containment=None, confidence=0.95, estimate_ci=False):
+        return self.minhash.containment_ani(other.minhash, downsample=downsample, containment=containment,
+                                            confidence=confidence, estimate_ci=estimate_ci)
+
+    def max_containment_ani(self, other, *, downsample=False, max_containment=None, confidence=0.95,
+                            estimate_ci=False):
+        return self.minhash.max_containment_ani(other.minhash, downsample=downsample,
+                                                max_containment=max_containment, confidence=confidence,
+                                                estimate_ci=estimate_ci)
+
+    def avg_containment_ani(self, other, *, downsample=False):
+        return self.minhash.avg_containment_ani(other.minhash, downsample=downsample)
+
+    # -- copies, pickling, freezing (signature.py:236-290) --------------------------------------
+    def __getstate__(self):
+        return (self.minhash, self.name, self.filename)
+
+    def __setstate__(self, tup):
+        mh, name, filename = tup
+        self.__del__()
+        self._objptr = lib.signature_new()
+        self._shared = False
+        if name:
+            self._methodcall(lib.signature_set_name, name.encode("utf-8"))
+        if filename:
+            self._methodcall(lib.signature_set_filename, filename.encode("utf-8"))
+        self._methodcall(lib.signature_set_mh, mh._get_objptr())
+
+    def __reduce__(self):
+        return (SourmashSignature, (self.minhash, self.name, self.filename))
+
+    def __copy__(self):
+        return SourmashSignature(self.minhash, name=self.name, filename=self.filename)
+
+    copy = __copy__
+
+    def to_frozen(self):
+        "Frozen copy of this signature."
+        new_ss = self.copy()
+        new_ss.__class__ = FrozenSourmashSignature
+        return new_ss
+
     def to_mutable(self):
-        return SourmashSignature(self.minhash.to_mutable(), name=self.name, filename=self.filename)
+        "Mutable copy of this signature."
+        return self.copy()
+
+    def into_frozen(self):
+        "Freeze this signature in place."
+        self.__class__ = FrozenSourmashSignature
+
+
+class FrozenSourmashSignature(SourmashSignature):
+    "Immutable signature (signature.py:293-352 of the reference): what the loaders return."
+
+    @SourmashSignature.minhash.setter
+    def minhash(self, value):
+        raise ValueError("cannot set .minhash on FrozenSourmashSignature")
+
+    @SourmashSignature._name.setter
+    def _name(self, value):
+        raise ValueError("cannot set ._name on FrozenSourmashSignature")
+
+    @SourmashSignature.name.setter
+    def name(self, value):
+        raise ValueError("cannot set .name on FrozenSourmashSignature")
+
+    @SourmashSignature.filename.setter
+    def filename(self, value):
+        raise ValueError("cannot set .filename on FrozenSourmashSignature")
+
+    def add_sequence(self, sequence, force=False):
+        raise ValueError("cannot add sequence data to FrozenSourmashSignature")
+
+    def add_protein(self, sequence):
+        raise ValueError("cannot add protein sequence to FrozenSourmashSignature")
+
+    def __copy__(self):
+        return self
+
+    copy = __copy__
+
+    def to_frozen(self):
+        return self
+
+    def to_mutable(self):
+        mut = SourmashSignature.__new__(SourmashSignature)
+        mut._objptr = None
+        mut.__setstate__(self.__getstate__())
+        return mut
+
+    def into_frozen(self):
+        self.__class__ = FrozenSourmashSignature
+
+    @contextlib.contextmanager
+    def update(self):
+        "Context manager yielding a mutable copy that is frozen again on exit."
+        new_copy = self.to_mutable()
+        yield new_copy
+        new_copy.into_frozen()
 
 
 class ComputeParameters(RustObject):
@@ -199,7 +306,7 @@ def load_signatures_from_json(data, *, ksize=None, select_moltype=None, ignore_m
         if do_raise:
             raise
         return
-    sigs = [SourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
+    sigs = [FrozenSourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
     lib.signatures_array_free(arr, size[0])
     yield from sigs
 
@@ -221,7 +328,8 @@ def load_one_signature_from_json(data, *, ksize=None, select_moltype=None, ignor
 
 
 def save_signatures_to_json(siglist, fp=None, compression=0):
-    "Serialise signatures in the reference's .sig JSON layout; returns the text if fp is None."
+    """Serialise signatures in the reference's .sig JSON layout (compact, serde field order);
+    returns bytes if fp is None, like the reference (signature.py:487-527)."""
     siglist = list(siglist)
     ptrs = ffi.new("SourmashSignature *[]", [sig._get_objptr() for sig in siglist])
     size = ffi.new("uintptr_t *")
@@ -230,12 +338,10 @@ def save_signatures_to_json(siglist, fp=None, compression=0):
         result = bytes(ffi.buffer(raw, size[0]))
     finally:
         lib.nodegraph_buffer_free(raw, size[0])
-    if not compression:
-        result = result.decode("utf-8")
     if fp is None:
         return result
     try:
         fp.write(result)
     except TypeError:
-        fp.write(result.decode("utf-8") if isinstance(result, bytes) else result.encode("utf-8"))
+        fp.write(result.decode("utf-8"))
     return None

@@ -214,8 +214,9 @@ def test_signature_container_and_json_roundtrip(golden, tmp_path):
     back = list(smb.load_signatures_from_json(text))
     assert back[0] == sig and back[1] == sig2 and back[0].name == "forty-seven"
     assert back[1].minhash.track_abundance and back[1].minhash == b
+    assert isinstance(text, bytes)                   # like the reference (ffi.string of the saved buffer)
     p = tmp_path / "x.sig"
-    p.write_text(text)
+    p.write_bytes(text)
     assert [s.md5sum() for s in smb.load_signatures(str(p))] == [sig.md5sum(), sig2.md5sum()]
     assert len(list(smb.load_signatures_from_json(text, ksize=21))) == 0
 

@@ -114,8 +114,8 @@ def test_sig_unsorted_mins_abundances_escapes_and_filters():
         smb.signature.load_one_signature_from_json(text)
     # writer -> parser round trip, compact serde field order (signature.rs:401-445, minhash.rs:103-131)
     out = smb.save_signatures_to_json(sigs[:1])
-    assert out.startswith('[{"class":"sourmash_signature","email":"","hash_function":"0.murmur64","filename":null,"name":')
-    assert out.endswith('"molecule":"DNA"}],"version":0.4}]')
+    assert out.startswith(b'[{"class":"sourmash_signature","email":"","hash_function":"0.murmur64","filename":null,"name":')
+    assert out.endswith(b'"molecule":"DNA"}],"version":0.4}]')
     d = json.loads(out)[0]
     assert d["name"] == doc[0]["name"] and d["signatures"][0]["mins"] == [10, 20, 30]
     assert d["signatures"][0]["abundances"] == [1, 2, 3]
@@ -123,6 +123,17 @@ def test_sig_unsorted_mins_abundances_escapes_and_filters():
     back = list(smb.load_signatures(smb.save_signatures_to_json(sigs, compression=6)))
     assert [b.md5sum() for b in back] == [s.md5sum() for s in sigs]
     assert [b.minhash.hashes for b in back] == [s.minhash.hashes for s in sigs]
+
+
+def test_writer_reproduces_a_reference_written_file_byte_for_byte():
+    """genome-s10.fa.gz.sig was written by the reference's serde writer: loading it and saving it
+    again gives the same bytes (field order, separators, number formatting, md5sums), except that
+    the file predates the `Display for HashFunctions` that spells the DNA molecule in capitals
+    (src/core/src/encodings.rs:55-69)."""
+    path = os.path.join(GOLDEN, "genome-s10.fa.gz.sig")
+    raw = open(path, "rb").read()
+    out = smb.save_signatures_to_json(list(smb.load_signatures(path)))
+    assert out == raw.replace(b'"molecule":"dna"', b'"molecule":"DNA"')
 
 
 def test_reference_written_files_roundtrip_through_the_writer(tmp_path):
