@@ -230,3 +230,25 @@ def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, name
                      match_containment_ani_low=mc.ani_low, match_containment_ani_high=mc.ani_high)
         out.append(d)
     return out
+
+
+def write_gather_csv(rows, fp, *, estimate_ani_ci=False):
+    """Write GatherRow objects as the reference's `gather -o` CSV: same columns in the same order
+    (search.py:480-523), empty cells for values that are None, query md5 shortened to 8 characters
+    (prep_gather_result, search.py:633-637)."""
+    import csv
+    cols = GATHER_COLUMNS + (CI_COLUMNS if estimate_ani_ci else [])
+    w = csv.DictWriter(fp, fieldnames=cols)
+    w.writeheader()
+    for g in rows:
+        w.writerow(g.to_dict(estimate_ani_ci))
+
+
+def write_prefetch_csv(results, fp, *, estimate_ani_ci=False):
+    "Write prefetch_database() results as the reference's `prefetch -o` CSV (search.py:364-395)."
+    import csv
+    cols = PREFETCH_COLUMNS + (CI_COLUMNS if estimate_ani_ci else [])
+    w = csv.DictWriter(fp, fieldnames=cols, extrasaction="ignore")
+    w.writeheader()
+    for d in results:
+        w.writerow({k: v for k, v in d.items() if v is not None})

@@ -294,3 +294,32 @@ def test_residue_encodings_and_protein_guards(golden):
     assert smb.MinHash(0, 2, dayhoff=True, scaled=1).seq_to_hashes("ACTGA") == []
     with pytest.raises(ValueError):
         smb.MinHash(0, 21, scaled=1).seq_to_hashes("ATGAGAGACGATAGACAGATGACC", is_protein=True)
+
+
+def test_gather_and_prefetch_csv_layout():
+    """CSV writers: the reference's column order (search.py:364-388, 480-523), None -> empty cell."""
+    import csv
+    import io
+    from sourmash_b200.gather import (CI_COLUMNS, GATHER_COLUMNS, PREFETCH_COLUMNS, GatherRow, write_gather_csv,
+                                      write_prefetch_csv)
+    rows = [GatherRow(row=3, intersect_bp=5000, f_orig_query=0.5, f_match=0.25, f_unique_to_query=0.5,
+                      f_unique_weighted=0.5, name="g3", md5="abc", gather_result_rank=0, remaining_bp=5000,
+                      query_md5="12345678", query_bp=10000, ksize=31, scaled=1000, query_n_hashes=10,
+                      query_containment_ani=0.97, total_weighted_hashes=10, sum_weighted_found=5),
+            GatherRow(row=1, gather_result_rank=1, average_abund=2.5, median_abund=2.0, std_abund=0.5,
+                      query_abundance=True, n_unique_weighted_found=7)]
+    buf = io.StringIO()
+    write_gather_csv(rows, buf)
+    got = list(csv.reader(io.StringIO(buf.getvalue())))
+    assert got[0] == GATHER_COLUMNS and len(got) == 3
+    rec = dict(zip(got[0], got[1]))
+    assert rec["intersect_bp"] == "5000" and rec["name"] == "g3" and rec["average_abund"] == "" and \\
+        rec["query_containment_ani"] == "0.97" and rec["match_containment_ani"] == ""
+    assert dict(zip(got[0], got[2]))["median_abund"] == "2.0"
+    buf = io.StringIO()
+    write_gather_csv(rows, buf, estimate_ani_ci=True)
+    assert next(csv.reader(io.StringIO(buf.getvalue()))) == GATHER_COLUMNS + CI_COLUMNS
+    buf = io.StringIO()
+    write_prefetch_csv([{"row": 0, "intersect_bp": 100, "jaccard": 0.5, "match_name": "m", "ksize": 21}], buf)
+    got = list(csv.reader(io.StringIO(buf.getvalue())))
+    assert got[0] == PREFETCH_COLUMNS and got[1][got[0].index("jaccard")] == "0.5" and "row" not in got[0]
