@@ -313,7 +313,7 @@ def test_gather_and_prefetch_csv_layout():
     got = list(csv.reader(io.StringIO(buf.getvalue())))
     assert got[0] == GATHER_COLUMNS and len(got) == 3
     rec = dict(zip(got[0], got[1]))
-    assert rec["intersect_bp"] == "5000" and rec["name"] == "g3" and rec["average_abund"] == "" and \\
+    assert rec["intersect_bp"] == "5000" and rec["name"] == "g3" and rec["average_abund"] == "" and \
         rec["query_containment_ani"] == "0.97" and rec["match_containment_ani"] == ""
     assert dict(zip(got[0], got[2]))["median_abund"] == "2.0"
     buf = io.StringIO()
