@@ -2,6 +2,7 @@
 object model (sorted containers, num/scaled bookkeeping, md5, errors, pickling, JSON) behaves
 like the reference -- checked against the oracle's KmerMinHash restatement.  No compute calls
 (those need the GPU and live in test_gpu_*.py)."""
+import os
 import pickle
 
 import numpy as np
@@ -323,3 +324,40 @@ def test_gather_and_prefetch_csv_layout():
     write_prefetch_csv([{"row": 0, "intersect_bp": 100, "jaccard": 0.5, "match_name": "m", "ksize": 21}], buf)
     got = list(csv.reader(io.StringIO(buf.getvalue())))
     assert got[0] == PREFETCH_COLUMNS and got[1][got[0].index("jaccard")] == "0.5" and "row" not in got[0]
+
+
+def test_cli_plugin_protocol_and_argument_wiring(tmp_path):
+    """The sourmash.cli_script plugin classes (reference protocol: src/sourmash/plugins.py:91-186):
+    command / description attributes, parser construction, -q/-d, param strings; a command run
+    without a GPU fails loudly instead of falling back."""
+    import argparse
+    from sourmash_b200 import plugin
+    from sourmash_b200.exceptions import SourmashError
+    parser, objs = plugin.build_parser()
+    assert sorted(objs) == ["b200compare", "b200gather", "b200prefetch", "b200sketch"]
+    for cls in plugin.COMMANDS:
+        assert cls.command and cls.description and issubclass(cls, plugin.CommandLinePlugin)
+        sp = argparse.ArgumentParser()
+        cls(sp)                                             # what sourmash's add_cli_scripts does
+        assert {"quiet", "debug"} <= {a.dest for a in sp._actions}
+    a = parser.parse_args(["b200sketch", "x.fa", "y.fa.gz", "-p", "k=21,k=31,scaled=1000,abund", "-o", "o.sig", "-q"])
+    assert a.filenames == ["x.fa", "y.fa.gz"] and a.quiet and a.moltype == "dna"
+    P = plugin.parse_param_string(a.param_string)
+    assert P == {"ksizes": [21, 31], "scaled": 1000, "num": None, "seed": 42, "track_abundance": True}
+    assert plugin.parse_param_string("k=7,num=500,seed=3,noabund")["num"] == 500
+    with pytest.raises(ValueError):
+        plugin.parse_param_string("k=31,scaled=100,num=5")
+    with pytest.raises(ValueError):
+        plugin.parse_param_string("k=31,bogus=1")
+    a = parser.parse_args(["b200gather", "q.sig", "a.sig", "b.sig", "-k", "31", "--threshold-bp", "0", "-o", "g.csv"])
+    assert a.query == "q.sig" and a.databases == ["a.sig", "b.sig"] and a.threshold_bp == 0 and a.ksize == 31
+    # pyproject registers exactly these classes under the reference's entry-point group
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyproject.toml")).read()
+    assert '[project.entry-points."sourmash.cli_script"]' in text
+    for cls in plugin.COMMANDS:
+        assert f'{cls.command} = "sourmash_b200.plugin:{cls.__name__}"' in text
+    if smb.batch.device_count() == 0:                       # no silent CPU fallback behind the CLI either
+        fa = tmp_path / "g.fa"
+        fa.write_text(">r\\n" + "ACGT" * 30 + "\\n")
+        with pytest.raises(SourmashError):
+            plugin.main(["b200sketch", str(fa), "-p", "k=21,scaled=1", "-o", str(tmp_path / "o.sig"), "-q"])
