@@ -386,6 +386,11 @@ typedef struct {
 } SmbSketchInfo;
 SmbSigs *smb_sigs_read(const char *const *paths, uintptr_t n_paths, int32_t n_threads);
 SmbSigs *smb_sigs_parse(const char *data, uintptr_t len);          /* JSON text or gzip of it */
+/* the same batch from objects already in memory (first sketch of every signature, like
+ * SourmashSignature.minhash): N sketches out of N objects in one call instead of
+ * N x (signature_first_mh + kmerminhash_get_mins + getters) */
+SmbSigs *smb_sigs_from_signatures(const SourmashSignature *const *sigs, uintptr_t n);
+SmbSigs *smb_sigs_from_minhashes(const SourmashKmerMinHash *const *mhs, uintptr_t n);
 void smb_sigs_free(SmbSigs *s);
 uintptr_t smb_sigs_n_signatures(const SmbSigs *s);
 uintptr_t smb_sigs_n_sketches(const SmbSigs *s);

@@ -38,6 +38,19 @@ def _sizes_accurate(mhs, relative_error=0.20, confidence=0.95):
     return out
 
 
+def _sizes_accurate_arrays(sizes, scaleds, relative_error=0.20, confidence=0.95):
+    "size_is_accurate() for sketches given as (number of hashes, scaled) arrays."
+    if not np.all(scaleds):
+        raise TypeError("Error: can only calculate ANI for scaled MinHashes")
+    out = np.zeros(len(sizes), dtype=bool)
+    cache = {}
+    for i, key in enumerate(zip((int(x) for x in sizes), (int(x) for x in scaleds))):
+        if key not in cache:
+            cache[key] = bool(DU.set_size_exact_prob(key[0] * key[1], key[1], relative_error=relative_error) >= confidence)
+        out[i] = cache[key]
+    return out
+
+
 def _p_nothing_in_common(dist, n_unique_kmers, ksize, scaled):
     "get_exp_probability_nothing_common for arrays (distance_utils.py:247-270)."
     q = 1 - (1 - dist) ** ksize
@@ -49,11 +62,48 @@ def _flat_minhashes(siglist):
     return [s.minhash if hasattr(s, "minhash") else s for s in siglist]
 
 
-def _check_and_build(siglist, *, downsample, need_scaled=False):
-    """Validate compatibility like the per-pair calls would, return (SketchSet, num, scaled, sizes)."""
-    mhs = _flat_minhashes(siglist)
-    if not mhs:
-        return None, 0, 0, np.zeros(0, np.int64)
+def _collect(siglist, *, downsample, need_scaled=False, with_abunds=False):
+    """Validate compatibility like the per-pair calls would and return the sketches as host CSR:
+    dict(hashes, offsets, abunds, num, scaled, sizes, has_abund, ksize).  The sketches of all
+    objects come out of the library in one call (SignatureSet.from_objects); mixed lists fall back
+    to one call per object."""
+    from .sigset import SignatureSet
+    objs = list(siglist)
+    ss = SignatureSet.from_objects(objs)
+    if ss is None:
+        return _collect_per_object(objs, downsample=downsample, need_scaled=need_scaled, with_abunds=with_abunds)
+    n = len(ss)
+    pyscaled = ss.python_scaled()
+    # the reference's per-pair checks, in its order, reported for the first offending sketch
+    bad = (ss.ksize != ss.ksize[0]) | (ss.hash_function != ss.hash_function[0]) | (ss.seed != ss.seed[0]) | \
+        (ss.num != ss.num[0])
+    if bad.any():
+        i = int(np.argmax(bad))
+        if ss.ksize[i] != ss.ksize[0]:
+            raise ValueError("different ksizes cannot be compared")
+        if ss.hash_function[i] != ss.hash_function[0]:
+            raise ValueError("DNA/prot minhashes cannot be compared")
+        if ss.seed[i] != ss.seed[0]:
+            raise ValueError("mismatch in seed; comparison fail")
+        raise TypeError(f"incompatible num values: self={int(ss.num[0])} other={int(ss.num[i])}")
+    if need_scaled and not pyscaled.all():
+        raise TypeError("Error: can only calculate containment for scaled MinHashes")
+    scaled = int(pyscaled.max())
+    cut = 0
+    if len(np.unique(pyscaled)) > 1:
+        if not downsample:
+            raise ValueError("mismatch in scaled; comparison fail")
+        cut = B.max_hash_for_scaled(scaled)
+    h, off, ab = ss.csr_host(cut, with_abunds=True)
+    ksize = int(ss.ksize[0]) if int(ss.hash_function[0]) == 1 else int(ss.ksize[0]) // 3
+    return {"hashes": h, "offsets": off, "abunds": ab if with_abunds else None, "num": int(ss.num[0]),
+            "scaled": scaled, "sizes": np.diff(off.astype(np.int64)), "has_abund": ss.has_abund.copy(), "ksize": ksize,
+            "orig_sizes": ss.n_mins.astype(np.int64), "orig_scaled": pyscaled, "_keepalive": ss}
+
+
+def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
+    "Same contract through one FFI round trip per object (MinHash-like objects of other origins)."
+    mhs = _flat_minhashes(objs)
     first = mhs[0]
     for mh in mhs[1:]:
         if mh.ksize != first.ksize:
@@ -68,31 +118,51 @@ def _check_and_build(siglist, *, downsample, need_scaled=False):
         raise TypeError("Error: can only calculate containment for scaled MinHashes")
     scaleds = {mh.scaled for mh in mhs}
     scaled = max(scaleds)
+    has_ab = np.array([bool(mh.track_abundance) for mh in mhs])
+    orig_sizes = np.array([len(mh) for mh in mhs], dtype=np.int64)
+    orig_scaled = np.array([mh.scaled for mh in mhs], dtype=np.uint64)
     if len(scaleds) > 1:
         if not downsample:
             raise ValueError("mismatch in scaled; comparison fail")
         mhs = [mh.downsample(scaled=scaled) if mh.scaled != scaled else mh for mh in mhs]
     rows = [mh._mins_array() for mh in mhs]
-    sset = B.SketchSet.from_rows(rows)
-    return sset, first.num, scaled, np.array([len(r) for r in rows], dtype=np.int64)
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    h = np.concatenate(rows) if rows else np.zeros(0, np.uint64)
+    ab = None
+    if with_abunds:
+        ab = np.concatenate([mh._abunds_array() if mh.track_abundance else np.ones(len(r), dtype=np.uint64)
+                             for mh, r in zip(mhs, rows)]) if rows else np.zeros(0, np.uint64)
+    return {"hashes": h, "offsets": off, "abunds": ab, "num": first.num, "scaled": scaled,
+            "sizes": np.diff(off.astype(np.int64)), "has_abund": has_ab, "ksize": first.ksize,
+            "orig_sizes": orig_sizes, "orig_scaled": orig_scaled}
+
+
+def _check_and_build(siglist, *, downsample, need_scaled=False):
+    """Validate compatibility like the per-pair calls would, return (SketchSet, num, scaled, sizes)."""
+    if not len(siglist):
+        return None, 0, 0, np.zeros(0, np.int64)
+    c = _collect(siglist, downsample=downsample, need_scaled=need_scaled)
+    sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
+    return sset, c["num"], c["scaled"], c["sizes"]
 
 
 def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=None, return_ani=False):
     """Similarity matrix (n, n) float64, ones on the diagonal -- ``compare_all_pairs`` /
     ``compare_serial`` / ``compare_parallel`` of the reference (compare.py:14-64,241-358).
     ``n_jobs`` is accepted for signature compatibility; the GPU does the whole matrix."""
-    mhs = _flat_minhashes(siglist)
-    n = len(mhs)
+    n = len(siglist)
     if n == 0:
         return np.ones((0, 0))
-    has_ab = np.array([bool(mh.track_abundance) for mh in mhs])
+    c = _collect(siglist, downsample=downsample, with_abunds=not ignore_abundance)
+    has_ab, num, scaled, sizes = c["has_abund"], c["num"], c["scaled"], c["sizes"]
     if return_ani:
-        accurate = _sizes_accurate(mhs)                   # also raises for num sketches, like jaccard_ani
-    sset, num, scaled, sizes = _check_and_build(siglist, downsample=downsample)
+        accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"])   # raises for num sketches, like jaccard_ani
+    sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
     jac = B.compare_jaccard(sset, num=num)
     if return_ani:
         # compare.py:36-54: ANI from Jaccard for every pair; untrustworthy estimates become 0
-        ani, untrustworthy, false_neg = DU.jaccard_to_ani_matrix(jac, sizes, mhs[0].ksize, scaled,
+        ani, untrustworthy, false_neg = DU.jaccard_to_ani_matrix(jac, sizes, c["ksize"], scaled,
                                                                   size_accurate=accurate)
         if untrustworthy:
             notify(_JACCARD_WARNING)
@@ -101,14 +171,9 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
         return ani
     if ignore_abundance or not has_ab.any():
         return jac
-    # angular similarity where both sketches track abundance, Jaccard elsewhere (minhash.rs:682-702)
-    rows, abs_ = [], []
-    for mh in mhs:
-        if mh.scaled and mh.scaled != scaled:
-            mh = mh.downsample(scaled=scaled)
-        rows.append(mh._mins_array())
-        abs_.append(mh._abunds_array() if mh.track_abundance else np.ones(len(rows[-1]), dtype=np.uint64))
-    ang = B.compare_angular(B.SketchSet.from_rows(rows, abs_))
+    # angular similarity where both sketches track abundance, Jaccard elsewhere (minhash.rs:682-702);
+    # flat sketches carry abundance 1 in the abundance set (their cells are replaced by Jaccard)
+    ang = B.compare_angular(B.SketchSet.from_host(c["hashes"], c["offsets"], c["abunds"]))
     both = has_ab[:, None] & has_ab[None, :]
     out = np.where(both, ang, jac)
     np.fill_diagonal(out, 1.0)
@@ -136,20 +201,21 @@ def _clamp01(m):
     return np.where(m <= 0, 0.0, m)
 
 
-def _containment_parts(siglist, downsample):
-    sset, _, scaled, sizes = _check_and_build(siglist, downsample=downsample, need_scaled=True)
-    n = len(sizes)
-    if n == 0:
-        return None, sizes, scaled
+def _containment_parts(siglist, downsample, return_ani=False):
+    "(common counts as float64, sizes, scaled, ksize, size_is_accurate flags or None)"
+    if not len(siglist):
+        return None, np.zeros(0, np.int64), 0, 0, None
+    c = _collect(siglist, downsample=downsample, need_scaled=True)
+    accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"]) if return_ani else None
+    sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
     common = B.pairwise_common(sset).astype(np.float64)
-    return common, sizes, scaled
+    return common, c["sizes"], c["scaled"], c["ksize"], accurate
 
 
 def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
     """containments[i][j] = siglist[j].contained_by(siglist[i]) (compare.py:67-106); with
     ``return_ani`` the containment ANI of j in i (0.0 where it cannot be trusted)."""
-    accurate = _sizes_accurate(_flat_minhashes(siglist)) if return_ani else None
-    common, sizes, scaled = _containment_parts(siglist, downsample)
+    common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani)
     n = len(sizes)
     if n == 0:
         return np.ones((0, 0))
@@ -159,7 +225,6 @@ def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
     m = _clamp01(m)
     m[:, sizes == 0] = 0.0
     if return_ani:
-        ksize = _flat_minhashes(siglist)[0].ksize
         ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
         p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize),
                                  (sizes * scaled).astype(np.float64)[np.newaxis, :], ksize, scaled)
@@ -173,8 +238,7 @@ def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
 
 def compare_serial_max_containment(siglist, *, downsample=False, return_ani=False):
     """max_containment matrix (compare.py:109-147): common / (min(|A|,|B|) * bias(min))."""
-    accurate = _sizes_accurate(_flat_minhashes(siglist)) if return_ani else None
-    common, sizes, scaled = _containment_parts(siglist, downsample)
+    common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani)
     n = len(sizes)
     if n == 0:
         return np.ones((0, 0))
@@ -188,7 +252,6 @@ def compare_serial_max_containment(siglist, *, downsample=False, return_ani=Fals
     m = _clamp01(m)
     m[mins == 0] = 0.0
     if return_ani:
-        ksize = _flat_minhashes(siglist)[0].ksize
         ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
         p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize), (mins * scaled).astype(np.float64),
                                  ksize, scaled)
@@ -205,8 +268,9 @@ def compare_serial_avg_containment(siglist, *, downsample=False, return_ani=Fals
     ``return_ani`` the mean of the two containment ANIs, 0.0 if either cannot be trusted."""
     c = compare_serial_containment(siglist, downsample=downsample, return_ani=return_ani)
     m = (c + c.T) / 2
-    if return_ani:
-        accurate = _sizes_accurate(_flat_minhashes(siglist))
+    if return_ani and len(siglist):
+        c0 = _collect(siglist, downsample=downsample, need_scaled=True)
+        accurate = _sizes_accurate_arrays(c0["orig_sizes"], c0["orig_scaled"])
         m = np.where(accurate[:, None] & accurate[None, :], m, 0.0)
     np.fill_diagonal(m, 1.0)
     return m

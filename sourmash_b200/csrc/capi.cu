@@ -2311,6 +2311,45 @@ SmbSigs* smb_sigs_parse(const char* data, uintptr_t len) {
         return r.release();
     });
 }
+// in-memory objects -> the same CSR batch as the file parser (first sketch of every signature, like
+// SourmashSignature.minhash): lets compare / search pull N sketches out of N objects in one call
+static void batch_push(smb::SigBatch& B, const MH& m, const std::string& name, const std::string& filename) {
+    if (B.off.empty()) B.off.push_back(0);
+    smb::SigRecord rec;
+    rec.name = name; rec.filename = filename; rec.license = "CC0"; rec.klass = "sourmash_signature";
+    rec.has_name = !name.empty(); rec.has_filename = !filename.empty();
+    smb::SigSketch sk;
+    sk.sig_index = (uint32_t)B.sigs.size(); sk.file = 0;
+    sk.ksize = m.ksize; sk.num = m.num; sk.max_hash = m.max_hash; sk.seed = m.seed;
+    sk.hash_function = (uint32_t)m.hash_function; sk.has_abund = m.track;
+    B.sigs.push_back(std::move(rec));
+    B.sketches.push_back(std::move(sk));
+    B.mins.insert(B.mins.end(), m.mins.begin(), m.mins.end());
+    if (m.track) B.abunds.insert(B.abunds.end(), m.abunds.begin(), m.abunds.end());
+    else B.abunds.insert(B.abunds.end(), m.mins.size(), 1);
+    B.any_abund = B.any_abund || m.track;
+    B.off.push_back(B.mins.size());
+}
+SmbSigs* smb_sigs_from_signatures(const SourmashSignature* const* sigs, uintptr_t n) {
+    return guarded<SmbSigs*>([&]() -> SmbSigs* {
+        auto r = std::make_unique<SmbSigs>();
+        r->b.off.push_back(0);
+        for (uintptr_t i = 0; i < n; ++i) {
+            if (sigs[i]->sketches.empty())
+                fail(SOURMASH_ERROR_CODE_INTERNAL, "internal error: \"found unsupported sketch type\"");
+            batch_push(r->b, sigs[i]->sketches[0], sigs[i]->name, sigs[i]->filename);
+        }
+        return r.release();
+    });
+}
+SmbSigs* smb_sigs_from_minhashes(const SourmashKmerMinHash* const* mhs, uintptr_t n) {
+    return guarded<SmbSigs*>([&]() -> SmbSigs* {
+        auto r = std::make_unique<SmbSigs>();
+        r->b.off.push_back(0);
+        for (uintptr_t i = 0; i < n; ++i) batch_push(r->b, *mhs[i], "", "");
+        return r.release();
+    });
+}
 void smb_sigs_free(SmbSigs* s) { delete s; }
 uintptr_t smb_sigs_n_signatures(const SmbSigs* s) { return s->b.sigs.size(); }
 uintptr_t smb_sigs_n_sketches(const SmbSigs* s) { return s->b.sketches.size(); }

@@ -53,6 +53,42 @@ class SignatureSet:
         return cls(rustcall(lib.smb_sigs_read, arr, len(paths), int(n_threads)))
 
     @classmethod
+    def from_objects(cls, objs):
+        """Batch of SourmashSignature objects (their first sketch) or of MinHash objects, pulled out of
+        the library in one call.  Returns None for mixed / foreign lists (callers fall back)."""
+        from .minhash import MinHash
+        from .signature import SourmashSignature
+        objs = list(objs)
+        if objs and all(isinstance(o, SourmashSignature) for o in objs):
+            arr = ffi.new("SourmashSignature *[]", [o._get_objptr() for o in objs])
+            return cls(rustcall(lib.smb_sigs_from_signatures, arr, len(objs)))
+        if objs and all(isinstance(o, MinHash) for o in objs):
+            arr = ffi.new("SourmashKmerMinHash *[]", [o._get_objptr() for o in objs])
+            return cls(rustcall(lib.smb_sigs_from_minhashes, arr, len(objs)))
+        return None
+
+    def python_scaled(self):
+        "MinHash.scaled of every sketch (minhash.py:63-67: round((2**64-1)/max_hash), 0 for num sketches)."
+        out = np.zeros(len(self), dtype=np.uint64)
+        for mx in np.unique(self.max_hash):
+            if mx:
+                out[self.max_hash == mx] = min(int(round((2**64 - 1) / int(mx), 0)), 2**64 - 1)
+        return out
+
+    def csr_host(self, max_hash=0, with_abunds=False):
+        """(hashes, offsets[, abunds]) of all sketches on the host, every row cut at max_hash
+        (0: as stored) -- rows are sorted, so the cut is a prefix (downsample_scaled)."""
+        n = len(self)
+        if not max_hash:
+            h, off = self.mins, self.offsets
+            return (h, off, self.abunds) if with_abunds else (h, off)
+        keep = self.mins <= np.uint64(max_hash)
+        csum = np.concatenate([[0], np.cumsum(keep, dtype=np.int64)])
+        off = csum[self.offsets.astype(np.int64)].astype(np.uint64)
+        h = self.mins[keep]
+        return (h, off, self.abunds[keep]) if with_abunds else (h, off)
+
+    @classmethod
     def from_json(cls, data):
         buf = data.encode("utf-8") if isinstance(data, str) else bytes(data)
         return cls(rustcall(lib.smb_sigs_parse, buf, len(buf)))
