@@ -24,20 +24,6 @@ def notify(msg):
     print(msg, file=sys.stderr)
 
 
-def _sizes_accurate(mhs, relative_error=0.20, confidence=0.95):
-    "size_is_accurate() of every sketch, one vectorised binomial evaluation (minhash.py:1129-1150)."
-    if not all(mh.scaled for mh in mhs):
-        raise TypeError("Error: can only calculate ANI for scaled MinHashes")
-    out = np.zeros(len(mhs), dtype=bool)
-    cache = {}
-    for i, mh in enumerate(mhs):
-        key = (len(mh), mh.scaled)
-        if key not in cache:
-            cache[key] = bool(DU.set_size_exact_prob(key[0] * key[1], key[1], relative_error=relative_error) >= confidence)
-        out[i] = cache[key]
-    return out
-
-
 def _sizes_accurate_arrays(sizes, scaleds, relative_error=0.20, confidence=0.95):
     "size_is_accurate() for sketches given as (number of hashes, scaled) arrays."
     if not np.all(scaleds):
@@ -136,15 +122,6 @@ def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
     return {"hashes": h, "offsets": off, "abunds": ab, "num": first.num, "scaled": scaled,
             "sizes": np.diff(off.astype(np.int64)), "has_abund": has_ab, "ksize": first.ksize,
             "orig_sizes": orig_sizes, "orig_scaled": orig_scaled}
-
-
-def _check_and_build(siglist, *, downsample, need_scaled=False):
-    """Validate compatibility like the per-pair calls would, return (SketchSet, num, scaled, sizes)."""
-    if not len(siglist):
-        return None, 0, 0, np.zeros(0, np.int64)
-    c = _collect(siglist, downsample=downsample, need_scaled=need_scaled)
-    sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
-    return sset, c["num"], c["scaled"], c["sizes"]
 
 
 def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=None, return_ani=False):
