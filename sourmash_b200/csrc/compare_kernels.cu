@@ -15,6 +15,7 @@
 // plus two key compares per table ("directory galloping"), instead of a two-pointer walk
 // over |A|+|B| elements.  Counts are reduced with warp REDUX and written as u32.
 #include <stdlib.h>
+#include <string.h>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1162,8 +1163,160 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
     return e;
 }
 
+// ------------------------------------------------------------------------------------
+// Experimental cluster layout of the inverted join (off unless SMB_JOIN_LAYOUT=cluster).
+// Not measured yet: kept behind the switch until it has been validated on the GPU; the logic
+// is covered on the CPU by tests/test_host_emulation.py::test_join_cluster_layout_matches_oracle.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) join_rowkey_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                         u64 T, unsigned long long* __restrict__ rowkey) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T) return;
+    if (join_is_shared(keys, T, p)) atomicMin(rowkey + ids[p], (unsigned long long)keys[p]);
+}
+
+__global__ void __launch_bounds__(256) join_iota_kernel(u32* __restrict__ v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (u32)i;
+}
+
+__global__ void __launch_bounds__(256) join_invert_kernel(const u32* __restrict__ order, int n, u32* __restrict__ inv) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) inv[order[r]] = (u32)r;
+}
+
+// per-rank element counts (rank r holds row order[r]); slot n is the scan's total
+__global__ void __launch_bounds__(256) join_rank_counts_kernel(const u64* __restrict__ cnt, const u32* __restrict__ order,
+                                                              int n, u64* __restrict__ cnt_rank) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    cnt_rank[r] = r < n ? cnt[order[r]] : 0;
+}
+
+// like join_gather_kernel, rows visited in rank order and labelled with their rank
+__global__ void __launch_bounds__(256) join_gather_ranked_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
+                                                                const u64* __restrict__ beg, const u32* __restrict__ order,
+                                                                const u64* __restrict__ dst_off, int n_rows,
+                                                                u64* __restrict__ keys, u32* __restrict__ ids) {
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const u32 row = order[r];
+        const u64 src = off[row] + beg[row], d0 = dst_off[r], n = dst_off[r + 1] - d0;
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) { keys[d0 + i] = h[src + i]; ids[d0 + i] = (u32)r; }
+    }
+}
+
+// one warp per element: lanes take consecutive later elements of the group
+__global__ void __launch_bounds__(256) join_count_warp_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                             u64 T, u32* __restrict__ common, size_t ld) {
+    const u64 p = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= T) return;                                   // whole warps leave together
+    const u32 lane = lane_id();
+    for (u64 b0 = p + 1;; b0 += 32) {
+        const bool hit = join_walk_lane(keys, ids, T, p, b0, lane,
+                                        [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
+        if (!__all_sync(0xffffffffu, hit)) break;
+    }
+}
+
+// common[i][j] += rank-space count of (i, j), for i < j
+__global__ void __launch_bounds__(256) join_unpermute_add_kernel(const u32* __restrict__ ranked, const u32* __restrict__ inv,
+                                                                int n, size_t ld_ranked, u32* __restrict__ common, size_t ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int i = blockIdx.y; i < j; i += gridDim.y) {       // every (i, j), i < j, is visited exactly once
+        u32 lo, hi;
+        join_rank_cell(inv, (u32)i, (u32)j, lo, hi);
+        const u32 v = ranked[(size_t)lo * ld_ranked + hi];
+        if (v) common[(size_t)i * ld + j] += v;
+    }
+}
+
+static cudaError_t join_counts_clustered(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
+                                         u32* common, size_t ld, cudaStream_t s) {
+    cudaError_t e;
+    JoinScratch scratch(s);
+    // 1. row keys from the global sample (lowest 1/JOIN_SAMPLE of the key range): smallest shared hash
+    unsigned long long* d_rowkey = nullptr;
+    u32 *d_order_in = nullptr, *d_order = nullptr;
+    if ((e = scratch.alloc((void**)&d_rowkey, (size_t)n * 2 * sizeof(unsigned long long))) != cudaSuccess) return e;
+    unsigned long long* d_rowkey_sorted = d_rowkey + n;
+    if ((e = scratch.alloc((void**)&d_order_in, (size_t)n * 3 * sizeof(u32))) != cudaSuccess) return e;
+    d_order = d_order_in + n;
+    u32* d_inv = d_order + n;
+    cudaMemsetAsync(d_rowkey, 0xff, (size_t)n * sizeof(unsigned long long), s);
+    {
+        const u64 hi = max_key / JOIN_SAMPLE + 1;
+        JoinWork S;
+        e = join_sort_slice(h, off, n, 0, hi, 1, key_bit_length(hi), S, s);
+        S.stream = s;
+        if (e != cudaSuccess) return e;
+        if (S.T) { join_rowkey_kernel<<<(unsigned)((S.T + 255) / 256), 256, 0, s>>>(S.keys_b, S.ids_b, S.T, d_rowkey); count_launches(1); }
+    }
+    // 2. rank rows by (row key, row id): stable sort of the ids by key
+    join_iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_order_in, n); count_launches(1);
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, d_rowkey, d_rowkey_sorted, d_order_in, d_order, n, 0, 64, s);
+    void* d_tmp = nullptr;
+    if ((e = cudaMallocAsync(&d_tmp, sb ? sb : 16, s)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(d_tmp, sb, d_rowkey, d_rowkey_sorted, d_order_in, d_order, n, 0, 64, s);
+    cudaFreeAsync(d_tmp, s);
+    join_invert_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_order, n, d_inv); count_launches(2);
+    // 3. slice this shard's key range, gather in rank order, sort
+    u64 lo, hi;
+    bool bounded;
+    join_shard_range(max_key, shard, n_shards, lo, hi, bounded);
+    const size_t nn = (size_t)n + 1;
+    u64* d_beg = nullptr;
+    if ((e = cudaMallocAsync((void**)&d_beg, nn * 4 * sizeof(u64), s)) != cudaSuccess) return e;
+    u64 *d_cnt = d_beg + nn, *d_cnt_rank = d_cnt + nn, *d_doff = d_cnt_rank + nn;
+    join_row_range_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(h, off, n, lo, hi, bounded ? 1 : 0, d_beg, d_cnt);
+    join_rank_counts_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(d_cnt, d_order, n, d_cnt_rank);
+    count_launches(2);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt_rank, d_doff, (int)nn, s);
+    void* d_scan = nullptr;
+    if ((e = cudaMallocAsync(&d_scan, scan_bytes ? scan_bytes : 16, s)) != cudaSuccess) { cudaFreeAsync(d_beg, s); return e; }
+    cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_cnt_rank, d_doff, (int)nn, s);
+    u64 T = 0;
+    cudaMemcpyAsync(&T, d_doff + n, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    cudaFreeAsync(d_scan, s);
+    if (e != cudaSuccess || T == 0) { cudaFreeAsync(d_beg, s); return e; }
+    JoinWork W;
+    W.stream = s;
+    const size_t Tp = (size_t)((T + 63) & ~63ull);
+    if ((e = cudaMallocAsync(&W.mem, Tp * (2 * sizeof(u64) + 2 * sizeof(u32)), s)) != cudaSuccess) { cudaFreeAsync(d_beg, s); return e; }
+    W.keys_a = (u64*)W.mem; W.keys_b = W.keys_a + Tp;
+    W.ids_a = (u32*)(W.keys_b + Tp); W.ids_b = W.ids_a + Tp;
+    const int blocks = n < SMB_B200_SMS * 16 ? n : SMB_B200_SMS * 16;
+    join_gather_ranked_kernel<<<blocks, 256, 0, s>>>(h, off, d_beg, d_order, d_doff, n, W.keys_a, W.ids_a); count_launches(1);
+    cudaFreeAsync(d_beg, s);
+    const int key_bits = key_bit_length(max_key);
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
+    void* d_sort = nullptr;
+    if ((e = cudaMallocAsync(&d_sort, sort_bytes ? sort_bytes : 16, s)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
+    cudaFreeAsync(d_sort, s);
+    count_launches(1);
+    // 4. count in rank space, then add into the caller's matrix in row space
+    u32* d_ranked = nullptr;
+    if ((e = cudaMallocAsync((void**)&d_ranked, (size_t)n * n * sizeof(u32), s)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_ranked, 0, (size_t)n * n * sizeof(u32), s);
+    const u64 warps = T, threads = warps * 32;
+    join_count_warp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, T, d_ranked, (size_t)n);
+    dim3 grid((n + 255) / 256, n < 65535 ? n : 65535);
+    join_unpermute_add_kernel<<<grid, 256, 0, s>>>(d_ranked, d_inv, n, (size_t)n, common, ld);
+    count_launches(2);
+    cudaFreeAsync(d_ranked, s);
+    return cudaGetLastError();
+}
+
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                         u32* common, size_t ld, cudaStream_t s) {
+    const char* layout = getenv("SMB_JOIN_LAYOUT");
+    if (layout && !strcmp(layout, "cluster"))
+        return join_counts_clustered(h, off, n, max_key, shard, n_shards, common, ld, s);
     u64 lo, hi;
     bool bounded;
     join_shard_range(max_key, shard, n_shards, lo, hi, bounded);

@@ -42,3 +42,37 @@ __host__ __device__ __forceinline__ void join_shard_range(u64 max_key, int shard
 }
 
 }  // namespace smb
+
+// ---------------------------------------------------------------------------------------------
+// Experimental "cluster" layout (SMB_JOIN_LAYOUT=cluster, off by default):
+// rows are renumbered so that related rows get adjacent ranks, and one *warp* walks the group of
+// an element, lane l taking the (l+1)-th later element of the current 32-element chunk.  The cells
+// a warp instruction touches are then (rank_a, consecutive ranks): a few sectors instead of 32.
+// ---------------------------------------------------------------------------------------------
+namespace smb {
+
+// true if element p belongs to a group of two or more rows (its hash is shared)
+__host__ __device__ __forceinline__ bool join_is_shared(const u64* __restrict__ keys, u64 T, u64 p) {
+    const u64 k = keys[p];
+    return (p > 0 && keys[p - 1] == k) || (p + 1 < T && keys[p + 1] == k);
+}
+
+// lane `lane` of the warp that owns element p, chunk starting at b0 (= p + 1 + 32 * iteration):
+// emits the pair if its element is still in p's group; returns whether it was.
+template <class Emit>
+__host__ __device__ __forceinline__ bool join_walk_lane(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                        u64 T, u64 p, u64 b0, u32 lane, Emit&& emit) {
+    const u64 b = b0 + lane;
+    if (b >= T || keys[b] != keys[p]) return false;
+    emit(ids[p], ids[b]);
+    return true;
+}
+
+// cell of the rank-space matrix that holds the count of rows (i, j), i != j
+__host__ __device__ __forceinline__ void join_rank_cell(const u32* __restrict__ inv, u32 i, u32 j, u32& lo, u32& hi) {
+    const u32 ri = inv[i], rj = inv[j];
+    lo = ri < rj ? ri : rj;
+    hi = ri < rj ? rj : ri;
+}
+
+}  // namespace smb

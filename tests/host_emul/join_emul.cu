@@ -2,7 +2,9 @@
 // compiled here for the host) over a CSR sketch set: slice rows to the shard's key range, sort the
 // (hash, row) pairs stably by hash (std::stable_sort stands in for the radix sort), walk every
 // element.  Test infrastructure for the CPU-only suite.
-//   usage: join_emul <n_shards> <hashes.u64> <offsets.u64> <out.u32 (n*n, summed over shards)> <out_pairs.u64>
+//   usage: join_emul <n_shards> <hashes.u64> <offsets.u64> <out.u32 (n*n, summed over shards)> <out_pairs.u64> [cluster]
+// With "cluster" the experimental layout is emulated instead: row keys from the global sample, rows
+// ranked by (key, id), gather in rank order, one 32-lane "warp" per element, un-permute.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -28,7 +30,77 @@ static std::vector<T> slurp(const char* path) {
     return v;
 }
 
+// the sorted (hash, id) stream of the rows restricted to [lo, hi) (bounded) / [lo, inf), rows visited
+// in the order given and labelled with their position in it
+static void sorted_stream(const std::vector<u64>& h, const std::vector<u64>& off, const std::vector<u32>& order,
+                          u64 lo, u64 hi, bool bounded, std::vector<u64>& sk, std::vector<u32>& si) {
+    std::vector<u64> keys;
+    std::vector<u32> ids;
+    for (size_t r = 0; r < order.size(); ++r)
+        for (u64 i = off[order[r]]; i < off[order[r] + 1]; ++i)
+            if (h[i] >= lo && (!bounded || h[i] < hi)) { keys.push_back(h[i]); ids.push_back((u32)r); }
+    std::vector<size_t> perm(keys.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    sk.resize(keys.size()); si.resize(keys.size());
+    for (size_t i = 0; i < perm.size(); ++i) { sk[i] = keys[perm[i]]; si[i] = ids[perm[i]]; }
+}
+
+static int cluster_main(int n_shards, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path) {
+    const size_t n = off.size() - 1;
+    u64 max_key = 0;
+    for (u64 v : h) max_key = std::max(max_key, v);
+    std::vector<u32> ident(n);
+    std::iota(ident.begin(), ident.end(), 0);
+    // row keys from the sample
+    std::vector<u64> sk;
+    std::vector<u32> si;
+    sorted_stream(h, off, ident, 0, max_key / 64 + 1, true, sk, si);
+    std::vector<u64> rowkey(n, ~0ull);
+    for (u64 p = 0; p < sk.size(); ++p)
+        if (join_is_shared(sk.data(), sk.size(), p)) rowkey[si[p]] = std::min(rowkey[si[p]], sk[p]);
+    std::vector<u32> order(ident);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return rowkey[a] < rowkey[b]; });
+    std::vector<u32> inv(n);
+    for (size_t r = 0; r < n; ++r) inv[order[r]] = (u32)r;
+    std::vector<u32> common(n * n, 0);
+    for (int shard = 0; shard < n_shards; ++shard) {
+        u64 lo, hi;
+        bool bounded;
+        join_shard_range(max_key, shard, n_shards, lo, hi, bounded);
+        sorted_stream(h, off, order, lo, hi, bounded, sk, si);
+        const u64 T = sk.size();
+        std::vector<u32> ranked(n * n, 0);
+        for (u64 p = 0; p < T; ++p) {                       // one "warp" per element
+            for (u64 b0 = p + 1;; b0 += 32) {
+                bool all = true;
+                for (u32 lane = 0; lane < 32; ++lane)
+                    all &= join_walk_lane(sk.data(), si.data(), T, p, b0, lane,
+                                          [&](u32 a, u32 b) { ranked[(size_t)a * n + b] += 1; });
+                if (!all) break;
+            }
+        }
+        for (size_t j = 0; j < n; ++j)
+            for (size_t i = 0; i < j; ++i) {
+                u32 rl, rh;
+                join_rank_cell(inv.data(), (u32)i, (u32)j, rl, rh);
+                common[i * n + j] += ranked[(size_t)rl * n + rh];
+            }
+        for (size_t a = 0; a < n; ++a)                      // nothing may land outside the upper triangle
+            for (size_t b = 0; b <= a; ++b)
+                if (ranked[a * n + b]) return 5;
+    }
+    FILE* f = fopen(out_path, "wb");
+    fwrite(common.data(), 4, common.size(), f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 7) {
+        std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
+        return cluster_main(atoi(argv[1]), h, off, argv[4]);
+    }
     if (argc != 6) return 2;
     const int n_shards = atoi(argv[1]);
     std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);

@@ -171,14 +171,15 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards):
+    def run(rows, n_shards, cluster=False):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
-            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp])
-            return np.fromfile(fc, dtype=np.uint32).reshape(n, n), int(np.fromfile(fp, dtype=np.uint64)[0])
+            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + (["cluster"] if cluster else []))
+            got = np.fromfile(fc, dtype=np.uint32).reshape(n, n)
+            return got if cluster else (got, int(np.fromfile(fp, dtype=np.uint64)[0]))
     return run
 
 
@@ -202,3 +203,24 @@ def test_join_walk_matches_oracle(join_emul):
             assert np.array_equal(got[iu], want[iu]), shards
             assert int(np.tril(got).sum()) == 0                      # only the upper triangle is touched
             assert pairs == int(want[iu].sum())                       # sum of C(m,2) == sum of all intersections
+
+
+def test_join_cluster_layout_matches_oracle(join_emul):
+    """Experimental cluster layout (SMB_JOIN_LAYOUT=cluster): row keys, ranking, ranked gather, 32-lane
+    walk and un-permutation, emulated with the header's own functions."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(8)
+    h, off = synth_sketches(120, mean=300, sd=60, lo=100, hi=600, n_families=7, pool=400, seed=21)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(120)]
+    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64),
+                                      np.array([7] if i % 4 else [7, 2**61], dtype=np.uint64)])) for i in range(150)]
+    dense = [np.arange(i % 4, 30, dtype=np.uint64) for i in range(40)]
+    dense[3] = np.zeros(0, np.uint64)
+    for rows in (fam, wide, dense):
+        hh, oo = orc.to_csr(rows)
+        want = orc.pairwise_common(hh, oo)
+        iu = np.triu_indices(len(rows), 1)
+        for shards in (1, 3):
+            got = join_emul(rows, shards, cluster=True)
+            assert np.array_equal(got[iu], want[iu]), shards
+            assert int(np.tril(got).sum()) == 0
