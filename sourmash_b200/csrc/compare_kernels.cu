@@ -1312,6 +1312,37 @@ static cudaError_t join_counts_clustered(const u64* h, const u64* off, int n, u6
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------
+// Sorted stream kept across several count passes (experimental row-block pipeline of
+// smb_compare_jaccard, SMB_COMPARE_PASSES; off by default, see join_walk.cuh).
+// ------------------------------------------------------------------------------------
+struct JoinStream { JoinWork W; };
+
+__global__ void __launch_bounds__(256) join_count_rows_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                             u64 T, u32 r0, u32 r1, u32* __restrict__ common, size_t ld) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T) return;
+    join_walk_rows(keys, ids, T, p, r0, r1, [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
+}
+
+cudaError_t join_stream_create(const u64* h, const u64* off, int n, u64 max_key, JoinStream** out, cudaStream_t s) {
+    JoinStream* js = new JoinStream();
+    js->W.stream = s;
+    cudaError_t e = join_sort_slice(h, off, n, 0, 0, 0, key_bit_length(max_key), js->W, s);
+    if (e != cudaSuccess) { delete js; return e; }
+    *out = js;
+    return cudaSuccess;
+}
+cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_end, u32* common, size_t ld,
+                                   cudaStream_t s) {
+    if (js->W.T == 0 || row_end <= row_begin) return cudaSuccess;
+    join_count_rows_kernel<<<(unsigned)((js->W.T + 255) / 256), 256, 0, s>>>(js->W.keys_b, js->W.ids_b, js->W.T,
+                                                                           (u32)row_begin, (u32)row_end, common, ld);
+    count_launches(1);
+    return cudaGetLastError();
+}
+void join_stream_destroy(JoinStream* js) { delete js; }
+
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                         u32* common, size_t ld, cudaStream_t s) {
     const char* layout = getenv("SMB_JOIN_LAYOUT");

@@ -23,6 +23,18 @@ __host__ __device__ __forceinline__ void join_walk(const u64* __restrict__ keys,
     } while (b < T && keys[b] == k);
 }
 
+// Row-block passes (experimental, SMB_COMPARE_PASSES): the walk of element p only touches row
+// ids[p] of the matrix, so a pass that walks the elements whose row lies in [r0, r1) completes
+// exactly the cells (i, j > i) with i in [r0, r1).  After the passes for rows [0, r1) every cell
+// with min(i, j) < r1 is final, i.e. the full rows [0, r1) of the symmetric result are known.
+template <class Emit>
+__host__ __device__ __forceinline__ void join_walk_rows(const u64* __restrict__ keys, const u32* __restrict__ ids,
+                                                        u64 T, u64 p, u32 r0, u32 r1, Emit&& emit) {
+    const u32 a = ids[p];
+    if (a < r0 || a >= r1) return;
+    join_walk(keys, ids, T, p, emit);
+}
+
 // size of the group that starts at p (0 if p is not the first element of its group)
 __host__ __device__ __forceinline__ u64 join_group_size_at_head(const u64* __restrict__ keys, u64 T, u64 p) {
     const u64 k = keys[p];

@@ -47,6 +47,16 @@ cudaError_t join_estimate(const uint64_t* h, const uint64_t* off, int n, uint64_
 cudaError_t join_counts(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key, int shard,
                         int n_shards, uint32_t* common, size_t ld, cudaStream_t s);
 
+// Experimental: the sorted stream kept for several count passes, one per block of rows (cells
+// (i, j > i) with i in the block) -- lets finished blocks of rows be finalised and downloaded while
+// later blocks are still being counted.
+struct JoinStream;
+cudaError_t join_stream_create(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key, JoinStream** out,
+                               cudaStream_t s);
+cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_end, uint32_t* common, size_t ld,
+                                   cudaStream_t s);
+void join_stream_destroy(JoinStream* js);
+
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
 // elements in the longer row.
 void launch_pairwise_generic(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,

@@ -96,7 +96,37 @@ static int cluster_main(int n_shards, const std::vector<u64>& h, const std::vect
     return 0;
 }
 
+// row-block passes: pass k walks the elements whose row is in block k, then the *full* rows of block k
+// (both triangles, read as c[min][max]) are captured; nothing captured is ever revisited
+static int rows_main(int passes, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path) {
+    const size_t n = off.size() - 1;
+    std::vector<u32> ident(n);
+    std::iota(ident.begin(), ident.end(), 0);
+    std::vector<u64> sk;
+    std::vector<u32> si;
+    sorted_stream(h, off, ident, 0, 0, false, sk, si);
+    const u64 T = sk.size();
+    std::vector<u32> c(n * n, 0), captured(n * n, 0);
+    const size_t per = (n + passes - 1) / passes;
+    for (size_t r0 = 0; r0 < n; r0 += per) {
+        const size_t r1 = std::min(n, r0 + per);
+        for (u64 p = 0; p < T; ++p)
+            join_walk_rows(sk.data(), si.data(), T, p, (u32)r0, (u32)r1, [&](u32 a, u32 b) { c[(size_t)a * n + b] += 1; });
+        for (size_t i = r0; i < r1; ++i)
+            for (size_t j = 0; j < n; ++j)
+                if (i != j) captured[i * n + j] = c[std::min(i, j) * n + std::max(i, j)];
+    }
+    FILE* f = fopen(out_path, "wb");
+    fwrite(captured.data(), 4, captured.size(), f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 8) {                                        // ... <out> <unused> rows <passes>
+        std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
+        return rows_main(atoi(argv[7]), h, off, argv[4]);
+    }
     if (argc == 7) {
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
         return cluster_main(atoi(argv[1]), h, off, argv[4]);

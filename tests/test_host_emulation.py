@@ -171,15 +171,16 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards, cluster=False):
+    def run(rows, n_shards, cluster=False, row_passes=0):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
-            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + (["cluster"] if cluster else []))
+            extra = ["cluster"] if cluster else ["rows", str(row_passes)] if row_passes else []
+            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + extra)
             got = np.fromfile(fc, dtype=np.uint32).reshape(n, n)
-            return got if cluster else (got, int(np.fromfile(fp, dtype=np.uint64)[0]))
+            return got if (cluster or row_passes) else (got, int(np.fromfile(fp, dtype=np.uint64)[0]))
     return run
 
 
@@ -224,3 +225,18 @@ def test_join_cluster_layout_matches_oracle(join_emul):
             got = join_emul(rows, shards, cluster=True)
             assert np.array_equal(got[iu], want[iu]), shards
             assert int(np.tril(got).sum()) == 0
+
+
+def test_join_row_block_passes_finalise_rows_in_order(join_emul):
+    """Experimental row-block pipeline (SMB_COMPARE_PASSES): after the pass over a block of rows the
+    complete rows of that block (both triangles) are final."""
+    from sourmash_b200.synth import synth_sketches
+    h, off = synth_sketches(75, mean=300, sd=60, lo=100, hi=600, n_families=5, pool=400, seed=33)
+    rows = [h[int(off[i]):int(off[i + 1])] for i in range(75)]
+    want = orc.pairwise_common(h, off)
+    iu = np.triu_indices(75, 1)
+    full = np.zeros_like(want)
+    full[iu] = want[iu]
+    full = full + full.T                                   # symmetric, zero diagonal
+    for passes in (2, 8, 75):
+        assert np.array_equal(join_emul(rows, 1, row_passes=passes), full), passes
