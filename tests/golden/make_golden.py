@@ -96,6 +96,10 @@ shutil.copyfile(os.path.join(TD, "genome-s10.fa.gz"), os.path.join(HERE, "genome
 s10 = {}
 for rec, s in sketches(os.path.join(TD, "genome-s10.fa.gz.sig")):
     if s["molecule"].lower() != "dna":
+        # protein sketches of the same genome (six-frame translation, num=500): k stored x3
+        arrays[f"s10_prot_k{s['ksize']}"] = np.array(s["mins"], dtype=np.uint64)
+        meta.setdefault("genome_s10_protein", {})[str(s["ksize"])] = {
+            "num": s["num"], "md5sum": s["md5sum"], "seed": s["seed"], "molecule": s["molecule"], "n": len(s["mins"])}
         continue
     key = f"s10_k{s['ksize']}"
     arrays[key] = np.array(s["mins"], dtype=np.uint64)

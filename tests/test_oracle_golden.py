@@ -205,3 +205,17 @@ def test_protein_2x2_similarities(golden, golden_dir):
     assert round(orc.jaccard(aa[1], tr[0], num=500), 3) == want["aa2_trans1"]
     assert round(orc.jaccard(aa[0], tr[1], num=500), 3) == want["aa1_trans2"]
     assert round(orc.jaccard(aa[1], tr[1], num=500), 3) == want["aa2_trans2"]
+
+
+def test_translate_golden_genome_s10(golden, s10_records):
+    """genome-s10.fa.gz.sig also carries protein sketches (k = 7 and 10 residues, num=500) that the
+    reference computed from the DNA by six-frame translation: a 500 kbp golden for that path."""
+    info = golden["meta"]["genome_s10_protein"]
+    assert sorted(info) == ["21", "30"]
+    for k3, meta in info.items():
+        assert meta["molecule"] == "protein" and meta["num"] == 500
+        mh = orc.OracleMinHash(scaled=0, ksize=int(k3), num=500, seed=meta["seed"])
+        for _, seq in s10_records:
+            mh.add_protein_family(seq, "protein", False)
+        assert np.array_equal(mh.mins(), golden["arrays"][f"s10_prot_k{k3}"])
+        assert mh.md5sum() == meta["md5sum"]
