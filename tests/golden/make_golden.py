@@ -107,6 +107,20 @@ for rec, s in sketches(os.path.join(TD, "genome-s10.fa.gz.sig")):
                             "max_hash": s.get("max_hash", 0), "n": len(s["mins"])}
 meta["genome_s10"] = s10
 
+# --- the scaled_siglist of tests/test_compare.py:28-40 (ANI matrices :94-190): byte copies ------
+for f in ("2.fa.sig", "2+63.fa.sig", "63.fa.sig"):
+    shutil.copyfile(os.path.join(TD, f), os.path.join(HERE, f))
+meta["compare_ani_k31"] = {   # np.testing.assert_array_almost_equal(..., decimal=3) in the reference
+    "order": ["2.fa.sig", "2+63.fa.sig", "47.fa.sig", "63.fa.sig"],
+    "jaccard": [[1.0, 0.978, 0.0, 0.0], [0.978, 1.0, 0.96973012, 0.99262776],
+                [0.0, 0.96973012, 1.0, 0.97697011], [0.0, 0.99262776, 0.97697011, 1.0]],
+    "containment": [[1, 0.966, 0.0, 0.0], [1, 1.0, 0.97715525, 1.0],
+                    [0.0, 0.96377054, 1.0, 0.97678608], [0.0, 0.98667513, 0.97715525, 1.0]],
+    "max_containment": [[1.0, 1.0, 0.0, 0.0], [1.0, 1.0, 0.97715525, 1.0],
+                        [0.0, 0.97715525, 1.0, 0.97715525], [0.0, 1.0, 0.97715525, 1.0]],
+    "avg_containment": [[1.0, 0.983, 0.0, 0.0], [0.983, 1.0, 0.97046289, 0.99333757],
+                        [0.0, 0.97046289, 1.0, 0.97697067], [0.0, 0.99333757, 0.97697067, 1.0]]}
+
 # --- two reference-written .sig files, byte copies, for the JSON loader tests ----------------
 shutil.copyfile(os.path.join(TD, "47.fa.sig"), os.path.join(HERE, "47.fa.sig"))
 shutil.copyfile(os.path.join(TD, "genome-s10.fa.gz.sig"), os.path.join(HERE, "genome-s10.fa.gz.sig"))

@@ -171,3 +171,21 @@ def test_containment_and_ani_glue(cpu_kernels):
     with pytest.raises(TypeError, match="can only calculate ANI"):
         num = [smb.SourmashSignature(smb.MinHash(50, 31), name=f"n{i}") for i in range(3)]
         C.compare_all_pairs(num, True, return_ani=True)
+
+
+def test_reference_ani_matrices(cpu_kernels, golden):
+    """The four ANI matrices the reference asserts for 2.fa / 2+63.fa / 47.fa / 63.fa at k=31
+    (tests/test_compare.py:94-190, decimal=3), from the reference-written .sig fixtures through the
+    native loader and the matrix post-processing (kernels replaced by the oracle on the CPU)."""
+    import os
+    from tests.conftest import GOLDEN
+    kat = golden["meta"]["compare_ani_k31"]
+    sigs = []
+    for f in kat["order"]:
+        these = [s for s in smb.load_signatures(os.path.join(GOLDEN, f), ksize=31) if s.minhash.scaled]
+        sigs.extend(these)
+    assert len(sigs) == 4
+    np.testing.assert_array_almost_equal(C.compare_all_pairs(sigs, True, return_ani=True), np.array(kat["jaccard"]), decimal=3)
+    np.testing.assert_array_almost_equal(C.compare_serial_containment(sigs, return_ani=True), np.array(kat["containment"], dtype=float), decimal=3)
+    np.testing.assert_array_almost_equal(C.compare_serial_max_containment(sigs, return_ani=True), np.array(kat["max_containment"]), decimal=3)
+    np.testing.assert_array_almost_equal(C.compare_serial_avg_containment(sigs, return_ani=True), np.array(kat["avg_containment"]), decimal=3)
