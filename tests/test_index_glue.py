@@ -126,3 +126,69 @@ def test_prefetch_and_best_containment(cpu_kernels, index_obj, three):  # :396-5
         assert score == 1.0 and match.minhash == ss2.minhash
     with pytest.raises(ValueError):
         list(LinearIndex().prefetch(ss2, threshold_bp=0))              # "no signatures to search"
+
+
+class _FakeSession:
+    "batch.GatherSession with Python sets (same begin / peek / intersect / apply contract)."
+
+    def __init__(self, query, db, min_count=1):
+        self.rows = [set(int(x) for x in r) for r in db.rows()]
+        self.remaining_set = set(int(x) for x in query)
+        self.counts = [len(self.remaining_set & r) for r in self.rows]
+        self.counts = [c if c >= min_count else 0 for c in self.counts]
+        self.remaining = len(self.remaining_set)
+
+    def peek(self):
+        best = max(self.counts) if self.counts else 0
+        return (best, self.counts.index(best)) if best else (0, 0)
+
+    def intersect(self, row):
+        return np.array(sorted(self.remaining_set & self.rows[row]), dtype=np.uint64)
+
+    def apply(self, isect):
+        s = set(int(x) for x in isect)
+        self.counts = [c - len(s & r) if c else 0 for c, r in zip(self.counts, self.rows)]
+        self.remaining_set -= s
+        self.remaining = len(self.remaining_set)
+        return self.remaining
+
+
+def test_gather_report_on_the_reference_fixture(cpu_kernels, monkeypatch, golden):
+    """gather_databases / prefetch_database report logic on the 12-genome fixture
+    (tests/test_index_protocol.py:1057-1097), the session replaced by Python sets."""
+    import glob
+    from sourmash_b200 import gather as G
+    from sourmash_b200.sigset import SignatureSet
+    monkeypatch.setattr(B, "GatherSession", _FakeSession)
+    d = os.path.join(GOLDEN, "gather")
+    query = smb.signature.load_one_signature_from_json(os.path.join(d, "combined.sig"), ksize=21)
+    ss = SignatureSet.from_files(sorted(glob.glob(os.path.join(d, "GCF*.sig"))))
+    rows = ss.select(ksize=21)
+    db = _FakeSet([ss.row(i) for i in rows])
+    names = [ss.name(i) for i in rows]
+    report = G.gather_databases(query.minhash, db, names=names, md5s=[ss.md5sum(i) for i in rows])
+    want = golden["meta"]["gather_k21_expected"]
+    assert [[g.name.split()[0], g.unique_intersect_bp // g.scaled] for g in report] == want
+    q = set(query.minhash.hashes)
+    covered = 0
+    for rank, g in enumerate(report):
+        m = set(int(x) for x in ss.row(rows[g.row]))
+        assert g.gather_result_rank == rank and g.intersect_bp == len(q & m) * g.scaled
+        assert g.f_orig_query == len(q & m) / len(q) and g.f_unique_to_query == (g.unique_intersect_bp // g.scaled) / len(q)
+        assert g.f_unique_weighted == g.f_unique_to_query and g.average_abund is None and not g.query_abundance
+        covered += g.unique_intersect_bp // g.scaled
+        assert g.remaining_bp == (len(q) - covered) * g.scaled and g.sum_weighted_found == covered
+        assert 0 < g.f_match <= g.f_match_orig <= 1
+        assert g.query_containment_ani is None or 0.8 < g.query_containment_ani <= 1.0
+    pre = G.prefetch_database(query.minhash, db, 0, names=names)
+    assert len(pre) == 12 and [p["row"] for p in pre] == list(range(12))
+    by_row = {g.row: g for g in report}
+    for p in pre:
+        assert p["intersect_bp"] == by_row[p["row"]].intersect_bp and p["f_query_match"] == by_row[p["row"]].f_match_orig
+    assert [p["row"] for p in G.prefetch_database(query.minhash, db, 100000, names=names)] == \
+        [p["row"] for p in pre if p["intersect_bp"] >= 100000]
+    with_thr = G.gather_databases(query.minhash, db, threshold_bp=50000, names=names)
+    scaled = query.minhash.scaled
+    assert scaled == 10000
+    assert [[g.name.split()[0], g.unique_intersect_bp // g.scaled] for g in with_thr] == [w for w in want if w[1] * scaled >= 50000]
+    assert len(with_thr) == 11
