@@ -385,6 +385,10 @@ typedef struct {
   uint64_t n_mins;
 } SmbSketchInfo;
 SmbSigs *smb_sigs_read(const char *const *paths, uintptr_t n_paths, int32_t n_threads);
+/* flags for .zip inputs: 1 = ignore the manifest (use_manifest=False), 2 = without a manifest try
+ * every member, not only *.sig / *.sig.gz (traverse_yield_all=True) */
+SmbSigs *smb_sigs_read_opts(const char *const *paths, uintptr_t n_paths, int32_t n_threads,
+                            uint32_t flags);
 SmbSigs *smb_sigs_parse(const char *data, uintptr_t len);          /* JSON text or gzip of it */
 /* the same batch from objects already in memory (first sketch of every signature, like
  * SourmashSignature.minhash): N sketches out of N objects in one call instead of
@@ -397,14 +401,21 @@ uintptr_t smb_sigs_n_sketches(const SmbSigs *s);
 bool smb_sigs_any_abund(const SmbSigs *s);
 void smb_sigs_sketch_info(const SmbSigs *s, uintptr_t i, SmbSketchInfo *out);
 void smb_sigs_sketch_info_all(const SmbSigs *s, SmbSketchInfo *out);   /* out[n_sketches] */
-SourmashStr smb_sigs_sketch_md5(const SmbSigs *s, uintptr_t i);
+SourmashStr smb_sigs_sketch_md5(const SmbSigs *s, uintptr_t i);      /* the md5sum field as stored */
+/* md5 of every sketch computed from its hashes (KmerMinHash::md5sum): out[32 * n_sketches] hex, no NULs */
+void smb_sigs_md5_all(const SmbSigs *s, char *out);
 SourmashStr smb_sigs_sig_name(const SmbSigs *s, uintptr_t j);
 SourmashStr smb_sigs_sig_filename(const SmbSigs *s, uintptr_t j);
 SourmashStr smb_sigs_sig_license(const SmbSigs *s, uintptr_t j);
+SourmashStr smb_sigs_sig_location(const SmbSigs *s, uintptr_t j);  /* zip member the signature came from, else "" */
 const uint64_t *smb_sigs_offsets(const SmbSigs *s);                /* n_sketches + 1 */
 const uint64_t *smb_sigs_mins(const SmbSigs *s);
 const uint64_t *smb_sigs_abunds(const SmbSigs *s);                 /* 1 where a sketch has none */
 SourmashKmerMinHash *smb_sigs_minhash(const SmbSigs *s, uintptr_t i);   /* new owned object */
+/* rows (NULL: all) as one SourmashSignature per sketch, like signatures_load_*: array freed with
+ * signatures_array_free, objects with signature_free */
+SourmashSignature **smb_sigs_signatures(const SmbSigs *s, const uint32_t *rows, uintptr_t n_rows,
+                                        uintptr_t *size);
 /* rows (NULL: all) -> device-resident CSR; max_hash != 0 keeps the prefix h <= max_hash of every
  * row (downsample_scaled, sketch/minhash.rs:777-798) */
 SmbSketchSet *smb_sigs_to_sketchset(const SmbSigs *s, const uint32_t *rows, uintptr_t n_rows,
@@ -424,6 +435,25 @@ const uint8_t *signatures_save_buffer(const SourmashSignature *const *ptr, uintp
 SourmashStr signature_save_json(const SourmashSignature *ptr);
 void nodegraph_buffer_free(uint8_t *ptr, uintptr_t insize);
 void signatures_array_free(SourmashSignature **ptr, uintptr_t size);
+
+/* --- .zip collections: src/core/src/ffi/storage.rs:15-141 (include/sourmash.h:469-486) -------
+ * Read-only view of a zip file of signatures (members in central-directory order, zip64
+ * included).  zipstorage_load resolves `path`, then `subdir + path` (storage/mod.rs:339-363);
+ * a missing member fails with SOURMASH_ERROR_CODE_STORAGE; the buffer is freed with
+ * nodegraph_buffer_free.  The string arrays are read as paths[i][0], like the reference's.
+ * smb_sigs_read accepts such files directly and loads every member the reference's
+ * ZipFileLinearIndex.signatures() would yield (src/sourmash/index/__init__.py:639-683):
+ * SOURMASH-MANIFEST.csv locations filtered by its md5 column, else every *.sig / *.sig.gz. */
+typedef struct SourmashZipStorage SourmashZipStorage;
+SourmashZipStorage *zipstorage_new(const char *ptr, uintptr_t insize);
+void zipstorage_free(SourmashZipStorage *ptr);
+const uint8_t *zipstorage_load(const SourmashZipStorage *ptr, const char *path_ptr,
+                               uintptr_t insize, uintptr_t *size);
+SourmashStr **zipstorage_filenames(const SourmashZipStorage *ptr, uintptr_t *size);
+SourmashStr **zipstorage_list_sbts(const SourmashZipStorage *ptr, uintptr_t *size);
+void zipstorage_set_subdir(SourmashZipStorage *ptr, const char *path_ptr, uintptr_t insize);
+SourmashStr zipstorage_path(const SourmashZipStorage *ptr);
+SourmashStr zipstorage_subdir(const SourmashZipStorage *ptr);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@
 #include "kernels.h"
 #include "ingest.h"
 #include "md5.h"
+#include "zipread.h"
 
 namespace smb {
 static std::atomic<uint64_t> g_launches{0};
@@ -1046,6 +1047,11 @@ struct SourmashSignature {                 // signature.rs:401-445
 };
 struct SmbRecords { smb::RecordBatch b; };
 struct SmbSigs { smb::SigBatch b; };
+struct SourmashZipStorage {
+    smb::ZipArchive zip;
+    std::string path, subdir;
+    bool has_subdir = false;
+};
 
 namespace {
 
@@ -1176,6 +1182,15 @@ MH mh_from_batch(const smb::SigBatch& B, size_t i) {
     if (sk.has_abund) m.abunds.assign(B.abunds.begin() + B.off[i], B.abunds.begin() + B.off[i + 1]);
     return m;
 }
+// sketch i with the metadata of the signature object it was stored in
+SourmashSignature* sig_from_batch(const smb::SigBatch& B, size_t i) {
+    const smb::SigRecord& r = B.sigs[B.sketches[i].sig_index];
+    auto* sig = new SourmashSignature();
+    sig->name = r.name; sig->filename = r.filename; sig->license = r.license; sig->email = r.email;
+    sig->klass = r.klass; sig->hash_function = r.hash_function; sig->version = r.version;
+    sig->sketches.push_back(mh_from_batch(B, i));
+    return sig;
+}
 // Signature::load_signatures (signature.rs:583-658): one signature per sketch, filtered by ksize
 // (as stored) and molecule type
 SourmashSignature** sigs_from_batch(const smb::SigBatch& B, uintptr_t ksize, const char* select_moltype,
@@ -1192,12 +1207,7 @@ SourmashSignature** sigs_from_batch(const smb::SigBatch& B, uintptr_t ksize, con
         const smb::SigSketch& sk = B.sketches[i];
         if (ksize != 0 && sk.ksize != ksize) continue;
         if (want_hf && (int)sk.hash_function != want_hf) continue;
-        const smb::SigRecord& r = B.sigs[sk.sig_index];
-        auto* sig = new SourmashSignature();
-        sig->name = r.name; sig->filename = r.filename; sig->license = r.license; sig->email = r.email;
-        sig->klass = r.klass; sig->hash_function = r.hash_function; sig->version = r.version;
-        sig->sketches.push_back(mh_from_batch(B, i));
-        out.push_back(sig);
+        out.push_back(sig_from_batch(B, i));
     }
     *size = out.size();
     auto** arr = (SourmashSignature**)malloc(std::max<size_t>(out.size(), 1) * sizeof(void*));
@@ -2318,13 +2328,17 @@ SourmashSignature** smb_signatures_from_sketchset(const SmbSketchSet* set, const
     });
 }
 
-SmbSigs* smb_sigs_read(const char* const* paths, uintptr_t n_paths, int32_t n_threads) {
+SmbSigs* smb_sigs_read_opts(const char* const* paths, uintptr_t n_paths, int32_t n_threads, uint32_t flags) {
     return guarded<SmbSigs*>([&]() -> SmbSigs* {
         auto r = std::make_unique<SmbSigs>();
-        std::string err = smb::read_signature_files(paths, n_paths, n_threads > 0 ? n_threads : default_threads(), r->b);
+        std::string err = smb::read_signature_files(paths, n_paths, n_threads > 0 ? n_threads : default_threads(),
+                                                    flags, r->b);
         if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
         return r.release();
     });
+}
+SmbSigs* smb_sigs_read(const char* const* paths, uintptr_t n_paths, int32_t n_threads) {
+    return smb_sigs_read_opts(paths, n_paths, n_threads, 0);
 }
 SmbSigs* smb_sigs_parse(const char* data, uintptr_t len) {
     return guarded<SmbSigs*>([&]() -> SmbSigs* {
@@ -2392,9 +2406,31 @@ void smb_sigs_sketch_info_all(const SmbSigs* s, SmbSketchInfo* out) {
     for (uintptr_t i = 0; i < s->b.sketches.size(); ++i) smb_sigs_sketch_info(s, i, out + i);
 }
 SourmashStr smb_sigs_sketch_md5(const SmbSigs* s, uintptr_t i) { return make_str(s->b.sketches[i].md5sum); }
+void smb_sigs_md5_all(const SmbSigs* s, char* out) {
+    // identities computed from the hashes (what ss.md5sum() returns), not the md5sum field of the file
+    guarded_void([&] {
+        const smb::SigBatch& B = s->b;
+        const size_t n = B.sketches.size();
+        std::atomic<size_t> next{0};
+        auto worker = [&] {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n) return;
+                const std::string d = smb::sketch_md5(B.sketches[i].ksize, B.mins.data() + B.off[i], (size_t)(B.off[i + 1] - B.off[i]));
+                memcpy(out + 32 * i, d.data(), 32);
+            }
+        };
+        const size_t nt = std::min<size_t>((size_t)default_threads(), std::max<size_t>(n / 64, 1));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& t : pool) t.join();
+    });
+}
 SourmashStr smb_sigs_sig_name(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].name); }
 SourmashStr smb_sigs_sig_filename(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].filename); }
 SourmashStr smb_sigs_sig_license(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].license); }
+SourmashStr smb_sigs_sig_location(const SmbSigs* s, uintptr_t j) { return make_str(s->b.sigs[j].location); }
 const uint64_t* smb_sigs_offsets(const SmbSigs* s) { return s->b.off.data(); }
 const uint64_t* smb_sigs_mins(const SmbSigs* s) { return s->b.mins.data(); }
 const uint64_t* smb_sigs_abunds(const SmbSigs* s) { return s->b.abunds.data(); }
@@ -2402,6 +2438,23 @@ SourmashKmerMinHash* smb_sigs_minhash(const SmbSigs* s, uintptr_t i) {
     return guarded<SourmashKmerMinHash*>([&] { return new MH(mh_from_batch(s->b, i)); });
 }
 // rows (NULL: all) of the parsed sketches -> device CSR, optionally cut at max_hash (0: as stored)
+SourmashSignature** smb_sigs_signatures(const SmbSigs* s, const uint32_t* rows, uintptr_t n_rows, uintptr_t* size) {
+    return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
+        const size_t n = rows ? n_rows : s->b.sketches.size();
+        auto** arr = (SourmashSignature**)malloc(std::max<size_t>(n, 1) * sizeof(void*));
+        for (size_t r = 0; r < n; ++r) {
+            const size_t i = rows ? rows[r] : r;
+            if (i >= s->b.sketches.size()) {
+                for (size_t q = 0; q < r; ++q) delete arr[q];
+                free(arr);
+                fail(SOURMASH_ERROR_CODE_INTERNAL, "sketch row out of range");
+            }
+            arr[r] = sig_from_batch(s->b, i);
+        }
+        *size = n;
+        return arr;
+    });
+}
 SmbSketchSet* smb_sigs_to_sketchset(const SmbSigs* s, const uint32_t* rows, uintptr_t n_rows, uint64_t max_hash,
                                     bool with_abunds) {
     return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
@@ -2428,7 +2481,7 @@ SourmashSignature** signatures_load_path(const char* ptr, bool, uintptr_t ksize,
     return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
         smb::SigBatch B;
         const char* paths[1] = {ptr};
-        std::string err = smb::read_signature_files(paths, 1, 1, B);
+        std::string err = smb::read_signature_files(paths, 1, 1, 0, B);
         if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
         return sigs_from_batch(B, ksize, select_moltype, size);
     });
@@ -2466,5 +2519,79 @@ SourmashStr signature_save_json(const SourmashSignature* ptr) {
 }
 void nodegraph_buffer_free(uint8_t* ptr, uintptr_t) { free(ptr); }
 void signatures_array_free(SourmashSignature** ptr, uintptr_t) { free(ptr); }
+
+// ------------------------------------------------------------------------------------------
+// ZipStorage: src/core/src/ffi/storage.rs:15-141 over storage/mod.rs:314-448 (read-only)
+// ------------------------------------------------------------------------------------------
+static std::string utf8_arg(const char* p, uintptr_t n) {
+    if (!p) fail(SOURMASH_ERROR_CODE_INTERNAL, "null string argument");
+    return std::string(p, n);
+}
+static SourmashStr** str_array(const std::vector<std::string>& v, uintptr_t* size) {
+    // array of boxed strings like the reference's Box<[*mut SourmashStr]>; read with paths[i][0]
+    SourmashStr** arr = (SourmashStr**)malloc(sizeof(SourmashStr*) * std::max<size_t>(v.size(), 1));
+    for (size_t i = 0; i < v.size(); ++i) {
+        arr[i] = (SourmashStr*)malloc(sizeof(SourmashStr));
+        *arr[i] = make_str(v[i]);
+    }
+    *size = v.size();
+    return arr;
+}
+
+SourmashZipStorage* zipstorage_new(const char* ptr, uintptr_t insize) {
+    return guarded<SourmashZipStorage*>([&]() -> SourmashZipStorage* {
+        auto z = std::make_unique<SourmashZipStorage>();
+        z->path = utf8_arg(ptr, insize);
+        std::string err = z->zip.open(z->path.c_str());
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_IO, err);
+        // storage/mod.rs:324-335 find_subdirs: exactly one directory entry becomes the default subdir
+        size_t n_dirs = 0;
+        for (const auto& m : z->zip.members) if (m.is_dir()) { ++n_dirs; z->subdir = m.name; }
+        z->has_subdir = n_dirs == 1;
+        if (!z->has_subdir) z->subdir.clear();
+        return z.release();
+    });
+}
+void zipstorage_free(SourmashZipStorage* ptr) { delete ptr; }
+const uint8_t* zipstorage_load(const SourmashZipStorage* ptr, const char* path_ptr, uintptr_t insize, uintptr_t* size) {
+    return guarded<const uint8_t*>([&]() -> const uint8_t* {
+        const std::string path = utf8_arg(path_ptr, insize);
+        const smb::ZipMember* m = ptr->zip.find(path);                       // storage/mod.rs:342-352
+        if (!m && ptr->has_subdir) m = ptr->zip.find(ptr->subdir + path);
+        if (!m) fail(SOURMASH_ERROR_CODE_STORAGE, "Path can't be found: " + path);
+        std::string data;
+        std::string err = ptr->zip.read(*m, data);
+        if (!err.empty()) fail(SOURMASH_ERROR_CODE_STORAGE, "Error reading data from " + path + " (" + err + ")");
+        uint8_t* buf = (uint8_t*)malloc(std::max<size_t>(data.size(), 1));
+        memcpy(buf, data.data(), data.size());
+        *size = data.size();
+        return buf;                                                          // freed with nodegraph_buffer_free
+    });
+}
+SourmashStr** zipstorage_filenames(const SourmashZipStorage* ptr, uintptr_t* size) {
+    return guarded<SourmashStr**>([&]() -> SourmashStr** {
+        std::vector<std::string> v;
+        for (const auto& m : ptr->zip.members) v.push_back(m.name);
+        return str_array(v, size);
+    });
+}
+SourmashStr** zipstorage_list_sbts(const SourmashZipStorage* ptr, uintptr_t* size) {
+    return guarded<SourmashStr**>([&]() -> SourmashStr** {
+        std::vector<std::string> v;
+        for (const auto& m : ptr->zip.members) {
+            const std::string& s = m.name;
+            if (s.size() >= 9 && s.compare(s.size() - 9, 9, ".sbt.json") == 0) v.push_back(s);
+        }
+        return str_array(v, size);
+    });
+}
+void zipstorage_set_subdir(SourmashZipStorage* ptr, const char* path_ptr, uintptr_t insize) {
+    guarded_void([&] {
+        ptr->subdir = utf8_arg(path_ptr, insize);
+        ptr->has_subdir = true;
+    });
+}
+SourmashStr zipstorage_path(const SourmashZipStorage* ptr) { return make_str(ptr->path); }
+SourmashStr zipstorage_subdir(const SourmashZipStorage* ptr) { return make_str(ptr->has_subdir ? ptr->subdir : std::string()); }
 
 }  // extern "C"

@@ -19,8 +19,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_set>
+
+#include "md5.h"
+#include "zipread.h"
 
 namespace smb {
 
@@ -489,28 +494,155 @@ std::string parse_signature_json(const char* text, size_t len, uint32_t file_ind
     return J.err;
 }
 
-std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, SigBatch& out) {
-    std::vector<SigBatch> parts(n_paths);
-    std::vector<std::string> errs(n_paths);
-    std::atomic<size_t> next{0};
-    auto worker = [&] {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n_paths) return;
-            Bytes data;
-            errs[i] = slurp(paths[i], data);
-            if (errs[i].empty()) {
-                errs[i] = parse_signature_json((const char*)data.data(), data.size(), (uint32_t)i, parts[i]);
-                if (!errs[i].empty()) errs[i] = std::string(paths[i]) + ": " + errs[i];
+// md5 of one parsed sketch, the identity manifests list (KmerMinHash::md5sum, minhash.rs:290-307:
+// the decimal ksize followed by every hash in decimal)
+std::string sketch_md5(uint32_t ksize, const uint64_t* mins, size_t n) {
+    Md5 ctx;
+    char buf[4096];
+    size_t fill = (size_t)snprintf(buf, sizeof buf, "%u", ksize);
+    for (size_t i = 0; i < n; ++i) {
+        if (fill > sizeof buf - 24) { ctx.update((const uint8_t*)buf, fill); fill = 0; }
+        char tmp[24];
+        int len = 0;
+        uint64_t v = mins[i];
+        do { tmp[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (len) buf[fill++] = tmp[--len];
+    }
+    ctx.update((const uint8_t*)buf, fill);
+    return ctx.hexdigest();
+}
+
+namespace {
+
+// keep only the sketches whose md5 the manifest lists (`if ss in manifest`, index/__init__.py:651-657);
+// signature records left without a sketch go too
+void keep_listed(SigBatch& B, const std::unordered_set<std::string>& md5s) {
+    const size_t n = B.sketches.size();
+    std::vector<char> keep(n);
+    bool all = true;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t lo = B.off[i], hi = B.off[i + 1];
+        keep[i] = md5s.count(sketch_md5(B.sketches[i].ksize, B.mins.data() + lo, (size_t)(hi - lo))) != 0;
+        all = all && keep[i];
+    }
+    if (all) return;
+    SigBatch R;
+    R.off.push_back(0);
+    std::vector<int64_t> new_sig(B.sigs.size(), -1);
+    for (size_t i = 0; i < n; ++i) {
+        if (!keep[i]) continue;
+        SigSketch sk = std::move(B.sketches[i]);
+        if (new_sig[sk.sig_index] < 0) { new_sig[sk.sig_index] = (int64_t)R.sigs.size(); R.sigs.push_back(std::move(B.sigs[sk.sig_index])); }
+        sk.sig_index = (uint32_t)new_sig[sk.sig_index];
+        R.mins.insert(R.mins.end(), B.mins.begin() + (ptrdiff_t)B.off[i], B.mins.begin() + (ptrdiff_t)B.off[i + 1]);
+        R.abunds.insert(R.abunds.end(), B.abunds.begin() + (ptrdiff_t)B.off[i], B.abunds.begin() + (ptrdiff_t)B.off[i + 1]);
+        R.off.push_back(R.mins.size());
+        R.any_abund = R.any_abund || sk.has_abund;
+        R.sketches.push_back(std::move(sk));
+    }
+    B = std::move(R);
+}
+
+bool ends_with(const std::string& s, const char* suffix) {
+    const size_t n = strlen(suffix);
+    return s.size() >= n && !memcmp(s.data() + s.size() - n, suffix, n);
+}
+
+struct ZipInput {                       // one .zip path: the mapped archive and what its manifest lists
+    ZipArchive zip;
+    bool has_manifest = false;
+    std::unordered_set<std::string> md5s;
+};
+struct SigTask { uint32_t path; const ZipMember* member; const ZipInput* zin; };   // member == nullptr: the file itself
+
+}  // namespace
+
+std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, uint32_t flags, SigBatch& out) {
+    // 1. classify: a .zip collection expands into one task per member, in the order the reference
+    //    visits them -- the manifest's distinct locations when SOURMASH-MANIFEST.csv exists
+    //    (index/__init__.py:644-657), else every member named *.sig / *.sig.gz in directory
+    //    order (index/__init__.py:659-683)
+    std::vector<std::unique_ptr<ZipInput>> zips(n_paths);
+    std::vector<SigTask> tasks;
+    tasks.reserve(n_paths);
+    for (size_t i = 0; i < n_paths; ++i) {
+        unsigned char magic[4] = {0, 0, 0, 0};
+        FILE* fh = fopen(paths[i], "rb");
+        if (!fh) return std::string("cannot open ") + paths[i];
+        const size_t got = fread(magic, 1, 4, fh);
+        fclose(fh);
+        if (!ZipArchive::has_magic(magic, got)) { tasks.push_back({(uint32_t)i, nullptr, nullptr}); continue; }
+        zips[i] = std::make_unique<ZipInput>();
+        ZipInput& Z = *zips[i];
+        std::string e = Z.zip.open(paths[i]);
+        if (!e.empty()) return e;
+        const ZipMember* mf = (flags & SIGS_NO_MANIFEST) ? nullptr : Z.zip.find("SOURMASH-MANIFEST.csv");
+        if (mf) {
+            std::string text;
+            ManifestIndex M;
+            e = Z.zip.read(*mf, text);
+            if (e.empty()) e = parse_manifest_csv(text, M);
+            if (!e.empty()) return std::string(paths[i]) + ": " + e;
+            Z.has_manifest = true;
+            Z.md5s.insert(M.md5s.begin(), M.md5s.end());
+            for (const auto& loc : M.locations) {
+                const ZipMember* m = Z.zip.find(loc);
+                if (!m) return std::string(paths[i]) + ": manifest lists '" + loc + "', which is not in the archive";
+                tasks.push_back({(uint32_t)i, m, &Z});
+            }
+        } else {
+            for (const auto& m : Z.zip.members) {
+                if (m.is_dir()) continue;
+                if ((flags & SIGS_ALL_MEMBERS) || ends_with(m.name, ".sig") || ends_with(m.name, ".sig.gz"))
+                    tasks.push_back({(uint32_t)i, &m, &Z});
             }
         }
+    }
+    // 2. parse: one task at a time per thread
+    const size_t n_tasks = tasks.size();
+    std::vector<SigBatch> parts(n_tasks);
+    std::vector<std::string> errs(n_tasks);
+    std::atomic<size_t> next{0};
+    auto worker = [&] {
+        std::string raw, text;
+        for (;;) {
+            const size_t t = next.fetch_add(1);
+            if (t >= n_tasks) return;
+            const SigTask& T = tasks[t];
+            const char* path = paths[T.path];
+            if (!T.member) {
+                Bytes data;
+                errs[t] = slurp(path, data);
+                if (errs[t].empty()) {
+                    errs[t] = parse_signature_json((const char*)data.data(), data.size(), T.path, parts[t]);
+                    if (!errs[t].empty()) errs[t] = std::string(path) + ": " + errs[t];
+                }
+                continue;
+            }
+            raw.clear(); text.clear();
+            errs[t] = T.zin->zip.read(*T.member, raw);
+            if (!errs[t].empty()) { errs[t] = std::string(path) + ": " + errs[t]; continue; }
+            // a member that does not hold signatures is passed over, like load_signatures_from_json
+            // without do_raise (src/sourmash/signature.py:350-380,412-418,466-468)
+            const std::string* doc = &raw;
+            if (raw.size() >= 2 && (uint8_t)raw[0] == 0x1f && (uint8_t)raw[1] == 0x8b) {
+                if (!inflate_all((const uint8_t*)raw.data(), raw.size(), 15 + 32, 0, text).empty()) continue;
+                doc = &text;
+            } else if (raw.find("sourmash_signature") == std::string::npos) {
+                continue;
+            }
+            if (!parse_signature_json(doc->data(), doc->size(), T.path, parts[t]).empty()) { parts[t] = SigBatch(); continue; }
+            if (T.zin->has_manifest) keep_listed(parts[t], T.zin->md5s);
+            for (auto& s : parts[t].sigs) s.location = T.member->name;
+        }
     };
-    size_t nt = std::min<size_t>((size_t)std::max(1, n_threads), std::max<size_t>(n_paths, 1));
+    size_t nt = std::min<size_t>((size_t)std::max(1, n_threads), std::max<size_t>(n_tasks, 1));
     std::vector<std::thread> pool;
     for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
     for (auto& e : errs) if (!e.empty()) return e;
+    // 3. concatenate in task order
     if (out.off.empty()) out.off.push_back(0);
     size_t tot = 0, nsk = 0;
     for (auto& p : parts) { tot += p.mins.size(); nsk += p.sketches.size(); }
@@ -526,6 +658,8 @@ std::string read_signature_files(const char* const* paths, size_t n_paths, int n
         out.mins.insert(out.mins.end(), p.mins.begin(), p.mins.end());
         out.abunds.insert(out.abunds.end(), p.abunds.begin(), p.abunds.end());
         out.any_abund = out.any_abund || p.any_abund;
+        SigBatch().mins.swap(p.mins);                    // give the part's memory back as we go
+        SigBatch().abunds.swap(p.abunds);
     }
     return "";
 }

@@ -43,6 +43,7 @@ struct SigSketch {
 struct SigRecord {                      // one signature object (signature.rs:401-445)
     uint32_t file = 0;
     std::string name, filename, license, email, klass, hash_function;
+    std::string location;               // member name when the file is a .zip collection (internal_location)
     double version = 0.4;
     bool has_name = false, has_filename = false;
 };
@@ -55,8 +56,16 @@ struct SigBatch {
     bool any_abund = false;
 };
 
-// Parses .sig / .sig.gz files (JSON array of signatures, or one signature object).
-std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, SigBatch& out);
+// Parses .sig / .sig.gz files (JSON array of signatures, or one signature object) and .zip
+// collections of them (zipread.h; members in the order ZipFileLinearIndex.signatures() visits them).
+enum : uint32_t {
+    SIGS_NO_MANIFEST = 1,   // ignore SOURMASH-MANIFEST.csv (ZipFileLinearIndex use_manifest=False)
+    SIGS_ALL_MEMBERS = 2,   // without a manifest, try every member, not only *.sig / *.sig.gz (traverse_yield_all)
+};
+std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, uint32_t flags,
+                                 SigBatch& out);
+// md5 identity of a sketch (KmerMinHash::md5sum, minhash.rs:290-307)
+std::string sketch_md5(uint32_t ksize, const uint64_t* mins, size_t n);
 // Same from memory (one document).
 std::string parse_signature_json(const char* text, size_t len, uint32_t file_index, SigBatch& out);
 

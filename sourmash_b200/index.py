@@ -10,11 +10,36 @@ from collections import namedtuple
 import numpy as np
 
 from . import batch as B
+from .manifest import CollectionManifest, _check_select_parameters
 from .minhash import flatten_and_intersect_scaled
 from .search import calc_threshold_from_bp, make_containment_query, make_jaccard_search_query
 
 IndexSearchResult = namedtuple("IndexSearchResult", "score, signature, location")
 GatherResult = namedtuple("GatherResult", "match, intersect_size, containment, location")
+
+
+def select_signature(ss, *, ksize=None, moltype=None, scaled=0, num=0, containment=False, abund=None,
+                     picklist=None):
+    "Does this signature match the requirements?  (index/__init__.py:349-395)"
+    mh = ss.minhash
+    if ksize and ksize != mh.ksize:
+        return False
+    if moltype and moltype != mh.moltype:
+        return False
+    if containment:
+        if not scaled:
+            raise ValueError("'containment' requires 'scaled' in Index.select'")
+        if not mh.scaled:
+            return False
+    if scaled and mh.num:
+        return False
+    if num and (mh.scaled or num != mh.num):
+        return False
+    if abund and not mh.track_abundance:
+        return False
+    if picklist is not None and ss not in picklist:
+        return False
+    return True
 
 
 class LinearIndex:
@@ -35,7 +60,7 @@ class LinearIndex:
         return iter(self._signatures)
 
     def signatures_with_location(self):
-        for ss in self._signatures:
+        for ss in self.signatures():
             yield ss, self.location
 
     def __len__(self):
@@ -47,6 +72,25 @@ class LinearIndex:
     def insert(self, node):
         self._signatures.append(node)
         self._device = None
+
+    def save(self, path):
+        from .signature import save_signatures_to_json
+        with open(path, "w") as fp:
+            save_signatures_to_json(self.signatures(), fp)
+
+    @classmethod
+    def load(cls, location, filename=None):
+        "Signatures of one .sig / .sig.gz file (LinearIndex.load, index/__init__.py:438-446)."
+        from .signature import load_signatures_from_json
+        return cls(load_signatures_from_json(location, do_raise=True), filename=filename or location)
+
+    def select(self, **kwargs):
+        "New LinearIndex with the signatures matching the requirements (index/__init__.py:448-460)."
+        _check_select_parameters(**kwargs)
+        return LinearIndex([ss for ss in self._signatures if select_signature(ss, **kwargs)], self.location)
+
+    def _subject(self, idx):
+        return self._signatures[idx]
 
     # -- device cache ----------------------------------------------------------------------
     def _groups(self):
@@ -98,7 +142,7 @@ class LinearIndex:
         for idx, qs, sh, ss_size, tot in scored:
             score = search_fn.score_fn(qs, sh, ss_size, tot)
             if search_fn.passes(score):
-                subj = self._signatures[idx]
+                subj = self._subject(idx)
                 if search_fn.collect(score, subj):
                     yield IndexSearchResult(score, subj, self.location)
 
@@ -133,6 +177,146 @@ class LinearIndex:
         results = self.prefetch(query, threshold_bp, best_only=True, **kwargs)
         results = sorted(results, key=lambda x: (-x.score, x.signature.md5sum()))
         return results[0] if results else None
+
+
+class ZipFileLinearIndex(LinearIndex):
+    """A read-only .zip collection of signatures (reference: ZipFileLinearIndex,
+    index/__init__.py:529-733), selected through its manifest when it has one.
+
+    The reference loads members lazily, one Python object per sketch per pass.  Here the whole
+    collection is parsed once by the library (``sigset.SignatureSet``: members inflated and parsed
+    on all host threads into one CSR) and searched from HBM; ``SourmashSignature`` objects are only
+    built for the subjects a search returns, or when ``signatures()`` is iterated."""
+
+    is_database = True
+
+    def __init__(self, storage, *, selection_dict=None, traverse_yield_all=False, manifest=None,
+                 use_manifest=True, _sigset=None):
+        from .sigset import SignatureSet
+        self.storage = storage
+        self.selection_dict = selection_dict
+        self.traverse_yield_all = traverse_yield_all
+        self.use_manifest = use_manifest
+        self.filename = storage.path
+        self._device = None
+        self._objects = {}
+        self._sigset = _sigset if _sigset is not None else SignatureSet.from_files(
+            [storage.path], use_manifest=use_manifest, traverse_yield_all=traverse_yield_all)
+        ss = self._sigset
+        self.manifest = None
+        if use_manifest:
+            self.manifest = manifest if manifest is not None else self._load_manifest()
+        if self.manifest is not None:
+            assert not self.selection_dict, self.selection_dict
+            # `for filename in manifest.locations(): ... if ss in manifest` (index/__init__.py:644-657)
+            locations, md5s = set(self.manifest.locations()), self.manifest._md5_set
+            self._rows = np.array([i for i, (md5, loc) in enumerate(zip(ss.md5sums(), ss.locations()))
+                                   if md5 in md5s and loc in locations], dtype=np.uint32)
+        else:
+            self._rows = self._select_rows(**(selection_dict or {}))
+
+    def _load_manifest(self):
+        from io import StringIO
+        try:
+            data = self.storage.load("SOURMASH-MANIFEST.csv")
+        except (KeyError, FileNotFoundError):
+            return None
+        return CollectionManifest.load_from_csv(StringIO(data.decode("utf-8")))
+
+    def _select_rows(self, *, ksize=None, moltype=None, scaled=0, num=0, containment=False, abund=None,
+                     picklist=None):
+        "select_signature over the metadata columns of the parsed collection."
+        if picklist is not None:
+            raise NotImplementedError("picklists are outside the GPU path")
+        ss = self._sigset
+        is_dna = ss.hash_function == 1
+        keep = np.ones(len(ss), bool)
+        if ksize:
+            keep &= np.where(is_dna, ss.ksize, ss.ksize // 3) == ksize
+        if moltype:
+            keep &= ss.hash_function == {"DNA": 1, "protein": 2, "dayhoff": 3, "hp": 4}[moltype]
+        if containment:
+            if not scaled:
+                raise ValueError("'containment' requires 'scaled' in Index.select'")
+            keep &= ss.max_hash != 0
+        if scaled:
+            keep &= ss.num == 0
+        if num:
+            keep &= (ss.max_hash == 0) & (ss.num == num)
+        if abund:
+            keep &= ss.has_abund
+        return np.nonzero(keep)[0].astype(np.uint32)
+
+    @classmethod
+    def load(cls, location, traverse_yield_all=False, use_manifest=True):
+        import os
+
+        from .sbt_storage import ZipStorage
+        if not os.path.exists(location):
+            raise FileNotFoundError(location)
+        return cls(ZipStorage(location), traverse_yield_all=traverse_yield_all, use_manifest=use_manifest)
+
+    @property
+    def location(self):
+        return self.storage.path
+
+    def __len__(self):
+        return len(self.manifest) if self.manifest is not None else len(self._rows)
+
+    def __bool__(self):
+        return len(self._rows) > 0
+
+    def insert(self, signature):
+        raise NotImplementedError
+
+    def save(self, path):
+        raise NotImplementedError
+
+    def _subject(self, idx):
+        if idx not in self._objects:
+            self._objects[idx] = self._sigset.signatures(self._rows[idx:idx + 1])[0]
+        return self._objects[idx]
+
+    def signatures(self):
+        missing = [i for i in range(len(self._rows)) if i not in self._objects]
+        if missing:
+            for i, obj in zip(missing, self._sigset.signatures(self._rows[missing])):
+                self._objects[i] = obj
+        for i in range(len(self._rows)):
+            yield self._objects[i]
+
+    def _signatures_with_internal(self):
+        "(signature, member name) of everything in the file, selection ignored (index/__init__.py:620-637)."
+        ss = self._sigset
+        for i, obj in enumerate(ss.signatures()):
+            yield obj, ss.location(i)
+
+    def select(self, **kwargs):
+        _check_select_parameters(**kwargs)
+        if self.manifest is not None:
+            return ZipFileLinearIndex(self.storage, traverse_yield_all=self.traverse_yield_all,
+                                      manifest=self.manifest.select_to_manifest(**kwargs), use_manifest=True,
+                                      _sigset=self._sigset)
+        if self.selection_dict:
+            d = dict(self.selection_dict)
+            for k, v in kwargs.items():
+                if k in d and d[k] is not None and d[k] != v:
+                    raise ValueError(f"incompatible select on '{k}'")
+                d[k] = v
+            kwargs = d
+        return ZipFileLinearIndex(self.storage, selection_dict=kwargs, traverse_yield_all=self.traverse_yield_all,
+                                  manifest=None, use_manifest=False, _sigset=self._sigset)
+
+    def _groups(self):
+        "Selected rows grouped by scaled (or num), each group one CSR upload straight from the parser's arrays."
+        if self._device is None:
+            ss, groups = self._sigset, {}
+            scaled = ss.python_scaled()
+            for pos, row in enumerate(self._rows.tolist()):
+                key = ("scaled", int(scaled[row])) if ss.max_hash[row] else ("num", int(ss.num[row]))
+                groups.setdefault(key, []).append(pos)
+            self._device = {k: (pos, ss.to_sketchset(self._rows[pos])) for k, pos in groups.items()}
+        return self._device
 
 
 class CounterGather:

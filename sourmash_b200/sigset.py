@@ -46,11 +46,15 @@ class SignatureSet:
             lib.smb_sigs_free(p)
 
     @classmethod
-    def from_files(cls, paths, n_threads=0):
+    def from_files(cls, paths, n_threads=0, *, use_manifest=True, traverse_yield_all=False):
+        """Parse .sig / .sig.gz files and .zip collections of them.  A zip contributes the members
+        ZipFileLinearIndex.signatures() of the reference would yield (index/__init__.py:639-683);
+        the two keywords are that class's options."""
         paths = [str(p).encode("utf-8") for p in paths]
         keep = [ffi.new("char[]", p) for p in paths]
         arr = ffi.new("char *[]", keep)
-        return cls(rustcall(lib.smb_sigs_read, arr, len(paths), int(n_threads)))
+        flags = (0 if use_manifest else 1) | (2 if traverse_yield_all else 0)
+        return cls(rustcall(lib.smb_sigs_read_opts, arr, len(paths), int(n_threads), flags))
 
     @classmethod
     def from_objects(cls, objs):
@@ -105,6 +109,28 @@ class SignatureSet:
     def filename(self, i):
         return decode_str(lib.smb_sigs_sig_filename(self._ptr, int(self.sig_index[i])))
 
+    def location(self, i):
+        "Zip member the sketch was stored in (the manifest's internal_location); '' for plain files."
+        return decode_str(lib.smb_sigs_sig_location(self._ptr, int(self.sig_index[i])))
+
+    def locations(self):
+        "location(i) of every sketch (one lookup per signature object, cached)."
+        if getattr(self, "_locs", None) is None:
+            per_sig = {}
+            self._locs = [per_sig[j] if j in per_sig else per_sig.setdefault(
+                j, decode_str(lib.smb_sigs_sig_location(self._ptr, j))) for j in self.sig_index.tolist()]
+        return self._locs
+
+    def md5sums(self):
+        "md5 of every sketch, computed from its hashes (what SourmashSignature.md5sum() returns)."
+        if getattr(self, "_md5s", None) is None:
+            n = len(self)
+            buf = ffi.new("char[]", max(32 * n, 1))
+            rustcall(lib.smb_sigs_md5_all, self._ptr, buf)
+            raw = bytes(ffi.buffer(buf, 32 * n)).decode("ascii")
+            self._md5s = [raw[32 * i:32 * i + 32] for i in range(n)]
+        return self._md5s
+
     def md5sum(self, i):
         return decode_str(lib.smb_sigs_sketch_md5(self._ptr, int(i)))
 
@@ -125,6 +151,20 @@ class SignatureSet:
         if num is not None:
             keep &= self.num == num
         return np.nonzero(keep)[0].astype(np.uint32)
+
+    def signatures(self, rows=None):
+        "Rows (default: all) as FrozenSourmashSignature objects, one per sketch, built in one call."
+        from .signature import FrozenSourmashSignature
+        size = ffi.new("uintptr_t *")
+        if rows is None:
+            arr = rustcall(lib.smb_sigs_signatures, self._ptr, ffi.NULL, 0, size)
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.uint32)
+            arr = rustcall(lib.smb_sigs_signatures, self._ptr, ffi.cast("uint32_t *", rows.ctypes.data), len(rows), size)
+        try:
+            return [FrozenSourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
+        finally:
+            lib.signatures_array_free(arr, size[0])
 
     def minhash(self, i):
         "One sketch as a (frozen) MinHash object."
