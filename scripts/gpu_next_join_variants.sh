@@ -1,0 +1,49 @@
+#!/bin/bash
+# Next round, first GPU call: validate and measure the experimental layouts of the inverted join that
+# are in the tree behind switches (default off; logic covered on the CPU by tests/test_host_emulation.py):
+#   SMB_JOIN_LAYOUT=stripe   CTAs own complete result rows in shared memory, no global atomics, fused
+#                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh)
+#   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
+#   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+TAG=${1:-r2a}
+# 1. correctness: the compare / join tests with each layout switched on and the join forced (they
+#    compare with the oracle bit for bit); a memcheck run of the stripe kernels on a small matrix
+for L in stripe cluster; do
+  echo "== tests with SMB_JOIN_LAYOUT=$L"
+  SMB_COMPARE_ALGO=join SMB_JOIN_LAYOUT=$L timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py \
+      tests/test_gpu_api.py -q -m gpu -k "join or compare" 2>&1 | tail -4
+done
+SMB_COMPARE_ALGO=join SMB_JOIN_LAYOUT=stripe timeout 600 compute-sanitizer --tool memcheck python -c "
+import numpy as np, oracle as orc
+from sourmash_b200 import batch as B
+from sourmash_b200.synth import synth_sketches
+h, off = synth_sketches(1500, mean=400, sd=80, lo=50, hi=800, n_families=12, pool=500, seed=5)
+m = B.compare_jaccard(B.SketchSet.from_host(h, off))
+assert np.array_equal(m, orc.compare_all_pairs(h, off, nthreads=8)); print('stripe 1500x1500 identical')
+" 2>&1 | tail -3
+# 2. A/B on the 10 000-sketch matrix
+for L in plain stripe cluster; do
+  SMB_JOIN_LAYOUT=$L timeout 200 python bench.py --workload compare --steps 5 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/bench_join_${L}_${TAG}.json 2> /dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_join_${L}_${TAG}.json')); print('${L}: ms %.2f kernel_ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step']))"
+done
+# 2b. row-block passes for the end-to-end path (SMB_COMPARE_PASSES): correctness through the host API, then e2e
+SMB_COMPARE_PASSES=8 timeout 300 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_kernels.py -q -m gpu -k "compare or join" 2>&1 | tail -3
+for P in 0 4 8 16; do
+  SMB_COMPARE_PASSES=$P timeout 200 python bench.py --workload compare --steps 5 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/bench_passes_${P}_${TAG}.json 2> /dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_passes_${P}_${TAG}.json')); print('passes ${P}: e2e %.1f ms'%d['e2e']['ms_per_step'])"
+done
+# 3. where the time goes
+for L in stripe cluster; do
+  SMB_JOIN_LAYOUT=$L ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_red.sum \
+      --clock-control none -c 200 --csv --log-file gpurun_out/launches_${L}_${TAG}.csv \
+      python bench.py --workload compare --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2> gpurun_out/launches_${L}_${TAG}.err
+  tail -1 gpurun_out/launches_${L}_${TAG}.err
+done
+SMB_JOIN_LAYOUT=stripe ncu --set full --clock-control none --import-source on -k regex:join_stripe_kernel -c 1 \
+    -o gpurun_out/stripe_${TAG} python bench.py --workload compare --steps 1 --warmup 0 --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out | tail -12

@@ -1828,9 +1828,48 @@ void smb_finalize_jaccard_rows_dev(const SmbSketchSet* set, const uint32_t* d_co
     });
 }
 
+// Experimental stripe layout of the join (SMB_JOIN_LAYOUT=stripe, off by default): float64 rows come
+// straight out of the count kernel, block of rows by block of rows; with `host_out` every finished
+// block is downloaded on the copy stream while the next one is counted.  Returns false when the
+// layout does not apply (the caller continues with the default path).
+static bool compare_jaccard_stripe(const SmbSketchSet* set, uint64_t max_key, double* d_out, double* host_out,
+                                   cudaStream_t s) {
+    const size_t n = set->n_rows;
+    smb::JoinStripe* js = nullptr;
+    if (t_profiling) t_timer_pairwise.begin(s);
+    CK(smb::join_stripe_create(set->d_hashes, set->d_off, (int)n, set->total(), max_key, &js, s));
+    if (!js) { if (t_profiling) t_timer_pairwise.end(s); return false; }
+    std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
+    if (!host_out) {
+        CK(smb::join_stripe_rows(js, set->d_off, 0, (int)n, d_out, s));
+        if (t_profiling) t_timer_pairwise.end(s);
+        return true;
+    }
+    cudaStream_t cs = copy_stream();
+    const size_t per = (n + 15) / 16;
+    for (size_t r0 = 0; r0 < n; r0 += per) {
+        const size_t r1 = std::min(n, r0 + per);
+        CK(smb::join_stripe_rows(js, set->d_off, (int)r0, (int)r1, d_out + r0 * n, s));
+        cudaEvent_t ev = pool_event();
+        CK(cudaEventRecord(ev, s));
+        CK(cudaStreamWaitEvent(cs, ev, 0));
+        CK(cudaMemcpyAsync(host_out + r0 * n, d_out + r0 * n, (r1 - r0) * n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    }
+    if (t_profiling) t_timer_pairwise.end(s);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(cs));
+    sync(s);
+    return true;
+}
+
 static void compare_jaccard_impl(const SmbSketchSet* set, uint32_t num, double* d_out, cudaStream_t s) {
     const size_t n = set->n_rows;
     if (n == 0) return;
+    if (num == 0 && smb::join_stripe_enabled()) {
+        const uint64_t mk = set_max_key(*set, s);
+        t_last_join = plan_join(*set, mk, s);
+        if (t_last_join.use && compare_jaccard_stripe(set, mk, d_out, nullptr, s)) return;
+    }
     DevBuf<uint32_t> d_c(n * n, s), d_u;
     if (num) d_u.alloc(n * n, s);
     pairwise_counts_dev(*set, nullptr, num, d_c.p, num ? d_u.p : nullptr, n, s);
@@ -1856,6 +1895,7 @@ void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
             if (t_last_join.use) {
                 // counts by inverted join, then finalise blocks of rows and download each block on
                 // the copy stream while the next one is being finalised
+                if (smb::join_stripe_enabled() && compare_jaccard_stripe(set, mk, d_out.p, out, s)) return;
                 DevBuf<uint32_t> d_c(n * n, s);
                 cudaStream_t cs = copy_stream();
                 const char* passes_env = getenv("SMB_COMPARE_PASSES");

@@ -26,6 +26,7 @@
 #include "kernels.h"
 #include "split_table.cuh"
 #include "join_walk.cuh"
+#include "join_stripe.cuh"
 
 namespace smb {
 
@@ -1342,6 +1343,175 @@ cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_
     return cudaGetLastError();
 }
 void join_stream_destroy(JoinStream* js) { delete js; }
+
+// ------------------------------------------------------------------------------------
+// Experimental stripe layout of the inverted join (off unless SMB_JOIN_LAYOUT=stripe; logic in
+// join_stripe.cuh, checked on the CPU by tests/test_host_emulation.py::test_join_stripe_*).
+// Not measured yet: kept behind the switch until it has been validated on the GPU.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stripe_iota_kernel(u32* __restrict__ v, u64 T) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (u64)gridDim.x * blockDim.x) v[i] = (u32)i;
+}
+
+// sorted (key, CSR element) stream -> tags (row | head flag) and the inverse permutation
+__global__ void __launch_bounds__(256) stripe_tag_kernel(const u64* __restrict__ sorted_keys, const u32* __restrict__ src,
+                                                        const u64* __restrict__ off, int n, u64 T,
+                                                        u32* __restrict__ tags, u32* __restrict__ pos) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < T; q += (u64)gridDim.x * blockDim.x) {
+        const u32 e = src[q];
+        tags[q] = stripe_make_tag(sorted_keys, q, stripe_row_of(off, n, e));
+        pos[e] = (u32)q;
+    }
+}
+
+struct StripeArgs {
+    const u32* tags;
+    const u32* pos;
+    const u64* off;          // CSR offsets of the set: element ranges and sizes of the rows
+    u64 T;
+    int n, rows_per_block, row_begin, row_end;
+    double* out;             // row `row_begin` first, leading dimension n
+};
+
+// One CTA = rows [r0, r1) of the result.  Warps take 32 consecutive elements of the block at a time;
+// the group scans of two elements are in flight together (four independent tag loads per lane).
+__global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
+    extern __shared__ __align__(16) unsigned char stripe_smem[];
+    u64* s_off = reinterpret_cast<u64*>(stripe_smem);                       // [rows + 1]
+    u32* stripe = reinterpret_cast<u32*>(stripe_smem + 40 * sizeof(u64));   // [rows][n]
+    const int r0 = a.row_begin + (int)blockIdx.x * a.rows_per_block;
+    const int r1 = min(a.row_end, r0 + a.rows_per_block);
+    const int rows = r1 - r0;
+    const u32 n = (u32)a.n;
+    for (int r = threadIdx.x; r <= rows; r += blockDim.x) s_off[r] = a.off[r0 + r];
+    for (u32 i = threadIdx.x; i < (u32)rows * n; i += blockDim.x) stripe[i] = 0;
+    __syncthreads();
+    const u64 e_begin = s_off[0], e_end = s_off[rows];
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const u32* __restrict__ tags = a.tags;
+
+    // the first chunk in both directions of one element, then the rare continuations (groups > 32)
+    auto finish = [&](u64 q, u32* row, u32 self, u32 tf, bool sf, u32 tb, bool sb, bool vb) {
+        u32 m = __ballot_sync(0xffffffffu, sf);
+        if (stripe_fwd_active(m, lane)) atomicAdd(row + (tf & ~STRIPE_HEAD), 1u);
+        for (u32 it = 1; stripe_continue(m); ++it) {
+            const bool st = stripe_fwd_stop(tags, a.T, q, it, lane, tf);
+            m = __ballot_sync(0xffffffffu, st);
+            if (stripe_fwd_active(m, lane)) atomicAdd(row + (tf & ~STRIPE_HEAD), 1u);
+        }
+        if (self & STRIPE_HEAD) return;                   // q opens its group: nothing in front of it
+        m = __ballot_sync(0xffffffffu, sb);
+        if (stripe_bwd_active(m, lane, vb)) atomicAdd(row + (tb & ~STRIPE_HEAD), 1u);
+        for (u32 it = 1; stripe_continue(m); ++it) {
+            const bool st = stripe_bwd_stop(tags, q, it, lane, tb, vb);
+            m = __ballot_sync(0xffffffffu, st);
+            if (stripe_bwd_active(m, lane, vb)) atomicAdd(row + (tb & ~STRIPE_HEAD), 1u);
+        }
+    };
+
+    for (u64 base = e_begin + (u64)warp * 32; base < e_end; base += (u64)n_warps * 32) {
+        const u64 e = base + lane;
+        const bool have = e < e_end;
+        const u32 my_q = have ? a.pos[e] : 0u;
+        const u32 my_row = have ? stripe_local_row(s_off, rows, e) : 0u;
+        const u32 cnt = (u32)min((u64)32, e_end - base);
+        for (u32 j = 0; j < cnt; j += 2) {
+            const bool two = j + 1 < cnt;
+            const u64 q0 = __shfl_sync(0xffffffffu, my_q, j);
+            const u64 q1 = __shfl_sync(0xffffffffu, my_q, two ? j + 1 : j);
+            u32* row0 = stripe + (size_t)__shfl_sync(0xffffffffu, my_row, j) * n;
+            u32* row1 = stripe + (size_t)__shfl_sync(0xffffffffu, my_row, two ? j + 1 : j) * n;
+            u32 tf0, tb0, tf1 = 0, tb1 = 0;
+            bool vb0, vb1 = false, sf1 = true, sb1 = true;
+            const u32 self0 = tags[q0];
+            const bool sf0 = stripe_fwd_stop(tags, a.T, q0, 0, lane, tf0);
+            const bool sb0 = stripe_bwd_stop(tags, q0, 0, lane, tb0, vb0);
+            u32 self1 = STRIPE_HEAD;
+            if (two) {
+                self1 = tags[q1];
+                sf1 = stripe_fwd_stop(tags, a.T, q1, 0, lane, tf1);
+                sb1 = stripe_bwd_stop(tags, q1, 0, lane, tb1, vb1);
+            }
+            finish(q0, row0, self0, tf0, sf0, tb0, sb0, vb0);
+            if (two) finish(q1, row1, self1, tf1, sf1, tb1, sb1, vb1);
+        }
+    }
+    __syncthreads();
+    // counts -> float64 rows, written once
+    for (u32 i = threadIdx.x; i < (u32)rows * n; i += blockDim.x) {
+        const u32 al = i / n, j = i - al * n;
+        const int row = r0 + (int)al;
+        const double v = stripe_jaccard(stripe[i], s_off[al + 1] - s_off[al], a.off[j + 1] - a.off[j], (u32)row == j);
+        a.out[(size_t)(row - a.row_begin) * n + j] = v;
+    }
+}
+
+struct JoinStripe {
+    cudaStream_t stream = 0;
+    void* mem = nullptr;      // tags + pos
+    u32 *tags = nullptr, *pos = nullptr;
+    u64 T = 0;
+    int n = 0, rows_per_block = 0;
+    size_t smem = 0;
+    ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
+};
+
+// *out stays null (with cudaSuccess) when the layout does not apply: more than 2^32 - 1 elements,
+// or a stripe row of n counters that does not fit in shared memory.
+cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 max_key, JoinStripe** out, cudaStream_t s) {
+    *out = nullptr;
+    const size_t smem = (size_t)MAX_DYN_SMEM;
+    const int R = n > 0 ? stripe_rows_per_block(smem, n) : 0;
+    if (R < 1 || T == 0 || T >= 0xffffffffull) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(join_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        if (ea != cudaSuccess) return ea;
+        attr_set = true;
+    }
+    auto js = new JoinStripe();
+    js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;
+    js->smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
+    cudaError_t e;
+    const size_t Tp = (size_t)((T + 63) & ~63ull);
+    if ((e = cudaMallocAsync(&js->mem, Tp * 2 * sizeof(u32), s)) != cudaSuccess) { delete js; return e; }
+    js->tags = (u32*)js->mem; js->pos = js->tags + Tp;
+    // sort the hashes where they lie (the CSR is the unsorted stream), payload = element index
+    JoinScratch scratch(s);
+    u64* keys_sorted = nullptr;
+    u32* vals = nullptr;
+    if ((e = scratch.alloc((void**)&keys_sorted, Tp * sizeof(u64))) != cudaSuccess) { delete js; return e; }
+    if ((e = scratch.alloc((void**)&vals, Tp * 2 * sizeof(u32))) != cudaSuccess) { delete js; return e; }
+    u32* vals_sorted = vals + Tp;
+    const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
+    stripe_iota_kernel<<<grid, 256, 0, s>>>(vals, T); count_launches(1);
+    const int key_bits = key_bit_length(max_key);
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
+    void* d_sort = nullptr;
+    if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) { delete js; return e; }
+    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
+    count_launches(1);
+    stripe_tag_kernel<<<grid, 256, 0, s>>>(keys_sorted, vals_sorted, off, n, T, js->tags, js->pos); count_launches(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) { delete js; return e; }
+    *out = js;
+    return cudaSuccess;
+}
+
+// float64 Jaccard rows [row_begin, row_end) of the all-vs-all matrix into d_out (row_begin first)
+cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin, int row_end, double* d_out,
+                             cudaStream_t s) {
+    if (row_end <= row_begin) return cudaSuccess;
+    StripeArgs a{js->tags, js->pos, off, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out};
+    const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
+    join_stripe_kernel<<<blocks, 1024, js->smem, s>>>(a); count_launches(1);
+    return cudaGetLastError();
+}
+void join_stripe_destroy(JoinStripe* js) { delete js; }
+bool join_stripe_enabled() {
+    const char* layout = getenv("SMB_JOIN_LAYOUT");
+    return layout && !strcmp(layout, "stripe");
+}
 
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                         u32* common, size_t ld, cudaStream_t s) {

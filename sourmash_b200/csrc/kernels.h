@@ -56,6 +56,16 @@ cudaError_t join_stream_create(const uint64_t* h, const uint64_t* off, int n, ui
 cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_end, uint32_t* common, size_t ld,
                                    cudaStream_t s);
 void join_stream_destroy(JoinStream* js);
+// Experimental stripe layout (SMB_JOIN_LAYOUT=stripe, off by default; join_stripe.cuh): CTAs own
+// complete rows of the result in shared memory and write float64 Jaccard rows directly.
+// join_stripe_create leaves *out null when the layout does not apply (caller uses join_counts).
+struct JoinStripe;
+bool join_stripe_enabled();
+cudaError_t join_stripe_create(const uint64_t* h, const uint64_t* off, int n, uint64_t n_elements, uint64_t max_key,
+                               JoinStripe** out, cudaStream_t s);
+cudaError_t join_stripe_rows(const JoinStripe* js, const uint64_t* off, int row_begin, int row_end, double* d_out,
+                             cudaStream_t s);
+void join_stripe_destroy(JoinStripe* js);
 
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's
 // elements in the longer row.

@@ -3,6 +3,9 @@
 // (hash, row) pairs stably by hash (std::stable_sort stands in for the radix sort), walk every
 // element.  Test infrastructure for the CPU-only suite.
 //   usage: join_emul <n_shards> <hashes.u64> <offsets.u64> <out.u32 (n*n, summed over shards)> <out_pairs.u64> [cluster]
+//          join_emul <R> <hashes.u64> <offsets.u64> <out.f64 (n*n jaccard)> <unused> stripe <n_warps> <unused>
+// With "stripe" the experimental stripe layout (join_stripe.cuh) is emulated: CTAs of R rows, warps
+// of 32 lanes with a host-side ballot, counters in a per-CTA stripe, float64 rows written directly.
 // With "cluster" the experimental layout is emulated instead: row keys from the global sample, rows
 // ranked by (key, id), gather in rank order, one 32-lane "warp" per element, un-permute.
 #include <stdio.h>
@@ -13,6 +16,7 @@
 #include <vector>
 
 #include "../../sourmash_b200/csrc/join_walk.cuh"
+#include "../../sourmash_b200/csrc/join_stripe.cuh"
 
 using namespace smb;
 
@@ -122,7 +126,74 @@ static int rows_main(int passes, const std::vector<u64>& h, const std::vector<u6
     return 0;
 }
 
+// stripe layout: the kernel's loop structure (compare_kernels.cu join_stripe_kernel) with the lanes of a
+// warp run one after the other and the ballot assembled on the host
+static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path) {
+    const int n = (int)off.size() - 1;
+    const u64 T = h.size();
+    std::vector<u32> src(T);
+    std::iota(src.begin(), src.end(), 0);
+    std::stable_sort(src.begin(), src.end(), [&](u32 a, u32 b) { return h[a] < h[b]; });
+    std::vector<u64> sk(T);
+    for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    std::vector<u32> tags(T), pos(T);
+    for (u64 q = 0; q < T; ++q) {
+        tags[q] = stripe_make_tag(sk.data(), q, stripe_row_of(off.data(), n, src[q]));
+        pos[src[q]] = (u32)q;
+    }
+    std::vector<double> out((size_t)n * n, -1.0);
+    for (int r0 = 0; r0 < n; r0 += R) {
+        const int r1 = std::min(n, r0 + R), rows = r1 - r0;
+        std::vector<u64> s_off(off.begin() + r0, off.begin() + r1 + 1);
+        std::vector<u32> stripe((size_t)rows * n, 0);
+        const u64 e_begin = s_off[0], e_end = s_off[rows];
+        auto scan = [&](u64 q, u32* row) {
+            u32 tag[32];
+            bool valid[32];
+            for (u32 it = 0;; ++it) {                                   // forward
+                u32 m = 0;
+                for (u32 l = 0; l < 32; ++l) m |= (stripe_fwd_stop(tags.data(), T, q, it, l, tag[l]) ? 1u : 0u) << l;
+                for (u32 l = 0; l < 32; ++l) if (stripe_fwd_active(m, l)) row[tag[l] & ~STRIPE_HEAD] += 1;
+                if (!stripe_continue(m)) break;
+            }
+            if (tags[q] & STRIPE_HEAD) return;
+            for (u32 it = 0;; ++it) {                                   // backward
+                u32 m = 0;
+                for (u32 l = 0; l < 32; ++l) m |= (stripe_bwd_stop(tags.data(), q, it, l, tag[l], valid[l]) ? 1u : 0u) << l;
+                for (u32 l = 0; l < 32; ++l) if (stripe_bwd_active(m, l, valid[l])) row[tag[l] & ~STRIPE_HEAD] += 1;
+                if (!stripe_continue(m)) break;
+            }
+        };
+        for (int warp = 0; warp < n_warps; ++warp)
+            for (u64 base = e_begin + (u64)warp * 32; base < e_end; base += (u64)n_warps * 32) {
+                u32 my_q[32], my_row[32];
+                for (u32 l = 0; l < 32; ++l) {
+                    const u64 e = base + l;
+                    const bool have = e < e_end;
+                    my_q[l] = have ? pos[e] : 0u;
+                    my_row[l] = have ? stripe_local_row(s_off.data(), rows, e) : 0u;
+                }
+                const u32 cnt = (u32)std::min<u64>(32, e_end - base);
+                for (u32 j = 0; j < cnt; ++j) scan(my_q[j], stripe.data() + (size_t)my_row[j] * n);
+            }
+        for (u32 i = 0; i < (u32)rows * (u32)n; ++i) {
+            const u32 al = i / (u32)n, j = i - al * (u32)n;
+            const int row = r0 + (int)al;
+            if (out[(size_t)row * n + j] != -1.0) return 6;              // every cell written once
+            out[(size_t)row * n + j] = stripe_jaccard(stripe[i], s_off[al + 1] - s_off[al], off[j + 1] - off[j], (u32)row == j);
+        }
+    }
+    FILE* f = fopen(out_path, "wb");
+    fwrite(out.data(), 8, out.size(), f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 9) {                                        // <R> ... <out> <unused> stripe <n_warps> <unused>
+        std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
+        return stripe_main(atoi(argv[1]), atoi(argv[7]), h, off, argv[4]);
+    }
     if (argc == 8) {                                        // ... <out> <unused> rows <passes>
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
         return rows_main(atoi(argv[7]), h, off, argv[4]);

@@ -171,12 +171,15 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards, cluster=False, row_passes=0):
+    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
+            if stripe_warps:                               # n_shards carries the rows per CTA
+                subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp, "stripe", str(stripe_warps), "-"])
+                return np.fromfile(fc, dtype=np.float64).reshape(n, n)
             extra = ["cluster"] if cluster else ["rows", str(row_passes)] if row_passes else []
             subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + extra)
             got = np.fromfile(fc, dtype=np.uint32).reshape(n, n)
@@ -240,3 +243,45 @@ def test_join_row_block_passes_finalise_rows_in_order(join_emul):
     full = full + full.T                                   # symmetric, zero diagonal
     for passes in (2, 8, 75):
         assert np.array_equal(join_emul(rows, 1, row_passes=passes), full), passes
+
+
+def test_join_stripe_layout_matches_oracle(join_emul):
+    """Experimental stripe layout (SMB_JOIN_LAYOUT=stripe, csrc/join_stripe.cuh): tags / inverse
+    permutation, both-direction 32-lane group scans cut by the ballot of the stop predicate, per-CTA
+    stripes and the fused float64 finalize -- the complete Jaccard matrix, bit for bit."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(12)
+    h, off = synth_sketches(90, mean=300, sd=60, lo=100, hi=600, n_families=2, pool=400, seed=17)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(90)]        # groups of ~30 rows: around one chunk
+    big = np.uint64(2**64 - 1)
+    # one hash shared by 150 rows (several chunks in both directions), one by exactly 33 and 65 rows
+    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64),
+                                      np.array([7], dtype=np.uint64),
+                                      np.array([2**61] if i < 33 else [], dtype=np.uint64),
+                                      np.array([2**62] if i >= 85 else [], dtype=np.uint64),
+                                      np.array([0, big] if i % 5 == 0 else [], dtype=np.uint64)])) for i in range(150)]
+    dense = [np.arange(i % 4, 30, dtype=np.uint64) for i in range(40)]
+    dense[0] = np.zeros(0, np.uint64)
+    dense[3] = np.zeros(0, np.uint64)
+    dense[39] = np.zeros(0, np.uint64)
+    tiny = [np.array([5], np.uint64)]
+    pair = [np.array([1, 2, 3], np.uint64), np.array([2, 3, 4], np.uint64)]
+    for rows in (fam, wide, dense, tiny, pair):
+        hh, oo = orc.to_csr(rows)
+        want = orc.compare_all_pairs(hh, oo, nthreads=2)
+        for rows_per_cta, warps in ((1, 1), (5, 3), (32, 4), (7, 32)):
+            got = join_emul(rows, rows_per_cta, stripe_warps=warps)
+            assert np.array_equal(got, want), (len(rows), rows_per_cta, warps)
+
+
+def test_join_stripe_helpers():
+    "rows per CTA for the shared-memory budget the kernel uses (227 KB): 10 000 columns -> 5 rows."
+    exe = os.path.join(tempfile.gettempdir(), "smb_stripe_rows")
+    src = os.path.join(tempfile.gettempdir(), "smb_stripe_rows.cu")
+    with open(src, "w") as fh:
+        fh.write('#include <stdio.h>\n#include "%s"\nint main() { int ns[] = {1, 64, 1024, 10000, 58000, 58100, 200000};'
+                 ' for (int n : ns) printf("%%d ", smb::stripe_rows_per_block(227 * 1024, n)); return 0; }\n'
+                 % os.path.join(os.path.dirname(HERE), "sourmash_b200", "csrc", "join_stripe.cuh"))
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+    got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [32, 32, 32, 5, 1, 0, 0]
