@@ -19,5 +19,5 @@ except Exception as e:
     print("no json:", e); print(open("gpurun_out/bench_n${N}.json").read()[:2000])
 PY
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-    scripts/multi_gpu_verify.py > gpurun_out/verify_n${N}.log 2>&1
+    tests/tools/multi_gpu_verify.py > gpurun_out/verify_n${N}.log 2>&1
 grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_n${N}.log | head -10

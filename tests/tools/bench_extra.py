@@ -6,7 +6,7 @@
   files      end-to-end `sketch dna` from FASTA files (native reader -> pinned buffer -> GPU -> .sig JSON)
   sigs       bulk .sig load (native parser) -> SketchSet -> N x N compare
 
-    python scripts/bench_extra.py [--what protein,files,sigs]
+    python tests/tools/bench_extra.py [--what protein,files,sigs]
 """
 import argparse
 import gzip
@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 ap = argparse.ArgumentParser()

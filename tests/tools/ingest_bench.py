@@ -2,7 +2,7 @@
 """Host-side ingest throughput: native readers of csrc/ingest.cu against the
 per-object / per-record Python path they replace.  CPU only; prints one JSON line.
 
-    python scripts/ingest_bench.py [--sigs 2000] [--genomes 16]
+    python tests/tools/ingest_bench.py [--sigs 2000] [--genomes 16]
 """
 import argparse
 import gzip
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sourmash_b200.sigset import SignatureSet            # noqa: E402
 from sourmash_b200.sketch import RecordBatch             # noqa: E402
 from sourmash_b200.synth import synth_genome, synth_sketches  # noqa: E402

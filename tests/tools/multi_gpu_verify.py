@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Correctness of the N-GPU paths against the oracle (run under torchrun on N GPUs):
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_verify.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/multi_gpu_verify.py
 
 Every rank runs CompareShard on a 700-sketch problem and checks its block of rows of the
 float64 matrix bit-for-bit against the oracle; the sketch shards are all-gathered and
@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import oracle as orc  # noqa: E402
