@@ -57,6 +57,27 @@ with tempfile.TemporaryDirectory() as td:
     out["sig"] = {"files": a.sigs, "MB": round(nbytes / 1e6, 1), "native_s": round(t_native, 3),
                   "native_MBps": round(nbytes / 1e6 / t_native, 1), "python_json_s": round(t_py, 3),
                   "speedup": round(t_py / t_native, 1)}
+    # ---- the same signatures as one .zip collection (members signatures/<i>.sig.gz, like `sig cat -o x.zip`) ----
+    import zipfile
+    zpath = os.path.join(td, "db.zip")
+    with zipfile.ZipFile(zpath, "w", compression=zipfile.ZIP_STORED) as z:
+        for i, p in enumerate(paths):
+            with open(p, "rb") as fh:
+                z.writestr(f"signatures/{i}.sig.gz", gzip.compress(fh.read(), compresslevel=6))
+    t0 = time.perf_counter()
+    zs = SignatureSet.from_files([zpath], a.threads)
+    t_native = time.perf_counter() - t0
+    assert len(zs) == a.sigs and np.array_equal(zs.mins, h)
+    t0 = time.perf_counter()
+    with zipfile.ZipFile(zpath) as z:                      # python zipfile + gzip + json, a tenth of the members
+        for name in z.namelist()[: max(a.sigs // 10, 1)]:
+            for rec in json.loads(gzip.decompress(z.read(name))):
+                for sk in rec["signatures"]:
+                    rows.append(np.array(sk["mins"], dtype=np.uint64))
+    t_py = (time.perf_counter() - t0) * (a.sigs / max(a.sigs // 10, 1))
+    out["zip"] = {"members": a.sigs, "MB": round(os.path.getsize(zpath) / 1e6, 1), "json_MB": round(nbytes / 1e6, 1),
+                  "native_s": round(t_native, 3), "python_zipfile_json_s": round(t_py, 3),
+                  "speedup": round(t_py / t_native, 1)}
     # ---- FASTA.gz genomes ------------------------------------------------------------------
     fpaths = []
     for g in range(a.genomes):
