@@ -411,6 +411,10 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "algorithm": plan, "note": knote},
     }
+    traffic = res["roofline"]["traffic"]
+    if traffic:                                           # what actually crossed the HBM interface (ncu), same launches
+        res["roofline"]["dram"] = {"bytes_per_launch": traffic, "achieved": traffic / world / (kms / 1e3) / 1e9,
+                                   "unit": "GB/s", "frac": traffic / world / (kms / 1e3) / 1e9 / hbm_peak}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # CPU baseline: rank 0 at N=1 only
         ncores = host_cores()
         units, dt, sample = cpu_compare_sample(h, off, ncores, int(1.5e5 * ncores))
