@@ -302,6 +302,12 @@ void smb_pairwise_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint
  * upper-triangular count matrix */
 void smb_finalize_jaccard_rows_dev(const SmbSketchSet *set, const uint32_t *d_common,
                                    uint64_t row_begin, uint64_t row_end, double *d_out);
+/* float64 rows [row_begin, row_end) of the all-vs-all Jaccard matrix of a scaled set into d_out
+ * ((row_end - row_begin) x n, device memory).  With the experimental stripe layout of the join
+ * (SMB_JOIN_LAYOUT=stripe) only those rows are counted, so one process per GPU can take a block
+ * of rows without exchanging counts; otherwise the whole count matrix is computed first. */
+void smb_compare_jaccard_rows_dev(const SmbSketchSet *set, uint64_t row_begin, uint64_t row_end,
+                                  double *d_out);
 /* Index.find inner loop (src/sourmash/index/__init__.py:115-170): one query vs every row */
 void smb_one_vs_many(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
                      uint32_t *common_out);

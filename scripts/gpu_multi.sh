@@ -21,3 +21,11 @@ PY
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     tests/tools/multi_gpu_verify.py > gpurun_out/verify_n${N}.log 2>&1
 grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_n${N}.log | head -10
+# experimental: stripe layout, every rank counts its own block of rows (no all-reduce); verify, then bench
+SMB_JOIN_LAYOUT=stripe timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
+    tests/tools/multi_gpu_verify.py > gpurun_out/verify_stripe_n${N}.log 2>&1
+grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_stripe_n${N}.log | head -5
+SMB_JOIN_LAYOUT=stripe timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
+    bench.py --gpus $N --workload compare --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stripe_n${N}.json 2> gpurun_out/bench_stripe_n${N}.err
+python -c "
+import json; d=json.loads([l for l in open('gpurun_out/bench_stripe_n${N}.json') if l.startswith('{')][-1]); print('stripe n=${N}: ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['e2e']['ms_per_step']))"

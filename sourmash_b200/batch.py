@@ -261,6 +261,12 @@ def finalize_jaccard_rows_device(sset, d_common_ptr, row_begin, row_end, d_out_p
              int(row_begin), int(row_end), ffi.cast("double *", int(d_out_ptr)))
 
 
+def compare_jaccard_rows_device(sset, row_begin, row_end, d_out_ptr):
+    "Rows [row_begin, row_end) of the all-vs-all Jaccard matrix into device memory (see the header)."
+    rustcall(lib.smb_compare_jaccard_rows_dev, sset._ptr, int(row_begin), int(row_end),
+             ffi.cast("double *", int(d_out_ptr)))
+
+
 def one_vs_many(query, db):
     q = _u64(query)
     out = np.zeros(len(db), dtype=np.uint32)

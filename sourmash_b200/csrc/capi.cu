@@ -1878,6 +1878,34 @@ static void compare_jaccard_impl(const SmbSketchSet* set, uint32_t num, double* 
     CK(cudaGetLastError());
 }
 
+void smb_compare_jaccard_rows_dev(const SmbSketchSet* set, uint64_t row_begin, uint64_t row_end, double* d_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (row_end > n) row_end = n;
+        if (row_begin >= row_end) return;
+        const uint64_t mk = set_max_key(*set, s);
+        if (smb::join_stripe_enabled() && set->total()) {
+            // stripe layout: only the requested rows are counted (a rank of a multi-GPU compare takes
+            // a block of rows and exchanges no counts)
+            smb::JoinStripe* js = nullptr;
+            if (t_profiling) t_timer_pairwise.begin(s);
+            CK(smb::join_stripe_create(set->d_hashes, set->d_off, (int)n, set->total(), mk, &js, s));
+            if (js) {
+                std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
+                CK(smb::join_stripe_rows(js, set->d_off, (int)row_begin, (int)row_end, d_out, s));
+                if (t_profiling) t_timer_pairwise.end(s);
+                return;
+            }
+            if (t_profiling) t_timer_pairwise.end(s);
+        }
+        DevBuf<uint32_t> d_c(n * n, s);
+        pairwise_counts_dev(*set, nullptr, 0, d_c.p, nullptr, n, s);
+        smb::launch_finalize_rows(d_c.p, n, set->d_off, (int)n, (int)row_begin, (int)row_end, d_out, s);
+        CK(cudaGetLastError());
+    });
+}
+
 void smb_compare_jaccard_dev(const SmbSketchSet* set, uint32_t num, double* d_out) {
     guarded_void([&] { cudaStream_t s = need_gpu(); compare_jaccard_impl(set, num, d_out, s); });
 }

@@ -7,6 +7,8 @@ The reference has no distributed path at all; sharding follows SUR
 Host-side logic (shard bounds, padded all-gather + compaction, offsets) is backend agnostic
 and is what the gloo tests exercise; the compute calls need a GPU.
 """
+import os
+
 import numpy as np
 
 
@@ -78,7 +80,10 @@ class CompareShard:
         self.pin_s = torch.from_numpy(sizes.copy()).pin_memory()
         self.d_local = self.pin_h.to(self.device)
         self.d_sizes = self.pin_s.to(self.device)
-        self.d_common = torch.zeros((n, n), dtype=torch.int32, device=self.device)
+        # experimental (SMB_JOIN_LAYOUT=stripe): every rank counts only its own block of rows, so there is
+        # no partial count matrix and no all-reduce
+        self.rows_direct = os.environ.get("SMB_JOIN_LAYOUT") == "stripe"
+        self.d_common = None if self.rows_direct else torch.zeros((n, n), dtype=torch.int32, device=self.device)
         self.d_out = torch.empty((hi - lo, n), dtype=torch.float64, device=self.device)
         self.pin_out = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
         self.h2d_bytes = int(local.nbytes + sizes.nbytes)
@@ -94,11 +99,14 @@ class CompareShard:
         h_off[1:] = np.cumsum(sizes)
         d_off = torch.from_numpy(h_off.view(np.int64)).to(self.device)
         sset = B.SketchSet.from_device(hashes.data_ptr(), d_off.data_ptr(), h_off, keepalive=(hashes, d_off))
-        self.d_common.zero_()
-        B.pairwise_counts_shard_device(sset, self.rank, self.world, self.d_common.data_ptr())
-        dist.all_reduce(self.d_common)
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        B.finalize_jaccard_rows_device(sset, self.d_common.data_ptr(), lo, hi, self.d_out.data_ptr())
+        if self.rows_direct:
+            B.compare_jaccard_rows_device(sset, lo, hi, self.d_out.data_ptr())
+        else:
+            self.d_common.zero_()
+            B.pairwise_counts_shard_device(sset, self.rank, self.world, self.d_common.data_ptr())
+            dist.all_reduce(self.d_common)
+            B.finalize_jaccard_rows_device(sset, self.d_common.data_ptr(), lo, hi, self.d_out.data_ptr())
         if e2e:
             self.pin_out.copy_(self.d_out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
