@@ -92,29 +92,48 @@ def _size_ok(n, scaled, cache):
 
 
 def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, estimate_ani_ci=False,
-                     names=None, md5s=None, filenames=None, query_name="", query_filename="", max_rounds=None):
+                     names=None, md5s=None, filenames=None, query_name="", query_filename="", max_rounds=None,
+                     noident_hashes=None):
     """Min-set-cover of ``query_mh`` by the rows of the GPU-resident SketchSet ``db`` (same ksize,
     seed and scaled as the query; use ``SketchSet.downsample`` / ``SignatureSet.to_sketchset``).
     Returns the list of GatherRow in pick order -- the reference's GatherDatabases loop with the
-    columns of GatherResult.gatherresultdict."""
+    columns of GatherResult.gatherresultdict.
+
+    ``noident_hashes``: hashes of the query known to match nothing (what ``sourmash gather`` collects
+    from its prefetch stage, commands.py:894-922,973): they are taken out of the query that is searched,
+    but stay in the denominators -- query_bp, query_n_hashes, f_orig_query, f_unique_to_query,
+    total_weighted_hashes -- and in remaining_bp (GatherDatabases.__init__ / __next__,
+    search.py:803-818,910-944; GatherResult.build_gather_result, search.py:553-590)."""
     if not query_mh.scaled:
         raise TypeError("query signature must be calculated with scaled")
     scaled, ksize = query_mh.scaled, query_mh.ksize
     q_hashes = query_mh._mins_array()
     track = bool(query_mh.track_abundance) and not ignore_abundance
     q_abunds = query_mh._abunds_array() if track else np.ones(len(q_hashes), dtype=np.uint64)
-    orig_len = len(q_hashes)
+    noident_len = noident_weight = 0
+    if noident_hashes is not None and len(noident_hashes):
+        noident = np.unique(np.asarray(noident_hashes, dtype=np.uint64))
+        noident = noident[noident <= np.uint64(B.max_hash_for_scaled(scaled))]      # noident_mh.downsample(scaled)
+        gone = np.isin(q_hashes, noident)
+        noident_len = len(noident)
+        # abundances come from the query; a noident hash that is not in the query has none (KeyError there)
+        if int(gone.sum()) != noident_len:
+            raise KeyError("noident hashes must be part of the query")
+        noident_weight = int(q_abunds[gone].sum(dtype=object)) if track else noident_len
+        q_hashes, q_abunds = q_hashes[~gone], q_abunds[~gone]
+    search_len = len(q_hashes)
+    orig_len = search_len + noident_len                       # orig_query_len, search.py:912
     rows = []
-    if orig_len == 0 or len(db) == 0:
+    if search_len == 0 or len(db) == 0:
         return rows
-    total_weighted = int(q_abunds.sum(dtype=object)) if track else orig_len
+    total_weighted = (int(q_abunds.sum(dtype=object)) if track else search_len) + noident_weight
     query_md5 = query_mh.md5sum()[:8]
     sizes = db.sizes()
     counts0 = B.one_vs_many(q_hashes, db)                     # |match ∩ original query| for every row
     cache = {}
     q_size_ok = _size_ok(orig_len, scaled, cache)
-    alive = np.ones(orig_len, dtype=bool)                      # hashes of the query not yet covered
-    remaining = orig_len
+    alive = np.ones(search_len, dtype=bool)                    # hashes of the searched query not yet covered
+    remaining = search_len
     sess = B.GatherSession(q_hashes, db, min_count=1)
     if max_rounds is None:
         max_rounds = len(db)
@@ -144,7 +163,7 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
         g.f_unique_to_query = u / orig_len
         g.f_match_orig = _contained_by(c0, m, scaled)          # match.contained_by(original query)
         g.f_match = _contained_by(u, m, scaled)                # match.contained_by(remaining query)
-        g.remaining_bp = (remaining - u) * scaled
+        g.remaining_bp = (noident_len + remaining - u) * scaled
         if track:
             g.query_abundance = True
             g.n_unique_weighted_found = int(ab.sum(dtype=object))
@@ -153,7 +172,8 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
             g.average_abund, g.median_abund, g.std_abund = np.mean(vals), np.median(vals), np.std(vals)
         else:
             g.f_unique_weighted = g.f_unique_to_query
-        g.sum_weighted_found = total_weighted - (int(q_abunds[alive].sum(dtype=object)) if track else int(alive.sum()))
+        g.sum_weighted_found = total_weighted - noident_weight - \
+            (int(q_abunds[alive].sum(dtype=object)) if track else int(alive.sum()))
         # ANI columns: FracMinHashComparison(original query, match) (search.py:389-420, sketchcomparison.py:162-236)
         ok = q_size_ok and _size_ok(m, scaled, cache)
         qc = DU.containment_to_distance(_contained_by(c0, orig_len, scaled), ksize, scaled,

@@ -192,3 +192,57 @@ def test_gather_report_on_the_reference_fixture(cpu_kernels, monkeypatch, golden
     assert scaled == 10000
     assert [[g.name.split()[0], g.unique_intersect_bp // g.scaled] for g in with_thr] == [w for w in want if w[1] * scaled >= 50000]
     assert len(with_thr) == 11
+
+
+@pytest.mark.parametrize("track", [False, True])
+def test_gather_noident_keeps_denominators(cpu_kernels, monkeypatch, track):
+    """noident hashes (search.py:803-818,910-944,553-590): searched query = query - noident, while
+    query_bp / query_n_hashes / f_orig_query / f_unique_to_query / total_weighted_hashes keep counting
+    them and remaining_bp carries them."""
+    import glob
+    from sourmash_b200 import gather as G
+    from sourmash_b200.sigset import SignatureSet
+    monkeypatch.setattr(B, "GatherSession", _FakeSession)
+    d = os.path.join(GOLDEN, "gather")
+    base = smb.signature.load_one_signature_from_json(os.path.join(d, "combined.sig"), ksize=21).minhash
+    ss = SignatureSet.from_files(sorted(glob.glob(os.path.join(d, "GCF*.sig"))))
+    rows = ss.select(ksize=21)
+    db = _FakeSet([ss.row(i) for i in rows])
+    in_db = set(int(x) for i in rows for x in ss.row(i))
+    extra = [h for h in range(1000, 1060) if h not in in_db and h not in set(base.hashes)]
+    assert len(extra) == 60
+    hashes = sorted(base.hashes)
+    abund = {h: 1 + (h % 7) for h in hashes + extra}
+    plain = smb.MinHash(0, 21, scaled=base.scaled, track_abundance=track)
+    padded = smb.MinHash(0, 21, scaled=base.scaled, track_abundance=track)
+    if track:
+        plain.set_abundances({h: abund[h] for h in hashes})
+        padded.set_abundances(abund)
+    else:
+        plain.add_many(hashes)
+        padded.add_many(hashes + extra)
+    ref = G.gather_databases(plain, db)
+    got = G.gather_databases(padded, db, noident_hashes=extra)
+    n, n_pad = len(hashes), len(hashes) + 60
+    w = sum(abund[h] for h in hashes) if track else n
+    w_pad = w + (sum(abund[h] for h in extra) if track else 60)
+    assert len(got) == len(ref) == 12
+    for a, b in zip(got, ref):
+        assert (a.row, a.intersect_bp, a.unique_intersect_bp, a.f_match, a.f_match_orig) == \
+            (b.row, b.intersect_bp, b.unique_intersect_bp, b.f_match, b.f_match_orig)
+        assert a.query_n_hashes == n_pad and a.query_bp == n_pad * a.scaled and b.query_n_hashes == n
+        assert a.f_orig_query == (b.intersect_bp // b.scaled) / n_pad
+        assert a.f_unique_to_query == (b.unique_intersect_bp // b.scaled) / n_pad
+        assert a.remaining_bp == b.remaining_bp + 60 * a.scaled
+        assert a.total_weighted_hashes == w_pad and b.total_weighted_hashes == w
+        assert a.sum_weighted_found == b.sum_weighted_found                 # noident is never "found"
+        if track:
+            assert a.n_unique_weighted_found == b.n_unique_weighted_found
+            assert a.f_unique_weighted == b.n_unique_weighted_found / w_pad
+            assert (a.average_abund, a.median_abund, a.std_abund) == (b.average_abund, b.median_abund, b.std_abund)
+        else:
+            assert a.f_unique_weighted == a.f_unique_to_query
+    # without the noident argument the padding is searched like any other hash: same picks, other threshold base
+    assert [g.row for g in G.gather_databases(padded, db)] == [g.row for g in ref]
+    with pytest.raises(KeyError):
+        G.gather_databases(plain, db, noident_hashes=extra)                # not part of the query
