@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
     cmd = [nvcc_path()] + NVCC_FLAGS + ["-shared", "-o", LIB] + \
-        [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in SOURCES] + ["-lz"]
+        [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in SOURCES] + ["-lz", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)

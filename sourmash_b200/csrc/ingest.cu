@@ -8,6 +8,7 @@
 #include "ingest.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -51,16 +52,91 @@ struct Bytes {
     size_t size() const { return n; }
 };
 
-// whole file into memory; gzip members are inflated (magic 1f 8b), anything else is read as is
+// bzip2 input (the reference reads .bz2 through screed / niffler): the image ships libbz2.so.1.0 without
+// its header, so the three streaming entry points are bound at first use; the struct is bzlib.h's.
+struct BzStream {
+    char* next_in; unsigned avail_in, total_in_lo32, total_in_hi32;
+    char* next_out; unsigned avail_out, total_out_lo32, total_out_hi32;
+    void* state;
+    void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+struct BzApi {
+    int (*init)(BzStream*, int, int) = nullptr;
+    int (*run)(BzStream*) = nullptr;
+    int (*end)(BzStream*) = nullptr;
+    bool ok = false;
+};
+const BzApi& bz_api() {
+    static const BzApi api = [] {
+        BzApi a;
+        void* h = dlopen("libbz2.so.1.0", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libbz2.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return a;
+        a.init = (int (*)(BzStream*, int, int))dlsym(h, "BZ2_bzDecompressInit");
+        a.run = (int (*)(BzStream*))dlsym(h, "BZ2_bzDecompress");
+        a.end = (int (*)(BzStream*))dlsym(h, "BZ2_bzDecompressEnd");
+        a.ok = a.init && a.run && a.end;
+        return a;
+    }();
+    return api;
+}
+inline bool is_bz2(const unsigned char* m, size_t n) { return n >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h'; }
+
+// concatenated streams (pbzip2 output) are one file
+std::string bunzip(const uint8_t* src, size_t n, Bytes& data) {
+    const BzApi& bz = bz_api();
+    if (!bz.ok) return "bzip2 input needs libbz2.so.1.0, which could not be loaded";
+    if (!data.reserve(n * 5 + (1 << 16))) return "out of host memory";
+    size_t fed = 0;
+    while (fed < n) {
+        if (!is_bz2(src + fed, n - fed)) break;                 // trailing bytes after the last stream
+        BzStream zs;
+        memset(&zs, 0, sizeof zs);
+        if (bz.init(&zs, 0, 0) != 0) return "BZ2_bzDecompressInit failed";
+        const size_t start = fed;
+        int r = 0;
+        for (;;) {
+            if (zs.avail_in == 0 && fed < n) {
+                const size_t c = std::min<size_t>(n - fed, 1u << 30);
+                zs.next_in = (char*)(src + fed); zs.avail_in = (unsigned)c; fed += c;
+            }
+            if (data.cap - data.n < (1u << 16) && !data.reserve(data.cap * 2)) { bz.end(&zs); return "out of host memory"; }
+            const size_t room = std::min<size_t>(data.cap - data.n, 1u << 30);
+            zs.next_out = (char*)data.p + data.n; zs.avail_out = (unsigned)room;
+            const unsigned in_before = zs.avail_in;
+            r = bz.run(&zs);
+            data.n += room - zs.avail_out;
+            if (r == 4) break;                                  // BZ_STREAM_END
+            if (r != 0 || (fed >= n && zs.avail_in == 0 && in_before == 0 && zs.avail_out == room)) {
+                bz.end(&zs);
+                return "bzip2 stream is corrupt or truncated";
+            }
+        }
+        fed -= zs.avail_in;                                      // unread input belongs to the next stream
+        bz.end(&zs);
+        if (fed == start) break;
+    }
+    return "";
+}
+
+// whole file into memory; gzip (magic 1f 8b) and bzip2 ("BZh") files are decompressed, anything else is read as is
 std::string slurp(const char* path, Bytes& data) {
     FILE* fh = fopen(path, "rb");
     if (!fh) return std::string("cannot open ") + path;
-    unsigned char magic[2] = {0, 0};
-    size_t got = fread(magic, 1, 2, fh);
+    unsigned char magic[3] = {0, 0, 0};
+    size_t got = fread(magic, 1, 3, fh);
     fseek(fh, 0, SEEK_END);
     const long fsize = ftell(fh);
     fseek(fh, 0, SEEK_SET);
-    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    const bool gz = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (is_bz2(magic, got)) {
+        Bytes raw;
+        if (!raw.reserve((size_t)std::max<long>(fsize, 0) + 16)) { fclose(fh); return "out of host memory"; }
+        raw.n = fread(raw.p, 1, (size_t)std::max<long>(fsize, 0), fh);
+        fclose(fh);
+        std::string e = bunzip(raw.p, raw.n, data);
+        return e.empty() ? e : std::string(path) + ": " + e;
+    }
     if (!gz) {
         if (!data.reserve((size_t)std::max<long>(fsize, 0) + 16)) { fclose(fh); return "out of host memory"; }
         data.n = fread(data.p, 1, (size_t)std::max<long>(fsize, 0), fh);
@@ -100,10 +176,10 @@ void load_file(const char* path, Loaded& L) {
     if (fd < 0) { L.error = std::string("cannot open ") + path; return; }
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); L.error = std::string("cannot stat ") + path; return; }
-    unsigned char magic[2] = {0, 0};
-    const ssize_t got = pread(fd, magic, 2, 0);
-    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-    if (!gz && st.st_size > 0 && S_ISREG(st.st_mode)) {
+    unsigned char magic[3] = {0, 0, 0};
+    const ssize_t got = pread(fd, magic, 3, 0);
+    const bool packed = (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) || is_bz2(magic, got > 0 ? (size_t)got : 0);
+    if (!packed && st.st_size > 0 && S_ISREG(st.st_mode)) {
         void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m != MAP_FAILED) {
             madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);

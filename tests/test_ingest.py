@@ -263,3 +263,33 @@ def test_native_reader_on_the_reference_sequence_files():
         assert [s for _, s in got] == [s for _, s in want], p
         checked += 1
     assert checked > 10, checked
+
+
+def test_bzip2_inputs(tmp_path):
+    "bzip2 sequence and signature files (single stream, concatenated streams, truncated)."
+    import bz2
+    fa = b">a first\nACGTACGTNN\nACG\n>b\nGGGGCCCC\n"
+    one = tmp_path / "x.fa.bz2"
+    one.write_bytes(bz2.compress(fa))
+    assert read_sequences(one) == [("a first", b"ACGTACGTNNACG"), ("b", b"GGGGCCCC")]
+    two = tmp_path / "multi.fa.bz2"                                   # pbzip2-style: two streams back to back
+    two.write_bytes(bz2.compress(fa[:28]) + bz2.compress(fa[28:]))
+    assert read_sequences(two) == read_sequences(one)
+    big = os.urandom(1 << 16).hex().upper().encode().replace(b"0", b"A").replace(b"1", b"C")   # incompressible-ish
+    rec = b">big\n" + b"\n".join(big[i:i + 80] for i in range(0, len(big), 80)) + b"\n"
+    bigf = tmp_path / "big.fa.bz2"
+    bigf.write_bytes(bz2.compress(rec, compresslevel=1))
+    assert read_sequences(bigf) == [("big", big)]
+    src = os.path.join(GOLDEN, "47.fa.sig")
+    with open(src, "rb") as fh:
+        raw = fh.read()
+    sigbz = tmp_path / "47.fa.sig.bz2"
+    sigbz.write_bytes(bz2.compress(raw))
+    a, b = SignatureSet.from_files([str(sigbz)]), SignatureSet.from_files([src])
+    assert np.array_equal(a.mins, b.mins) and np.array_equal(a.offsets, b.offsets) and a.md5sums() == b.md5sums()
+    cut = tmp_path / "cut.fa.bz2"
+    cut.write_bytes(bigf.read_bytes()[:-200])
+    with pytest.raises(Exception, match="corrupt or truncated"):
+        read_sequences(cut)
+    mixed = RecordBatch([str(one), os.path.join(GOLDEN, "genome-s10.fa.gz"), str(two)], n_threads=2)
+    assert mixed.names()[:2] == ["a first", "b"] and mixed.names()[-2:] == ["a first", "b"]
