@@ -1463,11 +1463,9 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
     const size_t smem = (size_t)MAX_DYN_SMEM;
     const int R = n > 0 ? stripe_rows_per_block(smem, n) : 0;
     if (R < 1 || T == 0 || T >= 0xffffffffull) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per device, so not cached in a flag
         cudaError_t ea = cudaFuncSetAttribute(join_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
         if (ea != cudaSuccess) return ea;
-        attr_set = true;
     }
     auto js = new JoinStripe();
     js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;

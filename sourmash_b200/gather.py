@@ -272,3 +272,95 @@ def write_prefetch_csv(results, fp, *, estimate_ani_ci=False):
     w.writeheader()
     for d in results:
         w.writerow({k: v for k, v in d.items() if v is not None})
+
+
+SEARCH_COLUMNS = ["similarity", "md5", "filename", "name", "query_filename", "query_name", "query_md5", "ani"]  # search.py:292-303
+SEARCH_CI_COLUMNS = ["ani_low", "ani_high"]
+
+
+def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_max_containment=False, best_only=False,
+                    estimate_ani_ci=False, names=None, md5s=None, filenames=None, query_name="", query_filename="",
+                    location=None):
+    """`sourmash search` of a flat scaled query against the rows of the GPU-resident SketchSet ``db``
+    (same ksize / seed / scaled as the query): Jaccard, containment of the query or max-containment
+    at or above ``threshold``, best first, one entry per md5
+    (search_databases_with_flat_query, search.py:686-733, over Index.find / JaccardSearch,
+    index/__init__.py:115-170, search.py:91-169).  Returns dictionaries with the columns of
+    SearchResult (search.py:283-355): ``ani`` from the containment handed in (containment), the
+    bias-corrected max containment (max-containment) or the Jaccard value; the confidence interval
+    only for the two containment searches, like the reference.  One launch of the one-vs-many kernel."""
+    if do_containment and do_max_containment:
+        raise TypeError("'do_containment' and 'do_max_containment' cannot both be True")
+    if query_mh.track_abundance:
+        raise TypeError("this search cannot be done with an abund signature")
+    if not query_mh.scaled:
+        raise TypeError("this search requires a scaled signature")
+    scaled, ksize = query_mh.scaled, query_mh.ksize
+    q = query_mh._mins_array()
+    nq = len(q)
+    counts = B.one_vs_many(q, db).astype(np.int64)
+    sizes = db.sizes().astype(np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if do_containment:
+            score = counts / nq if nq else np.zeros(len(counts))
+        elif do_max_containment:
+            d = np.minimum(nq, sizes)
+            score = np.where(d > 0, counts / np.maximum(d, 1), 0.0)
+        else:
+            tot = nq + sizes - counts
+            score = np.where(tot > 0, counts / np.maximum(tot, 1), 0.0)
+    threshold = float(threshold or 0)
+    picked = []
+    for r in range(len(counts)):                               # index order; best_only ratchets the threshold
+        s = float(score[r])
+        if s and s >= threshold:
+            if best_only:
+                threshold = max(threshold, s)
+            picked.append(r)
+    seen, uniq = set(), []
+    for r in picked:
+        key = md5s[r] if md5s is not None else r
+        if key not in seen:
+            seen.add(key)
+            uniq.append(r)
+    uniq.sort(key=lambda r: -float(score[r]))                  # stable: ties keep database order
+    cache = {}
+    q_ok = _size_ok(nq, scaled, cache)
+    query_md5 = query_mh.md5sum()[:8]
+    ci = estimate_ani_ci and (do_containment or do_max_containment)
+    out = []
+    for r in uniq:
+        c, m, s = int(counts[r]), int(sizes[r]), float(score[r])
+        if do_containment:
+            res = DU.containment_to_distance(s, ksize, scaled, n_unique_kmers=nq * scaled, estimate_ci=ci)
+        elif do_max_containment:
+            res = DU.containment_to_distance(_contained_by(c, min(nq, m), scaled), ksize, scaled,
+                                             n_unique_kmers=min(nq, m) * scaled, estimate_ci=ci)
+        else:
+            res = DU.jaccard_to_distance(s, ksize, scaled, n_unique_kmers=round((nq + m) / 2 * scaled))
+        if not (q_ok and _size_ok(m, scaled, cache)):
+            res.size_is_inaccurate = True
+        d = {"row": int(r), "similarity": s, "query_name": query_name, "query_filename": query_filename,
+             "query_md5": query_md5, "ani": res.ani,
+             "potential_false_negative": bool(res.p_exceeds_threshold)}
+        if md5s is not None:
+            d["md5"] = md5s[r]
+        if names is not None:
+            d["name"] = names[r]
+        # BaseResult.get_cmpinfo (search.py:230-234): the location passed by the search wins, else the
+        # filename stored in the match
+        d["filename"] = location if location is not None else (filenames[r] if filenames is not None else None)
+        if ci:
+            d["ani_low"], d["ani_high"] = res.ani_low, res.ani_high
+        out.append(d)
+    return out
+
+
+def write_search_csv(results, fp, *, estimate_ani_ci=False):
+    "Write search_database() results as the reference's `search -o` CSV (search.py:292-307)."
+    import csv
+    cols = SEARCH_COLUMNS + (SEARCH_CI_COLUMNS if estimate_ani_ci else [])
+    w = csv.DictWriter(fp, fieldnames=cols, extrasaction="ignore")
+    w.writeheader()
+    for d in results:
+        w.writerow({k: v for k, v in d.items() if v is not None})

@@ -172,7 +172,7 @@ class Command_B200Gather(CommandLinePlugin):
     def __init__(self, p):
         super().__init__(p)
         p.add_argument("query", help="query .sig")
-        p.add_argument("databases", nargs="+", help="database .sig / .sig.gz files")
+        p.add_argument("databases", nargs="+", help="database .sig / .sig.gz files or .zip collections")
         _select_args(p)
         p.add_argument("--threshold-bp", type=float, default=50000.0)
         p.add_argument("--ignore-abundance", action="store_true")
@@ -201,7 +201,7 @@ class Command_B200Prefetch(CommandLinePlugin):
     def __init__(self, p):
         super().__init__(p)
         p.add_argument("query", help="query .sig")
-        p.add_argument("databases", nargs="+", help="database .sig / .sig.gz files")
+        p.add_argument("databases", nargs="+", help="database .sig / .sig.gz files or .zip collections")
         _select_args(p)
         p.add_argument("--threshold-bp", type=float, default=50000.0)
         p.add_argument("--estimate-ani-ci", action="store_true")
@@ -219,7 +219,45 @@ class Command_B200Prefetch(CommandLinePlugin):
         return 0
 
 
-COMMANDS = [Command_B200Sketch, Command_B200Compare, Command_B200Gather, Command_B200Prefetch]
+class Command_B200Search(CommandLinePlugin):
+    command = "b200search"
+    description = "search a query sketch against database sketches on a B200 GPU (search CSV)"
+
+    def __init__(self, p):
+        super().__init__(p)
+        p.add_argument("query", help="query .sig")
+        p.add_argument("databases", nargs="+", help="database .sig / .sig.gz files or .zip collections")
+        _select_args(p)
+        p.add_argument("-t", "--threshold", type=float, default=0.08, help="minimum score to report (default 0.08)")
+        p.add_argument("--containment", action="store_true", help="score by containment of the query")
+        p.add_argument("--max-containment", action="store_true", help="score by max containment")
+        p.add_argument("--best-only", action="store_true", help="report only the best match")
+        p.add_argument("-n", "--num-results", type=int, default=3, help="matches to print (0: all; the CSV has all)")
+        p.add_argument("--estimate-ani-ci", action="store_true")
+        p.add_argument("-o", "--output", default=None, help="CSV of the matches")
+
+    def main(self, args):
+        super().main(args)
+        from .gather import search_database, write_search_csv
+        if args.containment and args.max_containment:
+            raise ValueError("--containment and --max-containment are mutually exclusive")
+        qmh, sset, meta = _load_query_and_db(args)
+        res = search_database(qmh.flatten() if qmh.track_abundance else qmh, sset, threshold=args.threshold,
+                              do_containment=args.containment, do_max_containment=args.max_containment,
+                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci, **meta)
+        if args.best_only:
+            res = res[:1]
+        _notify(args, f"{len(res)} matches above threshold {args.threshold:0.3f}")
+        shown = res if not args.num_results else res[:args.num_results]
+        for d in shown:
+            _notify(args, f"{d['similarity'] * 100:6.1f}%       {d.get('name') or d.get('md5', '')}")
+        if args.output:
+            with open(args.output, "w", newline="") as fp:
+                write_search_csv(res, fp, estimate_ani_ci=args.estimate_ani_ci)
+        return 0
+
+
+COMMANDS = [Command_B200Sketch, Command_B200Compare, Command_B200Search, Command_B200Gather, Command_B200Prefetch]
 
 
 def build_parser():

@@ -334,7 +334,7 @@ def test_cli_plugin_protocol_and_argument_wiring(tmp_path):
     from sourmash_b200 import plugin
     from sourmash_b200.exceptions import SourmashError
     parser, objs = plugin.build_parser()
-    assert sorted(objs) == ["b200compare", "b200gather", "b200prefetch", "b200sketch"]
+    assert sorted(objs) == ["b200compare", "b200gather", "b200prefetch", "b200search", "b200sketch"]
     for cls in plugin.COMMANDS:
         assert cls.command and cls.description and issubclass(cls, plugin.CommandLinePlugin)
         sp = argparse.ArgumentParser()
@@ -351,6 +351,8 @@ def test_cli_plugin_protocol_and_argument_wiring(tmp_path):
         plugin.parse_param_string("k=31,bogus=1")
     a = parser.parse_args(["b200gather", "q.sig", "a.sig", "b.sig", "-k", "31", "--threshold-bp", "0", "-o", "g.csv"])
     assert a.query == "q.sig" and a.databases == ["a.sig", "b.sig"] and a.threshold_bp == 0 and a.ksize == 31
+    a = parser.parse_args(["b200search", "q.sig", "db.zip", "--containment", "-t", "0.1", "-n", "0", "-o", "s.csv"])
+    assert a.containment and not a.max_containment and a.threshold == 0.1 and a.num_results == 0 and a.databases == ["db.zip"]
     # pyproject registers exactly these classes under the reference's entry-point group
     text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyproject.toml")).read()
     assert '[project.entry-points."sourmash.cli_script"]' in text

@@ -246,3 +246,59 @@ def test_gather_noident_keeps_denominators(cpu_kernels, monkeypatch, track):
     assert [g.row for g in G.gather_databases(padded, db)] == [g.row for g in ref]
     with pytest.raises(KeyError):
         G.gather_databases(plain, db, noident_hashes=extra)                # not part of the query
+
+
+def test_search_database_matches_index_search(cpu_kernels, three):
+    """gather.search_database (one launch over a SketchSet) == LinearIndex.search object by object:
+    scores, order, thresholds, best-only, one entry per md5; SearchResult CSV columns (search.py:283-355)."""
+    import csv
+    import glob
+    import io
+    from sourmash_b200 import distance_utils as DU
+    from sourmash_b200 import gather as G
+    from sourmash_b200.sigset import SignatureSet
+    d = os.path.join(GOLDEN, "gather")
+    query = smb.signature.load_one_signature_from_json(os.path.join(d, "combined.sig"), ksize=21)
+    paths = sorted(glob.glob(os.path.join(d, "GCF*.sig")))
+    ss = SignatureSet.from_files(paths + paths[:2])                    # two duplicates: one entry per md5
+    rows = ss.select(ksize=21)
+    db = _FakeSet([ss.row(i) for i in rows])
+    meta = dict(names=[ss.name(i) for i in rows], md5s=[ss.md5sum(i) for i in rows],
+                filenames=[ss.filename(i) for i in rows], query_name=query.name, query_filename=query.filename)
+    lin = LinearIndex(ss.signatures(rows))
+    qset = set(query.minhash.hashes)
+    for kw in ({}, {"do_containment": True}, {"do_max_containment": True}):
+        for thr in (0.0, 0.05, 0.2):
+            got = G.search_database(query.minhash, db, threshold=thr, **kw, **meta)
+            ref, seen = [], set()
+            for r in lin.search(query, threshold=thr, **kw):
+                if r.signature.md5sum() not in seen:
+                    seen.add(r.signature.md5sum())
+                    ref.append(r)
+            assert [(g["similarity"], g["md5"]) for g in got] == [(r.score, r.signature.md5sum()) for r in ref], (kw, thr)
+            assert len({g["md5"] for g in got}) == len(got) <= 12
+            assert all(a["similarity"] >= b["similarity"] for a, b in zip(got, got[1:]))
+    cont = G.search_database(query.minhash, db, threshold=0.0, do_containment=True, estimate_ani_ci=True, **meta)
+    assert len(cont) == 12
+    for g in cont:
+        m = set(int(x) for x in ss.row(rows[g["row"]]))
+        assert g["similarity"] == len(qset & m) / len(qset)
+        want = DU.containment_to_distance(g["similarity"], 21, query.minhash.scaled,
+                                          n_unique_kmers=len(qset) * query.minhash.scaled, estimate_ci=True)
+        assert g["query_md5"] == query.md5sum()[:8] and g["name"] == meta["names"][g["row"]]
+        assert g["ani"] in (None, want.ani) and (g["ani"] is None or (g["ani_low"] <= g["ani"] <= g["ani_high"]))
+    jac = G.search_database(query.minhash, db, threshold=0.0, estimate_ani_ci=True, **meta)
+    assert all("ani_low" not in g for g in jac)                            # no interval for Jaccard searches
+    best = G.search_database(query.minhash, db, threshold=0.0, do_containment=True, best_only=True, **meta)
+    assert best[0]["md5"] == cont[0]["md5"] and best[0]["similarity"] == max(g["similarity"] for g in cont)
+    buf = io.StringIO()
+    G.write_search_csv(cont, buf, estimate_ani_ci=True)
+    table = list(csv.reader(io.StringIO(buf.getvalue())))
+    assert table[0] == G.SEARCH_COLUMNS + G.SEARCH_CI_COLUMNS and len(table) == 13
+    assert table[1][0] == str(cont[0]["similarity"]) and table[1][1] == cont[0]["md5"]
+    with pytest.raises(TypeError):
+        G.search_database(query.minhash, db, do_containment=True, do_max_containment=True)
+    ss2, ss47, ss63 = three
+    small = _FakeSet([s.minhash._mins_array() for s in (ss2, ss47, ss63)])
+    sr = G.search_database(ss47.minhash, small, threshold=0.1, md5s=[s.md5sum() for s in three])    # test_index_protocol.py:206-230
+    assert [g["md5"] for g in sr] == [ss47.md5sum(), ss63.md5sum()] and sr[0]["similarity"] == 1.0 and round(sr[1]["similarity"], 2) == 0.32
