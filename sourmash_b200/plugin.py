@@ -78,6 +78,8 @@ class Command_B200Sketch(CommandLinePlugin):
                        "default for a protein-family moltype is six-frame translation (sketch translate)")
         p.add_argument("--singleton", action="store_true", help="one signature per record")
         p.add_argument("--name-from-first", action="store_true")
+        p.add_argument("--merge", "--name", dest="merge", default=None, metavar="NAME",
+                       help="one signature named NAME from all records of all files")
         p.add_argument("--check-sequence", action="store_true", help="fail on invalid DNA instead of skipping")
         p.add_argument("-o", "--output", required=True, help=".sig (or .sig.gz) file for all signatures")
 
@@ -96,7 +98,7 @@ class Command_B200Sketch(CommandLinePlugin):
         sigs = sketch_fasta_files(args.filenames, ksizes=P["ksizes"], scaled=scaled or 0, num=num or 0, seed=P["seed"],
                                   track_abundance=P["track_abundance"], singleton=args.singleton,
                                   name_from_first=args.name_from_first, check_sequence=args.check_sequence,
-                                  moltype=args.moltype, input_is_protein=args.input_is_protein)
+                                  moltype=args.moltype, input_is_protein=args.input_is_protein, merge=args.merge)
         compression = 1 if args.output.endswith(".gz") else 0
         with open(args.output, "wb") as fp:
             save_signatures_to_json(sigs, fp, compression=compression)
@@ -116,7 +118,7 @@ class Command_B200Compare(CommandLinePlugin):
 
     def __init__(self, p):
         super().__init__(p)
-        p.add_argument("signatures", nargs="+", help=".sig / .sig.gz files")
+        p.add_argument("signatures", nargs="+", help=".sig / .sig.gz files or .zip collections")
         _select_args(p)
         p.add_argument("-o", "--output", default=None, help="numpy matrix (+ <output>.labels.txt)")
         p.add_argument("--csv", default=None, help="labelled matrix as CSV")

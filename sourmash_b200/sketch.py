@@ -95,19 +95,28 @@ def _signature_from_rows(rows, abunds, ksizes, scaled, num, seed, track, name, f
 
 def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, seed=42, track_abundance=False,
                        singleton=False, name_from_first=False, check_sequence=False, moltype="DNA",
-                       input_is_protein=False, n_threads=0):
+                       input_is_protein=False, n_threads=0, merge=None):
     """Sketch every input file on the GPU; returns a list of SourmashSignature (one sketch per ksize).
 
     ``moltype`` "protein" / "dayhoff" / "hp" with ``input_is_protein`` is `sketch protein`; without
     it the DNA is translated in six frames (`sketch translate`); ksizes are then in residues.
     ``check_sequence=True`` reproduces ``--check-sequence`` (force=False: the first invalid k-mer
     raises ValueError) through the per-record ABI call; the default skips invalid k-mers like
-    the reference CLI (command_sketch.py:827-832)."""
+    the reference CLI (command_sketch.py:827-832).  ``merge="name"`` is ``--merge``: every record of
+    every file goes into one signature with that name, filename = the last input
+    (_compute_merged, command_sketch.py:791-824)."""
     ksizes = list(ksizes)
     rb = RecordBatch(filenames, n_threads)
     rec_names = rb.names() if (singleton or name_from_first) else None
     names, files = [], []
-    if singleton:
+    if merge is not None:
+        if singleton:
+            raise ValueError("cannot specify both 'singleton' and 'merge'")
+        if len(rb) == 0:
+            return []                                      # "no sequences found": nothing is saved
+        owner = np.zeros(len(rb), dtype=np.uint32)
+        names, files = [merge], [rb.paths[-1]]
+    elif singleton:
         owner = np.arange(len(rb), dtype=np.uint32)
         names = rec_names
         files = [rb.paths[int(f)] for f in rb.files]

@@ -400,6 +400,11 @@ def test_sketch_fasta_files_matches_golden_signatures(smb, golden):
     om.add_sequence(recs[0][1], force=True)
     assert single[0].minhash._mins_array().tolist() == om.mins().tolist()
     assert single[0].minhash._abunds_array().tolist() == om.abunds().tolist()
+    # --merge: all records of all files in one signature (command_sketch.py:791-824)
+    merged, = sketch_fasta_files([ecoli, s10], ksizes=[31], scaled=1000, merge="both")
+    k31 = [next(m for m in s.sketches() if m.ksize == 31) for s in sigs]
+    assert merged.name == "both" and merged.filename == s10
+    assert merged.minhash._mins_array().tolist() == sorted(set(k31[0].hashes) | set(k31[1].hashes))
     # --check-sequence semantics
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as fh:
