@@ -5,6 +5,8 @@
 #                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh)
 #   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
 #   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
+#   SMB_SEARCH_LAYOUT=ranges one CTA per key range, query bitmap of the range in shared memory, for the
+#                            one-vs-many pass of search / prefetch / gather (csrc/range_search.cuh)
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
 TAG=${1:-r2a}
 # 1. correctness: the compare / join tests with each layout switched on and the join forced (they
@@ -46,4 +48,16 @@ for L in stripe cluster; do
 done
 SMB_JOIN_LAYOUT=stripe ncu --set full --clock-control none --import-source on -k regex:join_stripe_kernel -c 1 \
     -o gpurun_out/stripe_${TAG} python bench.py --workload compare --steps 1 --warmup 0 --no-cpu-baseline > /dev/null 2>&1
+# 4. range-partitioned search pass: correctness (every test that goes through one-vs-many), then A/B
+echo "== tests with SMB_SEARCH_LAYOUT=ranges"
+SMB_SEARCH_LAYOUT=ranges timeout 900 python -m pytest tests -q -m gpu -k "one_vs_many or search or gather or index or prefetch or zip" 2>&1 | tail -4
+for L in plain ranges; do
+  for W in search gather; do
+    SMB_SEARCH_LAYOUT=$L timeout 400 python bench.py --workload $W --steps 3 --warmup 3 > gpurun_out/bench_${W}_${L}_${TAG}.json 2> /dev/null
+    python -c "
+import json; d=json.load(open('gpurun_out/bench_${W}_${L}_${TAG}.json')); print('${W} ${L}: %.2f ms'%d['ms_per_step'])"
+  done
+done
+SMB_SEARCH_LAYOUT=ranges ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,lts__t_sectors_srcunit_tex_op_read.sum --clock-control none -c 60 --csv \
+    --log-file gpurun_out/launches_ranges_${TAG}.csv python bench.py --workload search --steps 1 --warmup 1 > /dev/null 2> gpurun_out/launches_ranges_${TAG}.err
 ls -la gpurun_out | tail -12

@@ -26,6 +26,7 @@
 #include "kernels.h"
 #include "ingest.h"
 #include "md5.h"
+#include "range_search.cuh"
 #include "zipread.h"
 
 namespace smb {
@@ -253,6 +254,11 @@ struct SmbSketchSet {
     uint64_t max_len = 0;
     mutable uint64_t max_key = 0;         // largest hash of any row (lazily computed on the device)
     mutable bool max_key_known = false;
+    // experimental range-partitioned search (SMB_SEARCH_LAYOUT=ranges): slice bounds of every row for
+    // range_P equal key ranges of width range_width, built at the first search of the resident set
+    mutable DevBuf<uint32_t> range_bounds;
+    mutable int range_P = 0;
+    mutable uint64_t range_width = 0;
     uint64_t total() const { return h_off.empty() ? 0 : h_off.back(); }
     void finish_offsets() {
         max_len = 0;
@@ -2085,6 +2091,21 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
         const uint64_t nb = (q_max >> shift) + 1;
         DevBuf<uint32_t> d_dir(nb + 2, s);
         smb::launch_build_global_dir(d_q, nq, shift, nb, d_dir.p, s);
+        if (smb::range_search_enabled() && db.max_len < 0xffffffffull) {
+            // experimental: one CTA per key range, query bitmap of the range in shared memory
+            const int P = SMB_B200_SMS;
+            const uint64_t width = smb::range_width(set_max_key(db, s), P);
+            if (db.range_P != P || db.range_width != width) {
+                db.range_bounds.alloc((size_t)(P + 1) * (size_t)nB, s);
+                smb::launch_range_bounds(db.d_hashes, db.d_off, nB, width, P, db.range_bounds.p, s);
+                db.range_P = P; db.range_width = width;
+            }
+            smb::launch_one_vs_many_ranges(d_q, nq, d_dir.p, shift, nb, db.d_hashes, db.d_off, nB,
+                                           db.range_bounds.p, width, P, d_counts, s);
+            CK(cudaGetLastError());
+            sync(s);
+            return;
+        }
         // L2-resident occupancy bitmap, 8x finer than the directory (1 byte per bucket)
         const int fine_log2 = 3;
         DevBuf<uint32_t> d_bm(((size_t)nb << fine_log2) / 32 + 2, s);

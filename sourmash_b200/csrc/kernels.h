@@ -36,6 +36,17 @@ void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const ui
                           int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
                           size_t ldo, bool symmetric, TileShard tiles, cudaStream_t s);
 
+// Experimental range-partitioned one-vs-many pass (SMB_SEARCH_LAYOUT=ranges, off by default;
+// range_search.cuh): the key space is cut into P equal ranges, CTA p keeps the query bitmap of its
+// range in shared memory and streams the rows' slices of that range.  `bounds` ([P + 1][n] u32) is
+// built once per resident set; `out` must be zeroed; `dir` is launch_build_global_dir's directory.
+bool range_search_enabled();
+void launch_range_bounds(const uint64_t* h, const uint64_t* off, int n, uint64_t width, int P, uint32_t* bounds,
+                         cudaStream_t s);
+void launch_one_vs_many_ranges(const uint64_t* q, uint64_t nq, const uint32_t* dir, int shift, uint64_t nbk,
+                               const uint64_t* hB, const uint64_t* offB, int nB, const uint32_t* bounds,
+                               uint64_t width, int P, uint32_t* out, cudaStream_t s);
+
 // All-vs-all counts by inverted join (compare_kernels.cu): sort the (hash, row) pairs of the set,
 // one increment per pair of rows sharing a hash.  join_estimate sorts the lowest 1/JOIN_SAMPLE of
 // the key range and extrapolates the number of increments / elements (d_out2: 2 x u64 scratch);
