@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 N_SKETCHES = 10_000
 KSIZES = (21, 31, 51)
 N_GENOMES = 100
+SM_COUNT = 148                                        # B200
 GENOME_LEN = 5_000_000
 SCALED = 1000
 
@@ -483,8 +484,18 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "traffic": ncu_traffic("hash_kmers_kernel"), "kernel_ms": kms,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "note": "integer-issue bound by construction (~150 int ops per k-mer vs 1 B): "
-                             "HBM fraction is expected to be small"},
+                             "HBM fraction is expected to be small; roofline.issue is the bound that applies"},
     }
+    wipk = ncu_traffic("hash_kmers_kernel_warp_instr_per_kmer")
+    if wipk:
+        # the bound that applies: warp instructions issued (ncu count of the same three launches, per k-mer)
+        # against 4 issue slots per SM per clock at the SM clock sampled during the timed region
+        clk = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        issued = wipk * my_kmers / (kms / 1e3)
+        res["roofline"]["issue"] = {"warp_instructions_per_kmer": wipk, "achieved": issued / 1e9,
+                                    "peak": SM_COUNT * 4 * clk / 1e9, "unit": "G warp-instr/s",
+                                    "frac": issued / (SM_COUNT * 4 * clk),
+                                    "source": ncu_traffic("hash_kmers_kernel_warp_instr_source")}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = host_cores()
         units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, ng)
