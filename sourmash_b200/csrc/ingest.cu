@@ -119,22 +119,119 @@ std::string bunzip(const uint8_t* src, size_t n, Bytes& data) {
     return "";
 }
 
-// whole file into memory; gzip (magic 1f 8b) and bzip2 ("BZh") files are decompressed, anything else is read as is
+// xz and zstd, the other two formats niffler sniffs: same arrangement, liblzma.so.5 / libzstd.so.1 bound at first use
+struct LzmaStream {                       // lzma/base.h lzma_stream (136 bytes), tail padded
+    const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+    uint8_t* next_out; size_t avail_out; uint64_t total_out;
+    const void* allocator; void* internal;
+    void* reserved_ptr[4]; uint64_t reserved_int[2]; size_t reserved_size[2]; int reserved_enum[2];
+    uint64_t pad[8];
+};
+struct LzmaApi {
+    int (*decoder)(LzmaStream*, uint64_t, uint32_t) = nullptr;
+    int (*code)(LzmaStream*, int) = nullptr;
+    void (*end)(LzmaStream*) = nullptr;
+    bool ok = false;
+};
+const LzmaApi& lzma_api() {
+    static const LzmaApi api = [] {
+        LzmaApi a;
+        void* h = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return a;
+        a.decoder = (int (*)(LzmaStream*, uint64_t, uint32_t))dlsym(h, "lzma_stream_decoder");
+        a.code = (int (*)(LzmaStream*, int))dlsym(h, "lzma_code");
+        a.end = (void (*)(LzmaStream*))dlsym(h, "lzma_end");
+        a.ok = a.decoder && a.code && a.end;
+        return a;
+    }();
+    return api;
+}
+inline bool is_xz(const unsigned char* m, size_t n) { return n >= 6 && !memcmp(m, "\xfd" "7zXZ\0", 6); }
+
+std::string unxz(const uint8_t* src, size_t n, Bytes& data) {
+    const LzmaApi& lz = lzma_api();
+    if (!lz.ok) return "xz input needs liblzma.so.5, which could not be loaded";
+    if (!data.reserve(n * 5 + (1 << 16))) return "out of host memory";
+    LzmaStream zs;
+    memset(&zs, 0, sizeof zs);
+    if (lz.decoder(&zs, UINT64_MAX, 0x08u /* LZMA_CONCATENATED */) != 0) return "lzma_stream_decoder failed";
+    zs.next_in = src; zs.avail_in = n;
+    for (;;) {
+        if (data.cap - data.n < (1u << 16) && !data.reserve(data.cap * 2)) { lz.end(&zs); return "out of host memory"; }
+        zs.next_out = data.p + data.n; zs.avail_out = data.cap - data.n;
+        const int r = lz.code(&zs, zs.avail_in == 0 ? 3 /* LZMA_FINISH */ : 0 /* LZMA_RUN */);
+        data.n = data.cap - zs.avail_out;
+        if (r == 1) break;                                       // LZMA_STREAM_END
+        if (r != 0) { lz.end(&zs); return "xz stream is corrupt or truncated"; }
+    }
+    lz.end(&zs);
+    return "";
+}
+
+struct ZstdBuf { void* p; size_t size, pos; };
+struct ZstdApi {
+    void* (*create)() = nullptr;
+    size_t (*free)(void*) = nullptr;
+    size_t (*run)(void*, ZstdBuf*, ZstdBuf*) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+};
+const ZstdApi& zstd_api() {
+    static const ZstdApi api = [] {
+        ZstdApi a;
+        void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return a;
+        a.create = (void* (*)())dlsym(h, "ZSTD_createDStream");
+        a.free = (size_t (*)(void*))dlsym(h, "ZSTD_freeDStream");
+        a.run = (size_t (*)(void*, ZstdBuf*, ZstdBuf*))dlsym(h, "ZSTD_decompressStream");
+        a.is_error = (unsigned (*)(size_t))dlsym(h, "ZSTD_isError");
+        a.ok = a.create && a.free && a.run && a.is_error;
+        return a;
+    }();
+    return api;
+}
+inline bool is_zstd(const unsigned char* m, size_t n) { return n >= 4 && m[0] == 0x28 && m[1] == 0xb5 && m[2] == 0x2f && m[3] == 0xfd; }
+
+std::string unzstd(const uint8_t* src, size_t n, Bytes& data) {
+    const ZstdApi& z = zstd_api();
+    if (!z.ok) return "zstd input needs libzstd.so.1, which could not be loaded";
+    if (!data.reserve(n * 5 + (1 << 16))) return "out of host memory";
+    void* ds = z.create();
+    if (!ds) return "ZSTD_createDStream failed";
+    ZstdBuf in{(void*)src, n, 0};
+    size_t hint = 1;
+    for (;;) {
+        if (data.cap - data.n < (1u << 16) && !data.reserve(data.cap * 2)) { z.free(ds); return "out of host memory"; }
+        ZstdBuf out{data.p + data.n, data.cap - data.n, 0};
+        const size_t in_before = in.pos;
+        hint = z.run(ds, &out, &in);
+        data.n += out.pos;
+        if (z.is_error(hint)) { z.free(ds); return "zstd stream is corrupt"; }
+        if (in.pos >= in.size && out.pos < out.size) break;      // input eaten and the output flushed
+        if (in.pos == in_before && out.pos == 0) { z.free(ds); return "zstd stream is corrupt or truncated"; }
+    }
+    z.free(ds);
+    if (hint != 0) return "zstd stream is corrupt or truncated"; // a frame was left unfinished
+    return "";
+}
+
+// whole file into memory; gzip (magic 1f 8b), bzip2 ("BZh"), xz and zstd files are decompressed, anything else is read as is
 std::string slurp(const char* path, Bytes& data) {
     FILE* fh = fopen(path, "rb");
     if (!fh) return std::string("cannot open ") + path;
-    unsigned char magic[3] = {0, 0, 0};
-    size_t got = fread(magic, 1, 3, fh);
+    unsigned char magic[6] = {0, 0, 0, 0, 0, 0};
+    size_t got = fread(magic, 1, 6, fh);
     fseek(fh, 0, SEEK_END);
     const long fsize = ftell(fh);
     fseek(fh, 0, SEEK_SET);
     const bool gz = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-    if (is_bz2(magic, got)) {
+    if (is_bz2(magic, got) || is_xz(magic, got) || is_zstd(magic, got)) {
         Bytes raw;
         if (!raw.reserve((size_t)std::max<long>(fsize, 0) + 16)) { fclose(fh); return "out of host memory"; }
         raw.n = fread(raw.p, 1, (size_t)std::max<long>(fsize, 0), fh);
         fclose(fh);
-        std::string e = bunzip(raw.p, raw.n, data);
+        std::string e = is_bz2(magic, got) ? bunzip(raw.p, raw.n, data)
+                        : is_xz(magic, got) ? unxz(raw.p, raw.n, data) : unzstd(raw.p, raw.n, data);
         return e.empty() ? e : std::string(path) + ": " + e;
     }
     if (!gz) {
@@ -176,9 +273,11 @@ void load_file(const char* path, Loaded& L) {
     if (fd < 0) { L.error = std::string("cannot open ") + path; return; }
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); L.error = std::string("cannot stat ") + path; return; }
-    unsigned char magic[3] = {0, 0, 0};
-    const ssize_t got = pread(fd, magic, 3, 0);
-    const bool packed = (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) || is_bz2(magic, got > 0 ? (size_t)got : 0);
+    unsigned char magic[6] = {0, 0, 0, 0, 0, 0};
+    const ssize_t got = pread(fd, magic, 6, 0);
+    const size_t gn = got > 0 ? (size_t)got : 0;
+    const bool packed = (gn >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) || is_bz2(magic, gn) || is_xz(magic, gn) ||
+                        is_zstd(magic, gn);
     if (!packed && st.st_size > 0 && S_ISREG(st.st_mode)) {
         void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m != MAP_FAILED) {

@@ -293,3 +293,62 @@ def test_bzip2_inputs(tmp_path):
         read_sequences(cut)
     mixed = RecordBatch([str(one), os.path.join(GOLDEN, "genome-s10.fa.gz"), str(two)], n_threads=2)
     assert mixed.names()[:2] == ["a first", "b"] and mixed.names()[-2:] == ["a first", "b"]
+
+
+def test_xz_and_zstd_inputs(tmp_path):
+    "the other two compression formats the reference's readers sniff (niffler): xz and zstd."
+    import ctypes
+    import lzma
+    fa = b">a first\nACGTACGTNN\nACG\n>b\nGGGGCCCC\n"
+    want = [("a first", b"ACGTACGTNNACG"), ("b", b"GGGGCCCC")]
+    xz = tmp_path / "x.fa.xz"
+    xz.write_bytes(lzma.compress(fa))
+    assert read_sequences(xz) == want
+    multi = tmp_path / "multi.fa.xz"                                    # concatenated streams
+    multi.write_bytes(lzma.compress(fa[:28]) + lzma.compress(fa[28:]))
+    assert read_sequences(multi) == want
+    big = os.urandom(1 << 16).hex().upper().encode().replace(b"0", b"A").replace(b"1", b"C")
+    rec = b">big\n" + b"\n".join(big[i:i + 80] for i in range(0, len(big), 80)) + b"\n"
+    bigxz = tmp_path / "big.fa.xz"
+    bigxz.write_bytes(lzma.compress(rec, preset=0))
+    assert read_sequences(bigxz) == [("big", big)]
+    cut = tmp_path / "cut.fa.xz"
+    cut.write_bytes(bigxz.read_bytes()[:-300])
+    with pytest.raises(Exception, match="corrupt or truncated"):
+        read_sequences(cut)
+    src = os.path.join(GOLDEN, "47.fa.sig")
+    with open(src, "rb") as fh:
+        raw = fh.read()
+    sigxz = tmp_path / "47.fa.sig.xz"
+    sigxz.write_bytes(lzma.compress(raw))
+    assert np.array_equal(SignatureSet.from_files([str(sigxz)]).mins, SignatureSet.from_files([src]).mins)
+    try:
+        z = ctypes.CDLL("libzstd.so.1")
+    except OSError:
+        pytest.skip("libzstd.so.1 not present")
+    z.ZSTD_compressBound.restype = ctypes.c_size_t
+    z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    z.ZSTD_compress.restype = ctypes.c_size_t
+    z.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+
+    def zcompress(data):
+        cap = z.ZSTD_compressBound(len(data))
+        buf = ctypes.create_string_buffer(cap)
+        n = z.ZSTD_compress(buf, cap, data, len(data), 3)
+        return buf.raw[:n]
+    zs = tmp_path / "x.fa.zst"
+    zs.write_bytes(zcompress(fa))
+    assert read_sequences(zs) == want
+    zs2 = tmp_path / "two.fa.zst"                                       # two frames back to back
+    zs2.write_bytes(zcompress(fa[:28]) + zcompress(fa[28:]))
+    assert read_sequences(zs2) == want
+    bigz = tmp_path / "big.fa.zst"
+    bigz.write_bytes(zcompress(rec))
+    assert read_sequences(bigz) == [("big", big)]
+    cutz = tmp_path / "cut.fa.zst"
+    cutz.write_bytes(bigz.read_bytes()[:-300])
+    with pytest.raises(Exception, match="corrupt or truncated"):
+        read_sequences(cutz)
+    sigz = tmp_path / "47.fa.sig.zst"
+    sigz.write_bytes(zcompress(raw))
+    assert np.array_equal(SignatureSet.from_files([str(sigz)]).mins, SignatureSet.from_files([src]).mins)
