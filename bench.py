@@ -504,6 +504,20 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     return res
 
 
+def _maybe_index(args, B, db):
+    """--index: build the inverted index of the resident database once, outside the timed region (it
+    belongs to loading the database, like the upload); the build time is reported beside the result."""
+    if not getattr(args, "index", False):
+        return {}
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_keys = db.build_index()
+    torch.cuda.synchronize()
+    return {"index": {"distinct_hashes": int(n_keys), "build_ms": (time.perf_counter() - t0) * 1e3,
+                      "note": "inverted index (hash -> rows) of the resident database, built once at load"}}
+
+
 def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
     """configs[3] / configs[4] shapes (parity-test cases, not the headline): one query vs a
     large resident database; reported for completeness, single GPU only."""
@@ -520,6 +534,7 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
         query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=10_000_000, dtype=np.uint64)] +
                                          [rows[j][: len(rows[j]) // 2] for j in planted]))
         db = B.SketchSet.from_host(db_h, db_off)
+        index_info = _maybe_index(args, B, db)
         pq = B.pinned_empty(len(query), np.uint64)
         pq.array[:] = query
         ms, launches, clocks, ex = timed(lambda: int(B.one_vs_many(pq.array, db).sum()), args.steps, args.warmup)
@@ -528,7 +543,7 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
                 "config": {"workload": "configs[3]: 1e7-hash query vs 300000-sketch DB (12 GB resident), containment counts",
                            "db_hashes": int(len(db_h)), "query_hashes": int(len(query))},
                 "subjects_per_s": n_db / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9, "gpu_launches": launches,
-                "note": "query uploaded from pinned host memory every step; counts downloaded"}
+                "note": "query uploaded from pinned host memory every step; counts downloaded", **index_info}
     n_db = 50_000
     reps = n_db // N_SKETCHES
     db_h = np.tile(h, reps)
@@ -537,6 +552,7 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
     query = np.unique(np.concatenate([rows[j][rng.random(len(rows[j])) < 0.6] for j in planted] +
                                      [rng.integers(1, MAX_HASH_1000, size=20_000, dtype=np.uint64)]))
     db = B.SketchSet.from_host(db_h, db_off)
+    index_info = _maybe_index(args, B, db)
     res = {}
 
     def step():
@@ -548,7 +564,7 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
     return {"metric": "gather wall time", "value": ms, "unit": "ms", "higher_is_better": False, "ms_per_step": ms,
             "config": {"workload": "configs[4]: ~1e5-hash query vs 50000-sketch DB, 200 planted overlapping matches, "
                                    "threshold 50 hashes", "query_hashes": int(len(query)), "db_hashes": int(len(db_h))},
-            "rounds": res["rounds"], "rounds_per_s": res["rounds"] / (ms / 1e3), "gpu_launches": launches}
+            "rounds": res["rounds"], "rounds_per_s": res["rounds"] / (ms / 1e3), "gpu_launches": launches, **index_info}
 
 
 def main():
@@ -559,6 +575,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=["compare", "sketch", "both", "search", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index", action="store_true",
+                    help="search / gather workloads: query through the inverted index of the resident database")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "compare" if args.impl == "reference" else "both"

@@ -278,6 +278,16 @@ SmbSketchSet *smb_sketch_streams_dev(const uint8_t *d_bases, const uint64_t *h_s
                                      uint32_t num, uint64_t seed, bool track_abundance,
                                      uint64_t *n_kmers_out);
 
+/* Inverted index (hash -> rows) over a resident set, for databases that are queried repeatedly:
+ * once built, smb_one_vs_many and the gather session on this set probe the index -- one directory
+ * lookup per *query* hash and one increment per match -- instead of streaming every row of the set
+ * (the job of the reference's RevIndex, src/core/src/index/revindex/, for the same counts).
+ * Costs about 1.5x the set's size in HBM; at most 2^31 - 1 hashes.  Returns the number of distinct
+ * hashes.  Results are identical with and without the index. */
+uint64_t smb_sketchset_build_index(SmbSketchSet *set);
+void smb_sketchset_drop_index(SmbSketchSet *set);
+bool smb_sketchset_has_index(const SmbSketchSet *set);
+
 /* intersection ------------------------------------------------------------------------ */
 /* common[i*n_b + j] = |A_i ∩ B_j| (b == NULL: b = a, only i<j computed, mirrored, diagonal
  * = |A_i|).  num > 0 selects bottom-k semantics (minhash.rs:593-617) and fills usize_out

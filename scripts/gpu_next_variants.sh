@@ -5,10 +5,14 @@
 #                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh)
 #   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
 #   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
+#   SketchSet.build_index()  inverted index of a resident set: search / gather counts for work proportional
+#                            to the query (csrc/db_index.cuh); bench.py --workload search|gather --index
 #   SMB_SEARCH_LAYOUT=ranges one CTA per key range, query bitmap of the range in shared memory, for the
 #                            one-vs-many pass of search / prefetch / gather (csrc/range_search.cuh)
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
 TAG=${1:-r2a}
+# 0. the explicit parity tests of the experimental paths (skipped in the default suite)
+SMB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -q -m gpu 2>&1 | tail -8
 # 1. correctness: the compare / join tests with each layout switched on and the join forced (they
 #    compare with the oracle bit for bit); a memcheck run of the stripe kernels on a small matrix
 for L in stripe cluster; do
@@ -57,6 +61,11 @@ for L in plain ranges; do
     python -c "
 import json; d=json.load(open('gpurun_out/bench_${W}_${L}_${TAG}.json')); print('${W} ${L}: %.2f ms'%d['ms_per_step'])"
   done
+done
+for W in search gather; do
+  timeout 600 python bench.py --workload $W --index --steps 3 --warmup 3 > gpurun_out/bench_${W}_index_${TAG}.json 2> /dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_${W}_index_${TAG}.json')); print('${W} index: %.3f ms, build %.1f ms, %d distinct hashes'%(d['ms_per_step'], d['index']['build_ms'], d['index']['distinct_hashes']))"
 done
 SMB_SEARCH_LAYOUT=ranges ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,lts__t_sectors_srcunit_tex_op_read.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/launches_ranges_${TAG}.csv python bench.py --workload search --steps 1 --warmup 1 > /dev/null 2> gpurun_out/launches_ranges_${TAG}.err

@@ -154,6 +154,19 @@ class SketchSet:
         h, off = self.to_host()
         return [h[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
 
+    def build_index(self):
+        """Build the inverted index (hash -> rows) of this resident set; search / prefetch / gather
+        counts on it then cost work proportional to the query instead of a pass over the set.
+        Returns the number of distinct hashes."""
+        return int(rustcall(lib.smb_sketchset_build_index, self._ptr))
+
+    def drop_index(self):
+        rustcall(lib.smb_sketchset_drop_index, self._ptr)
+
+    @property
+    def has_index(self):
+        return bool(lib.smb_sketchset_has_index(self._ptr))
+
     def downsample(self, max_hash):
         return SketchSet(rustcall(lib.smb_sketchset_downsample, self._ptr, int(max_hash)))
 

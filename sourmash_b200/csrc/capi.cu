@@ -259,6 +259,10 @@ struct SmbSketchSet {
     mutable DevBuf<uint32_t> range_bounds;
     mutable int range_P = 0;
     mutable uint64_t range_width = 0;
+    // inverted index (hash -> rows), built on request by smb_sketchset_build_index: the one-vs-many
+    // counts of search / prefetch / gather then cost work proportional to the query (db_index.cuh)
+    smb::DbIndex* index = nullptr;
+    ~SmbSketchSet() { if (index) smb::db_index_destroy(index); }
     uint64_t total() const { return h_off.empty() ? 0 : h_off.back(); }
     void finish_offsets() {
         max_len = 0;
@@ -2060,6 +2064,11 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
     // otherwise a global-memory directory over the query.
     const int nB = (int)db.n_rows;
     if (nB == 0 || nq == 0) return;                  // callers zero the counters: nothing is shared
+    if (db.index) {                                  // resident set with an inverted index: probe it
+        smb::launch_index_count(db.index, d_q, nq, d_counts, s);
+        CK(cudaGetLastError());
+        return;
+    }
     SmbSketchSet q;
     q.n_rows = 1; q.h_off = {0, (uint64_t)nq};
     q.own_off.alloc(2, s); q.own_off.upload(q.h_off.data(), 2);
@@ -2118,6 +2127,27 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
     sync(s);      // q's offsets upload reads a host temporary
 }
 
+uint64_t smb_sketchset_build_index(SmbSketchSet* set) {
+    return guarded<uint64_t>([&]() -> uint64_t {
+        cudaStream_t s = need_gpu();
+        if (set->index) return smb::db_index_n_keys(set->index);
+        if (set->n_rows == 0 || set->total() == 0) return 0;
+        const uint64_t mk = set_max_key(*set, s);
+        smb::DbIndex* ix = nullptr;
+        CK(smb::db_index_build(set->d_hashes, set->d_off, (int)set->n_rows, set->total(), mk, &ix, s));
+        if (!ix) fail(SOURMASH_ERROR_CODE_MSG, "set too large for an inverted index (more than 2^31 - 1 hashes)");
+        sync(s);
+        set->index = ix;
+        return smb::db_index_n_keys(ix);
+    });
+}
+void smb_sketchset_drop_index(SmbSketchSet* set) {
+    guarded_void([&] {
+        if (set->index) { smb::db_index_destroy(set->index); set->index = nullptr; }
+    });
+}
+bool smb_sketchset_has_index(const SmbSketchSet* set) { return set->index != nullptr; }
+
 void smb_one_vs_many(const uint64_t* query, uintptr_t n_query, const SmbSketchSet* db,
                      uint32_t* common_out) {
     guarded_void([&] {
@@ -2162,7 +2192,7 @@ SmbGatherState* smb_gather_begin_min(const uint64_t* query, uintptr_t n_query, c
         sync(s);
         std::vector<uint32_t> keep;
         for (size_t j = 0; j < nB; ++j) if (cnt[j] >= min_count) keep.push_back((uint32_t)j);
-        if (keep.size() * 4 < nB * 3) {
+        if (!db->index && keep.size() * 4 < nB * 3) {      // (an indexed set is never streamed: keep it whole)
             const size_t m = keep.size();
             auto sub = std::make_unique<SmbSketchSet>();
             sub->n_rows = m;
@@ -2305,7 +2335,11 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
             const uint64_t* r = cdb->d_hashes + cdb->h_off[row];
             const size_t rn = cdb->h_off[row + 1] - cdb->h_off[row];
             smb::launch_intersect_alive(st->q.p, st->nq, st->alive.p, r, rn, st->isect.p, st->d_n.p, s);
-            if (small_rows) {
+            if (cdb->index) {                                   // probe the inverted index, length stays on the device
+                st->delta.zero();
+                smb::launch_index_count_n(cdb->index, st->isect.p, st->d_n.p, rn, st->delta.p, s);
+                smb::launch_mark_dead_n(st->q.p, st->nq, st->alive.p, st->isect.p, st->d_n.p, s);
+            } else if (small_rows) {
                 smb::launch_make_row_offsets(st->d_n.p, d_qoff.p, s);
                 st->delta.zero();
                 one_vs_many_small_async(st->isect.p, d_qoff.p, rn, q_max, *cdb, st->delta.p, s);

@@ -18,9 +18,11 @@
 #include <string.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <memory>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -28,6 +30,7 @@
 #include "join_walk.cuh"
 #include "join_stripe.cuh"
 #include "range_search.cuh"
+#include "db_index.cuh"
 
 namespace smb {
 
@@ -1635,6 +1638,134 @@ void join_stripe_destroy(JoinStripe* js) { delete js; }
 bool join_stripe_enabled() {
     const char* layout = getenv("SMB_JOIN_LAYOUT");
     return layout && !strcmp(layout, "stripe");
+}
+
+// ------------------------------------------------------------------------------------
+// Inverted index over a resident set (db_index.cuh): built on request, then one-vs-many counts cost
+// one directory probe per query hash and one increment per match instead of a pass over the set.
+// Logic checked on the CPU by tests/test_host_emulation.py::test_db_index_*; not measured yet.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) index_rowid_kernel(const u64* __restrict__ off, int n_rows, u32* __restrict__ ids) {
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x)
+        for (u64 i = off[r] + threadIdx.x; i < off[r + 1]; i += blockDim.x) ids[i] = (u32)r;
+}
+// run lengths -> start offsets: start[u] = sum of counts[0..u); done in place by an exclusive scan
+struct DbIndex {
+    cudaStream_t stream = 0;
+    void *m_keys = nullptr, *m_start = nullptr, *m_rows = nullptr, *m_dir = nullptr;
+    DbIndexView view{};
+    u64 n_elements = 0;
+    ~DbIndex() {
+        if (m_keys) cudaFreeAsync(m_keys, stream);
+        if (m_start) cudaFreeAsync(m_start, stream);
+        if (m_rows) cudaFreeAsync(m_rows, stream);
+        if (m_dir) cudaFreeAsync(m_dir, stream);
+    }
+};
+
+cudaError_t db_index_build(const u64* h, const u64* off, int n, u64 T, u64 max_key, DbIndex** out, cudaStream_t s) {
+    *out = nullptr;
+    if (n <= 0 || T == 0 || T > 0x7fffffffull) return cudaSuccess;       // CUB's run-length encode counts in int
+    auto ix = new DbIndex();
+    ix->stream = s; ix->n_elements = T;
+    std::unique_ptr<DbIndex> guard(ix);
+    cudaError_t e;
+    JoinScratch scratch(s);
+    u64* keys_sorted = nullptr;
+    u32* ids = nullptr;
+    if ((e = scratch.alloc((void**)&keys_sorted, T * sizeof(u64))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&ids, T * sizeof(u32))) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&ix->m_rows, T * sizeof(u32), s)) != cudaSuccess) return e;
+    const int blocks = n < SMB_B200_SMS * 16 ? n : SMB_B200_SMS * 16;
+    index_rowid_kernel<<<blocks, 256, 0, s>>>(off, n, ids); count_launches(1);
+    {   // (hash, row) pairs sorted by hash where they lie; stable, so rows ascend inside a group
+        const int key_bits = key_bit_length(max_key);
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, h, keys_sorted, ids, (u32*)ix->m_rows, (long long)T, 0, key_bits, s);
+        void* tmp = nullptr;
+        if ((e = cudaMallocAsync(&tmp, bytes ? bytes : 16, s)) != cudaSuccess) return e;
+        cub::DeviceRadixSort::SortPairs(tmp, bytes, h, keys_sorted, ids, (u32*)ix->m_rows, (long long)T, 0, key_bits, s);
+        cudaFreeAsync(tmp, s);
+        count_launches(1);
+    }
+    // distinct keys + group sizes, then sizes -> offsets
+    if ((e = cudaMallocAsync(&ix->m_keys, T * sizeof(u64), s)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&ix->m_start, (T + 1) * sizeof(u32), s)) != cudaSuccess) return e;
+    u64* d_runs = (u64*)ids;                                               // ids is free again: reuse 8 bytes of it
+    {
+        size_t bytes = 0;
+        cub::DeviceRunLengthEncode::Encode(nullptr, bytes, keys_sorted, (u64*)ix->m_keys, (u32*)ix->m_start, d_runs, (int)T, s);
+        void* tmp = nullptr;
+        if ((e = cudaMallocAsync(&tmp, bytes ? bytes : 16, s)) != cudaSuccess) return e;
+        cub::DeviceRunLengthEncode::Encode(tmp, bytes, keys_sorted, (u64*)ix->m_keys, (u32*)ix->m_start, d_runs, (int)T, s);
+        cudaFreeAsync(tmp, s);
+        count_launches(1);
+    }
+    u64 n_keys = 0;
+    cudaMemcpyAsync(&n_keys, d_runs, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    {
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, (u32*)ix->m_start, (u32*)ix->m_start, (int)(n_keys + 1), s);
+        void* tmp = nullptr;
+        if ((e = cudaMallocAsync(&tmp, bytes ? bytes : 16, s)) != cudaSuccess) return e;
+        // element n_keys is scratch: whatever it holds, the exclusive sum puts the total (= T) there
+        cub::DeviceScan::ExclusiveSum(tmp, bytes, (u32*)ix->m_start, (u32*)ix->m_start, (int)(n_keys + 1), s);
+        cudaFreeAsync(tmp, s);
+        count_launches(1);
+    }
+    u32 shift;
+    u64 nbk;
+    db_index_dir_plan(n_keys, max_key, shift, nbk);
+    if ((e = cudaMallocAsync(&ix->m_dir, (nbk + 2) * sizeof(u32), s)) != cudaSuccess) return e;
+    launch_build_global_dir((const u64*)ix->m_keys, n_keys, (int)shift, nbk, (u32*)ix->m_dir, s);
+    ix->view = DbIndexView{(const u64*)ix->m_keys, n_keys, (const u32*)ix->m_start, (const u32*)ix->m_rows,
+                           (const u32*)ix->m_dir, shift, nbk};
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *out = guard.release();
+    return cudaSuccess;
+}
+void db_index_destroy(DbIndex* ix) { delete ix; }
+u64 db_index_n_keys(const DbIndex* ix) { return ix->view.n_keys; }
+
+// counts[row] += 1 for every (query hash, row) pair the index holds.  One lane per query hash; groups
+// of up to 32 rows are walked by their lane, longer ones by the whole warp.
+__global__ void __launch_bounds__(256) index_count_kernel(DbIndexView ix, const u64* __restrict__ q, u64 nq,
+                                                         const u32* __restrict__ d_nq, u32* __restrict__ counts) {
+    if (d_nq) nq = *d_nq;                                  // length produced on the device by an earlier kernel
+    const u32 lane = lane_id();
+    const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 base = warp0 * 32; base < nq; base += n_warps * 32) {
+        const u64 i = base + lane;
+        u32 b = 0, e = 0;
+        if (i < nq) {
+            const long long u = db_index_find(ix, q[i]);
+            if (u >= 0) { b = ix.start[u]; e = ix.start[u + 1]; }
+        }
+        const bool wide = e - b > 32;
+        if (!wide) for (u32 j = b; j < e; ++j) atomicAdd(counts + ix.rows[j], 1u);
+        u32 todo = __ballot_sync(0xffffffffu, wide);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const u32 gb = __shfl_sync(0xffffffffu, b, src), ge = __shfl_sync(0xffffffffu, e, src);
+            for (u32 j = gb + lane; j < ge; j += 32) atomicAdd(counts + ix.rows[j], 1u);
+        }
+    }
+}
+void launch_index_count(const DbIndex* ix, const u64* q, u64 nq, u32* counts, cudaStream_t s) {
+    if (nq == 0 || ix->view.n_keys == 0) return;
+    u64 blocks = (nq + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
+    index_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(ix->view, q, nq, nullptr, counts); count_launches(1);
+}
+// the same with the number of query hashes read from device memory (at most max_nq): no host round trip
+void launch_index_count_n(const DbIndex* ix, const u64* q, const u32* d_nq, u64 max_nq, u32* counts, cudaStream_t s) {
+    if (max_nq == 0 || ix->view.n_keys == 0) return;
+    u64 blocks = (max_nq + 255) / 256;
+    if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
+    index_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(ix->view, q, max_nq, d_nq, counts); count_launches(1);
 }
 
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,

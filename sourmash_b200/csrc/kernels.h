@@ -36,6 +36,19 @@ void launch_pairwise_tile(const PairwisePlan& plan, const uint64_t* hA, const ui
                           int nA, const uint64_t* hB, const uint64_t* offB, int nB, uint32_t* out,
                           size_t ldo, bool symmetric, TileShard tiles, cudaStream_t s);
 
+// Inverted index over a resident set (db_index.cuh): hash -> rows.  db_index_build leaves *out null
+// when the set is empty or has more than 2^31 - 1 elements.  launch_index_count adds, for every query
+// hash, 1 to the counter of every row that holds it (counters zeroed by the caller): the same counts
+// as the one-vs-many passes, for work proportional to the query and its matches.
+struct DbIndex;
+cudaError_t db_index_build(const uint64_t* h, const uint64_t* off, int n, uint64_t n_elements, uint64_t max_key,
+                           DbIndex** out, cudaStream_t s);
+void db_index_destroy(DbIndex* ix);
+uint64_t db_index_n_keys(const DbIndex* ix);
+void launch_index_count(const DbIndex* ix, const uint64_t* q, uint64_t nq, uint32_t* counts, cudaStream_t s);
+void launch_index_count_n(const DbIndex* ix, const uint64_t* q, const uint32_t* d_nq, uint64_t max_nq, uint32_t* counts,
+                          cudaStream_t s);
+
 // Experimental range-partitioned one-vs-many pass (SMB_SEARCH_LAYOUT=ranges, off by default;
 // range_search.cuh): the key space is cut into P equal ranges, CTA p keeps the query bitmap of its
 // range in shared memory and streams the rows' slices of that range.  `bounds` ([P + 1][n] u32) is

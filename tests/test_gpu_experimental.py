@@ -1,0 +1,135 @@
+"""GPU parity tests of the paths that are in the tree behind switches and have not run on a GPU yet
+(DESIGN.md section 10): the stripe layout of the inverted join, the range-partitioned one-vs-many
+pass and the inverted index of a resident set.  Their logic is covered on the CPU by
+tests/test_host_emulation.py; these tests are the first thing to run on the device
+(scripts/gpu_next_variants.sh sets SMB_TEST_EXPERIMENTAL=1) and are skipped otherwise, so that an
+unvalidated experimental path can never turn the default suite red."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_sketches
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("SMB_TEST_EXPERIMENTAL"),
+                                 reason="experimental paths: set SMB_TEST_EXPERIMENTAL=1 (scripts/gpu_next_variants.sh)")]
+
+
+@pytest.fixture(scope="module")
+def B():
+    from sourmash_b200 import batch
+    return batch
+
+
+def _edge_rows():
+    rng = np.random.Generator(np.random.PCG64(77))
+    big = np.uint64(2**64 - 1)
+    rows = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, big - 1, big], np.uint64),
+            np.array([big], np.uint64), np.arange(1, 300, dtype=np.uint64), np.arange(1, 300, dtype=np.uint64),
+            np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
+    rows += [np.array([7, 1000 + i], dtype=np.uint64) for i in range(100)]      # one hash shared by 100 rows
+    return rows
+
+
+@pytest.mark.parametrize("n,fam", [(96, 6), (700, 9), (1500, 12)])
+def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam):
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", "stripe")
+    h, off = synth_sketches(n, mean=400, sd=80, lo=0, hi=800, n_families=fam, pool=500, seed=n)
+    want = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    assert np.array_equal(B.compare_jaccard(sset), want)                     # host path: row blocks + copies
+    import torch
+    d_out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    B.compare_jaccard_device(sset, d_out.data_ptr())                         # resident path: one launch
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    lo, hi = n // 3, n // 3 + 37
+    d_rows = torch.empty((hi - lo, n), dtype=torch.float64, device="cuda")
+    B.compare_jaccard_rows_device(sset, lo, hi, d_rows.data_ptr())          # a block of rows (multi-GPU unit)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_rows.cpu().numpy(), want[lo:hi])
+
+
+def test_stripe_layout_edge_rows(B, monkeypatch):
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", "stripe")
+    rows = _edge_rows() * 12                                                  # > 1024 rows: the host path takes the join
+    h, off = orc.to_csr(rows)
+    assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(h, off)), orc.compare_all_pairs(h, off, nthreads=8))
+
+
+def test_rows_device_without_stripe_equals_full_matrix(B):
+    "smb_compare_jaccard_rows_dev on the default path (whole count matrix, then the rows)."
+    import torch
+    h, off = synth_sketches(300, mean=300, sd=60, lo=0, hi=600, n_families=5, pool=400, seed=4)
+    want = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    d_rows = torch.empty((50, 300), dtype=torch.float64, device="cuda")
+    B.compare_jaccard_rows_device(sset, 120, 170, d_rows.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_rows.cpu().numpy(), want[120:170])
+
+
+def _big_query(rows, seed=4000, extra=400_000):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=extra, dtype=np.uint64)] + rows[:40]))
+
+
+def test_range_search_matches_oracle(B, monkeypatch):
+    monkeypatch.setenv("SMB_SEARCH_LAYOUT", "ranges")
+    h, off = synth_sketches(3000, mean=2000, sd=200, lo=0, hi=3000, n_families=5, pool=2500, seed=3)
+    rows = rows_of(h, off)
+    db = B.SketchSet.from_host(h, off)
+    q = _big_query(rows)                                                      # too large for shared memory: global path
+    want = orc.one_vs_many(q, h, off).astype(np.uint32)
+    assert np.array_equal(B.one_vs_many(q, db), want)
+    assert np.array_equal(B.one_vs_many(q, db), want)                        # second call: cached bounds
+    q2 = np.unique(np.concatenate([q[::3], np.array([MAX_HASH_1000 + 5, 2**63, 2**64 - 1], dtype=np.uint64)]))
+    assert np.array_equal(B.one_vs_many(q2, db), orc.one_vs_many(q2, h, off).astype(np.uint32))
+    eh, eoff = orc.to_csr(_edge_rows())
+    edb = B.SketchSet.from_host(eh, eoff)
+    rng = np.random.Generator(np.random.PCG64(5))
+    qe = np.unique(np.concatenate([rng.integers(0, 2**64 - 1, size=300_000, dtype=np.uint64), eh]))
+    assert np.array_equal(B.one_vs_many(qe, edb), orc.one_vs_many(qe, eh, eoff).astype(np.uint32))
+
+
+def test_db_index_search_and_gather(B):
+    from tests.test_gpu_kernels import _gather_oracle
+    h, off = synth_sketches(3000, mean=2000, sd=200, lo=0, hi=3000, n_families=5, pool=2500, seed=3)
+    rows = rows_of(h, off)
+    db = B.SketchSet.from_host(h, off)
+    queries = [rows[7], _big_query(rows), np.zeros(0, np.uint64), np.array([1, 2**64 - 1], dtype=np.uint64)]
+    plain = [B.one_vs_many(q, db) for q in queries]
+    g_query = np.unique(np.concatenate([rows[4], rows[9][:1500], rows[25][500:2500], rows[30][::2]]))
+    ids0, sizes0 = B.gather(g_query, db, threshold=5)
+    n_keys = db.build_index()
+    assert db.has_index and n_keys == len(np.unique(h)) and db.build_index() == n_keys
+    for q, p in zip(queries, plain):
+        got = B.one_vs_many(q, db)
+        assert np.array_equal(got, p)
+        if len(q):
+            assert np.array_equal(got, orc.one_vs_many(q, h, off).astype(np.uint32))
+    ids1, sizes1 = B.gather(g_query, db, threshold=5)
+    assert ids1.tolist() == ids0.tolist() and sizes1.tolist() == sizes0.tolist()
+    assert list(zip(ids1.tolist(), sizes1.tolist())) == _gather_oracle(g_query, rows, threshold=5)
+    sess = B.GatherSession(g_query, db, min_count=5)                          # step API on the indexed set
+    picked = []
+    while True:
+        cnt, row = sess.peek()
+        if cnt < 5:
+            break
+        isect = sess.intersect(row)
+        picked.append((row, len(isect)))
+        if sess.apply(isect) == 0:
+            break
+    assert picked == list(zip(ids0.tolist(), sizes0.tolist()))
+    db.drop_index()
+    assert not db.has_index and np.array_equal(B.one_vs_many(queries[1], db), plain[1])
+    eh, eoff = orc.to_csr(_edge_rows())
+    edb = B.SketchSet.from_host(eh, eoff)
+    edb.build_index()
+    for q in (np.array([7], dtype=np.uint64), np.unique(eh), np.array([0, 2**64 - 1], dtype=np.uint64)):
+        assert np.array_equal(B.one_vs_many(q, edb), orc.one_vs_many(q, eh, eoff).astype(np.uint32))

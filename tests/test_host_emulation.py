@@ -329,3 +329,47 @@ def test_range_search_matches_oracle(ranges_emul):
         for P, max_bits in ((148, 1 << 20), (7, 64), (2, 1 << 20), (148, 1), (33, 4096)):
             got, _ = ranges_emul(query, rows, P, max_bits)
             assert np.array_equal(got, want), (len(rows), len(query), P, max_bits)
+
+
+# ---------------------------------------------------------------------------------------------
+# inverted index over a resident set (csrc/db_index.cuh): smb_sketchset_build_index
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def index_emul():
+    exe = os.path.join(tempfile.gettempdir(), "smb_index_emul")
+    src = os.path.join(HERE, "host_emul", "index_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(query, rows):
+        hashes, offsets = orc.to_csr(rows)
+        with tempfile.TemporaryDirectory() as td:
+            fq, fh, fo, fc = (os.path.join(td, x) for x in ("q", "h", "o", "c"))
+            np.asarray(query, dtype=np.uint64).tofile(fq); hashes.tofile(fh); offsets.tofile(fo)
+            subprocess.check_call([exe, fq, fh, fo, fc])
+            return np.fromfile(fc, dtype=np.uint32)
+    return run
+
+
+def test_db_index_counts_match_oracle(index_emul):
+    """Distinct keys / offsets / rows / directory of the inverted index and the per-query-hash lookup:
+    the counts equal the oracle's one-vs-many (so search, prefetch and every gather round do)."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(6)
+    mx = orc.max_hash_for_scaled(1000)
+    h, off = synth_sketches(80, mean=400, sd=80, lo=50, hi=800, n_families=5, pool=500, seed=43)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(80)]
+    big = np.uint64(2**64 - 1)
+    edge = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, big - 1, big], np.uint64),
+            np.array([big], np.uint64), np.arange(1, 300, dtype=np.uint64), np.arange(1, 300, dtype=np.uint64),
+            np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
+    wide = [np.array([7, 1000 + i], dtype=np.uint64) for i in range(100)]                 # one hash in 100 rows
+    queries = [np.unique(np.concatenate([fam[3], fam[17][:200], rng.integers(1, mx, size=3000, dtype=np.uint64),
+                                         np.array([mx + 5, 2**63, 2**64 - 1], dtype=np.uint64)])),
+               np.unique(np.concatenate([edge[2], edge[6][::3], np.array([1, 299, 300, 2**40], dtype=np.uint64)])),
+               np.array([7], dtype=np.uint64), np.zeros(0, np.uint64), np.array([0, big], dtype=np.uint64)]
+    for rows in (fam, edge, wide, [edge[0]], [edge[0], edge[0]]):
+        hh, oo = orc.to_csr(rows)
+        for query in queries:
+            want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32) if len(hh) \
+                else np.zeros(len(rows), np.uint32)
+            assert np.array_equal(index_emul(query, rows), want), (len(rows), len(query))
