@@ -105,6 +105,12 @@ class LinearIndex:
                             for k, v in groups.items()}
         return self._device
 
+    def build_device_index(self):
+        """Build the inverted index (hash -> rows) of every resident group of this collection
+        (batch.SketchSet.build_index): later search / prefetch / gather calls at the collection's own
+        scaled probe it instead of streaming the rows.  Returns the number of distinct hashes."""
+        return sum(sset.build_index() for _, sset in self._groups().values() if len(sset))
+
     # -- the 1 x N scoring loop ------------------------------------------------------------
     def find(self, search_fn, query, **kwargs):
         """Yield IndexSearchResult for subjects passing search_fn, in index order

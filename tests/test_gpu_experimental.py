@@ -133,3 +133,23 @@ def test_db_index_search_and_gather(B):
     edb.build_index()
     for q in (np.array([7], dtype=np.uint64), np.unique(eh), np.array([0, 2**64 - 1], dtype=np.uint64)):
         assert np.array_equal(B.one_vs_many(q, edb), orc.one_vs_many(q, eh, eoff).astype(np.uint32))
+
+
+def test_db_index_behind_linear_index(B):
+    "LinearIndex.build_device_index: search / prefetch / gather results unchanged."
+    import glob
+    import sourmash_b200 as smb
+    from sourmash_b200.index import LinearIndex, gather
+    from tests.conftest import GOLDEN
+    d = os.path.join(GOLDEN, "gather")
+    query = smb.signature.load_one_signature_from_json(os.path.join(d, "combined.sig"), ksize=21)
+    sigs = [smb.signature.load_one_signature_from_json(p, ksize=21) for p in sorted(glob.glob(os.path.join(d, "GCF*.sig")))]
+    plain, indexed = LinearIndex(sigs), LinearIndex(sigs)
+    assert indexed.build_device_index() == len(set(h for s in sigs for h in s.minhash.hashes))
+
+    def view(results):
+        return [(r.score, r.signature.md5sum()) for r in results]
+    assert view(indexed.search(query, threshold=0.0, do_containment=True)) == view(plain.search(query, threshold=0.0, do_containment=True))
+    assert view(indexed.prefetch(query, 50000)) == view(plain.prefetch(query, 50000))
+    assert [(g.match.md5sum(), g.intersect_size) for g in gather(query, indexed)] == \
+        [(g.match.md5sum(), g.intersect_size) for g in gather(query, plain)]
