@@ -486,7 +486,11 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "note": "integer-issue bound by construction (~150 int ops per k-mer vs 1 B): "
                              "HBM fraction is expected to be small; roofline.issue is the bound that applies"},
     }
-    wipk = ncu_traffic("hash_kmers_kernel_warp_instr_per_kmer")
+    fused = os.environ.get("SMB_SKETCH_FUSED") == "1"      # experimental one-pass kernel, A/B runs only
+    if fused:
+        res["roofline"]["kernel"] = "hash_kmers_fused_kernel (1 launch, k=21,31,51)"
+        res["roofline"]["traffic"] = None
+    wipk = None if fused else ncu_traffic("hash_kmers_kernel_warp_instr_per_kmer")
     if wipk:
         # the bound that applies: warp instructions issued (ncu count of the same three launches, per k-mer)
         # against 4 issue slots per SM per clock at the SM clock sampled during the timed region

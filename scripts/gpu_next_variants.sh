@@ -5,6 +5,7 @@
 #                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh)
 #   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
 #   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
+#   SMB_SKETCH_FUSED=1       sketch: k = 21, 31, 51 in one pass over the bases (csrc/kmer_roll.cuh)
 #   SketchSet.build_index()  inverted index of a resident set: search / gather counts for work proportional
 #                            to the query (csrc/db_index.cuh); bench.py --workload search|gather --index
 #   SMB_SEARCH_LAYOUT=ranges one CTA per key range, query bitmap of the range in shared memory, for the
@@ -34,6 +35,12 @@ for L in plain stripe cluster; do
       > gpurun_out/bench_join_${L}_${TAG}.json 2> /dev/null
   python -c "
 import json; d=json.load(open('gpurun_out/bench_join_${L}_${TAG}.json')); print('${L}: ms %.2f kernel_ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step']))"
+done
+for F in 0 1; do
+  SMB_SKETCH_FUSED=$F timeout 300 python bench.py --workload sketch --steps 5 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/bench_sketch_fused${F}_${TAG}.json 2> /dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_sketch_fused${F}_${TAG}.json')); d=d.get('sketch', d); print('sketch fused=${F}: ms %.2f kernel_ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step']))"
 done
 # 2b. row-block passes for the end-to-end path (SMB_COMPARE_PASSES): correctness through the host API, then e2e
 SMB_COMPARE_PASSES=8 timeout 300 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_kernels.py -q -m gpu -k "compare or join" 2>&1 | tail -3

@@ -412,6 +412,28 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
             smb::launch_hash_kmers_range(L, P.ksizes[j], (int)j, r0, r1, g0, g1, s);
     };
 
+    // experimental: the default dna parameter string k=21,31,51 hashed in one pass (SMB_SKETCH_FUSED)
+    int fused_rows[3] = {-1, -1, -1};
+    bool fused = smb::sketch_fused_enabled() && !P.aa_mode() && nk == 3;
+    if (fused) {
+        for (size_t j = 0; j < nk; ++j) {
+            const int slot = P.ksizes[j] == 21 ? 0 : P.ksizes[j] == 31 ? 1 : P.ksizes[j] == 51 ? 2 : -1;
+            if (slot >= 0) fused_rows[slot] = (int)j;
+        }
+        fused = fused_rows[0] >= 0 && fused_rows[1] >= 0 && fused_rows[2] >= 0;
+    }
+    auto launch_all_k = [&](smb::HashLaunch& L, uint32_t r0, uint32_t r1, uint32_t g0, uint32_t g1) {
+        if (fused) {
+            const uint64_t thr3[3] = {kthr[fused_rows[0]], kthr[fused_rows[1]], kthr[fused_rows[2]]};
+            smb::launch_hash_kmers_fused_range(L, fused_rows, thr3, r0, r1, s);
+            return;
+        }
+        for (size_t j = 0; j < nk; ++j) {
+            L.max_hash = kthr[j];
+            launch_k(L, j, r0, r1, g0, g1);
+        }
+    };
+
     bool uploaded = false;
     for (int attempt = 0; attempt < 4; ++attempt) {
         for (size_t r = 0; r < n_rows; ++r) cand_off[r + 1] = cand_off[r] + cap[r];
@@ -450,18 +472,12 @@ std::unique_ptr<SmbSketchSet> sketch_streams(const StreamList& in, const SketchP
                 cudaEvent_t ev = pool_event();
                 CK(cudaEventRecord(ev, cs));
                 CK(cudaStreamWaitEvent(s, ev, 0));
-                for (size_t j = 0; j < nk; ++j) {
-                    L.max_hash = kthr[j];
-                    launch_k(L, j, tile_r[g0], tile_r[g1], tile_g[g0], tile_g[g1]);
-                }
+                launch_all_k(L, tile_r[g0], tile_r[g1], tile_g[g0], tile_g[g1]);
                 g0 = g1;
             }
             uploaded = true;
         } else {
-            for (size_t j = 0; j < nk; ++j) {
-                L.max_hash = kthr[j];
-                launch_k(L, j, 0, tile_r[ns], 0, tile_g[ns]);
-            }
+            launch_all_k(L, 0, tile_r[ns], 0, tile_g[ns]);
         }
         if (t_profiling) t_timer_hash.end(s);
         CK(cudaGetLastError());

@@ -179,6 +179,11 @@ void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cud
 // same, restricted to a range of tiles (a group of streams) -- lets uploads and hashing overlap
 void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index, uint32_t tile_lo_r,
                              uint32_t tile_hi_r, uint32_t tile_lo_g, uint32_t tile_hi_g, cudaStream_t s);
+// Experimental (SMB_SKETCH_FUSED, off by default): k = 21, 31 and 51 in one pass over the bases (one rolling
+// 51-state, the shorter k-mers as prefixes); row_index[i] / max_hash[i] belong to k = 21, 31, 51
+bool sketch_fused_enabled();
+void launch_hash_kmers_fused_range(const HashLaunch& L, const int row_index[3], const uint64_t max_hash[3],
+                                   uint32_t tile_lo, uint32_t tile_hi, cudaStream_t s);
 // per-window hashes of stream 0 in order; 0 marks an invalid window (seq_to_hashes)
 void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s);
 // protein-family sketches (aa_kmers.cuh): windows of kaa residues, read as they are

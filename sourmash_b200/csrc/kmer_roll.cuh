@@ -77,8 +77,8 @@ struct Roll {
         run = 0;
     }
 
-    // push one raw input byte
-    __host__ __device__ __forceinline__ void push(u32 x) {
+    // push one raw input byte; returns whether it is a valid base
+    __host__ __device__ __forceinline__ bool push(u32 x) {
         const u32 up = x & 0xDFu;                        // to_ascii_uppercase for letters
         const u32 c2 = (up >> 1) & 3u;                   // A0 C1 T2 G3
         const u32 expect = pick_byte(0x47544341u, c2);   // "ACTG"[c2]
@@ -106,6 +106,7 @@ struct Roll {
         for (int i = 0; i < NC - 1; ++i) cr[i] = fshr(cr[i], cr[i + 1], 2);
         cr[NC - 1] >>= 2;
         cr[(2 * K - 2) / 32] |= (code ^ 3u) << ((2 * K - 2) % 32);
+        return ok;
     }
 
     __host__ __device__ __forceinline__ bool fwd_is_canonical() const {
@@ -213,6 +214,74 @@ __host__ __device__ __forceinline__ void hash_thread_windows(const u8* __restric
         for (int b = 0; b < 4; ++b, ++w) {
             st.push((word >> (8 * b)) & 0xffu);
             emit(w, st.run >= (u32)K, st.hash(seed));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k = 21, 31 and 51 in one pass (experimental, SMB_SKETCH_FUSED; sketch_kernels.cu).  The three
+// k-mers that START at the same base are prefixes of the 51-mer, so one rolling 51-state serves
+// all of them:
+//   forward   bytes 0..k-1 of fw51: whole words plus a masked last word (21 = 5 x 4 + 1, 31 = 7 x 4 + 3)
+//   revcomp   the last k bytes of rc51: bytes 20..50 for k = 31 (word aligned), bytes 30..50 for
+//             k = 21 (a 16-bit funnel shift per word)
+//   order     2-bit codes: forward = the top 2k bits of cf51, revcomp = the low 2k bits of cr51
+//   validity  a 64-bit shift register of "valid base" flags; the k-prefix needs bits 50 .. 51-k
+// emit(w, which, valid, h): which = 0, 1, 2 for k = 21, 31, 51; windows in the order of the start w.
+// ---------------------------------------------------------------------------------------
+template <class Emit>
+__host__ __device__ __forceinline__ void hash_thread_windows_fused(const u8* __restrict__ base, u64 Lp, u32 lead,
+                                                                   u64 w0, int W, u64 seed, Emit&& emit) {
+    constexpr int K = 51;
+    const u64 nwin = Lp >= 21 ? Lp - 21 + 1 : 0;              // starts that have at least a 21-mer
+    if (w0 >= nwin) return;
+    constexpr int Q = (K - 1) / 4, R = (K - 1) % 4;
+    WordStream ws(base, Lp, lead, w0);
+    Roll<K> st;
+    st.init();
+    u64 vmask = 0;                                            // bit i: the base i positions before the newest is valid
+#pragma unroll 1
+    for (int q = 0; q < Q; ++q) {
+        const u32 word = ws.next();
+#pragma unroll
+        for (int b = 0; b < 4; ++b) vmask = (vmask << 1) | (st.push((word >> (8 * b)) & 0xffu) ? 1ull : 0ull);
+    }
+    u32 cur = ws.next();
+#pragma unroll
+    for (int b = 0; b < R; ++b) vmask = (vmask << 1) | (st.push((cur >> (8 * b)) & 0xffu) ? 1ull : 0ull);
+    constexpr u64 M51 = (1ull << 51) - 1, M31 = M51 & ~((1ull << 20) - 1), M21 = M51 & ~((1ull << 30) - 1);
+    u64 w = w0;
+#pragma unroll 1
+    for (int q = 0; q < (W >> 2); ++q) {
+        const u32 nxt = ws.next();
+        const u32 word = R ? fshr(cur, nxt, 8 * R) : cur;
+        cur = nxt;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b, ++w) {
+            vmask = (vmask << 1) | (st.push((word >> (8 * b)) & 0xffu) ? 1ull : 0ull);
+            // k = 21
+            {
+                const u32 f0 = fshr(st.cf[1], st.cf[2], 28), f1 = fshr(st.cf[2], st.cf[3], 28);     // cf51 >> 60
+                const u32 r0 = st.cr[0], r1 = st.cr[1] & 0x3ffu;                                   // low 42 bits of cr51
+                const bool fwd = f1 != r1 ? f1 < r1 : f0 <= r0;
+                u32 sel[6];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) sel[i] = fwd ? st.fw[i] : fshr(st.rc[7 + i], st.rc[8 + i], 16);
+                sel[5] = fwd ? (st.fw[5] & 0xffu) : (st.rc[12] >> 16);
+                emit(w, 0, (vmask & M21) == M21, murmur_words<21>(sel, seed));
+            }
+            // k = 31
+            {
+                const u32 f0 = fshr(st.cf[1], st.cf[2], 8), f1 = fshr(st.cf[2], st.cf[3], 8);       // cf51 >> 40
+                const u32 r0 = st.cr[0], r1 = st.cr[1] & 0x3fffffffu;                              // low 62 bits of cr51
+                const bool fwd = f1 != r1 ? f1 < r1 : f0 <= r0;
+                u32 sel[8];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sel[i] = fwd ? st.fw[i] : st.rc[5 + i];
+                sel[7] = fwd ? (st.fw[7] & 0xffffffu) : st.rc[12];
+                emit(w, 1, (vmask & M31) == M31, murmur_words<31>(sel, seed));
+            }
+            emit(w, 2, (vmask & M51) == M51, st.hash(seed));
         }
     }
 }

@@ -15,6 +15,8 @@
 // bases are read with 16-byte vector loads; survivors (h <= max_hash, h != 0) are staged in a
 // shared-memory buffer and flushed with one atomicAdd per CTA.  A block-level bitonic sort +
 // unique materialises each sketch row.
+#include <stdlib.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -100,6 +102,73 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
     for (u32 i = tid; i < n; i += HASH_THREADS) {
         u64 g = (u64)s_base + i;
         if (g < capr) a.cand[off + g] = s_buf[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Experimental (SMB_SKETCH_FUSED, off by default; kmer_roll.cuh hash_thread_windows_fused): k = 21, 31
+// and 51 of `sourmash sketch dna`'s default parameter string in ONE pass over the bases -- one
+// rolling 51-state, the shorter k-mers read off it as prefixes -- instead of three launches that each
+// decode and roll the same bases.  Logic checked on the CPU by
+// tests/test_host_emulation.py::test_roll_fused_21_31_51_matches_oracle; not measured yet.
+// ---------------------------------------------------------------------------------------
+struct FusedArgs {
+    HashArgs a;                   // row_index / max_hash unused
+    int row_index[3];             // output row of k = 21, 31, 51 inside a sketch's group of rows
+    u64 max_hash[3];
+};
+
+__global__ void __launch_bounds__(HASH_THREADS) hash_kmers_fused_kernel(FusedArgs f) {
+    __shared__ u64 s_buf[3][STAGE_CAP];
+    __shared__ u32 s_cnt[3];
+    __shared__ u32 s_base[3];
+    __shared__ int s_stream;
+    const HashArgs& a = f.a;
+    const int tid = threadIdx.x;
+    if (tid < 3) s_cnt[tid] = 0;
+    if (tid == 0) s_stream = find_stream(a.tile_start, a.n_streams, blockIdx.x + a.tile_base);
+    __syncthreads();
+    const int stream = s_stream;
+    const u64 s0 = a.stream_off[stream];
+    const u64 b0 = s0 & ~15ull;
+    const u32 lead = (u32)(s0 - b0);
+    const u64 Lp = (u64)lead + a.stream_len[stream];
+    const u8* __restrict__ base = a.bases + b0;
+    const u64 tile = blockIdx.x + a.tile_base - a.tile_start[stream];
+    const u64 w0 = (tile * HASH_THREADS + tid) * (u64)a.W;
+    const int sk = a.stream_row ? (int)a.stream_row[stream] : stream;
+    const int row0 = sk * a.row_stride;
+
+    hash_thread_windows_fused(base, Lp, lead, w0, a.W, a.seed, [&](u64, int which, bool valid, u64 h) {
+        if (valid && h != 0ull && h <= f.max_hash[which]) {
+            const u32 slot = atomicAdd(&s_cnt[which], 1u);
+            if (slot < STAGE_CAP) {
+                s_buf[which][slot] = h;
+            } else {                                  // staging full: append directly
+                const int row = row0 + f.row_index[which];
+                const u32 g = atomicAdd(&a.cand_cnt[row], 1u);
+                const u64 capr = a.cand_off[row + 1] - a.cand_off[row];
+                if (g < capr) a.cand[a.cand_off[row] + g] = h;
+            }
+        }
+    });
+    __syncthreads();
+    if (tid < 3) {
+        const u32 n = min(s_cnt[tid], (u32)STAGE_CAP);
+        s_cnt[tid] = n;
+        s_base[tid] = n ? atomicAdd(&a.cand_cnt[row0 + f.row_index[tid]], n) : 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+        const u32 n = s_cnt[which];
+        const int row = row0 + f.row_index[which];
+        const u64 off = a.cand_off[row];
+        const u64 capr = a.cand_off[row + 1] - off;
+        for (u32 i = tid; i < n; i += HASH_THREADS) {
+            const u64 g = (u64)s_base[which] + i;
+            if (g < capr) a.cand[off + g] = s_buf[which][i];
+        }
     }
 }
 
@@ -213,6 +282,22 @@ void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index,
     HashArgs a = make_hash_args(L, rolled, lo);
     a.row_index = row_index;
     launch_hash_one_k<false>(a, ksize, rolled, hi - lo, s);
+}
+
+bool sketch_fused_enabled() {
+    const char* e = getenv("SMB_SKETCH_FUSED");
+    return e && e[0] == '1';
+}
+// k = 21, 31, 51 in one launch over tiles [tile_lo, tile_hi) of the rolled tiling; row_index[i] / max_hash[i]
+// belong to k = 21, 31, 51 in this order
+void launch_hash_kmers_fused_range(const HashLaunch& L, const int row_index[3], const uint64_t max_hash[3],
+                                   uint32_t tile_lo, uint32_t tile_hi, cudaStream_t s) {
+    if (tile_hi <= tile_lo) return;
+    FusedArgs f{};
+    f.a = make_hash_args(L, true, tile_lo);
+    for (int i = 0; i < 3; ++i) { f.row_index[i] = row_index[i]; f.max_hash[i] = max_hash[i]; }
+    hash_kmers_fused_kernel<<<tile_hi - tile_lo, HASH_THREADS, 0, s>>>(f);
+    count_launches(1);
 }
 
 void launch_window_hashes(const HashLaunch& L, uint32_t ksize, uint64_t* raw_out, cudaStream_t s) {

@@ -153,3 +153,35 @@ def test_db_index_behind_linear_index(B):
     assert view(indexed.prefetch(query, 50000)) == view(plain.prefetch(query, 50000))
     assert [(g.match.md5sum(), g.intersect_size) for g in gather(query, indexed)] == \
         [(g.match.md5sum(), g.intersect_size) for g in gather(query, plain)]
+
+
+def test_fused_sketch_kernel_matches_default_and_oracle(B, monkeypatch):
+    "SMB_SKETCH_FUSED: k = 21, 31, 51 in one pass == three passes == the oracle (scaled, num, abundance)."
+    from sourmash_b200.synth import synth_genome
+    genomes = [synth_genome(60_000 + 1000 * i, seed=10 + i, n_every=97 if i == 1 else 0) for i in range(4)]
+    genomes.append(synth_genome(40, seed=3))                               # shorter than 51: only k = 21 and 31
+    genomes.append(synth_genome(20, seed=4))                               # shorter than every k
+    genomes[2][5000:5400] = np.frombuffer(bytes(genomes[2][5000:5400]).lower(), dtype=np.uint8)
+    genomes[3][777] = ord("R")
+    seqs = np.concatenate(genomes)
+    offs = np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
+    for ks in ([21, 31, 51], [51, 21, 31]):
+        for kw in (dict(scaled=100), dict(scaled=1), dict(num=500), dict(scaled=50, track_abundance=True)):
+            monkeypatch.delenv("SMB_SKETCH_FUSED", raising=False)
+            plain, nk0 = B.sketch_sequences(seqs, offs, ks, **kw)
+            monkeypatch.setenv("SMB_SKETCH_FUSED", "1")
+            fused, nk1 = B.sketch_sequences(seqs, offs, ks, **kw)
+            assert nk0 == nk1
+            a, b = plain.rows(), fused.rows()
+            assert len(a) == len(b) == len(genomes) * 3
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (ks, kw)
+            if kw.get("track_abundance"):
+                assert np.array_equal(plain.to_host(with_abunds=True)[2], fused.to_host(with_abunds=True)[2])
+    monkeypatch.setenv("SMB_SKETCH_FUSED", "1")
+    sset, _ = B.sketch_sequences(seqs, offs, [21, 31, 51], scaled=100)
+    rows = sset.rows()
+    mx = orc.max_hash_for_scaled(100)
+    for gi, g in enumerate(genomes):
+        for ki, k in enumerate((21, 31, 51)):
+            assert np.array_equal(rows[gi * 3 + ki], orc.sketch_scaled(g, k, mx)), (gi, k)

@@ -44,6 +44,28 @@ def test_roll_matches_oracle(emul, k):
         assert np.array_equal(got, want), (k, W, lead)
 
 
+def test_roll_fused_21_31_51_matches_oracle(emul):
+    """The fused pass (one rolling 51-state, the 21- and 31-mers as prefixes; experimental
+    SMB_SKETCH_FUSED): all three hash streams equal the oracle, invalid bases and stream ends included."""
+    for n, seed in ((5000, 7), (51, 8), (52, 9), (50, 10), (31, 11), (30, 12), (21, 13), (20, 14), (137, 15)):
+        g = synth_genome(max(n, 64), seed=seed, n_every=61)[:n]
+        if n >= 200:
+            g[100:160] = np.frombuffer(bytes(g[100:160]).lower(), dtype=np.uint8)
+            g[1000] = ord("R"); g[1001] = 0; g[1050] = ord("n"); g[1071] = ord("N"); g[-25] = ord("N")
+        want = []
+        for k in (21, 31, 51):
+            if n >= k:
+                hs, err = orc.seq_to_hashes(bytes(g), k, force=True, keep_zeros=True)
+                assert err is None
+                want.append(np.asarray(hs, dtype=np.uint64))
+            else:
+                want.append(np.zeros(0, np.uint64))
+        want = np.concatenate(want)
+        for W, lead in ((16, 0), (64, 5), (128, 15)):
+            got = emul(g, 0, W, lead)
+            assert np.array_equal(got, want), (n, W, lead)
+
+
 def test_roll_short_and_exact_lengths(emul):
     for k in (21, 31):
         for n in (k - 1, k, k + 1, 15, 16, 17, 47, 48, 49):
