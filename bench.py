@@ -386,9 +386,10 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                  "definition, 8*(|A|+|B|) per pair + 4 B out" % (plan["est_increments"], plan["est_elements"]))
         tkey = "inverted_join"
         layout = os.environ.get("SMB_JOIN_LAYOUT", "")
-        if layout in ("stripe", "cluster"):                # experimental layouts, A/B runs only
+        if layout in ("stripe", "stripe_upper", "cluster"):   # experimental layouts, A/B runs only
             plan = dict(plan, layout=layout)
             kname = {"stripe": "inverted join, stripe layout (cub::DeviceRadixSort + stripe_tag_kernel + join_stripe_kernel)",
+                     "stripe_upper": "inverted join, stripe layout, upper triangle + stripe_mirror_kernel",
                      "cluster": "inverted join, cluster layout (join_count_warp_kernel)"}[layout]
             tkey = "inverted_join_" + layout
     else:

@@ -2,7 +2,8 @@
 # Next round, first GPU call: validate and measure the experimental layouts of the inverted join that
 # are in the tree behind switches (default off; logic covered on the CPU by tests/test_host_emulation.py):
 #   SMB_JOIN_LAYOUT=stripe   CTAs own complete result rows in shared memory, no global atomics, fused
-#                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh)
+#                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh);
+#                            stripe_upper: only (i, j > i) counted, the rest mirrored tile by tile
 #   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
 #   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
 #   SMB_SKETCH_FUSED=1       sketch: k = 21, 31, 51 in one pass over the bases (csrc/kmer_roll.cuh)
@@ -30,7 +31,7 @@ m = B.compare_jaccard(B.SketchSet.from_host(h, off))
 assert np.array_equal(m, orc.compare_all_pairs(h, off, nthreads=8)); print('stripe 1500x1500 identical')
 " 2>&1 | tail -3
 # 2. A/B on the 10 000-sketch matrix
-for L in plain stripe cluster; do
+for L in plain stripe stripe_upper cluster; do
   SMB_JOIN_LAYOUT=$L timeout 200 python bench.py --workload compare --steps 5 --warmup 3 --no-cpu-baseline \
       > gpurun_out/bench_join_${L}_${TAG}.json 2> /dev/null
   python -c "

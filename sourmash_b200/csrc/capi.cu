@@ -1868,6 +1868,7 @@ static bool compare_jaccard_stripe(const SmbSketchSet* set, uint64_t max_key, do
     std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
     if (!host_out) {
         CK(smb::join_stripe_rows(js, set->d_off, 0, (int)n, d_out, s));
+        CK(smb::join_stripe_mirror(js, 0, (int)n, d_out, s));
         if (t_profiling) t_timer_pairwise.end(s);
         return true;
     }
@@ -1876,6 +1877,7 @@ static bool compare_jaccard_stripe(const SmbSketchSet* set, uint64_t max_key, do
     for (size_t r0 = 0; r0 < n; r0 += per) {
         const size_t r1 = std::min(n, r0 + per);
         CK(smb::join_stripe_rows(js, set->d_off, (int)r0, (int)r1, d_out + r0 * n, s));
+        CK(smb::join_stripe_mirror(js, (int)r0, (int)r1, d_out, s));
         cudaEvent_t ev = pool_event();
         CK(cudaEventRecord(ev, s));
         CK(cudaStreamWaitEvent(cs, ev, 0));
@@ -1919,6 +1921,7 @@ void smb_compare_jaccard_rows_dev(const SmbSketchSet* set, uint64_t row_begin, u
             CK(smb::join_stripe_create(set->d_hashes, set->d_off, (int)n, set->total(), mk, &js, s));
             if (js) {
                 std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
+                smb::join_stripe_two_directions(js);           // a block of rows on its own has no rows above to mirror
                 CK(smb::join_stripe_rows(js, set->d_off, (int)row_begin, (int)row_end, d_out, s));
                 if (t_profiling) t_timer_pairwise.end(s);
                 return;

@@ -1500,6 +1500,7 @@ struct StripeArgs {
     u64 T;
     int n, rows_per_block, row_begin, row_end;
     double* out;             // row `row_begin` first, leading dimension n
+    int upper_only;          // 1: count and write only cells (i, j >= i); stripe_mirror_kernel fills the rest
 };
 
 // One CTA = rows [r0, r1) of the result.  Warps take 32 consecutive elements of the block at a time;
@@ -1528,7 +1529,8 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
             m = __ballot_sync(0xffffffffu, st);
             if (stripe_fwd_active(m, lane)) atomicAdd(row + (tf & ~STRIPE_HEAD), 1u);
         }
-        if (self & STRIPE_HEAD) return;                   // q opens its group: nothing in front of it
+        if (a.upper_only || (self & STRIPE_HEAD)) return; // (rows ascend inside a group: the elements in front of q
+                                                          //  are the columns j < i) / q opens its group
         m = __ballot_sync(0xffffffffu, sb);
         if (stripe_bwd_active(m, lane, vb)) atomicAdd(row + (tb & ~STRIPE_HEAD), 1u);
         for (u32 it = 1; stripe_continue(m); ++it) {
@@ -1570,9 +1572,27 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     for (u32 i = threadIdx.x; i < (u32)rows * n; i += blockDim.x) {
         const u32 al = i / n, j = i - al * n;
         const int row = r0 + (int)al;
+        if (a.upper_only && j < (u32)row) continue;
         const double v = stripe_jaccard(stripe[i], s_off[al + 1] - s_off[al], a.off[j + 1] - a.off[j], (u32)row == j);
         a.out[(size_t)(row - a.row_begin) * n + j] = v;
     }
+}
+
+// out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 32 x 32 tiles through shared memory, reads
+// and writes both coalesced.  `full` points at row 0 of the whole matrix (rows < row_end are complete
+// in their upper part).
+__global__ void __launch_bounds__(1024) stripe_mirror_kernel(double* __restrict__ full, int n, int row_begin, int row_end) {
+    __shared__ double tile[32][33];
+    const int ti = row_begin / 32 + (int)blockIdx.y;       // tile row (destination rows)
+    const int tj = (int)blockIdx.x;                        // tile column (destination columns), tj <= ti
+    if (tj > ti) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source tile = rows of tile column tj, columns of tile row ti (the upper part)
+    const int sr = tj * 32 + ty, sc = ti * 32 + tx;
+    tile[ty][tx] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : 0.0;
+    __syncthreads();
+    const int dr = ti * 32 + ty, dc = tj * 32 + tx;
+    if (dr >= row_begin && dr < row_end && dc < dr && dc < n) full[(size_t)dr * n + dc] = tile[tx][ty];
 }
 
 struct JoinStripe {
@@ -1580,7 +1600,7 @@ struct JoinStripe {
     void* mem = nullptr;      // tags + pos
     u32 *tags = nullptr, *pos = nullptr;
     u64 T = 0;
-    int n = 0, rows_per_block = 0;
+    int n = 0, rows_per_block = 0, upper_only = 0;
     size_t smem = 0;
     ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
 };
@@ -1598,6 +1618,10 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
     }
     auto js = new JoinStripe();
     js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;
+    {   // SMB_JOIN_LAYOUT=stripe_upper: count only (i, j > i) and mirror -- half the scans and atomics
+        const char* layout = getenv("SMB_JOIN_LAYOUT");
+        js->upper_only = layout && !strcmp(layout, "stripe_upper");
+    }
     js->smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
     cudaError_t e;
     const size_t Tp = (size_t)((T + 63) & ~63ull);
@@ -1629,15 +1653,26 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
 cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
-    StripeArgs a{js->tags, js->pos, off, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out};
+    StripeArgs a{js->tags, js->pos, off, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out, js->upper_only};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
     join_stripe_kernel<<<blocks, 1024, js->smem, s>>>(a); count_launches(1);
     return cudaGetLastError();
 }
+// upper-only mode: the cells (i, j < i) of rows [row_begin, row_end) from the finished upper parts of rows
+// < row_end; d_full = row 0 of the whole n x n matrix.  No-op in the two-direction mode.
+cudaError_t join_stripe_mirror(const JoinStripe* js, int row_begin, int row_end, double* d_full, cudaStream_t s) {
+    if (!js->upper_only || row_end <= row_begin) return cudaSuccess;
+    const int t0 = row_begin / 32, t1 = (row_end + 31) / 32;
+    dim3 grid((unsigned)t1, (unsigned)(t1 - t0));
+    stripe_mirror_kernel<<<grid, 1024, 0, s>>>(d_full, js->n, row_begin, row_end); count_launches(1);
+    return cudaGetLastError();
+}
+bool join_stripe_upper_only(const JoinStripe* js) { return js->upper_only != 0; }
+void join_stripe_two_directions(JoinStripe* js) { js->upper_only = 0; }
 void join_stripe_destroy(JoinStripe* js) { delete js; }
 bool join_stripe_enabled() {
     const char* layout = getenv("SMB_JOIN_LAYOUT");
-    return layout && !strcmp(layout, "stripe");
+    return layout && (!strcmp(layout, "stripe") || !strcmp(layout, "stripe_upper"));
 }
 
 // ------------------------------------------------------------------------------------

@@ -89,6 +89,12 @@ cudaError_t join_stripe_create(const uint64_t* h, const uint64_t* off, int n, ui
                                JoinStripe** out, cudaStream_t s);
 cudaError_t join_stripe_rows(const JoinStripe* js, const uint64_t* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s);
+// SMB_JOIN_LAYOUT=stripe_upper: join_stripe_rows counts / writes only the cells (i, j >= i); join_stripe_mirror
+// then fills (i, j < i) of rows [row_begin, row_end) from the rows above (d_full = row 0 of the n x n matrix).
+// A block of rows computed on its own (smb_compare_jaccard_rows_dev) uses the two-direction mode.
+cudaError_t join_stripe_mirror(const JoinStripe* js, int row_begin, int row_end, double* d_full, cudaStream_t s);
+bool join_stripe_upper_only(const JoinStripe* js);
+void join_stripe_two_directions(JoinStripe* js);
 void join_stripe_destroy(JoinStripe* js);
 
 // Fallback for arbitrary row sizes: one warp per pair, binary search of the shorter row's

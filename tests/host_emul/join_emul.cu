@@ -3,7 +3,7 @@
 // (hash, row) pairs stably by hash (std::stable_sort stands in for the radix sort), walk every
 // element.  Test infrastructure for the CPU-only suite.
 //   usage: join_emul <n_shards> <hashes.u64> <offsets.u64> <out.u32 (n*n, summed over shards)> <out_pairs.u64> [cluster]
-//          join_emul <R> <hashes.u64> <offsets.u64> <out.f64 (n*n jaccard)> <unused> stripe <n_warps> <unused>
+//          join_emul <R> <hashes.u64> <offsets.u64> <out.f64 (n*n jaccard)> <unused> stripe <n_warps> <mirror_chunk_rows | 0>
 // With "stripe" the experimental stripe layout (join_stripe.cuh) is emulated: CTAs of R rows, warps
 // of 32 lanes with a host-side ballot, counters in a per-CTA stripe, float64 rows written directly.
 // With "cluster" the experimental layout is emulated instead: row keys from the global sample, rows
@@ -128,7 +128,8 @@ static int rows_main(int passes, const std::vector<u64>& h, const std::vector<u6
 
 // stripe layout: the kernel's loop structure (compare_kernels.cu join_stripe_kernel) with the lanes of a
 // warp run one after the other and the ballot assembled on the host
-static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path) {
+static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path,
+                       int upper_only, int chunk_rows) {
     const int n = (int)off.size() - 1;
     const u64 T = h.size();
     std::vector<u32> src(T);
@@ -156,7 +157,7 @@ static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std:
                 for (u32 l = 0; l < 32; ++l) if (stripe_fwd_active(m, l)) row[tag[l] & ~STRIPE_HEAD] += 1;
                 if (!stripe_continue(m)) break;
             }
-            if (tags[q] & STRIPE_HEAD) return;
+            if (upper_only || (tags[q] & STRIPE_HEAD)) return;
             for (u32 it = 0;; ++it) {                                   // backward
                 u32 m = 0;
                 for (u32 l = 0; l < 32; ++l) m |= (stripe_bwd_stop(tags.data(), q, it, l, tag[l], valid[l]) ? 1u : 0u) << l;
@@ -179,8 +180,35 @@ static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std:
         for (u32 i = 0; i < (u32)rows * (u32)n; ++i) {
             const u32 al = i / (u32)n, j = i - al * (u32)n;
             const int row = r0 + (int)al;
+            if (upper_only && j < (u32)row) continue;
             if (out[(size_t)row * n + j] != -1.0) return 6;              // every cell written once
             out[(size_t)row * n + j] = stripe_jaccard(stripe[i], s_off[al + 1] - s_off[al], off[j + 1] - off[j], (u32)row == j);
+        }
+    }
+    if (upper_only) {
+        // stripe_mirror_kernel, chunk of rows by chunk of rows like the host path: 32 x 32 tiles, tile row ti
+        // (destination rows) x tile column tj <= ti, thread (tx, ty) reads (tj*32+ty, ti*32+tx), writes (ti*32+ty, tj*32+tx)
+        for (int rb = 0; rb < n; rb += chunk_rows) {
+            const int re = std::min(n, rb + chunk_rows);
+            const int t0 = rb / 32, t1 = (re + 31) / 32;
+            for (int ti = t0; ti < t1; ++ti)
+                for (int tj = 0; tj < t1; ++tj) {
+                    if (tj > ti) continue;
+                    double tile[32][33];
+                    for (int ty = 0; ty < 32; ++ty)
+                        for (int tx = 0; tx < 32; ++tx) {
+                            const int sr = tj * 32 + ty, sc = ti * 32 + tx;
+                            tile[ty][tx] = (sr < n && sc < n) ? out[(size_t)sr * n + sc] : 0.0;
+                        }
+                    for (int ty = 0; ty < 32; ++ty)
+                        for (int tx = 0; tx < 32; ++tx) {
+                            const int dr = ti * 32 + ty, dc = tj * 32 + tx;
+                            if (dr >= rb && dr < re && dc < dr && dc < n) {
+                                if (out[(size_t)dr * n + dc] != -1.0) return 7;      // lower cells are written once
+                                out[(size_t)dr * n + dc] = tile[tx][ty];
+                            }
+                        }
+                }
         }
     }
     FILE* f = fopen(out_path, "wb");
@@ -192,7 +220,8 @@ static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std:
 int main(int argc, char** argv) {
     if (argc == 9) {                                        // <R> ... <out> <unused> stripe <n_warps> <unused>
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
-        return stripe_main(atoi(argv[1]), atoi(argv[7]), h, off, argv[4]);
+        const int chunk = atoi(argv[8]);                    // 0: two directions; > 0: upper only, mirrored in chunks of rows
+        return stripe_main(atoi(argv[1]), atoi(argv[7]), h, off, argv[4], chunk > 0, chunk);
     }
     if (argc == 8) {                                        // ... <out> <unused> rows <passes>
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);

@@ -33,10 +33,11 @@ def _edge_rows():
     return rows
 
 
+@pytest.mark.parametrize("layout", ["stripe", "stripe_upper"])
 @pytest.mark.parametrize("n,fam", [(96, 6), (700, 9), (1500, 12)])
-def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam):
+def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam, layout):
     monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
-    monkeypatch.setenv("SMB_JOIN_LAYOUT", "stripe")
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
     h, off = synth_sketches(n, mean=400, sd=80, lo=0, hi=800, n_families=fam, pool=500, seed=n)
     want = orc.compare_all_pairs(h, off, nthreads=8)
     sset = B.SketchSet.from_host(h, off)
@@ -53,9 +54,10 @@ def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam):
     assert np.array_equal(d_rows.cpu().numpy(), want[lo:hi])
 
 
-def test_stripe_layout_edge_rows(B, monkeypatch):
+@pytest.mark.parametrize("layout", ["stripe", "stripe_upper"])
+def test_stripe_layout_edge_rows(B, monkeypatch, layout):
     monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
-    monkeypatch.setenv("SMB_JOIN_LAYOUT", "stripe")
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
     rows = _edge_rows() * 12                                                  # > 1024 rows: the host path takes the join
     h, off = orc.to_csr(rows)
     assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(h, off)), orc.compare_all_pairs(h, off, nthreads=8))

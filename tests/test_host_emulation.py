@@ -193,14 +193,14 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0):
+    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0, mirror_chunk=0):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
             if stripe_warps:                               # n_shards carries the rows per CTA
-                subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp, "stripe", str(stripe_warps), "-"])
+                subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp, "stripe", str(stripe_warps), str(mirror_chunk)])
                 return np.fromfile(fc, dtype=np.float64).reshape(n, n)
             extra = ["cluster"] if cluster else ["rows", str(row_passes)] if row_passes else []
             subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + extra)
@@ -294,6 +294,10 @@ def test_join_stripe_layout_matches_oracle(join_emul):
         for rows_per_cta, warps in ((1, 1), (5, 3), (32, 4), (7, 32)):
             got = join_emul(rows, rows_per_cta, stripe_warps=warps)
             assert np.array_equal(got, want), (len(rows), rows_per_cta, warps)
+        # SMB_JOIN_LAYOUT=stripe_upper: forward scans only, (i, j < i) mirrored tile by tile, in chunks of rows
+        for rows_per_cta, chunk in ((5, 1000), (3, 10), (32, 33), (1, 1)):
+            got = join_emul(rows, rows_per_cta, stripe_warps=2, mirror_chunk=chunk)
+            assert np.array_equal(got, want), (len(rows), rows_per_cta, chunk)
 
 
 def test_join_stripe_helpers():
