@@ -3,7 +3,8 @@
 # are in the tree behind switches (default off; logic covered on the CPU by tests/test_host_emulation.py):
 #   SMB_JOIN_LAYOUT=stripe   CTAs own complete result rows in shared memory, no global atomics, fused
 #                            finalize, row blocks downloadable as they finish (csrc/join_stripe.cuh);
-#                            stripe_upper: only (i, j > i) counted, the rest mirrored tile by tile
+#                            stripe_upper: only (i, j > i) counted, the rest mirrored tile by tile;
+#                            SMB_JOIN_SORT=low32: the stream sorted on the low key words (4 passes) + repair
 #   SMB_JOIN_LAYOUT=cluster  related rows at adjacent ranks, warp per element (csrc/join_walk.cuh)
 #   SMB_COMPARE_PASSES=k     row-block count passes for the end-to-end path
 #   SMB_SKETCH_FUSED=1       sketch: k = 21, 31, 51 in one pass over the bases (csrc/kmer_roll.cuh)
@@ -42,6 +43,12 @@ for F in 0 1; do
       > gpurun_out/bench_sketch_fused${F}_${TAG}.json 2> /dev/null
   python -c "
 import json; d=json.load(open('gpurun_out/bench_sketch_fused${F}_${TAG}.json')); d=d.get('sketch', d); print('sketch fused=${F}: ms %.2f kernel_ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step']))"
+done
+for L in stripe stripe_upper; do
+  SMB_JOIN_SORT=low32 SMB_JOIN_LAYOUT=$L timeout 200 python bench.py --workload compare --steps 5 --warmup 3 --no-cpu-baseline \
+      > gpurun_out/bench_join_${L}_low32_${TAG}.json 2> /dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_join_${L}_low32_${TAG}.json')); print('${L} + low32 sort: ms %.2f kernel_ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step']))"
 done
 # 2b. row-block passes for the end-to-end path (SMB_COMPARE_PASSES): correctness through the host API, then e2e
 SMB_COMPARE_PASSES=8 timeout 300 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_kernels.py -q -m gpu -k "compare or join" 2>&1 | tail -3

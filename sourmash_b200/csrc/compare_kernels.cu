@@ -20,6 +20,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <memory>
@@ -1220,12 +1222,12 @@ struct JoinWork {
 // stream-ordered scratch allocations released at scope exit, error paths included
 struct JoinScratch {
     cudaStream_t s;
-    void* p[3] = {nullptr, nullptr, nullptr};
+    void* p[16] = {};
     int n = 0;
     explicit JoinScratch(cudaStream_t st) : s(st) {}
     cudaError_t alloc(void** out, size_t bytes) {
         cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
-        if (e == cudaSuccess) p[n++] = *out;
+        if (e == cudaSuccess && n < 16) p[n++] = *out;
         return e;
     }
     ~JoinScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s); }
@@ -1493,6 +1495,97 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u64* __restrict__
     }
 }
 
+// ---- SMB_JOIN_SORT=low32: the sorted (key, element) stream from a 32-bit sort + repair of mixed runs ----
+__global__ void __launch_bounds__(256) stripe_low32_kernel(const u64* __restrict__ h, u64 T, u32* __restrict__ low,
+                                                          u32* __restrict__ vals) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (u64)gridDim.x * blockDim.x) {
+        low[i] = (u32)h[i];
+        vals[i] = (u32)i;
+    }
+}
+__global__ void __launch_bounds__(256) stripe_gather_keys_kernel(const u64* __restrict__ h, const u32* __restrict__ src,
+                                                                u64 T, u64* __restrict__ keys) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < T; q += (u64)gridDim.x * blockDim.x) keys[q] = h[src[q]];
+}
+__global__ void __launch_bounds__(256) stripe_mixed_runs_kernel(const u32* __restrict__ low_sorted, const u64* __restrict__ keys,
+                                                               u64 T, u8* __restrict__ flags) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < T; q += (u64)gridDim.x * blockDim.x) {
+        bool mixed;
+        const u64 m = stripe_run_at_head(low_sorted, keys, T, q, mixed);
+        if (mixed) for (u64 j = 0; j < m; ++j) flags[q + j] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) stripe_repair_load_kernel(const u32* __restrict__ where, u64 n_sel, const u64* __restrict__ keys,
+                                                                const u32* __restrict__ src, u64* __restrict__ rot,
+                                                                u32* __restrict__ sel_src) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_sel; j += (u64)gridDim.x * blockDim.x) {
+        rot[j] = stripe_rotated_key(keys[where[j]]);
+        sel_src[j] = src[where[j]];
+    }
+}
+__global__ void __launch_bounds__(256) stripe_repair_store_kernel(const u32* __restrict__ where, u64 n_sel, const u64* __restrict__ rot_sorted,
+                                                                 const u32* __restrict__ src_sorted, u64* __restrict__ keys,
+                                                                 u32* __restrict__ src) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_sel; j += (u64)gridDim.x * blockDim.x) {
+        keys[where[j]] = stripe_rotated_key(rot_sorted[j]);          // rotating twice by 32 is the identity
+        src[where[j]] = src_sorted[j];
+    }
+}
+
+// keys_sorted[q] / src[q]: the hashes in ascending-group order with their CSR element index.  Groups of
+// equal hashes are contiguous and rows ascend inside a group; the groups themselves come in the order
+// of their low words (any order of the groups serves the stripe layout).
+static cudaError_t stripe_stream_low32(const u64* h, u64 T, u64* keys_sorted, u32* src, JoinScratch& scratch, cudaStream_t s) {
+    cudaError_t e;
+    const size_t Tp = (size_t)((T + 63) & ~63ull);
+    u32 *low = nullptr, *vals = nullptr;
+    if ((e = scratch.alloc((void**)&low, Tp * 2 * sizeof(u32))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&vals, Tp * sizeof(u32))) != cudaSuccess) return e;
+    u32* low_sorted = low + Tp;
+    const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
+    stripe_low32_kernel<<<grid, 256, 0, s>>>(h, T, low, vals); count_launches(1);
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, low, low_sorted, vals, src, (long long)T, 0, 32, s);
+    void* tmp = nullptr;
+    if ((e = scratch.alloc(&tmp, bytes)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(tmp, bytes, low, low_sorted, vals, src, (long long)T, 0, 32, s);
+    count_launches(1);
+    stripe_gather_keys_kernel<<<grid, 256, 0, s>>>(h, src, T, keys_sorted); count_launches(1);
+    // runs of equal low words that mix different hashes
+    u8* flags = nullptr;
+    if ((e = scratch.alloc((void**)&flags, Tp)) != cudaSuccess) return e;
+    cudaMemsetAsync(flags, 0, Tp, s);
+    stripe_mixed_runs_kernel<<<grid, 256, 0, s>>>(low_sorted, keys_sorted, T, flags); count_launches(1);
+    u32* where = vals;                                           // vals is free again: positions of the flagged elements
+    u64* d_nsel = (u64*)low;                                     // low (unsorted) is free again
+    thrust::counting_iterator<u32> positions(0);
+    bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, positions, flags, where, d_nsel, (int)T, s);
+    void* tmp2 = nullptr;
+    if ((e = scratch.alloc(&tmp2, bytes)) != cudaSuccess) return e;
+    cub::DeviceSelect::Flagged(tmp2, bytes, positions, flags, where, d_nsel, (int)T, s);
+    count_launches(1);
+    u64 n_sel = 0;
+    cudaMemcpyAsync(&n_sel, d_nsel, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if (n_sel == 0) return cudaSuccess;
+    // re-sort the flagged elements on (low word, high word): runs stay where they are, ordered inside
+    u64* rot = nullptr;
+    u32* sel_src = nullptr;
+    if ((e = scratch.alloc((void**)&rot, n_sel * 2 * sizeof(u64))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&sel_src, n_sel * 2 * sizeof(u32))) != cudaSuccess) return e;
+    const unsigned g2 = (unsigned)std::min<u64>((n_sel + 255) / 256, (u64)SMB_B200_SMS * 32);
+    stripe_repair_load_kernel<<<g2, 256, 0, s>>>(where, n_sel, keys_sorted, src, rot, sel_src); count_launches(1);
+    bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, rot, rot + n_sel, sel_src, sel_src + n_sel, (long long)n_sel, 0, 64, s);
+    void* tmp3 = nullptr;
+    if ((e = scratch.alloc(&tmp3, bytes)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(tmp3, bytes, rot, rot + n_sel, sel_src, sel_src + n_sel, (long long)n_sel, 0, 64, s);
+    count_launches(1);
+    stripe_repair_store_kernel<<<g2, 256, 0, s>>>(where, n_sel, rot + n_sel, sel_src + n_sel, keys_sorted, src); count_launches(1);
+    return cudaGetLastError();
+}
+
 struct StripeArgs {
     const u32* tags;
     const u32* pos;
@@ -1635,14 +1728,20 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
     if ((e = scratch.alloc((void**)&vals, Tp * 2 * sizeof(u32))) != cudaSuccess) { delete js; return e; }
     u32* vals_sorted = vals + Tp;
     const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
-    stripe_iota_kernel<<<grid, 256, 0, s>>>(vals, T); count_launches(1);
-    const int key_bits = key_bit_length(max_key);
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
-    void* d_sort = nullptr;
-    if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) { delete js; return e; }
-    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
-    count_launches(1);
+    const char* sort_mode = getenv("SMB_JOIN_SORT");
+    if (sort_mode && !strcmp(sort_mode, "low32") && T <= 0x7fffffffull) {
+        // 4 radix passes over 4-byte keys, then the rare runs that mix hashes are repaired
+        if ((e = stripe_stream_low32(h, T, keys_sorted, vals_sorted, scratch, s)) != cudaSuccess) { delete js; return e; }
+    } else {
+        stripe_iota_kernel<<<grid, 256, 0, s>>>(vals, T); count_launches(1);
+        const int key_bits = key_bit_length(max_key);
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
+        void* d_sort = nullptr;
+        if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) { delete js; return e; }
+        cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
+        count_launches(1);
+    }
     stripe_tag_kernel<<<grid, 256, 0, s>>>(keys_sorted, vals_sorted, off, n, T, js->tags, js->pos); count_launches(1);
     if ((e = cudaGetLastError()) != cudaSuccess) { delete js; return e; }
     *out = js;

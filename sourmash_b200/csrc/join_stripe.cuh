@@ -72,6 +72,26 @@ __host__ __device__ __forceinline__ u32 stripe_local_row(const u64* __restrict__
     return a;
 }
 
+// ---- sorting on the low 32 key bits only (SMB_JOIN_SORT=low32: 4 radix passes of 4-byte keys instead
+// of 7 passes of 8-byte keys) ----
+// Elements with equal low words form a run; nearly every run is one group of equal hashes.  The few
+// runs that mix different hashes (expected: distinct^2 / 2^33) are re-sorted on the rotated key
+// (low word first, then the high word), which keeps them in place as runs and orders them inside.
+__host__ __device__ __forceinline__ u64 stripe_rotated_key(u64 k) { return (k << 32) | (k >> 32); }
+
+// length of the run of equal low words that starts at q (0 if q is not its first element), and whether
+// the run holds more than one distinct key
+__host__ __device__ __forceinline__ u64 stripe_run_at_head(const u32* __restrict__ low_sorted, const u64* __restrict__ keys,
+                                                           u64 T, u64 q, bool& mixed) {
+    mixed = false;
+    const u32 lw = low_sorted[q];
+    if (q > 0 && low_sorted[q - 1] == lw) return 0;
+    const u64 k0 = keys[q];
+    u64 m = 1;
+    while (q + m < T && low_sorted[q + m] == lw) { mixed = mixed || keys[q + m] != k0; ++m; }
+    return m;
+}
+
 // the finalize step of compare (finalize_rows_kernel): ones on the diagonal, common / max(1, union)
 __host__ __device__ __forceinline__ double stripe_jaccard(u32 common, u64 size_i, u64 size_j, bool diagonal) {
     if (diagonal) return 1.0;

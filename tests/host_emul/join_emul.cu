@@ -3,13 +3,14 @@
 // (hash, row) pairs stably by hash (std::stable_sort stands in for the radix sort), walk every
 // element.  Test infrastructure for the CPU-only suite.
 //   usage: join_emul <n_shards> <hashes.u64> <offsets.u64> <out.u32 (n*n, summed over shards)> <out_pairs.u64> [cluster]
-//          join_emul <R> <hashes.u64> <offsets.u64> <out.f64 (n*n jaccard)> <unused> stripe <n_warps> <mirror_chunk_rows | 0>
+//          join_emul <R> <hashes.u64> <offsets.u64> <out.f64 (n*n jaccard)> <low32 | -> stripe <n_warps> <mirror_chunk_rows | 0>
 // With "stripe" the experimental stripe layout (join_stripe.cuh) is emulated: CTAs of R rows, warps
 // of 32 lanes with a host-side ballot, counters in a per-CTA stripe, float64 rows written directly.
 // With "cluster" the experimental layout is emulated instead: row keys from the global sample, rows
 // ranked by (key, id), gather in rank order, one 32-lane "warp" per element, un-permute.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <numeric>
@@ -129,14 +130,44 @@ static int rows_main(int passes, const std::vector<u64>& h, const std::vector<u6
 // stripe layout: the kernel's loop structure (compare_kernels.cu join_stripe_kernel) with the lanes of a
 // warp run one after the other and the ballot assembled on the host
 static int stripe_main(int R, int n_warps, const std::vector<u64>& h, const std::vector<u64>& off, const char* out_path,
-                       int upper_only, int chunk_rows) {
+                       int upper_only, int chunk_rows, bool low32) {
     const int n = (int)off.size() - 1;
     const u64 T = h.size();
     std::vector<u32> src(T);
     std::iota(src.begin(), src.end(), 0);
-    std::stable_sort(src.begin(), src.end(), [&](u32 a, u32 b) { return h[a] < h[b]; });
     std::vector<u64> sk(T);
-    for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    if (!low32) {
+        std::stable_sort(src.begin(), src.end(), [&](u32 a, u32 b) { return h[a] < h[b]; });
+        for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    } else {
+        // SMB_JOIN_SORT=low32 (compare_kernels.cu stripe_stream_low32): stable sort on the low words, gather the
+        // keys, flag the runs that mix hashes, re-sort the flagged elements on the rotated key, put them back
+        std::stable_sort(src.begin(), src.end(), [&](u32 a, u32 b) { return (u32)h[a] < (u32)h[b]; });
+        std::vector<u32> low(T);
+        for (u64 q = 0; q < T; ++q) { sk[q] = h[src[q]]; low[q] = (u32)sk[q]; }
+        std::vector<char> flags(T, 0);
+        for (u64 q = 0; q < T; ++q) {
+            bool mixed;
+            const u64 m = stripe_run_at_head(low.data(), sk.data(), T, q, mixed);
+            if (mixed) for (u64 j = 0; j < m; ++j) flags[q + j] = 1;
+        }
+        std::vector<u32> where;
+        for (u64 q = 0; q < T; ++q) if (flags[q]) where.push_back((u32)q);
+        std::vector<size_t> order(where.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            return stripe_rotated_key(sk[where[a]]) < stripe_rotated_key(sk[where[b]]); });
+        std::vector<u64> k2(where.size());
+        std::vector<u32> s2(where.size());
+        for (size_t j = 0; j < where.size(); ++j) { k2[j] = stripe_rotated_key(stripe_rotated_key(sk[where[order[j]]])); s2[j] = src[where[order[j]]]; }
+        for (size_t j = 0; j < where.size(); ++j) { sk[where[j]] = k2[j]; src[where[j]] = s2[j]; }
+        // what the stripe layout needs from the stream: equal hashes contiguous, rows ascending inside a group
+        for (u64 q = 1; q < T; ++q) {
+            if (sk[q] == sk[q - 1] && stripe_row_of(off.data(), n, src[q]) <= stripe_row_of(off.data(), n, src[q - 1])) return 8;
+            if (sk[q] != sk[q - 1]) for (u64 p2 = q + 1; p2 < T && (u32)sk[p2] == (u32)sk[q - 1]; ++p2) if (sk[p2] == sk[q - 1]) return 8;
+        }
+        if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "repaired %zu elements\n", where.size());
+    }
     std::vector<u32> tags(T), pos(T);
     for (u64 q = 0; q < T; ++q) {
         tags[q] = stripe_make_tag(sk.data(), q, stripe_row_of(off.data(), n, src[q]));
@@ -221,7 +252,7 @@ int main(int argc, char** argv) {
     if (argc == 9) {                                        // <R> ... <out> <unused> stripe <n_warps> <unused>
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);
         const int chunk = atoi(argv[8]);                    // 0: two directions; > 0: upper only, mirrored in chunks of rows
-        return stripe_main(atoi(argv[1]), atoi(argv[7]), h, off, argv[4], chunk > 0, chunk);
+        return stripe_main(atoi(argv[1]), atoi(argv[7]), h, off, argv[4], chunk > 0, chunk, !strcmp(argv[5], "low32"));
     }
     if (argc == 8) {                                        // ... <out> <unused> rows <passes>
         std::vector<u64> h = slurp<u64>(argv[2]), off = slurp<u64>(argv[3]);

@@ -63,6 +63,25 @@ def test_stripe_layout_edge_rows(B, monkeypatch, layout):
     assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(h, off)), orc.compare_all_pairs(h, off, nthreads=8))
 
 
+def test_stripe_low32_sort_with_clashing_low_words(B, monkeypatch):
+    "SMB_JOIN_SORT=low32: 32-bit sort + repair of the runs that mix hashes, under both stripe modes."
+    rng = np.random.Generator(np.random.PCG64(21))
+    h, off = synth_sketches(1200, mean=300, sd=60, lo=0, hi=600, n_families=8, pool=400, seed=23)
+    rows = rows_of(h, off)
+    lowword = np.uint64(0x1234abcd)
+    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
+    for i in range(0, 1200, 3):                                           # hashes sharing their low word, spread over rows
+        extra = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0] + [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)]
+        rows[i] = np.unique(np.concatenate([rows[i], np.array(extra, dtype=np.uint64)]))
+    hh, oo = orc.to_csr(rows)
+    want = orc.compare_all_pairs(hh, oo, nthreads=8)
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    monkeypatch.setenv("SMB_JOIN_SORT", "low32")
+    for layout in ("stripe", "stripe_upper"):
+        monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
+        assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(hh, oo)), want), layout
+
+
 def test_rows_device_without_stripe_equals_full_matrix(B):
     "smb_compare_jaccard_rows_dev on the default path (whole count matrix, then the rows)."
     import torch

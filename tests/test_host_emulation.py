@@ -193,14 +193,15 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0, mirror_chunk=0):
+    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0, mirror_chunk=0, low32=False):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
             if stripe_warps:                               # n_shards carries the rows per CTA
-                subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp, "stripe", str(stripe_warps), str(mirror_chunk)])
+                subprocess.check_call([exe, str(n_shards), fh, fo, fc, "low32" if low32 else "-", "stripe", str(stripe_warps),
+                                       str(mirror_chunk)])
                 return np.fromfile(fc, dtype=np.float64).reshape(n, n)
             extra = ["cluster"] if cluster else ["rows", str(row_passes)] if row_passes else []
             subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + extra)
@@ -297,6 +298,30 @@ def test_join_stripe_layout_matches_oracle(join_emul):
         # SMB_JOIN_LAYOUT=stripe_upper: forward scans only, (i, j < i) mirrored tile by tile, in chunks of rows
         for rows_per_cta, chunk in ((5, 1000), (3, 10), (32, 33), (1, 1)):
             got = join_emul(rows, rows_per_cta, stripe_warps=2, mirror_chunk=chunk)
+            assert np.array_equal(got, want), (len(rows), rows_per_cta, chunk)
+
+
+def test_join_stripe_low32_sort_repairs_mixed_runs(join_emul):
+    """SMB_JOIN_SORT=low32: the stream sorted on the low key words only, runs that mix different hashes
+    re-sorted on the rotated key -- hashes sharing their low word across rows, in both row orders, next
+    to ordinary sets; both stripe modes downstream."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(21)
+    h, off = synth_sketches(60, mean=300, sd=60, lo=100, hi=600, n_families=3, pool=400, seed=23)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(60)]
+    lowword = np.uint64(0x1234abcd)
+    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
+    clash = []
+    for i in range(40):                                               # five hashes with one low word, spread over the rows
+        mine = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0]
+        other = [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)]               # a second clashing low word
+        clash.append(np.unique(np.array(mine + other + rng.integers(1, 2**60, size=4, dtype=np.uint64).tolist(), dtype=np.uint64)))
+    clash[5] = np.zeros(0, np.uint64)
+    for rows in (fam, clash, fam[:20] + clash):
+        hh, oo = orc.to_csr(rows)
+        want = orc.compare_all_pairs(hh, oo, nthreads=2)
+        for rows_per_cta, chunk in ((5, 0), (3, 7), (32, 1000)):
+            got = join_emul(rows, rows_per_cta, stripe_warps=3, mirror_chunk=chunk, low32=True)
             assert np.array_equal(got, want), (len(rows), rows_per_cta, chunk)
 
 
