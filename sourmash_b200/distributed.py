@@ -131,6 +131,10 @@ class ShardedDatabase:
         self.device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
             else torch.device("cpu")
 
+    def build_index(self):
+        "Inverted index of this rank's block of rows (batch.SketchSet.build_index): counts and gather rounds probe it."
+        return self.sset.build_index() if len(self.sset) else 0
+
     def search_counts(self, query):
         "|query ∩ S_j| for every row of the whole database, on every rank."
         torch, dist = self.torch, self.dist
