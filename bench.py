@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 N_SKETCHES = 10_000
 KSIZES = (21, 31, 51)
 N_GENOMES = 100
+COMPARE_WORKLOAD = ("configs[2]: compare 10000 synthetic sketches (k=31, scaled=1000, ~5000 hashes, "
+                    "100 families) all-vs-all jaccard float64 matrix")
+SKETCH_WORKLOAD = "configs[1]: sketch dna k=21,31,51 scaled=1000 on 100 synthetic 5 Mbp genomes"
 SM_COUNT = 148                                        # B200
 GENOME_LEN = 5_000_000
 SCALED = 1000
@@ -220,8 +223,9 @@ def run_reference(args):
             if i >= args.warmup:
                 times.append(dt)
         metric, unit = "sketch-pairs/sec (compare)", "pairs/s"
-        config = {"workload": "configs[2]: compare 10000 synthetic sketches k=31 scaled=1000 all-vs-all jaccard",
-                  "n_sketches": N_SKETCHES}
+        config = {"workload": COMPARE_WORKLOAD, "n_sketches": N_SKETCHES,
+                  "pairs_per_step": N_SKETCHES * (N_SKETCHES - 1) // 2,
+                  "parallelism": "%d host threads (OpenMP over rows)" % ncores}
     else:
         ng = N_GENOMES                           # the whole configs[1] workload (a few seconds on 16 cores)
         seqs, offs = sketch_workload(ng)
@@ -231,7 +235,7 @@ def run_reference(args):
             if i >= args.warmup:
                 times.append(dt)
         metric, unit = "k-mers hashed/sec (sketch)", "k-mers/s"
-        config = {"workload": "configs[1]: sketch dna k=21,31,51 scaled=1000, 100 synthetic 5 Mbp genomes"}
+        config = {"workload": SKETCH_WORKLOAD, "parallelism": "%d host threads (one genome per thread)" % ncores}
     ms = 1000.0 * float(np.mean(times))
     value = units / (ms / 1000.0)
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
@@ -400,8 +404,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
         "metric": "sketch-pairs/sec (compare)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[2]: compare 10000 synthetic sketches (k=31, scaled=1000, ~5000 hashes, "
-                               "100 families) all-vs-all jaccard float64 matrix",
+        "config": {"workload": COMPARE_WORKLOAD,
                    "n_sketches": n, "pairs_per_step": n_pairs, "parallelism": parallelism,
                    "l2_policy": "inputs 400 MB + 800 MB output per step exceed the 126 MB L2; no flush"},
         "e2e": {"value": n_pairs / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
@@ -473,7 +476,7 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
         "metric": "k-mers hashed/sec (sketch)", "value": total_kmers / (ms / 1e3), "unit": "k-mers/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[1]: sketch dna k=21,31,51 scaled=1000 on 100 synthetic 5 Mbp genomes",
+        "config": {"workload": SKETCH_WORKLOAD,
                    "kmers_per_step": total_kmers,
                    "parallelism": "1 gpu" if world == 1 else f"{world} gpus: genomes round-robin, sketches all-gathered",
                    "l2_policy": "500 MB of bases per pass exceed the 126 MB L2; no flush"},
