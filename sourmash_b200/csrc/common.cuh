@@ -13,6 +13,16 @@ typedef uint8_t u8;
 // Number of SMs on a B200; grids for persistent-style kernels are sized in multiples of it.
 #define SMB_B200_SMS 148
 
+// Shared memory of kernels that tests/host_emul/simt.h also runs on the CPU (SMB_SIMT_EMUL: one CTA at a
+// time as cooperative fibers, so block-shared storage is plain static storage there).
+#ifdef SMB_SIMT_EMUL
+#define SMB_SHARED static
+#define SMB_DYN_SHARED(T, name) T* name = reinterpret_cast<T*>(smb_emu::dyn_smem())
+#else
+#define SMB_SHARED __shared__
+#define SMB_DYN_SHARED(T, name) extern __shared__ __align__(16) T name[]
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
 

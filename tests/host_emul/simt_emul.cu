@@ -1,0 +1,144 @@
+// simt_emul.cu -- runs the KERNELS of sourmash_b200/csrc/experimental_kernels.cuh on the CPU through the SIMT
+// emulator of simt.h (CTAs as cooperative fibers, real __syncthreads / warp collectives / shared memory) and
+// writes their results for comparison with the oracle.  The launch geometry is shrunk (fewer threads, smaller
+// shared memory) but the code is the code the GPU runs.  Test infrastructure for the CPU-only suite.
+//   simt_emul stripe <R> <upper 0|1> <threads> <hashes.u64> <offsets.u64> <out.f64 n*n>
+//   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
+//   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
+#define SMB_SIMT_EMUL 1
+#include "simt.h"
+
+#include <numeric>
+
+#include "../../sourmash_b200/csrc/experimental_kernels.cuh"
+
+using namespace smb;
+
+template <class T>
+static std::vector<T> slurp(const char* path) {
+    FILE* f = fopen(path, "rb");
+    std::vector<T> v;
+    if (!f) return v;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    v.resize((size_t)n / sizeof(T));
+    if (n && fread(v.data(), 1, (size_t)n, f) != (size_t)n) v.clear();
+    fclose(f);
+    return v;
+}
+template <class T>
+static void dump(const char* path, const std::vector<T>& v) {
+    FILE* f = fopen(path, "wb");
+    fwrite(v.data(), sizeof(T), v.size(), f);
+    fclose(f);
+}
+
+static int stripe_main(int R, int upper, int threads, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    const u64 T = h.size();
+    // the sorted stream: iota kernel, a stable host sort standing in for cub::DeviceRadixSort, tag kernel
+    std::vector<u32> vals(T + 1), src(T + 1), tags(T + 1), pos(T + 1);
+    smb_emu::launch(3, 64, 0, [&] { stripe_iota_kernel(vals.data(), T); });
+    for (u64 i = 0; i < T; ++i) if (vals[i] != (u32)i) return 3;
+    std::copy(vals.begin(), vals.begin() + T, src.begin());
+    std::stable_sort(src.begin(), src.begin() + T, [&](u32 a, u32 b) { return h[a] < h[b]; });
+    std::vector<u64> sk(T + 1);
+    for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel(sk.data(), src.data(), off.data(), n, T, tags.data(), pos.data()); });
+    std::vector<double> out((size_t)n * n, -1.0);
+    const size_t smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
+    // two launches over row chunks, like the host path of smb_compare_jaccard
+    const int half = n / 2;
+    for (int c = 0; c < 2; ++c) {
+        const int r0 = c ? half : 0, r1 = c ? n : half;
+        if (r1 <= r0) continue;
+        StripeArgs a{tags.data(), pos.data(), off.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, upper};
+        const int blocks = (r1 - r0 + R - 1) / R;
+        smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel(a); });
+        if (upper) {
+            const int t0 = r0 / 32, t1 = (r1 + 31) / 32;
+            smb_emu::launch(smb_emu::Dim3(t1, t1 - t0), 1024, 0, [&] { stripe_mirror_kernel(out.data(), n, r0, r1); });
+        }
+    }
+    dump(fout, out);
+    return 0;
+}
+
+static std::vector<u32> host_dir(const std::vector<u64>& keys, u32 shift, u64 nbk) {
+    std::vector<u32> dir(nbk + 2);
+    for (u64 b = 0; b <= nbk; ++b)
+        dir[b] = (u32)(std::lower_bound(keys.begin(), keys.end(), b, [&](u64 k, u64 bb) { return (k >> shift) < bb; }) - keys.begin());
+    return dir;
+}
+
+static int ranges_main(int P, u64 max_bits, int threads, const char* fq, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> q = slurp<u64>(fq), h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    u64 max_key = 0, q_max = q.empty() ? 0 : q.back();
+    for (u64 v : h) max_key = std::max(max_key, v);
+    const u64 width = range_width(max_key, P);
+    std::vector<u32> bounds((size_t)(P + 1) * n + 1);
+    h.push_back(0);                                             // keep h.data() valid for empty sets
+    smb_emu::launch(3, 64, 0, [&] { range_bounds_kernel(h.data(), off.data(), n, width, P, bounds.data()); });
+    u32 shift;
+    u64 nbk;
+    db_index_dir_plan(q.size(), q_max, shift, nbk);             // same geometry rules as the query directory
+    std::vector<u32> dir = host_dir(q, shift, nbk);
+    std::vector<u32> out(n, 0);
+    RangeArgs a{q.data(), (u64)q.size(), dir.data(), shift, nbk, h.data(), off.data(), n, bounds.data(), width, P, 0, 0, out.data()};
+    a.bm_shift = range_bitmap_shift(width, max_bits);
+    a.bm_words = (u32)((((width - 1) >> a.bm_shift) + 1 + 31) / 32);
+    q.push_back(0);
+    a.q = q.data();
+    if (a.nq) smb_emu::launch(P, threads, (size_t)a.bm_words * 4, [&] { one_vs_many_ranges_kernel(a); });
+    dump(fout, out);
+    return 0;
+}
+
+static int index_main(int threads, const char* fq, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> q = slurp<u64>(fq), h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    const u64 T = h.size();
+    std::vector<u32> ids(T + 1);
+    smb_emu::launch(5, 64, 0, [&] { index_rowid_kernel(off.data(), n, ids.data()); });
+    std::vector<size_t> perm(T);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return h[a] < h[b]; });
+    std::vector<u64> keys;
+    std::vector<u32> start, rows(T + 1);
+    for (u64 p = 0; p < T; ++p) {
+        rows[p] = ids[perm[p]];
+        if (p == 0 || h[perm[p]] != h[perm[p - 1]]) { keys.push_back(h[perm[p]]); start.push_back((u32)p); }
+    }
+    start.push_back((u32)T);
+    u64 max_key = 0;
+    for (u64 v : h) max_key = std::max(max_key, v);
+    u32 shift;
+    u64 nbk;
+    db_index_dir_plan(keys.size(), max_key, shift, nbk);
+    std::vector<u32> dir = host_dir(keys, shift, nbk);
+    keys.push_back(0);
+    DbIndexView ix{keys.data(), (u64)keys.size() - 1, start.data(), rows.data(), dir.data(), shift, nbk};
+    std::vector<u32> out(2 * (size_t)n + 1, 0);
+    const u64 nq = q.size();
+    q.push_back(0);
+    if (nq && ix.n_keys) {
+        smb_emu::launch(3, threads, 0, [&] { index_count_kernel(ix, q.data(), nq, nullptr, out.data()); });
+        u32 d_nq = (u32)nq;                                      // the gather loop's variant: length read on the "device"
+        smb_emu::launch(2, threads, 0, [&] { index_count_kernel(ix, q.data(), nq + 1000, &d_nq, out.data() + n); });
+    }
+    out.resize(2 * (size_t)n);
+    dump(fout, out);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7]);
+    if (argc == 9 && !strcmp(argv[1], "ranges"))
+        return ranges_main(atoi(argv[2]), strtoull(argv[3], nullptr, 10), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
+    if (argc == 7 && !strcmp(argv[1], "index")) return index_main(atoi(argv[2]), argv[3], argv[4], argv[5], argv[6]);
+    fprintf(stderr, "usage: see the head of simt_emul.cu\n");
+    return 2;
+}

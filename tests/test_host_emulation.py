@@ -424,3 +424,86 @@ def test_db_index_counts_match_oracle(index_emul):
             want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32) if len(hh) \
                 else np.zeros(len(rows), np.uint32)
             assert np.array_equal(index_emul(query, rows), want), (len(rows), len(query))
+
+
+# ---------------------------------------------------------------------------------------------
+# the experimental KERNELS themselves on the CPU (tests/host_emul/simt.h: CTAs as cooperative fibers with
+# real __syncthreads / warp collectives / shared memory), csrc/experimental_kernels.cuh
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def simt():
+    exe = os.path.join(tempfile.gettempdir(), "smb_simt_emul")
+    src = os.path.join(HERE, "host_emul", "simt_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(mode, rows, *args, query=None, dtype=np.uint32):
+        hashes, offsets = orc.to_csr(rows)
+        with tempfile.TemporaryDirectory() as td:
+            fq, fh, fo, fc = (os.path.join(td, x) for x in ("q", "h", "o", "c"))
+            hashes.tofile(fh); offsets.tofile(fo)
+            cmd = [exe, mode] + [str(a) for a in args]
+            if query is not None:
+                np.asarray(query, dtype=np.uint64).tofile(fq)
+                cmd.append(fq)
+            subprocess.check_call(cmd + [fh, fo, fc])
+            return np.fromfile(fc, dtype=dtype)
+    return run
+
+
+def test_simt_stripe_kernels_match_oracle(simt):
+    """join_stripe_kernel + stripe_mirror_kernel + stripe_tag_kernel as written: block geometry, the warp's
+    32-element chunks, two scans in flight, shared-memory stripe, fused finalize, row chunks."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(31)
+    h, off = synth_sketches(70, mean=120, sd=30, lo=20, hi=250, n_families=2, pool=160, seed=29)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(70)]
+    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=2, dtype=np.uint64), np.array([7], dtype=np.uint64),
+                                      np.array([2**61] if i < 33 else [], dtype=np.uint64)])) for i in range(80)]
+    wide[3] = np.zeros(0, np.uint64)
+    for rows in (fam, wide):
+        hh, oo = orc.to_csr(rows)
+        want = orc.compare_all_pairs(hh, oo, nthreads=2)
+        n = len(rows)
+        for R, upper, threads in ((5, 0, 64), (3, 1, 96), (32, 0, 32), (7, 1, 128)):
+            got = simt("stripe", rows, R, upper, threads, dtype=np.float64).reshape(n, n)
+            assert np.array_equal(got, want), (n, R, upper, threads)
+
+
+def test_simt_range_search_kernels_match_oracle(simt):
+    "range_bounds_kernel + one_vs_many_ranges_kernel as written (slices in flight, bitmap in shared memory, directory walk)."
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(9)
+    mx = orc.max_hash_for_scaled(1000)
+    h, off = synth_sketches(75, mean=300, sd=60, lo=0, hi=700, n_families=3, pool=400, seed=47)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(75)]
+    fam[11] = np.unique(rng.integers(1, mx, size=3000, dtype=np.uint64))             # a row with slices longer than 64
+    big = np.uint64(2**64 - 1)
+    edge = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, big - 1, big], np.uint64),
+            np.arange(1, 300, dtype=np.uint64), np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
+    q_fam = np.unique(np.concatenate([fam[3], fam[17][:100], fam[11][::2], rng.integers(1, mx, size=2000, dtype=np.uint64),
+                                      np.array([mx + 5, 2**63], dtype=np.uint64)]))
+    q_edge = np.unique(np.concatenate([edge[2], edge[4][::3], np.array([1, 299, 300], dtype=np.uint64)]))
+    for rows, query in ((fam, q_fam), (edge, q_edge), (fam, fam[5][:1])):
+        hh, oo = orc.to_csr(rows)
+        want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32)
+        for P, max_bits, threads in ((5, 1 << 16, 64), (2, 64, 96), (9, 4096, 32)):
+            got = simt("ranges", rows, P, max_bits, threads, query=query)
+            assert np.array_equal(got, want), (len(rows), P, max_bits, threads)
+
+
+def test_simt_index_kernels_match_oracle(simt):
+    "index_rowid_kernel + index_count_kernel as written (own-lane groups, warp-wide groups, length read on the device)."
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(10)
+    h, off = synth_sketches(60, mean=200, sd=40, lo=0, hi=400, n_families=3, pool=260, seed=53)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(60)]
+    wide = [np.array([7, 1000 + i], dtype=np.uint64) for i in range(100)]            # one hash in 100 rows: the warp-wide path
+    wide[4] = np.zeros(0, np.uint64)
+    queries = {"fam": np.unique(np.concatenate([fam[3], fam[17][:100], rng.integers(1, 2**54, size=500, dtype=np.uint64)])),
+               "wide": np.array([7, 1003, 1050, 5], dtype=np.uint64)}
+    for rows, query in ((fam, queries["fam"]), (wide, queries["wide"]), (fam, queries["wide"])):
+        hh, oo = orc.to_csr(rows)
+        want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32)
+        for threads in (32, 96):
+            got = simt("index", rows, threads, query=query).reshape(2, len(rows))
+            assert np.array_equal(got[0], want) and np.array_equal(got[1], want), (len(rows), threads)
