@@ -2,7 +2,7 @@
 // emulator of simt.h (CTAs as cooperative fibers, real __syncthreads / warp collectives / shared memory) and
 // writes their results for comparison with the oracle.  The launch geometry is shrunk (fewer threads, smaller
 // shared memory) but the code is the code the GPU runs.  Test infrastructure for the CPU-only suite.
-//   simt_emul stripe <R> <upper 0|1> <threads> <hashes.u64> <offsets.u64> <out.f64 n*n>
+//   simt_emul stripe|stripe_low32 <R> <upper 0|1> <threads> <hashes.u64> <offsets.u64> <out.f64 n*n>
 //   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
 //   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
 #define SMB_SIMT_EMUL 1
@@ -34,7 +34,7 @@ static void dump(const char* path, const std::vector<T>& v) {
     fclose(f);
 }
 
-static int stripe_main(int R, int upper, int threads, const char* fh, const char* fo, const char* fout) {
+static int stripe_main(int R, int upper, int threads, const char* fh, const char* fo, const char* fout, bool low32) {
     std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
     const int n = (int)off.size() - 1;
     const u64 T = h.size();
@@ -42,10 +42,38 @@ static int stripe_main(int R, int upper, int threads, const char* fh, const char
     std::vector<u32> vals(T + 1), src(T + 1), tags(T + 1), pos(T + 1);
     smb_emu::launch(3, 64, 0, [&] { stripe_iota_kernel(vals.data(), T); });
     for (u64 i = 0; i < T; ++i) if (vals[i] != (u32)i) return 3;
-    std::copy(vals.begin(), vals.begin() + T, src.begin());
-    std::stable_sort(src.begin(), src.begin() + T, [&](u32 a, u32 b) { return h[a] < h[b]; });
     std::vector<u64> sk(T + 1);
-    for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    if (!low32) {
+        std::copy(vals.begin(), vals.begin() + T, src.begin());
+        std::stable_sort(src.begin(), src.begin() + T, [&](u32 a, u32 b) { return h[a] < h[b]; });
+        for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
+    } else {
+        // SMB_JOIN_SORT=low32, stripe_stream_low32 of compare_kernels.cu: its kernels, host stand-ins for the cub calls
+        std::vector<u32> low(T + 1), low_sorted(T + 1);
+        h.push_back(0);
+        smb_emu::launch(3, 64, 0, [&] { stripe_low32_kernel(h.data(), T, low.data(), vals.data()); });
+        std::vector<u32> perm(T);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return low[a] < low[b]; });         // SortPairs(low, vals)
+        for (u64 q = 0; q < T; ++q) { low_sorted[q] = low[perm[q]]; src[q] = vals[perm[q]]; }
+        smb_emu::launch(2, 96, 0, [&] { stripe_gather_keys_kernel(h.data(), src.data(), T, sk.data()); });
+        std::vector<u8> flags(T + 1, 0);
+        smb_emu::launch(4, 32, 0, [&] { stripe_mixed_runs_kernel(low_sorted.data(), sk.data(), T, flags.data()); });
+        std::vector<u32> where;                                                                            // DeviceSelect::Flagged
+        for (u64 q = 0; q < T; ++q) if (flags[q]) where.push_back((u32)q);
+        const u64 n_sel = where.size();
+        if (n_sel) {
+            std::vector<u64> rot(n_sel), rot_sorted(n_sel);
+            std::vector<u32> sel(n_sel), sel_sorted(n_sel);
+            smb_emu::launch(2, 64, 0, [&] { stripe_repair_load_kernel(where.data(), n_sel, sk.data(), src.data(), rot.data(), sel.data()); });
+            std::vector<u32> o2(n_sel);
+            std::iota(o2.begin(), o2.end(), 0);
+            std::stable_sort(o2.begin(), o2.end(), [&](u32 a, u32 b) { return rot[a] < rot[b]; });         // SortPairs(rot, sel)
+            for (u64 j = 0; j < n_sel; ++j) { rot_sorted[j] = rot[o2[j]]; sel_sorted[j] = sel[o2[j]]; }
+            smb_emu::launch(2, 64, 0, [&] { stripe_repair_store_kernel(where.data(), n_sel, rot_sorted.data(), sel_sorted.data(), sk.data(), src.data()); });
+        }
+        if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "repaired %llu elements\n", (unsigned long long)n_sel);
+    }
     smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel(sk.data(), src.data(), off.data(), n, T, tags.data(), pos.data()); });
     std::vector<double> out((size_t)n * n, -1.0);
     const size_t smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
@@ -135,7 +163,8 @@ static int index_main(int threads, const char* fq, const char* fh, const char* f
 }
 
 int main(int argc, char** argv) {
-    if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7]);
+    if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], false);
+    if (argc == 8 && !strcmp(argv[1], "stripe_low32")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], true);
     if (argc == 9 && !strcmp(argv[1], "ranges"))
         return ranges_main(atoi(argv[2]), strtoull(argv[3], nullptr, 10), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
     if (argc == 7 && !strcmp(argv[1], "index")) return index_main(atoi(argv[2]), argv[3], argv[4], argv[5], argv[6]);

@@ -469,6 +469,24 @@ def test_simt_stripe_kernels_match_oracle(simt):
             assert np.array_equal(got, want), (n, R, upper, threads)
 
 
+def test_simt_stripe_low32_kernels(simt):
+    "the kernels of the 32-bit sort + repair (low words, key gather, mixed runs, repair load / store) as written."
+    rng = np.random.default_rng(33)
+    lowword = np.uint64(0x1234abcd)
+    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
+    rows = []
+    for i in range(45):
+        mine = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0]
+        rows.append(np.unique(np.array(mine + [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)] +
+                                       rng.integers(1, 2**60, size=30, dtype=np.uint64).tolist(), dtype=np.uint64)))
+    rows[6] = np.zeros(0, np.uint64)
+    hh, oo = orc.to_csr(rows)
+    want = orc.compare_all_pairs(hh, oo, nthreads=2)
+    for R, upper, threads in ((5, 0, 64), (4, 1, 96)):
+        got = simt("stripe_low32", rows, R, upper, threads, dtype=np.float64).reshape(45, 45)
+        assert np.array_equal(got, want), (R, upper, threads)
+
+
 def test_simt_range_search_kernels_match_oracle(simt):
     "range_bounds_kernel + one_vs_many_ranges_kernel as written (slices in flight, bitmap in shared memory, directory walk)."
     from sourmash_b200.synth import synth_sketches
