@@ -525,3 +525,53 @@ def test_simt_index_kernels_match_oracle(simt):
         for threads in (32, 96):
             got = simt("index", rows, threads, query=query).reshape(2, len(rows))
             assert np.array_equal(got[0], want) and np.array_equal(got[1], want), (len(rows), threads)
+
+
+@pytest.fixture(scope="module")
+def simt_sketch():
+    exe = os.path.join(tempfile.gettempdir(), "smb_simt_sketch_emul")
+    src = os.path.join(HERE, "host_emul", "simt_sketch_emul.cu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+
+    def run(k, W, max_hash, lead, genomes):
+        seqs = np.concatenate(genomes) if genomes else np.zeros(0, np.uint8)
+        offs = np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
+        with tempfile.TemporaryDirectory() as td:
+            fs, fo, fc = (os.path.join(td, x) for x in ("s", "o", "c"))
+            np.asarray(seqs, dtype=np.uint8).tofile(fs); offs.tofile(fo)
+            subprocess.check_call([exe, str(k), str(W), str(max_hash), str(lead), fs, fo, fc])
+            raw = np.fromfile(fc, dtype=np.uint64)
+        rows, at = [], 0
+        while at < len(raw):
+            n = int(raw[at]); rows.append(raw[at + 1:at + 1 + n]); at += 1 + n
+        return rows
+    return run
+
+
+def test_simt_hash_kernels_match_oracle(simt_sketch):
+    """hash_kmers_kernel<K> and the one-pass hash_kmers_fused_kernel as written: tiling over unaligned streams,
+    per-thread windows, shared-memory survivor staging with its overflow path (every hash kept), flushes,
+    launches over tile ranges -- the candidate sets equal the oracle's."""
+    genomes = [synth_genome(2600, seed=61, n_every=83), synth_genome(900, seed=62), synth_genome(40, seed=63),
+               synth_genome(20, seed=64), synth_genome(5000, seed=65)]
+    genomes[0][300:380] = np.frombuffer(bytes(genomes[0][300:380]).lower(), dtype=np.uint8)
+    genomes[4][1234] = ord("R"); genomes[4][-30] = ord("N")
+
+    def expected(g, k, max_hash):
+        if len(g) < k:
+            return np.zeros(0, np.uint64)
+        hs, err = orc.seq_to_hashes(bytes(g), k, force=True, keep_zeros=True)
+        hs = np.asarray(hs, dtype=np.uint64)
+        return np.unique(hs[(hs != 0) & (hs <= np.uint64(max_hash))])
+    for max_hash in (2**64 - 1, orc.max_hash_for_scaled(20)):                 # keep all (staging overflows) / a sketch threshold
+        for W, lead in ((16, 5), (32, 0)):
+            for k in (21, 31, 51):
+                got = simt_sketch(k, W, max_hash, lead, genomes)
+                assert len(got) == len(genomes)
+                for g, row in zip(genomes, got):
+                    assert np.array_equal(row, expected(g, k, max_hash)), (k, W, lead, len(g))
+            fused = simt_sketch(0, W, max_hash, lead, genomes)
+            assert len(fused) == 3 * len(genomes)
+            for gi, g in enumerate(genomes):
+                for ki, k in enumerate((21, 31, 51)):
+                    assert np.array_equal(fused[gi * 3 + ki], expected(g, k, max_hash)), ("fused", k, W, lead, len(g))
