@@ -1058,69 +1058,6 @@ void launch_counter_update_argmax(u32* counters, const u32* delta, int n,
 // Multi-GPU: rank r joins the hashes of key range r (every hash lives in exactly one range), the
 // partial matrices add up.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) join_row_range_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
-                                                            int n_rows, u64 key_lo, u64 key_hi, int bounded_hi,
-                                                            u64* __restrict__ beg, u64* __restrict__ cnt) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > n_rows) return;
-    if (r == n_rows) { cnt[r] = 0; return; }              // extra slot: the scan then yields the total
-    const u64* row = h + off[r];
-    const u64 len = off[r + 1] - off[r];
-    u64 lo = 0, hi = len;
-    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (row[mid] < key_lo) lo = mid + 1; else hi = mid; }
-    const u64 b = lo;
-    u64 e = len;
-    if (bounded_hi) {
-        lo = b; hi = len;
-        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (row[mid] < key_hi) lo = mid + 1; else hi = mid; }
-        e = lo;
-    }
-    beg[r] = b;
-    cnt[r] = e - b;
-}
-
-__global__ void __launch_bounds__(256) join_gather_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
-                                                         const u64* __restrict__ beg, const u64* __restrict__ dst_off,
-                                                         int n_rows, u64* __restrict__ keys, u32* __restrict__ ids) {
-    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        const u64 src = off[r] + beg[r], d0 = dst_off[r], n = dst_off[r + 1] - d0;
-        for (u64 i = threadIdx.x; i < n; i += blockDim.x) { keys[d0 + i] = h[src + i]; ids[d0 + i] = (u32)r; }
-    }
-}
-
-// out[0] += sum over groups of C(m,2); out[1] = max m
-__global__ void __launch_bounds__(256) join_estimate_kernel(const u64* __restrict__ keys, u64 T,
-                                                           unsigned long long* __restrict__ out) {
-    unsigned long long pairs = 0, mmax = 0;
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < T; p += (u64)gridDim.x * blockDim.x) {
-        const u64 m = join_group_size_at_head(keys, T, p);
-        pairs += m * (m - (m ? 1 : 0)) / 2;
-        mmax = m > mmax ? m : mmax;
-    }
-    for (int d = 16; d; d >>= 1) {
-        pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, mmax, d);
-        mmax = o > mmax ? o : mmax;
-    }
-    if (lane_id() == 0) { if (pairs) atomicAdd(out, pairs); if (mmax) atomicMax(out + 1, mmax); }
-}
-
-// Every element pairs with the later elements of its group: ids ascend inside a group, so
-// (ids[p], ids[b]) is an upper-triangle cell.  Increments are fire-and-forget reductions (RED)
-// resolved in L2, and their rate is what bounds the kernel: 1.455e9 reductions in 16.7 ms =
-// 8.7e10 /s = 0.31 per clock per SM on the 10 000-sketch matrix, and three rewrites that attack
-// everything else left the time unchanged to 0.1 % (profiles/r1q_join.txt, r1s_join.txt):
-// evict-first stream loads + evict-last reductions (DRAM write-back 7.1 -> 1.4 GB, same time) and
-// walking the groups from a shared-memory tile instead of dependent L2 loads (long-scoreboard
-// stalls 105 -> 33 per issue, same time).  Going faster needs fewer reductions (accumulating in
-// shared-memory tiles of the matrix), see DESIGN.md section 4.5.
-__global__ void __launch_bounds__(256) join_count_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
-                                                        u64 T, u32* __restrict__ common, size_t ld) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= T) return;
-    join_walk(keys, ids, T, p, [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
-}
-
 // Slice rows to [key_lo, key_hi) (bounded_hi == 0: no upper bound), sort the (hash, row) pairs.
 // Returns the number of elements; *keys_out / *ids_out point into `work`, which the caller frees.
 struct JoinWork {
@@ -1212,69 +1149,6 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
 // Not measured yet: kept behind the switch until it has been validated on the GPU; the logic
 // is covered on the CPU by tests/test_host_emulation.py::test_join_cluster_layout_matches_oracle.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) join_rowkey_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
-                                                         u64 T, unsigned long long* __restrict__ rowkey) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= T) return;
-    if (join_is_shared(keys, T, p)) atomicMin(rowkey + ids[p], (unsigned long long)keys[p]);
-}
-
-__global__ void __launch_bounds__(256) join_iota_kernel(u32* __restrict__ v, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (u32)i;
-}
-
-__global__ void __launch_bounds__(256) join_invert_kernel(const u32* __restrict__ order, int n, u32* __restrict__ inv) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) inv[order[r]] = (u32)r;
-}
-
-// per-rank element counts (rank r holds row order[r]); slot n is the scan's total
-__global__ void __launch_bounds__(256) join_rank_counts_kernel(const u64* __restrict__ cnt, const u32* __restrict__ order,
-                                                              int n, u64* __restrict__ cnt_rank) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > n) return;
-    cnt_rank[r] = r < n ? cnt[order[r]] : 0;
-}
-
-// like join_gather_kernel, rows visited in rank order and labelled with their rank
-__global__ void __launch_bounds__(256) join_gather_ranked_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
-                                                                const u64* __restrict__ beg, const u32* __restrict__ order,
-                                                                const u64* __restrict__ dst_off, int n_rows,
-                                                                u64* __restrict__ keys, u32* __restrict__ ids) {
-    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        const u32 row = order[r];
-        const u64 src = off[row] + beg[row], d0 = dst_off[r], n = dst_off[r + 1] - d0;
-        for (u64 i = threadIdx.x; i < n; i += blockDim.x) { keys[d0 + i] = h[src + i]; ids[d0 + i] = (u32)r; }
-    }
-}
-
-// one warp per element: lanes take consecutive later elements of the group
-__global__ void __launch_bounds__(256) join_count_warp_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
-                                                             u64 T, u32* __restrict__ common, size_t ld) {
-    const u64 p = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (p >= T) return;                                   // whole warps leave together
-    const u32 lane = lane_id();
-    for (u64 b0 = p + 1;; b0 += 32) {
-        const bool hit = join_walk_lane(keys, ids, T, p, b0, lane,
-                                        [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
-        if (!__all_sync(0xffffffffu, hit)) break;
-    }
-}
-
-// common[i][j] += rank-space count of (i, j), for i < j
-__global__ void __launch_bounds__(256) join_unpermute_add_kernel(const u32* __restrict__ ranked, const u32* __restrict__ inv,
-                                                                int n, size_t ld_ranked, u32* __restrict__ common, size_t ld) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    for (int i = blockIdx.y; i < j; i += gridDim.y) {       // every (i, j), i < j, is visited exactly once
-        u32 lo, hi;
-        join_rank_cell(inv, (u32)i, (u32)j, lo, hi);
-        const u32 v = ranked[(size_t)lo * ld_ranked + hi];
-        if (v) common[(size_t)i * ld + j] += v;
-    }
-}
-
 static cudaError_t join_counts_clustered(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                                          u32* common, size_t ld, cudaStream_t s) {
     cudaError_t e;
@@ -1361,13 +1235,6 @@ static cudaError_t join_counts_clustered(const u64* h, const u64* off, int n, u6
 // smb_compare_jaccard, SMB_COMPARE_PASSES; off by default, see join_walk.cuh).
 // ------------------------------------------------------------------------------------
 struct JoinStream { JoinWork W; };
-
-__global__ void __launch_bounds__(256) join_count_rows_kernel(const u64* __restrict__ keys, const u32* __restrict__ ids,
-                                                             u64 T, u32 r0, u32 r1, u32* __restrict__ common, size_t ld) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= T) return;
-    join_walk_rows(keys, ids, T, p, r0, r1, [&](u32 a, u32 b) { atomicAdd(common + (size_t)a * ld + b, 1u); });
-}
 
 cudaError_t join_stream_create(const u64* h, const u64* off, int n, u64 max_key, JoinStream** out, cudaStream_t s) {
     JoinStream* js = new JoinStream();

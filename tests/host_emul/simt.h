@@ -187,6 +187,21 @@ template <class T> inline T __shfl_sync(uint32_t, T v, int src) {
     memcpy(&out, &c.snap[src & 31], sizeof(T));
     return out;
 }
+template <class T> inline T __shfl_xor_sync(uint32_t, T v, int lane_mask) {
+    uint64_t raw = 0;
+    static_assert(sizeof(T) <= 8, "shfl payload");
+    memcpy(&raw, &v, sizeof(T));
+    const unsigned me = smb_emu::st().cur->linear & 31u;
+    const smb_emu::WarpColl& c = smb_emu::collective(raw);
+    T out;
+    memcpy(&out, &c.snap[(me ^ (unsigned)lane_mask) & 31], sizeof(T));
+    return out;
+}
+inline bool __all_sync(uint32_t, bool pred) {
+    const smb_emu::WarpColl& c = smb_emu::collective(pred ? 1 : 0);
+    for (int l = 0; l < 32; ++l) if (((c.snap_mask >> l) & 1u) && !c.snap[l]) return false;
+    return true;
+}
 inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     const smb_emu::WarpColl& c = smb_emu::collective(v);
     uint32_t s = 0;
@@ -196,5 +211,7 @@ inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
 inline int __ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 using std::max;
 using std::min;

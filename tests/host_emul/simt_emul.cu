@@ -4,6 +4,8 @@
 // shared memory) but the code is the code the GPU runs.  Test infrastructure for the CPU-only suite.
 //   simt_emul stripe|stripe_low32 <R> <upper 0|1> <threads> <hashes.u64> <offsets.u64> <out.f64 n*n>
 //   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
+//   simt_emul join|cluster <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>      (upper-triangle counts)
+//   simt_emul rows <passes> <hashes.u64> <offsets.u64> <out.u32 n*n>                         (full rows as captured)
 //   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
 #define SMB_SIMT_EMUL 1
 #include "simt.h"
@@ -94,6 +96,98 @@ static int stripe_main(int R, int upper, int threads, const char* fh, const char
     return 0;
 }
 
+// ---- inverted join: the default pipeline, the cluster layout, the row-block passes (kernels as written; the
+// exclusive scan and the radix sort of the product are host loops here) ----
+struct Slice { std::vector<u64> keys; std::vector<u32> ids; };
+static Slice sorted_slice(const std::vector<u64>& h, const std::vector<u64>& off, int n, u64 lo, u64 hi, bool bounded,
+                          const std::vector<u32>* order) {
+    std::vector<u64> beg(n + 1), cnt(n + 1), doff(n + 2, 0);
+    smb_emu::launch((n + 1 + 63) / 64, 64, 0, [&] { join_row_range_kernel(h.data(), off.data(), n, lo, hi, bounded ? 1 : 0, beg.data(), cnt.data()); });
+    std::vector<u64> cnt_rank(n + 1);
+    if (order) smb_emu::launch((n + 1 + 63) / 64, 64, 0, [&] { join_rank_counts_kernel(cnt.data(), order->data(), n, cnt_rank.data()); });
+    const std::vector<u64>& c = order ? cnt_rank : cnt;
+    for (int r = 0; r <= n; ++r) doff[r + 1] = doff[r] + c[r];                     // cub::DeviceScan::ExclusiveSum
+    const u64 T = doff[n];
+    std::vector<u64> keys(T + 1);
+    std::vector<u32> ids(T + 1);
+    if (order) smb_emu::launch(7, 64, 0, [&] { join_gather_ranked_kernel(h.data(), off.data(), beg.data(), order->data(), doff.data(), n, keys.data(), ids.data()); });
+    else smb_emu::launch(7, 64, 0, [&] { join_gather_kernel(h.data(), off.data(), beg.data(), doff.data(), n, keys.data(), ids.data()); });
+    std::vector<size_t> perm(T);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });   // cub::DeviceRadixSort::SortPairs
+    Slice S;
+    S.keys.resize(T + 1); S.ids.resize(T + 1);
+    for (u64 i = 0; i < T; ++i) { S.keys[i] = keys[perm[i]]; S.ids[i] = ids[perm[i]]; }
+    S.keys.resize(T); S.ids.resize(T);
+    return S;
+}
+
+static int join_main(const char* mode, int arg, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    u64 max_key = 0;
+    for (u64 v : h) max_key = std::max(max_key, v);
+    h.push_back(0);
+    std::vector<u32> common((size_t)n * n + 1, 0);
+    if (!strcmp(mode, "join")) {                                             // arg = number of key-range shards
+        unsigned long long est[2] = {0, 0}, total = 0;
+        for (int shard = 0; shard < arg; ++shard) {
+            u64 lo, hi;
+            bool bounded;
+            join_shard_range(max_key, shard, arg, lo, hi, bounded);
+            Slice S = sorted_slice(h, off, n, lo, hi, bounded, nullptr);
+            const u64 T = S.keys.size();
+            S.keys.push_back(0); S.ids.push_back(0);
+            if (!T) continue;
+            smb_emu::launch((T + 63) / 64, 64, 0, [&] { join_count_kernel(S.keys.data(), S.ids.data(), T, common.data(), (size_t)n); });
+            smb_emu::launch(3, 96, 0, [&] { join_estimate_kernel(S.keys.data(), T, est); });
+        }
+        for (size_t i = 0; i < (size_t)n * n; ++i) total += common[i];
+        if (est[0] != total) return 3;                                       // sum of C(m,2) == number of increments
+    } else if (!strcmp(mode, "rows")) {                                      // arg = number of row-block passes
+        Slice S = sorted_slice(h, off, n, 0, 0, false, nullptr);
+        const u64 T = S.keys.size();
+        S.keys.push_back(0); S.ids.push_back(0);
+        std::vector<u32> captured((size_t)n * n + 1, 0);
+        const int per = (n + arg - 1) / arg;
+        for (int r0 = 0; r0 < n; r0 += per) {
+            const int r1 = std::min(n, r0 + per);
+            if (T) smb_emu::launch((T + 63) / 64, 64, 0, [&] { join_count_rows_kernel(S.keys.data(), S.ids.data(), T, (u32)r0, (u32)r1, common.data(), (size_t)n); });
+            for (int i = r0; i < r1; ++i)
+                for (int j = 0; j < n; ++j)
+                    if (i != j) captured[(size_t)i * n + j] = common[(size_t)std::min(i, j) * n + std::max(i, j)];
+        }
+        common = captured;
+    } else {                                                                 // cluster; arg = shards
+        std::vector<unsigned long long> rowkey(n + 1, ~0ull);
+        {
+            Slice S = sorted_slice(h, off, n, 0, max_key / 64 + 1, true, nullptr);
+            const u64 T = S.keys.size();
+            S.keys.push_back(0); S.ids.push_back(0);
+            if (T) smb_emu::launch((T + 63) / 64, 64, 0, [&] { join_rowkey_kernel(S.keys.data(), S.ids.data(), T, rowkey.data()); });
+        }
+        std::vector<u32> order(n + 1), inv(n + 1);
+        smb_emu::launch((n + 63) / 64, 64, 0, [&] { join_iota_kernel(order.data(), n); });
+        std::stable_sort(order.begin(), order.begin() + n, [&](u32 a, u32 b) { return rowkey[a] < rowkey[b]; });  // SortPairs(rowkey, iota)
+        smb_emu::launch((n + 63) / 64, 64, 0, [&] { join_invert_kernel(order.data(), n, inv.data()); });
+        for (int shard = 0; shard < arg; ++shard) {
+            u64 lo, hi;
+            bool bounded;
+            join_shard_range(max_key, shard, arg, lo, hi, bounded);
+            Slice S = sorted_slice(h, off, n, lo, hi, bounded, &order);
+            const u64 T = S.keys.size();
+            S.keys.push_back(0); S.ids.push_back(0);
+            std::vector<u32> ranked((size_t)n * n + 1, 0);
+            if (T) smb_emu::launch((T * 32 + 63) / 64, 64, 0, [&] { join_count_warp_kernel(S.keys.data(), S.ids.data(), T, ranked.data(), (size_t)n); });
+            smb_emu::launch(smb_emu::Dim3((n + 63) / 64, std::min(n, 5)), 64, 0,
+                            [&] { join_unpermute_add_kernel(ranked.data(), inv.data(), n, (size_t)n, common.data(), (size_t)n); });
+        }
+    }
+    common.resize((size_t)n * n);
+    dump(fout, common);
+    return 0;
+}
+
 static std::vector<u32> host_dir(const std::vector<u64>& keys, u32 shift, u64 nbk) {
     std::vector<u32> dir(nbk + 2);
     for (u64 b = 0; b <= nbk; ++b)
@@ -168,6 +262,8 @@ int main(int argc, char** argv) {
     if (argc == 9 && !strcmp(argv[1], "ranges"))
         return ranges_main(atoi(argv[2]), strtoull(argv[3], nullptr, 10), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
     if (argc == 7 && !strcmp(argv[1], "index")) return index_main(atoi(argv[2]), argv[3], argv[4], argv[5], argv[6]);
+    if (argc == 6 && (!strcmp(argv[1], "join") || !strcmp(argv[1], "rows") || !strcmp(argv[1], "cluster")))
+        return join_main(argv[1], atoi(argv[2]), argv[3], argv[4], argv[5]);
     fprintf(stderr, "usage: see the head of simt_emul.cu\n");
     return 2;
 }

@@ -469,6 +469,34 @@ def test_simt_stripe_kernels_match_oracle(simt):
             assert np.array_equal(got, want), (n, R, upper, threads)
 
 
+def test_simt_join_kernels_match_oracle(simt):
+    """The inverted join as launched: row slices, gather, count (the default compare path), the estimate
+    kernel's invariant, key-range shards; the cluster layout's kernels; the row-block passes."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(3)
+    h, off = synth_sketches(70, mean=200, sd=40, lo=50, hi=400, n_families=4, pool=260, seed=9)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(70)]
+    big = np.uint64(2**64 - 1)
+    edge = [np.unique(np.concatenate([rng.integers(0, 2**64 - 1, size=int(rng.integers(0, 20)), dtype=np.uint64),
+                                      np.array([0, 5, big] if i % 3 == 0 else [5], dtype=np.uint64)])) for i in range(45)]
+    edge[7] = np.zeros(0, np.uint64)
+    edge[9] = edge[8].copy()
+    for rows in (fam, edge):
+        n = len(rows)
+        hh, oo = orc.to_csr(rows)
+        want = orc.pairwise_common(hh, oo)
+        iu = np.triu_indices(n, 1)
+        full = np.zeros_like(want)
+        full[iu] = want[iu]
+        for shards in (1, 3):
+            got = simt("join", rows, shards).reshape(n, n)
+            assert np.array_equal(got[iu], want[iu]) and int(np.tril(got).sum()) == 0, ("join", shards)
+            got = simt("cluster", rows, shards).reshape(n, n)
+            assert np.array_equal(got[iu], want[iu]) and int(np.tril(got).sum()) == 0, ("cluster", shards)
+        for passes in (1, 4, n):
+            assert np.array_equal(simt("rows", rows, passes).reshape(n, n), full + full.T), ("rows", passes)
+
+
 def test_simt_stripe_low32_kernels(simt):
     "the kernels of the 32-bit sort + repair (low words, key gather, mixed runs, repair load / store) as written."
     rng = np.random.default_rng(33)
