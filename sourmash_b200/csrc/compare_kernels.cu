@@ -34,6 +34,7 @@
 #include "range_search.cuh"
 #include "db_index.cuh"
 #include "experimental_kernels.cuh"
+#include "search_kernels.cuh"
 
 namespace smb {
 
@@ -472,15 +473,6 @@ void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* of
 // ------------------------------------------------------------------------------------
 // generic fallback: warp per pair, binary search of the shorter row in the longer row
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ bool row_contains(const u64* __restrict__ r, u64 n, u64 x) {
-    u64 lo = 0, hi = n;
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        u64 v = ld_nc_u64(r + mid);
-        if (v < x) lo = mid + 1; else hi = mid;
-    }
-    return lo < n && ld_nc_u64(r + lo) == x;
-}
 
 __global__ void __launch_bounds__(256) pairwise_generic_kernel(
     const u64* __restrict__ hA, const u64* __restrict__ offA, int nA, const u64* __restrict__ hB,
@@ -702,34 +694,9 @@ void launch_finalize_rows(const u32* common, size_t n, const u64* off, int n_row
 // lets every key that opens a bucket write its index and fill short runs of empty buckets
 // behind it, pass 3 resolves the remaining (long) empty runs by binary search -- no thread ever
 // walks a long gap serially, whatever the key distribution.
-static constexpr u32 DIR_UNSET = 0xffffffffu;
 
-__global__ void __launch_bounds__(256) global_dir_fill_kernel(u32* __restrict__ dir, u64 n_entries, u32 v) {
-    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_entries; b += (u64)gridDim.x * blockDim.x)
-        dir[b] = v;
-}
 
-__global__ void __launch_bounds__(256) global_dir_heads_kernel(const u64* __restrict__ q, u64 nq, u32 shift,
-                                                              u32* __restrict__ dir) {
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
-        const u64 bp = q[p] >> shift;
-        const long long bprev = p == 0 ? -1 : (long long)(q[p - 1] >> shift);
-        if ((long long)bp == bprev) continue;
-        long long lo = (long long)bp - 32;                      // short gaps: fill directly
-        if (lo < bprev + 1) lo = bprev + 1;
-        for (long long b = lo; b <= (long long)bp; ++b) dir[b] = (u32)p;
-    }
-}
 
-__global__ void __launch_bounds__(256) global_dir_resolve_kernel(const u64* __restrict__ q, u64 nq, u32 shift,
-                                                                u64 nb, u32* __restrict__ dir) {
-    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += (u64)gridDim.x * blockDim.x) {
-        if (dir[b] != DIR_UNSET) continue;
-        u64 lo = 0, hi = nq;                                    // first key with bucket >= b
-        while (lo < hi) { u64 mid = (lo + hi) >> 1; if ((q[mid] >> shift) < b) lo = mid + 1; else hi = mid; }
-        dir[b] = (u32)lo;
-    }
-}
 
 void launch_build_global_dir(const u64* q, u64 nq, int shift, u64 nb, u32* dir, cudaStream_t s) {
     const u64 cap_blocks = (u64)SMB_B200_SMS * 32;
@@ -742,29 +709,6 @@ void launch_build_global_dir(const u64* q, u64 nq, int shift, u64 nb, u32* dir, 
     global_dir_resolve_kernel<<<(unsigned)b1, 256, 0, s>>>(q, nq, (u32)shift, nb, dir); count_launches(1);
 }
 
-// occupancy bitmap over the query: bit (key >> bm_shift) set iff some query key maps there.  It
-// is 8-16x smaller than directory + keys, stays in L2, and rejects most probes of a subject
-// element before the directory / key lines (DRAM for a 1e7-hash query) are touched.
-__global__ void __launch_bounds__(256) build_query_bitmap_kernel(const u64* __restrict__ q, u64 nq,
-                                                                u32 sh, int fine_log2,
-                                                                u32* __restrict__ bitmap) {
-    // bitmap is 2^fine_log2 times finer than the directory
-    const u32 bm_shift = sh >= (u32)fine_log2 ? sh - (u32)fine_log2 : 0u;
-    // q is sorted, so the keys of one 32-bit bitmap word are a contiguous run: the first key of
-    // a run ORs the whole run together and stores the word -- no atomics, one writer per word.
-    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nq; p += (u64)gridDim.x * blockDim.x) {
-        const u64 bit = q[p] >> bm_shift;
-        const u64 word = bit >> 5;
-        if (p > 0 && ((q[p - 1] >> bm_shift) >> 5) == word) continue;
-        u32 acc = 1u << (bit & 31);
-        for (u64 r = p + 1; r < nq; ++r) {
-            const u64 b2 = q[r] >> bm_shift;
-            if ((b2 >> 5) != word) break;
-            acc |= 1u << (b2 & 31);
-        }
-        bitmap[word] = acc;
-    }
-}
 
 void launch_build_query_bitmap(const u64* q, u64 nq, int shift, int fine_log2,
                                u32* bitmap, cudaStream_t s) {
@@ -774,56 +718,6 @@ void launch_build_query_bitmap(const u64* q, u64 nq, int shift, int fine_log2,
     build_query_bitmap_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, (u32)shift, fine_log2, bitmap); count_launches(1);
 }
 
-__global__ void __launch_bounds__(256) one_vs_many_global_kernel(
-    const u64* __restrict__ q, u64 nq, const u32* __restrict__ dir, u32 shift, u64 nbk,
-    const u32* __restrict__ bitmap, int fine_log2, const u64* __restrict__ hB,
-    const u64* __restrict__ offB, int nB, u32* __restrict__ out) {
-    const u32 bm_shift = shift >= (u32)fine_log2 ? shift - (u32)fine_log2 : 0u;
-    const int lane = lane_id();
-    const int wstride = gridDim.x * (blockDim.x >> 5);
-    constexpr int U = 4;
-    for (int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nB; j += wstride) {
-        const u64* row = hB + offB[j];
-        const u64 n = offB[j + 1] - offB[j];
-        u32 c = 0;
-        for (u64 base = 0; base < n; base += 32 * U) {
-            u64 x[U];
-            u32 word[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {                       // U independent loads in flight
-                const u64 e = base + (u64)u * 32 + lane;
-                x[u] = e < n ? ld_nc_u64(row + e) : SMB_U64_MAX;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool in_range = (x[u] >> shift) < nbk;    // false for padding / beyond the query
-                word[u] = 0u;
-                if (in_range) {
-                    if (bitmap) {
-                        const u64 bit = x[u] >> bm_shift;
-                        word[u] = (__ldg(bitmap + (bit >> 5)) >> (bit & 31)) & 1u;
-                    } else {
-                        word[u] = 1u;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (word[u]) {                                   // ~4 % of the elements get here
-                    const u64 b = x[u] >> shift;
-                    u64 p = dir[b];
-                    const u64 pe = dir[b + 1];
-                    for (; p < pe; ++p) {
-                        const u64 k = ld_nc_u64(q + p);
-                        if (k >= x[u]) { c += (k == x[u]); break; }
-                    }
-                }
-            }
-        }
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) out[j] = c;
-    }
-}
 
 void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, int shift, u64 nb,
                                const u32* bitmap, int fine_log2, const u64* hB,
@@ -874,100 +768,14 @@ bool range_search_enabled() {
 // ------------------------------------------------------------------------------------
 // row-level set operations used by gather (single block; rows are a few 1e3..1e6 keys)
 // ------------------------------------------------------------------------------------
-template <bool KEEP_COMMON>
-__global__ void __launch_bounds__(1024) setop_rows_kernel(const u64* __restrict__ a, u64 na,
-                                                         const u64* __restrict__ b, u64 nb,
-                                                         u64* __restrict__ out,
-                                                         u32* __restrict__ d_n) {
-    // stable compaction of a's elements that are (KEEP_COMMON ? in : not in) b.
-    __shared__ u32 warp_tot[32];
-    __shared__ u32 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (u64 base = 0; base < na; base += blockDim.x) {
-        u64 e = base + threadIdx.x;
-        bool valid = e < na;
-        u64 x = valid ? a[e] : 0;
-        bool in_b = valid && row_contains(b, nb, x);
-        bool keep = valid && (KEEP_COMMON ? in_b : !in_b);
-        u32 bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        u32 before = 0;
-        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
-        u32 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
-        if (keep) out[pos] = x;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 t = 0;
-            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += warp_tot[w2];
-            carry += t;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *d_n = carry;
-}
 
-// gather keeps its query fixed and flags consumed hashes instead of re-materialising the
-// remaining query every round: intersect = row elements present in q and still alive.
-__device__ __forceinline__ long long row_find(const u64* __restrict__ r, u64 n, u64 x) {
-    u64 lo = 0, hi = n;
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        if (ld_nc_u64(r + mid) < x) lo = mid + 1; else hi = mid;
-    }
-    return (lo < n && ld_nc_u64(r + lo) == x) ? (long long)lo : -1;
-}
 
-__global__ void __launch_bounds__(1024) intersect_alive_kernel(const u64* __restrict__ q, u64 nq,
-                                                              const u8* __restrict__ alive,
-                                                              const u64* __restrict__ row, u64 rn,
-                                                              u64* __restrict__ out, u32* __restrict__ d_n) {
-    __shared__ u32 warp_tot[32];
-    __shared__ u32 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (u64 base = 0; base < rn; base += blockDim.x) {
-        u64 e = base + threadIdx.x;
-        bool keep = false;
-        u64 x = 0;
-        if (e < rn) {
-            x = row[e];
-            long long pos = row_find(q, nq, x);
-            keep = pos >= 0 && alive[pos];
-        }
-        u32 bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        u32 before = 0;
-        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
-        u32 pos_out = carry + before + __popc(bal & ((1u << lane) - 1u));
-        if (keep) out[pos_out] = x;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 t = 0;
-            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += warp_tot[w2];
-            carry += t;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *d_n = carry;
-}
 
 void launch_intersect_alive(const u64* q, u64 nq, const u8* alive, const u64* row, u64 rn, u64* out,
                             u32* d_n, cudaStream_t s) {
     intersect_alive_kernel<<<1, 1024, 0, s>>>(q, nq, alive, row, rn, out, d_n); count_launches(1);
 }
 
-__global__ void __launch_bounds__(256) mark_dead_kernel(const u64* __restrict__ q, u64 nq, u8* __restrict__ alive,
-                                                       const u64* __restrict__ gone, u64 n) {
-    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
-        long long pos = row_find(q, nq, gone[e]);
-        if (pos >= 0) alive[pos] = 0;
-    }
-}
 
 void launch_mark_dead(const u64* q, u64 nq, u8* alive, const u64* gone, u64 n, cudaStream_t s) {
     if (n == 0) return;
@@ -976,22 +784,10 @@ void launch_mark_dead(const u64* q, u64 nq, u8* alive, const u64* gone, u64 n, c
     mark_dead_kernel<<<(unsigned)blocks, 256, 0, s>>>(q, nq, alive, gone, n); count_launches(1);
 }
 
-__global__ void make_row_offsets_kernel(const u32* __restrict__ d_n, u64* __restrict__ off2) {
-    off2[0] = 0;
-    off2[1] = *d_n;
-}
 void launch_make_row_offsets(const u32* d_n, u64* d_off2, cudaStream_t s) {
     make_row_offsets_kernel<<<1, 1, 0, s>>>(d_n, d_off2); count_launches(1);
 }
 
-__global__ void __launch_bounds__(256) mark_dead_n_kernel(const u64* __restrict__ q, u64 nq, u8* __restrict__ alive,
-                                                         const u64* __restrict__ gone, const u32* __restrict__ d_n) {
-    const u64 n = *d_n;
-    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
-        long long pos = row_find(q, nq, gone[e]);
-        if (pos >= 0) alive[pos] = 0;
-    }
-}
 void launch_mark_dead_n(const u64* q, u64 nq, u8* alive, const u64* gone, const u32* d_n, cudaStream_t s) {
     mark_dead_n_kernel<<<64, 256, 0, s>>>(q, nq, alive, gone, d_n); count_launches(1);
 }
@@ -1006,38 +802,6 @@ void launch_subtract_rows(const u64* a, u64 na, const u64* b, u64 nb, u64* out, 
     setop_rows_kernel<false><<<1, 1024, 0, s>>>(a, na, b, nb, out, d_n); count_launches(1);
 }
 
-// counters[j] -= delta[j] (delta nullable), then argmax with lowest-index tie break
-// (Counter.most_common()[0] on insertion-ordered dict: src/sourmash/index/__init__.py:841).
-__global__ void __launch_bounds__(1024) counter_update_argmax_kernel(
-    u32* __restrict__ counters, const u32* __restrict__ delta, int n,
-    unsigned long long* __restrict__ d_best) {
-    // key = (value << 32) | (0xffffffff - index): max key == max value, then min index
-    unsigned long long best = 0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        u32 v = counters[j];
-        if (delta) { u32 d = delta[j]; v = d > v ? 0u : v - d; counters[j] = v; }
-        unsigned long long key = ((unsigned long long)v << 32) | (unsigned long long)(0xffffffffu - (u32)j);
-        best = key > best ? key : best;
-    }
-    for (int d = 16; d; d >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-        best = o > best ? o : best;
-    }
-    __shared__ unsigned long long sb[32];
-    if (lane_id() == 0) sb[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        best = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : 0ULL;
-        for (int d = 16; d; d >>= 1) {
-            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-            best = o > best ? o : best;
-        }
-        if (threadIdx.x == 0) {
-            d_best[0] = best >> 32;                                   // value
-            d_best[1] = 0xffffffffu - (u32)(best & 0xffffffffu);      // index
-        }
-    }
-}
 
 void launch_counter_update_argmax(u32* counters, const u32* delta, int n,
                                   unsigned long long* d_best, cudaStream_t s) {

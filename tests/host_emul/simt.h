@@ -209,6 +209,7 @@ inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     return s;
 }
 inline int __ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
+inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }

@@ -6,6 +6,7 @@
 //   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
 //   simt_emul join|cluster <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>      (upper-triangle counts)
 //   simt_emul rows <passes> <hashes.u64> <offsets.u64> <out.u32 n*n>                         (full rows as captured)
+//   simt_emul gather <use_index 0|1> <threshold> <query.u64> <hashes.u64> <offsets.u64> <out.u32 (row, size) pairs>
 //   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
 #define SMB_SIMT_EMUL 1
 #include "simt.h"
@@ -13,6 +14,7 @@
 #include <numeric>
 
 #include "../../sourmash_b200/csrc/experimental_kernels.cuh"
+#include "../../sourmash_b200/csrc/search_kernels.cuh"
 
 using namespace smb;
 
@@ -256,7 +258,98 @@ static int index_main(int threads, const char* fq, const char* fh, const char* f
     return 0;
 }
 
+// ---- search / gather: the default kernels as launched (directory + bitmap over the query, global one-vs-many
+// pass, and the rounds of the gather session), optionally with the inverted index for the per-round counts ----
+static void device_dir(const std::vector<u64>& keys, u64 nk, u32 shift, u64 nb, std::vector<u32>& dir) {
+    dir.assign(nb + 2, 0);
+    smb_emu::launch(3, 64, 0, [&] { global_dir_fill_kernel(dir.data(), nb + 1, DIR_UNSET); });
+    if (nk) smb_emu::launch(3, 64, 0, [&] { global_dir_heads_kernel(keys.data(), nk, shift, dir.data()); });
+    smb_emu::launch(3, 64, 0, [&] { global_dir_resolve_kernel(keys.data(), nk, shift, nb, dir.data()); });
+}
+// one_vs_many_dev's large-query branch (capi.cu)
+static void one_vs_many_global(const u64* q, u64 nq, const std::vector<u64>& h, const std::vector<u64>& off, int n, u32* counts) {
+    if (!nq || !n) return;
+    const u64 q_max = q[nq - 1];
+    int nb_log2 = 12;
+    while (nb_log2 < 26 && (1ull << nb_log2) < 2 * nq) ++nb_log2;
+    u32 shift = 0;
+    while (shift < 63 && (q_max >> shift) >= (1ull << nb_log2)) ++shift;
+    const u64 nb = (q_max >> shift) + 1;
+    std::vector<u64> qv(q, q + nq);
+    qv.push_back(0);
+    std::vector<u32> dir;
+    device_dir(qv, nq, shift, nb, dir);
+    const int fine_log2 = 3;
+    std::vector<u32> bm((((size_t)nb << fine_log2) / 32) + 2, 0);
+    smb_emu::launch(3, 64, 0, [&] { build_query_bitmap_kernel(qv.data(), nq, shift, fine_log2, bm.data()); });
+    smb_emu::launch(4, 64, 0, [&] { one_vs_many_global_kernel(qv.data(), nq, dir.data(), shift, nb, bm.data(), fine_log2, h.data(), off.data(), n, counts); });
+}
+
+static int gather_main(int use_index, u32 threshold, const char* fq, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> q = slurp<u64>(fq), h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    const u64 nq = q.size(), T = h.size();
+    u64 max_len = 1;
+    for (int r = 0; r < n; ++r) max_len = std::max<u64>(max_len, off[r + 1] - off[r]);
+    h.push_back(0); q.push_back(0);
+    // inverted index of the database, its directory built by the device kernels
+    std::vector<u64> keys;
+    std::vector<u32> start, rows(T + 1), idir;
+    DbIndexView ix{};
+    if (use_index && T) {
+        std::vector<u32> ids(T + 1);
+        smb_emu::launch(5, 64, 0, [&] { index_rowid_kernel(off.data(), n, ids.data()); });
+        std::vector<size_t> perm(T);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return h[a] < h[b]; });
+        for (u64 p = 0; p < T; ++p) {
+            rows[p] = ids[perm[p]];
+            if (p == 0 || h[perm[p]] != h[perm[p - 1]]) { keys.push_back(h[perm[p]]); start.push_back((u32)p); }
+        }
+        start.push_back((u32)T);
+        u64 max_key = 0;
+        for (u64 i = 0; i < T; ++i) max_key = std::max(max_key, h[i]);
+        u32 shift;
+        u64 nbk;
+        db_index_dir_plan(keys.size(), max_key, shift, nbk);
+        const u64 nkeys = keys.size();
+        keys.push_back(0);
+        device_dir(keys, nkeys, shift, nbk, idir);
+        ix = DbIndexView{keys.data(), nkeys, start.data(), rows.data(), idir.data(), shift, nbk};
+    }
+    auto counts_of = [&](const u64* x, u64 nx, const u32* d_nx, u32* out) {
+        if (use_index && T) smb_emu::launch(2, 64, 0, [&] { index_count_kernel(ix, x, d_nx ? max_len : nx, d_nx, out); });
+        else one_vs_many_global(x, d_nx ? *d_nx : nx, h, off, n, out);
+    };
+    std::vector<u32> counts(n + 1, 0), delta(n + 1, 0);
+    std::vector<u8> alive(nq + 1, 1);
+    std::vector<u64> isect(max_len + 1);
+    u32 d_n = 0;
+    unsigned long long best[2] = {0, 0};
+    if (nq) counts_of(q.data(), nq, nullptr, counts.data());
+    std::vector<u32> result;
+    bool have_delta = false;
+    u64 remaining = nq;
+    for (int round = 0; round < n && nq; ++round) {
+        smb_emu::launch(1, 64, 0, [&] { counter_update_argmax_kernel(counts.data(), have_delta ? delta.data() : nullptr, n, best); });
+        if (best[0] < threshold || best[0] == 0) break;
+        const u32 row = (u32)best[1];
+        smb_emu::launch(1, 96, 0, [&] { intersect_alive_kernel(q.data(), nq, alive.data(), h.data() + off[row], off[row + 1] - off[row], isect.data(), &d_n); });
+        if (d_n != best[0]) return 3;                        // the counter of the winner == its live intersection
+        result.push_back(row); result.push_back(d_n);
+        std::fill(delta.begin(), delta.end(), 0u);
+        counts_of(isect.data(), d_n, &d_n, delta.data());
+        smb_emu::launch(2, 64, 0, [&] { mark_dead_n_kernel(q.data(), nq, alive.data(), isect.data(), &d_n); });
+        have_delta = true;
+        remaining -= d_n;
+        if (!remaining) break;
+    }
+    dump(fout, result);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 8 && !strcmp(argv[1], "gather")) return gather_main(atoi(argv[2]), (u32)atoi(argv[3]), argv[4], argv[5], argv[6], argv[7]);
     if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], false);
     if (argc == 8 && !strcmp(argv[1], "stripe_low32")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], true);
     if (argc == 9 && !strcmp(argv[1], "ranges"))

@@ -603,3 +603,39 @@ def test_simt_hash_kernels_match_oracle(simt_sketch):
             for gi, g in enumerate(genomes):
                 for ki, k in enumerate((21, 31, 51)):
                     assert np.array_equal(fused[gi * 3 + ki], expected(g, k, max_hash)), ("fused", k, W, lead, len(g))
+
+
+def test_simt_gather_loop_matches_oracle(simt):
+    """The gather session as launched -- directory + bitmap kernels over the query, the global one-vs-many
+    pass, counter update + argmax, live intersection, consumed flags -- and the same rounds with the inverted
+    index doing the counts (directory of the index built by the device kernels): identical picks."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(14)
+    h, off = synth_sketches(50, mean=250, sd=50, lo=80, hi=500, n_families=3, pool=320, seed=71)
+    rows = [h[int(off[i]):int(off[i + 1])] for i in range(50)]
+    rows[17] = rows[4].copy()                                  # an exact tie: the lowest row wins
+    rows[30] = np.zeros(0, np.uint64)
+    query = np.unique(np.concatenate([rows[4], rows[9][:150], rows[25][50:250], rows[41][::2],
+                                      rng.integers(1, 2**54, size=300, dtype=np.uint64)]))
+
+    def oracle(threshold):
+        q = query.copy()
+        counts = np.array([orc.count_common(q, r) for r in rows], dtype=np.int64)
+        out = []
+        while True:
+            j = int(np.argmax(counts))
+            if counts[j] < threshold or counts[j] == 0:
+                break
+            isect = np.intersect1d(q, rows[j])
+            out += [j, len(isect)]
+            counts = counts - np.array([orc.count_common(isect, r) for r in rows], dtype=np.int64)
+            q = np.setdiff1d(q, isect)
+            if not len(q):
+                break
+        return out
+    for threshold in (1, 40):
+        want = oracle(threshold)
+        assert len(want) >= 6
+        for use_index in (0, 1):
+            got = simt("gather", rows, use_index, threshold, query=query)
+            assert got.tolist() == want, (threshold, use_index)
