@@ -1,5 +1,6 @@
 // sketch_device.cuh -- the rolled hashing kernels of sketch_kernels.cu (hash_kmers_kernel<K>, and the
-// experimental one-pass hash_kmers_fused_kernel) with their argument block.  In a header so that
+// experimental one-pass hash_kmers_fused_kernel) with their argument block, and the kernels that turn
+// the candidates of a row into a sketch row (block-wide bitonic sort, unique, run lengths).  In a header so that
 // tests/host_emul/simt_sketch_emul.cu can compile the kernels themselves for the host (tests/host_emul/simt.h)
 // and run them -- tiling, survivor staging, flushes included -- against the oracle without a GPU.
 #pragma once
@@ -152,6 +153,101 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_fused_kernel(FusedArg
             if (g < capr) a.cand[off + g] = s_buf[which][i];
         }
     }
+}
+
+// ---- row materialisation: sort + unique (+ run lengths) of each row's candidates (moved from sketch_kernels.cu) ----
+static constexpr int SORT_THREADS = 1024;
+static constexpr int SORT_MAX = 16384;            // rows up to this many candidates sort in smem
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_unique_small_kernel(
+    u64* __restrict__ cand, const u64* __restrict__ cand_off, const u32* __restrict__ cand_cnt,
+    u32* __restrict__ out_cnt, u64* __restrict__ abund) {
+    SMB_DYN_SHARED(unsigned char, smem_raw);
+    const int r = blockIdx.x;
+    const u64 off = cand_off[r];
+    const u64 capr = cand_off[r + 1] - off;
+    u32 n = cand_cnt[r];
+    if ((u64)n > capr || n > SORT_MAX) return;          // overflowed / big row: handled on host path
+    if (n == 0) { if (threadIdx.x == 0) out_cnt[r] = 0; return; }
+    u32 np2 = 1; while (np2 < n) np2 <<= 1;
+    u64* s = reinterpret_cast<u64*>(smem_raw);
+    u32* heads = reinterpret_cast<u32*>(smem_raw + (size_t)np2 * 8);
+    const int tid = threadIdx.x;
+    for (u32 i = tid; i < np2; i += SORT_THREADS) s[i] = i < n ? cand[off + i] : SMB_U64_MAX;
+    __syncthreads();
+    for (u32 k = 2; k <= np2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = tid; i < np2; i += SORT_THREADS) {
+                u32 ixj = i ^ j;
+                if (ixj > i) {
+                    u64 x = s[i], y = s[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { s[i] = y; s[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // unique: stable compaction of run heads
+    SMB_SHARED u32 warp_tot[32];
+    SMB_SHARED u32 carry;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (u32 base = 0; base < n; base += SORT_THREADS) {
+        u32 i = base + tid;
+        bool head = i < n && (i == 0 || s[i] != s[i - 1]);
+        u32 bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u32 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (head) { cand[off + pos] = s[i]; heads[pos] = i; }
+        __syncthreads();
+        if (tid == 0) { u32 t = 0; for (int w2 = 0; w2 < SORT_THREADS / 32; ++w2) t += warp_tot[w2]; carry += t; }
+        __syncthreads();
+    }
+    const u32 m = carry;
+    if (abund) {
+        for (u32 p = tid; p < m; p += SORT_THREADS) {
+            u32 nxt = p + 1 < m ? heads[p + 1] : n;
+            abund[off + p] = (u64)(nxt - heads[p]);
+        }
+    }
+    if (tid == 0) out_cnt[r] = m;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) unique_sorted_row_kernel(
+    const u64* __restrict__ sorted, u64 n, u64* __restrict__ out, u64* __restrict__ abund,
+    u64* __restrict__ head_idx, u32* __restrict__ out_cnt) {
+    SMB_SHARED u32 warp_tot[32];
+    SMB_SHARED u64 carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n; base += SORT_THREADS) {
+        u64 i = base + tid;
+        bool head = i < n && (i == 0 || sorted[i] != sorted[i - 1]);
+        u32 bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        u64 pos = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (head) { out[pos] = sorted[i]; head_idx[pos] = i; }
+        __syncthreads();
+        if (tid == 0) { u32 t = 0; for (int w2 = 0; w2 < SORT_THREADS / 32; ++w2) t += warp_tot[w2]; carry += t; }
+        __syncthreads();
+    }
+    const u64 m = carry;
+    if (abund) {
+        for (u64 p = tid; p < m; p += SORT_THREADS) {
+            u64 nxt = p + 1 < m ? head_idx[p + 1] : n;
+            abund[p] = nxt - head_idx[p];
+        }
+    }
+    if (tid == 0) *out_cnt = (u32)m;
 }
 
 }  // namespace smb

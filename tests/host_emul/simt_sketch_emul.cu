@@ -6,6 +6,8 @@
 //   simt_sketch_emul <k: 21|31|51, or 0 = fused 21+31+51> <W> <max_hash> <lead> <seqs.u8> <offsets.u64> <out.u64>
 // `lead` junk bytes precede the first stream, so that streams start at unaligned addresses.
 // out: for every row (stream-major, then k ascending for the fused pass): count, then the hashes.
+// With SMB_EMUL_DEVICE_SORT set the rows are materialised by sort_unique_small_kernel / unique_sorted_row_kernel
+// and every row is followed by its abundances (run lengths).
 #define SMB_SIMT_EMUL 1
 #include "simt.h"
 
@@ -74,9 +76,30 @@ int main(int argc, char** argv) {
         else if (k == 51) smb_emu::launch(tiles, HASH_THREADS, 0, [&] { hash_kmers_kernel<51, false>(a); });
         else return 4;
     }
+    for (int r = 0; r < n_rows; ++r) if (cnt[r] > cand_off[r + 1] - cand_off[r]) return 5;   // more candidates than windows
     FILE* f = fopen(argv[7], "wb");
+    if (getenv("SMB_EMUL_DEVICE_SORT")) {
+        // row materialisation on the "device": sort_unique_small_kernel (rows up to SORT_MAX candidates) and, for a
+        // longer row, a host sort standing in for cub + unique_sorted_row_kernel; abundances = run lengths
+        std::vector<u32> ucnt(n_rows + 1, 0);
+        std::vector<u64> abund(cand.size() + 1, 0);
+        const size_t smem = (size_t)SORT_MAX * 8 + (size_t)SORT_MAX * 4;
+        smb_emu::launch(n_rows, SORT_THREADS, smem, [&] { sort_unique_small_kernel(cand.data(), cand_off.data(), cnt.data(), ucnt.data(), abund.data()); });
+        for (int r = 0; r < n_rows; ++r) {
+            if (cnt[r] > (u32)SORT_MAX) {
+                std::vector<u64> sorted(cand.begin() + cand_off[r], cand.begin() + cand_off[r] + cnt[r]), heads(cnt[r] + 1);
+                std::sort(sorted.begin(), sorted.end());
+                smb_emu::launch(1, SORT_THREADS, 0, [&] { unique_sorted_row_kernel(sorted.data(), (u64)cnt[r], cand.data() + cand_off[r], abund.data() + cand_off[r], heads.data(), ucnt.data() + r); });
+            }
+            const u64 n = ucnt[r];
+            fwrite(&n, 8, 1, f);
+            fwrite(cand.data() + cand_off[r], 8, n, f);
+            fwrite(abund.data() + cand_off[r], 8, n, f);
+        }
+        fclose(f);
+        return 0;
+    }
     for (int r = 0; r < n_rows; ++r) {
-        if (cnt[r] > cand_off[r + 1] - cand_off[r]) return 5;              // more candidates than windows
         std::vector<u64> v(cand.begin() + cand_off[r], cand.begin() + cand_off[r] + cnt[r]);
         std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());

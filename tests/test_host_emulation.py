@@ -561,17 +561,22 @@ def simt_sketch():
     src = os.path.join(HERE, "host_emul", "simt_sketch_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(k, W, max_hash, lead, genomes):
+    def run(k, W, max_hash, lead, genomes, device_sort=False):
         seqs = np.concatenate(genomes) if genomes else np.zeros(0, np.uint8)
         offs = np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
         with tempfile.TemporaryDirectory() as td:
             fs, fo, fc = (os.path.join(td, x) for x in ("s", "o", "c"))
             np.asarray(seqs, dtype=np.uint8).tofile(fs); offs.tofile(fo)
-            subprocess.check_call([exe, str(k), str(W), str(max_hash), str(lead), fs, fo, fc])
+            env = dict(os.environ, SMB_EMUL_DEVICE_SORT="1") if device_sort else None
+            subprocess.check_call([exe, str(k), str(W), str(max_hash), str(lead), fs, fo, fc], env=env)
             raw = np.fromfile(fc, dtype=np.uint64)
         rows, at = [], 0
         while at < len(raw):
-            n = int(raw[at]); rows.append(raw[at + 1:at + 1 + n]); at += 1 + n
+            n = int(raw[at])
+            if device_sort:
+                rows.append((raw[at + 1:at + 1 + n], raw[at + 1 + n:at + 1 + 2 * n])); at += 1 + 2 * n
+            else:
+                rows.append(raw[at + 1:at + 1 + n]); at += 1 + n
         return rows
     return run
 
@@ -639,3 +644,31 @@ def test_simt_gather_loop_matches_oracle(simt):
         for use_index in (0, 1):
             got = simt("gather", rows, use_index, threshold, query=query)
             assert got.tolist() == want, (threshold, use_index)
+
+
+def test_simt_sketch_rows_with_abundances(simt_sketch):
+    """hash kernel -> sort_unique_small_kernel (block-wide bitonic sort, unique, run lengths) and, for a row with
+    more candidates than fit in shared memory, unique_sorted_row_kernel: the sketch rows and their abundances
+    equal the oracle's (repeats planted so that abundances exceed one)."""
+    unit = synth_genome(700, seed=81)
+    genomes = [np.concatenate([unit, unit, unit[:300], synth_genome(500, seed=82)]),       # repeated k-mers
+               synth_genome(1200, seed=83, n_every=101), synth_genome(25, seed=84),
+               np.concatenate([synth_genome(9000, seed=85)] * 2)]                          # > SORT_MAX candidates when all are kept
+    for max_hash in (2**64 - 1, orc.max_hash_for_scaled(10)):
+        for k in (21, 0):
+            got = simt_sketch(k, 16, max_hash, 3, genomes, device_sort=True)
+            ks = (21, 31, 51) if k == 0 else (k,)
+            assert len(got) == len(genomes) * len(ks)
+            for gi, g in enumerate(genomes):
+                for ki, kk in enumerate(ks):
+                    hashes, abunds = got[gi * len(ks) + ki]
+                    if len(g) < kk:
+                        assert len(hashes) == 0
+                        continue
+                    hs, _ = orc.seq_to_hashes(bytes(g), kk, force=True, keep_zeros=True)
+                    hs = np.asarray(hs, dtype=np.uint64)
+                    keep = hs[(hs != 0) & (hs <= np.uint64(max_hash))]
+                    want_h, want_a = np.unique(keep, return_counts=True)
+                    assert np.array_equal(hashes, want_h) and np.array_equal(abunds, want_a.astype(np.uint64)), (max_hash, k, gi, kk)
+    hs, _ = orc.seq_to_hashes(bytes(genomes[3]), 21, force=True, keep_zeros=True)
+    assert int((np.asarray(hs, dtype=np.uint64) != 0).sum()) > 16384      # that row took the big-row path when all were kept
