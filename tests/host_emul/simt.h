@@ -197,6 +197,11 @@ template <class T> inline T __shfl_xor_sync(uint32_t, T v, int lane_mask) {
     memcpy(&out, &c.snap[(me ^ (unsigned)lane_mask) & 31], sizeof(T));
     return out;
 }
+inline bool __any_sync(uint32_t, bool pred) {
+    const smb_emu::WarpColl& c = smb_emu::collective(pred ? 1 : 0);
+    for (int l = 0; l < 32; ++l) if (((c.snap_mask >> l) & 1u) && c.snap[l]) return true;
+    return false;
+}
 inline bool __all_sync(uint32_t, bool pred) {
     const smb_emu::WarpColl& c = smb_emu::collective(pred ? 1 : 0);
     for (int l = 0; l < 32; ++l) if (((c.snap_mask >> l) & 1u) && !c.snap[l]) return false;

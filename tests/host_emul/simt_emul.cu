@@ -6,6 +6,7 @@
 //   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
 //   simt_emul join|cluster <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>      (upper-triangle counts)
 //   simt_emul rows <passes> <hashes.u64> <offsets.u64> <out.u32 n*n>                         (full rows as captured)
+//   simt_emul tile <TA 1..4> <variant 1 split | 0 u64 occ | 2 u64> <threads> <cols_per_cta> <symmetric 0|1> <hashes.u64> <offsets.u64> <out.u32>
 //   simt_emul gather <use_index 0|1> <threshold> <query.u64> <hashes.u64> <offsets.u64> <out.u32 (row, size) pairs>
 //   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
 #define SMB_SIMT_EMUL 1
@@ -15,6 +16,7 @@
 
 #include "../../sourmash_b200/csrc/experimental_kernels.cuh"
 #include "../../sourmash_b200/csrc/search_kernels.cuh"
+#include "../../sourmash_b200/csrc/tile_kernels.cuh"
 
 using namespace smb;
 
@@ -348,7 +350,49 @@ static int gather_main(int use_index, u32 threshold, const char* fq, const char*
     return 0;
 }
 
+// ---- the pair-by-pair intersection kernels as launched (launch_tile_ta of compare_kernels.cu) ----
+template <int TA>
+static void run_tile(const TileArgs& a, size_t smem, int threads, int variant) {
+    const int tiles = (a.nA + TA - 1) / TA;
+    smb_emu::Dim3 grid(tiles, (a.nB + a.cols_per_cta - 1) / a.cols_per_cta);
+    if (variant == 1) smb_emu::launch(grid, threads, smem, [&] { pairwise_tile_split_kernel<TA, 4>(a); });
+    else if (variant == 0) smb_emu::launch(grid, threads, smem, [&] { pairwise_tile_kernel<TA, 4, true>(a); });
+    else smb_emu::launch(grid, threads, smem, [&] { pairwise_tile_kernel<TA, 4, false>(a); });
+}
+static int tile_main(int ta, int variant, int threads, int cols, int symmetric, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    u64 max_len = 0, max_key = 0;
+    for (int r = 0; r < n; ++r) max_len = std::max<u64>(max_len, off[r + 1] - off[r]);
+    for (u64 v : h) if (v != SMB_U64_MAX) max_key = std::max(max_key, v);
+    if (!h.empty() && h.back() == SMB_U64_MAX && max_key == 0) max_key = SMB_U64_MAX;
+    for (u64 v : h) max_key = std::max(max_key, v);               // the planner sees the raw maximum (set_max_key)
+    PairwisePlan plan = plan_pairwise_impl(max_len, max_key, cols);
+    if (plan.tables_per_cta == 0) return 3;
+    if (ta > plan.tables_per_cta) return 4;
+    const size_t key_bytes = ((size_t)plan.cap + 2) * 8;
+    const size_t smem = (size_t)ta * (key_bytes + ((size_t)plan.nb + 2) * 2);
+    h.push_back(0);
+    // symmetric: A == B, upper triangle; otherwise the first half of the rows against the second half
+    const int nA = symmetric ? n : n / 2, nB = symmetric ? n : n - n / 2;
+    const u64* offB = symmetric ? off.data() : off.data() + nA;
+    std::vector<u32> out((size_t)nA * nB + 1, 0xdeadbeefu);
+    TileArgs a{h.data(), off.data(), nA, h.data(), offB, nB, out.data(), (size_t)nB, plan.shift, plan.nb, plan.cap,
+               plan.cols_per_cta, symmetric, 0, 1, -1};
+    switch (ta) {
+        case 1: run_tile<1>(a, smem, threads, variant); break;
+        case 2: run_tile<2>(a, smem, threads, variant); break;
+        case 3: run_tile<3>(a, smem, threads, variant); break;
+        default: run_tile<4>(a, smem, threads, variant); break;
+    }
+    out.resize((size_t)nA * nB);
+    dump(fout, out);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 10 && !strcmp(argv[1], "tile"))
+        return tile_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8], argv[9]);
     if (argc == 8 && !strcmp(argv[1], "gather")) return gather_main(atoi(argv[2]), (u32)atoi(argv[3]), argv[4], argv[5], argv[6], argv[7]);
     if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], false);
     if (argc == 8 && !strcmp(argv[1], "stripe_low32")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], true);

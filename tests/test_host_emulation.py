@@ -672,3 +672,32 @@ def test_simt_sketch_rows_with_abundances(simt_sketch):
                     assert np.array_equal(hashes, want_h) and np.array_equal(abunds, want_a.astype(np.uint64)), (max_hash, k, gi, kk)
     hs, _ = orc.seq_to_hashes(bytes(genomes[3]), 21, force=True, keep_zeros=True)
     assert int((np.asarray(hs, dtype=np.uint64) != 0).sum()) > 16384      # that row took the big-row path when all were kept
+
+
+def test_simt_tile_kernels_match_oracle(simt):
+    """pairwise_tile_split_kernel (the pair-by-pair intersection kernel) and its u64 predecessor as launched:
+    table build in shared memory behind barriers, streamed rows, crowded buckets, UINT64_MAX handling, symmetric
+    (upper triangle) and A x B modes, every TA, column blocks."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(17)
+    h, off = synth_sketches(26, mean=400, sd=100, lo=5, hi=900, n_families=3, pool=520, seed=91)
+    fam = [h[int(off[i]):int(off[i + 1])] for i in range(26)]
+    big = np.uint64(2**64 - 1)
+    edge = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, 3, big], np.uint64), np.array([big], np.uint64),
+            np.array([big - 1, big], np.uint64), np.arange(1, 500, dtype=np.uint64),
+            np.unique(rng.integers(0, 2**63, size=700, dtype=np.uint64)),
+            np.array([(7 << 32) | 5, (8 << 32) | 5, (9 << 32) | 5, (9 << 32) | 6], dtype=np.uint64),
+            np.array([(8 << 32) | 5, (9 << 32) | 6, (10 << 32) | 5], dtype=np.uint64),
+            np.unique(rng.integers(0, 1000, size=300, dtype=np.uint64))]
+    for rows in (fam, edge):
+        n = len(rows)
+        hh, oo = orc.to_csr(rows)
+        want = orc.pairwise_common(hh, oo)
+        iu = np.triu_indices(n, 1)
+        for ta, variant, threads, cols in ((4, 1, 256, 512), (3, 1, 128, 7), (1, 1, 64, 512), (2, 0, 128, 512), (4, 2, 64, 5)):
+            got = simt("tile", rows, ta, variant, threads, cols, 1).reshape(n, n)
+            assert np.array_equal(got[iu], want[iu]), ("symmetric", n, ta, variant, threads, cols)
+            nA = n // 2
+            got = simt("tile", rows, ta, variant, threads, cols, 0).reshape(nA, n - nA)
+            cross = np.array([[orc.count_common(rows[i], rows[nA + j]) for j in range(n - nA)] for i in range(nA)], dtype=np.uint32)
+            assert np.array_equal(got, cross), ("AxB", n, ta, variant)
