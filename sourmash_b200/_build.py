@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsourmash_b200.so")
 SOURCES = ["capi.cu", "sketch_kernels.cu", "compare_kernels.cu", "ingest.cu"]
 HEADERS = ["common.cuh", "kernels.h", "md5.h", "kmer_roll.cuh", "split_table.cuh", "aa_kmers.cuh", "ingest.h",
-           "join_walk.cuh", "join_stripe.cuh", "range_search.cuh", "db_index.cuh", "experimental_kernels.cuh", "sketch_device.cuh", "search_kernels.cuh", "tile_kernels.cuh", "zipread.h", os.path.join("..", "..", "include", "sourmash_b200.h")]
+           "join_walk.cuh", "join_stripe.cuh", "range_search.cuh", "db_index.cuh", "experimental_kernels.cuh", "sketch_device.cuh", "search_kernels.cuh", "tile_kernels.cuh", "pair_kernels.cuh", "zipread.h", os.path.join("..", "..", "include", "sourmash_b200.h")]
 OBJ_DIR = os.path.join(CSRC, "build")                 # git-ignored; only the linked .so ships
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

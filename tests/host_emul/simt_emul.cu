@@ -7,6 +7,7 @@
 //   simt_emul join|cluster <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>      (upper-triangle counts)
 //   simt_emul rows <passes> <hashes.u64> <offsets.u64> <out.u32 n*n>                         (full rows as captured)
 //   simt_emul tile <TA 1..4> <variant 1 split | 0 u64 occ | 2 u64> <threads> <cols_per_cta> <symmetric 0|1> <hashes.u64> <offsets.u64> <out.u32>
+//   simt_emul pairs <num> <hashes.u64> <offsets.u64> <out.f64 3*n*n: jaccard (generic kernel) | jaccard num | angular>
 //   simt_emul gather <use_index 0|1> <threshold> <query.u64> <hashes.u64> <offsets.u64> <out.u32 (row, size) pairs>
 //   simt_emul index  <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 2n: direct | length on "device">
 #define SMB_SIMT_EMUL 1
@@ -17,6 +18,8 @@
 #include "../../sourmash_b200/csrc/experimental_kernels.cuh"
 #include "../../sourmash_b200/csrc/search_kernels.cuh"
 #include "../../sourmash_b200/csrc/tile_kernels.cuh"
+#include "../../sourmash_b200/csrc/pair_kernels.cuh"
+#include <math.h>
 
 using namespace smb;
 
@@ -390,7 +393,45 @@ static int tile_main(int ta, int variant, int threads, int cols, int symmetric, 
     return 0;
 }
 
+// ---- the remaining pair kernels: generic, bottom-k, angular, finalize (compare_jaccard_impl / smb_compare_angular) ----
+static int pairs_main(u32 num, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+    const int n = (int)off.size() - 1;
+    const size_t nn = (size_t)n * n;
+    h.push_back(0);
+    unsigned long long d_max = 0, want_max = 0;
+    smb_emu::launch(2, 64, 0, [&] { max_last_kernel(h.data(), off.data(), n, nullptr, nullptr, 0, &d_max); });
+    for (int r = 0; r < n; ++r) if (off[r + 1] > off[r]) want_max = std::max<unsigned long long>(want_max, h[off[r + 1] - 1]);
+    if (d_max != want_max) return 3;
+    std::vector<u32> common(nn + 1, 0), common_num(nn + 1, 0), usize(nn + 1, 0);
+    std::vector<double> out(3 * nn + 1, -1.0);
+    // scaled: generic kernel (rows of any size) + finalize, whole matrix and a block of rows
+    smb_emu::launch(3, 64, 0, [&] { pairwise_generic_kernel(h.data(), off.data(), n, h.data(), off.data(), n, common.data(), (size_t)n, 1); });
+    smb_emu::launch(smb_emu::Dim3((n + 63) / 64, n), 64, 0,
+                    [&] { finalize_matrix_kernel(common.data(), nullptr, (size_t)n, off.data(), off.data(), n, n, 0, 1, out.data()); });
+    {
+        const int r0 = n / 3, r1 = std::min(n, r0 + 7);
+        std::vector<double> rows((size_t)(r1 - r0) * n + 1, -1.0);
+        smb_emu::launch(smb_emu::Dim3((n + 63) / 64, r1 - r0), 64, 0, [&] { finalize_rows_kernel(common.data(), (size_t)n, off.data(), r0, r1, rows.data()); });
+        for (int i = r0; i < r1; ++i) for (int j = 0; j < n; ++j) if (rows[(size_t)(i - r0) * n + j] != out[(size_t)i * n + j]) return 4;
+    }
+    // bottom-k: num kernel + finalize mode 1
+    smb_emu::launch(3, 64, 0, [&] { pairwise_num_kernel(h.data(), off.data(), n, h.data(), off.data(), n, num, common_num.data(), usize.data(), (size_t)n, 1); });
+    smb_emu::launch(smb_emu::Dim3((n + 63) / 64, n), 64, 0,
+                    [&] { finalize_matrix_kernel(common_num.data(), usize.data(), (size_t)n, off.data(), off.data(), n, n, 1, 1, out.data() + nn); });
+    // abundances 1 + hash % 5: angular similarity
+    std::vector<u64> ab(h.size());
+    for (size_t i = 0; i < h.size(); ++i) ab[i] = 1 + h[i] % 5;
+    std::vector<unsigned long long> sumsq(n + 1, 0);
+    smb_emu::launch(2, 64, 0, [&] { row_sumsq_kernel(ab.data(), off.data(), n, sumsq.data()); });
+    smb_emu::launch(3, 64, 0, [&] { pairwise_angular_kernel(h.data(), ab.data(), off.data(), n, sumsq.data(), out.data() + 2 * nn); });
+    out.resize(3 * nn);
+    dump(fout, out);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 6 && !strcmp(argv[1], "pairs")) return pairs_main((u32)atoi(argv[2]), argv[3], argv[4], argv[5]);
     if (argc == 10 && !strcmp(argv[1], "tile"))
         return tile_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8], argv[9]);
     if (argc == 8 && !strcmp(argv[1], "gather")) return gather_main(atoi(argv[2]), (u32)atoi(argv[3]), argv[4], argv[5], argv[6], argv[7]);

@@ -701,3 +701,27 @@ def test_simt_tile_kernels_match_oracle(simt):
             got = simt("tile", rows, ta, variant, threads, cols, 0).reshape(nA, n - nA)
             cross = np.array([[orc.count_common(rows[i], rows[nA + j]) for j in range(n - nA)] for i in range(nA)], dtype=np.uint32)
             assert np.array_equal(got, cross), ("AxB", n, ta, variant)
+
+
+def test_simt_pair_kernels_match_oracle(simt):
+    """generic pair kernel, bottom-k kernel, angular kernels and the finalize kernels as launched: the float64
+    matrices of compare (scaled and num) bit for bit, angular within 1e-12."""
+    from sourmash_b200.synth import synth_sketches
+    rng = np.random.default_rng(19)
+    h, off = synth_sketches(28, mean=150, sd=40, lo=0, hi=300, n_families=3, pool=200, seed=97)
+    rows = [h[int(off[i]):int(off[i + 1])] for i in range(28)]
+    rows[5] = np.zeros(0, np.uint64)
+    rows[9] = rows[8].copy()
+    rows[11] = np.unique(rng.integers(0, 2**64 - 1, size=400, dtype=np.uint64))
+    n = len(rows)
+    hh, oo = orc.to_csr(rows)
+    for num in (50, 500):
+        got = simt("pairs", rows, num, dtype=np.float64).reshape(3, n, n)
+        assert np.array_equal(got[0], orc.compare_all_pairs(hh, oo, nthreads=2))
+        if num == 500:                                                       # every row is a valid num=500 sketch
+            assert np.array_equal(got[1], orc.compare_all_pairs(hh, oo, num=num, nthreads=2))
+        ab = [1 + (r % np.uint64(5)) for r in rows]
+        for i in range(n):
+            for j in range(n):
+                want = 1.0 if i == j else orc.angular_similarity(rows[i], ab[i], rows[j], ab[j])
+                assert abs(got[2][i, j] - want) < 1e-12, (i, j)
