@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(256) one_vs_many_global_kernel(
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool in_range = (x[u] >> shift) < nbk;    // false for padding / beyond the query
+                // beyond the query's key range nothing can match; lanes past the row's end are padding -- tested by
+                // index, not by value: a query that holds UINT64_MAX (scaled = 1) covers the padding key too
+                const bool in_range = base + (u64)u * 32 + lane < n && (x[u] >> shift) < nbk;
                 word[u] = 0u;
                 if (in_range) {
                     if (bitmap) {

@@ -27,7 +27,12 @@
 
 namespace smb_emu {
 
-struct Dim3 { unsigned x = 1, y = 1, z = 1; Dim3() {} Dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct Dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    Dim3() {}
+    Dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+    Dim3(const dim3& d) : x(d.x), y(d.y), z(d.z) {}
+};
 
 struct Fiber {
     ucontext_t ctx;
@@ -221,3 +226,7 @@ template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; 
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 using std::max;
 using std::min;
+// the typed overload cuda_runtime.h only offers to nvcc
+template <class T> inline cudaError_t cudaFuncSetAttribute(T* f, cudaFuncAttribute a, int v) {
+    return ::cudaFuncSetAttribute(reinterpret_cast<const void*>(f), a, v);
+}

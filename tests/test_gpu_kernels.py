@@ -189,6 +189,21 @@ def test_one_vs_many_small_and_large_query(B):
     assert np.array_equal(B.one_vs_many(q_large, db), orc.one_vs_many(q_large, h, off).astype(np.uint32))
 
 
+def test_one_vs_many_large_query_holding_uint64_max(B):
+    """A query too large for shared memory that holds UINT64_MAX (scaled = 1): the padding lanes of the global pass
+    carry that key too and must not count (found by the emulated build, tests/test_emulated_library.py)."""
+    h, off = synth_sketches(300, mean=300, sd=60, lo=0, hi=600, n_families=4, pool=400, seed=5)
+    rows = rows_of(h, off)
+    rng = np.random.Generator(np.random.PCG64(6))
+    q = np.unique(np.concatenate([rng.integers(1, 2**54, size=60_000, dtype=np.uint64)] + rows[:30] +
+                                 [np.array([2**63, 2**64 - 1], dtype=np.uint64)]))
+    db = B.SketchSet.from_host(h, off)
+    assert np.array_equal(B.one_vs_many(q, db), orc.one_vs_many(q, h, off).astype(np.uint32))
+    rows[5] = np.unique(np.concatenate([rows[5], np.array([2**64 - 1], dtype=np.uint64)]))     # and a row that holds it
+    h2, off2 = orc.to_csr(rows)
+    assert np.array_equal(B.one_vs_many(q, B.SketchSet.from_host(h2, off2)), orc.one_vs_many(q, h2, off2).astype(np.uint32))
+
+
 def _gather_oracle(query, rows, threshold=1):
     """CounterGather semantics (index/__init__.py:777-909) with the oracle's count_common."""
     q = np.array(query, dtype=np.uint64)
