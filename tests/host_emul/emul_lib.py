@@ -98,9 +98,6 @@ def emulated_sources(dst):
             text = rewrite_shared(text) if "SMB_SHARED" not in text else text
         with open(os.path.join(dst, name), "w") as fh:
             fh.write(text)
-    inc = os.path.join(os.path.dirname(dst), "include")
-    os.makedirs(inc, exist_ok=True)
-    shutil.copy(os.path.join(ROOT, "include", "sourmash_b200.h"), os.path.join(inc, "sourmash_b200.h"))
 
 
 def _newest_input():
@@ -121,9 +118,7 @@ def build(verbose=False):
     work = os.path.join(top, "sourmash_b200", "csrc")          # keeps the ../../include/sourmash_b200.h relation
     shutil.rmtree(top, ignore_errors=True)
     emulated_sources(work)
-    shutil.copy(os.path.join(ROOT, "include", "sourmash_b200.h"), os.path.join(top, "include", "sourmash_b200.h")) \
-        if os.path.isdir(os.path.join(top, "include")) else None
-    os.makedirs(os.path.join(top, "include"), exist_ok=True)
+    os.makedirs(os.path.join(top, "include"), exist_ok=True)            # csrc includes ../../include/sourmash_b200.h
     shutil.copy(os.path.join(ROOT, "include", "sourmash_b200.h"), os.path.join(top, "include", "sourmash_b200.h"))
     flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-w", "-DSMB_SIMT_EMUL=1", "-include", os.path.join(HERE, "simt.h"),
              "-I", os.path.join(HERE, "mock"), "-I", "/usr/local/cuda/include", "-I", work]
