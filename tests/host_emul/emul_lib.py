@@ -111,6 +111,13 @@ def _newest_input():
 
 def build(verbose=False):
     "Returns the path of the emulated shared library, (re)building it when an input is newer."
+    import fcntl
+    with open(os.path.join(tempfile.gettempdir(), "smb_emul_lib.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)                  # concurrent test processes build it once
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     top = os.path.join(tempfile.gettempdir(), "smb_emul_lib")
     lib = os.path.join(top, "libsourmash_b200_emul.so")
     if os.path.exists(lib) and os.path.getmtime(lib) >= _newest_input():
