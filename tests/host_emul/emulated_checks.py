@@ -110,6 +110,29 @@ def compare_host_path_row_chunks():
 
 
 @check
+def compare_shards_sum_to_full():
+    "the multi-GPU building blocks: partial counts of key-range / tile shards add up; rows finalised from the sum"
+    n = 200
+    h, off = synth_sketches(n, mean=150, sd=40, lo=30, hi=300, n_families=5, pool=200, seed=8)
+    sset = B.SketchSet.from_host(h, off)
+    want = orc.pairwise_common(h, off, nthreads=4)
+    jac = orc.compare_all_pairs(h, off, nthreads=4)
+    iu = np.triu_indices(n, 1)
+    for algo in ("join", "tile"):
+        with env(SMB_COMPARE_ALGO=algo):
+            for shards in (1, 3):
+                total = np.zeros((n, n), dtype=np.uint32)
+                for r in range(shards):
+                    part = np.zeros((n, n), dtype=np.uint32)
+                    B.pairwise_counts_shard_device(sset, r, shards, part.ctypes.data)
+                    total += part
+                assert np.array_equal(total[iu], want[iu]), (algo, shards)
+            rows = np.full((60, n), -1.0)
+            B.finalize_jaccard_rows_device(sset, total.ctypes.data, 70, 130, rows.ctypes.data)
+            assert np.array_equal(rows, jac[70:130]), algo
+
+
+@check
 def search_layouts_and_index():
     h, off = synth_sketches(400, mean=300, sd=60, lo=0, hi=600, n_families=4, pool=400, seed=5)
     rows = rows_of(h, off)

@@ -23,8 +23,9 @@ def _run(*names):
 
 @pytest.mark.timeout(1800)
 def test_emulated_compare_paths():
-    out = _run("compare_default_and_join", "compare_stripe_layouts_resident", "compare_host_path_row_chunks")
-    assert out.count("ok  ") == 3
+    out = _run("compare_default_and_join", "compare_stripe_layouts_resident", "compare_host_path_row_chunks",
+               "compare_shards_sum_to_full")
+    assert out.count("ok  ") == 4
 
 
 @pytest.mark.timeout(1800)

@@ -23,6 +23,29 @@ def B():
     return batch
 
 
+class _DeviceMatrix:
+    """float64 device buffer for the *_device entry points: a torch CUDA tensor on a GPU box; plain host memory
+    when the suite runs against the emulated library (tests/host_emul/run_gpu_tests_emulated.py), whose
+    "device" pointers are host pointers."""
+
+    def __init__(self, shape):
+        import torch
+        if torch.cuda.is_available():
+            self._t = torch.empty(shape, dtype=torch.float64, device="cuda")
+            self.ptr = self._t.data_ptr()
+        else:
+            self._t = None
+            self._a = np.full(shape, -1.0)
+            self.ptr = self._a.ctypes.data
+
+    def numpy(self):
+        if self._t is None:
+            return self._a
+        import torch
+        torch.cuda.synchronize()
+        return self._t.cpu().numpy()
+
+
 def _edge_rows():
     rng = np.random.Generator(np.random.PCG64(77))
     big = np.uint64(2**64 - 1)
@@ -42,16 +65,13 @@ def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam, layout):
     want = orc.compare_all_pairs(h, off, nthreads=8)
     sset = B.SketchSet.from_host(h, off)
     assert np.array_equal(B.compare_jaccard(sset), want)                     # host path: row blocks + copies
-    import torch
-    d_out = torch.empty((n, n), dtype=torch.float64, device="cuda")
-    B.compare_jaccard_device(sset, d_out.data_ptr())                         # resident path: one launch
-    torch.cuda.synchronize()
-    assert np.array_equal(d_out.cpu().numpy(), want)
+    d_out = _DeviceMatrix((n, n))
+    B.compare_jaccard_device(sset, d_out.ptr)                                # resident path: one launch
+    assert np.array_equal(d_out.numpy(), want)
     lo, hi = n // 3, n // 3 + 37
-    d_rows = torch.empty((hi - lo, n), dtype=torch.float64, device="cuda")
-    B.compare_jaccard_rows_device(sset, lo, hi, d_rows.data_ptr())          # a block of rows (multi-GPU unit)
-    torch.cuda.synchronize()
-    assert np.array_equal(d_rows.cpu().numpy(), want[lo:hi])
+    d_rows = _DeviceMatrix((hi - lo, n))
+    B.compare_jaccard_rows_device(sset, lo, hi, d_rows.ptr)                 # a block of rows (multi-GPU unit)
+    assert np.array_equal(d_rows.numpy(), want[lo:hi])
 
 
 @pytest.mark.parametrize("layout", ["stripe", "stripe_upper"])
@@ -84,14 +104,12 @@ def test_stripe_low32_sort_with_clashing_low_words(B, monkeypatch):
 
 def test_rows_device_without_stripe_equals_full_matrix(B):
     "smb_compare_jaccard_rows_dev on the default path (whole count matrix, then the rows)."
-    import torch
     h, off = synth_sketches(300, mean=300, sd=60, lo=0, hi=600, n_families=5, pool=400, seed=4)
     want = orc.compare_all_pairs(h, off, nthreads=8)
     sset = B.SketchSet.from_host(h, off)
-    d_rows = torch.empty((50, 300), dtype=torch.float64, device="cuda")
-    B.compare_jaccard_rows_device(sset, 120, 170, d_rows.data_ptr())
-    torch.cuda.synchronize()
-    assert np.array_equal(d_rows.cpu().numpy(), want[120:170])
+    d_rows = _DeviceMatrix((50, 300))
+    B.compare_jaccard_rows_device(sset, 120, 170, d_rows.ptr)
+    assert np.array_equal(d_rows.numpy(), want[120:170])
 
 
 def _big_query(rows, seed=4000, extra=400_000):
