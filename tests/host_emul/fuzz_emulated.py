@@ -1,6 +1,6 @@
 """Randomised differential campaign of the emulated library against the oracle (adversarial keys: 0, UINT64_MAX,
 dense small integers, clashing low words, empty / huge rows; queries below and above the shared-memory limit).
-Test infrastructure; run by hand:  [SMB_FUZZ_SWITCHED=1] python tests/host_emul/fuzz_emulated.py [seconds] [seed] [sets|sketch]"""
+Test infrastructure; run by hand:  [SMB_FUZZ_SWITCHED=1] python tests/host_emul/fuzz_emulated.py [seconds] [seed] [sets|sketch|protein]"""
 import os
 import sys
 import time
@@ -117,6 +117,38 @@ def sketch_trial(rng):
     os.environ.pop("SMB_SKETCH_FUSED")
 
 
+def protein_trial(rng):
+    "protein / dayhoff / hp sketches from residues or from DNA translated in six frames, any k, scaled / num"
+    moltype = str(rng.choice(["protein", "dayhoff", "hp"]))
+    translate = bool(rng.random() < 0.5)
+    recs = []
+    for _ in range(int(rng.integers(1, 5))):
+        n = int(rng.choice([0, 2, 20, 21, 64, 400, 2000]))
+        if translate:
+            g = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+            junk = b"NnRacgt"
+        else:
+            g = rng.choice(np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8), size=n)
+            junk = b"XxBZ*acd"
+        for _ in range(int(rng.integers(0, 4))):
+            if n:
+                g[int(rng.integers(0, n))] = rng.choice(np.frombuffer(junk, dtype=np.uint8))
+        recs.append(g.astype(np.uint8))
+    seqs = np.concatenate(recs) if recs else np.zeros(0, np.uint8)
+    offs = np.cumsum([0] + [len(g) for g in recs]).astype(np.uint64)
+    ks = sorted(set(int(x) for x in rng.choice([1, 2, 7, 10, 16, 21, 33, 42], size=2)))
+    scaled = int(rng.choice([1, 5, 40]))
+    sset, _ = B.sketch_sequences(seqs, offs, ks, scaled=scaled, moltype=moltype, input_is_protein=not translate)
+    rows = sset.rows()
+    mx = orc.max_hash_for_scaled(scaled)
+    for gi, g in enumerate(recs):
+        for ki, k in enumerate(ks):
+            fn = orc.seq_to_hashes_translate if translate else orc.seq_to_hashes_protein
+            hs = np.asarray(fn(bytes(g), k, moltype, keep_zeros=False), dtype=np.uint64)
+            want = np.unique(hs[hs <= np.uint64(mx)])
+            assert np.array_equal(rows[gi * len(ks) + ki], want), ("protein", moltype, translate, k, scaled, len(g))
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -124,7 +156,7 @@ def main():
     rng = np.random.Generator(np.random.PCG64(seed))
     t0, k = time.time(), 0
     while time.time() - t0 < seconds:
-        (sketch_trial if what == "sketch" else trial)(rng)
+        {"sketch": sketch_trial, "protein": protein_trial}.get(what, trial)(rng)
         k += 1
     print("%d trials in %.0f s, no difference" % (k, time.time() - t0))
 
