@@ -45,3 +45,13 @@ def test_package_does_not_know_the_emulated_library():
                 with open(os.path.join(base, f)) as fh:
                     text = fh.read()
                 assert "emul_lib" not in text and "libsourmash_b200_emul" not in text, f
+
+
+@pytest.mark.timeout(900)
+def test_emulated_sharded_search_and_gather_world2():
+    """distributed.ShardedDatabase with the real batch module on two gloo ranks (one of them probing the inverted
+    index): all-gathered counts and the gather rounds' exchanges give the single-process result on both ranks."""
+    script = os.path.join(HERE, "host_emul", "emulated_sharded.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "passed on 2 ranks" in r.stdout
