@@ -306,6 +306,8 @@ def run_b200(args):
         if rank == 0:
             r.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "data": "synthetic", "dtype": "u64"})
             emit_json(r)
+        if dist is not None:
+            dist.destroy_process_group()
         return
     out = {}
     if args.workload in ("compare", "both"):
@@ -533,6 +535,8 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
     h, off = synth_sketches(N_SKETCHES)
     rows = rows_of(h, off)
     rng = np.random.Generator(np.random.PCG64(4000))
+    if world > 1:
+        return bench_search_gather_sharded(args, torch, dist, B, rank, world, timed, which, h, off, rows, rng)
     if which == "search":
         n_db = 300_000
         reps = n_db // N_SKETCHES
@@ -573,6 +577,54 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
             "config": {"workload": "configs[4]: ~1e5-hash query vs 50000-sketch DB, 200 planted overlapping matches, "
                                    "threshold 50 hashes", "query_hashes": int(len(query)), "db_hashes": int(len(db_h))},
             "rounds": res["rounds"], "rounds_per_s": res["rounds"] / (ms / 1e3), "gpu_launches": launches, **index_info}
+
+
+def bench_search_gather_sharded(args, torch, dist, B, rank, world, timed, which, h, off, rows, rng):
+    """configs[3] / configs[4] on N GPUs: the database sharded by subject (rank r keeps rows
+    [b[r], b[r+1]) resident, built locally), the query replicated; search = local counts + one all-gather; gather =
+    the session rounds with (best count, row) all-gathered and the winner's intersection broadcast
+    (sourmash_b200.distributed.ShardedDatabase).  Same databases and queries as the single-GPU workloads."""
+    from sourmash_b200.distributed import ShardedDatabase, shard_bounds
+    from sourmash_b200.synth import MAX_HASH_1000
+    n_db = 300_000 if which == "search" else 50_000
+    b = shard_bounds(n_db, world)
+    lo, hi = b[rank], b[rank + 1]
+    sizes = np.diff(off.astype(np.int64))
+    idx = np.arange(lo, hi) % N_SKETCHES                                     # the tiled database, this rank's rows only
+    local_off = np.concatenate([[0], np.cumsum(sizes[idx])]).astype(np.uint64)
+    local_h = np.concatenate([rows[j] for j in idx]) if len(idx) else np.zeros(0, np.uint64)
+    local = B.SketchSet.from_host(local_h, local_off)
+    index_info = _maybe_index(args, B, local)
+    db = ShardedDatabase(torch, dist, B, local, n_db, lo)
+    if which == "search":
+        planted = rng.choice(N_SKETCHES, size=100, replace=False)
+        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=10_000_000, dtype=np.uint64)] +
+                                         [rows[j][: len(rows[j]) // 2] for j in planted]))
+        ms, launches, clocks, ex = timed(lambda: int(db.search_counts(query).sum()), args.steps, args.warmup)
+        return {"metric": "query-vs-DB passes/sec (search)", "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms,
+                "config": {"workload": "configs[3]: 1e7-hash query vs 300000-sketch DB sharded by subject over %d GPUs" % world,
+                           "db_hashes_per_rank": int(len(local_h)), "query_hashes": int(len(query)),
+                           "parallelism": "%d gpus: database sharded by subject, query replicated, counts all-gathered" % world},
+                "subjects_per_s": n_db / (ms / 1e3), "gpu_launches": launches, "scaling": "strong", **index_info}
+    planted = rng.choice(N_SKETCHES, size=200, replace=False)
+    query = np.unique(np.concatenate([rows[j][rng.random(len(rows[j])) < 0.6] for j in planted] +
+                                     [rng.integers(1, MAX_HASH_1000, size=20_000, dtype=np.uint64)]))
+    res = {}
+
+    def step():
+        ids, _sizes = db.gather(query, threshold=50)
+        res["rounds"] = len(ids)
+        return len(ids)
+
+    ms, launches, clocks, ex = timed(step, args.steps, args.warmup)
+    return {"metric": "gather wall time", "value": ms, "unit": "ms", "higher_is_better": False, "ms_per_step": ms,
+            "config": {"workload": "configs[4]: ~1e5-hash query vs 50000-sketch DB sharded by subject over %d GPUs, "
+                                   "200 planted overlapping matches, threshold 50 hashes" % world,
+                       "query_hashes": int(len(query)), "db_hashes_per_rank": int(len(local_h)),
+                       "parallelism": "%d gpus: database sharded by subject; per round an all-gather of (count, row) and a "
+                                      "broadcast of the winner's intersection" % world},
+            "rounds": res["rounds"], "rounds_per_s": res["rounds"] / (ms / 1e3), "gpu_launches": launches,
+            "scaling": "strong", **index_info}
 
 
 def main():

@@ -29,3 +29,12 @@ SMB_JOIN_LAYOUT=stripe timeout 600 python -m torch.distributed.run --nnodes=1 --
     bench.py --gpus $N --workload compare --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stripe_n${N}.json 2> gpurun_out/bench_stripe_n${N}.err
 python -c "
 import json; d=json.loads([l for l in open('gpurun_out/bench_stripe_n${N}.json') if l.startswith('{')][-1]); print('stripe n=${N}: ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['e2e']['ms_per_step']))"
+# configs[3] / configs[4] sharded by subject over the N GPUs (ShardedDatabase), without and with the inverted index
+for W in search gather; do
+  for IDX in "" "--index"; do
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 \
+        bench.py --gpus $N --workload $W $IDX --steps 3 --warmup 3 > gpurun_out/bench_${W}${IDX}_n${N}.json 2> gpurun_out/bench_${W}${IDX}_n${N}.err
+    python -c "
+import json; d=json.loads([l for l in open('gpurun_out/bench_${W}${IDX}_n${N}.json') if l.startswith('{')][-1]); print('${W} ${IDX} n=${N}: %.2f ms'%d['ms_per_step'], d.get('index',''))"
+  done
+done
