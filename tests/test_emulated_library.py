@@ -55,3 +55,11 @@ def test_emulated_sharded_search_and_gather_world2():
     r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "passed on 2 ranks" in r.stdout
+
+
+def test_emulated_smoke_hook():
+    "__graft_entry__.smoke() -- the driver's GPU smoke test -- against the emulated library"
+    code = ("import sys; sys.path.insert(0, %r); import emulated_boot; emulated_boot.install(); sys.path.insert(0, %r); "
+            "import __graft_entry__ as g; g.smoke()") % (os.path.join(HERE, "host_emul"), os.path.dirname(HERE))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
