@@ -1,0 +1,130 @@
+"""Dry run of bench.py's B200 arm without a GPU: the emulated library plays the device, a stand-in for the few
+torch.cuda calls bench.py makes supplies streams / events / "device" tensors (host memory), and the workloads are
+shrunk by patching bench's size constants from outside.  NOT a measurement -- it only proves that every code path of
+bench.py assembles its JSON line (keys, types) without raising, for each workload and switch.
+Run by tests/test_emulated_library.py.
+
+    python tests/host_emul/bench_dryrun.py
+"""
+import io
+import json
+import os
+import sys
+import time
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import emulated_boot  # noqa: E402
+
+emulated_boot.install()
+
+import torch  # noqa: E402
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = 0.0
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return max((other.t - self.t) * 1e3, 1e-3)
+
+
+_real_empty, _real_zeros, _real_tensor = torch.empty, torch.zeros, torch.tensor
+
+
+def _strip_device(fn):
+    def wrapped(*a, **kw):
+        kw.pop("device", None)
+        return fn(*a, **kw)
+    return wrapped
+
+
+torch.empty, torch.zeros, torch.tensor = _strip_device(_real_empty), _strip_device(_real_zeros), _strip_device(_real_tensor)
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda i: None
+torch.cuda.current_stream = lambda *a: _Stream()
+torch.cuda.synchronize = lambda *a: None
+torch.cuda.Event = _Event
+torch.cuda.current_device = lambda: 0
+_real_device = torch.device
+torch.Tensor.pin_memory = lambda self, *a, **kw: self
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import bench  # noqa: E402
+
+# tiny stand-ins for the two workload generators (the emulated device is ~10^4 x slower than a B200)
+import numpy as np  # noqa: E402
+
+from sourmash_b200.synth import synth_genome, synth_sketches  # noqa: E402
+
+
+def _small_compare():
+    return synth_sketches(160, mean=60, sd=15, lo=0, hi=120, n_families=5, pool=80, seed=1)
+
+
+def _small_sketch(n_genomes=3):
+    genomes = [synth_genome(12_000, seed=1000 + g) for g in range(3)]
+    return np.concatenate(genomes), np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
+
+
+bench.compare_workload, bench.sketch_workload = _small_compare, _small_sketch
+bench.N_SKETCHES, bench.N_GENOMES, bench.GENOME_LEN = 160, 3, 12_000
+_orig_device = torch.device
+torch.device = lambda *a, **kw: _orig_device("cpu")
+
+LINES = []
+bench.emit_json = lambda obj: LINES.append(json.loads(json.dumps(obj)))
+
+
+def run(workload, env=None, extra=()):
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        args = types.SimpleNamespace(gpus=1, steps=1, warmup=3, impl="b200", workload=workload, no_cpu_baseline=True,
+                                     index="--index" in extra)
+        n0 = len(LINES)
+        bench.run_b200(args)
+        assert len(LINES) == n0 + 1, "one JSON line per run"
+        return LINES[-1]
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def main():
+    base_keys = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"}
+    line = run("both", {"SMB_COMPARE_ALGO": "join"})
+    assert base_keys <= set(line) and "sketch" in line and base_keys <= set(line["sketch"]), sorted(set(line))
+    for part in (line, line["sketch"]):
+        r = part["roofline"]
+        assert {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "kernel_ms"} <= set(r)
+        assert part["e2e"]["h2d_bytes_per_step"] > 0 and part["e2e"]["d2h_bytes_per_step"] > 0 and part["gpu_launches"] > 0
+    assert "dram" in line["roofline"] and "issue" in line["sketch"]["roofline"]
+    assert line["roofline"]["algorithm"]["algo"] == "join"
+    for layout, sort in (("stripe", ""), ("stripe_upper", "low32"), ("cluster", "")):
+        d = run("compare", {"SMB_COMPARE_ALGO": "join", "SMB_JOIN_LAYOUT": layout, "SMB_JOIN_SORT": sort})
+        assert d["roofline"]["algorithm"].get("layout") == layout and layout.split("_")[0] in d["roofline"]["kernel"]
+    d = run("compare", {"SMB_COMPARE_ALGO": "tile"})
+    assert d["roofline"]["kernel"] == "pairwise_tile_split_kernel"
+    d = run("sketch", {"SMB_SKETCH_FUSED": "1"})
+    assert "fused" in d["roofline"]["kernel"] and "issue" not in d["roofline"]
+    print("bench dry run ok: %d JSON lines assembled" % len(LINES))
+
+
+if __name__ == "__main__":
+    main()

@@ -63,3 +63,13 @@ def test_emulated_smoke_hook():
             "import __graft_entry__ as g; g.smoke()") % (os.path.join(HERE, "host_emul"), os.path.dirname(HERE))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+@pytest.mark.timeout(900)
+def test_bench_b200_arm_dry_run():
+    """bench.py's B200 arm against the emulated library with tiny workloads and a stand-in for its torch.cuda calls:
+    not a measurement, a proof that every workload / switch assembles its JSON line (roofline, dram, issue, e2e,
+    launches, clocks) without raising -- the driver's end-of-round bench must not die on a KeyError."""
+    script = os.path.join(HERE, "host_emul", "bench_dryrun.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0 and "bench dry run ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
