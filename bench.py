@@ -31,6 +31,7 @@ N_GENOMES = 100
 COMPARE_WORKLOAD = ("configs[2]: compare 10000 synthetic sketches (k=31, scaled=1000, ~5000 hashes, "
                     "100 families) all-vs-all jaccard float64 matrix")
 SKETCH_WORKLOAD = "configs[1]: sketch dna k=21,31,51 scaled=1000 on 100 synthetic 5 Mbp genomes"
+N_DB_SEARCH, N_DB_GATHER, N_QUERY_SEARCH = 300_000, 50_000, 10_000_000   # configs[3] / configs[4] shapes
 SM_COUNT = 148                                        # B200
 GENOME_LEN = 5_000_000
 SCALED = 1000
@@ -538,12 +539,12 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
     if world > 1:
         return bench_search_gather_sharded(args, torch, dist, B, rank, world, timed, which, h, off, rows, rng)
     if which == "search":
-        n_db = 300_000
+        n_db = N_DB_SEARCH
         reps = n_db // N_SKETCHES
         db_h = np.tile(h, reps)
         db_off = np.concatenate([[0], np.cumsum(np.tile(np.diff(off.astype(np.int64)), reps))]).astype(np.uint64)
         planted = rng.choice(N_SKETCHES, size=100, replace=False)
-        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=10_000_000, dtype=np.uint64)] +
+        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=N_QUERY_SEARCH, dtype=np.uint64)] +
                                          [rows[j][: len(rows[j]) // 2] for j in planted]))
         db = B.SketchSet.from_host(db_h, db_off)
         index_info = _maybe_index(args, B, db)
@@ -556,7 +557,7 @@ def bench_search_gather(args, torch, dist, B, rank, world, timed, which):
                            "db_hashes": int(len(db_h)), "query_hashes": int(len(query))},
                 "subjects_per_s": n_db / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9, "gpu_launches": launches,
                 "note": "query uploaded from pinned host memory every step; counts downloaded", **index_info}
-    n_db = 50_000
+    n_db = N_DB_GATHER
     reps = n_db // N_SKETCHES
     db_h = np.tile(h, reps)
     db_off = np.concatenate([[0], np.cumsum(np.tile(np.diff(off.astype(np.int64)), reps))]).astype(np.uint64)
@@ -586,7 +587,7 @@ def bench_search_gather_sharded(args, torch, dist, B, rank, world, timed, which,
     (sourmash_b200.distributed.ShardedDatabase).  Same databases and queries as the single-GPU workloads."""
     from sourmash_b200.distributed import ShardedDatabase, shard_bounds
     from sourmash_b200.synth import MAX_HASH_1000
-    n_db = 300_000 if which == "search" else 50_000
+    n_db = N_DB_SEARCH if which == "search" else N_DB_GATHER
     b = shard_bounds(n_db, world)
     lo, hi = b[rank], b[rank + 1]
     sizes = np.diff(off.astype(np.int64))
@@ -598,7 +599,7 @@ def bench_search_gather_sharded(args, torch, dist, B, rank, world, timed, which,
     db = ShardedDatabase(torch, dist, B, local, n_db, lo)
     if which == "search":
         planted = rng.choice(N_SKETCHES, size=100, replace=False)
-        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=10_000_000, dtype=np.uint64)] +
+        query = np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=N_QUERY_SEARCH, dtype=np.uint64)] +
                                          [rows[j][: len(rows[j]) // 2] for j in planted]))
         ms, launches, clocks, ex = timed(lambda: int(db.search_counts(query).sum()), args.steps, args.warmup)
         return {"metric": "query-vs-DB passes/sec (search)", "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms,

@@ -80,6 +80,12 @@ def _small_sketch(n_genomes=3):
 
 bench.compare_workload, bench.sketch_workload = _small_compare, _small_sketch
 bench.N_SKETCHES, bench.N_GENOMES, bench.GENOME_LEN = 160, 3, 12_000
+# search / gather workloads: a 480-sketch database of ~60-hash rows, a 40 000-hash search query
+import sourmash_b200.synth as _synth  # noqa: E402
+
+_real_synth = _synth.synth_sketches
+_synth.synth_sketches = lambda n, **kw: _real_synth(n, mean=60, sd=15, lo=10, hi=120, n_families=20, pool=80, seed=7)
+bench.N_DB_SEARCH, bench.N_DB_GATHER, bench.N_QUERY_SEARCH = 480, 480, 40_000
 _orig_device = torch.device
 torch.device = lambda *a, **kw: _orig_device("cpu")
 
@@ -123,6 +129,15 @@ def main():
     assert d["roofline"]["kernel"] == "pairwise_tile_split_kernel"
     d = run("sketch", {"SMB_SKETCH_FUSED": "1"})
     assert "fused" in d["roofline"]["kernel"] and "issue" not in d["roofline"]
+    bench.N_SKETCHES = 240                                  # the tiled databases: 2 x 240 sketches
+    for workload in ("search", "gather"):
+        plain = run(workload)
+        ranged = run(workload, {"SMB_SEARCH_LAYOUT": "ranges"})
+        indexed = run(workload, extra=("--index",))
+        assert {"metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "n_gpus"} <= set(plain)
+        assert "index" in indexed and indexed["index"]["distinct_hashes"] > 0 and "index" not in plain
+        if workload == "gather":
+            assert plain["rounds"] == ranged["rounds"] == indexed["rounds"] > 10
     print("bench dry run ok: %d JSON lines assembled" % len(LINES))
 
 
