@@ -210,6 +210,7 @@ typedef struct SmbSketchSet SmbSketchSet;
 
 /* device / context ------------------------------------------------------------------- */
 int32_t smb_device_count(void);                 /* 0 if no usable CUDA device (no error set) */
+const char* smb_device_probe_error(void);       /* the CUDA runtime's message when the probe failed, else "" (static storage) */
 void smb_set_device(int32_t device);            /* per-thread; default = current CUDA device  */
 void smb_set_stream(void *cuda_stream);         /* run subsequent work on this cudaStream_t   */
 void smb_synchronize(void);

@@ -23,6 +23,11 @@ def device_count():
     return int(lib.smb_device_count())
 
 
+def device_probe_error():
+    "What cudaGetDeviceCount said when no device was found ('' when the probe succeeded)."
+    return ffi.string(lib.smb_device_probe_error()).decode(errors="replace")
+
+
 def set_device(i):
     lib.smb_set_device(int(i))
 

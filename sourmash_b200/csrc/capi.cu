@@ -621,8 +621,9 @@ void pairwise_counts_dev(const SmbSketchSet& A, const SmbSketchSet* Bp, uint32_t
     const uint64_t max_key = std::max(set_max_key(A, s), symmetric ? 0 : set_max_key(B, s));
     smb::PairwisePlan plan = smb::plan_pairwise(A.max_len, max_key, nB);
     if (plan.tables_per_cta == 0) {
+        // rows too large for shared memory; a shard takes the rows i % n_shards == shard
         smb::launch_pairwise_generic(A.d_hashes, A.d_off, nA, B.d_hashes, B.d_off, nB, d_common, ldo,
-                                     symmetric, s);
+                                     symmetric, tiles, s);
         return;
     }
     if (t_profiling) t_timer_pairwise.begin(s);
@@ -1606,6 +1607,7 @@ void computeparams_set_seed(SourmashComputeParameters* p, uint64_t new_seed) { p
 // Part 2: batched entry points
 // ==========================================================================================
 int32_t smb_device_count(void) { probe_devices(); return g_device_count; }
+const char* smb_device_probe_error(void) { probe_devices(); return g_probe_error.c_str(); }
 void smb_set_device(int32_t device) { t_device = device; }
 void smb_set_stream(void* cuda_stream) { t_stream = (cudaStream_t)cuda_stream; }
 void smb_synchronize(void) { guarded_void([&] { cudaStream_t s = need_gpu(); sync(s); }); }

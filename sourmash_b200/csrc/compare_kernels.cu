@@ -118,13 +118,14 @@ void launch_pairwise_tile(const PairwisePlan& plan, const u64* hA, const u64* of
 
 void launch_pairwise_generic(const u64* hA, const u64* offA, int nA, const u64* hB,
                              const u64* offB, int nB, u32* out, size_t ldo, bool symmetric,
-                             cudaStream_t s) {
+                             TileShard tiles, cudaStream_t s) {
     if (nA <= 0 || nB <= 0) return;
     u64 npairs = (u64)nA * (u64)nB;
     u64 blocks = (npairs + 7) / 8;
     if (blocks > (u64)SMB_B200_SMS * 16) blocks = (u64)SMB_B200_SMS * 16;
     pairwise_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(hA, offA, nA, hB, offB, nB, out, ldo,
-                                                            symmetric ? 1 : 0); count_launches(1);
+                                                            symmetric ? 1 : 0, tiles.shard,
+                                                            tiles.n_shards > 0 ? tiles.n_shards : 1); count_launches(1);
 }
 
 // ------------------------------------------------------------------------------------

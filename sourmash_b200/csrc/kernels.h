@@ -101,7 +101,7 @@ void join_stripe_destroy(JoinStripe* js);
 // elements in the longer row.
 void launch_pairwise_generic(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,
                              const uint64_t* offB, int nB, uint32_t* out, size_t ldo,
-                             bool symmetric, cudaStream_t s);
+                             bool symmetric, TileShard tiles, cudaStream_t s);
 
 // Bottom-k ("num") sketches: common = |A ∩ B ∩ M|, usize = |M|, M = first `num` of A ∪ B.
 void launch_pairwise_num(const uint64_t* hA, const uint64_t* offA, int nA, const uint64_t* hB,

@@ -28,13 +28,17 @@ __global__ void max_last_kernel(const u64* __restrict__ hA, const u64* __restric
 
 __global__ void __launch_bounds__(256) pairwise_generic_kernel(
     const u64* __restrict__ hA, const u64* __restrict__ offA, int nA, const u64* __restrict__ hB,
-    const u64* __restrict__ offB, int nB, u32* __restrict__ out, size_t ldo, int symmetric) {
+    const u64* __restrict__ offB, int nB, u32* __restrict__ out, size_t ldo, int symmetric,
+    int shard, int n_shards) {
+    // shard s of n_shards takes the rows i of A with i % n_shards == s (the partial matrices of the
+    // shards are summed by the caller, so every pair must be counted by exactly one shard)
     const u64 npairs = (u64)nA * (u64)nB;
     const u64 wstride = (u64)gridDim.x * (blockDim.x >> 5);
     const int lane = lane_id();
     for (u64 w = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < npairs; w += wstride) {
         int i = (int)(w / (u64)nB), j = (int)(w % (u64)nB);
         if (symmetric && j <= i) continue;
+        if (n_shards > 1 && i % n_shards != shard) continue;
         const u64* ra = hA + offA[i]; u64 na = offA[i + 1] - offA[i];
         const u64* rb = hB + offB[j]; u64 nb = offB[j + 1] - offB[j];
         if (na > nb) { const u64* tr = ra; ra = rb; rb = tr; u64 tn = na; na = nb; nb = tn; }

@@ -130,6 +130,23 @@ def compare_shards_sum_to_full():
             rows = np.full((60, n), -1.0)
             B.finalize_jaccard_rows_device(sset, total.ctypes.data, 70, 130, rows.ctypes.data)
             assert np.array_equal(rows, jac[70:130]), algo
+    # rows too large for the shared-memory tables (warp-per-pair kernel): the shards must still split
+    # the pairs, not each count all of them (round-1 advisor finding: counts came out x world_size)
+    rng = np.random.Generator(np.random.PCG64(77))
+    pool = np.unique(rng.integers(1, 1 << 62, size=60_000, dtype=np.uint64))
+    big = [np.sort(rng.choice(pool, size=40_000, replace=False)) for _ in range(3)]
+    bh = np.concatenate(big)
+    boff = np.array([0, 40_000, 80_000, 120_000], dtype=np.uint64)
+    bset = B.SketchSet.from_host(bh, boff)
+    bwant = orc.pairwise_common(bh, boff, nthreads=4)
+    biu = np.triu_indices(3, 1)
+    for shards in (1, 2):
+        total = np.zeros((3, 3), dtype=np.uint32)
+        for r in range(shards):
+            part = np.zeros((3, 3), dtype=np.uint32)
+            B.pairwise_counts_shard_device(bset, r, shards, part.ctypes.data)
+            total += part
+        assert np.array_equal(total[biu], bwant[biu]), ("large rows", shards, total, bwant)
 
 
 @check

@@ -406,7 +406,7 @@ static int pairs_main(u32 num, const char* fh, const char* fo, const char* fout)
     std::vector<u32> common(nn + 1, 0), common_num(nn + 1, 0), usize(nn + 1, 0);
     std::vector<double> out(3 * nn + 1, -1.0);
     // scaled: generic kernel (rows of any size) + finalize, whole matrix and a block of rows
-    smb_emu::launch(3, 64, 0, [&] { pairwise_generic_kernel(h.data(), off.data(), n, h.data(), off.data(), n, common.data(), (size_t)n, 1); });
+    smb_emu::launch(3, 64, 0, [&] { pairwise_generic_kernel(h.data(), off.data(), n, h.data(), off.data(), n, common.data(), (size_t)n, 1, 0, 1); });
     smb_emu::launch(smb_emu::Dim3((n + 63) / 64, n), 64, 0,
                     [&] { finalize_matrix_kernel(common.data(), nullptr, (size_t)n, off.data(), off.data(), n, n, 0, 1, out.data()); });
     {
