@@ -221,7 +221,12 @@ def main():
     out = {}
     for w in which:
         t = time.time()
-        {"compare": ab_compare, "sketch": ab_sketch, "search": ab_search, "gather": ab_gather}[w](out)
+        try:
+            {"compare": ab_compare, "sketch": ab_sketch, "search": ab_search, "gather": ab_gather}[w](out)
+        except Exception:                                          # noqa: BLE001 -- the other workloads still run
+            import traceback
+            out[w] = {"error": traceback.format_exc()[-1500:]}
+            log(out[w]["error"])
         log("[ab] %s done in %.1fs" % (w, time.time() - t))
         torch.cuda.empty_cache()
     print(json.dumps(out, indent=1))
