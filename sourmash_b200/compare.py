@@ -75,16 +75,17 @@ def _collect(siglist, *, downsample, need_scaled=False, with_abunds=False):
     if need_scaled and not pyscaled.all():
         raise TypeError("Error: can only calculate containment for scaled MinHashes")
     scaled = int(pyscaled.max())
-    cut = 0
+    cut, raw = 0, None
     if len(np.unique(pyscaled)) > 1:
         if not downsample:
             raise ValueError("mismatch in scaled; comparison fail")
         cut = B.max_hash_for_scaled(scaled)
+        raw = ss.csr_host(0, with_abunds=True)            # the sketches as given: pairs are compared at max(scaled_i, scaled_j)
     h, off, ab = ss.csr_host(cut, with_abunds=True)
     ksize = int(ss.ksize[0]) if int(ss.hash_function[0]) == 1 else int(ss.ksize[0]) // 3
     return {"hashes": h, "offsets": off, "abunds": ab if with_abunds else None, "num": int(ss.num[0]),
             "scaled": scaled, "sizes": np.diff(off.astype(np.int64)), "has_abund": ss.has_abund.copy(), "ksize": ksize,
-            "orig_sizes": ss.n_mins.astype(np.int64), "orig_scaled": pyscaled, "_keepalive": ss}
+            "orig_sizes": ss.n_mins.astype(np.int64), "orig_scaled": pyscaled, "raw": raw, "_keepalive": ss}
 
 
 def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
@@ -107,9 +108,16 @@ def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
     has_ab = np.array([bool(mh.track_abundance) for mh in mhs])
     orig_sizes = np.array([len(mh) for mh in mhs], dtype=np.int64)
     orig_scaled = np.array([mh.scaled for mh in mhs], dtype=np.uint64)
+    raw = None
     if len(scaleds) > 1:
         if not downsample:
             raise ValueError("mismatch in scaled; comparison fail")
+        raw_rows = [mh._mins_array() for mh in mhs]
+        raw_off = np.zeros(len(raw_rows) + 1, dtype=np.uint64)
+        raw_off[1:] = np.cumsum([len(r) for r in raw_rows])
+        raw = (np.concatenate(raw_rows), raw_off,
+               np.concatenate([mh._abunds_array() if mh.track_abundance else np.ones(len(r), dtype=np.uint64)
+                               for mh, r in zip(mhs, raw_rows)]))
         mhs = [mh.downsample(scaled=scaled) if mh.scaled != scaled else mh for mh in mhs]
     rows = [mh._mins_array() for mh in mhs]
     off = np.zeros(len(rows) + 1, dtype=np.uint64)
@@ -121,7 +129,49 @@ def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
                              for mh, r in zip(mhs, rows)]) if rows else np.zeros(0, np.uint64)
     return {"hashes": h, "offsets": off, "abunds": ab, "num": first.num, "scaled": scaled,
             "sizes": np.diff(off.astype(np.int64)), "has_abund": has_ab, "ksize": first.ksize,
-            "orig_sizes": orig_sizes, "orig_scaled": orig_scaled}
+            "orig_sizes": orig_sizes, "orig_scaled": orig_scaled, "raw": raw}
+
+
+_MIXED_ANI = ("ANI matrices need one scaled value: downsample the sketches to a common scaled first, as `sourmash compare` "
+              "does before it calls compare_all_pairs (reference commands.py:167-194)")
+
+
+def _mixed_pair_tables(c, *, jaccard=False, angular=False):
+    """Sketches with different scaled values and ``downsample=True``: the reference compares EVERY PAIR at
+    max(scaled_i, scaled_j) -- `similarity(other, downsample=True)` / `count_common(other, True)` downsample
+    the finer sketch of the pair (minhash.rs:539-547,682-702) -- not everything at the coarsest scaled of the
+    list.  One batched call per distinct scaled value S over the sketches with scaled <= S, cut at S; the pairs
+    whose coarser member has scaled S take their cells from that call.
+    Returns dict(common=u32 (n,n), jaccard / angular = float64 (n,n) or None)."""
+    h, off, ab = c["raw"]
+    scaleds = np.asarray(c["orig_scaled"]).astype(np.int64)
+    n = len(scaleds)
+    out = {"common": np.zeros((n, n), dtype=np.uint32), "jaccard": np.ones((n, n)) if jaccard else None,
+           "angular": np.ones((n, n)) if angular else None}
+    for S in sorted(set(scaleds.tolist())):
+        idx = np.nonzero(scaleds <= S)[0]
+        if len(idx) < 2:
+            continue
+        cut = np.uint64(B.max_hash_for_scaled(S))
+        lens = [int(np.searchsorted(h[int(off[i]):int(off[i + 1])], cut, side="right")) for i in idx]
+        sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+        sub_off[1:] = np.cumsum(lens)
+        sub_h = np.concatenate([h[int(off[i]):int(off[i]) + m] for i, m in zip(idx, lens)])
+        here = (scaleds[idx][:, None] == S) | (scaleds[idx][None, :] == S)      # pairs decided at this scaled
+        cells = np.ix_(idx, idx)
+
+        def put(name, block):
+            full = out[name][cells]
+            full[here] = block[here]
+            out[name][cells] = full
+        sset = B.SketchSet.from_host(sub_h, sub_off)
+        put("common", B.pairwise_common(sset))
+        if jaccard:
+            put("jaccard", B.compare_jaccard(sset))
+        if angular:
+            sub_ab = np.concatenate([ab[int(off[i]):int(off[i]) + m] for i, m in zip(idx, lens)])
+            put("angular", B.compare_angular(B.SketchSet.from_host(sub_h, sub_off, sub_ab)))
+    return out
 
 
 def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=None, return_ani=False):
@@ -133,6 +183,14 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
         return np.ones((0, 0))
     c = _collect(siglist, downsample=downsample, with_abunds=not ignore_abundance)
     has_ab, num, scaled, sizes = c["has_abund"], c["num"], c["scaled"], c["sizes"]
+    if c.get("raw") is not None:                         # different scaled values: every pair at its own max scaled
+        if return_ani:
+            raise ValueError(_MIXED_ANI)
+        want_ang = not ignore_abundance and bool(has_ab.any())
+        t = _mixed_pair_tables(c, jaccard=True, angular=want_ang)
+        out = np.where(has_ab[:, None] & has_ab[None, :], t["angular"], t["jaccard"]) if want_ang else t["jaccard"]
+        np.fill_diagonal(out, 1.0)
+        return out
     if return_ani:
         accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"])   # raises for num sketches, like jaccard_ani
     sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
@@ -166,11 +224,18 @@ def compare_parallel(siglist, ignore_abundance, downsample, n_jobs, return_ani=F
 
 
 def _bias_factors(sizes, scaled):
-    "bias_factor(n) = 1 - (1 - 1/scaled) ** float(n * scaled), Python floats (minhash.py:830-833)"
+    """bias_factor(n) = 1 - (1 - 1/scaled) ** float(n * scaled), Python floats (minhash.py:830-833);
+    `scaled` is one value or an array shaped like `sizes` (the scaled of the sketch whose method is called)."""
+    sizes = np.asarray(sizes)
+    scaleds = np.broadcast_to(np.asarray(scaled), sizes.shape)
     table = {}
-    for n in set(int(x) for x in sizes):
-        table[n] = 1.0 - (1.0 - 1.0 / scaled) ** float(n * scaled) if n else 1.0
-    return np.array([table[int(x)] for x in sizes], dtype=np.float64)
+    flat = np.empty(sizes.size, dtype=np.float64)
+    for k, (n, sc) in enumerate(zip(sizes.ravel().tolist(), scaleds.ravel().tolist())):
+        key = (int(n), int(sc))
+        if key not in table:
+            table[key] = 1.0 - (1.0 - 1.0 / key[1]) ** float(key[0] * key[1]) if key[0] else 1.0
+        flat[k] = table[key]
+    return flat.reshape(sizes.shape)
 
 
 def _clamp01(m):
@@ -183,6 +248,14 @@ def _containment_parts(siglist, downsample, return_ani=False):
     if not len(siglist):
         return None, np.zeros(0, np.int64), 0, 0, None
     c = _collect(siglist, downsample=downsample, need_scaled=True)
+    if c.get("raw") is not None:
+        # different scaled values: counts per pair at max(scaled_i, scaled_j) (count_common(other, downsample=True)),
+        # while contained_by / max_containment keep len(self) and self.scaled of the sketches AS GIVEN in the
+        # denominator (minhash.py:827-841,889-905)
+        if return_ani:
+            raise ValueError(_MIXED_ANI)
+        common = _mixed_pair_tables(c)["common"].astype(np.float64)
+        return common, c["orig_sizes"], np.asarray(c["orig_scaled"]).astype(np.int64), c["ksize"], None
     accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"]) if return_ani else None
     sset = B.SketchSet.from_host(c["hashes"], c["offsets"])
     common = B.pairwise_common(sset).astype(np.float64)
@@ -220,10 +293,15 @@ def compare_serial_max_containment(siglist, *, downsample=False, return_ani=Fals
     if n == 0:
         return np.ones((0, 0))
     mins = np.minimum(sizes[:, None], sizes[None, :])
-    flat = mins.ravel()
-    bias = _bias_factors(np.unique(flat), scaled)
-    lut = dict(zip(np.unique(flat).tolist(), bias.tolist()))
-    denom = mins.astype(np.float64) * np.vectorize(lut.get, otypes=[np.float64])(mins)
+    if np.ndim(scaled):
+        # cell (i, j), i < j, is siglist[j].max_containment(siglist[i]): the bias uses the scaled of the sketch
+        # with the HIGHER index (compare.py:131-140), mirrored into (j, i)
+        hi = np.maximum(np.arange(n)[:, None], np.arange(n)[None, :])
+        denom = mins.astype(np.float64) * _bias_factors(mins, np.asarray(scaled)[hi])
+    else:
+        flat = np.unique(mins.ravel())
+        lut = dict(zip(flat.tolist(), _bias_factors(flat, scaled).tolist()))
+        denom = mins.astype(np.float64) * np.vectorize(lut.get, otypes=[np.float64])(mins)
     with np.errstate(divide="ignore", invalid="ignore"):
         m = common / denom
     m = _clamp01(m)

@@ -105,6 +105,18 @@ class LinearIndex:
                             for k, v in groups.items()}
         return self._device
 
+    def _subject_params(self):
+        "(ksize, moltype, seed) of every subject, in index order"
+        return [(ss.minhash.ksize, ss.minhash.moltype, ss.minhash.seed) for ss in self._signatures]
+
+    def _first_incompatible(self, query_mh):
+        "index of the first subject the query cannot be compared with (None: all compatible)"
+        want = (query_mh.ksize, query_mh.moltype, query_mh.seed)
+        for idx, got in enumerate(self._subject_params()):
+            if got != want:
+                return idx
+        return None
+
     def build_device_index(self):
         """Build the inverted index (hash -> rows) of every resident group of this collection
         (batch.SketchSet.build_index): later search / prefetch / gather calls at the collection's own
@@ -118,6 +130,10 @@ class LinearIndex:
         search_fn.check_is_compatible(query)
         query_mh = query.minhash
         assert not query_mh.track_abundance
+        # The reference scores subject by subject and `intersection_and_union_size` raises
+        # TypeError("incompatible MinHash objects") at the first subject whose ksize / molecule / seed
+        # differ from the query's (minhash.py:649-654): results of earlier subjects have been yielded by then.
+        first_bad = self._first_incompatible(query_mh)
         scored = []
         for (kind, val), (indices, sset) in self._groups().items():
             if query_mh.scaled:
@@ -146,6 +162,8 @@ class LinearIndex:
                 scored.append((idx, int(qsize[pos]), int(shared[pos]), int(sizes[pos]), int(total[pos])))
         scored.sort()
         for idx, qs, sh, ss_size, tot in scored:
+            if first_bad is not None and idx >= first_bad:
+                raise TypeError("incompatible MinHash objects")
             score = search_fn.score_fn(qs, sh, ss_size, tot)
             if search_fn.passes(score):
                 subj = self._subject(idx)
@@ -312,6 +330,16 @@ class ZipFileLinearIndex(LinearIndex):
             kwargs = d
         return ZipFileLinearIndex(self.storage, selection_dict=kwargs, traverse_yield_all=self.traverse_yield_all,
                                   manifest=None, use_manifest=False, _sigset=self._sigset)
+
+    def _subject_params(self):
+        "(ksize, moltype, seed) of the selected sketches from the parser's metadata columns (no objects built)"
+        ss = self._sigset
+        out = []
+        for row in self._rows.tolist():
+            mol = ss.moltype(row)
+            k = int(ss.ksize[row])
+            out.append((k if mol == "DNA" else k // 3, mol, int(ss.seed[row])))   # protein-family sketches store 3*k
+        return out
 
     def _groups(self):
         "Selected rows grouped by scaled (or num), each group one CSR upload straight from the parser's arrays."

@@ -156,6 +156,7 @@ def _load_query_and_db(args):
     rows = db.select(ksize=query.minhash.ksize if query.minhash.is_dna else query.minhash.ksize * 3,
                      moltype=args.moltype)
     rows = rows[db.max_hash[rows] != 0]
+    rows = rows[db.seed[rows] == query.minhash.seed]      # check_compatible: ksize, molecule AND seed (minhash.rs:886-912)
     if len(rows) == 0:
         raise ValueError("no compatible scaled signatures in the databases")
     scaled = max(int(args.scaled or 0), query.minhash.scaled,

@@ -279,12 +279,20 @@ def test_compare_downsample_mixed_scaled(smb):
     sigs = [_sig(smb, r, f"s{i}", scaled=1000 if i % 2 else 2000) for i, r in enumerate(rows)]
     with pytest.raises(ValueError, match="mismatch in scaled"):
         C.compare_all_pairs(sigs, True)
+    # the reference downsamples per pair to max(scaled_i, scaled_j) (similarity(other, downsample=True),
+    # minhash.rs:682-702): two scaled=1000 sketches are compared at 1000 although the list holds 2000s
     m = C.compare_all_pairs(sigs, True, downsample=True)
-    mx = orc.max_hash_for_scaled(2000)
-    ds = [orc.downsample(r, mx) for r in rows]
+    ds = {sc: [orc.downsample(r, orc.max_hash_for_scaled(sc)) for r in rows] for sc in (1000, 2000)}
     for i in range(6):
         for j in range(i + 1, 6):
-            assert m[i, j] == m[j, i] == orc.jaccard(ds[i], ds[j])
+            sc = 1000 if (i % 2 and j % 2) else 2000
+            assert m[i, j] == m[j, i] == orc.jaccard(ds[sc][i], ds[sc][j])
+            assert m[i, j] == sigs[i].minhash.similarity(sigs[j].minhash, ignore_abundance=True, downsample=True)
+    cm = C.compare_serial_containment(sigs, downsample=True)
+    for i in range(6):
+        for j in range(6):
+            if i != j:                                      # compare.py:97-99
+                assert cm[i, j] == sigs[j].minhash.contained_by(sigs[i].minhash, downsample=True)
 
 
 # ---------------------------------------------------------------- search / prefetch / gather
