@@ -168,6 +168,7 @@ void signature_add_sequence(SourmashSignature *ptr, const char *sequence, bool f
 void signature_add_protein(SourmashSignature *ptr, const char *sequence);
 SourmashKmerMinHash *signature_first_mh(const SourmashSignature *ptr);
 SourmashKmerMinHash **signature_get_mhs(const SourmashSignature *ptr, uintptr_t *size);
+void smb_mh_array_free(SourmashKmerMinHash** arr);   /* the array signature_get_mhs malloc'd (not the sketches); the reference header has no counterpart and leaks it */
 void signature_set_mh(SourmashSignature *ptr, const SourmashKmerMinHash *other);
 void signature_push_mh(SourmashSignature *ptr, const SourmashKmerMinHash *other);
 SourmashStr signature_get_name(const SourmashSignature *ptr);

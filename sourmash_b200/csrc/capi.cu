@@ -1557,6 +1557,8 @@ SourmashKmerMinHash** signature_get_mhs(const SourmashSignature* ptr, uintptr_t*
     *size = n;
     return arr;
 }
+// frees the pointer ARRAY signature_get_mhs returned (the sketches it points at are owned by the caller)
+void smb_mh_array_free(SourmashKmerMinHash** arr) { free(arr); }
 void signature_set_mh(SourmashSignature* ptr, const SourmashKmerMinHash* other) {
     ptr->sketches.clear();
     ptr->sketches.push_back(*other);

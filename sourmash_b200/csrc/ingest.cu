@@ -518,10 +518,19 @@ struct Json {
     }
     bool number(double& v) {
         ws();
+        // the buffer need not be NUL-terminated (mapped files, zip members): parse a bounded copy of the token
+        char tok[64];
+        size_t m = 0;
+        while (p + m < end && m + 1 < sizeof tok &&
+               ((p[m] >= '0' && p[m] <= '9') || p[m] == '+' || p[m] == '-' || p[m] == '.' || p[m] == 'e' || p[m] == 'E')) {
+            tok[m] = p[m];
+            ++m;
+        }
+        tok[m] = 0;
         char* e = nullptr;
-        v = strtod(p, &e);
-        if (e == p) return fail("expected a number");
-        p = e;
+        v = strtod(tok, &e);
+        if (e == tok) return fail("expected a number");
+        p += e - tok;
         return true;
     }
     bool u64_array(std::vector<uint64_t>& dst) {
@@ -535,7 +544,10 @@ struct Json {
             return expect(']');
         }
     }
+    int depth = 0;                                  // nesting of skip(): hostile input cannot exhaust the stack
     bool skip() {                                   // any value
+        struct Level { int& d; explicit Level(int& x) : d(x) { ++d; } ~Level() { --d; } } level(depth);
+        if (depth > 256) return fail("JSON nested too deeply");
         ws();
         if (p >= end) return fail("unexpected end of JSON");
         if (*p == '"') { std::string s; return string(s); }

@@ -111,7 +111,7 @@ class ZipArchive {
         uint64_t n_entries = rd16(p + eocd + 10), cd_size = rd32(p + eocd + 12), cd_off = rd32(p + eocd + 16);
         if (eocd >= 20 && rd32(p + eocd - 20) == 0x07064b50u) {                  // zip64 locator
             const uint64_t at64 = rd64(p + eocd - 20 + 8);
-            if (at64 + 56 > n || rd32(p + at64) != 0x06064b50u) return "bad zip64 end-of-central-directory record";
+            if (at64 > n || n - at64 < 56 || rd32(p + at64) != 0x06064b50u) return "bad zip64 end-of-central-directory record";
             n_entries = rd64(p + at64 + 32); cd_size = rd64(p + at64 + 40); cd_off = rd64(p + at64 + 48);
         }
         if (cd_off > n || cd_size > n - cd_off) return "central directory lies outside the file";
@@ -166,7 +166,10 @@ class ZipArchive {
         if (m.method == 0) {
             out.append((const char*)p_ + data, (size_t)m.csize);
         } else if (m.method == 8) {
-            std::string e = inflate_all(p_ + data, (size_t)m.csize, -15, (size_t)m.usize + 16, out);
+            // the declared size is only a hint for the first allocation: deflate expands at most ~1032x, so a
+            // crafted header cannot ask for more than the compressed bytes could possibly produce
+            const uint64_t most = m.csize * 1032 + (1u << 16);
+            std::string e = inflate_all(p_ + data, (size_t)m.csize, -15, (size_t)std::min<uint64_t>(m.usize, most) + 16, out);
             if (!e.empty()) return m.name + ": " + e;
         } else {
             return m.name + ": unsupported compression method " + std::to_string(m.method);

@@ -41,7 +41,10 @@ class SourmashSignature(RustObject):
         "All sketches of this signature (clones)."
         size = ffi.new("uintptr_t *")
         arr = self._methodcall(lib.signature_get_mhs, size)
-        return [FrozenMinHash._from_objptr(arr[i]) for i in range(size[0])]
+        try:
+            return [FrozenMinHash._from_objptr(arr[i]) for i in range(size[0])]
+        finally:
+            lib.smb_mh_array_free(arr)                     # the pointer array; the clones now belong to the wrappers
 
     def __len__(self):
         return self._methodcall(lib.signature_len)

@@ -302,3 +302,35 @@ def test_search_database_matches_index_search(cpu_kernels, three):
     small = _FakeSet([s.minhash._mins_array() for s in (ss2, ss47, ss63)])
     sr = G.search_database(ss47.minhash, small, threshold=0.1, md5s=[s.md5sum() for s in three])    # test_index_protocol.py:206-230
     assert [g["md5"] for g in sr] == [ss47.md5sum(), ss63.md5sum()] and sr[0]["similarity"] == 1.0 and round(sr[1]["similarity"], 2) == 0.32
+
+
+def test_find_refuses_incompatible_subjects(cpu_kernels, three):
+    """Index.find scores subject by subject and `intersection_and_union_size` raises
+    TypeError("incompatible MinHash objects") when ksize / molecule / seed differ from the query's
+    (reference minhash.py:649-654, index/__init__.py:151-158); matches of earlier subjects are
+    yielded first.  Round-1 advisor finding: a k=21 query 'matched' a k=31 subject."""
+    ss2, ss47, ss63 = three
+    k21 = smb.MinHash(0, 21, scaled=1000)
+    k21.add_many(ss47.minhash.hashes)                                   # the same hashes under another ksize
+    q21 = smb.SourmashSignature(k21, name="k21")
+    lidx = LinearIndex([ss47, ss63])
+    with pytest.raises(TypeError, match="incompatible MinHash objects"):
+        lidx.search(q21, threshold=0.1)
+    with pytest.raises(TypeError, match="incompatible MinHash objects"):
+        list(lidx.prefetch(q21, threshold_bp=0))
+    with pytest.raises(TypeError, match="incompatible MinHash objects"):
+        lidx.counter_gather(q21, threshold_bp=0)
+    seeded = smb.MinHash(0, 31, scaled=1000, seed=43)
+    seeded.add_many(ss47.minhash.hashes)
+    with pytest.raises(TypeError, match="incompatible MinHash objects"):
+        lidx.search(smb.SourmashSignature(seeded, name="seed43"), threshold=0.1)
+    # a mixed collection: subjects in front of the first incompatible one are still reported
+    mixed = LinearIndex([ss47, smb.SourmashSignature(k21, name="k21"), ss63])
+    from sourmash_b200.search import make_jaccard_search_query
+    it = mixed.find(make_jaccard_search_query(threshold=0.1), ss47)
+    first = next(it)
+    assert first.signature.minhash == ss47.minhash and first.score == 1.0
+    with pytest.raises(TypeError, match="incompatible MinHash objects"):
+        next(it)
+    # compatible queries are unaffected
+    assert len(lidx.search(ss47, threshold=0.1)) == 2
