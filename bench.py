@@ -174,12 +174,40 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
+def git_blob_hash(path):
+    "the id `git hash-object` gives the file: sha1 over 'blob <size>\\0' + content"
+    import hashlib
+    with open(path, "rb") as fh:
+        data = fh.read()
+    return hashlib.sha1(b"blob %d\0" % len(data) + data).hexdigest()
+
+
+def ncu_record(key):
+    """An ncu-measured constant (DRAM bytes per launch, warp instructions per k-mer) from profiles/ncu_traffic.json,
+    or None when it is absent or STALE: every entry lists the kernel source files it was measured on with their
+    git blob ids, and counts only while those files are byte-identical (scripts/record_traffic.py writes entries)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        with open(p) as fh:
-            return json.load(fh).get(kernel)
-    return None
+    if not os.path.exists(p):
+        return None
+    with open(p) as fh:
+        entry = json.load(fh).get("entries", {}).get(key)
+    if not entry or not entry.get("files"):
+        return None
+    for rel, blob in entry["files"].items():
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path) or git_blob_hash(path) != blob:
+            return None
+    return entry
+
+
+def ncu_traffic(key):
+    entry = ncu_record(key)
+    return entry["value"] if entry else None
+
+
+def ncu_source(key):
+    entry = ncu_record(key)
+    return entry.get("source") if entry else None
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -387,18 +415,18 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     achieved = alg_bytes / (kms / 1e3) / 1e9
     plan = B.last_compare_plan()
     if plan["algo"] == "join":
-        kname = "inverted join (join_gather + cub::DeviceRadixSort + join_count_kernel)"
-        knote = ("counts by sorting the (hash,row) pairs and incrementing one cell per pair of rows sharing a hash "
+        knote = ("counts by sorting the hashes of the set once and incrementing one counter per pair of rows sharing a hash "
                  "(planner estimate: %.3g increments over %.3g elements); algorithmic bytes keep SURVEY 8d's "
                  "definition, 8*(|A|+|B|) per pair + 4 B out" % (plan["est_increments"], plan["est_elements"]))
-        tkey = "inverted_join"
-        layout = os.environ.get("SMB_JOIN_LAYOUT", "")
-        if layout in ("stripe", "stripe_upper", "cluster"):   # experimental layouts, A/B runs only
-            plan = dict(plan, layout=layout)
-            kname = {"stripe": "inverted join, stripe layout (cub::DeviceRadixSort + stripe_tag_kernel + join_stripe_kernel)",
-                     "stripe_upper": "inverted join, stripe layout, upper triangle + stripe_mirror_kernel",
-                     "cluster": "inverted join, cluster layout (join_count_warp_kernel)"}[layout]
-            tkey = "inverted_join_" + layout
+        if os.environ.get("SMB_JOIN_LAYOUT", "") == "plain":      # A/B runs only: the global-reduction join
+            kname = "inverted join, global reductions (join_gather + cub::DeviceRadixSort + join_count_kernel)"
+            tkey = "inverted_join"
+            plan = dict(plan, layout="plain")
+        else:
+            kname = ("inverted join, stripe layout (stripe_keys + cub::DeviceRadixSort on 32-bit keys + stripe_tag + "
+                     "join_stripe_kernel + stripe_mirror; counters in shared memory, no global atomics)")
+            tkey = "inverted_join_stripe"
+            plan = dict(plan, layout=os.environ.get("SMB_JOIN_LAYOUT") or "stripe")
     else:
         kname, tkey = "pairwise_tile_split_kernel", "pairwise_tile_split_kernel"
         knote = ("algorithmic bytes = 8*(|A|+|B|) per pair + 4 B out; rows are reused from shared "
@@ -493,11 +521,11 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
                      "note": "integer-issue bound by construction (~150 int ops per k-mer vs 1 B): "
                              "HBM fraction is expected to be small; roofline.issue is the bound that applies"},
     }
-    fused = os.environ.get("SMB_SKETCH_FUSED") == "1"      # experimental one-pass kernel, A/B runs only
+    fused = os.environ.get("SMB_SKETCH_FUSED") != "0"      # default: k=21,31,51 in one pass; =0: three launches (A/B runs)
     if fused:
         res["roofline"]["kernel"] = "hash_kmers_fused_kernel (1 launch, k=21,31,51)"
-        res["roofline"]["traffic"] = None
-    wipk = None if fused else ncu_traffic("hash_kmers_kernel_warp_instr_per_kmer")
+        res["roofline"]["traffic"] = ncu_traffic("hash_kmers_fused_kernel")
+    wipk = ncu_traffic("hash_kmers_fused_kernel_warp_instr_per_kmer" if fused else "hash_kmers_kernel_warp_instr_per_kmer")
     if wipk:
         # the bound that applies: warp instructions issued (ncu count of the same three launches, per k-mer)
         # against 4 issue slots per SM per clock at the SM clock sampled during the timed region
@@ -506,7 +534,7 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
         res["roofline"]["issue"] = {"warp_instructions_per_kmer": wipk, "achieved": issued / 1e9,
                                     "peak": SM_COUNT * 4 * clk / 1e9, "unit": "G warp-instr/s",
                                     "frac": issued / (SM_COUNT * 4 * clk),
-                                    "source": ncu_traffic("hash_kmers_kernel_warp_instr_source")}
+                                    "source": ncu_source("hash_kmers_fused_kernel_warp_instr_per_kmer" if fused else "hash_kmers_kernel_warp_instr_per_kmer")}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = host_cores()
         units, dt, sample = cpu_sketch_sample(seqs, offs, ncores, ng)

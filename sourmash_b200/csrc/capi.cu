@@ -1858,10 +1858,10 @@ void smb_finalize_jaccard_rows_dev(const SmbSketchSet* set, const uint32_t* d_co
     });
 }
 
-// Experimental stripe layout of the join (SMB_JOIN_LAYOUT=stripe, off by default): float64 rows come
-// straight out of the count kernel, block of rows by block of rows; with `host_out` every finished
-// block is downloaded on the copy stream while the next one is counted.  Returns false when the
-// layout does not apply (the caller continues with the default path).
+// Stripe layout of the join (join_stripe.cuh, the default; SMB_JOIN_LAYOUT=plain switches it off): float64
+// rows come straight out of the count kernel, block of rows by block of rows; with `host_out` every
+// finished block is downloaded on the copy stream while the next one is counted.  Returns false when the
+// layout does not apply (the caller continues with the global-reduction join).
 static bool compare_jaccard_stripe(const SmbSketchSet* set, uint64_t max_key, double* d_out, double* host_out,
                                    cudaStream_t s) {
     const size_t n = set->n_rows;
@@ -1877,7 +1877,9 @@ static bool compare_jaccard_stripe(const SmbSketchSet* set, uint64_t max_key, do
         return true;
     }
     cudaStream_t cs = copy_stream();
-    const size_t per = (n + 15) / 16;
+    // the download (PCIe) takes several times longer than the counting: a small first block starts it early,
+    // the later blocks are large enough to fill the GPU for a few waves of CTAs each
+    const size_t per = std::max<size_t>((n + 7) / 8, 1);
     for (size_t r0 = 0; r0 < n; r0 += per) {
         const size_t r1 = std::min(n, r0 + per);
         CK(smb::join_stripe_rows(js, set->d_off, (int)r0, (int)r1, d_out + r0 * n, s));
@@ -1959,34 +1961,6 @@ void smb_compare_jaccard(const SmbSketchSet* set, uint32_t num, double* out) {
                 if (smb::join_stripe_enabled() && compare_jaccard_stripe(set, mk, d_out.p, out, s)) return;
                 DevBuf<uint32_t> d_c(n * n, s);
                 cudaStream_t cs = copy_stream();
-                const char* passes_env = getenv("SMB_COMPARE_PASSES");
-                const int passes = passes_env ? std::min(64, atoi(passes_env)) : 0;
-                if (passes > 1) {
-                    // experimental (off by default): count block k of rows, then finalise and download it
-                    // while block k+1 is being counted (join_walk.cuh: after the passes for rows [0, r1)
-                    // the full rows [0, r1) of the result are final)
-                    if (t_profiling) t_timer_pairwise.begin(s);
-                    CK(cudaMemsetAsync(d_c.p, 0, n * n * sizeof(uint32_t), s));
-                    smb::JoinStream* js = nullptr;
-                    CK(smb::join_stream_create(set->d_hashes, set->d_off, (int)n, mk, &js, s));
-                    std::unique_ptr<smb::JoinStream, void (*)(smb::JoinStream*)> guard(js, smb::join_stream_destroy);
-                    const size_t per = (n + passes - 1) / passes;
-                    for (size_t r0 = 0; r0 < n; r0 += per) {
-                        const size_t r1 = std::min(n, r0 + per);
-                        CK(smb::join_stream_count_rows(js, (int)r0, (int)r1, d_c.p, n, s));
-                        smb::launch_finalize_rows(d_c.p, n, set->d_off, (int)n, (int)r0, (int)r1, d_out.p + r0 * n, s);
-                        cudaEvent_t ev = pool_event();
-                        CK(cudaEventRecord(ev, s));
-                        CK(cudaStreamWaitEvent(cs, ev, 0));
-                        CK(cudaMemcpyAsync(out + r0 * n, d_out.p + r0 * n, (r1 - r0) * n * sizeof(double),
-                                           cudaMemcpyDeviceToHost, cs));
-                    }
-                    if (t_profiling) t_timer_pairwise.end(s);
-                    CK(cudaGetLastError());
-                    CK(cudaStreamSynchronize(cs));
-                    sync(s);
-                    return;
-                }
                 if (t_profiling) t_timer_pairwise.begin(s);
                 CK(cudaMemsetAsync(d_c.p, 0, n * n * sizeof(uint32_t), s));
                 CK(smb::join_counts(set->d_hashes, set->d_off, (int)n, mk, 0, 1, d_c.p, n, s));

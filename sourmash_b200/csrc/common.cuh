@@ -31,6 +31,18 @@ __device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
 }
 #endif
 
+// Streaming accesses (evict-first): data that is read or written exactly once should not push the reused
+// working set (the tag stream of the stripe join, a query bitmap) out of L2.
+#ifdef SMB_SIMT_EMUL
+inline u32 ld_stream_u32(const u32* p) { return *p; }
+inline u64 ld_stream_u64(const u64* p) { return *p; }
+inline void st_stream_f64(double* p, double v) { *p = v; }
+#elif defined(__CUDACC__)
+__device__ __forceinline__ u32 ld_stream_u32(const u32* p) { return __ldcs(p); }
+__device__ __forceinline__ u64 ld_stream_u64(const u64* p) { return __ldcs(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ void st_stream_f64(double* p, double v) { __stcs(p, v); }
+#endif
+
 // MurmurHash3 x64-128 building blocks (device + host), see murmur.cuh.
 __host__ __device__ __forceinline__ u64 smb_rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
 __host__ __device__ __forceinline__ u64 smb_fmix64(u64 x) {

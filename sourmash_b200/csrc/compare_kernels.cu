@@ -20,8 +20,6 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <memory>
@@ -30,10 +28,12 @@
 #include "kernels.h"
 #include "split_table.cuh"
 #include "join_walk.cuh"
+#include "join_kernels.cuh"
 #include "join_stripe.cuh"
 #include "range_search.cuh"
+#include "range_kernels.cuh"
 #include "db_index.cuh"
-#include "experimental_kernels.cuh"
+#include "db_index_kernels.cuh"
 #include "search_kernels.cuh"
 #include "tile_kernels.cuh"
 #include "pair_kernels.cuh"
@@ -257,7 +257,9 @@ void launch_one_vs_many_ranges(const u64* q, u64 nq, const u32* dir, int shift, 
     RangeArgs a{q, nq, dir, (u32)shift, nbk, hB, offB, nB, bounds, width, P, 0, 0, out};
     plan_range_bitmap(width, &a.bm_shift, &a.bm_words);
     const size_t smem = (size_t)a.bm_words * sizeof(u32);
-    cudaFuncSetAttribute(one_vs_many_ranges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    // only what the bitmap needs: the kernel also has static shared memory, and dynamic + static must stay
+    // within the 227 KB a CTA may use (asking for all 227 KB as dynamic made every launch fail)
+    cudaFuncSetAttribute(one_vs_many_ranges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     one_vs_many_ranges_kernel<<<P, 1024, smem, s>>>(a); count_launches(1);
 }
 bool range_search_enabled() {
@@ -409,232 +411,92 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
 }
 
 // ------------------------------------------------------------------------------------
-// Experimental cluster layout of the inverted join (off unless SMB_JOIN_LAYOUT=cluster).
-// Not measured yet: kept behind the switch until it has been validated on the GPU; the logic
-// is covered on the CPU by tests/test_host_emulation.py::test_join_cluster_layout_matches_oracle.
+// Stripe layout of the inverted join (join_stripe.cuh): the default all-vs-all path.  CTAs own complete
+// rows of the result as shared-memory counters; no count matrix in HBM, no global atomics, float64 rows
+// written once.  SMB_JOIN_LAYOUT=plain selects the global-reduction join (join_counts) for A/B runs,
+// SMB_JOIN_LAYOUT=stripe_full counts both directions in every launch (no mirror pass).
 // ------------------------------------------------------------------------------------
-static cudaError_t join_counts_clustered(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
-                                         u32* common, size_t ld, cudaStream_t s) {
-    cudaError_t e;
-    JoinScratch scratch(s);
-    // 1. row keys from the global sample (lowest 1/JOIN_SAMPLE of the key range): smallest shared hash
-    unsigned long long* d_rowkey = nullptr;
-    u32 *d_order_in = nullptr, *d_order = nullptr;
-    if ((e = scratch.alloc((void**)&d_rowkey, (size_t)n * 2 * sizeof(unsigned long long))) != cudaSuccess) return e;
-    unsigned long long* d_rowkey_sorted = d_rowkey + n;
-    if ((e = scratch.alloc((void**)&d_order_in, (size_t)n * 3 * sizeof(u32))) != cudaSuccess) return e;
-    d_order = d_order_in + n;
-    u32* d_inv = d_order + n;
-    cudaMemsetAsync(d_rowkey, 0xff, (size_t)n * sizeof(unsigned long long), s);
-    {
-        const u64 hi = max_key / JOIN_SAMPLE + 1;
-        JoinWork S;
-        e = join_sort_slice(h, off, n, 0, hi, 1, key_bit_length(hi), S, s);
-        S.stream = s;
-        if (e != cudaSuccess) return e;
-        if (S.T) { join_rowkey_kernel<<<(unsigned)((S.T + 255) / 256), 256, 0, s>>>(S.keys_b, S.ids_b, S.T, d_rowkey); count_launches(1); }
-    }
-    // 2. rank rows by (row key, row id): stable sort of the ids by key
-    join_iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_order_in, n); count_launches(1);
-    size_t sb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sb, d_rowkey, d_rowkey_sorted, d_order_in, d_order, n, 0, 64, s);
-    void* d_tmp = nullptr;
-    if ((e = cudaMallocAsync(&d_tmp, sb ? sb : 16, s)) != cudaSuccess) return e;
-    cub::DeviceRadixSort::SortPairs(d_tmp, sb, d_rowkey, d_rowkey_sorted, d_order_in, d_order, n, 0, 64, s);
-    cudaFreeAsync(d_tmp, s);
-    join_invert_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_order, n, d_inv); count_launches(2);
-    // 3. slice this shard's key range, gather in rank order, sort
-    u64 lo, hi;
-    bool bounded;
-    join_shard_range(max_key, shard, n_shards, lo, hi, bounded);
-    const size_t nn = (size_t)n + 1;
-    u64* d_beg = nullptr;
-    if ((e = cudaMallocAsync((void**)&d_beg, nn * 4 * sizeof(u64), s)) != cudaSuccess) return e;
-    u64 *d_cnt = d_beg + nn, *d_cnt_rank = d_cnt + nn, *d_doff = d_cnt_rank + nn;
-    join_row_range_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(h, off, n, lo, hi, bounded ? 1 : 0, d_beg, d_cnt);
-    join_rank_counts_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(d_cnt, d_order, n, d_cnt_rank);
-    count_launches(2);
-    size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt_rank, d_doff, (int)nn, s);
-    void* d_scan = nullptr;
-    if ((e = cudaMallocAsync(&d_scan, scan_bytes ? scan_bytes : 16, s)) != cudaSuccess) { cudaFreeAsync(d_beg, s); return e; }
-    cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_cnt_rank, d_doff, (int)nn, s);
-    u64 T = 0;
-    cudaMemcpyAsync(&T, d_doff + n, sizeof(u64), cudaMemcpyDeviceToHost, s);
-    e = cudaStreamSynchronize(s);
-    cudaFreeAsync(d_scan, s);
-    if (e != cudaSuccess || T == 0) { cudaFreeAsync(d_beg, s); return e; }
-    JoinWork W;
-    W.stream = s;
-    const size_t Tp = (size_t)((T + 63) & ~63ull);
-    if ((e = cudaMallocAsync(&W.mem, Tp * (2 * sizeof(u64) + 2 * sizeof(u32)), s)) != cudaSuccess) { cudaFreeAsync(d_beg, s); return e; }
-    W.keys_a = (u64*)W.mem; W.keys_b = W.keys_a + Tp;
-    W.ids_a = (u32*)(W.keys_b + Tp); W.ids_b = W.ids_a + Tp;
-    const int blocks = n < SMB_B200_SMS * 16 ? n : SMB_B200_SMS * 16;
-    join_gather_ranked_kernel<<<blocks, 256, 0, s>>>(h, off, d_beg, d_order, d_doff, n, W.keys_a, W.ids_a); count_launches(1);
-    cudaFreeAsync(d_beg, s);
-    const int key_bits = key_bit_length(max_key);
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
-    void* d_sort = nullptr;
-    if ((e = cudaMallocAsync(&d_sort, sort_bytes ? sort_bytes : 16, s)) != cudaSuccess) return e;
-    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, W.keys_a, W.keys_b, W.ids_a, W.ids_b, (long long)T, 0, key_bits, s);
-    cudaFreeAsync(d_sort, s);
-    count_launches(1);
-    // 4. count in rank space, then add into the caller's matrix in row space
-    u32* d_ranked = nullptr;
-    if ((e = cudaMallocAsync((void**)&d_ranked, (size_t)n * n * sizeof(u32), s)) != cudaSuccess) return e;
-    cudaMemsetAsync(d_ranked, 0, (size_t)n * n * sizeof(u32), s);
-    const u64 warps = T, threads = warps * 32;
-    join_count_warp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(W.keys_b, W.ids_b, T, d_ranked, (size_t)n);
-    dim3 grid((n + 255) / 256, n < 65535 ? n : 65535);
-    join_unpermute_add_kernel<<<grid, 256, 0, s>>>(d_ranked, d_inv, n, (size_t)n, common, ld);
-    count_launches(2);
-    cudaFreeAsync(d_ranked, s);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------
-// Sorted stream kept across several count passes (experimental row-block pipeline of
-// smb_compare_jaccard, SMB_COMPARE_PASSES; off by default, see join_walk.cuh).
-// ------------------------------------------------------------------------------------
-struct JoinStream { JoinWork W; };
-
-cudaError_t join_stream_create(const u64* h, const u64* off, int n, u64 max_key, JoinStream** out, cudaStream_t s) {
-    JoinStream* js = new JoinStream();
-    js->W.stream = s;
-    cudaError_t e = join_sort_slice(h, off, n, 0, 0, 0, key_bit_length(max_key), js->W, s);
-    if (e != cudaSuccess) { delete js; return e; }
-    *out = js;
-    return cudaSuccess;
-}
-cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_end, u32* common, size_t ld,
-                                   cudaStream_t s) {
-    if (js->W.T == 0 || row_end <= row_begin) return cudaSuccess;
-    join_count_rows_kernel<<<(unsigned)((js->W.T + 255) / 256), 256, 0, s>>>(js->W.keys_b, js->W.ids_b, js->W.T,
-                                                                           (u32)row_begin, (u32)row_end, common, ld);
-    count_launches(1);
-    return cudaGetLastError();
-}
-void join_stream_destroy(JoinStream* js) { delete js; }
-
-// ------------------------------------------------------------------------------------
-// Experimental stripe layout of the inverted join (off unless SMB_JOIN_LAYOUT=stripe; logic in
-// join_stripe.cuh, checked on the CPU by tests/test_host_emulation.py::test_join_stripe_*).
-// Not measured yet: kept behind the switch until it has been validated on the GPU.
-// ------------------------------------------------------------------------------------
-// ---- SMB_JOIN_SORT=low32: the sorted (key, element) stream from a 32-bit sort + repair of mixed runs ----
-// keys_sorted[q] / src[q]: the hashes in ascending-group order with their CSR element index.  Groups of
-// equal hashes are contiguous and rows ascend inside a group; the groups themselves come in the order
-// of their low words (any order of the groups serves the stripe layout).
-static cudaError_t stripe_stream_low32(const u64* h, u64 T, u64* keys_sorted, u32* src, JoinScratch& scratch, cudaStream_t s) {
-    cudaError_t e;
-    const size_t Tp = (size_t)((T + 63) & ~63ull);
-    u32 *low = nullptr, *vals = nullptr;
-    if ((e = scratch.alloc((void**)&low, Tp * 2 * sizeof(u32))) != cudaSuccess) return e;
-    if ((e = scratch.alloc((void**)&vals, Tp * sizeof(u32))) != cudaSuccess) return e;
-    u32* low_sorted = low + Tp;
-    const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
-    stripe_low32_kernel<<<grid, 256, 0, s>>>(h, T, low, vals); count_launches(1);
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, low, low_sorted, vals, src, (long long)T, 0, 32, s);
-    void* tmp = nullptr;
-    if ((e = scratch.alloc(&tmp, bytes)) != cudaSuccess) return e;
-    cub::DeviceRadixSort::SortPairs(tmp, bytes, low, low_sorted, vals, src, (long long)T, 0, 32, s);
-    count_launches(1);
-    stripe_gather_keys_kernel<<<grid, 256, 0, s>>>(h, src, T, keys_sorted); count_launches(1);
-    // runs of equal low words that mix different hashes
-    u8* flags = nullptr;
-    if ((e = scratch.alloc((void**)&flags, Tp)) != cudaSuccess) return e;
-    cudaMemsetAsync(flags, 0, Tp, s);
-    stripe_mixed_runs_kernel<<<grid, 256, 0, s>>>(low_sorted, keys_sorted, T, flags); count_launches(1);
-    u32* where = vals;                                           // vals is free again: positions of the flagged elements
-    u64* d_nsel = (u64*)low;                                     // low (unsorted) is free again
-    thrust::counting_iterator<u32> positions(0);
-    bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, bytes, positions, flags, where, d_nsel, (int)T, s);
-    void* tmp2 = nullptr;
-    if ((e = scratch.alloc(&tmp2, bytes)) != cudaSuccess) return e;
-    cub::DeviceSelect::Flagged(tmp2, bytes, positions, flags, where, d_nsel, (int)T, s);
-    count_launches(1);
-    u64 n_sel = 0;
-    cudaMemcpyAsync(&n_sel, d_nsel, sizeof(u64), cudaMemcpyDeviceToHost, s);
-    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-    if (n_sel == 0) return cudaSuccess;
-    // re-sort the flagged elements on (low word, high word): runs stay where they are, ordered inside
-    u64* rot = nullptr;
-    u32* sel_src = nullptr;
-    if ((e = scratch.alloc((void**)&rot, n_sel * 2 * sizeof(u64))) != cudaSuccess) return e;
-    if ((e = scratch.alloc((void**)&sel_src, n_sel * 2 * sizeof(u32))) != cudaSuccess) return e;
-    const unsigned g2 = (unsigned)std::min<u64>((n_sel + 255) / 256, (u64)SMB_B200_SMS * 32);
-    stripe_repair_load_kernel<<<g2, 256, 0, s>>>(where, n_sel, keys_sorted, src, rot, sel_src); count_launches(1);
-    bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, rot, rot + n_sel, sel_src, sel_src + n_sel, (long long)n_sel, 0, 64, s);
-    void* tmp3 = nullptr;
-    if ((e = scratch.alloc(&tmp3, bytes)) != cudaSuccess) return e;
-    cub::DeviceRadixSort::SortPairs(tmp3, bytes, rot, rot + n_sel, sel_src, sel_src + n_sel, (long long)n_sel, 0, 64, s);
-    count_launches(1);
-    stripe_repair_store_kernel<<<g2, 256, 0, s>>>(where, n_sel, rot + n_sel, sel_src + n_sel, keys_sorted, src); count_launches(1);
-    return cudaGetLastError();
-}
-
 struct JoinStripe {
     cudaStream_t stream = 0;
-    void* mem = nullptr;      // tags + pos
-    u32 *tags = nullptr, *pos = nullptr;
+    void* mem = nullptr;      // tags + pos + sizes
+    void* tags = nullptr;
+    u32 *pos = nullptr, *sizes = nullptr;
     u64 T = 0;
-    int n = 0, rows_per_block = 0, upper_only = 0;
+    int n = 0, rows_per_block = 0, upper_only = 1, tag16 = 0;
     size_t smem = 0;
     ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
 };
 
-// *out stays null (with cudaSuccess) when the layout does not apply: more than 2^32 - 1 elements,
-// or a stripe row of n counters that does not fit in shared memory.
+template <typename TagT>
+static cudaError_t stripe_set_smem() {
+    cudaError_t e = cudaFuncSetAttribute(join_stripe_kernel<TagT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(join_stripe_kernel<TagT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+}
+
+// *out stays null (with cudaSuccess) when the layout does not apply: 2^32 - 1 or more elements, or a row of n
+// counters that does not fit in shared memory.  Everything is enqueued on `s`; nothing synchronises.
 cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 max_key, JoinStripe** out, cudaStream_t s) {
     *out = nullptr;
-    const size_t smem = (size_t)MAX_DYN_SMEM;
-    const int R = n > 0 ? stripe_rows_per_block(smem, n) : 0;
+    const int R = n > 0 ? stripe_rows_per_block((size_t)MAX_DYN_SMEM, n) : 0;
     if (R < 1 || T == 0 || T >= 0xffffffffull) return cudaSuccess;
-    {   // per device, so not cached in a flag
-        cudaError_t ea = cudaFuncSetAttribute(join_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-        if (ea != cudaSuccess) return ea;
-    }
-    auto js = new JoinStripe();
-    js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;
-    {   // SMB_JOIN_LAYOUT=stripe_upper: count only (i, j > i) and mirror -- half the scans and atomics
-        const char* layout = getenv("SMB_JOIN_LAYOUT");
-        js->upper_only = layout && !strcmp(layout, "stripe_upper");
-    }
-    js->smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
     cudaError_t e;
-    const size_t Tp = (size_t)((T + 63) & ~63ull);
-    if ((e = cudaMallocAsync(&js->mem, Tp * 2 * sizeof(u32), s)) != cudaSuccess) { delete js; return e; }
-    js->tags = (u32*)js->mem; js->pos = js->tags + Tp;
-    // sort the hashes where they lie (the CSR is the unsorted stream), payload = element index
-    JoinScratch scratch(s);
-    u64* keys_sorted = nullptr;
-    u32* vals = nullptr;
-    if ((e = scratch.alloc((void**)&keys_sorted, Tp * sizeof(u64))) != cudaSuccess) { delete js; return e; }
-    if ((e = scratch.alloc((void**)&vals, Tp * 2 * sizeof(u32))) != cudaSuccess) { delete js; return e; }
-    u32* vals_sorted = vals + Tp;
-    const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
-    const char* sort_mode = getenv("SMB_JOIN_SORT");
-    if (sort_mode && !strcmp(sort_mode, "low32") && T <= 0x7fffffffull) {
-        // 4 radix passes over 4-byte keys, then the rare runs that mix hashes are repaired
-        if ((e = stripe_stream_low32(h, T, keys_sorted, vals_sorted, scratch, s)) != cudaSuccess) { delete js; return e; }
-    } else {
-        stripe_iota_kernel<<<grid, 256, 0, s>>>(vals, T); count_launches(1);
-        const int key_bits = key_bit_length(max_key);
-        size_t sort_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
-        void* d_sort = nullptr;
-        if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) { delete js; return e; }
-        cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, h, keys_sorted, vals, vals_sorted, (long long)T, 0, key_bits, s);
-        count_launches(1);
+    if ((e = stripe_set_smem<u16>()) != cudaSuccess) return e;      // per device, so not cached in a flag
+    if ((e = stripe_set_smem<u32>()) != cudaSuccess) return e;
+    auto js = new JoinStripe();
+    std::unique_ptr<JoinStripe> guard(js);
+    js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;
+    js->tag16 = n < 32768;
+    {
+        const char* layout = getenv("SMB_JOIN_LAYOUT");
+        js->upper_only = !(layout && !strcmp(layout, "stripe_full"));
+        const char* tag = getenv("SMB_STRIPE_TAGS");                 // A/B: force 32-bit tags
+        if (tag && !strcmp(tag, "u32")) js->tag16 = 0;
     }
-    stripe_tag_kernel<<<grid, 256, 0, s>>>(keys_sorted, vals_sorted, off, n, T, js->tags, js->pos); count_launches(1);
-    if ((e = cudaGetLastError()) != cudaSuccess) { delete js; return e; }
-    *out = js;
+    js->smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
+    const size_t Tp = (size_t)((T + 63) & ~63ull);
+    const size_t np = ((size_t)n + 63) & ~(size_t)63;
+    if ((e = cudaMallocAsync(&js->mem, Tp * 2 * sizeof(u32) + np * sizeof(u32), s)) != cudaSuccess) return e;
+    js->tags = js->mem;
+    js->pos = (u32*)js->mem + Tp;
+    js->sizes = js->pos + Tp;
+    JoinScratch scratch(s);
+    u32 *key_a = nullptr, *key_b = nullptr, *eblk = nullptr, *d_count = nullptr;
+    u64 *pay_a = nullptr, *pay_b = nullptr;
+    if ((e = scratch.alloc((void**)&key_a, Tp * 2 * sizeof(u32))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&pay_a, Tp * 2 * sizeof(u64))) != cudaSuccess) return e;
+    key_b = key_a + Tp; pay_b = pay_a + Tp;
+    const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
+    if ((e = scratch.alloc((void**)&eblk, (nblk + 1) * sizeof(u32))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&d_count, 16)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
+    const int low_bits = stripe_low_bits(max_key);
+    // 1. 32-bit sort keys (top bits of the hashes) + payloads (low bits, element index)
+    stripe_keys_kernel<<<grid, 256, 0, s>>>(h, T, low_bits, key_a, pay_a); count_launches(1);
+    // 2. four radix passes (fewer when the keys are short)
+    int key_bits = key_bit_length(max_key);
+    if (key_bits > 32) key_bits = 32;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_a, key_b, pay_a, pay_b, (long long)T, 0, key_bits, s);
+    void* d_sort = nullptr;
+    if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) return e;
+    cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, key_a, key_b, pay_a, pay_b, (long long)T, 0, key_bits, s);
+    count_launches(1);
+    // 3. runs of equal keys that hold more than one hash: found, then ordered in place (key_a is free: worklist)
+    if (low_bits) {
+        cudaMemsetAsync(d_count, 0, sizeof(u32), s);
+        stripe_descent_kernel<<<grid, 256, 0, s>>>(key_b, pay_b, T, key_a, d_count);
+        stripe_fix_kernel<<<SMB_B200_SMS, 64, 0, s>>>(key_b, pay_b, T, key_a, d_count);
+        count_launches(2);
+    }
+    // 4. tags + inverse permutation; row lengths
+    stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T, eblk);
+    stripe_sizes_kernel<<<(n + 255) / 256, 256, 0, s>>>(off, n, js->sizes);
+    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos);
+    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos);
+    count_launches(3);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *out = guard.release();
     return cudaSuccess;
 }
 
@@ -642,9 +504,16 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
 cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
-    StripeArgs a{js->tags, js->pos, off, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out, js->upper_only};
+    StripeArgs a{js->tags, js->pos, off, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
-    join_stripe_kernel<<<blocks, 1024, js->smem, s>>>(a); count_launches(1);
+    if (js->tag16) {
+        if (js->upper_only) join_stripe_kernel<u16, true><<<blocks, 1024, js->smem, s>>>(a);
+        else join_stripe_kernel<u16, false><<<blocks, 1024, js->smem, s>>>(a);
+    } else {
+        if (js->upper_only) join_stripe_kernel<u32, true><<<blocks, 1024, js->smem, s>>>(a);
+        else join_stripe_kernel<u32, false><<<blocks, 1024, js->smem, s>>>(a);
+    }
+    count_launches(1);
     return cudaGetLastError();
 }
 // upper-only mode: the cells (i, j < i) of rows [row_begin, row_end) from the finished upper parts of rows
@@ -661,7 +530,7 @@ void join_stripe_two_directions(JoinStripe* js) { js->upper_only = 0; }
 void join_stripe_destroy(JoinStripe* js) { delete js; }
 bool join_stripe_enabled() {
     const char* layout = getenv("SMB_JOIN_LAYOUT");
-    return layout && (!strcmp(layout, "stripe") || !strcmp(layout, "stripe_upper"));
+    return !(layout && !strcmp(layout, "plain"));
 }
 
 // ------------------------------------------------------------------------------------
@@ -764,9 +633,6 @@ void launch_index_count_n(const DbIndex* ix, const u64* q, const u32* d_nq, u64 
 
 cudaError_t join_counts(const u64* h, const u64* off, int n, u64 max_key, int shard, int n_shards,
                         u32* common, size_t ld, cudaStream_t s) {
-    const char* layout = getenv("SMB_JOIN_LAYOUT");
-    if (layout && !strcmp(layout, "cluster"))
-        return join_counts_clustered(h, off, n, max_key, shard, n_shards, common, ld, s);
     u64 lo, hi;
     bool bounded;
     join_shard_range(max_key, shard, n_shards, lo, hi, bounded);

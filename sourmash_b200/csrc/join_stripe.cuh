@@ -1,26 +1,41 @@
-// join_stripe.cuh -- lane-level logic of the "stripe" layout of the inverted join (experimental,
-// SMB_JOIN_LAYOUT=stripe, off by default; compare_kernels.cu), shared with
-// tests/host_emul/join_emul.cu so that the CPU-only suite checks it against the oracle.
+// join_stripe.cuh -- the stripe layout of the inverted join: the all-vs-all count matrix of `compare` with
+// no count matrix in HBM and no global atomics (compare_kernels.cu launches these kernels; in a header so
+// that tests/host_emul/simt_emul.cu runs the kernels themselves on the CPU against the oracle).
 //
-// The plain join (join_walk.cuh) sends one global reduction per (shared hash, pair of rows) to a
-// count matrix in HBM, and the rate of those reductions is its limit.  Here a CTA owns R complete
-// rows of the result as a stripe of counters in shared memory: for every hash of its rows it visits
-// the hash's whole group in the sorted stream and bumps stripe[row][other row] with shared-memory
-// atomics, then turns the finished stripe into float64 Jaccard values and writes each output row
-// once.  No count matrix in HBM, no global atomics, no separate zero / finalize passes, and rows
-// finish in CTA order (row blocks can be downloaded while later ones are still being counted).
+// What it computes: |A_i ∩ A_j| for every pair of rows, then jaccard = common / max(1, union) as float64 --
+// intersection_size + jaccard of the reference (src/core/src/sketch/minhash.rs:593-631,1765-1807) for the
+// n(n-1)/2 pairs that compare_serial walks one by one (src/sourmash/compare.py:36-54).
 //
-// Stream layout: the set's hashes sorted by value with their CSR element index as payload;
-//   tags[q] = row of sorted element q, bit 31 set on the first element of a group of equal hashes;
-//   pos[e]  = sorted position of CSR element e (row r owns e in [off[r], off[r + 1])).
-// The group of element q = the run around q between two head flags; a warp scans it 32 tags at a
-// time in both directions, the ballot of the "stop" predicate cuts the chunk at the group's end.
+// Idea: |A_i ∩ A_j| = number of hashes held by both rows.  Sort the hashes of the whole set once; equal
+// hashes become one contiguous *group* of the sorted stream, rows ascending inside it.  A CTA owns R complete
+// rows of the RESULT as u32 counters in shared memory (a "stripe", R x n); for every hash of its rows it looks
+// up the hash's group and bumps stripe[row][other row] for the other members with shared-memory atomics; the
+// finished stripe is turned into float64 Jaccard values and written once.  Work is proportional to the
+// number of (shared hash, pair) incidences -- unrelated pairs cost nothing.
+//
+// The sorted stream is stored as
+//   tags[q] = row of sorted element q, top bit set on the first element of a group   (u16 if n < 32768: the
+//             whole stream of a 10 000 x 5 000 set is then 100 MB and stays in the 126 MB L2)
+//   pos[e]  = sorted position of CSR element e
+// and is built with FOUR radix passes instead of seven: the sort key is the top 32 significant bits of the
+// hash, the remaining low bits travel in the 64-bit payload in front of the element index
+// (payload = low bits << 32 | e).  Elements with equal 32-bit keys form a run, kept in CSR order by the
+// stable sort; nearly every run is one group.  The rare runs that mix different hashes (expected
+// distinct^2 / 2^33) are recognised by a payload that is smaller than its predecessor's and sorted in place
+// by one thread each -- ascending payloads = ascending (low bits, element) = groups contiguous, rows ascending.
+// Because the key is a prefix of the hash, the stream is in hash order and every row walks it front to back.
 #pragma once
 #include "common.cuh"
 
 namespace smb {
 
-static constexpr u32 STRIPE_HEAD = 0x80000000u;
+static constexpr int STRIPE_EBLK_LOG2 = 9;            // element blocks of the row lookup table
+static constexpr int STRIPE_MAX_ROWS = 32;            // rows per CTA (upper bound)
+static constexpr int STRIPE_HEADER = 352;             // bytes in front of the counters: s_off[33] + control words, 16-aligned
+
+template <typename TagT> struct StripeTag;
+template <> struct StripeTag<u16> { static constexpr u32 HEAD = 0x8000u; };
+template <> struct StripeTag<u32> { static constexpr u32 HEAD = 0x80000000u; };
 
 // row that owns CSR element e: largest r with off[r] <= e (rows may be empty)
 __host__ __device__ __forceinline__ u32 stripe_row_of(const u64* __restrict__ off, int n, u64 e) {
@@ -32,66 +47,6 @@ __host__ __device__ __forceinline__ u32 stripe_row_of(const u64* __restrict__ of
     return (u32)lo;
 }
 
-__host__ __device__ __forceinline__ u32 stripe_make_tag(const u64* __restrict__ sorted_keys, u64 q, u32 row) {
-    const bool head = q == 0 || sorted_keys[q] != sorted_keys[q - 1];
-    return row | (head ? STRIPE_HEAD : 0u);
-}
-
-// Forward chunk `it` of element q, lane `lane`: looks at sorted element q + 1 + 32 it + lane.
-// Returns the stop predicate (end of stream, or the first element of the next group).
-__host__ __device__ __forceinline__ bool stripe_fwd_stop(const u32* __restrict__ tags, u64 T, u64 q, u32 it, u32 lane,
-                                                         u32& tag) {
-    const u64 b = q + 1 + 32ull * it + lane;
-    if (b >= T) { tag = 0; return true; }
-    tag = tags[b];
-    return (tag & STRIPE_HEAD) != 0;
-}
-// Backward chunk: looks at q - 1 - 32 it - lane.  The head of the group stops the scan but belongs
-// to the group; `valid` is false in front of the stream.
-__host__ __device__ __forceinline__ bool stripe_bwd_stop(const u32* __restrict__ tags, u64 q, u32 it, u32 lane, u32& tag,
-                                                         bool& valid) {
-    const u64 d = 1 + 32ull * it + lane;
-    if (d > q) { tag = 0; valid = false; return true; }
-    tag = tags[q - d];
-    valid = true;
-    return (tag & STRIPE_HEAD) != 0;
-}
-// stop_mask = ballot of the stop predicate over the warp
-__host__ __device__ __forceinline__ bool stripe_fwd_active(u32 stop_mask, u32 lane) {   // no stop at lanes <= lane
-    return (stop_mask & ((2u << lane) - 1u)) == 0;
-}
-__host__ __device__ __forceinline__ bool stripe_bwd_active(u32 stop_mask, u32 lane, bool valid) {   // no stop at lanes < lane
-    return valid && (stop_mask & ((1u << lane) - 1u)) == 0;
-}
-__host__ __device__ __forceinline__ bool stripe_continue(u32 stop_mask) { return stop_mask == 0; }
-
-// local row of element e inside a block whose rows start at elements s_off[0..rows] (ascending)
-__host__ __device__ __forceinline__ u32 stripe_local_row(const u64* __restrict__ s_off, int rows, u64 e) {
-    u32 a = 0;
-    for (int r = 1; r < rows; ++r) a += (s_off[r] <= e) ? 1u : 0u;
-    return a;
-}
-
-// ---- sorting on the low 32 key bits only (SMB_JOIN_SORT=low32: 4 radix passes of 4-byte keys instead
-// of 7 passes of 8-byte keys) ----
-// Elements with equal low words form a run; nearly every run is one group of equal hashes.  The few
-// runs that mix different hashes (expected: distinct^2 / 2^33) are re-sorted on the rotated key
-// (low word first, then the high word), which keeps them in place as runs and orders them inside.
-__host__ __device__ __forceinline__ u64 stripe_rotated_key(u64 k) { return (k << 32) | (k >> 32); }
-
-// length of the run of equal low words that starts at q (0 if q is not its first element), and whether
-// the run holds more than one distinct key
-__host__ __device__ __forceinline__ u64 stripe_run_at_head(const u32* __restrict__ low_sorted, const u64* __restrict__ keys,
-                                                           u64 T, u64 q, bool& mixed) {
-    mixed = false;
-    const u32 lw = low_sorted[q];
-    if (q > 0 && low_sorted[q - 1] == lw) return 0;
-    const u64 k0 = keys[q];
-    u64 m = 1;
-    while (q + m < T && low_sorted[q + m] == lw) { mixed = mixed || keys[q + m] != k0; ++m; }
-    return m;
-}
-
 // the finalize step of compare (finalize_rows_kernel): ones on the diagonal, common / max(1, union)
 __host__ __device__ __forceinline__ double stripe_jaccard(u32 common, u64 size_i, u64 size_j, bool diagonal) {
     if (diagonal) return 1.0;
@@ -101,10 +56,249 @@ __host__ __device__ __forceinline__ double stripe_jaccard(u32 common, u64 size_i
 
 // rows per CTA for a stripe of `ncols` u32 counters per row in `smem_bytes` of shared memory
 __host__ __device__ __forceinline__ int stripe_rows_per_block(size_t smem_bytes, int ncols) {
-    const size_t reserve = 40 * sizeof(u64);              // the block's row offsets
-    if (smem_bytes <= reserve) return 0;
-    const size_t r = (smem_bytes - reserve) / ((size_t)ncols * sizeof(u32));
-    return (int)(r > 32 ? 32 : r);
+    if (smem_bytes <= (size_t)STRIPE_HEADER || ncols <= 0) return 0;
+    const size_t r = (smem_bytes - STRIPE_HEADER) / ((size_t)ncols * sizeof(u32));
+    return (int)(r > (size_t)STRIPE_MAX_ROWS ? (size_t)STRIPE_MAX_ROWS : r);
+}
+
+// number of low hash bits that do not fit the 32-bit sort key (0 when every key fits)
+__host__ __device__ __forceinline__ int stripe_low_bits(u64 max_key) {
+    int bits = 1;
+    while (bits < 64 && (max_key >> bits)) ++bits;
+    return bits > 32 ? bits - 32 : 0;
+}
+
+// ---- stream construction ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stripe_keys_kernel(const u64* __restrict__ h, u64 T, int low_bits,
+                                                         u32* __restrict__ key32, u64* __restrict__ payload) {
+    const u64 low_mask = low_bits ? ((1ull << low_bits) - 1ull) : 0ull;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < T; e += (u64)gridDim.x * blockDim.x) {
+        const u64 x = h[e];
+        key32[e] = (u32)(x >> low_bits);
+        payload[e] = ((x & low_mask) << 32) | e;
+    }
+}
+
+// Runs (equal 32-bit keys) whose payloads do not ascend hold more than one hash, interleaved: the thread that
+// sees the FIRST descent of a run appends the run's head to the worklist (read-only pass; the list can hold
+// every element, so it never overflows).
+__global__ void __launch_bounds__(256) stripe_descent_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays, u64 T,
+                                                            u32* __restrict__ worklist, u32* __restrict__ d_count) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; q < T; q += (u64)gridDim.x * blockDim.x) {
+        const u32 k = key32s[q];
+        if (key32s[q - 1] != k || pays[q] >= pays[q - 1]) continue;
+        u64 p = q - 1;                                    // any earlier descent in this run?
+        bool first = true;
+        while (p > 0 && key32s[p - 1] == k) {
+            if (pays[p] < pays[p - 1]) { first = false; break; }
+            --p;
+        }
+        if (first) worklist[atomicAdd(d_count, 1u)] = (u32)p;      // p = head of the run
+    }
+}
+
+// one thread per listed run: insertion sort of its payloads (runs are short; a mixed run is two or three
+// interleaved ascending sequences)
+__global__ void __launch_bounds__(64) stripe_fix_kernel(const u32* __restrict__ key32s, u64* __restrict__ pays, u64 T,
+                                                       const u32* __restrict__ worklist, const u32* __restrict__ d_count) {
+    const u32 count = *d_count;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const u64 head = worklist[i];
+        const u32 k = key32s[head];
+        u64 tail = head + 1;
+        while (tail < T && key32s[tail] == k) ++tail;
+        for (u64 a = head + 1; a < tail; ++a) {
+            const u64 v = pays[a];
+            u64 b = a;
+            while (b > head && pays[b - 1] > v) { pays[b] = pays[b - 1]; --b; }
+            pays[b] = v;
+        }
+    }
+}
+
+// eblk[b] = row that owns element b << STRIPE_EBLK_LOG2
+__global__ void __launch_bounds__(256) stripe_eblk_kernel(const u64* __restrict__ off, int n, u64 T, u32* __restrict__ eblk) {
+    const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (u64)gridDim.x * blockDim.x) {
+        const u64 e = b << STRIPE_EBLK_LOG2;
+        eblk[b] = e < T ? stripe_row_of(off, n, e) : (u32)(n > 0 ? n - 1 : 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) stripe_sizes_kernel(const u64* __restrict__ off, int n, u32* __restrict__ sizes) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) sizes[r] = (u32)(off[r + 1] - off[r]);
+}
+
+// sorted (key, payload) stream -> tags (row | head flag) and the inverse permutation
+template <typename TagT>
+__global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays,
+                                                        const u64* __restrict__ off, const u32* __restrict__ eblk, u64 T,
+                                                        TagT* __restrict__ tags, u32* __restrict__ pos) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < T; q += (u64)gridDim.x * blockDim.x) {
+        const u64 p = pays[q];
+        const u32 e = (u32)p;
+        bool head = q == 0;
+        if (!head) head = key32s[q] != key32s[q - 1] || (p >> 32) != (pays[q - 1] >> 32);
+        u32 r = eblk[e >> STRIPE_EBLK_LOG2];
+        while (off[r + 1] <= (u64)e) ++r;                 // e < T = off[n]: stops at the owning row, empty rows skipped
+        tags[q] = (TagT)(r | (head ? StripeTag<TagT>::HEAD : 0u));
+        pos[e] = (u32)q;
+    }
+}
+
+// ---- the count kernel -------------------------------------------------------------------------------------
+struct StripeArgs {
+    const void* tags;        // u16 or u32 (template parameter of the kernel)
+    const u32* pos;
+    const u64* off;          // CSR offsets of the set
+    const u32* sizes;        // row lengths
+    u64 T;
+    int n, rows_per_block, row_begin, row_end;
+    double* out;             // row `row_begin` first, leading dimension n
+};
+
+// One CTA = rows [r0, r1) of the result.  Work items are (row, chunk of 32 consecutive elements), handed to the
+// warps chunk index first, so that all rows of the CTA -- and, as CTAs start together, all CTAs of a wave --
+// move through the hash-ordered stream together.  For every element with a successor in its group the warp
+// reads the 32 tags behind it (four elements' reads in flight) and the lanes in front of the next group head
+// increment their counters.  UPPER: only later members (= higher rows) are counted, i.e. the cells (i, j > i);
+// stripe_mirror_kernel fills the rest.  Otherwise the members in front are counted too (full rows, used when a
+// block of rows is computed on its own).
+template <typename TagT, bool UPPER>
+__global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
+    constexpr u32 HEAD = StripeTag<TagT>::HEAD;
+    SMB_DYN_SHARED(unsigned char, stripe_smem);
+    u64* s_off = reinterpret_cast<u64*>(stripe_smem);                       // [rows + 1]
+    u32* s_ctl = reinterpret_cast<u32*>(stripe_smem + (STRIPE_MAX_ROWS + 1) * sizeof(u64));   // [0] next item, [1] chunks of the longest row
+    u32* stripe = reinterpret_cast<u32*>(stripe_smem + STRIPE_HEADER);      // [rows][n]
+    const TagT* __restrict__ tags = reinterpret_cast<const TagT*>(a.tags);
+    const int r0 = a.row_begin + (int)blockIdx.x * a.rows_per_block;
+    const int r1 = min(a.row_end, r0 + a.rows_per_block);
+    const int rows = r1 - r0;
+    const u32 n = (u32)a.n;
+    for (u32 i = threadIdx.x; i <= (u32)rows; i += blockDim.x) s_off[i] = a.off[r0 + i];
+    if (threadIdx.x == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
+    for (u32 i = threadIdx.x; i < (u32)rows * n; i += blockDim.x) stripe[i] = 0;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < (u32)rows; i += blockDim.x) atomicMax(&s_ctl[1], (u32)((s_off[i + 1] - s_off[i] + 31) >> 5));
+    __syncthreads();
+    const u32 lane = lane_id();
+    const u32 n_items = s_ctl[1] * (u32)rows;
+    const u32 le_mask = (2u << lane) - 1u;                // lanes <= lane
+    const u32 lt_mask = (1u << lane) - 1u;                // lanes <  lane
+
+    for (;;) {
+        u32 k = 0;
+        if (lane == 0) k = atomicAdd(&s_ctl[0], 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_items) break;
+        const u32 c = k / (u32)rows, r = k - c * (u32)rows;
+        const u64 e0 = s_off[r] + ((u64)c << 5);
+        const u64 re = s_off[r + 1];
+        if (e0 >= re) continue;                            // a shorter row: no such chunk
+        const u64 e = e0 + lane;
+        const bool have = e < re;
+        const u32 my_q = have ? ld_stream_u32(a.pos + e) : 0u;
+        u32* row_ptr = stripe + (size_t)r * n;
+
+        // ---- members behind the element (higher rows)
+        u32 nxt = HEAD;
+        if (have && (u64)my_q + 1 < a.T) nxt = (u32)tags[(u64)my_q + 1];
+        u32 todo = __ballot_sync(0xffffffffu, (nxt & HEAD) == 0);
+        while (todo) {
+            int j[4];
+            u64 qq[4];
+            u32 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                j[u] = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - (todo ? 1u : 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                  // up to four independent tag reads in flight
+                qq[u] = __shfl_sync(0xffffffffu, my_q, j[u] < 0 ? 0 : j[u]);
+                const u64 b = qq[u] + 1 + lane;
+                t[u] = (j[u] >= 0 && b < a.T) ? (u32)tags[b] : HEAD;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j[u] < 0) continue;                    // uniform in the warp
+                u32 m = __ballot_sync(0xffffffffu, (t[u] & HEAD) != 0);
+                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t[u] & ~HEAD), 1u);
+                for (u32 it = 1; m == 0; ++it) {           // groups with more than 32 members behind
+                    const u64 b = qq[u] + 1 + 32ull * it + lane;
+                    const u32 tt = b < a.T ? (u32)tags[b] : HEAD;
+                    m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
+                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                }
+            }
+        }
+        if (UPPER) continue;
+
+        // ---- members in front of the element (lower rows); the head of the group is one of them
+        const u32 self = have ? (u32)tags[my_q] : HEAD;
+        todo = __ballot_sync(0xffffffffu, (self & HEAD) == 0);
+        while (todo) {
+            int j[2];
+            u64 qq[2];
+            u32 t[2];
+            bool v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                j[u] = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - (todo ? 1u : 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                qq[u] = __shfl_sync(0xffffffffu, my_q, j[u] < 0 ? 0 : j[u]);
+                v[u] = j[u] >= 0 && qq[u] >= 1 + (u64)lane;
+                t[u] = v[u] ? (u32)tags[qq[u] - 1 - lane] : HEAD;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (j[u] < 0) continue;
+                u32 m = __ballot_sync(0xffffffffu, !v[u] || (t[u] & HEAD) != 0);
+                if (v[u] && (m & lt_mask) == 0) atomicAdd(row_ptr + (t[u] & ~HEAD), 1u);
+                for (u32 it = 1; m == 0; ++it) {
+                    const u64 d = 1 + 32ull * it + lane;
+                    const bool vv = qq[u] >= d;
+                    const u32 tt = vv ? (u32)tags[qq[u] - d] : HEAD;
+                    m = __ballot_sync(0xffffffffu, !vv || (tt & HEAD) != 0);
+                    if (vv && (m & lt_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // counts -> float64 rows, written once (streaming stores: the matrix is not read again by this kernel)
+    for (int al = 0; al < rows; ++al) {
+        const int row = r0 + al;
+        const u64 si = s_off[al + 1] - s_off[al];
+        const u32* __restrict__ srow = stripe + (size_t)al * n;
+        double* __restrict__ orow = a.out + (size_t)(row - a.row_begin) * n;
+        for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
+            if (UPPER && j < (u32)row) continue;
+            st_stream_f64(orow + j, stripe_jaccard(srow[j], si, a.sizes[j], (u32)row == j));
+        }
+    }
+}
+
+// out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 32 x 32 tiles through shared memory, reads
+// and writes both coalesced.  `full` points at row 0 of the whole matrix (rows < row_end are complete
+// in their upper part).
+__global__ void __launch_bounds__(1024) stripe_mirror_kernel(double* __restrict__ full, int n, int row_begin, int row_end) {
+    SMB_SHARED double tile[32][33];
+    const int ti = row_begin / 32 + (int)blockIdx.y;       // tile row (destination rows)
+    const int tj = (int)blockIdx.x;                        // tile column (destination columns), tj <= ti
+    if (tj > ti) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source tile = rows of tile column tj, columns of tile row ti (the upper part)
+    const int sr = tj * 32 + ty, sc = ti * 32 + tx;
+    tile[ty][tx] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : 0.0;
+    __syncthreads();
+    const int dr = ti * 32 + ty, dc = tj * 32 + tx;
+    if (dr >= row_begin && dr < row_end && dc < dr && dc < n) full[(size_t)dr * n + dc] = tile[tx][ty];
 }
 
 }  // namespace smb

@@ -71,16 +71,7 @@ cudaError_t join_estimate(const uint64_t* h, const uint64_t* off, int n, uint64_
 cudaError_t join_counts(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key, int shard,
                         int n_shards, uint32_t* common, size_t ld, cudaStream_t s);
 
-// Experimental: the sorted stream kept for several count passes, one per block of rows (cells
-// (i, j > i) with i in the block) -- lets finished blocks of rows be finalised and downloaded while
-// later blocks are still being counted.
-struct JoinStream;
-cudaError_t join_stream_create(const uint64_t* h, const uint64_t* off, int n, uint64_t max_key, JoinStream** out,
-                               cudaStream_t s);
-cudaError_t join_stream_count_rows(const JoinStream* js, int row_begin, int row_end, uint32_t* common, size_t ld,
-                                   cudaStream_t s);
-void join_stream_destroy(JoinStream* js);
-// Experimental stripe layout (SMB_JOIN_LAYOUT=stripe, off by default; join_stripe.cuh): CTAs own
+// Stripe layout of the join (join_stripe.cuh; the default, SMB_JOIN_LAYOUT=plain switches it off): CTAs own
 // complete rows of the result in shared memory and write float64 Jaccard rows directly.
 // join_stripe_create leaves *out null when the layout does not apply (caller uses join_counts).
 struct JoinStripe;
@@ -89,9 +80,9 @@ cudaError_t join_stripe_create(const uint64_t* h, const uint64_t* off, int n, ui
                                JoinStripe** out, cudaStream_t s);
 cudaError_t join_stripe_rows(const JoinStripe* js, const uint64_t* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s);
-// SMB_JOIN_LAYOUT=stripe_upper: join_stripe_rows counts / writes only the cells (i, j >= i); join_stripe_mirror
-// then fills (i, j < i) of rows [row_begin, row_end) from the rows above (d_full = row 0 of the n x n matrix).
-// A block of rows computed on its own (smb_compare_jaccard_rows_dev) uses the two-direction mode.
+// join_stripe_rows counts / writes only the cells (i, j >= i); join_stripe_mirror then fills (i, j < i) of rows
+// [row_begin, row_end) from the rows above (d_full = row 0 of the n x n matrix).  A block of rows computed on
+// its own (smb_compare_jaccard_rows_dev) -- and SMB_JOIN_LAYOUT=stripe_full -- use the two-direction mode.
 cudaError_t join_stripe_mirror(const JoinStripe* js, int row_begin, int row_end, double* d_full, cudaStream_t s);
 bool join_stripe_upper_only(const JoinStripe* js);
 void join_stripe_two_directions(JoinStripe* js);

@@ -1,6 +1,6 @@
-// range_search.cuh -- logic of the range-partitioned one-vs-many pass (experimental,
-// SMB_SEARCH_LAYOUT=ranges, off by default; compare_kernels.cu), shared with
-// tests/host_emul/ranges_emul.cu so that the CPU-only suite checks it against the oracle.
+// range_search.cuh -- the range-partitioned one-vs-many pass (SMB_SEARCH_LAYOUT=ranges; compare_kernels.cu
+// launches it): helpers shared with tests/host_emul/ranges_emul.cu and the kernels themselves, which
+// tests/host_emul/simt_emul.cu runs on the CPU against the oracle.
 //
 // The default pass (one_vs_many_global_kernel) answers every subject element with a random probe of
 // a query bitmap that lives in L2: 1.5e9 single-sector L2 reads for a 12 GB database, several times

@@ -139,9 +139,12 @@ void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index,
     launch_hash_one_k<false>(a, ksize, rolled, hi - lo, s);
 }
 
+// k = 21, 31, 51 requested together are hashed by the one-pass kernel (measured on B200, profiles/r2a_ab.json:
+// 11.2 ms vs 12.4 ms for the three launches over 100 x 5 Mbp, identical sketches); SMB_SKETCH_FUSED=0 keeps
+// the three launches for A/B runs.
 bool sketch_fused_enabled() {
     const char* e = getenv("SMB_SKETCH_FUSED");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 // k = 21, 31, 51 in one launch over tiles [tile_lo, tile_hi) of the rolled tiling; row_index[i] / max_hash[i]
 // belong to k = 21, 31, 51 in this order

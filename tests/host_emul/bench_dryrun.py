@@ -120,15 +120,18 @@ def main():
         r = part["roofline"]
         assert {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "kernel_ms"} <= set(r)
         assert part["e2e"]["h2d_bytes_per_step"] > 0 and part["e2e"]["d2h_bytes_per_step"] > 0 and part["gpu_launches"] > 0
-    assert "dram" in line["roofline"] and "issue" in line["sketch"]["roofline"]
+    # measured constants count only while the kernel files they were measured on are unchanged (profiles/ncu_traffic.json)
+    assert ("dram" in line["roofline"]) == (line["roofline"]["traffic"] is not None)
     assert line["roofline"]["algorithm"]["algo"] == "join"
-    for layout, sort in (("stripe", ""), ("stripe_upper", "low32"), ("cluster", "")):
-        d = run("compare", {"SMB_COMPARE_ALGO": "join", "SMB_JOIN_LAYOUT": layout, "SMB_JOIN_SORT": sort})
-        assert d["roofline"]["algorithm"].get("layout") == layout and layout.split("_")[0] in d["roofline"]["kernel"]
+    for layout in ("stripe_full", "plain"):
+        d = run("compare", {"SMB_COMPARE_ALGO": "join", "SMB_JOIN_LAYOUT": layout})
+        assert d["roofline"]["algorithm"].get("layout") == layout
+        assert ("stripe layout" in d["roofline"]["kernel"]) == (layout != "plain"), d["roofline"]["kernel"]
     d = run("compare", {"SMB_COMPARE_ALGO": "tile"})
     assert d["roofline"]["kernel"] == "pairwise_tile_split_kernel"
-    d = run("sketch", {"SMB_SKETCH_FUSED": "1"})
-    assert "fused" in d["roofline"]["kernel"] and "issue" not in d["roofline"]
+    assert "fused" in line["sketch"]["roofline"]["kernel"]
+    d = run("sketch", {"SMB_SKETCH_FUSED": "0"})
+    assert "3 launches" in d["roofline"]["kernel"]
     bench.N_SKETCHES = 240                                  # the tiled databases: 2 x 240 sketches
     for workload in ("search", "gather"):
         plain = run(workload)

@@ -65,30 +65,31 @@ def compare_default_and_join():
             assert np.array_equal(B.compare_jaccard(sset), want), algo
             assert np.array_equal(_device_matrix(sset, 150), want), algo
             assert B.last_compare_plan()["algo"] == algo
-    with env(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT="cluster"):
+    with env(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT="plain"):         # the global-reduction join behind the stripe layout
         assert np.array_equal(B.compare_jaccard(sset), want)
+        assert np.array_equal(_device_matrix(sset, 150), want)
 
 
 @check
 def compare_stripe_layouts_resident():
     h, off = synth_sketches(150, mean=200, sd=40, lo=0, hi=400, n_families=4, pool=260, seed=3)
     rows = rows_of(h, off)
-    lowword = np.uint64(0x1234abcd)
-    for i in range(0, 150, 3):                        # hashes sharing their low word: the repair of the 32-bit sort
-        extra = [(np.uint64(v) << np.uint64(32)) | lowword for v in (9, 3, 7, 1) if (i + v) % 3]
+    top = np.uint64(0x001234ab) << np.uint64(32)      # below max_hash(1000) ~ 2^54: the sort key is key >> 22
+    for i in range(0, 150, 3):                        # hashes equal in their top 32 significant bits: the repair of the 32-bit sort
+        extra = [top | np.uint64(v) for v in (9, 3, 7, 1) if (i + v) % 3]
         rows[i] = np.unique(np.concatenate([rows[i], np.array(extra, dtype=np.uint64)]))
     rows[7] = np.zeros(0, np.uint64)
     h, off = orc.to_csr(rows)
     want = orc.compare_all_pairs(h, off, nthreads=4)
     sset = B.SketchSet.from_host(h, off)
-    for layout in ("stripe", "stripe_upper"):
-        for sort in (None, "low32"):
-            with env(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT=layout, SMB_JOIN_SORT=sort):
-                assert np.array_equal(B.compare_jaccard(sset), want), (layout, sort)
-                assert np.array_equal(_device_matrix(sset, 150), want), (layout, sort)
+    for layout in (None, "stripe_full"):              # default: upper triangle + mirror; stripe_full: both directions
+        for tags in (None, "u32"):
+            with env(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT=layout, SMB_STRIPE_TAGS=tags):
+                assert np.array_equal(B.compare_jaccard(sset), want), (layout, tags)
+                assert np.array_equal(_device_matrix(sset, 150), want), (layout, tags)
                 block = np.full((37, 150), -1.0)
                 B.compare_jaccard_rows_device(sset, 50, 87, block.ctypes.data)
-                assert np.array_equal(block, want[50:87]), (layout, sort)
+                assert np.array_equal(block, want[50:87]), (layout, tags)
     block = np.full((37, 150), -1.0)                  # the default path of the rows entry point
     B.compare_jaccard_rows_device(sset, 50, 87, block.ctypes.data)
     assert np.array_equal(block, want[50:87])
@@ -102,11 +103,9 @@ def compare_host_path_row_chunks():
     sset = B.SketchSet.from_host(h, off)
     with env(SMB_COMPARE_ALGO="join"):
         assert np.array_equal(B.compare_jaccard(sset), want)
-        for layout, sort in (("stripe", None), ("stripe_upper", "low32")):
-            with env(SMB_JOIN_LAYOUT=layout, SMB_JOIN_SORT=sort):
+        for layout in ("stripe_full", "plain"):
+            with env(SMB_JOIN_LAYOUT=layout):
                 assert np.array_equal(B.compare_jaccard(sset), want), layout
-        with env(SMB_COMPARE_PASSES="5"):
-            assert np.array_equal(B.compare_jaccard(sset), want)
 
 
 @check
@@ -229,7 +228,7 @@ def sketch_default_and_fused():
     seqs = np.concatenate(genomes)
     offs = np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
     mx = orc.max_hash_for_scaled(20)
-    for fused in (None, "1"):
+    for fused in (None, "0"):                         # default: one pass over the bases; "0": one launch per ksize
         with env(SMB_SKETCH_FUSED=fused):
             for ks in ([21, 31, 51], [51, 21, 31]):
                 sset, nk = B.sketch_sequences(seqs, offs, ks, scaled=20)

@@ -52,10 +52,10 @@ def trial(rng):
         got = B.compare_jaccard(db)
         assert np.array_equal(got, want), ("compare", algo, n, scale)
     if SWITCHED:                                                                     # the paths behind switches
-        for layout, sort in (("stripe", "full"), ("stripe_upper", "low32"), ("cluster", "full")):
-            os.environ["SMB_JOIN_LAYOUT"], os.environ["SMB_JOIN_SORT"] = layout, sort
-            assert np.array_equal(B.compare_jaccard(db), want), ("compare", layout, sort, n, scale)
-        os.environ.pop("SMB_JOIN_LAYOUT"); os.environ.pop("SMB_JOIN_SORT")
+        for layout, tags in (("stripe_full", "u16"), ("stripe_upper", "u32"), ("plain", "u16")):
+            os.environ["SMB_JOIN_LAYOUT"], os.environ["SMB_STRIPE_TAGS"] = layout, tags
+            assert np.array_equal(B.compare_jaccard(db), want), ("compare", layout, tags, n, scale)
+        os.environ.pop("SMB_JOIN_LAYOUT"); os.environ.pop("SMB_STRIPE_TAGS")
         os.environ["SMB_SEARCH_LAYOUT"] = "ranges"
         if rng.random() < 0.5 and len(h) and len(h) < 2**31:
             db.build_index()

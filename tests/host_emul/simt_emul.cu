@@ -1,11 +1,10 @@
-// simt_emul.cu -- runs the KERNELS of sourmash_b200/csrc/experimental_kernels.cuh on the CPU through the SIMT
+// simt_emul.cu -- runs the KERNELS of sourmash_b200/csrc/*.cuh on the CPU through the SIMT
 // emulator of simt.h (CTAs as cooperative fibers, real __syncthreads / warp collectives / shared memory) and
 // writes their results for comparison with the oracle.  The launch geometry is shrunk (fewer threads, smaller
 // shared memory) but the code is the code the GPU runs.  Test infrastructure for the CPU-only suite.
-//   simt_emul stripe|stripe_low32 <R> <upper 0|1> <threads> <hashes.u64> <offsets.u64> <out.f64 n*n>
+//   simt_emul stripe <R> <upper 0|1> <threads> <tag bits 16|32> <sort-key bits> <hashes.u64> <offsets.u64> <out.f64 n*n>
 //   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
-//   simt_emul join|cluster <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>      (upper-triangle counts)
-//   simt_emul rows <passes> <hashes.u64> <offsets.u64> <out.u32 n*n>                         (full rows as captured)
+//   simt_emul join <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>              (upper-triangle counts)
 //   simt_emul tile <TA 1..4> <variant 1 split | 0 u64 occ | 2 u64> <threads> <cols_per_cta> <symmetric 0|1> <hashes.u64> <offsets.u64> <out.u32>
 //   simt_emul pairs <num> <hashes.u64> <offsets.u64> <out.f64 3*n*n: jaccard (generic kernel) | jaccard num | angular>
 //   simt_emul gather <use_index 0|1> <threshold> <query.u64> <hashes.u64> <offsets.u64> <out.u32 (row, size) pairs>
@@ -15,7 +14,10 @@
 
 #include <numeric>
 
-#include "../../sourmash_b200/csrc/experimental_kernels.cuh"
+#include "../../sourmash_b200/csrc/join_kernels.cuh"
+#include "../../sourmash_b200/csrc/join_stripe.cuh"
+#include "../../sourmash_b200/csrc/range_kernels.cuh"
+#include "../../sourmash_b200/csrc/db_index_kernels.cuh"
 #include "../../sourmash_b200/csrc/search_kernels.cuh"
 #include "../../sourmash_b200/csrc/tile_kernels.cuh"
 #include "../../sourmash_b200/csrc/pair_kernels.cuh"
@@ -43,57 +45,57 @@ static void dump(const char* path, const std::vector<T>& v) {
     fclose(f);
 }
 
-static int stripe_main(int R, int upper, int threads, const char* fh, const char* fo, const char* fout, bool low32) {
-    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+// The stripe pipeline as join_stripe_create / join_stripe_rows launch it (compare_kernels.cu), kernel by kernel;
+// a stable host sort stands in for cub::DeviceRadixSort::SortPairs.  `sort_bits` < 64 shortens the sort key
+// below the 32 bits the product uses, so that runs mixing different hashes -- rare with 32-bit keys -- occur
+// in every small test set and the descent / fix kernels are exercised.
+template <typename TagT>
+static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<u64>& h, const std::vector<u64>& off,
+                      const char* fout) {
     const int n = (int)off.size() - 1;
     const u64 T = h.size();
-    // the sorted stream: iota kernel, a stable host sort standing in for cub::DeviceRadixSort, tag kernel
-    std::vector<u32> vals(T + 1), src(T + 1), tags(T + 1), pos(T + 1);
-    smb_emu::launch(3, 64, 0, [&] { stripe_iota_kernel(vals.data(), T); });
-    for (u64 i = 0; i < T; ++i) if (vals[i] != (u32)i) return 3;
-    std::vector<u64> sk(T + 1);
-    if (!low32) {
-        std::copy(vals.begin(), vals.begin() + T, src.begin());
-        std::stable_sort(src.begin(), src.begin() + T, [&](u32 a, u32 b) { return h[a] < h[b]; });
-        for (u64 q = 0; q < T; ++q) sk[q] = h[src[q]];
-    } else {
-        // SMB_JOIN_SORT=low32, stripe_stream_low32 of compare_kernels.cu: its kernels, host stand-ins for the cub calls
-        std::vector<u32> low(T + 1), low_sorted(T + 1);
-        h.push_back(0);
-        smb_emu::launch(3, 64, 0, [&] { stripe_low32_kernel(h.data(), T, low.data(), vals.data()); });
-        std::vector<u32> perm(T);
-        std::iota(perm.begin(), perm.end(), 0);
-        std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return low[a] < low[b]; });         // SortPairs(low, vals)
-        for (u64 q = 0; q < T; ++q) { low_sorted[q] = low[perm[q]]; src[q] = vals[perm[q]]; }
-        smb_emu::launch(2, 96, 0, [&] { stripe_gather_keys_kernel(h.data(), src.data(), T, sk.data()); });
-        std::vector<u8> flags(T + 1, 0);
-        smb_emu::launch(4, 32, 0, [&] { stripe_mixed_runs_kernel(low_sorted.data(), sk.data(), T, flags.data()); });
-        std::vector<u32> where;                                                                            // DeviceSelect::Flagged
-        for (u64 q = 0; q < T; ++q) if (flags[q]) where.push_back((u32)q);
-        const u64 n_sel = where.size();
-        if (n_sel) {
-            std::vector<u64> rot(n_sel), rot_sorted(n_sel);
-            std::vector<u32> sel(n_sel), sel_sorted(n_sel);
-            smb_emu::launch(2, 64, 0, [&] { stripe_repair_load_kernel(where.data(), n_sel, sk.data(), src.data(), rot.data(), sel.data()); });
-            std::vector<u32> o2(n_sel);
-            std::iota(o2.begin(), o2.end(), 0);
-            std::stable_sort(o2.begin(), o2.end(), [&](u32 a, u32 b) { return rot[a] < rot[b]; });         // SortPairs(rot, sel)
-            for (u64 j = 0; j < n_sel; ++j) { rot_sorted[j] = rot[o2[j]]; sel_sorted[j] = sel[o2[j]]; }
-            smb_emu::launch(2, 64, 0, [&] { stripe_repair_store_kernel(where.data(), n_sel, rot_sorted.data(), sel_sorted.data(), sk.data(), src.data()); });
-        }
-        if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "repaired %llu elements\n", (unsigned long long)n_sel);
+    u64 max_key = 0;
+    for (u64 v : h) max_key = std::max(max_key, v);
+    int key_bits = 1;
+    while (key_bits < 64 && (max_key >> key_bits)) ++key_bits;
+    int low_bits = stripe_low_bits(max_key);
+    if (sort_bits < 32 && key_bits > sort_bits) low_bits = std::min(32, key_bits - sort_bits);   // test hook: coarser keys (the payload holds at most 32 low bits)
+    h.push_back(0);
+    std::vector<u32> key32(T + 1), key32s(T + 1), worklist(T + 1), pos(T + 1, 0xffffffffu), sizes(n + 1);
+    std::vector<u64> pays(T + 1), payss(T + 1);
+    smb_emu::launch(3, 64, 0, [&] { stripe_keys_kernel(h.data(), T, low_bits, key32.data(), pays.data()); });
+    std::vector<u32> perm(T);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return key32[a] < key32[b]; });
+    for (u64 q = 0; q < T; ++q) { key32s[q] = key32[perm[q]]; payss[q] = pays[perm[q]]; }
+    u32 count = 0;
+    if (low_bits) {
+        smb_emu::launch(3, 64, 0, [&] { stripe_descent_kernel(key32s.data(), payss.data(), T, worklist.data(), &count); });
+        smb_emu::launch(2, 32, 0, [&] { stripe_fix_kernel(key32s.data(), payss.data(), T, worklist.data(), &count); });
     }
-    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel(sk.data(), src.data(), off.data(), n, T, tags.data(), pos.data()); });
+    if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "mixed runs repaired: %u\n", count);
+    // the stream must now be the hashes in ascending order, rows ascending inside a group
+    for (u64 q = 0; q + 1 < T; ++q) {
+        const u64 a = h[(u32)payss[q]], b = h[(u32)payss[q + 1]];
+        if (a > b || (a == b && (u32)payss[q] > (u32)payss[q + 1])) return 5;
+    }
+    const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
+    std::vector<u32> eblk(nblk + 1);
+    smb_emu::launch(2, 64, 0, [&] { stripe_eblk_kernel(off.data(), n, T, eblk.data()); });
+    smb_emu::launch((n + 63) / 64 + 1, 64, 0, [&] { stripe_sizes_kernel(off.data(), n, sizes.data()); });
+    std::vector<TagT> tags(T + 1);
+    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data()); });
     std::vector<double> out((size_t)n * n, -1.0);
-    const size_t smem = 40 * sizeof(u64) + (size_t)R * n * sizeof(u32);
+    const size_t smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
     // two launches over row chunks, like the host path of smb_compare_jaccard
     const int half = n / 2;
     for (int c = 0; c < 2; ++c) {
         const int r0 = c ? half : 0, r1 = c ? n : half;
         if (r1 <= r0) continue;
-        StripeArgs a{tags.data(), pos.data(), off.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, upper};
+        StripeArgs a{tags.data(), pos.data(), off.data(), sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n};
         const int blocks = (r1 - r0 + R - 1) / R;
-        smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel(a); });
+        if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true>(a); });
+        else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false>(a); });
         if (upper) {
             const int t0 = r0 / 32, t1 = (r1 + 31) / 32;
             smb_emu::launch(smb_emu::Dim3(t1, t1 - t0), 1024, 0, [&] { stripe_mirror_kernel(out.data(), n, r0, r1); });
@@ -102,23 +104,25 @@ static int stripe_main(int R, int upper, int threads, const char* fh, const char
     dump(fout, out);
     return 0;
 }
+static int stripe_main(int R, int upper, int threads, int tag_bits, int sort_bits, const char* fh, const char* fo, const char* fout) {
+    std::vector<u64> h = slurp<u64>(fh), off = slurp<u64>(fo);
+    if (R > STRIPE_MAX_ROWS) return 6;
+    return tag_bits == 16 ? stripe_run<u16>(R, upper, threads, sort_bits, h, off, fout)
+                          : stripe_run<u32>(R, upper, threads, sort_bits, h, off, fout);
+}
 
 // ---- inverted join: the default pipeline, the cluster layout, the row-block passes (kernels as written; the
 // exclusive scan and the radix sort of the product are host loops here) ----
 struct Slice { std::vector<u64> keys; std::vector<u32> ids; };
-static Slice sorted_slice(const std::vector<u64>& h, const std::vector<u64>& off, int n, u64 lo, u64 hi, bool bounded,
-                          const std::vector<u32>* order) {
+static Slice sorted_slice(const std::vector<u64>& h, const std::vector<u64>& off, int n, u64 lo, u64 hi, bool bounded) {
     std::vector<u64> beg(n + 1), cnt(n + 1), doff(n + 2, 0);
     smb_emu::launch((n + 1 + 63) / 64, 64, 0, [&] { join_row_range_kernel(h.data(), off.data(), n, lo, hi, bounded ? 1 : 0, beg.data(), cnt.data()); });
-    std::vector<u64> cnt_rank(n + 1);
-    if (order) smb_emu::launch((n + 1 + 63) / 64, 64, 0, [&] { join_rank_counts_kernel(cnt.data(), order->data(), n, cnt_rank.data()); });
-    const std::vector<u64>& c = order ? cnt_rank : cnt;
+    const std::vector<u64>& c = cnt;
     for (int r = 0; r <= n; ++r) doff[r + 1] = doff[r] + c[r];                     // cub::DeviceScan::ExclusiveSum
     const u64 T = doff[n];
     std::vector<u64> keys(T + 1);
     std::vector<u32> ids(T + 1);
-    if (order) smb_emu::launch(7, 64, 0, [&] { join_gather_ranked_kernel(h.data(), off.data(), beg.data(), order->data(), doff.data(), n, keys.data(), ids.data()); });
-    else smb_emu::launch(7, 64, 0, [&] { join_gather_kernel(h.data(), off.data(), beg.data(), doff.data(), n, keys.data(), ids.data()); });
+    smb_emu::launch(7, 64, 0, [&] { join_gather_kernel(h.data(), off.data(), beg.data(), doff.data(), n, keys.data(), ids.data()); });
     std::vector<size_t> perm(T);
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });   // cub::DeviceRadixSort::SortPairs
@@ -142,7 +146,7 @@ static int join_main(const char* mode, int arg, const char* fh, const char* fo, 
             u64 lo, hi;
             bool bounded;
             join_shard_range(max_key, shard, arg, lo, hi, bounded);
-            Slice S = sorted_slice(h, off, n, lo, hi, bounded, nullptr);
+            Slice S = sorted_slice(h, off, n, lo, hi, bounded);
             const u64 T = S.keys.size();
             S.keys.push_back(0); S.ids.push_back(0);
             if (!T) continue;
@@ -151,45 +155,7 @@ static int join_main(const char* mode, int arg, const char* fh, const char* fo, 
         }
         for (size_t i = 0; i < (size_t)n * n; ++i) total += common[i];
         if (est[0] != total) return 3;                                       // sum of C(m,2) == number of increments
-    } else if (!strcmp(mode, "rows")) {                                      // arg = number of row-block passes
-        Slice S = sorted_slice(h, off, n, 0, 0, false, nullptr);
-        const u64 T = S.keys.size();
-        S.keys.push_back(0); S.ids.push_back(0);
-        std::vector<u32> captured((size_t)n * n + 1, 0);
-        const int per = (n + arg - 1) / arg;
-        for (int r0 = 0; r0 < n; r0 += per) {
-            const int r1 = std::min(n, r0 + per);
-            if (T) smb_emu::launch((T + 63) / 64, 64, 0, [&] { join_count_rows_kernel(S.keys.data(), S.ids.data(), T, (u32)r0, (u32)r1, common.data(), (size_t)n); });
-            for (int i = r0; i < r1; ++i)
-                for (int j = 0; j < n; ++j)
-                    if (i != j) captured[(size_t)i * n + j] = common[(size_t)std::min(i, j) * n + std::max(i, j)];
-        }
-        common = captured;
-    } else {                                                                 // cluster; arg = shards
-        std::vector<unsigned long long> rowkey(n + 1, ~0ull);
-        {
-            Slice S = sorted_slice(h, off, n, 0, max_key / 64 + 1, true, nullptr);
-            const u64 T = S.keys.size();
-            S.keys.push_back(0); S.ids.push_back(0);
-            if (T) smb_emu::launch((T + 63) / 64, 64, 0, [&] { join_rowkey_kernel(S.keys.data(), S.ids.data(), T, rowkey.data()); });
-        }
-        std::vector<u32> order(n + 1), inv(n + 1);
-        smb_emu::launch((n + 63) / 64, 64, 0, [&] { join_iota_kernel(order.data(), n); });
-        std::stable_sort(order.begin(), order.begin() + n, [&](u32 a, u32 b) { return rowkey[a] < rowkey[b]; });  // SortPairs(rowkey, iota)
-        smb_emu::launch((n + 63) / 64, 64, 0, [&] { join_invert_kernel(order.data(), n, inv.data()); });
-        for (int shard = 0; shard < arg; ++shard) {
-            u64 lo, hi;
-            bool bounded;
-            join_shard_range(max_key, shard, arg, lo, hi, bounded);
-            Slice S = sorted_slice(h, off, n, lo, hi, bounded, &order);
-            const u64 T = S.keys.size();
-            S.keys.push_back(0); S.ids.push_back(0);
-            std::vector<u32> ranked((size_t)n * n + 1, 0);
-            if (T) smb_emu::launch((T * 32 + 63) / 64, 64, 0, [&] { join_count_warp_kernel(S.keys.data(), S.ids.data(), T, ranked.data(), (size_t)n); });
-            smb_emu::launch(smb_emu::Dim3((n + 63) / 64, std::min(n, 5)), 64, 0,
-                            [&] { join_unpermute_add_kernel(ranked.data(), inv.data(), n, (size_t)n, common.data(), (size_t)n); });
-        }
-    }
+    } else return 2;
     common.resize((size_t)n * n);
     dump(fout, common);
     return 0;
@@ -435,12 +401,12 @@ int main(int argc, char** argv) {
     if (argc == 10 && !strcmp(argv[1], "tile"))
         return tile_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8], argv[9]);
     if (argc == 8 && !strcmp(argv[1], "gather")) return gather_main(atoi(argv[2]), (u32)atoi(argv[3]), argv[4], argv[5], argv[6], argv[7]);
-    if (argc == 8 && !strcmp(argv[1], "stripe")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], false);
-    if (argc == 8 && !strcmp(argv[1], "stripe_low32")) return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], true);
+    if (argc == 10 && !strcmp(argv[1], "stripe"))
+        return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8], argv[9]);
     if (argc == 9 && !strcmp(argv[1], "ranges"))
         return ranges_main(atoi(argv[2]), strtoull(argv[3], nullptr, 10), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
     if (argc == 7 && !strcmp(argv[1], "index")) return index_main(atoi(argv[2]), argv[3], argv[4], argv[5], argv[6]);
-    if (argc == 6 && (!strcmp(argv[1], "join") || !strcmp(argv[1], "rows") || !strcmp(argv[1], "cluster")))
+    if (argc == 6 && !strcmp(argv[1], "join"))
         return join_main(argv[1], atoi(argv[2]), argv[3], argv[4], argv[5]);
     fprintf(stderr, "usage: see the head of simt_emul.cu\n");
     return 2;

@@ -1,6 +1,5 @@
-"""GPU parity tests of the paths that are in the tree behind switches and have not run on a GPU yet
-(DESIGN.md section 10): the stripe layout of the inverted join, the range-partitioned one-vs-many
-pass and the inverted index of a resident set.  Their logic is covered on the CPU by
+"""GPU parity tests of the paths that sit behind switches: the range-partitioned
+one-vs-many pass and the inverted index of a resident set.  Their logic is covered on the CPU by
 tests/test_host_emulation.py; these tests are the first thing to run on the device
 (scripts/gpu_next_variants.sh sets SMB_TEST_EXPERIMENTAL=1) and are skipped otherwise, so that an
 unvalidated experimental path can never turn the default suite red."""
@@ -54,62 +53,6 @@ def _edge_rows():
             np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
     rows += [np.array([7, 1000 + i], dtype=np.uint64) for i in range(100)]      # one hash shared by 100 rows
     return rows
-
-
-@pytest.mark.parametrize("layout", ["stripe", "stripe_upper"])
-@pytest.mark.parametrize("n,fam", [(96, 6), (700, 9), (1500, 12)])
-def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam, layout):
-    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
-    monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
-    h, off = synth_sketches(n, mean=400, sd=80, lo=0, hi=800, n_families=fam, pool=500, seed=n)
-    want = orc.compare_all_pairs(h, off, nthreads=8)
-    sset = B.SketchSet.from_host(h, off)
-    assert np.array_equal(B.compare_jaccard(sset), want)                     # host path: row blocks + copies
-    d_out = _DeviceMatrix((n, n))
-    B.compare_jaccard_device(sset, d_out.ptr)                                # resident path: one launch
-    assert np.array_equal(d_out.numpy(), want)
-    lo, hi = n // 3, n // 3 + 37
-    d_rows = _DeviceMatrix((hi - lo, n))
-    B.compare_jaccard_rows_device(sset, lo, hi, d_rows.ptr)                 # a block of rows (multi-GPU unit)
-    assert np.array_equal(d_rows.numpy(), want[lo:hi])
-
-
-@pytest.mark.parametrize("layout", ["stripe", "stripe_upper"])
-def test_stripe_layout_edge_rows(B, monkeypatch, layout):
-    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
-    monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
-    rows = _edge_rows() * 12                                                  # > 1024 rows: the host path takes the join
-    h, off = orc.to_csr(rows)
-    assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(h, off)), orc.compare_all_pairs(h, off, nthreads=8))
-
-
-def test_stripe_low32_sort_with_clashing_low_words(B, monkeypatch):
-    "SMB_JOIN_SORT=low32: 32-bit sort + repair of the runs that mix hashes, under both stripe modes."
-    rng = np.random.Generator(np.random.PCG64(21))
-    h, off = synth_sketches(1200, mean=300, sd=60, lo=0, hi=600, n_families=8, pool=400, seed=23)
-    rows = rows_of(h, off)
-    lowword = np.uint64(0x1234abcd)
-    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
-    for i in range(0, 1200, 3):                                           # hashes sharing their low word, spread over rows
-        extra = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0] + [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)]
-        rows[i] = np.unique(np.concatenate([rows[i], np.array(extra, dtype=np.uint64)]))
-    hh, oo = orc.to_csr(rows)
-    want = orc.compare_all_pairs(hh, oo, nthreads=8)
-    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
-    monkeypatch.setenv("SMB_JOIN_SORT", "low32")
-    for layout in ("stripe", "stripe_upper"):
-        monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
-        assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(hh, oo)), want), layout
-
-
-def test_rows_device_without_stripe_equals_full_matrix(B):
-    "smb_compare_jaccard_rows_dev on the default path (whole count matrix, then the rows)."
-    h, off = synth_sketches(300, mean=300, sd=60, lo=0, hi=600, n_families=5, pool=400, seed=4)
-    want = orc.compare_all_pairs(h, off, nthreads=8)
-    sset = B.SketchSet.from_host(h, off)
-    d_rows = _DeviceMatrix((50, 300))
-    B.compare_jaccard_rows_device(sset, 120, 170, d_rows.ptr)
-    assert np.array_equal(d_rows.numpy(), want[120:170])
 
 
 def _big_query(rows, seed=4000, extra=400_000):
@@ -195,7 +138,7 @@ def test_db_index_behind_linear_index(B):
 
 
 def test_fused_sketch_kernel_matches_default_and_oracle(B, monkeypatch):
-    "SMB_SKETCH_FUSED: k = 21, 31, 51 in one pass == three passes == the oracle (scaled, num, abundance)."
+    "k = 21, 31, 51 in one pass (the default) == three launches (SMB_SKETCH_FUSED=0) == the oracle (scaled, num, abundance)."
     from sourmash_b200.synth import synth_genome
     genomes = [synth_genome(60_000 + 1000 * i, seed=10 + i, n_every=97 if i == 1 else 0) for i in range(4)]
     genomes.append(synth_genome(40, seed=3))                               # shorter than 51: only k = 21 and 31
@@ -206,9 +149,9 @@ def test_fused_sketch_kernel_matches_default_and_oracle(B, monkeypatch):
     offs = np.cumsum([0] + [len(g) for g in genomes]).astype(np.uint64)
     for ks in ([21, 31, 51], [51, 21, 31]):
         for kw in (dict(scaled=100), dict(scaled=1), dict(num=500), dict(scaled=50, track_abundance=True)):
-            monkeypatch.delenv("SMB_SKETCH_FUSED", raising=False)
+            monkeypatch.setenv("SMB_SKETCH_FUSED", "0")
             plain, nk0 = B.sketch_sequences(seqs, offs, ks, **kw)
-            monkeypatch.setenv("SMB_SKETCH_FUSED", "1")
+            monkeypatch.delenv("SMB_SKETCH_FUSED", raising=False)
             fused, nk1 = B.sketch_sequences(seqs, offs, ks, **kw)
             assert nk0 == nk1
             a, b = plain.rows(), fused.rows()
@@ -217,7 +160,7 @@ def test_fused_sketch_kernel_matches_default_and_oracle(B, monkeypatch):
                 assert np.array_equal(x, y), (ks, kw)
             if kw.get("track_abundance"):
                 assert np.array_equal(plain.to_host(with_abunds=True)[2], fused.to_host(with_abunds=True)[2])
-    monkeypatch.setenv("SMB_SKETCH_FUSED", "1")
+    monkeypatch.delenv("SMB_SKETCH_FUSED", raising=False)
     sset, _ = B.sketch_sequences(seqs, offs, [21, 31, 51], scaled=100)
     rows = sset.rows()
     mx = orc.max_hash_for_scaled(100)

@@ -1,0 +1,139 @@
+"""GPU parity tests of the stripe layout of the inverted join -- the default all-vs-all path of compare
+(csrc/join_stripe.cuh): resident, host (row blocks + copies) and block-of-rows entry points, both tag
+widths, both count modes, the global-reduction join behind it, edge rows, groups longer than a warp, and
+hashes a 32-bit sort key cannot tell apart.  Everything is compared with the oracle bit for bit; the same
+kernels run on the CPU in tests/test_host_emulation.py::test_simt_stripe_*."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from sourmash_b200.synth import rows_of, synth_sketches
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    from sourmash_b200 import batch
+    return batch
+
+
+class _DeviceMatrix:
+    """float64 device buffer for the *_device entry points: a torch CUDA tensor on a GPU box; plain host memory
+    when the suite runs against the emulated library (tests/host_emul/run_gpu_tests_emulated.py)."""
+
+    def __init__(self, shape):
+        import torch
+        if torch.cuda.is_available():
+            self._t = torch.empty(shape, dtype=torch.float64, device="cuda")
+            self.ptr = self._t.data_ptr()
+        else:
+            self._t = None
+            self._a = np.full(shape, -1.0)
+            self.ptr = self._a.ctypes.data
+
+    def numpy(self):
+        if self._t is None:
+            return self._a
+        import torch
+        torch.cuda.synchronize()
+        return self._t.cpu().numpy()
+
+
+def _edge_rows():
+    rng = np.random.Generator(np.random.PCG64(77))
+    big = np.uint64(2**64 - 1)
+    rows = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, big - 1, big], np.uint64),
+            np.array([big], np.uint64), np.arange(1, 300, dtype=np.uint64), np.arange(1, 300, dtype=np.uint64),
+            np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
+    rows += [np.array([7, 1000 + i], dtype=np.uint64) for i in range(100)]      # one hash shared by 100 rows
+    return rows
+
+
+def _check_all_entry_points(B, h, off, want=None):
+    n = len(off) - 1
+    want = orc.compare_all_pairs(h, off, nthreads=8) if want is None else want
+    sset = B.SketchSet.from_host(h, off)
+    assert np.array_equal(B.compare_jaccard(sset), want)                     # host path: row blocks + copies
+    d_out = _DeviceMatrix((n, n))
+    B.compare_jaccard_device(sset, d_out.ptr)                                # resident path
+    assert np.array_equal(d_out.numpy(), want)
+    lo, hi = n // 3, min(n, n // 3 + 37)
+    d_rows = _DeviceMatrix((hi - lo, n))
+    B.compare_jaccard_rows_device(sset, lo, hi, d_rows.ptr)                 # a block of complete rows (multi-GPU unit)
+    assert np.array_equal(d_rows.numpy(), want[lo:hi])
+
+
+@pytest.mark.parametrize("layout,tags", [(None, None), (None, "u32"), ("stripe_full", None), ("plain", None)])
+@pytest.mark.parametrize("n,fam", [(96, 6), (700, 9), (1500, 12)])
+def test_stripe_layout_matches_oracle(B, monkeypatch, n, fam, layout, tags):
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    if layout:
+        monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
+    if tags:
+        monkeypatch.setenv("SMB_STRIPE_TAGS", tags)
+    h, off = synth_sketches(n, mean=400, sd=80, lo=0, hi=800, n_families=fam, pool=500, seed=n)
+    _check_all_entry_points(B, h, off)
+
+
+@pytest.mark.parametrize("layout", [None, "stripe_full"])
+def test_stripe_layout_edge_rows(B, monkeypatch, layout):
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    if layout:
+        monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
+    rows = _edge_rows() * 12                                                  # > 1024 rows: the host path takes the join
+    h, off = orc.to_csr(rows)
+    _check_all_entry_points(B, h, off)
+
+
+def test_stripe_repairs_runs_of_equal_sort_keys(B, monkeypatch):
+    """The stream is sorted on the top 32 significant bits of the hashes; hashes that agree there and differ
+    below form one run of the sort and are put in order afterwards (stripe_descent_kernel / stripe_fix_kernel).
+    Planted: scaled=1000-sized keys (22 low bits) and full 64-bit keys (32 low bits), interleaved over rows."""
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    h, off = synth_sketches(1200, mean=300, sd=60, lo=0, hi=600, n_families=8, pool=400, seed=23)
+    base = rows_of(h, off)
+    for top, lows in ((np.uint64(0x001234ab) << np.uint64(32), (9, 3, 7, 1, 5)),                    # < max_hash(1000)
+                      (np.uint64(0xfedc0001) << np.uint64(32), (0x1234abcd, 1, 0xffffffff, 77))):   # 64-bit keys
+        rows = [r.copy() for r in base]
+        for i in range(0, 1200, 3):
+            extra = [top | np.uint64(v) for j, v in enumerate(lows) if (i + j) % 3 != 0]
+            rows[i] = np.unique(np.concatenate([rows[i], np.array(extra, dtype=np.uint64)]))
+        # a long mixed run: two hashes with one sort key, each in ~170 rows
+        for i in range(0, 1200, 7):
+            rows[i] = np.unique(np.concatenate([rows[i], np.array([top | np.uint64(0x3ff001 + (i // 7) % 2)], dtype=np.uint64)]))
+        hh, oo = orc.to_csr(rows)
+        want = orc.compare_all_pairs(hh, oo, nthreads=8)
+        for layout in (None, "stripe_full"):
+            if layout:
+                monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
+            else:
+                monkeypatch.delenv("SMB_JOIN_LAYOUT", raising=False)
+            assert np.array_equal(B.compare_jaccard(B.SketchSet.from_host(hh, oo)), want), (hex(int(top)), layout)
+
+
+def test_stripe_groups_longer_than_a_warp_and_short_keys(B, monkeypatch):
+    "one hash in 3300 rows (a hundred 32-tag chunks per element); keys below 2^32 (no low bits, fewer radix passes)"
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    rng = np.random.Generator(np.random.PCG64(5))
+    rows = [np.unique(np.concatenate([rng.integers(1, 2**20, size=int(rng.integers(0, 60)), dtype=np.uint64),
+                                      np.array([424242] if i < 3300 else [], dtype=np.uint64)]))
+            for i in range(3400)]
+    rows[17] = np.zeros(0, np.uint64)
+    h, off = orc.to_csr(rows)
+    want = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    assert np.array_equal(B.compare_jaccard(sset), want)
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", "stripe_full")
+    assert np.array_equal(B.compare_jaccard(sset), want)
+
+
+def test_rows_device_on_the_global_reduction_join(B, monkeypatch):
+    "smb_compare_jaccard_rows_dev when the stripe layout is switched off (whole count matrix, then the rows)."
+    monkeypatch.setenv("SMB_JOIN_LAYOUT", "plain")
+    h, off = synth_sketches(300, mean=300, sd=60, lo=0, hi=600, n_families=5, pool=400, seed=4)
+    want = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    d_rows = _DeviceMatrix((50, 300))
+    B.compare_jaccard_rows_device(sset, 120, 170, d_rows.ptr)
+    assert np.array_equal(d_rows.numpy(), want[120:170])

@@ -193,20 +193,15 @@ def join_emul():
     src = os.path.join(HERE, "host_emul", "join_emul.cu")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
 
-    def run(rows, n_shards, cluster=False, row_passes=0, stripe_warps=0, mirror_chunk=0, low32=False):
+    def run(rows, n_shards):
         hashes, offsets = orc.to_csr(rows)
         n = len(rows)
         with tempfile.TemporaryDirectory() as td:
             fh, fo, fc, fp = (os.path.join(td, x) for x in ("h", "o", "c", "p"))
             hashes.tofile(fh); offsets.tofile(fo)
-            if stripe_warps:                               # n_shards carries the rows per CTA
-                subprocess.check_call([exe, str(n_shards), fh, fo, fc, "low32" if low32 else "-", "stripe", str(stripe_warps),
-                                       str(mirror_chunk)])
-                return np.fromfile(fc, dtype=np.float64).reshape(n, n)
-            extra = ["cluster"] if cluster else ["rows", str(row_passes)] if row_passes else []
-            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp] + extra)
+            subprocess.check_call([exe, str(n_shards), fh, fo, fc, fp])
             got = np.fromfile(fc, dtype=np.uint32).reshape(n, n)
-            return got if (cluster or row_passes) else (got, int(np.fromfile(fp, dtype=np.uint64)[0]))
+            return got, int(np.fromfile(fp, dtype=np.uint64)[0])
     return run
 
 
@@ -232,108 +227,16 @@ def test_join_walk_matches_oracle(join_emul):
             assert pairs == int(want[iu].sum())                       # sum of C(m,2) == sum of all intersections
 
 
-def test_join_cluster_layout_matches_oracle(join_emul):
-    """Experimental cluster layout (SMB_JOIN_LAYOUT=cluster): row keys, ranking, ranked gather, 32-lane
-    walk and un-permutation, emulated with the header's own functions."""
-    from sourmash_b200.synth import synth_sketches
-    rng = np.random.default_rng(8)
-    h, off = synth_sketches(120, mean=300, sd=60, lo=100, hi=600, n_families=7, pool=400, seed=21)
-    fam = [h[int(off[i]):int(off[i + 1])] for i in range(120)]
-    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64),
-                                      np.array([7] if i % 4 else [7, 2**61], dtype=np.uint64)])) for i in range(150)]
-    dense = [np.arange(i % 4, 30, dtype=np.uint64) for i in range(40)]
-    dense[3] = np.zeros(0, np.uint64)
-    for rows in (fam, wide, dense):
-        hh, oo = orc.to_csr(rows)
-        want = orc.pairwise_common(hh, oo)
-        iu = np.triu_indices(len(rows), 1)
-        for shards in (1, 3):
-            got = join_emul(rows, shards, cluster=True)
-            assert np.array_equal(got[iu], want[iu]), shards
-            assert int(np.tril(got).sum()) == 0
-
-
-def test_join_row_block_passes_finalise_rows_in_order(join_emul):
-    """Experimental row-block pipeline (SMB_COMPARE_PASSES): after the pass over a block of rows the
-    complete rows of that block (both triangles) are final."""
-    from sourmash_b200.synth import synth_sketches
-    h, off = synth_sketches(75, mean=300, sd=60, lo=100, hi=600, n_families=5, pool=400, seed=33)
-    rows = [h[int(off[i]):int(off[i + 1])] for i in range(75)]
-    want = orc.pairwise_common(h, off)
-    iu = np.triu_indices(75, 1)
-    full = np.zeros_like(want)
-    full[iu] = want[iu]
-    full = full + full.T                                   # symmetric, zero diagonal
-    for passes in (2, 8, 75):
-        assert np.array_equal(join_emul(rows, 1, row_passes=passes), full), passes
-
-
-def test_join_stripe_layout_matches_oracle(join_emul):
-    """Experimental stripe layout (SMB_JOIN_LAYOUT=stripe, csrc/join_stripe.cuh): tags / inverse
-    permutation, both-direction 32-lane group scans cut by the ballot of the stop predicate, per-CTA
-    stripes and the fused float64 finalize -- the complete Jaccard matrix, bit for bit."""
-    from sourmash_b200.synth import synth_sketches
-    rng = np.random.default_rng(12)
-    h, off = synth_sketches(90, mean=300, sd=60, lo=100, hi=600, n_families=2, pool=400, seed=17)
-    fam = [h[int(off[i]):int(off[i + 1])] for i in range(90)]        # groups of ~30 rows: around one chunk
-    big = np.uint64(2**64 - 1)
-    # one hash shared by 150 rows (several chunks in both directions), one by exactly 33 and 65 rows
-    wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64),
-                                      np.array([7], dtype=np.uint64),
-                                      np.array([2**61] if i < 33 else [], dtype=np.uint64),
-                                      np.array([2**62] if i >= 85 else [], dtype=np.uint64),
-                                      np.array([0, big] if i % 5 == 0 else [], dtype=np.uint64)])) for i in range(150)]
-    dense = [np.arange(i % 4, 30, dtype=np.uint64) for i in range(40)]
-    dense[0] = np.zeros(0, np.uint64)
-    dense[3] = np.zeros(0, np.uint64)
-    dense[39] = np.zeros(0, np.uint64)
-    tiny = [np.array([5], np.uint64)]
-    pair = [np.array([1, 2, 3], np.uint64), np.array([2, 3, 4], np.uint64)]
-    for rows in (fam, wide, dense, tiny, pair):
-        hh, oo = orc.to_csr(rows)
-        want = orc.compare_all_pairs(hh, oo, nthreads=2)
-        for rows_per_cta, warps in ((1, 1), (5, 3), (32, 4), (7, 32)):
-            got = join_emul(rows, rows_per_cta, stripe_warps=warps)
-            assert np.array_equal(got, want), (len(rows), rows_per_cta, warps)
-        # SMB_JOIN_LAYOUT=stripe_upper: forward scans only, (i, j < i) mirrored tile by tile, in chunks of rows
-        for rows_per_cta, chunk in ((5, 1000), (3, 10), (32, 33), (1, 1)):
-            got = join_emul(rows, rows_per_cta, stripe_warps=2, mirror_chunk=chunk)
-            assert np.array_equal(got, want), (len(rows), rows_per_cta, chunk)
-
-
-def test_join_stripe_low32_sort_repairs_mixed_runs(join_emul):
-    """SMB_JOIN_SORT=low32: the stream sorted on the low key words only, runs that mix different hashes
-    re-sorted on the rotated key -- hashes sharing their low word across rows, in both row orders, next
-    to ordinary sets; both stripe modes downstream."""
-    from sourmash_b200.synth import synth_sketches
-    rng = np.random.default_rng(21)
-    h, off = synth_sketches(60, mean=300, sd=60, lo=100, hi=600, n_families=3, pool=400, seed=23)
-    fam = [h[int(off[i]):int(off[i + 1])] for i in range(60)]
-    lowword = np.uint64(0x1234abcd)
-    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
-    clash = []
-    for i in range(40):                                               # five hashes with one low word, spread over the rows
-        mine = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0]
-        other = [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)]               # a second clashing low word
-        clash.append(np.unique(np.array(mine + other + rng.integers(1, 2**60, size=4, dtype=np.uint64).tolist(), dtype=np.uint64)))
-    clash[5] = np.zeros(0, np.uint64)
-    for rows in (fam, clash, fam[:20] + clash):
-        hh, oo = orc.to_csr(rows)
-        want = orc.compare_all_pairs(hh, oo, nthreads=2)
-        for rows_per_cta, chunk in ((5, 0), (3, 7), (32, 1000)):
-            got = join_emul(rows, rows_per_cta, stripe_warps=3, mirror_chunk=chunk, low32=True)
-            assert np.array_equal(got, want), (len(rows), rows_per_cta, chunk)
-
-
 def test_join_stripe_helpers():
-    "rows per CTA for the shared-memory budget the kernel uses (227 KB): 10 000 columns -> 5 rows."
+    "rows per CTA for the shared-memory budget the kernel uses (227 KB minus its 352-byte header): 10 000 columns -> 5 rows."
     exe = os.path.join(tempfile.gettempdir(), "smb_stripe_rows")
     src = os.path.join(tempfile.gettempdir(), "smb_stripe_rows.cu")
     with open(src, "w") as fh:
         fh.write('#include <stdio.h>\n#include "%s"\nint main() { int ns[] = {1, 64, 1024, 10000, 58000, 58100, 200000};'
                  ' for (int n : ns) printf("%%d ", smb::stripe_rows_per_block(227 * 1024, n)); return 0; }\n'
                  % os.path.join(os.path.dirname(HERE), "sourmash_b200", "csrc", "join_stripe.cuh"))
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-DSMB_SIMT_EMUL=1", "-include", os.path.join(HERE, "host_emul", "simt.h"),
+                           "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
     got = [int(x) for x in subprocess.check_output([exe]).split()]
     assert got == [32, 32, 32, 5, 1, 0, 0]
 
@@ -428,7 +331,7 @@ def test_db_index_counts_match_oracle(index_emul):
 
 # ---------------------------------------------------------------------------------------------
 # the experimental KERNELS themselves on the CPU (tests/host_emul/simt.h: CTAs as cooperative fibers with
-# real __syncthreads / warp collectives / shared memory), csrc/experimental_kernels.cuh
+# real __syncthreads / warp collectives / shared memory), csrc/join_kernels.cuh, join_stripe.cuh, range_kernels.cuh, db_index_kernels.cuh
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def simt():
@@ -451,8 +354,11 @@ def simt():
 
 
 def test_simt_stripe_kernels_match_oracle(simt):
-    """join_stripe_kernel + stripe_mirror_kernel + stripe_tag_kernel as written: block geometry, the warp's
-    32-element chunks, two scans in flight, shared-memory stripe, fused finalize, row chunks."""
+    """The stripe pipeline kernel by kernel as join_stripe_create / join_stripe_rows launch it: 32-bit keys +
+    payloads, (host-sorted,) descent detection and in-place repair of runs that mix hashes, element-block
+    row table, u16 / u32 tags + inverse permutation, the count kernel (dynamic (row, chunk) items, four group
+    reads in flight, upper-only and two-direction modes, shared-memory stripe, fused float64 finalize), mirror,
+    row chunks.  Sort keys shortened to 8 / 3 bits make mixed runs the rule rather than a 1-in-10^4 event."""
     from sourmash_b200.synth import synth_sketches
     rng = np.random.default_rng(31)
     h, off = synth_sketches(70, mean=120, sd=30, lo=20, hi=250, n_families=2, pool=160, seed=29)
@@ -460,18 +366,55 @@ def test_simt_stripe_kernels_match_oracle(simt):
     wide = [np.unique(np.concatenate([rng.integers(1, 2**60, size=2, dtype=np.uint64), np.array([7], dtype=np.uint64),
                                       np.array([2**61] if i < 33 else [], dtype=np.uint64)])) for i in range(80)]
     wide[3] = np.zeros(0, np.uint64)
-    for rows in (fam, wide):
+    big = np.uint64(2**64 - 1)
+    edge = [np.unique(np.concatenate([rng.integers(0, 2**64 - 1, size=int(rng.integers(0, 20)), dtype=np.uint64),
+                                      np.array([0, 5, big] if i % 3 == 0 else [5], dtype=np.uint64)])) for i in range(45)]
+    edge[7] = np.zeros(0, np.uint64)
+    edge[9] = edge[8].copy()
+    small = [np.arange(1 + i % 3, 40 + i, dtype=np.uint64) for i in range(37)]          # dense small integers: no low bits at all
+    small[0] = np.zeros(0, np.uint64)
+    small[36] = np.zeros(0, np.uint64)
+    # one hash shared by 150 rows (several 32-tag chunks in both directions), one by exactly 33 and one by 65 rows
+    many = [np.unique(np.concatenate([rng.integers(1, 2**60, size=3, dtype=np.uint64), np.array([7], dtype=np.uint64),
+                                      np.array([2**61] if i < 33 else [], dtype=np.uint64),
+                                      np.array([2**62] if i >= 85 else [], dtype=np.uint64)])) for i in range(150)]
+    tiny = [np.array([5], np.uint64)]
+    pair = [np.array([1, 2, 3], np.uint64), np.array([2, 3, 4], np.uint64)]
+    for rows in (fam, wide, edge, small, many, tiny, pair):
         hh, oo = orc.to_csr(rows)
         want = orc.compare_all_pairs(hh, oo, nthreads=2)
         n = len(rows)
-        for R, upper, threads in ((5, 0, 64), (3, 1, 96), (32, 0, 32), (7, 1, 128)):
-            got = simt("stripe", rows, R, upper, threads, dtype=np.float64).reshape(n, n)
-            assert np.array_equal(got, want), (n, R, upper, threads)
+        for R, upper, threads, tag_bits, sort_bits in ((5, 0, 64, 16, 32), (3, 1, 96, 32, 32), (32, 0, 32, 16, 8),
+                                                       (7, 1, 128, 16, 3), (4, 1, 64, 32, 8)):
+            got = simt("stripe", rows, R, upper, threads, tag_bits, sort_bits, dtype=np.float64).reshape(n, n)
+            assert np.array_equal(got, want), (n, R, upper, threads, tag_bits, sort_bits)
+
+
+def test_simt_stripe_repairs_runs_that_mix_hashes(simt, capfd):
+    "hashes that agree in their top 32 bits and differ below (what a 32-bit sort key cannot separate), interleaved over rows"
+    rng = np.random.default_rng(33)
+    top = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7)]
+    lows = [np.uint64(0x1234abcd), np.uint64(0x00000001), np.uint64(0xffffffff)]
+    rows = []
+    for i in range(45):
+        mine = [t | lo for ti, t in enumerate(top) for li, lo in enumerate(lows) if (i + ti + 2 * li) % 3 != 0]
+        rows.append(np.unique(np.array(mine + rng.integers(1, 2**63, size=30, dtype=np.uint64).tolist(), dtype=np.uint64)))
+    rows[6] = np.zeros(0, np.uint64)
+    hh, oo = orc.to_csr(rows)
+    want = orc.compare_all_pairs(hh, oo, nthreads=2)
+    os.environ["SMB_EMUL_REPORT"] = "1"
+    try:
+        for R, upper, threads, tag_bits in ((5, 0, 64, 16), (4, 1, 96, 32)):
+            got = simt("stripe", rows, R, upper, threads, tag_bits, 32, dtype=np.float64).reshape(45, 45)
+            assert np.array_equal(got, want), (R, upper, threads)
+    finally:
+        del os.environ["SMB_EMUL_REPORT"]
+    assert "mixed runs repaired: 3" in capfd.readouterr().err
 
 
 def test_simt_join_kernels_match_oracle(simt):
-    """The inverted join as launched: row slices, gather, count (the default compare path), the estimate
-    kernel's invariant, key-range shards; the cluster layout's kernels; the row-block passes."""
+    """The global-reduction join as launched (the stripe layout's fallback and the key-range-sharded form):
+    row slices, gather, count, the estimate kernel's invariant, key-range shards."""
     from sourmash_b200.synth import synth_sketches
     rng = np.random.default_rng(3)
     h, off = synth_sketches(70, mean=200, sd=40, lo=50, hi=400, n_families=4, pool=260, seed=9)
@@ -491,28 +434,6 @@ def test_simt_join_kernels_match_oracle(simt):
         for shards in (1, 3):
             got = simt("join", rows, shards).reshape(n, n)
             assert np.array_equal(got[iu], want[iu]) and int(np.tril(got).sum()) == 0, ("join", shards)
-            got = simt("cluster", rows, shards).reshape(n, n)
-            assert np.array_equal(got[iu], want[iu]) and int(np.tril(got).sum()) == 0, ("cluster", shards)
-        for passes in (1, 4, n):
-            assert np.array_equal(simt("rows", rows, passes).reshape(n, n), full + full.T), ("rows", passes)
-
-
-def test_simt_stripe_low32_kernels(simt):
-    "the kernels of the 32-bit sort + repair (low words, key gather, mixed runs, repair load / store) as written."
-    rng = np.random.default_rng(33)
-    lowword = np.uint64(0x1234abcd)
-    his = [np.uint64(v) << np.uint64(32) for v in (9, 3, 7, 1, 5)]
-    rows = []
-    for i in range(45):
-        mine = [his[j] | lowword for j in range(5) if (i + j) % 3 != 0]
-        rows.append(np.unique(np.array(mine + [(np.uint64(i % 4 + 1) << np.uint64(32)) | np.uint64(77)] +
-                                       rng.integers(1, 2**60, size=30, dtype=np.uint64).tolist(), dtype=np.uint64)))
-    rows[6] = np.zeros(0, np.uint64)
-    hh, oo = orc.to_csr(rows)
-    want = orc.compare_all_pairs(hh, oo, nthreads=2)
-    for R, upper, threads in ((5, 0, 64), (4, 1, 96)):
-        got = simt("stripe_low32", rows, R, upper, threads, dtype=np.float64).reshape(45, 45)
-        assert np.array_equal(got, want), (R, upper, threads)
 
 
 def test_simt_range_search_kernels_match_oracle(simt):

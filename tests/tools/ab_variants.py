@@ -23,8 +23,7 @@ import bench  # noqa: E402
 from sourmash_b200 import batch as B  # noqa: E402
 from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_sketches  # noqa: E402
 
-SWITCHES = ("SMB_JOIN_LAYOUT", "SMB_JOIN_SORT", "SMB_COMPARE_ALGO", "SMB_COMPARE_PASSES", "SMB_SKETCH_FUSED",
-            "SMB_SEARCH_LAYOUT", "SMB_STRIPE_ROWS", "SMB_STRIPE_U16")
+SWITCHES = ("SMB_JOIN_LAYOUT", "SMB_COMPARE_ALGO", "SMB_SKETCH_FUSED", "SMB_SEARCH_LAYOUT", "SMB_STRIPE_TAGS")
 
 
 def log(*a):
@@ -61,12 +60,11 @@ def ab_compare(out):
     set_env({})
     B.compare_jaccard_device(sset, d_ref.data_ptr())
     torch.cuda.synchronize()
-    variants = [("plain", {}),
-                ("stripe", {"SMB_JOIN_LAYOUT": "stripe"}),
-                ("stripe+low32", {"SMB_JOIN_LAYOUT": "stripe", "SMB_JOIN_SORT": "low32"}),
-                ("stripe_upper", {"SMB_JOIN_LAYOUT": "stripe_upper"}),
-                ("stripe_upper+low32", {"SMB_JOIN_LAYOUT": "stripe_upper", "SMB_JOIN_SORT": "low32"}),
-                ("cluster", {"SMB_JOIN_LAYOUT": "cluster"})]
+    variants = [("stripe (default: u16 tags, upper + mirror)", {}),
+                ("stripe, u32 tags", {"SMB_STRIPE_TAGS": "u32"}),
+                ("stripe_full (both directions)", {"SMB_JOIN_LAYOUT": "stripe_full"}),
+                ("plain (global reductions)", {"SMB_JOIN_LAYOUT": "plain"}),
+                ("tile kernel", {"SMB_COMPARE_ALGO": "tile"})]
     res = {}
     for name, env in variants:
         set_env(env)
@@ -76,7 +74,7 @@ def ab_compare(out):
             torch.cuda.synchronize()
             same = bool(torch.equal(d_out, d_ref))
             ms = timed(lambda: B.compare_jaccard_device(sset, d_out.data_ptr()))
-            res[name] = {"ms": ms, "identical_to_plain": same, "pipeline_ms": B.last_kernel_ms(0)}
+            res[name] = {"ms": ms, "identical_to_first": same, "pipeline_ms": B.last_kernel_ms(0)}
         except Exception as exc:                                   # noqa: BLE001
             res[name] = {"error": repr(exc)[:300]}
         log("compare", name, res[name])
@@ -86,9 +84,7 @@ def ab_compare(out):
     po.array[:] = off
     pout = B.pinned_empty((n, n), np.float64)
     ref_host = d_ref.cpu().numpy()
-    for name, env in [("plain", {}), ("passes8", {"SMB_COMPARE_PASSES": 8}),
-                      ("stripe_upper+low32", {"SMB_JOIN_LAYOUT": "stripe_upper", "SMB_JOIN_SORT": "low32"}),
-                      ("stripe+low32", {"SMB_JOIN_LAYOUT": "stripe", "SMB_JOIN_SORT": "low32"})]:
+    for name, env in [("stripe (default)", {}), ("plain (global reductions)", {"SMB_JOIN_LAYOUT": "plain"})]:
         set_env(env)
         try:
             def e2e():
@@ -96,7 +92,7 @@ def ab_compare(out):
                 B.compare_jaccard(s2, out=pout.array)
             e2e()
             same = bool(np.array_equal(pout.array, ref_host))
-            res["e2e " + name] = {"ms": timed(e2e, steps=3, warmup=1), "identical_to_plain": same}
+            res["e2e " + name] = {"ms": timed(e2e, steps=3, warmup=1), "identical_to_first": same}
         except Exception as exc:                                   # noqa: BLE001
             res["e2e " + name] = {"error": repr(exc)[:300]}
         log("compare e2e", name, res["e2e " + name])
@@ -111,7 +107,7 @@ def ab_sketch(out):
     lens = np.diff(offs.astype(np.int64)).astype(np.uint64)
     B.set_profiling(True)
     res, ref = {}, None
-    for name, env in [("three launches", {}), ("fused", {"SMB_SKETCH_FUSED": 1})]:
+    for name, env in [("one pass (default)", {}), ("three launches", {"SMB_SKETCH_FUSED": 0})]:
         set_env(env)
         try:
             sset, nk = B.sketch_streams_device(d_bases.data_ptr(), offs[:-1], lens, bench.KSIZES, scaled=bench.SCALED)
