@@ -315,14 +315,17 @@ void smb_pairwise_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint
 void smb_finalize_jaccard_rows_dev(const SmbSketchSet *set, const uint32_t *d_common,
                                    uint64_t row_begin, uint64_t row_end, double *d_out);
 /* float64 rows [row_begin, row_end) of the all-vs-all Jaccard matrix of a scaled set into d_out
- * ((row_end - row_begin) x n, device memory).  With the experimental stripe layout of the join
- * (SMB_JOIN_LAYOUT=stripe) only those rows are counted, so one process per GPU can take a block
- * of rows without exchanging counts; otherwise the whole count matrix is computed first. */
+ * ((row_end - row_begin) x n, device memory).  With the stripe layout of the join (the default) only those
+ * rows are counted, so one process per GPU can take a block of rows without exchanging counts; with
+ * SMB_JOIN_LAYOUT=plain the whole count matrix is computed first. */
 void smb_compare_jaccard_rows_dev(const SmbSketchSet *set, uint64_t row_begin, uint64_t row_end,
                                   double *d_out);
 /* Index.find inner loop (src/sourmash/index/__init__.py:115-170): one query vs every row */
 void smb_one_vs_many(const uint64_t *query, uintptr_t n_query, const SmbSketchSet *db,
                      uint32_t *common_out);
+/* the same with the (sorted) query and the n_rows counters in device memory: nothing crosses PCIe */
+void smb_one_vs_many_dev(const uint64_t *d_query, uintptr_t n_query, const SmbSketchSet *db,
+                         uint32_t *d_common_out);
 /* gather (CounterGather + GatherDatabases, src/sourmash/index/__init__.py:777-909,
  * src/sourmash/search.py:877-949): iterative min-set-cover.  Returns number of rounds;
  * match_ids/isect_sizes receive, per round, the chosen row and |match ∩ remaining query|.

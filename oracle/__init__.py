@@ -72,6 +72,7 @@ def _load():
     lib.orc_compare_all_pairs.argtypes = [u64p, u64p, sz, C.c_uint32, sz, sz, f64p, C.c_int]
     lib.orc_pairwise_common.argtypes = [u64p, u64p, sz, sz, sz, u32p, C.c_int]
     lib.orc_one_vs_many.argtypes = [u64p, sz, u64p, u64p, sz, u64p, C.c_int]
+    lib.orc_one_vs_many_bsearch.argtypes = [u64p, sz, u64p, u64p, sz, u64p, C.c_int]
     lib.orc_sketch_scaled.restype = sz
     lib.orc_sketch_scaled.argtypes = [u8p, sz, C.c_uint32, C.c_uint64, C.c_uint64, u64p, sz,
                                       C.POINTER(C.c_uint64)]
@@ -298,6 +299,15 @@ def one_vs_many(q, hashes, offsets, nthreads=1):
     n = len(offsets) - 1
     out = np.zeros(n, dtype=np.uint64)
     lib.orc_one_vs_many(q, len(q), _u64(hashes), _u64(offsets), n, out, nthreads)
+    return out
+
+
+def one_vs_many_bsearch(q, hashes, offsets, nthreads=1):
+    "one_vs_many for a query much larger than the subjects: same counts, O(|S| log |Q|) per subject (oracle.c)"
+    q = _u64(q)
+    n = len(offsets) - 1
+    out = np.zeros(n, dtype=np.uint64)
+    lib.orc_one_vs_many_bsearch(q, len(q), _u64(hashes), _u64(offsets), n, out, nthreads)
     return out
 
 

@@ -47,6 +47,8 @@ void orc_pairwise_common(const uint64_t *hashes, const uint64_t *offsets, size_t
                          size_t first_row, size_t n_rows, uint32_t *out, int nthreads);
 void orc_one_vs_many(const uint64_t *q, size_t nq, const uint64_t *hashes,
                      const uint64_t *offsets, size_t n, uint64_t *common, int nthreads);
+void orc_one_vs_many_bsearch(const uint64_t *q, size_t nq, const uint64_t *hashes,
+                             const uint64_t *offsets, size_t n, uint64_t *common, int nthreads);
 size_t orc_sketch_scaled(const uint8_t *seq, size_t len, uint32_t k, uint64_t seed,
                          uint64_t max_hash, uint64_t *dst, size_t dst_cap, uint64_t *n_kmers);
 void orc_sketch_batch(const uint8_t *seqs, const uint64_t *seq_off, size_t n_seqs, uint32_t k,

@@ -292,6 +292,12 @@ def one_vs_many(query, db):
     return out
 
 
+def one_vs_many_device(d_query_ptr, n_query, db, d_counts_ptr):
+    "|query ∩ row| for every row, query (sorted u64) and the u32 counters resident in device memory."
+    rustcall(lib.smb_one_vs_many_dev, ffi.cast("uint64_t *", int(d_query_ptr)), int(n_query), db._ptr,
+             ffi.cast("uint32_t *", int(d_counts_ptr)))
+
+
 def gather(query, db, threshold=1, max_rounds=None):
     """Iterative min-set-cover; returns (match_ids, intersect_sizes) in pick order."""
     q = _u64(query)

@@ -254,15 +254,17 @@ struct SmbSketchSet {
     uint64_t max_len = 0;
     mutable uint64_t max_key = 0;         // largest hash of any row (lazily computed on the device)
     mutable bool max_key_known = false;
-    // experimental range-partitioned search (SMB_SEARCH_LAYOUT=ranges): slice bounds of every row for
-    // range_P equal key ranges of width range_width, built at the first search of the resident set
-    mutable DevBuf<uint32_t> range_bounds;
-    mutable int range_P = 0;
-    mutable uint64_t range_width = 0;
+    // range-major copy of the set (range_kernels.cuh), built at the first search with a query too large for shared
+    // memory and kept with the resident set: the streaming one-vs-many pass reads it instead of the rows
+    mutable smb::RangeMajor* range_major = nullptr;
+    mutable bool range_major_tried = false;
     // inverted index (hash -> rows), built on request by smb_sketchset_build_index: the one-vs-many
     // counts of search / prefetch / gather then cost work proportional to the query (db_index.cuh)
     smb::DbIndex* index = nullptr;
-    ~SmbSketchSet() { if (index) smb::db_index_destroy(index); }
+    ~SmbSketchSet() {
+        if (index) smb::db_index_destroy(index);
+        if (range_major) smb::range_major_destroy(range_major);
+    }
     uint64_t total() const { return h_off.empty() ? 0 : h_off.back(); }
     void finish_offsets() {
         max_len = 0;
@@ -2089,7 +2091,20 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
         smb::launch_pairwise_tile(one, q.d_hashes, q.d_off, 1, db.d_hashes, db.d_off, nB, d_counts,
                                   (size_t)nB, false, smb::TileShard{0, 1}, s);
     } else {
-        // large query: directory over the query's own key range (subject keys beyond it are skipped)
+        if (smb::range_search_enabled()) {
+            // large query: stream the range-major copy of the resident set (built once, kept with the set)
+            if (!db.range_major && !db.range_major_tried) {
+                db.range_major_tried = true;
+                CK(smb::range_major_build(db.d_hashes, db.d_off, nB, db.total(), set_max_key(db, s), &db.range_major, s));
+            }
+            if (db.range_major) {
+                smb::launch_one_vs_many_range_major(db.range_major, d_q, nq, d_counts, s);
+                CK(cudaGetLastError());
+                sync(s);      // q's offsets upload reads a host temporary
+                return;
+            }
+        }
+        // directory over the query's own key range (subject keys beyond it are skipped)
         int nb_log2 = 12;
         while (nb_log2 < 26 && (1ull << nb_log2) < 2 * (uint64_t)nq) ++nb_log2;
         int shift = 0;
@@ -2097,21 +2112,6 @@ static void one_vs_many_dev(const uint64_t* d_q, size_t nq, const SmbSketchSet& 
         const uint64_t nb = (q_max >> shift) + 1;
         DevBuf<uint32_t> d_dir(nb + 2, s);
         smb::launch_build_global_dir(d_q, nq, shift, nb, d_dir.p, s);
-        if (smb::range_search_enabled() && db.max_len < 0xffffffffull) {
-            // experimental: one CTA per key range, query bitmap of the range in shared memory
-            const int P = SMB_B200_SMS;
-            const uint64_t width = smb::range_width(set_max_key(db, s), P);
-            if (db.range_P != P || db.range_width != width) {
-                db.range_bounds.alloc((size_t)(P + 1) * (size_t)nB, s);
-                smb::launch_range_bounds(db.d_hashes, db.d_off, nB, width, P, db.range_bounds.p, s);
-                db.range_P = P; db.range_width = width;
-            }
-            smb::launch_one_vs_many_ranges(d_q, nq, d_dir.p, shift, nb, db.d_hashes, db.d_off, nB,
-                                           db.range_bounds.p, width, P, d_counts, s);
-            CK(cudaGetLastError());
-            sync(s);
-            return;
-        }
         // L2-resident occupancy bitmap, 8x finer than the directory (1 byte per bucket)
         const int fine_log2 = 3;
         DevBuf<uint32_t> d_bm(((size_t)nb << fine_log2) / 32 + 2, s);
@@ -2158,6 +2158,16 @@ void smb_one_vs_many(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
         one_vs_many_dev(d_q.p, n_query, *db, d_counts.p, s);
         d_counts.download(common_out, nB);
         sync(s);
+    });
+}
+
+void smb_one_vs_many_dev(const uint64_t* d_query, uintptr_t n_query, const SmbSketchSet* db, uint32_t* d_common_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t nB = db->n_rows;
+        if (nB == 0) return;
+        CK(cudaMemsetAsync(d_common_out, 0, nB * sizeof(uint32_t), s));
+        one_vs_many_dev(d_query, n_query, *db, d_common_out, s);
     });
 }
 

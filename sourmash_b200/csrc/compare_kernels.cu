@@ -40,6 +40,20 @@
 
 namespace smb {
 
+// stream-ordered scratch allocations released at scope exit, error paths included
+struct JoinScratch {
+    cudaStream_t s;
+    void* p[16] = {};
+    int n = 0;
+    explicit JoinScratch(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
+        if (e == cudaSuccess && n < 16) p[n++] = *out;
+        return e;
+    }
+    ~JoinScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s); }
+};
+
 static int tile_threads() {
     static int v = [] { const char* e = getenv("SMB_TILE_THREADS"); int t = e ? atoi(e) : 1024; return (t == 256 || t == 512 || t == 1024) ? t : 1024; }();
     return v;
@@ -230,41 +244,72 @@ void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, int shift, 
 }
 
 // ------------------------------------------------------------------------------------
-// Experimental range-partitioned one-vs-many pass (off unless SMB_SEARCH_LAYOUT=ranges; logic in
-// range_search.cuh, checked on the CPU by tests/test_host_emulation.py::test_range_search_*).
-// Not measured yet: kept behind the switch until it has been validated on the GPU.
+// Range-major copy of a resident set + the streaming one-vs-many pass over it (range_kernels.cuh): the path for
+// queries too large for shared memory.  SMB_SEARCH_LAYOUT=global keeps the global-directory kernel (A/B runs).
 // ------------------------------------------------------------------------------------
-// bounds[p * n + r] = index inside row r where range p starts (p = 0..P)
-void launch_range_bounds(const u64* h, const u64* off, int n, u64 width, int P, u32* bounds, cudaStream_t s) {
-    if (n <= 0) return;
-    const u64 total = (u64)n * (u64)(P + 1);
-    u64 blocks = (total + 255) / 256;
-    if (blocks > (u64)SMB_B200_SMS * 64) blocks = (u64)SMB_B200_SMS * 64;
-    range_bounds_kernel<<<(unsigned)blocks, 256, 0, s>>>(h, off, n, width, P, bounds); count_launches(1);
+struct RangeMajor {
+    cudaStream_t stream = 0;
+    void *m_rm = nullptr, *m_slice = nullptr;
+    int n = 0, P = 0;
+    u64 width = 0, T = 0;
+    u32 bm_shift = 0;
+    ~RangeMajor() {
+        if (m_rm) cudaFreeAsync(m_rm, stream);
+        if (m_slice) cudaFreeAsync(m_slice, stream);
+    }
+};
+
+int range_major_parts(u64 T) {
+    const char* e = getenv("SMB_RM_RANGES");              // tests: few ranges on small sets
+    if (e && atoi(e) > 0) return atoi(e);
+    // three CTAs per SM, a whole number of waves; fewer, larger parts for small sets
+    return T >= (32u << 20) ? SMB_B200_SMS * 9 : SMB_B200_SMS * 3;
 }
 
-// smallest bitmap (in 32-bit words) the kernel may be given for `width`: at most 1 Mi bits (128 KB)
-void plan_range_bitmap(u64 width, u32* bm_shift, u32* bm_words) {
-    const u64 max_bits = 1ull << 20;
-    *bm_shift = range_bitmap_shift(width, max_bits);
-    *bm_words = (u32)((((width - 1) >> *bm_shift) + 1 + 31) / 32);
+// *out stays null (with cudaSuccess) when the layout does not apply (positions must fit 32 bits)
+cudaError_t range_major_build(const u64* h, const u64* off, int n, u64 T, u64 max_key, RangeMajor** out, cudaStream_t s) {
+    *out = nullptr;
+    const int P = range_major_parts(T);
+    if (n <= 0 || T == 0 || T >= 0xffffffffull || (u64)n * (u64)(P + 1) >= 0x7fffffffull) return cudaSuccess;
+    auto rm = new RangeMajor();
+    std::unique_ptr<RangeMajor> guard(rm);
+    rm->stream = s; rm->n = n; rm->P = P; rm->T = T;
+    rm->width = range_width(max_key, P);
+    rm->bm_shift = range_bitmap_shift(rm->width, 1ull << RM_BITMAP_LOG2);
+    cudaError_t e;
+    const size_t cells = (size_t)n * (size_t)P;
+    if ((e = cudaMallocAsync(&rm->m_rm, (T + 64) * sizeof(u64), s)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&rm->m_slice, (cells + 1) * sizeof(u32), s)) != cudaSuccess) return e;
+    JoinScratch scratch(s);
+    u32 *bounds = nullptr, *cnt = nullptr;
+    if ((e = scratch.alloc((void**)&bounds, (cells + n) * sizeof(u32))) != cudaSuccess) return e;
+    if ((e = scratch.alloc((void**)&cnt, (cells + 1) * sizeof(u32))) != cudaSuccess) return e;
+    rm_bounds_kernel<<<SMB_B200_SMS * 16, 256, 0, s>>>(h, off, n, rm->width, P, bounds);
+    const unsigned grid = (unsigned)std::min<u64>((cells + 256) / 256, (u64)SMB_B200_SMS * 32);
+    rm_counts_kernel<<<grid, 256, 0, s>>>(bounds, n, P, cnt);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, (u32*)rm->m_slice, (long long)(cells + 1), s);
+    void* d_scan = nullptr;
+    if ((e = scratch.alloc(&d_scan, scan_bytes)) != cudaSuccess) return e;
+    cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cnt, (u32*)rm->m_slice, (long long)(cells + 1), s);
+    rm_scatter_kernel<<<grid, 256, 0, s>>>(h, off, bounds, (const u32*)rm->m_slice, n, P, (u64*)rm->m_rm);
+    count_launches(4);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *out = guard.release();
+    return cudaSuccess;
 }
+void range_major_destroy(RangeMajor* rm) { delete rm; }
 
-void launch_one_vs_many_ranges(const u64* q, u64 nq, const u32* dir, int shift, u64 nbk, const u64* hB,
-                               const u64* offB, int nB, const u32* bounds, u64 width, int P, u32* out,
-                               cudaStream_t s) {
-    if (nB <= 0 || nq == 0) return;
-    RangeArgs a{q, nq, dir, (u32)shift, nbk, hB, offB, nB, bounds, width, P, 0, 0, out};
-    plan_range_bitmap(width, &a.bm_shift, &a.bm_words);
-    const size_t smem = (size_t)a.bm_words * sizeof(u32);
-    // only what the bitmap needs: the kernel also has static shared memory, and dynamic + static must stay
-    // within the 227 KB a CTA may use (asking for all 227 KB as dynamic made every launch fail)
-    cudaFuncSetAttribute(one_vs_many_ranges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    one_vs_many_ranges_kernel<<<P, 1024, smem, s>>>(a); count_launches(1);
+void launch_one_vs_many_range_major(const RangeMajor* rm, const u64* q, u64 nq, u32* out, cudaStream_t s) {
+    if (nq == 0 || rm->n == 0) return;
+    RangeMajorArgs a{q, nq, (const u64*)rm->m_rm, (const u32*)rm->m_slice, rm->n, rm->P, rm->width, (u32)RM_BITMAP_LOG2, rm->bm_shift, out};
+    const size_t smem = ((size_t)1 << (RM_BITMAP_LOG2 - 3)) + (size_t)(RM_THREADS / 32) * RM_QUEUE * sizeof(u32);
+    cudaFuncSetAttribute(one_vs_many_range_major_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    one_vs_many_range_major_kernel<<<rm->P, RM_THREADS, smem, s>>>(a); count_launches(1);
 }
 bool range_search_enabled() {
     const char* layout = getenv("SMB_SEARCH_LAYOUT");
-    return layout && !strcmp(layout, "ranges");
+    return !(layout && !strcmp(layout, "global"));
 }
 
 // ------------------------------------------------------------------------------------
@@ -334,20 +379,6 @@ struct JoinWork {
     u32 *ids_a = nullptr, *ids_b = nullptr;
     u64 T = 0;
 };
-// stream-ordered scratch allocations released at scope exit, error paths included
-struct JoinScratch {
-    cudaStream_t s;
-    void* p[16] = {};
-    int n = 0;
-    explicit JoinScratch(cudaStream_t st) : s(st) {}
-    cudaError_t alloc(void** out, size_t bytes) {
-        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
-        if (e == cudaSuccess && n < 16) p[n++] = *out;
-        return e;
-    }
-    ~JoinScratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s); }
-};
-
 static cudaError_t join_sort_slice(const u64* h, const u64* off, int n, u64 key_lo, u64 key_hi,
                                    int bounded_hi, int key_bits, JoinWork& W, cudaStream_t s) {
     JoinScratch scratch(s);
@@ -439,7 +470,7 @@ static cudaError_t stripe_set_smem() {
 cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 max_key, JoinStripe** out, cudaStream_t s) {
     *out = nullptr;
     const int R = n > 0 ? stripe_rows_per_block((size_t)MAX_DYN_SMEM, n) : 0;
-    if (R < 1 || T == 0 || T >= 0xffffffffull) return cudaSuccess;
+    if (R < 1 || T == 0 || T >= 0xffffff00ull) return cudaSuccess;   // 32-bit stream positions, read-ahead included
     cudaError_t e;
     if ((e = stripe_set_smem<u16>()) != cudaSuccess) return e;      // per device, so not cached in a flag
     if ((e = stripe_set_smem<u32>()) != cudaSuccess) return e;
@@ -456,9 +487,10 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
     js->smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
     const size_t Tp = (size_t)((T + 63) & ~63ull);
     const size_t np = ((size_t)n + 63) & ~(size_t)63;
-    if ((e = cudaMallocAsync(&js->mem, Tp * 2 * sizeof(u32) + np * sizeof(u32), s)) != cudaSuccess) return e;
+    const size_t Tt = Tp + STRIPE_TAG_PAD;                          // the tag stream + its padding of head flags
+    if ((e = cudaMallocAsync(&js->mem, (Tt + Tp + np) * sizeof(u32), s)) != cudaSuccess) return e;
     js->tags = js->mem;
-    js->pos = (u32*)js->mem + Tp;
+    js->pos = (u32*)js->mem + Tt;
     js->sizes = js->pos + Tp;
     JoinScratch scratch(s);
     u32 *key_a = nullptr, *key_b = nullptr, *eblk = nullptr, *d_count = nullptr;

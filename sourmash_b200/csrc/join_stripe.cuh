@@ -32,6 +32,7 @@ namespace smb {
 static constexpr int STRIPE_EBLK_LOG2 = 9;            // element blocks of the row lookup table
 static constexpr int STRIPE_MAX_ROWS = 32;            // rows per CTA (upper bound)
 static constexpr int STRIPE_HEADER = 352;             // bytes in front of the counters: s_off[33] + control words, 16-aligned
+static constexpr int STRIPE_TAG_PAD = 128;            // head flags stored behind the end of the tag stream
 
 template <typename TagT> struct StripeTag;
 template <> struct StripeTag<u16> { static constexpr u32 HEAD = 0x8000u; };
@@ -130,21 +131,48 @@ __global__ void __launch_bounds__(256) stripe_sizes_kernel(const u64* __restrict
     if (r < n) sizes[r] = (u32)(off[r + 1] - off[r]);
 }
 
-// sorted (key, payload) stream -> tags (row | head flag) and the inverse permutation
+// sorted (key, payload) stream -> tags (row | head flag) and the inverse permutation.  Four stream positions per
+// thread, their loads issued together: the kernel is a chain of dependent loads (payload -> block table -> row
+// offsets) and is bound by latency, not by bytes.
 template <typename TagT>
 __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays,
                                                         const u64* __restrict__ off, const u32* __restrict__ eblk, u64 T,
                                                         TagT* __restrict__ tags, u32* __restrict__ pos) {
-    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < T; q += (u64)gridDim.x * blockDim.x) {
-        const u64 p = pays[q];
-        const u32 e = (u32)p;
-        bool head = q == 0;
-        if (!head) head = key32s[q] != key32s[q - 1] || (p >> 32) != (pays[q - 1] >> 32);
-        u32 r = eblk[e >> STRIPE_EBLK_LOG2];
-        while (off[r + 1] <= (u64)e) ++r;                 // e < T = off[n]: stops at the owning row, empty rows skipped
-        tags[q] = (TagT)(r | (head ? StripeTag<TagT>::HEAD : 0u));
-        pos[e] = (u32)q;
+    constexpr int U = 4;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 q0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; q0 < T; q0 += stride * U) {
+        u64 p[U], pp[U];
+        u32 k[U], kp[U], r[U];
+        u64 nx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u64 q = q0 + (u64)u * stride;
+            const bool in = q < T;
+            p[u] = in ? pays[q] : 0;
+            k[u] = in ? key32s[q] : 0;
+            pp[u] = (in && q) ? pays[q - 1] : ~0ull;
+            kp[u] = (in && q) ? key32s[q - 1] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = eblk[(u32)p[u] >> STRIPE_EBLK_LOG2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) nx[u] = off[r[u] + 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u64 q = q0 + (u64)u * stride;
+            if (q >= T) continue;
+            const u32 e = (u32)p[u];
+            const bool head = q == 0 || k[u] != kp[u] || (p[u] >> 32) != (pp[u] >> 32);
+            u32 rr = r[u];
+            u64 end = nx[u];
+            while (end <= (u64)e) end = off[++rr + 1];    // e < T = off[n]: stops at the owning row, empty rows skipped
+            tags[q] = (TagT)(rr | (head ? StripeTag<TagT>::HEAD : 0u));
+            pos[e] = (u32)q;
+        }
     }
+    // STRIPE_TAG_PAD head flags behind the end: the count kernel reads ahead of a group without bounds checks
+    const u64 gt = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt < (u64)STRIPE_TAG_PAD) tags[T + gt] = (TagT)StripeTag<TagT>::HEAD;
 }
 
 // ---- the count kernel -------------------------------------------------------------------------------------
@@ -187,6 +215,9 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     const u32 n_items = s_ctl[1] * (u32)rows;
     const u32 le_mask = (2u << lane) - 1u;                // lanes <= lane
     const u32 lt_mask = (1u << lane) - 1u;                // lanes <  lane
+    // tags[q + 1 + lane]: the stream is padded with head flags behind its end (stripe_tag_kernel), and T < 2^32 - 128,
+    // so forward reads need no bounds checks and 32-bit positions do not wrap
+    const TagT* __restrict__ fwd = tags + 1 + lane;
 
     for (;;) {
         u32 k = 0;
@@ -202,35 +233,45 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
         const u32 my_q = have ? ld_stream_u32(a.pos + e) : 0u;
         u32* row_ptr = stripe + (size_t)r * n;
 
-        // ---- members behind the element (higher rows)
+        // ---- members behind the element (higher rows): 64 tags per element are requested at once (groups of
+        // the benchmark have ~35 members behind an element on average), two elements per round
         u32 nxt = HEAD;
-        if (have && (u64)my_q + 1 < a.T) nxt = (u32)tags[(u64)my_q + 1];
+        if (have) nxt = (u32)tags[(size_t)my_q + 1];
         u32 todo = __ballot_sync(0xffffffffu, (nxt & HEAD) == 0);
         while (todo) {
-            int j[4];
-            u64 qq[4];
-            u32 t[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                j[u] = todo ? __ffs(todo) - 1 : -1;
-                todo &= todo - (todo ? 1u : 0u);
+            const int j0 = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int j1 = todo ? __ffs(todo) - 1 : -1;
+            todo &= todo - (todo ? 1u : 0u);
+            const u32 q0 = __shfl_sync(0xffffffffu, my_q, j0);
+            const u32 q1 = __shfl_sync(0xffffffffu, my_q, j1 < 0 ? j0 : j1);
+            const u32 t00 = (u32)fwd[q0], t01 = (u32)fwd[q0 + 32];
+            u32 t10 = HEAD, t11 = HEAD;
+            if (j1 >= 0) { t10 = (u32)fwd[q1]; t11 = (u32)fwd[q1 + 32]; }
+            {
+                u32 m = __ballot_sync(0xffffffffu, (t00 & HEAD) != 0);
+                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t00 & ~HEAD), 1u);
+                if (m == 0) {
+                    m = __ballot_sync(0xffffffffu, (t01 & HEAD) != 0);
+                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t01 & ~HEAD), 1u);
+                    for (u32 it = 2; m == 0; ++it) {       // more than 64 members behind
+                        const u32 tt = (u32)fwd[q0 + 32 * it];
+                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
+                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                    }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                  // up to four independent tag reads in flight
-                qq[u] = __shfl_sync(0xffffffffu, my_q, j[u] < 0 ? 0 : j[u]);
-                const u64 b = qq[u] + 1 + lane;
-                t[u] = (j[u] >= 0 && b < a.T) ? (u32)tags[b] : HEAD;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j[u] < 0) continue;                    // uniform in the warp
-                u32 m = __ballot_sync(0xffffffffu, (t[u] & HEAD) != 0);
-                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t[u] & ~HEAD), 1u);
-                for (u32 it = 1; m == 0; ++it) {           // groups with more than 32 members behind
-                    const u64 b = qq[u] + 1 + 32ull * it + lane;
-                    const u32 tt = b < a.T ? (u32)tags[b] : HEAD;
-                    m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
-                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+            if (j1 >= 0) {                                 // uniform in the warp
+                u32 m = __ballot_sync(0xffffffffu, (t10 & HEAD) != 0);
+                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t10 & ~HEAD), 1u);
+                if (m == 0) {
+                    m = __ballot_sync(0xffffffffu, (t11 & HEAD) != 0);
+                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t11 & ~HEAD), 1u);
+                    for (u32 it = 2; m == 0; ++it) {
+                        const u32 tt = (u32)fwd[q1 + 32 * it];
+                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
+                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                    }
                 }
             }
         }
@@ -240,33 +281,16 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
         const u32 self = have ? (u32)tags[my_q] : HEAD;
         todo = __ballot_sync(0xffffffffu, (self & HEAD) == 0);
         while (todo) {
-            int j[2];
-            u64 qq[2];
-            u32 t[2];
-            bool v[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                j[u] = todo ? __ffs(todo) - 1 : -1;
-                todo &= todo - (todo ? 1u : 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                qq[u] = __shfl_sync(0xffffffffu, my_q, j[u] < 0 ? 0 : j[u]);
-                v[u] = j[u] >= 0 && qq[u] >= 1 + (u64)lane;
-                t[u] = v[u] ? (u32)tags[qq[u] - 1 - lane] : HEAD;
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (j[u] < 0) continue;
-                u32 m = __ballot_sync(0xffffffffu, !v[u] || (t[u] & HEAD) != 0);
-                if (v[u] && (m & lt_mask) == 0) atomicAdd(row_ptr + (t[u] & ~HEAD), 1u);
-                for (u32 it = 1; m == 0; ++it) {
-                    const u64 d = 1 + 32ull * it + lane;
-                    const bool vv = qq[u] >= d;
-                    const u32 tt = vv ? (u32)tags[qq[u] - d] : HEAD;
-                    m = __ballot_sync(0xffffffffu, !vv || (tt & HEAD) != 0);
-                    if (vv && (m & lt_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
-                }
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const u32 q = __shfl_sync(0xffffffffu, my_q, j);
+            u32 m = 0;
+            for (u32 it = 0; m == 0; ++it) {
+                const u32 d = 1 + 32 * it + lane;
+                const bool vv = q >= d;
+                const u32 tt = vv ? (u32)tags[q - d] : HEAD;
+                m = __ballot_sync(0xffffffffu, !vv || (tt & HEAD) != 0);
+                if (vv && (m & lt_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
             }
         }
     }

@@ -49,16 +49,16 @@ void launch_index_count(const DbIndex* ix, const uint64_t* q, uint64_t nq, uint3
 void launch_index_count_n(const DbIndex* ix, const uint64_t* q, const uint32_t* d_nq, uint64_t max_nq, uint32_t* counts,
                           cudaStream_t s);
 
-// Experimental range-partitioned one-vs-many pass (SMB_SEARCH_LAYOUT=ranges, off by default;
-// range_search.cuh): the key space is cut into P equal ranges, CTA p keeps the query bitmap of its
-// range in shared memory and streams the rows' slices of that range.  `bounds` ([P + 1][n] u32) is
-// built once per resident set; `out` must be zeroed; `dir` is launch_build_global_dir's directory.
-bool range_search_enabled();
-void launch_range_bounds(const uint64_t* h, const uint64_t* off, int n, uint64_t width, int P, uint32_t* bounds,
-                         cudaStream_t s);
-void launch_one_vs_many_ranges(const uint64_t* q, uint64_t nq, const uint32_t* dir, int shift, uint64_t nbk,
-                               const uint64_t* hB, const uint64_t* offB, int nB, const uint32_t* bounds,
-                               uint64_t width, int P, uint32_t* out, cudaStream_t s);
+// Range-major copy of a resident set and the streaming one-vs-many pass over it (range_kernels.cuh): the key
+// space is cut into P equal ranges, part p of the copy holds every row's elements of range p back to back, CTA p
+// keeps a Bloom bitmap of the query keys of its range in shared memory and streams its part.  range_major_build
+// leaves *out null when the layout does not apply (the caller uses the global-directory kernel).
+struct RangeMajor;
+bool range_search_enabled();                          // false with SMB_SEARCH_LAYOUT=global
+cudaError_t range_major_build(const uint64_t* h, const uint64_t* off, int n, uint64_t n_elements, uint64_t max_key,
+                              RangeMajor** out, cudaStream_t s);
+void range_major_destroy(RangeMajor* rm);
+void launch_one_vs_many_range_major(const RangeMajor* rm, const uint64_t* q, uint64_t nq, uint32_t* out, cudaStream_t s);
 
 // All-vs-all counts by inverted join (compare_kernels.cu): sort the (hash, row) pairs of the set,
 // one increment per pair of rows sharing a hash.  join_estimate sorts the lowest 1/JOIN_SAMPLE of

@@ -1,35 +1,119 @@
-// range_kernels.cuh -- kernels of the range-partitioned one-vs-many pass (helpers: range_search.cuh);
-// compare_kernels.cu launches them, tests/host_emul/simt_emul.cu runs them on the CPU against the oracle.
+// range_kernels.cuh -- the streaming one-vs-many pass for a query too large for shared memory: the inner loop
+// of Index.find / prefetch / the first gather round against a metagenome-sized query
+// (src/sourmash/index/__init__.py:115-170, count_common of src/core/src/sketch/minhash.rs:539-558 per subject).
+// compare_kernels.cu launches these kernels, tests/host_emul/simt_emul.cu runs them on the CPU against the oracle.
+//
+// Problem: |Q ∩ S_j| for every row S_j of a resident database (300 000 rows x ~5 000 sorted u64 = 12 GB) and a
+// query of 10^7 hashes.  Every database element must be read once (the HBM roofline) and tested for membership
+// in Q.  A membership filter for 10^7 keys does not fit shared memory, so the KEY SPACE is cut into P equal
+// ranges and the database is kept in a second, RANGE-MAJOR order (built once per resident set, like an index):
+//   rm[ part p ] = the elements of range p of row 0, of row 1, ..., of row n-1, back to back
+//   slice[p * n + r] = position in rm where row r's elements of range p start     (u32, one table)
+// CTA p builds a two-probe Bloom bitmap of the query keys of ITS range in shared memory (~7 500 keys in 512 Kbit:
+// 0.1 % false positives), then streams part p front to back -- fully coalesced, every lane busy, 8 loads in flight
+// per thread -- and probes the bitmap.  The rare hits (true matches + false positives) go to a per-warp queue and
+// are settled in bulk: exact binary search in the query's slice, then the row is found from `slice` and its counter
+// incremented.  Algorithmic bytes: 8 (|Q| + sum |S_j|), each read once.
 #pragma once
 #include "common.cuh"
 #include "range_search.cuh"
 
 namespace smb {
 
-__global__ void __launch_bounds__(256) range_bounds_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
-                                                          int n, u64 width, int P, u32* __restrict__ bounds) {
-    const u64 total = (u64)n * (u64)(P + 1);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
-        const int p = (int)(i / (u64)n), r = (int)(i - (u64)p * n);
-        bounds[i] = (u32)range_bound(h + off[r], off[r + 1] - off[r], width, p, P);
+static constexpr int RM_THREADS = 512;                // 3 CTAs per SM: 3 x (64 KB bitmap + 4 KB queues) of shared memory
+static constexpr int RM_BITMAP_LOG2 = 19;             // 512 Kbit = 64 KB
+static constexpr int RM_QUEUE = 128;                  // candidates per warp
+static constexpr int RM_UNROLL = 8;                   // 8-byte loads in flight per thread
+static constexpr u64 RM_HASH2 = 0x9E3779B97F4A7C15ull;
+
+// range of key x for ranges of `width` keys (x <= max_key, so the result is < P by construction of width)
+__host__ __device__ __forceinline__ u32 rm_range_of(u64 x, u64 width) { return (u32)(x / width); }
+
+// bounds[p * n + r] = index inside row r of its first element with range >= p  (p = 0 .. P): one warp per row walks
+// the row once; where the range id steps from a to b the bounds a+1 .. b are the current index
+__global__ void __launch_bounds__(256) rm_bounds_kernel(const u64* __restrict__ h, const u64* __restrict__ off, int n,
+                                                       u64 width, int P, u32* __restrict__ bounds) {
+    const u32 lane = lane_id();
+    const int warp0 = (int)(((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int n_warps = (int)(((u64)gridDim.x * blockDim.x) >> 5);
+    for (int r = warp0; r < n; r += n_warps) {
+        const u64* __restrict__ row = h + off[r];
+        const u64 len = off[r + 1] - off[r];
+        long long carry = -1;                             // range of the element in front of the chunk
+        for (u64 i0 = 0; i0 <= len; i0 += 32) {           // index len is a virtual element of range P (closes every bound)
+            const u64 i = i0 + lane;
+            long long pid = -2;                           // lanes behind the virtual element: nothing to do
+            if (i < len) pid = (long long)rm_range_of(row[i], width);
+            else if (i == len) pid = P;
+            long long prev = __shfl_sync(0xffffffffu, pid, lane ? lane - 1 : 0);
+            if (lane == 0) prev = carry;
+            if (pid >= 0)
+                for (long long p = prev + 1; p <= pid; ++p) bounds[(size_t)p * n + r] = (u32)i;
+            carry = __shfl_sync(0xffffffffu, pid, 31);
+        }
     }
 }
 
-struct RangeArgs {
+// cnt[p * n + r] = number of elements of row r in range p (cub::DeviceScan::ExclusiveSum turns it into `slice`)
+__global__ void __launch_bounds__(256) rm_counts_kernel(const u32* __restrict__ bounds, int n, int P, u32* __restrict__ cnt) {
+    const u64 total = (u64)n * (u64)P;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += (u64)gridDim.x * blockDim.x)
+        cnt[i] = i < total ? bounds[i + n] - bounds[i] : 0u;    // one extra slot: the scan leaves the total there
+}
+
+// one thread per (range, row) slice: a few elements, read where the row lies, written back to back
+__global__ void __launch_bounds__(256) rm_scatter_kernel(const u64* __restrict__ h, const u64* __restrict__ off,
+                                                        const u32* __restrict__ bounds, const u32* __restrict__ slice,
+                                                        int n, int P, u64* __restrict__ rm) {
+    const u64 total = (u64)n * (u64)P;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const int r = (int)(i % (u64)n);
+        const u32 b0 = bounds[i], b1 = bounds[i + n];
+        const u64* __restrict__ src = h + off[r] + b0;
+        u64* __restrict__ dst = rm + slice[i];
+        for (u32 k = 0; k < b1 - b0; ++k) dst[k] = src[k];
+    }
+}
+
+struct RangeMajorArgs {
     const u64* q; u64 nq;                 // the query, sorted
-    const u32* dir; u32 shift; u64 nbk;   // directory over the query (launch_build_global_dir)
-    const u64* hB; const u64* offB; int nB;
-    const u32* bounds;                    // [P + 1][nB]
-    u64 width; int P; u32 bm_shift, bm_words;
-    u32* out;                             // zeroed by the caller; CTAs add their range's matches
+    const u64* rm;                        // range-major database
+    const u32* slice;                     // [P * n + 1]
+    int n, P;
+    u64 width;
+    u32 bm_log2;                          // bits of the bitmap = 2^bm_log2 (RM_BITMAP_LOG2; tests use tiny bitmaps: false positives)
+    u32 bm_shift;                         // (x - lo) >> bm_shift < 2^bm_log2
+    u32* out;                             // zeroed by the caller
 };
 
+__device__ __forceinline__ u32 rm_bit1(u64 d, u32 bm_shift) { return (u32)(d >> bm_shift); }
+__device__ __forceinline__ u32 rm_bit2(u64 d, u32 bm_log2) { return (u32)((d * RM_HASH2) >> (64 - bm_log2)); }
+
+// settle the queued candidates of one warp: exact test against the query slice, then row attribution
+__device__ __forceinline__ void rm_drain(const RangeMajorArgs& a, const u32* __restrict__ queue, u32 count, u64 qlo, u64 qhi,
+                                         const u32* __restrict__ slice_p, u32 lane) {
+    for (u32 i = lane; i < count; i += 32) {
+        const u32 pos = queue[i];
+        const u64 x = a.rm[pos];
+        u64 lo = qlo, hi = qhi;
+        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (a.q[mid] < x) lo = mid + 1; else hi = mid; }
+        if (lo >= qhi || a.q[lo] != x) continue;          // a false positive of the bitmap
+        int l = 0, r = a.n;                               // last row whose slice starts at or in front of pos
+        while (r - l > 1) { const int mid = (l + r) >> 1; if (slice_p[mid] <= pos) l = mid; else r = mid; }
+        atomicAdd(a.out + l, 1u);
+    }
+}
+
 // one CTA per key range
-__global__ void __launch_bounds__(1024, 1) one_vs_many_ranges_kernel(RangeArgs a) {
-    SMB_DYN_SHARED(u32, range_bm);
+__global__ void __launch_bounds__(RM_THREADS, 3) one_vs_many_range_major_kernel(RangeMajorArgs a) {
+    SMB_DYN_SHARED(u32, rm_smem);                          // [2^bm_log2 / 32] bitmap words, then the warps' queues
     SMB_SHARED u64 s_q[2];
+    u32* bitmap = rm_smem;
+    const u32 BM_WORDS = a.bm_log2 > 5 ? 1u << (a.bm_log2 - 5) : 1u;
     const int p = blockIdx.x;
     const u64 lo = (u64)p * a.width;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    u32* queue = rm_smem + BM_WORDS + warp * RM_QUEUE;
     if (threadIdx.x == 0) {
         // query keys of this range: lo <= k, k - lo < width (monotone predicate, no overflow)
         const u64 qlo = range_lower_bound(a.q, a.nq, lo);
@@ -37,63 +121,52 @@ __global__ void __launch_bounds__(1024, 1) one_vs_many_ranges_kernel(RangeArgs a
         while (l < hgh) { const u64 mid = (l + hgh) >> 1; if (a.q[mid] - lo < a.width) l = mid + 1; else hgh = mid; }
         s_q[0] = qlo; s_q[1] = l;
     }
-    for (u32 i = threadIdx.x; i < a.bm_words; i += blockDim.x) range_bm[i] = 0;
+    for (u32 i = threadIdx.x; i < BM_WORDS; i += blockDim.x) bitmap[i] = 0;
     __syncthreads();
-    for (u64 i = s_q[0] + threadIdx.x; i < s_q[1]; i += blockDim.x) {
-        const u64 bit = range_bit(a.q[i], lo, a.bm_shift);
-        atomicOr(range_bm + (bit >> 5), 1u << (bit & 31));
+    const u64 qlo = s_q[0], qhi = s_q[1];
+    if (qlo == qhi) return;                                // no query key in this range: nothing can match
+    for (u64 i = qlo + threadIdx.x; i < qhi; i += blockDim.x) {
+        const u64 d = a.q[i] - lo;
+        const u32 b1 = rm_bit1(d, a.bm_shift), b2 = rm_bit2(d, a.bm_log2);
+        atomicOr(bitmap + (b1 >> 5), 1u << (b1 & 31));
+        atomicOr(bitmap + (b2 >> 5), 1u << (b2 & 31));
     }
     __syncthreads();
-    if (s_q[0] == s_q[1]) return;                          // no query key in this range: nothing can match
-    const u32 lane = lane_id(), warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const u32* __restrict__ b0p = a.bounds + (size_t)p * a.nB;
-    const u32* __restrict__ b1p = b0p + a.nB;
-    constexpr int U = 4;                                   // row slices in flight per warp
-    for (int rbase = (int)warp * 32; rbase < a.nB; rbase += (int)n_warps * 32) {
-        const int r = rbase + (int)lane;
-        u64 my_start = 0;
-        u32 my_len = 0;
-        if (r < a.nB) { const u32 b0 = b0p[r]; my_len = b1p[r] - b0; my_start = a.offB[r] + b0; }
-        const int cnt = min(32, a.nB - rbase);
-        for (int j = 0; j < cnt; j += U) {
-            u64 x[U][2];
-            u32 len[U];
-            u64 start[U];
+    const u32* __restrict__ slice_p = a.slice + (size_t)p * a.n;
+    const u64 begin = slice_p[0], end = slice_p[a.n];      // slice[(p + 1) * n] = start of the next part (or the total)
+    u32 qn = 0;                                            // candidates in this warp's queue (warp-uniform)
+    const u64 step = (u64)blockDim.x * RM_UNROLL;
+    for (u64 base = begin + (u64)warp * 32 * RM_UNROLL; base < end; base += step) {
+        u64 x[RM_UNROLL];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {                  // U x 2 independent loads in flight
-                const int jj = min(j + u, cnt - 1);
-                start[u] = __shfl_sync(0xffffffffu, my_start, jj);
-                len[u] = (j + u < cnt) ? __shfl_sync(0xffffffffu, my_len, jj) : 0u;
-                x[u][0] = lane < len[u] ? ld_nc_u64(a.hB + start[u] + lane) : 0;
-                x[u][1] = lane + 32 < len[u] ? ld_nc_u64(a.hB + start[u] + lane + 32) : 0;
-            }
+        for (int u = 0; u < RM_UNROLL; ++u) {
+            const u64 i = base + (u64)u * 32 + lane;
+            x[u] = i < end ? ld_stream_u64(a.rm + i) : lo; // padding lanes are never candidates (tested by index below)
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (len[u] == 0) continue;                 // uniform in the warp
-                u32 c = 0;
-                for (u32 base = 0; base < len[u]; base += 64) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const u32 e = base + 32u * half + lane;
-                        if (e >= len[u]) continue;
-                        const u64 xv = base == 0 ? x[u][half] : ld_nc_u64(a.hB + start[u] + e);
-                        const u64 bit = range_bit(xv, lo, a.bm_shift);
-                        if (!((range_bm[bit >> 5] >> (bit & 31)) & 1u)) continue;
-                        const u64 b = xv >> a.shift;       // bitmap hit: locate the key through the directory
-                        if (b >= a.nbk) continue;
-                        u64 pp = a.dir[b];
-                        const u64 pe = a.dir[b + 1];
-                        for (; pp < pe; ++pp) {
-                            const u64 k = ld_nc_u64(a.q + pp);
-                            if (k >= xv) { c += (k == xv); break; }
-                        }
+        for (int u = 0; u < RM_UNROLL; ++u) {
+            const u64 i = base + (u64)u * 32 + lane;
+            const u64 d = x[u] - lo;
+            const u32 b1 = rm_bit1(d, a.bm_shift);
+            bool hit = i < end && ((bitmap[b1 >> 5] >> (b1 & 31)) & 1u);
+            if (__any_sync(0xffffffffu, hit)) {
+                if (hit) { const u32 b2 = rm_bit2(d, a.bm_log2); hit = (bitmap[b2 >> 5] >> (b2 & 31)) & 1u; }
+                const u32 m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
+                        __syncwarp();
+                        rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+                        __syncwarp();
+                        qn = 0;
                     }
+                    if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)i;
+                    qn += (u32)__popc(m);
                 }
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0 && c) atomicAdd(a.out + rbase + j + u, c);
             }
         }
     }
+    __syncwarp();
+    rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
 }
 
 }  // namespace smb

@@ -150,6 +150,16 @@ class ShardedDatabase:
         out = out.cpu().numpy().reshape(self.world, -1)
         return np.concatenate([out[r, : all_sizes[r]] for r in range(self.world)]).astype(np.uint32)
 
+    def search_counts_device(self, d_query, d_local_counts, d_all_counts=None):
+        """The same with the query (int64 view of the sorted u64 hashes) and the counters resident on the device: the
+        local pass writes `d_local_counts` (int32 [local rows]); with `d_all_counts` (int32 [world * max local rows])
+        one all-gather of equally sized blocks follows (shards of shard_bounds() differ by at most one row; a rank with
+        fewer rows leaves its last slot unused).  No host round trip."""
+        self.B.one_vs_many_device(d_query.data_ptr(), d_query.numel(), self.sset, d_local_counts.data_ptr())
+        if d_all_counts is not None:
+            self.dist.all_gather_into_tensor(d_all_counts, d_local_counts)
+        return d_all_counts
+
     def gather(self, query, threshold=1, max_rounds=None):
         "Returns (global match rows, intersect sizes) in pick order -- identical on every rank."
         torch, dist = self.torch, self.dist

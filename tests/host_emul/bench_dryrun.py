@@ -86,6 +86,12 @@ import sourmash_b200.synth as _synth  # noqa: E402
 _real_synth = _synth.synth_sketches
 _synth.synth_sketches = lambda n, **kw: _real_synth(n, mean=60, sd=15, lo=10, hi=120, n_families=20, pool=80, seed=7)
 bench.N_DB_SEARCH, bench.N_DB_GATHER, bench.N_QUERY_SEARCH = 480, 480, 40_000
+bench.DB_BACKEND, bench.DB_BLOCK_ROWS = "numpy", 160      # rows drawn on the host
+os.environ["SMB_RM_RANGES"] = "5"                         # few key ranges for the range-major copy of a tiny database
+_real_plan, _real_gather = _synth.database_plan, _synth.gather_workload
+_synth.database_plan = lambda n, seed, planted_frac=0.0, **kw: _real_plan(n, seed, planted_frac=max(planted_frac, 0.05) if planted_frac else 0.0,
+                                                                         mean=60, sd=15, lo=10, hi=120)
+_synth.gather_workload = lambda n_db, **kw: _real_gather(n_db, n_clusters=4, members=5, pool=70, noise=200)
 _orig_device = torch.device
 torch.device = lambda *a, **kw: _orig_device("cpu")
 
@@ -93,11 +99,11 @@ LINES = []
 bench.emit_json = lambda obj: LINES.append(json.loads(json.dumps(obj)))
 
 
-def run(workload, env=None, extra=()):
+def run(workload, env=None, extra=(), cpu_baseline=False):
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
     try:
-        args = types.SimpleNamespace(gpus=1, steps=1, warmup=3, impl="b200", workload=workload, no_cpu_baseline=True,
+        args = types.SimpleNamespace(gpus=1, steps=1, warmup=3, impl="b200", workload=workload, no_cpu_baseline=not cpu_baseline,
                                      index="--index" in extra)
         n0 = len(LINES)
         bench.run_b200(args)
@@ -114,7 +120,9 @@ def run(workload, env=None, extra=()):
 def main():
     base_keys = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"}
-    line = run("both", {"SMB_COMPARE_ALGO": "join"})
+    line = run("both", {"SMB_COMPARE_ALGO": "join"}, cpu_baseline=True)      # with the CPU arm: its rows / sketches are the parity check
+    assert line["parity_checked_pairs"] > 0 and line["sketch"]["parity_checked_sketches"] == 9
+    assert len(line["sketch"]["variants"]) == 2 and all(v["parity_checked_sketches"] for v in line["sketch"]["variants"].values())
     assert base_keys <= set(line) and "sketch" in line and base_keys <= set(line["sketch"]), sorted(set(line))
     for part in (line, line["sketch"]):
         r = part["roofline"]
@@ -134,13 +142,14 @@ def main():
     assert "3 launches" in d["roofline"]["kernel"]
     bench.N_SKETCHES = 240                                  # the tiled databases: 2 x 240 sketches
     for workload in ("search", "gather"):
-        plain = run(workload)
-        ranged = run(workload, {"SMB_SEARCH_LAYOUT": "ranges"})
+        plain = run(workload, cpu_baseline=True)
+        assert plain.get("parity_checked_subjects", 0) > 0 or plain.get("parity_checked_rounds", 0) > 0
+        ranged = run(workload, {"SMB_SEARCH_LAYOUT": "global"})
         indexed = run(workload, extra=("--index",))
         assert {"metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "n_gpus"} <= set(plain)
         assert "index" in indexed and indexed["index"]["distinct_hashes"] > 0 and "index" not in plain
         if workload == "gather":
-            assert plain["rounds"] == ranged["rounds"] == indexed["rounds"] > 10
+            assert plain["rounds"] == ranged["rounds"] == indexed["rounds"] > 2, (plain["rounds"], ranged["rounds"], indexed["rounds"])
     print("bench dry run ok: %d JSON lines assembled" % len(LINES))
 
 

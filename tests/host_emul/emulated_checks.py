@@ -160,10 +160,11 @@ def search_layouts_and_index():
     want_small = orc.one_vs_many(q_small, h, off).astype(np.uint32)
     want_large = orc.one_vs_many(q_large, h, off).astype(np.uint32)
     assert np.array_equal(B.one_vs_many(q_small, db), want_small)
-    assert np.array_equal(B.one_vs_many(q_large, db), want_large)              # global directory + bitmap path
-    with env(SMB_SEARCH_LAYOUT="ranges"):
+    with env(SMB_RM_RANGES="7"):                                               # a large query streams the range-major copy of the set
         assert np.array_equal(B.one_vs_many(q_large, db), want_large)
-        assert np.array_equal(B.one_vs_many(q_large[::2], db), orc.one_vs_many(q_large[::2], h, off).astype(np.uint32))   # cached bounds
+        assert np.array_equal(B.one_vs_many(q_large[::2], db), orc.one_vs_many(q_large[::2], h, off).astype(np.uint32))   # cached layout
+    with env(SMB_SEARCH_LAYOUT="global"):                                      # global directory + bitmap kernel
+        assert np.array_equal(B.one_vs_many(q_large, db), want_large)
     n_keys = db.build_index()
     assert db.has_index and n_keys == len(np.unique(h)) and db.build_index() == n_keys
     assert np.array_equal(B.one_vs_many(q_small, db), want_small)

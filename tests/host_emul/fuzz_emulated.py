@@ -56,7 +56,7 @@ def trial(rng):
             os.environ["SMB_JOIN_LAYOUT"], os.environ["SMB_STRIPE_TAGS"] = layout, tags
             assert np.array_equal(B.compare_jaccard(db), want), ("compare", layout, tags, n, scale)
         os.environ.pop("SMB_JOIN_LAYOUT"); os.environ.pop("SMB_STRIPE_TAGS")
-        os.environ["SMB_SEARCH_LAYOUT"] = "ranges"
+        os.environ["SMB_SEARCH_LAYOUT"] = "global"
         if rng.random() < 0.5 and len(h) and len(h) < 2**31:
             db.build_index()
     os.environ.pop("SMB_COMPARE_ALGO")

@@ -218,6 +218,7 @@ inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     for (int l = 0; l < 32; ++l) if ((c.snap_mask >> l) & 1u) s += (uint32_t)c.snap[l];
     return s;
 }
+inline void __syncwarp(uint32_t = 0xffffffffu) { smb_emu::collective(0); }
 inline int __ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
 inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }

@@ -3,7 +3,7 @@
 // writes their results for comparison with the oracle.  The launch geometry is shrunk (fewer threads, smaller
 // shared memory) but the code is the code the GPU runs.  Test infrastructure for the CPU-only suite.
 //   simt_emul stripe <R> <upper 0|1> <threads> <tag bits 16|32> <sort-key bits> <hashes.u64> <offsets.u64> <out.f64 n*n>
-//   simt_emul ranges <P> <max_bits> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
+//   simt_emul ranges <P> <bitmap log2> <threads> <query.u64> <hashes.u64> <offsets.u64> <out.u32 n>
 //   simt_emul join <key-range shards> <hashes.u64> <offsets.u64> <out.u32 n*n>              (upper-triangle counts)
 //   simt_emul tile <TA 1..4> <variant 1 split | 0 u64 occ | 2 u64> <threads> <cols_per_cta> <symmetric 0|1> <hashes.u64> <offsets.u64> <out.u32>
 //   simt_emul pairs <num> <hashes.u64> <offsets.u64> <out.f64 3*n*n: jaccard (generic kernel) | jaccard num | angular>
@@ -83,7 +83,7 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     std::vector<u32> eblk(nblk + 1);
     smb_emu::launch(2, 64, 0, [&] { stripe_eblk_kernel(off.data(), n, T, eblk.data()); });
     smb_emu::launch((n + 63) / 64 + 1, 64, 0, [&] { stripe_sizes_kernel(off.data(), n, sizes.data()); });
-    std::vector<TagT> tags(T + 1);
+    std::vector<TagT> tags(T + STRIPE_TAG_PAD + 1);
     smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data()); });
     std::vector<double> out((size_t)n * n, -1.0);
     const size_t smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
@@ -168,26 +168,34 @@ static std::vector<u32> host_dir(const std::vector<u64>& keys, u32 shift, u64 nb
     return dir;
 }
 
-static int ranges_main(int P, u64 max_bits, int threads, const char* fq, const char* fh, const char* fo, const char* fout) {
+// The range-major pass as range_major_build / launch_one_vs_many_range_major launch it (compare_kernels.cu): bounds,
+// counts, (host) exclusive scan, scatter, then the streaming kernel.  `bm_log2` far below the product's 19 makes
+// false positives of the bitmap -- and with them the exact test of the drain -- common.
+static int ranges_main(int P, int bm_log2, int threads, const char* fq, const char* fh, const char* fo, const char* fout) {
     std::vector<u64> q = slurp<u64>(fq), h = slurp<u64>(fh), off = slurp<u64>(fo);
     const int n = (int)off.size() - 1;
-    u64 max_key = 0, q_max = q.empty() ? 0 : q.back();
+    const u64 T = h.size();
+    u64 max_key = 0;
     for (u64 v : h) max_key = std::max(max_key, v);
     const u64 width = range_width(max_key, P);
-    std::vector<u32> bounds((size_t)(P + 1) * n + 1);
+    const size_t cells = (size_t)n * P;
+    std::vector<u32> bounds(cells + n + 1, 0xdeadbeefu), cnt(cells + 2), slice(cells + 2);
     h.push_back(0);                                             // keep h.data() valid for empty sets
-    smb_emu::launch(3, 64, 0, [&] { range_bounds_kernel(h.data(), off.data(), n, width, P, bounds.data()); });
-    u32 shift;
-    u64 nbk;
-    db_index_dir_plan(q.size(), q_max, shift, nbk);             // same geometry rules as the query directory
-    std::vector<u32> dir = host_dir(q, shift, nbk);
-    std::vector<u32> out(n, 0);
-    RangeArgs a{q.data(), (u64)q.size(), dir.data(), shift, nbk, h.data(), off.data(), n, bounds.data(), width, P, 0, 0, out.data()};
-    a.bm_shift = range_bitmap_shift(width, max_bits);
-    a.bm_words = (u32)((((width - 1) >> a.bm_shift) + 1 + 31) / 32);
+    smb_emu::launch(3, 64, 0, [&] { rm_bounds_kernel(h.data(), off.data(), n, width, P, bounds.data()); });
+    smb_emu::launch(2, 96, 0, [&] { rm_counts_kernel(bounds.data(), n, P, cnt.data()); });
+    u32 run = 0;
+    for (size_t i = 0; i <= cells; ++i) { slice[i] = run; run += cnt[i]; }       // cub::DeviceScan::ExclusiveSum
+    if (slice[cells] != (u32)T) return 3;                                        // every element lies in exactly one range
+    std::vector<u64> rm(T + 64, 0);
+    smb_emu::launch(3, 64, 0, [&] { rm_scatter_kernel(h.data(), off.data(), bounds.data(), slice.data(), n, P, rm.data()); });
+    std::vector<u32> out(n + 1, 0);
+    const u64 nq = q.size();
     q.push_back(0);
-    a.q = q.data();
-    if (a.nq) smb_emu::launch(P, threads, (size_t)a.bm_words * 4, [&] { one_vs_many_ranges_kernel(a); });
+    RangeMajorArgs a{q.data(), nq, rm.data(), slice.data(), n, P, width, (u32)bm_log2,
+                     range_bitmap_shift(width, 1ull << bm_log2), out.data()};
+    const size_t smem = (bm_log2 > 5 ? ((size_t)1 << (bm_log2 - 3)) : 4) + (size_t)(threads / 32) * RM_QUEUE * sizeof(u32);
+    if (nq && n) smb_emu::launch(P, threads, smem, [&] { one_vs_many_range_major_kernel(a); });
+    out.resize(n);
     dump(fout, out);
     return 0;
 }
@@ -404,7 +412,7 @@ int main(int argc, char** argv) {
     if (argc == 10 && !strcmp(argv[1], "stripe"))
         return stripe_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8], argv[9]);
     if (argc == 9 && !strcmp(argv[1], "ranges"))
-        return ranges_main(atoi(argv[2]), strtoull(argv[3], nullptr, 10), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
+        return ranges_main(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], argv[6], argv[7], argv[8]);
     if (argc == 7 && !strcmp(argv[1], "index")) return index_main(atoi(argv[2]), argv[3], argv[4], argv[5], argv[6]);
     if (argc == 6 && !strcmp(argv[1], "join"))
         return join_main(argv[1], atoi(argv[2]), argv[3], argv[4], argv[5]);

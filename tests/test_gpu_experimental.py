@@ -60,8 +60,11 @@ def _big_query(rows, seed=4000, extra=400_000):
     return np.unique(np.concatenate([rng.integers(1, MAX_HASH_1000, size=extra, dtype=np.uint64)] + rows[:40]))
 
 
-def test_range_search_matches_oracle(B, monkeypatch):
-    monkeypatch.setenv("SMB_SEARCH_LAYOUT", "ranges")
+@pytest.mark.parametrize("layout", [None, "global"])
+def test_large_query_search_matches_oracle(B, monkeypatch, layout):
+    "query too large for shared memory: the streaming pass over the range-major copy (default) / the global-directory kernel"
+    if layout:
+        monkeypatch.setenv("SMB_SEARCH_LAYOUT", layout)
     h, off = synth_sketches(3000, mean=2000, sd=200, lo=0, hi=3000, n_families=5, pool=2500, seed=3)
     rows = rows_of(h, off)
     db = B.SketchSet.from_host(h, off)

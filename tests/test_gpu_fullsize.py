@@ -136,3 +136,71 @@ def test_gather_large_properties(B, config3):
     # first pick is the best single overlap (lowest index among ties)
     cm = B.one_vs_many(query, db)
     assert ids[0] == int(np.argmax(cm)) and sizes[0] == cm.max()
+
+
+def test_compare_10k_first_256_rows_equal_the_oracle(B, config3):
+    """configs[2]: 256 complete rows of the 10 000 x 10 000 matrix (2.5 million pairs) against the CPU oracle's
+    compare_serial restatement, float64 bit for bit -- resident entry point and host entry point."""
+    import os
+    import torch
+    h, off = config3
+    n = len(off) - 1
+    want = orc.compare_all_pairs(h, off, first_row=0, n_rows=256, nthreads=os.cpu_count() or 8)[:256]
+    sset = B.SketchSet.from_host(h, off)
+    d_out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    B.compare_jaccard_device(sset, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out[:256].cpu().numpy()
+    iu = np.triu_indices(256, 1, n)
+    assert np.array_equal(got[iu], want[iu])
+    full = d_out.cpu().numpy()
+    assert np.array_equal(full, full.T) and np.array_equal(full[:, :256].T[iu], want[iu])     # mirrored cells too
+    assert np.array_equal(B.compare_jaccard(sset), full)                                          # host path: identical matrix
+
+
+@pytest.mark.timeout(1500)
+def test_search_300k_subjects_all_counts_equal_the_oracle(B):
+    """configs[3] at FULL size: a 1e7-hash query against 300 000 resident sketches (12 GB), every one of the
+    300 000 counters compared with the CPU oracle (binary-search form of count_common, held equal to the faithful walk
+    in tests/test_oracle_golden.py; the faithful walk itself checks the first 2 000 subjects)."""
+    import os
+    import torch
+    import bench
+    from sourmash_b200.synth import database_plan, search_query
+    query = search_query(bench.N_QUERY_SEARCH)
+    sizes, frac = database_plan(bench.N_DB_SEARCH, 4001, planted_frac=0.01)
+    db, d_h, h_off = bench.build_database(torch, B, sizes, frac, query, 4002, 0, bench.N_DB_SEARCH)
+    got = B.one_vs_many(query, db)
+    hh = d_h.cpu().numpy().view(np.uint64)
+    ncores = os.cpu_count() or 8
+    want = orc.one_vs_many_bsearch(query, hh, h_off, nthreads=ncores)
+    assert np.array_equal(got.astype(np.uint64), want)
+    planted = np.nonzero(frac > 0)[0]
+    assert 2000 < len(planted) < 4000 and np.all(got[planted] >= (frac[planted] * sizes[planted]).astype(np.int64))
+    assert got[np.setdiff1d(np.arange(len(got)), planted)].max() <= 3          # random subjects share next to nothing
+    assert np.array_equal(orc.one_vs_many(query, hh[: int(h_off[2000])], h_off[:2001], nthreads=ncores), want[:2000])
+    # the device entry point and the global-directory kernel give the same counters
+    d_q = torch.from_numpy(query.view(np.int64)).cuda()
+    d_c = torch.zeros(len(got), dtype=torch.int32, device="cuda")
+    B.one_vs_many_device(d_q.data_ptr(), len(query), db, d_c.data_ptr())
+    assert np.array_equal(d_c.cpu().numpy().astype(np.uint32), got)
+    os.environ["SMB_SEARCH_LAYOUT"] = "global"
+    try:
+        assert np.array_equal(B.one_vs_many(query, db), got)
+    finally:
+        del os.environ["SMB_SEARCH_LAYOUT"]
+
+
+def test_gather_50k_picks_equal_the_cpu_rounds(B):
+    "configs[4] (SURVEY 8d): ~1e5-hash metagenome vs 50 000 sketches, 200 planted in overlapping clusters; the pick list = the CPU rounds"
+    import torch
+    import bench
+    from sourmash_b200.synth import gather_workload
+    query, sizes, frac, overrides = gather_workload(bench.N_DB_GATHER)
+    db, d_h, h_off = bench.build_database(torch, B, sizes, frac, query, 5002, 0, bench.N_DB_GATHER, overrides)
+    ids, isizes = B.gather(query, db, threshold=50)
+    want = bench._gather_on_host(query, overrides, 50)
+    assert list(zip(ids.tolist(), isizes.tolist())) == want and len(want) > 150
+    cm = B.one_vs_many(query, db)
+    others = np.setdiff1d(np.arange(len(cm)), np.array(sorted(overrides)))
+    assert cm[others].max() < 50                                               # only planted rows can reach the threshold

@@ -242,50 +242,6 @@ def test_join_stripe_helpers():
 
 
 # ---------------------------------------------------------------------------------------------
-# range-partitioned one-vs-many pass (csrc/range_search.cuh), experimental SMB_SEARCH_LAYOUT=ranges
-# ---------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def ranges_emul():
-    exe = os.path.join(tempfile.gettempdir(), "smb_ranges_emul")
-    src = os.path.join(HERE, "host_emul", "ranges_emul.cu")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-x", "c++", src, "-o", exe])
-
-    def run(query, rows, P, max_bits):
-        hashes, offsets = orc.to_csr(rows)
-        with tempfile.TemporaryDirectory() as td:
-            fq, fh, fo, fc = (os.path.join(td, x) for x in ("q", "h", "o", "c"))
-            np.asarray(query, dtype=np.uint64).tofile(fq); hashes.tofile(fh); offsets.tofile(fo)
-            subprocess.check_call([exe, str(P), str(max_bits), fq, fh, fo, fc])
-            return np.fromfile(fc, dtype=np.uint32), (hashes, offsets)
-    return run
-
-
-def test_range_search_matches_oracle(ranges_emul):
-    """Equal key ranges, per-row slice bounds, per-range query bitmaps (coarse ones included, so that
-    false positives reach the key compare), the unbounded last range, query keys outside the
-    database's key space, empty rows / ranges -- counts equal to the oracle's one-vs-many."""
-    from sourmash_b200.synth import synth_sketches
-    rng = np.random.default_rng(5)
-    mx = orc.max_hash_for_scaled(1000)
-    h, off = synth_sketches(60, mean=400, sd=80, lo=50, hi=800, n_families=4, pool=500, seed=41)
-    fam = [h[int(off[i]):int(off[i + 1])] for i in range(60)]
-    big = np.uint64(2**64 - 1)
-    edge = [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([0, 1, 2, big - 1, big], np.uint64),
-            np.array([big], np.uint64), np.arange(1, 300, dtype=np.uint64),
-            np.unique(rng.integers(0, 2**64 - 1, size=500, dtype=np.uint64))]
-    q_fam = np.unique(np.concatenate([fam[3], fam[17][:200], fam[44][100:], rng.integers(1, mx, size=3000, dtype=np.uint64),
-                                      np.array([mx + 5, 2**63, 2**64 - 1], dtype=np.uint64)]))     # keys beyond the database
-    q_edge = np.unique(np.concatenate([edge[2], edge[5][::3], np.array([1, 299, 300, 2**40], dtype=np.uint64)]))
-    q_low = np.unique(rng.integers(0, 1000, size=200, dtype=np.uint64))                                 # query far below the db
-    for rows, query in ((fam, q_fam), (edge, q_edge), (edge, q_low), (fam, q_low), ([edge[0]], q_edge), (fam, fam[0][:1])):
-        hh, oo = orc.to_csr(rows)
-        want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32)
-        for P, max_bits in ((148, 1 << 20), (7, 64), (2, 1 << 20), (148, 1), (33, 4096)):
-            got, _ = ranges_emul(query, rows, P, max_bits)
-            assert np.array_equal(got, want), (len(rows), len(query), P, max_bits)
-
-
-# ---------------------------------------------------------------------------------------------
 # inverted index over a resident set (csrc/db_index.cuh): smb_sketchset_build_index
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
@@ -437,7 +393,10 @@ def test_simt_join_kernels_match_oracle(simt):
 
 
 def test_simt_range_search_kernels_match_oracle(simt):
-    "range_bounds_kernel + one_vs_many_ranges_kernel as written (slices in flight, bitmap in shared memory, directory walk)."
+    """The range-major layout and its streaming pass as written: rm_bounds / rm_counts / rm_scatter_kernel (every element
+    in exactly one part, rows in order inside a part) and one_vs_many_range_major_kernel (two-probe bitmap in shared
+    memory, eight loads in flight, per-warp candidate queues and their drain: exact test, row attribution).  Bitmaps of
+    2^6 .. 2^16 bits instead of 2^19 make false positives common; a 64-candidate burst overflows a queue mid-loop."""
     from sourmash_b200.synth import synth_sketches
     rng = np.random.default_rng(9)
     mx = orc.max_hash_for_scaled(1000)
@@ -450,12 +409,17 @@ def test_simt_range_search_kernels_match_oracle(simt):
     q_fam = np.unique(np.concatenate([fam[3], fam[17][:100], fam[11][::2], rng.integers(1, mx, size=2000, dtype=np.uint64),
                                       np.array([mx + 5, 2**63], dtype=np.uint64)]))
     q_edge = np.unique(np.concatenate([edge[2], edge[4][::3], np.array([1, 299, 300], dtype=np.uint64)]))
-    for rows, query in ((fam, q_fam), (edge, q_edge), (fam, fam[5][:1])):
+    q_beyond = np.unique(np.concatenate([fam[3], np.array([mx + 5, 2**63, 2**64 - 1], dtype=np.uint64)]))   # keys beyond the database
+    q_low = np.unique(rng.integers(0, 1000, size=200, dtype=np.uint64))                                       # query far below the db
+    dense = [np.arange(1, 2000, dtype=np.uint64) for _ in range(40)]                                         # every element a match:
+    q_dense = np.arange(1, 2000, dtype=np.uint64)                                                            # the queues overflow and drain
+    for rows, query in ((fam, q_fam), (edge, q_edge), (fam, fam[5][:1]), (fam, q_beyond), (fam, q_low), (edge, q_low),
+                        ([edge[0]], q_edge), (dense, q_dense)):
         hh, oo = orc.to_csr(rows)
         want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32)
-        for P, max_bits, threads in ((5, 1 << 16, 64), (2, 64, 96), (9, 4096, 32)):
-            got = simt("ranges", rows, P, max_bits, threads, query=query)
-            assert np.array_equal(got, want), (len(rows), P, max_bits, threads)
+        for P, bm_log2, threads in ((5, 16, 64), (2, 6, 96), (9, 12, 32), (3, 8, 64)):
+            got = simt("ranges", rows, P, bm_log2, threads, query=query)
+            assert np.array_equal(got, want), (len(rows), P, bm_log2, threads)
 
 
 def test_simt_index_kernels_match_oracle(simt):

@@ -219,3 +219,20 @@ def test_translate_golden_genome_s10(golden, s10_records):
             mh.add_protein_family(seq, "protein", False)
         assert np.array_equal(mh.mins(), golden["arrays"][f"s10_prot_k{k3}"])
         assert mh.md5sum() == meta["md5sum"]
+
+
+def test_one_vs_many_bsearch_equals_the_two_pointer_walk():
+    """oracle.one_vs_many_bsearch (used to check full-size configs[3] results) gives the counts of the faithful
+    count_common walk: random, planted, empty, extreme-key rows and queries."""
+    rng = np.random.default_rng(11)
+    big = np.uint64(2**64 - 1)
+    q = np.unique(np.concatenate([rng.integers(0, 2**64 - 1, size=20_000, dtype=np.uint64), np.array([0, big], dtype=np.uint64)]))
+    rows = [np.unique(rng.integers(0, 2**64 - 1, size=int(rng.integers(0, 400)), dtype=np.uint64)) for _ in range(60)]
+    rows += [np.unique(np.concatenate([r, q[rng.integers(0, len(q), size=50)]])) for r in rows[:20]]
+    rows += [np.zeros(0, np.uint64), np.array([0], np.uint64), np.array([big], np.uint64), q.copy(), q[::7].copy()]
+    h, off = orc.to_csr(rows)
+    for query in (q, q[:1], np.zeros(0, np.uint64), rows[3]):
+        a = orc.one_vs_many(query, h, off, nthreads=2)
+        b = orc.one_vs_many_bsearch(query, h, off, nthreads=2)
+        assert np.array_equal(a, b)
+    assert int(orc.one_vs_many_bsearch(q, h, off)[-2]) == len(q)

@@ -151,7 +151,7 @@ def ab_search(out):
     pq.array[:] = query
     res = {}
     alg = 8.0 * (db.total_hashes + len(query))
-    for name, env, index in [("global directory + bitmap", {}, False), ("ranges", {"SMB_SEARCH_LAYOUT": "ranges"}, False),
+    for name, env, index in [("range-major stream (default)", {}, False), ("global directory + bitmap", {"SMB_SEARCH_LAYOUT": "global"}, False),
                              ("inverted index", {}, True)]:
         set_env(env)
         try:
@@ -185,7 +185,7 @@ def ab_gather(out):
                                      [rng.integers(1, MAX_HASH_1000, size=20_000, dtype=np.uint64)]))
     db = tiled_db(h, off, reps)
     res, ref = {}, None
-    for name, env, index in [("plain", {}, False), ("ranges", {"SMB_SEARCH_LAYOUT": "ranges"}, False),
+    for name, env, index in [("default", {}, False), ("global directory", {"SMB_SEARCH_LAYOUT": "global"}, False),
                              ("inverted index", {}, True)]:
         set_env(env)
         try:
