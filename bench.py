@@ -408,7 +408,8 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
         ms_e2e, _, _, _ = timed(lambda: cs.step(e2e=True), max(2, args.steps // 2), 1)
         h2d, d2h = cs.h2d_bytes, cs.d2h_bytes
         alg_bytes = alg_bytes / world
-        parallelism = f"{world} gpus: sketches all-gathered, row tiles cyclic, counts all-reduced"
+        parallelism = (f"{world} gpus: sketches all-gathered, hash space split into {world} key ranges (sort + tags + whole-row "
+                       "counting of one range per rank), partial counters reduce-scattered by row block, rows finalised per rank")
 
     value = n_pairs / (ms / 1e3)
     kms = float(np.mean(kernel_ms))
@@ -485,11 +486,13 @@ def bench_sketch(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
     B.set_profiling(True)
     kernel_ms = []
 
+    gather_cache = {}
+
     def gather_shards(sset):
         if dist is None:
             return
         from sourmash_b200.distributed import allgather_sketchset
-        allgather_sketchset(torch, dist, B, sset)
+        allgather_sketchset(torch, dist, B, sset, cache=gather_cache)
 
     last = {}
 

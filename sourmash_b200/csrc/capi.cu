@@ -1848,6 +1848,48 @@ void smb_pairwise_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint
     });
 }
 
+void smb_compare_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint32_t n_shards, uint32_t* d_counts) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (n == 0) return;
+        if (n_shards == 0 || shard >= n_shards) fail(SOURMASH_ERROR_CODE_MSG, "bad shard index");
+        const uint64_t mk = set_max_key(*set, s);
+        if (smb::join_stripe_enabled() && set->total()) {
+            t_last_join = plan_join(*set, mk, s);
+            if (t_last_join.use) {
+                smb::JoinStripe* js = nullptr;
+                if (t_profiling) t_timer_pairwise.begin(s);
+                CK(smb::join_stripe_create_shard(set->d_hashes, set->d_off, (int)n, set->total(), mk, (int)shard, (int)n_shards, &js, s));
+                if (js) {
+                    std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
+                    CK(smb::join_stripe_counts(js, 0, (int)n, d_counts, s));
+                    if (t_profiling) t_timer_pairwise.end(s);
+                    return;
+                }
+                if (t_profiling) t_timer_pairwise.end(s);
+            }
+        }
+        // tile kernel / global-reduction join: upper-triangle shards, completed to whole rows
+        CK(cudaMemsetAsync(d_counts, 0, n * n * sizeof(uint32_t), s));
+        pairwise_counts_dev(*set, nullptr, 0, d_counts, nullptr, n, s, smb::TileShard{(int)shard, (int)n_shards});
+        smb::launch_mirror_counts(d_counts, (int)n, s);
+        CK(cudaGetLastError());
+    });
+}
+
+void smb_finalize_counts_rows_dev(const SmbSketchSet* set, const uint32_t* d_counts_rows, uint64_t row_begin, uint64_t row_end,
+                                  double* d_out) {
+    guarded_void([&] {
+        cudaStream_t s = need_gpu();
+        const size_t n = set->n_rows;
+        if (row_end > n) row_end = n;
+        if (row_begin >= row_end) return;
+        smb::launch_finalize_counts_rows(d_counts_rows, set->d_off, (int)n, (int)row_begin, (int)row_end, d_out, s);
+        CK(cudaGetLastError());
+    });
+}
+
 void smb_finalize_jaccard_rows_dev(const SmbSketchSet* set, const uint32_t* d_common, uint64_t row_begin,
                                    uint64_t row_end, double* d_out) {
     guarded_void([&] {

@@ -449,11 +449,12 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
 // ------------------------------------------------------------------------------------
 struct JoinStripe {
     cudaStream_t stream = 0;
-    void* mem = nullptr;      // tags + pos + sizes
+    void* mem = nullptr;      // tags + pos + sizes (+ the slice ranges of a key-range shard)
     void* tags = nullptr;
     u32 *pos = nullptr, *sizes = nullptr;
-    u64 T = 0;
-    int n = 0, rows_per_block = 0, upper_only = 1, tag16 = 0;
+    const u64 *ebeg = nullptr, *eend = nullptr;
+    u64 T = 0;                // elements in the stream (all of the set, or one key range of it)
+    int n = 0, rows_per_block = 0, upper_only = 1, tag16 = 0, sharded = 0;
     size_t smem = 0;
     ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
 };
@@ -465,46 +466,96 @@ static cudaError_t stripe_set_smem() {
     return cudaFuncSetAttribute(join_stripe_kernel<TagT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
-// *out stays null (with cudaSuccess) when the layout does not apply: 2^32 - 1 or more elements, or a row of n
-// counters that does not fit in shared memory.  Everything is enqueued on `s`; nothing synchronises.
-cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 max_key, JoinStripe** out, cudaStream_t s) {
+// *out stays null (with cudaSuccess) when the layout does not apply: 2^32 - 256 or more elements, or a row of n
+// counters that does not fit in shared memory.  n_shards > 1: the stream holds only the hashes of key range
+// `shard` (every hash lies in exactly one range, so the counts of the shards add up); that costs one 8-byte
+// readback (the number of elements in the range sizes the sort).  Otherwise nothing synchronises.
+cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_all, u64 max_key, int shard, int n_shards,
+                                     JoinStripe** out, cudaStream_t s) {
     *out = nullptr;
     const int R = n > 0 ? stripe_rows_per_block((size_t)MAX_DYN_SMEM, n) : 0;
-    if (R < 1 || T == 0 || T >= 0xffffff00ull) return cudaSuccess;   // 32-bit stream positions, read-ahead included
+    if (R < 1 || T_all == 0 || T_all >= 0xffffff00ull) return cudaSuccess;   // 32-bit stream positions, read-ahead included
     cudaError_t e;
     if ((e = stripe_set_smem<u16>()) != cudaSuccess) return e;      // per device, so not cached in a flag
     if ((e = stripe_set_smem<u32>()) != cudaSuccess) return e;
     auto js = new JoinStripe();
     std::unique_ptr<JoinStripe> guard(js);
-    js->stream = s; js->T = T; js->n = n; js->rows_per_block = R;
+    js->stream = s; js->n = n; js->rows_per_block = R;
     js->tag16 = n < 32768;
+    js->sharded = n_shards > 1;
     {
         const char* layout = getenv("SMB_JOIN_LAYOUT");
-        js->upper_only = !(layout && !strcmp(layout, "stripe_full"));
+        js->upper_only = !(layout && !strcmp(layout, "stripe_full")) && !js->sharded;
         const char* tag = getenv("SMB_STRIPE_TAGS");                 // A/B: force 32-bit tags
         if (tag && !strcmp(tag, "u32")) js->tag16 = 0;
     }
     js->smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
+    JoinScratch scratch(s);
+    const size_t np = ((size_t)n + 64) & ~(size_t)63;
+    // the slices of the rows that fall into the shard's key range, and how many elements that is
+    u64 T = T_all;
+    u64 *d_beg = nullptr, *d_cnt = nullptr, *d_doff = nullptr;
+    if (js->sharded) {
+        u64 lo, hi;
+        bool bounded;
+        join_shard_range(max_key, shard, n_shards, lo, hi, bounded);
+        const size_t nn = (size_t)n + 1;
+        if ((e = scratch.alloc((void**)&d_beg, nn * 3 * sizeof(u64))) != cudaSuccess) return e;
+        d_cnt = d_beg + nn; d_doff = d_cnt + nn;
+        join_row_range_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(h, off, n, lo, hi, bounded ? 1 : 0, d_beg, d_cnt);
+        count_launches(1);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt, d_doff, (int)nn, s);
+        void* d_scan = nullptr;
+        if ((e = scratch.alloc(&d_scan, scan_bytes)) != cudaSuccess) return e;
+        cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_cnt, d_doff, (int)nn, s);
+        cudaMemcpyAsync(&T, d_doff + n, sizeof(u64), cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    }
+    js->T = T;
     const size_t Tp = (size_t)((T + 63) & ~63ull);
-    const size_t np = ((size_t)n + 63) & ~(size_t)63;
+    const size_t Tall_p = (size_t)((T_all + 63) & ~63ull);
     const size_t Tt = Tp + STRIPE_TAG_PAD;                          // the tag stream + its padding of head flags
-    if ((e = cudaMallocAsync(&js->mem, (Tt + Tp + np) * sizeof(u32), s)) != cudaSuccess) return e;
+    // tags | pos (indexed by CSR element: the whole set's size) | sizes | slice ranges of a shard
+    if ((e = cudaMallocAsync(&js->mem, (Tt + Tall_p + np) * sizeof(u32) + (js->sharded ? 2 * np * sizeof(u64) : 0), s)) != cudaSuccess)
+        return e;
     js->tags = js->mem;
     js->pos = (u32*)js->mem + Tt;
-    js->sizes = js->pos + Tp;
-    JoinScratch scratch(s);
+    js->sizes = js->pos + Tall_p;
+    stripe_sizes_kernel<<<(n + 255) / 256, 256, 0, s>>>(off, n, js->sizes); count_launches(1);
+    if (js->sharded) {
+        u64* eb = (u64*)(js->sizes + np);
+        stripe_slice_ranges_kernel<<<(n + 255) / 256, 256, 0, s>>>(off, d_beg, d_cnt, n, eb, eb + np); count_launches(1);
+        js->ebeg = eb; js->eend = eb + np;
+    } else {
+        js->ebeg = off; js->eend = off + 1;
+    }
+    if (T == 0) {                                                   // no hash in this key range: every partial count is zero
+        if (js->tag16) stripe_tag_kernel<u16><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u16*)js->tags, js->pos);
+        else stripe_tag_kernel<u32><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u32*)js->tags, js->pos);
+        count_launches(1);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        *out = guard.release();
+        return cudaSuccess;
+    }
     u32 *key_a = nullptr, *key_b = nullptr, *eblk = nullptr, *d_count = nullptr;
     u64 *pay_a = nullptr, *pay_b = nullptr;
     if ((e = scratch.alloc((void**)&key_a, Tp * 2 * sizeof(u32))) != cudaSuccess) return e;
     if ((e = scratch.alloc((void**)&pay_a, Tp * 2 * sizeof(u64))) != cudaSuccess) return e;
     key_b = key_a + Tp; pay_b = pay_a + Tp;
-    const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
+    const u64 nblk = (T_all >> STRIPE_EBLK_LOG2) + 1;
     if ((e = scratch.alloc((void**)&eblk, (nblk + 1) * sizeof(u32))) != cudaSuccess) return e;
     if ((e = scratch.alloc((void**)&d_count, 16)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)std::min<u64>((T + 255) / 256, (u64)SMB_B200_SMS * 32);
     const int low_bits = stripe_low_bits(max_key);
     // 1. 32-bit sort keys (top bits of the hashes) + payloads (low bits, element index)
-    stripe_keys_kernel<<<grid, 256, 0, s>>>(h, T, low_bits, key_a, pay_a); count_launches(1);
+    if (js->sharded) {
+        const int blocks = n < SMB_B200_SMS * 16 ? n : SMB_B200_SMS * 16;
+        stripe_keys_slice_kernel<<<blocks, 256, 0, s>>>(h, js->ebeg, d_doff, n, low_bits, key_a, pay_a);
+    } else {
+        stripe_keys_kernel<<<grid, 256, 0, s>>>(h, T, low_bits, key_a, pay_a);
+    }
+    count_launches(1);
     // 2. four radix passes (fewer when the keys are short)
     int key_bits = key_bit_length(max_key);
     if (key_bits > 32) key_bits = 32;
@@ -521,32 +572,57 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
         stripe_fix_kernel<<<SMB_B200_SMS, 64, 0, s>>>(key_b, pay_b, T, key_a, d_count);
         count_launches(2);
     }
-    // 4. tags + inverse permutation; row lengths
-    stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T, eblk);
-    stripe_sizes_kernel<<<(n + 255) / 256, 256, 0, s>>>(off, n, js->sizes);
+    // 4. tags + inverse permutation
+    stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T_all, eblk);
     if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos);
     else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos);
-    count_launches(3);
+    count_launches(2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *out = guard.release();
     return cudaSuccess;
+}
+cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 max_key, JoinStripe** out, cudaStream_t s) {
+    return join_stripe_create_shard(h, off, n, T, max_key, 0, 1, out, s);
+}
+
+static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_end, double* d_out, u32* d_counts, cudaStream_t s) {
+    if (row_end <= row_begin) return cudaSuccess;
+    StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out, d_counts};
+    const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
+    const bool upper = js->upper_only && !d_counts;
+    if (js->tag16) {
+        if (upper) join_stripe_kernel<u16, true><<<blocks, 1024, js->smem, s>>>(a);
+        else join_stripe_kernel<u16, false><<<blocks, 1024, js->smem, s>>>(a);
+    } else {
+        if (upper) join_stripe_kernel<u32, true><<<blocks, 1024, js->smem, s>>>(a);
+        else join_stripe_kernel<u32, false><<<blocks, 1024, js->smem, s>>>(a);
+    }
+    count_launches(1);
+    return cudaGetLastError();
+}
+// raw counters (both directions, whole rows) of rows [row_begin, row_end): the partial counts of a key-range shard
+cudaError_t join_stripe_counts(const JoinStripe* js, int row_begin, int row_end, u32* d_counts, cudaStream_t s) {
+    return stripe_launch(js, row_begin, row_end, nullptr, d_counts, s);
+}
+// counters of rows [row_begin, row_end) summed over the shards -> float64 Jaccard rows
+void launch_finalize_counts_rows(const u32* d_counts, const u64* off, int n, int row_begin, int row_end, double* d_out,
+                                 cudaStream_t s) {
+    if (row_end <= row_begin || n <= 0) return;
+    dim3 grid((n + 255) / 256, row_end - row_begin);
+    stripe_finalize_counts_kernel<<<grid, 256, 0, s>>>(d_counts, off, n, row_begin, row_end, d_out); count_launches(1);
+}
+// c[j][i] = c[i][j] for j > i: the upper-triangle counters of the tile kernel / the global-reduction join as whole rows
+void launch_mirror_counts(u32* d_counts, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    const int t = (n + 31) / 32;
+    stripe_mirror_kernel<u32><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>(d_counts, n, 0, n); count_launches(1);
 }
 
 // float64 Jaccard rows [row_begin, row_end) of the all-vs-all matrix into d_out (row_begin first)
 cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s) {
-    if (row_end <= row_begin) return cudaSuccess;
-    StripeArgs a{js->tags, js->pos, off, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out};
-    const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
-    if (js->tag16) {
-        if (js->upper_only) join_stripe_kernel<u16, true><<<blocks, 1024, js->smem, s>>>(a);
-        else join_stripe_kernel<u16, false><<<blocks, 1024, js->smem, s>>>(a);
-    } else {
-        if (js->upper_only) join_stripe_kernel<u32, true><<<blocks, 1024, js->smem, s>>>(a);
-        else join_stripe_kernel<u32, false><<<blocks, 1024, js->smem, s>>>(a);
-    }
-    count_launches(1);
-    return cudaGetLastError();
+    (void)off;
+    return stripe_launch(js, row_begin, row_end, d_out, nullptr, s);
 }
 // upper-only mode: the cells (i, j < i) of rows [row_begin, row_end) from the finished upper parts of rows
 // < row_end; d_full = row 0 of the whole n x n matrix.  No-op in the two-direction mode.
@@ -554,7 +630,7 @@ cudaError_t join_stripe_mirror(const JoinStripe* js, int row_begin, int row_end,
     if (!js->upper_only || row_end <= row_begin) return cudaSuccess;
     const int t0 = row_begin / 32, t1 = (row_end + 31) / 32;
     dim3 grid((unsigned)t1, (unsigned)(t1 - t0));
-    stripe_mirror_kernel<<<grid, 1024, 0, s>>>(d_full, js->n, row_begin, row_end); count_launches(1);
+    stripe_mirror_kernel<double><<<grid, 1024, 0, s>>>(d_full, js->n, row_begin, row_end); count_launches(1);
     return cudaGetLastError();
 }
 bool join_stripe_upper_only(const JoinStripe* js) { return js->upper_only != 0; }

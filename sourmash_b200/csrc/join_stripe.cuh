@@ -31,7 +31,7 @@ namespace smb {
 
 static constexpr int STRIPE_EBLK_LOG2 = 9;            // element blocks of the row lookup table
 static constexpr int STRIPE_MAX_ROWS = 32;            // rows per CTA (upper bound)
-static constexpr int STRIPE_HEADER = 352;             // bytes in front of the counters: s_off[33] + control words, 16-aligned
+static constexpr int STRIPE_HEADER = 544;             // bytes in front of the counters: s_beg[32] + s_end[32] + control words, 16-aligned
 static constexpr int STRIPE_TAG_PAD = 128;            // head flags stored behind the end of the tag stream
 
 template <typename TagT> struct StripeTag;
@@ -179,11 +179,13 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__
 struct StripeArgs {
     const void* tags;        // u16 or u32 (template parameter of the kernel)
     const u32* pos;
-    const u64* off;          // CSR offsets of the set
-    const u32* sizes;        // row lengths
-    u64 T;
+    const u64* ebeg;         // per row: the CSR elements [ebeg[r], eend[r]) that are in the stream -- the whole row
+    const u64* eend;         //   (off, off + 1), or its slice of one key range when the stream holds a shard of the keys
+    const u32* sizes;        // row lengths (whole rows: the Jaccard denominators)
+    u64 T;                   // elements in the stream
     int n, rows_per_block, row_begin, row_end;
-    double* out;             // row `row_begin` first, leading dimension n
+    double* out;             // float64 Jaccard rows, row `row_begin` first, leading dimension n (null: counts only)
+    u32* out_counts;         // raw counters of the rows instead (a key-range shard's partial counts), same layout
 };
 
 // One CTA = rows [r0, r1) of the result.  Work items are (row, chunk of 32 consecutive elements), handed to the
@@ -197,19 +199,20 @@ template <typename TagT, bool UPPER>
 __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     constexpr u32 HEAD = StripeTag<TagT>::HEAD;
     SMB_DYN_SHARED(unsigned char, stripe_smem);
-    u64* s_off = reinterpret_cast<u64*>(stripe_smem);                       // [rows + 1]
-    u32* s_ctl = reinterpret_cast<u32*>(stripe_smem + (STRIPE_MAX_ROWS + 1) * sizeof(u64));   // [0] next item, [1] chunks of the longest row
+    u64* s_beg = reinterpret_cast<u64*>(stripe_smem);                       // [rows]
+    u64* s_end = s_beg + STRIPE_MAX_ROWS;                                   // [rows]
+    u32* s_ctl = reinterpret_cast<u32*>(stripe_smem + 2 * STRIPE_MAX_ROWS * sizeof(u64));   // [0] next item, [1] chunks of the longest row
     u32* stripe = reinterpret_cast<u32*>(stripe_smem + STRIPE_HEADER);      // [rows][n]
     const TagT* __restrict__ tags = reinterpret_cast<const TagT*>(a.tags);
     const int r0 = a.row_begin + (int)blockIdx.x * a.rows_per_block;
     const int r1 = min(a.row_end, r0 + a.rows_per_block);
     const int rows = r1 - r0;
     const u32 n = (u32)a.n;
-    for (u32 i = threadIdx.x; i <= (u32)rows; i += blockDim.x) s_off[i] = a.off[r0 + i];
+    for (u32 i = threadIdx.x; i < (u32)rows; i += blockDim.x) { s_beg[i] = a.ebeg[r0 + i]; s_end[i] = a.eend[r0 + i]; }
     if (threadIdx.x == 0) { s_ctl[0] = 0; s_ctl[1] = 0; }
     for (u32 i = threadIdx.x; i < (u32)rows * n; i += blockDim.x) stripe[i] = 0;
     __syncthreads();
-    for (u32 i = threadIdx.x; i < (u32)rows; i += blockDim.x) atomicMax(&s_ctl[1], (u32)((s_off[i + 1] - s_off[i] + 31) >> 5));
+    for (u32 i = threadIdx.x; i < (u32)rows; i += blockDim.x) atomicMax(&s_ctl[1], (u32)((s_end[i] - s_beg[i] + 31) >> 5));
     __syncthreads();
     const u32 lane = lane_id();
     const u32 n_items = s_ctl[1] * (u32)rows;
@@ -225,8 +228,8 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_items) break;
         const u32 c = k / (u32)rows, r = k - c * (u32)rows;
-        const u64 e0 = s_off[r] + ((u64)c << 5);
-        const u64 re = s_off[r + 1];
+        const u64 e0 = s_beg[r] + ((u64)c << 5);
+        const u64 re = s_end[r];
         if (e0 >= re) continue;                            // a shorter row: no such chunk
         const u64 e = e0 + lane;
         const bool have = e < re;
@@ -298,8 +301,13 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     // counts -> float64 rows, written once (streaming stores: the matrix is not read again by this kernel)
     for (int al = 0; al < rows; ++al) {
         const int row = r0 + al;
-        const u64 si = s_off[al + 1] - s_off[al];
         const u32* __restrict__ srow = stripe + (size_t)al * n;
+        if (a.out_counts) {                                // a shard of the keys: partial counts, summed over the shards later
+            u32* __restrict__ crow = a.out_counts + (size_t)(row - a.row_begin) * n;
+            for (u32 j = threadIdx.x; j < n; j += blockDim.x) crow[j] = srow[j];
+            continue;
+        }
+        const u64 si = a.sizes[row];
         double* __restrict__ orow = a.out + (size_t)(row - a.row_begin) * n;
         for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
             if (UPPER && j < (u32)row) continue;
@@ -308,18 +316,54 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     }
 }
 
+// a shard's row slices -> 32-bit sort keys + payloads (element index = position in the whole CSR), written back to back
+__global__ void __launch_bounds__(256) stripe_keys_slice_kernel(const u64* __restrict__ h, const u64* __restrict__ ebeg,
+                                                               const u64* __restrict__ dst_off, int n, int low_bits,
+                                                               u32* __restrict__ key32, u64* __restrict__ payload) {
+    const u64 low_mask = low_bits ? ((1ull << low_bits) - 1ull) : 0ull;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const u64 src = ebeg[r], d0 = dst_off[r], m = dst_off[r + 1] - d0;
+        for (u64 i = threadIdx.x; i < m; i += blockDim.x) {
+            const u64 x = h[src + i];
+            key32[d0 + i] = (u32)(x >> low_bits);
+            payload[d0 + i] = ((x & low_mask) << 32) | (src + i);
+        }
+    }
+}
+
+// ebeg[r] = off[r] + beg[r], eend[r] = ebeg[r] + cnt[r]: the slices of join_row_range_kernel as CSR element ranges
+__global__ void __launch_bounds__(256) stripe_slice_ranges_kernel(const u64* __restrict__ off, const u64* __restrict__ beg,
+                                                                 const u64* __restrict__ cnt, int n, u64* __restrict__ ebeg,
+                                                                 u64* __restrict__ eend) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    ebeg[r] = off[r] + beg[r];
+    eend[r] = off[r] + beg[r] + cnt[r];
+}
+
+// counters of rows [row_begin, row_end) (row_begin first, whole rows), summed over the shards -> float64 Jaccard rows
+__global__ void __launch_bounds__(256) stripe_finalize_counts_kernel(const u32* __restrict__ counts, const u64* __restrict__ off,
+                                                                    int n, int row_begin, int row_end, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = row_begin + (int)blockIdx.y;
+    if (j >= n || i >= row_end) return;
+    const size_t cell = (size_t)(i - row_begin) * n + j;
+    st_stream_f64(out + cell, stripe_jaccard(counts[cell], off[i + 1] - off[i], off[j + 1] - off[j], i == j));
+}
+
 // out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 32 x 32 tiles through shared memory, reads
 // and writes both coalesced.  `full` points at row 0 of the whole matrix (rows < row_end are complete
 // in their upper part).
-__global__ void __launch_bounds__(1024) stripe_mirror_kernel(double* __restrict__ full, int n, int row_begin, int row_end) {
-    SMB_SHARED double tile[32][33];
+template <typename T>
+__global__ void __launch_bounds__(1024) stripe_mirror_kernel(T* __restrict__ full, int n, int row_begin, int row_end) {
+    SMB_SHARED T tile[32][33];
     const int ti = row_begin / 32 + (int)blockIdx.y;       // tile row (destination rows)
     const int tj = (int)blockIdx.x;                        // tile column (destination columns), tj <= ti
     if (tj > ti) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // source tile = rows of tile column tj, columns of tile row ti (the upper part)
     const int sr = tj * 32 + ty, sc = ti * 32 + tx;
-    tile[ty][tx] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : 0.0;
+    tile[ty][tx] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : T(0);
     __syncthreads();
     const int dr = ti * 32 + ty, dc = tj * 32 + tx;
     if (dr >= row_begin && dr < row_end && dc < dr && dc < n) full[(size_t)dr * n + dc] = tile[tx][ty];

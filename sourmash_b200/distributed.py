@@ -1,14 +1,14 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
 
-The reference has no distributed path at all; sharding follows SURVEY §8e:
-  * sketching shards by genome, followed by ONE variable-length all-gather of the shards;
-  * compare replicates the gathered sketches, deals row tiles cyclically to ranks, sums the
-    partial count matrices with an all-reduce, and every rank finalises a block of rows.
-Host-side logic (shard bounds, padded all-gather + compaction, offsets) is backend agnostic
-and is what the gloo tests exercise; the compute calls need a GPU.
+The reference has no distributed path at all; sharding follows SURVEY 8e:
+  * sketching shards by genome, followed by ONE variable-length all-gather of the shards (`ShardGather`);
+  * compare all-gathers the sketches, splits the HASH SPACE into key ranges -- rank r sorts, tags and counts
+    only the hashes of range r, for whole rows -- sums the partial counters with one reduce-scatter by row block
+    and finalises its block of rows (`CompareShard`);
+  * search / gather shard the database by subject (`ShardedDatabase`).
+Host-side logic (shard bounds, padded all-gather + compaction, offsets, tie breaks) is backend agnostic and is
+what the gloo tests exercise; the compute calls need a GPU.
 """
-import os
-
 import numpy as np
 
 
@@ -17,55 +17,84 @@ def shard_bounds(n, world):
     return [n * r // world for r in range(world + 1)]
 
 
+class ShardGather:
+    """Variable-length all-gather of CSR shards (rank order == row order) with the bookkeeping done ONCE: the
+    sizes of the shards are exchanged at construction (one small collective and one host read), after which
+    `gather()` is a single all-gather of padded hash blocks plus `world` device-to-device slice copies -- no
+    host synchronisation in the step.  Row lengths are known on the host when sketches exist (they are the CSR
+    offsets), so the exchange belongs to setting the job up."""
+
+    def __init__(self, torch, dist, n_local_hashes, local_sizes, device):
+        self.torch, self.dist, self.device = torch, dist, device
+        world = dist.get_world_size()
+        sizes = np.asarray(local_sizes, dtype=np.int64)
+        meta = torch.tensor([int(n_local_hashes), len(sizes)], dtype=torch.int64, device=device)
+        metas = torch.empty(2 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(metas, meta)
+        metas = metas.cpu().numpy().reshape(world, 2)
+        self.n_hashes, self.n_rows = metas[:, 0].copy(), metas[:, 1].copy()
+        self.pad_h = max(int(self.n_hashes.max()), 1)
+        pad_r = max(int(self.n_rows.max()), 1)
+        mine = torch.zeros(pad_r, dtype=torch.int64, device=device)
+        mine[: len(sizes)] = torch.from_numpy(sizes).to(device)
+        all_s = torch.empty(world * pad_r, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_s, mine)
+        all_s = all_s.cpu().numpy().reshape(world, pad_r)
+        self.sizes = np.concatenate([all_s[r, : self.n_rows[r]] for r in range(world)]) if world else sizes
+        self.offsets = np.zeros(len(self.sizes) + 1, dtype=np.uint64)
+        self.offsets[1:] = np.cumsum(self.sizes)
+        self.total = int(self.n_hashes.sum())
+        self.d_offsets = torch.from_numpy(self.offsets.view(np.int64)).to(device)
+        self._padded = torch.zeros(self.pad_h, dtype=torch.int64, device=device)
+        self._all = torch.empty(world * self.pad_h, dtype=torch.int64, device=device)
+        self.hashes = torch.empty(max(self.total, 1), dtype=torch.int64, device=device)
+
+    def gather(self, local_hashes):
+        "all ranks' hashes, compacted, in `self.hashes[:total]` (int64 view of the u64 hashes)"
+        world, pad = len(self.n_hashes), self.pad_h
+        self._padded[: local_hashes.numel()] = local_hashes
+        self.dist.all_gather_into_tensor(self._all, self._padded)
+        pos = 0
+        for r in range(world):
+            nh = int(self.n_hashes[r])
+            self.hashes[pos:pos + nh] = self._all[r * pad: r * pad + nh]
+            pos += nh
+        return self.hashes[: self.total]
+
+
 def allgather_csr(torch, dist, local_hashes, local_sizes, device):
-    """All-gather variable-length CSR shards (rank order == row order).
-
-    local_hashes: int64 tensor (hashes viewed as int64) on `device`; local_sizes: int64 tensor.
-    Returns (hashes int64 tensor [total], sizes int64 numpy [n_rows_total]).
-    """
-    world = dist.get_world_size()
-    meta = torch.tensor([local_hashes.numel(), local_sizes.numel()], dtype=torch.int64, device=device)
-    metas = torch.empty(2 * world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(metas, meta)
-    metas = metas.cpu().numpy().reshape(world, 2)
-    max_h, max_r = int(metas[:, 0].max()), int(metas[:, 1].max())
-    pad_h = torch.zeros(max(max_h, 1), dtype=torch.int64, device=device)
-    pad_h[: local_hashes.numel()] = local_hashes
-    pad_s = torch.zeros(max(max_r, 1), dtype=torch.int64, device=device)
-    pad_s[: local_sizes.numel()] = local_sizes
-    all_h = torch.empty(world * pad_h.numel(), dtype=torch.int64, device=device)
-    all_s = torch.empty(world * pad_s.numel(), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(all_h, pad_h)
-    dist.all_gather_into_tensor(all_s, pad_s)
-    total = int(metas[:, 0].sum())
-    hashes = torch.empty(max(total, 1), dtype=torch.int64, device=device)
-    sizes = []
-    pos = 0
-    all_s_host = all_s.cpu().numpy()
-    for r in range(world):
-        nh, nr = int(metas[r, 0]), int(metas[r, 1])
-        hashes[pos:pos + nh] = all_h[r * pad_h.numel(): r * pad_h.numel() + nh]
-        sizes.append(all_s_host[r * pad_s.numel(): r * pad_s.numel() + nr])
-        pos += nh
-    return hashes[:total], np.concatenate(sizes) if sizes else np.zeros(0, np.int64)
+    """One-shot form of ShardGather: returns (hashes int64 tensor [total], sizes int64 numpy [n_rows_total])."""
+    sizes = local_sizes.cpu().numpy() if hasattr(local_sizes, "cpu") else np.asarray(local_sizes)
+    g = ShardGather(torch, dist, local_hashes.numel(), sizes, device)
+    return g.gather(local_hashes), g.sizes
 
 
-def allgather_sketchset(torch, dist, B, sset):
-    """All-gather a per-rank SketchSet into a full SketchSet on every rank."""
+def allgather_sketchset(torch, dist, B, sset, cache=None):
+    """All-gather a per-rank SketchSet into a full SketchSet on every rank.  `cache` (a dict the caller keeps) holds
+    the ShardGather of a step that repeats with the same shard sizes."""
     device = torch.device("cuda", torch.cuda.current_device())
     off = sset.offsets()
-    local = torch.empty(max(int(off[-1]), 1), dtype=torch.int64, device=device)
+    sizes = np.diff(off.astype(np.int64))
+    key = (int(off[-1]), len(sizes))
+    g = cache.get("g") if cache is not None and cache.get("key") == key and np.array_equal(cache.get("sizes"), sizes) else None
+    if g is None:
+        g = ShardGather(torch, dist, int(off[-1]), sizes, device)
+        if cache is not None:
+            cache.update(g=g, key=key, sizes=sizes, local=torch.empty(max(int(off[-1]), 1), dtype=torch.int64, device=device))
+    local = cache["local"] if cache is not None else torch.empty(max(int(off[-1]), 1), dtype=torch.int64, device=device)
     sset.copy_to_device(local.data_ptr())
-    sizes = torch.from_numpy(np.diff(off.astype(np.int64))).to(device)
-    hashes, all_sizes = allgather_csr(torch, dist, local[: int(off[-1])], sizes, device)
-    h_off = np.zeros(len(all_sizes) + 1, dtype=np.uint64)
-    h_off[1:] = np.cumsum(all_sizes)
-    d_off = torch.from_numpy(h_off.view(np.int64)).to(device)
-    return B.SketchSet.from_device(hashes.data_ptr(), d_off.data_ptr(), h_off, keepalive=(hashes, d_off))
+    hashes = g.gather(local[: int(off[-1])])
+    return B.SketchSet.from_device(hashes.data_ptr(), g.d_offsets.data_ptr(), g.offsets, keepalive=(hashes, g.d_offsets, g))
 
 
 class CompareShard:
-    """One rank's part of an N-GPU all-vs-all compare (see module docstring)."""
+    """One rank's part of an N-GPU all-vs-all compare.
+
+    step(): (1) all-gather of the sketch shards (as if every rank had sketched its own genomes); (2) this rank's
+    KEY RANGE of the hash space: sort, tags and whole-row counting of the hashes in range `rank` only
+    (smb_compare_counts_shard_dev) -- every stage shrinks with 1 / world; (3) one reduce-scatter of the partial
+    counters by row block (the only exchange of results: u32, (world - 1) / world of n^2 * 4 bytes per rank);
+    (4) float64 Jaccard rows of this rank's block.  gloo has no reduce-scatter: all-reduce + slice there."""
 
     def __init__(self, torch, dist, B, hashes, offsets, rank, world):
         self.torch, self.dist, self.B, self.rank, self.world = torch, dist, B, rank, world
@@ -77,13 +106,13 @@ class CompareShard:
         local = hashes[int(offsets[lo]):int(offsets[hi])].view(np.int64)
         sizes = np.diff(offsets.astype(np.int64))[lo:hi]
         self.pin_h = torch.from_numpy(local.copy()).pin_memory()
-        self.pin_s = torch.from_numpy(sizes.copy()).pin_memory()
         self.d_local = self.pin_h.to(self.device)
-        self.d_sizes = self.pin_s.to(self.device)
-        # experimental (SMB_JOIN_LAYOUT=stripe): every rank counts only its own block of rows, so there is
-        # no partial count matrix and no all-reduce
-        self.rows_direct = os.environ.get("SMB_JOIN_LAYOUT") == "stripe"
-        self.d_common = None if self.rows_direct else torch.zeros((n, n), dtype=torch.int32, device=self.device)
+        self.gatherer = ShardGather(torch, dist, len(local), sizes, self.device)
+        self.per = max(b1 - b0 for b0, b1 in zip(self.bounds[:-1], self.bounds[1:]))      # rows per reduce-scatter block
+        self.even = all(b1 - b0 == self.per for b0, b1 in zip(self.bounds[:-1], self.bounds[1:]))
+        rows_padded = self.per * world if self.even else n
+        self.d_partial = torch.zeros((rows_padded, n), dtype=torch.int32, device=self.device)
+        self.d_counts = torch.zeros((self.per, n), dtype=torch.int32, device=self.device)
         self.d_out = torch.empty((hi - lo, n), dtype=torch.float64, device=self.device)
         self.pin_out = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
         self.h2d_bytes = int(local.nbytes + sizes.nbytes)
@@ -93,20 +122,18 @@ class CompareShard:
         torch, dist, B = self.torch, self.dist, self.B
         if e2e:
             self.d_local.copy_(self.pin_h, non_blocking=True)
-            self.d_sizes.copy_(self.pin_s, non_blocking=True)
-        hashes, sizes = allgather_csr(torch, dist, self.d_local, self.d_sizes, self.device)
-        h_off = np.zeros(self.n + 1, dtype=np.uint64)
-        h_off[1:] = np.cumsum(sizes)
-        d_off = torch.from_numpy(h_off.view(np.int64)).to(self.device)
-        sset = B.SketchSet.from_device(hashes.data_ptr(), d_off.data_ptr(), h_off, keepalive=(hashes, d_off))
+        g = self.gatherer
+        hashes = g.gather(self.d_local)
+        sset = B.SketchSet.from_device(hashes.data_ptr(), g.d_offsets.data_ptr(), g.offsets, keepalive=(hashes, g.d_offsets))
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        if self.rows_direct:
-            B.compare_jaccard_rows_device(sset, lo, hi, self.d_out.data_ptr())
-        else:
-            self.d_common.zero_()
-            B.pairwise_counts_shard_device(sset, self.rank, self.world, self.d_common.data_ptr())
-            dist.all_reduce(self.d_common)
-            B.finalize_jaccard_rows_device(sset, self.d_common.data_ptr(), lo, hi, self.d_out.data_ptr())
+        B.compare_counts_shard_device(sset, self.rank, self.world, self.d_partial.data_ptr())
+        if self.even and dist.get_backend() == "nccl":
+            dist.reduce_scatter_tensor(self.d_counts, self.d_partial)
+            counts = self.d_counts
+        else:                                               # uneven blocks / gloo: sum everything, keep this rank's rows
+            dist.all_reduce(self.d_partial)
+            counts = self.d_partial[lo:hi].contiguous()
+        B.finalize_counts_rows_device(sset, counts.data_ptr(), lo, hi, self.d_out.data_ptr())
         if e2e:
             self.pin_out.copy_(self.d_out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -135,17 +162,26 @@ class ShardedDatabase:
         "Inverted index of this rank's block of rows (batch.SketchSet.build_index): counts and gather rounds probe it."
         return self.sset.build_index() if len(self.sset) else 0
 
+    def _shard_sizes(self):
+        "rows per rank (one small collective, cached: the sharding of a resident database does not change)"
+        if getattr(self, "_sizes", None) is None:
+            torch, dist = self.torch, self.dist
+            mine = torch.tensor([len(self.sset), int(self.sset.sizes().max()) if len(self.sset) else 0],
+                                dtype=torch.int64, device=self.device)
+            allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allv, mine)
+            allv = allv.cpu().numpy().reshape(self.world, 2)
+            self._sizes, self._max_row = allv[:, 0].copy(), int(allv[:, 1].max())
+        return self._sizes
+
     def search_counts(self, query):
-        "|query ∩ S_j| for every row of the whole database, on every rank."
+        "|query ∩ S_j| for every row of the whole database, on every rank (host arrays in and out)."
         torch, dist = self.torch, self.dist
-        local = self.B.one_vs_many(query, self.sset).astype(np.int64)
-        sizes = torch.tensor([len(local)], dtype=torch.int64, device=self.device)
-        all_sizes = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(all_sizes, sizes)
-        all_sizes = all_sizes.cpu().numpy()
-        pad = torch.zeros(int(all_sizes.max()) if len(all_sizes) else 1, dtype=torch.int64, device=self.device)
+        all_sizes = self._shard_sizes()
+        local = self.B.one_vs_many(query, self.sset).astype(np.int32)
+        pad = torch.zeros(max(int(all_sizes.max()), 1), dtype=torch.int32, device=self.device)
         pad[: len(local)] = torch.from_numpy(local).to(self.device)
-        out = torch.empty(self.world * pad.numel(), dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * pad.numel(), dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(out, pad)
         out = out.cpu().numpy().reshape(self.world, -1)
         return np.concatenate([out[r, : all_sizes[r]] for r in range(self.world)]).astype(np.uint32)
@@ -161,39 +197,40 @@ class ShardedDatabase:
         return d_all_counts
 
     def gather(self, query, threshold=1, max_rounds=None):
-        "Returns (global match rows, intersect sizes) in pick order -- identical on every rank."
+        """Returns (global match rows, intersect sizes) in pick order -- identical on every rank.
+        One collective per round: every rank contributes a fixed-size record (best count, global row, the row's
+        intersection with the remaining query); the host of every rank reads the records once, picks the winner
+        (largest count, lowest global row on ties == first inserted in the reference's Counter) and applies the
+        winner's intersection to its own counters."""
         torch, dist = self.torch, self.dist
         threshold = max(int(threshold), 1)
+        self._shard_sizes()
+        rec_len = 3 + max(self._max_row, 1)
         session = self.B.GatherSession(query, self.sset, threshold)
         ids, sizes = [], []
         max_rounds = self.n_total if max_rounds is None else max_rounds
+        rec = torch.zeros(rec_len, dtype=torch.int64, device=self.device)
+        all_rec = torch.empty(self.world * rec_len, dtype=torch.int64, device=self.device)
         while len(ids) < max_rounds:
             cnt, row = session.peek() if len(self.sset) else (0, 0)
-            mine = torch.tensor([cnt, self.row_begin + row], dtype=torch.int64, device=self.device)
-            allv = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(allv, mine)
-            allv = allv.cpu().numpy().reshape(self.world, 2)
-            best = int(allv[:, 0].max())
+            host_rec = np.zeros(rec_len, dtype=np.int64)
+            host_rec[0], host_rec[1] = cnt, self.row_begin + row
+            if cnt >= threshold:
+                isect = np.asarray(session.intersect(row), dtype=np.uint64)
+                host_rec[2] = len(isect)
+                host_rec[3:3 + len(isect)] = isect.view(np.int64)
+            rec.copy_(torch.from_numpy(host_rec))
+            dist.all_gather_into_tensor(all_rec, rec)
+            recs = all_rec.cpu().numpy().reshape(self.world, rec_len)
+            best = int(recs[:, 0].max())
             if best < threshold:
                 break
-            # ties: lowest global row (== first inserted in the reference's Counter)
-            cand = allv[allv[:, 0] == best]
-            grow = int(cand[:, 1].min())
-            owner = int(np.nonzero((allv[:, 0] == best) & (allv[:, 1] == grow))[0][0])
-            if owner == self.rank:
-                isect = session.intersect(grow - self.row_begin)
-                n = torch.tensor([len(isect)], dtype=torch.int64, device=self.device)
-            else:
-                isect, n = None, torch.zeros(1, dtype=torch.int64, device=self.device)
-            dist.broadcast(n, src=owner)
-            buf = torch.empty(int(n.item()), dtype=torch.int64, device=self.device)
-            if owner == self.rank and len(isect):
-                buf.copy_(torch.from_numpy(isect.view(np.int64)))
-            if buf.numel():
-                dist.broadcast(buf, src=owner)
-            isect = buf.cpu().numpy().view(np.uint64)
+            cand = np.nonzero(recs[:, 0] == best)[0]
+            owner = int(cand[np.argmin(recs[cand, 1])])
+            grow, n_isect = int(recs[owner, 1]), int(recs[owner, 2])
+            isect = recs[owner, 3:3 + n_isect].copy().view(np.uint64)
             ids.append(grow)
-            sizes.append(len(isect))
+            sizes.append(n_isect)
             if session.apply(isect) == 0:
                 break
         return np.array(ids, dtype=np.uint32), np.array(sizes, dtype=np.uint32)

@@ -129,6 +129,24 @@ def compare_shards_sum_to_full():
             rows = np.full((60, n), -1.0)
             B.finalize_jaccard_rows_device(sset, total.ctypes.data, 70, 130, rows.ctypes.data)
             assert np.array_equal(rows, jac[70:130]), algo
+    # whole-row counters by shard (the unit of a reduce-scatter by row blocks): stripe layout = key-range shards of the
+    # sorted stream; plain join / tile kernel = upper-triangle shards, mirrored
+    off_diag = ~np.eye(n, dtype=bool)
+    for envs in (dict(SMB_COMPARE_ALGO="join"), dict(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT="plain"),
+                 dict(SMB_COMPARE_ALGO="tile"), dict(SMB_COMPARE_ALGO="join", SMB_STRIPE_TAGS="u32")):
+        with env(**envs):
+            for shards in (1, 3, 8):
+                total = np.zeros((n, n), dtype=np.uint32)
+                for r in range(shards):
+                    part = np.full((n, n), 0xdeadbeef, dtype=np.uint32)            # every cell must be written
+                    B.compare_counts_shard_device(sset, r, shards, part.ctypes.data)
+                    np.fill_diagonal(part, 0)
+                    total += part
+                assert np.array_equal(total[off_diag], want[off_diag]), (envs, shards)
+            rows = np.full((60, n), -1.0)
+            block = np.ascontiguousarray(total[70:130])
+            B.finalize_counts_rows_device(sset, block.ctypes.data, 70, 130, rows.ctypes.data)
+            assert np.array_equal(rows, jac[70:130]), envs
     # rows too large for the shared-memory tables (warp-per-pair kernel): the shards must still split
     # the pairs, not each count all of them (round-1 advisor finding: counts came out x world_size)
     rng = np.random.Generator(np.random.PCG64(77))

@@ -92,13 +92,13 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     for (int c = 0; c < 2; ++c) {
         const int r0 = c ? half : 0, r1 = c ? n : half;
         if (r1 <= r0) continue;
-        StripeArgs a{tags.data(), pos.data(), off.data(), sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n};
+        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr};
         const int blocks = (r1 - r0 + R - 1) / R;
         if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true>(a); });
         else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false>(a); });
         if (upper) {
             const int t0 = r0 / 32, t1 = (r1 + 31) / 32;
-            smb_emu::launch(smb_emu::Dim3(t1, t1 - t0), 1024, 0, [&] { stripe_mirror_kernel(out.data(), n, r0, r1); });
+            smb_emu::launch(smb_emu::Dim3(t1, t1 - t0), 1024, 0, [&] { stripe_mirror_kernel<double>(out.data(), n, r0, r1); });
         }
     }
     dump(fout, out);

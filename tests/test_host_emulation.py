@@ -228,11 +228,11 @@ def test_join_walk_matches_oracle(join_emul):
 
 
 def test_join_stripe_helpers():
-    "rows per CTA for the shared-memory budget the kernel uses (227 KB minus its 352-byte header): 10 000 columns -> 5 rows."
+    "rows per CTA for the shared-memory budget the kernel uses (227 KB minus its 544-byte header): 10 000 columns -> 5 rows."
     exe = os.path.join(tempfile.gettempdir(), "smb_stripe_rows")
     src = os.path.join(tempfile.gettempdir(), "smb_stripe_rows.cu")
     with open(src, "w") as fh:
-        fh.write('#include <stdio.h>\n#include "%s"\nint main() { int ns[] = {1, 64, 1024, 10000, 58000, 58100, 200000};'
+        fh.write('#include <stdio.h>\n#include "%s"\nint main() { int ns[] = {1, 64, 1024, 10000, 57900, 58000, 200000};'
                  ' for (int n : ns) printf("%%d ", smb::stripe_rows_per_block(227 * 1024, n)); return 0; }\n'
                  % os.path.join(os.path.dirname(HERE), "sourmash_b200", "csrc", "join_stripe.cuh"))
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-DSMB_SIMT_EMUL=1", "-include", os.path.join(HERE, "host_emul", "simt.h"),

@@ -28,14 +28,16 @@ B.set_device(local)
 B.set_stream(torch.cuda.current_stream().cuda_stream)
 
 # ---- compare
-h, off = synth_sketches(700, mean=1500, sd=300, lo=100, hi=3000, n_families=7, pool=1800, seed=4)
-cs = CompareShard(torch, dist, B, h, off, rank, world)
-cs.step(e2e=True)
-lo, hi = cs.bounds[rank], cs.bounds[rank + 1]
-want = orc.compare_all_pairs(h, off, nthreads=8)
-got = cs.pin_out.numpy()
-assert got.shape == (hi - lo, 700)
-assert np.array_equal(got, want[lo:hi]), f"rank {rank}: compare rows {lo}:{hi} differ"
+for n_cmp in (704, 700):              # 704: equal row blocks (reduce-scatter); 700: uneven blocks at 8 ranks (all-reduce + slice)
+    h, off = synth_sketches(n_cmp, mean=1500, sd=300, lo=100, hi=3000, n_families=7, pool=1800, seed=4)
+    cs = CompareShard(torch, dist, B, h, off, rank, world)
+    for _ in range(2):                # the second step reuses every buffer
+        cs.step(e2e=True)
+    lo, hi = cs.bounds[rank], cs.bounds[rank + 1]
+    want = orc.compare_all_pairs(h, off, nthreads=8)
+    got = cs.pin_out.numpy()
+    assert got.shape == (hi - lo, n_cmp)
+    assert np.array_equal(got, want[lo:hi]), f"rank {rank}: compare rows {lo}:{hi} of {n_cmp} differ"
 
 # ---- sketch shards + all-gather
 NG = 2 * world + 1
@@ -62,6 +64,15 @@ sdb = ShardedDatabase(torch, dist, B, shard, 400, bb[rank])
 query = np.unique(np.concatenate([rws[5], rws[123][:500], rws[250][100:700], rws[399][::2], rws[77][:30]]))
 whole = B.SketchSet.from_host(hh, oo)
 assert np.array_equal(sdb.search_counts(query), B.one_vs_many(query, whole))
+big_q = np.unique(np.concatenate([query, np.random.Generator(np.random.PCG64(3)).integers(1, 2**54, size=300_000, dtype=np.uint64)]))
+d_q = torch.from_numpy(big_q.view(np.int64)).cuda()
+per = max(bb[i + 1] - bb[i] for i in range(world))
+d_loc = torch.zeros(per, dtype=torch.int32, device="cuda")
+d_all = torch.zeros(per * world, dtype=torch.int32, device="cuda")
+sdb.search_counts_device(d_q, d_loc, d_all)                       # large query: range-major pass per shard, counters all-gathered on the device
+got_all = d_all.cpu().numpy().reshape(world, per)
+got_all = np.concatenate([got_all[r, : bb[r + 1] - bb[r]] for r in range(world)])
+assert np.array_equal(got_all.astype(np.uint32), B.one_vs_many(big_q, whole))
 ids, sizes = sdb.gather(query, threshold=3)
 ids1, sizes1 = B.gather(query, whole, threshold=3)
 assert np.array_equal(ids, ids1) and np.array_equal(sizes, sizes1) and len(ids) >= 4, (ids, ids1)
