@@ -1,40 +1,32 @@
 #!/bin/bash
-# N-GPU bench (torchrun, NCCL) -- run with: gpurun --gpus N -- 'bash scripts/gpu_multi.sh N'
+# N-GPU verification + bench (torchrun, NCCL) -- run with: gpurun --gpus N -- 'bash scripts/gpu_multi.sh N [tag] [workloads]'
+# For every N in the list (default: just N) : multi_gpu_verify.py (results bit-identical to the oracle / the single-GPU
+# result), then bench.py for the default line (compare + sketch) and the search / gather workloads.
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-N=${1:-2}
-nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n${N}.json 2> gpurun_out/bench_n${N}.err
-echo "rc=$?"
-tail -15 gpurun_out/bench_n${N}.err
-python - <<PY
+NS=${1:-2}; TAG=${2:-r2}; WL=${3:-"both search gather"}
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+PORT=29511
+for N in $NS; do
+  if [ "$N" -gt 1 ]; then
+    RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"
+    PORT=$((PORT+1))
+    timeout 600 $RUN $PORT tests/tools/multi_gpu_verify.py > gpurun_out/verify_n${N}_${TAG}.log 2>&1
+    grep -E "multi-GPU verify|Error|assert|Traceback" gpurun_out/verify_n${N}_${TAG}.log | head -6
+  else
+    RUN=""
+  fi
+  for W in $WL; do
+    PORT=$((PORT+1))
+    if [ "$N" -gt 1 ]; then CMD="$RUN $PORT bench.py"; else CMD="python bench.py"; fi
+    timeout 900 $CMD --gpus $N --workload $W --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${W}_n${N}_${TAG}.json 2> gpurun_out/bench_${W}_n${N}_${TAG}.err
+    python - <<PY
 import json
 try:
-    lines=[l for l in open("gpurun_out/bench_n${N}.json") if l.startswith("{")]
-    print("stdout lines:", sum(1 for _ in open("gpurun_out/bench_n${N}.json")))
-    d=json.loads(lines[-1])
+    d=json.loads([l for l in open("gpurun_out/bench_${W}_n${N}_${TAG}.json") if l.startswith("{")][-1])
     for x in (d, d.get("sketch", {})):
-        if x: print(x["metric"], "n_gpus", x["n_gpus"], "value %.4g"%x["value"], "ms %.2f"%x["ms_per_step"], "e2e %.4g (%.1f ms)"%(x["e2e"]["value"], x["e2e"]["ms_per_step"]), "kernel_ms %.2f"%x["roofline"]["kernel_ms"])
+        if x: print("N=$N", x["metric"][:40], "value %.4g"%x["value"], "ms %.3f"%x["ms_per_step"], "e2e %.1f ms"%x["e2e"]["ms_per_step"], "clocks", (x.get("clocks") or {}).get("samples"))
 except Exception as e:
-    print("no json:", e); print(open("gpurun_out/bench_n${N}.json").read()[:2000])
+    print("N=$N $W: no json:", e); print(open("gpurun_out/bench_${W}_n${N}_${TAG}.err").read()[-1500:])
 PY
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-    tests/tools/multi_gpu_verify.py > gpurun_out/verify_n${N}.log 2>&1
-grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_n${N}.log | head -10
-# experimental: stripe layout, every rank counts its own block of rows (no all-reduce); verify, then bench
-SMB_JOIN_LAYOUT=stripe timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
-    tests/tools/multi_gpu_verify.py > gpurun_out/verify_stripe_n${N}.log 2>&1
-grep -E "multi-GPU verify|Error|assert" gpurun_out/verify_stripe_n${N}.log | head -5
-SMB_JOIN_LAYOUT=stripe timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
-    bench.py --gpus $N --workload compare --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stripe_n${N}.json 2> gpurun_out/bench_stripe_n${N}.err
-python -c "
-import json; d=json.loads([l for l in open('gpurun_out/bench_stripe_n${N}.json') if l.startswith('{')][-1]); print('stripe n=${N}: ms %.2f e2e %.1f ms'%(d['ms_per_step'], d['e2e']['ms_per_step']))"
-# configs[3] / configs[4] sharded by subject over the N GPUs (ShardedDatabase), without and with the inverted index
-for W in search gather; do
-  for IDX in "" "--index"; do
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 \
-        bench.py --gpus $N --workload $W $IDX --steps 3 --warmup 3 > gpurun_out/bench_${W}${IDX}_n${N}.json 2> gpurun_out/bench_${W}${IDX}_n${N}.err
-    python -c "
-import json; d=json.loads([l for l in open('gpurun_out/bench_${W}${IDX}_n${N}.json') if l.startswith('{')][-1]); print('${W} ${IDX} n=${N}: %.2f ms'%d['ms_per_step'], d.get('index',''))"
   done
 done

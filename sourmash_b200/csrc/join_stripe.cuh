@@ -29,7 +29,9 @@
 
 namespace smb {
 
-static constexpr int STRIPE_EBLK_LOG2 = 9;            // element blocks of the row lookup table
+static constexpr int STRIPE_EBLK_LOG2 = 11;           // element blocks of the row lookup table: 25 000 entries for 5e7 elements, so
+                                                      // the table and the row offsets it leads to stay in L1 (the tag kernel is bound
+                                                      // by L2 transactions: its scattered 4-byte writes of pos[] are enough of those)
 static constexpr int STRIPE_MAX_ROWS = 32;            // rows per CTA (upper bound)
 static constexpr int STRIPE_HEADER = 544;             // bytes in front of the counters: s_beg[32] + s_end[32] + control words, 16-aligned
 static constexpr int STRIPE_TAG_PAD = 128;            // head flags stored behind the end of the tag stream

@@ -24,7 +24,7 @@ static constexpr int RM_THREADS = 512;                // 3 CTAs per SM: 3 x (64 
 static constexpr int RM_BITMAP_LOG2 = 19;             // 512 Kbit = 64 KB
 static constexpr int RM_QUEUE = 128;                  // candidates per warp
 static constexpr int RM_UNROLL = 8;                   // 8-byte loads in flight per thread
-static constexpr u64 RM_HASH2 = 0x9E3779B97F4A7C15ull;
+static constexpr u32 RM_HASH2_32 = 0x9E3779B1u;       // second probe: multiplicative hash of the low word of (x - lo)
 
 // range of key x for ranges of `width` keys (x <= max_key, so the result is < P by construction of width)
 __host__ __device__ __forceinline__ u32 rm_range_of(u64 x, u64 width) { return (u32)(x / width); }
@@ -87,7 +87,7 @@ struct RangeMajorArgs {
 };
 
 __device__ __forceinline__ u32 rm_bit1(u64 d, u32 bm_shift) { return (u32)(d >> bm_shift); }
-__device__ __forceinline__ u32 rm_bit2(u64 d, u32 bm_log2) { return (u32)((d * RM_HASH2) >> (64 - bm_log2)); }
+__device__ __forceinline__ u32 rm_bit2(u64 d, u32 bm_log2) { return ((u32)d * RM_HASH2_32) >> (32u - bm_log2); }
 
 // settle the queued candidates of one warp: exact test against the query slice, then row attribution
 __device__ __forceinline__ void rm_drain(const RangeMajorArgs& a, const u32* __restrict__ queue, u32 count, u64 qlo, u64 qhi,
@@ -135,35 +135,61 @@ __global__ void __launch_bounds__(RM_THREADS, 3) one_vs_many_range_major_kernel(
     const u32* __restrict__ slice_p = a.slice + (size_t)p * a.n;
     const u64 begin = slice_p[0], end = slice_p[a.n];      // slice[(p + 1) * n] = start of the next part (or the total)
     u32 qn = 0;                                            // candidates in this warp's queue (warp-uniform)
+    const u32 sh2 = 32u - a.bm_log2;
     const u64 step = (u64)blockDim.x * RM_UNROLL;
-    for (u64 base = begin + (u64)warp * 32 * RM_UNROLL; base < end; base += step) {
-        u64 x[RM_UNROLL];
+
+    // Both probes for the eight elements of a lane, branch-free: bit 1 from the top bits of (x - lo), bit 2 from a
+    // multiplicative hash of its low word (hash bits: independent of the top bits).  hm = the lane's 8 verdicts.
+    auto probe8 = [&](const u64 (&x)[RM_UNROLL], u32 valid_mask) -> u32 {
+        u32 hm = 0;
 #pragma unroll
         for (int u = 0; u < RM_UNROLL; ++u) {
-            const u64 i = base + (u64)u * 32 + lane;
-            x[u] = i < end ? ld_stream_u64(a.rm + i) : lo; // padding lanes are never candidates (tested by index below)
-        }
-#pragma unroll
-        for (int u = 0; u < RM_UNROLL; ++u) {
-            const u64 i = base + (u64)u * 32 + lane;
             const u64 d = x[u] - lo;
-            const u32 b1 = rm_bit1(d, a.bm_shift);
-            bool hit = i < end && ((bitmap[b1 >> 5] >> (b1 & 31)) & 1u);
-            if (__any_sync(0xffffffffu, hit)) {
-                if (hit) { const u32 b2 = rm_bit2(d, a.bm_log2); hit = (bitmap[b2 >> 5] >> (b2 & 31)) & 1u; }
-                const u32 m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
-                        __syncwarp();
-                        rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
-                        __syncwarp();
-                        qn = 0;
-                    }
-                    if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)i;
-                    qn += (u32)__popc(m);
-                }
-            }
+            const u32 b1 = (u32)(d >> a.bm_shift);
+            const u32 b2 = ((u32)d * RM_HASH2_32) >> sh2;
+            const u32 h = (bitmap[b1 >> 5] >> (b1 & 31)) & (bitmap[b2 >> 5] >> (b2 & 31)) & 1u;
+            hm |= h << u;
         }
+        return hm & valid_mask;
+    };
+    // rare path: queue the hits of one iteration (positions base + 32 u + lane), draining when the queue is full
+    auto push8 = [&](u32 hm, u64 base) {
+#pragma unroll
+        for (int u = 0; u < RM_UNROLL; ++u) {
+            const bool hit = (hm >> u) & 1u;
+            const u32 m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0) continue;
+            if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
+                __syncwarp();
+                rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+                __syncwarp();
+                qn = 0;
+            }
+            if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(base + (u64)u * 32 + lane);
+            qn += (u32)__popc(m);
+        }
+    };
+
+    u64 base = begin + (u64)warp * 32 * RM_UNROLL;
+    for (; base + 32 * RM_UNROLL <= end; base += step) {   // whole iterations: no bounds tests
+        u64 x[RM_UNROLL];
+        const u64* __restrict__ src = a.rm + base + lane;
+#pragma unroll
+        for (int u = 0; u < RM_UNROLL; ++u) x[u] = ld_stream_u64(src + u * 32);
+        const u32 hm = probe8(x, 0xffu);
+        if (__any_sync(0xffffffffu, hm != 0)) push8(hm, base);
+    }
+    if (base < end) {                                      // the warp that holds the ragged end of the part
+        u64 x[RM_UNROLL];
+        u32 valid = 0;
+#pragma unroll
+        for (int u = 0; u < RM_UNROLL; ++u) {
+            const u64 i = base + (u64)u * 32 + lane;
+            x[u] = i < end ? ld_stream_u64(a.rm + i) : lo;
+            valid |= (i < end ? 1u : 0u) << u;
+        }
+        const u32 hm = probe8(x, valid);
+        if (__any_sync(0xffffffffu, hm != 0)) push8(hm, base);
     }
     __syncwarp();
     rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);

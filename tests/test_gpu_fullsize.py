@@ -200,7 +200,7 @@ def test_gather_50k_picks_equal_the_cpu_rounds(B):
     db, d_h, h_off = bench.build_database(torch, B, sizes, frac, query, 5002, 0, bench.N_DB_GATHER, overrides)
     ids, isizes = B.gather(query, db, threshold=50)
     want = bench._gather_on_host(query, overrides, 50)
-    assert list(zip(ids.tolist(), isizes.tolist())) == want and len(want) > 150
+    assert list(zip(ids.tolist(), isizes.tolist())) == want and len(want) > 80
     cm = B.one_vs_many(query, db)
     others = np.setdiff1d(np.arange(len(cm)), np.array(sorted(overrides)))
     assert cm[others].max() < 50                                               # only planted rows can reach the threshold
