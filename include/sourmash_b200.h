@@ -247,6 +247,8 @@ const uint64_t *smb_sketchset_device_offsets(const SmbSketchSet *set);
 /* new set holding, for every row, the prefix h <= max_hash (downsample_scaled,
  * sketch/minhash.rs:777-798) */
 SmbSketchSet *smb_sketchset_downsample(const SmbSketchSet *set, uint64_t max_hash);
+/* the given rows (any order) as a new resident set */
+SmbSketchSet *smb_sketchset_take_rows(const SmbSketchSet *set, const uint32_t *rows, uintptr_t n);
 
 /* sketching (replaces the per-record loop command_sketch.py:662-789 ->
  * signature_add_sequence -> SeqToHashes::next) --------------------------------------- */

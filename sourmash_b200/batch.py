@@ -175,6 +175,11 @@ class SketchSet:
     def downsample(self, max_hash):
         return SketchSet(rustcall(lib.smb_sketchset_downsample, self._ptr, int(max_hash)))
 
+    def take_rows(self, rows):
+        "The given rows (any order) as a new resident SketchSet."
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        return SketchSet(rustcall(lib.smb_sketchset_take_rows, self._ptr, _ptr(rows, "uint32_t *"), len(rows)))
+
     def copy_to_device(self, d_hashes_ptr, d_offsets_ptr=0):
         rustcall(lib.smb_sketchset_copy_to_device, self._ptr, ffi.cast("uint64_t *", int(d_hashes_ptr)),
                  ffi.cast("uint64_t *", int(d_offsets_ptr)))

@@ -1729,6 +1729,43 @@ SmbSketchSet* smb_sketchset_downsample(const SmbSketchSet* set, uint64_t max_has
     });
 }
 
+// rows `rows[0..n)` of a resident set (any order, repeats allowed) as a new resident set -- e.g. the few candidates of
+// a sharded prefetch that are replicated on every rank for the gather rounds
+SmbSketchSet* smb_sketchset_take_rows(const SmbSketchSet* set, const uint32_t* rows, uintptr_t n) {
+    return guarded<SmbSketchSet*>([&]() -> SmbSketchSet* {
+        cudaStream_t s = need_gpu();
+        auto out = std::make_unique<SmbSketchSet>();
+        out->n_rows = n;
+        out->h_off.assign(n + 1, 0);
+        std::vector<uint64_t> src_off(n + 1, 0);
+        std::vector<uint32_t> len(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) {
+            if (rows[i] >= set->n_rows) fail(SOURMASH_ERROR_CODE_MSG, "row index out of range");
+            src_off[i] = set->h_off[rows[i]];
+            len[i] = (uint32_t)(set->h_off[rows[i] + 1] - set->h_off[rows[i]]);
+            out->h_off[i + 1] = out->h_off[i] + len[i];
+        }
+        DevBuf<uint64_t> d_src(n + 1, s);
+        DevBuf<uint32_t> d_len(n + 1, s);
+        d_src.upload(src_off.data(), n + 1);
+        d_len.upload(len.data(), n + 1);
+        out->own_off.alloc(n + 1, s);
+        out->own_off.upload(out->h_off.data(), n + 1);
+        out->own_hashes.alloc(std::max<uint64_t>(out->total(), 1), s);
+        if (n) smb::launch_compact_rows(set->d_hashes, d_src.p, d_len.p, out->own_off.p, out->own_hashes.p, (int)n, s);
+        if (set->d_abunds) {
+            out->own_abunds.alloc(std::max<uint64_t>(out->total(), 1), s);
+            if (n) smb::launch_compact_rows(set->d_abunds, d_src.p, d_len.p, out->own_off.p, out->own_abunds.p, (int)n, s);
+        }
+        CK(cudaGetLastError());
+        sync(s);
+        out->d_off = out->own_off.p; out->d_hashes = out->own_hashes.p;
+        out->d_abunds = set->d_abunds ? out->own_abunds.p : nullptr;
+        out->finish_offsets();
+        return out.release();
+    });
+}
+
 static SketchParams make_params(const uint32_t* ksizes, uintptr_t n_ksizes, uint64_t scaled,
                                 uint32_t num, uint64_t seed, bool track) {
     SketchParams P;
@@ -1863,7 +1900,7 @@ void smb_compare_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint3
                 CK(smb::join_stripe_create_shard(set->d_hashes, set->d_off, (int)n, set->total(), mk, (int)shard, (int)n_shards, &js, s));
                 if (js) {
                     std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
-                    CK(smb::join_stripe_counts(js, 0, (int)n, d_counts, s));
+                    CK(smb::join_stripe_counts(js, d_counts, s));
                     if (t_profiling) t_timer_pairwise.end(s);
                     return;
                 }

@@ -36,8 +36,10 @@ __device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
 #ifdef SMB_SIMT_EMUL
 inline u32 ld_stream_u32(const u32* p) { return *p; }
 inline u64 ld_stream_u64(const u64* p) { return *p; }
+inline ulonglong2 ld_stream_u64x2(const ulonglong2* p) { return *p; }
 inline void st_stream_f64(double* p, double v) { *p = v; }
 #elif defined(__CUDACC__)
+__device__ __forceinline__ ulonglong2 ld_stream_u64x2(const ulonglong2* p) { return __ldcs(p); }
 __device__ __forceinline__ u32 ld_stream_u32(const u32* p) { return __ldcs(p); }
 __device__ __forceinline__ u64 ld_stream_u64(const u64* p) { return __ldcs(reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ void st_stream_f64(double* p, double v) { __stcs(p, v); }

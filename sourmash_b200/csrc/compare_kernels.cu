@@ -262,8 +262,8 @@ struct RangeMajor {
 int range_major_parts(u64 T) {
     const char* e = getenv("SMB_RM_RANGES");              // tests: few ranges on small sets
     if (e && atoi(e) > 0) return atoi(e);
-    // three CTAs per SM, a whole number of waves; fewer, larger parts for small sets
-    return T >= (32u << 20) ? SMB_B200_SMS * 9 : SMB_B200_SMS * 3;
+    // two CTAs per SM, a whole number of waves; fewer, larger parts for small sets
+    return T >= (32u << 20) ? SMB_B200_SMS * 10 : SMB_B200_SMS * 2;
 }
 
 // *out stays null (with cudaSuccess) when the layout does not apply (positions must fit 32 bits)
@@ -485,7 +485,7 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     js->sharded = n_shards > 1;
     {
         const char* layout = getenv("SMB_JOIN_LAYOUT");
-        js->upper_only = !(layout && !strcmp(layout, "stripe_full")) && !js->sharded;
+        js->upper_only = !(layout && !strcmp(layout, "stripe_full"));
         const char* tag = getenv("SMB_STRIPE_TAGS");                 // A/B: force 32-bit tags
         if (tag && !strcmp(tag, "u32")) js->tag16 = 0;
     }
@@ -589,7 +589,7 @@ static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_en
     if (row_end <= row_begin) return cudaSuccess;
     StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out, d_counts};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
-    const bool upper = js->upper_only && !d_counts;
+    const bool upper = js->upper_only;
     if (js->tag16) {
         if (upper) join_stripe_kernel<u16, true><<<blocks, 1024, js->smem, s>>>(a);
         else join_stripe_kernel<u16, false><<<blocks, 1024, js->smem, s>>>(a);
@@ -600,9 +600,13 @@ static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_en
     count_launches(1);
     return cudaGetLastError();
 }
-// raw counters (both directions, whole rows) of rows [row_begin, row_end): the partial counts of a key-range shard
-cudaError_t join_stripe_counts(const JoinStripe* js, int row_begin, int row_end, u32* d_counts, cudaStream_t s) {
-    return stripe_launch(js, row_begin, row_end, nullptr, d_counts, s);
+// raw counters of ALL rows (n x n, whole rows): the partial counts of a key-range shard.  Counted for the cells
+// (i, j > i) only and mirrored -- the counts of one key range are symmetric like the total -- unless SMB_JOIN_LAYOUT=stripe_full.
+cudaError_t join_stripe_counts(const JoinStripe* js, u32* d_counts, cudaStream_t s) {
+    cudaError_t e = stripe_launch(js, 0, js->n, nullptr, d_counts, s);
+    if (e != cudaSuccess) return e;
+    if (js->upper_only) launch_mirror_counts(d_counts, js->n, s);
+    return cudaGetLastError();
 }
 // counters of rows [row_begin, row_end) summed over the shards -> float64 Jaccard rows
 void launch_finalize_counts_rows(const u32* d_counts, const u64* off, int n, int row_begin, int row_end, double* d_out,

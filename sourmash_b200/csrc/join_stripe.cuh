@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
         const u32* __restrict__ srow = stripe + (size_t)al * n;
         if (a.out_counts) {                                // a shard of the keys: partial counts, summed over the shards later
             u32* __restrict__ crow = a.out_counts + (size_t)(row - a.row_begin) * n;
-            for (u32 j = threadIdx.x; j < n; j += blockDim.x) crow[j] = srow[j];
+            for (u32 j = threadIdx.x; j < n; j += blockDim.x)
+                if (!UPPER || j >= (u32)row) crow[j] = srow[j];     // UPPER: the caller mirrors (a shard's counts are symmetric)
             continue;
         }
         const u64 si = a.sizes[row];

@@ -20,7 +20,7 @@
 
 namespace smb {
 
-static constexpr int RM_THREADS = 512;                // 3 CTAs per SM: 3 x (64 KB bitmap + 4 KB queues) of shared memory
+static constexpr int RM_THREADS = 512;                // 2 CTAs per SM (registers: two batches of loads live per thread), 64 KB bitmap each
 static constexpr int RM_BITMAP_LOG2 = 19;             // 512 Kbit = 64 KB
 static constexpr int RM_QUEUE = 128;                  // candidates per warp
 static constexpr int RM_UNROLL = 8;                   // 8-byte loads in flight per thread
@@ -105,7 +105,7 @@ __device__ __forceinline__ void rm_drain(const RangeMajorArgs& a, const u32* __r
 }
 
 // one CTA per key range
-__global__ void __launch_bounds__(RM_THREADS, 3) one_vs_many_range_major_kernel(RangeMajorArgs a) {
+__global__ void __launch_bounds__(RM_THREADS, 2) one_vs_many_range_major_kernel(RangeMajorArgs a) {
     SMB_DYN_SHARED(u32, rm_smem);                          // [2^bm_log2 / 32] bitmap words, then the warps' queues
     SMB_SHARED u64 s_q[2];
     u32* bitmap = rm_smem;
@@ -136,24 +136,18 @@ __global__ void __launch_bounds__(RM_THREADS, 3) one_vs_many_range_major_kernel(
     const u64 begin = slice_p[0], end = slice_p[a.n];      // slice[(p + 1) * n] = start of the next part (or the total)
     u32 qn = 0;                                            // candidates in this warp's queue (warp-uniform)
     const u32 sh2 = 32u - a.bm_log2;
-    const u64 step = (u64)blockDim.x * RM_UNROLL;
 
-    // Both probes for the eight elements of a lane, branch-free: bit 1 from the top bits of (x - lo), bit 2 from a
-    // multiplicative hash of its low word (hash bits: independent of the top bits).  hm = the lane's 8 verdicts.
-    auto probe8 = [&](const u64 (&x)[RM_UNROLL], u32 valid_mask) -> u32 {
-        u32 hm = 0;
-#pragma unroll
-        for (int u = 0; u < RM_UNROLL; ++u) {
-            const u64 d = x[u] - lo;
-            const u32 b1 = (u32)(d >> a.bm_shift);
-            const u32 b2 = ((u32)d * RM_HASH2_32) >> sh2;
-            const u32 h = (bitmap[b1 >> 5] >> (b1 & 31)) & (bitmap[b2 >> 5] >> (b2 & 31)) & 1u;
-            hm |= h << u;
-        }
-        return hm & valid_mask;
+    // Both probes of one element, branch-free: bit 1 from the top bits of (x - lo), bit 2 from a multiplicative hash of
+    // its low word (hash bits: independent of the top bits)
+    auto probe = [&](u64 x) -> u32 {
+        const u64 d = x - lo;
+        const u32 b1 = (u32)(d >> a.bm_shift);
+        const u32 b2 = ((u32)d * RM_HASH2_32) >> sh2;
+        return (bitmap[b1 >> 5] >> (b1 & 31)) & (bitmap[b2 >> 5] >> (b2 & 31)) & 1u;
     };
-    // rare path: queue the hits of one iteration (positions base + 32 u + lane), draining when the queue is full
-    auto push8 = [&](u32 hm, u64 base) {
+    // rare path: queue the hits of one batch (bit u of hm = the lane's element at position pos0 + stride * u),
+    // draining when the queue is full
+    auto push = [&](u32 hm, u64 pos0, u32 stride) {
 #pragma unroll
         for (int u = 0; u < RM_UNROLL; ++u) {
             const bool hit = (hm >> u) & 1u;
@@ -165,31 +159,65 @@ __global__ void __launch_bounds__(RM_THREADS, 3) one_vs_many_range_major_kernel(
                 __syncwarp();
                 qn = 0;
             }
-            if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(base + (u64)u * 32 + lane);
+            if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(pos0 + (u64)stride * u);
             qn += (u32)__popc(m);
         }
     };
-
-    u64 base = begin + (u64)warp * 32 * RM_UNROLL;
-    for (; base + 32 * RM_UNROLL <= end; base += step) {   // whole iterations: no bounds tests
-        u64 x[RM_UNROLL];
-        const u64* __restrict__ src = a.rm + base + lane;
-#pragma unroll
-        for (int u = 0; u < RM_UNROLL; ++u) x[u] = ld_stream_u64(src + u * 32);
-        const u32 hm = probe8(x, 0xffu);
-        if (__any_sync(0xffffffffu, hm != 0)) push8(hm, base);
-    }
-    if (base < end) {                                      // the warp that holds the ragged end of the part
-        u64 x[RM_UNROLL];
-        u32 valid = 0;
+    // a batch of up to 32 * RM_UNROLL elements with bounds tests (the ragged head and tail of the part)
+    auto checked = [&](u64 s0, u64 s1) {
+        u32 hm = 0;
 #pragma unroll
         for (int u = 0; u < RM_UNROLL; ++u) {
-            const u64 i = base + (u64)u * 32 + lane;
-            x[u] = i < end ? ld_stream_u64(a.rm + i) : lo;
-            valid |= (i < end ? 1u : 0u) << u;
+            const u64 i = s0 + (u64)u * 32 + lane;
+            if (i < s1) hm |= probe(ld_stream_u64(a.rm + i)) << u;
         }
-        const u32 hm = probe8(x, valid);
-        if (__any_sync(0xffffffffu, hm != 0)) push8(hm, base);
+        if (__any_sync(0xffffffffu, hm != 0)) push(hm, s0 + lane, 32);
+    };
+
+    // main loop: 16-byte loads (positions are even), RM_UNROLL elements per lane per batch, and the NEXT batch's loads
+    // are issued before the current batch is probed -- the kernel lives on bytes in flight
+    constexpr int V = RM_UNROLL / 2;                       // 16-byte loads per lane per batch
+    const u64 abeg = (begin + 1) & ~1ull;
+    const u64 batch = 32ull * RM_UNROLL;
+    const u64 n_batches = end > abeg ? (end - abeg) / batch : 0;
+    const u32 n_warps = blockDim.x >> 5;
+    if (warp == 0 && abeg > begin && begin < end) checked(begin, abeg);               // one element in front of the aligned start
+    if (warp == n_warps - 1 && abeg + n_batches * batch < end) checked(abeg + n_batches * batch, end);
+    const ulonglong2* __restrict__ src = reinterpret_cast<const ulonglong2*>(a.rm + abeg) + lane;
+    ulonglong2 cur[V], nxt[V];
+    u64 k = warp;
+    if (k < n_batches) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) cur[v] = ld_stream_u64x2(src + (k * V + v) * 32);
+    }
+    for (; k < n_batches; k += n_warps) {
+        const u64 kn = k + n_warps;
+        if (kn < n_batches) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) nxt[v] = ld_stream_u64x2(src + (kn * V + v) * 32);
+        }
+        u32 hm = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) hm |= (probe(cur[v].x) << (2 * v)) | (probe(cur[v].y) << (2 * v + 1));
+        if (__any_sync(0xffffffffu, hm != 0)) {
+            // element (v, half) of the lane sits at abeg + k * batch + v * 64 + 2 * lane + half: bit u = 2 v + half
+#pragma unroll
+            for (int u = 0; u < RM_UNROLL; ++u) {
+                const bool hit = (hm >> u) & 1u;
+                const u32 m = __ballot_sync(0xffffffffu, hit);
+                if (m == 0) continue;
+                if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
+                    __syncwarp();
+                    rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+                    __syncwarp();
+                    qn = 0;
+                }
+                if (hit) queue[qn + __popc(m & ((1u << lane) - 1u))] = (u32)(abeg + k * batch + (u64)(u >> 1) * 64 + 2 * lane + (u & 1));
+                qn += (u32)__popc(m);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) cur[v] = nxt[v];
     }
     __syncwarp();
     rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);

@@ -196,8 +196,57 @@ class ShardedDatabase:
             self.dist.all_gather_into_tensor(d_all_counts, d_local_counts)
         return d_all_counts
 
+    REPLICATE_LIMIT = 1 << 26            # hashes: candidate rows are replicated when together they are smaller than this
+
     def gather(self, query, threshold=1, max_rounds=None):
         """Returns (global match rows, intersect sizes) in pick order -- identical on every rank.
+
+        The expensive part of gather is the prefetch pass over the database, and that is what the shards divide.  The
+        rounds only ever touch the rows whose overlap reached the threshold (CounterGather holds prefetch matches only,
+        index/__init__.py:302-320) -- typically a few hundred genomes -- so those rows are all-gathered once (their
+        global ids, lengths and hashes) and every rank runs the rounds on its own copy: identical picks everywhere, no
+        collective inside the loop.  Only when the candidates are a large part of the database does the loop stay
+        sharded (`gather_sharded_rounds`: one collective per round)."""
+        torch, dist = self.torch, self.dist
+        threshold = max(int(threshold), 1)
+        counts = self.B.one_vs_many(query, self.sset) if len(self.sset) else np.zeros(0, np.uint32)
+        cand = np.nonzero(counts >= threshold)[0].astype(np.uint32)
+        sizes = np.asarray(self.sset.sizes(), dtype=np.int64)[cand] if len(cand) else np.zeros(0, np.int64)
+        meta = torch.tensor([len(cand), int(sizes.sum())], dtype=torch.int64, device=self.device)
+        metas = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(metas, meta)
+        metas = metas.cpu().numpy().reshape(self.world, 2)
+        if int(metas[:, 1].sum()) > self.REPLICATE_LIMIT:
+            return self.gather_sharded_rounds(query, threshold, max_rounds)
+        if int(metas[:, 0].sum()) == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        # one padded all-gather: [global ids | lengths | hashes] of this rank's candidates
+        pad_r, pad_h = max(int(metas[:, 0].max()), 1), max(int(metas[:, 1].max()), 1)
+        rec = np.zeros(2 * pad_r + pad_h, dtype=np.int64)
+        rec[: len(cand)] = cand.astype(np.int64) + self.row_begin
+        rec[pad_r: pad_r + len(cand)] = sizes
+        if len(cand):
+            hh, _ = self.sset.take_rows(cand).to_host()
+            rec[2 * pad_r: 2 * pad_r + len(hh)] = np.asarray(hh, dtype=np.uint64).view(np.int64)
+        mine = torch.from_numpy(rec).to(self.device)
+        allv = torch.empty(self.world * len(rec), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allv, mine)
+        allv = allv.cpu().numpy().reshape(self.world, len(rec))
+        ids, lens, parts = [], [], []
+        for r in range(self.world):                       # rank order == global row order (contiguous shards)
+            nr, nh = int(metas[r, 0]), int(metas[r, 1])
+            ids.append(allv[r, :nr])
+            lens.append(allv[r, pad_r: pad_r + nr])
+            parts.append(allv[r, 2 * pad_r: 2 * pad_r + nh])
+        ids, lens = np.concatenate(ids), np.concatenate(lens)
+        off = np.zeros(len(ids) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        cset = self.B.SketchSet.from_host(np.concatenate(parts).view(np.uint64), off)
+        picks, isect = self.B.gather(query, cset, threshold=threshold, max_rounds=max_rounds)
+        return ids[np.asarray(picks, dtype=np.int64)].astype(np.uint32), np.asarray(isect, dtype=np.uint32)
+
+    def gather_sharded_rounds(self, query, threshold=1, max_rounds=None):
+        """The rounds with the counters left sharded (used when the candidates are too many to replicate).
         One collective per round: every rank contributes a fixed-size record (best count, global row, the row's
         intersection with the remaining query); the host of every rank reads the records once, picks the winner
         (largest count, lowest global row on ties == first inserted in the reference's Counter) and applies the

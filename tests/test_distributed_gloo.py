@@ -56,6 +56,11 @@ class _FakeSet:
         return len(self._rows)
     def sizes(self):
         return np.array([len(r) for r in self._rows], dtype=np.int64)
+    def take_rows(self, rows):
+        return _FakeSet([self._rows[int(i)] for i in rows])
+    def to_host(self):
+        import oracle as orc
+        return orc.to_csr(self._rows)
 
 
 class _FakeBatch:
@@ -65,6 +70,30 @@ class _FakeBatch:
     def one_vs_many(query, sset):
         import oracle as orc
         return np.array([orc.count_common(query, r) for r in sset._rows], dtype=np.uint32)
+
+    class SketchSet:
+        @staticmethod
+        def from_host(h, off):
+            return _FakeSet([h[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)])
+
+    @staticmethod
+    def gather(query, sset, threshold=1, max_rounds=None):
+        "single-process CounterGather rounds: largest remaining overlap first, lowest row on ties"
+        import oracle as orc
+        rows, cur = sset._rows, np.array(query, dtype=np.uint64)
+        cnt = np.array([orc.count_common(cur, r) for r in rows], dtype=np.int64)
+        ids, sizes = [], []
+        while len(cnt) and (max_rounds is None or len(ids) < max_rounds):
+            j = int(np.argmax(cnt))
+            if cnt[j] < max(threshold, 1):
+                break
+            isect = np.intersect1d(cur, rows[j])
+            ids.append(j); sizes.append(len(isect))
+            cnt = cnt - np.array([orc.count_common(isect, r) for r in rows], dtype=np.int64)
+            cur = np.setdiff1d(cur, isect)
+            if not len(cur):
+                break
+        return np.array(ids, dtype=np.uint32), np.array(sizes, dtype=np.uint32)
 
     class GatherSession:
         def __init__(self, query, sset, min_count=1):
@@ -117,6 +146,8 @@ def _sharded_worker(rank, world, port, q):
             if not len(cur):
                 break
         ok = ok and list(zip(ids.tolist(), sizes.tolist())) == want and ids[0] == 4
+        ids2, sizes2 = db.gather_sharded_rounds(query, threshold=5)          # the loop with sharded counters: same picks
+        ok = ok and list(zip(ids2.tolist(), sizes2.tolist())) == want
         q.put((rank, bool(ok), len(ids)))
     finally:
         dist.destroy_process_group()

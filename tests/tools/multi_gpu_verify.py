@@ -76,6 +76,8 @@ assert np.array_equal(got_all.astype(np.uint32), B.one_vs_many(big_q, whole))
 ids, sizes = sdb.gather(query, threshold=3)
 ids1, sizes1 = B.gather(query, whole, threshold=3)
 assert np.array_equal(ids, ids1) and np.array_equal(sizes, sizes1) and len(ids) >= 4, (ids, ids1)
+ids2, sizes2 = sdb.gather_sharded_rounds(query, threshold=3)        # the rounds with sharded counters (one collective per round)
+assert np.array_equal(ids2, ids1) and np.array_equal(sizes2, sizes1)
 dist.barrier()
 if rank == 0:
     print(f"multi-GPU verify ok on {world} GPUs: compare rows bit-identical to the oracle, "
