@@ -150,10 +150,11 @@ def sketch_workload(n_genomes=N_GENOMES):
 
 
 def host_cores():
-    """Usable host threads: the smallest of cpu_count, the affinity mask and the cgroup CPU quota."""
+    """Usable host threads: the smallest of cpu_count, the affinity mask (the one the process started with) and the
+    cgroup CPU quota."""
     n = os.cpu_count() or 1
     try:
-        n = min(n, len(os.sched_getaffinity(0)))
+        n = min(n, len(_ALL_CPUS if _ALL_CPUS is not None else os.sched_getaffinity(0)))
     except Exception:
         pass
     try:
@@ -214,6 +215,7 @@ def ncu_source(key):
 def cpu_compare_sample(h, off, ncores, target_pairs):
     """Time the oracle's compare_serial restatement on rows [0, R) (all columns j > i)."""
     import oracle as orc
+    all_host_cpus()
     n = len(off) - 1
     rows, pairs = 0, 0
     while rows < n and pairs < target_pairs:
@@ -227,6 +229,7 @@ def cpu_compare_sample(h, off, ncores, target_pairs):
 
 def cpu_sketch_sample(seqs, offs, ncores, n_genomes):
     import oracle as orc
+    all_host_cpus()
     sub_off = offs[: n_genomes + 1]
     sub = seqs[: int(sub_off[-1])]
     mx = orc.max_hash_for_scaled(SCALED)
@@ -277,6 +280,35 @@ def run_reference(args):
     emit_json(line)
 
 
+_ALL_CPUS = None
+
+
+def all_host_cpus():
+    "give the process back every CPU it started with (the CPU arm uses all host threads it can)"
+    if _ALL_CPUS is not None:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except OSError:
+            pass
+
+
+def bind_to_gpu_cpus(torch, local_rank):
+    """Pin this process to the CPUs next to its GPU (what `numactl` does for a PCIe-bound job): the pinned host buffers
+    of the end-to-end legs are then allocated on the GPU's own NUMA node.  Best effort: returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        global _ALL_CPUS
+        _ALL_CPUS = os.sched_getaffinity(0)
+        before = len(_ALL_CPUS)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return "cpu affinity %d -> %d cpus (GPU-local)" % (before, len(os.sched_getaffinity(0)))
+    except Exception as exc:                                       # noqa: BLE001
+        return "cpu affinity unchanged (%s)" % type(exc).__name__
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -286,6 +318,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    log("[bench] rank %d: %s" % (rank, bind_to_gpu_cpus(torch, local_rank)))
     dist = None
     if world > 1:
         # keep stdout clean for the single JSON line: NCCL's banner / debug output goes to stderr
@@ -737,6 +770,7 @@ def _bench_search(args, torch, dist, B, rank, world, timed, query, db, d_h, h_of
         # CPU arm on a bounded sample: the reference's walk (count_common per subject) over the first rows; its counts
         # are also the parity check of the GPU counters for those rows
         import oracle as orc
+        all_host_cpus()
         ncores = host_cores()
         n_sample = min(hi - lo, 60 * ncores)
         hh, oo = _rows_to_host(torch, db, d_h, h_off, n_sample)
@@ -805,6 +839,7 @@ def _bench_gather(args, torch, dist, B, rank, world, timed, query, db, d_h, h_of
     if rank == 0 and not args.no_cpu_baseline:
         # only planted rows can reach the threshold (a random row shares ~0 hashes with the query): the CPU rounds run
         # over them; equality of the pick list (rows and intersection sizes, in order) is the parity check
+        all_host_cpus()
         t = time.perf_counter()
         want = _gather_on_host(query, overrides, 50)
         dt = time.perf_counter() - t

@@ -45,13 +45,23 @@ class ShardGather:
         self.offsets[1:] = np.cumsum(self.sizes)
         self.total = int(self.n_hashes.sum())
         self.d_offsets = torch.from_numpy(self.offsets.view(np.int64)).to(device)
-        self._padded = torch.zeros(self.pad_h, dtype=torch.int64, device=device)
-        self._all = torch.empty(world * self.pad_h, dtype=torch.int64, device=device)
         self.hashes = torch.empty(max(self.total, 1), dtype=torch.int64, device=device)
+        starts = np.concatenate([[0], np.cumsum(self.n_hashes)])
+        # every rank's shard lands where it belongs in the gathered array: the views of an all_gather with shards of
+        # different sizes (NCCL: one grouped broadcast per rank straight into its view -- no padding, no compaction copy)
+        self._views = [self.hashes[int(starts[r]):int(starts[r + 1])] for r in range(world)]
+        self._uneven_ok = dist.get_backend() == "nccl" and all(int(x) > 0 for x in self.n_hashes)
+        if not self._uneven_ok:                           # gloo (CPU tests) / an empty shard: padded blocks + compaction
+            self._padded = torch.zeros(self.pad_h, dtype=torch.int64, device=device)
+            self._all = torch.empty(world * self.pad_h, dtype=torch.int64, device=device)
 
     def gather(self, local_hashes):
         "all ranks' hashes, compacted, in `self.hashes[:total]` (int64 view of the u64 hashes)"
-        world, pad = len(self.n_hashes), self.pad_h
+        world = len(self.n_hashes)
+        if self._uneven_ok:
+            self.dist.all_gather(self._views, local_hashes)
+            return self.hashes[: self.total]
+        pad = self.pad_h
         self._padded[: local_hashes.numel()] = local_hashes
         self.dist.all_gather_into_tensor(self._all, self._padded)
         pos = 0
