@@ -316,9 +316,11 @@ void smb_pairwise_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint
  * writes its partial counters of every cell (i, j), i != j, into d_counts (n*n u32, every cell written, nothing to
  * zero).  With the stripe layout the shard is key range `shard` of the hash space -- sort, tags and counting all
  * shrink with 1/n_shards; otherwise the upper-triangle shards above, mirrored.  Partial matrices add up. */
-void smb_compare_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint32_t n_shards, uint32_t *d_counts);
+void smb_compare_counts_shard_dev(const SmbSketchSet *set, uint32_t shard, uint32_t n_shards, void *d_counts, uint32_t bits);
+/* (bits = 32: uint32_t counters; bits = 16: uint16_t counters, allowed when every row is shorter than 65 536 hashes --
+ * half the bytes to exchange; two of them added as one uint32_t never carry into each other) */
 /* summed whole-row counters of rows [row_begin, row_end) (row_begin first, leading dimension n) -> float64 Jaccard rows */
-void smb_finalize_counts_rows_dev(const SmbSketchSet *set, const uint32_t *d_counts_rows, uint64_t row_begin,
+void smb_finalize_counts_rows_dev(const SmbSketchSet *set, const void *d_counts_rows, uint32_t bits, uint64_t row_begin,
                                   uint64_t row_end, double *d_out);
 /* d_out[(i - row_begin) * n + j] = jaccard(i, j) for row_begin <= i < row_end, from a complete
  * upper-triangular count matrix */

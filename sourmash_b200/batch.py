@@ -279,14 +279,14 @@ def pairwise_counts_shard_device(sset, shard, n_shards, d_common_ptr):
              ffi.cast("uint32_t *", int(d_common_ptr)))
 
 
-def compare_counts_shard_device(sset, shard, n_shards, d_counts_ptr):
-    "Partial counters of shard `shard` as whole rows (n*n u32, device): they add up over the shards (see the header)."
-    rustcall(lib.smb_compare_counts_shard_dev, sset._ptr, int(shard), int(n_shards), ffi.cast("uint32_t *", int(d_counts_ptr)))
+def compare_counts_shard_device(sset, shard, n_shards, d_counts_ptr, bits=32):
+    "Partial counters of shard `shard` as whole rows (n*n counters of `bits` bits, device): they add up over the shards (see the header)."
+    rustcall(lib.smb_compare_counts_shard_dev, sset._ptr, int(shard), int(n_shards), ffi.cast("void *", int(d_counts_ptr)), int(bits))
 
 
-def finalize_counts_rows_device(sset, d_counts_rows_ptr, row_begin, row_end, d_out_ptr):
+def finalize_counts_rows_device(sset, d_counts_rows_ptr, row_begin, row_end, d_out_ptr, bits=32):
     "Summed whole-row counters of rows [row_begin, row_end) -> float64 Jaccard rows (device memory)."
-    rustcall(lib.smb_finalize_counts_rows_dev, sset._ptr, ffi.cast("uint32_t *", int(d_counts_rows_ptr)), int(row_begin),
+    rustcall(lib.smb_finalize_counts_rows_dev, sset._ptr, ffi.cast("void *", int(d_counts_rows_ptr)), int(bits), int(row_begin),
              int(row_end), ffi.cast("double *", int(d_out_ptr)))
 
 

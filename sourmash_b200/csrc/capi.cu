@@ -1885,12 +1885,14 @@ void smb_pairwise_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint
     });
 }
 
-void smb_compare_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint32_t n_shards, uint32_t* d_counts) {
+void smb_compare_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint32_t n_shards, void* d_counts, uint32_t bits) {
     guarded_void([&] {
         cudaStream_t s = need_gpu();
         const size_t n = set->n_rows;
         if (n == 0) return;
         if (n_shards == 0 || shard >= n_shards) fail(SOURMASH_ERROR_CODE_MSG, "bad shard index");
+        if (bits != 32 && bits != 16) fail(SOURMASH_ERROR_CODE_MSG, "counter width must be 32 or 16 bits");
+        if (bits == 16 && set->max_len >= 65536) fail(SOURMASH_ERROR_CODE_MSG, "16-bit counters need rows shorter than 65536 hashes");
         const uint64_t mk = set_max_key(*set, s);
         if (smb::join_stripe_enabled() && set->total()) {
             t_last_join = plan_join(*set, mk, s);
@@ -1900,29 +1902,34 @@ void smb_compare_counts_shard_dev(const SmbSketchSet* set, uint32_t shard, uint3
                 CK(smb::join_stripe_create_shard(set->d_hashes, set->d_off, (int)n, set->total(), mk, (int)shard, (int)n_shards, &js, s));
                 if (js) {
                     std::unique_ptr<smb::JoinStripe, void (*)(smb::JoinStripe*)> guard(js, smb::join_stripe_destroy);
-                    CK(smb::join_stripe_counts(js, d_counts, s));
+                    CK(smb::join_stripe_counts(js, d_counts, (int)bits, s));
                     if (t_profiling) t_timer_pairwise.end(s);
                     return;
                 }
                 if (t_profiling) t_timer_pairwise.end(s);
             }
         }
-        // tile kernel / global-reduction join: upper-triangle shards, completed to whole rows
-        CK(cudaMemsetAsync(d_counts, 0, n * n * sizeof(uint32_t), s));
-        pairwise_counts_dev(*set, nullptr, 0, d_counts, nullptr, n, s, smb::TileShard{(int)shard, (int)n_shards});
-        smb::launch_mirror_counts(d_counts, (int)n, s);
+        // tile kernel / global-reduction join: upper-triangle shards (u32), completed to whole rows, narrowed if asked
+        DevBuf<uint32_t> wide;
+        uint32_t* d32 = (uint32_t*)d_counts;
+        if (bits == 16) { wide.alloc(n * n, s); d32 = wide.p; }
+        CK(cudaMemsetAsync(d32, 0, n * n * sizeof(uint32_t), s));
+        pairwise_counts_dev(*set, nullptr, 0, d32, nullptr, n, s, smb::TileShard{(int)shard, (int)n_shards});
+        smb::launch_mirror_counts(d32, 32, (int)n, s);
+        if (bits == 16) smb::launch_narrow_counts(d32, (uint64_t)n * n, (uint16_t*)d_counts, s);
         CK(cudaGetLastError());
+        if (bits == 16) sync(s);                           // `wide` is released when this scope ends
     });
 }
 
-void smb_finalize_counts_rows_dev(const SmbSketchSet* set, const uint32_t* d_counts_rows, uint64_t row_begin, uint64_t row_end,
-                                  double* d_out) {
+void smb_finalize_counts_rows_dev(const SmbSketchSet* set, const void* d_counts_rows, uint32_t bits, uint64_t row_begin,
+                                  uint64_t row_end, double* d_out) {
     guarded_void([&] {
         cudaStream_t s = need_gpu();
         const size_t n = set->n_rows;
         if (row_end > n) row_end = n;
         if (row_begin >= row_end) return;
-        smb::launch_finalize_counts_rows(d_counts_rows, set->d_off, (int)n, (int)row_begin, (int)row_end, d_out, s);
+        smb::launch_finalize_counts_rows(d_counts_rows, (int)bits, set->d_off, (int)n, (int)row_begin, (int)row_end, d_out, s);
         CK(cudaGetLastError());
     });
 }

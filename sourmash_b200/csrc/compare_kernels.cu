@@ -585,9 +585,11 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
     return join_stripe_create_shard(h, off, n, T, max_key, 0, 1, out, s);
 }
 
-static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_end, double* d_out, u32* d_counts, cudaStream_t s) {
+static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_end, double* d_out, u32* d_counts, u16* d_counts16,
+                                 cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
-    StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out, d_counts};
+    StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out,
+                 d_counts, d_counts16};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
     const bool upper = js->upper_only;
     if (js->tag16) {
@@ -602,31 +604,41 @@ static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_en
 }
 // raw counters of ALL rows (n x n, whole rows): the partial counts of a key-range shard.  Counted for the cells
 // (i, j > i) only and mirrored -- the counts of one key range are symmetric like the total -- unless SMB_JOIN_LAYOUT=stripe_full.
-cudaError_t join_stripe_counts(const JoinStripe* js, u32* d_counts, cudaStream_t s) {
-    cudaError_t e = stripe_launch(js, 0, js->n, nullptr, d_counts, s);
+cudaError_t join_stripe_counts(const JoinStripe* js, void* d_counts, int bits, cudaStream_t s) {
+    cudaError_t e = bits == 16 ? stripe_launch(js, 0, js->n, nullptr, nullptr, (u16*)d_counts, s)
+                               : stripe_launch(js, 0, js->n, nullptr, (u32*)d_counts, nullptr, s);
     if (e != cudaSuccess) return e;
-    if (js->upper_only) launch_mirror_counts(d_counts, js->n, s);
+    if (js->upper_only) launch_mirror_counts(d_counts, bits, js->n, s);
     return cudaGetLastError();
 }
 // counters of rows [row_begin, row_end) summed over the shards -> float64 Jaccard rows
-void launch_finalize_counts_rows(const u32* d_counts, const u64* off, int n, int row_begin, int row_end, double* d_out,
+void launch_finalize_counts_rows(const void* d_counts, int bits, const u64* off, int n, int row_begin, int row_end, double* d_out,
                                  cudaStream_t s) {
     if (row_end <= row_begin || n <= 0) return;
     dim3 grid((n + 255) / 256, row_end - row_begin);
-    stripe_finalize_counts_kernel<<<grid, 256, 0, s>>>(d_counts, off, n, row_begin, row_end, d_out); count_launches(1);
+    if (bits == 16) stripe_finalize_counts_kernel<u16><<<grid, 256, 0, s>>>((const u16*)d_counts, off, n, row_begin, row_end, d_out);
+    else stripe_finalize_counts_kernel<u32><<<grid, 256, 0, s>>>((const u32*)d_counts, off, n, row_begin, row_end, d_out);
+    count_launches(1);
 }
-// c[j][i] = c[i][j] for j > i: the upper-triangle counters of the tile kernel / the global-reduction join as whole rows
-void launch_mirror_counts(u32* d_counts, int n, cudaStream_t s) {
+// c[j][i] = c[i][j] for j > i: upper-triangle counters completed to whole rows
+void launch_mirror_counts(void* d_counts, int bits, int n, cudaStream_t s) {
     if (n <= 0) return;
     const int t = (n + 31) / 32;
-    stripe_mirror_kernel<u32><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>(d_counts, n, 0, n); count_launches(1);
+    if (bits == 16) stripe_mirror_kernel<u16><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>((u16*)d_counts, n, 0, n);
+    else stripe_mirror_kernel<u32><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>((u32*)d_counts, n, 0, n);
+    count_launches(1);
+}
+void launch_narrow_counts(const u32* in, u64 total, u16* out, cudaStream_t s) {
+    if (!total) return;
+    stripe_narrow_counts_kernel<<<(unsigned)std::min<u64>((total + 255) / 256, (u64)SMB_B200_SMS * 32), 256, 0, s>>>(in, total, out);
+    count_launches(1);
 }
 
 // float64 Jaccard rows [row_begin, row_end) of the all-vs-all matrix into d_out (row_begin first)
 cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s) {
     (void)off;
-    return stripe_launch(js, row_begin, row_end, d_out, nullptr, s);
+    return stripe_launch(js, row_begin, row_end, d_out, nullptr, nullptr, s);
 }
 // upper-only mode: the cells (i, j < i) of rows [row_begin, row_end) from the finished upper parts of rows
 // < row_end; d_full = row 0 of the whole n x n matrix.  No-op in the two-direction mode.

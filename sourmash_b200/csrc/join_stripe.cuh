@@ -188,6 +188,7 @@ struct StripeArgs {
     int n, rows_per_block, row_begin, row_end;
     double* out;             // float64 Jaccard rows, row `row_begin` first, leading dimension n (null: counts only)
     u32* out_counts;         // raw counters of the rows instead (a key-range shard's partial counts), same layout
+    u16* out_counts16;       // ... as 16-bit counters (rows shorter than 65 536 hashes: half the bytes to exchange)
 };
 
 // One CTA = rows [r0, r1) of the result.  Work items are (row, chunk of 32 consecutive elements), handed to the
@@ -310,6 +311,12 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
                 if (!UPPER || j >= (u32)row) crow[j] = srow[j];     // UPPER: the caller mirrors (a shard's counts are symmetric)
             continue;
         }
+        if (a.out_counts16) {
+            u16* __restrict__ crow = a.out_counts16 + (size_t)(row - a.row_begin) * n;
+            for (u32 j = threadIdx.x; j < n; j += blockDim.x)
+                if (!UPPER || j >= (u32)row) crow[j] = (u16)srow[j];
+            continue;
+        }
         const u64 si = a.sizes[row];
         double* __restrict__ orow = a.out + (size_t)(row - a.row_begin) * n;
         for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
@@ -344,14 +351,20 @@ __global__ void __launch_bounds__(256) stripe_slice_ranges_kernel(const u64* __r
     eend[r] = off[r] + beg[r] + cnt[r];
 }
 
+// u32 counters -> u16 (the upper-triangle shards of the tile kernel / the global-reduction join, narrowed for the exchange)
+__global__ void __launch_bounds__(256) stripe_narrow_counts_kernel(const u32* __restrict__ in, u64 total, u16* __restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) out[i] = (u16)in[i];
+}
+
 // counters of rows [row_begin, row_end) (row_begin first, whole rows), summed over the shards -> float64 Jaccard rows
-__global__ void __launch_bounds__(256) stripe_finalize_counts_kernel(const u32* __restrict__ counts, const u64* __restrict__ off,
+template <typename CountT>
+__global__ void __launch_bounds__(256) stripe_finalize_counts_kernel(const CountT* __restrict__ counts, const u64* __restrict__ off,
                                                                     int n, int row_begin, int row_end, double* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = row_begin + (int)blockIdx.y;
     if (j >= n || i >= row_end) return;
     const size_t cell = (size_t)(i - row_begin) * n + j;
-    st_stream_f64(out + cell, stripe_jaccard(counts[cell], off[i + 1] - off[i], off[j + 1] - off[j], i == j));
+    st_stream_f64(out + cell, stripe_jaccard((u32)counts[cell], off[i + 1] - off[i], off[j + 1] - off[j], i == j));
 }
 
 // out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 32 x 32 tiles through shared memory, reads

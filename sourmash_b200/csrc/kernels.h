@@ -83,9 +83,10 @@ cudaError_t join_stripe_create(const uint64_t* h, const uint64_t* off, int n, ui
 // of a block of rows into float64 Jaccard rows; launch_mirror_counts completes upper-triangle counters to whole rows.
 cudaError_t join_stripe_create_shard(const uint64_t* h, const uint64_t* off, int n, uint64_t n_elements, uint64_t max_key,
                                      int shard, int n_shards, JoinStripe** out, cudaStream_t s);
-void launch_mirror_counts(uint32_t* d_counts, int n, cudaStream_t s);
-cudaError_t join_stripe_counts(const JoinStripe* js, uint32_t* d_counts, cudaStream_t s);
-void launch_finalize_counts_rows(const uint32_t* d_counts, const uint64_t* off, int n, int row_begin, int row_end,
+void launch_mirror_counts(void* d_counts, int bits, int n, cudaStream_t s);          // bits: 32 or 16 (counter width)
+void launch_narrow_counts(const uint32_t* in, uint64_t total, uint16_t* out, cudaStream_t s);
+cudaError_t join_stripe_counts(const JoinStripe* js, void* d_counts, int bits, cudaStream_t s);
+void launch_finalize_counts_rows(const void* d_counts, int bits, const uint64_t* off, int n, int row_begin, int row_end,
                                  double* d_out, cudaStream_t s);
 cudaError_t join_stripe_rows(const JoinStripe* js, const uint64_t* off, int row_begin, int row_end, double* d_out,
                              cudaStream_t s);

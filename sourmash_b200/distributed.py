@@ -103,7 +103,8 @@ class CompareShard:
     step(): (1) all-gather of the sketch shards (as if every rank had sketched its own genomes); (2) this rank's
     KEY RANGE of the hash space: sort, tags and whole-row counting of the hashes in range `rank` only
     (smb_compare_counts_shard_dev) -- every stage shrinks with 1 / world; (3) one reduce-scatter of the partial
-    counters by row block (the only exchange of results: u32, (world - 1) / world of n^2 * 4 bytes per rank);
+    counters by row block (the only exchange of results: (world - 1) / world of n^2 * 2 bytes per rank with 16-bit
+    counters, * 4 with 32-bit ones);
     (4) float64 Jaccard rows of this rank's block.  gloo has no reduce-scatter: all-reduce + slice there."""
 
     def __init__(self, torch, dist, B, hashes, offsets, rank, world):
@@ -121,8 +122,13 @@ class CompareShard:
         self.per = max(b1 - b0 for b0, b1 in zip(self.bounds[:-1], self.bounds[1:]))      # rows per reduce-scatter block
         self.even = all(b1 - b0 == self.per for b0, b1 in zip(self.bounds[:-1], self.bounds[1:]))
         rows_padded = self.per * world if self.even else n
-        self.d_partial = torch.zeros((rows_padded, n), dtype=torch.int32, device=self.device)
-        self.d_counts = torch.zeros((self.per, n), dtype=torch.int32, device=self.device)
+        # 16-bit counters when every sketch is shorter than 65 536 hashes (a count never exceeds the shorter row): half
+        # the bytes through NVLink.  The reduce-scatter adds them two at a time as int32 -- sums stay below 65 536, so
+        # nothing carries from one counter into its neighbour.
+        self.bits = 16 if (n % 2 == 0 and int(self.gatherer.sizes.max() if len(self.gatherer.sizes) else 0) < 65536) else 32
+        cdtype = torch.int16 if self.bits == 16 else torch.int32
+        self.d_partial = torch.zeros((rows_padded, n), dtype=cdtype, device=self.device)
+        self.d_counts = torch.zeros((self.per, n), dtype=cdtype, device=self.device)
         self.d_out = torch.empty((hi - lo, n), dtype=torch.float64, device=self.device)
         self.pin_out = torch.empty((hi - lo, n), dtype=torch.float64).pin_memory()
         self.h2d_bytes = int(local.nbytes + sizes.nbytes)
@@ -136,14 +142,15 @@ class CompareShard:
         hashes = g.gather(self.d_local)
         sset = B.SketchSet.from_device(hashes.data_ptr(), g.d_offsets.data_ptr(), g.offsets, keepalive=(hashes, g.d_offsets))
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        B.compare_counts_shard_device(sset, self.rank, self.world, self.d_partial.data_ptr())
+        B.compare_counts_shard_device(sset, self.rank, self.world, self.d_partial.data_ptr(), bits=self.bits)
+        wide = (lambda t: t.view(torch.int32)) if self.bits == 16 else (lambda t: t)
         if self.even and dist.get_backend() == "nccl":
-            dist.reduce_scatter_tensor(self.d_counts, self.d_partial)
+            dist.reduce_scatter_tensor(wide(self.d_counts), wide(self.d_partial))
             counts = self.d_counts
         else:                                               # uneven blocks / gloo: sum everything, keep this rank's rows
-            dist.all_reduce(self.d_partial)
+            dist.all_reduce(wide(self.d_partial))
             counts = self.d_partial[lo:hi].contiguous()
-        B.finalize_counts_rows_device(sset, counts.data_ptr(), lo, hi, self.d_out.data_ptr())
+        B.finalize_counts_rows_device(sset, counts.data_ptr(), lo, hi, self.d_out.data_ptr(), bits=self.bits)
         if e2e:
             self.pin_out.copy_(self.d_out, non_blocking=True)
             torch.cuda.current_stream().synchronize()

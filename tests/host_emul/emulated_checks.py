@@ -135,18 +135,21 @@ def compare_shards_sum_to_full():
     for envs in (dict(SMB_COMPARE_ALGO="join"), dict(SMB_COMPARE_ALGO="join", SMB_JOIN_LAYOUT="plain"),
                  dict(SMB_COMPARE_ALGO="tile"), dict(SMB_COMPARE_ALGO="join", SMB_STRIPE_TAGS="u32")):
         with env(**envs):
-            for shards in (1, 3, 8):
-                total = np.zeros((n, n), dtype=np.uint32)
-                for r in range(shards):
-                    part = np.full((n, n), 0xdeadbeef, dtype=np.uint32)            # every cell must be written
-                    B.compare_counts_shard_device(sset, r, shards, part.ctypes.data)
-                    np.fill_diagonal(part, 0)
-                    total += part
-                assert np.array_equal(total[off_diag], want[off_diag]), (envs, shards)
-            rows = np.full((60, n), -1.0)
-            block = np.ascontiguousarray(total[70:130])
-            B.finalize_counts_rows_device(sset, block.ctypes.data, 70, 130, rows.ctypes.data)
-            assert np.array_equal(rows, jac[70:130]), envs
+            for bits, dt in ((32, np.uint32), (16, np.uint16)):
+                for shards in (1, 3, 8):
+                    total = np.zeros((n, n), dtype=dt)
+                    for r in range(shards):
+                        part = np.full((n, n), 0xbeef, dtype=dt)                       # every cell must be written
+                        B.compare_counts_shard_device(sset, r, shards, part.ctypes.data, bits=bits)
+                        np.fill_diagonal(part, 0)
+                        total += part
+                    assert np.array_equal(total[off_diag], want[off_diag].astype(dt)), (envs, bits, shards)
+                    if bits == 16:                        # what the reduce-scatter does: pairs of counters added as one u32
+                        assert np.array_equal((total.view(np.uint32) + 0).view(np.uint16), total)
+                rows = np.full((60, n), -1.0)
+                block = np.ascontiguousarray(total[70:130])
+                B.finalize_counts_rows_device(sset, block.ctypes.data, 70, 130, rows.ctypes.data, bits=bits)
+                assert np.array_equal(rows, jac[70:130]), (envs, bits)
     # rows too large for the shared-memory tables (warp-per-pair kernel): the shards must still split
     # the pairs, not each count all of them (round-1 advisor finding: counts came out x world_size)
     rng = np.random.Generator(np.random.PCG64(77))

@@ -92,7 +92,7 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     for (int c = 0; c < 2; ++c) {
         const int r0 = c ? half : 0, r1 = c ? n : half;
         if (r1 <= r0) continue;
-        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr};
+        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr};
         const int blocks = (r1 - r0 + R - 1) / R;
         if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true>(a); });
         else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false>(a); });

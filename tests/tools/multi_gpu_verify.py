@@ -28,7 +28,7 @@ B.set_device(local)
 B.set_stream(torch.cuda.current_stream().cuda_stream)
 
 # ---- compare
-for n_cmp in (704, 700):              # 704: equal row blocks (reduce-scatter); 700: uneven blocks at 8 ranks (all-reduce + slice)
+for n_cmp in (704, 700, 701):         # 704: equal row blocks (reduce-scatter, 16-bit counters); 700: uneven blocks at 8 ranks (all-reduce + slice); 701: odd n (32-bit counters)
     h, off = synth_sketches(n_cmp, mean=1500, sd=300, lo=100, hi=3000, n_families=7, pool=1800, seed=4)
     cs = CompareShard(torch, dist, B, h, off, rank, world)
     for _ in range(2):                # the second step reuses every buffer
