@@ -449,9 +449,8 @@ cudaError_t join_estimate(const u64* h, const u64* off, int n, u64 max_key, unsi
 // ------------------------------------------------------------------------------------
 struct JoinStripe {
     cudaStream_t stream = 0;
-    void* mem = nullptr;      // tags + rem + pos + sizes (+ the slice ranges of a key-range shard)
+    void* mem = nullptr;      // tags + pos + sizes (+ the slice ranges of a key-range shard)
     void* tags = nullptr;
-    u16* rem = nullptr;
     u32 *pos = nullptr, *sizes = nullptr;
     const u64 *ebeg = nullptr, *eend = nullptr;
     u64 T = 0;                // elements in the stream (all of the set, or one key range of it)
@@ -517,12 +516,11 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     const size_t Tp = (size_t)((T + 63) & ~63ull);
     const size_t Tall_p = (size_t)((T_all + 63) & ~63ull);
     const size_t Tt = Tp + STRIPE_TAG_PAD;                          // the tag stream + its padding of head flags
-    // tags | rem (u16: half a u32 slot each) | pos (indexed by CSR element: the whole set's size) | sizes | slice ranges of a shard
-    if ((e = cudaMallocAsync(&js->mem, (Tt + Tt / 2 + Tall_p + np) * sizeof(u32) + (js->sharded ? 2 * np * sizeof(u64) : 0), s)) != cudaSuccess)
+    // tags | pos (indexed by CSR element: the whole set's size) | sizes | slice ranges of a shard
+    if ((e = cudaMallocAsync(&js->mem, (Tt + Tall_p + np) * sizeof(u32) + (js->sharded ? 2 * np * sizeof(u64) : 0), s)) != cudaSuccess)
         return e;
     js->tags = js->mem;
-    js->rem = (u16*)((u32*)js->mem + Tt);
-    js->pos = (u32*)js->mem + Tt + Tt / 2;
+    js->pos = (u32*)js->mem + Tt;
     js->sizes = js->pos + Tall_p;
     stripe_sizes_kernel<<<(n + 255) / 256, 256, 0, s>>>(off, n, js->sizes); count_launches(1);
     if (js->sharded) {
@@ -576,15 +574,9 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     }
     // 4. tags + inverse permutation
     stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T_all, eblk);
-    const unsigned rgrid = (unsigned)std::min<u64>((T + STRIPE_REM_CHUNK - 1) / STRIPE_REM_CHUNK, (u64)SMB_B200_SMS * 64);
-    if (js->tag16) {
-        stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos);
-        stripe_rem_kernel<u16><<<rgrid, STRIPE_REM_THREADS, 0, s>>>((const u16*)js->tags, T, js->rem);
-    } else {
-        stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos);
-        stripe_rem_kernel<u32><<<rgrid, STRIPE_REM_THREADS, 0, s>>>((const u32*)js->tags, T, js->rem);
-    }
-    count_launches(3);
+    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos);
+    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos);
+    count_launches(2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *out = guard.release();
     return cudaSuccess;
@@ -596,7 +588,7 @@ cudaError_t join_stripe_create(const u64* h, const u64* off, int n, u64 T, u64 m
 static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_end, double* d_out, u32* d_counts, u16* d_counts16,
                                  cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
-    StripeArgs a{js->tags, js->rem, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out,
+    StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out,
                  d_counts, d_counts16};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
     const bool upper = js->upper_only;

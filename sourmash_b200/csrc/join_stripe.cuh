@@ -177,53 +177,9 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__
     if (gt < (u64)STRIPE_TAG_PAD) tags[T + gt] = (TagT)StripeTag<TagT>::HEAD;
 }
 
-// rem[q] = number of members of q's group that lie BEHIND q in the stream (the distance to the next head flag, minus
-// one).  The count kernel then knows how many tags to read behind an element before it reads any of them: no head tests,
-// no ballots, and the reads do not depend on each other.  One CTA per chunk of STRIPE_REM_CHUNK positions: every thread
-// finds the first head flag in its 8 positions, a suffix-min over the threads (and a short look-ahead behind the chunk:
-// the stream ends in head flags) gives each thread the next head flag behind its positions.
-static constexpr int STRIPE_REM_ITEMS = 8;
-static constexpr int STRIPE_REM_THREADS = 256;
-static constexpr int STRIPE_REM_CHUNK = STRIPE_REM_ITEMS * STRIPE_REM_THREADS;
-
-template <typename TagT>
-__global__ void __launch_bounds__(STRIPE_REM_THREADS) stripe_rem_kernel(const TagT* __restrict__ tags, u64 T, u16* __restrict__ rem) {
-    constexpr u32 HEAD = StripeTag<TagT>::HEAD;
-    SMB_SHARED u32 s_first[STRIPE_REM_THREADS + 1];        // first head flag at or behind thread t's positions (chunk-relative)
-    for (u64 c0 = (u64)blockIdx.x * STRIPE_REM_CHUNK; c0 < T; c0 += (u64)gridDim.x * STRIPE_REM_CHUNK) {
-        const u32 t = threadIdx.x;
-        const u64 p0 = c0 + (u64)t * STRIPE_REM_ITEMS;
-        u32 heads = 0;                                     // bit i: position p0 + i carries a head flag (positions >= T do: padding)
-#pragma unroll
-        for (int i = 0; i < STRIPE_REM_ITEMS; ++i)
-            heads |= ((p0 + i >= T || ((u32)tags[p0 + i] & HEAD)) ? 1u : 0u) << i;
-        constexpr u32 NONE = 0xffffffffu;
-        s_first[t] = heads ? (u32)(t * STRIPE_REM_ITEMS + (__ffs(heads) - 1)) : NONE;
-        if (t == 0) {                                      // first head flag behind the chunk (the padding guarantees one)
-            u64 p = c0 + STRIPE_REM_CHUNK;
-            while (p < T && !((u32)tags[p] & HEAD)) ++p;
-            s_first[STRIPE_REM_THREADS] = (u32)(p - c0);
-        }
-        __syncthreads();
-        // suffix minimum over the threads behind t (serial over at most a few entries: a group is ~70 positions = 9 threads;
-        // the loop stops at the first thread that holds a head flag)
-        u32 next = NONE;
-        for (u32 k = t + 1; k <= STRIPE_REM_THREADS; ++k) { next = s_first[k]; if (next != NONE) break; }
-        __syncthreads();
-#pragma unroll
-        for (int i = STRIPE_REM_ITEMS - 1; i >= 0; --i) {  // walk the thread's positions back to front
-            const u64 p = p0 + i;
-            const u32 rel = t * STRIPE_REM_ITEMS + (u32)i;
-            if (p < T) rem[p] = (u16)(next - rel - 1);     // groups hold at most n <= 58 000 rows: fits 16 bits
-            if ((heads >> i) & 1u) next = rel;
-        }
-    }
-}
-
 // ---- the count kernel -------------------------------------------------------------------------------------
 struct StripeArgs {
     const void* tags;        // u16 or u32 (template parameter of the kernel)
-    const u16* rem;          // members behind each stream position (stripe_rem_kernel)
     const u32* pos;
     const u64* ebeg;         // per row: the CSR elements [ebeg[r], eend[r]) that are in the stream -- the whole row
     const u64* eend;         //   (off, off + 1), or its slice of one key range when the stream holds a shard of the keys
@@ -263,6 +219,7 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
     __syncthreads();
     const u32 lane = lane_id();
     const u32 n_items = s_ctl[1] * (u32)rows;
+    const u32 le_mask = (2u << lane) - 1u;                // lanes <= lane
     const u32 lt_mask = (1u << lane) - 1u;                // lanes <  lane
     // tags[q + 1 + lane]: the stream is padded with head flags behind its end (stripe_tag_kernel), and T < 2^32 - 128,
     // so forward reads need no bounds checks and 32-bit positions do not wrap
@@ -282,30 +239,47 @@ __global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
         const u32 my_q = have ? ld_stream_u32(a.pos + e) : 0u;
         u32* row_ptr = stripe + (size_t)r * n;
 
-        // ---- members behind the element (higher rows).  rem says how many there are, so the tag reads of two
-        // elements (64 tags each) are issued together and nothing waits for a vote.
-        const u32 my_r = have ? (u32)a.rem[my_q] : 0u;
-        u32 todo = __ballot_sync(0xffffffffu, my_r != 0);
+        // ---- members behind the element (higher rows): 64 tags per element are requested at once (groups of
+        // the benchmark have ~35 members behind an element on average), two elements per round
+        u32 nxt = HEAD;
+        if (have) nxt = (u32)tags[(size_t)my_q + 1];
+        u32 todo = __ballot_sync(0xffffffffu, (nxt & HEAD) == 0);
         while (todo) {
             const int j0 = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int j1 = todo ? __ffs(todo) - 1 : j0;
-            const bool two = todo != 0;
+            const int j1 = todo ? __ffs(todo) - 1 : -1;
             todo &= todo - (todo ? 1u : 0u);
-            const u32 q0 = __shfl_sync(0xffffffffu, my_q, j0), r0 = __shfl_sync(0xffffffffu, my_r, j0);
-            const u32 q1 = __shfl_sync(0xffffffffu, my_q, j1), r1 = two ? __shfl_sync(0xffffffffu, my_r, j1) : 0u;
-            const bool a00 = lane < r0, a01 = lane + 32 < r0, a10 = lane < r1, a11 = lane + 32 < r1;
-            u32 t00 = 0, t01 = 0, t10 = 0, t11 = 0;
-            if (a00) t00 = (u32)fwd[q0];
-            if (a01) t01 = (u32)fwd[q0 + 32];
-            if (a10) t10 = (u32)fwd[q1];
-            if (a11) t11 = (u32)fwd[q1 + 32];
-            if (a00) atomicAdd(row_ptr + (t00 & ~HEAD), 1u);
-            if (a01) atomicAdd(row_ptr + (t01 & ~HEAD), 1u);
-            if (a10) atomicAdd(row_ptr + (t10 & ~HEAD), 1u);
-            if (a11) atomicAdd(row_ptr + (t11 & ~HEAD), 1u);
-            for (u32 b = lane + 64; b < r0; b += 32) atomicAdd(row_ptr + ((u32)fwd[q0 + b - lane] & ~HEAD), 1u);   // > 64 members behind
-            for (u32 b = lane + 64; b < r1; b += 32) atomicAdd(row_ptr + ((u32)fwd[q1 + b - lane] & ~HEAD), 1u);
+            const u32 q0 = __shfl_sync(0xffffffffu, my_q, j0);
+            const u32 q1 = __shfl_sync(0xffffffffu, my_q, j1 < 0 ? j0 : j1);
+            const u32 t00 = (u32)fwd[q0], t01 = (u32)fwd[q0 + 32];
+            u32 t10 = HEAD, t11 = HEAD;
+            if (j1 >= 0) { t10 = (u32)fwd[q1]; t11 = (u32)fwd[q1 + 32]; }
+            {
+                u32 m = __ballot_sync(0xffffffffu, (t00 & HEAD) != 0);
+                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t00 & ~HEAD), 1u);
+                if (m == 0) {
+                    m = __ballot_sync(0xffffffffu, (t01 & HEAD) != 0);
+                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t01 & ~HEAD), 1u);
+                    for (u32 it = 2; m == 0; ++it) {       // more than 64 members behind
+                        const u32 tt = (u32)fwd[q0 + 32 * it];
+                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
+                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                    }
+                }
+            }
+            if (j1 >= 0) {                                 // uniform in the warp
+                u32 m = __ballot_sync(0xffffffffu, (t10 & HEAD) != 0);
+                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t10 & ~HEAD), 1u);
+                if (m == 0) {
+                    m = __ballot_sync(0xffffffffu, (t11 & HEAD) != 0);
+                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t11 & ~HEAD), 1u);
+                    for (u32 it = 2; m == 0; ++it) {
+                        const u32 tt = (u32)fwd[q1 + 32 * it];
+                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
+                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                    }
+                }
+            }
         }
         if (UPPER) continue;
 

@@ -85,13 +85,6 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     smb_emu::launch((n + 63) / 64 + 1, 64, 0, [&] { stripe_sizes_kernel(off.data(), n, sizes.data()); });
     std::vector<TagT> tags(T + STRIPE_TAG_PAD + 1);
     smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data()); });
-    std::vector<u16> rem(T + STRIPE_TAG_PAD + 1, 0xdead);
-    smb_emu::launch(3, STRIPE_REM_THREADS, 0, [&] { stripe_rem_kernel<TagT>(tags.data(), T, rem.data()); });
-    for (u64 q = 0; q < T; ++q) {                              // rem = distance to the next group head, minus one
-        u64 p = q + 1;
-        while (p < T && !(tags[p] & StripeTag<TagT>::HEAD)) ++p;
-        if (rem[q] != (u16)(p - q - 1)) return 7;
-    }
     std::vector<double> out((size_t)n * n, -1.0);
     const size_t smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
     // two launches over row chunks, like the host path of smb_compare_jaccard
@@ -99,7 +92,7 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     for (int c = 0; c < 2; ++c) {
         const int r0 = c ? half : 0, r1 = c ? n : half;
         if (r1 <= r0) continue;
-        StripeArgs a{tags.data(), rem.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr};
+        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr};
         const int blocks = (r1 - r0 + R - 1) / R;
         if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true>(a); });
         else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false>(a); });
