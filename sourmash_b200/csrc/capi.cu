@@ -2404,6 +2404,40 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
         const bool small_rows = smb::plan_pairwise(cdb->max_len, std::max(q_max, set_max_key(*cdb, s)),
                                                    (int)cdb->n_rows).tables_per_cta > 0;
         DevBuf<uint64_t> d_qoff(2, s);
+        if (small_rows && !cdb->index && max_rounds <= 0xffffffffull) {
+            // Rounds picked on the device (search_kernels.cuh): argmax + pick, intersect the picked row with the live
+            // query, one-vs-many of the intersection over the candidates, flag the consumed hashes -- five launches per
+            // round and NO readback; the host enqueues rounds in batches and looks at the pick counter once per batch.
+            const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, cdb->n_rows);   // a row is picked at most once
+            DevBuf<uint32_t> d_rows(cap + 1, s), d_sizes(cap + 1, s), d_state(2, s);
+            d_state.zero();
+            st->delta.zero();
+            smb::GatherPicks g{d_rows.p, d_sizes.p, d_state.p, threshold, cap};
+            uint32_t state[2] = {0, 0};
+            const uint32_t batch = 16;
+            for (uint32_t issued = 0; !state[1] && issued < cap + 1; issued += batch) {
+                for (uint32_t k = 0; k < batch; ++k) {
+                    smb::launch_counter_update_argmax_pick(st->counts.p, st->delta.p, (int)cdb->n_rows, g, s);
+                    smb::launch_intersect_alive_pick(st->q.p, st->nq, st->alive.p, cdb->d_hashes, cdb->d_off, g, st->isect.p, st->d_n.p, s);
+                    smb::launch_make_row_offsets(st->d_n.p, d_qoff.p, s);
+                    st->delta.zero();
+                    one_vs_many_small_async(st->isect.p, d_qoff.p, cdb->max_len, q_max, *cdb, st->delta.p, s);
+                    smb::launch_mark_dead_n(st->q.p, st->nq, st->alive.p, st->isect.p, st->d_n.p, s);
+                }
+                CK(cudaGetLastError());
+                d_state.download(state, 2);
+                sync(s);
+                if (state[0] >= cap) break;
+            }
+            const uint32_t rounds = state[0];
+            std::vector<uint32_t> rows(rounds), sizes(rounds);
+            if (rounds) { d_rows.download(rows.data(), rounds); d_sizes.download(sizes.data(), rounds); sync(s); }
+            for (uint32_t r = 0; r < rounds; ++r) {
+                match_ids[r] = st->rowmap.empty() ? rows[r] : st->rowmap[rows[r]];
+                isect_sizes[r] = sizes[r];
+            }
+            return rounds;
+        }
         DevBuf<unsigned long long> d_info(4, s);               // {best count, best row, previous |intersect|}
         uintptr_t rounds = 0;
         bool have_delta = false;

@@ -145,6 +145,15 @@ void launch_mark_dead(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint
 // device-side glue for the sync-free gather round: offsets {0, *d_n} of a 1-row CSR, and
 // mark_dead with the count read from the device
 void launch_make_row_offsets(const uint32_t* d_n, uint64_t* d_off2, cudaStream_t s);
+// gather rounds picked on the device (search_kernels.cuh): the argmax appends (row, count) to the pick list and raises
+// `done` below the threshold; the intersect kernel takes its row from the last pick
+#ifndef SMB_GATHER_PICKS_DEFINED
+#define SMB_GATHER_PICKS_DEFINED
+struct GatherPicks { uint32_t* rows; uint32_t* sizes; uint32_t* state; uint32_t threshold, max_rounds; };
+#endif
+void launch_counter_update_argmax_pick(uint32_t* counters, const uint32_t* delta, int n, const GatherPicks& g, cudaStream_t s);
+void launch_intersect_alive_pick(const uint64_t* q, uint64_t nq, const uint8_t* alive, const uint64_t* hashes,
+                                 const uint64_t* off, const GatherPicks& g, uint64_t* out, uint32_t* d_n, cudaStream_t s);
 void launch_mark_dead_n(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* gone,
                         const uint32_t* d_n, cudaStream_t s);
 

@@ -261,4 +261,101 @@ __global__ void __launch_bounds__(1024) counter_update_argmax_kernel(
     }
 }
 
+
+// ---- gather rounds driven from the device (smb_gather, candidate rows that fit the shared-memory table) ----------------
+// The host loop above reads the winner of every round back (24 bytes + a stream synchronisation) to pick the row pointer.
+// Here the row is picked ON the device: the argmax kernel appends (row, count) to a pick list and raises `done` when the
+// best remaining overlap falls below the threshold; the intersect kernel takes its row from that pick; a finished loop
+// turns every later kernel into a no-op (the intersection has length 0).  The host enqueues rounds in batches and looks
+// at `state` once per batch.   state[0] = rounds picked, state[1] = done flag.
+#ifndef SMB_GATHER_PICKS_DEFINED
+#define SMB_GATHER_PICKS_DEFINED
+struct GatherPicks {
+    uint32_t* rows;       // [max_rounds] picked row per round
+    uint32_t* sizes;      // [max_rounds] |row ∩ remaining query| per round
+    uint32_t* state;      // [2]
+    uint32_t threshold, max_rounds;
+};
+#endif
+
+__global__ void __launch_bounds__(1024) counter_update_argmax_pick_kernel(u32* __restrict__ counters, const u32* __restrict__ delta,
+                                                                         int n, GatherPicks g) {
+    SMB_SHARED unsigned long long sb[32];
+    const bool done = g.state[1] != 0;
+    unsigned long long best = 0;
+    if (!done) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            u32 v = counters[j];
+            const u32 d = delta[j];
+            v = d > v ? 0u : v - d;
+            counters[j] = v;
+            const unsigned long long key = ((unsigned long long)v << 32) | (unsigned long long)(0xffffffffu - (u32)j);
+            best = key > best ? key : best;
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o > best ? o : best;
+    }
+    if (lane_id() == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : 0ULL;
+        for (int d = 16; d; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+            best = o > best ? o : best;
+        }
+        if (threadIdx.x == 0 && !done) {
+            const u32 value = (u32)(best >> 32), row = 0xffffffffu - (u32)(best & 0xffffffffu);
+            const u32 r = g.state[0];
+            if (value < g.threshold || value == 0 || r >= g.max_rounds) g.state[1] = 1;
+            else { g.rows[r] = row; g.sizes[r] = 0; g.state[0] = r + 1; }
+        }
+    }
+}
+
+// intersect_alive_kernel for the row the last pick names (nothing, and *d_n = 0, once the loop is done)
+__global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* __restrict__ q, u64 nq, const u8* __restrict__ alive,
+                                                                   const u64* __restrict__ hashes, const u64* __restrict__ off,
+                                                                   GatherPicks g, u64* __restrict__ out, u32* __restrict__ d_n) {
+    SMB_SHARED u32 warp_tot[32];
+    SMB_SHARED u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const bool done = g.state[1] != 0 || g.state[0] == 0;
+    const u32 round = done ? 0u : g.state[0] - 1;
+    const u32 r = done ? 0u : g.rows[round];
+    const u64* __restrict__ row = hashes + off[r];
+    const u64 rn = done ? 0 : off[r + 1] - off[r];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    for (u64 base = 0; base < rn; base += blockDim.x) {
+        const u64 e = base + threadIdx.x;
+        bool keep = false;
+        u64 x = 0;
+        if (e < rn) {
+            x = row[e];
+            const long long pos = row_find(q, nq, x);
+            keep = pos >= 0 && alive[pos];
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        const u32 pos_out = carry + before + __popc(bal & ((1u << lane) - 1u));
+        if (keep) out[pos_out] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 t = 0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += warp_tot[w2];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *d_n = carry;
+        if (!done) g.sizes[round] = carry;
+    }
+}
+
 }  // namespace smb

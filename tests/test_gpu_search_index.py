@@ -1,8 +1,7 @@
-"""GPU parity tests of the paths that sit behind switches: the range-partitioned
-one-vs-many pass and the inverted index of a resident set.  Their logic is covered on the CPU by
-tests/test_host_emulation.py; these tests are the first thing to run on the device
-(scripts/gpu_next_variants.sh sets SMB_TEST_EXPERIMENTAL=1) and are skipped otherwise, so that an
-unvalidated experimental path can never turn the default suite red."""
+"""GPU parity tests of the one-vs-many paths beyond the shared-memory table: the streaming pass over the range-major copy
+of a resident set (queries too large for shared memory), the global-directory kernel behind SMB_SEARCH_LAYOUT=global, the
+inverted index of a resident set, and the one-pass k = 21, 31, 51 hash kernel against the three launches.  All against
+the oracle; the same kernels run on the CPU in tests/test_host_emulation.py."""
 import os
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 import oracle as orc
 from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_sketches
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("SMB_TEST_EXPERIMENTAL"),
-                                 reason="experimental paths: set SMB_TEST_EXPERIMENTAL=1 (scripts/gpu_next_variants.sh)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
