@@ -477,7 +477,7 @@ def bench_compare(args, torch, dist, B, rank, world, timed, hbm_peak, peak_src):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(tkey),
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(tkey) if world == 1 else None,
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "algorithm": plan, "note": knote},
     }
@@ -762,7 +762,9 @@ def _bench_search(args, torch, dist, B, rank, world, timed, query, db, d_h, h_of
                         ("one_vs_many_global_kernel" if os.environ.get("SMB_SEARCH_LAYOUT") == "global" else
                          "one_vs_many_range_major_kernel (streams the range-major copy of the database)"),
                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak * world, "unit": "GB/s",
-                        "frac": achieved / (hbm_peak * world), "traffic": None, "kernel_ms": ms,
+                        "frac": achieved / (hbm_peak * world), "kernel_ms": ms,
+                        "traffic": ncu_traffic("one_vs_many_range_major_kernel")
+                        if world == 1 and not index_info and os.environ.get("SMB_SEARCH_LAYOUT") != "global" else None,
                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                         "note": "whole pass timed (query and database resident): kernel_ms == ms_per_step"},
            **index_info}

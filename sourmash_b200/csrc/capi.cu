@@ -2138,7 +2138,9 @@ static void one_vs_many_small_async(const uint64_t* d_q, const uint64_t* d_qoff,
     while (sh < 63 && (max_key >> sh) >= max_entries) ++sh;
     one.shift = sh; one.nb = (int)((max_key >> sh) + 1);
     one.smem_bytes = key_bytes + ((size_t)one.nb + 2) * 2;
-    one.cols_per_cta = std::max(64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
+    // a few hundred candidate rows (the gather rounds): many small CTAs, each building the (small) table again, beat four
+    // CTAs of 64 rows -- the launch is latency bound, not work bound
+    one.cols_per_cta = std::max(nB < 4096 ? 8 : 64, std::min(512, (nB + SMB_B200_SMS * 2 - 1) / (SMB_B200_SMS * 2)));
     smb::launch_pairwise_tile(one, d_q, d_qoff, 1, db.d_hashes, db.d_off, nB, d_counts, (size_t)nB, false,
                               smb::TileShard{0, 1}, s);
 }

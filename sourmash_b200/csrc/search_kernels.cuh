@@ -314,10 +314,14 @@ __global__ void __launch_bounds__(1024) counter_update_argmax_pick_kernel(u32* _
     }
 }
 
-// intersect_alive_kernel for the row the last pick names (nothing, and *d_n = 0, once the loop is done)
+// intersect_alive_kernel for the row the last pick names (nothing, and *d_n = 0, once the loop is done).  One CTA (the
+// output must stay in row order); every thread takes FOUR consecutive elements per pass and runs their four binary
+// searches in lock step -- a fixed number of branch-free halving steps -- so that four loads are in flight per thread
+// instead of one: the kernel is a chain of ~17 dependent L2 loads per element and nothing else.
 __global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* __restrict__ q, u64 nq, const u8* __restrict__ alive,
                                                                    const u64* __restrict__ hashes, const u64* __restrict__ off,
                                                                    GatherPicks g, u64* __restrict__ out, u32* __restrict__ d_n) {
+    constexpr int K = 4;
     SMB_SHARED u32 warp_tot[32];
     SMB_SHARED u32 carry;
     if (threadIdx.x == 0) carry = 0;
@@ -328,22 +332,43 @@ __global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* _
     const u64* __restrict__ row = hashes + off[r];
     const u64 rn = done ? 0 : off[r + 1] - off[r];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (u64 base = 0; base < rn; base += blockDim.x) {
-        const u64 e = base + threadIdx.x;
-        bool keep = false;
-        u64 x = 0;
-        if (e < rn) {
-            x = row[e];
-            const long long pos = row_find(q, nq, x);
-            keep = pos >= 0 && alive[pos];
+    int steps = 0;                                         // halving steps that cover nq positions
+    while ((1ull << steps) < nq + 1) ++steps;
+    for (u64 base = 0; base < rn; base += (u64)blockDim.x * K) {
+        u64 x[K], lo[K];
+        bool in[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const u64 e = base + (u64)threadIdx.x * K + k;
+            in[k] = e < rn;
+            x[k] = in[k] ? row[e] : 0;
+            lo[k] = 0;                                     // number of query keys < x, found from the top bit down
         }
-        const u32 bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
+        for (int b = steps - 1; b >= 0; --b) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const u64 probe = lo[k] + (1ull << b);     // q[probe - 1] < x  <=>  at least `probe` keys are smaller
+                if (probe <= nq && ld_nc_u64(q + probe - 1) < x[k]) lo[k] = probe;
+            }
+        }
+        u32 keep = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (in[k] && lo[k] < nq && ld_nc_u64(q + lo[k]) == x[k] && alive[lo[k]]) keep |= 1u << k;
+        // ordered compaction: counts of the threads in front (warp prefix, then the warps in front)
+        u32 mine = (u32)__popc(keep), incl = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_sync(0xffffffffu, incl, lane >= d ? lane - d : lane);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         u32 before = 0;
         for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
-        const u32 pos_out = carry + before + __popc(bal & ((1u << lane) - 1u));
-        if (keep) out[pos_out] = x;
+        u32 pos_out = carry + before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if ((keep >> k) & 1u) out[pos_out++] = x[k];
         __syncthreads();
         if (threadIdx.x == 0) {
             u32 t = 0;
