@@ -195,7 +195,7 @@ void launch_hash_kmers_k(const HashLaunch& L, uint32_t ksize, int row_index, cud
 // same, restricted to a range of tiles (a group of streams) -- lets uploads and hashing overlap
 void launch_hash_kmers_range(const HashLaunch& L, uint32_t ksize, int row_index, uint32_t tile_lo_r,
                              uint32_t tile_hi_r, uint32_t tile_lo_g, uint32_t tile_hi_g, cudaStream_t s);
-// Experimental (SMB_SKETCH_FUSED, off by default): k = 21, 31 and 51 in one pass over the bases (one rolling
+// Default when k = 21, 31 and 51 are requested together (SMB_SKETCH_FUSED=0 switches it off): one pass over the bases (one rolling
 // 51-state, the shorter k-mers as prefixes); row_index[i] / max_hash[i] belong to k = 21, 31, 51
 bool sketch_fused_enabled();
 void launch_hash_kmers_fused_range(const HashLaunch& L, const int row_index[3], const uint64_t max_hash[3],

@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_kmers_kernel(HashArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Experimental (SMB_SKETCH_FUSED, off by default; kmer_roll.cuh hash_thread_windows_fused): k = 21, 31
+// The default for k = 21, 31, 51 requested together (SMB_SKETCH_FUSED=0 switches it off; kmer_roll.cuh hash_thread_windows_fused): k = 21, 31
 // and 51 of `sourmash sketch dna`'s default parameter string in ONE pass over the bases -- one
 // rolling 51-state, the shorter k-mers read off it as prefixes -- instead of three launches that each
 // decode and roll the same bases.  Logic checked on the CPU by
-// tests/test_host_emulation.py::test_roll_fused_21_31_51_matches_oracle; not measured yet.
+// tests/test_host_emulation.py::test_roll_fused_21_31_51_matches_oracle; measured 11.2 ms against 12.4 ms (profiles/r2a_ab.json).
 // ---------------------------------------------------------------------------------------
 struct FusedArgs {
     HashArgs a;                   // row_index / max_hash unused

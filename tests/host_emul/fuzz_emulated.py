@@ -52,7 +52,7 @@ def trial(rng):
         got = B.compare_jaccard(db)
         assert np.array_equal(got, want), ("compare", algo, n, scale)
     if SWITCHED:                                                                     # the paths behind switches
-        for layout, tags in (("stripe_full", "u16"), ("stripe_upper", "u32"), ("plain", "u16")):
+        for layout, tags in (("stripe_full", "u16"), ("stripe", "u32"), ("plain", "u16")):
             os.environ["SMB_JOIN_LAYOUT"], os.environ["SMB_STRIPE_TAGS"] = layout, tags
             assert np.array_equal(B.compare_jaccard(db), want), ("compare", layout, tags, n, scale)
         os.environ.pop("SMB_JOIN_LAYOUT"); os.environ.pop("SMB_STRIPE_TAGS")

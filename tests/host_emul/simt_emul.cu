@@ -111,7 +111,7 @@ static int stripe_main(int R, int upper, int threads, int tag_bits, int sort_bit
                           : stripe_run<u32>(R, upper, threads, sort_bits, h, off, fout);
 }
 
-// ---- inverted join: the default pipeline, the cluster layout, the row-block passes (kernels as written; the
+// ---- global-reduction join (the stripe layout's fallback): row slices, gather, count, estimate (kernels as written; the
 // exclusive scan and the radix sort of the product are host loops here) ----
 struct Slice { std::vector<u64> keys; std::vector<u32> ids; };
 static Slice sorted_slice(const std::vector<u64>& h, const std::vector<u64>& off, int n, u64 lo, u64 hi, bool bounded) {
