@@ -137,3 +137,54 @@ def test_rows_device_on_the_global_reduction_join(B, monkeypatch):
     d_rows = _DeviceMatrix((50, 300))
     B.compare_jaccard_rows_device(sset, 120, 170, d_rows.ptr)
     assert np.array_equal(d_rows.numpy(), want[120:170])
+
+
+@pytest.mark.parametrize("algo,layout", [("join", None), ("join", "plain"), ("tile", None)])
+def test_key_range_shards_add_up_to_whole_row_counters(B, monkeypatch, algo, layout):
+    """The multi-GPU unit on one GPU: the whole-row partial counters of 1 / 3 / 8 shards (key ranges of the sorted stream
+    for the stripe layout, upper-triangle shards mirrored for the others) sum to the oracle's counts, as 32- and 16-bit
+    counters; 16-bit counters added two at a time as uint32 (what the reduce-scatter does) give the same; summed counters
+    of a block of rows finalise to the oracle's float64 rows."""
+    import torch
+    monkeypatch.setenv("SMB_COMPARE_ALGO", algo)
+    if layout:
+        monkeypatch.setenv("SMB_JOIN_LAYOUT", layout)
+    n = 600
+    h, off = synth_sketches(n, mean=400, sd=80, lo=0, hi=800, n_families=9, pool=500, seed=77)
+    want = orc.pairwise_common(h, off, nthreads=8)
+    jac = orc.compare_all_pairs(h, off, nthreads=8)
+    sset = B.SketchSet.from_host(h, off)
+    off_diag = ~np.eye(n, dtype=bool)
+    for bits, tdt, ndt in ((32, torch.int32, np.uint32), (16, torch.int16, np.uint16)):
+        for shards in (1, 3, 8):
+            total = torch.zeros((n, n), dtype=tdt, device="cuda")
+            for r in range(shards):
+                part = torch.full((n, n), -1, dtype=tdt, device="cuda")            # every cell must be written
+                B.compare_counts_shard_device(sset, r, shards, part.data_ptr(), bits=bits)
+                if bits == 32:
+                    total += part
+                else:                                              # pairs of 16-bit counters added as one int32, like ncclSum on the int32 view
+                    total = (total.view(torch.int32) + part.view(torch.int32)).view(torch.int16)
+            got = total.cpu().numpy().view(ndt)
+            assert np.array_equal(got[off_diag], want[off_diag].astype(ndt)), (algo, layout, bits, shards)
+        rows = torch.full((60, n), -1.0, dtype=torch.float64, device="cuda")
+        block = total[70:130].contiguous()
+        B.finalize_counts_rows_device(sset, block.data_ptr(), 70, 130, rows.data_ptr(), bits=bits)
+        assert np.array_equal(rows.cpu().numpy(), jac[70:130]), (algo, layout, bits)
+
+
+def test_take_rows_and_device_query_entry_points(B):
+    import torch
+    h, off = synth_sketches(300, mean=500, sd=80, lo=0, hi=900, n_families=5, pool=600, seed=5)
+    sset = B.SketchSet.from_host(h, off)
+    pick = np.array([7, 0, 299, 7, 150], dtype=np.uint32)
+    sub = sset.take_rows(pick)
+    hh, oo = sub.to_host()
+    rows = [h[int(off[i]):int(off[i + 1])] for i in pick]
+    assert np.array_equal(oo, np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint64))
+    assert np.array_equal(hh, np.concatenate(rows))
+    q = np.unique(np.concatenate([rows[0], rows[2][::2]]))
+    d_q = torch.from_numpy(q.view(np.int64)).cuda()
+    d_c = torch.full((300,), -1, dtype=torch.int32, device="cuda")
+    B.one_vs_many_device(d_q.data_ptr(), len(q), sset, d_c.data_ptr())
+    assert np.array_equal(d_c.cpu().numpy().astype(np.uint64), orc.one_vs_many(q, h, off))
