@@ -2408,8 +2408,8 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
         DevBuf<uint64_t> d_qoff(2, s);
         if (small_rows && !cdb->index && max_rounds <= 0xffffffffull) {
             // Rounds picked on the device (search_kernels.cuh): argmax + pick, intersect the picked row with the live
-            // query, one-vs-many of the intersection over the candidates, flag the consumed hashes -- five launches per
-            // round and NO readback; the host enqueues rounds in batches and looks at the pick counter once per batch.
+            // query (consuming its hashes on the spot), one-vs-many of the intersection over the candidates -- four launches
+            // and a memset per round and NO readback; the host enqueues rounds in batches and looks at the pick counter once per batch.
             const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, cdb->n_rows);   // a row is picked at most once
             DevBuf<uint32_t> d_rows(cap + 1, s), d_sizes(cap + 1, s), d_state(2, s);
             d_state.zero();
@@ -2424,7 +2424,6 @@ uintptr_t smb_gather(const uint64_t* query, uintptr_t n_query, const SmbSketchSe
                     smb::launch_make_row_offsets(st->d_n.p, d_qoff.p, s);
                     st->delta.zero();
                     one_vs_many_small_async(st->isect.p, d_qoff.p, cdb->max_len, q_max, *cdb, st->delta.p, s);
-                    smb::launch_mark_dead_n(st->q.p, st->nq, st->alive.p, st->isect.p, st->d_n.p, s);
                 }
                 CK(cudaGetLastError());
                 d_state.download(state, 2);

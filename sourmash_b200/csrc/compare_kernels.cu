@@ -334,7 +334,7 @@ void launch_mark_dead(const u64* q, u64 nq, u8* alive, const u64* gone, u64 n, c
 void launch_counter_update_argmax_pick(u32* counters, const u32* delta, int n, const GatherPicks& g, cudaStream_t s) {
     counter_update_argmax_pick_kernel<<<1, 1024, 0, s>>>(counters, delta, n, g); count_launches(1);
 }
-void launch_intersect_alive_pick(const u64* q, u64 nq, const u8* alive, const u64* hashes, const u64* off, const GatherPicks& g,
+void launch_intersect_alive_pick(const u64* q, u64 nq, u8* alive, const u64* hashes, const u64* off, const GatherPicks& g,
                                  u64* out, u32* d_n, cudaStream_t s) {
     intersect_alive_pick_kernel<<<1, 1024, 0, s>>>(q, nq, alive, hashes, off, g, out, d_n); count_launches(1);
 }

@@ -152,7 +152,7 @@ void launch_make_row_offsets(const uint32_t* d_n, uint64_t* d_off2, cudaStream_t
 struct GatherPicks { uint32_t* rows; uint32_t* sizes; uint32_t* state; uint32_t threshold, max_rounds; };
 #endif
 void launch_counter_update_argmax_pick(uint32_t* counters, const uint32_t* delta, int n, const GatherPicks& g, cudaStream_t s);
-void launch_intersect_alive_pick(const uint64_t* q, uint64_t nq, const uint8_t* alive, const uint64_t* hashes,
+void launch_intersect_alive_pick(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* hashes,
                                  const uint64_t* off, const GatherPicks& g, uint64_t* out, uint32_t* d_n, cudaStream_t s);
 void launch_mark_dead_n(const uint64_t* q, uint64_t nq, uint8_t* alive, const uint64_t* gone,
                         const uint32_t* d_n, cudaStream_t s);

@@ -315,13 +315,15 @@ __global__ void __launch_bounds__(1024) counter_update_argmax_pick_kernel(u32* _
 }
 
 // intersect_alive_kernel for the row the last pick names (nothing, and *d_n = 0, once the loop is done).  One CTA (the
-// output must stay in row order); every thread takes FOUR consecutive elements per pass and runs their four binary
-// searches in lock step -- a fixed number of branch-free halving steps -- so that four loads are in flight per thread
+// output must stay in row order); every thread takes EIGHT consecutive elements per pass and runs their binary
+// searches in lock step -- a fixed number of branch-free halving steps -- so that eight loads are in flight per thread
 // instead of one: the kernel is a chain of ~17 dependent L2 loads per element and nothing else.
-__global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* __restrict__ q, u64 nq, const u8* __restrict__ alive,
+// The kept hashes are consumed on the spot (alive[pos] = 0: the job of mark_dead_n_kernel in the host-driven loop) -- the
+// one-vs-many pass that follows reads the intersection, not the flags.
+__global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* __restrict__ q, u64 nq, u8* __restrict__ alive,
                                                                    const u64* __restrict__ hashes, const u64* __restrict__ off,
                                                                    GatherPicks g, u64* __restrict__ out, u32* __restrict__ d_n) {
-    constexpr int K = 4;
+    constexpr int K = 8;                                   // 8 192 elements per pass: a genome-sized row in one
     SMB_SHARED u32 warp_tot[32];
     SMB_SHARED u32 carry;
     if (threadIdx.x == 0) carry = 0;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(1024) intersect_alive_pick_kernel(const u64* _
         u32 keep = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if (in[k] && lo[k] < nq && ld_nc_u64(q + lo[k]) == x[k] && alive[lo[k]]) keep |= 1u << k;
+            if (in[k] && lo[k] < nq && ld_nc_u64(q + lo[k]) == x[k] && alive[lo[k]]) { keep |= 1u << k; alive[lo[k]] = 0; }
         // ordered compaction: counts of the threads in front (warp prefix, then the warps in front)
         u32 mine = (u32)__popc(keep), incl = mine;
         for (int d = 1; d < 32; d <<= 1) {
