@@ -249,13 +249,14 @@ void launch_one_vs_many_global(const u64* q, u64 nq, const u32* dir, int shift, 
 // ------------------------------------------------------------------------------------
 struct RangeMajor {
     cudaStream_t stream = 0;
-    void *m_rm = nullptr, *m_slice = nullptr;
-    int n = 0, P = 0;
+    void *m_rm = nullptr, *m_slice = nullptr, *m_coarse = nullptr;
+    int n = 0, P = 0, nc = 0;
     u64 width = 0, T = 0;
     u32 bm_shift = 0;
     ~RangeMajor() {
         if (m_rm) cudaFreeAsync(m_rm, stream);
         if (m_slice) cudaFreeAsync(m_slice, stream);
+        if (m_coarse) cudaFreeAsync(m_coarse, stream);
     }
 };
 
@@ -293,7 +294,11 @@ cudaError_t range_major_build(const u64* h, const u64* off, int n, u64 T, u64 ma
     if ((e = scratch.alloc(&d_scan, scan_bytes)) != cudaSuccess) return e;
     cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cnt, (u32*)rm->m_slice, (long long)(cells + 1), s);
     rm_scatter_kernel<<<grid, 256, 0, s>>>(h, off, bounds, (const u32*)rm->m_slice, n, P, (u64*)rm->m_rm);
-    count_launches(4);
+    rm->nc = (n >> RM_COARSE_LOG2) + 2;
+    if ((e = cudaMallocAsync(&rm->m_coarse, (size_t)P * rm->nc * sizeof(u32), s)) != cudaSuccess) return e;
+    rm_coarse_kernel<<<(unsigned)std::min<u64>(((u64)P * rm->nc + 255) / 256, (u64)SMB_B200_SMS * 32), 256, 0, s>>>(
+        (const u32*)rm->m_slice, n, P, rm->nc, (u32*)rm->m_coarse);
+    count_launches(5);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *out = guard.release();
     return cudaSuccess;
@@ -302,7 +307,7 @@ void range_major_destroy(RangeMajor* rm) { delete rm; }
 
 void launch_one_vs_many_range_major(const RangeMajor* rm, const u64* q, u64 nq, u32* out, cudaStream_t s) {
     if (nq == 0 || rm->n == 0) return;
-    RangeMajorArgs a{q, nq, (const u64*)rm->m_rm, (const u32*)rm->m_slice, rm->n, rm->P, rm->width, (u32)RM_BITMAP_LOG2, rm->bm_shift, out};
+    RangeMajorArgs a{q, nq, (const u64*)rm->m_rm, (const u32*)rm->m_slice, (const u32*)rm->m_coarse, rm->nc, rm->n, rm->P, rm->width, (u32)RM_BITMAP_LOG2, rm->bm_shift, out};
     const size_t smem = ((size_t)1 << (RM_BITMAP_LOG2 - 3)) + (size_t)(RM_THREADS / 32) * RM_QUEUE * sizeof(u32);
     cudaFuncSetAttribute(one_vs_many_range_major_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     one_vs_many_range_major_kernel<<<rm->P, RM_THREADS, smem, s>>>(a); count_launches(1);

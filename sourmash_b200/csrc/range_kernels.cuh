@@ -75,10 +75,25 @@ __global__ void __launch_bounds__(256) rm_scatter_kernel(const u64* __restrict__
     }
 }
 
+static constexpr int RM_COARSE_LOG2 = 6;              // every 64th row's slice start is repeated in a small table
+
+// coarse[p * nc + k] = slice[p * n + min(k << RM_COARSE_LOG2, n)], k = 0 .. nc - 1 (nc = (n >> RM_COARSE_LOG2) + 2): the row
+// attribution of a match searches this table (19 KB per part, cache resident) and then one 64-row window of `slice`
+// instead of all of a part's 1.2 MB of it
+__global__ void __launch_bounds__(256) rm_coarse_kernel(const u32* __restrict__ slice, int n, int P, int nc, u32* __restrict__ coarse) {
+    const u64 total = (u64)P * (u64)nc;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const u64 p = i / (u64)nc, k = i - p * (u64)nc;
+        const u64 r = (k << RM_COARSE_LOG2) < (u64)n ? (k << RM_COARSE_LOG2) : (u64)n;
+        coarse[i] = slice[p * (u64)n + r];
+    }
+}
+
 struct RangeMajorArgs {
     const u64* q; u64 nq;                 // the query, sorted
     const u64* rm;                        // range-major database
     const u32* slice;                     // [P * n + 1]
+    const u32* coarse; int nc;            // [P * nc]
     int n, P;
     u64 width;
     u32 bm_log2;                          // bits of the bitmap = 2^bm_log2 (RM_BITMAP_LOG2; tests use tiny bitmaps: false positives)
@@ -91,14 +106,18 @@ __device__ __forceinline__ u32 rm_bit2(u64 d, u32 bm_log2) { return ((u32)d * RM
 
 // settle the queued candidates of one warp: exact test against the query slice, then row attribution
 __device__ __forceinline__ void rm_drain(const RangeMajorArgs& a, const u32* __restrict__ queue, u32 count, u64 qlo, u64 qhi,
-                                         const u32* __restrict__ slice_p, u32 lane) {
+                                         const u32* __restrict__ slice_p, const u32* __restrict__ coarse_p, u32 lane) {
     for (u32 i = lane; i < count; i += 32) {
         const u32 pos = queue[i];
         const u64 x = a.rm[pos];
         u64 lo = qlo, hi = qhi;
         while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (a.q[mid] < x) lo = mid + 1; else hi = mid; }
         if (lo >= qhi || a.q[lo] != x) continue;          // a false positive of the bitmap
-        int l = 0, r = a.n;                               // last row whose slice starts at or in front of pos
+        // last row whose slice starts at or in front of pos: first the 64-row window (coarse table), then inside it
+        int l = 0, r = a.nc;
+        while (r - l > 1) { const int mid = (l + r) >> 1; if (coarse_p[mid] <= pos) l = mid; else r = mid; }
+        l <<= RM_COARSE_LOG2;
+        r = l + (1 << RM_COARSE_LOG2) < a.n ? l + (1 << RM_COARSE_LOG2) : a.n;
         while (r - l > 1) { const int mid = (l + r) >> 1; if (slice_p[mid] <= pos) l = mid; else r = mid; }
         atomicAdd(a.out + l, 1u);
     }
@@ -133,6 +152,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) one_vs_many_range_major_kernel(
     }
     __syncthreads();
     const u32* __restrict__ slice_p = a.slice + (size_t)p * a.n;
+    const u32* __restrict__ coarse_p = a.coarse + (size_t)p * a.nc;
     const u64 begin = slice_p[0], end = slice_p[a.n];      // slice[(p + 1) * n] = start of the next part (or the total)
     u32 qn = 0;                                            // candidates in this warp's queue (warp-uniform)
     const u32 sh2 = 32u - a.bm_log2;
@@ -155,7 +175,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) one_vs_many_range_major_kernel(
             if (m == 0) continue;
             if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
                 __syncwarp();
-                rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+                rm_drain(a, queue, qn, qlo, qhi, slice_p, coarse_p, lane);
                 __syncwarp();
                 qn = 0;
             }
@@ -208,7 +228,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) one_vs_many_range_major_kernel(
                 if (m == 0) continue;
                 if (qn + (u32)__popc(m) > (u32)RM_QUEUE) {
                     __syncwarp();
-                    rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+                    rm_drain(a, queue, qn, qlo, qhi, slice_p, coarse_p, lane);
                     __syncwarp();
                     qn = 0;
                 }
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) one_vs_many_range_major_kernel(
         for (int v = 0; v < V; ++v) cur[v] = nxt[v];
     }
     __syncwarp();
-    rm_drain(a, queue, qn, qlo, qhi, slice_p, lane);
+    rm_drain(a, queue, qn, qlo, qhi, slice_p, coarse_p, lane);
 }
 
 }  // namespace smb

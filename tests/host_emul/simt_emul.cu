@@ -191,7 +191,10 @@ static int ranges_main(int P, int bm_log2, int threads, const char* fq, const ch
     std::vector<u32> out(n + 1, 0);
     const u64 nq = q.size();
     q.push_back(0);
-    RangeMajorArgs a{q.data(), nq, rm.data(), slice.data(), n, P, width, (u32)bm_log2,
+    const int nc = (n >> RM_COARSE_LOG2) + 2;
+    std::vector<u32> coarse((size_t)P * nc + 1);
+    smb_emu::launch(2, 64, 0, [&] { rm_coarse_kernel(slice.data(), n, P, nc, coarse.data()); });
+    RangeMajorArgs a{q.data(), nq, rm.data(), slice.data(), coarse.data(), nc, n, P, width, (u32)bm_log2,
                      range_bitmap_shift(width, 1ull << bm_log2), out.data()};
     const size_t smem = (bm_log2 > 5 ? ((size_t)1 << (bm_log2 - 3)) : 4) + (size_t)(threads / 32) * RM_QUEUE * sizeof(u32);
     if (nq && n) smb_emu::launch(P, threads, smem, [&] { one_vs_many_range_major_kernel(a); });

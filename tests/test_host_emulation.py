@@ -413,8 +413,10 @@ def test_simt_range_search_kernels_match_oracle(simt):
     q_low = np.unique(rng.integers(0, 1000, size=200, dtype=np.uint64))                                       # query far below the db
     dense = [np.arange(1, 2000, dtype=np.uint64) for _ in range(40)]                                         # every element a match:
     q_dense = np.arange(1, 2000, dtype=np.uint64)                                                            # the queues overflow and drain
+    many = [np.unique(rng.integers(1, mx, size=int(rng.integers(0, 25)), dtype=np.uint64)) for _ in range(330)]   # > 5 windows of
+    q_many = np.unique(np.concatenate(many[::3] + [rng.integers(1, mx, size=500, dtype=np.uint64)]))               # the coarse row table
     for rows, query in ((fam, q_fam), (edge, q_edge), (fam, fam[5][:1]), (fam, q_beyond), (fam, q_low), (edge, q_low),
-                        ([edge[0]], q_edge), (dense, q_dense)):
+                        ([edge[0]], q_edge), (dense, q_dense), (many, q_many)):
         hh, oo = orc.to_csr(rows)
         want = orc.one_vs_many(np.asarray(query, dtype=np.uint64), hh, oo).astype(np.uint32)
         for P, bm_log2, threads in ((5, 16, 64), (2, 6, 96), (9, 12, 32), (3, 8, 64)):
