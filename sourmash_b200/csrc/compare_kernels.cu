@@ -468,15 +468,28 @@ struct JoinStripe {
     const u64 *ebeg = nullptr, *eend = nullptr;
     u64 T = 0;                // elements in the stream (all of the set, or one key range of it)
     int n = 0, rows_per_block = 0, upper_only = 1, tag16 = 0, sharded = 0;
+    int ctas_per_sm = 1;      // 2: rows_per_block sized for two resident CTAs (64 warps per SM; the count kernel is bound by issue latency)
     size_t smem = 0;
     ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
 };
 
+// shared memory of one CTA when two are to be resident: 2 x (dynamic + 1 KB reserved per CTA) <= 228 KB per SM
+static constexpr size_t STRIPE_SMEM_TWO_CTAS = 112 * 1024;
+template <typename TagT, bool UPPER, int CTAS>
+static cudaError_t stripe_set_smem_one() {
+    cudaError_t e = cudaFuncSetAttribute(join_stripe_kernel<TagT, UPPER, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CTAS == 2 ? (int)STRIPE_SMEM_TWO_CTAS : MAX_DYN_SMEM);
+    if (e != cudaSuccess || CTAS != 2) return e;
+    return cudaFuncSetAttribute(join_stripe_kernel<TagT, UPPER, CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+}
 template <typename TagT>
 static cudaError_t stripe_set_smem() {
-    cudaError_t e = cudaFuncSetAttribute(join_stripe_kernel<TagT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(join_stripe_kernel<TagT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    cudaError_t e;
+    if ((e = stripe_set_smem_one<TagT, true, 1>()) != cudaSuccess) return e;
+    if ((e = stripe_set_smem_one<TagT, false, 1>()) != cudaSuccess) return e;
+    if ((e = stripe_set_smem_one<TagT, true, 2>()) != cudaSuccess) return e;
+    return stripe_set_smem_one<TagT, false, 2>();
 }
 
 // *out stays null (with cudaSuccess) when the layout does not apply: 2^32 - 256 or more elements, or a row of n
@@ -486,14 +499,20 @@ static cudaError_t stripe_set_smem() {
 cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_all, u64 max_key, int shard, int n_shards,
                                      JoinStripe** out, cudaStream_t s) {
     *out = nullptr;
-    const int R = n > 0 ? stripe_rows_per_block((size_t)MAX_DYN_SMEM, n) : 0;
+    int R = n > 0 ? stripe_rows_per_block((size_t)MAX_DYN_SMEM, n) : 0;
+    int ctas = 1;
+    {   // two CTAs per SM when a row block of at least one row fits half the shared memory (SMB_STRIPE_CTAS=1: A/B switch)
+        const int R2 = n > 0 ? stripe_rows_per_block(STRIPE_SMEM_TWO_CTAS, n) : 0;
+        const char* c = getenv("SMB_STRIPE_CTAS");
+        if (R2 >= 1 && !(c && !strcmp(c, "1"))) { R = R2; ctas = 2; }
+    }
     if (R < 1 || T_all == 0 || T_all >= 0xffffff00ull) return cudaSuccess;   // 32-bit stream positions, read-ahead included
     cudaError_t e;
     if ((e = stripe_set_smem<u16>()) != cudaSuccess) return e;      // per device, so not cached in a flag
     if ((e = stripe_set_smem<u32>()) != cudaSuccess) return e;
     auto js = new JoinStripe();
     std::unique_ptr<JoinStripe> guard(js);
-    js->stream = s; js->n = n; js->rows_per_block = R;
+    js->stream = s; js->n = n; js->rows_per_block = R; js->ctas_per_sm = ctas;
     js->tag16 = n < 32768;
     js->sharded = n_shards > 1;
     {
@@ -544,8 +563,8 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
         js->ebeg = off; js->eend = off + 1;
     }
     if (T == 0) {                                                   // no hash in this key range: every partial count is zero
-        if (js->tag16) stripe_tag_kernel<u16><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u16*)js->tags, js->pos);
-        else stripe_tag_kernel<u32><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u32*)js->tags, js->pos);
+        if (js->tag16) stripe_tag_kernel<u16><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u16*)js->tags, js->pos, nullptr, nullptr);
+        else stripe_tag_kernel<u32><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u32*)js->tags, js->pos, nullptr, nullptr);
         count_launches(1);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         *out = guard.release();
@@ -578,18 +597,19 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     if ((e = scratch.alloc(&d_sort, sort_bytes)) != cudaSuccess) return e;
     cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, key_a, key_b, pay_a, pay_b, (long long)T, 0, key_bits, s);
     count_launches(1);
-    // 3. runs of equal keys that hold more than one hash: found, then ordered in place (key_a is free: worklist)
-    if (low_bits) {
-        cudaMemsetAsync(d_count, 0, sizeof(u32), s);
-        stripe_descent_kernel<<<grid, 256, 0, s>>>(key_b, pay_b, T, key_a, d_count);
-        stripe_fix_kernel<<<SMB_B200_SMS, 64, 0, s>>>(key_b, pay_b, T, key_a, d_count);
-        count_launches(2);
-    }
-    // 4. tags + inverse permutation
+    // 3. tags + inverse permutation.  Runs of equal keys that hold more than one hash are noticed on the way (key_a is
+    //    free: worklist) and redone in order, one warp per run (pay_a is free: the ordered payloads of those runs)
+    u32* worklist = low_bits ? key_a : nullptr;
+    if (low_bits) cudaMemsetAsync(d_count, 0, sizeof(u32), s);
     stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T_all, eblk);
-    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos);
-    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos);
+    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos, worklist, d_count);
+    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos, worklist, d_count);
     count_launches(2);
+    if (low_bits) {
+        if (js->tag16) stripe_fix_kernel<u16><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u16*)js->tags, js->pos);
+        else stripe_fix_kernel<u32><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u32*)js->tags, js->pos);
+        count_launches(1);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *out = guard.release();
     return cudaSuccess;
@@ -605,13 +625,16 @@ static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_en
                  d_counts, d_counts16};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
     const bool upper = js->upper_only;
+    const bool two = js->ctas_per_sm == 2;
+#define SMB_STRIPE_LAUNCH(TAG, UP, C) join_stripe_kernel<TAG, UP, C><<<blocks, 1024, js->smem, s>>>(a)
     if (js->tag16) {
-        if (upper) join_stripe_kernel<u16, true><<<blocks, 1024, js->smem, s>>>(a);
-        else join_stripe_kernel<u16, false><<<blocks, 1024, js->smem, s>>>(a);
+        if (upper) { if (two) SMB_STRIPE_LAUNCH(u16, true, 2); else SMB_STRIPE_LAUNCH(u16, true, 1); }
+        else { if (two) SMB_STRIPE_LAUNCH(u16, false, 2); else SMB_STRIPE_LAUNCH(u16, false, 1); }
     } else {
-        if (upper) join_stripe_kernel<u32, true><<<blocks, 1024, js->smem, s>>>(a);
-        else join_stripe_kernel<u32, false><<<blocks, 1024, js->smem, s>>>(a);
+        if (upper) { if (two) SMB_STRIPE_LAUNCH(u32, true, 2); else SMB_STRIPE_LAUNCH(u32, true, 1); }
+        else { if (two) SMB_STRIPE_LAUNCH(u32, false, 2); else SMB_STRIPE_LAUNCH(u32, false, 1); }
     }
+#undef SMB_STRIPE_LAUNCH
     count_launches(1);
     return cudaGetLastError();
 }
@@ -636,7 +659,7 @@ void launch_finalize_counts_rows(const void* d_counts, int bits, const u64* off,
 // c[j][i] = c[i][j] for j > i: upper-triangle counters completed to whole rows
 void launch_mirror_counts(void* d_counts, int bits, int n, cudaStream_t s) {
     if (n <= 0) return;
-    const int t = (n + 31) / 32;
+    const int t = (n + STRIPE_MIRROR_TILE - 1) / STRIPE_MIRROR_TILE;
     if (bits == 16) stripe_mirror_kernel<u16><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>((u16*)d_counts, n, 0, n);
     else stripe_mirror_kernel<u32><<<dim3((unsigned)t, (unsigned)t), 1024, 0, s>>>((u32*)d_counts, n, 0, n);
     count_launches(1);
@@ -657,7 +680,7 @@ cudaError_t join_stripe_rows(const JoinStripe* js, const u64* off, int row_begin
 // < row_end; d_full = row 0 of the whole n x n matrix.  No-op in the two-direction mode.
 cudaError_t join_stripe_mirror(const JoinStripe* js, int row_begin, int row_end, double* d_full, cudaStream_t s) {
     if (!js->upper_only || row_end <= row_begin) return cudaSuccess;
-    const int t0 = row_begin / 32, t1 = (row_end + 31) / 32;
+    const int t0 = row_begin / STRIPE_MIRROR_TILE, t1 = (row_end + STRIPE_MIRROR_TILE - 1) / STRIPE_MIRROR_TILE;
     dim3 grid((unsigned)t1, (unsigned)(t1 - t0));
     stripe_mirror_kernel<double><<<grid, 1024, 0, s>>>(d_full, js->n, row_begin, row_end); count_launches(1);
     return cudaGetLastError();

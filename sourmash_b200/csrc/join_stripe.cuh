@@ -82,43 +82,6 @@ __global__ void __launch_bounds__(256) stripe_keys_kernel(const u64* __restrict_
     }
 }
 
-// Runs (equal 32-bit keys) whose payloads do not ascend hold more than one hash, interleaved: the thread that
-// sees the FIRST descent of a run appends the run's head to the worklist (read-only pass; the list can hold
-// every element, so it never overflows).
-__global__ void __launch_bounds__(256) stripe_descent_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays, u64 T,
-                                                            u32* __restrict__ worklist, u32* __restrict__ d_count) {
-    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; q < T; q += (u64)gridDim.x * blockDim.x) {
-        const u32 k = key32s[q];
-        if (key32s[q - 1] != k || pays[q] >= pays[q - 1]) continue;
-        u64 p = q - 1;                                    // any earlier descent in this run?
-        bool first = true;
-        while (p > 0 && key32s[p - 1] == k) {
-            if (pays[p] < pays[p - 1]) { first = false; break; }
-            --p;
-        }
-        if (first) worklist[atomicAdd(d_count, 1u)] = (u32)p;      // p = head of the run
-    }
-}
-
-// one thread per listed run: insertion sort of its payloads (runs are short; a mixed run is two or three
-// interleaved ascending sequences)
-__global__ void __launch_bounds__(64) stripe_fix_kernel(const u32* __restrict__ key32s, u64* __restrict__ pays, u64 T,
-                                                       const u32* __restrict__ worklist, const u32* __restrict__ d_count) {
-    const u32 count = *d_count;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const u64 head = worklist[i];
-        const u32 k = key32s[head];
-        u64 tail = head + 1;
-        while (tail < T && key32s[tail] == k) ++tail;
-        for (u64 a = head + 1; a < tail; ++a) {
-            const u64 v = pays[a];
-            u64 b = a;
-            while (b > head && pays[b - 1] > v) { pays[b] = pays[b - 1]; --b; }
-            pays[b] = v;
-        }
-    }
-}
-
 // eblk[b] = row that owns element b << STRIPE_EBLK_LOG2
 __global__ void __launch_bounds__(256) stripe_eblk_kernel(const u64* __restrict__ off, int n, u64 T, u32* __restrict__ eblk) {
     const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
@@ -133,13 +96,32 @@ __global__ void __launch_bounds__(256) stripe_sizes_kernel(const u64* __restrict
     if (r < n) sizes[r] = (u32)(off[r + 1] - off[r]);
 }
 
+// Runs (equal 32-bit keys) whose payloads do not ascend hold more than one hash, interleaved.  The tag kernel
+// below sees every (predecessor, element) pair of the stream anyway: the thread that meets the FIRST descent of a
+// run appends the run's head to a worklist (the list can hold every element, so it never overflows), and
+// stripe_fix_kernel redoes the tags and positions of the listed runs -- one warp per run: the payloads are
+// ranked against each other (they are distinct: they end in the element index) and written in order to `tmp`
+// (the sort's input buffer, free by now; a run uses the slots of its own stream positions), then the run's
+// tags and positions are derived from the ordered payloads.  Ascending payloads = ascending (low bits, element)
+// = groups contiguous, rows ascending.
+__device__ __forceinline__ void stripe_note_descent(const u32* __restrict__ key32s, const u64* __restrict__ pays, u64 q, u32 k,
+                                                    u32* __restrict__ worklist, u32* __restrict__ d_count) {
+    u64 p = q - 1;                                        // q: a descent (same key as q - 1, smaller payload).  Any earlier one in this run?
+    while (p > 0 && key32s[p - 1] == k) {
+        if (pays[p] < pays[p - 1]) return;
+        --p;
+    }
+    worklist[atomicAdd(d_count, 1u)] = (u32)p;            // p = head of the run
+}
+
 // sorted (key, payload) stream -> tags (row | head flag) and the inverse permutation.  Four stream positions per
 // thread, their loads issued together: the kernel is a chain of dependent loads (payload -> block table -> row
 // offsets) and is bound by latency, not by bytes.
 template <typename TagT>
 __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays,
                                                         const u64* __restrict__ off, const u32* __restrict__ eblk, u64 T,
-                                                        TagT* __restrict__ tags, u32* __restrict__ pos) {
+                                                        TagT* __restrict__ tags, u32* __restrict__ pos,
+                                                        u32* __restrict__ worklist, u32* __restrict__ d_count) {
     constexpr int U = 4;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 q0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; q0 < T; q0 += stride * U) {
@@ -170,11 +152,50 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__
             while (end <= (u64)e) end = off[++rr + 1];    // e < T = off[n]: stops at the owning row, empty rows skipped
             tags[q] = (TagT)(rr | (head ? StripeTag<TagT>::HEAD : 0u));
             pos[e] = (u32)q;
+            // a run that mixes hashes (null worklist: the keys hold every bit, no such runs)
+            if (worklist && q && k[u] == kp[u] && p[u] < pp[u]) stripe_note_descent(key32s, pays, q, k[u], worklist, d_count);
         }
     }
     // STRIPE_TAG_PAD head flags behind the end: the count kernel reads ahead of a group without bounds checks
     const u64 gt = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gt < (u64)STRIPE_TAG_PAD) tags[T + gt] = (TagT)StripeTag<TagT>::HEAD;
+}
+
+// the listed runs again, in order (see stripe_note_descent)
+template <typename TagT>
+__global__ void __launch_bounds__(128) stripe_fix_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays, u64 T,
+                                                        const u32* __restrict__ worklist, const u32* __restrict__ d_count,
+                                                        const u64* __restrict__ off, int n, u64* tmp, TagT* tags, u32* pos) {
+    const u32 count = *d_count;
+    const u32 lane = lane_id();
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
+        const u64 head = worklist[i];
+        const u32 k = key32s[head];
+        u64 tail = head + 1;                              // end of the run: 32 positions probed at a time
+        for (;;) {
+            const u64 q = tail + lane;
+            const bool same = q < T && key32s[q] == k;
+            const u32 m = __ballot_sync(0xffffffffu, !same);
+            if (m) { tail += (u64)(__ffs((int)m) - 1); break; }
+            tail += 32;
+        }
+        for (u64 a = head + lane; a < tail; a += 32) {
+            const u64 v = pays[a];
+            u64 rank = 0;
+            for (u64 b = head; b < tail; ++b) rank += pays[b] < v ? 1u : 0u;
+            tmp[head + rank] = v;
+        }
+        __syncwarp();                                     // tmp[head, tail) written by this warp, read by it below
+        for (u64 q = head + lane; q < tail; q += 32) {
+            const u64 v = tmp[q];
+            const bool first = q == head || (tmp[q - 1] >> 32) != (v >> 32);
+            const u32 e = (u32)v;
+            tags[q] = (TagT)(stripe_row_of(off, n, (u64)e) | (first ? StripeTag<TagT>::HEAD : 0u));
+            pos[e] = (u32)q;
+        }
+        __syncwarp();
+    }
 }
 
 // ---- the count kernel -------------------------------------------------------------------------------------
@@ -198,8 +219,8 @@ struct StripeArgs {
 // increment their counters.  UPPER: only later members (= higher rows) are counted, i.e. the cells (i, j > i);
 // stripe_mirror_kernel fills the rest.  Otherwise the members in front are counted too (full rows, used when a
 // block of rows is computed on its own).
-template <typename TagT, bool UPPER>
-__global__ void __launch_bounds__(1024, 1) join_stripe_kernel(StripeArgs a) {
+template <typename TagT, bool UPPER, int CTAS>
+__global__ void __launch_bounds__(1024, CTAS) join_stripe_kernel(StripeArgs a) {
     constexpr u32 HEAD = StripeTag<TagT>::HEAD;
     SMB_DYN_SHARED(unsigned char, stripe_smem);
     u64* s_beg = reinterpret_cast<u64*>(stripe_smem);                       // [rows]
@@ -367,22 +388,35 @@ __global__ void __launch_bounds__(256) stripe_finalize_counts_kernel(const Count
     st_stream_f64(out + cell, stripe_jaccard((u32)counts[cell], off[i + 1] - off[i], off[j + 1] - off[j], i == j));
 }
 
-// out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 32 x 32 tiles through shared memory, reads
-// and writes both coalesced.  `full` points at row 0 of the whole matrix (rows < row_end are complete
-// in their upper part).
+// out[i][j] = out[j][i] for i in [row_begin, row_end), j < i: 64 x 64 tiles through shared memory (four cells
+// per thread, so that a CTA has 32 KB of float64 in flight: with 32 x 32 tiles the kernel was bound by latency
+// at 2.4 TB/s), reads and writes both coalesced.  `full` points at row 0 of the whole matrix (rows < row_end
+// are complete in their upper part).
+static constexpr int STRIPE_MIRROR_TILE = 64;
 template <typename T>
 __global__ void __launch_bounds__(1024) stripe_mirror_kernel(T* __restrict__ full, int n, int row_begin, int row_end) {
-    SMB_SHARED T tile[32][33];
-    const int ti = row_begin / 32 + (int)blockIdx.y;       // tile row (destination rows)
+    constexpr int W = STRIPE_MIRROR_TILE;
+    SMB_SHARED T tile[W][W + 1];
+    const int ti = row_begin / W + (int)blockIdx.y;        // tile row (destination rows)
     const int tj = (int)blockIdx.x;                        // tile column (destination columns), tj <= ti
     if (tj > ti) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // source tile = rows of tile column tj, columns of tile row ti (the upper part)
-    const int sr = tj * 32 + ty, sc = ti * 32 + tx;
-    tile[ty][tx] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : T(0);
+#pragma unroll
+    for (int a = 0; a < W; a += 32)
+#pragma unroll
+        for (int b = 0; b < W; b += 32) {
+            const int sr = tj * W + ty + a, sc = ti * W + tx + b;
+            tile[ty + a][tx + b] = (sr < n && sc < n) ? full[(size_t)sr * n + sc] : T(0);
+        }
     __syncthreads();
-    const int dr = ti * 32 + ty, dc = tj * 32 + tx;
-    if (dr >= row_begin && dr < row_end && dc < dr && dc < n) full[(size_t)dr * n + dc] = tile[tx][ty];
+#pragma unroll
+    for (int a = 0; a < W; a += 32)
+#pragma unroll
+        for (int b = 0; b < W; b += 32) {
+            const int dr = ti * W + ty + a, dc = tj * W + tx + b;
+            if (dr >= row_begin && dr < row_end && dc < dr && dc < n) full[(size_t)dr * n + dc] = tile[tx + b][ty + a];
+        }
 }
 
 }  // namespace smb

@@ -68,23 +68,34 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return key32[a] < key32[b]; });
     for (u64 q = 0; q < T; ++q) { key32s[q] = key32[perm[q]]; payss[q] = pays[perm[q]]; }
-    u32 count = 0;
-    if (low_bits) {
-        smb_emu::launch(3, 64, 0, [&] { stripe_descent_kernel(key32s.data(), payss.data(), T, worklist.data(), &count); });
-        smb_emu::launch(2, 32, 0, [&] { stripe_fix_kernel(key32s.data(), payss.data(), T, worklist.data(), &count); });
-    }
-    if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "mixed runs repaired: %u\n", count);
-    // the stream must now be the hashes in ascending order, rows ascending inside a group
-    for (u64 q = 0; q + 1 < T; ++q) {
-        const u64 a = h[(u32)payss[q]], b = h[(u32)payss[q + 1]];
-        if (a > b || (a == b && (u32)payss[q] > (u32)payss[q + 1])) return 5;
-    }
     const u64 nblk = (T >> STRIPE_EBLK_LOG2) + 1;
     std::vector<u32> eblk(nblk + 1);
     smb_emu::launch(2, 64, 0, [&] { stripe_eblk_kernel(off.data(), n, T, eblk.data()); });
     smb_emu::launch((n + 63) / 64 + 1, 64, 0, [&] { stripe_sizes_kernel(off.data(), n, sizes.data()); });
     std::vector<TagT> tags(T + STRIPE_TAG_PAD + 1);
-    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data()); });
+    u32 count = 0;
+    u32* wl = low_bits ? worklist.data() : nullptr;
+    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data(), wl, &count); });
+    if (low_bits)            // pays (the sort's input) is free: the ordered payloads of the repaired runs
+        smb_emu::launch(2, 64, 0, [&] { stripe_fix_kernel<TagT>(key32s.data(), payss.data(), T, worklist.data(), &count, off.data(), n, pays.data(), tags.data(), pos.data()); });
+    if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "mixed runs repaired: %u\n", count);
+    // the stream must now be the hashes in ascending order, rows ascending inside a group: pos[] a permutation, tags = owning
+    // row, head flag exactly where the hash changes
+    {
+        std::vector<u32> inv(T, 0xffffffffu);
+        for (u64 e = 0; e < T; ++e) {
+            if (pos[e] >= T || inv[pos[e]] != 0xffffffffu) return 5;
+            inv[pos[e]] = (u32)e;
+        }
+        constexpr u32 HEAD = StripeTag<TagT>::HEAD;
+        for (u64 q = 0; q < T; ++q) {
+            const u64 x = h[inv[q]];
+            if (q + 1 < T) { const u64 y = h[inv[q + 1]]; if (x > y || (x == y && inv[q] > inv[q + 1])) return 5; }
+            const bool head = q == 0 || h[inv[q - 1]] != x;
+            if (((u32)tags[q] & HEAD ? true : false) != head) return 7;
+            if (((u32)tags[q] & ~HEAD) != stripe_row_of(off.data(), n, inv[q])) return 8;
+        }
+    }
     std::vector<double> out((size_t)n * n, -1.0);
     const size_t smem = (size_t)STRIPE_HEADER + (size_t)R * n * sizeof(u32);
     // two launches over row chunks, like the host path of smb_compare_jaccard
@@ -94,10 +105,10 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
         if (r1 <= r0) continue;
         StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr};
         const int blocks = (r1 - r0 + R - 1) / R;
-        if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true>(a); });
-        else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false>(a); });
+        if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true, 1>(a); });
+        else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false, 2>(a); });
         if (upper) {
-            const int t0 = r0 / 32, t1 = (r1 + 31) / 32;
+            const int t0 = r0 / STRIPE_MIRROR_TILE, t1 = (r1 + STRIPE_MIRROR_TILE - 1) / STRIPE_MIRROR_TILE;
             smb_emu::launch(smb_emu::Dim3(t1, t1 - t0), 1024, 0, [&] { stripe_mirror_kernel<double>(out.data(), n, r0, r1); });
         }
     }

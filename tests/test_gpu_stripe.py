@@ -88,7 +88,7 @@ def test_stripe_layout_edge_rows(B, monkeypatch, layout):
 
 def test_stripe_repairs_runs_of_equal_sort_keys(B, monkeypatch):
     """The stream is sorted on the top 32 significant bits of the hashes; hashes that agree there and differ
-    below form one run of the sort and are put in order afterwards (stripe_descent_kernel / stripe_fix_kernel).
+    below form one run of the sort; stripe_tag_kernel notices such runs and stripe_fix_kernel redoes them in order.
     Planted: scaled=1000-sized keys (22 low bits) and full 64-bit keys (32 low bits), interleaved over rows."""
     monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
     h, off = synth_sketches(1200, mean=300, sd=60, lo=0, hi=600, n_families=8, pool=400, seed=23)
@@ -188,3 +188,34 @@ def test_take_rows_and_device_query_entry_points(B):
     d_c = torch.full((300,), -1, dtype=torch.int32, device="cuda")
     B.one_vs_many_device(d_q.data_ptr(), len(q), sset, d_c.data_ptr())
     assert np.array_equal(d_c.cpu().numpy().astype(np.uint64), orc.one_vs_many(q, h, off))
+
+
+def _jaccard_rows_from_counts(h, off, lo, hi):
+    "rows [lo, hi) of compare_serial's matrix from the oracle's one-vs-many counts (n x n does not fit for n ~ 3e4)"
+    sizes = np.diff(off).astype(np.uint64)
+    want = np.empty((hi - lo, len(sizes)), dtype=np.float64)
+    for i in range(lo, hi):
+        common = orc.one_vs_many(h[int(off[i]):int(off[i + 1])], h, off, nthreads=8)
+        union = sizes[i] + sizes - common
+        want[i - lo] = common.astype(np.float64) / np.maximum(union, 1).astype(np.float64)
+        want[i - lo, i] = 1.0
+    return want
+
+
+@pytest.mark.parametrize("n,ctas", [(27000, None), (29000, None), (1500, "1")])
+def test_stripe_row_blocks_for_one_and_two_ctas_per_sm(B, monkeypatch, n, ctas):
+    """The count kernel runs two CTAs per SM when a row block of >= 1 row fits half the shared memory (n <= 28 536 columns
+    of u32 counters), else one; SMB_STRIPE_CTAS=1 forces one.  27 000 columns: one-row blocks, two CTAs; 29 000: two-row
+    blocks, one CTA."""
+    monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
+    if ctas:
+        monkeypatch.setenv("SMB_STRIPE_CTAS", ctas)
+    rng = np.random.Generator(np.random.PCG64(n))
+    pool = rng.integers(1, 2**54, size=4000, dtype=np.uint64)
+    rows = [np.unique(rng.choice(pool, size=int(rng.integers(0, 30)))) for _ in range(n)]
+    h, off = orc.to_csr(rows)
+    sset = B.SketchSet.from_host(h, off)
+    for lo, hi in ((0, 3), (n // 2 - 1, n // 2 + 6), (n - 5, n)):
+        d_rows = _DeviceMatrix((hi - lo, n))
+        B.compare_jaccard_rows_device(sset, lo, hi, d_rows.ptr)
+        assert np.array_equal(d_rows.numpy(), _jaccard_rows_from_counts(h, off, lo, hi)), (n, lo, hi)

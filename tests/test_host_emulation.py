@@ -311,8 +311,8 @@ def simt():
 
 def test_simt_stripe_kernels_match_oracle(simt):
     """The stripe pipeline kernel by kernel as join_stripe_create / join_stripe_rows launch it: 32-bit keys +
-    payloads, (host-sorted,) descent detection and in-place repair of runs that mix hashes, element-block
-    row table, u16 / u32 tags + inverse permutation, the count kernel (dynamic (row, chunk) items, four group
+    payloads, (host-sorted,) element-block row table, u16 / u32 tags + inverse permutation with descent detection, the
+    warp-per-run repair of runs that mix hashes, the count kernel (dynamic (row, chunk) items, four group
     reads in flight, upper-only and two-direction modes, shared-memory stripe, fused float64 finalize), mirror,
     row chunks.  Sort keys shortened to 8 / 3 bits make mixed runs the rule rather than a 1-in-10^4 event."""
     from sourmash_b200.synth import synth_sketches
