@@ -212,6 +212,22 @@ struct StripeArgs {
     u16* out_counts16;       // ... as 16-bit counters (rows shorter than 65 536 hashes: half the bytes to exchange)
 };
 
+// A counter of the stripe is bumped through the 32-bit shared-memory address of its row: one address add and one
+// ATOMS per increment.  (atomicAdd on the generic pointer made the compiler rebuild the shared-window base --
+// S2UR, UMOV, ULEA, IMAD, LEA -- for every increment under its 32-register budget: 13 instructions against 9.)
+#ifdef SMB_SIMT_EMUL
+typedef u32* StripeRowRef;                                            // the emulator has no shared address space
+inline StripeRowRef stripe_row_ref(u32* row) { return row; }
+inline void stripe_inc_if(StripeRowRef row, u32 col, bool on) { if (on) atomicAdd(row + col, 1u); }
+#else
+typedef u32 StripeRowRef;
+__device__ __forceinline__ StripeRowRef stripe_row_ref(u32* row) { return (u32)__cvta_generic_to_shared(row); }
+__device__ __forceinline__ void stripe_inc_if(StripeRowRef row, u32 col, bool on) {
+    // (ptxas keeps a short branch around the ATOMS either way: its increment form aggregates over the converged lanes)
+    if (on) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(row + (col << 2)) : "memory");
+}
+#endif
+
 // One CTA = rows [r0, r1) of the result.  Work items are (row, chunk of 32 consecutive elements), handed to the
 // warps chunk index first, so that all rows of the CTA -- and, as CTAs start together, all CTAs of a wave --
 // move through the hash-ordered stream together.  For every element with a successor in its group the warp
@@ -261,43 +277,49 @@ __global__ void __launch_bounds__(1024, CTAS) join_stripe_kernel(StripeArgs a) {
         u32* row_ptr = stripe + (size_t)r * n;
 
         // ---- members behind the element (higher rows): 64 tags per element are requested at once (groups of
-        // the benchmark have ~35 members behind an element on average), two elements per round
+        // the benchmark have ~35 members behind an element on average), two elements per round.  A lane counts
+        // its tag when no group head lies at or in front of it (m & le_mask == 0); the row index of a tag that is
+        // not counted is still a valid column (the padding tags are HEAD | 0), so addresses need no guard.
+        const StripeRowRef row_ref = stripe_row_ref(row_ptr);
+        const u32 lane1 = lane + 1u;
         u32 nxt = HEAD;
         if (have) nxt = (u32)tags[(size_t)my_q + 1];
-        u32 todo = __ballot_sync(0xffffffffu, (nxt & HEAD) == 0);
+        u32 todo = __ballot_sync(0xffffffffu, nxt < HEAD);
         while (todo) {
             const int j0 = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int j1 = todo ? __ffs(todo) - 1 : -1;
-            todo &= todo - (todo ? 1u : 0u);
-            const u32 q0 = __shfl_sync(0xffffffffu, my_q, j0);
-            const u32 q1 = __shfl_sync(0xffffffffu, my_q, j1 < 0 ? j0 : j1);
-            const u32 t00 = (u32)fwd[q0], t01 = (u32)fwd[q0 + 32];
+            const bool two = todo != 0;                    // uniform in the warp
+            const int j1 = two ? __ffs(todo) - 1 : j0;
+            todo &= todo - 1;                              // 0 stays 0
+            // 32-bit position + lane + 1 (no wrap: T < 2^32 - 128), widened once per element
+            const TagT* __restrict__ p0 = tags + (__shfl_sync(0xffffffffu, my_q, j0) + lane1);
+            const TagT* __restrict__ p1 = tags + (__shfl_sync(0xffffffffu, my_q, j1) + lane1);
+            const u32 t00 = (u32)p0[0], t01 = (u32)p0[32];
             u32 t10 = HEAD, t11 = HEAD;
-            if (j1 >= 0) { t10 = (u32)fwd[q1]; t11 = (u32)fwd[q1 + 32]; }
+            if (two) { t10 = (u32)p1[0]; t11 = (u32)p1[32]; }
             {
-                u32 m = __ballot_sync(0xffffffffu, (t00 & HEAD) != 0);
-                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t00 & ~HEAD), 1u);
+                u32 m = __ballot_sync(0xffffffffu, t00 >= HEAD);
+                stripe_inc_if(row_ref, t00 & (HEAD - 1u), (m & le_mask) == 0);
                 if (m == 0) {
-                    m = __ballot_sync(0xffffffffu, (t01 & HEAD) != 0);
-                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t01 & ~HEAD), 1u);
+                    m = __ballot_sync(0xffffffffu, t01 >= HEAD);
+                    stripe_inc_if(row_ref, t01 & (HEAD - 1u), (m & le_mask) == 0);
                     for (u32 it = 2; m == 0; ++it) {       // more than 64 members behind
-                        const u32 tt = (u32)fwd[q0 + 32 * it];
-                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
-                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                        const u32 tt = (u32)p0[32 * it];
+                        m = __ballot_sync(0xffffffffu, tt >= HEAD);
+                        stripe_inc_if(row_ref, tt & (HEAD - 1u), (m & le_mask) == 0);
                     }
                 }
             }
-            if (j1 >= 0) {                                 // uniform in the warp
-                u32 m = __ballot_sync(0xffffffffu, (t10 & HEAD) != 0);
-                if ((m & le_mask) == 0) atomicAdd(row_ptr + (t10 & ~HEAD), 1u);
+            if (two) {
+                u32 m = __ballot_sync(0xffffffffu, t10 >= HEAD);
+                stripe_inc_if(row_ref, t10 & (HEAD - 1u), (m & le_mask) == 0);
                 if (m == 0) {
-                    m = __ballot_sync(0xffffffffu, (t11 & HEAD) != 0);
-                    if ((m & le_mask) == 0) atomicAdd(row_ptr + (t11 & ~HEAD), 1u);
+                    m = __ballot_sync(0xffffffffu, t11 >= HEAD);
+                    stripe_inc_if(row_ref, t11 & (HEAD - 1u), (m & le_mask) == 0);
                     for (u32 it = 2; m == 0; ++it) {
-                        const u32 tt = (u32)fwd[q1 + 32 * it];
-                        m = __ballot_sync(0xffffffffu, (tt & HEAD) != 0);
-                        if ((m & le_mask) == 0) atomicAdd(row_ptr + (tt & ~HEAD), 1u);
+                        const u32 tt = (u32)p1[32 * it];
+                        m = __ballot_sync(0xffffffffu, tt >= HEAD);
+                        stripe_inc_if(row_ref, tt & (HEAD - 1u), (m & le_mask) == 0);
                     }
                 }
             }
