@@ -21,8 +21,8 @@
 // hash, the remaining low bits travel in the 64-bit payload in front of the element index
 // (payload = low bits << 32 | e).  Elements with equal 32-bit keys form a run, kept in CSR order by the
 // stable sort; nearly every run is one group.  The rare runs that mix different hashes (expected
-// distinct^2 / 2^33) are recognised by a payload that is smaller than its predecessor's and sorted in place
-// by one thread each -- ascending payloads = ascending (low bits, element) = groups contiguous, rows ascending.
+// distinct^2 / 2^33) are recognised by a payload that is smaller than its predecessor's and redone in order
+// by one warp each -- ascending payloads = ascending (low bits, element) = groups contiguous, rows ascending.
 // Because the key is a prefix of the hash, the stream is in hash order and every row walks it front to back.
 #pragma once
 #include "common.cuh"

@@ -48,7 +48,7 @@ static void dump(const char* path, const std::vector<T>& v) {
 // The stripe pipeline as join_stripe_create / join_stripe_rows launch it (compare_kernels.cu), kernel by kernel;
 // a stable host sort stands in for cub::DeviceRadixSort::SortPairs.  `sort_bits` < 64 shortens the sort key
 // below the 32 bits the product uses, so that runs mixing different hashes -- rare with 32-bit keys -- occur
-// in every small test set and the descent / fix kernels are exercised.
+// in every small test set and the descent detection of the tag kernel / the fix kernel are exercised.
 template <typename TagT>
 static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<u64>& h, const std::vector<u64>& off,
                       const char* fout) {
