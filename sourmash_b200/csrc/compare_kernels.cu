@@ -468,6 +468,7 @@ struct JoinStripe {
     const u64 *ebeg = nullptr, *eend = nullptr;
     u64 T = 0;                // elements in the stream (all of the set, or one key range of it)
     int n = 0, rows_per_block = 0, upper_only = 1, tag16 = 0, sharded = 0;
+    unsigned swz = 0;         // tags hold stripe_col(row, swz): counters of rows a fixed stride apart spread over the banks
     int ctas_per_sm = 1;      // 2: rows_per_block sized for two resident CTAs (64 warps per SM; the count kernel is bound by issue latency)
     size_t smem = 0;
     ~JoinStripe() { if (mem) cudaFreeAsync(mem, stream); }
@@ -513,6 +514,10 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     auto js = new JoinStripe();
     std::unique_ptr<JoinStripe> guard(js);
     js->stream = s; js->n = n; js->rows_per_block = R; js->ctas_per_sm = ctas;
+    {
+        const char* z = getenv("SMB_STRIPE_SWIZZLE");                // A/B: 0 = counters in column order
+        js->swz = (z && !strcmp(z, "0")) ? 0u : ((unsigned)n & ~31u);
+    }
     js->tag16 = n < 32768;
     js->sharded = n_shards > 1;
     {
@@ -563,8 +568,8 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
         js->ebeg = off; js->eend = off + 1;
     }
     if (T == 0) {                                                   // no hash in this key range: every partial count is zero
-        if (js->tag16) stripe_tag_kernel<u16><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u16*)js->tags, js->pos, nullptr, nullptr);
-        else stripe_tag_kernel<u32><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u32*)js->tags, js->pos, nullptr, nullptr);
+        if (js->tag16) stripe_tag_kernel<u16><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u16*)js->tags, js->pos, nullptr, nullptr, 0u);
+        else stripe_tag_kernel<u32><<<1, 256, 0, s>>>(nullptr, nullptr, off, nullptr, 0, (u32*)js->tags, js->pos, nullptr, nullptr, 0u);
         count_launches(1);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         *out = guard.release();
@@ -602,12 +607,12 @@ cudaError_t join_stripe_create_shard(const u64* h, const u64* off, int n, u64 T_
     u32* worklist = low_bits ? key_a : nullptr;
     if (low_bits) cudaMemsetAsync(d_count, 0, sizeof(u32), s);
     stripe_eblk_kernel<<<(unsigned)std::min<u64>((nblk + 255) / 256, (u64)SMB_B200_SMS * 8), 256, 0, s>>>(off, n, T_all, eblk);
-    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos, worklist, d_count);
-    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos, worklist, d_count);
+    if (js->tag16) stripe_tag_kernel<u16><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u16*)js->tags, js->pos, worklist, d_count, js->swz);
+    else stripe_tag_kernel<u32><<<grid, 256, 0, s>>>(key_b, pay_b, off, eblk, T, (u32*)js->tags, js->pos, worklist, d_count, js->swz);
     count_launches(2);
     if (low_bits) {
-        if (js->tag16) stripe_fix_kernel<u16><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u16*)js->tags, js->pos);
-        else stripe_fix_kernel<u32><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u32*)js->tags, js->pos);
+        if (js->tag16) stripe_fix_kernel<u16><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u16*)js->tags, js->pos, js->swz);
+        else stripe_fix_kernel<u32><<<SMB_B200_SMS * 4, 128, 0, s>>>(key_b, pay_b, T, worklist, d_count, off, n, pay_a, (u32*)js->tags, js->pos, js->swz);
         count_launches(1);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -622,7 +627,7 @@ static cudaError_t stripe_launch(const JoinStripe* js, int row_begin, int row_en
                                  cudaStream_t s) {
     if (row_end <= row_begin) return cudaSuccess;
     StripeArgs a{js->tags, js->pos, js->ebeg, js->eend, js->sizes, js->T, js->n, js->rows_per_block, row_begin, row_end, d_out,
-                 d_counts, d_counts16};
+                 d_counts, d_counts16, js->swz};
     const int blocks = (row_end - row_begin + js->rows_per_block - 1) / js->rows_per_block;
     const bool upper = js->upper_only;
     const bool two = js->ctas_per_sm == 2;

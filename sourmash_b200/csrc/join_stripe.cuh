@@ -57,6 +57,14 @@ __host__ __device__ __forceinline__ double stripe_jaccard(u32 common, u64 size_i
     return (double)common / (double)(un > 1 ? un : 1);
 }
 
+// Column of a stripe that holds the counter of row j.  Inside every whole block of 32 columns the low five bits are
+// XORed with the block index: rows a fixed stride apart (related genomes listed at regular distances -- the benchmark's
+// families are rows f, f + 100, f + 200, ...: 8 banks for 25 lanes, 5 wavefronts per ATOMS) spread over all banks.
+// The tags of the stream carry this column, so the count kernel pays nothing; its output stage reads counter
+// stripe_col(j) for column j (a permutation inside each block: conflict-free).  `swz` = number of columns in whole
+// blocks (the last partial block stays as it is), 0 = no swizzle.
+__host__ __device__ __forceinline__ u32 stripe_col(u32 j, u32 swz) { return j < swz ? j ^ ((j >> 5) & 31u) : j; }
+
 // rows per CTA for a stripe of `ncols` u32 counters per row in `smem_bytes` of shared memory
 __host__ __device__ __forceinline__ int stripe_rows_per_block(size_t smem_bytes, int ncols) {
     if (smem_bytes <= (size_t)STRIPE_HEADER || ncols <= 0) return 0;
@@ -121,7 +129,7 @@ template <typename TagT>
 __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays,
                                                         const u64* __restrict__ off, const u32* __restrict__ eblk, u64 T,
                                                         TagT* __restrict__ tags, u32* __restrict__ pos,
-                                                        u32* __restrict__ worklist, u32* __restrict__ d_count) {
+                                                        u32* __restrict__ worklist, u32* __restrict__ d_count, u32 swz) {
     constexpr int U = 4;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 q0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; q0 < T; q0 += stride * U) {
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__
             u32 rr = r[u];
             u64 end = nx[u];
             while (end <= (u64)e) end = off[++rr + 1];    // e < T = off[n]: stops at the owning row, empty rows skipped
-            tags[q] = (TagT)(rr | (head ? StripeTag<TagT>::HEAD : 0u));
+            tags[q] = (TagT)(stripe_col(rr, swz) | (head ? StripeTag<TagT>::HEAD : 0u));
             pos[e] = (u32)q;
             // a run that mixes hashes (null worklist: the keys hold every bit, no such runs)
             if (worklist && q && k[u] == kp[u] && p[u] < pp[u]) stripe_note_descent(key32s, pays, q, k[u], worklist, d_count);
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(256) stripe_tag_kernel(const u32* __restrict__
 template <typename TagT>
 __global__ void __launch_bounds__(128) stripe_fix_kernel(const u32* __restrict__ key32s, const u64* __restrict__ pays, u64 T,
                                                         const u32* __restrict__ worklist, const u32* __restrict__ d_count,
-                                                        const u64* __restrict__ off, int n, u64* tmp, TagT* tags, u32* pos) {
+                                                        const u64* __restrict__ off, int n, u64* tmp, TagT* tags, u32* pos, u32 swz) {
     const u32 count = *d_count;
     const u32 lane = lane_id();
     const u32 warps = gridDim.x * (blockDim.x >> 5);
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(128) stripe_fix_kernel(const u32* __restrict__
             const u64 v = tmp[q];
             const bool first = q == head || (tmp[q - 1] >> 32) != (v >> 32);
             const u32 e = (u32)v;
-            tags[q] = (TagT)(stripe_row_of(off, n, (u64)e) | (first ? StripeTag<TagT>::HEAD : 0u));
+            tags[q] = (TagT)(stripe_col(stripe_row_of(off, n, (u64)e), swz) | (first ? StripeTag<TagT>::HEAD : 0u));
             pos[e] = (u32)q;
         }
         __syncwarp();
@@ -210,6 +218,7 @@ struct StripeArgs {
     double* out;             // float64 Jaccard rows, row `row_begin` first, leading dimension n (null: counts only)
     u32* out_counts;         // raw counters of the rows instead (a key-range shard's partial counts), same layout
     u16* out_counts16;       // ... as 16-bit counters (rows shorter than 65 536 hashes: half the bytes to exchange)
+    u32 swz;                 // the tags hold stripe_col(row, swz)
 };
 
 // A counter of the stripe is bumped through the 32-bit shared-memory address of its row: one address add and one
@@ -278,8 +287,9 @@ __global__ void __launch_bounds__(1024, CTAS) join_stripe_kernel(StripeArgs a) {
 
         // ---- members behind the element (higher rows): 64 tags per element are requested at once (groups of
         // the benchmark have ~35 members behind an element on average), two elements per round.  A lane counts
-        // its tag when no group head lies at or in front of it (m & le_mask == 0); the row index of a tag that is
-        // not counted is still a valid column (the padding tags are HEAD | 0), so addresses need no guard.
+        // its tag when no group head lies at or in front of it (m & le_mask == 0); a tag is the stripe column of its row
+        // (stripe_col), and that of a tag that is not counted is still a valid column (the padding tags are HEAD | 0), so
+        // addresses need no guard.
         const StripeRowRef row_ref = stripe_row_ref(row_ptr);
         const u32 lane1 = lane + 1u;
         u32 nxt = HEAD;
@@ -351,20 +361,20 @@ __global__ void __launch_bounds__(1024, CTAS) join_stripe_kernel(StripeArgs a) {
         if (a.out_counts) {                                // a shard of the keys: partial counts, summed over the shards later
             u32* __restrict__ crow = a.out_counts + (size_t)(row - a.row_begin) * n;
             for (u32 j = threadIdx.x; j < n; j += blockDim.x)
-                if (!UPPER || j >= (u32)row) crow[j] = srow[j];     // UPPER: the caller mirrors (a shard's counts are symmetric)
+                if (!UPPER || j >= (u32)row) crow[j] = srow[stripe_col(j, a.swz)];     // UPPER: the caller mirrors (a shard's counts are symmetric)
             continue;
         }
         if (a.out_counts16) {
             u16* __restrict__ crow = a.out_counts16 + (size_t)(row - a.row_begin) * n;
             for (u32 j = threadIdx.x; j < n; j += blockDim.x)
-                if (!UPPER || j >= (u32)row) crow[j] = (u16)srow[j];
+                if (!UPPER || j >= (u32)row) crow[j] = (u16)srow[stripe_col(j, a.swz)];
             continue;
         }
         const u64 si = a.sizes[row];
         double* __restrict__ orow = a.out + (size_t)(row - a.row_begin) * n;
         for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
             if (UPPER && j < (u32)row) continue;
-            st_stream_f64(orow + j, stripe_jaccard(srow[j], si, a.sizes[j], (u32)row == j));
+            st_stream_f64(orow + j, stripe_jaccard(srow[stripe_col(j, a.swz)], si, a.sizes[j], (u32)row == j));
         }
     }
 }

@@ -75,9 +75,10 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     std::vector<TagT> tags(T + STRIPE_TAG_PAD + 1);
     u32 count = 0;
     u32* wl = low_bits ? worklist.data() : nullptr;
-    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data(), wl, &count); });
+    const u32 swz = (R & 1) ? ((u32)n & ~31u) : 0u;          // both column orders over the test configurations
+    smb_emu::launch(2, 96, 0, [&] { stripe_tag_kernel<TagT>(key32s.data(), payss.data(), off.data(), eblk.data(), T, tags.data(), pos.data(), wl, &count, swz); });
     if (low_bits)            // pays (the sort's input) is free: the ordered payloads of the repaired runs
-        smb_emu::launch(2, 64, 0, [&] { stripe_fix_kernel<TagT>(key32s.data(), payss.data(), T, worklist.data(), &count, off.data(), n, pays.data(), tags.data(), pos.data()); });
+        smb_emu::launch(2, 64, 0, [&] { stripe_fix_kernel<TagT>(key32s.data(), payss.data(), T, worklist.data(), &count, off.data(), n, pays.data(), tags.data(), pos.data(), swz); });
     if (getenv("SMB_EMUL_REPORT")) fprintf(stderr, "mixed runs repaired: %u\n", count);
     // the stream must now be the hashes in ascending order, rows ascending inside a group: pos[] a permutation, tags = owning
     // row, head flag exactly where the hash changes
@@ -93,7 +94,7 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
             if (q + 1 < T) { const u64 y = h[inv[q + 1]]; if (x > y || (x == y && inv[q] > inv[q + 1])) return 5; }
             const bool head = q == 0 || h[inv[q - 1]] != x;
             if (((u32)tags[q] & HEAD ? true : false) != head) return 7;
-            if (((u32)tags[q] & ~HEAD) != stripe_row_of(off.data(), n, inv[q])) return 8;
+            if (((u32)tags[q] & ~HEAD) != stripe_col(stripe_row_of(off.data(), n, inv[q]), swz)) return 8;
         }
     }
     std::vector<double> out((size_t)n * n, -1.0);
@@ -103,7 +104,7 @@ static int stripe_run(int R, int upper, int threads, int sort_bits, std::vector<
     for (int c = 0; c < 2; ++c) {
         const int r0 = c ? half : 0, r1 = c ? n : half;
         if (r1 <= r0) continue;
-        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr};
+        StripeArgs a{tags.data(), pos.data(), off.data(), off.data() + 1, sizes.data(), T, n, R, r0, r1, out.data() + (size_t)r0 * n, nullptr, nullptr, swz};
         const int blocks = (r1 - r0 + R - 1) / R;
         if (upper) smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, true, 1>(a); });
         else smb_emu::launch(blocks, threads, smem, [&] { join_stripe_kernel<TagT, false, 2>(a); });

@@ -202,14 +202,17 @@ def _jaccard_rows_from_counts(h, off, lo, hi):
     return want
 
 
-@pytest.mark.parametrize("n,ctas", [(27000, None), (29000, None), (1500, "1")])
-def test_stripe_row_blocks_for_one_and_two_ctas_per_sm(B, monkeypatch, n, ctas):
+@pytest.mark.parametrize("n,ctas,swizzle", [(27000, None, None), (29000, None, None), (1500, "1", None), (1500, None, "0"), (1483, None, None)])
+def test_stripe_row_blocks_for_one_and_two_ctas_per_sm(B, monkeypatch, n, ctas, swizzle):
     """The count kernel runs two CTAs per SM when a row block of >= 1 row fits half the shared memory (n <= 28 536 columns
     of u32 counters), else one; SMB_STRIPE_CTAS=1 forces one.  27 000 columns: one-row blocks, two CTAs; 29 000: two-row
-    blocks, one CTA."""
+    blocks, one CTA.  SMB_STRIPE_SWIZZLE=0: counters in column order instead of stripe_col's bank-spreading order (1 483
+    columns: a last partial block of 11, left in place)."""
     monkeypatch.setenv("SMB_COMPARE_ALGO", "join")
     if ctas:
         monkeypatch.setenv("SMB_STRIPE_CTAS", ctas)
+    if swizzle:
+        monkeypatch.setenv("SMB_STRIPE_SWIZZLE", swizzle)
     rng = np.random.Generator(np.random.PCG64(n))
     pool = rng.integers(1, 2**54, size=4000, dtype=np.uint64)
     rows = [np.unique(rng.choice(pool, size=int(rng.integers(0, 30)))) for _ in range(n)]

@@ -23,7 +23,7 @@ import bench  # noqa: E402
 from sourmash_b200 import batch as B  # noqa: E402
 from sourmash_b200.synth import MAX_HASH_1000, rows_of, synth_sketches  # noqa: E402
 
-SWITCHES = ("SMB_JOIN_LAYOUT", "SMB_COMPARE_ALGO", "SMB_SKETCH_FUSED", "SMB_SEARCH_LAYOUT", "SMB_STRIPE_TAGS", "SMB_STRIPE_CTAS")
+SWITCHES = ("SMB_JOIN_LAYOUT", "SMB_COMPARE_ALGO", "SMB_SKETCH_FUSED", "SMB_SEARCH_LAYOUT", "SMB_STRIPE_TAGS", "SMB_STRIPE_CTAS", "SMB_STRIPE_SWIZZLE")
 
 
 def log(*a):
@@ -60,7 +60,8 @@ def ab_compare(out):
     set_env({})
     B.compare_jaccard_device(sset, d_ref.data_ptr())
     torch.cuda.synchronize()
-    variants = [("stripe (default: u16 tags, upper + mirror, two CTAs per SM)", {}),
+    variants = [("stripe (default: u16 tags, upper + mirror, two CTAs per SM, swizzled counter columns)", {}),
+                ("stripe, counters in column order", {"SMB_STRIPE_SWIZZLE": "0"}),
                 ("stripe, one CTA per SM (five-row blocks)", {"SMB_STRIPE_CTAS": "1"}),
                 ("stripe, u32 tags", {"SMB_STRIPE_TAGS": "u32"}),
                 ("stripe_full (both directions)", {"SMB_JOIN_LAYOUT": "stripe_full"}),
