@@ -37,8 +37,8 @@ def random_row(rng, scale):
 
 
 def trial(rng):
-    n = int(rng.integers(1, 40))
-    scale = int(rng.choice([5, 60, 600]))
+    n = int(rng.integers(1, 40)) if rng.random() < 0.7 else int(rng.integers(40, 130))   # > 32 rows: whole blocks of swizzled counter columns
+    scale = int(rng.choice([5, 60, 600])) if n < 40 else int(rng.choice([5, 60]))
     rows = [random_row(rng, scale) for _ in range(n)]
     for _ in range(int(rng.integers(0, 4))):                                        # related rows
         i, j = rng.integers(0, n, size=2)
@@ -56,6 +56,10 @@ def trial(rng):
             os.environ["SMB_JOIN_LAYOUT"], os.environ["SMB_STRIPE_TAGS"] = layout, tags
             assert np.array_equal(B.compare_jaccard(db), want), ("compare", layout, tags, n, scale)
         os.environ.pop("SMB_JOIN_LAYOUT"); os.environ.pop("SMB_STRIPE_TAGS")
+        for key in ("SMB_STRIPE_CTAS", "SMB_STRIPE_SWIZZLE"):                        # one CTA per SM / counters in column order
+            os.environ[key] = "1" if key.endswith("CTAS") else "0"
+            assert np.array_equal(B.compare_jaccard(db), want), ("compare", key, n, scale)
+            os.environ.pop(key)
         os.environ["SMB_SEARCH_LAYOUT"] = "global"
         if rng.random() < 0.5 and len(h) and len(h) < 2**31:
             db.build_index()
