@@ -1507,15 +1507,12 @@ SourmashSignature* signature_from_params(const SourmashComputeParameters* p) {
 }
 uintptr_t signature_len(const SourmashSignature* ptr) { return ptr->sketches.size(); }
 bool signature_eq(const SourmashSignature* a, const SourmashSignature* b) {
-    // signature.rs PartialEq (:883-905): class/license/name-independent metadata + sketches' mins
-    if (a->sketches.size() != b->sketches.size()) return false;
-    for (size_t i = 0; i < a->sketches.size(); ++i) {
-        const MH &x = a->sketches[i], &y = b->sketches[i];
-        if (x.ksize != y.ksize || x.num != y.num || x.max_hash != y.max_hash || x.seed != y.seed ||
-            x.hash_function != y.hash_function || x.mins != y.mins) return false;
-        if (x.track && y.track && x.abunds != y.abunds) return false;
-    }
-    return true;
+    // signature.rs:869-888 (PartialEq): class, email, hash_function, filename and name, and the FIRST sketch of each --
+    // sketches compare by md5sum (sketch/minhash.rs:66-71: ksize + mins; abundances, seed and max_hash do not enter)
+    const bool metadata = a->klass == b->klass && a->email == b->email && a->hash_function == b->hash_function &&
+                          a->filename == b->filename && a->name == b->name;
+    if (a->sketches.empty() || b->sketches.empty()) return metadata;     // (the reference indexes signatures[0] and panics here)
+    return metadata && a->sketches[0].md5sum() == b->sketches[0].md5sum();
 }
 void signature_add_sequence(SourmashSignature* ptr, const char* sequence, bool force) {
     // signature.rs:661-677: every sketch of the signature sees the sequence.  One upload, one

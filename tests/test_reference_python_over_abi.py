@@ -1,11 +1,13 @@
 """The reference's OWN Python object model over this library's C ABI.
 
-/root/reference/src/sourmash/{minhash,signature,utils,exceptions,distance_utils,logging}.py are loaded IN PLACE
+/root/reference/src/sourmash/{minhash,signature,utils,exceptions,distance_utils,logging,compare,sketchcomparison,np_utils}.py
+are loaded IN PLACE
 (symlinks, nothing is copied) as a package `sourmash` whose `_lowlevel` is a cffi ABI-mode binding built from
 the REFERENCE header /root/reference/include/sourmash.h -- exactly what maturin generates for the Rust cdylib
 (pyproject.toml:138-155) -- but dlopen()s libsourmash_b200 instead.  The reference's own test modules
-(tests/test_minhash.py, test_jaccard.py, test__minhash_hypothesis.py, unmodified, read in place with their
-test-data) are then run by pytest in a subprocess.
+(tests/test_minhash.py, test_jaccard.py, test__minhash_hypothesis.py, test_signature.py, test_compare.py --
+the reference's compare.py loops, multiprocessing included -- and test_sketchcomparison.py, unmodified, read in
+place with their test-data) are then run by pytest in a subprocess.
 
 No GPU here and no /root/reference on the GPU box, so the "device" is the emulated build of the library
 (tests/host_emul/emul_lib.py: the product's capi.cu host glue and kernels compiled for the CPU, kernel
@@ -15,7 +17,7 @@ real hardware are pinned separately by the -m gpu tests against the same oracle 
 
 Stubs (ours, tiny): `deprecation` (a decorator that warns), `screed` (rc, FASTA records), the five fixtures of the
 reference's conftest.py that these modules use.  REFERENCE_DESELECT lists reference tests that are not run, each
-with its reason; it is empty for test_minhash.py -- all 311 cases pass."""
+with its reason; it is empty -- all 311 cases of test_minhash.py and all cases of the other five modules pass."""
 import os
 import subprocess
 import sys
@@ -52,9 +54,11 @@ VERSION = "0.0.0+libsourmash_b200"
 from .minhash import MinHash, get_minhash_default_seed, get_minhash_max_hash
 DEFAULT_SEED = get_minhash_default_seed()
 MAX_HASH = get_minhash_max_hash()
-from .signature import (load_signatures_from_json as load_signatures, load_one_signature_from_json as load_one_signature,
-                        SourmashSignature, save_signatures_to_json as save_signatures)
+from .signature import load_signatures_from_json, load_one_signature_from_json, SourmashSignature, save_signatures_to_json
+load_signatures, load_one_signature, save_signatures = load_signatures_from_json, load_one_signature_from_json, save_signatures_to_json
 from . import signature
+def load_file_as_signatures(filename, **kw):       # the reference's goes through sourmash_args / save_load (format sniffing:
+    return load_signatures_from_json(filename, **kw)   # out of scope); the tests here only hand it .sig JSON files
 '''
 
 PLUGIN = '''
@@ -111,7 +115,8 @@ STUBS = {
 def _stub_package(tmp, lib_path):
     pkg = os.path.join(tmp, "sourmash")
     os.makedirs(pkg)
-    for name in ("minhash.py", "signature.py", "utils.py", "exceptions.py", "distance_utils.py", "logging.py"):
+    for name in ("minhash.py", "signature.py", "utils.py", "exceptions.py", "distance_utils.py", "logging.py",
+                 "compare.py", "sketchcomparison.py", "np_utils.py"):
         os.symlink(os.path.join(REF, "src", "sourmash", name), os.path.join(pkg, name))
     with open(os.path.join(pkg, "_lowlevel.py"), "w") as fh:
         fh.write(LOWLEVEL.format(header=os.path.join(REF, "include", "sourmash.h"), lib=lib_path))
@@ -127,7 +132,8 @@ def _stub_package(tmp, lib_path):
     # the reference's test modules and helpers, read in place
     tests = os.path.join(tmp, "reftests")
     os.makedirs(tests)
-    for name in ("test_minhash.py", "test_jaccard.py", "test__minhash_hypothesis.py", "sourmash_tst_utils.py", "test-data"):
+    for name in ("test_minhash.py", "test_jaccard.py", "test__minhash_hypothesis.py", "test_signature.py", "test_compare.py",
+                 "test_sketchcomparison.py", "sourmash_tst_utils.py", "test-data"):
         os.symlink(os.path.join(REF, "tests", name), os.path.join(tests, name))
     return tests
 
@@ -184,9 +190,30 @@ def test_reference_jaccard_and_hypothesis_tests_pass_over_this_abi(tmp_path):
     assert counts["failed"] == 0 and counts["passed"] >= 15, tail
 
 
+@pytest.mark.timeout(1800)
+def test_reference_signature_compare_and_sketchcomparison_tests_pass_over_this_abi(tmp_path):
+    """tests/test_signature.py (48 functions: SourmashSignature over signature_* / signatures_load_* / save), test_compare.py
+    (the reference's compare_serial*, compare_parallel and compare_all_pairs loops calling this ABI pair by pair) and
+    test_sketchcomparison.py (FracMinHashComparison / NumMinHashComparison: containment, ANI, downsampling), unmodified.
+    `sourmash.load_file_as_signatures` is the stub package's three-line JSON loader (the reference's own sniffs formats
+    through sourmash_args / save_load: out of scope)."""
+    mods = ["test_signature.py", "test_compare.py", "test_sketchcomparison.py"]
+    deselect = []
+    for mod in mods:
+        for d in REFERENCE_DESELECT.get(mod, ()):
+            deselect += ["--deselect", "reftests/%s::%s" % (mod, d)]
+    r = _run_reference_tests(tmp_path, mods, deselect)
+    counts, tail = _counts(r.stdout)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert counts["failed"] == 0 and counts["error"] + counts["errors"] == 0 and counts["passed"] >= 140, tail
+
+
 # Reference tests that are NOT run, each with the reason; everything else in the modules must pass.
 REFERENCE_DESELECT = {
     "test_minhash.py": [],
     "test_jaccard.py": [],
     "test__minhash_hypothesis.py": [],
+    "test_signature.py": [],
+    "test_compare.py": [],
+    "test_sketchcomparison.py": [],
 }
