@@ -1,13 +1,14 @@
 """The reference's OWN Python object model over this library's C ABI.
 
-/root/reference/src/sourmash/{minhash,signature,utils,exceptions,distance_utils,logging,compare,sketchcomparison,np_utils}.py
-are loaded IN PLACE
+/root/reference/src/sourmash/{minhash,signature,utils,exceptions,distance_utils,logging,compare,sketchcomparison,np_utils,
+search,manifest,picklist,sbt_storage,save_load,sourmash_args,plugins,sqlite_utils}.py and index/__init__.py are loaded IN PLACE
 (symlinks, nothing is copied) as a package `sourmash` whose `_lowlevel` is a cffi ABI-mode binding built from
 the REFERENCE header /root/reference/include/sourmash.h -- exactly what maturin generates for the Rust cdylib
 (pyproject.toml:138-155) -- but dlopen()s libsourmash_b200 instead.  The reference's own test modules
 (tests/test_minhash.py, test_jaccard.py, test__minhash_hypothesis.py, test_signature.py, test_compare.py --
-the reference's compare.py loops, multiprocessing included -- and test_sketchcomparison.py, unmodified, read in
-place with their test-data) are then run by pytest in a subprocess.
+the reference's compare.py loops, multiprocessing included --, test_sketchcomparison.py, test_search.py and the
+in-scope classes of test_index_protocol.py, unmodified, read in place with their test-data) are then run by pytest
+in a subprocess.
 
 No GPU here and no /root/reference on the GPU box, so the "device" is the emulated build of the library
 (tests/host_emul/emul_lib.py: the product's capi.cu host glue and kernels compiled for the CPU, kernel
@@ -57,8 +58,8 @@ MAX_HASH = get_minhash_max_hash()
 from .signature import load_signatures_from_json, load_one_signature_from_json, SourmashSignature, save_signatures_to_json
 load_signatures, load_one_signature, save_signatures = load_signatures_from_json, load_one_signature_from_json, save_signatures_to_json
 from . import signature
-def load_file_as_signatures(filename, **kw):       # the reference's goes through sourmash_args / save_load (format sniffing:
-    return load_signatures_from_json(filename, **kw)   # out of scope); the tests here only hand it .sig JSON files
+from . import sbt_storage
+from .sourmash_args import load_file_as_index, load_file_as_signatures      # __init__.py:153-154
 '''
 
 PLUGIN = '''
@@ -72,6 +73,11 @@ for _name, _params in (("track_abundance", [True, False]), ("dayhoff", [True, Fa
             return request.param
         return fx
     globals()[_name] = _make(_params)
+
+@pytest.fixture
+def runtmp(tmp_path):                                   # conftest.py:16-19
+    from sourmash_tst_utils import RunnerContext
+    return RunnerContext(str(tmp_path))
 '''
 
 STUBS = {
@@ -112,12 +118,33 @@ STUBS = {
         '''),
 }
 
+# Modules test_index_protocol.py imports at its top whose subjects are OUT OF SCOPE (SBT needs the nodegraph FFI,
+# RevIndex the revindex_* FFI, SqliteIndex needs `bitstring`, LCA databases are taxonomy): placeholders, so that the module imports; every test that
+# would build one of them is deselected below by its fixture id.
+OUT_OF_SCOPE_STUBS = {
+    "sbt.py": "class SBT: pass\nclass GraphFactory:\n    def __init__(self, *a, **k): pass\n",
+    "sbtmh.py": "def load_sbt_index(*a, **k): raise NotImplementedError\n",
+    "lca/__init__.py": "",
+    "lca/lca_db.py": "class LCA_Database: pass\ndef load_single_database(*a, **k): raise NotImplementedError\n",
+    "index/sqlite_index.py": "class SqliteIndex: pass\ndef load_sqlite_index(*a, **k): return None\n",
+    "index/revindex.py": "class RevIndex: pass\n",               # the Rust RevIndex (revindex_* symbols): out of scope
+}
+
+
 def _stub_package(tmp, lib_path):
     pkg = os.path.join(tmp, "sourmash")
     os.makedirs(pkg)
     for name in ("minhash.py", "signature.py", "utils.py", "exceptions.py", "distance_utils.py", "logging.py",
-                 "compare.py", "sketchcomparison.py", "np_utils.py"):
+                 "compare.py", "sketchcomparison.py", "np_utils.py", "search.py", "manifest.py", "picklist.py", "sbt_storage.py",
+                 "sourmash_args.py", "save_load.py", "plugins.py", "sqlite_utils.py"):
         os.symlink(os.path.join(REF, "src", "sourmash", name), os.path.join(pkg, name))
+    os.makedirs(os.path.join(pkg, "index"))                       # the Index classes (LinearIndex, ZipFileLinearIndex, CounterGather ...)
+    os.symlink(os.path.join(REF, "src", "sourmash", "index", "__init__.py"), os.path.join(pkg, "index", "__init__.py"))
+    for rel, text in OUT_OF_SCOPE_STUBS.items():                  # importable names only; their tests are deselected
+        path = os.path.join(pkg, rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as fh:
+            fh.write(text)
     with open(os.path.join(pkg, "_lowlevel.py"), "w") as fh:
         fh.write(LOWLEVEL.format(header=os.path.join(REF, "include", "sourmash.h"), lib=lib_path))
     with open(os.path.join(pkg, "__init__.py"), "w") as fh:
@@ -133,7 +160,7 @@ def _stub_package(tmp, lib_path):
     tests = os.path.join(tmp, "reftests")
     os.makedirs(tests)
     for name in ("test_minhash.py", "test_jaccard.py", "test__minhash_hypothesis.py", "test_signature.py", "test_compare.py",
-                 "test_sketchcomparison.py", "sourmash_tst_utils.py", "test-data"):
+                 "test_sketchcomparison.py", "test_search.py", "test_index_protocol.py", "sourmash_tst_utils.py", "test-data"):
         os.symlink(os.path.join(REF, "tests", name), os.path.join(tests, name))
     return tests
 
@@ -195,8 +222,7 @@ def test_reference_signature_compare_and_sketchcomparison_tests_pass_over_this_a
     """tests/test_signature.py (48 functions: SourmashSignature over signature_* / signatures_load_* / save), test_compare.py
     (the reference's compare_serial*, compare_parallel and compare_all_pairs loops calling this ABI pair by pair) and
     test_sketchcomparison.py (FracMinHashComparison / NumMinHashComparison: containment, ANI, downsampling), unmodified.
-    `sourmash.load_file_as_signatures` is the stub package's three-line JSON loader (the reference's own sniffs formats
-    through sourmash_args / save_load: out of scope)."""
+    `sourmash.load_file_as_signatures` is the reference's own (sourmash_args / save_load, loaded in place like the rest)."""
     mods = ["test_signature.py", "test_compare.py", "test_sketchcomparison.py"]
     deselect = []
     for mod in mods:
@@ -206,6 +232,27 @@ def test_reference_signature_compare_and_sketchcomparison_tests_pass_over_this_a
     counts, tail = _counts(r.stdout)
     assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
     assert counts["failed"] == 0 and counts["error"] + counts["errors"] == 0 and counts["passed"] >= 140, tail
+
+
+# test_index_protocol.py parametrises every test over 11 Index builders and 3 CounterGather flavours; the ones built on
+# SURVEY section 2's OUT-OF-SCOPE index engines are not run: SBT (needs the nodegraph FFI), LCA_Database (taxonomy),
+# SqliteIndex (needs `bitstring`), CounterGather_LCA.  What runs: LinearIndex, LazyLinearIndex, ZipFileLinearIndex (over
+# this library's zipstorage_*), MultiIndex, StandaloneManifestIndex, CounterGather, CounterGather_LinearIndex.
+INDEX_PROTOCOL_IN_SCOPE = "not sbt and not SBT and not lca and not LCA and not sqlite and not Sqlite"
+
+
+@pytest.mark.timeout(1800)
+def test_reference_search_and_index_protocol_tests_pass_over_this_abi(tmp_path):
+    """tests/test_search.py (39 functions: the reference's JaccardSearch / search / gather helpers and LinearIndex.find loops)
+    and tests/test_index_protocol.py -- the reference's conformance suite for Index and CounterGather classes -- for every
+    in-scope class (18 tests x 5 Index builders + 22 x 2 CounterGather flavours = 134 cases), unmodified; the reference's
+    own index/__init__.py, search.py, manifest.py, picklist.py, sbt_storage.py, save_load.py, sourmash_args.py loaded in
+    place.  Every count_common / intersection / downsample / zip read they make goes through this library."""
+    r = _run_reference_tests(tmp_path, ["test_search.py", "test_index_protocol.py"], ["-k", INDEX_PROTOCOL_IN_SCOPE])
+    counts, tail = _counts(r.stdout)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert counts["failed"] == 0 and counts["error"] + counts["errors"] == 0 and counts["passed"] >= 39 + 134, tail
+    assert counts["deselected"] == 130, tail                     # exactly the out-of-scope parametrisations
 
 
 # Reference tests that are NOT run, each with the reason; everything else in the modules must pass.
