@@ -2729,7 +2729,9 @@ SourmashSignature** signatures_load_path(const char* ptr, bool, uintptr_t ksize,
     return guarded<SourmashSignature**>([&]() -> SourmashSignature** {
         smb::SigBatch B;
         const char* paths[1] = {ptr};
-        std::string err = smb::read_signature_files(paths, 1, 1, 0, B);
+        // one JSON file, possibly compressed; a .zip collection is NOT accepted here (the reference's loaders rely on that:
+        // save_load.py tries this before the zipfile loader, tests/test_index.py::test_zipfile_load_database_fail_if_not_zip)
+        std::string err = smb::read_signature_files(paths, 1, 1, smb::SIGS_NO_ZIP, B);
         if (!err.empty()) fail(SOURMASH_ERROR_CODE_SERDE_ERROR, err);
         return sigs_from_batch(B, ksize, select_moltype, size);
     });

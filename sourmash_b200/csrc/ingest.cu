@@ -758,7 +758,7 @@ std::string read_signature_files(const char* const* paths, size_t n_paths, int n
         if (!fh) return std::string("cannot open ") + paths[i];
         const size_t got = fread(magic, 1, 4, fh);
         fclose(fh);
-        if (!ZipArchive::has_magic(magic, got)) { tasks.push_back({(uint32_t)i, nullptr, nullptr}); continue; }
+        if ((flags & SIGS_NO_ZIP) || !ZipArchive::has_magic(magic, got)) { tasks.push_back({(uint32_t)i, nullptr, nullptr}); continue; }
         zips[i] = std::make_unique<ZipInput>();
         ZipInput& Z = *zips[i];
         std::string e = Z.zip.open(paths[i]);

@@ -61,6 +61,8 @@ struct SigBatch {
 enum : uint32_t {
     SIGS_NO_MANIFEST = 1,   // ignore SOURMASH-MANIFEST.csv (ZipFileLinearIndex use_manifest=False)
     SIGS_ALL_MEMBERS = 2,   // without a manifest, try every member, not only *.sig / *.sig.gz (traverse_yield_all)
+    SIGS_NO_ZIP = 4,        // every path is one (possibly compressed) JSON file: a .zip archive is a parse error, as it is for
+                            // the reference's Signature::from_path (signature.rs:569-590) behind signatures_load_path
 };
 std::string read_signature_files(const char* const* paths, size_t n_paths, int n_threads, uint32_t flags,
                                  SigBatch& out);

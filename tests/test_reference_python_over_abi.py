@@ -66,7 +66,8 @@ PLUGIN = '''
 """the fixtures of /root/reference/tests/conftest.py that the hot-path test modules use (that conftest imports matplotlib)"""
 import pytest
 for _name, _params in (("track_abundance", [True, False]), ("dayhoff", [True, False]), ("hp", [True, False]),
-                       ("keep_identifiers", [True, False]), ("keep_versions", [True, False])):
+                       ("keep_identifiers", [True, False]), ("keep_versions", [True, False]), ("use_manifest", [True, False]),
+                       ("n_children", [2, 5, 10])):
     def _make(params):
         @pytest.fixture(params=params)
         def fx(request):
@@ -114,7 +115,13 @@ STUBS = {
                         chunks.append(line)
             if name is not None:
                 recs.append(_Rec(name, "".join(chunks)))
-            return recs
+            return _Records(recs)
+        class _Records:                                             # an iterator that is also a context manager, like screed's
+            def __init__(self, recs): self._it = iter(recs)
+            def __iter__(self): return self
+            def __next__(self): return next(self._it)
+            def __enter__(self): return self
+            def __exit__(self, *a): return False
         '''),
 }
 
@@ -123,9 +130,9 @@ STUBS = {
 # would build one of them is deselected below by its fixture id.
 OUT_OF_SCOPE_STUBS = {
     "sbt.py": "class SBT: pass\nclass GraphFactory:\n    def __init__(self, *a, **k): pass\n",
-    "sbtmh.py": "def load_sbt_index(*a, **k): raise NotImplementedError\n",
+    "sbtmh.py": "def load_sbt_index(*a, **k): raise ValueError('not an SBT (SBT is out of scope here)')\n",
     "lca/__init__.py": "",
-    "lca/lca_db.py": "class LCA_Database: pass\ndef load_single_database(*a, **k): raise NotImplementedError\n",
+    "lca/lca_db.py": "class LCA_Database: pass\ndef load_single_database(*a, **k): raise ValueError('not an LCA database (out of scope here)')\n",
     "index/sqlite_index.py": "class SqliteIndex: pass\ndef load_sqlite_index(*a, **k): return None\n",
     "index/revindex.py": "class RevIndex: pass\n",               # the Rust RevIndex (revindex_* symbols): out of scope
 }
@@ -160,7 +167,8 @@ def _stub_package(tmp, lib_path):
     tests = os.path.join(tmp, "reftests")
     os.makedirs(tests)
     for name in ("test_minhash.py", "test_jaccard.py", "test__minhash_hypothesis.py", "test_signature.py", "test_compare.py",
-                 "test_sketchcomparison.py", "test_search.py", "test_index_protocol.py", "sourmash_tst_utils.py", "test-data"):
+                 "test_sketchcomparison.py", "test_search.py", "test_index_protocol.py", "test_index.py", "test_api.py",
+                 "test_manifest.py", "test_picklist.py", "sourmash_tst_utils.py", "test-data"):
         os.symlink(os.path.join(REF, "tests", name), os.path.join(tests, name))
     return tests
 
@@ -255,8 +263,35 @@ def test_reference_search_and_index_protocol_tests_pass_over_this_abi(tmp_path):
     assert counts["deselected"] == 130, tail                     # exactly the out-of-scope parametrisations
 
 
+@pytest.mark.timeout(1800)
+def test_reference_index_tests_pass_over_this_abi(tmp_path):
+    """tests/test_index.py: LinearIndex, LazyLinearIndex, ZipFileLinearIndex (manifests, select, traverse), MultiIndex
+    (directories, pathlists), StandaloneManifestIndex, CounterGather -- the reference's classes over this library, zip reads
+    through zipstorage_*.  Not run: the SBT / LCA / Sqlite / RevIndex tests (out-of-scope engines, by name) and the tests
+    listed in REFERENCE_DESELECT (they shell out to the `sourmash` CLI or read .lca.json databases)."""
+    deselect = ["-k", INDEX_PROTOCOL_IN_SCOPE + " and not revindex and not RevIndex and not simple_index"]
+    mods = ["test_index.py", "test_api.py", "test_manifest.py", "test_picklist.py"]      # + the public API, manifests, picklists
+    for mod in mods:
+        for d in REFERENCE_DESELECT.get(mod, ()):
+            deselect += ["--deselect", "reftests/%s::%s" % (mod, d)]
+    r = _run_reference_tests(tmp_path, mods, deselect)
+    counts, tail = _counts(r.stdout)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert counts["failed"] == 0 and counts["error"] + counts["errors"] == 0 and counts["passed"] >= 95, tail
+
+
 # Reference tests that are NOT run, each with the reason; everything else in the modules must pass.
+_CLI = "runs the `sourmash` command line (CLI: out of scope, not installed in the stub package)"
+_LCA = "loads a .lca.json database (LCA: out of scope)"
 REFERENCE_DESELECT = {
+    "test_index.py": [  # 13 x _CLI, 2 x _LCA
+        "test_index_same_md5sum_fsstorage", "test_zipfile_does_not_exist", "test_zipfile_protein_command_search",
+        "test_zipfile_hp_command_search", "test_zipfile_dayhoff_command_search", "test_zipfile_protein_command_search_combined",
+        "test_zipfile_hp_command_search_combined", "test_zipfile_dayhoff_command_search_combined",
+        "test_zipfile_dayhoff_command_search_protein", "test_standalone_manifest_lazy_load",
+        "test_standalone_manifest_lazy_load_2_prefix", "test_standalone_manifest_search", "test_standalone_manifest_prefetch_lazy",
+        "test_lazy_index_wraps_multi_index_location", "test_standalone_manifest_load_from_dir"],
+    "test_api.py": ["test_load_index_1", "test_load_index_2"],      # an SBT, an LCA database: out of scope
     "test_minhash.py": [],
     "test_jaccard.py": [],
     "test__minhash_hypothesis.py": [],

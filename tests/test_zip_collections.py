@@ -174,8 +174,11 @@ def test_collection_equals_plain_files(tmp_path, manifest, deflate):
     mixed = SignatureSet.from_files([GATHER[0], path, GATHER[1]])
     assert len(mixed) == len(plain) + 2 * (len(plain) // len(GATHER))
     assert mixed.file.tolist() == [0] * (len(plain) // len(GATHER)) + [1] * len(plain) + [2] * (len(plain) // len(GATHER))
-    # the reference-ABI loader accepts the archive too
-    assert len(list(smb.signature.load_signatures_from_json(path))) == len(plain)
+    # ... but the reference-ABI JSON loader does NOT take an archive: signatures_load_path parses one (compressed) JSON file
+    # like Signature::from_path, and the reference's loader chain (save_load.py) relies on it failing for a zip
+    assert list(smb.signature.load_signatures_from_json(path)) == []
+    with pytest.raises(Exception):
+        list(smb.signature.load_signatures_from_json(path, do_raise=True))
 
 
 def test_manifest_order_and_md5_filter(tmp_path):
