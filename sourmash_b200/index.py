@@ -5,7 +5,7 @@ Mirrors the reference's ``Index`` protocol (src/sourmash/index/__init__.py:115-3
 of ``Index.find`` and the per-dataset loop of ``CounterGather.consume`` become single
 one-vs-many kernel launches over a SketchSet kept in HBM.
 """
-from collections import namedtuple
+from collections import namedtuple, Counter
 
 import numpy as np
 
@@ -46,6 +46,7 @@ class LinearIndex:
     "A list of signatures searched on the GPU (reference: LinearIndex, index/__init__.py:380-470)."
 
     is_database = False
+    manifest = None                   # Index protocol (index/__init__.py:65-68): None, or a manifest that makes select() cheap
 
     def __init__(self, _signatures=None, filename=None):
         self._signatures = list(_signatures) if _signatures else []
@@ -170,6 +171,24 @@ class LinearIndex:
                 if search_fn.collect(score, subj):
                     yield IndexSearchResult(score, subj, self.location)
 
+    def search_abund(self, query, *, threshold=None, **kwargs):
+        """Matches by angular similarity of abundance sketches, best first (Index.search_abund, index/__init__.py:172-200):
+        one `similarity(..., downsample=True)` per subject, as there."""
+        if not query.minhash.track_abundance:
+            raise TypeError("'search_abund' requires query signature with abundance information")
+        if threshold is None:
+            raise TypeError("'search_abund' requires 'threshold'")
+        threshold = float(threshold)
+        matches = []
+        for subj, loc in self.signatures_with_location():
+            if not subj.minhash.track_abundance:
+                raise TypeError("'search_abund' requires subject signatures with abundance information")
+            score = query.similarity(subj, downsample=True)
+            if score >= threshold:
+                matches.append(IndexSearchResult(score, subj, loc))
+        matches.sort(key=lambda x: -x.score)
+        return matches
+
     def search(self, query, *, threshold=None, do_containment=False, do_max_containment=False,
                best_only=False, **kwargs):
         "Sorted (best first) matches at or above threshold (Index.search, :202-239)."
@@ -288,7 +307,12 @@ class ZipFileLinearIndex(LinearIndex):
         return len(self.manifest) if self.manifest is not None else len(self._rows)
 
     def __bool__(self):
-        return len(self._rows) > 0
+        "Any matching signature?  Looks at the first one only, never at len() (index/__init__.py:584-591)."
+        try:
+            next(iter(self.signatures()))
+        except StopIteration:
+            return False
+        return True
 
     def insert(self, signature):
         raise NotImplementedError
@@ -367,7 +391,7 @@ class CounterGather:
         self.scaled = query_mh.scaled
         self.siglist = {}
         self.locations = {}
-        self.counter = {}            # md5 -> overlap, insertion ordered (ties: first added wins)
+        self.counter = Counter()     # md5 -> overlap, insertion ordered (ties: first added wins), a Counter like the reference's
         self.query_started = 0
         self._pending = []           # signatures added but not yet counted
         self._sset = None
@@ -488,3 +512,51 @@ def gather(query, index, threshold_bp=0):
         cur = cur.downsample(scaled=counter.scaled).to_mutable() if counter.scaled > cur.scaled else cur
         cur.remove_many(sr.signature.minhash.downsample(scaled=cur.scaled) if
                         sr.signature.minhash.scaled < cur.scaled else sr.signature.minhash)
+
+
+def load_file_as_index(filename, yield_all_files=False, _use_manifest=True):
+    """A collection of signatures by location -- the loaders of the reference's chain (save_load.py:46-66, 140-233) that are
+    in scope: a directory -> LinearIndex over the *.sig / *.sig.gz files below it (every file with ``yield_all_files``),
+    a .zip collection -> ZipFileLinearIndex, a .sig JSON file (plain or compressed) -> LinearIndex.  SBT, LCA and sqlite
+    databases, standalone manifests and path lists are not handled.  Failure is the reference's ValueError."""
+    import os
+    err = ValueError(f"Error while reading signatures from '{filename}'.")
+    if not os.path.exists(filename):
+        raise err
+    if os.path.isdir(filename):
+        found = []
+        for root, _dirs, files in sorted(os.walk(filename)):
+            for name in sorted(files):
+                if yield_all_files or name.endswith(".sig") or name.endswith(".sig.gz"):
+                    path = os.path.join(root, name)
+                    try:
+                        found.extend(LinearIndex.load(path).signatures())
+                    except Exception:
+                        if not yield_all_files:            # forced traversal skips what does not parse
+                            raise err
+        return LinearIndex(found, filename)
+    try:
+        return LinearIndex.load(filename)
+    except Exception:
+        pass
+    if filename.endswith(".zip"):
+        try:
+            return ZipFileLinearIndex.load(filename, traverse_yield_all=yield_all_files, use_manifest=_use_manifest)
+        except Exception:
+            pass
+    raise err
+
+
+def load_file_as_signatures(filename, *, select_moltype=None, ksize=None, picklist=None, yield_all_files=False, progress=None,
+                            pattern=None, _use_manifest=True):
+    """Iterator over the signatures at ``filename`` that match (sourmash_args.py:765-816).  Picklists and name patterns are
+    out of scope: passing one raises."""
+    if picklist is not None or pattern is not None:
+        raise NotImplementedError("picklists / patterns are not supported by sourmash_b200.load_file_as_signatures")
+    if progress:
+        progress.notify(filename)
+    db = load_file_as_index(filename, yield_all_files=yield_all_files, _use_manifest=_use_manifest)
+
+    def gen():
+        yield from db.select(moltype=select_moltype, ksize=ksize).signatures()
+    return gen()

@@ -30,6 +30,12 @@ def get_minhash_default_seed():
     return MINHASH_DEFAULT_SEED
 
 
+def _deprecated(name, details):
+    "what the reference's @deprecated decorator does once the version is reached: a DeprecationWarning"
+    import warnings
+    warnings.warn("%s is deprecated. %s" % (name, details), DeprecationWarning, stacklevel=3)
+
+
 def get_minhash_max_hash():
     "Largest possible hash value (2**64 - 1)."
     return MINHASH_MAX_HASH
@@ -354,10 +360,13 @@ class MinHash(RustObject):
         return _HashesWrapper({k: 1 for k in mins})
 
     def get_mins(self, with_abundance=False):
-        "Deprecated in the reference; kept for compatibility."
+        "Deprecated in the reference (minhash.py:498-511: since 3.5, 'Use .hashes property instead.'); warns like it."
+        _deprecated("get_mins", "Use .hashes property instead.")
         return self.hashes if with_abundance else self.hashes.keys()
 
     def get_hashes(self):
+        "Deprecated in the reference (minhash.py:513-521); warns like it."
+        _deprecated("get_hashes", "Use .hashes property instead.")
         return self.hashes.keys()
 
     @property
@@ -465,13 +474,11 @@ class MinHash(RustObject):
     def jaccard(self, other, downsample=False):
         "Jaccard similarity."
         if self.num != other.num:
-            raise TypeError(f"incompatible num values: self={self.num} other={other.num}")
+            raise TypeError(f"must have same num: {self.num} != {other.num}")          # minhash.py:742-744
         return self._methodcall(lib.kmerminhash_similarity, other._get_objptr(), True, downsample)
 
     def similarity(self, other, ignore_abundance=False, downsample=False):
-        "Angular similarity if both track abundance (and not ignored), else Jaccard."
-        if self.num != other.num:
-            raise TypeError(f"incompatible num values: self={self.num} other={other.num}")
+        "Angular similarity if both track abundance (and not ignored), else Jaccard (no num check here: minhash.py:787-806)."
         return self._methodcall(lib.kmerminhash_similarity, other._get_objptr(), ignore_abundance, downsample)
 
     def angular_similarity(self, other):

@@ -283,41 +283,63 @@ class ComputeParameters(RustObject):
 # signatures_load_path / signatures_load_buffer / signatures_save_buffer
 # (signature.py:383-527 -> ffi/signature.rs:219-343).
 # ---------------------------------------------------------------------------------------------
-def load_signatures_from_json(data, *, ksize=None, select_moltype=None, ignore_md5sum=False, do_raise=False):
+def load_signatures_from_json(data, ksize=None, select_moltype=None, ignore_md5sum=False, do_raise=False):
     """Yield SourmashSignature objects (one per sketch) from a .sig / .sig.gz path, JSON text,
     bytes (optionally gzipped) or a file object.  ``ksize`` is compared with the stored value
-    (3 x residues for protein-family sketches), like the reference (signature.rs:611-616)."""
+    (3 x residues for protein-family sketches), like the reference (signature.rs:611-616).
+    What counts as which kind of input, and which failures are swallowed unless ``do_raise``, follow
+    signature.py:350-471: anything with read / fileno / mode is read (a failing read is swallowed too), text or bytes
+    holding "sourmash_signature" or starting with the gzip magic is a buffer, an existing path is a path, the rest is an error."""
     if not data:
         return
-    if hasattr(data, "read"):
-        if hasattr(data, "mode") and "t" in data.mode and hasattr(data, "buffer"):
-            data = data.buffer
-        data = data.read()
-    moltype = ffi.NULL if select_moltype is None else select_moltype.encode("utf-8")
+    file_like = hasattr(data, "read") or hasattr(data, "fileno") or hasattr(data, "mode")
+    is_buffer = False
+    if not file_like and hasattr(data, "find"):
+        try:
+            is_buffer = data.find("sourmash_signature") > 0
+        except TypeError:
+            is_buffer = data.find(b"sourmash_signature") > 0 or data.startswith(b"\x1f\x8b")
+    is_path = False
+    if not file_like and not is_buffer:
+        try:
+            is_path = os.path.exists(data)
+        except (ValueError, TypeError):
+            is_path = False
+        if not is_path:
+            if do_raise:
+                raise ValueError("Error in parsing signature; quitting. Cannot open file or invalid signature")
+            return
+    moltype = select_moltype
+    if moltype is None:
+        moltype = ffi.NULL
+    elif hasattr(moltype, "encode"):
+        moltype = moltype.encode("utf-8")
     size = ffi.new("uintptr_t *")
     try:
-        if isinstance(data, (str, os.PathLike)) and os.path.exists(str(data)):
-            arr = rustcall(lib.signatures_load_path, str(data).encode("utf-8"), ignore_md5sum,
-                           int(ksize or 0), moltype, size)
+        if file_like:
+            if hasattr(data, "mode") and "t" in data.mode:      # text handle: the bytes underneath
+                data = data.buffer
+            buf = data.read()
+            data.close()
+            data = buf
+        if is_path:
+            arr = rustcall(lib.signatures_load_path, os.fspath(data).encode("utf-8"), ignore_md5sum, int(ksize or 0), moltype, size)
         else:
-            if isinstance(data, os.PathLike):
-                raise ValueError(f"cannot open {data}")
-            buf = data.encode("utf-8") if isinstance(data, str) else bytes(data)
-            arr = rustcall(lib.signatures_load_buffer, buf, len(buf), ignore_md5sum,
-                           int(ksize or 0), moltype, size)
+            buf = data.encode("utf-8") if hasattr(data, "encode") else bytes(data)
+            arr = rustcall(lib.signatures_load_buffer, buf, len(buf), ignore_md5sum, int(ksize or 0), moltype, size)
+        sigs = [FrozenSourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
+        lib.signatures_array_free(arr, size[0])
     except Exception:
         if do_raise:
             raise
         return
-    sigs = [FrozenSourmashSignature._from_objptr(arr[i]) for i in range(size[0])]
-    lib.signatures_array_free(arr, size[0])
     yield from sigs
 
 
 load_signatures = load_signatures_from_json
 
 
-def load_one_signature_from_json(data, *, ksize=None, select_moltype=None, ignore_md5sum=False):
+def load_one_signature_from_json(data, ksize=None, select_moltype=None, ignore_md5sum=False):
     it = load_signatures_from_json(data, ksize=ksize, select_moltype=select_moltype, ignore_md5sum=ignore_md5sum)
     try:
         first = next(it)
