@@ -93,7 +93,7 @@ def _size_ok(n, scaled, cache):
 
 def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, estimate_ani_ci=False,
                      names=None, md5s=None, filenames=None, query_name="", query_filename="", max_rounds=None,
-                     noident_hashes=None):
+                     noident_hashes=None, locations=None):
     """Min-set-cover of ``query_mh`` by the rows of the GPU-resident SketchSet ``db`` (same ksize,
     seed and scaled as the query; use ``SketchSet.downsample`` / ``SignatureSet.to_sketchset``).
     Returns the list of GatherRow in pick order -- the reference's GatherDatabases loop with the
@@ -156,7 +156,8 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
                       query_bp=orig_len * scaled, query_n_hashes=orig_len, total_weighted_hashes=total_weighted)
         g.name = names[r] if names is not None else None
         g.md5 = md5s[r] if md5s is not None else None
-        g.filename = filenames[r] if filenames is not None else None
+        # the location the match was loaded from wins, else the filename stored in the match (search.py:230-235)
+        g.filename = locations[r] if locations is not None else (filenames[r] if filenames is not None else None)
         g.intersect_bp = c0 * scaled
         g.unique_intersect_bp = u * scaled
         g.f_orig_query = c0 / orig_len
@@ -280,7 +281,7 @@ SEARCH_CI_COLUMNS = ["ani_low", "ani_high"]
 
 def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_max_containment=False, best_only=False,
                     estimate_ani_ci=False, names=None, md5s=None, filenames=None, query_name="", query_filename="",
-                    location=None):
+                    location=None, locations=None, groups=None):
     """`sourmash search` of a flat scaled query against the rows of the GPU-resident SketchSet ``db``
     (same ksize / seed / scaled as the query): Jaccard, containment of the query or max-containment
     at or above ``threshold``, best first, one entry per md5
@@ -309,9 +310,16 @@ def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_ma
         else:
             tot = nq + sizes - counts
             score = np.where(tot > 0, counts / np.maximum(tot, 1), 0.0)
-    threshold = float(threshold or 0)
+    # index order; best_only ratchets the threshold (JaccardSearchBestOnly.collect, search.py:163-169) -- inside one
+    # database: the reference searches database after database, each with a search function of its own
+    # (search_databases_with_flat_query, search.py:676-691), so with ``groups`` (database id of every row) the ratchet
+    # starts again at every new database
+    floor = float(threshold or 0)
+    threshold = floor
     picked = []
-    for r in range(len(counts)):                               # index order; best_only ratchets the threshold
+    for r in range(len(counts)):
+        if groups is not None and r and groups[r] != groups[r - 1]:
+            threshold = floor
         s = float(score[r])
         if s and s >= threshold:
             if best_only:
@@ -349,7 +357,10 @@ def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_ma
             d["name"] = names[r]
         # BaseResult.get_cmpinfo (search.py:230-234): the location passed by the search wins, else the
         # filename stored in the match
-        d["filename"] = location if location is not None else (filenames[r] if filenames is not None else None)
+        if locations is not None:                     # one location per row (several database files behind one SketchSet)
+            d["filename"] = locations[r]
+        else:
+            d["filename"] = location if location is not None else (filenames[r] if filenames is not None else None)
         if ci:
             d["ani_low"], d["ani_high"] = res.ani_low, res.ani_high
         out.append(d)

@@ -165,6 +165,8 @@ def _load_query_and_db(args):
     sset = db.to_sketchset(rows, scaled=scaled)
     meta = dict(names=[db.name(i) for i in rows], md5s=[db.md5sum(i) for i in rows],
                 filenames=[db.filename(i) for i in rows], query_name=query.name, query_filename=query.filename)
+    # where each row was loaded from: the `filename` column of the reference's search / gather CSVs (the match's location)
+    meta["locations"] = [args.databases[int(db.file[i])] for i in rows]
     return qmh, sset, meta
 
 
@@ -214,6 +216,7 @@ class Command_B200Prefetch(CommandLinePlugin):
         super().main(args)
         from .gather import prefetch_database, write_prefetch_csv
         qmh, sset, meta = _load_query_and_db(args)
+        meta.pop("locations")                              # prefetch reports the filename stored in the match (match_filename)
         res = prefetch_database(qmh, sset, args.threshold_bp, estimate_ani_ci=args.estimate_ani_ci, **meta)
         _notify(args, f"total of {len(res)} matching signatures")
         if args.output:
@@ -247,11 +250,12 @@ class Command_B200Search(CommandLinePlugin):
         qmh, sset, meta = _load_query_and_db(args)
         res = search_database(qmh.flatten() if qmh.track_abundance else qmh, sset, threshold=args.threshold,
                               do_containment=args.containment, do_max_containment=args.max_containment,
-                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci, **meta)
-        if args.best_only:
-            res = res[:1]
+                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci,
+                              groups=meta["locations"], **meta)             # one database per input file, like the reference's CLI
         _notify(args, f"{len(res)} matches above threshold {args.threshold:0.3f}")
         shown = res if not args.num_results else res[:args.num_results]
+        if args.best_only:                                         # commands.py: --best-only prints one match; the CSV has all
+            shown = res[:1]
         for d in shown:
             _notify(args, f"{d['similarity'] * 100:6.1f}%       {d.get('name') or d.get('md5', '')}")
         if args.output:
