@@ -107,6 +107,35 @@ def test_sketch_commands_write_equal_signatures(cli, kind, params, files):
     assert len(want) > 100 and got == want
 
 
+@pytest.mark.parametrize("flags,files", [
+    (["--singleton"], ["short.fa"]),
+    (["--name-from-first"], ["short.fa", "short2.fa"]),
+    (["--merge", "all of them"], ["short.fa", "short2.fa", "short3.fa"]),
+    (["--singleton", "--name-from-first"], ["ecoli.genes.fna"]),
+])
+def test_sketch_naming_modes_write_equal_signatures(cli, flags, files):
+    "--singleton (one signature per record), --name-from-first, --merge NAME: names, filenames and sketches (command_sketch.py:662-789)"
+    paths = [os.path.join(DATA, f) for f in files]
+    tag = "naming_" + "".join(f.strip("-")[:4] for f in flags if f.startswith("--"))
+    cli("sketch", "dna", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_ref.sig", *flags)
+    cli("scripts", "b200sketch", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_b200.sig", *flags)
+    want, got = cli.load(tag + "_ref.sig"), cli.load(tag + "_b200.sig")
+    assert len(want) > 100 and got == want
+
+
+def test_sketch_of_fastq_and_invalid_bases(cli):
+    "a FASTQ file; records with N and IUPAC codes (skipped k-mers, force = the CLI default)"
+    reads = [("r1", "ACGTTGCAACGTTGCATGCATGCAAGCTNNACGTACGATCGATCGTACGATGCATGCA"),
+             ("r2 second", "acgtacgtRYacgtagctagctagcatcgatcgatcgatgcatgcatgcatgcag")]
+    with open(os.path.join(cli.work, "reads.fq"), "w") as fh:
+        for name, seq in reads:
+            fh.write("@%s\n%s\n+\n%s\n" % (name, seq, "I" * len(seq)))
+    cli("sketch", "dna", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_ref.sig")
+    cli("scripts", "b200sketch", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_b200.sig")
+    want, got = cli.load("fq_ref.sig"), cli.load("fq_b200.sig")
+    assert len(want) > 100 and got == want
+
+
 def test_compare_command_writes_the_same_matrix(cli):
     sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
     cli("compare", *sigs, "-k", "21", "-o", "ref.npy", "--csv", "ref_cmp.csv")
