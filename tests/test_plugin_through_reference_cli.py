@@ -75,7 +75,18 @@ def cli(tmp_path_factory):
         assert r.returncode == 0, r.stderr[-3000:]
         return r.stdout
 
-    run.work, run.load = work, load
+    def together(*cmdlines):
+        "several command lines at once (each is a process that spends a second importing the reference package)"
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(cmdlines)) as pool:
+            return list(pool.map(lambda c: run(*c), cmdlines))
+
+    def loads(*paths):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(paths)) as pool:
+            return list(pool.map(load, paths))
+
+    run.work, run.load, run.loads, run.together = work, load, loads, together
     return run
 
 
@@ -96,14 +107,14 @@ def test_the_reference_lists_the_plugin_commands(cli):
 def test_sketch_commands_write_equal_signatures(cli, kind, params, files):
     paths = [os.path.join(DATA, f) for f in files]
     tag = "%s_%s" % (kind, abs(hash(params)) % 10**6)
-    cli("sketch", kind, "-p", params, *paths, "-o", tag + "_ref.sig")
-    extra = []
+    extra, plugin_params = [], params
     if kind != "dna":
         moltype = "dayhoff" if "dayhoff" in params else "hp" if ",hp" in params else "protein"
         extra = ["--moltype", moltype] + (["--input-is-protein"] if kind == "protein" else [])
-        params = params.replace(",dayhoff", "").replace(",hp", "")
-    cli("scripts", "b200sketch", "-p", params, *paths, "-o", tag + "_b200.sig", *extra)
-    want, got = cli.load(tag + "_ref.sig"), cli.load(tag + "_b200.sig")
+        plugin_params = params.replace(",dayhoff", "").replace(",hp", "")
+    cli.together(["sketch", kind, "-p", params, *paths, "-o", tag + "_ref.sig"],
+                 ["scripts", "b200sketch", "-p", plugin_params, *paths, "-o", tag + "_b200.sig", *extra])
+    want, got = cli.loads(tag + "_ref.sig", tag + "_b200.sig")
     assert len(want) > 100 and got == want
 
 
@@ -117,9 +128,9 @@ def test_sketch_naming_modes_write_equal_signatures(cli, flags, files):
     "--singleton (one signature per record), --name-from-first, --merge NAME: names, filenames and sketches (command_sketch.py:662-789)"
     paths = [os.path.join(DATA, f) for f in files]
     tag = "naming_" + "".join(f.strip("-")[:4] for f in flags if f.startswith("--"))
-    cli("sketch", "dna", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_ref.sig", *flags)
-    cli("scripts", "b200sketch", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_b200.sig", *flags)
-    want, got = cli.load(tag + "_ref.sig"), cli.load(tag + "_b200.sig")
+    cli.together(["sketch", "dna", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_ref.sig", *flags],
+                 ["scripts", "b200sketch", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_b200.sig", *flags])
+    want, got = cli.loads(tag + "_ref.sig", tag + "_b200.sig")
     assert len(want) > 100 and got == want
 
 
@@ -130,16 +141,16 @@ def test_sketch_of_fastq_and_invalid_bases(cli):
     with open(os.path.join(cli.work, "reads.fq"), "w") as fh:
         for name, seq in reads:
             fh.write("@%s\n%s\n+\n%s\n" % (name, seq, "I" * len(seq)))
-    cli("sketch", "dna", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_ref.sig")
-    cli("scripts", "b200sketch", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_b200.sig")
-    want, got = cli.load("fq_ref.sig"), cli.load("fq_b200.sig")
+    cli.together(["sketch", "dna", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_ref.sig"],
+                 ["scripts", "b200sketch", "-p", "k=11,scaled=1", "reads.fq", "-o", "fq_b200.sig"])
+    want, got = cli.loads("fq_ref.sig", "fq_b200.sig")
     assert len(want) > 100 and got == want
 
 
 def test_compare_command_writes_the_same_matrix(cli):
     sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
-    cli("compare", *sigs, "-k", "21", "-o", "ref.npy", "--csv", "ref_cmp.csv")
-    cli("scripts", "b200compare", *sigs, "-k", "21", "-o", "b200.npy", "--csv", "b200_cmp.csv")
+    cli.together(["compare", *sigs, "-k", "21", "-o", "ref.npy", "--csv", "ref_cmp.csv"],
+                 ["scripts", "b200compare", *sigs, "-k", "21", "-o", "b200.npy", "--csv", "b200_cmp.csv"])
     w = cli.work
     a, b = np.load(os.path.join(w, "ref.npy")), np.load(os.path.join(w, "b200.npy"))
     assert a.shape == (12, 12) and np.array_equal(a, b) and 0 < a[a < 1].max() < 1
@@ -156,8 +167,8 @@ def _same_file(cli, a, b, min_rows):
 def test_search_command_writes_the_same_csv(cli, flags):
     sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
     tag = "search" + "".join(flags).replace("-", "")
-    cli("search", sigs[0], *sigs, "-k", "21", "--threshold", "0.01", "-o", tag + "_ref.csv", *flags)
-    cli("scripts", "b200search", sigs[0], *sigs, "-k", "21", "--threshold", "0.01", "-o", tag + "_b200.csv", *flags)
+    cli.together(["search", sigs[0], *sigs, "-k", "21", "--threshold", "0.01", "-o", tag + "_ref.csv", *flags],
+                 ["scripts", "b200search", sigs[0], *sigs, "-k", "21", "--threshold", "0.01", "-o", tag + "_b200.csv", *flags])
     _same_file(cli, tag + "_ref.csv", tag + "_b200.csv", 1 if "--best-only" in flags else 5)
 
 
@@ -167,8 +178,8 @@ def test_gather_and_prefetch_commands_write_the_same_csv(cli, threshold_bp):
     sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
     for cmd in ("gather", "prefetch"):
         tag = "%s_%s" % (cmd, threshold_bp)
-        cli(cmd, query, *sigs, "-k", "21", "--threshold-bp", threshold_bp, "-o", tag + "_ref.csv")
-        cli("scripts", "b200" + cmd, query, *sigs, "-k", "21", "--threshold-bp", threshold_bp, "-o", tag + "_b200.csv")
+        cli.together([cmd, query, *sigs, "-k", "21", "--threshold-bp", threshold_bp, "-o", tag + "_ref.csv"],
+                     ["scripts", "b200" + cmd, query, *sigs, "-k", "21", "--threshold-bp", threshold_bp, "-o", tag + "_b200.csv"])
         _same_file(cli, tag + "_ref.csv", tag + "_b200.csv", 5)
 
 
@@ -176,8 +187,8 @@ def test_gather_of_an_abundance_query_writes_the_same_csv(cli):
     "weighted columns (average_abund, f_unique_weighted, ...): a query with abundances against flat genomes"
     query = os.path.join(DATA, "track_abund", "47.fa.sig")
     dbs = [os.path.join(DATA, f) for f in ("47.fa.sig", "63.fa.sig", "2.fa.sig")]
-    cli("gather", query, *dbs, "-k", "31", "--threshold-bp", "0", "-o", "abund_ref.csv")
-    cli("scripts", "b200gather", query, *dbs, "-k", "31", "--threshold-bp", "0", "-o", "abund_b200.csv")
+    cli.together(["gather", query, *dbs, "-k", "31", "--threshold-bp", "0", "-o", "abund_ref.csv"],
+                 ["scripts", "b200gather", query, *dbs, "-k", "31", "--threshold-bp", "0", "-o", "abund_b200.csv"])
     _same_file(cli, "abund_ref.csv", "abund_b200.csv", 1)
 
 
@@ -188,8 +199,8 @@ def test_search_of_one_multi_signature_database(cli, flags):
     if not os.path.exists(os.path.join(cli.work, "all12.sig")):
         cli("sig", "cat", *sigs[::-1], "-o", "all12.sig")              # reversed: the query's own sketch comes last
     tag = "one" + "".join(flags).replace("-", "")
-    cli("search", sigs[3], "all12.sig", "-k", "21", "--threshold", "0.01", "-o", tag + "_ref.csv", *flags)
-    cli("scripts", "b200search", sigs[3], "all12.sig", "-k", "21", "--threshold", "0.01", "-o", tag + "_b200.csv", *flags)
+    cli.together(["search", sigs[3], "all12.sig", "-k", "21", "--threshold", "0.01", "-o", tag + "_ref.csv", *flags],
+                 ["scripts", "b200search", sigs[3], "all12.sig", "-k", "21", "--threshold", "0.01", "-o", tag + "_b200.csv", *flags])
     _same_file(cli, tag + "_ref.csv", tag + "_b200.csv", 1)
     if flags:
         rows = open(os.path.join(cli.work, tag + "_ref.csv")).read().count("\n") - 1
