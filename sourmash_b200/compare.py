@@ -71,6 +71,8 @@ def _collect(siglist, *, downsample, need_scaled=False, with_abunds=False):
             raise ValueError("DNA/prot minhashes cannot be compared")
         if ss.seed[i] != ss.seed[0]:
             raise ValueError("mismatch in seed; comparison fail")
+        if (ss.num[0] == 0) != (ss.num[i] == 0):         # a scaled sketch against a num sketch: max_hash differs (minhash.rs:886-912)
+            raise ValueError("mismatch in scaled; comparison fail")
         raise TypeError(f"incompatible num values: self={int(ss.num[0])} other={int(ss.num[i])}")
     if need_scaled and not pyscaled.all():
         raise TypeError("Error: can only calculate containment for scaled MinHashes")
@@ -99,6 +101,8 @@ def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
             raise ValueError("DNA/prot minhashes cannot be compared")
         if mh.seed != first.seed:
             raise ValueError("mismatch in seed; comparison fail")
+        if bool(mh.num) != bool(first.num):
+            raise ValueError("mismatch in scaled; comparison fail")
         if mh.num != first.num:
             raise TypeError(f"incompatible num values: self={first.num} other={mh.num}")
     if need_scaled and not all(mh.scaled for mh in mhs):
@@ -181,6 +185,17 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
     n = len(siglist)
     if n == 0:
         return np.ones((0, 0))
+    nums = {int(mh.num) for mh in _flat_minhashes(siglist)}
+    if len(nums) > 1 and 0 not in nums and not return_ani:
+        # num sketches of different sizes: the reference does not refuse them, and what it computes depends on which side is
+        # `self` (the union is cut at self.num, minhash.rs:596-617).  No batched form: its own loop, pair by pair through the
+        # ABI -- cells (i, j) and (j, i) both take siglist[i].similarity(siglist[j]) for i < j (compare.py:36-54)
+        mhs = _flat_minhashes(siglist)
+        out = np.ones((n, n))
+        for i in range(n):
+            for j in range(i + 1, n):
+                out[i][j] = out[j][i] = mhs[i].similarity(mhs[j], ignore_abundance=ignore_abundance, downsample=downsample)
+        return out
     c = _collect(siglist, downsample=downsample, with_abunds=not ignore_abundance)
     has_ab, num, scaled, sizes = c["has_abund"], c["num"], c["scaled"], c["sizes"]
     if c.get("raw") is not None:                         # different scaled values: every pair at its own max scaled

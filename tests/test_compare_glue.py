@@ -81,7 +81,7 @@ def test_error_semantics_and_order():
     seed = smb.SourmashSignature(smb.MinHash(0, 31, scaled=1000, seed=43), name="seed")
     num = smb.SourmashSignature(smb.MinHash(500, 31), name="num")
     for bad, exc, msg in ((other_k, ValueError, "different ksizes"), (seed, ValueError, "mismatch in seed"),
-                          (num, TypeError, "incompatible num values: self=0 other=500")):
+                          (num, ValueError, "mismatch in scaled")):         # scaled vs num: max_hash differs
         with pytest.raises(exc, match=msg):
             C._collect(sigs + [bad], downsample=False)
     prot93 = smb.SourmashSignature(smb.MinHash(0, 31, scaled=1000, is_protein=True), name="p")
@@ -243,3 +243,4 @@ def test_reference_ani_matrices(cpu_kernels, golden):
     np.testing.assert_array_almost_equal(C.compare_serial_containment(sigs, return_ani=True), np.array(kat["containment"], dtype=float), decimal=3)
     np.testing.assert_array_almost_equal(C.compare_serial_max_containment(sigs, return_ani=True), np.array(kat["max_containment"]), decimal=3)
     np.testing.assert_array_almost_equal(C.compare_serial_avg_containment(sigs, return_ani=True), np.array(kat["avg_containment"]), decimal=3)
+

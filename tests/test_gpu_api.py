@@ -422,3 +422,23 @@ def test_sketch_fasta_files_matches_golden_signatures(smb, golden):
     ok, = sketch_fasta_files([fh.name], ksizes=[5], scaled=1)
     assert len(ok.minhash) > 0
     os.unlink(fh.name)
+
+
+def test_compare_of_num_sketches_of_different_sizes_follows_the_reference_pair_by_pair(smb):
+    """The reference does not refuse num sketches of different num: cells (i, j) and (j, i) are siglist[i].similarity(siglist[j])
+    for i < j, and that value depends on which sketch is self (compare.py:36-54, minhash.rs:596-617).  A scaled sketch against
+    a num sketch is 'mismatch in scaled', as there."""
+    from sourmash_b200 import compare as CMP
+    a, b, c = smb.MinHash(10, 21), smb.MinHash(20, 21), smb.MinHash(10, 21)
+    for i in range(40):
+        a.add_hash(i * 3 + 1); b.add_hash(i * 2 + 1); c.add_hash(i * 5 + 1)
+    sigs = [smb.SourmashSignature(m, name=n) for m, n in ((a, "a"), (b, "b"), (c, "c"))]
+    m = CMP.compare_all_pairs(sigs, True)
+    assert m[0][1] == m[1][0] == a.similarity(b) == 0.3 and m[1][2] == m[2][1] == b.similarity(c) and m[0][2] == a.similarity(c)
+    assert b.similarity(a) == 0.25                                  # why this cannot be one symmetric batched matrix
+    with pytest.raises(TypeError, match="incompatible num values"):
+        CMP._collect(sigs, downsample=False)
+    scaled = smb.SourmashSignature(_mh(smb, range(1, 100, 3), ksize=21, scaled=1), name="s")
+    for order in ([scaled, sigs[1]], [sigs[1], scaled]):
+        with pytest.raises(ValueError, match="mismatch in scaled; comparison fail"):
+            CMP.compare_all_pairs(order, True)
