@@ -216,6 +216,10 @@ void smb_set_device(int32_t device);            /* per-thread; default = current
 void smb_set_stream(void *cuda_stream);         /* run subsequent work on this cudaStream_t   */
 void smb_synchronize(void);
 uint64_t smb_kernel_launches(void);             /* number of kernels launched by this library */
+/* out[i] = pow(x[i], e) with the C library's pow -- the function behind Python's float ** float, which the reference's
+ * ANI formulas use pair by pair (distance_utils.py:258-407: c ** (1/k)); numpy's vectorised power may differ in the last
+ * bit, so the matrix forms of those formulas call this (host only, no device work). */
+void smb_pow_f64(const double *x, double e, double *out, uintptr_t n);
 void smb_set_profiling(bool on);                /* record CUDA events around the dominant kernels */
 double smb_last_kernel_ms(int32_t which);       /* 0: last pairwise tile kernel, 1: last hash pass */
 /* planner of the last all-vs-all count (this thread): {1 = inverted join / 0 = tile kernel,

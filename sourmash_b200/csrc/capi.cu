@@ -1609,6 +1609,9 @@ void computeparams_set_seed(SourmashComputeParameters* p, uint64_t new_seed) { p
 // ==========================================================================================
 int32_t smb_device_count(void) { probe_devices(); return g_device_count; }
 const char* smb_device_probe_error(void) { probe_devices(); return g_probe_error.c_str(); }
+void smb_pow_f64(const double* x, double e, double* out, uintptr_t n) {     // host libm, element by element: what CPython's float_pow calls
+    for (uintptr_t i = 0; i < n; ++i) out[i] = ::pow(x[i], e);
+}
 void smb_set_device(int32_t device) { t_device = device; }
 void smb_set_stream(void* cuda_stream) { t_stream = (cudaStream_t)cuda_stream; }
 void smb_synchronize(void) { guarded_void([&] { cudaStream_t s = need_gpu(); sync(s); }); }
@@ -2107,6 +2110,10 @@ void smb_compare_angular(const SmbSketchSet* set, double* out) {
         cudaStream_t s = need_gpu();
         const size_t n = set->n_rows;
         if (n == 0) return;
+        if (set->total() == 0) {                 // every sketch empty (no abundance buffer exists for zero hashes): all norms are 0,
+            std::fill(out, out + n * n, 0.0);    // every pair is 0.0 (minhash.rs:674-676)
+            return;
+        }
         if (!set->d_abunds)
             fail(SOURMASH_ERROR_CODE_NEEDS_ABUNDANCE_TRACKING, "sketch needs abundance for this operation");
         DevBuf<double> d_out(n * n, s);

@@ -240,6 +240,16 @@ def jaccard_to_distance(jaccard, ksize, scaled, *, n_unique_kmers=None, sequence
 
 
 # ------------------------------------------------------------------------------ whole matrices
+def _pow(values, exponent):
+    """values ** exponent, element by element with the C library's pow -- bit-identical to the Python floats of the
+    per-pair formulas (numpy's vectorised power is allowed to differ in the last bit)."""
+    from ._lowlevel import ffi, lib
+    a = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.empty_like(a)
+    lib.smb_pow_f64(ffi.cast("double *", a.ctypes.data), float(exponent), ffi.cast("double *", out.ctypes.data), a.size)
+    return out
+
+
 def jaccard_to_ani_matrix(jaccard, sizes, ksize, scaled, *, err_threshold=1e-4, prob_threshold=1e-3,
                           size_accurate=None):
     """ANI for every pair of an N x N Jaccard matrix (what ``compare --ani`` reports:
@@ -253,9 +263,9 @@ def jaccard_to_ani_matrix(jaccard, sizes, ksize, scaled, *, err_threshold=1e-4, 
     L = np.rint((sizes[:, None] + sizes[None, :]) / 2 * scaled)          # round(avg sketch size * scaled)
     k = float(ksize)
     with np.errstate(divide="ignore", invalid="ignore"):
-        r = 1.0 - (2.0 * J / (1 + J)) ** (1.0 / k)
+        r = 1.0 - _pow(2.0 * J / (1 + J), 1.0 / k)
         r = np.where(J == 0, 1.0, np.where(J == 1, 0.0, r))
-        q = 1 - (1 - r) ** ksize
+        q = 1 - _pow(1 - r, ksize)
         var = (L * (1 - q) * (q * (2 * k + (2 / r) - 1) - 2 * k) + k * (k - 1) * (1 - q) ** 2
                + (2 * (1 - q) / (r ** 2)) * ((1 + (k - 1) * (1 - q)) * r - q))
         var = np.where(r == 0, 0.0, var)
@@ -278,7 +288,7 @@ def containment_to_ani_matrix(containment, ksize, *, size_accurate_rows=None, si
     "Point-estimate ANI 1 - (1 - c**(1/k)) for a matrix of containments (no intervals)."
     C = np.asarray(containment, dtype=np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
-        r = 1.0 - C ** (1.0 / ksize)
+        r = 1.0 - _pow(C, 1.0 / ksize)
     r = np.where(C == 0, 1.0, np.where(C == 1, 0.0, r))
     ani = 1.0 - r
     if size_accurate_rows is not None and size_accurate_cols is not None:

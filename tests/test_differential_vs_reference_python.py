@@ -1,0 +1,177 @@
+"""Randomised differential test: the reference's Python (its per-pair loops over this library's ABI) against this package's
+batched functions, on the same random signature lists, in one process.
+
+Both packages are importable side by side (`sourmash` = the reference loaded in place, as in
+test_reference_python_over_abi.py; `sourmash_b200` = this package), both bound to the emulated library.  For every random
+list -- equal or mixed scaled, flat and abundance sketches, empty sketches, num sketches -- the matrices of
+compare_all_pairs / compare_serial_containment / _max_containment / _avg_containment (with and without ANI) must be equal
+bit for bit, and LinearIndex.search / prefetch and a gather loop must return the same matches with the same scores."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import test_reference_python_over_abi as over_abi  # noqa: E402
+
+REF = over_abi.REF
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "sourmash")),
+                                reason="needs the reference checkout (this container only)")
+
+TRIALS = r'''
+import sys
+import warnings
+import numpy as np
+import sourmash as ref
+import sourmash.compare as ref_compare
+import sourmash.index as ref_index
+import sourmash_b200 as smb
+import sourmash_b200.compare as our_compare
+import sourmash_b200.index as our_index
+
+seed, n_trials = int(sys.argv[1]), int(sys.argv[2])
+rng = np.random.default_rng(seed)
+stats = {"compare": 0, "containment": 0, "ani": 0, "search": 0, "prefetch": 0, "gather": 0, "errors": 0}   # comparisons made
+
+
+def make(pkg, spec):
+    mh = pkg.MinHash(n=spec["num"], ksize=spec["ksize"], scaled=spec["scaled"], track_abundance=spec["abund"])
+    if spec["abund"]:
+        mh.set_abundances(dict(zip(spec["hashes"], spec["abunds"])))
+    else:
+        mh.add_many(spec["hashes"])
+    return pkg.SourmashSignature(mh, name=spec["name"], filename=spec["name"] + ".fa").to_frozen()   # what loading a file gives
+
+
+def random_list(rng):
+    n = int(rng.integers(2, 8))
+    kind = rng.choice(["scaled", "scaled", "mixed_scaled", "num", "abund"])
+    pool = rng.integers(1, 2**64 - 1, size=int(rng.integers(20, 400)), dtype=np.uint64)
+    specs = []
+    for i in range(n):
+        scaled, num = 1000, 0
+        if kind == "mixed_scaled":
+            scaled = int(rng.choice([500, 1000, 2000]))
+        if kind == "num":
+            scaled, num = 0, 50
+        hashes = rng.choice(pool, size=int(rng.integers(0, len(pool))), replace=False)
+        if scaled:
+            hashes = hashes[hashes <= np.uint64((2**64 - 1) // scaled)] if rng.random() < 0.5 else hashes % np.uint64((2**64) // scaled)
+        hashes = np.unique(hashes)
+        if rng.random() < 0.08:
+            hashes = hashes[:0]                                     # an empty sketch
+        abund = kind == "abund" and rng.random() < 0.8
+        specs.append(dict(num=num, ksize=21, scaled=scaled, abund=bool(abund), name="s%d" % i,
+                          hashes=[int(h) for h in hashes], abunds=[int(a) for a in rng.integers(1, 30, size=len(hashes))]))
+    return kind, specs
+
+
+def outcome(fn):
+    "('ok', value) or ('raises', exception type name, message)"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            return ("ok", fn())
+        except Exception as exc:                                    # noqa: BLE001 -- the comparison IS about what is raised
+            return ("raises", type(exc).__name__, str(exc))
+
+
+def same(a, b, what, specs):
+    if a[0] != b[0]:
+        raise AssertionError("%s: reference %r, here %r\n%r" % (what, a[:3], b[:3], specs))
+    if a[0] == "raises":
+        if a[1] != b[1]:
+            raise AssertionError("%s raises %s(%s) in the reference, %s(%s) here" % (what, a[1], a[2], b[1], b[2]))
+        stats["errors"] += 1
+        return
+    if isinstance(a[1], np.ndarray):
+        if not (a[1].shape == b[1].shape and np.array_equal(a[1], b[1], equal_nan=True)):
+            raise AssertionError("%s differs\nreference\n%r\nhere\n%r\n%r" % (what, a[1], b[1], specs))
+    elif a[1] != b[1]:
+        raise AssertionError("%s differs\nreference %r\nhere      %r\n%r" % (what, a[1], b[1], specs))
+
+
+for trial in range(n_trials):
+    kind, specs = random_list(rng)
+    R, O = [make(ref, s) for s in specs], [make(smb, s) for s in specs]
+    down = kind == "mixed_scaled"
+    for ignore in (True, False):
+        same(outcome(lambda: ref_compare.compare_all_pairs(R, ignore, downsample=down, n_jobs=None)),
+             outcome(lambda: our_compare.compare_all_pairs(O, ignore, downsample=down, n_jobs=None)),
+             "compare_all_pairs(ignore_abundance=%s) on %s" % (ignore, kind), specs)
+        stats["compare"] += 1
+    for name in ("compare_serial_containment", "compare_serial_max_containment", "compare_serial_avg_containment"):
+        same(outcome(lambda: getattr(ref_compare, name)(R, downsample=down)),
+             outcome(lambda: getattr(our_compare, name)(O, downsample=down)), "%s on %s" % (name, kind), specs)
+        stats["containment"] += 1
+        if kind == "scaled":
+            same(outcome(lambda: getattr(ref_compare, name)(R, return_ani=True)),
+                 outcome(lambda: getattr(our_compare, name)(O, return_ani=True)), "%s(return_ani) on %s" % (name, kind), specs)
+            stats["ani"] += 1
+    if kind == "scaled":
+        same(outcome(lambda: ref_compare.compare_all_pairs(R, True, return_ani=True, n_jobs=None)),
+             outcome(lambda: our_compare.compare_all_pairs(O, True, return_ani=True, n_jobs=None)), "compare_all_pairs(return_ani)", specs)
+        stats["ani"] += 1
+    # one-vs-many: the first signature against an index of the rest
+    if kind in ("scaled", "mixed_scaled") and len(specs[0]["hashes"]):
+        ri, oi = ref_index.LinearIndex(R[1:], "db"), our_index.LinearIndex(O[1:], "db")
+
+        def names(results):
+            return [(float(r.score), r.signature.name, r.location) for r in results]
+        for kw in (dict(threshold=0.0), dict(threshold=0.05, do_containment=True), dict(threshold=0.05, do_max_containment=True),
+                   dict(threshold=0.0, best_only=True)):
+            same(outcome(lambda: names(ri.search(R[0], **kw))), outcome(lambda: names(oi.search(O[0], **kw))),
+                 "LinearIndex.search(%r) on %s" % (kw, kind), specs)
+            stats["search"] += 1
+        same(outcome(lambda: names(ri.prefetch(R[0], threshold_bp=0))), outcome(lambda: names(oi.prefetch(O[0], threshold_bp=0))),
+             "LinearIndex.prefetch on %s" % kind, specs)
+        stats["prefetch"] += 1
+
+        def gather_rounds(index, query):
+            counter = index.counter_gather(query, 0)
+            cur, out = query.minhash.flatten().to_mutable(), []
+            while True:
+                res = counter.peek(cur)
+                if not res:
+                    return out
+                sr, intersect = res
+                out.append((float(sr.score), sr.signature.name, len(intersect)))
+                counter.consume(intersect)
+                cur = cur.downsample(scaled=counter.scaled).to_mutable() if counter.scaled > cur.scaled else cur
+                cur.remove_many(intersect.downsample(scaled=cur.scaled) if intersect.scaled < cur.scaled else intersect)
+        same(outcome(lambda: gather_rounds(ri, R[0])), outcome(lambda: gather_rounds(oi, O[0])), "gather rounds on %s" % kind, specs)
+        stats["gather"] += 1
+    if kind == "abund":
+        ri, oi = ref_index.LinearIndex(R[1:], "db"), our_index.LinearIndex(O[1:], "db")
+        same(outcome(lambda: [(float(r.score), r.signature.name) for r in ri.search_abund(R[0], threshold=0.0)]),
+             outcome(lambda: [(float(r.score), r.signature.name) for r in oi.search_abund(O[0], threshold=0.0)]),
+             "LinearIndex.search_abund", specs)
+        stats["search"] += 1
+print("DIFFERENTIAL OK", stats)
+'''
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_batched_functions_equal_the_reference_loops_on_random_lists(tmp_path, seed):
+    sys.path.insert(0, os.path.join(HERE, "host_emul"))
+    try:
+        import emul_lib
+    finally:
+        sys.path.pop(0)
+    tmp = str(tmp_path)
+    over_abi._stub_package(tmp, emul_lib.build())
+    site = os.path.join(tmp, "site")
+    with open(os.path.join(site, "sitecustomize.py"), "w") as fh:       # this package binds the emulated library too
+        fh.write("import sys\nsys.path.insert(0, %r); sys.path.insert(0, %r)\nimport emulated_boot\nemulated_boot.install()\n"
+                 % (os.path.join(HERE, "host_emul"), ROOT))
+    script = os.path.join(tmp, "trials.py")
+    with open(script, "w") as fh:
+        fh.write(TRIALS)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([site, os.path.join(tmp, "reftests")]), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, script, str(seed), "25"], capture_output=True, text=True, env=env, cwd=tmp, timeout=1500)
+    assert r.returncode == 0 and "DIFFERENTIAL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
