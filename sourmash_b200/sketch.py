@@ -129,6 +129,8 @@ def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, se
         names = [first_of.get(i, "") for i in range(len(rb.paths))]
         files = list(rb.paths)
     n_sk = len(names)
+    # a file without records gives no signature ("no sequences found in ...", command_sketch.py:697-700)
+    keep = [bool(c) for c in np.bincount(owner, minlength=n_sk)] if (merge is None and not singleton) else [True] * n_sk
     if check_sequence and moltype.lower() == "dna":
         sigs = []
         empty = [np.zeros(0, np.uint64)] * len(ksizes)
@@ -137,12 +139,10 @@ def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, se
             for i in np.nonzero(owner == s)[0]:
                 sig.add_sequence(rb.sequence(int(i)), force=False)
             sigs.append(sig)
-        return sigs
+        return [sig for sig, k in zip(sigs, keep) if k]
     nk = len(ksizes)
-    if len(rb) == 0:                                       # nothing to hash: empty sketches
-        empty = [np.zeros(0, np.uint64)] * nk
-        return [_signature_from_rows(empty, empty, ksizes, scaled, num, seed, track_abundance, names[s], files[s], moltype)
-                for s in range(n_sk)]
+    if len(rb) == 0:                                       # no records anywhere: nothing to save
+        return []
     sset, _ = rb.sketch(owner, n_sk, ksizes, moltype=moltype, input_is_protein=input_is_protein, scaled=scaled,
                         num=num, seed=seed, track_abundance=track_abundance)
     hf = B._HASH_FUNCTIONS[moltype.lower()]
@@ -157,4 +157,4 @@ def sketch_fasta_files(filenames, *, ksizes=(21, 31, 51), scaled=1000, num=0, se
             sig._name = names[s_]
         if files[s_]:
             sig.filename = files[s_]
-    return sigs
+    return [sig for sig, k in zip(sigs, keep) if k]

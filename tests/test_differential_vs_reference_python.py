@@ -151,6 +151,58 @@ for trial in range(n_trials):
              outcome(lambda: [(float(r.score), r.signature.name) for r in oi.search_abund(O[0], threshold=0.0)]),
              "LinearIndex.search_abund", specs)
         stats["search"] += 1
+# ---- sketching: the reference's record-by-record add_sequence / add_protein against this package's batched file sketcher
+import gzip
+from sourmash_b200.sketch import sketch_fasta_files
+stats["sketch"] = 0
+for trial in range(max(4, n_trials // 5)):
+    mode = rng.choice(["dna", "dna", "dna_abund_num", "protein", "dayhoff", "hp", "translate"])
+    n_files = int(rng.integers(1, 4))
+    paths, records = [], []
+    for f in range(n_files):
+        recs = []
+        for r in range(int(rng.integers(0, 5))):
+            L = int(rng.choice([0, 5, 20, 21, 60, 300, 2500]))
+            if mode in ("protein", "dayhoff", "hp"):
+                seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYX*"), size=L))
+            else:
+                seq = "".join(rng.choice(list("ACGT"), size=L))
+                if L and rng.random() < 0.5:                       # invalid bases, lower case
+                    pos = rng.integers(0, L, size=max(1, L // 40))
+                    seq = "".join(("N" if i in set(pos.tolist()) else c) for i, c in enumerate(seq))
+                if rng.random() < 0.3:
+                    seq = seq.lower()
+            recs.append(("f%dr%d some description" % (f, r), seq))
+        path = "sk%d_%d.fa%s" % (trial, f, ".gz" if rng.random() < 0.3 else "")
+        text = "".join(">%s\n%s\n" % (n, "\n".join(sq[i:i + 70] for i in range(0, len(sq), 70))) for n, sq in recs)
+        (gzip.open if path.endswith(".gz") else open)(path, "wt").write(text)
+        paths.append(path); records.append(recs)
+    if mode in ("dna", "dna_abund_num"):
+        ksizes, kw = [21, 31, 51], dict(is_protein=False)
+    else:
+        ksizes, kw = [7, 10], dict(is_protein=mode in ("protein", "translate"), dayhoff=mode == "dayhoff", hp=mode == "hp")
+    scaled, num, abund = (0, 30, True) if mode == "dna_abund_num" else (int(rng.choice([1, 10, 100])), 0, bool(rng.random() < 0.3))
+    ours = sketch_fasta_files(paths, ksizes=ksizes, scaled=scaled, num=num, track_abundance=abund,
+                              moltype={"dna": "dna", "dna_abund_num": "dna", "translate": "protein"}.get(mode, mode),
+                              input_is_protein=mode in ("protein", "dayhoff", "hp"))
+    got = sorted((ss.filename, mh.ksize, sorted(mh.hashes.items())) for ss in ours for mh in ss.sketches())   # one signature per file
+    want = []
+    for path, recs in zip(paths, records):
+        if not recs:
+            continue                                                # no sequences found: no signature
+        for k in ksizes:
+            mh = ref.MinHash(n=num, ksize=k, scaled=scaled, track_abundance=abund, **kw)
+            for _name, seq in recs:
+                if mode in ("protein", "dayhoff", "hp"):
+                    mh.add_protein(seq)
+                else:
+                    mh.add_sequence(seq, force=True)                # translate: is_protein sketch fed DNA = six frames
+            want.append((path, k, sorted(mh.hashes.items())))
+    want.sort()
+    if got != want:
+        raise AssertionError("sketch (%s, scaled=%s num=%s abund=%s) differs for %r\nreference %r\nhere      %r" % (
+            mode, scaled, num, abund, records, [(w[0], w[1], len(w[2])) for w in want], [(g[0], g[1], len(g[2])) for g in got]))
+    stats["sketch"] += 1
 print("DIFFERENTIAL OK", stats)
 '''
 
