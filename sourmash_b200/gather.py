@@ -12,6 +12,8 @@ hashes, in ascending hash order like ``MinHash.hashes``.
 """
 from dataclasses import dataclass
 
+import math
+
 import numpy as np
 
 from . import batch as B
@@ -93,7 +95,7 @@ def _size_ok(n, scaled, cache):
 
 def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, estimate_ani_ci=False,
                      names=None, md5s=None, filenames=None, query_name="", query_filename="", max_rounds=None,
-                     noident_hashes=None, locations=None):
+                     noident_hashes=None, locations=None, query_orig=None):
     """Min-set-cover of ``query_mh`` by the rows of the GPU-resident SketchSet ``db`` (same ksize,
     seed and scaled as the query; use ``SketchSet.downsample`` / ``SignatureSet.to_sketchset``).
     Returns the list of GatherRow in pick order -- the reference's GatherDatabases loop with the
@@ -127,14 +129,21 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
     if search_len == 0 or len(db) == 0:
         return rows
     total_weighted = (int(q_abunds.sum(dtype=object)) if track else search_len) + noident_weight
-    query_md5 = query_mh.md5sum()[:8]
+    # query_orig = (number of hashes, scaled, md5sum) of the query AS GIVEN, when ``query_mh`` is a downsampled copy of it: the
+    # reference reports the given query's md5 and multiplies the hash count (at the comparison's scaled) by the GIVEN scaled
+    # for query_bp (GatherResult.build_gather_result, search.py:553-561; BaseResult.get_cmpinfo, :222-243)
+    query_md5 = (query_orig[2] if query_orig else query_mh.md5sum())[:8]
+    query_bp_scaled = int(query_orig[1]) if query_orig else scaled
     sizes = db.sizes()
     counts0 = B.one_vs_many(q_hashes, db)                     # |match ∩ original query| for every row
     cache = {}
     q_size_ok = _size_ok(orig_len, scaled, cache)
     alive = np.ones(search_len, dtype=bool)                    # hashes of the searched query not yet covered
     remaining = search_len
-    sess = B.GatherSession(q_hashes, db, min_count=1)
+    # which rows enter the rounds at all: the reference fills its counters by a prefetch of the query as given
+    # (commands.py:906-911 -> CounterGather via Index.counter_gather); later rounds only ask count >= n_threshold_hashes
+    min_count = _min_count_of_given_query(threshold_bp, query_orig, orig_len) if (query_orig is not None and threshold_bp) else 1
+    sess = B.GatherSession(q_hashes, db, min_count=min_count)
     if max_rounds is None:
         max_rounds = len(db)
     while remaining > 0 and len(rows) < max_rounds:
@@ -153,7 +162,7 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
         left = sess.apply(isect)
         g = GatherRow(row=int(r), gather_result_rank=len(rows), ksize=ksize, moltype=query_mh.moltype,
                       scaled=scaled, query_name=query_name, query_filename=query_filename, query_md5=query_md5,
-                      query_bp=orig_len * scaled, query_n_hashes=orig_len, total_weighted_hashes=total_weighted)
+                      query_bp=orig_len * query_bp_scaled, query_n_hashes=orig_len, total_weighted_hashes=total_weighted)
         g.name = names[r] if names is not None else None
         g.md5 = md5s[r] if md5s is not None else None
         # the location the match was loaded from wins, else the filename stored in the match (search.py:230-235)
@@ -202,8 +211,23 @@ PREFETCH_COLUMNS = [  # search.py:364-388
     "average_containment_ani", "max_containment_ani", "potential_false_negative"]
 
 
+def _min_count_of_given_query(threshold_bp, query_orig, query_len):
+    """Smallest overlap (in hashes of the comparison) that passes the reference's prefetch threshold when the query was given at a
+    finer scaled than the comparison runs at: Index.prefetch turns threshold_bp into a containment
+    (threshold_bp / scaled) / len(query) with the GIVEN query's scaled and length (make_containment_query, search.py:77-88;
+    calc_threshold_from_bp :15-37) and Index.find compares it with shared / len(query downsampled) (index/__init__.py:151-164)
+    -- so the bar in base pairs moves with the sampling noise of the downsampled query.  Same float operations as there."""
+    frac = (float(threshold_bp) / int(query_orig[1])) / int(query_orig[0])
+    c = max(1, int(math.ceil(frac * query_len)))
+    while c > 1 and (c - 1) / query_len >= frac:
+        c -= 1
+    while c / query_len < frac:
+        c += 1
+    return c
+
+
 def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, names=None, md5s=None, filenames=None,
-                      query_name="", query_filename=""):
+                      query_name="", query_filename="", query_orig=None, match_orig=None):
     """All rows of ``db`` sharing at least ``threshold_bp`` with the query, in database order, as
     dictionaries with the reference's prefetch columns (search.py:953-998 + PrefetchResult
     :357-470).  One pass of the one-vs-many kernel; everything else is per-match scalar work."""
@@ -220,8 +244,16 @@ def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, name
     cache = {}
     q_ok = _size_ok(nq, scaled, cache)
     out = []
-    query_md5 = query_mh.md5sum()[:8]
-    for r in np.nonzero(counts.astype(np.int64) * scaled >= max(threshold_bp, 1))[0]:
+    # sizes of the sketches AS GIVEN (PrefetchResult.init_sigcomparison, search.py:401-416: query_bp / match_bp are
+    # unique_dataset_hashes of the given sketches, query_n_hashes their given length; the comparison itself is at `scaled`):
+    # query_orig = (n hashes, scaled, md5sum), match_orig = (n hashes per row, scaled per row)
+    query_md5 = (query_orig[2] if query_orig else query_mh.md5sum())[:8]
+    query_n, query_bp = (int(query_orig[0]), int(query_orig[0]) * int(query_orig[1])) if query_orig else (nq, nq * scaled)
+    if query_orig is not None and threshold_bp:
+        passing = counts.astype(np.int64) >= _min_count_of_given_query(threshold_bp, query_orig, nq)
+    else:
+        passing = counts.astype(np.int64) * scaled >= max(threshold_bp, 1)
+    for r in np.nonzero(passing)[0]:
         c, m = int(counts[r]), int(sizes[r])
         qc_c, mc_c = _contained_by(c, nq, scaled), _contained_by(c, m, scaled)
         qc = DU.containment_to_distance(qc_c, ksize, scaled, n_unique_kmers=nq * scaled, estimate_ci=estimate_ani_ci)
@@ -229,8 +261,9 @@ def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, name
         qc.size_is_inaccurate = mc.size_is_inaccurate = not (q_ok and _size_ok(m, scaled, cache))
         d = {"row": int(r), "intersect_bp": c * scaled, "jaccard": c / max(1, nq + m - c),
              "max_containment": _contained_by(c, min(nq, m), scaled), "f_query_match": mc_c, "f_match_query": qc_c,
-             "match_bp": m * scaled, "query_bp": nq * scaled, "ksize": ksize, "moltype": query_mh.moltype,
-             "scaled": scaled, "query_n_hashes": nq, "query_abundance": bool(query_mh.track_abundance),
+             "match_bp": int(match_orig[0][r]) * int(match_orig[1][r]) if match_orig is not None else m * scaled,
+             "query_bp": query_bp, "ksize": ksize, "moltype": query_mh.moltype,
+             "scaled": scaled, "query_n_hashes": query_n, "query_abundance": bool(query_mh.track_abundance),
              "query_name": query_name, "query_filename": query_filename, "query_md5": query_md5,
              "potential_false_negative": bool(qc.p_exceeds_threshold or mc.p_exceeds_threshold)}
         if names is not None:
@@ -281,7 +314,7 @@ SEARCH_CI_COLUMNS = ["ani_low", "ani_high"]
 
 def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_max_containment=False, best_only=False,
                     estimate_ani_ci=False, names=None, md5s=None, filenames=None, query_name="", query_filename="",
-                    location=None, locations=None, groups=None):
+                    location=None, locations=None, groups=None, query_orig=None):
     """`sourmash search` of a flat scaled query against the rows of the GPU-resident SketchSet ``db``
     (same ksize / seed / scaled as the query): Jaccard, containment of the query or max-containment
     at or above ``threshold``, best first, one entry per md5
@@ -334,7 +367,7 @@ def search_database(query_mh, db, *, threshold=0.08, do_containment=False, do_ma
     uniq.sort(key=lambda r: -float(score[r]))                  # stable: ties keep database order
     cache = {}
     q_ok = _size_ok(nq, scaled, cache)
-    query_md5 = query_mh.md5sum()[:8]
+    query_md5 = (query_orig[2] if query_orig else query_mh.md5sum())[:8]      # the query as given (get_cmpinfo, search.py:222-243)
     ci = estimate_ani_ci and (do_containment or do_max_containment)
     out = []
     for r in uniq:

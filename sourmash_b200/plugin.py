@@ -20,6 +20,8 @@ import argparse
 import csv
 import sys
 
+import numpy as np
+
 try:                                                    # pragma: no cover - depends on the host install
     from sourmash.plugins import CommandLinePlugin
 except Exception:                                       # sourmash itself is optional here
@@ -167,6 +169,9 @@ def _load_query_and_db(args):
                 filenames=[db.filename(i) for i in rows], query_name=query.name, query_filename=query.filename)
     # where each row was loaded from: the `filename` column of the reference's search / gather CSVs (the match's location)
     meta["locations"] = [args.databases[int(db.file[i])] for i in rows]
+    # the sketches as given: the reports quote their sizes and the query's md5, the comparisons run at `scaled`
+    meta["query_orig"] = (len(query.minhash), query.minhash.scaled, query.md5sum())
+    meta["match_orig"] = (db.n_mins[rows].astype(np.int64), db.python_scaled()[rows].astype(np.int64))
     return qmh, sset, meta
 
 
@@ -188,6 +193,7 @@ class Command_B200Gather(CommandLinePlugin):
         super().main(args)
         from .gather import gather_databases, write_gather_csv
         qmh, sset, meta = _load_query_and_db(args)
+        meta.pop("match_orig")
         rows = gather_databases(qmh, sset, threshold_bp=args.threshold_bp, ignore_abundance=args.ignore_abundance,
                                 estimate_ani_ci=args.estimate_ani_ci, **meta)
         for g in rows:
@@ -217,6 +223,8 @@ class Command_B200Prefetch(CommandLinePlugin):
         from .gather import prefetch_database, write_prefetch_csv
         qmh, sset, meta = _load_query_and_db(args)
         meta.pop("locations")                              # prefetch reports the filename stored in the match (match_filename)
+        if qmh.track_abundance:                             # prefetch works on the flattened query (commands.py: prefetch)
+            qmh = qmh.flatten()
         res = prefetch_database(qmh, sset, args.threshold_bp, estimate_ani_ci=args.estimate_ani_ci, **meta)
         _notify(args, f"total of {len(res)} matching signatures")
         if args.output:
@@ -238,20 +246,19 @@ class Command_B200Search(CommandLinePlugin):
         p.add_argument("--containment", action="store_true", help="score by containment of the query")
         p.add_argument("--max-containment", action="store_true", help="score by max containment")
         p.add_argument("--best-only", action="store_true", help="report only the best match")
+        p.add_argument("--ignore-abundance", action="store_true", help="search an abundance query by its hashes only")
         p.add_argument("-n", "--num-results", type=int, default=3, help="matches to print (0: all; the CSV has all)")
         p.add_argument("--estimate-ani-ci", action="store_true")
         p.add_argument("-o", "--output", default=None, help="CSV of the matches")
 
     def main(self, args):
         super().main(args)
-        from .gather import search_database, write_search_csv
+        from .gather import write_search_csv
         if args.containment and args.max_containment:
             raise ValueError("--containment and --max-containment are mutually exclusive")
-        qmh, sset, meta = _load_query_and_db(args)
-        res = search_database(qmh.flatten() if qmh.track_abundance else qmh, sset, threshold=args.threshold,
-                              do_containment=args.containment, do_max_containment=args.max_containment,
-                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci,
-                              groups=meta["locations"], **meta)             # one database per input file, like the reference's CLI
+        res = self._abundance_search(args)                 # None: a flat query, or --ignore-abundance
+        if res is None:
+            res = self._flat_search(args)
         _notify(args, f"{len(res)} matches above threshold {args.threshold:0.3f}")
         shown = res if not args.num_results else res[:args.num_results]
         if args.best_only:                                         # commands.py: --best-only prints one match; the CSV has all
@@ -262,6 +269,49 @@ class Command_B200Search(CommandLinePlugin):
             with open(args.output, "w", newline="") as fp:
                 write_search_csv(res, fp, estimate_ani_ci=args.estimate_ani_ci)
         return 0
+
+    @staticmethod
+    def _abundance_search(args):
+        """A query with abundances, kept: angular similarity against subjects with abundances, database by database, one entry
+        per md5, best first (commands.py:652-684 -> search_databases_with_abund_query, search.py:723-748 -> Index.search_abund);
+        containment searches and flat subjects are errors there, and here."""
+        from .index import load_file_as_index
+        from .signature import load_signatures_from_json
+        moltype = None if args.moltype == "DNA" else args.moltype
+        queries = list(load_signatures_from_json(args.query, ksize=args.ksize, select_moltype=moltype or "DNA"))
+        if len(queries) != 1 or not queries[0].minhash.track_abundance or args.ignore_abundance:
+            return None
+        query = queries[0]
+        if args.containment or args.max_containment:
+            print("ERROR: cannot do containment searches on an abund signature; maybe specify --ignore-abundance?", file=sys.stderr)
+            raise SystemExit(-1)
+        ksize = query.minhash.ksize
+        found, seen = [], set()
+        try:
+            for path in args.databases:
+                db = load_file_as_index(path).select(ksize=ksize, moltype=args.moltype)
+                for score, match, location in db.search_abund(query, threshold=args.threshold):
+                    if match.md5sum() not in seen:
+                        seen.add(match.md5sum())
+                        found.append((score, match, location))
+        except TypeError as exc:
+            print(f"ERROR: {exc}", file=sys.stderr)
+            raise SystemExit(-1)
+        found.sort(key=lambda x: -x[0])
+        return [{"similarity": score, "md5": match.md5sum(), "filename": location, "name": match.name,
+                 "query_filename": query.filename, "query_name": query.name, "query_md5": query.md5sum()[:8], "ani": None}
+                for score, match, location in found]
+
+    @staticmethod
+    def _flat_search(args):
+        from .gather import search_database
+        qmh, sset, meta = _load_query_and_db(args)
+        meta.pop("match_orig")
+        res = search_database(qmh.flatten() if qmh.track_abundance else qmh, sset, threshold=args.threshold,
+                              do_containment=args.containment, do_max_containment=args.max_containment,
+                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci,
+                              groups=meta["locations"], **meta)             # one database per input file, like the reference's CLI
+        return res
 
 
 COMMANDS = [Command_B200Sketch, Command_B200Compare, Command_B200Search, Command_B200Gather, Command_B200Prefetch]

@@ -5,7 +5,10 @@ Both packages are importable side by side (`sourmash` = the reference loaded in 
 test_reference_python_over_abi.py; `sourmash_b200` = this package), both bound to the emulated library.  For every random
 list -- equal or mixed scaled, flat and abundance sketches, empty sketches, num sketches -- the matrices of
 compare_all_pairs / compare_serial_containment / _max_containment / _avg_containment (with and without ANI) must be equal
-bit for bit, and LinearIndex.search / prefetch and a gather loop must return the same matches with the same scores."""
+bit for bit, and LinearIndex.search / search_abund / prefetch and a gather loop must return the same matches with the same
+scores.  Then random FASTA files are sketched both ways (every molecule type), and random query / database sets go through
+the reference's `gather`, `prefetch` and `search` commands and the plugin's: the CSV files must be byte-identical (query at a
+finer, equal or coarser scaled than the databases; abundance queries with and without --ignore-abundance; thresholds)."""
 import os
 import subprocess
 import sys
@@ -203,6 +206,82 @@ for trial in range(max(4, n_trials // 5)):
         raise AssertionError("sketch (%s, scaled=%s num=%s abund=%s) differs for %r\nreference %r\nhere      %r" % (
             mode, scaled, num, abund, records, [(w[0], w[1], len(w[2])) for w in want], [(g[0], g[1], len(g[2])) for g in got]))
     stats["sketch"] += 1
+# ---- reports: the reference's gather / prefetch / search commands against the plugin commands, CSV files byte for byte
+import contextlib, io
+from sourmash.__main__ import main as sourmash_main
+stats["reports"] = 0
+
+
+def cli(*args):
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        try:
+            sourmash_main([str(a) for a in args])
+        except SystemExit as exc:
+            return exc.code or 0
+        except Exception as exc:                                    # noqa: BLE001
+            return type(exc).__name__
+    return 0
+
+
+def read(path):
+    try:
+        return open(path).read()
+    except FileNotFoundError:
+        return None
+
+
+for trial in range(max(3, n_trials // 8)):
+    top = (2**64 - 1) // 1000
+    pool = np.unique(rng.integers(1, top, size=3000, dtype=np.uint64))
+    n_subj = int(rng.integers(2, 9))
+    # one scaled per database set, finer / equal / coarser than the query's 1000 (databases of DIFFERENT scaled values are
+    # the one case the plugin does not follow: the reference lowers the resolution as coarser matches get picked, DESIGN 8)
+    db_scaled = int(rng.choice([500, 1000, 2000]))
+    subjects, files = [], []
+    for i in range(n_subj):
+        own = rng.choice(pool, size=int(rng.integers(30, 600)), replace=False)
+        mh = ref.MinHash(n=0, ksize=31, scaled=db_scaled)
+        mh.add_many([int(h) for h in own])
+        ss = ref.SourmashSignature(mh, name="subject %d" % i, filename="subj%d.fa" % i)
+        subjects.append(ss)
+        path = "rep%d_s%d.sig" % (trial, i)
+        with open(path, "w") as fp:
+            ref.save_signatures([ss], fp)
+        files.append(path)
+    qh = {}
+    for ss in subjects[: max(1, n_subj - 1)]:                      # the query: parts of most subjects + hashes of its own
+        for h in list(ss.minhash.hashes)[:: int(rng.integers(1, 4))]:
+            qh[h] = int(rng.integers(1, 40))
+    for h in rng.integers(1, top, size=int(rng.integers(0, 200)), dtype=np.uint64):
+        qh[int(h)] = int(rng.integers(1, 5))
+    abund = bool(rng.random() < 0.6)
+    qmh = ref.MinHash(n=0, ksize=31, scaled=1000, track_abundance=abund)
+    if abund:
+        qmh.set_abundances(qh)
+    else:
+        qmh.add_many(list(qh))
+    qpath = "rep%d_query.sig" % trial
+    with open(qpath, "w") as fp:
+        ref.save_signatures([ref.SourmashSignature(qmh, name="the query", filename="query.fa")], fp)
+    tbp = int(rng.choice([0, 20000, 100000]))
+    runs = [("gather", ["--threshold-bp", tbp] + (["--ignore-abundance"] if abund and rng.random() < 0.4 else [])),
+            ("prefetch", ["--threshold-bp", tbp]),
+            ("search", ["--threshold", "0.02"] + ([[], ["--containment"], ["--max-containment"]][int(rng.integers(0, 3))])
+             + (["--ignore-abundance"] if abund and rng.random() < 0.6 else []))]
+    for cmd, flags in runs:
+        a, b = "rep%d_%s_ref.csv" % (trial, cmd), "rep%d_%s_b200.csv" % (trial, cmd)
+        ra = cli(cmd, qpath, *files, "-o", a, *flags)
+        rb = cli("scripts", "b200" + cmd, qpath, *files, "-o", b, *flags)
+        ta, tb = read(a), read(b)
+        if ra == "AssertionError":                                  # an `assert` of the reference's own tripped: nothing to follow
+            continue
+        if (ra == 0) != (rb == 0) or ta != tb:
+            la, lb = (ta or "").splitlines(), (tb or "").splitlines()
+            diff = [(x, y) for x, y in zip(la, lb) if x != y][:2] or [("%d lines" % len(la), "%d lines" % len(lb))]
+            raise AssertionError("%s %r (abund query: %s, %d subjects, db scaled %d): exit %r / %r\n%s\n%s" % (
+                cmd, flags, abund, n_subj, db_scaled, ra, rb, la[:1],
+                "\n".join("reference %s\nplugin    %s" % d for d in diff)))
+        stats["reports"] += 1
 print("DIFFERENTIAL OK", stats)
 '''
 
@@ -221,9 +300,16 @@ def test_batched_functions_equal_the_reference_loops_on_random_lists(tmp_path, s
     with open(os.path.join(site, "sitecustomize.py"), "w") as fh:       # this package binds the emulated library too
         fh.write("import sys\nsys.path.insert(0, %r); sys.path.insert(0, %r)\nimport emulated_boot\nemulated_boot.install()\n"
                  % (os.path.join(HERE, "host_emul"), ROOT))
+    info = os.path.join(site, "sourmash_b200-0.1.0.dist-info")         # the plugin commands, for the report comparisons
+    os.makedirs(info)
+    with open(os.path.join(info, "METADATA"), "w") as fh:
+        fh.write("Metadata-Version: 2.1\nName: sourmash_b200\nVersion: 0.1.0\n")
+    with open(os.path.join(info, "entry_points.txt"), "w") as fh:
+        fh.write("[sourmash.cli_script]\n" + "".join("b200%s = sourmash_b200.plugin:Command_B200%s\n" % (c.lower(), c)
+                                                      for c in ("Sketch", "Compare", "Search", "Gather", "Prefetch")))
     script = os.path.join(tmp, "trials.py")
     with open(script, "w") as fh:
         fh.write(TRIALS)
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([site, os.path.join(tmp, "reftests")]), PYTHONDONTWRITEBYTECODE="1")
-    r = subprocess.run([sys.executable, script, str(seed), "25"], capture_output=True, text=True, env=env, cwd=tmp, timeout=1500)
+    r = subprocess.run([sys.executable, script, str(seed), "32"], capture_output=True, text=True, env=env, cwd=tmp, timeout=1500)
     assert r.returncode == 0 and "DIFFERENTIAL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
