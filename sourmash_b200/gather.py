@@ -142,8 +142,21 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
     remaining = search_len
     # which rows enter the rounds at all: the reference fills its counters by a prefetch of the query as given
     # (commands.py:906-911 -> CounterGather via Index.counter_gather); later rounds only ask count >= n_threshold_hashes
-    min_count = _min_count_of_given_query(threshold_bp, query_orig, orig_len) if (query_orig is not None and threshold_bp) else 1
-    sess = B.GatherSession(q_hashes, db, min_count=min_count)
+    min_count = 1
+    if query_orig is not None and threshold_bp:
+        try:                                                   # unattainable for the query as given: no database yields a counter
+            calc_threshold_from_bp(threshold_bp, int(query_orig[1]), int(query_orig[0]))      # (commands.py:909-914)
+        except ValueError:
+            return rows
+        min_count = _min_count_of_given_query(threshold_bp, query_orig, orig_len)
+    rowmap = None
+    if min_count > 1:                                          # the session's min_count is a hint; the rule is enforced here
+        rowmap = np.nonzero(counts0.astype(np.int64) >= min_count)[0].astype(np.uint32)
+        if len(rowmap) == 0:
+            return rows
+        sess = B.GatherSession(q_hashes, db.take_rows(rowmap), min_count=1)
+    else:
+        sess = B.GatherSession(q_hashes, db, min_count=1)
     if max_rounds is None:
         max_rounds = len(db)
     while remaining > 0 and len(rows) < max_rounds:
@@ -155,6 +168,8 @@ def gather_databases(query_mh, db, *, threshold_bp=0, ignore_abundance=False, es
         if best == 0 or best < n_threshold:
             break
         isect = sess.intersect(r)                              # remaining query ∩ row r (ascending)
+        if rowmap is not None:
+            r = int(rowmap[r])                                 # row of the caller's database
         u, m, c0 = len(isect), int(sizes[r]), int(counts0[r])
         pos = np.searchsorted(q_hashes, isect)
         ab = q_abunds[pos]
@@ -238,7 +253,10 @@ def prefetch_database(query_mh, db, threshold_bp, *, estimate_ani_ci=False, name
     nq = len(q)
     if nq == 0:
         raise ValueError("query is empty!?")
-    calc_threshold_from_bp(threshold_bp, scaled, nq)           # ValueError if unattainable (search.py:15-37)
+    if query_orig is not None:                                 # ValueError if unattainable (search.py:15-37), judged on the query as given
+        calc_threshold_from_bp(threshold_bp, int(query_orig[1]), int(query_orig[0]))
+    else:
+        calc_threshold_from_bp(threshold_bp, scaled, nq)
     counts = B.one_vs_many(q, db)
     sizes = db.sizes()
     cache = {}
@@ -292,6 +310,8 @@ def write_gather_csv(rows, fp, *, estimate_ani_ci=False):
     (prep_gather_result, search.py:633-637)."""
     import csv
     cols = GATHER_COLUMNS + (CI_COLUMNS if estimate_ani_ci else [])
+    if not rows:
+        return                                             # the reference writes the header with the first result: no results, empty file
     w = csv.DictWriter(fp, fieldnames=cols)
     w.writeheader()
     for g in rows:
@@ -302,6 +322,8 @@ def write_prefetch_csv(results, fp, *, estimate_ani_ci=False):
     "Write prefetch_database() results as the reference's `prefetch -o` CSV (search.py:364-395)."
     import csv
     cols = PREFETCH_COLUMNS + (CI_COLUMNS if estimate_ani_ci else [])
+    if not results:
+        return                                             # no results: an empty file, like the reference
     w = csv.DictWriter(fp, fieldnames=cols, extrasaction="ignore")
     w.writeheader()
     for d in results:
@@ -404,6 +426,8 @@ def write_search_csv(results, fp, *, estimate_ani_ci=False):
     "Write search_database() results as the reference's `search -o` CSV (search.py:292-307)."
     import csv
     cols = SEARCH_COLUMNS + (SEARCH_CI_COLUMNS if estimate_ani_ci else [])
+    if not results:
+        return                                             # no results: an empty file, like the reference
     w = csv.DictWriter(fp, fieldnames=cols, extrasaction="ignore")
     w.writeheader()
     for d in results:

@@ -199,7 +199,7 @@ class Command_B200Gather(CommandLinePlugin):
         for g in rows:
             _notify(args, f"{g.intersect_bp / 1e3:9.1f} kbp {g.f_orig_query * 100:6.1f}% {g.f_match * 100:6.1f}%  {g.name}")
         _notify(args, f"found {len(rows)} matches total")
-        if args.output:
+        if args.output and rows:                            # no matches: the reference leaves without creating the file
             with open(args.output, "w", newline="") as fp:
                 write_gather_csv(rows, fp, estimate_ani_ci=args.estimate_ani_ci)
         return 0
@@ -221,6 +221,8 @@ class Command_B200Prefetch(CommandLinePlugin):
     def main(self, args):
         super().main(args)
         from .gather import prefetch_database, write_prefetch_csv
+        if args.output:
+            open(args.output, "w").close()                  # created before the search, as in the reference (empty if it fails)
         qmh, sset, meta = _load_query_and_db(args)
         meta.pop("locations")                              # prefetch reports the filename stored in the match (match_filename)
         if qmh.track_abundance:                             # prefetch works on the flattened query (commands.py: prefetch)
