@@ -116,6 +116,7 @@ def test_sketch_commands_write_equal_signatures(cli, kind, params, files):
                  ["scripts", "b200sketch", "-p", plugin_params, *paths, "-o", tag + "_b200.sig", *extra])
     want, got = cli.loads(tag + "_ref.sig", tag + "_b200.sig")
     assert len(want) > 100 and got == want
+    assert open(os.path.join(cli.work, tag + "_ref.sig")).read() == open(os.path.join(cli.work, tag + "_b200.sig")).read()   # the .sig files themselves
 
 
 @pytest.mark.parametrize("flags,files", [
@@ -132,6 +133,7 @@ def test_sketch_naming_modes_write_equal_signatures(cli, flags, files):
                  ["scripts", "b200sketch", "-p", "k=21,k=31,scaled=10", *paths, "-o", tag + "_b200.sig", *flags])
     want, got = cli.loads(tag + "_ref.sig", tag + "_b200.sig")
     assert len(want) > 100 and got == want
+    assert open(os.path.join(cli.work, tag + "_ref.sig")).read() == open(os.path.join(cli.work, tag + "_b200.sig")).read()   # the .sig files themselves
 
 
 def test_sketch_of_fastq_and_invalid_bases(cli):
