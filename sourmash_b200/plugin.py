@@ -124,14 +124,23 @@ class Command_B200Compare(CommandLinePlugin):
         _select_args(p)
         p.add_argument("-o", "--output", default=None, help="numpy matrix (+ <output>.labels.txt)")
         p.add_argument("--csv", default=None, help="labelled matrix as CSV")
+        p.add_argument("--ignore-abundance", action="store_true", help="Jaccard also for sketches with abundances (default: angular similarity)")
+        p.add_argument("--containment", action="store_true", help="containment matrix")
+        p.add_argument("--max-containment", action="store_true", help="max-containment matrix")
+        p.add_argument("--avg-containment", action="store_true", help="average-containment matrix")
+        p.add_argument("--estimate-ani", "--ani", dest="estimate_ani", action="store_true", help="ANI estimated from the chosen measure")
+        p.add_argument("--distance-matrix", action="store_true", help="1 - similarity")
+
+    _matrix = staticmethod(lambda args: _compare_matrix(args))
 
     def main(self, args):
         super().main(args)
-        import numpy as np
-        from .sigset import compare_signature_files
-        matrix, labels = compare_signature_files(args.signatures, ksize=args.ksize, moltype=args.moltype,
-                                                 scaled=args.scaled)
-        _notify(args, f"min similarity in matrix: {np.min(matrix):.3f}")
+        matrix, labels = self._matrix(args)
+        if args.distance_matrix:
+            matrix = 1 - matrix
+            _notify(args, f"max distance in matrix: {np.max(matrix):.3f}")
+        else:
+            _notify(args, f"min similarity in matrix: {np.min(matrix):.3f}")
         if args.output:                                                  # commands.py:253-262
             with open(args.output + ".labels.txt", "w") as fp:
                 fp.write("\n".join(labels))
@@ -144,6 +153,53 @@ class Command_B200Compare(CommandLinePlugin):
                 for i in range(len(labels)):
                     w.writerow([str(matrix[i][j]) for j in range(len(labels))])
         return 0
+
+
+def _compare_matrix(args):
+    """The matrix `sourmash compare` computes for these flags (commands.py:100-214).  Flat sketches, or --ignore-abundance:
+    parsed natively and compared in one pass (sigset.compare_signature_files).  Abundance sketches (angular similarity), the
+    containment matrices and ANI: signature objects built in one call, brought to the coarsest scaled like there, then the
+    batched functions of compare.py."""
+    from . import compare as C
+    from .sigset import SignatureSet, compare_signature_files
+    kinds = [args.containment, args.max_containment, args.avg_containment]
+    if sum(kinds) > 1:
+        print("ERROR: cannot specify more than one containment argument!", file=sys.stderr)
+        raise SystemExit(-1)
+    ss = SignatureSet.from_files(args.signatures)
+    rows = ss.select(ksize=args.ksize, moltype=args.moltype)
+    if len(rows) == 0:
+        raise ValueError("no signatures match the selection")
+    is_scaled = bool((ss.max_hash[rows] != 0).all())
+    if any(kinds) and not is_scaled:
+        print("must use scaled signatures with --containment, --max-containment, and --avg-containment", file=sys.stderr)
+        raise SystemExit(-1)
+    if args.estimate_ani and not is_scaled:
+        print("must use scaled signatures with --estimate-ani", file=sys.stderr)
+        raise SystemExit(-1)
+    keeps_abundance = bool(ss.has_abund[rows].any()) and not args.ignore_abundance
+    if not (any(kinds) or args.estimate_ani or keeps_abundance):
+        return compare_signature_files(args.signatures, ksize=args.ksize, moltype=args.moltype, scaled=args.scaled)
+    if len(set(int(x) for x in ss.ksize[rows])) != 1:
+        raise ValueError("multiple k-mer sizes loaded; please specify one with ksize")
+    sigs = ss.signatures(rows)
+    labels = [str(x) for x in sigs]
+    if is_scaled:
+        coarsest = max([int(x.minhash.scaled) for x in sigs] + [int(args.scaled or 0)])
+        down = []
+        for x in sigs:
+            if x.minhash.scaled != coarsest:
+                with x.update() as x:
+                    x.minhash = x.minhash.downsample(scaled=coarsest)
+            down.append(x)
+        sigs = down
+    if args.containment:
+        return C.compare_serial_containment(sigs, return_ani=args.estimate_ani), labels
+    if args.max_containment:
+        return C.compare_serial_max_containment(sigs, return_ani=args.estimate_ani), labels
+    if args.avg_containment:
+        return C.compare_serial_avg_containment(sigs, return_ani=args.estimate_ani), labels
+    return C.compare_all_pairs(sigs, args.ignore_abundance, return_ani=args.estimate_ani), labels
 
 
 def _load_query_and_db(args):

@@ -160,6 +160,32 @@ def test_compare_command_writes_the_same_matrix(cli):
     assert list(csv.reader(open(os.path.join(w, "ref_cmp.csv")))) == list(csv.reader(open(os.path.join(w, "b200_cmp.csv"))))
 
 
+@pytest.mark.parametrize("flags", [["--containment"], ["--max-containment"], ["--avg-containment"], ["--estimate-ani"],
+                                   ["--containment", "--estimate-ani"], ["--max-containment", "--estimate-ani"],
+                                   ["--distance-matrix"], ["--scaled", "2000"]])
+def test_compare_flags_write_the_same_matrix(cli, flags):
+    "the other matrices of `sourmash compare`: containment forms, ANI, distances, a coarser --scaled"
+    sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))[:6]
+    tag = "cmp" + "".join(flags).replace("-", "")
+    cli.together(["compare", *sigs, "-k", "21", "-o", tag + "_ref.npy", "--csv", tag + "_ref.csv", *flags],
+                 ["scripts", "b200compare", *sigs, "-k", "21", "-o", tag + "_b200.npy", "--csv", tag + "_b200.csv", *flags])
+    w = cli.work
+    a, b = np.load(os.path.join(w, tag + "_ref.npy")), np.load(os.path.join(w, tag + "_b200.npy"))
+    assert a.shape == (6, 6) and np.array_equal(a, b)
+    assert open(os.path.join(w, tag + "_ref.csv")).read() == open(os.path.join(w, tag + "_b200.csv")).read()
+
+
+@pytest.mark.parametrize("flags", [[], ["--ignore-abundance"], ["--containment"]])
+def test_compare_of_abundance_sketches(cli, flags):
+    "sketches with abundances: angular similarity unless --ignore-abundance; a flat sketch among them; containment ignores abundances"
+    sigs = [os.path.join(DATA, "track_abund", f) for f in ("47.fa.sig", "63.fa.sig")] + [os.path.join(DATA, "2.fa.sig")]
+    tag = "cmpab" + "".join(flags).replace("-", "")
+    cli.together(["compare", *sigs, "-k", "31", "-o", tag + "_ref.npy", *flags],
+                 ["scripts", "b200compare", *sigs, "-k", "31", "-o", tag + "_b200.npy", *flags])
+    a, b = np.load(os.path.join(cli.work, tag + "_ref.npy")), np.load(os.path.join(cli.work, tag + "_b200.npy"))
+    assert a.shape == (3, 3) and np.array_equal(a, b) and 0 < a[0, 1] < 1
+
+
 def _same_file(cli, a, b, min_rows):
     ta, tb = open(os.path.join(cli.work, a)).read(), open(os.path.join(cli.work, b)).read()
     assert ta.count("\n") > min_rows and ta == tb
