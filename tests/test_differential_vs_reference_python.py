@@ -287,7 +287,7 @@ print("DIFFERENTIAL OK", stats)
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("seed", [1])
 def test_batched_functions_equal_the_reference_loops_on_random_lists(tmp_path, seed):
     sys.path.insert(0, os.path.join(HERE, "host_emul"))
     try:
