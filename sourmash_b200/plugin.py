@@ -224,7 +224,9 @@ def _load_query_and_db(args):
     meta = dict(names=[db.name(i) for i in rows], md5s=[db.md5sum(i) for i in rows],
                 filenames=[db.filename(i) for i in rows], query_name=query.name, query_filename=query.filename)
     # where each row was loaded from: the `filename` column of the reference's search / gather CSVs (the match's location)
-    meta["locations"] = [args.databases[int(db.file[i])] for i in rows]
+    import os
+    where = [os.path.abspath(p) if p.endswith(".zip") else p for p in args.databases]      # a zip collection reports its absolute path
+    meta["locations"] = [where[int(db.file[i])] for i in rows]
     # the sketches as given: the reports quote their sizes and the query's md5, the comparisons run at `scaled`
     meta["query_orig"] = (len(query.minhash), query.minhash.scaled, query.md5sum())
     meta["match_orig"] = (db.n_mins[rows].astype(np.int64), db.python_scaled()[rows].astype(np.int64))

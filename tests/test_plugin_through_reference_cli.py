@@ -233,3 +233,22 @@ def test_search_of_one_multi_signature_database(cli, flags):
     if flags:
         rows = open(os.path.join(cli.work, tag + "_ref.csv")).read().count("\n") - 1
         assert 1 <= rows < 8                                            # fewer than without the ratchet
+
+
+def test_a_zip_collection_as_the_database(cli):
+    "the twelve genomes in one .zip (written by the reference's `sig cat`): every command, same files; a zip reports its absolute path"
+    sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
+    query = os.path.join(DATA, "gather", "combined.sig")
+    cli("sig", "cat", *sigs, "-o", "all12.zip")
+    cli.together(["gather", query, "all12.zip", "-k", "21", "--threshold-bp", "0", "-o", "zip_gather_ref.csv"],
+                 ["scripts", "b200gather", query, "all12.zip", "-k", "21", "--threshold-bp", "0", "-o", "zip_gather_b200.csv"],
+                 ["prefetch", query, "all12.zip", "-k", "21", "--threshold-bp", "0", "-o", "zip_prefetch_ref.csv"],
+                 ["scripts", "b200prefetch", query, "all12.zip", "-k", "21", "--threshold-bp", "0", "-o", "zip_prefetch_b200.csv"])
+    cli.together(["search", sigs[0], "all12.zip", "-k", "21", "--threshold", "0.01", "-o", "zip_search_ref.csv"],
+                 ["scripts", "b200search", sigs[0], "all12.zip", "-k", "21", "--threshold", "0.01", "-o", "zip_search_b200.csv"],
+                 ["compare", "all12.zip", "-k", "21", "-o", "zip_ref.npy"],
+                 ["scripts", "b200compare", "all12.zip", "-k", "21", "-o", "zip_b200.npy"])
+    for name in ("gather", "prefetch", "search"):
+        _same_file(cli, "zip_%s_ref.csv" % name, "zip_%s_b200.csv" % name, 5)
+    assert np.array_equal(np.load(os.path.join(cli.work, "zip_ref.npy")), np.load(os.path.join(cli.work, "zip_b200.npy")))
+    assert open(os.path.join(cli.work, "zip_ref.npy.labels.txt")).read() == open(os.path.join(cli.work, "zip_b200.npy.labels.txt")).read()
