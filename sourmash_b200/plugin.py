@@ -166,7 +166,8 @@ def _compare_matrix(args):
     if sum(kinds) > 1:
         print("ERROR: cannot specify more than one containment argument!", file=sys.stderr)
         raise SystemExit(-1)
-    ss = SignatureSet.from_files(args.signatures)
+    files, _origin = _expand(args.signatures)
+    ss = SignatureSet.from_files(files)
     rows = ss.select(ksize=args.ksize, moltype=args.moltype)
     if len(rows) == 0:
         raise ValueError("no signatures match the selection")
@@ -179,7 +180,7 @@ def _compare_matrix(args):
         raise SystemExit(-1)
     keeps_abundance = bool(ss.has_abund[rows].any()) and not args.ignore_abundance
     if not (any(kinds) or args.estimate_ani or keeps_abundance):
-        return compare_signature_files(args.signatures, ksize=args.ksize, moltype=args.moltype, scaled=args.scaled)
+        return compare_signature_files(files, ksize=args.ksize, moltype=args.moltype, scaled=args.scaled)
     if len(set(int(x) for x in ss.ksize[rows])) != 1:
         raise ValueError("multiple k-mer sizes loaded; please specify one with ksize")
     sigs = ss.signatures(rows)
@@ -202,6 +203,24 @@ def _compare_matrix(args):
     return C.compare_all_pairs(sigs, args.ignore_abundance, return_ani=args.estimate_ani), labels
 
 
+def _expand(paths):
+    """Files behind the arguments, and the argument each came from: a directory stands for the .sig / .sig.gz files below it, in
+    the reference's traversal order (traverse_find_sigs, sourmash_args.py:275-295) -- one database, many locations."""
+    import os
+    files, origin = [], []
+    for k, p in enumerate(paths):
+        if os.path.isdir(p):
+            for root, _dirs, names in os.walk(p):
+                for name in sorted(names):
+                    if name.endswith((".sig", ".sig.gz")):
+                        files.append(os.path.join(root, name))
+                        origin.append(k)
+        else:
+            files.append(p)
+            origin.append(k)
+    return files, origin
+
+
 def _load_query_and_db(args):
     from .signature import load_signatures_from_json
     from .sigset import SignatureSet
@@ -210,7 +229,11 @@ def _load_query_and_db(args):
     if len(queries) != 1:
         raise ValueError(f"need exactly one query sketch in '{args.query}' (found {len(queries)}); select with -k")
     query = queries[0]
-    db = SignatureSet.from_files(args.databases)
+    if args.scaled and int(args.scaled) > query.minhash.scaled:        # --scaled: the query itself is downsampled first, and that
+        with query.update() as query:                                  # sketch is "the query" of the reports (commands.py: gather)
+            query.minhash = query.minhash.downsample(scaled=int(args.scaled))
+    files, origin = _expand(args.databases)
+    db = SignatureSet.from_files(files)
     rows = db.select(ksize=query.minhash.ksize if query.minhash.is_dna else query.minhash.ksize * 3,
                      moltype=args.moltype)
     rows = rows[db.max_hash[rows] != 0]
@@ -225,8 +248,9 @@ def _load_query_and_db(args):
                 filenames=[db.filename(i) for i in rows], query_name=query.name, query_filename=query.filename)
     # where each row was loaded from: the `filename` column of the reference's search / gather CSVs (the match's location)
     import os
-    where = [os.path.abspath(p) if p.endswith(".zip") else p for p in args.databases]      # a zip collection reports its absolute path
+    where = [os.path.abspath(p) if p.endswith(".zip") else p for p in files]               # a zip collection reports its absolute path
     meta["locations"] = [where[int(db.file[i])] for i in rows]
+    meta["groups"] = [origin[int(db.file[i])] for i in rows]                                # the database (argument) of every row
     # the sketches as given: the reports quote their sizes and the query's md5, the comparisons run at `scaled`
     meta["query_orig"] = (len(query.minhash), query.minhash.scaled, query.md5sum())
     meta["match_orig"] = (db.n_mins[rows].astype(np.int64), db.python_scaled()[rows].astype(np.int64))
@@ -252,6 +276,7 @@ class Command_B200Gather(CommandLinePlugin):
         from .gather import gather_databases, write_gather_csv
         qmh, sset, meta = _load_query_and_db(args)
         meta.pop("match_orig")
+        meta.pop("groups")
         rows = gather_databases(qmh, sset, threshold_bp=args.threshold_bp, ignore_abundance=args.ignore_abundance,
                                 estimate_ani_ci=args.estimate_ani_ci, **meta)
         for g in rows:
@@ -283,6 +308,7 @@ class Command_B200Prefetch(CommandLinePlugin):
             open(args.output, "w").close()                  # created before the search, as in the reference (empty if it fails)
         qmh, sset, meta = _load_query_and_db(args)
         meta.pop("locations")                              # prefetch reports the filename stored in the match (match_filename)
+        meta.pop("groups")
         if qmh.track_abundance:                             # prefetch works on the flattened query (commands.py: prefetch)
             qmh = qmh.flatten()
         res = prefetch_database(qmh, sset, args.threshold_bp, estimate_ani_ci=args.estimate_ani_ci, **meta)
@@ -369,8 +395,7 @@ class Command_B200Search(CommandLinePlugin):
         meta.pop("match_orig")
         res = search_database(qmh.flatten() if qmh.track_abundance else qmh, sset, threshold=args.threshold,
                               do_containment=args.containment, do_max_containment=args.max_containment,
-                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci,
-                              groups=meta["locations"], **meta)             # one database per input file, like the reference's CLI
+                              best_only=args.best_only, estimate_ani_ci=args.estimate_ani_ci, **meta)   # `groups`: one database per argument
         return res
 
 

@@ -252,3 +252,34 @@ def test_a_zip_collection_as_the_database(cli):
         _same_file(cli, "zip_%s_ref.csv" % name, "zip_%s_b200.csv" % name, 5)
     assert np.array_equal(np.load(os.path.join(cli.work, "zip_ref.npy")), np.load(os.path.join(cli.work, "zip_b200.npy")))
     assert open(os.path.join(cli.work, "zip_ref.npy.labels.txt")).read() == open(os.path.join(cli.work, "zip_b200.npy.labels.txt")).read()
+
+
+def test_a_directory_as_the_database_and_the_scaled_option(cli):
+    """A directory (with a sub-directory) of .sig files is one database whose matches report the file they came from; --scaled
+    downsamples the query first, and the reports then quote that sketch; protein sketches."""
+    import shutil
+    sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
+    query = os.path.join(DATA, "gather", "combined.sig")
+    db = os.path.join(cli.work, "dbdir")
+    os.makedirs(os.path.join(db, "sub"))
+    for i, p in enumerate(sigs):
+        shutil.copy(p, os.path.join(db, "sub") if i % 3 == 0 else db)
+    cli.together(["gather", query, "dbdir", "-k", "21", "--threshold-bp", "0", "-o", "dir_gather_ref.csv"],
+                 ["scripts", "b200gather", query, "dbdir", "-k", "21", "--threshold-bp", "0", "-o", "dir_gather_b200.csv"],
+                 ["search", sigs[0], "dbdir", "--best-only", "-k", "21", "--threshold", "0.01", "-o", "dir_search_ref.csv"],
+                 ["scripts", "b200search", sigs[0], "dbdir", "--best-only", "-k", "21", "--threshold", "0.01", "-o", "dir_search_b200.csv"])
+    cli.together(["gather", query, *sigs, "-k", "21", "--threshold-bp", "0", "--scaled", "20000", "-o", "sc_gather_ref.csv"],
+                 ["scripts", "b200gather", query, *sigs, "-k", "21", "--threshold-bp", "0", "--scaled", "20000", "-o", "sc_gather_b200.csv"],
+                 ["compare", "dbdir", "-k", "21", "-o", "dir_ref.npy"],
+                 ["scripts", "b200compare", "dbdir", "-k", "21", "-o", "dir_b200.npy"])
+    _same_file(cli, "dir_gather_ref.csv", "dir_gather_b200.csv", 5)
+    _same_file(cli, "dir_search_ref.csv", "dir_search_b200.csv", 1)
+    _same_file(cli, "sc_gather_ref.csv", "sc_gather_b200.csv", 3)
+    assert np.array_equal(np.load(os.path.join(cli.work, "dir_ref.npy")), np.load(os.path.join(cli.work, "dir_b200.npy")))
+    prot = sorted(glob.glob(os.path.join(DATA, "prot", "protein", "*.sig")))
+    cli.together(["search", prot[0], *prot, "--protein", "--threshold", "0.0", "-o", "prot_search_ref.csv"],
+                 ["scripts", "b200search", prot[0], *prot, "--moltype", "protein", "--threshold", "0.0", "-o", "prot_search_b200.csv"],
+                 ["gather", prot[0], *prot, "--protein", "--threshold-bp", "0", "-o", "prot_gather_ref.csv"],
+                 ["scripts", "b200gather", prot[0], *prot, "--moltype", "protein", "--threshold-bp", "0", "-o", "prot_gather_b200.csv"])
+    _same_file(cli, "prot_search_ref.csv", "prot_search_b200.csv", 1)
+    _same_file(cli, "prot_gather_ref.csv", "prot_gather_b200.csv", 0)
