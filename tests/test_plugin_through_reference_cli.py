@@ -283,3 +283,18 @@ def test_a_directory_as_the_database_and_the_scaled_option(cli):
                  ["scripts", "b200gather", prot[0], *prot, "--moltype", "protein", "--threshold-bp", "0", "-o", "prot_gather_b200.csv"])
     _same_file(cli, "prot_search_ref.csv", "prot_search_b200.csv", 1)
     _same_file(cli, "prot_gather_ref.csv", "prot_gather_b200.csv", 0)
+
+
+def test_confidence_interval_columns(cli):
+    "--estimate-ani-ci: the four (gather, prefetch) / two (containment search) extra columns"
+    query = os.path.join(DATA, "gather", "combined.sig")
+    sigs = sorted(glob.glob(os.path.join(DATA, "gather", "GCF*.sig")))
+    pairs = []
+    for cmd, first, flags in (("gather", query, ["--threshold-bp", "0"]), ("prefetch", query, ["--threshold-bp", "0"]),
+                              ("search", sigs[0], ["--threshold", "0.01", "--containment"])):
+        pairs += [[cmd, first, *sigs, "-k", "21", "--estimate-ani-ci", "-o", "ci_%s_ref.csv" % cmd, *flags],
+                  ["scripts", "b200" + cmd, first, *sigs, "-k", "21", "--estimate-ani-ci", "-o", "ci_%s_b200.csv" % cmd, *flags]]
+    cli.together(*pairs)
+    for cmd in ("gather", "prefetch", "search"):
+        _same_file(cli, "ci_%s_ref.csv" % cmd, "ci_%s_b200.csv" % cmd, 5)
+        assert "ani_low" in open(os.path.join(cli.work, "ci_%s_ref.csv" % cmd)).readline()
