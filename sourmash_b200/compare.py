@@ -185,18 +185,21 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
     n = len(siglist)
     if n == 0:
         return np.ones((0, 0))
-    nums = {int(mh.num) for mh in _flat_minhashes(siglist)}
-    if len(nums) > 1 and 0 not in nums and not return_ani:
-        # num sketches of different sizes: the reference does not refuse them, and what it computes depends on which side is
-        # `self` (the union is cut at self.num, minhash.rs:596-617).  No batched form: its own loop, pair by pair through the
-        # ABI -- cells (i, j) and (j, i) both take siglist[i].similarity(siglist[j]) for i < j (compare.py:36-54)
+    try:
+        c = _collect(siglist, downsample=downsample, with_abunds=not ignore_abundance)
+    except TypeError as exc:
+        if return_ani or "incompatible num values" not in str(exc):
+            raise
+        # num sketches of different sizes (found by _collect without touching the objects one by one): the reference does
+        # not refuse them, and what it computes depends on which side is `self` (the union is cut at self.num,
+        # minhash.rs:596-617).  No batched form: its own loop, pair by pair through the ABI -- cells (i, j) and (j, i) both
+        # take siglist[i].similarity(siglist[j]) for i < j (compare.py:36-54)
         mhs = _flat_minhashes(siglist)
         out = np.ones((n, n))
         for i in range(n):
             for j in range(i + 1, n):
                 out[i][j] = out[j][i] = mhs[i].similarity(mhs[j], ignore_abundance=ignore_abundance, downsample=downsample)
         return out
-    c = _collect(siglist, downsample=downsample, with_abunds=not ignore_abundance)
     has_ab, num, scaled, sizes = c["has_abund"], c["num"], c["scaled"], c["sizes"]
     if c.get("raw") is not None:                         # different scaled values: every pair at its own max scaled
         if return_ani:
