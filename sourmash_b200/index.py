@@ -307,7 +307,11 @@ class ZipFileLinearIndex(LinearIndex):
         return len(self.manifest) if self.manifest is not None else len(self._rows)
 
     def __bool__(self):
-        "Any matching signature?  Looks at the first one only, never at len() (index/__init__.py:584-591)."
+        """Any matching signature?  Never len() (index/__init__.py:584-591).  The selected rows are known here without building
+        a single object; a subclass without them (the reference's test fakes one) is asked for its first signature."""
+        rows = getattr(self, "_rows", None)
+        if rows is not None:
+            return len(rows) > 0
         try:
             next(iter(self.signatures()))
         except StopIteration:
