@@ -134,6 +134,14 @@ for trial in range(n_trials):
              "LinearIndex.prefetch on %s" % kind, specs)
         stats["prefetch"] += 1
 
+        def best(index, query, tbp):
+            r = index.best_containment(query, threshold_bp=tbp)
+            return None if not r else (float(r.score), r.signature.name, r.location)
+        for tbp in (0, 5000):
+            same(outcome(lambda: best(ri, R[0], tbp)), outcome(lambda: best(oi, O[0], tbp)),
+                 "LinearIndex.best_containment(threshold_bp=%d) on %s" % (tbp, kind), specs)
+            stats["search"] += 1
+
         def gather_rounds(index, query):
             counter = index.counter_gather(query, 0)
             cur, out = query.minhash.flatten().to_mutable(), []
