@@ -295,7 +295,7 @@ print("DIFFERENTIAL OK", stats)
 
 
 @pytest.mark.timeout(1800)
-@pytest.mark.parametrize("seed", [1])
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("SMB_DIFF_SEEDS", "1").split(",")])   # longer campaigns by hand
 def test_batched_functions_equal_the_reference_loops_on_random_lists(tmp_path, seed):
     sys.path.insert(0, os.path.join(HERE, "host_emul"))
     try:
@@ -319,5 +319,5 @@ def test_batched_functions_equal_the_reference_loops_on_random_lists(tmp_path, s
     with open(script, "w") as fh:
         fh.write(TRIALS)
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([site, os.path.join(tmp, "reftests")]), PYTHONDONTWRITEBYTECODE="1")
-    r = subprocess.run([sys.executable, script, str(seed), "40"], capture_output=True, text=True, env=env, cwd=tmp, timeout=1500)
+    r = subprocess.run([sys.executable, script, str(seed), os.environ.get("SMB_DIFF_TRIALS", "40")], capture_output=True, text=True, env=env, cwd=tmp, timeout=int(os.environ.get("SMB_DIFF_TIMEOUT", "1500")))
     assert r.returncode == 0 and "DIFFERENTIAL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
