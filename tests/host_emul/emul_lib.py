@@ -118,7 +118,10 @@ def build(verbose=False):
 
 
 def _build_locked(verbose):
-    top = os.path.join(tempfile.gettempdir(), "smb_emul_lib")
+    # SMB_EMUL_ASAN=1: a second build with AddressSanitizer + UBSan for the host code (parsers, glue); load it with
+    # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 (tests/tools/fuzz_ingest.py does)
+    asan = os.environ.get("SMB_EMUL_ASAN") == "1"
+    top = os.path.join(tempfile.gettempdir(), "smb_emul_lib_asan" if asan else "smb_emul_lib")
     lib = os.path.join(top, "libsourmash_b200_emul.so")
     if os.path.exists(lib) and os.path.getmtime(lib) >= _newest_input():
         return lib
@@ -129,6 +132,8 @@ def _build_locked(verbose):
     shutil.copy(os.path.join(ROOT, "include", "sourmash_b200.h"), os.path.join(top, "include", "sourmash_b200.h"))
     flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-w", "-DSMB_SIMT_EMUL=1", "-include", os.path.join(HERE, "simt.h"),
              "-I", os.path.join(HERE, "mock"), "-I", "/usr/local/cuda/include", "-I", work]
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if asan else []
+    flags += san
     objs, procs = [], []
     for src in [s[:-3] + ".cpp" for s in SOURCES]:
         obj = os.path.join(work, src[:-4] + ".o")
@@ -146,7 +151,7 @@ def _build_locked(verbose):
             failed += out
     if failed:
         raise RuntimeError("emulated build failed:\n" + failed[-6000:])
-    subprocess.check_call(["g++", "-shared", "-o", lib] + objs + [mock_obj, "-lz", "-ldl", "-lpthread"])
+    subprocess.check_call(["g++", "-shared", "-o", lib] + san + objs + [mock_obj, "-lz", "-ldl", "-lpthread"])
     if verbose:
         print("built", lib)
     return lib
