@@ -121,7 +121,8 @@ def _build_locked(verbose):
     # SMB_EMUL_ASAN=1: a second build with AddressSanitizer + UBSan for the host code (parsers, glue); load it with
     # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 (tests/tools/fuzz_ingest.py does)
     asan = os.environ.get("SMB_EMUL_ASAN") == "1"
-    top = os.path.join(tempfile.gettempdir(), "smb_emul_lib_asan" if asan else "smb_emul_lib")
+    tsan = not asan and os.environ.get("SMB_EMUL_TSAN") == "1"       # ThreadSanitizer: the multi-threaded file readers
+    top = os.path.join(tempfile.gettempdir(), "smb_emul_lib_asan" if asan else "smb_emul_lib_tsan" if tsan else "smb_emul_lib")
     lib = os.path.join(top, "libsourmash_b200_emul.so")
     if os.path.exists(lib) and os.path.getmtime(lib) >= _newest_input():
         return lib
@@ -133,6 +134,8 @@ def _build_locked(verbose):
     flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-w", "-DSMB_SIMT_EMUL=1", "-include", os.path.join(HERE, "simt.h"),
              "-I", os.path.join(HERE, "mock"), "-I", "/usr/local/cuda/include", "-I", work]
     san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if asan else []
+    if tsan:
+        san = ["-fsanitize=thread", "-fno-omit-frame-pointer"]
     flags += san
     objs, procs = [], []
     for src in [s[:-3] + ".cpp" for s in SOURCES]:
