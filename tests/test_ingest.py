@@ -352,3 +352,15 @@ def test_xz_and_zstd_inputs(tmp_path):
     sigz = tmp_path / "47.fa.sig.zst"
     sigz.write_bytes(zcompress(raw))
     assert np.array_equal(SignatureSet.from_files([str(sigz)]).mins, SignatureSet.from_files([src]).mins)
+
+
+@pytest.mark.timeout(300)
+def test_malformed_inputs_give_parse_errors_not_crashes():
+    """tests/tools/fuzz_ingest.py for a few seconds with a fixed seed: mutated .sig / .zip / FASTA / FASTQ inputs, each batch
+    parsed in a child process -- an exception through the ABI is fine, a signal or a hang is not (longer runs, also under
+    AddressSanitizer: profiles/r2q_cpu_side_checks.md)."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "fuzz_ingest.py")
+    r = subprocess.run([sys.executable, tool, "8", "5"], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "no findings" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -83,6 +83,14 @@ def seeds():
     for p in zips[:6]:
         with open(p, "rb") as fh:
             out.append(("zip", ".zip", fh.read()))
+    import io
+    import zipfile
+    for method in (zipfile.ZIP_STORED, zipfile.ZIP_DEFLATED):       # collections made here (the only zip seeds where the
+        buf = io.BytesIO()                                          # reference checkout is absent): no manifest, two members
+        with zipfile.ZipFile(buf, "w", method) as z:
+            for name in ("2.fa.sig", "47.fa.sig"):
+                z.write(os.path.join(GOLDEN, name), "signatures/" + name)
+        out.append(("zip", ".zip", buf.getvalue()))
     fa = b">r1 first\nACGTACGTNNACGT\nACGT\n>r2\n\nGGGG\r\n>r3\n" + b"ACGT" * 300 + b"\n"
     fq = b"@r1 x\nACGTN\n+\nIIIII\n@r2\nAC\nGT\n+r2\nII\nII\n@r3\nTTTT\n+\n@@@@\n"
     out += [("fa", ".fa", fa), ("fa", ".fa.gz", gzip.compress(fa)), ("fa", ".fq", fq), ("fa", ".fq.gz", gzip.compress(fq))]
