@@ -136,8 +136,23 @@ def _collect_per_object(objs, *, downsample, need_scaled, with_abunds):
             "orig_sizes": orig_sizes, "orig_scaled": orig_scaled, "raw": raw}
 
 
-_MIXED_ANI = ("ANI matrices need one scaled value: downsample the sketches to a common scaled first, as `sourmash compare` "
-              "does before it calls compare_all_pairs (reference commands.py:167-194)")
+def _scaled_groups(c):
+    """Sketches with different scaled values: one group per distinct value S -- the sketches with scaled <= S, cut at S
+    (what downsample(scaled=S) keeps of a sorted row is a prefix).  Yields (S, rows of the group, their lengths at S,
+    hashes, offsets, mask of the pairs whose coarser member has scaled S: the pairs the reference compares at S)."""
+    h, off, _ab = c["raw"]
+    scaleds = np.asarray(c["orig_scaled"]).astype(np.int64)
+    for S in sorted(set(scaleds.tolist())):
+        idx = np.nonzero(scaleds <= S)[0]
+        if len(idx) < 2:
+            continue
+        cut = np.uint64(B.max_hash_for_scaled(S))
+        lens = [int(np.searchsorted(h[int(off[i]):int(off[i + 1])], cut, side="right")) for i in idx]
+        sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+        sub_off[1:] = np.cumsum(lens)
+        sub_h = np.concatenate([h[int(off[i]):int(off[i]) + m] for i, m in zip(idx, lens)])
+        here = (scaleds[idx][:, None] == S) | (scaleds[idx][None, :] == S)      # pairs decided at this scaled
+        yield S, idx, lens, sub_h, sub_off, here
 
 
 def _mixed_pair_tables(c, *, jaccard=False, angular=False):
@@ -152,16 +167,7 @@ def _mixed_pair_tables(c, *, jaccard=False, angular=False):
     n = len(scaleds)
     out = {"common": np.zeros((n, n), dtype=np.uint32), "jaccard": np.ones((n, n)) if jaccard else None,
            "angular": np.ones((n, n)) if angular else None}
-    for S in sorted(set(scaleds.tolist())):
-        idx = np.nonzero(scaleds <= S)[0]
-        if len(idx) < 2:
-            continue
-        cut = np.uint64(B.max_hash_for_scaled(S))
-        lens = [int(np.searchsorted(h[int(off[i]):int(off[i + 1])], cut, side="right")) for i in idx]
-        sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
-        sub_off[1:] = np.cumsum(lens)
-        sub_h = np.concatenate([h[int(off[i]):int(off[i]) + m] for i, m in zip(idx, lens)])
-        here = (scaleds[idx][:, None] == S) | (scaleds[idx][None, :] == S)      # pairs decided at this scaled
+    for S, idx, lens, sub_h, sub_off, here in _scaled_groups(c):
         cells = np.ix_(idx, idx)
 
         def put(name, block):
@@ -203,7 +209,12 @@ def compare_all_pairs(siglist, ignore_abundance, *, downsample=False, n_jobs=Non
     has_ab, num, scaled, sizes = c["has_abund"], c["num"], c["scaled"], c["sizes"]
     if c.get("raw") is not None:                         # different scaled values: every pair at its own max scaled
         if return_ani:
-            raise ValueError(_MIXED_ANI)
+            ani, untrustworthy, false_neg = _mixed_ani(c, "jaccard")
+            if untrustworthy:
+                notify(_JACCARD_WARNING)
+            if false_neg:
+                notify(_FALSE_NEG_WARNING)
+            return ani
         want_ang = not ignore_abundance and bool(has_ab.any())
         t = _mixed_pair_tables(c, jaccard=True, angular=want_ang)
         out = np.where(has_ab[:, None] & has_ab[None, :], t["angular"], t["jaccard"]) if want_ang else t["jaccard"]
@@ -261,7 +272,11 @@ def _clamp01(m):
     return np.where(m <= 0, 0.0, m)
 
 
-def _containment_parts(siglist, downsample, return_ani=False):
+class _MixedAni(Exception):
+    "carries the finished ANI matrix of a list with different scaled values out of _containment_parts"
+
+
+def _containment_parts(siglist, downsample, return_ani=False, kind="containment"):
     "(common counts as float64, sizes, scaled, ksize, size_is_accurate flags or None)"
     if not len(siglist):
         return None, np.zeros(0, np.int64), 0, 0, None
@@ -269,9 +284,12 @@ def _containment_parts(siglist, downsample, return_ani=False):
     if c.get("raw") is not None:
         # different scaled values: counts per pair at max(scaled_i, scaled_j) (count_common(other, downsample=True)),
         # while contained_by / max_containment keep len(self) and self.scaled of the sketches AS GIVEN in the
-        # denominator (minhash.py:827-841,889-905)
+        # denominator (minhash.py:827-841,889-905); the ANI forms take everything from the downsampled pair (_mixed_ani)
         if return_ani:
-            raise ValueError(_MIXED_ANI)
+            m, _untrustworthy, false_neg = _mixed_ani(c, kind)
+            if false_neg:
+                notify(_FALSE_NEG_WARNING)
+            raise _MixedAni(m)
         common = _mixed_pair_tables(c)["common"].astype(np.float64)
         return common, c["orig_sizes"], np.asarray(c["orig_scaled"]).astype(np.int64), c["ksize"], None
     accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"]) if return_ani else None
@@ -283,30 +301,93 @@ def _containment_parts(siglist, downsample, return_ani=False):
 def compare_serial_containment(siglist, *, downsample=False, return_ani=False):
     """containments[i][j] = siglist[j].contained_by(siglist[i]) (compare.py:67-106); with
     ``return_ani`` the containment ANI of j in i (0.0 where it cannot be trusted)."""
-    common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani)
+    try:
+        common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani)
+    except _MixedAni as done:
+        return done.args[0]
     n = len(sizes)
     if n == 0:
         return np.ones((0, 0))
+    m, false_neg = _containment_block(common, sizes, scaled, ksize, accurate, return_ani)
+    if false_neg:
+        notify(_FALSE_NEG_WARNING)
+    np.fill_diagonal(m, 1.0)
+    return m
+
+
+def _containment_block(common, sizes, scaled, ksize, accurate, return_ani, cells=None):
+    "containment (or its ANI) of column sketch j in row sketch i from the common counts; (matrix, false-negative flag)"
     denom = sizes.astype(np.float64) * _bias_factors(sizes, scaled)       # per column j
     with np.errstate(divide="ignore", invalid="ignore"):
         m = common / denom[np.newaxis, :]
     m = _clamp01(m)
     m[:, sizes == 0] = 0.0
-    if return_ani:
-        ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
-        p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize),
-                                 (sizes * scaled).astype(np.float64)[np.newaxis, :], ksize, scaled)
-        np.fill_diagonal(p, 0.0)
-        if (p > 1e-3).any():
-            notify(_FALSE_NEG_WARNING)
-        m = ani
-    np.fill_diagonal(m, 1.0)
-    return m
+    if not return_ani:
+        return m, False
+    ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
+    p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize),
+                             (sizes * scaled).astype(np.float64)[np.newaxis, :], ksize, scaled)
+    np.fill_diagonal(p, 0.0)
+    return ani, bool(((p > 1e-3) if cells is None else (p > 1e-3) & cells).any())
+
+
+def _max_containment_block(common, sizes, scaled, ksize, accurate, return_ani, cells=None):
+    "the same for max_containment with ONE scaled value: common / (min(|A|, |B|) * bias(min))"
+    mins = np.minimum(sizes[:, None], sizes[None, :])
+    flat = np.unique(mins.ravel())
+    lut = dict(zip(flat.tolist(), _bias_factors(flat, scaled).tolist()))
+    denom = mins.astype(np.float64) * np.vectorize(lut.get, otypes=[np.float64])(mins)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = common / denom
+    m = _clamp01(m)
+    m[mins == 0] = 0.0
+    if not return_ani:
+        return m, False
+    ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
+    p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize), (mins * scaled).astype(np.float64), ksize, scaled)
+    np.fill_diagonal(p, 0.0)
+    return ani, bool(((p > 1e-3) if cells is None else (p > 1e-3) & cells).any())
+
+
+def _mixed_ani(c, kind):
+    """ANI matrices of sketches with different scaled values (``downsample=True``): jaccard_ani / containment_ani /
+    max_containment_ani downsample BOTH sketches of a pair to max(scaled_i, scaled_j) and take every quantity -- the
+    similarity, the sketch sizes, the scaled of the formulas -- from the downsampled pair (minhash.py:749-785,843-945);
+    only size_is_accurate() is asked of the sketches as given (of the downsampled ones by avg_containment_ani, which the
+    reference computes through FracMinHashComparison).  One batched call per distinct scaled value, the formulas
+    of the one-scaled case on it, and every pair keeps the cell of its own scaled.
+    Returns (matrix with a unit diagonal, jaccard-untrustworthy flag, false-negative flag)."""
+    n = len(c["orig_scaled"])
+    accurate = _sizes_accurate_arrays(c["orig_sizes"], c["orig_scaled"])
+    out, untrustworthy, false_neg = np.ones((n, n)), False, False
+    for S, idx, lens, sub_h, sub_off, here in _scaled_groups(c):
+        sset = B.SketchSet.from_host(sub_h, sub_off)
+        sizes, acc = np.asarray(lens, dtype=np.int64), accurate[idx]
+        if kind == "jaccard":
+            block, u, f = DU.jaccard_to_ani_matrix(B.compare_jaccard(sset), sizes, c["ksize"], S, size_accurate=acc, cells=here)
+            untrustworthy |= u
+        elif kind == "avg_containment":                     # mean of the two directed ANIs; accuracy of the downsampled pair
+            acc = _sizes_accurate_arrays(sizes, np.full(len(sizes), S, dtype=np.int64))
+            block, f = _containment_block(B.pairwise_common(sset).astype(np.float64), sizes, S, c["ksize"], acc, True, cells=here)
+            block = np.where(acc[:, None] & acc[None, :], (block + block.T) / 2, 0.0)
+        else:
+            fn = _containment_block if kind == "containment" else _max_containment_block
+            block, f = fn(B.pairwise_common(sset).astype(np.float64), sizes, S, c["ksize"], acc, True, cells=here)
+        false_neg |= f
+        cells = np.ix_(idx, idx)
+        full = out[cells]
+        full[here] = block[here]
+        out[cells] = full
+    np.fill_diagonal(out, 1.0)
+    return out, untrustworthy, false_neg
 
 
 def compare_serial_max_containment(siglist, *, downsample=False, return_ani=False):
     """max_containment matrix (compare.py:109-147): common / (min(|A|,|B|) * bias(min))."""
-    common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani)
+    try:
+        common, sizes, scaled, ksize, accurate = _containment_parts(siglist, downsample, return_ani, kind="max_containment")
+    except _MixedAni as done:
+        return done.args[0]
     n = len(sizes)
     if n == 0:
         return np.ones((0, 0))
@@ -316,22 +397,14 @@ def compare_serial_max_containment(siglist, *, downsample=False, return_ani=Fals
         # with the HIGHER index (compare.py:131-140), mirrored into (j, i)
         hi = np.maximum(np.arange(n)[:, None], np.arange(n)[None, :])
         denom = mins.astype(np.float64) * _bias_factors(mins, np.asarray(scaled)[hi])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            m = common / denom
+        m = _clamp01(m)
+        m[mins == 0] = 0.0
     else:
-        flat = np.unique(mins.ravel())
-        lut = dict(zip(flat.tolist(), _bias_factors(flat, scaled).tolist()))
-        denom = mins.astype(np.float64) * np.vectorize(lut.get, otypes=[np.float64])(mins)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        m = common / denom
-    m = _clamp01(m)
-    m[mins == 0] = 0.0
-    if return_ani:
-        ani = DU.containment_to_ani_matrix(m, ksize, size_accurate_rows=accurate, size_accurate_cols=accurate)
-        p = _p_nothing_in_common(1.0 - DU.containment_to_ani_matrix(m, ksize), (mins * scaled).astype(np.float64),
-                                 ksize, scaled)
-        np.fill_diagonal(p, 0.0)
-        if (p > 1e-3).any():
+        m, false_neg = _max_containment_block(common, sizes, scaled, ksize, accurate, return_ani)
+        if false_neg:
             notify(_FALSE_NEG_WARNING)
-        m = ani
     np.fill_diagonal(m, 1.0)
     return m
 
@@ -339,11 +412,20 @@ def compare_serial_max_containment(siglist, *, downsample=False, return_ani=Fals
 def compare_serial_avg_containment(siglist, *, downsample=False, return_ani=False):
     """avg_containment matrix (compare.py:150-187): mean of the two directed containments; with
     ``return_ani`` the mean of the two containment ANIs, 0.0 if either cannot be trusted."""
-    c = compare_serial_containment(siglist, downsample=downsample, return_ani=return_ani)
-    m = (c + c.T) / 2
+    accurate = None
     if return_ani and len(siglist):
         c0 = _collect(siglist, downsample=downsample, need_scaled=True)
+        if c0.get("raw") is not None:
+            # different scaled values: the reference goes through FracMinHashComparison here (compare.py:150-187), which
+            # downsamples the pair first and asks size_is_accurate() of the DOWNSAMPLED sketches (sketchcomparison.py:99-236)
+            m, _untrustworthy, false_neg = _mixed_ani(c0, "avg_containment")
+            if false_neg:
+                notify(_FALSE_NEG_WARNING)
+            return m
         accurate = _sizes_accurate_arrays(c0["orig_sizes"], c0["orig_scaled"])
+    c = compare_serial_containment(siglist, downsample=downsample, return_ani=return_ani)
+    m = (c + c.T) / 2
+    if accurate is not None:
         m = np.where(accurate[:, None] & accurate[None, :], m, 0.0)
     np.fill_diagonal(m, 1.0)
     return m

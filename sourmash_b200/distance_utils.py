@@ -251,11 +251,12 @@ def _pow(values, exponent):
 
 
 def jaccard_to_ani_matrix(jaccard, sizes, ksize, scaled, *, err_threshold=1e-4, prob_threshold=1e-3,
-                          size_accurate=None):
+                          size_accurate=None, cells=None):
     """ANI for every pair of an N x N Jaccard matrix (what ``compare --ani`` reports:
     compare.py:36-54 -> MinHash.jaccard_ani).  ``sizes[i]`` = number of hashes of sketch i.
     Untrustworthy estimates (error bound above err_threshold, or a sketch whose size estimate
-    is inaccurate) become 0.0 like in compare_serial; the diagonal is 1.0.
+    is inaccurate) become 0.0 like in compare_serial; the diagonal is 1.0.  ``cells`` (bool N x N) limits the two warning
+    flags to those pairs (a caller that keeps only part of the matrix).
     Returns (ani, jaccard_ani_untrustworthy, potential_false_negatives)."""
     J = np.asarray(jaccard, dtype=np.float64)
     n = J.shape[0]
@@ -278,6 +279,8 @@ def jaccard_to_ani_matrix(jaccard, sizes, ksize, scaled, *, err_threshold=1e-4, 
         bad = bad | ~(acc[:, None] & acc[None, :])
     ani = np.where(bad, 0.0, 1.0 - r)
     off = ~np.eye(n, dtype=bool)
+    if cells is not None:
+        off &= np.asarray(cells, dtype=bool)
     untrustworthy = bool((err > err_threshold)[off].any())
     false_neg = bool((p_nothing > prob_threshold)[off].any())
     np.fill_diagonal(ani, 1.0)

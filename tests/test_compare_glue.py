@@ -114,8 +114,21 @@ def test_compare_all_pairs_glue(cpu_kernels):
             assert got[i, j] == want, (i, j, sc)
     assert any(got[i, j] != orc.jaccard(rows_at[1000][i], rows_at[1000][j])            # ... and that is observable
                for i in range(len(sigs)) for j in range(i) if max(sigs[i].minhash.scaled, sigs[j].minhash.scaled) == 200)
-    with pytest.raises(ValueError, match="need one scaled value"):
-        C.compare_all_pairs(sigs, True, downsample=True, return_ani=True)
+    # ANI of such a list: every pair as jaccard_ani(other, downsample=True) sees it -- both sketches cut at the pair's max
+    # scaled, size_is_accurate() of the sketches as given (minhash.py:749-785) -- i.e. the one-scaled path on that pair
+    ani = C.compare_all_pairs(sigs, True, downsample=True, return_ani=True)
+    acc = C._sizes_accurate_arrays(np.array([len(s.minhash) for s in sigs]), np.array([s.minhash.scaled for s in sigs]))
+    seen = set()
+    for i in range(len(sigs)):
+        for j in range(i + 1, len(sigs)):
+            sc = max(sigs[i].minhash.scaled, sigs[j].minhash.scaled)
+            pair = [smb.SourmashSignature(s.minhash.downsample(scaled=sc), name=s.name) for s in (sigs[i], sigs[j])]
+            c2 = C._collect(pair, downsample=False)
+            want, _u, _f = C.DU.jaccard_to_ani_matrix(orc.compare_all_pairs(c2["hashes"], c2["offsets"]), c2["sizes"], 31, sc,
+                                                      size_accurate=acc[[i, j]])
+            assert ani[i, j] == ani[j, i] == want[0, 1], (i, j, sc)
+            seen.add((sc, bool(want[0, 1] > 0)))
+    assert {sc for sc, _ in seen} == {200, 1000} and any(pos for _, pos in seen)
     # one scaled value (what `sourmash compare` hands over after its own downsampling): one batched call
     same = [smb.SourmashSignature(s.minhash.downsample(scaled=1000), name=s.name) for s in sigs]
     h, off = orc.to_csr(_rows(sigs, 1000))
@@ -188,8 +201,26 @@ def test_containment_and_ani_glue(cpu_kernels):
             hi = max(i, j)                                                   # siglist[hi].max_containment(siglist[lo], True)
             assert mixed["mc"][i, j] == cont(c, min(size[i], size[j]), sc_of[hi]), (i, j)
             assert mixed["ac"][i, j] == (cont(c, size[j], sc_of[j]) + cont(c, size[i], sc_of[i])) / 2
-    with pytest.raises(ValueError, match="need one scaled value"):
-        C.compare_serial_containment(sigs, downsample=True, return_ani=True)
+    # the ANI forms take everything from the pair downsampled to its max scaled (minhash.py:843-945): the one-scaled
+    # functions on that pair, except that containment_ani / max_containment_ani ask size_is_accurate() of the sketches as
+    # given and the avg form (FracMinHashComparison) of the downsampled ones
+    acc = C._sizes_accurate_arrays(np.array(size), np.array(sc_of))
+    got_ani = {name: fn(sigs, downsample=True, return_ani=True) for name, fn in (("c", C.compare_serial_containment),
+                                                                                  ("mc", C.compare_serial_max_containment),
+                                                                                  ("ac", C.compare_serial_avg_containment))}
+    for i in range(n):
+        for j in range(i + 1, n):
+            sc = max(sc_of[i], sc_of[j])
+            pair = [smb.SourmashSignature(s.minhash.downsample(scaled=sc), name=s.name) for s in (sigs[i], sigs[j])]
+            sizes2 = np.array([len(p.minhash) for p in pair], dtype=np.int64)
+            common2 = np.array([[sizes2[0], 0], [0, sizes2[1]]], dtype=np.float64)
+            common2[0, 1] = common2[1, 0] = orc.count_common(rows_at[sc][i], rows_at[sc][j])
+            want_c, _ = C._containment_block(common2, sizes2, sc, 31, acc[[i, j]], True)
+            want_mc, _ = C._max_containment_block(common2, sizes2, sc, 31, acc[[i, j]], True)
+            assert (got_ani["c"][i, j], got_ani["c"][j, i]) == (want_c[0, 1], want_c[1, 0]), (i, j)
+            assert got_ani["mc"][i, j] == got_ani["mc"][j, i] == want_mc[0, 1], (i, j)
+            assert got_ani["ac"][i, j] == got_ani["ac"][j, i] == C.compare_serial_avg_containment(pair, return_ani=True)[0, 1]
+    assert (got_ani["c"] > 0).sum() > n and np.array_equal(np.diagonal(got_ani["c"]), np.ones(n))
     # from here on: one scaled value, as `sourmash compare` hands the list over after its own downsampling
     given = sigs
     sigs = [smb.SourmashSignature(s.minhash.downsample(scaled=1000), name=s.name) for s in given]

@@ -111,13 +111,15 @@ for trial in range(n_trials):
         same(outcome(lambda: getattr(ref_compare, name)(R, downsample=down)),
              outcome(lambda: getattr(our_compare, name)(O, downsample=down)), "%s on %s" % (name, kind), specs)
         stats["containment"] += 1
-        if kind == "scaled":
-            same(outcome(lambda: getattr(ref_compare, name)(R, return_ani=True)),
-                 outcome(lambda: getattr(our_compare, name)(O, return_ani=True)), "%s(return_ani) on %s" % (name, kind), specs)
+        if kind in ("scaled", "mixed_scaled"):
+            same(outcome(lambda: getattr(ref_compare, name)(R, downsample=down, return_ani=True)),
+                 outcome(lambda: getattr(our_compare, name)(O, downsample=down, return_ani=True)),
+                 "%s(return_ani) on %s" % (name, kind), specs)
             stats["ani"] += 1
-    if kind == "scaled":
-        same(outcome(lambda: ref_compare.compare_all_pairs(R, True, return_ani=True, n_jobs=None)),
-             outcome(lambda: our_compare.compare_all_pairs(O, True, return_ani=True, n_jobs=None)), "compare_all_pairs(return_ani)", specs)
+    if kind in ("scaled", "mixed_scaled"):
+        same(outcome(lambda: ref_compare.compare_all_pairs(R, True, downsample=down, return_ani=True, n_jobs=None)),
+             outcome(lambda: our_compare.compare_all_pairs(O, True, downsample=down, return_ani=True, n_jobs=None)),
+             "compare_all_pairs(return_ani) on %s" % kind, specs)
         stats["ani"] += 1
     # one-vs-many: the first signature against an index of the rest
     if kind in ("scaled", "mixed_scaled") and len(specs[0]["hashes"]):
