@@ -414,7 +414,7 @@ def compare_serial_avg_containment(siglist, *, downsample=False, return_ani=Fals
     ``return_ani`` the mean of the two containment ANIs, 0.0 if either cannot be trusted."""
     accurate = None
     if return_ani and len(siglist):
-        c0 = _collect(siglist, downsample=downsample, need_scaled=True)
+        c0 = _collect(siglist, downsample=True, need_scaled=True)           # (the ANI form downsamples whatever the flag says)
         if c0.get("raw") is not None:
             # different scaled values: the reference goes through FracMinHashComparison here (compare.py:150-187), which
             # downsamples the pair first and asks size_is_accurate() of the DOWNSAMPLED sketches (sketchcomparison.py:99-236)

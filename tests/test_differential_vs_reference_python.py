@@ -116,6 +116,11 @@ for trial in range(n_trials):
                  outcome(lambda: getattr(our_compare, name)(O, downsample=down, return_ani=True)),
                  "%s(return_ani) on %s" % (name, kind), specs)
             stats["ani"] += 1
+    if kind == "mixed_scaled":             # without the flag the avg ANI form downsamples anyway (FracMinHashComparison)
+        for name in ("compare_serial_avg_containment",):
+            same(outcome(lambda: getattr(ref_compare, name)(R, return_ani=True)),
+                 outcome(lambda: getattr(our_compare, name)(O, return_ani=True)), "%s(return_ani, no downsample) on %s" % (name, kind), specs)
+            stats["ani"] += 1
     if kind in ("scaled", "mixed_scaled"):
         same(outcome(lambda: ref_compare.compare_all_pairs(R, True, downsample=down, return_ani=True, n_jobs=None)),
              outcome(lambda: our_compare.compare_all_pairs(O, True, downsample=down, return_ani=True, n_jobs=None)),
